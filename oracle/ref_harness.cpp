@@ -1,0 +1,343 @@
+// ref_harness: drives the UNMODIFIED reference CPU SDK (PhysX 5.6.1, built by oracle/ref_build.mk)
+// through its public API on a scene file (oracle/scene_format.h).  Test infrastructure only:
+// it is the parity oracle ("whole-scene oracle") and the CPU baseline
+// (eABP broadphase, CPU TGS/PGS solver, PxDefaultCpuDispatcher with T threads).
+//
+//   ref_harness run <scene.bin> --steps N [--threads T] [--states out.bin] [--bp out.bin]
+//                   [--contacts out.bin] [--warmup W] [--quiet]
+//
+// Outputs
+//   --states   float32 [N+1][nDyn][13]  (pos3 quat4 linVel3 angVel3; row 0 = initial state)
+//   --bp       per step: u32 nActors, float bounds[nActors][6] (tight world AABBs the step's
+//              broadphase sees), u32 nCreated, u32 nDeleted, then (u32 a,u32 b) pairs (a<b), both
+//              lists sorted.  Pairs come from a stage-level PxBroadPhase(eABP)+PxAABBManager fed
+//              those bounds with distance = contactOffset  (physx/include/PxBroadPhase.h:492-796).
+//   --contacts per step: u32 nPairs, then per pair: u32 actor0, u32 actor1, u32 nContacts and
+//              nContacts x {pos3, normal3, separation, impulse3}  (PxContactPair::extractContacts)
+//   --order    per step: u32 nEdges, then (u32 actor0, u32 actor1) in the order the island manager
+//              feeds contact managers to the solver (IG::Island edge lists walked exactly like
+//              DynamicsTGSContext::prepareBodiesAndConstraints, DyTGSDynamics.cpp:822-905), dumped
+//              AFTER the step (the lists the step used, plus edges removed/added at its very end).
+//   stdout     one JSON line with timing.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include "PxPhysicsAPI.h"
+// Internal headers are included (with access opened up) ONLY so that --order can dump the order in which
+// the reference's island manager hands contact managers to the solver; nothing internal is modified.
+#define private public
+#define protected public
+#include "NpScene.h"
+#include "ScScene.h"
+#include "PxsSimpleIslandManager.h"
+#include "PxsIslandSim.h"
+#include "PxsContactManager.h"
+#undef private
+#undef protected
+#include "scene_format.h"
+
+using namespace physx;
+
+static PxDefaultAllocator gAllocator;
+static PxDefaultErrorCallback gErrorCallback;
+
+struct ContactDump {
+  struct Pair { uint32_t a0, a1; std::vector<float> data; uint32_t n; };
+  std::vector<Pair> pairs;
+};
+static ContactDump gContacts;
+
+class EventCb : public PxSimulationEventCallback {
+public:
+  void onConstraintBreak(PxConstraintInfo*, PxU32) override {}
+  void onWake(PxActor**, PxU32) override {}
+  void onSleep(PxActor**, PxU32) override {}
+  void onTrigger(PxTriggerPair*, PxU32) override {}
+  void onAdvance(const PxRigidBody* const*, const PxTransform*, const PxU32) override {}
+  void onContact(const PxContactPairHeader& hdr, const PxContactPair* pairs, PxU32 nbPairs) override {
+    for (PxU32 i = 0; i < nbPairs; i++) {
+      const PxContactPair& cp = pairs[i];
+      if (cp.flags & (PxContactPairFlag::eREMOVED_SHAPE_0 | PxContactPairFlag::eREMOVED_SHAPE_1)) continue;
+      PxContactPairPoint pts[64];
+      PxU32 n = cp.extractContacts(pts, 64);
+      ContactDump::Pair p;
+      p.a0 = uint32_t(size_t(hdr.actors[0]->userData));
+      p.a1 = uint32_t(size_t(hdr.actors[1]->userData));
+      p.n = n;
+      for (PxU32 k = 0; k < n; k++) {
+        const float rec[10] = {pts[k].position.x, pts[k].position.y, pts[k].position.z,
+                               pts[k].normal.x, pts[k].normal.y, pts[k].normal.z, pts[k].separation,
+                               pts[k].impulse.x, pts[k].impulse.y, pts[k].impulse.z};
+        p.data.insert(p.data.end(), rec, rec + 10);
+      }
+      gContacts.pairs.push_back(p);
+    }
+  }
+};
+
+static bool gWantContacts = false;
+static PxFilterFlags filterShader(PxFilterObjectAttributes a0, PxFilterData, PxFilterObjectAttributes a1, PxFilterData,
+                                  PxPairFlags& pairFlags, const void* cb, PxU32) {
+  PX_UNUSED(a0); PX_UNUSED(a1);
+  pairFlags = PxPairFlag::eCONTACT_DEFAULT;
+  if (cb && *reinterpret_cast<const int*>(cb))
+    pairFlags |= PxPairFlag::eNOTIFY_TOUCH_FOUND | PxPairFlag::eNOTIFY_TOUCH_PERSISTS | PxPairFlag::eNOTIFY_CONTACT_POINTS;
+  return PxFilterFlag::eDEFAULT;
+}
+
+static std::vector<uint8_t> readFile(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { fprintf(stderr, "cannot open %s\n", path); exit(2); }
+  fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+  std::vector<uint8_t> b(n);
+  if (fread(b.data(), 1, n, f) != size_t(n)) { fprintf(stderr, "short read\n"); exit(2); }
+  fclose(f);
+  return b;
+}
+
+struct Hull { std::vector<PxVec3> verts; PxConvexMesh* mesh = nullptr; };
+
+int main(int argc, char** argv) {
+  if (argc < 3 || strcmp(argv[1], "run") != 0) {
+    fprintf(stderr, "usage: ref_harness run <scene.bin> --steps N [--threads T] [--states f] [--bp f] [--contacts f] [--warmup W] [--hulls f]\n");
+    return 2;
+  }
+  const char* scenePath = argv[2];
+  int steps = 100, threads = 1, warmup = 0;
+  const char *statesPath = nullptr, *bpPath = nullptr, *contactsPath = nullptr, *hullsPath = nullptr, *orderPath = nullptr;
+  for (int i = 3; i < argc; i++) {
+    std::string a = argv[i];
+    if (a == "--steps") steps = atoi(argv[++i]);
+    else if (a == "--threads") threads = atoi(argv[++i]);
+    else if (a == "--warmup") warmup = atoi(argv[++i]);
+    else if (a == "--states") statesPath = argv[++i];
+    else if (a == "--bp") bpPath = argv[++i];
+    else if (a == "--contacts") contactsPath = argv[++i];
+    else if (a == "--hulls") hullsPath = argv[++i];
+    else if (a == "--order") orderPath = argv[++i];
+  }
+  gWantContacts = contactsPath != nullptr;
+  static int wantContactsFlag; wantContactsFlag = gWantContacts ? 1 : 0;
+
+  std::vector<uint8_t> buf = readFile(scenePath);
+  const PxbSceneHeader& H = *reinterpret_cast<const PxbSceneHeader*>(buf.data());
+  if (H.magic != PXB_SCENE_MAGIC) { fprintf(stderr, "bad magic\n"); return 2; }
+  const PxbActorRec* recs = reinterpret_cast<const PxbActorRec*>(buf.data() + sizeof(PxbSceneHeader));
+  const uint8_t* hp = reinterpret_cast<const uint8_t*>(recs + H.nActors);
+
+  PxFoundation* foundation = PxCreateFoundation(PX_PHYSICS_VERSION, gAllocator, gErrorCallback);
+  PxTolerancesScale scale; scale.length = H.toleranceLength; scale.speed = 10.0f * H.toleranceLength;
+  PxPhysics* physics = PxCreatePhysics(PX_PHYSICS_VERSION, *foundation, scale, false, nullptr);
+
+  std::vector<Hull> hulls(H.nHulls);
+  for (uint32_t h = 0; h < H.nHulls; h++) {
+    uint32_t nv; memcpy(&nv, hp, 4); hp += 4;
+    hulls[h].verts.resize(nv);
+    memcpy(hulls[h].verts.data(), hp, nv * 12); hp += nv * 12;
+    PxConvexMeshDesc d;
+    d.points.count = nv; d.points.stride = sizeof(PxVec3); d.points.data = hulls[h].verts.data();
+    d.flags = PxConvexFlag::eCOMPUTE_CONVEX;
+    d.vertexLimit = 64;
+    PxCookingParams cp(scale); cp.buildGPUData = true;
+    hulls[h].mesh = PxCreateConvexMesh(cp, d, physics->getPhysicsInsertionCallback());
+    if (!hulls[h].mesh) { fprintf(stderr, "hull cook failed\n"); return 3; }
+  }
+  if (hullsPath) {
+    // cooked hull dump: per hull: u32 nVerts, u32 nPolys, verts xyz, per poly: plane(nx ny nz d), u32 nIdx, u32 idx[nIdx]
+    FILE* f = fopen(hullsPath, "wb");
+    for (auto& h : hulls) {
+      uint32_t nv = h.mesh->getNbVertices(), np = h.mesh->getNbPolygons();
+      fwrite(&nv, 4, 1, f); fwrite(&np, 4, 1, f);
+      fwrite(h.mesh->getVertices(), 12, nv, f);
+      const PxU8* ib = h.mesh->getIndexBuffer();
+      for (uint32_t p = 0; p < np; p++) {
+        PxHullPolygon poly; h.mesh->getPolygonData(p, poly);
+        fwrite(poly.mPlane, 4, 4, f);
+        uint32_t n = poly.mNbVerts; fwrite(&n, 4, 1, f);
+        for (uint32_t k = 0; k < n; k++) { uint32_t v = ib[poly.mIndexBase + k]; fwrite(&v, 4, 1, f); }
+      }
+    }
+    fclose(f);
+  }
+
+  PxSceneDesc sd(scale);
+  sd.gravity = PxVec3(H.gravity[0], H.gravity[1], H.gravity[2]);
+  PxDefaultCpuDispatcher* dispatcher = PxDefaultCpuDispatcherCreate(threads);
+  sd.cpuDispatcher = dispatcher;
+  sd.filterShader = filterShader;
+  sd.filterShaderData = &wantContactsFlag;
+  sd.filterShaderDataSize = sizeof(int);
+  sd.broadPhaseType = PxBroadPhaseType::eABP;
+  sd.solverType = H.solverType == PXB_SOLVER_TGS ? PxSolverType::eTGS : PxSolverType::ePGS;
+  sd.flags |= PxSceneFlag::eENABLE_PCM;
+  sd.bounceThresholdVelocity = H.bounceThreshold;
+  sd.frictionOffsetThreshold = H.frictionOffsetThreshold;
+  sd.frictionCorrelationDistance = H.frictionCorrelationDistance;
+  EventCb cb;
+  if (gWantContacts) sd.simulationEventCallback = &cb;
+  PxScene* scene = physics->createScene(sd);
+  PxMaterial* mat = physics->createMaterial(H.staticFriction, H.dynamicFriction, H.restitution);
+
+  std::vector<PxRigidActor*> actors(H.nActors);
+  std::vector<PxRigidDynamic*> dyn;
+  std::vector<PxShape*> shapes(H.nActors);
+  for (uint32_t i = 0; i < H.nActors; i++) {
+    const PxbActorRec& r = recs[i];
+    PxTransform pose(PxVec3(r.pos[0], r.pos[1], r.pos[2]), PxQuat(r.quat[0], r.quat[1], r.quat[2], r.quat[3]));
+    PxRigidActor* a;
+    if (r.flags & PXB_ACTOR_DYNAMIC) a = physics->createRigidDynamic(pose); else a = physics->createRigidStatic(pose);
+    PxShape* s = nullptr;
+    switch (r.geomType) {
+      case PXB_GEOM_SPHERE: s = PxRigidActorExt::createExclusiveShape(*a, PxSphereGeometry(r.dims[0]), *mat); break;
+      case PXB_GEOM_PLANE: s = PxRigidActorExt::createExclusiveShape(*a, PxPlaneGeometry(), *mat); break;
+      case PXB_GEOM_CAPSULE: s = PxRigidActorExt::createExclusiveShape(*a, PxCapsuleGeometry(r.dims[0], r.dims[1]), *mat); break;
+      case PXB_GEOM_BOX: s = PxRigidActorExt::createExclusiveShape(*a, PxBoxGeometry(r.dims[0], r.dims[1], r.dims[2]), *mat); break;
+      case PXB_GEOM_CONVEX: s = PxRigidActorExt::createExclusiveShape(*a, PxConvexMeshGeometry(hulls[r.hullIdx].mesh), *mat); break;
+      default: fprintf(stderr, "bad geom %u\n", r.geomType); return 2;
+    }
+    s->setContactOffset(H.contactOffset);
+    s->setRestOffset(H.restOffset);
+    shapes[i] = s;
+    a->userData = reinterpret_cast<void*>(size_t(i));
+    if (r.flags & PXB_ACTOR_DYNAMIC) {
+      PxRigidDynamic* d = static_cast<PxRigidDynamic*>(a);
+      d->setMass(r.mass);
+      d->setMassSpaceInertiaTensor(PxVec3(r.inertia[0], r.inertia[1], r.inertia[2]));
+      d->setCMassLocalPose(PxTransform(PxIdentity));
+      d->setLinearVelocity(PxVec3(r.linVel[0], r.linVel[1], r.linVel[2]));
+      d->setAngularVelocity(PxVec3(r.angVel[0], r.angVel[1], r.angVel[2]));
+      d->setLinearDamping(r.linDamping);
+      d->setAngularDamping(r.angDamping);
+      d->setMaxLinearVelocity(r.maxLinVel);
+      d->setMaxAngularVelocity(r.maxAngVel);
+      d->setMaxDepenetrationVelocity(r.maxDepenetrationVel);
+      d->setSolverIterationCounts(H.posIters, H.velIters);
+      d->setSleepThreshold(H.sleepThreshold);
+      if (H.sleepThreshold == 0.0f) d->setWakeCounter(1e9f);
+      dyn.push_back(d);
+    }
+    actors[i] = a;
+    scene->addActor(*a);
+  }
+
+  FILE* fs = statesPath ? fopen(statesPath, "wb") : nullptr;
+  FILE* fb = bpPath ? fopen(bpPath, "wb") : nullptr;
+  FILE* fc = contactsPath ? fopen(contactsPath, "wb") : nullptr;
+  FILE* fo = orderPath ? fopen(orderPath, "wb") : nullptr;
+  auto dumpOrder = [&]() {
+    if (!fo) return;
+    NpScene* np = static_cast<NpScene*>(scene);
+    IG::SimpleIslandManager* im = np->getScScene().getSimpleIslandManager();
+    const IG::IslandSim& is = im->getAccurateIslandSim();
+    std::vector<uint32_t> edges;
+    for (PxU32 i = 0; i < is.getNbActiveIslands(); i++) {
+      const IG::Island& isl = is.getIsland(is.getActiveIslands()[i]);
+      IG::EdgeIndex e = isl.mFirstEdge[IG::Edge::eCONTACT_MANAGER];
+      while (e != IG_INVALID_EDGE) {
+        PxsContactManager* cm = im->getContactManager(e);
+        if (cm) { edges.push_back(cm->getWorkUnit().mTransformCache0); edges.push_back(cm->getWorkUnit().mTransformCache1); }
+        e = is.getEdge(e).mNextIslandEdge;
+      }
+    }
+    uint32_t n = uint32_t(edges.size() / 2);
+    fwrite(&n, 4, 1, fo); fwrite(edges.data(), 4, edges.size(), fo);
+  };
+
+  auto dumpStates = [&]() {
+    if (!fs) return;
+    std::vector<float> row(dyn.size() * PXB_STATE_FLOATS);
+    for (size_t i = 0; i < dyn.size(); i++) {
+      PxTransform t = dyn[i]->getGlobalPose();
+      PxVec3 lv = dyn[i]->getLinearVelocity(), av = dyn[i]->getAngularVelocity();
+      float* o = &row[i * PXB_STATE_FLOATS];
+      o[0] = t.p.x; o[1] = t.p.y; o[2] = t.p.z; o[3] = t.q.x; o[4] = t.q.y; o[5] = t.q.z; o[6] = t.q.w;
+      o[7] = lv.x; o[8] = lv.y; o[9] = lv.z; o[10] = av.x; o[11] = av.y; o[12] = av.z;
+    }
+    fwrite(row.data(), 4, row.size(), fs);
+  };
+
+  // stage-level broadphase oracle
+  PxBroadPhase* bp = nullptr; PxAABBManager* aabb = nullptr;
+  if (fb) {
+    PxBroadPhaseDesc bpd(PxBroadPhaseType::eABP);
+    bp = PxCreateBroadPhase(bpd);
+    aabb = PxCreateAABBManager(*bp);
+  }
+  auto bpStep = [&](bool first) {
+    if (!fb) return;
+    std::vector<float> bounds(H.nActors * 6);
+    for (uint32_t i = 0; i < H.nActors; i++) {
+      PxBounds3 b;
+      PxGeometryQuery::computeGeomBounds(b, shapes[i]->getGeometry(), actors[i]->getGlobalPose() * shapes[i]->getLocalPose(), 0.0f, 1.0f);
+      memcpy(&bounds[i * 6], &b.minimum.x, 24);
+      const bool isDyn = recs[i].flags & PXB_ACTOR_DYNAMIC;
+      if (first) {
+        PxBpFilterGroup g = isDyn ? PxGetBroadPhaseDynamicFilterGroup(i) : PxGetBroadPhaseStaticFilterGroup();
+        aabb->addObject(i, b, g, H.contactOffset);
+      } else if (isDyn) {
+        aabb->updateObject(i, &b, nullptr);
+      }
+    }
+    aabb->update();
+    PxBroadPhaseResults res; aabb->fetchResults(res);
+    auto norm = [](const PxBroadPhasePair* p, PxU32 n) {
+      std::vector<std::pair<uint32_t, uint32_t>> v(n);
+      for (PxU32 i = 0; i < n; i++) v[i] = std::make_pair(std::min(p[i].mID0, p[i].mID1), std::max(p[i].mID0, p[i].mID1));
+      std::sort(v.begin(), v.end());
+      return v;
+    };
+    auto c = norm(res.mCreatedPairs, res.mNbCreatedPairs), d = norm(res.mDeletedPairs, res.mNbDeletedPairs);
+    uint32_t n = H.nActors, nc = uint32_t(c.size()), nd = uint32_t(d.size());
+    fwrite(&n, 4, 1, fb); fwrite(bounds.data(), 4, bounds.size(), fb);
+    fwrite(&nc, 4, 1, fb); fwrite(&nd, 4, 1, fb);
+    for (auto& p : c) { fwrite(&p.first, 4, 1, fb); fwrite(&p.second, 4, 1, fb); }
+    for (auto& p : d) { fwrite(&p.first, 4, 1, fb); fwrite(&p.second, 4, 1, fb); }
+  };
+
+  dumpStates();
+  double totalMs = 0; std::vector<double> stepMs;
+  for (int s = 0; s < steps + warmup; s++) {
+    bpStep(s == 0);
+    gContacts.pairs.clear();
+    auto t0 = std::chrono::steady_clock::now();
+    scene->simulate(H.dt);
+    scene->fetchResults(true);
+    auto t1 = std::chrono::steady_clock::now();
+    double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (s >= warmup) { totalMs += ms; stepMs.push_back(ms); }
+    dumpStates();
+    dumpOrder();
+    if (fc) {
+      std::sort(gContacts.pairs.begin(), gContacts.pairs.end(), [](const ContactDump::Pair& x, const ContactDump::Pair& y) {
+        return std::make_pair(x.a0, x.a1) < std::make_pair(y.a0, y.a1); });
+      uint32_t np = uint32_t(gContacts.pairs.size());
+      fwrite(&np, 4, 1, fc);
+      for (auto& p : gContacts.pairs) {
+        fwrite(&p.a0, 4, 1, fc); fwrite(&p.a1, 4, 1, fc); fwrite(&p.n, 4, 1, fc);
+        fwrite(p.data.data(), 4, p.data.size(), fc);
+      }
+    }
+  }
+  if (fs) fclose(fs);
+  if (fb) fclose(fb);
+  if (fc) fclose(fc);
+  if (fo) fclose(fo);
+  std::sort(stepMs.begin(), stepMs.end());
+  double med = stepMs.empty() ? 0 : stepMs[stepMs.size() / 2];
+  double p95 = stepMs.empty() ? 0 : stepMs[std::min(stepMs.size() - 1, size_t(stepMs.size() * 0.95))];
+  PxSimulationStatistics st; scene->getSimulationStatistics(st);
+  printf("{\"impl\": \"reference-cpu\", \"version\": \"5.6.1\", \"bodies\": %zu, \"steps\": %d, \"threads\": %d, \"solver\": \"%s\", "
+         "\"ms_per_step\": %.6f, \"ms_median\": %.6f, \"ms_p95\": %.6f, \"body_steps_per_s\": %.1f, \"nb_discrete_contact_pairs\": %u}\n",
+         dyn.size(), steps, threads, H.solverType == PXB_SOLVER_TGS ? "tgs" : "pgs",
+         totalMs / std::max(1, steps), med, p95, dyn.size() * double(steps) / (totalMs / 1000.0),
+         st.nbDiscreteContactPairsTotal);
+  scene->release();
+  dispatcher->release();
+  physics->release();
+  foundation->release();
+  return 0;
+}

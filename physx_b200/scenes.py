@@ -1,0 +1,185 @@
+"""Synthetic scene builders for the BASELINE.json configs and the scene file
+format shared with the oracle tools (oracle/scene_format.h).
+
+A scene is plain data: a header + one record per actor (one shape per actor, identity local pose).
+Mass properties are computed here in float32 (box: m = rho*8*hx*hy*hz, I = m/3*(hy^2+hz^2, ...),
+the closed forms PxRigidBodyExt::updateMassAndInertia evaluates for a box,
+physx/source/physxextensions/src/ExtRigidBodyExt.cpp) and set explicitly on both sides so the
+reference and this engine start from bit-identical inputs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+GEOM_SPHERE, GEOM_PLANE, GEOM_CAPSULE, GEOM_BOX, GEOM_CONVEX = 0, 1, 2, 3, 5
+ACTOR_DYNAMIC = 1
+SOLVER_PGS, SOLVER_TGS = 0, 1
+SCENE_MAGIC = 0x314E4353
+NO_ENV = 0xFFFFFFFF
+
+HEADER_DTYPE = np.dtype([
+    ("magic", "<u4"), ("nActors", "<u4"), ("nHulls", "<u4"), ("solverType", "<u4"),
+    ("gravity", "<f4", 3), ("dt", "<f4"), ("posIters", "<u4"), ("velIters", "<u4"),
+    ("staticFriction", "<f4"), ("dynamicFriction", "<f4"), ("restitution", "<f4"),
+    ("contactOffset", "<f4"), ("restOffset", "<f4"), ("sleepThreshold", "<f4"),
+    ("bounceThreshold", "<f4"), ("frictionOffsetThreshold", "<f4"),
+    ("frictionCorrelationDistance", "<f4"), ("toleranceLength", "<f4"), ("reserved", "<u4", 4),
+])
+
+ACTOR_DTYPE = np.dtype([
+    ("flags", "<u4"), ("geomType", "<u4"), ("envId", "<u4"), ("hullIdx", "<u4"),
+    ("pos", "<f4", 3), ("quat", "<f4", 4), ("dims", "<f4", 4),
+    ("linVel", "<f4", 3), ("angVel", "<f4", 3), ("mass", "<f4"), ("inertia", "<f4", 3),
+    ("linDamping", "<f4"), ("angDamping", "<f4"), ("maxLinVel", "<f4"), ("maxAngVel", "<f4"),
+    ("maxDepenetrationVel", "<f4"), ("reserved", "<f4", 2),
+])
+assert HEADER_DTYPE.itemsize == 96 and ACTOR_DTYPE.itemsize == 128
+
+STATE_FLOATS = 13  # pos3 quat4 linVel3 angVel3
+
+def normalize_quat_f32(q):
+    """PxQuat::getNormalized in float32, iterated to its fixed point.  The reference normalises every
+    pose handed to createRigidStatic/Dynamic (physx/source/physx/src/NpPhysics.cpp); scene files carry
+    quaternions that normalisation leaves unchanged so both sides start from identical bits."""
+    q = np.asarray(q, dtype=np.float32)
+    for _ in range(8):
+        m = np.float32(np.sqrt(np.float32(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3])))
+        q2 = (q * (np.float32(1.0) / m)).astype(np.float32)
+        if (q2 == q).all():
+            break
+        q = q2
+    return q
+
+
+# rotation taking local +X (PxPlaneGeometry normal) to world +Y: 90 deg about Z
+PLANE_UP_Y_QUAT = normalize_quat_f32([0.0, 0.0, np.sqrt(0.5), np.sqrt(0.5)])
+
+
+def default_header(solver=SOLVER_TGS, pos_iters=4, vel_iters=1, sleep_threshold=0.0):
+    h = np.zeros((), dtype=HEADER_DTYPE)
+    h["magic"] = SCENE_MAGIC
+    h["solverType"] = solver
+    h["gravity"] = (0.0, -9.81, 0.0)
+    h["dt"] = np.float32(1.0 / 60.0)
+    h["posIters"], h["velIters"] = pos_iters, vel_iters
+    h["staticFriction"], h["dynamicFriction"], h["restitution"] = 0.5, 0.5, 0.6
+    h["contactOffset"], h["restOffset"] = 0.02, 0.0
+    h["sleepThreshold"] = sleep_threshold
+    h["bounceThreshold"] = 2.0          # 0.2 * toleranceSpeed (PxSceneDesc.h)
+    h["frictionOffsetThreshold"] = 0.04
+    h["frictionCorrelationDistance"] = 0.025
+    h["toleranceLength"] = 1.0
+    return h
+
+
+def _new_actors(n):
+    a = np.zeros(n, dtype=ACTOR_DTYPE)
+    a["quat"][:, 3] = 1.0
+    a["envId"] = NO_ENV
+    a["maxLinVel"] = 1.0e16   # PX_MAX_F32-ish: PxRigidDynamic default is 1e32^0.5
+    a["maxAngVel"] = 100.0    # PxRigidDynamic default
+    a["maxDepenetrationVel"] = 1.0e32  # NpRigidDynamic default (PX_MAX_F32 in practice)
+    a["angDamping"] = 0.05    # PxRigidDynamic default
+    return a
+
+
+def set_box(a, idx, half_extents, density=10.0):
+    he = np.broadcast_to(np.asarray(half_extents, dtype=np.float32), (np.size(idx) if np.ndim(idx) else 1, 3)) \
+        if np.ndim(half_extents) == 1 else np.asarray(half_extents, dtype=np.float32)
+    a["geomType"][idx] = GEOM_BOX
+    a["flags"][idx] = ACTOR_DYNAMIC
+    a["dims"][idx, :3] = he
+    hx, hy, hz = he[..., 0], he[..., 1], he[..., 2]
+    m = (np.float32(density) * np.float32(8.0) * hx * hy * hz).astype(np.float32)
+    third = np.float32(1.0 / 3.0)
+    a["mass"][idx] = m
+    a["inertia"][idx, 0] = m * third * (hy * hy + hz * hz)
+    a["inertia"][idx, 1] = m * third * (hx * hx + hz * hz)
+    a["inertia"][idx, 2] = m * third * (hx * hx + hy * hy)
+
+
+def add_ground_plane(actors):
+    p = _new_actors(1)
+    p["geomType"] = GEOM_PLANE
+    p["quat"][0] = PLANE_UP_Y_QUAT
+    return np.concatenate([p, actors])
+
+
+class Scene:
+    def __init__(self, header, actors, hulls=()):
+        self.header = header.copy()
+        self.actors = actors
+        self.hulls = list(hulls)
+        self.header["nActors"] = len(actors)
+        self.header["nHulls"] = len(self.hulls)
+
+    @property
+    def n_dynamic(self):
+        return int(np.count_nonzero(self.actors["flags"] & ACTOR_DYNAMIC))
+
+    def tobytes(self):
+        out = [self.header.tobytes(), self.actors.tobytes()]
+        for h in self.hulls:
+            h = np.asarray(h, dtype="<f4").reshape(-1, 3)
+            out.append(np.uint32(len(h)).tobytes())
+            out.append(h.tobytes())
+        return b"".join(out)
+
+    def save(self, path):
+        with open(path, "wb") as f:
+            f.write(self.tobytes())
+
+    @staticmethod
+    def load(path):
+        buf = open(path, "rb").read()
+        h = np.frombuffer(buf, dtype=HEADER_DTYPE, count=1)[0].copy()
+        off = HEADER_DTYPE.itemsize
+        a = np.frombuffer(buf, dtype=ACTOR_DTYPE, count=int(h["nActors"]), offset=off).copy()
+        off += a.nbytes
+        hulls = []
+        for _ in range(int(h["nHulls"])):
+            nv = int(np.frombuffer(buf, "<u4", 1, off)[0]); off += 4
+            hulls.append(np.frombuffer(buf, "<f4", nv * 3, off).reshape(nv, 3).copy()); off += nv * 12
+        return Scene(h, a, hulls)
+
+
+def box_stacks(n_stacks=10, height=10, half_extent=0.5, spacing=4.0, jitter=0.0, seed=1234, **hdr):
+    """BASELINE config 1: SnippetHelloWorld-style stacks on a ground plane."""
+    rng = np.random.RandomState(seed)
+    n = n_stacks * height
+    a = _new_actors(n)
+    he = np.float32(half_extent)
+    k = 0
+    for s in range(n_stacks):
+        for j in range(height):
+            jx, jz = (rng.uniform(-jitter, jitter, 2) if jitter > 0 else (0.0, 0.0))
+            a["pos"][k] = (s * spacing + jx, he + 2 * he * j, jz)
+            k += 1
+    set_box(a, np.arange(n), np.array([he, he, he], dtype=np.float32))
+    return Scene(default_header(**hdr), add_ground_plane(a))
+
+
+def env_grid_stacks(n_envs=4096, stacks_per_env=8, height=8, half_extent=0.25, env_pitch=8.0,
+                    stack_spacing=1.0, jitter=0.01, seed=1234, **hdr):
+    """BASELINE config 2 / 5: E independent envs on a square grid, each `stacks_per_env` stacks of
+    `height` boxes, +-jitter seeded offsets in the ground plane, one shared ground plane."""
+    rng = np.random.RandomState(seed)
+    side = int(np.ceil(np.sqrt(n_envs)))
+    per_env = stacks_per_env * height
+    n = n_envs * per_env
+    a = _new_actors(n)
+    he = np.float32(half_extent)
+    env = np.repeat(np.arange(n_envs), per_env)
+    local = np.tile(np.arange(per_env), n_envs)
+    stack = local // height
+    level = local % height
+    ssx = int(np.ceil(np.sqrt(stacks_per_env)))
+    ex = (env % side).astype(np.float32) * np.float32(env_pitch)
+    ez = (env // side).astype(np.float32) * np.float32(env_pitch)
+    jit = rng.uniform(-jitter, jitter, size=(n, 2)).astype(np.float32) if jitter > 0 else np.zeros((n, 2), np.float32)
+    a["pos"][:, 0] = ex + (stack % ssx).astype(np.float32) * np.float32(stack_spacing) + jit[:, 0]
+    a["pos"][:, 1] = he + np.float32(2.0) * he * level.astype(np.float32)
+    a["pos"][:, 2] = ez + (stack // ssx).astype(np.float32) * np.float32(stack_spacing) + jit[:, 1]
+    a["envId"] = env.astype(np.uint32)
+    set_box(a, np.arange(n), np.array([he, he, he], dtype=np.float32))
+    return Scene(default_header(**hdr), add_ground_plane(a))
