@@ -1,0 +1,125 @@
+/* physx_b200.h -- C ABI of the B200-native rigid-body step (libphysx_b200.so).
+ *
+ * This is the boundary the PhysXGpu plugin shim binds (INTEGRATION.md shows the shim): plain pointers
+ * and sizes, no C++ or torch types.  Each entry point names the reference interface it stands in for.
+ * All functions return 0 (PXB_OK) on success or a negative PxbError; pxb_last_error() gives the text.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with PXB_ERR_NO_DEVICE.
+ *
+ * Pointers are HOST pointers unless the name says "_device"/"dev".  Actor records use the layout of
+ * oracle/scene_format.h::PxbActorRec (128 bytes) so scenes are bit-identical on both sides of a test.
+ */
+#ifndef PHYSX_B200_H
+#define PHYSX_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PXB_API __attribute__((visibility("default")))
+
+typedef enum {
+  PXB_OK = 0,
+  PXB_ERR_NO_DEVICE = -1,     /* no CUDA device / driver: the product never falls back to the CPU */
+  PXB_ERR_INVALID = -2,
+  PXB_ERR_CUDA = -3,          /* CUDA runtime failure; scene enters abort mode like PxCudaContext (cudamanager/src/CudaContextManager.cpp:845) */
+  PXB_ERR_CAPACITY = -4,      /* pair / contact capacity exceeded (PxGpuDynamicsMemoryConfig analogue) */
+  PXB_ERR_UNSUPPORTED = -5
+} PxbError;
+
+/* PxGeometryType values used by the hot path (physx/include/geometry/PxGeometry.h:48-62) */
+enum { PXB_GEOM_SPHERE = 0, PXB_GEOM_PLANE = 1, PXB_GEOM_CAPSULE = 2, PXB_GEOM_BOX = 3, PXB_GEOM_CONVEXMESH = 5 };
+enum { PXB_ACTOR_DYNAMIC = 1u };
+enum { PXB_SOLVER_PGS = 0, PXB_SOLVER_TGS = 1 };
+
+/* Scene description: the PxSceneDesc / PxGpuDynamicsMemoryConfig fields the hot path consumes
+ * (physx/include/PxSceneDesc.h:473-487, :1023-1075). */
+typedef struct {
+  float    gravity[3];
+  uint32_t solverType;                 /* PXB_SOLVER_TGS (PGS: planned, returns PXB_ERR_UNSUPPORTED) */
+  float    bounceThresholdVelocity;    /* PxSceneDesc::bounceThresholdVelocity */
+  float    frictionOffsetThreshold;    /* PxSceneDesc::frictionOffsetThreshold */
+  float    frictionCorrelationDistance;/* PxSceneDesc::frictionCorrelationDistance */
+  float    toleranceLength;            /* PxTolerancesScale::length */
+  float    staticFriction, dynamicFriction, restitution; /* the (single) combined material */
+  float    contactOffset, restOffset;  /* PxShape::setContactOffset / setRestOffset (uniform) */
+  uint32_t posIters, velIters;         /* PxRigidDynamic::setSolverIterationCounts (scene max) */
+  uint32_t maxActors;                  /* capacity */
+  uint32_t maxPairs;                   /* PxGpuDynamicsMemoryConfig::foundLostPairsCapacity / maxRigidPatchCount analogue; 0 = 8*maxActors */
+  int32_t  device;                     /* CUDA device ordinal (PxCudaContextManagerDesc) */
+  uint32_t reserved[8];
+} PxbSceneDesc;
+
+typedef struct PxbScene PxbScene;
+
+/* ---- lifecycle: PxPhysXGpu factory set (physx/source/physxgpu/include/PxPhysXGpu.h:101-200;
+ *      createGpuBroadPhase / createGpuNphaseImplementationContext / createGpuDynamicsContext /
+ *      createGpuSimulationController in PxgPhysXGpu.cpp:153-262) ---- */
+PXB_API int  pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out);
+PXB_API void pxb_scene_release(PxbScene* scene);
+PXB_API const char* pxb_last_error(void);
+PXB_API int  pxb_device_count(void);
+
+/* PxsSimulationController::addDynamics / addPxgShape + Bp::AABBManagerBase::addBounds
+ * (lowlevel/software/include/PxsSimulationController.h:122-354, lowlevelaabb/include/BpAABBManagerBase.h:175-330).
+ * `recs` = nb records of 128 bytes (PxbActorRec layout).  Actor index = order of addition. */
+PXB_API int  pxb_scene_add_actors(PxbScene* scene, const void* recs, uint32_t nb);
+PXB_API uint32_t pxb_scene_num_actors(const PxbScene* scene);
+PXB_API uint32_t pxb_scene_num_dynamic(const PxbScene* scene);
+
+/* ---- the step: PxScene::simulate()+fetchResults() hot path = Sc::Scene collide + advance chains
+ *      (simulationcontroller/src/ScPipeline.cpp:108-124), i.e. bounds -> Bp::BroadPhase::update ->
+ *      PxvNphaseImplementationContext::updateContactManager -> Dy::Context::update/updatePostPartitioning ->
+ *      integration.  pxb_scene_simulate only enqueues GPU work; pxb_scene_fetch_results waits for it. ---- */
+PXB_API int  pxb_scene_simulate(PxbScene* scene, float dt);
+PXB_API int  pxb_scene_fetch_results(PxbScene* scene, int block);
+
+/* Constraint input order for the NEXT simulate call: n (actorA, actorB) pairs in the order the island
+ * manager hands contact managers to the solver (IG::IslandSim edge lists as walked by
+ * DynamicsTGSContext::prepareBodiesAndConstraints, DyTGSDynamics.cpp:822-905; the plugin shim reads them
+ * from the IG::SimpleIslandManager& it is given).  n = 0 restores the canonical order (sorted pair key). */
+PXB_API int  pxb_scene_set_constraint_order(PxbScene* scene, const uint32_t* pairs, uint32_t n);
+
+/* ---- PxDirectGPUAPI mirror (physx/include/PxDirectGPUAPI.h:311-463; kernels updateBodiesAndShapes.cu:999-1253).
+ *      dataType: 0 = global pose (7 floats q.xyzw,p.xyz = PxTransform), 1 = linear velocity, 2 = angular velocity.
+ *      `indices` are dynamic-body indices (PxRigidDynamicGPUIndex analogue), NULL = 0..nb-1.
+ *      *_device variants take device pointers and run on the scene stream without synchronising. ---- */
+enum { PXB_RD_GLOBAL_POSE = 0, PXB_RD_LINEAR_VELOCITY = 1, PXB_RD_ANGULAR_VELOCITY = 2 };
+PXB_API int  pxb_get_rigid_dynamic_data(PxbScene* scene, void* data, const uint32_t* indices, int dataType, uint32_t nb);
+PXB_API int  pxb_set_rigid_dynamic_data(PxbScene* scene, const void* data, const uint32_t* indices, int dataType, uint32_t nb);
+PXB_API int  pxb_get_rigid_dynamic_data_device(PxbScene* scene, void* devData, const uint32_t* devIndices, int dataType, uint32_t nb);
+PXB_API int  pxb_set_rigid_dynamic_data_device(PxbScene* scene, const void* devData, const uint32_t* devIndices, int dataType, uint32_t nb);
+/* Packed state convenience: 13 floats per dynamic body (pos3 quat4 linVel3 angVel3), dynamic-body order. */
+PXB_API int  pxb_scene_get_states(PxbScene* scene, float* out);
+PXB_API int  pxb_scene_set_states(PxbScene* scene, const float* in);
+PXB_API void* pxb_scene_state_device_ptr(PxbScene* scene, int which); /* 0 pos4, 1 quat4, 2 linVel4, 3 angVel4 (per ACTOR float4 arrays) */
+PXB_API void* pxb_scene_stream(PxbScene* scene);                        /* cudaStream_t */
+
+/* ---- stage-level entry points (parity tests drive these with teacher-forced inputs) ----
+ * Bp::BroadPhase::update + getCreatedPairs/getDeletedPairs (lowlevelaabb/include/BpBroadPhase.h:98-222).
+ * `tightBounds` = 6 floats per actor (min xyz, max xyz) or NULL to compute them from the current poses
+ * (Gu::computeBounds, geomutils/src/GuBounds.cpp:354-400).  Pairs are (a,b) actor indices with a<b. */
+PXB_API int  pxb_scene_compute_bounds(PxbScene* scene);
+PXB_API int  pxb_scene_get_bounds(PxbScene* scene, float* out6);
+PXB_API int  pxb_scene_broadphase(PxbScene* scene, const float* tightBounds);
+PXB_API uint32_t pxb_scene_num_pairs(PxbScene* scene);
+PXB_API int  pxb_scene_get_pairs(PxbScene* scene, uint32_t* outPairs);       /* sorted */
+PXB_API uint32_t pxb_scene_num_created(PxbScene* scene);
+PXB_API uint32_t pxb_scene_num_deleted(PxbScene* scene);
+PXB_API int  pxb_scene_get_created(PxbScene* scene, uint32_t* outPairs);     /* sorted */
+PXB_API int  pxb_scene_get_deleted(PxbScene* scene, uint32_t* outPairs);     /* sorted */
+/* Contacts of the last step, one 24-float record per pair in pair order:
+ * [count, nx, ny, nz, 4 x (px, py, pz, separation, appliedForce)]; normal points body1 -> body0
+ * (PxsContactManagerOutput / PxContactPatch + PxContact stream analogue, physx/include/PxContact.h:57-148). */
+PXB_API int  pxb_scene_get_contacts(PxbScene* scene, float* out24);
+/* Solver statistics of the last step (PxSimulationStatistics::mNbPartitions analogue). */
+PXB_API uint32_t pxb_scene_last_num_partitions(PxbScene* scene);
+PXB_API uint32_t pxb_scene_last_num_constraints(PxbScene* scene);
+/* number of kernels launched by the last pxb_scene_simulate call */
+PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* scene);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1082 @@
+// pxb_engine.cu -- the B200-native rigid-body step: bounds -> grid broadphase -> PCM narrowphase ->
+// order-preserving graph colouring -> TGS contact solve -> integration, plus the C ABI (include/physx_b200.h).
+//
+// Everything between pxb_scene_simulate() and pxb_scene_fetch_results() runs on one CUDA stream with
+// all counts kept in device memory: there is no host synchronisation inside a step (the reference GPU
+// pipeline has three).  Stage <-> reference mapping:
+//   k_bounds            a1/a2  updateTransformCacheAndBoundArrayLaunch + translateAABBsLaunch  (oracle: Gu::computeBounds)
+//   radix sort + k_bp_* a3-a5  radixSort*/performIncrementalSAP/region kernels                  (oracle: ABP pair set)
+//   k_pair_*            a7     removeContactManagers_Stage*, prepareLostFoundPairs_*           (found/lost + persistent slots)
+//   k_narrowphase       a8-a11 sphereNphase/boxBoxNphase/convexConvex... kernels               (oracle: CPU PCM)
+//   k_colour_partition  a13    PxgIncrementalPartition (host) -> here on device, first-fit in solver input order
+//   k_preintegrate      a12    preIntegrationLaunchTGS
+//   k_prep              a14    constraintContactBlockPrePrepLaunch + contactConstraintBlockPrepareParallelLaunchTGS
+//   k_solve             a15/a16 solveBlockUnified + propagateAverageSolverBodyVelocityTGS loop  (ONE cooperative launch)
+//   k_finalize          a17/a18 writebackBlocksTGS + integrateCoreParallelLaunchTGS
+//   k_rd_get/k_rd_set   a19    get/setRigidDynamic* (PxDirectGPUAPI)
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <vector>
+#include <string>
+#include <algorithm>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+#include "../../include/physx_b200.h"
+#include "pxb_math.cuh"
+#include "pxb_np.cuh"
+#include "pxb_solver.cuh"
+#include "pxb_sort.cuh"
+
+namespace cg = cooperative_groups;
+
+#define NONE32 0xffffffffu
+#define MAX_PARTITIONS 96
+
+// ---------------------------------------------------------------------------------------------
+// host-side record (layout of oracle/scene_format.h::PxbActorRec, 128 bytes)
+struct ActorRec {
+  uint32_t flags, geomType, envId, hullIdx;
+  float pos[3], quat[4], dims[4], linVel[3], angVel[3], mass, inertia[3], linDamping, angDamping, maxLinVel, maxAngVel, maxDepenetrationVel, reserved[2];
+};
+static_assert(sizeof(ActorRec) == 128, "actor record layout");
+
+enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREETOP, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_COUNT = 16 };
+enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4 };
+
+struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };
+
+struct PxbScene {
+  PxbSceneDesc desc; cudaStream_t stream = nullptr; bool abort = false; bool stepping = false;
+  uint32_t nA = 0, nDyn = 0, capA = 0, capPairs = 0, bitsA = 1, nLarge = 0;
+  std::vector<ActorRec> recs; std::vector<int> dynIndex; std::vector<uint32_t> dynActor; std::vector<uint32_t> largeHost;
+  GridParams grid; bool gridDirty = true;
+  int numSMs = 148, coopBlocksColour = 0, coopBlocksSolve = 0;
+  // per actor
+  float4 *pos = 0, *quat = 0, *linVel = 0, *angVel = 0, *invInertia = 0, *damp = 0, *dims = 0, *aabbMin = 0, *aabbMax = 0;
+  uint32_t *geomFlags = 0, *envId = 0, *dynActorDev = 0, *largeList = 0;
+  float* tight = 0;
+  // solver body state (per actor)
+  float4 *sbLin = 0, *sbAng = 0, *sbDLin = 0, *sbDAng = 0, *sbIA = 0, *sbIB = 0, *sbP = 0, *sbQ = 0, *sbOrigAng = 0;
+  uint32_t *bodyCnt = 0, *bodyStart = 0, *bodyCursor = 0, *bodyNext = 0, *bodyMask = 0, *bodyHasCon = 0;
+  // broadphase
+  uint64_t *cellKey = 0, *cellKeyAlt = 0; uint32_t *cellVal = 0, *cellValAlt = 0; float4 *sMin = 0, *sMax = 0;
+  uint64_t* pairKeys[2] = {0, 0}; uint32_t* pairSlots[2] = {0, 0}; uint64_t* pairKeyAlt = 0; uint32_t *pairValTmp = 0, *pairValAlt = 0;
+  uint32_t* nPairsDev = 0;  // [2]
+  int cur = 0;
+  uint32_t *freeList = 0; uint64_t *createdKeys = 0, *deletedKeys = 0;
+  float4 *manifolds = 0, *frictions = 0;
+  // per pair (this frame)
+  float4 *cHdr = 0, *cPts = 0; uint2* pairBodies = 0; float* cForce = 0;
+  uint32_t *conFlag = 0, *conIdx = 0, *conPair = 0, *rankOfPair = 0; uint64_t *conSortKey = 0, *conSortKeyAlt = 0; uint32_t* conPairAlt = 0;
+  uint64_t* orderKeys = 0; uint32_t nOrder = 0, capOrder = 0;
+  uint32_t *conB0 = 0, *conB1 = 0, *conPos0 = 0, *conPos1 = 0, *conColour = 0, *conDone = 0, *bodyList = 0, *ordered = 0;
+  uint32_t *partCnt = 0, *partStart = 0, *partCursor = 0;
+  // rows (solve order)
+  float4 *rowA = 0, *rowB = 0; uint4* rowC = 0; float4 *ptA = 0, *ptB = 0, *ptC = 0, *frA = 0, *frB = 0, *frC = 0, *frD = 0;
+  uint32_t* counters = 0; uint32_t* hostCounters = 0;  // pinned mirror
+  RadixSortTemp rsTmp; uint32_t* scanSums = 0;
+  uint32_t launches = 0;
+  uint32_t hNPairs = 0, hNCreated = 0, hNDeleted = 0, hNCon = 0, hNPart = 0, hErr = 0;
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (s) s->abort = true; return fail(PXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+
+// a1/a2: world AABB of every actor (tight, then inflated by the contact offset) + grid cell key.
+// Formulas: Gu::computeBounds (geomutils/src/GuBounds.cpp:354-400, plane :210-260), inflation
+// BpBroadPhaseABP.cpp:1187-1197.
+__global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims,
+                         const uint32_t* __restrict__ geomFlags, const uint32_t* __restrict__ envId, float contactOffset, float* __restrict__ tight,
+                         int externalTight, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax, GridParams g, uint32_t envCount,
+                         uint64_t* __restrict__ cellKey, uint32_t* __restrict__ cellVal) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nA) return;
+  const uint32_t gf = geomFlags[a]; const uint32_t type = gf & 0xff;
+  float mn[3], mx[3];
+  if (externalTight) { for (int k = 0; k < 3; ++k) { mn[k] = tight[a * 6 + k]; mx[k] = tight[a * 6 + 3 + k]; } }
+  else {
+    const float4 p4 = pos[a]; const q4 q = Q4(quat[a]); const float4 d = dims[a];
+    const v3 p = V3(p4.x, p4.y, p4.z);
+    v3 e = V3(0, 0, 0); bool plane = false;
+    if (type == PXB_GEOM_SPHERE) e = V3(d.x, d.x, d.x);
+    else if (type == PXB_GEOM_CAPSULE) { const v3 dd = qbasis0(q) * d.y; e = V3(fabsf(dd.x) + d.x, fabsf(dd.y) + d.x, fabsf(dd.z) + d.x); }
+    else if (type == PXB_GEOM_BOX) {
+      const m33 b = mfromq(q);
+      const v3 c0 = b.c0 * d.x, c1 = b.c1 * d.y, c2 = b.c2 * d.z;
+      e = V3((fabsf(c0.x) + fabsf(c1.x)) + fabsf(c2.x), (fabsf(c0.y) + fabsf(c1.y)) + fabsf(c2.y), (fabsf(c0.z) + fabsf(c1.z)) + fabsf(c2.z));
+    } else if (type == PXB_GEOM_PLANE) plane = true;
+    if (!plane) { mn[0] = p.x - e.x; mn[1] = p.y - e.y; mn[2] = p.z - e.z; mx[0] = p.x + e.x; mx[1] = p.y + e.y; mx[2] = p.z + e.z; }
+    else {
+      const float big = FLT_MAX * 0.25f;
+      mn[0] = mn[1] = mn[2] = -big; mx[0] = mx[1] = mx[2] = big;
+      const v3 n = qbasis0(q); const float dd = -dot(p, n);
+      const float nx = fabsf(n.x), ny = fabsf(n.y), nz = fabsf(n.z); const float eps = 1e-6f, ome = 1.0f - eps;
+      if (nx > ome && ny < eps && nz < eps) { if (n.x > 0.f) mx[0] = -dd; else mn[0] = dd; }
+      else if (nx < eps && ny > ome && nz < eps) { if (n.y > 0.f) mx[1] = -dd; else mn[1] = dd; }
+      else if (nx < eps && ny < eps && nz > ome) { if (n.z > 0.f) mx[2] = -dd; else mn[2] = dd; }
+    }
+    for (int k = 0; k < 3; ++k) { tight[a * 6 + k] = mn[k]; tight[a * 6 + 3 + k] = mx[k]; }
+  }
+  const float co = contactOffset;
+  const uint32_t env = envId[a];
+  aabbMin[a] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(env));
+  aabbMax[a] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf));
+  uint64_t key = ~0ull;
+  if (!(gf & 0x200u)) {  // not a global/large object: grid key (env, cz, cy, cx), cx least significant
+    int cx = (int)floorf((mn[0] - co - g.ox) * g.invCell), cy = (int)floorf((mn[1] - co - g.oy) * g.invCell), cz = (int)floorf((mn[2] - co - g.oz) * g.invCell);
+    cx = max(0, min(g.nx - 1, cx)); cy = max(0, min(g.ny - 1, cy)); cz = max(0, min(g.nz - 1, cz));
+    const uint64_t e = (env == NONE32) ? 0ull : (uint64_t)min(env, envCount - 1);
+    key = ((e * (uint64_t)g.nz + (uint64_t)cz) * (uint64_t)g.ny + (uint64_t)cy) * (uint64_t)g.nx + (uint64_t)cx;
+  }
+  cellKey[a] = key; cellVal[a] = a;
+}
+
+__global__ void k_bp_gather(uint32_t nA, const uint32_t* __restrict__ sortedActor, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
+                            float4* __restrict__ sMin, float4* __restrict__ sMax) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nA) return;
+  const uint32_t a = sortedActor[i];
+  sMin[i] = aabbMin[a]; sMax[i] = aabbMax[a];
+}
+
+// pair filter: closed-interval overlap on all axes (PxgIntegerAABB::intersects / ABP intersect2D semantics),
+// at least one dynamic actor (BpFiltering.h:99-114 groups), equal-or-invalid environment ids (broadphase.cu:62-80)
+__device__ __forceinline__ bool bp_test(const float4& amin, const float4& amax, const float4& bmin, const float4& bmax) {
+  if (amin.x > bmax.x || bmin.x > amax.x || amin.y > bmax.y || bmin.y > amax.y || amin.z > bmax.z || bmin.z > amax.z) return false;
+  const uint32_t fa = __float_as_uint(amax.w), fb = __float_as_uint(bmax.w);
+  if (!((fa | fb) & 0x100u)) return false;
+  const uint32_t ea = __float_as_uint(amin.w), eb = __float_as_uint(bmin.w);
+  if (ea != NONE32 && eb != NONE32 && ea != eb) return false;
+  return true;
+}
+__device__ __forceinline__ void bp_emit(uint32_t a, uint32_t b, uint32_t bitsA, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt, uint32_t cap, uint32_t* __restrict__ err) {
+  const uint32_t lo = min(a, b), hi = max(a, b);
+  const uint32_t idx = atomicAdd(cnt, 1u);
+  if (idx < cap) keys[idx] = ((uint64_t)lo << bitsA) | hi; else atomicOr(err, (uint32_t)E_PAIR_OVERFLOW);
+}
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__ k, uint32_t n, uint64_t v) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (k[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// a4/a5: every grid object looks "forward" in (env, cz, cy, cx) order: its own row from itself on, and the
+// 4 following neighbour rows; because the cell edge is >= every object extent, overlapping objects differ
+// by at most one cell per axis, so each unordered pair is visited exactly once.
+__global__ void k_bp_pairs(uint32_t nA, const uint64_t* __restrict__ key, const uint32_t* __restrict__ sortedActor, const float4* __restrict__ sMin,
+                           const float4* __restrict__ sMax, GridParams g, uint32_t bitsA, uint64_t* __restrict__ pairKeys, uint32_t* __restrict__ counters, uint32_t cap) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nA) return;
+  const uint64_t k = key[i];
+  if (k == ~0ull) return;
+  const uint32_t a = sortedActor[i];
+  const float4 amin = sMin[i], amax = sMax[i];
+  const uint64_t nx = (uint64_t)g.nx, ny = (uint64_t)g.ny, nz = (uint64_t)g.nz;
+  const int cx = (int)(k % nx); const uint64_t r1 = k / nx; const int cy = (int)(r1 % ny); const uint64_t r2 = r1 / ny; const int cz = (int)(r2 % nz); const uint64_t e = r2 / nz;
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+  {  // own row, forward
+    const uint64_t last = r1 * nx + (uint64_t)x1;
+    for (uint32_t j = i + 1; j < nA && key[j] <= last; ++j)
+      if (bp_test(amin, amax, sMin[j], sMax[j])) bp_emit(a, sortedActor[j], bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
+  }
+  const int dzs[4] = {0, 1, 1, 1}, dys[4] = {1, -1, 0, 1};
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int yy = cy + dys[r], zz = cz + dzs[r];
+    if (yy < 0 || yy >= g.ny || zz >= g.nz) continue;
+    const uint64_t rowBase = ((e * nz + (uint64_t)zz) * ny + (uint64_t)yy) * nx;
+    const uint64_t first = rowBase + (uint64_t)x0, last = rowBase + (uint64_t)x1;
+    for (uint32_t j = lower_bound_u64(key, nA, first); j < nA && key[j] <= last; ++j)
+      if (bp_test(amin, amax, sMin[j], sMax[j])) bp_emit(a, sortedActor[j], bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
+  }
+}
+// global / oversize objects (planes, shapes larger than a cell, env-less actors in env scenes) against everything
+__global__ void k_bp_large(uint32_t nA, uint32_t nLarge, const uint32_t* __restrict__ largeList, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
+                           uint32_t bitsA, uint64_t* __restrict__ pairKeys, uint32_t* __restrict__ counters, uint32_t cap) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nA) return;
+  const float4 amin = aabbMin[a], amax = aabbMax[a];
+  const bool aLarge = (__float_as_uint(amax.w) & 0x200u) != 0;
+  for (uint32_t l = 0; l < nLarge; ++l) {
+    const uint32_t b = largeList[l];
+    if (b == a || (aLarge && a > b)) continue;
+    if (bp_test(amin, amax, aabbMin[b], aabbMax[b])) bp_emit(a, b, bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
+  }
+}
+__global__ void k_clamp_count(uint32_t* __restrict__ counters, uint32_t cap, uint32_t* __restrict__ nPairsCur) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { const uint32_t n = min(counters[C_NPAIRS_NEW], cap); counters[C_NPAIRS_NEW] = n; *nPairsCur = n; }
+}
+
+// a7: pair lifecycle.  Lost pairs give their persistent slot back, surviving pairs keep theirs, new pairs
+// take one from the free list and start with an empty manifold (PersistentContactManifold::initialize).
+__global__ void k_pair_lost(const uint64_t* __restrict__ oldKeys, const uint32_t* __restrict__ oldSlots, const uint32_t* __restrict__ nOldP,
+                            const uint64_t* __restrict__ newKeys, const uint32_t* __restrict__ nNewP, uint32_t* __restrict__ freeList,
+                            uint64_t* __restrict__ deletedKeys, uint32_t* __restrict__ counters) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nOld = *nOldP, nNew = *nNewP;
+  if (j >= nOld) return;
+  const uint64_t k = oldKeys[j];
+  const uint32_t p = lower_bound_u64(newKeys, nNew, k);
+  if (p < nNew && newKeys[p] == k) return;
+  freeList[atomicAdd(&counters[C_FREETOP], 1u)] = oldSlots[j];
+  deletedKeys[atomicAdd(&counters[C_NDELETED], 1u)] = k;
+}
+__global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_t* __restrict__ oldSlots, const uint32_t* __restrict__ nOldP,
+                             const uint64_t* __restrict__ newKeys, uint32_t* __restrict__ newSlots, const uint32_t* __restrict__ nNewP,
+                             const uint32_t* __restrict__ freeList, uint64_t* __restrict__ createdKeys, uint32_t* __restrict__ counters,
+                             float4* __restrict__ manifolds, float4* __restrict__ frictions) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nOld = *nOldP, nNew = *nNewP;
+  if (i >= nNew) return;
+  const uint64_t k = newKeys[i];
+  const uint32_t p = lower_bound_u64(oldKeys, nOld, k);
+  if (p < nOld && oldKeys[p] == k) { newSlots[i] = oldSlots[p]; return; }
+  const uint32_t top = atomicSub(&counters[C_FREETOP], 1u);
+  const uint32_t slot = freeList[top - 1];
+  newSlots[i] = slot;
+  createdKeys[atomicAdd(&counters[C_NCREATED], 1u)] = k;
+  float4* m = manifolds + (size_t)slot * PXB_MANIFOLD_F4;
+  m[0] = make_float4(__int_as_float(0), FLT_MAX, FLT_MAX, FLT_MAX); m[1] = make_float4(0, 0, 0, 1); m[2] = make_float4(0, 0, 0, 1); m[3] = make_float4(0, 0, 0, 1);
+  float4* f = frictions + (size_t)slot * PXB_FRICTION_F4;
+  f[0] = make_float4(0, 0, 0, __int_as_float(0)); f[1] = make_float4(0, 0, 0, __int_as_float(0)); f[2] = make_float4(0, 0, 0, __int_as_float(0));
+}
+
+// a8-a11: one thread per pair.  Driver logic of PxcNpBatch.cpp:364-498: body0 is the dynamic actor (for
+// two dynamics the later-created one, ScNPhaseCore.cpp:182-252), shapes are ordered by geometry type for
+// the contact function and the normal is flipped back afterwards (flipContacts).
+__global__ void __launch_bounds__(128) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
+                              const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
+                              float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
+                              uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *nPairsP) return;
+  const uint64_t key = pairKeys[i];
+  const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
+  uint32_t a0 = hi, a1 = lo;
+  const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
+  if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
+  const uint32_t g0 = (a0 == hi) ? gfHi : gfLo, g1 = (a0 == hi) ? gfLo : gfHi;
+  const uint32_t t0 = g0 & 0xff, t1 = g1 & 0xff;
+  const bool flip = t1 < t0;
+  const uint32_t s0 = flip ? a1 : a0, s1 = flip ? a0 : a1;
+  const uint32_t ty0 = flip ? t1 : t0, ty1 = flip ? t0 : t1;
+  const float4 p0 = pos[s0], p1 = pos[s1];
+  xf tm0, tm1; tm0.p = V3(p0.x, p0.y, p0.z); tm0.q = Q4(quat[s0]); tm1.p = V3(p1.x, p1.y, p1.z); tm1.q = Q4(quat[s1]);
+  const float4 d0 = dims[s0], d1 = dims[s1];
+  float4* rec = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4;
+  Manifold man; manifold_load(man, rec);
+  Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
+  for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
+  if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_BOX) pcm_plane_box(tm0, tm1, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
+  else if (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX) pcm_box_box(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
+  manifold_store(man, rec);
+  if (flip && out.count) out.normal = -out.normal;
+  cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]); cForce[(size_t)i * 4 + k] = 0.f; }
+  pairBodies[i] = make_uint2(a0, a1);
+  conFlag[i] = out.count > 0 ? 1u : 0u;
+}
+
+__global__ void k_compact(const uint32_t* __restrict__ nPairsP, const uint32_t* __restrict__ conFlag, const uint32_t* __restrict__ conIdx, uint32_t* __restrict__ conPair,
+                          const uint32_t* __restrict__ pairSlots, float4* __restrict__ frictions) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *nPairsP) return;
+  if (conFlag[i]) conPair[conIdx[i]] = i;
+  else frictions[(size_t)pairSlots[i] * PXB_FRICTION_F4 + 2].w = __int_as_float(0);  // no contacts: friction patch state is dropped
+}
+// host-provided solver input order -> per-pair rank
+__global__ void k_rank_init(const uint32_t* __restrict__ nPairsP, uint32_t* __restrict__ rankOfPair) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *nPairsP) rankOfPair[i] = 0x80000000u + i;
+}
+__global__ void k_rank_map(uint32_t nOrder, const uint64_t* __restrict__ orderKeys, const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ nPairsP, uint32_t* __restrict__ rankOfPair) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nOrder) return;
+  const uint32_t n = *nPairsP; const uint64_t key = orderKeys[k];
+  const uint32_t p = lower_bound_u64(pairKeys, n, key);
+  if (p < n && pairKeys[p] == key) rankOfPair[p] = k;
+}
+__global__ void k_con_sortkeys(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ conPair, const uint32_t* __restrict__ rankOfPair, uint64_t* __restrict__ keys) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < counters[C_NCON]) keys[c] = rankOfPair[conPair[c]];
+}
+
+// a13 (1/3): constraint -> bodies, per-body constraint counts
+__global__ void k_con_bodies(const uint32_t* __restrict__ counters_, uint32_t* __restrict__ counters, const uint32_t* __restrict__ conPair, const uint2* __restrict__ pairBodies,
+                             const uint32_t* __restrict__ geomFlags, uint32_t* __restrict__ conB0, uint32_t* __restrict__ conB1, uint32_t* __restrict__ conDone, uint32_t* __restrict__ bodyCnt) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= counters_[C_NCON]) return;
+  const uint2 b = pairBodies[conPair[c]];
+  const bool dyn1 = (geomFlags[b.y] & 0x100u) != 0;
+  conB0[c] = b.x; conB1[c] = dyn1 ? b.y : NONE32; conDone[c] = dyn1 ? 0u : 1u;
+  atomicAdd(&bodyCnt[b.x], 1u);
+  if (dyn1) { atomicAdd(&bodyCnt[b.y], 1u); atomicAdd(&counters[C_REMAINING], 1u); }
+}
+__global__ void k_con_fill(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ conB0, const uint32_t* __restrict__ conB1, const uint32_t* __restrict__ bodyStart,
+                           uint32_t* __restrict__ bodyCursor, uint32_t* __restrict__ bodyList) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= counters[C_NCON]) return;
+  const uint32_t a = conB0[c], b = conB1[c];
+  bodyList[bodyStart[a] + atomicAdd(&bodyCursor[a], 1u)] = c;
+  if (b != NONE32) bodyList[bodyStart[b] + atomicAdd(&bodyCursor[b], 1u)] = c;
+}
+// a13 (2/3): order each body's list by solver input order; position of each constraint among the body's
+// dynamic (resp. static) constraints
+__global__ void k_body_lists(uint32_t nA, const uint32_t* __restrict__ bodyStart, const uint32_t* __restrict__ bodyCnt, uint32_t* __restrict__ bodyList,
+                             const uint32_t* __restrict__ conB0, const uint32_t* __restrict__ conB1, uint32_t* __restrict__ conPos0, uint32_t* __restrict__ conPos1,
+                             uint32_t* __restrict__ bodyNext, uint32_t* __restrict__ bodyMask, uint32_t* __restrict__ bodyHasCon) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nA) return;
+  const uint32_t n = bodyCnt[a]; uint32_t* l = bodyList + bodyStart[a];
+  for (uint32_t i = 1; i < n; ++i) { const uint32_t v = l[i]; uint32_t j = i; while (j > 0 && l[j - 1] > v) { l[j] = l[j - 1]; --j; } l[j] = v; }
+  uint32_t dpos = 0, spos = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t c = l[i]; const bool isStatic = conB1[c] == NONE32;
+    if (conB0[c] == a) conPos0[c] = isStatic ? spos : dpos; else conPos1[c] = dpos;
+    if (isStatic) spos++; else dpos++;
+  }
+  bodyNext[a] = 0; bodyMask[a] = 0; bodyHasCon[a] = n > 0 ? 1u : 0u;
+}
+// a13 (3/3): first-fit colouring in solver input order, identical to the sequential
+// classifyConstraintDesc (DyConstraintPartition.cpp:475-568): a constraint takes the lowest colour free on
+// both bodies once every earlier constraint of both bodies is coloured.  Static contacts of a body go to
+// partitions maxDynamicColour(body)+k (:203-262).  Then partition-major ordering of the constraints.
+__global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__ counters, const uint32_t* __restrict__ conB0, const uint32_t* __restrict__ conB1,
+                                   const uint32_t* __restrict__ conPos0, const uint32_t* __restrict__ conPos1, uint32_t* __restrict__ conColour, uint32_t* __restrict__ conDone,
+                                   uint32_t* __restrict__ bodyNext, uint32_t* __restrict__ bodyMask, uint32_t* __restrict__ partCnt, uint32_t* __restrict__ partStart,
+                                   uint32_t* __restrict__ partCursor, uint32_t* __restrict__ ordered) {
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t nCon = counters[C_NCON];
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  for (uint32_t p = gtid; p < MAX_PARTITIONS + 1; p += gsize) { partCnt[p] = 0; }
+  for (;;) {
+    // every thread samples the counter between two grid barriers, so all of them take the same branch
+    const uint32_t remaining = ld_volatile(&counters[C_REMAINING]);
+    grid.sync();
+    if (remaining == 0) break;
+    for (uint32_t c = gtid; c < nCon; c += gsize) {
+      if (conDone[c]) continue;
+      const uint32_t a = conB0[c], b = conB1[c];
+      if (ld_volatile(&bodyNext[a]) != conPos0[c] || ld_volatile(&bodyNext[b]) != conPos1[c]) continue;
+      __threadfence();
+      const uint32_t ma = ld_volatile(&bodyMask[a]), mb = ld_volatile(&bodyMask[b]);
+      const uint32_t comb = ~ma & ~mb;
+      uint32_t col = 31;
+      if (comb) col = __ffs(comb) - 1; else atomicOr(&counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
+      conColour[c] = col; conDone[c] = 1u;
+      st_volatile(&bodyMask[a], ma | (1u << col)); st_volatile(&bodyMask[b], mb | (1u << col));
+      __threadfence();
+      st_volatile(&bodyNext[a], conPos0[c] + 1); st_volatile(&bodyNext[b], conPos1[c] + 1);
+      atomicSub(&counters[C_REMAINING], 1u);
+    }
+    grid.sync();
+  }
+  grid.sync();
+  for (uint32_t c = gtid; c < nCon; c += gsize) {
+    uint32_t col;
+    if (conB1[c] == NONE32) { const uint32_t m = bodyMask[conB0[c]]; col = (m ? 32u - __clz(m) : 0u) + conPos0[c]; conColour[c] = col; }
+    else col = conColour[c];
+    if (col >= MAX_PARTITIONS) { col = MAX_PARTITIONS - 1; conColour[c] = col; atomicOr(&counters[C_ERROR], (uint32_t)E_PARTITION_OVERFLOW); }
+    atomicAdd(&partCnt[col], 1u);
+  }
+  grid.sync();
+  if (gtid == 0) {
+    uint32_t s = 0, np = 0;
+    for (uint32_t p = 0; p < MAX_PARTITIONS; ++p) { const uint32_t c = partCnt[p]; partStart[p] = s; partCursor[p] = s; s += c; if (c) np = p + 1; }
+    partStart[MAX_PARTITIONS] = s; counters[C_NPART] = np;
+  }
+  grid.sync();
+  for (uint32_t c = gtid; c < nCon; c += gsize) ordered[atomicAdd(&partCursor[conColour[c]], 1u)] = c;
+}
+
+// a12: unconstrained velocities + solver body setup (preIntegrateBodies, DyTGSDynamics.cpp:992-1021)
+__global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynActor, const float4* __restrict__ pos, const float4* __restrict__ quat,
+                               float4* __restrict__ linVel, float4* __restrict__ angVel, const float4* __restrict__ invInertia, const float4* __restrict__ damp,
+                               float gx, float gy, float gz, float dt, float4* __restrict__ sbLin, float4* __restrict__ sbAng, float4* __restrict__ sbDLin,
+                               float4* __restrict__ sbDAng, float4* __restrict__ sbIA, float4* __restrict__ sbIB, float4* __restrict__ sbP, float4* __restrict__ sbQ,
+                               float4* __restrict__ sbOrigAng) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nDyn) return;
+  const uint32_t a = dynActor[d];
+  const float4 dm = damp[a]; const float4 ii = invInertia[a]; const float4 p4 = pos[a];
+  v3 lv = V3(linVel[a]), av = V3(angVel[a]);
+  unconstrained_velocity(V3(gx, gy, gz), dt, dm.x, dm.y, dm.z, dm.w, lv, av);
+  linVel[a] = F4(lv, 0.f); angVel[a] = F4(av, 0.f);
+  const m33 rot = mfromq(Q4(quat[a]));
+  const v3 sqrtInvI = V3(ii.x == 0.f ? 0.f : sqrtf(ii.x), ii.y == 0.f ? 0.f : sqrtf(ii.y), ii.z == 0.f ? 0.f : sqrtf(ii.z));
+  const v3 sqrtI = V3(sqrtInvI.x == 0.f ? 0.f : 1.0f / sqrtInvI.x, sqrtInvI.y == 0.f ? 0.f : 1.0f / sqrtInvI.y, sqrtInvI.z == 0.f ? 0.f : 1.0f / sqrtInvI.z);
+  m33 sI, sInertia; transform_inertia(sqrtInvI, rot, sI); transform_inertia(sqrtI, rot, sInertia);
+  sbLin[a] = F4(lv, 0.f); sbAng[a] = F4(mmul(sInertia, av), 0.f); sbDLin[a] = make_float4(0, 0, 0, 0); sbDAng[a] = make_float4(0, 0, 0, 0);
+  sbIA[a] = make_float4(sI.c0.x, sI.c0.y, sI.c0.z, sI.c1.y); sbIB[a] = make_float4(sI.c1.z, sI.c2.z, 0.f, 0.f);
+  sbP[a] = make_float4(p4.x, p4.y, p4.z, 0.f); sbQ[a] = make_float4(0, 0, 0, 1); sbOrigAng[a] = F4(av, 0.f);
+}
+__device__ __forceinline__ m33 load_sym(const float4 A, const float4 B) {
+  m33 m; m.c0 = V3(A.x, A.y, A.z); m.c1 = V3(A.y, A.w, B.x); m.c2 = V3(A.z, B.x, B.y); return m;
+}
+
+// a14: per constraint (in solve order): friction-patch correlation + solver rows
+__global__ void __launch_bounds__(128) k_prep(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ ordered, const uint32_t* __restrict__ conPair, const uint32_t* __restrict__ pairSlots,
+                       const uint2* __restrict__ pairBodies, const uint32_t* __restrict__ geomFlags, const float4* __restrict__ cHdr, const float4* __restrict__ cPts,
+                       const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ linVel, const float4* __restrict__ sbOrigAng,
+                       const float4* __restrict__ invInertia, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, float4* __restrict__ frictions, SolverParams P, uint32_t cap,
+                       float4* __restrict__ rowA, float4* __restrict__ rowB, uint4* __restrict__ rowC, float4* __restrict__ ptA, float4* __restrict__ ptB, float4* __restrict__ ptC,
+                       float4* __restrict__ frA, float4* __restrict__ frB, float4* __restrict__ frC, float4* __restrict__ frD) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= counters[C_NCON]) return;
+  const uint32_t c = ordered[k]; const uint32_t i = conPair[c];
+  const uint2 bb = pairBodies[i]; const uint32_t b0 = bb.x, b1 = bb.y;
+  const bool dyn1 = (geomFlags[b1] & 0x100u) != 0;
+  Contacts con; const float4 h = cHdr[i]; con.normal = V3(h.x, h.y, h.z); con.count = __float_as_int(h.w);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float4 p = cPts[(size_t)i * 4 + j]; con.point[j] = V3(p.x, p.y, p.z); con.sep[j] = p.w; }
+  xf f0, f1; { const float4 p = pos[b0]; f0.p = V3(p.x, p.y, p.z); f0.q = Q4(quat[b0]); const float4 q = pos[b1]; f1.p = V3(q.x, q.y, q.z); f1.q = Q4(quat[b1]); }
+  float4* frec = frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4;
+  FrictionPatch fp; friction_load(fp, frec);
+  friction_correlate(fp, con, f0, f1, P.staticFriction, P.dynamicFriction, P.restitution, P.correlationDistance, P.frictionOffsetThreshold + P.restDistance);
+  friction_store(fp, frec);
+  const float invMass0 = pos[b0].w, invMass1 = dyn1 ? pos[b1].w : 0.f;
+  const float pen0 = -invInertia[b0].w, pen1 = dyn1 ? -invInertia[b1].w : -FLT_MAX;
+  const float maxPenBias = fmax_(pen0, pen1);
+  const v3 linVel0 = V3(linVel[b0]), linVel1 = dyn1 ? V3(linVel[b1]) : V3(0, 0, 0);
+  const v3 angVel0 = V3(sbOrigAng[b0]), angVel1 = dyn1 ? V3(sbOrigAng[b1]) : V3(0, 0, 0);
+  const m33 sI0 = load_sym(sbIA[b0], sbIB[b0]);
+  m33 sI1; if (dyn1) sI1 = load_sym(sbIA[b1], sbIB[b1]); else { sI1.c0 = sI1.c1 = sI1.c2 = V3(0, 0, 0); }
+  const float invMass0_dom0 = 1.f * invMass0, invMass1_dom1 = (-1.f) * invMass1;
+  const float scale = fmin_(0.8f, P.biasCoefficient);
+  const float invDtp8 = P.invStepDt * scale, frictionBiasScale = P.invStepDt * scale;
+  const v3 normal = con.normal;
+  const float normalLenSq = adot(normal, normal);
+  const float norVel0 = adot(linVel0, normal), norVel1 = adot(linVel1, normal);
+  const float imn0 = invMass0_dom0 * normalLenSq, imn1 = invMass1_dom1 * normalLenSq;
+  const bool haveFriction = fp.anchorCount != 0;
+  const uint32_t numFriction = haveFriction ? (uint32_t)fp.anchorCount * 2u : 0u;
+  rowA[k] = F4(normal, maxPenBias);
+  rowB[k] = make_float4(invMass0_dom0, -invMass1_dom1, P.staticFriction, P.dynamicFriction);
+  rowC[k] = make_uint4(b0, dyn1 ? b1 : NONE32, (uint32_t)con.count | (numFriction << 8), i);
+  for (int j = 0; j < con.count; ++j) {
+    SPoint s; prep_point(s, con.point[j], con.sep[j], normal, f0.p, f1.p, sI0, sI1, angVel0, angVel1, norVel0, norVel1, imn0, imn1, P, invDtp8);
+    ptA[(size_t)j * cap + k] = F4(s.raXnI, s.velMultiplier); ptB[(size_t)j * cap + k] = F4(s.rbXnI, s.separation);
+    ptC[(size_t)j * cap + k] = make_float4(s.biasCoefficient, s.targetVelocity, s.recipResponse, 0.f);
+  }
+  if (haveFriction) {
+    const v3 linVrel = linVel0 - linVel1;
+    const v3 fb1 = V3(0.f, -normal.z, normal.y), fb2 = V3(-normal.y, normal.x, 0.f);
+    const v3 t0Fallback = (0.70710678f > fabsf(normal.x)) ? fb1 : fb2;
+    v3 t0 = linVrel - normal * adot(normal, linVrel);
+    t0 = (adot(t0, t0) > 0.0001f) ? t0 : t0Fallback;
+    t0 = anormalize(t0);
+    const v3 t1 = anormalize(cross(normal, t0));
+    const v3 relTr = f0.p - f1.p;
+    const float frictionScale = (fp.anchorCount == 2) ? 0.5f : 1.f;
+    for (int j = 0; j < fp.anchorCount; ++j) {
+      const v3 ra = aqrot(f0.q, fp.body0Anchors[j]), rb = aqrot(f1.q, fp.body1Anchors[j]);
+      const v3 error = (ra - rb) + relTr;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        SFriction f; prep_friction_row(f, ra, rb, error, t == 0 ? t0 : t1, sI0, sI1, imn0, imn1, scale, frictionScale, frictionBiasScale);
+        const size_t o = (size_t)(j * 2 + t) * cap + k;
+        frA[o] = F4(f.normal, f.error); frB[o] = F4(f.raXnI, f.targetVel); frC[o] = F4(f.rbXnI, f.velMultiplier);
+        frD[o] = make_float4(0.f, f.frictionScale, f.biasScale, 0.f);
+      }
+    }
+  }
+}
+
+// a15: one contact constraint (solveContact, DyTGSContactPrep.cpp:1581-1873)
+__device__ __forceinline__ void solve_constraint(uint32_t k, uint32_t cap, float minPen, float elapsedTime, const float4* __restrict__ rowA, const float4* __restrict__ rowB,
+                                                 const uint4* __restrict__ rowC, const float4* __restrict__ ptA, const float4* __restrict__ ptB, float4* __restrict__ ptC,
+                                                 const float4* __restrict__ frA, const float4* __restrict__ frB, const float4* __restrict__ frC, float4* __restrict__ frD,
+                                                 float4* __restrict__ sbLin, float4* __restrict__ sbAng, const float4* __restrict__ sbDLin, const float4* __restrict__ sbDAng,
+                                                 uint32_t* __restrict__ brokenFlags) {
+  const uint4 rc = rowC[k]; const uint32_t b0 = rc.x, b1 = rc.y;
+  const uint32_t numNormal = rc.z & 0xff, numFriction = (rc.z >> 8) & 0xff;
+  const float4 ra4 = rowA[k], rb4 = rowB[k];
+  const v3 n = V3(ra4.x, ra4.y, ra4.z); const float maxPenBias = ra4.w;
+  const float invMassA = rb4.x, invMassB = rb4.y;
+  v3 linVel0 = V3(sbLin[b0]), angState0 = V3(sbAng[b0]);
+  const v3 angMotion0 = V3(sbDAng[b0]); v3 relMotion = V3(sbDLin[b0]);
+  v3 linVel1 = V3(0, 0, 0), angState1 = V3(0, 0, 0), angMotion1 = V3(0, 0, 0);
+  if (b1 != NONE32) { linVel1 = V3(sbLin[b1]); angState1 = V3(sbAng[b1]); angMotion1 = V3(sbDAng[b1]); relMotion = relMotion - V3(sbDLin[b1]); }
+  float accum = 0.f;
+  {
+    const v3 nim0 = n * invMassA, nim1 = n * invMassB;
+    const float deltaV = adot(relMotion, n);
+    for (uint32_t j = 0; j < numNormal; ++j) {
+      const size_t o = (size_t)j * cap + k;
+      const float4 A = ptA[o], B = ptB[o]; float4 C = ptC[o];
+      const v3 raXnI = V3(A.x, A.y, A.z), rbXnI = V3(B.x, B.y, B.z);
+      const float deltaAng = adot(angMotion0, raXnI) - adot(angMotion1, rbXnI);
+      const float targetVel = C.y;
+      const float deltaBias = (deltaV + deltaAng) - targetVel * elapsedTime;
+      const float sep = fmax_(minPen, B.w + deltaBias);
+      const float bias = fmin_(-maxPenBias, C.x * sep);
+      const v3 dv = (vmul(linVel0, n) + vmul(angState0, raXnI)) - (vmul(linVel1, n) + vmul(angState1, rbXnI));
+      const float normalVel = (dv.x + dv.y) + dv.z;
+      const float biasNV = bias * C.z;
+      const float lambda = biasNV - (normalVel - targetVel) * A.w;
+      const float applied = C.w;
+      const float dF_ = fmax_(lambda, -applied);
+      const float newForce = fmin_(applied + dF_, FLT_MAX);
+      const float deltaF = newForce - applied;
+      linVel0 = scaleadd(nim0, deltaF, linVel0); linVel1 = negscalesub(nim1, deltaF, linVel1);
+      angState0 = scaleadd(raXnI, deltaF * 1.f, angState0); angState1 = negscalesub(rbXnI, deltaF * 1.f, angState1);
+      C.w = newForce; ptC[o] = C;
+      accum = accum + newForce;
+    }
+  }
+  if (numFriction) {
+    const float maxFrictionImpulse = rb4.z * accum, maxDynFrictionImpulse = rb4.w * accum;
+    bool broken = false;
+    for (uint32_t j = 0; j < numFriction; j += 2) {
+      const size_t o0 = (size_t)j * cap + k, o1 = (size_t)(j + 1) * cap + k;
+      const float4 A0 = frA[o0], B0 = frB[o0], C0 = frC[o0]; float4 D0 = frD[o0];
+      const float4 A1 = frA[o1], B1 = frB[o1], C1 = frC[o1]; float4 D1 = frD[o1];
+      const float frictionScale = D0.y, biasScale = D0.z;
+      const v3 normal0 = V3(A0.x, A0.y, A0.z), normal1 = V3(A1.x, A1.y, A1.z);
+      const v3 raXnI0 = V3(B0.x, B0.y, B0.z), rbXnI0 = V3(C0.x, C0.y, C0.z), raXnI1 = V3(B1.x, B1.y, B1.z), rbXnI1 = V3(C1.x, C1.y, C1.z);
+      const float applied0 = D0.x, applied1 = D1.x, targetVel0 = B0.w, targetVel1 = B1.w;
+      float deltaV0 = (adot(raXnI0, angMotion0) - adot(rbXnI0, angMotion1)) + adot(normal0, relMotion);
+      float deltaV1 = (adot(raXnI1, angMotion0) - adot(rbXnI1, angMotion1)) + adot(normal1, relMotion);
+      deltaV0 = deltaV0 - targetVel0 * elapsedTime; deltaV1 = deltaV1 - targetVel1 * elapsedTime;
+      const float bias0 = (A0.w + deltaV0) * biasScale, bias1 = (A1.w + deltaV1) * biasScale;
+      const float vm0 = C0.w, vm1 = C1.w;
+      const v3 d0 = (vmul(linVel0, normal0) + vmul(angState0, raXnI0)) - (vmul(linVel1, normal0) + vmul(angState1, rbXnI0));
+      const v3 d1 = (vmul(linVel0, normal1) + vmul(angState0, raXnI1)) - (vmul(linVel1, normal1) + vmul(angState1, rbXnI1));
+      const float normalVel0 = (d0.x + d0.y) + d0.z, normalVel1 = (d1.x + d1.y) + d1.z;
+      const float tmp10 = applied0 - (bias0 - targetVel0) * vm0, tmp11 = applied1 - (bias1 - targetVel1) * vm1;
+      const float total0 = tmp10 - normalVel0 * vm0, total1 = tmp11 - normalVel1 * vm1;
+      const float total = sqrtf(total0 * total0 + total1 * total1);
+      const bool clamp = total > (frictionScale * maxFrictionImpulse);
+      const float totalClamped = clamp ? fmin_(frictionScale * maxDynFrictionImpulse, total) : total;
+      const float ratio = (total > 0.f) ? (totalClamped / total) : 0.f;
+      const float new0 = total0 * ratio, new1 = total1 * ratio;
+      broken = broken || clamp;
+      const float dF0 = new0 - applied0, dF1 = new1 - applied1;
+      linVel0 = scaleadd(normal0 * invMassA, dF0, scaleadd(normal1 * invMassA, dF1, linVel0));
+      linVel1 = negscalesub(normal0 * invMassB, dF0, negscalesub(normal1 * invMassB, dF1, linVel1));
+      angState0 = scaleadd(raXnI0, dF0 * 1.f, scaleadd(raXnI1, dF1 * 1.f, angState0));
+      angState1 = negscalesub(rbXnI0, dF0 * 1.f, negscalesub(rbXnI1, dF1 * 1.f, angState1));
+      D0.x = new0; D1.x = new1; frD[o0] = D0; frD[o1] = D1;
+    }
+    brokenFlags[k] = broken ? 1u : 0u;  // hdr->broken is overwritten by every solve call (Store_From_BoolV)
+  }
+  sbLin[b0] = F4(linVel0, 0.f); sbAng[b0] = F4(angState0, 0.f);
+  if (b1 != NONE32) { sbLin[b1] = F4(linVel1, 0.f); sbAng[b1] = F4(angState1, 0.f); }
+}
+
+// a15/a16: the whole TGS iteration loop in ONE cooperative launch (iterativeSolveIsland, DyTGSDynamics.cpp:2515-2793):
+// position iterations = {solve every partition in order; integrate the sub-step}, then velocity iterations.
+__global__ void __launch_bounds__(256) k_solve(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ partStart, uint32_t cap, uint32_t posIters, uint32_t velIters, float stepDt,
+                        const float4* __restrict__ rowA, const float4* __restrict__ rowB, const uint4* __restrict__ rowC, const float4* __restrict__ ptA, const float4* __restrict__ ptB,
+                        float4* __restrict__ ptC, const float4* __restrict__ frA, const float4* __restrict__ frB, const float4* __restrict__ frC, float4* __restrict__ frD,
+                        float4* __restrict__ sbLin, float4* __restrict__ sbAng, float4* __restrict__ sbDLin, float4* __restrict__ sbDAng, const float4* __restrict__ sbIA,
+                        const float4* __restrict__ sbIB, float4* __restrict__ sbP, float4* __restrict__ sbQ, const uint32_t* __restrict__ bodyHasCon, uint32_t nDyn,
+                        const uint32_t* __restrict__ dynActor, uint32_t* __restrict__ brokenFlags) {
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t nPart = counters[C_NPART];
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  if (nPart == 0) return;
+  float elapsed = 0.f;
+  for (uint32_t it = 0; it < posIters + velIters; ++it) {
+    const bool vel = it >= posIters;
+    const float minPen = vel ? 0.f : -FLT_MAX;
+    for (uint32_t p = 0; p < nPart; ++p) {
+      const uint32_t b = partStart[p], e = partStart[p + 1];
+      for (uint32_t k = b + gtid; k < e; k += gsize)
+        solve_constraint(k, cap, minPen, elapsed, rowA, rowB, rowC, ptA, ptB, ptC, frA, frB, frC, frD, sbLin, sbAng, sbDLin, sbDAng, brokenFlags);
+      grid.sync();
+    }
+    if (!vel) {
+      for (uint32_t d = gtid; d < nDyn; d += gsize) {
+        const uint32_t a = dynActor[d];
+        if (!bodyHasCon[a]) continue;
+        v3 p = V3(sbP[a]); q4 dq = Q4(sbQ[a]); v3 dl = V3(sbDLin[a]), da = V3(sbDAng[a]);
+        integrate_core_step(V3(sbLin[a]), V3(sbAng[a]), load_sym(sbIA[a], sbIB[a]), stepDt, p, dq, dl, da);
+        sbP[a] = F4(p, 0.f); sbQ[a] = F4(dq); sbDLin[a] = F4(dl, 0.f); sbDAng[a] = F4(da, 0.f);
+      }
+      elapsed += stepDt;
+      grid.sync();
+    }
+  }
+}
+
+// a17/a18: copyBackBodies (DyTGSDynamics.cpp:1549-1580); bodies without constraints take one full-dt step (:2573-2577)
+__global__ void k_finalize_bodies(uint32_t nDyn, const uint32_t* __restrict__ dynActor, float dt, float4* __restrict__ pos, float4* __restrict__ quat, float4* __restrict__ linVel,
+                                  float4* __restrict__ angVel, const float4* __restrict__ sbLin, const float4* __restrict__ sbAng, const float4* __restrict__ sbIA,
+                                  const float4* __restrict__ sbIB, const float4* __restrict__ sbP, const float4* __restrict__ sbQ, const uint32_t* __restrict__ bodyHasCon) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nDyn) return;
+  const uint32_t a = dynActor[d];
+  const m33 sI = load_sym(sbIA[a], sbIB[a]);
+  v3 p = V3(sbP[a]); q4 dq = Q4(sbQ[a]);
+  const v3 lv = V3(sbLin[a]), as = V3(sbAng[a]);
+  if (!bodyHasCon[a]) { v3 dl = V3(0, 0, 0), da = V3(0, 0, 0); integrate_core_step(lv, as, sI, dt, p, dq, dl, da); }
+  const float invMass = pos[a].w;
+  const q4 q = qnormalized(qmul(dq, Q4(quat[a])));
+  pos[a] = make_float4(p.x, p.y, p.z, invMass); quat[a] = F4(q);
+  linVel[a] = F4(lv, 0.f); angVel[a] = F4(mmul(sI, as), 0.f);
+}
+// writeBackContact (DyTGSContactPrep.cpp:1875-1937): applied forces -> contact force stream, broken flag -> friction patch
+__global__ void k_writeback(const uint32_t* __restrict__ counters, uint32_t cap, const uint4* __restrict__ rowC, const float4* __restrict__ ptC, const uint32_t* __restrict__ brokenFlags,
+                            const uint32_t* __restrict__ pairSlots, float* __restrict__ cForce, float4* __restrict__ frictions) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= counters[C_NCON]) return;
+  const uint4 rc = rowC[k]; const uint32_t i = rc.w; const uint32_t numNormal = rc.z & 0xff, numFriction = (rc.z >> 8) & 0xff;
+  for (uint32_t j = 0; j < numNormal; ++j) cForce[(size_t)i * 4 + j] = ptC[(size_t)j * cap + k].w;
+  if (numFriction && brokenFlags[k]) frictions[(size_t)pairSlots[i] * PXB_FRICTION_F4 + 1].w = __int_as_float(1);
+}
+
+// a19: PxDirectGPUAPI get/set (gather/scatter by dynamic-body index)
+__global__ void k_rd_get(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, int type, const float4* __restrict__ pos, const float4* __restrict__ quat,
+                         const float4* __restrict__ linVel, const float4* __restrict__ angVel, float* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const uint32_t a = dynActor[idx ? idx[i] : i];
+  if (type == PXB_RD_GLOBAL_POSE) { const float4 q = quat[a], p = pos[a]; float* o = out + (size_t)i * 7; o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; o[4] = p.x; o[5] = p.y; o[6] = p.z; }
+  else { const float4 v = type == PXB_RD_LINEAR_VELOCITY ? linVel[a] : angVel[a]; float* o = out + (size_t)i * 3; o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+}
+__global__ void k_rd_set(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, int type, float4* __restrict__ pos, float4* __restrict__ quat,
+                         float4* __restrict__ linVel, float4* __restrict__ angVel, const float* __restrict__ in) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const uint32_t a = dynActor[idx ? idx[i] : i];
+  if (type == PXB_RD_GLOBAL_POSE) { const float* o = in + (size_t)i * 7; quat[a] = make_float4(o[0], o[1], o[2], o[3]); const float w = pos[a].w; pos[a] = make_float4(o[4], o[5], o[6], w); }
+  else { const float* o = in + (size_t)i * 3; const float4 v = make_float4(o[0], o[1], o[2], 0.f); if (type == PXB_RD_LINEAR_VELOCITY) linVel[a] = v; else angVel[a] = v; }
+}
+__global__ void k_states_get(uint32_t nDyn, const uint32_t* __restrict__ dynActor, const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ linVel,
+                             const float4* __restrict__ angVel, float* __restrict__ out) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nDyn) return;
+  const uint32_t a = dynActor[d]; float* o = out + (size_t)d * 13;
+  const float4 p = pos[a], q = quat[a], l = linVel[a], w = angVel[a];
+  o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = q.x; o[4] = q.y; o[5] = q.z; o[6] = q.w; o[7] = l.x; o[8] = l.y; o[9] = l.z; o[10] = w.x; o[11] = w.y; o[12] = w.z;
+}
+__global__ void k_states_set(uint32_t nDyn, const uint32_t* __restrict__ dynActor, float4* __restrict__ pos, float4* __restrict__ quat, float4* __restrict__ linVel,
+                             float4* __restrict__ angVel, const float* __restrict__ in) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nDyn) return;
+  const uint32_t a = dynActor[d]; const float* o = in + (size_t)d * 13;
+  const float w = pos[a].w;
+  pos[a] = make_float4(o[0], o[1], o[2], w); quat[a] = make_float4(o[3], o[4], o[5], o[6]); linVel[a] = make_float4(o[7], o[8], o[9], 0.f); angVel[a] = make_float4(o[10], o[11], o[12], 0.f);
+}
+__global__ void k_init_freelist(uint32_t cap, uint32_t* __restrict__ freeList) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) freeList[i] = cap - 1 - i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+template <typename T> static cudaError_t dalloc(T*& p, size_t n) { return cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)); }
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+static uint32_t bits_for(uint64_t n) { uint32_t b = 1; while ((1ull << b) < n) ++b; return b; }
+
+extern "C" {
+
+PXB_API const char* pxb_last_error(void) { return g_err.c_str(); }
+PXB_API int pxb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+static int scene_alloc(PxbScene* s) {
+  const size_t A = s->capA, Pn = s->capPairs;
+  CK(dalloc(s->pos, A)); CK(dalloc(s->quat, A)); CK(dalloc(s->linVel, A)); CK(dalloc(s->angVel, A)); CK(dalloc(s->invInertia, A)); CK(dalloc(s->damp, A));
+  CK(dalloc(s->dims, A)); CK(dalloc(s->aabbMin, A)); CK(dalloc(s->aabbMax, A)); CK(dalloc(s->geomFlags, A)); CK(dalloc(s->envId, A)); CK(dalloc(s->dynActorDev, A));
+  CK(dalloc(s->largeList, A)); CK(dalloc(s->tight, A * 6));
+  CK(dalloc(s->sbLin, A)); CK(dalloc(s->sbAng, A)); CK(dalloc(s->sbDLin, A)); CK(dalloc(s->sbDAng, A)); CK(dalloc(s->sbIA, A)); CK(dalloc(s->sbIB, A)); CK(dalloc(s->sbP, A));
+  CK(dalloc(s->sbQ, A)); CK(dalloc(s->sbOrigAng, A));
+  CK(dalloc(s->bodyCnt, A)); CK(dalloc(s->bodyStart, A)); CK(dalloc(s->bodyCursor, A)); CK(dalloc(s->bodyNext, A)); CK(dalloc(s->bodyMask, A)); CK(dalloc(s->bodyHasCon, A));
+  CK(dalloc(s->cellKey, A)); CK(dalloc(s->cellKeyAlt, A)); CK(dalloc(s->cellVal, A)); CK(dalloc(s->cellValAlt, A)); CK(dalloc(s->sMin, A)); CK(dalloc(s->sMax, A));
+  for (int k = 0; k < 2; ++k) { CK(dalloc(s->pairKeys[k], Pn)); CK(dalloc(s->pairSlots[k], Pn)); }
+  CK(dalloc(s->pairKeyAlt, Pn)); CK(dalloc(s->pairValTmp, Pn)); CK(dalloc(s->pairValAlt, Pn)); CK(dalloc(s->nPairsDev, 2));
+  CK(dalloc(s->freeList, Pn)); CK(dalloc(s->createdKeys, Pn)); CK(dalloc(s->deletedKeys, Pn));
+  CK(dalloc(s->manifolds, Pn * PXB_MANIFOLD_F4)); CK(dalloc(s->frictions, Pn * PXB_FRICTION_F4));
+  CK(dalloc(s->cHdr, Pn)); CK(dalloc(s->cPts, Pn * 4)); CK(dalloc(s->pairBodies, Pn)); CK(dalloc(s->cForce, Pn * 4));
+  CK(dalloc(s->conFlag, Pn)); CK(dalloc(s->conIdx, Pn)); CK(dalloc(s->conPair, Pn)); CK(dalloc(s->rankOfPair, Pn)); CK(dalloc(s->conSortKey, Pn)); CK(dalloc(s->conSortKeyAlt, Pn));
+  CK(dalloc(s->conPairAlt, Pn));
+  CK(dalloc(s->conB0, Pn)); CK(dalloc(s->conB1, Pn)); CK(dalloc(s->conPos0, Pn)); CK(dalloc(s->conPos1, Pn)); CK(dalloc(s->conColour, Pn)); CK(dalloc(s->conDone, Pn));
+  CK(dalloc(s->bodyList, Pn * 2)); CK(dalloc(s->ordered, Pn));
+  CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
+  CK(dalloc(s->rowA, Pn)); CK(dalloc(s->rowB, Pn)); CK(dalloc(s->rowC, Pn)); CK(dalloc(s->ptA, Pn * 4)); CK(dalloc(s->ptB, Pn * 4)); CK(dalloc(s->ptC, Pn * 4));
+  CK(dalloc(s->frA, Pn * 4)); CK(dalloc(s->frB, Pn * 4)); CK(dalloc(s->frC, Pn * 4)); CK(dalloc(s->frD, Pn * 4));
+  CK(dalloc(s->counters, C_COUNT)); CK(cudaMallocHost((void**)&s->hostCounters, sizeof(uint32_t) * (C_COUNT + 2)));
+  CK(dalloc(s->rsTmp.blockHist, RS_MAX_CTAS * 256)); CK(dalloc(s->scanSums, RS_MAX_CTAS));
+  CK(cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * C_COUNT, s->stream)); CK(cudaMemsetAsync(s->nPairsDev, 0, 8, s->stream));
+  CK(cudaMemsetAsync(s->sbLin, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->sbAng, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->sbDLin, 0, 16 * A, s->stream));
+  CK(cudaMemsetAsync(s->sbDAng, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->sbIA, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->sbIB, 0, 16 * A, s->stream));
+  CK(cudaMemsetAsync(s->sbOrigAng, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->bodyHasCon, 0, 4 * A, s->stream));
+  CK(cudaMemsetAsync(s->manifolds, 0, sizeof(float4) * Pn * PXB_MANIFOLD_F4, s->stream)); CK(cudaMemsetAsync(s->frictions, 0, sizeof(float4) * Pn * PXB_FRICTION_F4, s->stream));
+  k_init_freelist<<<cdiv((uint32_t)Pn, 256), 256, 0, s->stream>>>((uint32_t)Pn, s->freeList);
+  const uint32_t top = (uint32_t)Pn;
+  CK(cudaMemcpyAsync(s->counters + C_FREETOP, &top, 4, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return PXB_OK;
+}
+
+PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
+  PxbScene* s = nullptr;
+  if (!desc || !out) return fail(PXB_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PXB_ERR_NO_DEVICE, "no CUDA device: physx_b200 has no CPU fallback"); }
+  if (desc->solverType != PXB_SOLVER_TGS) return fail(PXB_ERR_UNSUPPORTED, "only the TGS solver is implemented");
+  if (desc->device < 0 || desc->device >= ndev) return fail(PXB_ERR_INVALID, "bad device ordinal");
+  s = new PxbScene(); s->desc = *desc;
+  CK(cudaSetDevice(desc->device));
+  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, desc->device));
+  s->numSMs = prop.multiProcessorCount;
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_colour_partition, 256, 0)); s->coopBlocksColour = std::max(1, std::min(occ, 4)) * s->numSMs;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, 2)) * s->numSMs;
+  s->capA = std::max(16u, desc->maxActors);
+  s->capPairs = desc->maxPairs ? desc->maxPairs : std::max(1024u, 8u * s->capA);
+  s->bitsA = bits_for(s->capA);
+  s->rsTmp.ctas = std::min<uint32_t>(RS_MAX_CTAS, (uint32_t)s->numSMs * 2);
+  const int rc = scene_alloc(s);
+  if (rc != PXB_OK) { delete s; return rc; }
+  *out = s;
+  return PXB_OK;
+}
+
+PXB_API void pxb_scene_release(PxbScene* s) {
+  if (!s) return;
+  cudaStreamSynchronize(s->stream);
+  void* ptrs[] = {s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
+                  s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
+                  s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
+                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->conFlag, s->conIdx,
+                  s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
+                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD, s->counters, s->rsTmp.blockHist, s->scanSums};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (s->hostCounters) cudaFreeHost(s->hostCounters);
+  cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+PXB_API uint32_t pxb_scene_num_actors(const PxbScene* s) { return s ? s->nA : 0; }
+PXB_API uint32_t pxb_scene_num_dynamic(const PxbScene* s) { return s ? s->nDyn : 0; }
+PXB_API void* pxb_scene_stream(PxbScene* s) { return s ? (void*)s->stream : nullptr; }
+PXB_API void* pxb_scene_state_device_ptr(PxbScene* s, int which) {
+  if (!s) return nullptr;
+  switch (which) { case 0: return s->pos; case 1: return s->quat; case 2: return s->linVel; case 3: return s->angVel; default: return nullptr; }
+}
+
+// bounding diameter of a shape (rotation independent), used to size the broadphase grid cell
+static float shape_diameter(const ActorRec& r) {
+  switch (r.geomType) {
+    case PXB_GEOM_SPHERE: return 2.f * r.dims[0];
+    case PXB_GEOM_CAPSULE: return 2.f * (r.dims[0] + r.dims[1]);
+    case PXB_GEOM_BOX: return 2.f * std::sqrt(r.dims[0] * r.dims[0] + r.dims[1] * r.dims[1] + r.dims[2] * r.dims[2]);
+    default: return INFINITY;
+  }
+}
+
+static void rebuild_grid(PxbScene* s) {
+  // cell edge = largest rotation-independent extent among regular shapes (+ inflation, + 2% slack); shapes more
+  // than 8x the median are classified "large" (tested against everything) so they do not blow the cell up.
+  std::vector<float> diam; diam.reserve(s->nA);
+  for (auto& r : s->recs) { const float d = shape_diameter(r); if (std::isfinite(d)) diam.push_back(d); }
+  float med = 1.f;
+  if (!diam.empty()) { std::vector<float> t = diam; std::nth_element(t.begin(), t.begin() + t.size() / 2, t.end()); med = t[t.size() / 2]; }
+  const float largeThresh = 8.f * med;
+  bool usesEnv = false; uint32_t maxEnv = 0;
+  for (auto& r : s->recs) if (r.envId != NONE32) { usesEnv = true; maxEnv = std::max(maxEnv, r.envId); }
+  float cell = 0.f; float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  s->largeHost.clear();
+  std::vector<uint32_t> gf(s->nA);
+  for (uint32_t a = 0; a < s->nA; ++a) {
+    const ActorRec& r = s->recs[a];
+    const float d = shape_diameter(r);
+    const bool global = !std::isfinite(d) || d > largeThresh || (usesEnv && r.envId == NONE32);
+    gf[a] = (r.geomType & 0xff) | ((r.flags & PXB_ACTOR_DYNAMIC) ? 0x100u : 0u) | (global ? 0x200u : 0u);
+    if (global) { s->largeHost.push_back(a); continue; }
+    cell = std::max(cell, d);
+    for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], r.pos[k]); mx[k] = std::max(mx[k], r.pos[k]); }
+  }
+  cell = (cell + 2.f * s->desc.contactOffset) * 1.02f; if (!(cell > 0.f)) cell = 1.f;
+  GridParams g; g.invCell = 1.0f / cell;
+  int n[3];
+  for (int k = 0; k < 3; ++k) {
+    if (!std::isfinite(mn[k])) { mn[k] = 0.f; mx[k] = 0.f; }
+    const float span = (mx[k] - mn[k]) + 16.f * cell;  // headroom: objects outside are clamped (still correct, just slower)
+    n[k] = std::max(4, (int)std::ceil(span / cell) + 1);
+  }
+  g.ox = mn[0] - 8.f * cell; g.oy = mn[1] - 8.f * cell; g.oz = mn[2] - 8.f * cell; g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
+  const uint64_t envCount = usesEnv ? (uint64_t)maxEnv + 1 : 1;
+  // keep the key within 62 bits
+  while ((long double)envCount * g.nx * g.ny * g.nz > 4.0e18L) { if (g.nx >= g.ny && g.nx >= g.nz) g.nx = (g.nx + 1) / 2; else if (g.ny >= g.nz) g.ny = (g.ny + 1) / 2; else g.nz = (g.nz + 1) / 2; }
+  g.keyBits = bits_for((uint64_t)envCount * (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz + 1);
+  s->grid = g; s->nLarge = (uint32_t)s->largeHost.size();
+  s->desc.reserved[0] = (uint32_t)envCount;
+  cudaMemcpyAsync(s->geomFlags, gf.data(), 4 * s->nA, cudaMemcpyHostToDevice, s->stream);
+  if (s->nLarge) cudaMemcpyAsync(s->largeList, s->largeHost.data(), 4 * s->nLarge, cudaMemcpyHostToDevice, s->stream);
+  cudaStreamSynchronize(s->stream);
+  s->gridDirty = false;
+}
+
+PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
+  if (!s || !recsIn) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->abort) return fail(PXB_ERR_CUDA, "scene is in abort mode");
+  if (s->nA + nb > s->capA) return fail(PXB_ERR_CAPACITY, "maxActors exceeded");
+  const ActorRec* in = (const ActorRec*)recsIn;
+  const uint32_t base = s->nA;
+  std::vector<float4> pos(nb), quat(nb), lin(nb), ang(nb), inv(nb), dmp(nb), dims(nb); std::vector<uint32_t> env(nb);
+  for (uint32_t i = 0; i < nb; ++i) {
+    const ActorRec& r = in[i];
+    if (r.geomType != PXB_GEOM_BOX && r.geomType != PXB_GEOM_PLANE && r.geomType != PXB_GEOM_SPHERE && r.geomType != PXB_GEOM_CAPSULE)
+      return fail(PXB_ERR_UNSUPPORTED, "geometry type not supported yet");
+    const bool dyn = r.flags & PXB_ACTOR_DYNAMIC;
+    s->recs.push_back(r);
+    if (dyn) { s->dynIndex.push_back((int)s->nDyn); s->dynActor.push_back(base + i); s->nDyn++; } else s->dynIndex.push_back(-1);
+    const float invMass = (dyn && r.mass > 0.f) ? 1.0f / r.mass : 0.f;
+    pos[i] = make_float4(r.pos[0], r.pos[1], r.pos[2], invMass); quat[i] = make_float4(r.quat[0], r.quat[1], r.quat[2], r.quat[3]);
+    lin[i] = make_float4(r.linVel[0], r.linVel[1], r.linVel[2], 0.f); ang[i] = make_float4(r.angVel[0], r.angVel[1], r.angVel[2], 0.f);
+    inv[i] = make_float4(dyn && r.inertia[0] > 0.f ? 1.0f / r.inertia[0] : 0.f, dyn && r.inertia[1] > 0.f ? 1.0f / r.inertia[1] : 0.f, dyn && r.inertia[2] > 0.f ? 1.0f / r.inertia[2] : 0.f, r.maxDepenetrationVel);
+    dmp[i] = make_float4(r.linDamping, r.angDamping, r.maxLinVel * r.maxLinVel, r.maxAngVel * r.maxAngVel);
+    dims[i] = make_float4(r.dims[0], r.dims[1], r.dims[2], r.dims[3]); env[i] = r.envId;
+  }
+  s->nA += nb;
+  CK(cudaMemcpyAsync(s->pos + base, pos.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->quat + base, quat.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->linVel + base, lin.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->angVel + base, ang.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->invInertia + base, inv.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->damp + base, dmp.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->dims + base, dims.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->envId + base, env.data(), 4 * nb, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->dynActorDev, s->dynActor.data(), 4 * s->nDyn, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  s->gridDirty = true;
+  return PXB_OK;
+}
+
+PXB_API int pxb_scene_set_constraint_order(PxbScene* s, const uint32_t* pairs, uint32_t n) {
+  if (!s) return fail(PXB_ERR_INVALID, "null scene");
+  s->nOrder = 0;
+  if (!n) return PXB_OK;
+  if (!pairs) return fail(PXB_ERR_INVALID, "null pairs");
+  if (n > s->capOrder) { if (s->orderKeys) cudaFree(s->orderKeys); s->capOrder = std::max(n, s->capPairs); CK(dalloc(s->orderKeys, s->capOrder)); }
+  std::vector<uint64_t> keys(n);
+  for (uint32_t k = 0; k < n; ++k) { const uint32_t a = std::min(pairs[2 * k], pairs[2 * k + 1]), b = std::max(pairs[2 * k], pairs[2 * k + 1]); keys[k] = ((uint64_t)a << s->bitsA) | b; }
+  CK(cudaMemcpyAsync(s->orderKeys, keys.data(), 8 * n, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  s->nOrder = n;
+  return PXB_OK;
+}
+
+#define LAUNCH(kernel, grid, block, ...) do { kernel<<<(grid), (block), 0, st>>>(__VA_ARGS__); s->launches++; } while (0)
+
+// stage 1: bounds + broadphase + pair lifecycle
+static int run_broadphase(PxbScene* s, bool externalTight) {
+  cudaStream_t st = s->stream;
+  if (s->gridDirty) rebuild_grid(s);
+  const uint32_t nA = s->nA, B = 256;
+  const int prev = s->cur; s->cur ^= 1; const int cur = s->cur;
+  CK(cudaMemsetAsync(s->counters + C_NPAIRS_NEW, 0, 4 * 3, st));  // NPAIRS_NEW, NCREATED, NDELETED
+  CK(cudaMemcpyAsync(s->counters + C_NA, &s->nA, 4, cudaMemcpyHostToDevice, st));
+  LAUNCH(k_bounds, cdiv(nA, B), B, nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, externalTight ? 1 : 0, s->aabbMin, s->aabbMax, s->grid,
+         s->desc.reserved[0], s->cellKey, s->cellVal);
+  const int r = radix_sort_pairs(s->cellKey, s->cellVal, s->cellKeyAlt, s->cellValAlt, s->counters + C_NA, s->grid.keyBits, s->rsTmp, st);
+  s->launches += 3 * ((s->grid.keyBits + 7) / 8);
+  const uint64_t* sk = r ? s->cellKeyAlt : s->cellKey; const uint32_t* sv = r ? s->cellValAlt : s->cellVal;
+  LAUNCH(k_bp_gather, cdiv(nA, B), B, nA, sv, s->aabbMin, s->aabbMax, s->sMin, s->sMax);
+  LAUNCH(k_bp_pairs, cdiv(nA, 128), 128, nA, sk, sv, s->sMin, s->sMax, s->grid, s->bitsA, s->pairKeys[cur], s->counters, s->capPairs);
+  if (s->nLarge) LAUNCH(k_bp_large, cdiv(nA, B), B, nA, s->nLarge, s->largeList, s->aabbMin, s->aabbMax, s->bitsA, s->pairKeys[cur], s->counters, s->capPairs);
+  LAUNCH(k_clamp_count, 1, 32, s->counters, s->capPairs, s->nPairsDev + cur);
+  const int r2 = radix_sort_pairs(s->pairKeys[cur], s->pairValTmp, s->pairKeyAlt, s->pairValAlt, s->nPairsDev + cur, 2 * s->bitsA, s->rsTmp, st);
+  s->launches += 3 * ((2 * s->bitsA + 7) / 8);
+  if (r2) std::swap(s->pairKeys[cur], s->pairKeyAlt);
+  const uint32_t gP = cdiv(s->capPairs, B);
+  LAUNCH(k_pair_lost, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->nPairsDev + cur, s->freeList, s->deletedKeys, s->counters);
+  LAUNCH(k_pair_found, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->pairSlots[cur], s->nPairsDev + cur, s->freeList, s->createdKeys, s->counters,
+         s->manifolds, s->frictions);
+  return PXB_OK;
+}
+
+static int read_counters(PxbScene* s) {
+  CK(cudaMemcpyAsync(s->hostCounters, s->counters, 4 * C_COUNT, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(s->hostCounters + C_COUNT, s->nPairsDev, 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  s->hNPairs = s->hostCounters[C_COUNT + s->cur]; s->hNCreated = s->hostCounters[C_NCREATED]; s->hNDeleted = s->hostCounters[C_NDELETED];
+  s->hNCon = s->hostCounters[C_NCON]; s->hNPart = s->hostCounters[C_NPART]; s->hErr = s->hostCounters[C_ERROR];
+  if (s->hErr & E_PAIR_OVERFLOW) return fail(PXB_ERR_CAPACITY, "broadphase pair capacity (maxPairs) exceeded");
+  if (s->hErr & (E_COLOUR_OVERFLOW | E_PARTITION_OVERFLOW)) return fail(PXB_ERR_CAPACITY, "more than 32 dynamic colours / 96 partitions needed");
+  return PXB_OK;
+}
+
+PXB_API int pxb_scene_simulate(PxbScene* s, float dt) {
+  if (!s) return fail(PXB_ERR_INVALID, "null scene");
+  if (s->abort) return fail(PXB_ERR_CUDA, "scene is in abort mode");
+  if (s->nA == 0) return PXB_OK;
+  if (!(dt > 0.f)) return fail(PXB_ERR_INVALID, "dt must be positive");
+  cudaStream_t st = s->stream; const uint32_t B = 256;
+  s->launches = 0;
+  int rc = run_broadphase(s, false); if (rc) return rc;
+  const int cur = s->cur; const uint32_t gP = cdiv(s->capPairs, B);
+  const uint32_t* nP = s->nPairsDev + cur;
+  const float contactDist = s->desc.contactOffset + s->desc.contactOffset;
+  LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
+         s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce);
+  exclusive_scan_u32(s->conFlag, s->conIdx, nP, s->counters + C_NCON, s->scanSums, s->rsTmp.ctas, st); s->launches += 3;
+  LAUNCH(k_compact, gP, B, nP, s->conFlag, s->conIdx, s->conPair, s->pairSlots[cur], s->frictions);
+  if (s->nOrder) {
+    LAUNCH(k_rank_init, gP, B, nP, s->rankOfPair);
+    LAUNCH(k_rank_map, cdiv(s->nOrder, B), B, s->nOrder, s->orderKeys, s->pairKeys[cur], nP, s->rankOfPair);
+    LAUNCH(k_con_sortkeys, gP, B, s->counters, s->conPair, s->rankOfPair, s->conSortKey);
+    const int r = radix_sort_pairs(s->conSortKey, s->conPair, s->conSortKeyAlt, s->conPairAlt, s->counters + C_NCON, 32, s->rsTmp, st); s->launches += 12;
+    if (r) std::swap(s->conPair, s->conPairAlt);
+  }
+  CK(cudaMemsetAsync(s->bodyCnt, 0, 4 * s->nA, st)); CK(cudaMemsetAsync(s->bodyCursor, 0, 4 * s->nA, st));
+  CK(cudaMemsetAsync(s->counters + C_NPART, 0, 8, st));  // NPART, REMAINING
+  LAUNCH(k_con_bodies, gP, B, s->counters, s->counters, s->conPair, s->pairBodies, s->geomFlags, s->conB0, s->conB1, s->conDone, s->bodyCnt);
+  exclusive_scan_u32(s->bodyCnt, s->bodyStart, s->counters + C_NA, s->counters + C_NDYNCON, s->scanSums, s->rsTmp.ctas, st); s->launches += 3;
+  LAUNCH(k_con_fill, gP, B, s->counters, s->conB0, s->conB1, s->bodyStart, s->bodyCursor, s->bodyList);
+  LAUNCH(k_body_lists, cdiv(s->nA, B), B, s->nA, s->bodyStart, s->bodyCnt, s->bodyList, s->conB0, s->conB1, s->conPos0, s->conPos1, s->bodyNext, s->bodyMask, s->bodyHasCon);
+  {
+    void* args[] = {&s->counters, &s->conB0, &s->conB1, &s->conPos0, &s->conPos1, &s->conColour, &s->conDone, &s->bodyNext, &s->bodyMask, &s->partCnt, &s->partStart, &s->partCursor, &s->ordered};
+    CK(cudaLaunchCooperativeKernel((void*)k_colour_partition, dim3(s->coopBlocksColour), dim3(256), args, 0, st)); s->launches++;
+  }
+  const float* g = s->desc.gravity;
+  LAUNCH(k_preintegrate, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, g[0], g[1], g[2], dt, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng,
+         s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng);
+  SolverParams P;
+  P.dt = dt; P.stepDt = dt / (float)s->desc.posIters; P.invStepDt = 1.f / P.stepDt; P.invTotalDt = 1.0f / dt;
+  P.biasCoefficient = 2.f * sqrtf(1.f / (float)s->desc.posIters);
+  P.bounceThreshold = -s->desc.bounceThresholdVelocity;  // Sc::Scene hands the solver the negated threshold (ScScene.cpp:1002)
+  P.frictionOffsetThreshold = s->desc.frictionOffsetThreshold; P.correlationDistance = s->desc.frictionCorrelationDistance;
+  P.restDistance = s->desc.restOffset + s->desc.restOffset; P.staticFriction = s->desc.staticFriction; P.dynamicFriction = s->desc.dynamicFriction; P.restitution = s->desc.restitution;
+  LAUNCH(k_prep, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
+         s->invInertia, s->sbIA, s->sbIB, s->frictions, P, s->capPairs, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD);
+  {
+    uint32_t cap = s->capPairs, posIters = s->desc.posIters, velIters = s->desc.velIters; float stepDt = P.stepDt; uint32_t nDyn = s->nDyn; uint32_t* broken = s->conDone;
+    void* args[] = {&s->counters, &s->partStart, &cap, &posIters, &velIters, &stepDt, &s->rowA, &s->rowB, &s->rowC, &s->ptA, &s->ptB, &s->ptC, &s->frA, &s->frB, &s->frC, &s->frD,
+                    &s->sbLin, &s->sbAng, &s->sbDLin, &s->sbDAng, &s->sbIA, &s->sbIB, &s->sbP, &s->sbQ, &s->bodyHasCon, &nDyn, &s->dynActorDev, &broken};
+    CK(cudaMemsetAsync(s->conDone, 0, 4 * (size_t)s->capPairs, st));
+    CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(s->coopBlocksSolve), dim3(256), args, 0, st)); s->launches++;
+  }
+  LAUNCH(k_writeback, gP, B, s->counters, s->capPairs, s->rowC, s->ptC, s->conDone, s->pairSlots[cur], s->cForce, s->frictions);
+  LAUNCH(k_finalize_bodies, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->bodyHasCon);
+  CK(cudaGetLastError());
+  s->stepping = true;
+  return PXB_OK;
+}
+
+PXB_API int pxb_scene_fetch_results(PxbScene* s, int block) {
+  if (!s) return fail(PXB_ERR_INVALID, "null scene");
+  if (!block) { const cudaError_t e = cudaStreamQuery(s->stream); if (e == cudaErrorNotReady) return 1; }
+  s->stepping = false;
+  return read_counters(s);
+}
+
+PXB_API int pxb_scene_compute_bounds(PxbScene* s) {
+  if (!s) return fail(PXB_ERR_INVALID, "null scene");
+  cudaStream_t st = s->stream;
+  if (s->gridDirty) rebuild_grid(s);
+  LAUNCH(k_bounds, cdiv(s->nA, 256), 256, s->nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, 0, s->aabbMin, s->aabbMax, s->grid, s->desc.reserved[0], s->cellKey, s->cellVal);
+  CK(cudaStreamSynchronize(st));
+  return PXB_OK;
+}
+PXB_API int pxb_scene_get_bounds(PxbScene* s, float* out6) {
+  if (!s || !out6) return fail(PXB_ERR_INVALID, "null argument");
+  CK(cudaMemcpyAsync(out6, s->tight, 24 * (size_t)s->nA, cudaMemcpyDeviceToHost, s->stream)); CK(cudaStreamSynchronize(s->stream));
+  return PXB_OK;
+}
+PXB_API int pxb_scene_broadphase(PxbScene* s, const float* tightBounds) {
+  if (!s) return fail(PXB_ERR_INVALID, "null scene");
+  if (s->abort) return fail(PXB_ERR_CUDA, "scene is in abort mode");
+  s->launches = 0;
+  if (tightBounds) { CK(cudaMemcpyAsync(s->tight, tightBounds, 24 * (size_t)s->nA, cudaMemcpyHostToDevice, s->stream)); }
+  const int rc = run_broadphase(s, tightBounds != nullptr); if (rc) return rc;
+  return read_counters(s);
+}
+static int copy_pairs(PxbScene* s, const uint64_t* dev, uint32_t n, uint32_t* out, bool sortThem) {
+  std::vector<uint64_t> k(n);
+  if (n) { CK(cudaMemcpyAsync(k.data(), dev, 8 * (size_t)n, cudaMemcpyDeviceToHost, s->stream)); CK(cudaStreamSynchronize(s->stream)); }
+  if (sortThem) std::sort(k.begin(), k.end());
+  for (uint32_t i = 0; i < n; ++i) { out[2 * i] = (uint32_t)(k[i] >> s->bitsA); out[2 * i + 1] = (uint32_t)(k[i] & ((1ull << s->bitsA) - 1ull)); }
+  return PXB_OK;
+}
+PXB_API uint32_t pxb_scene_num_pairs(PxbScene* s) { return s ? s->hNPairs : 0; }
+PXB_API uint32_t pxb_scene_num_created(PxbScene* s) { return s ? s->hNCreated : 0; }
+PXB_API uint32_t pxb_scene_num_deleted(PxbScene* s) { return s ? s->hNDeleted : 0; }
+PXB_API int pxb_scene_get_pairs(PxbScene* s, uint32_t* out) { if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->pairKeys[s->cur], s->hNPairs, out, false); }
+PXB_API int pxb_scene_get_created(PxbScene* s, uint32_t* out) { if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->createdKeys, s->hNCreated, out, true); }
+PXB_API int pxb_scene_get_deleted(PxbScene* s, uint32_t* out) { if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->deletedKeys, s->hNDeleted, out, true); }
+PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) {
+  if (!s || !out24) return fail(PXB_ERR_INVALID, "null argument");
+  const uint32_t n = s->hNPairs; if (!n) return PXB_OK;
+  std::vector<float4> h(n), p((size_t)n * 4); std::vector<float> f((size_t)n * 4);
+  CK(cudaMemcpyAsync(h.data(), s->cHdr, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->stream)); CK(cudaMemcpyAsync(p.data(), s->cPts, 64 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(f.data(), s->cForce, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->stream)); CK(cudaStreamSynchronize(s->stream));
+  for (uint32_t i = 0; i < n; ++i) {
+    float* o = out24 + (size_t)i * 24; memset(o, 0, 96);
+    int cnt; memcpy(&cnt, &h[i].w, 4);
+    o[0] = (float)cnt; o[1] = h[i].x; o[2] = h[i].y; o[3] = h[i].z;
+    for (int k = 0; k < cnt && k < 4; ++k) { const float4 q = p[(size_t)i * 4 + k]; float* r = o + 4 + k * 5; r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; r[4] = f[(size_t)i * 4 + k]; }
+  }
+  return PXB_OK;
+}
+PXB_API uint32_t pxb_scene_last_num_partitions(PxbScene* s) { return s ? s->hNPart : 0; }
+PXB_API uint32_t pxb_scene_last_num_constraints(PxbScene* s) { return s ? s->hNCon : 0; }
+PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* s) { return s ? s->launches : 0; }
+
+static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb, bool set) {
+  if (type < 0 || type > 2) return fail(PXB_ERR_INVALID, "bad dataType");
+  if (!devIdx && nb > s->nDyn) return fail(PXB_ERR_INVALID, "nb exceeds the number of dynamic bodies");
+  cudaStream_t st = s->stream;
+  if (!nb) return PXB_OK;
+  if (set) LAUNCH(k_rd_set, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (const float*)devData);
+  else LAUNCH(k_rd_get, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (float*)devData);
+  CK(cudaGetLastError());
+  return PXB_OK;
+}
+PXB_API int pxb_get_rigid_dynamic_data_device(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb) {
+  if (!s || !devData) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
+  return rd_common(s, devData, devIdx, type, nb, false);
+}
+PXB_API int pxb_set_rigid_dynamic_data_device(PxbScene* s, const void* devData, const uint32_t* devIdx, int type, uint32_t nb) {
+  if (!s || !devData) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
+  return rd_common(s, const_cast<void*>(devData), devIdx, type, nb, true);
+}
+static int rd_host(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb, bool set) {
+  if (!s || !data) return fail(PXB_ERR_INVALID, "null argument");
+  if (type < 0 || type > 2) return fail(PXB_ERR_INVALID, "bad dataType");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
+  if (!nb) return PXB_OK;
+  const size_t bytes = (size_t)nb * (type == 0 ? 28 : 12);
+  float* d = nullptr; uint32_t* di = nullptr;
+  CK(cudaMalloc((void**)&d, bytes));
+  if (idx) { for (uint32_t i = 0; i < nb; ++i) if (idx[i] >= s->nDyn) { cudaFree(d); return fail(PXB_ERR_INVALID, "index out of range"); }
+             CK(cudaMalloc((void**)&di, 4 * (size_t)nb)); CK(cudaMemcpyAsync(di, idx, 4 * (size_t)nb, cudaMemcpyHostToDevice, s->stream)); }
+  if (set) CK(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, s->stream));
+  int rc = rd_common(s, d, di, type, nb, set);
+  if (!rc && !set) CK(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  cudaFree(d); if (di) cudaFree(di);
+  return rc;
+}
+PXB_API int pxb_get_rigid_dynamic_data(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, data, idx, type, nb, false); }
+PXB_API int pxb_set_rigid_dynamic_data(PxbScene* s, const void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, const_cast<void*>(data), idx, type, nb, true); }
+
+PXB_API int pxb_scene_get_states(PxbScene* s, float* out) {
+  if (!s || !out) return fail(PXB_ERR_INVALID, "null argument");
+  if (!s->nDyn) return PXB_OK;
+  cudaStream_t st = s->stream; float* d = nullptr; CK(cudaMalloc((void**)&d, 52 * (size_t)s->nDyn));
+  LAUNCH(k_states_get, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, d);
+  CK(cudaMemcpyAsync(out, d, 52 * (size_t)s->nDyn, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); cudaFree(d);
+  return PXB_OK;
+}
+PXB_API int pxb_scene_set_states(PxbScene* s, const float* in) {
+  if (!s || !in) return fail(PXB_ERR_INVALID, "null argument");
+  if (!s->nDyn) return PXB_OK;
+  cudaStream_t st = s->stream; float* d = nullptr; CK(cudaMalloc((void**)&d, 52 * (size_t)s->nDyn));
+  CK(cudaMemcpyAsync(d, in, 52 * (size_t)s->nDyn, cudaMemcpyHostToDevice, st));
+  LAUNCH(k_states_set, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, d);
+  CK(cudaStreamSynchronize(st)); cudaFree(d);
+  return PXB_OK;
+}
+
+}  // extern "C"

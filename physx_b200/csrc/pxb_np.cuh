@@ -1,0 +1,497 @@
+// pxb_np.cuh -- narrowphase contact generation (stage 2 of the rigid-body step), device functions.
+//
+// Semantics follow the reference's CPU PCM path (persistent contact manifolds), which is what the
+// parity target is, not the reference GPU's stateless box-box:
+//   persistent manifold refresh / invalidation / reduction
+//       physx/source/geomutils/src/pcm/GuPersistentContactManifold.h:160-260, :695-752
+//       physx/source/geomutils/src/pcm/GuPersistentContactManifold.cpp:739-1174
+//   plane vs box   physx/source/geomutils/src/pcm/GuPCMContactPlaneBox.cpp:36-209
+//   box vs box     physx/source/geomutils/src/pcm/GuPCMContactBoxBox.cpp:42-971
+// Known deviations: (1) the reference's _mm_rcp_ps in the segment/AABB clip is an exact reciprocal
+// here; (2) the GJK/EPA single-point fallback of box-box (taken only when the SAT passes and face
+// clipping produces no point) is not implemented yet -- such a pair reports no contact that frame.
+#pragma once
+#include "pxb_math.cuh"
+
+#define PXB_MANIFOLD_CACHE 4
+#define PXB_MANIFOLD_F4 16   // float4 slots per persistent manifold record (14 used)
+
+struct MPoint { v3 a, b, n; float pen; };
+struct Manifold { int n; xf rel; q4 quatA, quatB; MPoint pts[PXB_MANIFOLD_CACHE]; };
+struct Contacts { int count; v3 normal; v3 point[PXB_MANIFOLD_CACHE]; float sep[PXB_MANIFOLD_CACHE]; };
+
+PXB_D void manifold_init(Manifold& m) {
+  m.n = 0; m.rel.q = Q4(0, 0, 0, 1); m.rel.p = V3(FLT_MAX, FLT_MAX, FLT_MAX);
+  m.quatA = Q4(0, 0, 0, 1); m.quatB = Q4(0, 0, 0, 1);
+  for (int i = 0; i < PXB_MANIFOLD_CACHE; ++i) { m.pts[i].a = V3(0, 0, 0); m.pts[i].b = V3(0, 0, 0); m.pts[i].n = V3(0, 0, 0); m.pts[i].pen = 0.f; }
+}
+
+// record layout: [0]=(n, rel.p) [1]=rel.q [2]=quatA [3]=quatB [4+..]=4 points x 10 floats
+PXB_D void manifold_load(Manifold& m, const float4* __restrict__ rec) {
+  const float4 h = rec[0], rq = rec[1], qa = rec[2], qb = rec[3];
+  m.n = __float_as_int(h.x); m.rel.p = V3(h.y, h.z, h.w); m.rel.q = Q4(rq); m.quatA = Q4(qa); m.quatB = Q4(qb);
+  float f[40];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) { const float4 v = rec[4 + i]; f[i * 4] = v.x; f[i * 4 + 1] = v.y; f[i * 4 + 2] = v.z; f[i * 4 + 3] = v.w; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m.pts[i].a = V3(f[i * 10], f[i * 10 + 1], f[i * 10 + 2]); m.pts[i].b = V3(f[i * 10 + 3], f[i * 10 + 4], f[i * 10 + 5]);
+    m.pts[i].n = V3(f[i * 10 + 6], f[i * 10 + 7], f[i * 10 + 8]); m.pts[i].pen = f[i * 10 + 9];
+  }
+}
+PXB_D void manifold_store(const Manifold& m, float4* __restrict__ rec) {
+  rec[0] = make_float4(__int_as_float(m.n), m.rel.p.x, m.rel.p.y, m.rel.p.z); rec[1] = F4(m.rel.q); rec[2] = F4(m.quatA); rec[3] = F4(m.quatB);
+  float f[40];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[i * 10] = m.pts[i].a.x; f[i * 10 + 1] = m.pts[i].a.y; f[i * 10 + 2] = m.pts[i].a.z; f[i * 10 + 3] = m.pts[i].b.x; f[i * 10 + 4] = m.pts[i].b.y;
+    f[i * 10 + 5] = m.pts[i].b.z; f[i * 10 + 6] = m.pts[i].n.x; f[i * 10 + 7] = m.pts[i].n.y; f[i * 10 + 8] = m.pts[i].n.z; f[i * 10 + 9] = m.pts[i].pen;
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) rec[4 + i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+}
+
+PXB_D float box_margin(v3 e, float toleranceLength) {  // GuVecBox.h:81-88
+  const float mn = fmin_(e.x, fmin_(e.y, e.z));
+  return fmin_(mn * 0.15f, toleranceLength * 0.15f);
+}
+
+PXB_D void manifold_refresh(Manifold& m, const mxf& aToB, float projectBreakingThreshold) {  // GuPersistentContactManifold.h:723-752
+  const float sq = projectBreakingThreshold * projectBreakingThreshold;
+  for (int i = m.n; i > 0; --i) {
+    MPoint& mp = m.pts[i - 1];
+    const v3 localAInB = amxftransform(aToB, mp.a);
+    const v3 v = localAInB - mp.b;
+    const float dist = adot(v, mp.n);
+    const v3 projected = negscalesub(mp.n, dist, localAInB);
+    const v3 diff = mp.b - projected;
+    const float d2 = adot(diff, diff);
+    if (d2 > sq) { m.n--; m.pts[i - 1] = m.pts[m.n]; }
+    else mp.pen = dist;
+  }
+}
+PXB_D float max_pos_delta(const Manifold& m, v3 curP) {
+  const v3 d = vabs(curP - m.rel.p);
+  return fmax_(d.x, fmax_(d.y, d.z));
+}
+PXB_D bool invalidate_plane(const Manifold& m, const xf& cur, float minMargin, float ratio) {  // :245-257
+  const float thresholdP = minMargin * ratio;
+  return (max_pos_delta(m, cur.p) > thresholdP) || (0.99996f > adot4(cur.q, m.rel.q));
+}
+PXB_D bool invalidate_boxconvex(const Manifold& m, const xf& cur, q4 quatA, q4 quatB, float minMargin, float radiusA, float radiusB) {  // :190-223
+  const float thr[5] = {0.5f, 0.125f, 0.25f, 0.375f, 0.375f};
+  const float qthr[5] = {0.9998f, 0.9999f, 0.9999f, 0.9999f, 0.9999f};
+  const float thresholdP = minMargin * thr[m.n];
+  const float deltaP = max_pos_delta(m, cur.p);
+  const float thresholdQ = qthr[m.n];
+  const float dqA = adot4(quatA, m.quatA), dqB = adot4(quatB, m.quatB);
+  bool gen = (deltaP > thresholdP) || (thresholdQ > dqA) || (thresholdQ > dqB);
+  if (!gen) {
+    const float aRad = dqA < 1.0f ? acosf(dqA) : 0.f;
+    const float bRad = dqB < 1.0f ? acosf(dqB) : 0.f;
+    gen = (aRad * radiusA > thresholdP) || (bRad * radiusB > thresholdP);
+  }
+  return gen;
+}
+
+// GuPersistentContactManifold.cpp:859-1005
+PXB_D void reduce_cluster(Manifold& m, const MPoint* p, int numPoints) {
+  uint32_t chosen = 0u;
+  float maxDist = FLT_MAX; int index = 0; int indices[4];
+  for (int i = 0; i < numPoints; ++i) if (maxDist > p[i].pen) { maxDist = p[i].pen; index = i; }
+  m.pts[0] = p[index]; chosen |= 1u << index; indices[0] = index;
+  v3 v = p[0].b - m.pts[0].b; maxDist = adot(v, v); index = 0;
+  for (int i = 1; i < numPoints; ++i) { v = p[i].b - m.pts[0].b; const float d = adot(v, v); if (d > maxDist) { maxDist = d; index = i; } }
+  m.pts[1] = p[index]; chosen |= 1u << index; indices[1] = index;
+  maxDist = -FLT_MAX; index = 0;
+  v = m.pts[1].b - m.pts[0].b;
+  const v3 cn0 = m.pts[0].n;
+  v3 norm = cross(v, cn0);
+  const float sqLen = adot(norm, norm);
+  if (sqLen > 0.f) { const float l = sqrtf(sqLen); norm = V3(norm.x / l, norm.y / l, norm.z / l); } else norm = cn0;
+  float minDist = FLT_MAX; int index1 = 0;
+  for (int i = 0; i < numPoints; ++i) if (!((chosen >> i) & 1u)) {
+    v = p[i].b - m.pts[0].b; const float d = adot(v, norm);
+    if (d > maxDist) { maxDist = d; index = i; }
+    if (minDist > d) { minDist = d; index1 = i; }
+  }
+  m.pts[2] = p[index]; chosen |= 1u << index; indices[2] = index;
+  if (minDist * maxDist > 0.f) {
+    maxDist = -FLT_MAX;
+    for (int i = 0; i < numPoints; ++i) if (!((chosen >> i) & 1u)) {
+      v = p[i].b - m.pts[0].b; const float d = adot(v, norm);
+      if (d > maxDist) { maxDist = d; index1 = i; }
+    }
+  }
+  m.pts[3] = p[index1]; chosen |= 1u << index1; indices[3] = index1;
+  for (int i = 0; i < numPoints; ++i) if (!((chosen >> i) & 1u)) {
+    maxDist = FLT_MAX; const float pen = p[i].pen; index = 0;
+    for (int j = 0; j < 4; ++j) { const v3 v1 = p[i].b - m.pts[j].b; const float dist = adot(v1, v1); if (maxDist > dist) { maxDist = dist; index = j; } }
+    if (p[indices[index]].pen > pen) indices[index] = i;
+  }
+  for (int k = 0; k < 4; ++k) m.pts[k] = p[indices[k]];
+}
+
+// GuPersistentContactManifold.cpp:1008-1174
+PXB_D void reduce_batch(Manifold& m, const MPoint* p, int numPoints, float toleranceLength) {
+  int chosenIdx[4]; uint8_t cand[16];
+  float maxPen = p[0].pen, minPen = maxPen;
+  int index = 0; cand[0] = 0; int candIndex = 0; int nbCand = numPoints;
+  for (int i = 1; i < numPoints; ++i) {
+    cand[i] = (uint8_t)i;
+    const float pen = p[i].pen;
+    minPen = fmax_(minPen, pen);
+    if (maxPen > pen) { maxPen = pen; index = i; candIndex = i; }
+  }
+  chosenIdx[0] = index;
+  nbCand--; cand[candIndex] = cand[nbCand];
+  v3 v = p[cand[0]].b - p[chosenIdx[0]].b;
+  float maxDist = adot(v, v); index = cand[0]; candIndex = 0;
+  for (int i = 1; i < nbCand; ++i) {
+    v = p[cand[i]].b - p[chosenIdx[0]].b; const float d = adot(v, v);
+    if (d > maxDist) { maxDist = d; index = cand[i]; candIndex = i; }
+  }
+  chosenIdx[1] = index;
+  nbCand--; cand[candIndex] = cand[nbCand];
+  v = p[chosenIdx[1]].b - p[chosenIdx[0]].b;
+  const v3 cn0 = p[chosenIdx[0]].n;
+  v3 norm = cross(v, cn0);
+  const float sqLen = adot(norm, norm);
+  if (sqLen > 0.f) { const float l = sqrtf(sqLen); norm = V3(norm.x / l, norm.y / l, norm.z / l); } else norm = cn0;
+  maxDist = -FLT_MAX; index = 0; candIndex = 0;
+  float minDist = FLT_MAX; int index1 = 0, candIndex1 = 0;
+  for (int i = 0; i < nbCand; ++i) {
+    v = p[cand[i]].b - p[chosenIdx[0]].b; const float d = adot(v, norm);
+    if (d > maxDist) { maxDist = d; index = cand[i]; candIndex = i; }
+    if (minDist > d) { minDist = d; index1 = cand[i]; candIndex1 = i; }
+  }
+  chosenIdx[2] = index;
+  nbCand--; cand[candIndex] = cand[nbCand];
+  if (nbCand == candIndex1) candIndex1 = candIndex;
+  if (minDist * maxDist > 0.f) {
+    maxDist = -FLT_MAX;
+    for (int i = 0; i < nbCand; ++i) {
+      v = p[cand[i]].b - p[chosenIdx[0]].b; const float d = adot(v, norm);
+      if (d > maxDist) { maxDist = d; index1 = cand[i]; candIndex1 = i; }
+    }
+  }
+  chosenIdx[3] = index1;
+  nbCand--; cand[candIndex1] = cand[nbCand];
+  const float eps = toleranceLength * 0.02f;
+  if ((eps > maxPen) && (minPen > eps)) {
+    for (int i = 0; i < 4; ++i) {
+      float pen = p[chosenIdx[i]].pen;
+      if (pen > eps) {
+        candIndex = 0xff;
+        for (int j = 0; j < nbCand; ++j) {
+          const float pen1 = p[cand[j]].pen;
+          if ((pen > pen1) && (eps > pen1)) { pen = pen1; candIndex = j; }
+        }
+        if (candIndex < nbCand) { const int orig = chosenIdx[i]; chosenIdx[i] = cand[candIndex]; cand[candIndex] = (uint8_t)orig; }
+      }
+      m.pts[i] = p[chosenIdx[i]];
+    }
+  } else {
+    for (int i = 0; i < 4; ++i) m.pts[i] = p[chosenIdx[i]];
+  }
+}
+
+PXB_D v3 manifold_world_normal(const Manifold& m, const xf& trB) {  // GuPersistentContactManifold.h:695-708
+  v3 n = m.pts[0].n;
+  for (int i = 1; i < m.n; ++i) n = n + m.pts[i].n;
+  const float sq = adot(n, n);
+  const v3 nn = (sq > FLT_EPSILON) ? n : m.pts[0].n;
+  return aqrot_normalize(trB.q, nn);
+}
+
+// plane (shape0) vs box (shape1): GuPCMContactPlaneBox.cpp:36-209
+PXB_D void pcm_plane_box(const xf& planeTm, const xf& boxTm, v3 be, float contactDist, float toleranceLength, Manifold& man, Contacts& out) {
+  const xf cur = axfinvmul(planeTm, boxTm);  // box to plane
+  const v3 negPlaneNormal = anormalize(-aqbasis0(planeTm.q));
+  const float margin = box_margin(be, toleranceLength);
+  const int initial = man.n;
+  const mxf aToB = amxffromxf(cur);
+  manifold_refresh(man, aToB, margin * 0.2f);
+  const bool lost = man.n != initial;
+  out.count = 0; out.normal = negPlaneNormal;
+  if (lost || invalidate_plane(man, cur, margin, 0.2f)) {
+    const v3 ln = V3(1.f, 0.f, 0.f);
+    man.n = 0; man.rel = cur;
+    const v3 t0 = aToB.r.c0 * be.x, t1 = aToB.r.c1 * be.y, t2 = aToB.r.c2 * be.z;
+    const v3 nt2 = -t2;
+    const float px = aToB.p.x;
+    const v3 t01 = t0 + t1, t02 = t0 - t1;
+    const float acceptance = contactDist - px;
+    MPoint mc[8]; int num = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      // corner order of the reference: (x,y,z) (x,y,-z) (x,-y,z) (x,-y,-z) (-x,y,z) (-x,y,-z) (-x,-y,z) (-x,-y,-z)
+      const v3 zt = (k & 1) ? nt2 : t2;
+      float s;
+      switch (k >> 1) { case 0: s = (zt + t01).x; break; case 1: s = (zt + t02).x; break; case 2: s = (zt - t02).x; break; default: s = (zt - t01).x; }
+      if (acceptance > s) {
+        const v3 corner = V3((k & 4) ? -be.x : be.x, (k & 2) ? -be.y : be.y, (k & 1) ? -be.z : be.z);
+        const float pen = s + px;
+        mc[num].a = corner; mc[num].b = negscalesub(ln, pen, amxftransform(aToB, corner)); mc[num].n = ln; mc[num].pen = pen; num++;
+      }
+    }
+    if (num <= PXB_MANIFOLD_CACHE) { for (int i = 0; i < num; ++i) man.pts[i] = mc[i]; man.n = num; }
+    else { reduce_cluster(man, mc, num); man.n = PXB_MANIFOLD_CACHE; }
+  }
+  for (int i = 0; i < man.n; ++i) {
+    const float dist = man.pts[i].pen;
+    if (contactDist >= dist) { out.point[out.count] = axftransform(planeTm, man.pts[i].b); out.sep[out.count] = dist; out.count++; }
+  }
+}
+
+// ---- box vs box ----
+PXB_D void incident_polygon(v3* pts, v3& faceNormal, v3 axis, const mxf& t, v3 ext) {  // GuPCMContactBoxBox.cpp:42-118
+  float ex = ext.x, ey = ext.y, ez = ext.z;
+  const v3 u0 = t.r.c0, u1 = t.r.c1, u2 = t.r.c2;
+  const float d0 = adot(u0, axis), d1 = adot(u1, axis), d2 = adot(u2, axis);
+  const float a0 = fabsf(d0), a1 = fabsf(d1), a2 = fabsf(d2);
+  v3 base, e1, e2;
+  if (a0 >= a1 && a0 >= a2) {
+    const bool con = d0 > 0.f; faceNormal = con ? -u0 : u0; ex = con ? -ex : ex;
+    const v3 r0 = u0 * ex, r1 = u1 * ey, r2 = u2 * ez;
+    base = t.p + r0; e1 = r1 + r2; e2 = r1 - r2;
+  } else if (a1 >= a2) {
+    const bool con = d1 > 0.f; faceNormal = con ? -u1 : u1; ey = con ? -ey : ey;
+    const v3 r0 = u0 * ex, r1 = u1 * ey, r2 = u2 * ez;
+    base = t.p + r1; e1 = r0 + r2; e2 = r0 - r2;
+  } else {
+    const bool con = d2 > 0.f; faceNormal = con ? -u2 : u2; ez = con ? -ez : ez;
+    const v3 r0 = u0 * ex, r1 = u1 * ey, r2 = u2 * ez;
+    base = t.p + r2; e1 = r0 + r1; e2 = r0 - r1;
+  }
+  pts[0] = base + e1; pts[1] = base + e2; pts[2] = base - e1; pts[3] = base - e2;
+}
+
+PXB_D float comp(v3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+PXB_D bool seg_aabb(v3 p0, v3 d, v3 mx, v3 mn, float& tmin, float& tmax) {  // :121-165
+  const float eps = 1e-6f;
+  bool par[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    par[k] = eps > fabsf(comp(d, k));
+    const bool outside = (comp(p0, k) > comp(mx, k)) || (comp(mn, k) > comp(p0, k));
+    if (par[k] && outside) return false;
+  }
+  float ft1 = -FLT_MAX, ft2 = FLT_MAX;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float odd = 1.0f / comp(d, k);  // reference: V3RecipFast (approximate)
+    const float t1 = par[k] ? 0.f : (comp(mn, k) - comp(p0, k)) * odd;
+    const float t2 = par[k] ? FLT_MAX : (comp(mx, k) - comp(p0, k)) * odd;
+    ft1 = fmax_(ft1, fmin_(t1, t2)); ft2 = fmin_(ft2, fmax_(t1, t2));
+  }
+  const float tminf = fmax_(ft1, 0.f), tmaxf = fmin_(1.f, ft2);
+  tmin = tminf; tmax = tmaxf;
+  return !((tminf > tmaxf) || (tminf > 1.f));
+}
+
+PXB_D bool poly_contains(const v3* verts, v3 p, v3 mn, v3 mx) {  // GuPCMContactGenUtil.cpp:35-103, 4 vertices
+  if ((mn.x > p.x) || (p.x > mx.x) || (mn.y > p.y) || (p.y > mx.y)) return false;
+  const float tx = p.x, ty = p.y; const float eps = FLT_EPSILON;
+  int inter = 0;
+  for (int i = 0, j = 3; i < 4; j = i++) {
+    const float jy = verts[j].y, iy = verts[i].y, jx = verts[j].x, ix = verts[i].x;
+    if ((tx == jx && ty == jy) || (tx == ix && ty == iy)) return true;
+    const bool yflag0 = jy > ty, yflag1 = iy > ty;
+    if (yflag0 != yflag1) {
+      const float jix = ix - jx, jiy = iy - jy, jty = ty - jy;
+      const float part1 = jty * jix, part2 = (jx + eps) * jiy, part3 = tx * jiy;
+      const bool c = jiy > 0.f;
+      const float tmp = part1 + part2;
+      const float comp1 = c ? tmp : part3, comp2 = c ? part3 : tmp;
+      if (comp1 >= comp2) { if (inter == 1) return false; inter++; }
+    }
+  }
+  return inter > 0;
+}
+
+PXB_D void calc_contacts(float extentX_, float extentY_, v3* pts, v3 incN, v3 localNormal, MPoint* mc, int& numContacts, float contactDist) {  // :168-330
+  const float extentX = extentX_ * 1.0001f, extentY = extentY_ * 1.0001f;
+  const float nExtentX = -extentX, nExtentY = -extentY;
+  bool pPen[4], pArea[4];
+  v3 bmin = V3(FLT_MAX, FLT_MAX, FLT_MAX), bmax = V3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+  int n = numContacts;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bmin = vmin(bmin, pts[i]); bmax = vmax(bmax, pts[i]);
+    const float z = -pts[i].z;
+    if (contactDist > z) {
+      pPen[i] = true;
+      const v3 ap = vabs(pts[i]);
+      if (extentX >= ap.x && extentY >= ap.y) { pArea[i] = true; mc[n].a = V3(pts[i].x, pts[i].y, 0.f); mc[n].b = pts[i]; mc[n].n = localNormal; mc[n].pen = z; n++; }
+      else pArea[i] = false;
+    } else { pPen[i] = false; pArea[i] = false; }
+  }
+  if (n == 4) { numContacts = n; return; }
+  {
+    const float denom = incN.z;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const v3 q = V3((k & 2) ? nExtentX : extentX, (k & 1) ? nExtentY : extentY, 0.f);
+      if (poly_contains(pts, q, bmin, bmax)) {
+        const float nom = adot(incN, pts[0] - q);
+        const float t = nom / denom; const float pen = -t;
+        if (contactDist > pen) { mc[n].a = q; mc[n].b = V3(q.x, q.y, t); mc[n].n = localNormal; mc[n].pen = pen; n++; }
+      }
+    }
+  }
+  const v3 ext = V3(extentX, extentY, FLT_MAX);
+  const v3 negExt = V3(nExtentX, nExtentY, -(contactDist + FLT_EPSILON));
+  for (int rStart = 0, rEnd = 3; rStart < 4; rEnd = rStart++) {
+    const v3 p0 = pts[rStart], p1 = pts[rEnd];
+    if (!pPen[rStart] && !pPen[rEnd]) continue;
+    const bool con0 = pPen[rStart] && pArea[rStart], con1 = pPen[rEnd] && pArea[rEnd];
+    if (con0 && con1) continue;
+    const v3 p0p1 = p1 - p0;
+    float tmin, tmax;
+    if (seg_aabb(p0, p0p1, ext, negExt, tmin, tmax)) {
+      if (!con0) { const v3 ip = scaleadd(p0p1, tmin, p0); mc[n].a = V3(ip.x, ip.y, 0.f); mc[n].b = ip; mc[n].n = localNormal; mc[n].pen = -ip.z; n++; }
+      if (!con1) { const v3 ip = scaleadd(p0p1, tmax, p0); mc[n].a = V3(ip.x, ip.y, 0.f); mc[n].b = ip; mc[n].n = localNormal; mc[n].pen = -ip.z; n++; }
+    }
+  }
+  numContacts = n;
+}
+
+PXB_D float sum3(v3 v) { return v.x + (v.y + v.z); }
+
+// GuPCMContactBoxBox.cpp:332-846; false when a separating axis exists
+PXB_D bool boxbox_generate(v3 e0, v3 e1, const mxf& t0, const mxf& t1, float contactDist, MPoint* mc, int& numContacts) {
+  const mxf t1To0 = amxfinvmul(t0, t1);
+  const m33 r01 = mtranspose(t1To0.r);
+  const float uEps = 1e-6f;
+  const v3 tt = t1To0.p;
+  const v3 col[3] = {t1To0.r.c0, t1To0.r.c1, t1To0.r.c2};
+  const v3 rr[3] = {r01.c0, r01.c1, r01.c2};
+  v3 abs1To0[3], abs0To1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    abs1To0[k] = V3(fabsf(col[k].x) + uEps, fabsf(col[k].y) + uEps, fabsf(col[k].z) + uEps);
+    abs0To1[k] = V3(fabsf(rr[k].x) + uEps, fabsf(rr[k].y) + uEps, fabsf(rr[k].z) + uEps);
+  }
+  float sign[6], overlap[6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    sign[k] = comp(tt, k);
+    const float rb = sum3(vmul(abs0To1[k], e1));
+    overlap[k] = ((comp(e0, k) + rb) - fabsf(sign[k])) + contactDist;
+    if (0.f > overlap[k]) return false;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    sign[3 + k] = adot(tt, col[k]);
+    const float ra = sum3(vmul(abs1To0[k], e0));
+    overlap[3 + k] = ((ra + comp(e1, k)) - fabsf(sign[3 + k])) + contactDist;
+    if (0.f > overlap[3 + k]) return false;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float absSign = fabsf(comp(col[j], i1) * comp(tt, i2) - comp(col[j], i2) * comp(tt, i1));
+      float ra, rb;
+      if (i == 0) ra = abs1To0[j].z * e0.y + abs1To0[j].y * e0.z;
+      else if (i == 1) ra = abs1To0[j].z * e0.x + abs1To0[j].x * e0.z;
+      else ra = abs1To0[j].y * e0.x + abs1To0[j].x * e0.y;
+      if (j == 0) rb = abs0To1[i].z * e1.y + abs0To1[i].y * e1.z;
+      else if (j == 1) rb = abs0To1[i].z * e1.x + abs0To1[i].x * e1.z;
+      else rb = abs0To1[i].y * e1.x + abs0To1[i].x * e1.y;
+      if (absSign > ((ra + rb) + contactDist)) return false;
+    }
+  }
+  int feature = 0; float minOverlap = overlap[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) if (minOverlap > overlap[i]) { minOverlap = overlap[i]; feature = i; }
+
+  float sgn = sign[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) if (feature == i) sgn = sign[i];
+  const bool neg = 0.f >= sgn;
+  const bool flip = feature >= 3;
+  const mxf& tr = flip ? t1 : t0;          // transform owning the reference face
+  const v3 er = flip ? e1 : e0;
+  const int ax = flip ? feature - 3 : feature;
+  const v3 A0 = tr.r.c0, A1 = tr.r.c1, A2 = tr.r.c2;
+  mxf nt; v3 mtd; float exx, eyy;
+  if (!flip) {
+    if (ax == 0) {
+      exx = er.z; eyy = er.y;
+      if (neg) { mtd = A0; nt.r.c0 = -A2; nt.r.c1 = A1; nt.r.c2 = A0; nt.p = negscalesub(A0, er.x, tr.p); }
+      else { mtd = -A0; nt.r.c0 = A2; nt.r.c1 = A1; nt.r.c2 = mtd; nt.p = scaleadd(A0, er.x, tr.p); }
+    } else if (ax == 1) {
+      exx = er.x; eyy = er.z;
+      if (neg) { mtd = A1; nt.r.c0 = A0; nt.r.c1 = -A2; nt.r.c2 = A1; nt.p = negscalesub(A1, er.y, tr.p); }
+      else { mtd = -A1; nt.r.c0 = A0; nt.r.c1 = A2; nt.r.c2 = mtd; nt.p = scaleadd(A1, er.y, tr.p); }
+    } else {
+      exx = er.x; eyy = er.y;
+      if (neg) { mtd = A2; nt.r.c0 = A0; nt.r.c1 = A1; nt.r.c2 = A2; nt.p = negscalesub(A2, er.z, tr.p); }
+      else { mtd = -A2; nt.r.c0 = A0; nt.r.c1 = -A1; nt.r.c2 = mtd; nt.p = scaleadd(A2, er.z, tr.p); }
+    }
+  } else {
+    if (ax == 0) {
+      exx = er.z; eyy = er.y;
+      if (neg) { mtd = A0; nt.r.c0 = A2; nt.r.c1 = A1; nt.r.c2 = -A0; nt.p = scaleadd(A0, er.x, tr.p); }
+      else { mtd = -A0; nt.r.c0 = -A2; nt.r.c1 = A1; nt.r.c2 = A0; nt.p = negscalesub(A0, er.x, tr.p); }
+    } else if (ax == 1) {
+      exx = er.x; eyy = er.z;
+      if (neg) { mtd = A1; nt.r.c0 = A0; nt.r.c1 = A2; nt.r.c2 = -A1; nt.p = scaleadd(A1, er.y, tr.p); }
+      else { mtd = -A1; nt.r.c0 = A0; nt.r.c1 = -A2; nt.r.c2 = A1; nt.p = negscalesub(A1, er.y, tr.p); }
+    } else {
+      exx = er.x; eyy = er.y;
+      if (neg) { mtd = A2; nt.r.c0 = A0; nt.r.c1 = -A1; nt.r.c2 = -A2; nt.p = scaleadd(A2, er.z, tr.p); }
+      else { mtd = -A2; nt.r.c0 = A0; nt.r.c1 = A1; nt.r.c2 = A2; nt.p = negscalesub(A2, er.z, tr.p); }
+    }
+  }
+  const v3 localNormal = amtmul(nt.r, mtd);
+  v3 pts[4]; v3 incN;
+  if (!flip) { const mxf o = amxfinvmul(nt, t1); incident_polygon(pts, incN, -localNormal, o, e1); }
+  else { const mxf o = amxfinvmul(nt, t0); incident_polygon(pts, incN, localNormal, o, e0); }
+  calc_contacts(exx, eyy, pts, incN, localNormal, mc, numContacts, contactDist);
+  const int n = numContacts;
+  if (n != 0) {
+    if (flip) for (int i = 0; i < n; ++i) { const v3 lb = mc[i].b; mc[i].b = mc[i].a; mc[i].a = lb; }
+    const mxf newTo1 = amxfinvmul(t1, nt), newTo0 = amxfinvmul(t0, nt);
+    const v3 nInB = mmul(newTo1.r, mc[0].n);
+    for (int i = 0; i < n; ++i) { mc[i].a = amxftransform(newTo0, mc[i].a); mc[i].b = amxftransform(newTo1, mc[i].b); mc[i].n = nInB; }
+  }
+  return true;
+}
+
+// GuPCMContactBoxBox.cpp:848-971
+PXB_D void pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contactDist, float toleranceLength, Manifold& man, Contacts& out) {
+  const xf cur = axfinvmul(tm1, tm0);  // A into B
+  const mxf aToB = amxffromxf(cur);
+  const float minMargin = fmin_(box_margin(e0, toleranceLength), box_margin(e1, toleranceLength));
+  const int initial = man.n;
+  manifold_refresh(man, aToB, minMargin * 0.8f);
+  const bool lost = man.n != initial;
+  const float radiusA = alen(e0), radiusB = alen(e1);
+  out.count = 0; out.normal = V3(0, 0, 0);
+  if (lost || invalidate_boxconvex(man, cur, tm0.q, tm1.q, minMargin, radiusA, radiusB)) {
+    man.rel = cur; man.quatA = tm0.q; man.quatB = tm1.q;
+    mxf tv0 = amxffromxf(tm0), tv1 = amxffromxf(tm1);
+    tv0.r.c0 = anormalize(tv0.r.c0); tv0.r.c1 = anormalize(tv0.r.c1); tv0.r.c2 = anormalize(tv0.r.c2);
+    tv1.r.c0 = anormalize(tv1.r.c0); tv1.r.c1 = anormalize(tv1.r.c1); tv1.r.c2 = anormalize(tv1.r.c2);
+    MPoint mc[16]; int num = 0;
+    if (boxbox_generate(e0, e1, tv0, tv1, contactDist, mc, num)) {
+      if (num > 0) {
+        if (num <= PXB_MANIFOLD_CACHE) { for (int i = 0; i < num; ++i) man.pts[i] = mc[i]; man.n = num; }
+        else { reduce_batch(man, mc, num, toleranceLength); man.n = PXB_MANIFOLD_CACHE; }
+        out.normal = anormalize(mmul(tv1.r, man.pts[0].n));
+        for (int i = 0; i < man.n; ++i) { out.point[out.count] = amxftransform(tv1, man.pts[i].b); out.sep[out.count] = man.pts[i].pen; out.count++; }
+      }
+    }
+  } else if (man.n > 0) {
+    out.normal = manifold_world_normal(man, tm1);
+    for (int i = 0; i < man.n; ++i) {
+      const float dist = man.pts[i].pen;
+      if (contactDist >= dist) { out.point[out.count] = axftransform(tm1, man.pts[i].b); out.sep[out.count] = dist; out.count++; }
+    }
+  }
+}

@@ -1,0 +1,242 @@
+"""Host-side mirror of the reference scene interface for the rigid-body step hot path.
+
+`Scene` wraps the C ABI of libphysx_b200.so (include/physx_b200.h) with the names a PhysX user knows:
+`simulate(dt)` / `fetchResults(block)` (PxScene, physx/include/PxScene.h), `getRigidDynamicData` /
+`setRigidDynamicData` (PxDirectGPUAPI, physx/include/PxDirectGPUAPI.h:311-463).  There is no CPU path:
+importing works anywhere (so the symbol checks run on a CPU box) but creating a Scene without a CUDA
+device raises `PhysxB200Error`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import scenes as _scenes
+
+_LIB_NAME = "libphysx_b200.so"
+_lib = None
+
+# every symbol include/physx_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "pxb_scene_create", "pxb_scene_release", "pxb_last_error", "pxb_device_count", "pxb_scene_add_actors",
+    "pxb_scene_num_actors", "pxb_scene_num_dynamic", "pxb_scene_simulate", "pxb_scene_fetch_results",
+    "pxb_scene_set_constraint_order", "pxb_get_rigid_dynamic_data", "pxb_set_rigid_dynamic_data",
+    "pxb_get_rigid_dynamic_data_device", "pxb_set_rigid_dynamic_data_device", "pxb_scene_get_states",
+    "pxb_scene_set_states", "pxb_scene_state_device_ptr", "pxb_scene_stream", "pxb_scene_compute_bounds",
+    "pxb_scene_get_bounds", "pxb_scene_broadphase", "pxb_scene_num_pairs", "pxb_scene_get_pairs",
+    "pxb_scene_num_created", "pxb_scene_num_deleted", "pxb_scene_get_created", "pxb_scene_get_deleted",
+    "pxb_scene_get_contacts", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
+    "pxb_scene_last_num_launches",
+]
+
+RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY = 0, 1, 2
+
+
+class PhysxB200Error(RuntimeError):
+    pass
+
+
+class SceneDesc(ctypes.Structure):
+    _fields_ = [
+        ("gravity", ctypes.c_float * 3), ("solverType", ctypes.c_uint32),
+        ("bounceThresholdVelocity", ctypes.c_float), ("frictionOffsetThreshold", ctypes.c_float),
+        ("frictionCorrelationDistance", ctypes.c_float), ("toleranceLength", ctypes.c_float),
+        ("staticFriction", ctypes.c_float), ("dynamicFriction", ctypes.c_float), ("restitution", ctypes.c_float),
+        ("contactOffset", ctypes.c_float), ("restOffset", ctypes.c_float),
+        ("posIters", ctypes.c_uint32), ("velIters", ctypes.c_uint32),
+        ("maxActors", ctypes.c_uint32), ("maxPairs", ctypes.c_uint32), ("device", ctypes.c_int32),
+        ("reserved", ctypes.c_uint32 * 8),
+    ]
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def load_library():
+    """Loads libphysx_b200.so; raises loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise PhysxB200Error(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(physx_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    vp, u32, i32, f32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_float
+    lib.pxb_scene_create.argtypes = [ctypes.POINTER(SceneDesc), ctypes.POINTER(vp)]
+    lib.pxb_scene_release.argtypes = [vp]
+    lib.pxb_scene_release.restype = None
+    lib.pxb_last_error.restype = ctypes.c_char_p
+    lib.pxb_scene_add_actors.argtypes = [vp, vp, u32]
+    for f in ("pxb_scene_num_actors", "pxb_scene_num_dynamic", "pxb_scene_num_pairs", "pxb_scene_num_created",
+              "pxb_scene_num_deleted", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
+              "pxb_scene_last_num_launches"):
+        getattr(lib, f).argtypes = [vp]
+        getattr(lib, f).restype = u32
+    lib.pxb_scene_simulate.argtypes = [vp, f32]
+    lib.pxb_scene_fetch_results.argtypes = [vp, i32]
+    lib.pxb_scene_set_constraint_order.argtypes = [vp, vp, u32]
+    for f in ("pxb_get_rigid_dynamic_data", "pxb_set_rigid_dynamic_data", "pxb_get_rigid_dynamic_data_device",
+              "pxb_set_rigid_dynamic_data_device"):
+        getattr(lib, f).argtypes = [vp, vp, vp, i32, u32]
+    for f in ("pxb_scene_get_states", "pxb_scene_set_states", "pxb_scene_get_bounds", "pxb_scene_broadphase",
+              "pxb_scene_get_pairs", "pxb_scene_get_created", "pxb_scene_get_deleted", "pxb_scene_get_contacts"):
+        getattr(lib, f).argtypes = [vp, vp]
+    lib.pxb_scene_compute_bounds.argtypes = [vp]
+    lib.pxb_scene_state_device_ptr.argtypes = [vp, i32]
+    lib.pxb_scene_state_device_ptr.restype = vp
+    lib.pxb_scene_stream.argtypes = [vp]
+    lib.pxb_scene_stream.restype = vp
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc):
+    if rc < 0:
+        raise PhysxB200Error(f"physx_b200 error {rc}: {lib.pxb_last_error().decode()}")
+    return rc
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Scene:
+    """One simulation scene resident on one GPU (one PxScene <-> one device, ScScene.cpp:718)."""
+
+    def __init__(self, scene: _scenes.Scene, device: int = 0, max_pairs: int = 0, max_actors: int = 0):
+        lib = load_library()
+        self._lib = lib
+        h = scene.header
+        d = SceneDesc()
+        d.gravity[:] = [float(x) for x in h["gravity"]]
+        d.solverType = int(h["solverType"])
+        d.bounceThresholdVelocity = float(h["bounceThreshold"])
+        d.frictionOffsetThreshold = float(h["frictionOffsetThreshold"])
+        d.frictionCorrelationDistance = float(h["frictionCorrelationDistance"])
+        d.toleranceLength = float(h["toleranceLength"])
+        d.staticFriction, d.dynamicFriction, d.restitution = float(h["staticFriction"]), float(h["dynamicFriction"]), float(h["restitution"])
+        d.contactOffset, d.restOffset = float(h["contactOffset"]), float(h["restOffset"])
+        d.posIters, d.velIters = int(h["posIters"]), int(h["velIters"])
+        d.maxActors = max(int(max_actors), len(scene.actors))
+        d.maxPairs = int(max_pairs)
+        d.device = int(device)
+        self.dt = float(h["dt"])
+        self._h = ctypes.c_void_p()
+        _check(lib, lib.pxb_scene_create(ctypes.byref(d), ctypes.byref(self._h)))
+        recs = np.ascontiguousarray(scene.actors)
+        _check(lib, lib.pxb_scene_add_actors(self._h, _ptr(recs), len(recs)))
+        self.num_actors = int(lib.pxb_scene_num_actors(self._h))
+        self.num_dynamic = int(lib.pxb_scene_num_dynamic(self._h))
+
+    def release(self):
+        if getattr(self, "_h", None):
+            self._lib.pxb_scene_release(self._h)
+            self._h = None
+
+    __del__ = release
+
+    # ---- PxScene ----
+    def simulate(self, dt: float | None = None):
+        _check(self._lib, self._lib.pxb_scene_simulate(self._h, float(self.dt if dt is None else dt)))
+
+    def fetchResults(self, block: bool = True):
+        return _check(self._lib, self._lib.pxb_scene_fetch_results(self._h, 1 if block else 0)) == 0
+
+    def step(self, dt: float | None = None):
+        self.simulate(dt)
+        self.fetchResults(True)
+
+    def setConstraintOrder(self, pairs):
+        """pairs: (n,2) actor indices in solver input order (island manager order); None/empty = canonical."""
+        if pairs is None or len(pairs) == 0:
+            _check(self._lib, self._lib.pxb_scene_set_constraint_order(self._h, None, 0))
+            return
+        p = np.ascontiguousarray(pairs, dtype=np.uint32)
+        _check(self._lib, self._lib.pxb_scene_set_constraint_order(self._h, _ptr(p), len(p)))
+
+    # ---- PxDirectGPUAPI ----
+    def getRigidDynamicData(self, data_type: int, indices=None, nb: int | None = None):
+        idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.uint32)
+        n = self.num_dynamic if (idx is None and nb is None) else (len(idx) if idx is not None else int(nb))
+        out = np.zeros((n, 7 if data_type == RD_GLOBAL_POSE else 3), np.float32)
+        _check(self._lib, self._lib.pxb_get_rigid_dynamic_data(self._h, _ptr(out), _ptr(idx), data_type, n))
+        return out
+
+    def setRigidDynamicData(self, data_type: int, data, indices=None):
+        d = np.ascontiguousarray(data, dtype=np.float32)
+        idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.uint32)
+        _check(self._lib, self._lib.pxb_set_rigid_dynamic_data(self._h, _ptr(d), _ptr(idx), data_type, len(d)))
+
+    def getRigidDynamicDataDevice(self, data_type: int, dev_ptr: int, nb: int, dev_indices: int = 0):
+        _check(self._lib, self._lib.pxb_get_rigid_dynamic_data_device(self._h, dev_ptr, dev_indices or None, data_type, nb))
+
+    def setRigidDynamicDataDevice(self, data_type: int, dev_ptr: int, nb: int, dev_indices: int = 0):
+        _check(self._lib, self._lib.pxb_set_rigid_dynamic_data_device(self._h, dev_ptr, dev_indices or None, data_type, nb))
+
+    def stream(self) -> int:
+        return int(self._lib.pxb_scene_stream(self._h) or 0)
+
+    # ---- packed state / stage level ----
+    def getStates(self):
+        out = np.zeros((self.num_dynamic, _scenes.STATE_FLOATS), np.float32)
+        _check(self._lib, self._lib.pxb_scene_get_states(self._h, _ptr(out)))
+        return out
+
+    def setStates(self, st):
+        st = np.ascontiguousarray(st, dtype=np.float32)
+        assert st.shape == (self.num_dynamic, _scenes.STATE_FLOATS)
+        _check(self._lib, self._lib.pxb_scene_set_states(self._h, _ptr(st)))
+
+    def computeBounds(self):
+        _check(self._lib, self._lib.pxb_scene_compute_bounds(self._h))
+        out = np.zeros((self.num_actors, 6), np.float32)
+        _check(self._lib, self._lib.pxb_scene_get_bounds(self._h, _ptr(out)))
+        return out
+
+    def getBounds(self):
+        out = np.zeros((self.num_actors, 6), np.float32)
+        _check(self._lib, self._lib.pxb_scene_get_bounds(self._h, _ptr(out)))
+        return out
+
+    def broadphase(self, tight_bounds=None):
+        b = None if tight_bounds is None else np.ascontiguousarray(tight_bounds, dtype=np.float32)
+        _check(self._lib, self._lib.pxb_scene_broadphase(self._h, _ptr(b)))
+
+    def _pairs(self, count_fn, get_fn):
+        n = int(count_fn(self._h))
+        out = np.zeros((n, 2), np.uint32)
+        if n:
+            _check(self._lib, get_fn(self._h, _ptr(out)))
+        return out
+
+    def getPairs(self):
+        return self._pairs(self._lib.pxb_scene_num_pairs, self._lib.pxb_scene_get_pairs)
+
+    def getCreatedPairs(self):
+        return self._pairs(self._lib.pxb_scene_num_created, self._lib.pxb_scene_get_created)
+
+    def getDeletedPairs(self):
+        return self._pairs(self._lib.pxb_scene_num_deleted, self._lib.pxb_scene_get_deleted)
+
+    def getContacts(self):
+        n = int(self._lib.pxb_scene_num_pairs(self._h))
+        out = np.zeros((n, 24), np.float32)
+        if n:
+            _check(self._lib, self._lib.pxb_scene_get_contacts(self._h, _ptr(out)))
+        return out
+
+    @property
+    def num_partitions(self):
+        return int(self._lib.pxb_scene_last_num_partitions(self._h))
+
+    @property
+    def num_constraints(self):
+        return int(self._lib.pxb_scene_last_num_constraints(self._h))
+
+    @property
+    def num_launches(self):
+        return int(self._lib.pxb_scene_last_num_launches(self._h))
