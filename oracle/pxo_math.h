@@ -169,13 +169,18 @@ static inline mxf amxfinvmul(const mxf* a, const mxf* b) { /* PxMatTransformV::t
   return r;
 }
 /* PxMatTransformV(const PxTransformV&): 3-output QuatGetMat33V, PxVecMathSSE.h:54-69 */
-static inline mxf amxffromxf(const xf* t) {
-  const q4 q = t->q; mxf m; m.p = t->p;
+static inline m33 am33fromq(q4 q);
+static inline mxf amxffromxf(const xf* t) { mxf m; m.p = t->p; m.r = am33fromq(t->q); return m; }
+/* also PxMat33Padded(const PxQuat&), physx/include/foundation/PxSIMDHelpers.h:45-60 */
+static inline m33 am33fromq(q4 q) {
+  struct { m33 r; } m_; 
+#define m m_
   const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z, w2 = q.w + q.w;
   const float wx = x2 * q.w, wy = y2 * q.w, wz = z2 * q.w, ww1 = w2 * q.w + (-1.0f);
   m.r.c0 = V3(q.x * x2 + ww1, q.y * x2 + wz, q.z * x2 + (-wy));
   m.r.c1 = V3(q.x * y2 + (-wz), q.y * y2 + ww1, q.z * y2 + wx);
   m.r.c2 = V3(q.x * z2 + wy, q.y * z2 + (-wx), q.z * z2 + ww1);
-  return m;
+  return m.r;
+#undef m
 }
 #endif

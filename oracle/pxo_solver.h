@@ -77,7 +77,7 @@ static inline void pxo_unconstrained_velocity(v3 gravity, float dt, float linDam
 
 /* DyTGSDynamics.cpp:154-243 (no gyroscopic forces, no lock flags) */
 static inline void pxo_solver_body_init(PxoSolverBody* b, v3 lv, v3 av, float invMass, v3 invInertia, const xf* pose, float maxDepenVel) {
-  const m33 rot = m33fromq(pose->q);
+  const m33 rot = am33fromq(pose->q); /* PxMat33Padded rotation(globalPose.q) */
   const v3 sqrtInvI = V3(invInertia.x == 0.f ? 0.f : sqrtf(invInertia.x), invInertia.y == 0.f ? 0.f : sqrtf(invInertia.y), invInertia.z == 0.f ? 0.f : sqrtf(invInertia.z));
   const v3 sqrtI = V3(sqrtInvI.x == 0.f ? 0.f : 1.0f / sqrtInvI.x, sqrtInvI.y == 0.f ? 0.f : 1.0f / sqrtInvI.y, sqrtInvI.z == 0.f ? 0.f : 1.0f / sqrtInvI.z);
   pxo_transform_inertia(sqrtInvI, &rot, &b->sqrtInvInertia);

@@ -108,7 +108,7 @@ __global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const floa
     if (type == PXB_GEOM_SPHERE) e = V3(d.x, d.x, d.x);
     else if (type == PXB_GEOM_CAPSULE) { const v3 dd = qbasis0(q) * d.y; e = V3(fabsf(dd.x) + d.x, fabsf(dd.y) + d.x, fabsf(dd.z) + d.x); }
     else if (type == PXB_GEOM_BOX) {
-      const m33 b = mfromq(q);
+      const m33 b = amfromq(q);
       const v3 c0 = b.c0 * d.x, c1 = b.c1 * d.y, c2 = b.c2 * d.z;
       e = V3((fabsf(c0.x) + fabsf(c1.x)) + fabsf(c2.x), (fabsf(c0.y) + fabsf(c1.y)) + fabsf(c2.y), (fabsf(c0.z) + fabsf(c1.z)) + fabsf(c2.z));
     } else if (type == PXB_GEOM_PLANE) plane = true;
@@ -410,7 +410,7 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
   v3 lv = V3(linVel[a]), av = V3(angVel[a]);
   unconstrained_velocity(V3(gx, gy, gz), dt, dm.x, dm.y, dm.z, dm.w, lv, av);
   linVel[a] = F4(lv, 0.f); angVel[a] = F4(av, 0.f);
-  const m33 rot = mfromq(Q4(quat[a]));
+  const m33 rot = amfromq(Q4(quat[a]));
   const v3 sqrtInvI = V3(ii.x == 0.f ? 0.f : sqrtf(ii.x), ii.y == 0.f ? 0.f : sqrtf(ii.y), ii.z == 0.f ? 0.f : sqrtf(ii.z));
   const v3 sqrtI = V3(sqrtInvI.x == 0.f ? 0.f : 1.0f / sqrtInvI.x, sqrtInvI.y == 0.f ? 0.f : 1.0f / sqrtInvI.y, sqrtInvI.z == 0.f ? 0.f : 1.0f / sqrtInvI.z);
   m33 sI, sInertia; transform_inertia(sqrtInvI, rot, sI); transform_inertia(sqrtI, rot, sInertia);

@@ -132,12 +132,13 @@ PXB_D mxf amxfinvmul(const mxf& a, const mxf& b) {                              
   r.p = amtmul(a.r, b.p - a.p);
   return r;
 }
-PXB_D mxf amxffromxf(const xf& t) {                                                             // 3-output QuatGetMat33V
-  const q4 q = t.q; mxf m; m.p = t.p;
+PXB_D m33 amfromq(q4 q) {                        // 3-output QuatGetMat33V (PxVecMathSSE.h:54-69) = PxMat33Padded(const PxQuat&)
   const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z, w2 = q.w + q.w;
   const float wx = x2 * q.w, wy = y2 * q.w, wz = z2 * q.w, ww1 = w2 * q.w + (-1.0f);
-  m.r.c0 = V3(q.x * x2 + ww1, q.y * x2 + wz, q.z * x2 + (-wy));
-  m.r.c1 = V3(q.x * y2 + (-wz), q.y * y2 + ww1, q.z * y2 + wx);
-  m.r.c2 = V3(q.x * z2 + wy, q.y * z2 + (-wx), q.z * z2 + ww1);
-  return m;
+  m33 r;
+  r.c0 = V3(q.x * x2 + ww1, q.y * x2 + wz, q.z * x2 + (-wy));
+  r.c1 = V3(q.x * y2 + (-wz), q.y * y2 + ww1, q.z * y2 + wx);
+  r.c2 = V3(q.x * z2 + wy, q.y * z2 + (-wx), q.z * z2 + ww1);
+  return r;
 }
+PXB_D mxf amxffromxf(const xf& t) { mxf m; m.p = t.p; m.r = amfromq(t.q); return m; }

@@ -183,3 +183,24 @@ def env_grid_stacks(n_envs=4096, stacks_per_env=8, height=8, half_extent=0.25, e
     a["envId"] = env.astype(np.uint32)
     set_box(a, np.arange(n), np.array([he, he, he], dtype=np.float32))
     return Scene(default_header(**hdr), add_ground_plane(a))
+
+
+def random_unit_quats(rng, n):
+    q = rng.normal(size=(n, 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True).astype(np.float32)
+    return np.stack([normalize_quat_f32(x) for x in q]).astype(np.float32)
+
+
+def tumbling_boxes(n=12, seed=7, half_extent=0.25, **hdr):
+    """Boxes with random orientations and spins dropped from a loose column: exercises pair creation /
+    deletion, manifold invalidation and regeneration, edge clipping and non-axis-aligned contacts."""
+    rng = np.random.RandomState(seed)
+    a = _new_actors(n)
+    he = np.array([half_extent, half_extent * 0.8, half_extent * 1.3], dtype=np.float32)
+    a["pos"][:, 0] = rng.uniform(-0.3, 0.3, n)
+    a["pos"][:, 1] = 0.6 + 0.75 * np.arange(n)
+    a["pos"][:, 2] = rng.uniform(-0.3, 0.3, n)
+    a["quat"] = random_unit_quats(rng, n)
+    a["angVel"] = rng.uniform(-2, 2, (n, 3))
+    set_box(a, np.arange(n), he)
+    return Scene(default_header(**hdr), add_ground_plane(a))

@@ -1,0 +1,78 @@
+"""Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference CPU SDK
+(oracle/_ref/ref_harness, built from /root/reference by oracle/ref_build.mk) on small seeded scenes.
+Run in the build container (needs oracle/_ref/):   python tests/golden/make_golden.py
+Fixture = .npz with the scene bytes, per-step states, per-step solver constraint input order (island
+manager order), per-step tight bounds + ABP created/deleted pairs, and per-step contact sets.
+Reference version: 5.6.1.51c1f783."""
+import os
+import struct
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from physx_b200 import scenes  # noqa: E402
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+
+def run_reference(scene, steps, threads=1):
+    with tempfile.TemporaryDirectory() as d:
+        sp = os.path.join(d, "s.bin")
+        scene.save(sp)
+        subprocess.run([HARNESS, "run", sp, "--steps", str(steps), "--threads", str(threads), "--states", d + "/st", "--order", d + "/ord",
+                        "--bp", d + "/bp", "--contacts", d + "/con"], check=True, capture_output=True)
+        nd, na = scene.n_dynamic, len(scene.actors)
+        states = np.fromfile(d + "/st", "<f4").reshape(steps + 1, nd, 13)
+        ob = open(d + "/ord", "rb").read(); off = 0; order_flat = []; order_off = [0]
+        for _ in range(steps):
+            n, = struct.unpack_from("<I", ob, off); off += 4
+            order_flat.append(np.frombuffer(ob, "<u4", n * 2, off).reshape(n, 2)); off += n * 8
+            order_off.append(order_off[-1] + n)
+        bb = open(d + "/bp", "rb").read(); off = 0; bounds = []; cr = []; cro = [0]; de = []; deo = [0]
+        for _ in range(steps):
+            n, = struct.unpack_from("<I", bb, off); off += 4
+            bounds.append(np.frombuffer(bb, "<f4", n * 6, off).reshape(n, 6)); off += n * 24
+            nc, ndl = struct.unpack_from("<II", bb, off); off += 8
+            cr.append(np.frombuffer(bb, "<u4", nc * 2, off).reshape(nc, 2)); off += nc * 8
+            de.append(np.frombuffer(bb, "<u4", ndl * 2, off).reshape(ndl, 2)); off += ndl * 8
+            cro.append(cro[-1] + nc); deo.append(deo[-1] + ndl)
+        cb = open(d + "/con", "rb").read(); off = 0; con_pairs = []; con_off = [0]; con_pts = []; pt_off = [0]
+        for _ in range(steps):
+            n, = struct.unpack_from("<I", cb, off); off += 4
+            for _p in range(n):
+                a0, a1, k = struct.unpack_from("<III", cb, off); off += 12
+                con_pairs.append((a0, a1, k))
+                con_pts.append(np.frombuffer(cb, "<f4", k * 10, off).reshape(k, 10)[:, :7]); off += k * 40
+                pt_off.append(pt_off[-1] + k)
+            con_off.append(con_off[-1] + n)
+        return dict(scene=np.frombuffer(scene.tobytes(), np.uint8), states=states,
+                    order=np.concatenate(order_flat) if order_flat else np.zeros((0, 2), np.uint32), order_off=np.array(order_off),
+                    bounds=np.stack(bounds), created=np.concatenate(cr), created_off=np.array(cro), deleted=np.concatenate(de) if de else np.zeros((0, 2), np.uint32),
+                    deleted_off=np.array(deo), con_pairs=np.array(con_pairs, np.uint32).reshape(-1, 3), con_off=np.array(con_off),
+                    con_pts=np.concatenate(con_pts).astype(np.float32) if con_pts else np.zeros((0, 7), np.float32), pt_off=np.array(pt_off))
+
+
+def main():
+    out = os.path.dirname(os.path.abspath(__file__))
+    cases = {
+        # BASELINE config 1 at reduced size: 4 stacks x 8 boxes, jittered (every island has its own edge order)
+        "stacks_4x8_jitter": (scenes.box_stacks(n_stacks=4, height=8, half_extent=0.25, spacing=1.0, jitter=0.01), 120),
+        # SnippetHelloWorld-style exact stacking (zero gap, zero jitter), unit boxes
+        "stacks_3x5_exact": (scenes.box_stacks(n_stacks=3, height=5, half_extent=0.5, spacing=4.0, jitter=0.0), 60),
+        # boxes dropped from a height with initial spin: pairs are created and lost, manifolds rebuilt
+        "tumble_12": (scenes.tumbling_boxes(n=12, seed=7), 150),
+        # BASELINE config 2 shape at 4 envs
+        "envs_4": (scenes.env_grid_stacks(n_envs=4, jitter=0.01), 30),
+    }
+    for name, (sc, steps) in cases.items():
+        data = run_reference(sc, steps)
+        np.savez_compressed(os.path.join(out, name + ".npz"), **data)
+        print(name, "bodies", sc.n_dynamic, "steps", steps, "bytes", os.path.getsize(os.path.join(out, name + ".npz")))
+
+
+if __name__ == "__main__":
+    main()
