@@ -116,6 +116,11 @@ PXB_API int  pxb_scene_get_contacts(PxbScene* scene, float* out24);
 /* Solver statistics of the last step (PxSimulationStatistics::mNbPartitions analogue). */
 PXB_API uint32_t pxb_scene_last_num_partitions(PxbScene* scene);
 PXB_API uint32_t pxb_scene_last_num_constraints(PxbScene* scene);
+/* Optional per-stage device timing of the last step with CUDA events on the scene stream (no reference
+ * analogue: the reference has no device-side timers).  ms7 = [broadphase, narrowphase,
+ * colouring, prep, solve, writeback+integration, whole step]. */
+PXB_API int  pxb_scene_set_profiling(PxbScene* scene, int enable);
+PXB_API int  pxb_scene_get_stage_times(PxbScene* scene, float* ms7);
 /* number of kernels launched by the last pxb_scene_simulate call */
 PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* scene);
 

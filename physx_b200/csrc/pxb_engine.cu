@@ -22,6 +22,7 @@
 #include <cstring>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include "../../include/physx_b200.h"
 #include "pxb_math.cuh"
 #include "pxb_np.cuh"
@@ -77,6 +78,9 @@ struct PxbScene {
   uint32_t* counters = 0; uint32_t* hostCounters = 0;  // pinned mirror
   RadixSortTemp rsTmp; uint32_t* scanSums = 0;
   uint32_t launches = 0;
+  float* stage = 0; uint32_t* stageIdx = 0;
+  bool useGraph = true; cudaGraphExec_t graphExec[2] = {0, 0}; float graphDt = 0.f; uint32_t graphLaunches[2] = {0, 0};
+  bool profiling = false; cudaEvent_t ev[8] = {0, 0, 0, 0, 0, 0, 0, 0}; float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
   uint32_t hNPairs = 0, hNCreated = 0, hNDeleted = 0, hNCon = 0, hNPart = 0, hErr = 0;
 };
 
@@ -357,36 +361,54 @@ __global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__
   const uint32_t nCon = counters[C_NCON];
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   for (uint32_t p = gtid; p < MAX_PARTITIONS + 1; p += gsize) { partCnt[p] = 0; }
+  const uint32_t perCta = (nCon + gridDim.x - 1) / gridDim.x;
+  const uint32_t cb = min(nCon, blockIdx.x * perCta), ce = min(nCon, cb + perCta);
   for (;;) {
     // every thread samples the counter between two grid barriers, so all of them take the same branch
     const uint32_t remaining = ld_volatile(&counters[C_REMAINING]);
     grid.sync();
     if (remaining == 0) break;
-    for (uint32_t c = gtid; c < nCon; c += gsize) {
-      if (conDone[c]) continue;
-      const uint32_t a = conB0[c], b = conB1[c];
-      if (ld_volatile(&bodyNext[a]) != conPos0[c] || ld_volatile(&bodyNext[b]) != conPos1[c]) continue;
-      __threadfence();
-      const uint32_t ma = ld_volatile(&bodyMask[a]), mb = ld_volatile(&bodyMask[b]);
-      const uint32_t comb = ~ma & ~mb;
-      uint32_t col = 31;
-      if (comb) col = __ffs(comb) - 1; else atomicOr(&counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
-      conColour[c] = col; conDone[c] = 1u;
-      st_volatile(&bodyMask[a], ma | (1u << col)); st_volatile(&bodyMask[b], mb | (1u << col));
-      __threadfence();
-      st_volatile(&bodyNext[a], conPos0[c] + 1); st_volatile(&bodyNext[b], conPos1[c] + 1);
-      atomicSub(&counters[C_REMAINING], 1u);
+    // Each CTA owns a contiguous range of constraints (solver input order keeps an island's constraints
+    // together), and runs the dependency fixed point locally with CTA barriers; only chains that cross a
+    // CTA boundary need another grid-wide round.
+    for (;;) {
+      int progress = 0;
+      for (uint32_t c = cb + threadIdx.x; c < ce; c += blockDim.x) {
+        if (conDone[c]) continue;
+        const uint32_t a = conB0[c], b = conB1[c];
+        if (ld_volatile(&bodyNext[a]) != conPos0[c] || ld_volatile(&bodyNext[b]) != conPos1[c]) continue;
+        __threadfence();
+        const uint32_t ma = ld_volatile(&bodyMask[a]), mb = ld_volatile(&bodyMask[b]);
+        const uint32_t comb = ~ma & ~mb;
+        uint32_t col = 31;
+        if (comb) col = __ffs(comb) - 1; else atomicOr(&counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
+        conColour[c] = col; conDone[c] = 1u;
+        st_volatile(&bodyMask[a], ma | (1u << col)); st_volatile(&bodyMask[b], mb | (1u << col));
+        __threadfence();
+        st_volatile(&bodyNext[a], conPos0[c] + 1); st_volatile(&bodyNext[b], conPos1[c] + 1);
+        atomicSub(&counters[C_REMAINING], 1u);
+        progress = 1;
+      }
+      if (!__syncthreads_or(progress)) break;
     }
     grid.sync();
   }
   grid.sync();
-  for (uint32_t c = gtid; c < nCon; c += gsize) {
+  // partition-major ordering: per-CTA histogram in shared memory, one global atomic per (CTA, partition)
+  __shared__ uint32_t shCnt[MAX_PARTITIONS];
+  __shared__ uint32_t shBase[MAX_PARTITIONS];
+  for (uint32_t p = threadIdx.x; p < MAX_PARTITIONS; p += blockDim.x) shCnt[p] = 0;
+  __syncthreads();
+  for (uint32_t c = cb + threadIdx.x; c < ce; c += blockDim.x) {
     uint32_t col;
-    if (conB1[c] == NONE32) { const uint32_t m = bodyMask[conB0[c]]; col = (m ? 32u - __clz(m) : 0u) + conPos0[c]; conColour[c] = col; }
+    if (conB1[c] == NONE32) { const uint32_t m = bodyMask[conB0[c]]; col = (m ? 32u - __clz(m) : 0u) + conPos0[c]; }
     else col = conColour[c];
-    if (col >= MAX_PARTITIONS) { col = MAX_PARTITIONS - 1; conColour[c] = col; atomicOr(&counters[C_ERROR], (uint32_t)E_PARTITION_OVERFLOW); }
-    atomicAdd(&partCnt[col], 1u);
+    if (col >= MAX_PARTITIONS) { col = MAX_PARTITIONS - 1; atomicOr(&counters[C_ERROR], (uint32_t)E_PARTITION_OVERFLOW); }
+    conColour[c] = col;
+    atomicAdd(&shCnt[col], 1u);
   }
+  __syncthreads();
+  for (uint32_t p = threadIdx.x; p < MAX_PARTITIONS; p += blockDim.x) if (shCnt[p]) atomicAdd(&partCnt[p], shCnt[p]);
   grid.sync();
   if (gtid == 0) {
     uint32_t s = 0, np = 0;
@@ -394,7 +416,9 @@ __global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__
     partStart[MAX_PARTITIONS] = s; counters[C_NPART] = np;
   }
   grid.sync();
-  for (uint32_t c = gtid; c < nCon; c += gsize) ordered[atomicAdd(&partCursor[conColour[c]], 1u)] = c;
+  for (uint32_t p = threadIdx.x; p < MAX_PARTITIONS; p += blockDim.x) { const uint32_t n = shCnt[p]; shBase[p] = n ? atomicAdd(&partCursor[p], n) : 0u; shCnt[p] = 0; }
+  __syncthreads();
+  for (uint32_t c = cb + threadIdx.x; c < ce; c += blockDim.x) { const uint32_t col = conColour[c]; ordered[shBase[col] + atomicAdd(&shCnt[col], 1u)] = c; }
 }
 
 // a12: unconstrained velocities + solver body setup (preIntegrateBodies, DyTGSDynamics.cpp:992-1021)
@@ -704,8 +728,9 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
   CK(dalloc(s->rowA, Pn)); CK(dalloc(s->rowB, Pn)); CK(dalloc(s->rowC, Pn)); CK(dalloc(s->ptA, Pn * 4)); CK(dalloc(s->ptB, Pn * 4)); CK(dalloc(s->ptC, Pn * 4));
   CK(dalloc(s->frA, Pn * 4)); CK(dalloc(s->frB, Pn * 4)); CK(dalloc(s->frC, Pn * 4)); CK(dalloc(s->frD, Pn * 4));
+  CK(dalloc(s->stage, A * 7)); CK(dalloc(s->stageIdx, A));
   CK(dalloc(s->counters, C_COUNT)); CK(cudaMallocHost((void**)&s->hostCounters, sizeof(uint32_t) * (C_COUNT + 2)));
-  CK(dalloc(s->rsTmp.blockHist, RS_MAX_CTAS * 256)); CK(dalloc(s->scanSums, RS_MAX_CTAS));
+  CK(dalloc(s->rsTmp.blockHist, RS_MAX_CTAS * 256)); CK(dalloc(s->rsTmp.digitTotals, 256)); CK(dalloc(s->scanSums, RS_MAX_CTAS));
   CK(cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * C_COUNT, s->stream)); CK(cudaMemsetAsync(s->nPairsDev, 0, 8, s->stream));
   CK(cudaMemsetAsync(s->sbLin, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->sbAng, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->sbDLin, 0, 16 * A, s->stream));
   CK(cudaMemsetAsync(s->sbDAng, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->sbIA, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->sbIB, 0, 16 * A, s->stream));
@@ -737,21 +762,24 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->capPairs = desc->maxPairs ? desc->maxPairs : std::max(1024u, 8u * s->capA);
   s->bitsA = bits_for(s->capA);
   s->rsTmp.ctas = std::min<uint32_t>(RS_MAX_CTAS, (uint32_t)s->numSMs * 2);
+  { const char* ng = getenv("PXB_NO_GRAPH"); if (ng && ng[0] == '1') s->useGraph = false; }
   const int rc = scene_alloc(s);
   if (rc != PXB_OK) { delete s; return rc; }
   *out = s;
   return PXB_OK;
 }
 
+static void drop_graphs(PxbScene* s);
 PXB_API void pxb_scene_release(PxbScene* s) {
   if (!s) return;
   cudaStreamSynchronize(s->stream);
+  drop_graphs(s);
   void* ptrs[] = {s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
-                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD, s->counters, s->rsTmp.blockHist, s->scanSums};
+                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
   cudaStreamDestroy(s->stream);
@@ -846,6 +874,7 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
   CK(cudaMemcpyAsync(s->invInertia + base, inv.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->damp + base, dmp.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->dims + base, dims.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->envId + base, env.data(), 4 * nb, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->dynActorDev, s->dynActor.data(), 4 * s->nDyn, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->counters + C_NA, &s->nA, 4, cudaMemcpyHostToDevice, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   s->gridDirty = true;
   return PXB_OK;
@@ -874,19 +903,22 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
   const uint32_t nA = s->nA, B = 256;
   const int prev = s->cur; s->cur ^= 1; const int cur = s->cur;
   CK(cudaMemsetAsync(s->counters + C_NPAIRS_NEW, 0, 4 * 3, st));  // NPAIRS_NEW, NCREATED, NDELETED
-  CK(cudaMemcpyAsync(s->counters + C_NA, &s->nA, 4, cudaMemcpyHostToDevice, st));
   LAUNCH(k_bounds, cdiv(nA, B), B, nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, externalTight ? 1 : 0, s->aabbMin, s->aabbMax, s->grid,
          s->desc.reserved[0], s->cellKey, s->cellVal);
   const int r = radix_sort_pairs(s->cellKey, s->cellVal, s->cellKeyAlt, s->cellValAlt, s->counters + C_NA, s->grid.keyBits, s->rsTmp, st);
   s->launches += 3 * ((s->grid.keyBits + 7) / 8);
   const uint64_t* sk = r ? s->cellKeyAlt : s->cellKey; const uint32_t* sv = r ? s->cellValAlt : s->cellVal;
   LAUNCH(k_bp_gather, cdiv(nA, B), B, nA, sv, s->aabbMin, s->aabbMax, s->sMin, s->sMax);
-  LAUNCH(k_bp_pairs, cdiv(nA, 128), 128, nA, sk, sv, s->sMin, s->sMax, s->grid, s->bitsA, s->pairKeys[cur], s->counters, s->capPairs);
-  if (s->nLarge) LAUNCH(k_bp_large, cdiv(nA, B), B, nA, s->nLarge, s->largeList, s->aabbMin, s->aabbMax, s->bitsA, s->pairKeys[cur], s->counters, s->capPairs);
+  // the emission buffer is chosen so that the last radix pass lands in pairKeys[cur] (no pointer swaps: the
+  // launch sequence only depends on the parity `cur`, which keeps it CUDA-graph capturable)
+  const bool oddPasses = (((2 * s->bitsA + 7) / 8) & 1u) != 0;
+  uint64_t* emit = oddPasses ? s->pairKeyAlt : s->pairKeys[cur];
+  uint64_t* other = oddPasses ? s->pairKeys[cur] : s->pairKeyAlt;
+  LAUNCH(k_bp_pairs, cdiv(nA, 128), 128, nA, sk, sv, s->sMin, s->sMax, s->grid, s->bitsA, emit, s->counters, s->capPairs);
+  if (s->nLarge) LAUNCH(k_bp_large, cdiv(nA, B), B, nA, s->nLarge, s->largeList, s->aabbMin, s->aabbMax, s->bitsA, emit, s->counters, s->capPairs);
   LAUNCH(k_clamp_count, 1, 32, s->counters, s->capPairs, s->nPairsDev + cur);
-  const int r2 = radix_sort_pairs(s->pairKeys[cur], s->pairValTmp, s->pairKeyAlt, s->pairValAlt, s->nPairsDev + cur, 2 * s->bitsA, s->rsTmp, st);
+  radix_sort_pairs(emit, s->pairValTmp, other, s->pairValAlt, s->nPairsDev + cur, 2 * s->bitsA, s->rsTmp, st);
   s->launches += 3 * ((2 * s->bitsA + 7) / 8);
-  if (r2) std::swap(s->pairKeys[cur], s->pairKeyAlt);
   const uint32_t gP = cdiv(s->capPairs, B);
   LAUNCH(k_pair_lost, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->nPairsDev + cur, s->freeList, s->deletedKeys, s->counters);
   LAUNCH(k_pair_found, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->pairSlots[cur], s->nPairsDev + cur, s->freeList, s->createdKeys, s->counters,
@@ -905,19 +937,19 @@ static int read_counters(PxbScene* s) {
   return PXB_OK;
 }
 
-PXB_API int pxb_scene_simulate(PxbScene* s, float dt) {
-  if (!s) return fail(PXB_ERR_INVALID, "null scene");
-  if (s->abort) return fail(PXB_ERR_CUDA, "scene is in abort mode");
-  if (s->nA == 0) return PXB_OK;
-  if (!(dt > 0.f)) return fail(PXB_ERR_INVALID, "dt must be positive");
+static int enqueue_step(PxbScene* s, float dt) {
   cudaStream_t st = s->stream; const uint32_t B = 256;
   s->launches = 0;
+#define MARK(i) do { if (s->profiling) CK(cudaEventRecord(s->ev[i], st)); } while (0)
+  MARK(0);
   int rc = run_broadphase(s, false); if (rc) return rc;
+  MARK(1);
   const int cur = s->cur; const uint32_t gP = cdiv(s->capPairs, B);
   const uint32_t* nP = s->nPairsDev + cur;
   const float contactDist = s->desc.contactOffset + s->desc.contactOffset;
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
          s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce);
+  MARK(2);
   exclusive_scan_u32(s->conFlag, s->conIdx, nP, s->counters + C_NCON, s->scanSums, s->rsTmp.ctas, st); s->launches += 3;
   LAUNCH(k_compact, gP, B, nP, s->conFlag, s->conIdx, s->conPair, s->pairSlots[cur], s->frictions);
   if (s->nOrder) {
@@ -937,6 +969,7 @@ PXB_API int pxb_scene_simulate(PxbScene* s, float dt) {
     void* args[] = {&s->counters, &s->conB0, &s->conB1, &s->conPos0, &s->conPos1, &s->conColour, &s->conDone, &s->bodyNext, &s->bodyMask, &s->partCnt, &s->partStart, &s->partCursor, &s->ordered};
     CK(cudaLaunchCooperativeKernel((void*)k_colour_partition, dim3(s->coopBlocksColour), dim3(256), args, 0, st)); s->launches++;
   }
+  MARK(3);
   const float* g = s->desc.gravity;
   LAUNCH(k_preintegrate, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, g[0], g[1], g[2], dt, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng,
          s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng);
@@ -948,6 +981,7 @@ PXB_API int pxb_scene_simulate(PxbScene* s, float dt) {
   P.restDistance = s->desc.restOffset + s->desc.restOffset; P.staticFriction = s->desc.staticFriction; P.dynamicFriction = s->desc.dynamicFriction; P.restitution = s->desc.restitution;
   LAUNCH(k_prep, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
          s->invInertia, s->sbIA, s->sbIB, s->frictions, P, s->capPairs, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD);
+  MARK(4);
   {
     uint32_t cap = s->capPairs, posIters = s->desc.posIters, velIters = s->desc.velIters; float stepDt = P.stepDt; uint32_t nDyn = s->nDyn; uint32_t* broken = s->conDone;
     void* args[] = {&s->counters, &s->partStart, &cap, &posIters, &velIters, &stepDt, &s->rowA, &s->rowB, &s->rowC, &s->ptA, &s->ptB, &s->ptC, &s->frA, &s->frB, &s->frC, &s->frD,
@@ -955,10 +989,67 @@ PXB_API int pxb_scene_simulate(PxbScene* s, float dt) {
     CK(cudaMemsetAsync(s->conDone, 0, 4 * (size_t)s->capPairs, st));
     CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(s->coopBlocksSolve), dim3(256), args, 0, st)); s->launches++;
   }
+  MARK(5);
   LAUNCH(k_writeback, gP, B, s->counters, s->capPairs, s->rowC, s->ptC, s->conDone, s->pairSlots[cur], s->cForce, s->frictions);
   LAUNCH(k_finalize_bodies, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->bodyHasCon);
+  MARK(6);
   CK(cudaGetLastError());
+  return PXB_OK;
+}
+
+static void drop_graphs(PxbScene* s) {
+  for (int k = 0; k < 2; ++k) if (s->graphExec[k]) { cudaGraphExecDestroy(s->graphExec[k]); s->graphExec[k] = 0; }
+}
+
+// The launch sequence of a step depends only on the buffer parity (all counts live in device memory), so it is
+// captured once per parity into a CUDA graph and replayed: ~55 kernel launches become one graph launch.
+// Teacher-forced constraint order, stage profiling and PXB_NO_GRAPH=1 use direct launches.
+PXB_API int pxb_scene_simulate(PxbScene* s, float dt) {
+  if (!s) return fail(PXB_ERR_INVALID, "null scene");
+  if (s->abort) return fail(PXB_ERR_CUDA, "scene is in abort mode");
+  if (s->nA == 0) return PXB_OK;
+  if (!(dt > 0.f)) return fail(PXB_ERR_INVALID, "dt must be positive");
+  if (s->gridDirty) { rebuild_grid(s); drop_graphs(s); }
+  const bool graphOk = s->useGraph && s->nOrder == 0 && !s->profiling;
+  if (!graphOk) { const int rc = enqueue_step(s, dt); if (rc) return rc; s->stepping = true; return PXB_OK; }
+  if (s->graphDt != dt) { drop_graphs(s); s->graphDt = dt; }
+  const int par = s->cur ^ 1;   // parity this step runs with
+  if (!s->graphExec[par]) {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); s->useGraph = false; return pxb_scene_simulate(s, dt); }
+    const int curBefore = s->cur;
+    const int rc = enqueue_step(s, dt);
+    const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    s->cur = curBefore;
+    if (rc != PXB_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&s->graphExec[par], graph, 0) != cudaSuccess) {
+      cudaGetLastError(); if (graph) cudaGraphDestroy(graph);
+      s->graphExec[par] = 0; s->useGraph = false; s->abort = false;   // capture not possible here: direct launches from now on
+      return pxb_scene_simulate(s, dt);
+    }
+    cudaGraphDestroy(graph);
+    s->graphLaunches[par] = s->launches;
+  }
+  s->cur = par; s->launches = s->graphLaunches[par];
+  CK(cudaGraphLaunch(s->graphExec[par], s->stream));
   s->stepping = true;
+  return PXB_OK;
+}
+
+// Per-stage device times of the last completed step (CUDA events on the scene stream), in ms:
+// [0] bounds+broadphase+pair lifecycle, [1] narrowphase, [2] constraint ordering+colouring, [3] preintegrate+prep,
+// [4] solve (the cooperative k_solve launch), [5] writeback+integration, [6] whole step.
+PXB_API int pxb_scene_set_profiling(PxbScene* s, int enable) {
+  if (!s) return fail(PXB_ERR_INVALID, "null scene");
+  if (enable && !s->ev[0]) for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&s->ev[i]));
+  s->profiling = enable != 0;
+  return PXB_OK;
+}
+PXB_API int pxb_scene_get_stage_times(PxbScene* s, float* ms7) {
+  if (!s || !ms7) return fail(PXB_ERR_INVALID, "null argument");
+  if (!s->profiling) return fail(PXB_ERR_INVALID, "profiling is off");
+  CK(cudaEventSynchronize(s->ev[6]));
+  for (int i = 0; i < 6; ++i) CK(cudaEventElapsedTime(&ms7[i], s->ev[i], s->ev[i + 1]));
+  CK(cudaEventElapsedTime(&ms7[6], s->ev[0], s->ev[6]));
   return PXB_OK;
 }
 
@@ -1012,7 +1103,8 @@ PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) {
   for (uint32_t i = 0; i < n; ++i) {
     float* o = out24 + (size_t)i * 24; memset(o, 0, 96);
     int cnt; memcpy(&cnt, &h[i].w, 4);
-    o[0] = (float)cnt; o[1] = h[i].x; o[2] = h[i].y; o[3] = h[i].z;
+    o[0] = (float)cnt;
+    if (cnt) { o[1] = h[i].x; o[2] = h[i].y; o[3] = h[i].z; }
     for (int k = 0; k < cnt && k < 4; ++k) { const float4 q = p[(size_t)i * 4 + k]; float* r = o + 4 + k * 5; r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; r[4] = f[(size_t)i * 4 + k]; }
   }
   return PXB_OK;
@@ -1047,15 +1139,14 @@ static int rd_host(PxbScene* s, void* data, const uint32_t* idx, int type, uint3
   if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
   if (!nb) return PXB_OK;
   const size_t bytes = (size_t)nb * (type == 0 ? 28 : 12);
-  float* d = nullptr; uint32_t* di = nullptr;
-  CK(cudaMalloc((void**)&d, bytes));
-  if (idx) { for (uint32_t i = 0; i < nb; ++i) if (idx[i] >= s->nDyn) { cudaFree(d); return fail(PXB_ERR_INVALID, "index out of range"); }
-             CK(cudaMalloc((void**)&di, 4 * (size_t)nb)); CK(cudaMemcpyAsync(di, idx, 4 * (size_t)nb, cudaMemcpyHostToDevice, s->stream)); }
+  if (nb > s->capA) return fail(PXB_ERR_INVALID, "nb exceeds the actor capacity");
+  float* d = s->stage; uint32_t* di = nullptr;   // persistent staging: no allocation on the per-step path
+  if (idx) { for (uint32_t i = 0; i < nb; ++i) if (idx[i] >= s->nDyn) return fail(PXB_ERR_INVALID, "index out of range");
+             di = s->stageIdx; CK(cudaMemcpyAsync(di, idx, 4 * (size_t)nb, cudaMemcpyHostToDevice, s->stream)); }
   if (set) CK(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, s->stream));
   int rc = rd_common(s, d, di, type, nb, set);
   if (!rc && !set) CK(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
-  cudaFree(d); if (di) cudaFree(di);
   return rc;
 }
 PXB_API int pxb_get_rigid_dynamic_data(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, data, idx, type, nb, false); }

@@ -4,7 +4,7 @@
 // Replaces the role of the reference's radix sort (physx/source/gpucommon/src/CUDA/RadixSort.cuh,
 // radixSortImpl.cu:37-237: 4 bits/pass, 2 kernels/pass, fixed grid) in the broadphase.
 // Design: 8 bits per pass, fixed persistent grid sized to the SM count, each CTA owns one contiguous
-// chunk per pass (histogram -> single-CTA scan of [CTA][256] counts -> stable scatter using
+// chunk per pass (histogram -> per-digit row scan of the [CTA][256] counts -> stable scatter using
 // warp-level __match_any_sync ranking).  Only ceil(keyBits/8) passes run.
 #pragma once
 #include <cuda_runtime.h>
@@ -32,33 +32,54 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
   blockHist[blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
 }
 
-// single CTA: exclusive scan of counts in (digit major, CTA minor) order; in place
-__global__ void __launch_bounds__(256) k_rs_scan(uint32_t* __restrict__ blockHist, uint32_t G) {
-  __shared__ uint32_t tot[256];
-  const uint32_t d = threadIdx.x;
-  uint32_t s = 0;
-  for (uint32_t g = 0; g < G; ++g) s += blockHist[g * 256 + d];
-  tot[d] = s;
+// One CTA per digit: exclusive scan of that digit's counts over the CTAs (in place) + the digit total.
+// The cross-digit prefix (256 values) is rebuilt by every scatter CTA in shared memory, so a pass is
+// hist -> row scan (256 tiny CTAs) -> scatter, with no serial single-CTA step.
+__global__ void __launch_bounds__(128) k_rs_scan(uint32_t* __restrict__ blockHist, uint32_t G, uint32_t* __restrict__ digitTotals) {
+  __shared__ uint32_t ws[4];
+  __shared__ uint32_t carry;
+  const uint32_t d = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) carry = 0;
   __syncthreads();
-  // exclusive scan of the 256 digit totals (Hillis-Steele)
-  uint32_t v = s;
-  for (uint32_t off = 1; off < 256; off <<= 1) {
-    const uint32_t t = d >= off ? tot[d - off] : 0;
+  for (uint32_t base = 0; base < G; base += 128) {
+    const uint32_t g = base + t;
+    const uint32_t v = g < G ? blockHist[g * 256 + d] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += y; }
+    if (lane == 31) ws[warp] = x;
     __syncthreads();
-    tot[d] += t;
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { const uint32_t c = ws[w]; if (w < (int)warp) woff += c; tot += c; }
+    if (g < G) blockHist[g * 256 + d] = carry + woff + x - v;
+    __syncthreads();
+    if (t == 0) carry += tot;
     __syncthreads();
   }
-  uint32_t base = tot[d] - v;
-  for (uint32_t g = 0; g < G; ++g) { const uint32_t c = blockHist[g * 256 + d]; blockHist[g * 256 + d] = base; base += c; }
+  if (t == 0) digitTotals[d] = carry;
 }
 
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
                                                            uint64_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
-                                                           const uint32_t* __restrict__ dN, uint32_t shift, const uint32_t* __restrict__ blockHist) {
+                                                           const uint32_t* __restrict__ dN, uint32_t shift, const uint32_t* __restrict__ blockHist,
+                                                           const uint32_t* __restrict__ digitTotals) {
   __shared__ uint32_t running[256];
   __shared__ uint32_t warpCnt[RS_WARPS][256];
+  __shared__ uint32_t wsum[RS_WARPS];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  running[tid] = blockHist[blockIdx.x * 256 + tid];
+  {  // exclusive prefix of the 256 digit totals (block-wide scan), plus this CTA's offset inside the digit
+    const uint32_t v = digitTotals[tid];
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += y; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) if (w < (int)warp) woff += wsum[w];
+    running[tid] = woff + x - v + blockHist[blockIdx.x * 256 + tid];
+  }
   uint32_t b, e; rs_chunk(*dN, b, e);
   for (uint32_t base = b; base < e; base += RS_THREADS) {
 #pragma unroll
@@ -84,7 +105,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
   }
 }
 
-struct RadixSortTemp { uint32_t* blockHist; uint32_t ctas; };
+struct RadixSortTemp { uint32_t* blockHist; uint32_t* digitTotals; uint32_t ctas; };
 
 // Sorts (keys, vals)[0..*dN) on `stream`. Returns 0 if the result is in (keys, vals), 1 if in (keysAlt, valsAlt).
 static inline int radix_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t* keysAlt, uint32_t* valsAlt, const uint32_t* dN,
@@ -95,8 +116,8 @@ static inline int radix_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t* key
     const uint64_t* kin = cur ? keysAlt : keys; const uint32_t* vin = cur ? valsAlt : vals;
     uint64_t* kout = cur ? keys : keysAlt; uint32_t* vout = cur ? vals : valsAlt;
     k_rs_hist<<<tmp.ctas, RS_THREADS, 0, stream>>>(kin, dN, p * 8, tmp.blockHist);
-    k_rs_scan<<<1, 256, 0, stream>>>(tmp.blockHist, tmp.ctas);
-    k_rs_scatter<<<tmp.ctas, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, dN, p * 8, tmp.blockHist);
+    k_rs_scan<<<256, 128, 0, stream>>>(tmp.blockHist, tmp.ctas, tmp.digitTotals);
+    k_rs_scatter<<<tmp.ctas, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, dN, p * 8, tmp.blockHist, tmp.digitTotals);
     cur ^= 1;
   }
   return cur;
@@ -114,8 +135,24 @@ __global__ void __launch_bounds__(RS_THREADS) k_scan_reduce(const uint32_t* __re
   if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < RS_WARPS; ++w) t += ws[w]; blockSums[blockIdx.x] = t; }
 }
 // single CTA; also writes the grand total to *dTotal
-__global__ void k_scan_sums(uint32_t* __restrict__ blockSums, uint32_t G, uint32_t* __restrict__ dTotal) {
-  if (threadIdx.x == 0) { uint32_t s = 0; for (uint32_t g = 0; g < G; ++g) { const uint32_t c = blockSums[g]; blockSums[g] = s; s += c; } *dTotal = s; }
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* __restrict__ blockSums, uint32_t G, uint32_t* __restrict__ dTotal) {
+  __shared__ uint32_t ws[32];
+  const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t v = t < G ? blockSums[t] : 0;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += y; }
+  if (lane == 31) ws[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = ws[lane]; uint32_t y = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t z = __shfl_up_sync(0xffffffffu, y, o); if ((int)lane >= o) y += z; }
+    ws[lane] = y - w;
+    if (lane == 31) *dTotal = y;
+  }
+  __syncthreads();
+  if (t < G) blockSums[t] = ws[warp] + x - v;
 }
 __global__ void __launch_bounds__(RS_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ dN, const uint32_t* __restrict__ blockSums) {
   __shared__ uint32_t ws[RS_WARPS];
@@ -142,6 +179,6 @@ __global__ void __launch_bounds__(RS_THREADS) k_scan_apply(const uint32_t* __res
 }
 static inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, const uint32_t* dN, uint32_t* dTotal, uint32_t* blockSums, uint32_t ctas, cudaStream_t stream) {
   k_scan_reduce<<<ctas, RS_THREADS, 0, stream>>>(in, dN, blockSums);
-  k_scan_sums<<<1, 32, 0, stream>>>(blockSums, ctas, dTotal);
+  k_scan_sums<<<1, 1024, 0, stream>>>(blockSums, ctas, dTotal);  // ctas <= RS_MAX_CTAS <= 1024
   k_scan_apply<<<ctas, RS_THREADS, 0, stream>>>(in, out, dN, blockSums);
 }

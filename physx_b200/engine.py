@@ -28,7 +28,7 @@ EXPORTS = [
     "pxb_scene_get_bounds", "pxb_scene_broadphase", "pxb_scene_num_pairs", "pxb_scene_get_pairs",
     "pxb_scene_num_created", "pxb_scene_num_deleted", "pxb_scene_get_created", "pxb_scene_get_deleted",
     "pxb_scene_get_contacts", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
-    "pxb_scene_last_num_launches",
+    "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY = 0, 1, 2
@@ -86,6 +86,8 @@ def load_library():
               "pxb_scene_get_pairs", "pxb_scene_get_created", "pxb_scene_get_deleted", "pxb_scene_get_contacts"):
         getattr(lib, f).argtypes = [vp, vp]
     lib.pxb_scene_compute_bounds.argtypes = [vp]
+    lib.pxb_scene_set_profiling.argtypes = [vp, i32]
+    lib.pxb_scene_get_stage_times.argtypes = [vp, vp]
     lib.pxb_scene_state_device_ptr.argtypes = [vp, i32]
     lib.pxb_scene_state_device_ptr.restype = vp
     lib.pxb_scene_stream.argtypes = [vp]
@@ -228,6 +230,16 @@ class Scene:
         if n:
             _check(self._lib, self._lib.pxb_scene_get_contacts(self._h, _ptr(out)))
         return out
+
+    STAGES = ("broadphase", "narrowphase", "colouring", "prep", "solve", "integrate", "step")
+
+    def setProfiling(self, on: bool = True):
+        _check(self._lib, self._lib.pxb_scene_set_profiling(self._h, 1 if on else 0))
+
+    def getStageTimes(self):
+        ms = np.zeros(7, np.float32)
+        _check(self._lib, self._lib.pxb_scene_get_stage_times(self._h, _ptr(ms)))
+        return dict(zip(self.STAGES, (float(x) for x in ms)))
 
     @property
     def num_partitions(self):

@@ -1,0 +1,124 @@
+"""Env-partitioned multi-GPU stepping (BASELINE config 5).
+
+Environments never interact (environment-id filter in the broadphase), so the path shards by environment:
+rank r owns envs [r*E/G, (r+1)*E/G) in its own scene on its own GPU -- one process per GPU, no physics
+coupling, no halo exchange.  The only collective is an NCCL all-gather of the per-env body-state tensors the
+Direct GPU API exposes (pose 7 floats, linear and angular velocity 3 floats each), so that every rank (the
+learner) sees the global [E*B, 7|3|3] tensors.  The reference has no multi-GPU mode (one PxScene <-> one
+device, physx/source/simulationcontroller/src/ScScene.cpp:718), so this module is new work.
+
+`torch.distributed` is plumbing only: the gather operates directly on the device buffers the engine's
+get-kernels fill (no staging copy through the host).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import scenes as _scenes
+
+STATE_COLS = {0: 7, 1: 3, 2: 3}  # RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY
+
+
+def env_range(n_envs: int, world_size: int, rank: int):
+    """Contiguous env shard of `rank`; remainders go to the lowest ranks."""
+    base, rem = divmod(n_envs, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_scene(scene: _scenes.Scene, world_size: int, rank: int) -> _scenes.Scene:
+    """Sub-scene with the actors of this rank's environments plus every env-less (shared) actor, e.g. the
+    ground plane.  Actor order is preserved, so local dynamic-body order = global order restricted to the shard."""
+    env = scene.actors["envId"]
+    n_envs = int(env[env != _scenes.NO_ENV].max()) + 1 if np.any(env != _scenes.NO_ENV) else 0
+    lo, hi = env_range(n_envs, world_size, rank)
+    keep = (env == _scenes.NO_ENV) | ((env >= lo) & (env < hi))
+    return _scenes.Scene(scene.header, scene.actors[keep].copy(), scene.hulls)
+
+
+def gather_layout(counts):
+    """Row offsets of every rank's block in the gathered tensor."""
+    off = np.concatenate([[0], np.cumsum(counts)])
+    return [(int(off[i]), int(off[i + 1])) for i in range(len(counts))]
+
+
+class StateGather:
+    """All-gathers one Direct-GPU-API state tensor across ranks.
+
+    `local_fill(dst_tensor)` must write this rank's [n_local, cols] float32 block into `dst_tensor`
+    (a view of the send region); on the GPU that is pxb_get_rigid_dynamic_data_device writing straight
+    into the NCCL send buffer.  Equal per-rank counts use all_gather_into_tensor (one NCCL call over
+    NVLink/NVSwitch); ragged counts fall back to all_gather with per-rank tensors."""
+
+    def __init__(self, dist, n_local: int, cols: int, device):
+        import torch
+        self.dist, self.torch = dist, torch
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        cnt = torch.tensor([n_local], dtype=torch.int64, device=device)
+        allc = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(allc, cnt)
+        self.counts = [int(c.item()) for c in allc]
+        self.layout = gather_layout(self.counts)
+        self.equal = len(set(self.counts)) == 1
+        self.cols = cols
+        self.global_tensor = torch.zeros((sum(self.counts), cols), dtype=torch.float32, device=device)
+        lo, hi = self.layout[self.rank]
+        self.local_view = self.global_tensor[lo:hi]
+
+    def __call__(self, local_fill):
+        local_fill(self.local_view)
+        if self.equal:
+            # in place: the send region is this rank's slice of the receive tensor (NCCL in-place all-gather)
+            src = self.local_view if self.global_tensor.is_cuda else self.local_view.clone()
+            self.dist.all_gather_into_tensor(self.global_tensor, src)
+        else:
+            # ragged shards: pad every block to the largest one, gather, then compact into the global tensor
+            mx = max(self.counts)
+            if not hasattr(self, "_padded"):
+                self._padded = self.torch.zeros((self.world * mx, self.cols), dtype=self.torch.float32, device=self.global_tensor.device)
+                self._send = self.torch.zeros((mx, self.cols), dtype=self.torch.float32, device=self.global_tensor.device)
+            self._send[:self.counts[self.rank]].copy_(self.local_view)
+            self.dist.all_gather_into_tensor(self._padded, self._send)
+            for r, (lo, hi) in enumerate(self.layout):
+                if r != self.rank:
+                    self.global_tensor[lo:hi].copy_(self._padded[r * mx:r * mx + (hi - lo)])
+        return self.global_tensor
+
+
+class EnvShardedScene:
+    """One rank's scene of an env-partitioned job + the state all-gather."""
+
+    def __init__(self, full_scene: _scenes.Scene, dist=None, device_index: int = 0):
+        import torch
+        from . import engine
+        self.dist = dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.local_scene_desc = shard_scene(full_scene, self.world, self.rank) if self.world > 1 else full_scene
+        self.scene = engine.Scene(self.local_scene_desc, device=device_index)
+        self.device = torch.device("cuda", device_index)
+        self.stream = torch.cuda.ExternalStream(self.scene.stream(), device=self.device)
+        self.gathers = {}
+        if dist is not None and self.world > 1:
+            for t, cols in STATE_COLS.items():
+                self.gathers[t] = StateGather(dist, self.scene.num_dynamic, cols, self.device)
+
+    def step(self):
+        self.scene.step()
+
+    def all_gather_state(self, data_type: int):
+        """Global [sum(n_dyn), cols] tensor of one state type; identical on every rank afterwards."""
+        import torch
+        if not self.gathers:
+            out = torch.empty((self.scene.num_dynamic, STATE_COLS[data_type]), dtype=torch.float32, device=self.device)
+            self.scene.getRigidDynamicDataDevice(data_type, out.data_ptr(), self.scene.num_dynamic)
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+            return out
+        g = self.gathers[data_type]
+
+        def fill(view):
+            # the engine's gather kernel writes straight into the NCCL send region on the scene stream
+            self.scene.getRigidDynamicDataDevice(data_type, view.data_ptr(), self.scene.num_dynamic)
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return g(fill)

@@ -1,0 +1,78 @@
+"""CPU tests (gloo, world_size 2) of the env-sharding and state all-gather host logic (physx_b200/multi_gpu.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from physx_b200 import multi_gpu, scenes
+
+
+def test_env_ranges_partition_exactly():
+    for n_envs in (1, 7, 8, 4096, 32768):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                lo, hi = multi_gpu.env_range(n_envs, world, r)
+                got.extend(range(lo, hi))
+            assert got == list(range(n_envs))
+
+
+def test_shard_scene_keeps_shared_actors_and_order():
+    sc = scenes.env_grid_stacks(n_envs=6)
+    seen = []
+    for r in range(4):
+        sh = multi_gpu.shard_scene(sc, 4, r)
+        assert sh.actors[0]["geomType"] == scenes.GEOM_PLANE           # the shared ground plane is in every shard
+        env = sh.actors["envId"][1:]
+        assert np.all(np.diff(env.astype(np.int64)) >= 0)
+        seen.extend(np.unique(env).tolist())
+        assert sh.n_dynamic == len(env)
+    assert sorted(seen) == list(range(6))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, counts, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_local = counts[rank]
+        for cols in (7, 3):
+            g = multi_gpu.StateGather(dist, n_local, cols, torch.device("cpu"))
+
+            def fill(view, cols=cols):
+                view.copy_(torch.arange(n_local * cols, dtype=torch.float32).reshape(n_local, cols) + 1000.0 * rank)
+            out = g(fill)
+            exp = torch.cat([torch.arange(c * cols, dtype=torch.float32).reshape(c, cols) + 1000.0 * r for r, c in enumerate(counts)])
+            assert g.layout == multi_gpu.gather_layout(counts)
+            assert torch.equal(out, exp), f"rank {rank} cols {cols}"
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [(5, 5), (4, 7)])
+def test_state_all_gather_world2_gloo(counts):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, counts, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
