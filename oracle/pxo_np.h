@@ -532,4 +532,195 @@ static inline int pxo_pcm_box_box(const xf* tm0, const xf* tm1, v3 ext0, v3 ext1
   }
   return 0;
 }
+
+/* ---------------- sphere / capsule family ---------------- */
+/* shape0 = sphere, shape1 = sphere: GuPCMContactSphereSphere.cpp:36-69 (stateless) */
+static inline void pxo_sphere_sphere(v3 p0, v3 p1, float r0, float r1, float cDist, PxoContacts* out) {
+  out->count = 0;
+  const v3 delta = v3sub(p0, p1);
+  const float distanceSq = adot(delta, delta);
+  const float radiusSum = r0 + r1, inflatedSum = radiusSum + cDist;
+  if (inflatedSum * inflatedSum > distanceSq) {
+    const float dist = sqrtf(distanceSq);
+    const v3 normal = (0.00001f >= dist) ? V3(1.f, 0.f, 0.f) : V3(delta.x / dist, delta.y / dist, delta.z / dist);
+    out->normal = normal; out->point[0] = v3scaleadd(normal, r1, p1); out->sep[0] = dist - radiusSum; out->count = 1;
+  }
+}
+/* shape0 = sphere, shape1 = plane: GuPCMContactSpherePlane.cpp:36-73 */
+static inline void pxo_sphere_plane(v3 p0, float radius, const xf* planeTm, float cDist, PxoContacts* out) {
+  out->count = 0;
+  const v3 c = aqrotinv(planeTm->q, v3sub(p0, planeTm->p));
+  const float separation = c.x - radius;
+  if (cDist >= separation) {
+    const v3 n = aqbasis0(planeTm->q);
+    out->normal = n; out->point[0] = v3negscalesub(n, radius, p0); out->sep[0] = separation; out->count = 1;
+  }
+}
+/* GuPCMContactSphereCapsule.cpp:38-54 */
+static inline float pxo_dist_point_segment_sq(v3 a, v3 b, v3 p, float* param) {
+  const v3 ap = v3sub(p, a), ab = v3sub(b, a);
+  const float nom = adot(ap, ab), denom = adot(ab, ab);
+  const float tValue = fmaxf_(fminf_(nom / denom, 1.f), 0.f);
+  const float t = (denom == 0.f) ? 0.f : tValue;
+  const v3 v = v3negscalesub(ab, t, ap);
+  *param = t;
+  return adot(v, v);
+}
+/* shape0 = sphere, shape1 = capsule: GuPCMContactSphereCapsule.cpp:56-102 */
+static inline void pxo_sphere_capsule(v3 sphereCenter, float sphereRadius, const xf* capTm, float capRadius, float halfHeight, float cDist, PxoContacts* out) {
+  out->count = 0;
+  const v3 tmp0 = v3scale(aqbasis0(capTm->q), halfHeight);
+  const v3 s = v3add(capTm->p, tmp0), e = v3sub(capTm->p, tmp0);
+  const float radiusSum = sphereRadius + capRadius, inflatedSum = radiusSum + cDist;
+  float t; const float squareDist = pxo_dist_point_segment_sq(s, e, sphereCenter, &t);
+  if (inflatedSum * inflatedSum > squareDist) {
+    const v3 p = v3scaleadd(v3sub(e, s), t, s);
+    const v3 dir = v3sub(sphereCenter, p);
+    const float len = alen(dir);
+    const v3 normal = (len > FLT_EPSILON) ? V3(dir.x / len, dir.y / len, dir.z / len) : V3(1.f, 0.f, 0.f);
+    out->normal = normal; out->point[0] = v3negscalesub(normal, sphereRadius, sphereCenter); out->sep[0] = sqrtf(squareDist) - radiusSum; out->count = 1;
+  }
+}
+/* shape0 = sphere, shape1 = box: GuPCMContactSphereBox.cpp:36-131 */
+static inline void pxo_sphere_box(v3 sphereOrigin, float radius, const xf* boxTm, v3 be, float cDist, PxoContacts* out) {
+  out->count = 0;
+  const v3 c = aqrotinv(boxTm->q, v3sub(sphereOrigin, boxTm->p));
+  const float inflatedSum = radius + cDist;
+  const v3 p = V3(fmaxf_(fminf_(c.x, be.x), -be.x), fmaxf_(fminf_(c.y, be.y), -be.y), fmaxf_(fminf_(c.z, be.z), -be.z)); /* V3Clamp = max(min(a,max),min) */
+  const v3 v = v3sub(c, p);
+  const float lengthSq = adot(v, v);
+  if (inflatedSum * inflatedSum > lengthSq) {
+    const v3 ac = v3abs(c);
+    if (be.x >= ac.x && be.y >= ac.y && be.z >= ac.z) {
+      const v3 d = v3sub(be, v3abs(p));
+      const int con0 = d.x >= d.z && d.y >= d.z && d.z >= d.z, con1 = d.x >= d.x && d.y >= d.x && d.z >= d.x;
+      const v3 sign = V3(p.x >= 0.f ? 1.f : -1.f, p.y >= 0.f ? 1.f : -1.f, p.z >= 0.f ? 1.f : -1.f);
+      const v3 locNorm = con0 ? V3(0.f * sign.x, 0.f * sign.y, 1.f * sign.z) : (con1 ? V3(1.f * sign.x, 0.f * sign.y, 0.f * sign.z) : V3(0.f * sign.x, 1.f * sign.y, 0.f * sign.z));
+      const float dist = -(con0 ? d.z : (con1 ? d.x : d.y));
+      const v3 normal = aqrot(boxTm->q, locNorm);
+      out->normal = normal; out->point[0] = v3sub(sphereOrigin, v3scale(normal, dist)); out->sep[0] = dist - radius; out->count = 1;
+    } else {
+      const float recipLength = 1.0f / sqrtf(lengthSq);
+      const float length = 1.0f / recipLength;
+      const v3 locNorm = v3scale(v, recipLength);
+      out->normal = aqrot(boxTm->q, locNorm); out->point[0] = axftransform(boxTm, p); out->sep[0] = length - radius; out->count = 1;
+    }
+  }
+}
+/* GuPersistentContactManifold.cpp:552-600, :1269-1290 (addManifoldPoint2 -> replaceManifoldPoint / reduceContactSegment) */
+static inline void pxo_add_manifold_point2(PxoManifold* m, v3 la, v3 lb, v3 n, float pen, float replaceBreakingThreshold) {
+  const float shortest = replaceBreakingThreshold * replaceBreakingThreshold;
+  for (int i = 0; i < m->n; ++i) {
+    const v3 dB = v3sub(m->pts[i].b, lb), dA = v3sub(m->pts[i].a, la);
+    if (shortest > fminf_(adot(dB, dB), adot(dA, dA))) { m->pts[i].a = la; m->pts[i].b = lb; m->pts[i].n = n; m->pts[i].pen = pen; return; }
+  }
+  if (m->n < 2) { m->pts[m->n].a = la; m->pts[m->n].b = lb; m->pts[m->n].n = n; m->pts[m->n].pen = pen; m->n++; return; }
+  const v3 v0 = v3sub(m->pts[0].b, lb), v1 = v3sub(m->pts[1].b, lb);
+  const int k = (adot(v0, v0) > adot(v1, v1)) ? 1 : 0;
+  m->pts[k].a = la; m->pts[k].b = lb; m->pts[k].n = n; m->pts[k].pen = pen;
+}
+/* shape0 = plane, shape1 = capsule: GuPCMContactPlaneCapsule.cpp:36-123 (persistent manifold, <= 2 points) */
+static inline void pxo_pcm_plane_capsule(const xf* planeTm, const xf* capTm, float radius, float halfHeight, float contactDist, PxoManifold* man, PxoContacts* out) {
+  const xf aToB = axfinvmul(planeTm, capTm);
+  const v3 planeNormal = anormalize(aqbasis0(planeTm->q));
+  const v3 contactNormal = v3neg(planeNormal);
+  const v3 localNormal = V3(1.f, 0.f, 0.f);
+  const v3 tmp = v3scale(aqbasis0(aToB.q), halfHeight);
+  const v3 s = v3add(aToB.p, tmp), e = v3sub(aToB.p, tmp);
+  const float inflatedRadius = radius + contactDist;
+  const float replaceBreakingThreshold = radius * 0.001f, projectBreakingThreshold = radius * 0.05f;
+  const int initial = man->n;
+  const mxf aToBm = amxffromxf(&aToB);
+  pxo_refresh(man, &aToBm, projectBreakingThreshold);
+  const int lost = man->n != initial;
+  if (lost || pxo_invalidate_plane(man, &aToB, radius, 0.02f)) {
+    man->n = 0; man->rel = aToB;
+    const float sd0 = s.x;
+    if (inflatedRadius > sd0) pxo_add_manifold_point2(man, aqrotinv(aToB.q, v3sub(s, aToB.p)), v3negscalesub(localNormal, sd0, s), localNormal, sd0, replaceBreakingThreshold);
+    const float sd1 = e.x;
+    if (inflatedRadius > sd1) pxo_add_manifold_point2(man, aqrotinv(aToB.q, v3sub(e, aToB.p)), v3negscalesub(localNormal, sd1, e), localNormal, sd1, replaceBreakingThreshold);
+  }
+  /* addManifoldContactsToContactBuffer(buffer, normal, projectionNormal, transf0, radius, contactOffset): .cpp:783-807 */
+  out->count = 0; out->normal = contactNormal;
+  for (int i = 0; i < man->n; ++i) {
+    const float dist = man->pts[i].pen - radius;
+    if (contactDist >= dist) { out->point[out->count] = v3negscalesub(planeNormal, radius, axftransform(capTm, man->pts[i].a)); out->sep[out->count] = dist; out->count++; }
+  }
+}
+/* GuDistanceSegmentSegment.cpp:411-469 */
+static inline float pxo_dist_seg_seg_sq(v3 p1, v3 d1, v3 p2, v3 d2, float* s, float* t) {
+  const float eps = FLT_EPSILON;
+  const v3 r = v3sub(p1, p2);
+  const float a = v3dot(d1, d1), e = v3dot(d2, d2), b = v3dot(d1, d2), c = v3dot(d1, r); /* V3Dot4: (x+y)+z */
+  const float aRecip = a > eps ? 1.0f / a : 0.f, eRecip = e > eps ? 1.0f / e : 0.f;
+  const float f = adot(d2, r);
+  const float denom = a * e - b * b;
+  const float temp = b * f - c * e;
+  const float s0 = fmaxf_(fminf_(temp / denom, 1.f), 0.f);
+  const float sTmp = (eps > denom) ? 0.5f : s0;
+  const float tTmp = (b * sTmp + f) * eRecip;
+  const float t2 = fmaxf_(fminf_(tTmp, 1.f), 0.f);
+  const float comp = (b * t2 - c) * aRecip;
+  const float s2 = fmaxf_(fminf_(comp, 1.f), 0.f);
+  *s = s2; *t = t2;
+  const v3 vv = v3sub(v3scaleadd(d1, s2, p1), v3scaleadd(d2, t2, p2));
+  return adot(vv, vv);
+}
+/* shape0 = capsule, shape1 = capsule: GuPCMContactCapsuleCapsule.cpp:78-275 (stateless, <= 4 contacts).
+ * Returns nonzero in *multiNormal when the contacts' normals are not all within PXC_SAME_NORMAL of the first
+ * one (the reference would then split them into several patches; we keep one patch -- see DESIGN.md). */
+static inline void pxo_capsule_capsule(const xf* tm0, const xf* tm1, float r0, float hh0, float r1, float hh1, float cDist, PxoContacts* out, int* multiNormal) {
+  out->count = 0; *multiNormal = 0;
+  const v3 positionOffset = v3scale(v3add(tm0->p, tm1->p), 0.5f);
+  const v3 p0 = v3sub(tm0->p, positionOffset), p1 = v3sub(tm1->p, positionOffset);
+  const v3 tmp0 = v3scale(aqbasis0(tm0->q), hh0);
+  const v3 s0 = v3add(p0, tmp0), e0 = v3sub(p0, tmp0), d0 = v3sub(e0, s0);
+  const v3 tmp1 = v3scale(aqbasis0(tm1->q), hh1);
+  const v3 s1 = v3add(p1, tmp1), e1 = v3sub(p1, tmp1), d1 = v3sub(e1, s1);
+  const float sumRadius = r0 + r1, inflatedSum = sumRadius + cDist, inflatedSumSquared = inflatedSum * inflatedSum;
+  const float a = adot(d0, d0), e = adot(d1, d1), eps = 1e-6f;
+  float t0, t1;
+  const float sqDist0 = pxo_dist_seg_seg_sq(s0, d0, s1, d1, &t0, &t1);
+  if (!(inflatedSumSquared >= sqDist0)) return;
+  v3 normals[4];
+  const float sa = sqrtf(a), se = sqrtf(e);
+  const v3 dir0 = (eps > a) ? V3(0, 0, 0) : V3(d0.x / sa, d0.y / sa, d0.z / sa);
+  const v3 dir1 = (eps > e) ? V3(0, 0, 0) : V3(d1.x / se, d1.y / se, d1.z / se);
+  const float cosv = fabsf(adot(dir0, dir1));
+  if (cosv > 0.9998f) {
+    /* pcmDistancePointSegmentTValue22(s0,e0, s1,e1, s1,e1,s0,e0): t = dot(p - a, ab)/dot(ab,ab) */
+    const v3 ab0 = v3sub(e0, s0), ab1 = v3sub(e1, s1);
+    const float den0 = adot(ab0, ab0), den1 = adot(ab1, ab1);
+    const float nom[4] = {v3dot(v3sub(s1, s0), ab0), v3dot(v3sub(e1, s0), ab0), v3dot(v3sub(s0, s1), ab1), v3dot(v3sub(e0, s1), ab1)};
+    const float den[4] = {den0, den0, den1, den1};
+    float t[4];
+    for (int k = 0; k < 4; ++k) t[k] = (den[k] == 0.f) ? 0.f : nom[k] / den[k];
+    for (int k = 0; k < 4; ++k) {
+      if (!(t[k] >= 0.f && 1.f >= t[k])) continue;
+      v3 proj, v, base;
+      if (k == 0) { proj = v3scaleadd(d0, t[0], s0); v = v3sub(proj, s1); base = proj; }
+      else if (k == 1) { proj = v3scaleadd(d0, t[1], s0); v = v3sub(proj, e1); base = proj; }
+      else if (k == 2) { proj = v3scaleadd(d1, t[2], s1); v = v3sub(s0, proj); base = s0; }
+      else { proj = v3scaleadd(d1, t[3], s1); v = v3sub(e0, proj); base = e0; }
+      const float sqDist = adot(v, v);
+      if (sqDist > eps && inflatedSumSquared > sqDist) {
+        const float dist = sqrtf(sqDist);
+        const v3 normal = V3(v.x / dist, v.y / dist, v.z / dist);
+        normals[out->count] = normal;
+        out->point[out->count] = v3add(v3negscalesub(normal, r0, base), positionOffset); out->sep[out->count] = dist - sumRadius; out->count++;
+      }
+    }
+    if (out->count) {
+      out->normal = normals[0];
+      for (int k = 1; k < out->count; ++k) if (!(v3dot(normals[k], normals[0]) >= 0.999f)) *multiNormal = 1;
+      return;
+    }
+  }
+  const v3 closestA = v3scaleadd(d0, t0, s0), closestB = v3scaleadd(d1, t1, s1);
+  const int con = eps > sqDist0;
+  const v3 _normal = con ? ((a > eps) ? d0 : V3(1.f, 0.f, 0.f)) : v3sub(closestA, closestB);
+  const v3 normal = anormalize(_normal);
+  out->normal = normal; out->point[0] = v3add(v3negscalesub(normal, r0, closestA), positionOffset);
+  out->sep[0] = (con ? 0.f : sqrtf(sqDist0)) - sumRadius; out->count = 1;
+}
 #endif

@@ -17,7 +17,9 @@
 //   --order    per step: u32 nEdges, then (u32 actor0, u32 actor1) in the order the island manager
 //              feeds contact managers to the solver (IG::Island edge lists walked exactly like
 //              DynamicsTGSContext::prepareBodiesAndConstraints, DyTGSDynamics.cpp:822-905), dumped
-//              AFTER the step (the lists the step used, plus edges removed/added at its very end).
+//              at the moment the solver task (ScScene.updateDynamics) is submitted, i.e. the lists the step's
+//              solve really uses (a custom inline PxCpuDispatcher intercepts the task; island splits caused
+//              by lost edges only happen after the solve, so a post-step dump would be wrong).
 //   stdout     one JSON line with timing.
 #include <cstdio>
 #include <cstdlib>
@@ -77,6 +79,17 @@ public:
       gContacts.pairs.push_back(p);
     }
   }
+};
+
+// Inline dispatcher (same behaviour as PxDefaultCpuDispatcherCreate(0)) that calls a hook right before the
+// solver task runs.
+struct InlineDispatcher : public PxCpuDispatcher {
+  void (*hook)(void*) = nullptr; void* user = nullptr;
+  void submitTask(PxBaseTask& task) override {
+    if (hook && task.getName() && !strcmp(task.getName(), "ScScene.updateDynamics")) hook(user);
+    task.run(); task.release();
+  }
+  uint32_t getWorkerCount() const override { return 0; }
 };
 
 static bool gWantContacts = false;
@@ -167,7 +180,8 @@ int main(int argc, char** argv) {
   PxSceneDesc sd(scale);
   sd.gravity = PxVec3(H.gravity[0], H.gravity[1], H.gravity[2]);
   PxDefaultCpuDispatcher* dispatcher = PxDefaultCpuDispatcherCreate(threads);
-  sd.cpuDispatcher = dispatcher;
+  static InlineDispatcher inlineDispatcher;
+  sd.cpuDispatcher = orderPath ? static_cast<PxCpuDispatcher*>(&inlineDispatcher) : static_cast<PxCpuDispatcher*>(dispatcher);
   sd.filterShader = filterShader;
   sd.filterShaderData = &wantContactsFlag;
   sd.filterShaderDataSize = sizeof(int);
@@ -228,7 +242,10 @@ int main(int argc, char** argv) {
   FILE* fb = bpPath ? fopen(bpPath, "wb") : nullptr;
   FILE* fc = contactsPath ? fopen(contactsPath, "wb") : nullptr;
   FILE* fo = orderPath ? fopen(orderPath, "wb") : nullptr;
-  auto dumpOrder = [&]() {
+  static FILE* sFo; static PxScene* sScene; sFo = fo; sScene = scene;
+  static void (*sDump)();
+  auto dumpOrder = []() {
+    FILE* fo = sFo; PxScene* scene = sScene;
     if (!fo) return;
     NpScene* np = static_cast<NpScene*>(scene);
     IG::SimpleIslandManager* im = np->getScScene().getSimpleIslandManager();
@@ -246,6 +263,7 @@ int main(int argc, char** argv) {
     uint32_t n = uint32_t(edges.size() / 2);
     fwrite(&n, 4, 1, fo); fwrite(edges.data(), 4, edges.size(), fo);
   };
+  sDump = dumpOrder;
 
   auto dumpStates = [&]() {
     if (!fs) return;
@@ -298,6 +316,7 @@ int main(int argc, char** argv) {
     for (auto& p : d) { fwrite(&p.first, 4, 1, fb); fwrite(&p.second, 4, 1, fb); }
   };
 
+  inlineDispatcher.hook = [](void*) { sDump(); };
   dumpStates();
   double totalMs = 0; std::vector<double> stepMs;
   for (int s = 0; s < steps + warmup; s++) {
@@ -310,7 +329,6 @@ int main(int argc, char** argv) {
     double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     if (s >= warmup) { totalMs += ms; stepMs.push_back(ms); }
     dumpStates();
-    dumpOrder();
     if (fc) {
       std::sort(gContacts.pairs.begin(), gContacts.pairs.end(), [](const ContactDump::Pair& x, const ContactDump::Pair& y) {
         return std::make_pair(x.a0, x.a1) < std::make_pair(y.a0, y.a1); });

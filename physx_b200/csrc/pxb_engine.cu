@@ -280,6 +280,12 @@ __global__ void __launch_bounds__(128) k_narrowphase(const uint64_t* __restrict_
   for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
   if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_BOX) pcm_plane_box(tm0, tm1, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
   else if (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX) pcm_box_box(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
+  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_SPHERE) np_sphere_sphere(tm0.p, tm1.p, d0.x, d1.x, contactDist, out);
+  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_PLANE) np_sphere_plane(tm0.p, d0.x, tm1, contactDist, out);
+  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_CAPSULE) np_sphere_capsule(tm0.p, d0.x, tm1, d1.x, d1.y, contactDist, out);
+  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_BOX) np_sphere_box(tm0.p, d0.x, tm1, V3(d1.x, d1.y, d1.z), contactDist, out);
+  else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CAPSULE) pcm_plane_capsule(tm0, tm1, d1.x, d1.y, contactDist, man, out);
+  else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_CAPSULE) np_capsule_capsule(tm0, tm1, d0.x, d0.y, d1.x, d1.y, contactDist, out);
   manifold_store(man, rec);
   if (flip && out.count) out.normal = -out.normal;
   cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
@@ -290,11 +296,17 @@ __global__ void __launch_bounds__(128) k_narrowphase(const uint64_t* __restrict_
 }
 
 __global__ void k_compact(const uint32_t* __restrict__ nPairsP, const uint32_t* __restrict__ conFlag, const uint32_t* __restrict__ conIdx, uint32_t* __restrict__ conPair,
-                          const uint32_t* __restrict__ pairSlots, float4* __restrict__ frictions) {
+                          const uint32_t* __restrict__ pairSlots, const float4* __restrict__ cHdr, float4* __restrict__ frictions) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *nPairsP) return;
   if (conFlag[i]) conPair[conIdx[i]] = i;
-  else frictions[(size_t)pairSlots[i] * PXB_FRICTION_F4 + 2].w = __int_as_float(0);  // no contacts: friction patch state is dropped
+  if (__float_as_int(cHdr[i].w) == 0) frictions[(size_t)pairSlots[i] * PXB_FRICTION_F4 + 2].w = __int_as_float(0);  // no contacts: friction patch state is dropped
+}
+// Pairs the host's island manager still lists stay in the constraint list even without contacts this frame: they are
+// empty constraints that still take a colour (lost-touch edges leave the island only after the solve).
+__global__ void k_flag_ordered(const uint32_t* __restrict__ nPairsP, const uint32_t* __restrict__ rankOfPair, uint32_t* __restrict__ conFlag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *nPairsP && rankOfPair[i] < 0x80000000u) conFlag[i] = 1u;
 }
 // host-provided solver input order -> per-pair rank
 __global__ void k_rank_init(const uint32_t* __restrict__ nPairsP, uint32_t* __restrict__ rankOfPair) {
@@ -461,6 +473,10 @@ __global__ void __launch_bounds__(128) k_prep(const uint32_t* __restrict__ count
   Contacts con; const float4 h = cHdr[i]; con.normal = V3(h.x, h.y, h.z); con.count = __float_as_int(h.w);
 #pragma unroll
   for (int j = 0; j < 4; ++j) { const float4 p = cPts[(size_t)i * 4 + j]; con.point[j] = V3(p.x, p.y, p.z); con.sep[j] = p.w; }
+  if (con.count == 0) {  // empty constraint kept only for the colouring (see k_flag_ordered)
+    rowA[k] = make_float4(0, 0, 0, 0); rowB[k] = make_float4(0, 0, 0, 0); rowC[k] = make_uint4(b0, dyn1 ? b1 : NONE32, 0u, i);
+    return;
+  }
   xf f0, f1; { const float4 p = pos[b0]; f0.p = V3(p.x, p.y, p.z); f0.q = Q4(quat[b0]); const float4 q = pos[b1]; f1.p = V3(q.x, q.y, q.z); f1.q = Q4(quat[b1]); }
   float4* frec = frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4;
   FrictionPatch fp; friction_load(fp, frec);
@@ -950,11 +966,14 @@ static int enqueue_step(PxbScene* s, float dt) {
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
          s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce);
   MARK(2);
-  exclusive_scan_u32(s->conFlag, s->conIdx, nP, s->counters + C_NCON, s->scanSums, s->rsTmp.ctas, st); s->launches += 3;
-  LAUNCH(k_compact, gP, B, nP, s->conFlag, s->conIdx, s->conPair, s->pairSlots[cur], s->frictions);
   if (s->nOrder) {
     LAUNCH(k_rank_init, gP, B, nP, s->rankOfPair);
     LAUNCH(k_rank_map, cdiv(s->nOrder, B), B, s->nOrder, s->orderKeys, s->pairKeys[cur], nP, s->rankOfPair);
+    LAUNCH(k_flag_ordered, gP, B, nP, s->rankOfPair, s->conFlag);
+  }
+  exclusive_scan_u32(s->conFlag, s->conIdx, nP, s->counters + C_NCON, s->scanSums, s->rsTmp.ctas, st); s->launches += 3;
+  LAUNCH(k_compact, gP, B, nP, s->conFlag, s->conIdx, s->conPair, s->pairSlots[cur], s->cHdr, s->frictions);
+  if (s->nOrder) {
     LAUNCH(k_con_sortkeys, gP, B, s->counters, s->conPair, s->rankOfPair, s->conSortKey);
     const int r = radix_sort_pairs(s->conSortKey, s->conPair, s->conSortKeyAlt, s->conPairAlt, s->counters + C_NCON, 32, s->rsTmp, st); s->launches += 12;
     if (r) std::swap(s->conPair, s->conPairAlt);

@@ -107,6 +107,13 @@ PXB_D v3 aqrot_noscale(q4 q, v3 v) {
   return scaleadd(u, adot(u, v), t);
 }
 PXB_D v3 aqrot(q4 q, v3 v) { return aqrot_noscale(q, v) * 2.0f; }                                // QuatRotate
+PXB_D v3 aqrotinv(q4 q, v3 v) {                                                                 // QuatRotateInv
+  const v3 u = V3(q.x, q.y, q.z);
+  const float w2 = q.w * q.w + (-0.5f);
+  const v3 a = v * w2;
+  const v3 t = negscalesub(cross(u, v), q.w, a);
+  return scaleadd(u, adot(u, v), t) * 2.0f;
+}
 PXB_D v3 aqrot_normalize(q4 q, v3 v) { return anormalize(aqrot_noscale(q, v)); }                // QuatRotateAndNormalize
 PXB_D q4 aqmul(q4 a, q4 b) {                                                                    // QuatMul
   const v3 ia = V3(a.x, a.y, a.z), ib = V3(b.x, b.y, b.z);

@@ -495,3 +495,167 @@ PXB_D void pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contact
     }
   }
 }
+
+// ---------------- sphere / capsule family (reference GPU kernel: sphereNphase_Kernel) ----------------
+// CPU PCM semantics: GuPCMContactSphereSphere.cpp:36-69, GuPCMContactSpherePlane.cpp:36-73, GuPCMContactSphereCapsule.cpp:38-102,
+// GuPCMContactSphereBox.cpp:36-131, GuPCMContactPlaneCapsule.cpp:36-123, GuPCMContactCapsuleCapsule.cpp:38-275,
+// GuDistanceSegmentSegment.cpp:411-469.
+PXB_D void np_sphere_sphere(v3 p0, v3 p1, float r0, float r1, float cDist, Contacts& out) {
+  const v3 delta = p0 - p1;
+  const float distanceSq = adot(delta, delta);
+  const float radiusSum = r0 + r1, inflatedSum = radiusSum + cDist;
+  if (inflatedSum * inflatedSum > distanceSq) {
+    const float dist = sqrtf(distanceSq);
+    const v3 normal = (0.00001f >= dist) ? V3(1.f, 0.f, 0.f) : V3(delta.x / dist, delta.y / dist, delta.z / dist);
+    out.normal = normal; out.point[0] = scaleadd(normal, r1, p1); out.sep[0] = dist - radiusSum; out.count = 1;
+  }
+}
+PXB_D void np_sphere_plane(v3 p0, float radius, const xf& planeTm, float cDist, Contacts& out) {
+  const v3 c = aqrotinv(planeTm.q, p0 - planeTm.p);
+  const float separation = c.x - radius;
+  if (cDist >= separation) { const v3 n = aqbasis0(planeTm.q); out.normal = n; out.point[0] = negscalesub(n, radius, p0); out.sep[0] = separation; out.count = 1; }
+}
+PXB_D float dist_point_segment_sq(v3 a, v3 b, v3 p, float& param) {
+  const v3 ap = p - a, ab = b - a;
+  const float nom = adot(ap, ab), denom = adot(ab, ab);
+  const float tValue = fmax_(fmin_(nom / denom, 1.f), 0.f);
+  const float t = (denom == 0.f) ? 0.f : tValue;
+  const v3 v = negscalesub(ab, t, ap);
+  param = t;
+  return adot(v, v);
+}
+PXB_D void np_sphere_capsule(v3 sphereCenter, float sphereRadius, const xf& capTm, float capRadius, float halfHeight, float cDist, Contacts& out) {
+  const v3 tmp0 = aqbasis0(capTm.q) * halfHeight;
+  const v3 s = capTm.p + tmp0, e = capTm.p - tmp0;
+  const float radiusSum = sphereRadius + capRadius, inflatedSum = radiusSum + cDist;
+  float t; const float squareDist = dist_point_segment_sq(s, e, sphereCenter, t);
+  if (inflatedSum * inflatedSum > squareDist) {
+    const v3 p = scaleadd(e - s, t, s);
+    const v3 dir = sphereCenter - p;
+    const float len = alen(dir);
+    const v3 normal = (len > FLT_EPSILON) ? V3(dir.x / len, dir.y / len, dir.z / len) : V3(1.f, 0.f, 0.f);
+    out.normal = normal; out.point[0] = negscalesub(normal, sphereRadius, sphereCenter); out.sep[0] = sqrtf(squareDist) - radiusSum; out.count = 1;
+  }
+}
+PXB_D void np_sphere_box(v3 sphereOrigin, float radius, const xf& boxTm, v3 be, float cDist, Contacts& out) {
+  const v3 c = aqrotinv(boxTm.q, sphereOrigin - boxTm.p);
+  const float inflatedSum = radius + cDist;
+  const v3 p = V3(fmax_(fmin_(c.x, be.x), -be.x), fmax_(fmin_(c.y, be.y), -be.y), fmax_(fmin_(c.z, be.z), -be.z));
+  const v3 v = c - p;
+  const float lengthSq = adot(v, v);
+  if (inflatedSum * inflatedSum > lengthSq) {
+    const v3 ac = vabs(c);
+    if (be.x >= ac.x && be.y >= ac.y && be.z >= ac.z) {
+      const v3 d = be - vabs(p);
+      const bool con0 = d.x >= d.z && d.y >= d.z, con1 = d.y >= d.x && d.z >= d.x;
+      const v3 sign = V3(p.x >= 0.f ? 1.f : -1.f, p.y >= 0.f ? 1.f : -1.f, p.z >= 0.f ? 1.f : -1.f);
+      const v3 locNorm = con0 ? V3(0.f * sign.x, 0.f * sign.y, 1.f * sign.z) : (con1 ? V3(1.f * sign.x, 0.f * sign.y, 0.f * sign.z) : V3(0.f * sign.x, 1.f * sign.y, 0.f * sign.z));
+      const float dist = -(con0 ? d.z : (con1 ? d.x : d.y));
+      const v3 normal = aqrot(boxTm.q, locNorm);
+      out.normal = normal; out.point[0] = sphereOrigin - normal * dist; out.sep[0] = dist - radius; out.count = 1;
+    } else {
+      const float recipLength = 1.0f / sqrtf(lengthSq);
+      const float length = 1.0f / recipLength;
+      out.normal = aqrot(boxTm.q, v * recipLength); out.point[0] = axftransform(boxTm, p); out.sep[0] = length - radius; out.count = 1;
+    }
+  }
+}
+PXB_D void add_manifold_point2(Manifold& m, v3 la, v3 lb, v3 n, float pen, float replaceBreakingThreshold) {
+  const float shortest = replaceBreakingThreshold * replaceBreakingThreshold;
+  for (int i = 0; i < m.n; ++i) {
+    const v3 dB = m.pts[i].b - lb, dA = m.pts[i].a - la;
+    if (shortest > fmin_(adot(dB, dB), adot(dA, dA))) { m.pts[i].a = la; m.pts[i].b = lb; m.pts[i].n = n; m.pts[i].pen = pen; return; }
+  }
+  if (m.n < 2) { m.pts[m.n].a = la; m.pts[m.n].b = lb; m.pts[m.n].n = n; m.pts[m.n].pen = pen; m.n++; return; }
+  const v3 v0 = m.pts[0].b - lb, v1 = m.pts[1].b - lb;
+  const int k = (adot(v0, v0) > adot(v1, v1)) ? 1 : 0;
+  m.pts[k].a = la; m.pts[k].b = lb; m.pts[k].n = n; m.pts[k].pen = pen;
+}
+PXB_D void pcm_plane_capsule(const xf& planeTm, const xf& capTm, float radius, float halfHeight, float contactDist, Manifold& man, Contacts& out) {
+  const xf aToB = axfinvmul(planeTm, capTm);
+  const v3 planeNormal = anormalize(aqbasis0(planeTm.q));
+  const v3 ln = V3(1.f, 0.f, 0.f);
+  const v3 tmp = aqbasis0(aToB.q) * halfHeight;
+  const v3 s = aToB.p + tmp, e = aToB.p - tmp;
+  const float inflatedRadius = radius + contactDist;
+  const int initial = man.n;
+  const mxf aToBm = amxffromxf(aToB);
+  manifold_refresh(man, aToBm, radius * 0.05f);
+  const bool lost = man.n != initial;
+  if (lost || invalidate_plane(man, aToB, radius, 0.02f)) {
+    man.n = 0; man.rel = aToB;
+    if (inflatedRadius > s.x) add_manifold_point2(man, aqrotinv(aToB.q, s - aToB.p), negscalesub(ln, s.x, s), ln, s.x, radius * 0.001f);
+    if (inflatedRadius > e.x) add_manifold_point2(man, aqrotinv(aToB.q, e - aToB.p), negscalesub(ln, e.x, e), ln, e.x, radius * 0.001f);
+  }
+  out.count = 0; out.normal = -planeNormal;
+  for (int i = 0; i < man.n; ++i) {
+    const float dist = man.pts[i].pen - radius;
+    if (contactDist >= dist) { out.point[out.count] = negscalesub(planeNormal, radius, axftransform(capTm, man.pts[i].a)); out.sep[out.count] = dist; out.count++; }
+  }
+}
+PXB_D float dist_seg_seg_sq(v3 p1, v3 d1, v3 p2, v3 d2, float& s, float& t) {
+  const float eps = FLT_EPSILON;
+  const v3 r = p1 - p2;
+  const float a = dot(d1, d1), e = dot(d2, d2), b = dot(d1, d2), c = dot(d1, r);
+  const float aRecip = a > eps ? 1.0f / a : 0.f, eRecip = e > eps ? 1.0f / e : 0.f;
+  const float f = adot(d2, r);
+  const float denom = a * e - b * b;
+  const float temp = b * f - c * e;
+  const float s0 = fmax_(fmin_(temp / denom, 1.f), 0.f);
+  const float sTmp = (eps > denom) ? 0.5f : s0;
+  const float tTmp = (b * sTmp + f) * eRecip;
+  const float t2 = fmax_(fmin_(tTmp, 1.f), 0.f);
+  const float comp = (b * t2 - c) * aRecip;
+  const float s2 = fmax_(fmin_(comp, 1.f), 0.f);
+  s = s2; t = t2;
+  const v3 vv = scaleadd(d1, s2, p1) - scaleadd(d2, t2, p2);
+  return adot(vv, vv);
+}
+// Contacts of one capsule pair share the first contact's normal (they fall into one patch when their normals
+// agree within PXC_SAME_NORMAL, which holds for the near-parallel case that produces several contacts).
+PXB_D void np_capsule_capsule(const xf& tm0, const xf& tm1, float r0, float hh0, float r1, float hh1, float cDist, Contacts& out) {
+  const v3 positionOffset = (tm0.p + tm1.p) * 0.5f;
+  const v3 p0 = tm0.p - positionOffset, p1 = tm1.p - positionOffset;
+  const v3 tmp0 = aqbasis0(tm0.q) * hh0;
+  const v3 s0 = p0 + tmp0, e0 = p0 - tmp0, d0 = e0 - s0;
+  const v3 tmp1 = aqbasis0(tm1.q) * hh1;
+  const v3 s1 = p1 + tmp1, e1 = p1 - tmp1, d1 = e1 - s1;
+  const float sumRadius = r0 + r1, inflatedSum = sumRadius + cDist, inflatedSumSquared = inflatedSum * inflatedSum;
+  const float a = adot(d0, d0), e = adot(d1, d1), eps = 1e-6f;
+  float t0, t1;
+  const float sqDist0 = dist_seg_seg_sq(s0, d0, s1, d1, t0, t1);
+  if (!(inflatedSumSquared >= sqDist0)) return;
+  const float sa = sqrtf(a), se = sqrtf(e);
+  const v3 dir0 = (eps > a) ? V3(0, 0, 0) : V3(d0.x / sa, d0.y / sa, d0.z / sa);
+  const v3 dir1 = (eps > e) ? V3(0, 0, 0) : V3(d1.x / se, d1.y / se, d1.z / se);
+  if (fabsf(adot(dir0, dir1)) > 0.9998f) {
+    const v3 ab0 = e0 - s0, ab1 = e1 - s1;
+    const float den0 = adot(ab0, ab0), den1 = adot(ab1, ab1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float nom, den;
+      if (k == 0) { nom = dot(s1 - s0, ab0); den = den0; } else if (k == 1) { nom = dot(e1 - s0, ab0); den = den0; }
+      else if (k == 2) { nom = dot(s0 - s1, ab1); den = den1; } else { nom = dot(e0 - s1, ab1); den = den1; }
+      const float t = (den == 0.f) ? 0.f : nom / den;
+      if (!(t >= 0.f && 1.f >= t)) continue;
+      v3 proj, v, base;
+      if (k == 0) { proj = scaleadd(d0, t, s0); v = proj - s1; base = proj; }
+      else if (k == 1) { proj = scaleadd(d0, t, s0); v = proj - e1; base = proj; }
+      else if (k == 2) { proj = scaleadd(d1, t, s1); v = s0 - proj; base = s0; }
+      else { proj = scaleadd(d1, t, s1); v = e0 - proj; base = e0; }
+      const float sqDist = adot(v, v);
+      if (sqDist > eps && inflatedSumSquared > sqDist) {
+        const float dist = sqrtf(sqDist);
+        const v3 normal = V3(v.x / dist, v.y / dist, v.z / dist);
+        if (out.count == 0) out.normal = normal;
+        out.point[out.count] = negscalesub(normal, r0, base) + positionOffset; out.sep[out.count] = dist - sumRadius; out.count++;
+      }
+    }
+    if (out.count) return;
+  }
+  const v3 closestA = scaleadd(d0, t0, s0), closestB = scaleadd(d1, t1, s1);
+  const bool con = eps > sqDist0;
+  const v3 nrm = anormalize(con ? ((a > eps) ? d0 : V3(1.f, 0.f, 0.f)) : (closestA - closestB));
+  out.normal = nrm; out.point[0] = negscalesub(nrm, r0, closestA) + positionOffset;
+  out.sep[0] = (con ? 0.f : sqrtf(sqDist0)) - sumRadius; out.count = 1;
+}

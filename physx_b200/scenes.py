@@ -204,3 +204,50 @@ def tumbling_boxes(n=12, seed=7, half_extent=0.25, **hdr):
     a["angVel"] = rng.uniform(-2, 2, (n, 3))
     set_box(a, np.arange(n), he)
     return Scene(default_header(**hdr), add_ground_plane(a))
+
+
+def set_sphere(a, idx, radius, density=10.0):
+    r = np.float32(radius)
+    a["geomType"][idx] = GEOM_SPHERE
+    a["flags"][idx] = ACTOR_DYNAMIC
+    a["dims"][idx, 0] = r
+    m = np.float32(density * 4.0 / 3.0 * np.pi) * r * r * r
+    a["mass"][idx] = m
+    a["inertia"][idx] = (np.float32(0.4) * m * r * r).astype(np.float32)[..., None] if np.ndim(m) else np.float32(0.4) * m * r * r
+
+
+def set_capsule(a, idx, radius, half_height, density=10.0):
+    """Capsule along local X (PxCapsuleGeometry); solid cylinder + two hemispheres."""
+    r, h = np.float32(radius), np.float32(half_height)
+    a["geomType"][idx] = GEOM_CAPSULE
+    a["flags"][idx] = ACTOR_DYNAMIC
+    a["dims"][idx, 0] = r
+    a["dims"][idx, 1] = h
+    mc = np.float32(density * np.pi) * r * r * (2 * h)
+    ms = np.float32(density * 4.0 / 3.0 * np.pi) * r * r * r
+    a["mass"][idx] = mc + ms
+    ix = mc * r * r * np.float32(0.5) + ms * r * r * np.float32(0.4)
+    iy = mc * (r * r * np.float32(0.25) + h * h * np.float32(1.0 / 3.0)) + ms * (r * r * np.float32(0.4) + h * h + np.float32(0.75) * h * r)
+    a["inertia"][idx, 0] = ix
+    a["inertia"][idx, 1] = iy
+    a["inertia"][idx, 2] = iy
+
+
+def mixed_primitives(n=18, seed=3, kinds=("sphere", "capsule", "box"), spread=0.5, **hdr):
+    """Spheres, capsules and boxes dropped in a loose column onto the ground plane (BASELINE config 3 shape
+    without the convex hulls): exercises every primitive pair of the sphere family."""
+    rng = np.random.RandomState(seed)
+    a = _new_actors(n)
+    a["pos"][:, 0] = rng.uniform(-spread, spread, n)
+    a["pos"][:, 1] = 0.5 + 0.45 * np.arange(n)
+    a["pos"][:, 2] = rng.uniform(-spread, spread, n)
+    a["quat"] = random_unit_quats(rng, n)
+    for i in range(n):
+        k = kinds[i % len(kinds)]
+        if k == "sphere":
+            set_sphere(a, i, rng.uniform(0.1, 0.2))
+        elif k == "capsule":
+            set_capsule(a, i, rng.uniform(0.08, 0.15), rng.uniform(0.1, 0.3))
+        else:
+            set_box(a, np.array([i]), np.array([rng.uniform(0.12, 0.25), rng.uniform(0.12, 0.25), rng.uniform(0.12, 0.25)], dtype=np.float32))
+    return Scene(default_header(**hdr), add_ground_plane(a))
