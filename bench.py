@@ -47,7 +47,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -142,14 +142,14 @@ def bench_ours(args):
     stream = torch.cuda.ExternalStream(scene.stream(), device=dev)
     gathers = {}
     if dist is not None:
-        for t, cols in multi_gpu.STATE_COLS.items():
-            gathers[t] = multi_gpu.StateGather(dist, nb, cols, dev)
+        # one packed [n, 13] tensor (pose + linear + angular velocity) -> ONE NCCL all-gather per step
+        gathers["packed"] = multi_gpu.StateGather(dist, nb, 13, dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
 
     def gather_all():
         for t, g in gathers.items():
             def fill(view, t=t):
-                scene.getRigidDynamicDataDevice(t, view.data_ptr(), nb)
+                scene.getStatesDevice(view.data_ptr())
                 torch.cuda.current_stream(dev).wait_stream(stream)
             g(fill)
 
@@ -263,7 +263,7 @@ def bench_ours(args):
             "config": {"workload": f"config 2: {n_envs} envs x {BOXES_PER_ENV} boxes = {nb} bodies per GPU, shared ground plane, GPU broadphase + TGS 4 pos/1 vel iterations, 60 Hz",
                        "bodies_total": total_bodies, "constraints_per_gpu": P, "partitions": scene.num_partitions,
                        "timing": "CUDA events on the scene stream per step, max over ranks; L2 flushed (256 MiB memset) between timed steps",
-                       "multi_gpu": "env-partitioned, one scene per GPU, per-step NCCL all-gather of pose/linear/angular velocity tensors" if world > 1 else "single scene"},
+                       "multi_gpu": "env-partitioned, one scene per GPU, per-step NCCL all-gather of the packed pose+linear+angular velocity tensor (13 floats/body)" if world > 1 else "single scene"},
             "roofline": {"kernel": "k_solve (all TGS iterations, one cooperative launch)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes, "kernel_ms": solve_ms},
             "stage_ms": stages,

@@ -33,6 +33,9 @@ namespace cg = cooperative_groups;
 
 #define NONE32 0xffffffffu
 #define MAX_PARTITIONS 96
+#ifndef PXB_SOLVE_CTAS_PER_SM
+#define PXB_SOLVE_CTAS_PER_SM 2   // measured on B200: 3 CTAs/SM (80 regs, spills, wider grid.sync) is 20% slower than 2
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // host-side record (layout of oracle/scene_format.h::PxbActorRec, 128 bytes)
@@ -614,7 +617,7 @@ __device__ __forceinline__ void solve_constraint(uint32_t k, uint32_t cap, float
 
 // a15/a16: the whole TGS iteration loop in ONE cooperative launch (iterativeSolveIsland, DyTGSDynamics.cpp:2515-2793):
 // position iterations = {solve every partition in order; integrate the sub-step}, then velocity iterations.
-__global__ void __launch_bounds__(256) k_solve(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ partStart, uint32_t cap, uint32_t posIters, uint32_t velIters, float stepDt,
+__global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ partStart, uint32_t cap, uint32_t posIters, uint32_t velIters, float stepDt,
                         const float4* __restrict__ rowA, const float4* __restrict__ rowB, const uint4* __restrict__ rowC, const float4* __restrict__ ptA, const float4* __restrict__ ptB,
                         float4* __restrict__ ptC, const float4* __restrict__ frA, const float4* __restrict__ frB, const float4* __restrict__ frC, float4* __restrict__ frD,
                         float4* __restrict__ sbLin, float4* __restrict__ sbAng, float4* __restrict__ sbDLin, float4* __restrict__ sbDAng, const float4* __restrict__ sbIA,
@@ -773,7 +776,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->numSMs = prop.multiProcessorCount;
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_colour_partition, 256, 0)); s->coopBlocksColour = std::max(1, std::min(occ, 4)) * s->numSMs;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, 2)) * s->numSMs;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
   s->capA = std::max(16u, desc->maxActors);
   s->capPairs = desc->maxPairs ? desc->maxPairs : std::max(1024u, 8u * s->capA);
   s->bitsA = bits_for(s->capA);
@@ -1171,6 +1174,17 @@ static int rd_host(PxbScene* s, void* data, const uint32_t* idx, int type, uint3
 PXB_API int pxb_get_rigid_dynamic_data(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, data, idx, type, nb, false); }
 PXB_API int pxb_set_rigid_dynamic_data(PxbScene* s, const void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, const_cast<void*>(data), idx, type, nb, true); }
 
+// Packed 13-float state of every dynamic body written straight into a DEVICE buffer (e.g. this rank's slice of
+// the NCCL all-gather receive tensor); asynchronous on the scene stream.
+PXB_API int pxb_scene_get_states_device(PxbScene* s, float* devOut) {
+  if (!s || !devOut) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
+  if (!s->nDyn) return PXB_OK;
+  cudaStream_t st = s->stream;
+  LAUNCH(k_states_get, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, devOut);
+  CK(cudaGetLastError());
+  return PXB_OK;
+}
 PXB_API int pxb_scene_get_states(PxbScene* s, float* out) {
   if (!s || !out) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;

@@ -29,6 +29,7 @@ EXPORTS = [
     "pxb_scene_num_created", "pxb_scene_num_deleted", "pxb_scene_get_created", "pxb_scene_get_deleted",
     "pxb_scene_get_contacts", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
+    "pxb_scene_get_states_device",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY = 0, 1, 2
@@ -86,6 +87,7 @@ def load_library():
               "pxb_scene_get_pairs", "pxb_scene_get_created", "pxb_scene_get_deleted", "pxb_scene_get_contacts"):
         getattr(lib, f).argtypes = [vp, vp]
     lib.pxb_scene_compute_bounds.argtypes = [vp]
+    lib.pxb_scene_get_states_device.argtypes = [vp, vp]
     lib.pxb_scene_set_profiling.argtypes = [vp, i32]
     lib.pxb_scene_get_stage_times.argtypes = [vp, vp]
     lib.pxb_scene_state_device_ptr.argtypes = [vp, i32]
@@ -178,6 +180,10 @@ class Scene:
 
     def setRigidDynamicDataDevice(self, data_type: int, dev_ptr: int, nb: int, dev_indices: int = 0):
         _check(self._lib, self._lib.pxb_set_rigid_dynamic_data_device(self._h, dev_ptr, dev_indices or None, data_type, nb))
+
+    def getStatesDevice(self, dev_ptr: int):
+        """13 floats per dynamic body (pos3 quat4 linVel3 angVel3) into a device buffer, async on the scene stream."""
+        _check(self._lib, self._lib.pxb_scene_get_states_device(self._h, dev_ptr))
 
     def stream(self) -> int:
         return int(self._lib.pxb_scene_stream(self._h) or 0)
