@@ -48,8 +48,12 @@ typedef struct {
   uint32_t maxActors;                  /* capacity */
   uint32_t maxPairs;                   /* PxGpuDynamicsMemoryConfig::foundLostPairsCapacity / maxRigidPatchCount analogue; 0 = 8*maxActors */
   int32_t  device;                     /* CUDA device ordinal (PxCudaContextManagerDesc) */
-  uint32_t reserved[8];
+  uint32_t reserved[8];                /* [0] internal; [1] = PXB_FLAG_* bits; [2] = rows per environment kept in shared memory (0 = adaptive) */
 } PxbSceneDesc;
+/* Scenes whose dynamic actors all carry an environment id (PxActor::setEnvironmentID, the RL many-env layout of
+ * BASELINE configs 2/5) run on the environment path: one warp / one CTA per environment with solver rows in shared
+ * memory (physx_b200/csrc/pxb_env.cuh).  Results are bit-identical to the device-wide path; this flag forces the latter. */
+enum { PXB_FLAG_NO_ENV_PATH = 1u };
 
 typedef struct PxbScene PxbScene;
 
@@ -124,6 +128,8 @@ PXB_API int  pxb_scene_set_profiling(PxbScene* scene, int enable);
 PXB_API int  pxb_scene_get_stage_times(PxbScene* scene, float* ms7);
 /* number of kernels launched by the last pxb_scene_simulate call */
 PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* scene);
+/* 1 if the last step ran on the environment path, 0 for the device-wide path */
+PXB_API int  pxb_scene_uses_env_path(PxbScene* scene);
 
 #ifdef __cplusplus
 }

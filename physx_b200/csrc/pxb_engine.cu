@@ -45,7 +45,7 @@ struct ActorRec {
 };
 static_assert(sizeof(ActorRec) == 128, "actor record layout");
 
-enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREETOP, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_COUNT = 16 };
+enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_COUNT = 16 };
 enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4 };
 
 struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };
@@ -85,6 +85,10 @@ struct PxbScene {
   bool useGraph = true; cudaGraphExec_t graphExec[2] = {0, 0}; float graphDt = 0.f; uint32_t graphLaunches[2] = {0, 0};
   bool profiling = false; cudaEvent_t ev[8] = {0, 0, 0, 0, 0, 0, 0, 0}; float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
   uint32_t hNPairs = 0, hNCreated = 0, hNDeleted = 0, hNCon = 0, hNPart = 0, hErr = 0;
+  // environment-partitioned path (pxb_env.cuh)
+  bool envEligible = false, envActive = false, envDisabled = false, everStepped = false; uint32_t ringMask = 0;
+  uint32_t nEnv = 0, envMaxList = 0, envConCap = 0, envConCapForced = 0, hMaxConEnv = 0, envSolveThreads = 64;
+  uint32_t *envStart = 0, *envList = 0, *actorLocal = 0; uint2* envSeg[2] = {0, 0};
 };
 
 static thread_local std::string g_err;
@@ -96,39 +100,40 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
-// a1/a2: world AABB of every actor (tight, then inflated by the contact offset) + grid cell key.
-// Formulas: Gu::computeBounds (geomutils/src/GuBounds.cpp:354-400, plane :210-260), inflation
-// BpBroadPhaseABP.cpp:1187-1197.
+// a1: tight world AABB of one shape.  Formulas: Gu::computeBounds (geomutils/src/GuBounds.cpp:354-400, plane :210-260).
+__device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d, float* mn, float* mx) {
+  v3 e = V3(0, 0, 0); bool plane = false;
+  if (type == PXB_GEOM_SPHERE) e = V3(d.x, d.x, d.x);
+  else if (type == PXB_GEOM_CAPSULE) { const v3 dd = qbasis0(q) * d.y; e = V3(fabsf(dd.x) + d.x, fabsf(dd.y) + d.x, fabsf(dd.z) + d.x); }
+  else if (type == PXB_GEOM_BOX) {
+    const m33 b = amfromq(q);
+    const v3 c0 = b.c0 * d.x, c1 = b.c1 * d.y, c2 = b.c2 * d.z;
+    e = V3((fabsf(c0.x) + fabsf(c1.x)) + fabsf(c2.x), (fabsf(c0.y) + fabsf(c1.y)) + fabsf(c2.y), (fabsf(c0.z) + fabsf(c1.z)) + fabsf(c2.z));
+  } else if (type == PXB_GEOM_PLANE) plane = true;
+  if (!plane) { mn[0] = p.x - e.x; mn[1] = p.y - e.y; mn[2] = p.z - e.z; mx[0] = p.x + e.x; mx[1] = p.y + e.y; mx[2] = p.z + e.z; }
+  else {
+    const float big = FLT_MAX * 0.25f;
+    mn[0] = mn[1] = mn[2] = -big; mx[0] = mx[1] = mx[2] = big;
+    const v3 n = qbasis0(q); const float dd = -dot(p, n);
+    const float nx = fabsf(n.x), ny = fabsf(n.y), nz = fabsf(n.z); const float eps = 1e-6f, ome = 1.0f - eps;
+    if (nx > ome && ny < eps && nz < eps) { if (n.x > 0.f) mx[0] = -dd; else mn[0] = dd; }
+    else if (nx < eps && ny > ome && nz < eps) { if (n.y > 0.f) mx[1] = -dd; else mn[1] = dd; }
+    else if (nx < eps && ny < eps && nz > ome) { if (n.z > 0.f) mx[2] = -dd; else mn[2] = dd; }
+  }
+}
+// a1/a2: world AABB of every actor (tight, then inflated by the contact offset, BpBroadPhaseABP.cpp:1187-1197) + grid cell key.
 __global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims,
                          const uint32_t* __restrict__ geomFlags, const uint32_t* __restrict__ envId, float contactOffset, float* __restrict__ tight,
                          int externalTight, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax, GridParams g, uint32_t envCount,
                          uint64_t* __restrict__ cellKey, uint32_t* __restrict__ cellVal) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nA) return;
-  const uint32_t gf = geomFlags[a]; const uint32_t type = gf & 0xff;
+  const uint32_t gf = geomFlags[a];
   float mn[3], mx[3];
   if (externalTight) { for (int k = 0; k < 3; ++k) { mn[k] = tight[a * 6 + k]; mx[k] = tight[a * 6 + 3 + k]; } }
   else {
-    const float4 p4 = pos[a]; const q4 q = Q4(quat[a]); const float4 d = dims[a];
-    const v3 p = V3(p4.x, p4.y, p4.z);
-    v3 e = V3(0, 0, 0); bool plane = false;
-    if (type == PXB_GEOM_SPHERE) e = V3(d.x, d.x, d.x);
-    else if (type == PXB_GEOM_CAPSULE) { const v3 dd = qbasis0(q) * d.y; e = V3(fabsf(dd.x) + d.x, fabsf(dd.y) + d.x, fabsf(dd.z) + d.x); }
-    else if (type == PXB_GEOM_BOX) {
-      const m33 b = amfromq(q);
-      const v3 c0 = b.c0 * d.x, c1 = b.c1 * d.y, c2 = b.c2 * d.z;
-      e = V3((fabsf(c0.x) + fabsf(c1.x)) + fabsf(c2.x), (fabsf(c0.y) + fabsf(c1.y)) + fabsf(c2.y), (fabsf(c0.z) + fabsf(c1.z)) + fabsf(c2.z));
-    } else if (type == PXB_GEOM_PLANE) plane = true;
-    if (!plane) { mn[0] = p.x - e.x; mn[1] = p.y - e.y; mn[2] = p.z - e.z; mx[0] = p.x + e.x; mx[1] = p.y + e.y; mx[2] = p.z + e.z; }
-    else {
-      const float big = FLT_MAX * 0.25f;
-      mn[0] = mn[1] = mn[2] = -big; mx[0] = mx[1] = mx[2] = big;
-      const v3 n = qbasis0(q); const float dd = -dot(p, n);
-      const float nx = fabsf(n.x), ny = fabsf(n.y), nz = fabsf(n.z); const float eps = 1e-6f, ome = 1.0f - eps;
-      if (nx > ome && ny < eps && nz < eps) { if (n.x > 0.f) mx[0] = -dd; else mn[0] = dd; }
-      else if (nx < eps && ny > ome && nz < eps) { if (n.y > 0.f) mx[1] = -dd; else mn[1] = dd; }
-      else if (nx < eps && ny < eps && nz > ome) { if (n.z > 0.f) mx[2] = -dd; else mn[2] = dd; }
-    }
+    const float4 p4 = pos[a];
+    tight_bounds(gf & 0xff, V3(p4.x, p4.y, p4.z), Q4(quat[a]), dims[a], mn, mx);
     for (int k = 0; k < 3; ++k) { tight[a * 6 + k] = mn[k]; tight[a * 6 + 3 + k] = mx[k]; }
   }
   const float co = contactOffset;
@@ -224,7 +229,7 @@ __global__ void k_clamp_count(uint32_t* __restrict__ counters, uint32_t cap, uin
 // a7: pair lifecycle.  Lost pairs give their persistent slot back, surviving pairs keep theirs, new pairs
 // take one from the free list and start with an empty manifold (PersistentContactManifold::initialize).
 __global__ void k_pair_lost(const uint64_t* __restrict__ oldKeys, const uint32_t* __restrict__ oldSlots, const uint32_t* __restrict__ nOldP,
-                            const uint64_t* __restrict__ newKeys, const uint32_t* __restrict__ nNewP, uint32_t* __restrict__ freeList,
+                            const uint64_t* __restrict__ newKeys, const uint32_t* __restrict__ nNewP, uint32_t* __restrict__ freeList, uint32_t ringMask,
                             uint64_t* __restrict__ deletedKeys, uint32_t* __restrict__ counters) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nOld = *nOldP, nNew = *nNewP;
@@ -232,12 +237,12 @@ __global__ void k_pair_lost(const uint64_t* __restrict__ oldKeys, const uint32_t
   const uint64_t k = oldKeys[j];
   const uint32_t p = lower_bound_u64(newKeys, nNew, k);
   if (p < nNew && newKeys[p] == k) return;
-  freeList[atomicAdd(&counters[C_FREETOP], 1u)] = oldSlots[j];
+  freeList[atomicAdd(&counters[C_FREE_TAIL], 1u) & ringMask] = oldSlots[j];
   deletedKeys[atomicAdd(&counters[C_NDELETED], 1u)] = k;
 }
 __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_t* __restrict__ oldSlots, const uint32_t* __restrict__ nOldP,
                              const uint64_t* __restrict__ newKeys, uint32_t* __restrict__ newSlots, const uint32_t* __restrict__ nNewP,
-                             const uint32_t* __restrict__ freeList, uint64_t* __restrict__ createdKeys, uint32_t* __restrict__ counters,
+                             const uint32_t* __restrict__ freeList, uint32_t ringMask, uint64_t* __restrict__ createdKeys, uint32_t* __restrict__ counters,
                              float4* __restrict__ manifolds, float4* __restrict__ frictions) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nOld = *nOldP, nNew = *nNewP;
@@ -245,8 +250,9 @@ __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_
   const uint64_t k = newKeys[i];
   const uint32_t p = lower_bound_u64(oldKeys, nOld, k);
   if (p < nOld && oldKeys[p] == k) { newSlots[i] = oldSlots[p]; return; }
-  const uint32_t top = atomicSub(&counters[C_FREETOP], 1u);
-  const uint32_t slot = freeList[top - 1];
+  const uint32_t h = atomicAdd(&counters[C_FREE_HEAD], 1u);   // free slots live in a ring: pops advance the head, pushes the tail
+  uint32_t slot = 0;
+  if ((int32_t)(counters[C_FREE_TAIL] - h) <= 0) atomicOr(&counters[C_ERROR], (uint32_t)E_PAIR_OVERFLOW); else slot = freeList[h & ringMask];
   newSlots[i] = slot;
   createdKeys[atomicAdd(&counters[C_NCREATED], 1u)] = k;
   float4* m = manifolds + (size_t)slot * PXB_MANIFOLD_F4;
@@ -265,6 +271,7 @@ __global__ void __launch_bounds__(128) k_narrowphase(const uint64_t* __restrict_
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *nPairsP) return;
   const uint64_t key = pairKeys[i];
+  if (key == ~0ull) { cHdr[i] = make_float4(0, 0, 0, __int_as_float(0)); conFlag[i] = 0u; pairBodies[i] = make_uint2(0, 0); return; }   // dropped segment (capacity error already flagged)
   const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
   uint32_t a0 = hi, a1 = lo;
   const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
@@ -461,37 +468,24 @@ __device__ __forceinline__ m33 load_sym(const float4 A, const float4 B) {
   m33 m; m.c0 = V3(A.x, A.y, A.z); m.c1 = V3(A.y, A.w, B.x); m.c2 = V3(A.z, B.x, B.y); return m;
 }
 
-// a14: per constraint (in solve order): friction-patch correlation + solver rows
-__global__ void __launch_bounds__(128) k_prep(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ ordered, const uint32_t* __restrict__ conPair, const uint32_t* __restrict__ pairSlots,
-                       const uint2* __restrict__ pairBodies, const uint32_t* __restrict__ geomFlags, const float4* __restrict__ cHdr, const float4* __restrict__ cPts,
-                       const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ linVel, const float4* __restrict__ sbOrigAng,
-                       const float4* __restrict__ invInertia, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, float4* __restrict__ frictions, SolverParams P, uint32_t cap,
-                       float4* __restrict__ rowA, float4* __restrict__ rowB, uint4* __restrict__ rowC, float4* __restrict__ ptA, float4* __restrict__ ptB, float4* __restrict__ ptC,
-                       float4* __restrict__ frA, float4* __restrict__ frB, float4* __restrict__ frC, float4* __restrict__ frD) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= counters[C_NCON]) return;
-  const uint32_t c = ordered[k]; const uint32_t i = conPair[c];
-  const uint2 bb = pairBodies[i]; const uint32_t b0 = bb.x, b1 = bb.y;
-  const bool dyn1 = (geomFlags[b1] & 0x100u) != 0;
+// a14: one constraint: friction-patch correlation + solver rows (createFinalizeSolverContactsStep, DyTGSContactPrep.cpp:1297-1490;
+// DyFrictionCorrelation.cpp:56-330).  `k` = row index (stride `cap`), `i` = pair index, b0/b1 = solver-body indices stored in the row.
+struct PrepBodies { xf f0, f1; float invMass0, invMass1, pen0, pen1; v3 linVel0, linVel1, angVel0, angVel1; m33 sI0, sI1; };
+__device__ __forceinline__ void prep_constraint(uint32_t k, uint32_t cap, uint32_t i, uint32_t b0, uint32_t b1, const PrepBodies& B, const float4* __restrict__ cHdr,
+                                                const float4* __restrict__ cPts, float4* __restrict__ frec, const SolverParams& P,
+                                                float4* __restrict__ rowA, float4* __restrict__ rowB, uint4* __restrict__ rowC, float4* __restrict__ ptA, float4* __restrict__ ptB,
+                                                float4* __restrict__ ptC, float4* __restrict__ frA, float4* __restrict__ frB, float4* __restrict__ frC, float4* __restrict__ frD) {
   Contacts con; const float4 h = cHdr[i]; con.normal = V3(h.x, h.y, h.z); con.count = __float_as_int(h.w);
 #pragma unroll
   for (int j = 0; j < 4; ++j) { const float4 p = cPts[(size_t)i * 4 + j]; con.point[j] = V3(p.x, p.y, p.z); con.sep[j] = p.w; }
-  if (con.count == 0) {  // empty constraint kept only for the colouring (see k_flag_ordered)
-    rowA[k] = make_float4(0, 0, 0, 0); rowB[k] = make_float4(0, 0, 0, 0); rowC[k] = make_uint4(b0, dyn1 ? b1 : NONE32, 0u, i);
-    return;
-  }
-  xf f0, f1; { const float4 p = pos[b0]; f0.p = V3(p.x, p.y, p.z); f0.q = Q4(quat[b0]); const float4 q = pos[b1]; f1.p = V3(q.x, q.y, q.z); f1.q = Q4(quat[b1]); }
-  float4* frec = frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4;
+  const xf& f0 = B.f0; const xf& f1 = B.f1;
   FrictionPatch fp; friction_load(fp, frec);
   friction_correlate(fp, con, f0, f1, P.staticFriction, P.dynamicFriction, P.restitution, P.correlationDistance, P.frictionOffsetThreshold + P.restDistance);
   friction_store(fp, frec);
-  const float invMass0 = pos[b0].w, invMass1 = dyn1 ? pos[b1].w : 0.f;
-  const float pen0 = -invInertia[b0].w, pen1 = dyn1 ? -invInertia[b1].w : -FLT_MAX;
-  const float maxPenBias = fmax_(pen0, pen1);
-  const v3 linVel0 = V3(linVel[b0]), linVel1 = dyn1 ? V3(linVel[b1]) : V3(0, 0, 0);
-  const v3 angVel0 = V3(sbOrigAng[b0]), angVel1 = dyn1 ? V3(sbOrigAng[b1]) : V3(0, 0, 0);
-  const m33 sI0 = load_sym(sbIA[b0], sbIB[b0]);
-  m33 sI1; if (dyn1) sI1 = load_sym(sbIA[b1], sbIB[b1]); else { sI1.c0 = sI1.c1 = sI1.c2 = V3(0, 0, 0); }
+  const float invMass0 = B.invMass0, invMass1 = B.invMass1;
+  const float maxPenBias = fmax_(B.pen0, B.pen1);
+  const v3 linVel0 = B.linVel0, linVel1 = B.linVel1, angVel0 = B.angVel0, angVel1 = B.angVel1;
+  const m33& sI0 = B.sI0; const m33& sI1 = B.sI1;
   const float invMass0_dom0 = 1.f * invMass0, invMass1_dom1 = (-1.f) * invMass1;
   const float scale = fmin_(0.8f, P.biasCoefficient);
   const float invDtp8 = P.invStepDt * scale, frictionBiasScale = P.invStepDt * scale;
@@ -503,7 +497,7 @@ __global__ void __launch_bounds__(128) k_prep(const uint32_t* __restrict__ count
   const uint32_t numFriction = haveFriction ? (uint32_t)fp.anchorCount * 2u : 0u;
   rowA[k] = F4(normal, maxPenBias);
   rowB[k] = make_float4(invMass0_dom0, -invMass1_dom1, P.staticFriction, P.dynamicFriction);
-  rowC[k] = make_uint4(b0, dyn1 ? b1 : NONE32, (uint32_t)con.count | (numFriction << 8), i);
+  rowC[k] = make_uint4(b0, b1, (uint32_t)con.count | (numFriction << 8), i);
   for (int j = 0; j < con.count; ++j) {
     SPoint s; prep_point(s, con.point[j], con.sep[j], normal, f0.p, f1.p, sI0, sI1, angVel0, angVel1, norVel0, norVel1, imn0, imn1, P, invDtp8);
     ptA[(size_t)j * cap + k] = F4(s.raXnI, s.velMultiplier); ptB[(size_t)j * cap + k] = F4(s.rbXnI, s.separation);
@@ -531,6 +525,32 @@ __global__ void __launch_bounds__(128) k_prep(const uint32_t* __restrict__ count
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(128) k_prep(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ ordered, const uint32_t* __restrict__ conPair, const uint32_t* __restrict__ pairSlots,
+                       const uint2* __restrict__ pairBodies, const uint32_t* __restrict__ geomFlags, const float4* __restrict__ cHdr, const float4* __restrict__ cPts,
+                       const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ linVel, const float4* __restrict__ sbOrigAng,
+                       const float4* __restrict__ invInertia, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, float4* __restrict__ frictions, SolverParams P, uint32_t cap,
+                       float4* __restrict__ rowA, float4* __restrict__ rowB, uint4* __restrict__ rowC, float4* __restrict__ ptA, float4* __restrict__ ptB, float4* __restrict__ ptC,
+                       float4* __restrict__ frA, float4* __restrict__ frB, float4* __restrict__ frC, float4* __restrict__ frD) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= counters[C_NCON]) return;
+  const uint32_t c = ordered[k]; const uint32_t i = conPair[c];
+  const uint2 bb = pairBodies[i]; const uint32_t b0 = bb.x, b1 = bb.y;
+  const bool dyn1 = (geomFlags[b1] & 0x100u) != 0;
+  if (__float_as_int(cHdr[i].w) == 0) {  // empty constraint kept only for the colouring (see k_flag_ordered)
+    rowA[k] = make_float4(0, 0, 0, 0); rowB[k] = make_float4(0, 0, 0, 0); rowC[k] = make_uint4(b0, dyn1 ? b1 : NONE32, 0u, i);
+    return;
+  }
+  PrepBodies B;
+  { const float4 p = pos[b0]; B.f0.p = V3(p.x, p.y, p.z); B.f0.q = Q4(quat[b0]); const float4 q = pos[b1]; B.f1.p = V3(q.x, q.y, q.z); B.f1.q = Q4(quat[b1]); }
+  B.invMass0 = pos[b0].w; B.invMass1 = dyn1 ? pos[b1].w : 0.f;
+  B.pen0 = -invInertia[b0].w; B.pen1 = dyn1 ? -invInertia[b1].w : -FLT_MAX;
+  B.linVel0 = V3(linVel[b0]); B.linVel1 = dyn1 ? V3(linVel[b1]) : V3(0, 0, 0);
+  B.angVel0 = V3(sbOrigAng[b0]); B.angVel1 = dyn1 ? V3(sbOrigAng[b1]) : V3(0, 0, 0);
+  B.sI0 = load_sym(sbIA[b0], sbIB[b0]);
+  if (dyn1) B.sI1 = load_sym(sbIA[b1], sbIB[b1]); else { B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
+  prep_constraint(k, cap, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, rowA, rowB, rowC, ptA, ptB, ptC, frA, frB, frC, frD);
 }
 
 // a15: one contact constraint (solveContact, DyTGSContactPrep.cpp:1581-1873)
@@ -712,11 +732,20 @@ __global__ void k_states_set(uint32_t nDyn, const uint32_t* __restrict__ dynActo
 }
 __global__ void k_init_freelist(uint32_t cap, uint32_t* __restrict__ freeList) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < cap) freeList[i] = cap - 1 - i;
+  if (i < cap) freeList[i] = i;
 }
+
+__global__ void k_env_begin(uint32_t* __restrict__ counters) {   // per-step counter reset of the environment path
+  if (threadIdx.x == 0) { counters[C_NPAIRS_NEW] = 0; counters[C_NCREATED] = 0; counters[C_NDELETED] = 0; counters[C_NCON] = 0; counters[C_NPART] = 0; counters[C_MAXCONENV] = 0;
+                          counters[C_FREE_SNAP] = counters[C_FREE_TAIL]; }
+}
+#include "pxb_env.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // host side
+static const size_t ENV_SMEM_MAX = 227 * 1024 - 2048;   // dynamic shared memory budget of k_env_solve (static part: partition tables)
+static size_t env_solve_smem(uint32_t maxList, uint32_t conCap) { return (size_t)maxList * (8 * sizeof(float4) + 3 * sizeof(uint32_t)) + (size_t)conCap * 31 * sizeof(float4); }
+static uint32_t env_con_cap_limit(uint32_t maxList) { return (uint32_t)((ENV_SMEM_MAX - (size_t)maxList * (8 * sizeof(float4) + 3 * sizeof(uint32_t))) / (31 * sizeof(float4))); }
 template <typename T> static cudaError_t dalloc(T*& p, size_t n) { return cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)); }
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 static uint32_t bits_for(uint64_t n) { uint32_t b = 1; while ((1ull << b) < n) ++b; return b; }
@@ -726,6 +755,7 @@ extern "C" {
 PXB_API const char* pxb_last_error(void) { return g_err.c_str(); }
 PXB_API int pxb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 
+static void drop_graphs(PxbScene* s);
 static int scene_alloc(PxbScene* s) {
   const size_t A = s->capA, Pn = s->capPairs;
   CK(dalloc(s->pos, A)); CK(dalloc(s->quat, A)); CK(dalloc(s->linVel, A)); CK(dalloc(s->angVel, A)); CK(dalloc(s->invInertia, A)); CK(dalloc(s->damp, A));
@@ -737,7 +767,8 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->cellKey, A)); CK(dalloc(s->cellKeyAlt, A)); CK(dalloc(s->cellVal, A)); CK(dalloc(s->cellValAlt, A)); CK(dalloc(s->sMin, A)); CK(dalloc(s->sMax, A));
   for (int k = 0; k < 2; ++k) { CK(dalloc(s->pairKeys[k], Pn)); CK(dalloc(s->pairSlots[k], Pn)); }
   CK(dalloc(s->pairKeyAlt, Pn)); CK(dalloc(s->pairValTmp, Pn)); CK(dalloc(s->pairValAlt, Pn)); CK(dalloc(s->nPairsDev, 2));
-  CK(dalloc(s->freeList, Pn)); CK(dalloc(s->createdKeys, Pn)); CK(dalloc(s->deletedKeys, Pn));
+  { uint32_t R = 1; while (R < Pn) R <<= 1; s->ringMask = R - 1; CK(dalloc(s->freeList, R)); }
+  CK(dalloc(s->createdKeys, Pn)); CK(dalloc(s->deletedKeys, Pn));
   CK(dalloc(s->manifolds, Pn * PXB_MANIFOLD_F4)); CK(dalloc(s->frictions, Pn * PXB_FRICTION_F4));
   CK(dalloc(s->cHdr, Pn)); CK(dalloc(s->cPts, Pn * 4)); CK(dalloc(s->pairBodies, Pn)); CK(dalloc(s->cForce, Pn * 4));
   CK(dalloc(s->conFlag, Pn)); CK(dalloc(s->conIdx, Pn)); CK(dalloc(s->conPair, Pn)); CK(dalloc(s->rankOfPair, Pn)); CK(dalloc(s->conSortKey, Pn)); CK(dalloc(s->conSortKeyAlt, Pn));
@@ -756,8 +787,9 @@ static int scene_alloc(PxbScene* s) {
   CK(cudaMemsetAsync(s->sbOrigAng, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->bodyHasCon, 0, 4 * A, s->stream));
   CK(cudaMemsetAsync(s->manifolds, 0, sizeof(float4) * Pn * PXB_MANIFOLD_F4, s->stream)); CK(cudaMemsetAsync(s->frictions, 0, sizeof(float4) * Pn * PXB_FRICTION_F4, s->stream));
   k_init_freelist<<<cdiv((uint32_t)Pn, 256), 256, 0, s->stream>>>((uint32_t)Pn, s->freeList);
-  const uint32_t top = (uint32_t)Pn;
-  CK(cudaMemcpyAsync(s->counters + C_FREETOP, &top, 4, cudaMemcpyHostToDevice, s->stream));
+  const uint32_t top = (uint32_t)Pn;   // ring of free persistent slots: head = 0, tail = Pn
+  CK(cudaMemcpyAsync(s->counters + C_FREE_TAIL, &top, 4, cudaMemcpyHostToDevice, s->stream));
+  CK(dalloc(s->actorLocal, A)); for (int k = 0; k < 2; ++k) { CK(dalloc(s->envSeg[k], A)); CK(cudaMemsetAsync(s->envSeg[k], 0, sizeof(uint2) * A, s->stream)); }
   CK(cudaStreamSynchronize(s->stream));
   return PXB_OK;
 }
@@ -776,19 +808,24 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->numSMs = prop.multiProcessorCount;
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_colour_partition, 256, 0)); s->coopBlocksColour = std::max(1, std::min(occ, 4)) * s->numSMs;
+  CK(cudaFuncSetAttribute(k_env_solve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
+  CK(cudaFuncSetAttribute(k_env_solve<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
+  CK(cudaFuncSetAttribute(k_env_solve<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
+  CK(cudaFuncSetAttribute(k_env_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * ENV_MAX_LIST * 36)));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
   s->capA = std::max(16u, desc->maxActors);
   s->capPairs = desc->maxPairs ? desc->maxPairs : std::max(1024u, 8u * s->capA);
   s->bitsA = bits_for(s->capA);
   s->rsTmp.ctas = std::min<uint32_t>(RS_MAX_CTAS, (uint32_t)s->numSMs * 2);
   { const char* ng = getenv("PXB_NO_GRAPH"); if (ng && ng[0] == '1') s->useGraph = false; }
+  if (desc->reserved[1] & PXB_FLAG_NO_ENV_PATH) s->envDisabled = true;
+  s->envConCapForced = desc->reserved[2];
   const int rc = scene_alloc(s);
   if (rc != PXB_OK) { delete s; return rc; }
   *out = s;
   return PXB_OK;
 }
 
-static void drop_graphs(PxbScene* s);
 PXB_API void pxb_scene_release(PxbScene* s) {
   if (!s) return;
   cudaStreamSynchronize(s->stream);
@@ -798,7 +835,8 @@ PXB_API void pxb_scene_release(PxbScene* s) {
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
-                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx};
+                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
+                  s->envStart, s->envList, s->actorLocal, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
   cudaStreamDestroy(s->stream);
@@ -821,6 +859,48 @@ static float shape_diameter(const ActorRec& r) {
     case PXB_GEOM_BOX: return 2.f * std::sqrt(r.dims[0] * r.dims[0] + r.dims[1] * r.dims[1] + r.dims[2] * r.dims[2]);
     default: return INFINITY;
   }
+}
+
+// Environment path eligibility + per-environment actor lists (CSR).  Eligible: every dynamic actor carries an
+// environment id, at most ENV_MAX_GLOBALS env-less actors (all static: the shared ground plane / walls), and no
+// environment lists more than ENV_MAX_LIST actors.  Each list = the environment's actors merged with the env-less
+// statics, ascending actor index, so row-major pair enumeration yields ascending pair keys.
+static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
+  s->envEligible = false;
+  const char* em = getenv("PXB_ENV_MODE");
+  if (!usesEnv || s->envDisabled || (em && em[0] == '0')) return;
+  if (maxEnv >= s->capA) return;   // sparse environment ids: stay on the device-wide path
+  std::vector<uint32_t> globals; const uint32_t nEnv = maxEnv + 1;
+  std::vector<uint32_t> cnt(nEnv, 0);
+  for (uint32_t a = 0; a < s->nA; ++a) {
+    const ActorRec& r = s->recs[a];
+    if (r.envId == NONE32) { if (r.flags & PXB_ACTOR_DYNAMIC) return; globals.push_back(a); if (globals.size() > ENV_MAX_GLOBALS) return; }
+    else cnt[r.envId]++;
+  }
+  const uint32_t G = (uint32_t)globals.size();
+  uint32_t maxList = 0;
+  for (uint32_t e = 0; e < nEnv; ++e) maxList = std::max(maxList, cnt[e] + G);
+  if (maxList > ENV_MAX_LIST) return;
+  std::vector<uint32_t> start(nEnv + 1, 0), local(s->nA, NONE32);
+  for (uint32_t e = 0; e < nEnv; ++e) start[e + 1] = start[e] + cnt[e] + G;
+  std::vector<uint32_t> list(start[nEnv]), cur(start.begin(), start.end() - 1), gi(nEnv, 0);
+  for (uint32_t a = 0; a < s->nA; ++a) {   // ascending a: merge the env-less statics in by index
+    const uint32_t e = s->recs[a].envId;
+    if (e == NONE32) continue;
+    while (gi[e] < G && globals[gi[e]] < a) list[cur[e]++] = globals[gi[e]++];
+    local[a] = cur[e] - start[e]; list[cur[e]++] = a;
+  }
+  for (uint32_t e = 0; e < nEnv; ++e) while (gi[e] < G) list[cur[e]++] = globals[gi[e]++];
+  if (s->envStart) cudaFree(s->envStart); if (s->envList) cudaFree(s->envList); s->envStart = s->envList = nullptr;
+  if (dalloc(s->envStart, nEnv + 1) != cudaSuccess || dalloc(s->envList, list.size()) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaMemcpyAsync(s->envStart, start.data(), 4 * (nEnv + 1), cudaMemcpyHostToDevice, s->stream);
+  cudaMemcpyAsync(s->envList, list.data(), 4 * list.size(), cudaMemcpyHostToDevice, s->stream);
+  cudaMemcpyAsync(s->actorLocal, local.data(), 4 * s->nA, cudaMemcpyHostToDevice, s->stream);
+  cudaStreamSynchronize(s->stream);
+  s->nEnv = nEnv; s->envMaxList = maxList; s->envEligible = true;
+  if (s->envConCap == 0) s->envConCap = std::max(32u, maxList);
+  if (s->envConCapForced) s->envConCap = std::min(s->envConCapForced, env_con_cap_limit(maxList));
+  const char* et = getenv("PXB_ENV_THREADS"); if (et) { const int t = atoi(et); if (t == 32 || t == 64 || t == 128) s->envSolveThreads = (uint32_t)t; }
 }
 
 static void rebuild_grid(PxbScene* s) {
@@ -864,6 +944,7 @@ static void rebuild_grid(PxbScene* s) {
   if (s->nLarge) cudaMemcpyAsync(s->largeList, s->largeHost.data(), 4 * s->nLarge, cudaMemcpyHostToDevice, s->stream);
   cudaStreamSynchronize(s->stream);
   s->gridDirty = false;
+  rebuild_env(s, usesEnv, maxEnv);
 }
 
 PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
@@ -915,12 +996,44 @@ PXB_API int pxb_scene_set_constraint_order(PxbScene* s, const uint32_t* pairs, u
 
 #define LAUNCH(kernel, grid, block, ...) do { kernel<<<(grid), (block), 0, st>>>(__VA_ARGS__); s->launches++; } while (0)
 
+static void drop_graphs(PxbScene* s);
+// Chooses between the environment path and the device-wide path for the coming step.  The pair list layout differs
+// (per-environment segments vs one sorted list); env -> global is converted by one radix sort, the opposite direction
+// is not needed (a scene that has stepped on the device-wide path stays there).
+static int select_path(PxbScene* s) {
+  const bool want = s->envEligible && !s->envDisabled && s->nOrder == 0;
+  if (want == s->envActive) return PXB_OK;
+  if (want) {
+    if (s->everStepped) { s->envDisabled = true; return PXB_OK; }
+    s->envActive = true; drop_graphs(s);
+    return PXB_OK;
+  }
+  // env -> global: sort (key, slot) of the current list
+  cudaStream_t st = s->stream; const int cur = s->cur;
+  const int r = radix_sort_pairs(s->pairKeys[cur], s->pairSlots[cur], s->pairKeyAlt, s->pairValAlt, s->nPairsDev + cur, 2 * s->bitsA, s->rsTmp, st);
+  if (r) { CK(cudaMemcpyAsync(s->pairKeys[cur], s->pairKeyAlt, 8 * (size_t)s->capPairs, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(s->pairSlots[cur], s->pairValAlt, 4 * (size_t)s->capPairs, cudaMemcpyDeviceToDevice, st)); }
+  s->envActive = false; s->envDisabled = true; drop_graphs(s);
+  return PXB_OK;
+}
+
 // stage 1: bounds + broadphase + pair lifecycle
 static int run_broadphase(PxbScene* s, bool externalTight) {
   cudaStream_t st = s->stream;
   if (s->gridDirty) rebuild_grid(s);
   const uint32_t nA = s->nA, B = 256;
   const int prev = s->cur; s->cur ^= 1; const int cur = s->cur;
+  if (s->envActive) {   // environment path: one warp per environment does bounds + pair finding + pair lifecycle
+    LAUNCH(k_env_begin, 1, 32, s->counters);
+    EnvBpArgs A;
+    A.nEnv = s->nEnv; A.maxList = s->envMaxList; A.bitsA = s->bitsA; A.cap = s->capPairs; A.ringMask = s->ringMask; A.externalTight = externalTight ? 1 : 0; A.contactOffset = s->desc.contactOffset;
+    A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight;
+    A.oldKeys = s->pairKeys[prev]; A.oldSlots = s->pairSlots[prev]; A.oldSeg = s->envSeg[prev]; A.newKeys = s->pairKeys[cur]; A.newSlots = s->pairSlots[cur]; A.newSeg = s->envSeg[cur];
+    A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions;
+    const size_t smem = (size_t)ENV_BP_WARPS * s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t));
+    k_env_bp<<<cdiv(s->nEnv, ENV_BP_WARPS), 32 * ENV_BP_WARPS, smem, st>>>(A); s->launches++;
+    LAUNCH(k_clamp_count, 1, 32, s->counters, s->capPairs, s->nPairsDev + cur);
+    return PXB_OK;
+  }
   CK(cudaMemsetAsync(s->counters + C_NPAIRS_NEW, 0, 4 * 3, st));  // NPAIRS_NEW, NCREATED, NDELETED
   LAUNCH(k_bounds, cdiv(nA, B), B, nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, externalTight ? 1 : 0, s->aabbMin, s->aabbMax, s->grid,
          s->desc.reserved[0], s->cellKey, s->cellVal);
@@ -939,8 +1052,8 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
   radix_sort_pairs(emit, s->pairValTmp, other, s->pairValAlt, s->nPairsDev + cur, 2 * s->bitsA, s->rsTmp, st);
   s->launches += 3 * ((2 * s->bitsA + 7) / 8);
   const uint32_t gP = cdiv(s->capPairs, B);
-  LAUNCH(k_pair_lost, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->nPairsDev + cur, s->freeList, s->deletedKeys, s->counters);
-  LAUNCH(k_pair_found, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->pairSlots[cur], s->nPairsDev + cur, s->freeList, s->createdKeys, s->counters,
+  LAUNCH(k_pair_lost, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->nPairsDev + cur, s->freeList, s->ringMask, s->deletedKeys, s->counters);
+  LAUNCH(k_pair_found, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->pairSlots[cur], s->nPairsDev + cur, s->freeList, s->ringMask, s->createdKeys, s->counters,
          s->manifolds, s->frictions);
   return PXB_OK;
 }
@@ -951,6 +1064,12 @@ static int read_counters(PxbScene* s) {
   CK(cudaStreamSynchronize(s->stream));
   s->hNPairs = s->hostCounters[C_COUNT + s->cur]; s->hNCreated = s->hostCounters[C_NCREATED]; s->hNDeleted = s->hostCounters[C_NDELETED];
   s->hNCon = s->hostCounters[C_NCON]; s->hNPart = s->hostCounters[C_NPART]; s->hErr = s->hostCounters[C_ERROR];
+  if (s->envActive && !s->envConCapForced) {   // size the shared-memory row store of k_env_solve to the largest environment seen (+12.5%); oversize environments fall back to global rows
+    s->hMaxConEnv = s->hostCounters[C_MAXCONENV];
+    const uint32_t lim = env_con_cap_limit(s->envMaxList);
+    uint32_t want = std::min(lim, std::max(32u, (s->hMaxConEnv + s->hMaxConEnv / 8 + 7u) & ~7u));
+    if (s->hMaxConEnv > s->envConCap ? want != s->envConCap : want * 2 <= s->envConCap) { s->envConCap = want; drop_graphs(s); }
+  }
   if (s->hErr & E_PAIR_OVERFLOW) return fail(PXB_ERR_CAPACITY, "broadphase pair capacity (maxPairs) exceeded");
   if (s->hErr & (E_COLOUR_OVERFLOW | E_PARTITION_OVERFLOW)) return fail(PXB_ERR_CAPACITY, "more than 32 dynamic colours / 96 partitions needed");
   return PXB_OK;
@@ -969,6 +1088,33 @@ static int enqueue_step(PxbScene* s, float dt) {
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
          s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce);
   MARK(2);
+  const float* g = s->desc.gravity;
+  SolverParams P;
+  P.dt = dt; P.stepDt = dt / (float)s->desc.posIters; P.invStepDt = 1.f / P.stepDt; P.invTotalDt = 1.0f / dt;
+  P.biasCoefficient = 2.f * sqrtf(1.f / (float)s->desc.posIters);
+  P.bounceThreshold = -s->desc.bounceThresholdVelocity;  // Sc::Scene hands the solver the negated threshold (ScScene.cpp:1002)
+  P.frictionOffsetThreshold = s->desc.frictionOffsetThreshold; P.correlationDistance = s->desc.frictionCorrelationDistance;
+  P.restDistance = s->desc.restOffset + s->desc.restOffset; P.staticFriction = s->desc.staticFriction; P.dynamicFriction = s->desc.dynamicFriction; P.restitution = s->desc.restitution;
+  if (s->envActive) {   // environment path: colouring + prep + all solver iterations + integration in one launch, rows in shared memory
+    MARK(3); MARK(4);
+    EnvSolveArgs A;
+    A.nEnv = s->nEnv; A.maxList = s->envMaxList; A.conCap = s->envConCap; A.cap = s->capPairs; A.posIters = s->desc.posIters; A.velIters = s->desc.velIters;
+    A.dt = dt; A.gx = g[0]; A.gy = g[1]; A.gz = g[2]; A.P = P;
+    A.envStart = s->envStart; A.envList = s->envList; A.actorLocal = s->actorLocal; A.seg = s->envSeg[cur];
+    A.pos = s->pos; A.quat = s->quat; A.linVel = s->linVel; A.angVel = s->angVel; A.invInertia = s->invInertia; A.damp = s->damp; A.geomFlags = s->geomFlags;
+    A.pairSlots = s->pairSlots[cur]; A.pairBodies = s->pairBodies; A.cHdr = s->cHdr; A.cPts = s->cPts; A.cForce = s->cForce; A.frictions = s->frictions;
+    A.conPair = s->conPair; A.conB0 = s->conB0; A.conB1 = s->conB1; A.conColour = s->conColour; A.ordered = s->ordered; A.broken = s->conDone;
+    A.rowA = s->rowA; A.rowB = s->rowB; A.rowC = s->rowC; A.ptA = s->ptA; A.ptB = s->ptB; A.ptC = s->ptC; A.frA = s->frA; A.frB = s->frB; A.frC = s->frC; A.frD = s->frD;
+    A.counters = s->counters;
+    const size_t smem = env_solve_smem(s->envMaxList, s->envConCap);
+    if (s->envSolveThreads == 32) k_env_solve<32><<<s->nEnv, 32, smem, st>>>(A);
+    else if (s->envSolveThreads == 128) k_env_solve<128><<<s->nEnv, 128, smem, st>>>(A);
+    else k_env_solve<64><<<s->nEnv, 64, smem, st>>>(A);
+    s->launches++;
+    MARK(5); MARK(6);
+    CK(cudaGetLastError());
+    return PXB_OK;
+  }
   if (s->nOrder) {
     LAUNCH(k_rank_init, gP, B, nP, s->rankOfPair);
     LAUNCH(k_rank_map, cdiv(s->nOrder, B), B, s->nOrder, s->orderKeys, s->pairKeys[cur], nP, s->rankOfPair);
@@ -992,15 +1138,8 @@ static int enqueue_step(PxbScene* s, float dt) {
     CK(cudaLaunchCooperativeKernel((void*)k_colour_partition, dim3(s->coopBlocksColour), dim3(256), args, 0, st)); s->launches++;
   }
   MARK(3);
-  const float* g = s->desc.gravity;
   LAUNCH(k_preintegrate, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, g[0], g[1], g[2], dt, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng,
          s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng);
-  SolverParams P;
-  P.dt = dt; P.stepDt = dt / (float)s->desc.posIters; P.invStepDt = 1.f / P.stepDt; P.invTotalDt = 1.0f / dt;
-  P.biasCoefficient = 2.f * sqrtf(1.f / (float)s->desc.posIters);
-  P.bounceThreshold = -s->desc.bounceThresholdVelocity;  // Sc::Scene hands the solver the negated threshold (ScScene.cpp:1002)
-  P.frictionOffsetThreshold = s->desc.frictionOffsetThreshold; P.correlationDistance = s->desc.frictionCorrelationDistance;
-  P.restDistance = s->desc.restOffset + s->desc.restOffset; P.staticFriction = s->desc.staticFriction; P.dynamicFriction = s->desc.dynamicFriction; P.restitution = s->desc.restitution;
   LAUNCH(k_prep, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
          s->invInertia, s->sbIA, s->sbIB, s->frictions, P, s->capPairs, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD);
   MARK(4);
@@ -1032,6 +1171,8 @@ PXB_API int pxb_scene_simulate(PxbScene* s, float dt) {
   if (s->nA == 0) return PXB_OK;
   if (!(dt > 0.f)) return fail(PXB_ERR_INVALID, "dt must be positive");
   if (s->gridDirty) { rebuild_grid(s); drop_graphs(s); }
+  if (int rc = select_path(s)) return rc;
+  if (!s->envActive) s->everStepped = true;
   const bool graphOk = s->useGraph && s->nOrder == 0 && !s->profiling;
   if (!graphOk) { const int rc = enqueue_step(s, dt); if (rc) return rc; s->stepping = true; return PXB_OK; }
   if (s->graphDt != dt) { drop_graphs(s); s->graphDt = dt; }
@@ -1100,6 +1241,9 @@ PXB_API int pxb_scene_broadphase(PxbScene* s, const float* tightBounds) {
   if (s->abort) return fail(PXB_ERR_CUDA, "scene is in abort mode");
   s->launches = 0;
   if (tightBounds) { CK(cudaMemcpyAsync(s->tight, tightBounds, 24 * (size_t)s->nA, cudaMemcpyHostToDevice, s->stream)); }
+  if (s->gridDirty) rebuild_grid(s);
+  if (int rc = select_path(s)) return rc;
+  if (!s->envActive) s->everStepped = true;
   const int rc = run_broadphase(s, tightBounds != nullptr); if (rc) return rc;
   return read_counters(s);
 }
@@ -1113,7 +1257,7 @@ static int copy_pairs(PxbScene* s, const uint64_t* dev, uint32_t n, uint32_t* ou
 PXB_API uint32_t pxb_scene_num_pairs(PxbScene* s) { return s ? s->hNPairs : 0; }
 PXB_API uint32_t pxb_scene_num_created(PxbScene* s) { return s ? s->hNCreated : 0; }
 PXB_API uint32_t pxb_scene_num_deleted(PxbScene* s) { return s ? s->hNDeleted : 0; }
-PXB_API int pxb_scene_get_pairs(PxbScene* s, uint32_t* out) { if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->pairKeys[s->cur], s->hNPairs, out, false); }
+PXB_API int pxb_scene_get_pairs(PxbScene* s, uint32_t* out) { if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->pairKeys[s->cur], s->hNPairs, out, s->envActive); }
 PXB_API int pxb_scene_get_created(PxbScene* s, uint32_t* out) { if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->createdKeys, s->hNCreated, out, true); }
 PXB_API int pxb_scene_get_deleted(PxbScene* s, uint32_t* out) { if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->deletedKeys, s->hNDeleted, out, true); }
 PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) {
@@ -1122,8 +1266,14 @@ PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) {
   std::vector<float4> h(n), p((size_t)n * 4); std::vector<float> f((size_t)n * 4);
   CK(cudaMemcpyAsync(h.data(), s->cHdr, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->stream)); CK(cudaMemcpyAsync(p.data(), s->cPts, 64 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaMemcpyAsync(f.data(), s->cForce, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->stream)); CK(cudaStreamSynchronize(s->stream));
-  for (uint32_t i = 0; i < n; ++i) {
-    float* o = out24 + (size_t)i * 24; memset(o, 0, 96);
+  std::vector<uint32_t> perm(n); for (uint32_t i = 0; i < n; ++i) perm[i] = i;
+  if (s->envActive) {   // the environment path keeps pairs per environment: report them in ascending key order like the device-wide path
+    std::vector<uint64_t> k(n); CK(cudaMemcpyAsync(k.data(), s->pairKeys[s->cur], 8 * (size_t)n, cudaMemcpyDeviceToHost, s->stream)); CK(cudaStreamSynchronize(s->stream));
+    std::sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return k[x] < k[y]; });
+  }
+  for (uint32_t r = 0; r < n; ++r) {
+    const uint32_t i = perm[r];
+    float* o = out24 + (size_t)r * 24; memset(o, 0, 96);
     int cnt; memcpy(&cnt, &h[i].w, 4);
     o[0] = (float)cnt;
     if (cnt) { o[1] = h[i].x; o[2] = h[i].y; o[3] = h[i].z; }
@@ -1134,6 +1284,7 @@ PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) {
 PXB_API uint32_t pxb_scene_last_num_partitions(PxbScene* s) { return s ? s->hNPart : 0; }
 PXB_API uint32_t pxb_scene_last_num_constraints(PxbScene* s) { return s ? s->hNCon : 0; }
 PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* s) { return s ? s->launches : 0; }
+PXB_API int pxb_scene_uses_env_path(PxbScene* s) { return s && s->envActive ? 1 : 0; }
 
 static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb, bool set) {
   if (type < 0 || type > 2) return fail(PXB_ERR_INVALID, "bad dataType");

@@ -29,7 +29,7 @@ EXPORTS = [
     "pxb_scene_num_created", "pxb_scene_num_deleted", "pxb_scene_get_created", "pxb_scene_get_deleted",
     "pxb_scene_get_contacts", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
-    "pxb_scene_get_states_device",
+    "pxb_scene_get_states_device", "pxb_scene_uses_env_path",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY = 0, 1, 2
@@ -88,6 +88,7 @@ def load_library():
         getattr(lib, f).argtypes = [vp, vp]
     lib.pxb_scene_compute_bounds.argtypes = [vp]
     lib.pxb_scene_get_states_device.argtypes = [vp, vp]
+    lib.pxb_scene_uses_env_path.argtypes = [vp]
     lib.pxb_scene_set_profiling.argtypes = [vp, i32]
     lib.pxb_scene_get_stage_times.argtypes = [vp, vp]
     lib.pxb_scene_state_device_ptr.argtypes = [vp, i32]
@@ -111,7 +112,7 @@ def _ptr(a):
 class Scene:
     """One simulation scene resident on one GPU (one PxScene <-> one device, ScScene.cpp:718)."""
 
-    def __init__(self, scene: _scenes.Scene, device: int = 0, max_pairs: int = 0, max_actors: int = 0):
+    def __init__(self, scene: _scenes.Scene, device: int = 0, max_pairs: int = 0, max_actors: int = 0, env_path: bool = True, env_row_cap: int = 0):
         lib = load_library()
         self._lib = lib
         h = scene.header
@@ -128,6 +129,8 @@ class Scene:
         d.maxActors = max(int(max_actors), len(scene.actors))
         d.maxPairs = int(max_pairs)
         d.device = int(device)
+        d.reserved[1] = 0 if env_path else 1   # PXB_FLAG_NO_ENV_PATH
+        d.reserved[2] = int(env_row_cap)
         self.dt = float(h["dt"])
         self._h = ctypes.c_void_p()
         _check(lib, lib.pxb_scene_create(ctypes.byref(d), ctypes.byref(self._h)))
@@ -254,6 +257,10 @@ class Scene:
     @property
     def num_constraints(self):
         return int(self._lib.pxb_scene_last_num_constraints(self._h))
+
+    @property
+    def uses_env_path(self):
+        return bool(self._lib.pxb_scene_uses_env_path(self._h))
 
     @property
     def num_launches(self):

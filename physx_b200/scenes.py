@@ -251,3 +251,38 @@ def mixed_primitives(n=18, seed=3, kinds=("sphere", "capsule", "box"), spread=0.
         else:
             set_box(a, np.array([i]), np.array([rng.uniform(0.12, 0.25), rng.uniform(0.12, 0.25), rng.uniform(0.12, 0.25)], dtype=np.float32))
     return Scene(default_header(**hdr), add_ground_plane(a))
+
+
+def env_ragged(n_envs=12, max_bodies=20, seed=5, static_blocks=True, env_pitch=6.0, **hdr):
+    """Environments of different sizes (including an empty one) with tumbling boxes / spheres / capsules, an optional
+    static box inside every other environment and two env-less statics (ground plane + a wall plane): exercises the
+    environment path's ragged lists, pair creation/deletion, static env members and several shared statics."""
+    rng = np.random.RandomState(seed)
+    recs = []
+    for e in range(n_envs):
+        nb = 0 if e == 3 else int(rng.randint(1, max_bodies + 1))
+        a = _new_actors(nb + (1 if (static_blocks and e % 2 == 0) else 0))
+        ex, ez = (e % 4) * env_pitch, (e // 4) * env_pitch
+        for i in range(nb):
+            kind = rng.randint(0, 3)
+            if kind == 0:
+                set_box(a, np.array([i]), np.array([rng.uniform(0.12, 0.3), rng.uniform(0.12, 0.3), rng.uniform(0.12, 0.3)], dtype=np.float32))
+            elif kind == 1:
+                set_sphere(a, i, rng.uniform(0.1, 0.25))
+            else:
+                set_capsule(a, i, rng.uniform(0.08, 0.15), rng.uniform(0.1, 0.3))
+            a["pos"][i] = (ex + rng.uniform(-0.4, 0.4), 0.5 + 0.5 * i, ez + rng.uniform(-0.4, 0.4))
+            a["angVel"][i] = rng.uniform(-2, 2, 3)
+        if nb:
+            a["quat"][:nb] = random_unit_quats(rng, nb)
+        if len(a) > nb:   # static box (flags = 0) that belongs to the environment
+            a["geomType"][nb] = GEOM_BOX
+            a["dims"][nb, :3] = (0.5, 0.2, 0.5)
+            a["pos"][nb] = (ex + 0.2, 0.2, ez)
+        a["envId"] = e
+        recs.append(a)
+    wall = _new_actors(1)   # env-less wall plane x >= -1.5 (normal +X = identity pose)
+    wall["geomType"] = GEOM_PLANE
+    wall["pos"][0] = (-1.5, 0.0, 0.0)
+    actors = np.concatenate(recs + [wall])
+    return Scene(default_header(**hdr), add_ground_plane(actors))

@@ -192,3 +192,65 @@ def test_gpu_teacher_forced_steps_match_reference(name):
         assert np.abs(st[:, :7] - ref[:, :7]).max() < 1e-5, f"pose, step {t}"
         assert np.abs(st[:, 7:10] - ref[:, 7:10]).max() < 1e-4 and np.abs(st[:, 10:] - ref[:, 10:]).max() < 1e-3, f"velocity, step {t}"
         assert util.contact_counts(gpu.getPairs(), gpu.getContacts()) == util.golden_contact_counts(z, t), f"manifolds, step {t}"
+
+
+def _env_scenes():
+    return {"envs_16": (scenes.env_grid_stacks(n_envs=16, jitter=0.01), 40),
+            "envs_37x3x5": (scenes.env_grid_stacks(n_envs=37, stacks_per_env=3, height=5, jitter=0.02), 40),
+            "ragged": (scenes.env_ragged(), 150)}
+
+
+@pytest.mark.parametrize("name", list(_env_scenes()))
+def test_env_path_is_bit_identical_to_device_wide_path(name):
+    """Environment path (one warp / CTA per environment, rows in shared memory) vs the device-wide path (grid broadphase,
+    global colouring, cooperative solve): same pairs, events, contacts and states, bit for bit, every step."""
+    sc, steps = _env_scenes()[name]
+    env, glob = engine.Scene(sc), engine.Scene(sc, env_path=False)
+    for t in range(steps):
+        env.step()
+        glob.step()
+        assert env.uses_env_path and not glob.uses_env_path
+        assert np.array_equal(env.getPairs(), glob.getPairs()), f"pairs, step {t}"
+        assert np.array_equal(env.getCreatedPairs(), glob.getCreatedPairs()), f"created, step {t}"
+        assert np.array_equal(env.getDeletedPairs(), glob.getDeletedPairs()), f"deleted, step {t}"
+        assert np.array_equal(env.getContacts(), glob.getContacts()), f"contacts + applied forces, step {t}"
+        assert env.num_constraints == glob.num_constraints and env.num_partitions == glob.num_partitions
+        assert np.array_equal(env.getStates(), glob.getStates()), f"states, step {t}"
+
+
+def test_env_path_matches_oracle_ragged(oracle):
+    sc = scenes.env_ragged()
+    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    for t in range(120):
+        gpu.step()
+        cpu.step()
+        assert gpu.uses_env_path
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
+        assert np.array_equal(gpu.getCreatedPairs(), cpu.getCreatedPairs()) and np.array_equal(gpu.getDeletedPairs(), cpu.getDeletedPairs()), f"events, step {t}"
+        cg, cc = gpu.getContacts(), cpu.getContacts()
+        assert np.array_equal(cg[:, 0], cc[:, 0]), f"contact counts, step {t}"
+        assert gpu.num_constraints == cpu.num_constraints and gpu.num_partitions == cpu.num_partitions
+        sg = gpu.getStates()
+        assert np.abs(sg - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
+        cpu.setStates(sg)
+
+
+def test_env_path_falls_back_when_order_is_given_and_small_row_store():
+    """(1) a host constraint order switches a running scene from the environment path to the device-wide path (pair list
+    converted, manifolds kept); (2) environments larger than the shared-memory row store use global rows, same results."""
+    sc = scenes.env_grid_stacks(n_envs=9, jitter=0.01)
+    a, b = engine.Scene(sc), engine.Scene(sc, env_path=False)
+    for _ in range(10):
+        a.step(); b.step()
+    assert a.uses_env_path
+    order = a.getPairs()
+    a.setConstraintOrder(order); b.setConstraintOrder(order)
+    for t in range(10):
+        a.step(); b.step()
+        assert not a.uses_env_path
+        assert np.array_equal(a.getCreatedPairs(), b.getCreatedPairs()) and len(a.getCreatedPairs()) == 0
+        assert np.array_equal(a.getStates(), b.getStates()), f"step {t}"
+    c, d = engine.Scene(sc, env_row_cap=8), engine.Scene(sc)   # 64 constraints per environment > 8 rows in shared memory
+    for t in range(20):
+        c.step(); d.step()
+        assert c.uses_env_path and np.array_equal(c.getStates(), d.getStates()) and np.array_equal(c.getContacts(), d.getContacts()), f"step {t}"
