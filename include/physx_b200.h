@@ -48,7 +48,7 @@ typedef struct {
   uint32_t maxActors;                  /* capacity */
   uint32_t maxPairs;                   /* PxGpuDynamicsMemoryConfig::foundLostPairsCapacity / maxRigidPatchCount analogue; 0 = 8*maxActors */
   int32_t  device;                     /* CUDA device ordinal (PxCudaContextManagerDesc) */
-  uint32_t reserved[8];                /* [0] internal; [1] = PXB_FLAG_* bits; [2] = rows per environment kept in shared memory (0 = adaptive) */
+  uint32_t reserved[8];                /* [0] internal; [1] = PXB_FLAG_* bits; [2]/[3] = test hooks of the environment path: constraint-list slots in shared memory / constraints per CTA (0 = adaptive) */
 } PxbSceneDesc;
 /* Scenes whose dynamic actors all carry an environment id (PxActor::setEnvironmentID, the RL many-env layout of
  * BASELINE configs 2/5) run on the environment path: one warp / one CTA per environment with solver rows in shared

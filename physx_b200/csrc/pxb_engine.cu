@@ -45,7 +45,7 @@ struct ActorRec {
 };
 static_assert(sizeof(ActorRec) == 128, "actor record layout");
 
-enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_COUNT = 16 };
+enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_COUNT = 16 };
 enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4 };
 
 struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };
@@ -87,8 +87,8 @@ struct PxbScene {
   uint32_t hNPairs = 0, hNCreated = 0, hNDeleted = 0, hNCon = 0, hNPart = 0, hErr = 0;
   // environment-partitioned path (pxb_env.cuh)
   bool envEligible = false, envActive = false, envDisabled = false, everStepped = false; uint32_t ringMask = 0;
-  uint32_t nEnv = 0, envMaxList = 0, envConCap = 0, envConCapForced = 0, hMaxConEnv = 0, envSolveThreads = 64;
-  uint32_t *envStart = 0, *envList = 0, *actorLocal = 0; uint2* envSeg[2] = {0, 0};
+  uint32_t nEnv = 0, envMaxList = 0, envConCap = 0, envConCapForced = 0, envThreadsForced = 0, hMaxConEnv = 0, hMaxPairEnv = 0, envSolveThreads = 64;
+  uint32_t *envStart = 0, *envList = 0, *actorLocal = 0; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
 };
 
 static thread_local std::string g_err;
@@ -736,7 +736,7 @@ __global__ void k_init_freelist(uint32_t cap, uint32_t* __restrict__ freeList) {
 }
 
 __global__ void k_env_begin(uint32_t* __restrict__ counters) {   // per-step counter reset of the environment path
-  if (threadIdx.x == 0) { counters[C_NPAIRS_NEW] = 0; counters[C_NCREATED] = 0; counters[C_NDELETED] = 0; counters[C_NCON] = 0; counters[C_NPART] = 0; counters[C_MAXCONENV] = 0;
+  if (threadIdx.x == 0) { counters[C_NPAIRS_NEW] = 0; counters[C_NCREATED] = 0; counters[C_NDELETED] = 0; counters[C_NCON] = 0; counters[C_NPART] = 0; counters[C_MAXCONENV] = 0; counters[C_MAXPAIRENV] = 0;
                           counters[C_FREE_SNAP] = counters[C_FREE_TAIL]; }
 }
 #include "pxb_env.cuh"
@@ -744,8 +744,9 @@ __global__ void k_env_begin(uint32_t* __restrict__ counters) {   // per-step cou
 // ---------------------------------------------------------------------------------------------
 // host side
 static const size_t ENV_SMEM_MAX = 227 * 1024 - 2048;   // dynamic shared memory budget of k_env_solve (static part: partition tables)
-static size_t env_solve_smem(uint32_t maxList, uint32_t conCap) { return (size_t)maxList * (8 * sizeof(float4) + 3 * sizeof(uint32_t)) + (size_t)conCap * 31 * sizeof(float4); }
-static uint32_t env_con_cap_limit(uint32_t maxList) { return (uint32_t)((ENV_SMEM_MAX - (size_t)maxList * (8 * sizeof(float4) + 3 * sizeof(uint32_t))) / (31 * sizeof(float4))); }
+static const size_t ENV_CON_BYTES = 5 * sizeof(uint32_t);   // 5 u32 lists per pair slot (rows live in registers)
+static size_t env_solve_smem(uint32_t maxList, uint32_t conCap) { return (size_t)maxList * (8 * sizeof(float4) + 3 * sizeof(uint32_t)) + (size_t)conCap * ENV_CON_BYTES; }
+static uint32_t env_con_cap_limit(uint32_t maxList) { return (uint32_t)((ENV_SMEM_MAX - (size_t)maxList * (8 * sizeof(float4) + 3 * sizeof(uint32_t))) / ENV_CON_BYTES); }
 template <typename T> static cudaError_t dalloc(T*& p, size_t n) { return cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)); }
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 static uint32_t bits_for(uint64_t n) { uint32_t b = 1; while ((1ull << b) < n) ++b; return b; }
@@ -755,6 +756,7 @@ extern "C" {
 PXB_API const char* pxb_last_error(void) { return g_err.c_str(); }
 PXB_API int pxb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 
+static uint32_t env_threads_for(uint32_t nCon) { return nCon <= 32 ? 32u : (nCon <= 64 ? 64u : (nCon <= 128 ? 128u : 256u)); }   // CTA size of k_env_solve: one thread per constraint when possible
 static void drop_graphs(PxbScene* s);
 static int scene_alloc(PxbScene* s) {
   const size_t A = s->capA, Pn = s->capPairs;
@@ -776,8 +778,8 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->conB0, Pn)); CK(dalloc(s->conB1, Pn)); CK(dalloc(s->conPos0, Pn)); CK(dalloc(s->conPos1, Pn)); CK(dalloc(s->conColour, Pn)); CK(dalloc(s->conDone, Pn));
   CK(dalloc(s->bodyList, Pn * 2)); CK(dalloc(s->ordered, Pn));
   CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
-  CK(dalloc(s->rowA, Pn)); CK(dalloc(s->rowB, Pn)); CK(dalloc(s->rowC, Pn)); CK(dalloc(s->ptA, Pn * 4)); CK(dalloc(s->ptB, Pn * 4)); CK(dalloc(s->ptC, Pn * 4));
-  CK(dalloc(s->frA, Pn * 4)); CK(dalloc(s->frB, Pn * 4)); CK(dalloc(s->frC, Pn * 4)); CK(dalloc(s->frD, Pn * 4));
+  CK(dalloc(s->rowA, Pn)); CK(dalloc(s->rowB, Pn)); CK(dalloc(s->rowC, Pn)); CK(dalloc(s->ptA, Pn * 28)); s->ptB = s->ptA + Pn * 4; s->ptC = s->ptA + Pn * 8;   // one allocation: the environment path views it as 25 x Pn (pxb_env.cuh Rows)
+  s->frA = s->ptA + Pn * 12; s->frB = s->ptA + Pn * 16; s->frC = s->ptA + Pn * 20; s->frD = s->ptA + Pn * 24;
   CK(dalloc(s->stage, A * 7)); CK(dalloc(s->stageIdx, A));
   CK(dalloc(s->counters, C_COUNT)); CK(cudaMallocHost((void**)&s->hostCounters, sizeof(uint32_t) * (C_COUNT + 2)));
   CK(dalloc(s->rsTmp.blockHist, RS_MAX_CTAS * 256)); CK(dalloc(s->rsTmp.digitTotals, 256)); CK(dalloc(s->scanSums, RS_MAX_CTAS));
@@ -811,7 +813,8 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   CK(cudaFuncSetAttribute(k_env_solve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
   CK(cudaFuncSetAttribute(k_env_solve<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
   CK(cudaFuncSetAttribute(k_env_solve<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
-  CK(cudaFuncSetAttribute(k_env_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * ENV_MAX_LIST * 36)));
+  CK(cudaFuncSetAttribute(k_env_solve<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
+  CK(cudaFuncSetAttribute(k_env_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
   s->capA = std::max(16u, desc->maxActors);
   s->capPairs = desc->maxPairs ? desc->maxPairs : std::max(1024u, 8u * s->capA);
@@ -819,7 +822,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->rsTmp.ctas = std::min<uint32_t>(RS_MAX_CTAS, (uint32_t)s->numSMs * 2);
   { const char* ng = getenv("PXB_NO_GRAPH"); if (ng && ng[0] == '1') s->useGraph = false; }
   if (desc->reserved[1] & PXB_FLAG_NO_ENV_PATH) s->envDisabled = true;
-  s->envConCapForced = desc->reserved[2];
+  s->envConCapForced = desc->reserved[2]; s->envThreadsForced = desc->reserved[3];
   const int rc = scene_alloc(s);
   if (rc != PXB_OK) { delete s; return rc; }
   *out = s;
@@ -835,7 +838,7 @@ PXB_API void pxb_scene_release(PxbScene* s) {
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
-                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
+                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
                   s->envStart, s->envList, s->actorLocal, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
@@ -898,9 +901,13 @@ static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
   cudaMemcpyAsync(s->actorLocal, local.data(), 4 * s->nA, cudaMemcpyHostToDevice, s->stream);
   cudaStreamSynchronize(s->stream);
   s->nEnv = nEnv; s->envMaxList = maxList; s->envEligible = true;
-  if (s->envConCap == 0) s->envConCap = std::max(32u, maxList);
+#ifdef PXB_ENV_TIMING
+  if (s->envTiming) cudaFree(s->envTiming); cudaMalloc((void**)&s->envTiming, (size_t)nEnv * 16 * 8); cudaMemset(s->envTiming, 0, (size_t)nEnv * 16 * 8);
+#endif
+  // first guess: about one constraint / two pairs per actor; adapted after every step from the device-side maxima (read_counters)
+  if (s->envConCap == 0) { s->envConCap = std::max(32u, 2 * maxList); s->envSolveThreads = env_threads_for(maxList); }
   if (s->envConCapForced) s->envConCap = std::min(s->envConCapForced, env_con_cap_limit(maxList));
-  const char* et = getenv("PXB_ENV_THREADS"); if (et) { const int t = atoi(et); if (t == 32 || t == 64 || t == 128) s->envSolveThreads = (uint32_t)t; }
+  if (s->envThreadsForced) s->envSolveThreads = env_threads_for(s->envThreadsForced);
 }
 
 static void rebuild_grid(PxbScene* s) {
@@ -1029,7 +1036,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight;
     A.oldKeys = s->pairKeys[prev]; A.oldSlots = s->pairSlots[prev]; A.oldSeg = s->envSeg[prev]; A.newKeys = s->pairKeys[cur]; A.newSlots = s->pairSlots[cur]; A.newSeg = s->envSeg[cur];
     A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions;
-    const size_t smem = (size_t)ENV_BP_WARPS * s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t));
+    const size_t smem = (size_t)ENV_BP_WARPS * (s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t)) + ENV_BP_STAGE * sizeof(uint64_t));
     k_env_bp<<<cdiv(s->nEnv, ENV_BP_WARPS), 32 * ENV_BP_WARPS, smem, st>>>(A); s->launches++;
     LAUNCH(k_clamp_count, 1, 32, s->counters, s->capPairs, s->nPairsDev + cur);
     return PXB_OK;
@@ -1064,11 +1071,13 @@ static int read_counters(PxbScene* s) {
   CK(cudaStreamSynchronize(s->stream));
   s->hNPairs = s->hostCounters[C_COUNT + s->cur]; s->hNCreated = s->hostCounters[C_NCREATED]; s->hNDeleted = s->hostCounters[C_NDELETED];
   s->hNCon = s->hostCounters[C_NCON]; s->hNPart = s->hostCounters[C_NPART]; s->hErr = s->hostCounters[C_ERROR];
-  if (s->envActive && !s->envConCapForced) {   // size the shared-memory row store of k_env_solve to the largest environment seen (+12.5%); oversize environments fall back to global rows
-    s->hMaxConEnv = s->hostCounters[C_MAXCONENV];
-    const uint32_t lim = env_con_cap_limit(s->envMaxList);
-    uint32_t want = std::min(lim, std::max(32u, (s->hMaxConEnv + s->hMaxConEnv / 8 + 7u) & ~7u));
-    if (s->hMaxConEnv > s->envConCap ? want != s->envConCap : want * 2 <= s->envConCap) { s->envConCap = want; drop_graphs(s); }
+  if (s->envActive) {   // fit k_env_solve to the largest environment seen: one thread per constraint (rows in registers), lists in shared memory
+    s->hMaxConEnv = s->hostCounters[C_MAXCONENV]; s->hMaxPairEnv = s->hostCounters[C_MAXPAIRENV];
+    if (!s->envThreadsForced) { const uint32_t t = env_threads_for(s->hMaxConEnv); if (t != s->envSolveThreads && s->hMaxConEnv) { s->envSolveThreads = t; drop_graphs(s); } }
+    if (!s->envConCapForced) {
+      const uint32_t want = std::min(env_con_cap_limit(s->envMaxList), std::max(32u, (s->hMaxPairEnv + 3u) & ~3u));
+      if (s->hMaxPairEnv > s->envConCap ? want != s->envConCap : want * 2 <= s->envConCap) { s->envConCap = want; drop_graphs(s); }
+    }
   }
   if (s->hErr & E_PAIR_OVERFLOW) return fail(PXB_ERR_CAPACITY, "broadphase pair capacity (maxPairs) exceeded");
   if (s->hErr & (E_COLOUR_OVERFLOW | E_PARTITION_OVERFLOW)) return fail(PXB_ERR_CAPACITY, "more than 32 dynamic colours / 96 partitions needed");
@@ -1104,12 +1113,13 @@ static int enqueue_step(PxbScene* s, float dt) {
     A.pos = s->pos; A.quat = s->quat; A.linVel = s->linVel; A.angVel = s->angVel; A.invInertia = s->invInertia; A.damp = s->damp; A.geomFlags = s->geomFlags;
     A.pairSlots = s->pairSlots[cur]; A.pairBodies = s->pairBodies; A.cHdr = s->cHdr; A.cPts = s->cPts; A.cForce = s->cForce; A.frictions = s->frictions;
     A.conPair = s->conPair; A.conB0 = s->conB0; A.conB1 = s->conB1; A.conColour = s->conColour; A.ordered = s->ordered; A.broken = s->conDone;
-    A.rowA = s->rowA; A.rowB = s->rowB; A.rowC = s->rowC; A.ptA = s->ptA; A.ptB = s->ptB; A.ptC = s->ptC; A.frA = s->frA; A.frB = s->frB; A.frC = s->frC; A.frD = s->frD;
-    A.counters = s->counters;
+    A.rowScratch = s->ptA;   // ptA|ptB|ptC|frA|frB|frC|frD are ONE allocation of 28 x cap float4 (scene_alloc); the environment path uses 25 of them
+    A.counters = s->counters; A.timing = s->envTiming;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap);
     if (s->envSolveThreads == 32) k_env_solve<32><<<s->nEnv, 32, smem, st>>>(A);
+    else if (s->envSolveThreads == 64) k_env_solve<64><<<s->nEnv, 64, smem, st>>>(A);
     else if (s->envSolveThreads == 128) k_env_solve<128><<<s->nEnv, 128, smem, st>>>(A);
-    else k_env_solve<64><<<s->nEnv, 64, smem, st>>>(A);
+    else k_env_solve<256><<<s->nEnv, 256, smem, st>>>(A);
     s->launches++;
     MARK(5); MARK(6);
     CK(cudaGetLastError());
@@ -1285,6 +1295,9 @@ PXB_API uint32_t pxb_scene_last_num_partitions(PxbScene* s) { return s ? s->hNPa
 PXB_API uint32_t pxb_scene_last_num_constraints(PxbScene* s) { return s ? s->hNCon : 0; }
 PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* s) { return s ? s->launches : 0; }
 PXB_API int pxb_scene_uses_env_path(PxbScene* s) { return s && s->envActive ? 1 : 0; }
+#ifdef PXB_ENV_TIMING
+extern "C" PXB_API int pxb_debug_env_timing(PxbScene* s, unsigned long long* out) { cudaStreamSynchronize(s->stream); cudaMemcpy(out, s->envTiming, (size_t)s->nEnv * 16 * 8, cudaMemcpyDeviceToHost); return (int)s->nEnv; }
+#endif
 
 static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb, bool set) {
   if (type < 0 || type > 2) return fail(PXB_ERR_INVALID, "bad dataType");

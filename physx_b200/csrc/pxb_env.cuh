@@ -29,8 +29,14 @@ struct EnvBpArgs {
   uint32_t *counters, *freeRing; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions;
 };
 
-__device__ __forceinline__ void env_pair_norm(uint32_t n, uint32_t& i, uint32_t& j) {
-  while (i + 1 < n && j >= n) { j = j - n + i + 2; ++i; }
+#define ENV_BP_STAGE 256   // pair keys staged per warp in shared memory before the segment base is known
+
+// branch-free AABB test of the environment path: closed-interval overlap on all axes (PxgIntegerAABB::intersects / ABP
+// intersect2D semantics) and at least one dynamic actor (BpFiltering.h:99-114).  Every list member is in the warp's own
+// environment or env-less, so the environment filter (broadphase.cu:62-80) always passes here.
+__device__ __forceinline__ bool env_bp_test(const float4& amin, const float4& amax, const float4& bmin, const float4& bmax) {
+  const bool sep = (amin.x > bmax.x) | (bmin.x > amax.x) | (amin.y > bmax.y) | (bmin.y > amax.y) | (amin.z > bmax.z) | (bmin.z > amax.z);
+  return !sep & (((__float_as_uint(amax.w) | __float_as_uint(bmax.w)) & 0x100u) != 0);
 }
 
 __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A) {
@@ -39,7 +45,8 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
   const uint32_t e = blockIdx.x * ENV_BP_WARPS + warp;
   if (e >= A.nEnv) return;   // warps are independent: no CTA-wide barrier below
   float4* sMin = envBpSmem + (size_t)warp * 2 * A.maxList; float4* sMax = sMin + A.maxList;
-  uint32_t* sAct = reinterpret_cast<uint32_t*>(envBpSmem + (size_t)ENV_BP_WARPS * 2 * A.maxList) + (size_t)warp * A.maxList;
+  uint64_t* sStage = reinterpret_cast<uint64_t*>(envBpSmem + (size_t)ENV_BP_WARPS * 2 * A.maxList) + (size_t)warp * ENV_BP_STAGE;
+  uint32_t* sAct = reinterpret_cast<uint32_t*>(envBpSmem + (size_t)ENV_BP_WARPS * 2 * A.maxList) + ENV_BP_WARPS * ENV_BP_STAGE * 2 + (size_t)warp * A.maxList;
   const uint32_t ls = A.envStart[e], n = A.envStart[e + 1] - ls;
   // a1/a2: bounds of this environment's actors (+ the shared env-less statics), inflated, into shared memory
   for (uint32_t k = lane; k < n; k += 32) {
@@ -57,36 +64,43 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
     sAct[k] = a;
   }
   __syncwarp();
-  // a4/a5: all pairs (i<j) of the list in row-major order = ascending (lo,hi) key order because the list is sorted by
-  // actor index.  Pass 1 counts, one atomic reserves the segment, pass 2 emits.
-  const uint32_t total = n * (n - 1) / 2;
+  // a4/a5: all pairs (i<j) of the list, row by row = ascending (lo,hi) key order because the list is sorted by actor
+  // index.  Keys are staged in shared memory; one atomic reserves the environment's segment of the flat pair list.
   uint32_t cnt = 0;
-  {
-    uint32_t i = 0, j = 1 + lane;
-    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-      env_pair_norm(n, i, j);
-      const bool hit = (i + 1 < n) && bp_test(sMin[i], sMax[i], sMin[j], sMax[j]);
-      cnt += __popc(__ballot_sync(0xffffffffu, hit));
-      j += 32;
+  for (uint32_t i = 0; i + 1 < n; ++i) {
+    const float4 amin = sMin[i], amax = sMax[i]; const uint64_t hiKey = (uint64_t)sAct[i] << A.bitsA;
+    for (uint32_t j0 = i + 1; j0 < n; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      const bool hit = j < n && env_bp_test(amin, amax, sMin[j], sMax[j]);
+      const uint32_t m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        const uint32_t w = cnt + __popc(m & ((1u << lane) - 1u));
+        if (hit && w < ENV_BP_STAGE) sStage[w] = hiKey | sAct[j];
+        cnt += __popc(m);
+      }
     }
   }
   uint32_t base = 0;
   if (lane == 0 && cnt) base = atomicAdd(&A.counters[C_NPAIRS_NEW], cnt);
   base = __shfl_sync(0xffffffffu, base, 0);
+  __syncwarp();
   if (base + cnt > A.cap) {   // capacity exceeded: report, keep the flat list crash-free (sentinel keys), drop the segment
     if (lane == 0) atomicOr(&A.counters[C_ERROR], (uint32_t)E_PAIR_OVERFLOW);
     for (uint32_t t = base + lane; t < min(base + cnt, A.cap); t += 32) { A.newKeys[t] = ~0ull; A.newSlots[t] = 0; }
     cnt = 0;
   }
-  {
-    uint32_t i = 0, j = 1 + lane, w = 0;
-    for (uint32_t t0 = 0; t0 < total && cnt; t0 += 32) {
-      env_pair_norm(n, i, j);
-      const bool hit = (i + 1 < n) && bp_test(sMin[i], sMax[i], sMin[j], sMax[j]);
-      const uint32_t m = __ballot_sync(0xffffffffu, hit);
-      if (hit) A.newKeys[base + w + __popc(m & ((1u << lane) - 1u))] = ((uint64_t)sAct[i] << A.bitsA) | sAct[j];
-      w += __popc(m);
-      j += 32;
+  if (cnt <= ENV_BP_STAGE) { for (uint32_t t = lane; t < cnt; t += 32) A.newKeys[base + t] = sStage[t]; }
+  else {   // more pairs than the staging area holds: enumerate again, straight into the segment
+    uint32_t w = 0;
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+      const float4 amin = sMin[i], amax = sMax[i]; const uint64_t hiKey = (uint64_t)sAct[i] << A.bitsA;
+      for (uint32_t j0 = i + 1; j0 < n; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool hit = j < n && env_bp_test(amin, amax, sMin[j], sMax[j]);
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (hit) A.newKeys[base + w + __popc(m & ((1u << lane) - 1u))] = hiKey | sAct[j];
+        w += __popc(m);
+      }
     }
   }
   __syncwarp();
@@ -128,38 +142,244 @@ struct EnvSolveArgs {
   float4 *pos, *quat, *linVel, *angVel; const float4 *invInertia, *damp; const uint32_t* geomFlags;
   const uint32_t* pairSlots; const uint2* pairBodies; const float4 *cHdr, *cPts; float* cForce; float4* frictions;
   uint32_t *conPair, *conB0, *conB1, *conColour, *ordered, *broken;   // per-pair-index scratch (global, L2 resident)
-  float4 *rowA, *rowB; uint4* rowC; float4 *ptA, *ptB, *ptC, *frA, *frB, *frC, *frD;  // global rows: only for environments that do not fit conCap
-  uint32_t* counters;
+  float4* rowScratch;   // 25 x cap float4, field-major: memory image of RegRows for environments with more constraints than threads
+  uint32_t* counters; unsigned long long* timing;
 };
+#ifdef PXB_ENV_TIMING
+#define ENV_T(i) do { __syncthreads(); if (threadIdx.x == 0) { const long long c_ = clock64(); A.timing[(size_t)blockIdx.x * 16 + (i)] = (unsigned long long)(c_ - t_prev); t_prev = c_; } } while (0)
+#else
+#define ENV_T(i) do { } while (0)
+#endif
 
-struct Rows { float4 *rowA, *rowB; uint4* rowC; float4 *ptA, *ptB, *ptC, *frA, *frB, *frC, *frD; uint32_t stride; };
+// Solver rows of ONE constraint in the environment path's compact layout (25 float4 = 400 B; the device-wide path's rows
+// are 31 float4): contact header, per point (raXnI, velMultiplier | rbXnI, separation), the per-point scalars packed by
+// field, the two friction directions shared by both anchors, per friction row (raXnI, error | rbXnI, velMultiplier) and the
+// accumulated impulses.  A thread that owns a constraint for the whole solve keeps this record in REGISTERS.
+struct RegRows {
+  float4 h0;            // normal.xyz, maxPenBias
+  float4 h1;            // invMass0*dom0, invMass1*dom1, staticFriction, dynamicFriction
+  uint4 h2;             // body0, body1 (NONE32 = static), numNormal | numFriction << 8, pair index
+  float4 pa[4], pb[4];  // raXnI.xyz, velMultiplier (= recipResponse) | rbXnI.xyz, separation
+  float4 pc0, pc1, ap;  // biasCoefficient[4], targetVelocity[4], appliedForce[4]
+  float4 t0, t1;        // friction direction 0 .xyz, frictionScale | direction 1 .xyz, biasScale
+  float4 fa[4], fb[4];  // raXnI.xyz, error | rbXnI.xyz, velMultiplier   (row = anchor*2 + direction)
+  float4 fap;           // applied friction impulses[4]
+  uint32_t broken;
+};
+PXB_D float f4get(const float4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+PXB_D void f4set(float4& v, int j, float x) { if (j == 0) v.x = x; else if (j == 1) v.y = x; else if (j == 2) v.z = x; else v.w = x; }
 
-template <int T>
-__device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows R, const uint32_t e, const uint32_t base, const uint32_t nCon, const uint32_t n, const uint32_t* __restrict__ list,
-                                               float4* bLin, float4* bAng, float4* bDLin, float4* bDAng, float4* bIA, float4* bIB, float4* bP, float4* bQ,
-                                               const uint32_t* sPartStart, const uint32_t nPart) {
-  const uint32_t tid = threadIdx.x;
-  // a14: contact prep, one thread per constraint in partition-major order
-  for (uint32_t pos = tid; pos < nCon; pos += T) {
-    const uint32_t k = A.ordered[base + pos]; const uint32_t i = base + A.conPair[base + k];
-    const uint32_t l0 = A.conB0[base + k], l1 = A.conB1[base + k];
-    const uint2 bb = A.pairBodies[i];
-    PrepBodies B;
-    { const float4 p = A.pos[bb.x]; B.f0.p = V3(p.x, p.y, p.z); B.f0.q = Q4(A.quat[bb.x]); B.invMass0 = p.w; const float4 q = A.pos[bb.y]; B.f1.p = V3(q.x, q.y, q.z); B.f1.q = Q4(A.quat[bb.y]); }
-    const bool dyn1 = l1 != NONE32;
-    B.invMass1 = dyn1 ? A.pos[bb.y].w : 0.f;
-    B.pen0 = -A.invInertia[bb.x].w; B.pen1 = dyn1 ? -A.invInertia[bb.y].w : -FLT_MAX;
-    B.linVel0 = V3(bLin[l0]); B.angVel0 = V3(bQ[l0]); B.sI0 = load_sym(bIA[l0], bIB[l0]);
-    if (dyn1) { B.linVel1 = V3(bLin[l1]); B.angVel1 = V3(bQ[l1]); B.sI1 = load_sym(bIA[l1], bIB[l1]); }
-    else { B.linVel1 = V3(0, 0, 0); B.angVel1 = V3(0, 0, 0); B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
-    prep_constraint(pos, R.stride, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.P,
-                    R.rowA, R.rowB, R.rowC, R.ptA, R.ptB, R.ptC, R.frA, R.frB, R.frC, R.frD);
-    A.broken[base + pos] = 0u;
+// a14 into registers: same arithmetic as prep_constraint (createFinalizeSolverContactsStep, DyTGSContactPrep.cpp:1297-1490;
+// friction correlation DyFrictionCorrelation.cpp:56-330).
+__device__ __forceinline__ void prep_constraint_regs(RegRows& r, uint32_t i, uint32_t b0, uint32_t b1, const PrepBodies& B, const float4* __restrict__ cHdr,
+                                                     const float4* __restrict__ cPts, float4* __restrict__ frec, const SolverParams& P) {
+  Contacts con; const float4 h = cHdr[i]; con.normal = V3(h.x, h.y, h.z); con.count = __float_as_int(h.w);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float4 p = cPts[(size_t)i * 4 + j]; con.point[j] = V3(p.x, p.y, p.z); con.sep[j] = p.w; }
+  const xf& f0 = B.f0; const xf& f1 = B.f1;
+  FrictionPatch fp; friction_load(fp, frec);
+  friction_correlate(fp, con, f0, f1, P.staticFriction, P.dynamicFriction, P.restitution, P.correlationDistance, P.frictionOffsetThreshold + P.restDistance);
+  friction_store(fp, frec);
+  const float maxPenBias = fmax_(B.pen0, B.pen1);
+  const v3 linVel0 = B.linVel0, linVel1 = B.linVel1, angVel0 = B.angVel0, angVel1 = B.angVel1;
+  const m33& sI0 = B.sI0; const m33& sI1 = B.sI1;
+  const float invMass0_dom0 = 1.f * B.invMass0, invMass1_dom1 = (-1.f) * B.invMass1;
+  const float scale = fmin_(0.8f, P.biasCoefficient);
+  const float invDtp8 = P.invStepDt * scale, frictionBiasScale = P.invStepDt * scale;
+  const v3 normal = con.normal;
+  const float normalLenSq = adot(normal, normal);
+  const float norVel0 = adot(linVel0, normal), norVel1 = adot(linVel1, normal);
+  const float imn0 = invMass0_dom0 * normalLenSq, imn1 = invMass1_dom1 * normalLenSq;
+  const bool haveFriction = fp.anchorCount != 0;
+  const uint32_t numFriction = haveFriction ? (uint32_t)fp.anchorCount * 2u : 0u;
+  r.h0 = F4(normal, maxPenBias);
+  r.h1 = make_float4(invMass0_dom0, -invMass1_dom1, P.staticFriction, P.dynamicFriction);
+  r.h2 = make_uint4(b0, b1, (uint32_t)con.count | (numFriction << 8), i);
+  r.pc0 = r.pc1 = r.ap = r.fap = make_float4(0, 0, 0, 0); r.t0 = r.t1 = make_float4(0, 0, 0, 0); r.broken = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    r.pa[j] = r.pb[j] = make_float4(0, 0, 0, 0);
+    if (j < con.count) {
+      SPoint s; prep_point(s, con.point[j], con.sep[j], normal, f0.p, f1.p, sI0, sI1, angVel0, angVel1, norVel0, norVel1, imn0, imn1, P, invDtp8);
+      r.pa[j] = F4(s.raXnI, s.velMultiplier); r.pb[j] = F4(s.rbXnI, s.separation);
+      f4set(r.pc0, j, s.biasCoefficient); f4set(r.pc1, j, s.targetVelocity);
+    }
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r.fa[j] = r.fb[j] = make_float4(0, 0, 0, 0);
+  if (haveFriction) {
+    const v3 linVrel = linVel0 - linVel1;
+    const v3 fb1 = V3(0.f, -normal.z, normal.y), fb2 = V3(-normal.y, normal.x, 0.f);
+    const v3 t0Fallback = (0.70710678f > fabsf(normal.x)) ? fb1 : fb2;
+    v3 t0 = linVrel - normal * adot(normal, linVrel);
+    t0 = (adot(t0, t0) > 0.0001f) ? t0 : t0Fallback;
+    t0 = anormalize(t0);
+    const v3 t1 = anormalize(cross(normal, t0));
+    const v3 relTr = f0.p - f1.p;
+    const float frictionScale = (fp.anchorCount == 2) ? 0.5f : 1.f;
+    r.t0 = F4(t0, frictionScale); r.t1 = F4(t1, frictionBiasScale);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (j < fp.anchorCount) {
+        const v3 ra = aqrot(f0.q, fp.body0Anchors[j]), rb = aqrot(f1.q, fp.body1Anchors[j]);
+        const v3 error = (ra - rb) + relTr;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          SFriction f; prep_friction_row(f, ra, rb, error, t == 0 ? t0 : t1, sI0, sI1, imn0, imn1, scale, frictionScale, frictionBiasScale);
+          r.fa[j * 2 + t] = F4(f.raXnI, f.error); r.fb[j * 2 + t] = F4(f.rbXnI, f.velMultiplier);
+        }
+      }
+    }
+  }
+}
+
+// a15 on a register-resident record: same arithmetic and operation order as solve_constraint (solveContact,
+// DyTGSContactPrep.cpp:1581-1873).  Friction rows have targetVel == 0 (prep_friction_row), so `x - 0*t` and `bias - 0` of
+// the reference are the identity and are dropped.
+__device__ __forceinline__ void solve_constraint_regs(RegRows& r, const float minPen, const float elapsedTime, float4* bLin, float4* bAng, const float4* bDLin, const float4* bDAng) {
+  const uint32_t b0 = r.h2.x, b1 = r.h2.y;
+  const int numNormal = (int)(r.h2.z & 0xff), numFriction = (int)((r.h2.z >> 8) & 0xff);
+  const v3 n = V3(r.h0.x, r.h0.y, r.h0.z); const float maxPenBias = r.h0.w;
+  const float invMassA = r.h1.x, invMassB = r.h1.y;
+  v3 linVel0 = V3(bLin[b0]), angState0 = V3(bAng[b0]);
+  const v3 angMotion0 = V3(bDAng[b0]); v3 relMotion = V3(bDLin[b0]);
+  v3 linVel1 = V3(0, 0, 0), angState1 = V3(0, 0, 0), angMotion1 = V3(0, 0, 0);
+  if (b1 != NONE32) { linVel1 = V3(bLin[b1]); angState1 = V3(bAng[b1]); angMotion1 = V3(bDAng[b1]); relMotion = relMotion - V3(bDLin[b1]); }
+  float accum = 0.f;
+  {
+    const v3 nim0 = n * invMassA, nim1 = n * invMassB;
+    const float deltaV = adot(relMotion, n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < numNormal) {
+        const float4 A = r.pa[j], B = r.pb[j];
+        const v3 raXnI = V3(A.x, A.y, A.z), rbXnI = V3(B.x, B.y, B.z);
+        const float deltaAng = adot(angMotion0, raXnI) - adot(angMotion1, rbXnI);
+        const float targetVel = f4get(r.pc1, j);
+        const float deltaBias = (deltaV + deltaAng) - targetVel * elapsedTime;
+        const float sep = fmax_(minPen, B.w + deltaBias);
+        const float bias = fmin_(-maxPenBias, f4get(r.pc0, j) * sep);
+        const v3 dv = (vmul(linVel0, n) + vmul(angState0, raXnI)) - (vmul(linVel1, n) + vmul(angState1, rbXnI));
+        const float normalVel = (dv.x + dv.y) + dv.z;
+        const float biasNV = bias * A.w;
+        const float lambda = biasNV - (normalVel - targetVel) * A.w;
+        const float applied = f4get(r.ap, j);
+        const float dF_ = fmax_(lambda, -applied);
+        const float newForce = fmin_(applied + dF_, FLT_MAX);
+        const float deltaF = newForce - applied;
+        linVel0 = scaleadd(nim0, deltaF, linVel0); linVel1 = negscalesub(nim1, deltaF, linVel1);
+        angState0 = scaleadd(raXnI, deltaF * 1.f, angState0); angState1 = negscalesub(rbXnI, deltaF * 1.f, angState1);
+        f4set(r.ap, j, newForce);
+        accum = accum + newForce;
+      }
+    }
+  }
+  if (numFriction) {
+    const float maxFrictionImpulse = r.h1.z * accum, maxDynFrictionImpulse = r.h1.w * accum;
+    const float frictionScale = r.t0.w, biasScale = r.t1.w;
+    const v3 normal0 = V3(r.t0.x, r.t0.y, r.t0.z), normal1 = V3(r.t1.x, r.t1.y, r.t1.z);
+    bool broken = false;
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+      if (j < numFriction) {
+        const float4 A0 = r.fa[j], B0 = r.fb[j], A1 = r.fa[j + 1], B1 = r.fb[j + 1];
+        const v3 raXnI0 = V3(A0.x, A0.y, A0.z), rbXnI0 = V3(B0.x, B0.y, B0.z), raXnI1 = V3(A1.x, A1.y, A1.z), rbXnI1 = V3(B1.x, B1.y, B1.z);
+        const float applied0 = f4get(r.fap, j), applied1 = f4get(r.fap, j + 1);
+        const float deltaV0 = (adot(raXnI0, angMotion0) - adot(rbXnI0, angMotion1)) + adot(normal0, relMotion);
+        const float deltaV1 = (adot(raXnI1, angMotion0) - adot(rbXnI1, angMotion1)) + adot(normal1, relMotion);
+        const float bias0 = (A0.w + deltaV0) * biasScale, bias1 = (A1.w + deltaV1) * biasScale;
+        const float vm0 = B0.w, vm1 = B1.w;
+        const v3 d0 = (vmul(linVel0, normal0) + vmul(angState0, raXnI0)) - (vmul(linVel1, normal0) + vmul(angState1, rbXnI0));
+        const v3 d1 = (vmul(linVel0, normal1) + vmul(angState0, raXnI1)) - (vmul(linVel1, normal1) + vmul(angState1, rbXnI1));
+        const float normalVel0 = (d0.x + d0.y) + d0.z, normalVel1 = (d1.x + d1.y) + d1.z;
+        const float tmp10 = applied0 - bias0 * vm0, tmp11 = applied1 - bias1 * vm1;
+        const float total0 = tmp10 - normalVel0 * vm0, total1 = tmp11 - normalVel1 * vm1;
+        const float total = sqrtf(total0 * total0 + total1 * total1);
+        const bool clamp = total > (frictionScale * maxFrictionImpulse);
+        const float totalClamped = clamp ? fmin_(frictionScale * maxDynFrictionImpulse, total) : total;
+        const float ratio = (total > 0.f) ? (totalClamped / total) : 0.f;
+        const float new0 = total0 * ratio, new1 = total1 * ratio;
+        broken = broken || clamp;
+        const float dF0 = new0 - applied0, dF1 = new1 - applied1;
+        linVel0 = scaleadd(normal0 * invMassA, dF0, scaleadd(normal1 * invMassA, dF1, linVel0));
+        linVel1 = negscalesub(normal0 * invMassB, dF0, negscalesub(normal1 * invMassB, dF1, linVel1));
+        angState0 = scaleadd(raXnI0, dF0 * 1.f, scaleadd(raXnI1, dF1 * 1.f, angState0));
+        angState1 = negscalesub(rbXnI0, dF0 * 1.f, negscalesub(rbXnI1, dF1 * 1.f, angState1));
+        f4set(r.fap, j, new0); f4set(r.fap, j + 1, new1);
+      }
+    }
+    r.broken = broken ? 1u : 0u;  // hdr->broken is overwritten by every solve call (Store_From_BoolV)
+  }
+  bLin[b0] = F4(linVel0, 0.f); bAng[b0] = F4(angState0, 0.f);
+  if (b1 != NONE32) { bLin[b1] = F4(linVel1, 0.f); bAng[b1] = F4(angState1, 0.f); }
+}
+
+// memory image of RegRows for environments with more constraints than threads: 25 float4 + 1 u32 per constraint, field-major
+struct Rows { float4* f; uint32_t* broken; uint32_t stride; };
+PXB_D void rows_store(const Rows& R, uint32_t k, const RegRows& r) {
+  const size_t s = R.stride; float4* f = R.f + k;
+  f[0] = r.h0; f[s] = r.h1; f[2 * s] = make_float4(__uint_as_float(r.h2.x), __uint_as_float(r.h2.y), __uint_as_float(r.h2.z), __uint_as_float(r.h2.w));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { f[(3 + j) * s] = r.pa[j]; f[(7 + j) * s] = r.pb[j]; f[(16 + j) * s] = r.fa[j]; f[(20 + j) * s] = r.fb[j]; }
+  f[11 * s] = r.pc0; f[12 * s] = r.pc1; f[13 * s] = r.ap; f[14 * s] = r.t0; f[15 * s] = r.t1; f[24 * s] = r.fap; R.broken[k] = r.broken;
+}
+PXB_D void rows_load(const Rows& R, uint32_t k, RegRows& r) {
+  const size_t s = R.stride; const float4* f = R.f + k;
+  r.h0 = f[0]; r.h1 = f[s]; { const float4 c = f[2 * s]; r.h2 = make_uint4(__float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z), __float_as_uint(c.w)); }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { r.pa[j] = f[(3 + j) * s]; r.pb[j] = f[(7 + j) * s]; r.fa[j] = f[(16 + j) * s]; r.fb[j] = f[(20 + j) * s]; }
+  r.pc0 = f[11 * s]; r.pc1 = f[12 * s]; r.ap = f[13 * s]; r.t0 = f[14 * s]; r.t1 = f[15 * s]; r.fap = f[24 * s]; r.broken = R.broken[k];
+}
+PXB_D void rows_store_state(const Rows& R, uint32_t k, const RegRows& r) { const size_t s = R.stride; R.f[13 * s + k] = r.ap; R.f[24 * s + k] = r.fap; R.broken[k] = r.broken; }
+
+struct ConLists { uint32_t *conPair, *b0, *b1, *colour, *ordered; };   // per-constraint scratch of one environment (shared memory, or global when it does not fit)
+
+__device__ __forceinline__ void env_prep_one(const EnvSolveArgs& A, const ConLists& L, uint32_t base, uint32_t pos, const float4* bLin, const float4* bIA, const float4* bIB, const float4* bQ, RegRows& r) {
+  const uint32_t k = L.ordered[pos]; const uint32_t i = base + L.conPair[k];
+  const uint32_t l0 = L.b0[k], l1 = L.b1[k];
+  const uint2 bb = A.pairBodies[i];
+  PrepBodies B;
+  { const float4 p = A.pos[bb.x]; B.f0.p = V3(p.x, p.y, p.z); B.f0.q = Q4(A.quat[bb.x]); B.invMass0 = p.w; const float4 q = A.pos[bb.y]; B.f1.p = V3(q.x, q.y, q.z); B.f1.q = Q4(A.quat[bb.y]); }
+  const bool dyn1 = l1 != NONE32;
+  B.invMass1 = dyn1 ? A.pos[bb.y].w : 0.f;
+  B.pen0 = -A.invInertia[bb.x].w; B.pen1 = dyn1 ? -A.invInertia[bb.y].w : -FLT_MAX;
+  B.linVel0 = V3(bLin[l0]); B.angVel0 = V3(bQ[l0]); B.sI0 = load_sym(bIA[l0], bIB[l0]);
+  if (dyn1) { B.linVel1 = V3(bLin[l1]); B.angVel1 = V3(bQ[l1]); B.sI1 = load_sym(bIA[l1], bIB[l1]); }
+  else { B.linVel1 = V3(0, 0, 0); B.angVel1 = V3(0, 0, 0); B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
+  prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.P);
+}
+// a17: writeBackContact (DyTGSContactPrep.cpp:1875-1937)
+__device__ __forceinline__ void env_writeback_one(const EnvSolveArgs& A, const RegRows& r) {
+  const uint32_t i = r.h2.w; const int numNormal = (int)(r.h2.z & 0xff), numFriction = (int)((r.h2.z >> 8) & 0xff);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) if (j < numNormal) A.cForce[(size_t)i * 4 + j] = f4get(r.ap, j);
+  if (numFriction && r.broken) A.frictions[(size_t)A.pairSlots[i] * PXB_FRICTION_F4 + 1].w = __int_as_float(1);
+}
+template <int T>
+__device__ __forceinline__ void env_integrate_substep(uint32_t n, float stepDt, float4* bLin, float4* bAng, float4* bDLin, float4* bDAng, const float4* bIA, const float4* bIB, float4* bP, float4* bQ) {
+  for (uint32_t b = threadIdx.x; b < n; b += T) {
+    if (!__float_as_uint(bP[b].w)) continue;
+    v3 p = V3(bP[b]); q4 dq = Q4(bQ[b]); v3 dl = V3(bDLin[b]), da = V3(bDAng[b]);
+    integrate_core_step(V3(bLin[b]), V3(bAng[b]), load_sym(bIA[b], bIB[b]), stepDt, p, dq, dl, da);
+    bP[b] = F4(p, __uint_as_float(1u)); bQ[b] = F4(dq); bDLin[b] = F4(dl, 0.f); bDAng[b] = F4(da, 0.f);
+  }
+}
+
+// prep + all TGS iterations + write-back of one environment (iterativeSolveIsland, DyTGSDynamics.cpp:2515-2793, with CTA
+// barriers between partitions).  REG: every thread owns exactly one constraint (nCon <= T) and keeps its rows in registers
+// for the whole solve; otherwise rows stream through the memory image R (global scratch, L2 resident).
+template <int T, bool REG>
+__device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows R, const ConLists L, const uint32_t base, const uint32_t nCon, const uint32_t n,
+                                               float4* bLin, float4* bAng, float4* bDLin, float4* bDAng, float4* bIA, float4* bIB, float4* bP, float4* bQ,
+                                               const uint32_t* sPartStart, const uint32_t nPart, long long& t_prev) {
+  const uint32_t tid = threadIdx.x;
+  RegRows mine;
+  if (REG) { if (tid < nCon) env_prep_one(A, L, base, tid, bLin, bIA, bIB, bQ, mine); }
+  else for (uint32_t pos = tid; pos < nCon; pos += T) { RegRows r; env_prep_one(A, L, base, pos, bLin, bIA, bIB, bQ, r); rows_store(R, pos, r); }
   __syncthreads();
+  ENV_T(4);
   for (uint32_t b = tid; b < n; b += T) bQ[b] = make_float4(0, 0, 0, 1);   // bQ carried the unconstrained angular velocity during prep
   __syncthreads();
-  // a15/a16: iterativeSolveIsland (DyTGSDynamics.cpp:2515-2793) with CTA barriers between partitions
   const float stepDt = A.P.stepDt;
   float elapsed = 0.f;
   for (uint32_t it = 0; it < A.posIters + A.velIters; ++it) {
@@ -167,40 +387,39 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
     const float minPen = vel ? 0.f : -FLT_MAX;
     for (uint32_t p = 0; p < nPart; ++p) {
       const uint32_t pb = sPartStart[p], pe = sPartStart[p + 1];
-      for (uint32_t k = pb + tid; k < pe; k += T)
-        solve_constraint(k, R.stride, minPen, elapsed, R.rowA, R.rowB, R.rowC, R.ptA, R.ptB, R.ptC, R.frA, R.frB, R.frC, R.frD, bLin, bAng, bDLin, bDAng, A.broken + base);
+      if (REG) { if (tid >= pb && tid < pe) solve_constraint_regs(mine, minPen, elapsed, bLin, bAng, bDLin, bDAng); }
+      else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_regs(r, minPen, elapsed, bLin, bAng, bDLin, bDAng); rows_store_state(R, k, r); }
       __syncthreads();
     }
     if (!vel) {
-      for (uint32_t b = tid; b < n; b += T) {
-        if (!__float_as_uint(bP[b].w)) continue;
-        v3 p = V3(bP[b]); q4 dq = Q4(bQ[b]); v3 dl = V3(bDLin[b]), da = V3(bDAng[b]);
-        integrate_core_step(V3(bLin[b]), V3(bAng[b]), load_sym(bIA[b], bIB[b]), stepDt, p, dq, dl, da);
-        bP[b] = F4(p, __uint_as_float(1u)); bQ[b] = F4(dq); bDLin[b] = F4(dl, 0.f); bDAng[b] = F4(da, 0.f);
-      }
+      env_integrate_substep<T>(n, stepDt, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ);
       elapsed += stepDt;
       __syncthreads();
     }
   }
-  // a17: writeBackContact
-  for (uint32_t pos = tid; pos < nCon; pos += T) {
-    const uint4 rc = R.rowC[pos]; const uint32_t i = rc.w; const uint32_t numNormal = rc.z & 0xff, numFriction = (rc.z >> 8) & 0xff;
-    for (uint32_t j = 0; j < numNormal; ++j) A.cForce[(size_t)i * 4 + j] = R.ptC[(size_t)j * R.stride + pos].w;
-    if (numFriction && A.broken[base + pos]) A.frictions[(size_t)A.pairSlots[i] * PXB_FRICTION_F4 + 1].w = __int_as_float(1);
-  }
+  ENV_T(5);
+  if (REG) { if (tid < nCon) env_writeback_one(A, mine); }
+  else for (uint32_t pos = tid; pos < nCon; pos += T) { RegRows r; rows_load(R, pos, r); env_writeback_one(A, r); }
 }
 
+// dynamic shared memory of k_env_solve (host mirror: env_solve_smem in pxb_engine.cu):
+//   8 x maxList float4 body state | u32: 3 x maxList body masks, 5 x conCap constraint lists
+// conCap = list capacity (pairs of the environment); environments with more pairs keep their lists in global scratch.
 template <int T>
-__global__ void __launch_bounds__(T) k_env_solve(const EnvSolveArgs A) {
+__global__ void __launch_bounds__(T, (T <= 64 ? 6 : (T <= 128 ? 3 : 1))) k_env_solve(const EnvSolveArgs A) {
   extern __shared__ float4 envSmem[];
   __shared__ uint32_t sPartCnt[MAX_PARTITIONS + 1], sPartStart[MAX_PARTITIONS + 1], sWarp[T / 32 + 1], sMisc[4];
   const uint32_t e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ls = A.envStart[e], n = A.envStart[e + 1] - ls; const uint32_t* list = A.envList + ls;
   const uint2 sg = A.seg[e]; const uint32_t base = sg.x, m = sg.y;
-  const uint32_t nb = A.maxList;
+  const uint32_t nb = A.maxList, lc = A.conCap;
   float4 *bLin = envSmem, *bAng = bLin + nb, *bDLin = bAng + nb, *bDAng = bDLin + nb, *bIA = bDAng + nb, *bIB = bIA + nb, *bP = bIB + nb, *bQ = bP + nb;
-  float4* rowsSmem = bQ + nb;
-  uint32_t* bMask = reinterpret_cast<uint32_t*>(rowsSmem + (size_t)31 * A.conCap); uint32_t* bFirst = bMask + nb; uint32_t* bStat = bFirst + nb;
+  uint32_t* bMask = reinterpret_cast<uint32_t*>(bQ + nb); uint32_t* bFirst = bMask + nb; uint32_t* bStat = bFirst + nb;
+  uint32_t* sLists = bStat + nb;
+  ConLists L;
+  if (m <= lc) { L.conPair = sLists; L.b0 = sLists + lc; L.b1 = sLists + 2 * lc; L.colour = sLists + 3 * lc; L.ordered = sLists + 4 * lc; }
+  else { L.conPair = A.conPair + base; L.b0 = A.conB0 + base; L.b1 = A.conB1 + base; L.colour = A.conColour + base; L.ordered = A.ordered + base; }
+  long long t_prev = clock64();
   // a12: preIntegrateBodies (DyTGSDynamics.cpp:992-1021) into shared memory
   for (uint32_t b = tid; b < n; b += T) {
     const uint32_t a = list[b];
@@ -220,6 +439,7 @@ __global__ void __launch_bounds__(T) k_env_solve(const EnvSolveArgs A) {
   for (uint32_t p = tid; p < MAX_PARTITIONS + 1; p += T) sPartCnt[p] = 0;
   if (tid == 0) { sMisc[0] = 0; sMisc[1] = 0; }
   __syncthreads();
+  ENV_T(0);
   // constraint list = this environment's pairs that produced contacts, in ascending key order (ordered compaction)
   uint32_t nCon = 0;
   for (uint32_t t0 = 0; t0 < m; t0 += T) {
@@ -238,13 +458,14 @@ __global__ void __launch_bounds__(T) k_env_solve(const EnvSolveArgs A) {
       const uint32_t k = off + __popc(bal & ((1u << lane) - 1u));
       const uint2 bb = A.pairBodies[base + t];
       const uint32_t l0 = A.actorLocal[bb.x]; const uint32_t l1 = (A.geomFlags[bb.y] & 0x100u) ? A.actorLocal[bb.y] : NONE32;
-      A.conPair[base + k] = t; A.conB0[base + k] = l0; A.conB1[base + k] = l1; A.conColour[base + k] = NONE32;
+      L.conPair[k] = t; L.b0[k] = l0; L.b1[k] = l1; L.colour[k] = NONE32;
       bP[l0].w = __uint_as_float(1u); if (l1 != NONE32) bP[l1].w = __uint_as_float(1u);   // hasConstraints (benign same-value races)
       if (l1 == NONE32) atomicAdd(&bStat[l0], 1u);
     }
     nCon += tot;
     __syncthreads();
   }
+  ENV_T(1);
   // a13: first-fit colouring in constraint order (classifyConstraintDesc, DyConstraintPartition.cpp:475-568).  A constraint
   // is ready once it is the lowest-numbered uncoloured constraint on both of its bodies; ready constraints are body-disjoint.
   for (;;) {
@@ -252,62 +473,58 @@ __global__ void __launch_bounds__(T) k_env_solve(const EnvSolveArgs A) {
     __syncthreads();
     int undone = 0;
     for (uint32_t k = tid; k < nCon; k += T) {
-      const uint32_t l1 = A.conB1[base + k];
-      if (l1 == NONE32 || A.conColour[base + k] != NONE32) continue;
-      atomicMin(&bFirst[A.conB0[base + k]], k); atomicMin(&bFirst[l1], k); undone = 1;
+      const uint32_t l1 = L.b1[k];
+      if (l1 == NONE32 || L.colour[k] != NONE32) continue;
+      atomicMin(&bFirst[L.b0[k]], k); atomicMin(&bFirst[l1], k); undone = 1;
     }
     if (!__syncthreads_or(undone)) break;
     for (uint32_t k = tid; k < nCon; k += T) {
-      const uint32_t l1 = A.conB1[base + k];
-      if (l1 == NONE32 || A.conColour[base + k] != NONE32) continue;
-      const uint32_t l0 = A.conB0[base + k];
+      const uint32_t l1 = L.b1[k];
+      if (l1 == NONE32 || L.colour[k] != NONE32) continue;
+      const uint32_t l0 = L.b0[k];
       if (bFirst[l0] != k || bFirst[l1] != k) continue;
       const uint32_t ma = bMask[l0], mb = bMask[l1]; const uint32_t comb = ~ma & ~mb;
       uint32_t col = 31;
       if (comb) col = __ffs(comb) - 1; else atomicOr(&A.counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
-      A.conColour[base + k] = col; bMask[l0] = ma | (1u << col); bMask[l1] = mb | (1u << col);
+      L.colour[k] = col; bMask[l0] = ma | (1u << col); bMask[l1] = mb | (1u << col);
     }
     __syncthreads();
   }
+  ENV_T(2);
   // static contacts of a body go to partitions maxDynamicColour(body) + rank among the body's static contacts (:203-262)
   for (uint32_t k = tid; k < nCon; k += T) {
     uint32_t col;
-    if (A.conB1[base + k] == NONE32) {
-      const uint32_t l0 = A.conB0[base + k]; uint32_t rank = 0;
-      if (bStat[l0] > 1) for (uint32_t kk = 0; kk < k; ++kk) if (A.conB1[base + kk] == NONE32 && A.conB0[base + kk] == l0) ++rank;
+    if (L.b1[k] == NONE32) {
+      const uint32_t l0 = L.b0[k]; uint32_t rank = 0;
+      if (bStat[l0] > 1) for (uint32_t kk = 0; kk < k; ++kk) if (L.b1[kk] == NONE32 && L.b0[kk] == l0) ++rank;
       const uint32_t mk = bMask[l0]; col = (mk ? 32u - __clz(mk) : 0u) + rank;
       if (col >= MAX_PARTITIONS) { col = MAX_PARTITIONS - 1; atomicOr(&A.counters[C_ERROR], (uint32_t)E_PARTITION_OVERFLOW); }
-      A.conColour[base + k] = col;
-    } else col = A.conColour[base + k];
+      L.colour[k] = col;
+    } else col = L.colour[k];
     atomicAdd(&sPartCnt[col], 1u);
   }
   __syncthreads();
   if (tid == 0) {
     uint32_t s = 0, np = 0;
-    for (uint32_t p = 0; p < MAX_PARTITIONS; ++p) { const uint32_t c = sPartCnt[p]; sPartStart[p] = s; sPartCnt[p] = s; s += c; if (c) np = p + 1; }
-    sPartStart[MAX_PARTITIONS] = s; sMisc[0] = np;
+    for (uint32_t p = 0; p < MAX_PARTITIONS; ++p) { const uint32_t c = sPartCnt[p]; sPartStart[p] = s; sPartCnt[p] = s; s += c; if (c) np = p + 1; if (s == nCon) { for (uint32_t q = p + 1; q <= MAX_PARTITIONS; ++q) sPartStart[q] = s; break; } }
+    sMisc[0] = np;
     if (nCon) { atomicAdd(&A.counters[C_NCON], nCon); atomicMax(&A.counters[C_NPART], np); atomicMax(&A.counters[C_MAXCONENV], nCon); }
+    if (m) atomicMax(&A.counters[C_MAXPAIRENV], m);
   }
   __syncthreads();
   const uint32_t nPart = sMisc[0];
-  for (uint32_t k = tid; k < nCon; k += T) A.ordered[base + atomicAdd(&sPartCnt[A.conColour[base + k]], 1u)] = k;
+  for (uint32_t k = tid; k < nCon; k += T) L.ordered[atomicAdd(&sPartCnt[L.colour[k]], 1u)] = k;
   __syncthreads();
+  ENV_T(3);
   if (nCon) {
-    Rows R;
-    if (nCon <= A.conCap) {
-      const uint32_t c = A.conCap; float4* r = rowsSmem;
-      R.rowA = r; R.rowB = r + c; R.rowC = reinterpret_cast<uint4*>(r + 2 * c); R.ptA = r + 3 * c; R.ptB = r + 7 * c; R.ptC = r + 11 * c;
-      R.frA = r + 15 * c; R.frB = r + 19 * c; R.frC = r + 23 * c; R.frD = r + 27 * c; R.stride = c;
-      env_solve_body<T>(A, R, e, base, nCon, n, list, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart);
-    } else {   // oversize environment: rows stream through global memory (L2), same arithmetic
-      R.rowA = A.rowA + base; R.rowB = A.rowB + base; R.rowC = A.rowC + base; R.ptA = A.ptA + base; R.ptB = A.ptB + base; R.ptC = A.ptC + base;
-      R.frA = A.frA + base; R.frB = A.frB + base; R.frC = A.frC + base; R.frD = A.frD + base; R.stride = A.cap;
-      env_solve_body<T>(A, R, e, base, nCon, n, list, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart);
-    }
+    Rows R; R.f = A.rowScratch + base; R.broken = A.broken + base; R.stride = A.cap;
+    if (nCon <= T) env_solve_body<T, true>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, t_prev);
+    else env_solve_body<T, false>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, t_prev);
   } else {
     for (uint32_t b = tid; b < n; b += T) bQ[b] = make_float4(0, 0, 0, 1);
   }
   __syncthreads();
+  ENV_T(6);
   // a18: copyBackBodies (DyTGSDynamics.cpp:1549-1580); bodies without constraints take one full-dt step (:2573-2577)
   for (uint32_t b = tid; b < n; b += T) {
     const uint32_t a = list[b];
@@ -321,4 +538,5 @@ __global__ void __launch_bounds__(T) k_env_solve(const EnvSolveArgs A) {
     A.pos[a] = make_float4(p.x, p.y, p.z, invMass); A.quat[a] = F4(q);
     A.linVel[a] = F4(lv, 0.f); A.angVel[a] = F4(mmul(sI, as), 0.f);
   }
+  ENV_T(7);
 }

@@ -112,7 +112,7 @@ def _ptr(a):
 class Scene:
     """One simulation scene resident on one GPU (one PxScene <-> one device, ScScene.cpp:718)."""
 
-    def __init__(self, scene: _scenes.Scene, device: int = 0, max_pairs: int = 0, max_actors: int = 0, env_path: bool = True, env_row_cap: int = 0):
+    def __init__(self, scene: _scenes.Scene, device: int = 0, max_pairs: int = 0, max_actors: int = 0, env_path: bool = True, env_row_cap: int = 0, env_threads: int = 0):
         lib = load_library()
         self._lib = lib
         h = scene.header
@@ -131,6 +131,7 @@ class Scene:
         d.device = int(device)
         d.reserved[1] = 0 if env_path else 1   # PXB_FLAG_NO_ENV_PATH
         d.reserved[2] = int(env_row_cap)
+        d.reserved[3] = int(env_threads)
         self.dt = float(h["dt"])
         self._h = ctypes.c_void_p()
         _check(lib, lib.pxb_scene_create(ctypes.byref(d), ctypes.byref(self._h)))

@@ -235,7 +235,7 @@ def test_env_path_matches_oracle_ragged(oracle):
         cpu.setStates(sg)
 
 
-def test_env_path_falls_back_when_order_is_given_and_small_row_store():
+def test_env_path_falls_back_when_order_is_given_and_oversize_environments():
     """(1) a host constraint order switches a running scene from the environment path to the device-wide path (pair list
     converted, manifolds kept); (2) environments larger than the shared-memory row store use global rows, same results."""
     sc = scenes.env_grid_stacks(n_envs=9, jitter=0.01)
@@ -250,7 +250,10 @@ def test_env_path_falls_back_when_order_is_given_and_small_row_store():
         assert not a.uses_env_path
         assert np.array_equal(a.getCreatedPairs(), b.getCreatedPairs()) and len(a.getCreatedPairs()) == 0
         assert np.array_equal(a.getStates(), b.getStates()), f"step {t}"
-    c, d = engine.Scene(sc, env_row_cap=8), engine.Scene(sc)   # 64 constraints per environment > 8 rows in shared memory
+    # 64 constraints per environment: 32 threads per CTA -> rows stream through global scratch instead of registers;
+    # 8 list slots -> constraint lists in global scratch instead of shared memory
+    c, c2, d = engine.Scene(sc, env_threads=32), engine.Scene(sc, env_row_cap=8), engine.Scene(sc)
     for t in range(20):
-        c.step(); d.step()
+        c.step(); c2.step(); d.step()
         assert c.uses_env_path and np.array_equal(c.getStates(), d.getStates()) and np.array_equal(c.getContacts(), d.getContacts()), f"step {t}"
+        assert c2.uses_env_path and np.array_equal(c2.getStates(), d.getStates()) and np.array_equal(c2.getContacts(), d.getContacts()), f"step {t}"
