@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 METRIC = "rigid-body-steps/sec"
 UNIT = "bodies*steps/s"
 BOXES_PER_ENV = 64
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_env_solve launch at config 2 (4096 envs x 64 boxes), from the committed
+# ncu --set full capture profiles/r01_env_kernels_full_raw.csv (a profiler number: quoted, never timed under ncu)
+ENV_SOLVE_DRAM_BYTES_PER_LAUNCH = 108_990_720
 
 
 def measured_peaks():
@@ -252,20 +255,36 @@ def bench_ours(args):
         C = 4 * P                            # contact points (box-plane / box-box face manifolds: 4)
         F = 4 * P                            # friction rows (2 anchors x 2 tangents)
         iters = int(sc.header["posIters"]) + int(sc.header["velIters"])
-        # solver bytes per iteration = 116 P + 60 C + 48 F + 72 N_b
+        # SURVEY.md §8d algorithmic bytes: solver per iteration 116 P + 60 C + 48 F + 72 N_b; contact prep reads 64 P + 16 C + 2*112 P
+        # and writes 116 P + 56 C + 44 F; integration 132 N_b.
         solve_bytes = (116 * P + 60 * C + 48 * F + 72 * nb) * iters
+        prep_bytes = (64 * P + 16 * C + 224 * P) + (116 * P + 56 * C + 44 * F)
+        integ_bytes = 132 * nb
         solve_ms = stage_acc["solve"] / prof_steps
-        achieved = solve_bytes / (solve_ms / 1e3) / 1e9
+        if scene.uses_env_path:
+            # environment path: ONE kernel does pre-integration, colouring, prep, all TGS iterations, write-back and integration
+            kernel_name = "k_env_solve (a12-a18 fused: prep + all TGS iterations + integration, one CTA per environment, rows in registers)"
+            kernel_bytes = prep_bytes + solve_bytes + integ_bytes
+            note = ("algorithmic bytes = SURVEY 8d prep + 5 solver iterations + integration; the kernel keeps every solver row on chip (registers), "
+                    "so only contacts, friction patches and body state cross HBM once: see `traffic` (ncu dram bytes per launch, profiles/r01_env_kernels_full_raw.csv)")
+            traffic = ENV_SOLVE_DRAM_BYTES_PER_LAUNCH if n_envs == 4096 else None
+        else:
+            kernel_name = "k_solve (all TGS iterations, one cooperative launch)"
+            kernel_bytes = solve_bytes
+            note = "device-wide path: rows re-streamed from HBM every iteration"
+            traffic = None
+        achieved = kernel_bytes / (solve_ms / 1e3) / 1e9
         stages = {k: round(v / prof_steps, 4) for k, v in stage_acc.items()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"config 2: {n_envs} envs x {BOXES_PER_ENV} boxes = {nb} bodies per GPU, shared ground plane, GPU broadphase + TGS 4 pos/1 vel iterations, 60 Hz",
-                       "bodies_total": total_bodies, "constraints_per_gpu": P, "partitions": scene.num_partitions,
+                       "bodies_total": total_bodies, "constraints_per_gpu": P, "partitions": scene.num_partitions, "path": "environment (pxb_env.cuh)" if scene.uses_env_path else "device-wide",
                        "timing": "CUDA events on the scene stream per step, max over ranks; L2 flushed (256 MiB memset) between timed steps",
                        "multi_gpu": "env-partitioned, one scene per GPU, per-step NCCL all-gather of the packed pose+linear+angular velocity tensor (13 floats/body)" if world > 1 else "single scene"},
-            "roofline": {"kernel": "k_solve (all TGS iterations, one cooperative launch)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes, "kernel_ms": solve_ms},
+            "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kernel_bytes, "kernel_ms": solve_ms,
+                         "dram_frac": (traffic / (solve_ms / 1e3) / 1e9 / peak) if traffic else None, "note": note},
             "stage_ms": stages,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nb * 24), "d2h_bytes_per_step": int(nb * (28 + 24)), "steps": e2e_steps,
                     "api": "pxb_set_rigid_dynamic_data(lin,ang) -> pxb_scene_simulate -> pxb_scene_fetch_results -> pxb_get_rigid_dynamic_data(pose,lin,ang), pinned host buffers"},

@@ -88,7 +88,7 @@ struct PxbScene {
   // environment-partitioned path (pxb_env.cuh)
   bool envEligible = false, envActive = false, envDisabled = false, everStepped = false; uint32_t ringMask = 0;
   uint32_t nEnv = 0, envMaxList = 0, envConCap = 0, envConCapForced = 0, envThreadsForced = 0, hMaxConEnv = 0, hMaxPairEnv = 0, envSolveThreads = 64;
-  uint32_t *envStart = 0, *envList = 0, *actorLocal = 0; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
+  uint32_t *envStart = 0, *envList = 0, *actorLocal = 0, *slotColour = 0; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
 };
 
 static thread_local std::string g_err;
@@ -791,7 +791,7 @@ static int scene_alloc(PxbScene* s) {
   k_init_freelist<<<cdiv((uint32_t)Pn, 256), 256, 0, s->stream>>>((uint32_t)Pn, s->freeList);
   const uint32_t top = (uint32_t)Pn;   // ring of free persistent slots: head = 0, tail = Pn
   CK(cudaMemcpyAsync(s->counters + C_FREE_TAIL, &top, 4, cudaMemcpyHostToDevice, s->stream));
-  CK(dalloc(s->actorLocal, A)); for (int k = 0; k < 2; ++k) { CK(dalloc(s->envSeg[k], A)); CK(cudaMemsetAsync(s->envSeg[k], 0, sizeof(uint2) * A, s->stream)); }
+  CK(dalloc(s->actorLocal, A)); CK(dalloc(s->slotColour, Pn)); CK(cudaMemsetAsync(s->slotColour, 0xff, 4 * Pn, s->stream)); for (int k = 0; k < 2; ++k) { CK(dalloc(s->envSeg[k], A)); CK(cudaMemsetAsync(s->envSeg[k], 0, sizeof(uint2) * A, s->stream)); }
   CK(cudaStreamSynchronize(s->stream));
   return PXB_OK;
 }
@@ -839,7 +839,7 @@ PXB_API void pxb_scene_release(PxbScene* s) {
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
-                  s->envStart, s->envList, s->actorLocal, s->envSeg[0], s->envSeg[1]};
+                  s->envStart, s->envList, s->actorLocal, s->slotColour, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
   cudaStreamDestroy(s->stream);
@@ -1035,7 +1035,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     A.nEnv = s->nEnv; A.maxList = s->envMaxList; A.bitsA = s->bitsA; A.cap = s->capPairs; A.ringMask = s->ringMask; A.externalTight = externalTight ? 1 : 0; A.contactOffset = s->desc.contactOffset;
     A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight;
     A.oldKeys = s->pairKeys[prev]; A.oldSlots = s->pairSlots[prev]; A.oldSeg = s->envSeg[prev]; A.newKeys = s->pairKeys[cur]; A.newSlots = s->pairSlots[cur]; A.newSeg = s->envSeg[cur];
-    A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions;
+    A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions; A.slotColour = s->slotColour;
     const size_t smem = (size_t)ENV_BP_WARPS * (s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t)) + ENV_BP_STAGE * sizeof(uint64_t));
     k_env_bp<<<cdiv(s->nEnv, ENV_BP_WARPS), 32 * ENV_BP_WARPS, smem, st>>>(A); s->launches++;
     LAUNCH(k_clamp_count, 1, 32, s->counters, s->capPairs, s->nPairsDev + cur);
@@ -1114,7 +1114,7 @@ static int enqueue_step(PxbScene* s, float dt) {
     A.pairSlots = s->pairSlots[cur]; A.pairBodies = s->pairBodies; A.cHdr = s->cHdr; A.cPts = s->cPts; A.cForce = s->cForce; A.frictions = s->frictions;
     A.conPair = s->conPair; A.conB0 = s->conB0; A.conB1 = s->conB1; A.conColour = s->conColour; A.ordered = s->ordered; A.broken = s->conDone;
     A.rowScratch = s->ptA;   // ptA|ptB|ptC|frA|frB|frC|frD are ONE allocation of 28 x cap float4 (scene_alloc); the environment path uses 25 of them
-    A.counters = s->counters; A.timing = s->envTiming;
+    A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap);
     if (s->envSolveThreads == 32) k_env_solve<32><<<s->nEnv, 32, smem, st>>>(A);
     else if (s->envSolveThreads == 64) k_env_solve<64><<<s->nEnv, 64, smem, st>>>(A);

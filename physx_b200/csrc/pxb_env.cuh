@@ -26,7 +26,7 @@ struct EnvBpArgs {
   const float4 *pos, *quat, *dims; const uint32_t *geomFlags, *envId; float* tight;
   const uint64_t* oldKeys; const uint32_t* oldSlots; const uint2* oldSeg;
   uint64_t* newKeys; uint32_t* newSlots; uint2* newSeg;
-  uint32_t *counters, *freeRing; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions;
+  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions;
 };
 
 #define ENV_BP_STAGE 256   // pair keys staged per warp in shared memory before the segment base is known
@@ -105,12 +105,14 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
   }
   __syncwarp();
   // a7: pair lifecycle against last frame's segment of the same environment (both sorted)
-  const uint2 os = A.oldSeg[e]; const uint32_t ob = os.x, oc = os.y;
+  const uint2 os = A.oldSeg[e]; const uint32_t ob = os.x, oc = os.y & 0x7fffffffu;
+  bool same = cnt == oc;   // segment identical to last frame's (steady state): k_env_solve may reuse last frame's colouring
   for (uint32_t t = lane; t < cnt; t += 32) {
     const uint64_t k = A.newKeys[base + t];
     uint32_t slot = NONE32;
     if (t < oc && A.oldKeys[ob + t] == k) slot = A.oldSlots[ob + t];
-    else { const uint32_t p = lower_bound_u64(A.oldKeys + ob, oc, k); if (p < oc && A.oldKeys[ob + p] == k) slot = A.oldSlots[ob + p]; }
+    else {
+      same = false; const uint32_t p = lower_bound_u64(A.oldKeys + ob, oc, k); if (p < oc && A.oldKeys[ob + p] == k) slot = A.oldSlots[ob + p]; }
     if (slot == NONE32) {
       // pops only consume ring entries that existed when the step began (C_FREE_SNAP), pushes of this step land behind them
       const uint32_t h = atomicAdd(&A.counters[C_FREE_HEAD], 1u);
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
       m[0] = make_float4(__int_as_float(0), FLT_MAX, FLT_MAX, FLT_MAX); m[1] = make_float4(0, 0, 0, 1); m[2] = make_float4(0, 0, 0, 1); m[3] = make_float4(0, 0, 0, 1);
       float4* f = A.frictions + (size_t)slot * PXB_FRICTION_F4;
       f[0] = make_float4(0, 0, 0, __int_as_float(0)); f[1] = make_float4(0, 0, 0, __int_as_float(0)); f[2] = make_float4(0, 0, 0, __int_as_float(0));
+      A.slotColour[slot] = NONE32;
     }
     A.newSlots[base + t] = slot;
   }
@@ -132,7 +135,8 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
     A.freeRing[atomicAdd(&A.counters[C_FREE_TAIL], 1u) & A.ringMask] = A.oldSlots[ob + t];
     A.deletedKeys[atomicAdd(&A.counters[C_NDELETED], 1u)] = k;
   }
-  if (lane == 0) A.newSeg[e] = make_uint2(base, cnt);
+  same = __all_sync(0xffffffffu, same);
+  if (lane == 0) A.newSeg[e] = make_uint2(base, cnt | (same ? 0x80000000u : 0u));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -142,6 +146,7 @@ struct EnvSolveArgs {
   float4 *pos, *quat, *linVel, *angVel; const float4 *invInertia, *damp; const uint32_t* geomFlags;
   const uint32_t* pairSlots; const uint2* pairBodies; const float4 *cHdr, *cPts; float* cForce; float4* frictions;
   uint32_t *conPair, *conB0, *conB1, *conColour, *ordered, *broken;   // per-pair-index scratch (global, L2 resident)
+  uint32_t* slotColour;   // per persistent pair slot: partition of the pair's constraint last frame (NONE32 = no contacts)
   float4* rowScratch;   // 25 x cap float4, field-major: memory image of RegRows for environments with more constraints than threads
   uint32_t* counters; unsigned long long* timing;
 };
@@ -405,13 +410,16 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
 // dynamic shared memory of k_env_solve (host mirror: env_solve_smem in pxb_engine.cu):
 //   8 x maxList float4 body state | u32: 3 x maxList body masks, 5 x conCap constraint lists
 // conCap = list capacity (pairs of the environment); environments with more pairs keep their lists in global scratch.
+#ifndef PXB_ENV_CTAS64
+#define PXB_ENV_CTAS64 6
+#endif
 template <int T>
-__global__ void __launch_bounds__(T, (T <= 64 ? 6 : (T <= 128 ? 3 : 1))) k_env_solve(const EnvSolveArgs A) {
+__global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB_ENV_CTAS64 / 2 : 1))) k_env_solve(const EnvSolveArgs A) {
   extern __shared__ float4 envSmem[];
   __shared__ uint32_t sPartCnt[MAX_PARTITIONS + 1], sPartStart[MAX_PARTITIONS + 1], sWarp[T / 32 + 1], sMisc[4];
   const uint32_t e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ls = A.envStart[e], n = A.envStart[e + 1] - ls; const uint32_t* list = A.envList + ls;
-  const uint2 sg = A.seg[e]; const uint32_t base = sg.x, m = sg.y;
+  const uint2 sg = A.seg[e]; const uint32_t base = sg.x, m = sg.y & 0x7fffffffu; const bool sameSeg = (sg.y >> 31) != 0;
   const uint32_t nb = A.maxList, lc = A.conCap;
   float4 *bLin = envSmem, *bAng = bLin + nb, *bDLin = bAng + nb, *bDAng = bDLin + nb, *bIA = bDAng + nb, *bIB = bIA + nb, *bP = bIB + nb, *bQ = bP + nb;
   uint32_t* bMask = reinterpret_cast<uint32_t*>(bQ + nb); uint32_t* bFirst = bMask + nb; uint32_t* bStat = bFirst + nb;
@@ -441,12 +449,18 @@ __global__ void __launch_bounds__(T, (T <= 64 ? 6 : (T <= 128 ? 3 : 1))) k_env_s
   __syncthreads();
   ENV_T(0);
   // constraint list = this environment's pairs that produced contacts, in ascending key order (ordered compaction)
-  uint32_t nCon = 0;
+  // Steady state: when the pair segment and the contact/no-contact state of every pair are unchanged, the ordered constraint
+  // list is last frame's, so last frame's partitions (kept per persistent pair slot) are the first-fit result again.
+  uint32_t nCon = 0; int stale = sameSeg ? 0 : 1;
   for (uint32_t t0 = 0; t0 < m; t0 += T) {
-    const uint32_t t = t0 + tid; bool f = false;
+    const uint32_t t = t0 + tid; bool f = false; uint32_t prevCol = NONE32;
     if (t < m) {
       f = __float_as_int(A.cHdr[base + t].w) > 0;
-      if (!f) A.frictions[(size_t)A.pairSlots[base + t] * PXB_FRICTION_F4 + 2].w = __int_as_float(0);   // no contacts: the friction patch is dropped
+      const uint32_t slot = A.pairSlots[base + t];
+      prevCol = A.slotColour[slot];
+      if (f != (prevCol != NONE32)) stale = 1;
+      if (!f) { A.frictions[(size_t)slot * PXB_FRICTION_F4 + 2].w = __int_as_float(0);   // no contacts: the friction patch is dropped
+                if (prevCol != NONE32) A.slotColour[slot] = NONE32; }
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, f);
     if (lane == 0) sWarp[warp] = __popc(bal);
@@ -458,14 +472,18 @@ __global__ void __launch_bounds__(T, (T <= 64 ? 6 : (T <= 128 ? 3 : 1))) k_env_s
       const uint32_t k = off + __popc(bal & ((1u << lane) - 1u));
       const uint2 bb = A.pairBodies[base + t];
       const uint32_t l0 = A.actorLocal[bb.x]; const uint32_t l1 = (A.geomFlags[bb.y] & 0x100u) ? A.actorLocal[bb.y] : NONE32;
-      L.conPair[k] = t; L.b0[k] = l0; L.b1[k] = l1; L.colour[k] = NONE32;
+      L.conPair[k] = t; L.b0[k] = l0; L.b1[k] = l1; L.colour[k] = prevCol;
       bP[l0].w = __uint_as_float(1u); if (l1 != NONE32) bP[l1].w = __uint_as_float(1u);   // hasConstraints (benign same-value races)
       if (l1 == NONE32) atomicAdd(&bStat[l0], 1u);
     }
     nCon += tot;
     __syncthreads();
   }
+  const bool recolour = __syncthreads_or(stale) != 0;
   ENV_T(1);
+  if (recolour) {
+  for (uint32_t k = tid; k < nCon; k += T) L.colour[k] = NONE32;
+  __syncthreads();
   // a13: first-fit colouring in constraint order (classifyConstraintDesc, DyConstraintPartition.cpp:475-568).  A constraint
   // is ready once it is the lowest-numbered uncoloured constraint on both of its bodies; ready constraints are body-disjoint.
   for (;;) {
@@ -501,8 +519,10 @@ __global__ void __launch_bounds__(T, (T <= 64 ? 6 : (T <= 128 ? 3 : 1))) k_env_s
       if (col >= MAX_PARTITIONS) { col = MAX_PARTITIONS - 1; atomicOr(&A.counters[C_ERROR], (uint32_t)E_PARTITION_OVERFLOW); }
       L.colour[k] = col;
     } else col = L.colour[k];
-    atomicAdd(&sPartCnt[col], 1u);
+    A.slotColour[A.pairSlots[base + L.conPair[k]]] = col;
   }
+  }   // recolour
+  for (uint32_t k = tid; k < nCon; k += T) atomicAdd(&sPartCnt[L.colour[k]], 1u);
   __syncthreads();
   if (tid == 0) {
     uint32_t s = 0, np = 0;

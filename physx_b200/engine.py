@@ -15,7 +15,7 @@ import numpy as np
 
 from . import scenes as _scenes
 
-_LIB_NAME = "libphysx_b200.so"
+_LIB_NAME = os.environ.get("PXB_LIB", "libphysx_b200.so")   # PXB_LIB: tooling hook to load an experimental build
 _lib = None
 
 # every symbol include/physx_b200.h declares (checked by tests/test_abi.py)
