@@ -143,24 +143,18 @@ def bench_ours(args):
     scene = engine.Scene(sc, device=local)
     nb = scene.num_dynamic
     stream = torch.cuda.ExternalStream(scene.stream(), device=dev)
-    gathers = {}
+    gather = None
     if dist is not None:
-        # one packed [n, 13] tensor (pose + linear + angular velocity) -> ONE NCCL all-gather per step
-        gathers["packed"] = multi_gpu.StateGather(dist, nb, 13, dev)
+        # one packed [n, 13] tensor (pose + linear + angular velocity) -> ONE NCCL all-gather per step, double-buffered on a
+        # communication stream so that it overlaps the next step's kernels
+        gather = multi_gpu.PipelinedStateGather(dist, nb, 13, dev, scene_stream=stream)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
-
-    def gather_all():
-        for t, g in gathers.items():
-            def fill(view, t=t):
-                scene.getStatesDevice(view.data_ptr())
-                torch.cuda.current_stream(dev).wait_stream(stream)
-            g(fill)
 
     def one_step():
         scene.simulate()
+        if gather is not None:
+            gather.step(lambda view: scene.getStatesDevice(view.data_ptr()))
         scene.fetchResults(True)
-        if gathers:
-            gather_all()
 
     for _ in range(max(args.warmup, 3)):
         one_step()
@@ -180,17 +174,21 @@ def bench_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         scene.simulate()
-        if gathers:
-            scene.fetchResults(True)
-            gather_all()
-            stream.wait_stream(torch.cuda.current_stream(dev))   # the collective ran on torch's stream: order it before the end event
-            e1.record(stream)
-        else:
-            e1.record(stream)
-            scene.fetchResults(True)
+        if gather is not None:
+            gather.step(lambda view: scene.getStatesDevice(view.data_ptr()))   # pack kernel on the scene stream, NCCL on the comm stream
+        e1.record(stream)
+        scene.fetchResults(True)
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
-        launches += scene.num_launches
+        launches += scene.num_launches + (1 if gather is not None else 0)
+    if gather is not None:
+        # the collectives of the last two steps may still be in flight: their completion is part of the timed region
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        gather.wait()
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
     torch.cuda.synchronize(dev)
     if dist is not None:
         dist.barrier()
@@ -281,7 +279,7 @@ def bench_ours(args):
             "config": {"workload": f"config 2: {n_envs} envs x {BOXES_PER_ENV} boxes = {nb} bodies per GPU, shared ground plane, GPU broadphase + TGS 4 pos/1 vel iterations, 60 Hz",
                        "bodies_total": total_bodies, "constraints_per_gpu": P, "partitions": scene.num_partitions, "path": "environment (pxb_env.cuh)" if scene.uses_env_path else "device-wide",
                        "timing": "CUDA events on the scene stream per step, max over ranks; L2 flushed (256 MiB memset) between timed steps",
-                       "multi_gpu": "env-partitioned, one scene per GPU, per-step NCCL all-gather of the packed pose+linear+angular velocity tensor (13 floats/body)" if world > 1 else "single scene"},
+                       "multi_gpu": "env-partitioned, one scene per GPU, per-step NCCL all-gather of the packed pose+linear+angular velocity tensor (13 floats/body), double-buffered on a communication stream (overlaps the next step)" if world > 1 else "single scene"},
             "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kernel_bytes, "kernel_ms": solve_ms,
                          "dram_frac": (traffic / (solve_ms / 1e3) / 1e9 / peak) if traffic else None, "note": note},

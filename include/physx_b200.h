@@ -97,7 +97,8 @@ PXB_API int  pxb_set_rigid_dynamic_data_device(PxbScene* scene, const void* devD
 /* Packed state convenience: 13 floats per dynamic body (pos3 quat4 linVel3 angVel3), dynamic-body order. */
 PXB_API int  pxb_scene_get_states(PxbScene* scene, float* out);
 PXB_API int  pxb_scene_set_states(PxbScene* scene, const float* in);
-PXB_API int  pxb_scene_get_states_device(PxbScene* scene, float* devOut); /* same record, device pointer, async on the scene stream */
+PXB_API int  pxb_scene_get_states_device(PxbScene* scene, float* devOut); /* same record, device pointer; stream-ordered on the scene stream (may follow pxb_scene_simulate
+                                                                              without a fetch: it packs the state that step produces, e.g. into an NCCL send buffer) */
 PXB_API void* pxb_scene_state_device_ptr(PxbScene* scene, int which); /* 0 pos4, 1 quat4, 2 linVel4, 3 angVel4 (per ACTOR float4 arrays) */
 PXB_API void* pxb_scene_stream(PxbScene* scene);                        /* cudaStream_t */
 

@@ -1342,8 +1342,7 @@ PXB_API int pxb_set_rigid_dynamic_data(PxbScene* s, const void* data, const uint
 // the NCCL all-gather receive tensor); asynchronous on the scene stream.
 PXB_API int pxb_scene_get_states_device(PxbScene* s, float* devOut) {
   if (!s || !devOut) return fail(PXB_ERR_INVALID, "null argument");
-  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
-  if (!s->nDyn) return PXB_OK;
+  if (!s->nDyn) return PXB_OK;   // stream-ordered: legal right after pxb_scene_simulate, it reads the state that step produces
   cudaStream_t st = s->stream;
   LAUNCH(k_states_get, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, devOut);
   CK(cudaGetLastError());

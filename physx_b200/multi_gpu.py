@@ -86,6 +86,58 @@ class StateGather:
         return self.global_tensor
 
 
+class PipelinedStateGather:
+    """Double-buffered all-gather of the packed state that overlaps the collective of step N with the kernels of
+    step N+1 ("overlappable with the next step's BP/NP").
+
+    Per step:  `pack(view)` enqueues the engine's pack kernel on the scene stream into this step's buffer, the
+    collective runs on a dedicated communication stream ordered after it by an event, and the scene stream only
+    waits for the collective that last used the buffer it is about to overwrite (two steps back).  On CPU tensors
+    (gloo tests) the same rotation runs synchronously."""
+
+    def __init__(self, dist, n_local: int, cols: int, device, scene_stream=None):
+        import torch
+        self.torch, self.dist = torch, dist
+        self.bufs = [StateGather(dist, n_local, cols, device) for _ in range(2)]
+        self.cuda = device.type == "cuda"
+        self.scene_stream = scene_stream
+        self.comm_stream = torch.cuda.Stream(device=device) if self.cuda else None
+        self.done = [None, None]
+        self.k = 0
+
+    def step(self, pack):
+        """pack(view): fill this rank's block (stream-ordered on the scene stream).  Returns the buffer index used."""
+        b = self.k & 1
+        g = self.bufs[b]
+        if not self.cuda:
+            g(pack)
+        else:
+            t = self.torch
+            if self.done[b] is not None:
+                self.scene_stream.wait_event(self.done[b])      # gather k-2 read/wrote this buffer
+            pack(g.local_view)
+            ready = t.cuda.Event()
+            ready.record(self.scene_stream)
+            self.comm_stream.wait_event(ready)
+            with t.cuda.stream(self.comm_stream):
+                g(lambda view: None)
+                self.done[b] = t.cuda.Event()
+                self.done[b].record(self.comm_stream)
+        self.k += 1
+        return b
+
+    def latest(self):
+        """Global tensor of the most recent step (caller must `wait()` or order its stream after `done`)."""
+        return self.bufs[(self.k - 1) & 1].global_tensor
+
+    def wait(self, stream=None):
+        """Orders `stream` (default: the scene stream) after every outstanding collective."""
+        if self.cuda:
+            for ev in self.done:
+                if ev is not None:
+                    (stream or self.scene_stream).wait_event(ev)
+
+
 class EnvShardedScene:
     """One rank's scene of an env-partitioned job + the state all-gather."""
 

@@ -57,6 +57,18 @@ def _worker(rank, world, port, counts, q):
             exp = torch.cat([torch.arange(c * cols, dtype=torch.float32).reshape(c, cols) + 1000.0 * r for r, c in enumerate(counts)])
             assert g.layout == multi_gpu.gather_layout(counts)
             assert torch.equal(out, exp), f"rank {rank} cols {cols}"
+        # double-buffered gather: buffers alternate, every step's global tensor is complete and the previous one stays intact
+        pg = multi_gpu.PipelinedStateGather(dist, n_local, 13, torch.device("cpu"))
+        prev = None
+        for step in range(3):
+            b = pg.step(lambda view, step=step: view.fill_(100.0 * step + rank))
+            assert b == step % 2
+            exp = torch.cat([torch.full((c, 13), 100.0 * step + r) for r, c in enumerate(counts)])
+            assert torch.equal(pg.latest(), exp), f"rank {rank} step {step}"
+            if prev is not None:
+                assert torch.equal(pg.bufs[(step - 1) % 2].global_tensor, prev)
+            prev = exp
+        pg.wait()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
