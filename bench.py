@@ -139,7 +139,8 @@ def bench_ours(args):
     torch.cuda.set_device(dev)
 
     n_envs = args.envs
-    sc = scenes.env_grid_stacks(n_envs=n_envs, seed=1234 + rank)  # every rank owns its own envs (weak scaling)
+    solver = scenes.SOLVER_PGS if args.solver == "pgs" else scenes.SOLVER_TGS
+    sc = scenes.env_grid_stacks(n_envs=n_envs, seed=1234 + rank, solver=solver)  # every rank owns its own envs (weak scaling)
     scene = engine.Scene(sc, device=local)
     nb = scene.num_dynamic
     stream = torch.cuda.ExternalStream(scene.stream(), device=dev)
@@ -276,7 +277,7 @@ def bench_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config 2: {n_envs} envs x {BOXES_PER_ENV} boxes = {nb} bodies per GPU, shared ground plane, GPU broadphase + TGS 4 pos/1 vel iterations, 60 Hz",
+            "config": {"workload": f"config 2: {n_envs} envs x {BOXES_PER_ENV} boxes = {nb} bodies per GPU, shared ground plane, GPU broadphase + {args.solver.upper()} 4 pos/1 vel iterations, 60 Hz",
                        "bodies_total": total_bodies, "constraints_per_gpu": P, "partitions": scene.num_partitions, "path": "environment (pxb_env.cuh)" if scene.uses_env_path else "device-wide",
                        "timing": "CUDA events on the scene stream per step, max over ranks; L2 flushed (256 MiB memset) between timed steps",
                        "multi_gpu": "env-partitioned, one scene per GPU, per-step NCCL all-gather of the packed pose+linear+angular velocity tensor (13 floats/body), double-buffered on a communication stream (overlaps the next step)" if world > 1 else "single scene"},
@@ -305,6 +306,7 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=1024, help="environments in the reference arm's bounded sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver", default="tgs", choices=["tgs", "pgs"], help="PxSolverType of the scene (headline metric: tgs)")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)

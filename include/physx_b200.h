@@ -37,7 +37,7 @@ enum { PXB_SOLVER_PGS = 0, PXB_SOLVER_TGS = 1 };
  * (physx/include/PxSceneDesc.h:473-487, :1023-1075). */
 typedef struct {
   float    gravity[3];
-  uint32_t solverType;                 /* PXB_SOLVER_TGS (PGS: planned, returns PXB_ERR_UNSUPPORTED) */
+  uint32_t solverType;                 /* PXB_SOLVER_TGS or PXB_SOLVER_PGS (PxSceneDesc::solverType) */
   float    bounceThresholdVelocity;    /* PxSceneDesc::bounceThresholdVelocity */
   float    frictionOffsetThreshold;    /* PxSceneDesc::frictionOffsetThreshold */
   float    frictionCorrelationDistance;/* PxSceneDesc::frictionCorrelationDistance */

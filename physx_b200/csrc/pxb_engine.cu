@@ -55,7 +55,7 @@ struct PxbScene {
   uint32_t nA = 0, nDyn = 0, capA = 0, capPairs = 0, bitsA = 1, nLarge = 0;
   std::vector<ActorRec> recs; std::vector<int> dynIndex; std::vector<uint32_t> dynActor; std::vector<uint32_t> largeHost;
   GridParams grid; bool gridDirty = true;
-  int numSMs = 148, coopBlocksColour = 0, coopBlocksSolve = 0;
+  int numSMs = 148, coopBlocksColour = 0, coopBlocksSolve = 0, coopBlocksSolvePgs = 0;
   // per actor
   float4 *pos = 0, *quat = 0, *linVel = 0, *angVel = 0, *invInertia = 0, *damp = 0, *dims = 0, *aabbMin = 0, *aabbMax = 0;
   uint32_t *geomFlags = 0, *envId = 0, *dynActorDev = 0, *largeList = 0;
@@ -448,7 +448,7 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
                                float4* __restrict__ linVel, float4* __restrict__ angVel, const float4* __restrict__ invInertia, const float4* __restrict__ damp,
                                float gx, float gy, float gz, float dt, float4* __restrict__ sbLin, float4* __restrict__ sbAng, float4* __restrict__ sbDLin,
                                float4* __restrict__ sbDAng, float4* __restrict__ sbIA, float4* __restrict__ sbIB, float4* __restrict__ sbP, float4* __restrict__ sbQ,
-                               float4* __restrict__ sbOrigAng) {
+                               float4* __restrict__ sbOrigAng, int pgs) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
@@ -460,7 +460,9 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
   const v3 sqrtInvI = V3(ii.x == 0.f ? 0.f : sqrtf(ii.x), ii.y == 0.f ? 0.f : sqrtf(ii.y), ii.z == 0.f ? 0.f : sqrtf(ii.z));
   const v3 sqrtI = V3(sqrtInvI.x == 0.f ? 0.f : 1.0f / sqrtInvI.x, sqrtInvI.y == 0.f ? 0.f : 1.0f / sqrtInvI.y, sqrtInvI.z == 0.f ? 0.f : 1.0f / sqrtInvI.z);
   m33 sI, sInertia; transform_inertia(sqrtInvI, rot, sI); transform_inertia(sqrtI, rot, sInertia);
-  sbLin[a] = F4(lv, 0.f); sbAng[a] = F4(mmul(sInertia, av), 0.f); sbDLin[a] = make_float4(0, 0, 0, 0); sbDAng[a] = make_float4(0, 0, 0, 0);
+  if (pgs) { sbLin[a] = make_float4(0, 0, 0, 0); sbAng[a] = make_float4(0, 0, 0, 0); }   // PGS solver bodies hold velocity deltas
+  else { sbLin[a] = F4(lv, 0.f); sbAng[a] = F4(mmul(sInertia, av), 0.f); }
+  sbDLin[a] = make_float4(0, 0, 0, 0); sbDAng[a] = make_float4(0, 0, 0, 0);
   sbIA[a] = make_float4(sI.c0.x, sI.c0.y, sI.c0.z, sI.c1.y); sbIB[a] = make_float4(sI.c1.z, sI.c2.z, 0.f, 0.f);
   sbP[a] = make_float4(p4.x, p4.y, p4.z, 0.f); sbQ[a] = make_float4(0, 0, 0, 1); sbOrigAng[a] = F4(av, 0.f);
 }
@@ -801,7 +803,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   if (!desc || !out) return fail(PXB_ERR_INVALID, "null argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PXB_ERR_NO_DEVICE, "no CUDA device: physx_b200 has no CPU fallback"); }
-  if (desc->solverType != PXB_SOLVER_TGS) return fail(PXB_ERR_UNSUPPORTED, "only the TGS solver is implemented");
+  if (desc->solverType != PXB_SOLVER_TGS && desc->solverType != PXB_SOLVER_PGS) return fail(PXB_ERR_INVALID, "unknown solver type");
   if (desc->device < 0 || desc->device >= ndev) return fail(PXB_ERR_INVALID, "bad device ordinal");
   s = new PxbScene(); s->desc = *desc;
   CK(cudaSetDevice(desc->device));
@@ -810,11 +812,12 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->numSMs = prop.multiProcessorCount;
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_colour_partition, 256, 0)); s->coopBlocksColour = std::max(1, std::min(occ, 4)) * s->numSMs;
-  CK(cudaFuncSetAttribute(k_env_solve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
-  CK(cudaFuncSetAttribute(k_env_solve<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
-  CK(cudaFuncSetAttribute(k_env_solve<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
-  CK(cudaFuncSetAttribute(k_env_solve<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX));
+#define ENV_ATTR(T) do { CK(cudaFuncSetAttribute(k_env_solve<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); \
+                         CK(cudaFuncSetAttribute(k_env_solve<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); } while (0)
+  ENV_ATTR(32); ENV_ATTR(64); ENV_ATTR(128); ENV_ATTR(256);
+#undef ENV_ATTR
   CK(cudaFuncSetAttribute(k_env_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_pgs, 256, 0)); s->coopBlocksSolvePgs = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
   s->capA = std::max(16u, desc->maxActors);
   s->capPairs = desc->maxPairs ? desc->maxPairs : std::max(1024u, 8u * s->capA);
@@ -1097,7 +1100,7 @@ static int enqueue_step(PxbScene* s, float dt) {
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
          s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce);
   MARK(2);
-  const float* g = s->desc.gravity;
+  const float* g = s->desc.gravity; const bool pgs = s->desc.solverType == PXB_SOLVER_PGS;
   SolverParams P;
   P.dt = dt; P.stepDt = dt / (float)s->desc.posIters; P.invStepDt = 1.f / P.stepDt; P.invTotalDt = 1.0f / dt;
   P.biasCoefficient = 2.f * sqrtf(1.f / (float)s->desc.posIters);
@@ -1116,10 +1119,9 @@ static int enqueue_step(PxbScene* s, float dt) {
     A.rowScratch = s->ptA;   // ptA|ptB|ptC|frA|frB|frC|frD are ONE allocation of 28 x cap float4 (scene_alloc); the environment path uses 25 of them
     A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap);
-    if (s->envSolveThreads == 32) k_env_solve<32><<<s->nEnv, 32, smem, st>>>(A);
-    else if (s->envSolveThreads == 64) k_env_solve<64><<<s->nEnv, 64, smem, st>>>(A);
-    else if (s->envSolveThreads == 128) k_env_solve<128><<<s->nEnv, 128, smem, st>>>(A);
-    else k_env_solve<256><<<s->nEnv, 256, smem, st>>>(A);
+#define ENV_LAUNCH(T) do { if (pgs) k_env_solve<T, true><<<s->nEnv, T, smem, st>>>(A); else k_env_solve<T, false><<<s->nEnv, T, smem, st>>>(A); } while (0)
+    if (s->envSolveThreads == 32) ENV_LAUNCH(32); else if (s->envSolveThreads == 64) ENV_LAUNCH(64); else if (s->envSolveThreads == 128) ENV_LAUNCH(128); else ENV_LAUNCH(256);
+#undef ENV_LAUNCH
     s->launches++;
     MARK(5); MARK(6);
     CK(cudaGetLastError());
@@ -1149,7 +1151,22 @@ static int enqueue_step(PxbScene* s, float dt) {
   }
   MARK(3);
   LAUNCH(k_preintegrate, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, g[0], g[1], g[2], dt, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng,
-         s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng);
+         s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, pgs ? 1 : 0);
+  if (pgs) {   // PGS: rows in the 25-float4 record image, velocity-delta solver bodies (pxb_pgs.cuh)
+    Rows R; R.f = s->ptA; R.broken = s->conDone; R.stride = s->capPairs;
+    LAUNCH(k_prep_pgs, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
+           s->invInertia, s->sbIA, s->sbIB, s->frictions, P, R);
+    MARK(4);
+    uint32_t posIters = s->desc.posIters, velIters = s->desc.velIters, nDyn = s->nDyn;
+    void* args[] = {&s->counters, &s->partStart, &posIters, &velIters, &R, &s->sbLin, &s->sbAng, &s->sbDLin, &s->sbDAng, &nDyn, &s->dynActorDev};
+    CK(cudaLaunchCooperativeKernel((void*)k_solve_pgs, dim3(s->coopBlocksSolvePgs), dim3(256), args, 0, st)); s->launches++;
+    MARK(5);
+    LAUNCH(k_writeback_pgs, gP, B, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions);
+    LAUNCH(k_finalize_bodies_pgs, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB);
+    MARK(6);
+    CK(cudaGetLastError());
+    return PXB_OK;
+  }
   LAUNCH(k_prep, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
          s->invInertia, s->sbIA, s->sbIB, s->frictions, P, s->capPairs, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD);
   MARK(4);

@@ -337,9 +337,13 @@ PXB_D void rows_load(const Rows& R, uint32_t k, RegRows& r) {
 }
 PXB_D void rows_store_state(const Rows& R, uint32_t k, const RegRows& r) { const size_t s = R.stride; R.f[13 * s + k] = r.ap; R.f[24 * s + k] = r.fap; R.broken[k] = r.broken; }
 
+#include "pxb_pgs.cuh"
+
 struct ConLists { uint32_t *conPair, *b0, *b1, *colour, *ordered; };   // per-constraint scratch of one environment (shared memory, or global when it does not fit)
 
-__device__ __forceinline__ void env_prep_one(const EnvSolveArgs& A, const ConLists& L, uint32_t base, uint32_t pos, const float4* bLin, const float4* bIA, const float4* bIB, const float4* bQ, RegRows& r) {
+// vLin / vAng: per-body pre-solver (unconstrained) linear and world angular velocity
+template <bool PGS>
+__device__ __forceinline__ void env_prep_one(const EnvSolveArgs& A, const ConLists& L, uint32_t base, uint32_t pos, const float4* vLin, const float4* bIA, const float4* bIB, const float4* vAng, RegRows& r) {
   const uint32_t k = L.ordered[pos]; const uint32_t i = base + L.conPair[k];
   const uint32_t l0 = L.b0[k], l1 = L.b1[k];
   const uint2 bb = A.pairBodies[i];
@@ -348,10 +352,11 @@ __device__ __forceinline__ void env_prep_one(const EnvSolveArgs& A, const ConLis
   const bool dyn1 = l1 != NONE32;
   B.invMass1 = dyn1 ? A.pos[bb.y].w : 0.f;
   B.pen0 = -A.invInertia[bb.x].w; B.pen1 = dyn1 ? -A.invInertia[bb.y].w : -FLT_MAX;
-  B.linVel0 = V3(bLin[l0]); B.angVel0 = V3(bQ[l0]); B.sI0 = load_sym(bIA[l0], bIB[l0]);
-  if (dyn1) { B.linVel1 = V3(bLin[l1]); B.angVel1 = V3(bQ[l1]); B.sI1 = load_sym(bIA[l1], bIB[l1]); }
+  B.linVel0 = V3(vLin[l0]); B.angVel0 = V3(vAng[l0]); B.sI0 = load_sym(bIA[l0], bIB[l0]);
+  if (dyn1) { B.linVel1 = V3(vLin[l1]); B.angVel1 = V3(vAng[l1]); B.sI1 = load_sym(bIA[l1], bIB[l1]); }
   else { B.linVel1 = V3(0, 0, 0); B.angVel1 = V3(0, 0, 0); B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
-  prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.P);
+  if (PGS) prep_constraint_pgs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.P);
+  else prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.P);
 }
 // a17: writeBackContact (DyTGSContactPrep.cpp:1875-1937)
 __device__ __forceinline__ void env_writeback_one(const EnvSolveArgs& A, const RegRows& r) {
@@ -373,33 +378,58 @@ __device__ __forceinline__ void env_integrate_substep(uint32_t n, float stepDt, 
 // prep + all TGS iterations + write-back of one environment (iterativeSolveIsland, DyTGSDynamics.cpp:2515-2793, with CTA
 // barriers between partitions).  REG: every thread owns exactly one constraint (nCon <= T) and keeps its rows in registers
 // for the whole solve; otherwise rows stream through the memory image R (global scratch, L2 resident).
-template <int T, bool REG>
+template <int T, bool REG, bool PGS>
 __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows R, const ConLists L, const uint32_t base, const uint32_t nCon, const uint32_t n,
                                                float4* bLin, float4* bAng, float4* bDLin, float4* bDAng, float4* bIA, float4* bIB, float4* bP, float4* bQ,
                                                const uint32_t* sPartStart, const uint32_t nPart, long long& t_prev) {
   const uint32_t tid = threadIdx.x;
   RegRows mine;
-  if (REG) { if (tid < nCon) env_prep_one(A, L, base, tid, bLin, bIA, bIB, bQ, mine); }
-  else for (uint32_t pos = tid; pos < nCon; pos += T) { RegRows r; env_prep_one(A, L, base, pos, bLin, bIA, bIB, bQ, r); rows_store(R, pos, r); }
+  const float4* vLin = PGS ? bDLin : bLin; const float4* vAng = PGS ? bDAng : bQ;
+  if (REG) { if (tid < nCon) env_prep_one<PGS>(A, L, base, tid, vLin, bIA, bIB, vAng, mine); }
+  else for (uint32_t pos = tid; pos < nCon; pos += T) { RegRows r; env_prep_one<PGS>(A, L, base, pos, vLin, bIA, bIB, vAng, r); rows_store(R, pos, r); }
   __syncthreads();
   ENV_T(4);
-  for (uint32_t b = tid; b < n; b += T) bQ[b] = make_float4(0, 0, 0, 1);   // bQ carried the unconstrained angular velocity during prep
-  __syncthreads();
-  const float stepDt = A.P.stepDt;
-  float elapsed = 0.f;
-  for (uint32_t it = 0; it < A.posIters + A.velIters; ++it) {
-    const bool vel = it >= A.posIters;
-    const float minPen = vel ? 0.f : -FLT_MAX;
-    for (uint32_t p = 0; p < nPart; ++p) {
-      const uint32_t pb = sPartStart[p], pe = sPartStart[p + 1];
-      if (REG) { if (tid >= pb && tid < pe) solve_constraint_regs(mine, minPen, elapsed, bLin, bAng, bDLin, bDAng); }
-      else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_regs(r, minPen, elapsed, bLin, bAng, bDLin, bDAng); rows_store_state(R, k, r); }
-      __syncthreads();
+  if (PGS) {
+    // solveV_Blocks (DySolverControl.cpp:163-405): position iterations (friction in the last three, the last one concludes),
+    // saveMotionVelocities, then max(velIters, 1) velocity iterations; bP / bQ keep the motion velocities for integrateCore
+    for (uint32_t it = A.posIters; it > 0; --it) {
+      const bool doFriction = it <= 3;
+      for (uint32_t p = 0; p < nPart; ++p) {
+        const uint32_t pb = sPartStart[p], pe = sPartStart[p + 1];
+        if (REG) { if (tid >= pb && tid < pe) { solve_constraint_pgs(mine, doFriction, bLin, bAng); if (it == 1) conclude_constraint_pgs(mine); } }
+        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_pgs(r, doFriction, bLin, bAng); if (it == 1) { conclude_constraint_pgs(r); rows_store(R, k, r); } else rows_store_state(R, k, r); }
+        __syncthreads();
+      }
     }
-    if (!vel) {
-      env_integrate_substep<T>(n, stepDt, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ);
-      elapsed += stepDt;
-      __syncthreads();
+    for (uint32_t b = tid; b < n; b += T) { bP[b] = bLin[b]; bQ[b] = bAng[b]; }
+    __syncthreads();
+    const uint32_t velIters = A.velIters ? A.velIters : 1u;
+    for (uint32_t it = 0; it < velIters; ++it)
+      for (uint32_t p = 0; p < nPart; ++p) {
+        const uint32_t pb = sPartStart[p], pe = sPartStart[p + 1];
+        if (REG) { if (tid >= pb && tid < pe) solve_constraint_pgs(mine, true, bLin, bAng); }
+        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_pgs(r, true, bLin, bAng); rows_store_state(R, k, r); }
+        __syncthreads();
+      }
+  } else {
+    for (uint32_t b = tid; b < n; b += T) bQ[b] = make_float4(0, 0, 0, 1);   // bQ carried the unconstrained angular velocity during prep
+    __syncthreads();
+    const float stepDt = A.P.stepDt;
+    float elapsed = 0.f;
+    for (uint32_t it = 0; it < A.posIters + A.velIters; ++it) {
+      const bool vel = it >= A.posIters;
+      const float minPen = vel ? 0.f : -FLT_MAX;
+      for (uint32_t p = 0; p < nPart; ++p) {
+        const uint32_t pb = sPartStart[p], pe = sPartStart[p + 1];
+        if (REG) { if (tid >= pb && tid < pe) solve_constraint_regs(mine, minPen, elapsed, bLin, bAng, bDLin, bDAng); }
+        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_regs(r, minPen, elapsed, bLin, bAng, bDLin, bDAng); rows_store_state(R, k, r); }
+        __syncthreads();
+      }
+      if (!vel) {
+        env_integrate_substep<T>(n, stepDt, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ);
+        elapsed += stepDt;
+        __syncthreads();
+      }
     }
   }
   ENV_T(5);
@@ -413,7 +443,7 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
 #ifndef PXB_ENV_CTAS64
 #define PXB_ENV_CTAS64 6
 #endif
-template <int T>
+template <int T, bool PGS>
 __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB_ENV_CTAS64 / 2 : 1))) k_env_solve(const EnvSolveArgs A) {
   extern __shared__ float4 envSmem[];
   __shared__ uint32_t sPartCnt[MAX_PARTITIONS + 1], sPartStart[MAX_PARTITIONS + 1], sWarp[T / 32 + 1], sMisc[4];
@@ -440,7 +470,11 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
     const v3 sqrtInvI = V3(ii.x == 0.f ? 0.f : sqrtf(ii.x), ii.y == 0.f ? 0.f : sqrtf(ii.y), ii.z == 0.f ? 0.f : sqrtf(ii.z));
     const v3 sqrtI = V3(sqrtInvI.x == 0.f ? 0.f : 1.0f / sqrtInvI.x, sqrtInvI.y == 0.f ? 0.f : 1.0f / sqrtInvI.y, sqrtInvI.z == 0.f ? 0.f : 1.0f / sqrtInvI.z);
     m33 sI, sInertia; transform_inertia(sqrtInvI, rot, sI); transform_inertia(sqrtI, rot, sInertia);
-    bLin[b] = F4(lv, 0.f); bAng[b] = F4(mmul(sInertia, av), 0.f); bDLin[b] = make_float4(0, 0, 0, 0); bDAng[b] = make_float4(0, 0, 0, 0);
+    if (PGS) {   // solver bodies hold velocity deltas (start at zero); bDLin / bDAng hold the pre-solver velocities (PxSolverBodyData)
+      bLin[b] = make_float4(0, 0, 0, 0); bAng[b] = make_float4(0, 0, 0, 0); bDLin[b] = F4(lv, 0.f); bDAng[b] = F4(av, 0.f);
+    } else {
+      bLin[b] = F4(lv, 0.f); bAng[b] = F4(mmul(sInertia, av), 0.f); bDLin[b] = make_float4(0, 0, 0, 0); bDAng[b] = make_float4(0, 0, 0, 0);
+    }
     bIA[b] = make_float4(sI.c0.x, sI.c0.y, sI.c0.z, sI.c1.y); bIB[b] = make_float4(sI.c1.z, sI.c2.z, 0.f, 0.f);
     bP[b] = make_float4(p4.x, p4.y, p4.z, __uint_as_float(0u)); bQ[b] = F4(av, 0.f);
   }
@@ -538,10 +572,10 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   ENV_T(3);
   if (nCon) {
     Rows R; R.f = A.rowScratch + base; R.broken = A.broken + base; R.stride = A.cap;
-    if (nCon <= T) env_solve_body<T, true>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, t_prev);
-    else env_solve_body<T, false>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, t_prev);
+    if (nCon <= T) env_solve_body<T, true, PGS>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, t_prev);
+    else env_solve_body<T, false, PGS>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, t_prev);
   } else {
-    for (uint32_t b = tid; b < n; b += T) bQ[b] = make_float4(0, 0, 0, 1);
+    for (uint32_t b = tid; b < n; b += T) { if (PGS) { bP[b] = make_float4(0, 0, 0, 0); bQ[b] = make_float4(0, 0, 0, 0); } else bQ[b] = make_float4(0, 0, 0, 1); }
   }
   __syncthreads();
   ENV_T(6);
@@ -550,6 +584,12 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
     const uint32_t a = list[b];
     if (!(A.geomFlags[a] & 0x100u)) continue;
     const m33 sI = load_sym(bIA[b], bIB[b]);
+    if (PGS) {   // integrate (DyDynamics.cpp:1398-1423): every body, with or without constraints
+      const float4 p4 = A.pos[a]; v3 p = V3(p4.x, p4.y, p4.z); q4 q = Q4(A.quat[a]); v3 lv = V3(bDLin[b]), av = V3(bDAng[b]);
+      integrate_core_pgs(p, q, lv, av, sI, V3(bP[b]), V3(bQ[b]), V3(bLin[b]), V3(bAng[b]), A.dt);
+      A.pos[a] = make_float4(p.x, p.y, p.z, p4.w); A.quat[a] = F4(q); A.linVel[a] = F4(lv, 0.f); A.angVel[a] = F4(av, 0.f);
+      continue;
+    }
     v3 p = V3(bP[b]); q4 dq = Q4(bQ[b]);
     const v3 lv = V3(bLin[b]), as = V3(bAng[b]);
     if (!__float_as_uint(bP[b].w)) { v3 dl = V3(0, 0, 0), da = V3(0, 0, 0); integrate_core_step(lv, as, sI, A.dt, p, dq, dl, da); }

@@ -67,7 +67,14 @@ def main():
         "tumble_12": (scenes.tumbling_boxes(n=12, seed=7), 150),
         # BASELINE config 2 shape at 4 envs
         "envs_4": (scenes.env_grid_stacks(n_envs=4, jitter=0.01), 30),
+        # PGS solver (PxSolverType::ePGS) on the same shapes
+        "pgs_stacks_3x6_jitter": (scenes.box_stacks(n_stacks=3, height=6, half_extent=0.25, spacing=1.0, jitter=0.01, solver=scenes.SOLVER_PGS), 100),
+        "pgs_envs_4": (scenes.env_grid_stacks(n_envs=4, stacks_per_env=4, height=4, jitter=0.01, solver=scenes.SOLVER_PGS), 40),
+        "pgs_spheres_capsules_12": (scenes.mixed_primitives(n=12, seed=3, kinds=("sphere", "capsule"), solver=scenes.SOLVER_PGS), 100),
     }
+    only = sys.argv[1:]
+    if only:
+        cases = {k: v for k, v in cases.items() if any(k.startswith(o) for o in only)}
     for name, (sc, steps) in cases.items():
         data = run_reference(sc, steps)
         np.savez_compressed(os.path.join(out, name + ".npz"), **data)

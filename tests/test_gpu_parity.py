@@ -257,3 +257,60 @@ def test_env_path_falls_back_when_order_is_given_and_oversize_environments():
         c.step(); c2.step(); d.step()
         assert c.uses_env_path and np.array_equal(c.getStates(), d.getStates()) and np.array_equal(c.getContacts(), d.getContacts()), f"step {t}"
         assert c2.uses_env_path and np.array_equal(c2.getStates(), d.getStates()) and np.array_equal(c2.getContacts(), d.getContacts()), f"step {t}"
+
+
+# ---- PGS solver ----
+def _pgs_scenes():
+    P = scenes.SOLVER_PGS
+    return {"stacks_4x8": (scenes.box_stacks(n_stacks=4, height=8, half_extent=0.25, spacing=1.0, jitter=0.01, solver=P), 100, False),
+            "envs_16": (scenes.env_grid_stacks(n_envs=16, jitter=0.01, solver=P), 60, True),
+            "ragged": (scenes.env_ragged(solver=P), 120, True),
+            "mixed_all": (scenes.mixed_primitives(n=24, seed=11, kinds=("sphere", "box", "capsule", "sphere"), solver=P), 120, False),
+            "vel_iters_0_and_3": (scenes.box_stacks(n_stacks=2, height=5, half_extent=0.25, spacing=1.0, jitter=0.01, solver=P, pos_iters=6, vel_iters=3), 40, False)}
+
+
+@pytest.mark.parametrize("name", list(_pgs_scenes()))
+def test_pgs_gpu_matches_oracle(oracle, name):
+    sc, steps, env = _pgs_scenes()[name]
+    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    glob = engine.Scene(sc, env_path=False) if env else None
+    for t in range(steps):
+        gpu.step()
+        cpu.step()
+        assert gpu.uses_env_path == env
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
+        cg, cc = gpu.getContacts(), cpu.getContacts()
+        assert np.array_equal(cg[:, 0], cc[:, 0]), f"contact counts, step {t}"
+        assert gpu.num_constraints == cpu.num_constraints and gpu.num_partitions == cpu.num_partitions
+        sg = gpu.getStates()
+        assert np.abs(sg - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
+        assert np.abs(cg - cc).max(initial=0) < 1e-4, f"contacts / applied forces, step {t}"
+        cpu.setStates(sg)
+        if glob is not None:   # environment path == device-wide path, bit for bit
+            glob.step()
+            assert np.array_equal(glob.getStates(), sg) and np.array_equal(glob.getContacts(), cg), f"env vs device-wide, step {t}"
+
+
+@pytest.mark.parametrize("name", ["pgs_stacks_3x6_jitter", "pgs_envs_4"])
+def test_pgs_gpu_matches_reference_golden(name):
+    z, sc = util.load_golden(name)
+    gpu = engine.Scene(sc)
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setConstraintOrder(util.golden_order(z, t))
+        gpu.step()
+        st, ref = gpu.getStates(), z["states"][t + 1]
+        assert util.rel_err(st[:, :3], ref[:, :3]) < TOL_POSE and util.rel_err(st[:, 3:7], ref[:, 3:7]) < TOL_POSE, f"pose, step {t}"
+        assert np.abs(st[:, 7:10] - ref[:, 7:10]).max() < TOL_LINVEL and np.abs(st[:, 10:] - ref[:, 10:]).max() < TOL_ANGVEL, f"velocity, step {t}"
+        assert util.contact_counts(gpu.getPairs(), gpu.getContacts()) == util.golden_contact_counts(z, t), f"manifolds, step {t}"
+
+
+def test_pgs_gpu_teacher_forced_steps_match_reference():
+    z, sc = util.load_golden("pgs_spheres_capsules_12")
+    gpu = engine.Scene(sc)
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setStates(z["states"][t])
+        gpu.setConstraintOrder(util.golden_order(z, t))
+        gpu.step()
+        st, ref = gpu.getStates(), z["states"][t + 1]
+        assert np.abs(st[:, :7] - ref[:, :7]).max() < 1e-5, f"pose, step {t}"
+        assert np.abs(st[:, 7:10] - ref[:, 7:10]).max() < 1e-4 and np.abs(st[:, 10:] - ref[:, 10:]).max() < 1e-3, f"velocity, step {t}"
