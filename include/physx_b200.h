@@ -53,7 +53,12 @@ typedef struct {
 /* Scenes whose dynamic actors all carry an environment id (PxActor::setEnvironmentID, the RL many-env layout of
  * BASELINE configs 2/5) run on the environment path: one warp / one CTA per environment with solver rows in shared
  * memory (physx_b200/csrc/pxb_env.cuh).  Results are bit-identical to the device-wide path; this flag forces the latter. */
-enum { PXB_FLAG_NO_ENV_PATH = 1u };
+enum { PXB_FLAG_NO_ENV_PATH = 1u,
+/* Documented relaxation for giant islands (BASELINE configs 3 / 4): the reference's partitioning is a sequential first-fit in
+ * solver input order (DyConstraintPartition.cpp:475-568) whose dependency chains grow with the island; with this flag the
+ * device-wide path colours constraints with Jones-Plassmann rounds instead (a valid, deterministic partitioning that is NOT the
+ * reference's first-fit, so trajectories are comparable to the reference only statistically).  Off by default. */
+       PXB_FLAG_RELAXED_PARTITIONING = 2u };
 
 typedef struct PxbScene PxbScene;
 

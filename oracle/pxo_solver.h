@@ -386,4 +386,44 @@ static inline int pxo_colour(const int* body0, const int* body1, int n, int nBod
   }
   return nPart;
 }
+/* PXB_FLAG_RELAXED_PARTITIONING (include/physx_b200.h): the same Jones-Plassmann rounds as k_colour_partition's relaxed branch
+ * (physx_b200/csrc/pxb_engine.cu), run sequentially.  Not a reference algorithm: it exists so the relaxed GPU mode stays testable
+ * bit for bit.  Static contacts are placed exactly as in pxo_colour. */
+static inline int pxo_colour_relaxed(const int* body0, const int* body1, int n, int nBodies, int* colour, uint32_t* bodyMask, int* bodyMaxDyn, int* bodyStatic) {
+  memset(bodyMask, 0, sizeof(uint32_t) * nBodies); memset(bodyMaxDyn, 0, sizeof(int) * nBodies); memset(bodyStatic, 0, sizeof(int) * nBodies);
+  uint64_t* best = (uint64_t*)calloc(nBodies ? nBodies : 1, sizeof(uint64_t));
+  int remaining = 0;
+  for (int i = 0; i < n; ++i) { colour[i] = -1; if (body0[i] >= 0 && body1[i] >= 0) remaining++; }
+  for (uint32_t round = 1; remaining > 0; ++round) {
+    for (int i = 0; i < n; ++i) {
+      if (colour[i] >= 0 || body0[i] < 0 || body1[i] < 0) continue;
+      const uint64_t bid = ((uint64_t)round << 32) | ((uint32_t)i * 2654435761u + 1u);
+      if (best[body0[i]] < bid) best[body0[i]] = bid;
+      if (best[body1[i]] < bid) best[body1[i]] = bid;
+    }
+    for (int i = 0; i < n; ++i) {
+      if (colour[i] >= 0 || body0[i] < 0 || body1[i] < 0) continue;
+      const uint64_t bid = ((uint64_t)round << 32) | ((uint32_t)i * 2654435761u + 1u);
+      const int a = body0[i], b = body1[i];
+      if (best[a] != bid || best[b] != bid) continue;
+      const uint32_t comb = ~bodyMask[a] & ~bodyMask[b];
+      if (comb == 0) { free(best); return -1; }
+      int p = 0; while (!((comb >> p) & 1u)) p++;
+      bodyMask[a] |= 1u << p; bodyMask[b] |= 1u << p;
+      colour[i] = p; remaining--;
+    }
+  }
+  free(best);
+  int nPart = 0;
+  for (int i = 0; i < n; ++i) {
+    const int a = body0[i], b = body1[i];
+    if (!(a >= 0 && b >= 0)) {
+      const int d = a >= 0 ? a : b; const uint32_t m = bodyMask[d]; int mx = 0; while (mx < 32 && (m >> mx)) mx++;
+      colour[i] = mx + bodyStatic[d]++;
+    }
+    if (colour[i] + 1 > nPart) nPart = colour[i] + 1;
+  }
+  (void)bodyMaxDyn;
+  return nPart;
+}
 #endif

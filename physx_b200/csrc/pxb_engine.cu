@@ -88,7 +88,7 @@ struct PxbScene {
   // environment-partitioned path (pxb_env.cuh)
   bool envEligible = false, envActive = false, envDisabled = false, everStepped = false; uint32_t ringMask = 0;
   uint32_t nEnv = 0, envMaxList = 0, envConCap = 0, envConCapForced = 0, envThreadsForced = 0, hMaxConEnv = 0, hMaxPairEnv = 0, envSolveThreads = 64;
-  uint32_t *envStart = 0, *envList = 0, *actorLocal = 0, *slotColour = 0; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
+  uint32_t *envStart = 0, *envList = 0, *actorLocal = 0, *slotColour = 0; unsigned long long* bodyBest = 0; bool relaxedPartitioning = false; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
 };
 
 static thread_local std::string g_err;
@@ -378,13 +378,44 @@ __global__ void k_body_lists(uint32_t nA, const uint32_t* __restrict__ bodyStart
 __global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__ counters, const uint32_t* __restrict__ conB0, const uint32_t* __restrict__ conB1,
                                    const uint32_t* __restrict__ conPos0, const uint32_t* __restrict__ conPos1, uint32_t* __restrict__ conColour, uint32_t* __restrict__ conDone,
                                    uint32_t* __restrict__ bodyNext, uint32_t* __restrict__ bodyMask, uint32_t* __restrict__ partCnt, uint32_t* __restrict__ partStart,
-                                   uint32_t* __restrict__ partCursor, uint32_t* __restrict__ ordered) {
+                                   uint32_t* __restrict__ partCursor, uint32_t* __restrict__ ordered, unsigned long long* __restrict__ bodyBest, int relaxed) {
   cg::grid_group grid = cg::this_grid();
   const uint32_t nCon = counters[C_NCON];
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   for (uint32_t p = gtid; p < MAX_PARTITIONS + 1; p += gsize) { partCnt[p] = 0; }
   const uint32_t perCta = (nCon + gridDim.x - 1) / gridDim.x;
   const uint32_t cb = min(nCon, blockIdx.x * perCta), ce = min(nCon, cb + perCta);
+  if (relaxed) {
+    // PXB_FLAG_RELAXED_PARTITIONING: Jones-Plassmann style rounds.  Every uncoloured constraint bids its priority (a fixed
+    // bijective hash of its index) on both bodies; the constraint that holds the highest bid on BOTH bodies takes the lowest
+    // colour free on both.  Winners of a round are body-disjoint, the result is a valid partitioning that depends only on the
+    // constraint list (deterministic; oracle/pxb_oracle.c runs the same rounds), but it is not the reference's first-fit.
+    for (uint32_t round = 1;; ++round) {
+      const uint32_t remaining = ld_volatile(&counters[C_REMAINING]);
+      grid.sync();
+      if (remaining == 0) break;
+      for (uint32_t c = cb + threadIdx.x; c < ce; c += blockDim.x) {
+        if (conDone[c]) continue;
+        const unsigned long long bid = ((unsigned long long)round << 32) | (c * 2654435761u + 1u);
+        atomicMax(&bodyBest[conB0[c]], bid); atomicMax(&bodyBest[conB1[c]], bid);
+      }
+      grid.sync();
+      uint32_t won = 0;
+      for (uint32_t c = cb + threadIdx.x; c < ce; c += blockDim.x) {
+        if (conDone[c]) continue;
+        const unsigned long long bid = ((unsigned long long)round << 32) | (c * 2654435761u + 1u);
+        const uint32_t a = conB0[c], b = conB1[c];
+        if (bodyBest[a] != bid || bodyBest[b] != bid) continue;
+        const uint32_t ma = bodyMask[a], mb = bodyMask[b]; const uint32_t comb = ~ma & ~mb;
+        uint32_t col = 31;
+        if (comb) col = __ffs(comb) - 1; else atomicOr(&counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
+        conColour[c] = col; conDone[c] = 1u; bodyMask[a] = ma | (1u << col); bodyMask[b] = mb | (1u << col);
+        ++won;
+      }
+      if (won) atomicSub(&counters[C_REMAINING], won);
+      grid.sync();
+    }
+  } else
   for (;;) {
     // every thread samples the counter between two grid barriers, so all of them take the same branch
     const uint32_t remaining = ld_volatile(&counters[C_REMAINING]);
@@ -793,7 +824,7 @@ static int scene_alloc(PxbScene* s) {
   k_init_freelist<<<cdiv((uint32_t)Pn, 256), 256, 0, s->stream>>>((uint32_t)Pn, s->freeList);
   const uint32_t top = (uint32_t)Pn;   // ring of free persistent slots: head = 0, tail = Pn
   CK(cudaMemcpyAsync(s->counters + C_FREE_TAIL, &top, 4, cudaMemcpyHostToDevice, s->stream));
-  CK(dalloc(s->actorLocal, A)); CK(dalloc(s->slotColour, Pn)); CK(cudaMemsetAsync(s->slotColour, 0xff, 4 * Pn, s->stream)); for (int k = 0; k < 2; ++k) { CK(dalloc(s->envSeg[k], A)); CK(cudaMemsetAsync(s->envSeg[k], 0, sizeof(uint2) * A, s->stream)); }
+  CK(dalloc(s->bodyBest, A)); CK(dalloc(s->actorLocal, A)); CK(dalloc(s->slotColour, Pn)); CK(cudaMemsetAsync(s->slotColour, 0xff, 4 * Pn, s->stream)); for (int k = 0; k < 2; ++k) { CK(dalloc(s->envSeg[k], A)); CK(cudaMemsetAsync(s->envSeg[k], 0, sizeof(uint2) * A, s->stream)); }
   CK(cudaStreamSynchronize(s->stream));
   return PXB_OK;
 }
@@ -825,6 +856,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->rsTmp.ctas = std::min<uint32_t>(RS_MAX_CTAS, (uint32_t)s->numSMs * 2);
   { const char* ng = getenv("PXB_NO_GRAPH"); if (ng && ng[0] == '1') s->useGraph = false; }
   if (desc->reserved[1] & PXB_FLAG_NO_ENV_PATH) s->envDisabled = true;
+  if (desc->reserved[1] & PXB_FLAG_RELAXED_PARTITIONING) { s->relaxedPartitioning = true; s->envDisabled = true; }
   s->envConCapForced = desc->reserved[2]; s->envThreadsForced = desc->reserved[3];
   const int rc = scene_alloc(s);
   if (rc != PXB_OK) { delete s; return rc; }
@@ -842,7 +874,7 @@ PXB_API void pxb_scene_release(PxbScene* s) {
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
-                  s->envStart, s->envList, s->actorLocal, s->slotColour, s->envSeg[0], s->envSeg[1]};
+                  s->envStart, s->envList, s->actorLocal, s->slotColour, s->bodyBest, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
   cudaStreamDestroy(s->stream);
@@ -1146,7 +1178,10 @@ static int enqueue_step(PxbScene* s, float dt) {
   LAUNCH(k_con_fill, gP, B, s->counters, s->conB0, s->conB1, s->bodyStart, s->bodyCursor, s->bodyList);
   LAUNCH(k_body_lists, cdiv(s->nA, B), B, s->nA, s->bodyStart, s->bodyCnt, s->bodyList, s->conB0, s->conB1, s->conPos0, s->conPos1, s->bodyNext, s->bodyMask, s->bodyHasCon);
   {
-    void* args[] = {&s->counters, &s->conB0, &s->conB1, &s->conPos0, &s->conPos1, &s->conColour, &s->conDone, &s->bodyNext, &s->bodyMask, &s->partCnt, &s->partStart, &s->partCursor, &s->ordered};
+    int relaxed = (s->relaxedPartitioning && s->nOrder == 0) ? 1 : 0;   // a host-provided solver order always gets the exact first-fit
+    if (relaxed) CK(cudaMemsetAsync(s->bodyBest, 0, 8 * (size_t)s->nA, st));
+    void* args[] = {&s->counters, &s->conB0, &s->conB1, &s->conPos0, &s->conPos1, &s->conColour, &s->conDone, &s->bodyNext, &s->bodyMask, &s->partCnt, &s->partStart, &s->partCursor, &s->ordered,
+                    &s->bodyBest, &relaxed};
     CK(cudaLaunchCooperativeKernel((void*)k_colour_partition, dim3(s->coopBlocksColour), dim3(256), args, 0, st)); s->launches++;
   }
   MARK(3);

@@ -129,7 +129,8 @@ class Scene:
         d.maxActors = max(int(max_actors), len(scene.actors))
         d.maxPairs = int(max_pairs)
         d.device = int(device)
-        d.reserved[1] = 0 if env_path else 1   # PXB_FLAG_NO_ENV_PATH
+        relaxed = bool(int(h["reserved"][0]) & 1)   # scene header reserved[0] bit 0: PXB_FLAG_RELAXED_PARTITIONING (shared with the oracle)
+        d.reserved[1] = (0 if env_path else 1) | (2 if relaxed else 0)   # PXB_FLAG_NO_ENV_PATH | PXB_FLAG_RELAXED_PARTITIONING
         d.reserved[2] = int(env_row_cap)
         d.reserved[3] = int(env_threads)
         self.dt = float(h["dt"])

@@ -55,7 +55,7 @@ def normalize_quat_f32(q):
 PLANE_UP_Y_QUAT = normalize_quat_f32([0.0, 0.0, np.sqrt(0.5), np.sqrt(0.5)])
 
 
-def default_header(solver=SOLVER_TGS, pos_iters=4, vel_iters=1, sleep_threshold=0.0):
+def default_header(solver=SOLVER_TGS, pos_iters=4, vel_iters=1, sleep_threshold=0.0, relaxed_partitioning=False):
     h = np.zeros((), dtype=HEADER_DTYPE)
     h["magic"] = SCENE_MAGIC
     h["solverType"] = solver
@@ -69,6 +69,7 @@ def default_header(solver=SOLVER_TGS, pos_iters=4, vel_iters=1, sleep_threshold=
     h["frictionOffsetThreshold"] = 0.04
     h["frictionCorrelationDistance"] = 0.025
     h["toleranceLength"] = 1.0
+    h["reserved"][0] = 1 if relaxed_partitioning else 0   # bit 0: PXB_FLAG_RELAXED_PARTITIONING (engine and oracle; ignored by the reference)
     return h
 
 
@@ -286,3 +287,57 @@ def env_ragged(n_envs=12, max_bodies=20, seed=5, static_blocks=True, env_pitch=6
     wall["pos"][0] = (-1.5, 0.0, 0.0)
     actors = np.concatenate(recs + [wall])
     return Scene(default_header(**hdr), add_ground_plane(actors))
+
+
+def add_bin(actors, half_size, wall_height=4.0, thickness=0.5):
+    """Ground plane + four static box walls around [-half_size, half_size]^2 (BASELINE configs 3 / 4: "falling into a bin")."""
+    w = _new_actors(4)
+    w["geomType"] = GEOM_BOX
+    t, h, L = np.float32(thickness), np.float32(wall_height), np.float32(half_size + thickness)
+    w["dims"][0, :3] = (t, h, L); w["pos"][0] = (-half_size - t, h, 0)
+    w["dims"][1, :3] = (t, h, L); w["pos"][1] = (half_size + t, h, 0)
+    w["dims"][2, :3] = (L, h, t); w["pos"][2] = (0, h, -half_size - t)
+    w["dims"][3, :3] = (L, h, t); w["pos"][3] = (0, h, half_size + t)
+    return add_ground_plane(np.concatenate([w, actors]))
+
+
+def box_pile(nx=100, ny=20, nz=100, half_extent=0.25, gap=0.001, seed=1, **hdr):
+    """BASELINE config 4: nx*ny*nz boxes in a lattice with small gaps settling in a walled bin -- one giant island with high
+    contact density (solver partitioning / colouring stress).  Device-wide path (no environment ids)."""
+    rng = np.random.RandomState(seed)
+    n = nx * ny * nz
+    a = _new_actors(n)
+    he = np.float32(half_extent)
+    pitch = np.float32(2 * half_extent + gap)
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    jit = rng.uniform(-gap * 0.4, gap * 0.4, size=(n, 2)).astype(np.float32)
+    a["pos"][:, 0] = (ix.ravel() - (nx - 1) / 2).astype(np.float32) * pitch + jit[:, 0]
+    a["pos"][:, 1] = he + iy.ravel().astype(np.float32) * pitch + np.float32(gap)
+    a["pos"][:, 2] = (iz.ravel() - (nz - 1) / 2).astype(np.float32) * pitch + jit[:, 1]
+    set_box(a, np.arange(n), np.array([he, he, he], dtype=np.float32))
+    return Scene(default_header(**hdr), add_bin(a, half_size=float(max(nx, nz) * pitch / 2 + 0.5)))
+
+
+def falling_primitives(nx=128, ny=64, nz=128, pitch=0.6, seed=2, kinds=("sphere", "capsule", "box"), **hdr):
+    """BASELINE config 3 shape (broadphase + narrowphase stress): nx*ny*nz mixed primitives with random orientations dropped
+    from a lattice into a walled bin.  (The convex-hull third of config 3 is replaced by boxes until a10 lands.)"""
+    rng = np.random.RandomState(seed)
+    n = nx * ny * nz
+    a = _new_actors(n)
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    a["pos"][:, 0] = (ix.ravel() - (nx - 1) / 2).astype(np.float32) * np.float32(pitch)
+    a["pos"][:, 1] = np.float32(0.5) + iy.ravel().astype(np.float32) * np.float32(pitch)
+    a["pos"][:, 2] = (iz.ravel() - (nz - 1) / 2).astype(np.float32) * np.float32(pitch)
+    q = rng.normal(size=(n, 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True).astype(np.float32)
+    a["quat"] = q   # unit to float rounding; the engine does not depend on the normalisation fixed point
+    kind = np.arange(n) % len(kinds)
+    for ki, k in enumerate(kinds):
+        idx = np.nonzero(kind == ki)[0]
+        if k == "sphere":
+            set_sphere(a, idx, rng.uniform(0.1, 0.2, len(idx)).astype(np.float32))
+        elif k == "capsule":
+            set_capsule(a, idx, rng.uniform(0.08, 0.15, len(idx)).astype(np.float32), rng.uniform(0.1, 0.3, len(idx)).astype(np.float32))
+        else:
+            set_box(a, idx, rng.uniform(0.1, 0.2, (len(idx), 3)).astype(np.float32))
+    return Scene(default_header(**hdr), add_bin(a, half_size=float(max(nx, nz) * pitch / 2 + 1.0)))

@@ -22,6 +22,8 @@ def _scenes_small():
         "envs_16": (scenes.env_grid_stacks(n_envs=16, jitter=0.01), 60),    # BASELINE config 2 shape
         "tumble_12": (scenes.tumbling_boxes(n=12, seed=7), 150),            # pairs created/lost, rotated contacts
         "free_fall": (_free_fall(), 5),
+        "pile_6x4x6": (scenes.box_pile(6, 4, 6), 60),                       # BASELINE config 4 shape: one dense island, walled bin
+        "fall_5x4x5": (scenes.falling_primitives(5, 4, 5), 120),            # BASELINE config 3 shape: mixed primitives into a bin
     }
 
 
@@ -34,7 +36,7 @@ def _free_fall():
 @pytest.mark.parametrize("name", list(_scenes_small()))
 def test_gpu_matches_oracle(oracle, name):
     sc, steps = _scenes_small()[name]
-    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    gpu, cpu = engine.Scene(sc, max_pairs=16 * len(sc.actors)), oracle.OracleScene(sc)
     exact = True
     for t in range(steps):
         gpu.step()
@@ -50,7 +52,7 @@ def test_gpu_matches_oracle(oracle, name):
         assert np.abs(sg - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
         exact = exact and np.array_equal(sg, cpu.getStates())
         cpu.setStates(sg)   # re-synchronise: every step is checked from identical inputs (sinf/cosf/acosf differ by an ulp between libm and CUDA)
-    if name not in ("tumble_12",):
+    if name not in ("tumble_12", "fall_5x4x5"):
         assert exact, "stack / free-fall scenes are expected to be bit-identical to the oracle"
 
 
@@ -314,3 +316,27 @@ def test_pgs_gpu_teacher_forced_steps_match_reference():
         st, ref = gpu.getStates(), z["states"][t + 1]
         assert np.abs(st[:, :7] - ref[:, :7]).max() < 1e-5, f"pose, step {t}"
         assert np.abs(st[:, 7:10] - ref[:, 7:10]).max() < 1e-4 and np.abs(st[:, 10:] - ref[:, 10:]).max() < 1e-3, f"velocity, step {t}"
+
+
+@pytest.mark.parametrize("name", ["pile_tgs", "pile_pgs", "fall_tgs"])
+def test_relaxed_partitioning_matches_oracle(oracle, name):
+    """PXB_FLAG_RELAXED_PARTITIONING (giant islands, BASELINE configs 3 / 4): Jones-Plassmann rounds instead of the sequential
+    first-fit.  The oracle runs the same rounds, so the GPU stays checkable bit for bit; the partitioning is valid (no body twice
+    in a partition) and the pile settles like the first-fit one."""
+    sc = {"pile_tgs": scenes.box_pile(6, 4, 6, relaxed_partitioning=True),
+          "pile_pgs": scenes.box_pile(5, 4, 5, relaxed_partitioning=True, solver=scenes.SOLVER_PGS),
+          "fall_tgs": scenes.falling_primitives(5, 4, 5, relaxed_partitioning=True)}[name]
+    gpu, cpu = engine.Scene(sc, max_pairs=16 * len(sc.actors)), oracle.OracleScene(sc)
+    for t in range(80):
+        gpu.step()
+        cpu.step()
+        assert not gpu.uses_env_path
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
+        assert gpu.num_constraints == cpu.num_constraints and gpu.num_partitions == cpu.num_partitions, f"partition count, step {t}"
+        sg = gpu.getStates()
+        assert np.abs(sg - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
+        assert np.abs(gpu.getContacts() - cpu.getContacts()).max(initial=0) < 1e-4, f"contacts / applied forces, step {t}"
+        cpu.setStates(sg)
+    if name.startswith("pile"):
+        st = gpu.getStates()
+        assert np.isfinite(st).all() and np.abs(st[:, 7:10]).max() < 0.5 and st[:, 1].min() > 0.2, "the pile rests in the bin"
