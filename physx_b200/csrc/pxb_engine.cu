@@ -264,7 +264,10 @@ __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_
 // a8-a11: one thread per pair.  Driver logic of PxcNpBatch.cpp:364-498: body0 is the dynamic actor (for
 // two dynamics the later-created one, ScNPhaseCore.cpp:182-252), shapes are ordered by geometry type for
 // the contact function and the normal is flipped back afterwards (flipContacts).
-__global__ void __launch_bounds__(128) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
+#ifndef PXB_NP_CTAS
+#define PXB_NP_CTAS 5
+#endif
+__global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
                               const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
                               float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
                               uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce) {
@@ -285,7 +288,10 @@ __global__ void __launch_bounds__(128) k_narrowphase(const uint64_t* __restrict_
   xf tm0, tm1; tm0.p = V3(p0.x, p0.y, p0.z); tm0.q = Q4(quat[s0]); tm1.p = V3(p1.x, p1.y, p1.z); tm1.q = Q4(quat[s1]);
   const float4 d0 = dims[s0], d1 = dims[s1];
   float4* rec = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4;
-  Manifold man; manifold_load(man, rec);
+  // only the PCM pair types keep a persistent manifold (plane-box, box-box, plane-capsule); the closed-form sphere family does not
+  const bool usesManifold = (ty0 == PXB_GEOM_PLANE && (ty1 == PXB_GEOM_BOX || ty1 == PXB_GEOM_CAPSULE)) || (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX);
+  Manifold man;
+  if (usesManifold) manifold_load(man, rec); else { man.n = 0; man.dirty = 0; }
   Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
   for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
   if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_BOX) pcm_plane_box(tm0, tm1, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
@@ -296,11 +302,11 @@ __global__ void __launch_bounds__(128) k_narrowphase(const uint64_t* __restrict_
   else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_BOX) np_sphere_box(tm0.p, d0.x, tm1, V3(d1.x, d1.y, d1.z), contactDist, out);
   else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CAPSULE) pcm_plane_capsule(tm0, tm1, d1.x, d1.y, contactDist, man, out);
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_CAPSULE) np_capsule_capsule(tm0, tm1, d0.x, d0.y, d1.x, d1.y, contactDist, out);
-  manifold_store(man, rec);
+  if (man.dirty) manifold_store(man, rec); else if (usesManifold && man.n > 0) manifold_store_pens(man, rec);   // steady state: only the penetrations change
   if (flip && out.count) out.normal = -out.normal;
   cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]); cForce[(size_t)i * 4 + k] = 0.f; }
+  for (int k = 0; k < 4; ++k) { cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]); }   // (cForce: every pair with contacts is a constraint and gets its forces from write-back)
   pairBodies[i] = make_uint2(a0, a1);
   conFlag[i] = out.count > 0 ? 1u : 0u;
 }
@@ -778,8 +784,8 @@ __global__ void k_env_begin(uint32_t* __restrict__ counters) {   // per-step cou
 // host side
 static const size_t ENV_SMEM_MAX = 227 * 1024 - 2048;   // dynamic shared memory budget of k_env_solve (static part: partition tables)
 static const size_t ENV_CON_BYTES = 5 * sizeof(uint32_t);   // 5 u32 lists per pair slot (rows live in registers)
-static size_t env_solve_smem(uint32_t maxList, uint32_t conCap) { return (size_t)maxList * (8 * sizeof(float4) + 3 * sizeof(uint32_t)) + (size_t)conCap * ENV_CON_BYTES; }
-static uint32_t env_con_cap_limit(uint32_t maxList) { return (uint32_t)((ENV_SMEM_MAX - (size_t)maxList * (8 * sizeof(float4) + 3 * sizeof(uint32_t))) / ENV_CON_BYTES); }
+static size_t env_solve_smem(uint32_t maxList, uint32_t conCap, uint32_t threads = 256) { return (size_t)maxList * (8 * sizeof(float4) + 3 * sizeof(uint32_t)) + (size_t)conCap * ENV_CON_BYTES + 16 + (size_t)threads * 12 * sizeof(float4); }
+static uint32_t env_con_cap_limit(uint32_t maxList) { return (uint32_t)((ENV_SMEM_MAX - env_solve_smem(maxList, 0)) / ENV_CON_BYTES); }
 template <typename T> static cudaError_t dalloc(T*& p, size_t n) { return cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)); }
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 static uint32_t bits_for(uint64_t n) { uint32_t b = 1; while ((1ull << b) < n) ++b; return b; }
@@ -1150,7 +1156,7 @@ static int enqueue_step(PxbScene* s, float dt) {
     A.conPair = s->conPair; A.conB0 = s->conB0; A.conB1 = s->conB1; A.conColour = s->conColour; A.ordered = s->ordered; A.broken = s->conDone;
     A.rowScratch = s->ptA;   // ptA|ptB|ptC|frA|frB|frC|frD are ONE allocation of 28 x cap float4 (scene_alloc); the environment path uses 25 of them
     A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour;
-    const size_t smem = env_solve_smem(s->envMaxList, s->envConCap);
+    const size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
 #define ENV_LAUNCH(T) do { if (pgs) k_env_solve<T, true><<<s->nEnv, T, smem, st>>>(A); else k_env_solve<T, false><<<s->nEnv, T, smem, st>>>(A); } while (0)
     if (s->envSolveThreads == 32) ENV_LAUNCH(32); else if (s->envSolveThreads == 64) ENV_LAUNCH(64); else if (s->envSolveThreads == 128) ENV_LAUNCH(128); else ENV_LAUNCH(256);
 #undef ENV_LAUNCH

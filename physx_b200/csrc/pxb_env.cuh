@@ -241,7 +241,17 @@ __device__ __forceinline__ void prep_constraint_regs(RegRows& r, uint32_t i, uin
 // a15 on a register-resident record: same arithmetic and operation order as solve_constraint (solveContact,
 // DyTGSContactPrep.cpp:1581-1873).  Friction rows have targetVel == 0 (prep_friction_row), so `x - 0*t` and `bias - 0` of
 // the reference are the identity and are dropped.
-__device__ __forceinline__ void solve_constraint_regs(RegRows& r, const float minPen, const float elapsedTime, float4* bLin, float4* bAng, const float4* bDLin, const float4* bDAng) {
+// FR: the friction half of the record (t0, t1, fa, fb, fap [, pc1 for PGS]) lives in shared memory as fr[field * frStride] (this
+// thread's column) instead of registers: it is only touched in the friction section, which keeps the register count at 128
+// and lets 8 instead of 6 environments be resident per SM.
+struct FrView { float4* p; uint32_t stride; };
+PXB_D void fr_spill(const FrView& v, const RegRows& r) {
+  v.p[0] = r.t0; v.p[v.stride] = r.t1; v.p[10 * v.stride] = r.fap; v.p[11 * v.stride] = r.pc1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v.p[(2 + j) * v.stride] = r.fa[j]; v.p[(6 + j) * v.stride] = r.fb[j]; }
+}
+template <bool FR>
+__device__ __forceinline__ void solve_constraint_regs(RegRows& r, const float minPen, const float elapsedTime, float4* bLin, float4* bAng, const float4* bDLin, const float4* bDAng, const FrView fr = FrView()) {
   const uint32_t b0 = r.h2.x, b1 = r.h2.y;
   const int numNormal = (int)(r.h2.z & 0xff), numFriction = (int)((r.h2.z >> 8) & 0xff);
   const v3 n = V3(r.h0.x, r.h0.y, r.h0.z); const float maxPenBias = r.h0.w;
@@ -281,15 +291,17 @@ __device__ __forceinline__ void solve_constraint_regs(RegRows& r, const float mi
   }
   if (numFriction) {
     const float maxFrictionImpulse = r.h1.z * accum, maxDynFrictionImpulse = r.h1.w * accum;
-    const float frictionScale = r.t0.w, biasScale = r.t1.w;
-    const v3 normal0 = V3(r.t0.x, r.t0.y, r.t0.z), normal1 = V3(r.t1.x, r.t1.y, r.t1.z);
+    const float4 T0 = FR ? fr.p[0] : r.t0, T1 = FR ? fr.p[fr.stride] : r.t1; float4 fap = FR ? fr.p[10 * fr.stride] : r.fap;
+    const float frictionScale = T0.w, biasScale = T1.w;
+    const v3 normal0 = V3(T0.x, T0.y, T0.z), normal1 = V3(T1.x, T1.y, T1.z);
     bool broken = false;
 #pragma unroll
     for (int j = 0; j < 4; j += 2) {
       if (j < numFriction) {
-        const float4 A0 = r.fa[j], B0 = r.fb[j], A1 = r.fa[j + 1], B1 = r.fb[j + 1];
+        const float4 A0 = FR ? fr.p[(2 + j) * fr.stride] : r.fa[j], B0 = FR ? fr.p[(6 + j) * fr.stride] : r.fb[j];
+        const float4 A1 = FR ? fr.p[(3 + j) * fr.stride] : r.fa[j + 1], B1 = FR ? fr.p[(7 + j) * fr.stride] : r.fb[j + 1];
         const v3 raXnI0 = V3(A0.x, A0.y, A0.z), rbXnI0 = V3(B0.x, B0.y, B0.z), raXnI1 = V3(A1.x, A1.y, A1.z), rbXnI1 = V3(B1.x, B1.y, B1.z);
-        const float applied0 = f4get(r.fap, j), applied1 = f4get(r.fap, j + 1);
+        const float applied0 = f4get(fap, j), applied1 = f4get(fap, j + 1);
         const float deltaV0 = (adot(raXnI0, angMotion0) - adot(rbXnI0, angMotion1)) + adot(normal0, relMotion);
         const float deltaV1 = (adot(raXnI1, angMotion0) - adot(rbXnI1, angMotion1)) + adot(normal1, relMotion);
         const float bias0 = (A0.w + deltaV0) * biasScale, bias1 = (A1.w + deltaV1) * biasScale;
@@ -310,9 +322,10 @@ __device__ __forceinline__ void solve_constraint_regs(RegRows& r, const float mi
         linVel1 = negscalesub(normal0 * invMassB, dF0, negscalesub(normal1 * invMassB, dF1, linVel1));
         angState0 = scaleadd(raXnI0, dF0 * 1.f, scaleadd(raXnI1, dF1 * 1.f, angState0));
         angState1 = negscalesub(rbXnI0, dF0 * 1.f, negscalesub(rbXnI1, dF1 * 1.f, angState1));
-        f4set(r.fap, j, new0); f4set(r.fap, j + 1, new1);
+        f4set(fap, j, new0); f4set(fap, j + 1, new1);
       }
     }
+    if (FR) fr.p[10 * fr.stride] = fap; else r.fap = fap;
     r.broken = broken ? 1u : 0u;  // hdr->broken is overwritten by every solve call (Store_From_BoolV)
   }
   bLin[b0] = F4(linVel0, 0.f); bAng[b0] = F4(angState0, 0.f);
@@ -381,11 +394,12 @@ __device__ __forceinline__ void env_integrate_substep(uint32_t n, float stepDt, 
 template <int T, bool REG, bool PGS>
 __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows R, const ConLists L, const uint32_t base, const uint32_t nCon, const uint32_t n,
                                                float4* bLin, float4* bAng, float4* bDLin, float4* bDAng, float4* bIA, float4* bIB, float4* bP, float4* bQ,
-                                               const uint32_t* sPartStart, const uint32_t nPart, long long& t_prev) {
+                                               const uint32_t* sPartStart, const uint32_t nPart, float4* sFr, long long& t_prev) {
   const uint32_t tid = threadIdx.x;
   RegRows mine;
   const float4* vLin = PGS ? bDLin : bLin; const float4* vAng = PGS ? bDAng : bQ;
-  if (REG) { if (tid < nCon) env_prep_one<PGS>(A, L, base, tid, vLin, bIA, bIB, vAng, mine); }
+  const FrView fr = {sFr + tid, T};
+  if (REG) { if (tid < nCon) { env_prep_one<PGS>(A, L, base, tid, vLin, bIA, bIB, vAng, mine); fr_spill(fr, mine); } }
   else for (uint32_t pos = tid; pos < nCon; pos += T) { RegRows r; env_prep_one<PGS>(A, L, base, pos, vLin, bIA, bIB, vAng, r); rows_store(R, pos, r); }
   __syncthreads();
   ENV_T(4);
@@ -396,8 +410,8 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
       const bool doFriction = it <= 3;
       for (uint32_t p = 0; p < nPart; ++p) {
         const uint32_t pb = sPartStart[p], pe = sPartStart[p + 1];
-        if (REG) { if (tid >= pb && tid < pe) { solve_constraint_pgs(mine, doFriction, bLin, bAng); if (it == 1) conclude_constraint_pgs(mine); } }
-        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_pgs(r, doFriction, bLin, bAng); if (it == 1) { conclude_constraint_pgs(r); rows_store(R, k, r); } else rows_store_state(R, k, r); }
+        if (REG) { if (tid >= pb && tid < pe) { solve_constraint_pgs<true>(mine, doFriction, bLin, bAng, fr); if (it == 1) conclude_constraint_pgs<true>(mine, fr); } }
+        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_pgs<false>(r, doFriction, bLin, bAng); if (it == 1) { conclude_constraint_pgs<false>(r); rows_store(R, k, r); } else rows_store_state(R, k, r); }
         __syncthreads();
       }
     }
@@ -407,8 +421,8 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
     for (uint32_t it = 0; it < velIters; ++it)
       for (uint32_t p = 0; p < nPart; ++p) {
         const uint32_t pb = sPartStart[p], pe = sPartStart[p + 1];
-        if (REG) { if (tid >= pb && tid < pe) solve_constraint_pgs(mine, true, bLin, bAng); }
-        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_pgs(r, true, bLin, bAng); rows_store_state(R, k, r); }
+        if (REG) { if (tid >= pb && tid < pe) solve_constraint_pgs<true>(mine, true, bLin, bAng, fr); }
+        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_pgs<false>(r, true, bLin, bAng); rows_store_state(R, k, r); }
         __syncthreads();
       }
   } else {
@@ -421,8 +435,8 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
       const float minPen = vel ? 0.f : -FLT_MAX;
       for (uint32_t p = 0; p < nPart; ++p) {
         const uint32_t pb = sPartStart[p], pe = sPartStart[p + 1];
-        if (REG) { if (tid >= pb && tid < pe) solve_constraint_regs(mine, minPen, elapsed, bLin, bAng, bDLin, bDAng); }
-        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_regs(r, minPen, elapsed, bLin, bAng, bDLin, bDAng); rows_store_state(R, k, r); }
+        if (REG) { if (tid >= pb && tid < pe) solve_constraint_regs<true>(mine, minPen, elapsed, bLin, bAng, bDLin, bDAng, fr); }
+        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_regs<false>(r, minPen, elapsed, bLin, bAng, bDLin, bDAng); rows_store_state(R, k, r); }
         __syncthreads();
       }
       if (!vel) {
@@ -438,10 +452,10 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
 }
 
 // dynamic shared memory of k_env_solve (host mirror: env_solve_smem in pxb_engine.cu):
-//   8 x maxList float4 body state | u32: 3 x maxList body masks, 5 x conCap constraint lists
+//   8 x maxList float4 body state | u32: 3 x maxList body masks, 5 x conCap constraint lists (padded to 16 B) | 12 x T float4 friction rows
 // conCap = list capacity (pairs of the environment); environments with more pairs keep their lists in global scratch.
 #ifndef PXB_ENV_CTAS64
-#define PXB_ENV_CTAS64 6
+#define PXB_ENV_CTAS64 8
 #endif
 template <int T, bool PGS>
 __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB_ENV_CTAS64 / 2 : 1))) k_env_solve(const EnvSolveArgs A) {
@@ -454,6 +468,7 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   float4 *bLin = envSmem, *bAng = bLin + nb, *bDLin = bAng + nb, *bDAng = bDLin + nb, *bIA = bDAng + nb, *bIB = bIA + nb, *bP = bIB + nb, *bQ = bP + nb;
   uint32_t* bMask = reinterpret_cast<uint32_t*>(bQ + nb); uint32_t* bFirst = bMask + nb; uint32_t* bStat = bFirst + nb;
   uint32_t* sLists = bStat + nb;
+  float4* sFr = reinterpret_cast<float4*>(sLists + 5 * lc + ((4 - ((3 * nb + 5 * lc) & 3)) & 3));   // 12 x T float4: friction half of the register rows
   ConLists L;
   if (m <= lc) { L.conPair = sLists; L.b0 = sLists + lc; L.b1 = sLists + 2 * lc; L.colour = sLists + 3 * lc; L.ordered = sLists + 4 * lc; }
   else { L.conPair = A.conPair + base; L.b0 = A.conB0 + base; L.b1 = A.conB1 + base; L.colour = A.conColour + base; L.ordered = A.ordered + base; }
@@ -572,8 +587,8 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   ENV_T(3);
   if (nCon) {
     Rows R; R.f = A.rowScratch + base; R.broken = A.broken + base; R.stride = A.cap;
-    if (nCon <= T) env_solve_body<T, true, PGS>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, t_prev);
-    else env_solve_body<T, false, PGS>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, t_prev);
+    if (nCon <= T) env_solve_body<T, true, PGS>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, sFr, t_prev);
+    else env_solve_body<T, false, PGS>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, sFr, t_prev);
   } else {
     for (uint32_t b = tid; b < n; b += T) { if (PGS) { bP[b] = make_float4(0, 0, 0, 0); bQ[b] = make_float4(0, 0, 0, 0); } else bQ[b] = make_float4(0, 0, 0, 1); }
   }

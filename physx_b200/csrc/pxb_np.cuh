@@ -17,39 +17,44 @@
 #define PXB_MANIFOLD_F4 16   // float4 slots per persistent manifold record (14 used)
 
 struct MPoint { v3 a, b, n; float pen; };
-struct Manifold { int n; xf rel; q4 quatA, quatB; MPoint pts[PXB_MANIFOLD_CACHE]; };
+struct Manifold { int n; xf rel; q4 quatA, quatB; MPoint pts[PXB_MANIFOLD_CACHE]; int dirty; };   // dirty: points / frames regenerated this frame (else only pens changed)
 struct Contacts { int count; v3 normal; v3 point[PXB_MANIFOLD_CACHE]; float sep[PXB_MANIFOLD_CACHE]; };
 
 PXB_D void manifold_init(Manifold& m) {
   m.n = 0; m.rel.q = Q4(0, 0, 0, 1); m.rel.p = V3(FLT_MAX, FLT_MAX, FLT_MAX);
-  m.quatA = Q4(0, 0, 0, 1); m.quatB = Q4(0, 0, 0, 1);
+  m.quatA = Q4(0, 0, 0, 1); m.quatB = Q4(0, 0, 0, 1); m.dirty = 1;
   for (int i = 0; i < PXB_MANIFOLD_CACHE; ++i) { m.pts[i].a = V3(0, 0, 0); m.pts[i].b = V3(0, 0, 0); m.pts[i].n = V3(0, 0, 0); m.pts[i].pen = 0.f; }
 }
 
-// record layout: [0]=(n, rel.p) [1]=rel.q [2]=quatA [3]=quatB [4+..]=4 points x 10 floats
+// record layout: [0]=(n, rel.p) [1]=rel.q [2]=quatA [3]=quatB [4]=pen of the 4 points [5..13]=4 points x 9 floats (a, b, n).
+// The penetrations sit in one float4 because they are the only thing a persisting manifold changes per frame
+// (refreshContactPoints, GuPersistentContactManifold.h:723-752): steady state writes 16-32 B per pair instead of 224 B.
 PXB_D void manifold_load(Manifold& m, const float4* __restrict__ rec) {
-  const float4 h = rec[0], rq = rec[1], qa = rec[2], qb = rec[3];
-  m.n = __float_as_int(h.x); m.rel.p = V3(h.y, h.z, h.w); m.rel.q = Q4(rq); m.quatA = Q4(qa); m.quatB = Q4(qb);
-  float f[40];
+  const float4 h = rec[0], rq = rec[1], qa = rec[2], qb = rec[3], pen = rec[4];
+  m.n = __float_as_int(h.x); m.rel.p = V3(h.y, h.z, h.w); m.rel.q = Q4(rq); m.quatA = Q4(qa); m.quatB = Q4(qb); m.dirty = 0;
+  float f[36];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) { const float4 v = rec[4 + i]; f[i * 4] = v.x; f[i * 4 + 1] = v.y; f[i * 4 + 2] = v.z; f[i * 4 + 3] = v.w; }
+  for (int i = 0; i < 9; ++i) { const float4 v = rec[5 + i]; f[i * 4] = v.x; f[i * 4 + 1] = v.y; f[i * 4 + 2] = v.z; f[i * 4 + 3] = v.w; }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    m.pts[i].a = V3(f[i * 10], f[i * 10 + 1], f[i * 10 + 2]); m.pts[i].b = V3(f[i * 10 + 3], f[i * 10 + 4], f[i * 10 + 5]);
-    m.pts[i].n = V3(f[i * 10 + 6], f[i * 10 + 7], f[i * 10 + 8]); m.pts[i].pen = f[i * 10 + 9];
+    m.pts[i].a = V3(f[i * 9], f[i * 9 + 1], f[i * 9 + 2]); m.pts[i].b = V3(f[i * 9 + 3], f[i * 9 + 4], f[i * 9 + 5]);
+    m.pts[i].n = V3(f[i * 9 + 6], f[i * 9 + 7], f[i * 9 + 8]);
   }
+  m.pts[0].pen = pen.x; m.pts[1].pen = pen.y; m.pts[2].pen = pen.z; m.pts[3].pen = pen.w;
 }
 PXB_D void manifold_store(const Manifold& m, float4* __restrict__ rec) {
   rec[0] = make_float4(__int_as_float(m.n), m.rel.p.x, m.rel.p.y, m.rel.p.z); rec[1] = F4(m.rel.q); rec[2] = F4(m.quatA); rec[3] = F4(m.quatB);
-  float f[40];
+  rec[4] = make_float4(m.pts[0].pen, m.pts[1].pen, m.pts[2].pen, m.pts[3].pen);
+  float f[36];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    f[i * 10] = m.pts[i].a.x; f[i * 10 + 1] = m.pts[i].a.y; f[i * 10 + 2] = m.pts[i].a.z; f[i * 10 + 3] = m.pts[i].b.x; f[i * 10 + 4] = m.pts[i].b.y;
-    f[i * 10 + 5] = m.pts[i].b.z; f[i * 10 + 6] = m.pts[i].n.x; f[i * 10 + 7] = m.pts[i].n.y; f[i * 10 + 8] = m.pts[i].n.z; f[i * 10 + 9] = m.pts[i].pen;
+    f[i * 9] = m.pts[i].a.x; f[i * 9 + 1] = m.pts[i].a.y; f[i * 9 + 2] = m.pts[i].a.z; f[i * 9 + 3] = m.pts[i].b.x; f[i * 9 + 4] = m.pts[i].b.y;
+    f[i * 9 + 5] = m.pts[i].b.z; f[i * 9 + 6] = m.pts[i].n.x; f[i * 9 + 7] = m.pts[i].n.y; f[i * 9 + 8] = m.pts[i].n.z;
   }
 #pragma unroll
-  for (int i = 0; i < 10; ++i) rec[4 + i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+  for (int i = 0; i < 9; ++i) rec[5 + i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
 }
+PXB_D void manifold_store_pens(const Manifold& m, float4* __restrict__ rec) { rec[4] = make_float4(m.pts[0].pen, m.pts[1].pen, m.pts[2].pen, m.pts[3].pen); }
 
 PXB_D float box_margin(v3 e, float toleranceLength) {  // GuVecBox.h:81-88
   const float mn = fmin_(e.x, fmin_(e.y, e.z));
@@ -216,7 +221,7 @@ PXB_D void pcm_plane_box(const xf& planeTm, const xf& boxTm, v3 be, float contac
   out.count = 0; out.normal = negPlaneNormal;
   if (lost || invalidate_plane(man, cur, margin, 0.2f)) {
     const v3 ln = V3(1.f, 0.f, 0.f);
-    man.n = 0; man.rel = cur;
+    man.n = 0; man.rel = cur; man.dirty = 1;
     const v3 t0 = aToB.r.c0 * be.x, t1 = aToB.r.c1 * be.y, t2 = aToB.r.c2 * be.z;
     const v3 nt2 = -t2;
     const float px = aToB.p.x;
@@ -474,7 +479,7 @@ PXB_D void pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contact
   const float radiusA = alen(e0), radiusB = alen(e1);
   out.count = 0; out.normal = V3(0, 0, 0);
   if (lost || invalidate_boxconvex(man, cur, tm0.q, tm1.q, minMargin, radiusA, radiusB)) {
-    man.rel = cur; man.quatA = tm0.q; man.quatB = tm1.q;
+    man.rel = cur; man.quatA = tm0.q; man.quatB = tm1.q; man.dirty = 1;
     mxf tv0 = amxffromxf(tm0), tv1 = amxffromxf(tm1);
     tv0.r.c0 = anormalize(tv0.r.c0); tv0.r.c1 = anormalize(tv0.r.c1); tv0.r.c2 = anormalize(tv0.r.c2);
     tv1.r.c0 = anormalize(tv1.r.c0); tv1.r.c1 = anormalize(tv1.r.c1); tv1.r.c2 = anormalize(tv1.r.c2);
@@ -583,7 +588,7 @@ PXB_D void pcm_plane_capsule(const xf& planeTm, const xf& capTm, float radius, f
   manifold_refresh(man, aToBm, radius * 0.05f);
   const bool lost = man.n != initial;
   if (lost || invalidate_plane(man, aToB, radius, 0.02f)) {
-    man.n = 0; man.rel = aToB;
+    man.n = 0; man.rel = aToB; man.dirty = 1;
     if (inflatedRadius > s.x) add_manifold_point2(man, aqrotinv(aToB.q, s - aToB.p), negscalesub(ln, s.x, s), ln, s.x, radius * 0.001f);
     if (inflatedRadius > e.x) add_manifold_point2(man, aqrotinv(aToB.q, e - aToB.p), negscalesub(ln, e.x, e), ln, e.x, radius * 0.001f);
   }

@@ -100,7 +100,8 @@ __device__ __forceinline__ void prep_constraint_pgs(RegRows& r, uint32_t i, uint
   }
 }
 
-__device__ __forceinline__ void solve_constraint_pgs(RegRows& r, const bool doFriction, float4* bLin, float4* bAng) {
+template <bool FR>
+__device__ __forceinline__ void solve_constraint_pgs(RegRows& r, const bool doFriction, float4* bLin, float4* bAng, const FrView fr = FrView()) {
   const uint32_t b0 = r.h2.x, b1 = r.h2.y;
   const int numNormal = (int)(r.h2.z & 0xff), numFriction = (int)((r.h2.z >> 8) & 0xff);
   const v3 n = V3(r.h0.x, r.h0.y, r.h0.z);
@@ -132,15 +133,16 @@ __device__ __forceinline__ void solve_constraint_pgs(RegRows& r, const bool doFr
   if (doFriction && numFriction) {
     const float maxFrictionImpulse = r.h1.z * accum, maxDynFrictionImpulse = r.h1.w * accum;
     const float negMaxDyn = -maxDynFrictionImpulse;
+    const float4 T0 = FR ? fr.p[0] : r.t0, T1 = FR ? fr.p[fr.stride] : r.t1, TV = FR ? fr.p[11 * fr.stride] : r.pc1; float4 fap = FR ? fr.p[10 * fr.stride] : r.fap;
     bool broken = false;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j < numFriction) {
-        const float4 T = (j & 1) ? r.t1 : r.t0;
+        const float4 T = (j & 1) ? T1 : T0;
         const v3 normal = V3(T.x, T.y, T.z);
-        const float4 A = r.fa[j], B = r.fb[j];
+        const float4 A = FR ? fr.p[(2 + j) * fr.stride] : r.fa[j], B = FR ? fr.p[(6 + j) * fr.stride] : r.fb[j];
         const v3 raXn = V3(A.x, A.y, A.z), rbXn = V3(B.x, B.y, B.z);
-        const float applied = f4get(r.fap, j), bias = B.w, velMultiplier = A.w, targetVel = f4get(r.pc1, j);
+        const float applied = f4get(fap, j), bias = B.w, velMultiplier = A.w, targetVel = f4get(TV, j);
         const v3 del0 = normal * invMassA, del1 = normal * invMassB;
         const v3 dv = (vmul(linVel0, normal) + vmul(angState0, raXn)) - (vmul(linVel1, normal) + vmul(angState1, rbXn));
         const float normalVel = (dv.x + dv.y) + dv.z;
@@ -153,9 +155,10 @@ __device__ __forceinline__ void solve_constraint_pgs(RegRows& r, const bool doFr
         const float deltaF = newApplied - applied;
         linVel0 = scaleadd(del0, deltaF, linVel0); linVel1 = negscalesub(del1, deltaF, linVel1);
         angState0 = scaleadd(raXn, deltaF * 1.f, angState0); angState1 = negscalesub(rbXn, deltaF * 1.f, angState1);
-        f4set(r.fap, j, newApplied);
+        f4set(fap, j, newApplied);
       }
     }
+    if (FR) fr.p[10 * fr.stride] = fap; else r.fap = fap;
     r.broken = broken ? 1u : 0u;
   }
   bLin[b0] = F4(linVel0, 0.f); bAng[b0] = F4(angState0, 0.f);
@@ -163,9 +166,10 @@ __device__ __forceinline__ void solve_constraint_pgs(RegRows& r, const bool doFr
 }
 
 // concludeContact: biased error -> unbiased error, friction bias -> 0
-__device__ __forceinline__ void conclude_constraint_pgs(RegRows& r) {
+template <bool FR>
+__device__ __forceinline__ void conclude_constraint_pgs(RegRows& r, const FrView fr = FrView()) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { r.pb[j].w = f4get(r.pc0, j); r.fb[j].w = 0.f; }
+  for (int j = 0; j < 4; ++j) { r.pb[j].w = f4get(r.pc0, j); if (FR) fr.p[(6 + j) * fr.stride].w = 0.f; else r.fb[j].w = 0.f; }
 }
 
 // integrateCore: pose from the motion velocity (deltas after the position iterations), velocity from the final deltas
@@ -232,8 +236,8 @@ __global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve_pgs(const 
       for (uint32_t k = b + gtid; k < e; k += gsize) {
         RegRows r; rows_load(R, k, r);
         if ((r.h2.z & 0xff) == 0) continue;
-        solve_constraint_pgs(r, doFriction, sbLin, sbAng);
-        if (it == 1) { conclude_constraint_pgs(r); rows_store(R, k, r); } else rows_store_state(R, k, r);
+        solve_constraint_pgs<false>(r, doFriction, sbLin, sbAng);
+        if (it == 1) { conclude_constraint_pgs<false>(r); rows_store(R, k, r); } else rows_store_state(R, k, r);
       }
       grid.sync();
     }
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve_pgs(const 
       for (uint32_t k = b + gtid; k < e; k += gsize) {
         RegRows r; rows_load(R, k, r);
         if ((r.h2.z & 0xff) == 0) continue;
-        solve_constraint_pgs(r, true, sbLin, sbAng);
+        solve_constraint_pgs<false>(r, true, sbLin, sbAng);
         rows_store_state(R, k, r);
       }
       grid.sync();
