@@ -140,7 +140,7 @@ def bench_ours(args):
 
     n_envs = args.envs
     solver = scenes.SOLVER_PGS if args.solver == "pgs" else scenes.SOLVER_TGS
-    sc = scenes.env_grid_stacks(n_envs=n_envs, seed=1234 + rank, solver=solver)  # every rank owns its own envs (weak scaling)
+    sc = scenes.env_grid_stacks(n_envs=n_envs, stacks_per_env=args.stacks, seed=1234 + rank, solver=solver)  # every rank owns its own envs (weak scaling)
     scene = engine.Scene(sc, device=local)
     nb = scene.num_dynamic
     stream = torch.cuda.ExternalStream(scene.stream(), device=dev)
@@ -266,7 +266,7 @@ def bench_ours(args):
             kernel_bytes = prep_bytes + solve_bytes + integ_bytes
             note = ("algorithmic bytes = SURVEY 8d prep + 5 solver iterations + integration; the kernel keeps every solver row on chip (registers), "
                     "so only contacts, friction patches and body state cross HBM once: see `traffic` (ncu dram bytes per launch, profiles/r01_env_kernels_full_raw.csv)")
-            traffic = ENV_SOLVE_DRAM_BYTES_PER_LAUNCH if n_envs == 4096 else None
+            traffic = ENV_SOLVE_DRAM_BYTES_PER_LAUNCH if (n_envs == 4096 and args.stacks == 8 and args.solver == "tgs") else None
         else:
             kernel_name = "k_solve (all TGS iterations, one cooperative launch)"
             kernel_bytes = solve_bytes
@@ -277,7 +277,7 @@ def bench_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config 2: {n_envs} envs x {BOXES_PER_ENV} boxes = {nb} bodies per GPU, shared ground plane, GPU broadphase + {args.solver.upper()} 4 pos/1 vel iterations, 60 Hz",
+            "config": {"workload": f"config {2 if args.stacks == 8 else 5}: {n_envs} envs x {args.stacks * 8} boxes = {nb} bodies per GPU, shared ground plane, GPU broadphase + {args.solver.upper()} 4 pos/1 vel iterations, 60 Hz",
                        "bodies_total": total_bodies, "constraints_per_gpu": P, "partitions": scene.num_partitions, "path": "environment (pxb_env.cuh)" if scene.uses_env_path else "device-wide",
                        "timing": "CUDA events on the scene stream per step, max over ranks; L2 flushed (256 MiB memset) between timed steps",
                        "multi_gpu": "env-partitioned, one scene per GPU, per-step NCCL all-gather of the packed pose+linear+angular velocity tensor (13 floats/body), double-buffered on a communication stream (overlaps the next step)" if world > 1 else "single scene"},
@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=1024, help="environments in the reference arm's bounded sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stacks", type=int, default=8, help="stacks of 8 boxes per environment (8 = config 2, 16 = the per-GPU shard of config 5)")
     ap.add_argument("--solver", default="tgs", choices=["tgs", "pgs"], help="PxSolverType of the scene (headline metric: tgs)")
     args = ap.parse_args()
     if args.impl == "reference":

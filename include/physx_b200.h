@@ -48,7 +48,8 @@ typedef struct {
   uint32_t maxActors;                  /* capacity */
   uint32_t maxPairs;                   /* PxGpuDynamicsMemoryConfig::foundLostPairsCapacity / maxRigidPatchCount analogue; 0 = 8*maxActors */
   int32_t  device;                     /* CUDA device ordinal (PxCudaContextManagerDesc) */
-  uint32_t reserved[8];                /* [0] internal; [1] = PXB_FLAG_* bits; [2]/[3] = test hooks of the environment path: constraint-list slots in shared memory / constraints per CTA (0 = adaptive) */
+  uint32_t reserved[8];                /* [0] internal; [1] = PXB_FLAG_* bits; [2]/[3] = test hooks of the environment path: constraint-list slots in shared memory / constraints per CTA (0 = adaptive);
+                                          [4] = sleep threshold as IEEE-754 float bits (PxRigidDynamic::setSleepThreshold, uniform; 0 = sleeping off) */
 } PxbSceneDesc;
 /* Scenes whose dynamic actors all carry an environment id (PxActor::setEnvironmentID, the RL many-env layout of
  * BASELINE configs 2/5) run on the environment path: one warp / one CTA per environment with solver rows in shared
@@ -134,6 +135,9 @@ PXB_API int  pxb_scene_set_profiling(PxbScene* scene, int enable);
 PXB_API int  pxb_scene_get_stage_times(PxbScene* scene, float* ms7);
 /* number of kernels launched by the last pxb_scene_simulate call */
 PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* scene);
+/* Sleeping (a18: integrateCoreParallelLaunchTGS sleepCheck / updateWakeCounter, DySleep.cpp:35-236): per DYNAMIC body the wake counter
+ * (PxRigidDynamic::getWakeCounter) and 1 if asleep (isSleeping).  Islands whose bodies are all ready are put to sleep on the device. */
+PXB_API int  pxb_scene_get_sleep_data(PxbScene* scene, float* wakeCounters, uint32_t* asleep);
 /* 1 if the last step ran on the environment path, 0 for the device-wide path */
 PXB_API int  pxb_scene_uses_env_path(PxbScene* scene);
 

@@ -121,7 +121,7 @@ int main(int argc, char** argv) {
   }
   const char* scenePath = argv[2];
   int steps = 100, threads = 1, warmup = 0;
-  const char *statesPath = nullptr, *bpPath = nullptr, *contactsPath = nullptr, *hullsPath = nullptr, *orderPath = nullptr;
+  const char *statesPath = nullptr, *bpPath = nullptr, *contactsPath = nullptr, *hullsPath = nullptr, *orderPath = nullptr, *sleepPath = nullptr;
   for (int i = 3; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--steps") steps = atoi(argv[++i]);
@@ -132,6 +132,7 @@ int main(int argc, char** argv) {
     else if (a == "--contacts") contactsPath = argv[++i];
     else if (a == "--hulls") hullsPath = argv[++i];
     else if (a == "--order") orderPath = argv[++i];
+    else if (a == "--sleep") sleepPath = argv[++i];   // per step, per dynamic actor: f32 wakeCounter, u32 isSleeping
   }
   gWantContacts = contactsPath != nullptr;
   static int wantContactsFlag; wantContactsFlag = gWantContacts ? 1 : 0;
@@ -242,6 +243,7 @@ int main(int argc, char** argv) {
   FILE* fb = bpPath ? fopen(bpPath, "wb") : nullptr;
   FILE* fc = contactsPath ? fopen(contactsPath, "wb") : nullptr;
   FILE* fo = orderPath ? fopen(orderPath, "wb") : nullptr;
+  FILE* fsl = sleepPath ? fopen(sleepPath, "wb") : nullptr;
   static FILE* sFo; static PxScene* sScene; sFo = fo; sScene = scene;
   static void (*sDump)();
   auto dumpOrder = []() {
@@ -329,6 +331,7 @@ int main(int argc, char** argv) {
     double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     if (s >= warmup) { totalMs += ms; stepMs.push_back(ms); }
     dumpStates();
+    if (fsl) for (size_t i = 0; i < dyn.size(); i++) { const float wc = dyn[i]->getWakeCounter(); const uint32_t sl = dyn[i]->isSleeping() ? 1u : 0u; fwrite(&wc, 4, 1, fsl); fwrite(&sl, 4, 1, fsl); }
     if (fc) {
       std::sort(gContacts.pairs.begin(), gContacts.pairs.end(), [](const ContactDump::Pair& x, const ContactDump::Pair& y) {
         return std::make_pair(x.a0, x.a1) < std::make_pair(y.a0, y.a1); });
@@ -344,6 +347,7 @@ int main(int argc, char** argv) {
   if (fb) fclose(fb);
   if (fc) fclose(fc);
   if (fo) fclose(fo);
+  if (fsl) fclose(fsl);
   std::sort(stepMs.begin(), stepMs.end());
   double med = stepMs.empty() ? 0 : stepMs[stepMs.size() / 2];
   double p95 = stepMs.empty() ? 0 : stepMs[std::min(stepMs.size() - 1, size_t(stepMs.size() * 0.95))];

@@ -88,7 +88,8 @@ struct PxbScene {
   // environment-partitioned path (pxb_env.cuh)
   bool envEligible = false, envActive = false, envDisabled = false, everStepped = false; uint32_t ringMask = 0;
   uint32_t nEnv = 0, envMaxList = 0, envConCap = 0, envConCapForced = 0, envThreadsForced = 0, hMaxConEnv = 0, hMaxPairEnv = 0, envSolveThreads = 64;
-  uint32_t *envStart = 0, *envList = 0, *actorLocal = 0, *slotColour = 0; unsigned long long* bodyBest = 0; bool relaxedPartitioning = false; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
+  uint32_t *envStart = 0, *envList = 0, *actorLocal = 0, *slotColour = 0; unsigned long long* bodyBest = 0; bool relaxedPartitioning = false;
+  float sleepThreshold = 0.f; float* wake = 0; float4 *accLin = 0, *accAng = 0; uint32_t *asleep = 0, *nInter = 0, *islandLabel = 0, *islandAwake = 0; int coopBlocksSleep = 0; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
 };
 
 static thread_local std::string g_err;
@@ -480,18 +481,100 @@ __global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__
   for (uint32_t c = cb + threadIdx.x; c < ce; c += blockDim.x) { const uint32_t col = conColour[c]; ordered[shBase[col] + atomicAdd(&shCnt[col], 1u)] = c; }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a18 sleeping.  Per body: Dy::sleepCheck / updateWakeCounter, non-stabilised branch (lowleveldynamics/src/DySleep.cpp:169-236;
+// GPU reference: sleepCheck / updateWakeCounter in gpusolver integration.cuh:40-435).  Per island (the host island manager's
+// job in the reference pipeline, IG::IslandSim): k_sleep_islands puts an island to sleep once every body in it is ready and
+// wakes sleeping bodies that touch an awake island.  Disabled (threshold 0) for throughput runs, SURVEY.md 8d.
+struct SleepArgs { float threshold, dt; float* wake; float4 *accLin, *accAng; uint32_t *asleep, *nInter; };
+__device__ __forceinline__ bool body_asleep(const SleepArgs& S, uint32_t a) { return S.threshold > 0.f && S.asleep[a] != 0u; }
+__device__ __forceinline__ void sleep_check_dev(const SleepArgs& S, uint32_t a, q4 q, float4 invInertia, float invMassIn, v3 motionLin, v3 motionAng) {
+  const float wakeCounterResetTime = 20.0f * 0.02f;
+  float wc = S.wake[a];
+  if (wc < wakeCounterResetTime * 0.5f || wc < S.dt) {
+    const v3 inertia = V3(invInertia.x > 0.f ? 1.0f / invInertia.x : 1.0f, invInertia.y > 0.f ? 1.0f / invInertia.y : 1.0f, invInertia.z > 0.f ? 1.0f / invInertia.z : 1.0f);
+    const v3 accL = V3(S.accLin[a]) + motionLin, accA = V3(S.accAng[a]) + qrotinv(q, motionAng);
+    const float invMass = invMassIn == 0.0f ? 1.0f : invMassIn;
+    const float angular = dot(vmul(accA, accA), inertia) * invMass, linear = lensq(accL);
+    const float normalizedEnergy = 0.5f * (angular + linear);
+    const float clusterFactor = (float)(1u + S.nInter[a]);
+    const float threshold = clusterFactor * S.threshold;
+    if (normalizedEnergy >= threshold) {
+      S.accLin[a] = make_float4(0, 0, 0, 0); S.accAng[a] = make_float4(0, 0, 0, 0);   // resetSleepFilter
+      const float ratio = normalizedEnergy / threshold;
+      const float factor = threshold == 0.0f ? 2.0f : (ratio < 2.0f ? ratio : 2.0f);
+      S.wake[a] = factor * 0.5f * wakeCounterResetTime + S.dt * (clusterFactor - 1.0f);
+      return;
+    }
+    S.accLin[a] = F4(accL, 0.f); S.accAng[a] = F4(accA, 0.f);
+  }
+  wc = wc - S.dt; if (!(wc > 0.0f)) wc = 0.0f;
+  S.wake[a] = wc;
+  if (wc == 0.0f) { S.accLin[a] = make_float4(0, 0, 0, 0); S.accAng[a] = make_float4(0, 0, 0, 0); }
+}
+// islands = connected components over touching dynamic-dynamic pairs (min-label hooking + pointer jumping, cooperative)
+__global__ void __launch_bounds__(256) k_sleep_islands(uint32_t nA, const uint32_t* __restrict__ nPairsP, const uint2* __restrict__ pairBodies, const float4* __restrict__ cHdr,
+                                                       const uint32_t* __restrict__ geomFlags, SleepArgs S, uint32_t* __restrict__ label, uint32_t* __restrict__ islandAwake,
+                                                       uint32_t* __restrict__ counters, float4* __restrict__ linVel, float4* __restrict__ angVel, uint32_t* __restrict__ conFlag) {
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  const uint32_t nPairs = *nPairsP;
+  for (uint32_t a = gtid; a < nA; a += gsize) { label[a] = a; S.nInter[a] = 0; islandAwake[a] = 0; }
+  grid.sync();
+  for (uint32_t i = gtid; i < nPairs; i += gsize) {   // numCountedInteractions: every broadphase pair of the body (ScBodySim.h:137)
+    const uint2 b = pairBodies[i];
+    if (geomFlags[b.x] & 0x100u) atomicAdd(&S.nInter[b.x], 1u);
+    if (geomFlags[b.y] & 0x100u) atomicAdd(&S.nInter[b.y], 1u);
+  }
+  for (;;) {
+    if (gtid == 0) counters[C_REMAINING] = 0;
+    grid.sync();
+    uint32_t changed = 0;
+    for (uint32_t i = gtid; i < nPairs; i += gsize) {
+      if (__float_as_int(cHdr[i].w) <= 0) continue;
+      const uint2 b = pairBodies[i];
+      if (!(geomFlags[b.x] & 0x100u) || !(geomFlags[b.y] & 0x100u)) continue;
+      const uint32_t la = label[b.x], lb = label[b.y];
+      if (la == lb) continue;
+      const uint32_t mn = min(la, lb), mx = max(la, lb);
+      atomicMin(&label[mx], mn); atomicMin(&label[b.x], mn); atomicMin(&label[b.y], mn);
+      changed = 1;
+    }
+    if (changed) counters[C_REMAINING] = 1;
+    grid.sync();
+    for (uint32_t a = gtid; a < nA; a += gsize) { uint32_t l = label[a]; while (label[l] != l) l = label[l]; label[a] = l; }
+    grid.sync();
+    if (counters[C_REMAINING] == 0) break;
+    grid.sync();
+  }
+  for (uint32_t a = gtid; a < nA; a += gsize) if ((geomFlags[a] & 0x100u) && !S.asleep[a] && S.wake[a] != 0.0f) islandAwake[label[a]] = 1u;   // a body that is not ready keeps its island awake
+  grid.sync();
+  for (uint32_t a = gtid; a < nA; a += gsize) {
+    if (!(geomFlags[a] & 0x100u)) continue;
+    if (islandAwake[label[a]]) S.asleep[a] = 0u;   // woken with the island; the wake counter is re-armed by this step's sleep check
+    else if (!S.asleep[a]) { S.asleep[a] = 1u; linVel[a] = make_float4(0, 0, 0, 0); angVel[a] = make_float4(0, 0, 0, 0); S.accLin[a] = make_float4(0, 0, 0, 0); S.accAng[a] = make_float4(0, 0, 0, 0); }
+  }
+  grid.sync();
+  for (uint32_t i = gtid; i < nPairs; i += gsize) {   // sleeping islands are not solved
+    const uint2 b = pairBodies[i];
+    const bool act0 = (geomFlags[b.x] & 0x100u) && !S.asleep[b.x], act1 = (geomFlags[b.y] & 0x100u) && !S.asleep[b.y];
+    if (!act0 && !act1) conFlag[i] = 0u;
+  }
+}
+
 // a12: unconstrained velocities + solver body setup (preIntegrateBodies, DyTGSDynamics.cpp:992-1021)
 __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynActor, const float4* __restrict__ pos, const float4* __restrict__ quat,
                                float4* __restrict__ linVel, float4* __restrict__ angVel, const float4* __restrict__ invInertia, const float4* __restrict__ damp,
                                float gx, float gy, float gz, float dt, float4* __restrict__ sbLin, float4* __restrict__ sbAng, float4* __restrict__ sbDLin,
                                float4* __restrict__ sbDAng, float4* __restrict__ sbIA, float4* __restrict__ sbIB, float4* __restrict__ sbP, float4* __restrict__ sbQ,
-                               float4* __restrict__ sbOrigAng, int pgs) {
+                               float4* __restrict__ sbOrigAng, int pgs, SleepArgs S) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
+  const bool asleep = body_asleep(S, a);
   const float4 dm = damp[a]; const float4 ii = invInertia[a]; const float4 p4 = pos[a];
   v3 lv = V3(linVel[a]), av = V3(angVel[a]);
-  unconstrained_velocity(V3(gx, gy, gz), dt, dm.x, dm.y, dm.z, dm.w, lv, av);
+  if (!asleep) unconstrained_velocity(V3(gx, gy, gz), dt, dm.x, dm.y, dm.z, dm.w, lv, av);
   linVel[a] = F4(lv, 0.f); angVel[a] = F4(av, 0.f);
   const m33 rot = amfromq(Q4(quat[a]));
   const v3 sqrtInvI = V3(ii.x == 0.f ? 0.f : sqrtf(ii.x), ii.y == 0.f ? 0.f : sqrtf(ii.y), ii.z == 0.f ? 0.f : sqrtf(ii.z));
@@ -713,18 +796,22 @@ __global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve(const uint
 // a17/a18: copyBackBodies (DyTGSDynamics.cpp:1549-1580); bodies without constraints take one full-dt step (:2573-2577)
 __global__ void k_finalize_bodies(uint32_t nDyn, const uint32_t* __restrict__ dynActor, float dt, float4* __restrict__ pos, float4* __restrict__ quat, float4* __restrict__ linVel,
                                   float4* __restrict__ angVel, const float4* __restrict__ sbLin, const float4* __restrict__ sbAng, const float4* __restrict__ sbIA,
-                                  const float4* __restrict__ sbIB, const float4* __restrict__ sbP, const float4* __restrict__ sbQ, const uint32_t* __restrict__ bodyHasCon) {
+                                  const float4* __restrict__ sbIB, const float4* __restrict__ sbP, const float4* __restrict__ sbQ, const uint32_t* __restrict__ bodyHasCon,
+                                  const float4* __restrict__ sbDLin, const float4* __restrict__ sbDAng, const float4* __restrict__ invInertia, SleepArgs S) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
+  if (body_asleep(S, a)) return;
   const m33 sI = load_sym(sbIA[a], sbIB[a]);
   v3 p = V3(sbP[a]); q4 dq = Q4(sbQ[a]);
   const v3 lv = V3(sbLin[a]), as = V3(sbAng[a]);
-  if (!bodyHasCon[a]) { v3 dl = V3(0, 0, 0), da = V3(0, 0, 0); integrate_core_step(lv, as, sI, dt, p, dq, dl, da); }
+  v3 dl = V3(sbDLin[a]), da = V3(sbDAng[a]);
+  if (!bodyHasCon[a]) { dl = V3(0, 0, 0); da = V3(0, 0, 0); integrate_core_step(lv, as, sI, dt, p, dq, dl, da); }
   const float invMass = pos[a].w;
   const q4 q = qnormalized(qmul(dq, Q4(quat[a])));
   pos[a] = make_float4(p.x, p.y, p.z, invMass); quat[a] = F4(q);
   linVel[a] = F4(lv, 0.f); angVel[a] = F4(mmul(sI, as), 0.f);
+  if (S.threshold > 0.f) { const float invDt = 1.0f / dt; sleep_check_dev(S, a, q, invInertia[a], invMass, dl * invDt, mmul(sI, da * invDt)); }   // motionVel of copyBackBodies
 }
 // writeBackContact (DyTGSContactPrep.cpp:1875-1937): applied forces -> contact force stream, broken flag -> friction patch
 __global__ void k_writeback(const uint32_t* __restrict__ counters, uint32_t cap, const uint4* __restrict__ rowC, const float4* __restrict__ ptC, const uint32_t* __restrict__ brokenFlags,
@@ -746,10 +833,11 @@ __global__ void k_rd_get(uint32_t nb, const uint32_t* __restrict__ idx, const ui
   else { const float4 v = type == PXB_RD_LINEAR_VELOCITY ? linVel[a] : angVel[a]; float* o = out + (size_t)i * 3; o[0] = v.x; o[1] = v.y; o[2] = v.z; }
 }
 __global__ void k_rd_set(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, int type, float4* __restrict__ pos, float4* __restrict__ quat,
-                         float4* __restrict__ linVel, float4* __restrict__ angVel, const float* __restrict__ in) {
+                         float4* __restrict__ linVel, float4* __restrict__ angVel, const float* __restrict__ in, float* __restrict__ wake, uint32_t* __restrict__ asleep) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nb) return;
   const uint32_t a = dynActor[idx ? idx[i] : i];
+  wake[a] = 20.0f * 0.02f; asleep[a] = 0u;   // setting pose / velocity wakes the body (PxRigidDynamic autowake, wakeCounterResetValue)
   if (type == PXB_RD_GLOBAL_POSE) { const float* o = in + (size_t)i * 7; quat[a] = make_float4(o[0], o[1], o[2], o[3]); const float w = pos[a].w; pos[a] = make_float4(o[4], o[5], o[6], w); }
   else { const float* o = in + (size_t)i * 3; const float4 v = make_float4(o[0], o[1], o[2], 0.f); if (type == PXB_RD_LINEAR_VELOCITY) linVel[a] = v; else angVel[a] = v; }
 }
@@ -762,10 +850,11 @@ __global__ void k_states_get(uint32_t nDyn, const uint32_t* __restrict__ dynActo
   o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = q.x; o[4] = q.y; o[5] = q.z; o[6] = q.w; o[7] = l.x; o[8] = l.y; o[9] = l.z; o[10] = w.x; o[11] = w.y; o[12] = w.z;
 }
 __global__ void k_states_set(uint32_t nDyn, const uint32_t* __restrict__ dynActor, float4* __restrict__ pos, float4* __restrict__ quat, float4* __restrict__ linVel,
-                             float4* __restrict__ angVel, const float* __restrict__ in) {
+                             float4* __restrict__ angVel, const float* __restrict__ in, float* __restrict__ wake, uint32_t* __restrict__ asleep) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d]; const float* o = in + (size_t)d * 13;
+  wake[a] = 20.0f * 0.02f; asleep[a] = 0u;
   const float w = pos[a].w;
   pos[a] = make_float4(o[0], o[1], o[2], w); quat[a] = make_float4(o[3], o[4], o[5], o[6]); linVel[a] = make_float4(o[7], o[8], o[9], 0.f); angVel[a] = make_float4(o[10], o[11], o[12], 0.f);
 }
@@ -830,6 +919,9 @@ static int scene_alloc(PxbScene* s) {
   k_init_freelist<<<cdiv((uint32_t)Pn, 256), 256, 0, s->stream>>>((uint32_t)Pn, s->freeList);
   const uint32_t top = (uint32_t)Pn;   // ring of free persistent slots: head = 0, tail = Pn
   CK(cudaMemcpyAsync(s->counters + C_FREE_TAIL, &top, 4, cudaMemcpyHostToDevice, s->stream));
+  CK(dalloc(s->wake, A)); CK(dalloc(s->accLin, A)); CK(dalloc(s->accAng, A)); CK(dalloc(s->asleep, A)); CK(dalloc(s->nInter, A)); CK(dalloc(s->islandLabel, A)); CK(dalloc(s->islandAwake, A));
+  CK(cudaMemsetAsync(s->accLin, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->accAng, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->asleep, 0, 4 * A, s->stream)); CK(cudaMemsetAsync(s->nInter, 0, 4 * A, s->stream));
+  { std::vector<float> w(A, 20.0f * 0.02f); CK(cudaMemcpyAsync(s->wake, w.data(), 4 * A, cudaMemcpyHostToDevice, s->stream)); CK(cudaStreamSynchronize(s->stream)); }   // PxRigidDynamic default wake counter
   CK(dalloc(s->bodyBest, A)); CK(dalloc(s->actorLocal, A)); CK(dalloc(s->slotColour, Pn)); CK(cudaMemsetAsync(s->slotColour, 0xff, 4 * Pn, s->stream)); for (int k = 0; k < 2; ++k) { CK(dalloc(s->envSeg[k], A)); CK(cudaMemsetAsync(s->envSeg[k], 0, sizeof(uint2) * A, s->stream)); }
   CK(cudaStreamSynchronize(s->stream));
   return PXB_OK;
@@ -854,6 +946,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   ENV_ATTR(32); ENV_ATTR(64); ENV_ATTR(128); ENV_ATTR(256);
 #undef ENV_ATTR
   CK(cudaFuncSetAttribute(k_env_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sleep_islands, 256, 0)); s->coopBlocksSleep = std::max(1, std::min(occ, 2)) * s->numSMs;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_pgs, 256, 0)); s->coopBlocksSolvePgs = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
   s->capA = std::max(16u, desc->maxActors);
@@ -864,6 +957,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   if (desc->reserved[1] & PXB_FLAG_NO_ENV_PATH) s->envDisabled = true;
   if (desc->reserved[1] & PXB_FLAG_RELAXED_PARTITIONING) { s->relaxedPartitioning = true; s->envDisabled = true; }
   s->envConCapForced = desc->reserved[2]; s->envThreadsForced = desc->reserved[3];
+  memcpy(&s->sleepThreshold, &desc->reserved[4], 4); if (!(s->sleepThreshold > 0.f)) s->sleepThreshold = 0.f;
   const int rc = scene_alloc(s);
   if (rc != PXB_OK) { delete s; return rc; }
   *out = s;
@@ -880,7 +974,7 @@ PXB_API void pxb_scene_release(PxbScene* s) {
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
-                  s->envStart, s->envList, s->actorLocal, s->slotColour, s->bodyBest, s->envSeg[0], s->envSeg[1]};
+                  s->envStart, s->envList, s->actorLocal, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
   cudaStreamDestroy(s->stream);
@@ -1137,6 +1231,12 @@ static int enqueue_step(PxbScene* s, float dt) {
   const float contactDist = s->desc.contactOffset + s->desc.contactOffset;
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
          s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce);
+  SleepArgs SA; SA.threshold = s->sleepThreshold; SA.dt = dt; SA.wake = s->wake; SA.accLin = s->accLin; SA.accAng = s->accAng; SA.asleep = s->asleep; SA.nInter = s->nInter;
+  if (s->sleepThreshold > 0.f) {   // island sleep / wake decisions for this step (needs this frame's touching pairs)
+    uint32_t nA = s->nA;
+    void* args[] = {&nA, &nP, &s->pairBodies, &s->cHdr, &s->geomFlags, &SA, &s->islandLabel, &s->islandAwake, &s->counters, &s->linVel, &s->angVel, &s->conFlag};
+    CK(cudaLaunchCooperativeKernel((void*)k_sleep_islands, dim3(s->coopBlocksSleep), dim3(256), args, 0, st)); s->launches++;
+  }
   MARK(2);
   const float* g = s->desc.gravity; const bool pgs = s->desc.solverType == PXB_SOLVER_PGS;
   SolverParams P;
@@ -1155,7 +1255,7 @@ static int enqueue_step(PxbScene* s, float dt) {
     A.pairSlots = s->pairSlots[cur]; A.pairBodies = s->pairBodies; A.cHdr = s->cHdr; A.cPts = s->cPts; A.cForce = s->cForce; A.frictions = s->frictions;
     A.conPair = s->conPair; A.conB0 = s->conB0; A.conB1 = s->conB1; A.conColour = s->conColour; A.ordered = s->ordered; A.broken = s->conDone;
     A.rowScratch = s->ptA;   // ptA|ptB|ptC|frA|frB|frC|frD are ONE allocation of 28 x cap float4 (scene_alloc); the environment path uses 25 of them
-    A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour;
+    A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour; A.S = SA;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
 #define ENV_LAUNCH(T) do { if (pgs) k_env_solve<T, true><<<s->nEnv, T, smem, st>>>(A); else k_env_solve<T, false><<<s->nEnv, T, smem, st>>>(A); } while (0)
     if (s->envSolveThreads == 32) ENV_LAUNCH(32); else if (s->envSolveThreads == 64) ENV_LAUNCH(64); else if (s->envSolveThreads == 128) ENV_LAUNCH(128); else ENV_LAUNCH(256);
@@ -1192,7 +1292,7 @@ static int enqueue_step(PxbScene* s, float dt) {
   }
   MARK(3);
   LAUNCH(k_preintegrate, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, g[0], g[1], g[2], dt, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng,
-         s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, pgs ? 1 : 0);
+         s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, pgs ? 1 : 0, SA);
   if (pgs) {   // PGS: rows in the 25-float4 record image, velocity-delta solver bodies (pxb_pgs.cuh)
     Rows R; R.f = s->ptA; R.broken = s->conDone; R.stride = s->capPairs;
     LAUNCH(k_prep_pgs, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
@@ -1203,7 +1303,7 @@ static int enqueue_step(PxbScene* s, float dt) {
     CK(cudaLaunchCooperativeKernel((void*)k_solve_pgs, dim3(s->coopBlocksSolvePgs), dim3(256), args, 0, st)); s->launches++;
     MARK(5);
     LAUNCH(k_writeback_pgs, gP, B, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions);
-    LAUNCH(k_finalize_bodies_pgs, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB);
+    LAUNCH(k_finalize_bodies_pgs, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->invInertia, SA);
     MARK(6);
     CK(cudaGetLastError());
     return PXB_OK;
@@ -1220,7 +1320,8 @@ static int enqueue_step(PxbScene* s, float dt) {
   }
   MARK(5);
   LAUNCH(k_writeback, gP, B, s->counters, s->capPairs, s->rowC, s->ptC, s->conDone, s->pairSlots[cur], s->cForce, s->frictions);
-  LAUNCH(k_finalize_bodies, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->bodyHasCon);
+  LAUNCH(k_finalize_bodies, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->bodyHasCon,
+         s->sbDLin, s->sbDAng, s->invInertia, SA);
   MARK(6);
   CK(cudaGetLastError());
   return PXB_OK;
@@ -1353,6 +1454,14 @@ PXB_API uint32_t pxb_scene_last_num_partitions(PxbScene* s) { return s ? s->hNPa
 PXB_API uint32_t pxb_scene_last_num_constraints(PxbScene* s) { return s ? s->hNCon : 0; }
 PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* s) { return s ? s->launches : 0; }
 PXB_API int pxb_scene_uses_env_path(PxbScene* s) { return s && s->envActive ? 1 : 0; }
+PXB_API int pxb_scene_get_sleep_data(PxbScene* s, float* wakeCounters, uint32_t* asleep) {
+  if (!s || !wakeCounters || !asleep) return fail(PXB_ERR_INVALID, "null argument");
+  std::vector<float> w(s->nA); std::vector<uint32_t> f(s->nA);
+  CK(cudaMemcpyAsync(w.data(), s->wake, 4 * (size_t)s->nA, cudaMemcpyDeviceToHost, s->stream)); CK(cudaMemcpyAsync(f.data(), s->asleep, 4 * (size_t)s->nA, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  for (uint32_t d = 0; d < s->nDyn; ++d) { wakeCounters[d] = w[s->dynActor[d]]; asleep[d] = f[s->dynActor[d]]; }
+  return PXB_OK;
+}
 #ifdef PXB_ENV_TIMING
 extern "C" PXB_API int pxb_debug_env_timing(PxbScene* s, unsigned long long* out) { cudaStreamSynchronize(s->stream); cudaMemcpy(out, s->envTiming, (size_t)s->nEnv * 16 * 8, cudaMemcpyDeviceToHost); return (int)s->nEnv; }
 #endif
@@ -1362,7 +1471,7 @@ static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int typ
   if (!devIdx && nb > s->nDyn) return fail(PXB_ERR_INVALID, "nb exceeds the number of dynamic bodies");
   cudaStream_t st = s->stream;
   if (!nb) return PXB_OK;
-  if (set) LAUNCH(k_rd_set, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (const float*)devData);
+  if (set) LAUNCH(k_rd_set, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (const float*)devData, s->wake, s->asleep);
   else LAUNCH(k_rd_get, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (float*)devData);
   CK(cudaGetLastError());
   return PXB_OK;
@@ -1419,7 +1528,7 @@ PXB_API int pxb_scene_set_states(PxbScene* s, const float* in) {
   if (!s->nDyn) return PXB_OK;
   cudaStream_t st = s->stream; float* d = nullptr; CK(cudaMalloc((void**)&d, 52 * (size_t)s->nDyn));
   CK(cudaMemcpyAsync(d, in, 52 * (size_t)s->nDyn, cudaMemcpyHostToDevice, st));
-  LAUNCH(k_states_set, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, d);
+  LAUNCH(k_states_set, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, d, s->wake, s->asleep);
   CK(cudaStreamSynchronize(st)); cudaFree(d);
   return PXB_OK;
 }

@@ -148,7 +148,7 @@ struct EnvSolveArgs {
   uint32_t *conPair, *conB0, *conB1, *conColour, *ordered, *broken;   // per-pair-index scratch (global, L2 resident)
   uint32_t* slotColour;   // per persistent pair slot: partition of the pair's constraint last frame (NONE32 = no contacts)
   float4* rowScratch;   // 25 x cap float4, field-major: memory image of RegRows for environments with more constraints than threads
-  uint32_t* counters; unsigned long long* timing;
+  uint32_t* counters; unsigned long long* timing; SleepArgs S;
 };
 #ifdef PXB_ENV_TIMING
 #define ENV_T(i) do { __syncthreads(); if (threadIdx.x == 0) { const long long c_ = clock64(); A.timing[(size_t)blockIdx.x * 16 + (i)] = (unsigned long long)(c_ - t_prev); t_prev = c_; } } while (0)
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   for (uint32_t b = tid; b < n; b += T) {
     const uint32_t a = list[b];
     bMask[b] = 0; bStat[b] = 0;
-    if (!(A.geomFlags[a] & 0x100u)) { bP[b] = make_float4(0, 0, 0, 0); continue; }
+    if (!(A.geomFlags[a] & 0x100u) || body_asleep(A.S, a)) { bP[b] = make_float4(0, 0, 0, 0); continue; }   // statics and sleeping bodies take no part
     const float4 dm = A.damp[a]; const float4 ii = A.invInertia[a]; const float4 p4 = A.pos[a];
     v3 lv = V3(A.linVel[a]), av = V3(A.angVel[a]);
     unconstrained_velocity(V3(A.gx, A.gy, A.gz), A.dt, dm.x, dm.y, dm.z, dm.w, lv, av);
@@ -504,12 +504,14 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   for (uint32_t t0 = 0; t0 < m; t0 += T) {
     const uint32_t t = t0 + tid; bool f = false; uint32_t prevCol = NONE32;
     if (t < m) {
-      f = __float_as_int(A.cHdr[base + t].w) > 0;
+      const bool touching = __float_as_int(A.cHdr[base + t].w) > 0;
+      f = touching;
+      if (f && A.S.threshold > 0.f) { const uint2 bb = A.pairBodies[base + t]; if (A.S.asleep[bb.x] && (!(A.geomFlags[bb.y] & 0x100u) || A.S.asleep[bb.y])) f = false; }   // sleeping islands are not solved
       const uint32_t slot = A.pairSlots[base + t];
       prevCol = A.slotColour[slot];
       if (f != (prevCol != NONE32)) stale = 1;
-      if (!f) { A.frictions[(size_t)slot * PXB_FRICTION_F4 + 2].w = __int_as_float(0);   // no contacts: the friction patch is dropped
-                if (prevCol != NONE32) A.slotColour[slot] = NONE32; }
+      if (!touching) A.frictions[(size_t)slot * PXB_FRICTION_F4 + 2].w = __int_as_float(0);   // no contacts: the friction patch is dropped (a sleeping pair keeps its patch)
+      if (!f && prevCol != NONE32) A.slotColour[slot] = NONE32;
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, f);
     if (lane == 0) sWarp[warp] = __popc(bal);
@@ -597,21 +599,25 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   // a18: copyBackBodies (DyTGSDynamics.cpp:1549-1580); bodies without constraints take one full-dt step (:2573-2577)
   for (uint32_t b = tid; b < n; b += T) {
     const uint32_t a = list[b];
-    if (!(A.geomFlags[a] & 0x100u)) continue;
+    if (!(A.geomFlags[a] & 0x100u) || body_asleep(A.S, a)) continue;
     const m33 sI = load_sym(bIA[b], bIB[b]);
     if (PGS) {   // integrate (DyDynamics.cpp:1398-1423): every body, with or without constraints
       const float4 p4 = A.pos[a]; v3 p = V3(p4.x, p4.y, p4.z); q4 q = Q4(A.quat[a]); v3 lv = V3(bDLin[b]), av = V3(bDAng[b]);
+      const v3 motionLin = lv + V3(bP[b]), motionAng = av + mmul(sI, V3(bQ[b]));
       integrate_core_pgs(p, q, lv, av, sI, V3(bP[b]), V3(bQ[b]), V3(bLin[b]), V3(bAng[b]), A.dt);
       A.pos[a] = make_float4(p.x, p.y, p.z, p4.w); A.quat[a] = F4(q); A.linVel[a] = F4(lv, 0.f); A.angVel[a] = F4(av, 0.f);
+      if (A.S.threshold > 0.f) sleep_check_dev(A.S, a, q, A.invInertia[a], p4.w, motionLin, motionAng);
       continue;
     }
     v3 p = V3(bP[b]); q4 dq = Q4(bQ[b]);
     const v3 lv = V3(bLin[b]), as = V3(bAng[b]);
-    if (!__float_as_uint(bP[b].w)) { v3 dl = V3(0, 0, 0), da = V3(0, 0, 0); integrate_core_step(lv, as, sI, A.dt, p, dq, dl, da); }
+    v3 dl = V3(bDLin[b]), da = V3(bDAng[b]);
+    if (!__float_as_uint(bP[b].w)) { dl = V3(0, 0, 0); da = V3(0, 0, 0); integrate_core_step(lv, as, sI, A.dt, p, dq, dl, da); }
     const float invMass = A.pos[a].w;
     const q4 q = qnormalized(qmul(dq, Q4(A.quat[a])));
     A.pos[a] = make_float4(p.x, p.y, p.z, invMass); A.quat[a] = F4(q);
     A.linVel[a] = F4(lv, 0.f); A.angVel[a] = F4(mmul(sI, as), 0.f);
+    if (A.S.threshold > 0.f) { const float invDt = 1.0f / A.dt; sleep_check_dev(A.S, a, q, A.invInertia[a], invMass, dl * invDt, mmul(sI, da * invDt)); }
   }
   ENV_T(7);
 }

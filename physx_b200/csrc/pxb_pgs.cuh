@@ -271,11 +271,15 @@ __global__ void k_writeback_pgs(const uint32_t* __restrict__ counters, Rows R, c
 
 __global__ void k_finalize_bodies_pgs(uint32_t nDyn, const uint32_t* __restrict__ dynActor, float dt, float4* __restrict__ pos, float4* __restrict__ quat, float4* __restrict__ linVel,
                                       float4* __restrict__ angVel, const float4* __restrict__ sbLin, const float4* __restrict__ sbAng, const float4* __restrict__ sbDLin,
-                                      const float4* __restrict__ sbDAng, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB) {
+                                      const float4* __restrict__ sbDAng, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, const float4* __restrict__ invInertia, SleepArgs S) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
+  if (body_asleep(S, a)) return;
   const float4 p4 = pos[a]; v3 p = V3(p4.x, p4.y, p4.z); q4 q = Q4(quat[a]); v3 lv = V3(linVel[a]), av = V3(angVel[a]);
-  integrate_core_pgs(p, q, lv, av, load_sym(sbIA[a], sbIB[a]), V3(sbDLin[a]), V3(sbDAng[a]), V3(sbLin[a]), V3(sbAng[a]), dt);
+  const m33 sI = load_sym(sbIA[a], sbIB[a]);
+  const v3 motionLin = lv + V3(sbDLin[a]), motionAng = av + mmul(sI, V3(sbDAng[a]));   // motionVelocityArray after integrateCore
+  integrate_core_pgs(p, q, lv, av, sI, V3(sbDLin[a]), V3(sbDAng[a]), V3(sbLin[a]), V3(sbAng[a]), dt);
   pos[a] = make_float4(p.x, p.y, p.z, p4.w); quat[a] = F4(q); linVel[a] = F4(lv, 0.f); angVel[a] = F4(av, 0.f);
+  if (S.threshold > 0.f) sleep_check_dev(S, a, q, invInertia[a], p4.w, motionLin, motionAng);
 }

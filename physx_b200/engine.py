@@ -29,7 +29,7 @@ EXPORTS = [
     "pxb_scene_num_created", "pxb_scene_num_deleted", "pxb_scene_get_created", "pxb_scene_get_deleted",
     "pxb_scene_get_contacts", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
-    "pxb_scene_get_states_device", "pxb_scene_uses_env_path",
+    "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY = 0, 1, 2
@@ -89,6 +89,7 @@ def load_library():
     lib.pxb_scene_compute_bounds.argtypes = [vp]
     lib.pxb_scene_get_states_device.argtypes = [vp, vp]
     lib.pxb_scene_uses_env_path.argtypes = [vp]
+    lib.pxb_scene_get_sleep_data.argtypes = [vp, vp, vp]
     lib.pxb_scene_set_profiling.argtypes = [vp, i32]
     lib.pxb_scene_get_stage_times.argtypes = [vp, vp]
     lib.pxb_scene_state_device_ptr.argtypes = [vp, i32]
@@ -132,6 +133,7 @@ class Scene:
         relaxed = bool(int(h["reserved"][0]) & 1)   # scene header reserved[0] bit 0: PXB_FLAG_RELAXED_PARTITIONING (shared with the oracle)
         d.reserved[1] = (0 if env_path else 1) | (2 if relaxed else 0)   # PXB_FLAG_NO_ENV_PATH | PXB_FLAG_RELAXED_PARTITIONING
         d.reserved[2] = int(env_row_cap)
+        d.reserved[4] = int(np.float32(h["sleepThreshold"]).view(np.uint32))   # sleep threshold as float bits (0 = sleeping off)
         d.reserved[3] = int(env_threads)
         self.dt = float(h["dt"])
         self._h = ctypes.c_void_p()
@@ -259,6 +261,12 @@ class Scene:
     @property
     def num_constraints(self):
         return int(self._lib.pxb_scene_last_num_constraints(self._h))
+
+    def getSleep(self):
+        """(wake counters f32[n_dyn], asleep flags u32[n_dyn]) -- PxRigidDynamic::getWakeCounter / isSleeping"""
+        w, a = np.zeros(self.num_dynamic, np.float32), np.zeros(self.num_dynamic, np.uint32)
+        _check(self._lib, self._lib.pxb_scene_get_sleep_data(self._h, _ptr(w), _ptr(a)))
+        return w, a
 
     @property
     def uses_env_path(self):

@@ -24,7 +24,8 @@ def run_reference(scene, steps, threads=1):
         sp = os.path.join(d, "s.bin")
         scene.save(sp)
         subprocess.run([HARNESS, "run", sp, "--steps", str(steps), "--threads", str(threads), "--states", d + "/st", "--order", d + "/ord",
-                        "--bp", d + "/bp", "--contacts", d + "/con"], check=True, capture_output=True)
+                        "--bp", d + "/bp", "--contacts", d + "/con", "--sleep", d + "/sl"], check=True, capture_output=True)
+        sl = np.fromfile(d + "/sl", dtype=[("wc", "<f4"), ("s", "<u4")]).reshape(steps, scene.n_dynamic)
         nd, na = scene.n_dynamic, len(scene.actors)
         states = np.fromfile(d + "/st", "<f4").reshape(steps + 1, nd, 13)
         ob = open(d + "/ord", "rb").read(); off = 0; order_flat = []; order_off = [0]
@@ -49,7 +50,7 @@ def run_reference(scene, steps, threads=1):
                 con_pts.append(np.frombuffer(cb, "<f4", k * 10, off).reshape(k, 10)[:, :7]); off += k * 40
                 pt_off.append(pt_off[-1] + k)
             con_off.append(con_off[-1] + n)
-        return dict(scene=np.frombuffer(scene.tobytes(), np.uint8), states=states,
+        return dict(scene=np.frombuffer(scene.tobytes(), np.uint8), states=states, wake=sl["wc"].copy(), asleep=sl["s"].copy(),
                     order=np.concatenate(order_flat) if order_flat else np.zeros((0, 2), np.uint32), order_off=np.array(order_off),
                     bounds=np.stack(bounds), created=np.concatenate(cr), created_off=np.array(cro), deleted=np.concatenate(de) if de else np.zeros((0, 2), np.uint32),
                     deleted_off=np.array(deo), con_pairs=np.array(con_pairs, np.uint32).reshape(-1, 3), con_off=np.array(con_off),
@@ -72,6 +73,11 @@ def main():
         "pgs_envs_4": (scenes.env_grid_stacks(n_envs=4, stacks_per_env=4, height=4, jitter=0.01, solver=scenes.SOLVER_PGS), 40),
         "pgs_spheres_capsules_12": (scenes.mixed_primitives(n=12, seed=3, kinds=("sphere", "capsule"), solver=scenes.SOLVER_PGS), 100),
     }
+    # sleeping enabled (PxRigidDynamic::setSleepThreshold 0.005): resting stacks fall asleep; a box dropped on a sleeping stack wakes it
+    cases["sleep_stacks_2x3"] = (scenes.box_stacks(n_stacks=2, height=3, half_extent=0.25, spacing=1.0, jitter=0.01, sleep_threshold=0.005), 60)
+    drop = scenes.box_stacks(n_stacks=1, height=3, half_extent=0.25, spacing=1.0, jitter=0.0, sleep_threshold=0.005)
+    drop.actors["pos"][3, 1] = 4.0
+    cases["sleep_drop"] = (drop, 80)
     only = sys.argv[1:]
     if only:
         cases = {k: v for k, v in cases.items() if any(k.startswith(o) for o in only)}

@@ -32,6 +32,7 @@ def lib():
         for f in ("pxo_scene_get_states", "pxo_scene_set_states", "pxo_scene_get_bounds", "pxo_scene_set_bounds",
                   "pxo_scene_get_pairs", "pxo_scene_get_created", "pxo_scene_get_deleted", "pxo_scene_get_contacts"):
             getattr(L, f).argtypes = [vp, vp]
+        L.pxo_scene_get_sleep.argtypes = [vp, vp, vp]
         L.pxo_scene_compute_bounds.argtypes = [vp]
         L.pxo_scene_broadphase.argtypes = [vp]
         _LIB = L
@@ -55,6 +56,12 @@ class OracleScene:
         if getattr(self, "h", None):
             self.L.pxo_scene_destroy(self.h)
             self.h = None
+
+    def getSleep(self):
+        """(wake counters f32[n_dyn], asleep flags u32[n_dyn]) -- PxRigidDynamic::getWakeCounter / isSleeping"""
+        w, a = np.zeros(self.num_dynamic, np.float32), np.zeros(self.num_dynamic, np.uint32)
+        self.L.pxo_scene_get_sleep(self.h, _p(w), _p(a))
+        return w, a
 
     def step(self, order=None):
         if order is None or len(order) == 0:

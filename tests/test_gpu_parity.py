@@ -340,3 +340,57 @@ def test_relaxed_partitioning_matches_oracle(oracle, name):
     if name.startswith("pile"):
         st = gpu.getStates()
         assert np.isfinite(st).all() and np.abs(st[:, 7:10]).max() < 0.5 and st[:, 1].min() > 0.2, "the pile rests in the bin"
+
+
+# ---- sleeping (a18) ----
+def _sleep_scenes():
+    drop = scenes.box_stacks(n_stacks=1, height=3, half_extent=0.25, spacing=1.0, jitter=0.0, sleep_threshold=0.005)
+    drop.actors["pos"][3, 1] = 4.0
+    envs = scenes.env_grid_stacks(n_envs=6, stacks_per_env=2, height=3, jitter=0.01, sleep_threshold=0.005)
+    envs.actors["pos"][1 + 6 * 2 + 5, 1] = 3.0        # env 2: one box starts high and lands on its sleeping stack later
+    return {"stacks": (scenes.box_stacks(n_stacks=2, height=3, half_extent=0.25, spacing=1.0, jitter=0.01, sleep_threshold=0.005), 60, False),
+            "drop": (drop, 110, False),
+            "envs": (envs, 110, True),
+            "envs_pgs": (scenes.env_grid_stacks(n_envs=5, stacks_per_env=2, height=3, jitter=0.01, sleep_threshold=0.005, solver=scenes.SOLVER_PGS), 70, True),
+            "stacks_pgs": (scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01, sleep_threshold=0.005, solver=scenes.SOLVER_PGS), 70, False)}
+
+
+@pytest.mark.parametrize("name", list(_sleep_scenes()))
+def test_sleeping_gpu_matches_oracle(oracle, name):
+    """Wake counters, asleep flags and states against the oracle (itself pinned against the reference's getWakeCounter /
+    isSleeping, tests/test_oracle_vs_reference.py): islands fall asleep and wake on the same step; no resynchronisation."""
+    sc, steps, env = _sleep_scenes()[name]
+    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    ever_slept = woke = False
+    prev = None
+    for t in range(steps):
+        gpu.step()
+        cpu.step()
+        assert gpu.uses_env_path == env
+        (wg, ag), (wc, ac) = gpu.getSleep(), cpu.getSleep()
+        assert np.array_equal(ag, ac), f"asleep flags, step {t}"
+        assert np.abs(wg - wc).max() < 1e-6, f"wake counters, step {t}"
+        sg = gpu.getStates()
+        assert np.abs(sg - cpu.getStates()).max() < 1e-4, f"state, step {t}"
+        if ag.any():
+            ever_slept = True
+            assert np.all(sg[ag == 1][:, 7:] == 0), "sleeping bodies have zero velocity"
+            if prev is not None:
+                still = (ag == 1) & (prev[1] == 1)
+                assert np.array_equal(sg[still][:, :7], prev[0][still][:, :7]), "sleeping bodies do not move"
+        if prev is not None and np.any((prev[1] == 1) & (ag == 0)):
+            woke = True
+        prev = (sg, ag)
+    assert ever_slept
+    if name in ("drop", "envs"):
+        assert woke, "the impact wakes the sleeping island"
+
+
+def test_sleeping_gpu_matches_reference_golden():
+    z, sc = util.load_golden("sleep_stacks_2x3")
+    gpu = engine.Scene(sc)
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setConstraintOrder(util.golden_order(z, t))
+        gpu.step()
+        w, a = gpu.getSleep()
+        assert np.array_equal(a, z["asleep"][t]) and np.abs(w - z["wake"][t]).max() < 1e-6, f"step {t}"
