@@ -232,13 +232,14 @@ def bench_ours(args):
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        lib.pxb_set_rigid_dynamic_data(h, lin_h.data_ptr(), None, engine.RD_LINEAR_VELOCITY, nb)   # H2D (identity action: values just read back)
-        lib.pxb_set_rigid_dynamic_data(h, ang_h.data_ptr(), None, engine.RD_ANGULAR_VELOCITY, nb)
+        # stream-ordered calls on pinned host buffers, ONE host synchronisation per step (fetchResults), as with PxDirectGPUAPI's events
+        lib.pxb_set_rigid_dynamic_data_async(h, lin_h.data_ptr(), engine.RD_LINEAR_VELOCITY, nb)   # H2D (identity action: values just read back)
+        lib.pxb_set_rigid_dynamic_data_async(h, ang_h.data_ptr(), engine.RD_ANGULAR_VELOCITY, nb)
         scene.simulate()
-        scene.fetchResults(True)
-        lib.pxb_get_rigid_dynamic_data(h, pose_h.data_ptr(), None, engine.RD_GLOBAL_POSE, nb)      # D2H
-        lib.pxb_get_rigid_dynamic_data(h, lin_h.data_ptr(), None, engine.RD_LINEAR_VELOCITY, nb)
-        lib.pxb_get_rigid_dynamic_data(h, ang_h.data_ptr(), None, engine.RD_ANGULAR_VELOCITY, nb)
+        lib.pxb_get_rigid_dynamic_data_async(h, pose_h.data_ptr(), engine.RD_GLOBAL_POSE, nb)      # D2H
+        lib.pxb_get_rigid_dynamic_data_async(h, lin_h.data_ptr(), engine.RD_LINEAR_VELOCITY, nb)
+        lib.pxb_get_rigid_dynamic_data_async(h, ang_h.data_ptr(), engine.RD_ANGULAR_VELOCITY, nb)
+        scene.fetchResults(True)                                                                   # waits for the step and the copies
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -286,7 +287,7 @@ def bench_ours(args):
                          "dram_frac": (traffic / (solve_ms / 1e3) / 1e9 / peak) if traffic else None, "note": note},
             "stage_ms": stages,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nb * 24), "d2h_bytes_per_step": int(nb * (28 + 24)), "steps": e2e_steps,
-                    "api": "pxb_set_rigid_dynamic_data(lin,ang) -> pxb_scene_simulate -> pxb_scene_fetch_results -> pxb_get_rigid_dynamic_data(pose,lin,ang), pinned host buffers"},
+                    "api": "pxb_set_rigid_dynamic_data_async(lin,ang) -> pxb_scene_simulate -> pxb_get_rigid_dynamic_data_async(pose,lin,ang) -> pxb_scene_fetch_results (one host sync per step), pinned host buffers"},
             "gpu_launches": launches, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

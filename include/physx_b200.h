@@ -98,6 +98,11 @@ PXB_API int  pxb_scene_set_constraint_order(PxbScene* scene, const uint32_t* pai
 enum { PXB_RD_GLOBAL_POSE = 0, PXB_RD_LINEAR_VELOCITY = 1, PXB_RD_ANGULAR_VELOCITY = 2 };
 PXB_API int  pxb_get_rigid_dynamic_data(PxbScene* scene, void* data, const uint32_t* indices, int dataType, uint32_t nb);
 PXB_API int  pxb_set_rigid_dynamic_data(PxbScene* scene, const void* data, const uint32_t* indices, int dataType, uint32_t nb);
+/* stream-ordered host variants: PINNED host buffers, no index list, no synchronisation; complete at the next
+ * pxb_scene_fetch_results / pxb_scene_sync (PxDirectGPUAPI is asynchronous as well: start / finish CUevents) */
+PXB_API int  pxb_get_rigid_dynamic_data_async(PxbScene* scene, void* pinnedData, int dataType, uint32_t nb);
+PXB_API int  pxb_set_rigid_dynamic_data_async(PxbScene* scene, const void* pinnedData, int dataType, uint32_t nb);
+PXB_API int  pxb_scene_sync(PxbScene* scene);
 PXB_API int  pxb_get_rigid_dynamic_data_device(PxbScene* scene, void* devData, const uint32_t* devIndices, int dataType, uint32_t nb);
 PXB_API int  pxb_set_rigid_dynamic_data_device(PxbScene* scene, const void* devData, const uint32_t* devIndices, int dataType, uint32_t nb);
 /* Packed state convenience: 13 floats per dynamic body (pos3 quat4 linVel3 angVel3), dynamic-body order. */

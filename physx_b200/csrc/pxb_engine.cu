@@ -908,7 +908,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
   CK(dalloc(s->rowA, Pn)); CK(dalloc(s->rowB, Pn)); CK(dalloc(s->rowC, Pn)); CK(dalloc(s->ptA, Pn * 28)); s->ptB = s->ptA + Pn * 4; s->ptC = s->ptA + Pn * 8;   // one allocation: the environment path views it as 25 x Pn (pxb_env.cuh Rows)
   s->frA = s->ptA + Pn * 12; s->frB = s->ptA + Pn * 16; s->frC = s->ptA + Pn * 20; s->frD = s->ptA + Pn * 24;
-  CK(dalloc(s->stage, A * 7)); CK(dalloc(s->stageIdx, A));
+  CK(dalloc(s->stage, A * 13 * 2)); CK(dalloc(s->stageIdx, A));   // staging: {get, set} x {pose 7, linear 3, angular 3} floats per actor
   CK(dalloc(s->counters, C_COUNT)); CK(cudaMallocHost((void**)&s->hostCounters, sizeof(uint32_t) * (C_COUNT + 2)));
   CK(dalloc(s->rsTmp.blockHist, RS_MAX_CTAS * 256)); CK(dalloc(s->rsTmp.digitTotals, 256)); CK(dalloc(s->scanSums, RS_MAX_CTAS));
   CK(cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * C_COUNT, s->stream)); CK(cudaMemsetAsync(s->nPairsDev, 0, 8, s->stream));
@@ -1486,24 +1486,32 @@ PXB_API int pxb_set_rigid_dynamic_data_device(PxbScene* s, const void* devData, 
   if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
   return rd_common(s, const_cast<void*>(devData), devIdx, type, nb, true);
 }
-static int rd_host(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb, bool set) {
+static int rd_host(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb, bool set, bool async) {
   if (!s || !data) return fail(PXB_ERR_INVALID, "null argument");
   if (type < 0 || type > 2) return fail(PXB_ERR_INVALID, "bad dataType");
-  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
+  if (s->stepping && !async) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
+  if (async && idx) return fail(PXB_ERR_INVALID, "the stream-ordered host variants take no index list");
   if (!nb) return PXB_OK;
   const size_t bytes = (size_t)nb * (type == 0 ? 28 : 12);
   if (nb > s->capA) return fail(PXB_ERR_INVALID, "nb exceeds the actor capacity");
-  float* d = s->stage; uint32_t* di = nullptr;   // persistent staging: no allocation on the per-step path
+  // persistent staging, one region per (direction, data type): no allocation on the per-step path and stream-ordered calls never share a buffer
+  float* d = s->stage + (size_t)s->capA * ((set ? 13 : 0) + (type == 0 ? 0 : (type == 1 ? 7 : 10))); uint32_t* di = nullptr;
   if (idx) { for (uint32_t i = 0; i < nb; ++i) if (idx[i] >= s->nDyn) return fail(PXB_ERR_INVALID, "index out of range");
              di = s->stageIdx; CK(cudaMemcpyAsync(di, idx, 4 * (size_t)nb, cudaMemcpyHostToDevice, s->stream)); }
   if (set) CK(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, s->stream));
   int rc = rd_common(s, d, di, type, nb, set);
   if (!rc && !set) CK(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, s->stream));
-  CK(cudaStreamSynchronize(s->stream));
+  if (!async) CK(cudaStreamSynchronize(s->stream));
   return rc;
 }
-PXB_API int pxb_get_rigid_dynamic_data(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, data, idx, type, nb, false); }
-PXB_API int pxb_set_rigid_dynamic_data(PxbScene* s, const void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, const_cast<void*>(data), idx, type, nb, true); }
+PXB_API int pxb_get_rigid_dynamic_data(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, data, idx, type, nb, false, false); }
+PXB_API int pxb_set_rigid_dynamic_data(PxbScene* s, const void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, const_cast<void*>(data), idx, type, nb, true, false); }
+// Stream-ordered host variants (the PxDirectGPUAPI calls are asynchronous too: they take start / finish CUevents,
+// PxDirectGPUAPI.h:311-463).  `data` must be PINNED host memory that stays valid until the next pxb_scene_fetch_results /
+// pxb_scene_sync; a set takes effect for the next simulate, a get issued after pxb_scene_simulate returns that step's result.
+PXB_API int pxb_get_rigid_dynamic_data_async(PxbScene* s, void* pinned, int type, uint32_t nb) { return rd_host(s, pinned, nullptr, type, nb, false, true); }
+PXB_API int pxb_set_rigid_dynamic_data_async(PxbScene* s, const void* pinned, int type, uint32_t nb) { return rd_host(s, const_cast<void*>(pinned), nullptr, type, nb, true, true); }
+PXB_API int pxb_scene_sync(PxbScene* s) { if (!s) return fail(PXB_ERR_INVALID, "null scene"); CK(cudaStreamSynchronize(s->stream)); return PXB_OK; }
 
 // Packed 13-float state of every dynamic body written straight into a DEVICE buffer (e.g. this rank's slice of
 // the NCCL all-gather receive tensor); asynchronous on the scene stream.

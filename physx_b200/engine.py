@@ -29,7 +29,7 @@ EXPORTS = [
     "pxb_scene_num_created", "pxb_scene_num_deleted", "pxb_scene_get_created", "pxb_scene_get_deleted",
     "pxb_scene_get_contacts", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
-    "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data",
+    "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY = 0, 1, 2
@@ -90,6 +90,9 @@ def load_library():
     lib.pxb_scene_get_states_device.argtypes = [vp, vp]
     lib.pxb_scene_uses_env_path.argtypes = [vp]
     lib.pxb_scene_get_sleep_data.argtypes = [vp, vp, vp]
+    lib.pxb_get_rigid_dynamic_data_async.argtypes = [vp, vp, i32, u32]
+    lib.pxb_set_rigid_dynamic_data_async.argtypes = [vp, vp, i32, u32]
+    lib.pxb_scene_sync.argtypes = [vp]
     lib.pxb_scene_set_profiling.argtypes = [vp, i32]
     lib.pxb_scene_get_stage_times.argtypes = [vp, vp]
     lib.pxb_scene_state_device_ptr.argtypes = [vp, i32]

@@ -394,3 +394,55 @@ def test_sleeping_gpu_matches_reference_golden():
         gpu.step()
         w, a = gpu.getSleep()
         assert np.array_equal(a, z["asleep"][t]) and np.abs(w - z["wake"][t]).max() < 1e-6, f"step {t}"
+
+
+def test_stream_ordered_host_api_matches_blocking_api():
+    """pxb_get/set_rigid_dynamic_data_async: enqueued around simulate with ONE host sync (fetchResults) per step, same results."""
+    import ctypes
+    sc = scenes.env_grid_stacks(n_envs=8)
+    a, b = engine.Scene(sc), engine.Scene(sc)
+    nb = a.num_dynamic
+    lin = np.zeros((nb, 3), np.float32); ang = np.zeros((nb, 3), np.float32); pose = np.zeros((nb, 7), np.float32)
+    rng = np.random.RandomState(0)
+    for t in range(5):
+        act = (rng.uniform(-0.2, 0.2, (nb, 3))).astype(np.float32)
+        b.setRigidDynamicData(engine.RD_LINEAR_VELOCITY, act)
+        b.step()
+        ptr = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+        assert a._lib.pxb_set_rigid_dynamic_data_async(a._h, ptr(act), engine.RD_LINEAR_VELOCITY, nb) == 0
+        a.simulate()
+        for arr, ty in ((pose, engine.RD_GLOBAL_POSE), (lin, engine.RD_LINEAR_VELOCITY), (ang, engine.RD_ANGULAR_VELOCITY)):
+            assert a._lib.pxb_get_rigid_dynamic_data_async(a._h, ptr(arr), ty, nb) == 0
+        a.fetchResults(True)
+        assert np.array_equal(pose, b.getRigidDynamicData(engine.RD_GLOBAL_POSE)), f"step {t}"
+        assert np.array_equal(lin, b.getRigidDynamicData(engine.RD_LINEAR_VELOCITY)) and np.array_equal(ang, b.getRigidDynamicData(engine.RD_ANGULAR_VELOCITY))
+
+
+def test_actors_added_to_a_running_env_scene():
+    """pxb_scene_add_actors between steps: the environment lists are rebuilt, existing pairs keep their manifolds (no spurious
+    created / deleted events) and the result equals the device-wide path's."""
+    sc = scenes.env_grid_stacks(n_envs=6, stacks_per_env=2, height=3, jitter=0.01)
+    extra = scenes.env_grid_stacks(n_envs=6, stacks_per_env=1, height=2, jitter=0.0).actors[1:].copy()   # 2 more boxes per env
+    extra["pos"][:, 0] += 3.0
+    scs = [engine.Scene(sc, max_actors=len(sc.actors) + len(extra)), engine.Scene(sc, max_actors=len(sc.actors) + len(extra), env_path=False)]
+    for g in scs:
+        for _ in range(10):
+            g.step()
+        assert g._lib.pxb_scene_add_actors(g._h, np.ascontiguousarray(extra).ctypes.data, len(extra)) == 0
+        g.num_dynamic = int(g._lib.pxb_scene_num_dynamic(g._h)); g.num_actors = int(g._lib.pxb_scene_num_actors(g._h))
+    for t in range(20):
+        for g in scs:
+            g.step()
+        assert scs[0].uses_env_path and not scs[1].uses_env_path
+        assert np.array_equal(scs[0].getPairs(), scs[1].getPairs()) and np.array_equal(scs[0].getCreatedPairs(), scs[1].getCreatedPairs()), f"step {t}"
+        assert np.array_equal(scs[0].getDeletedPairs(), scs[1].getDeletedPairs()) and len(scs[0].getDeletedPairs()) == 0
+        assert np.array_equal(scs[0].getStates(), scs[1].getStates()), f"states, step {t}"
+    assert len(scs[0].getStates()) == 6 * 6 + 12
+
+
+def test_env_path_pair_capacity_overflow_is_reported():
+    sc = scenes.env_grid_stacks(n_envs=16)
+    gpu = engine.Scene(sc, max_pairs=100)
+    with pytest.raises(engine.PhysxB200Error) as e:
+        gpu.step()
+    assert "capacity" in str(e.value)
