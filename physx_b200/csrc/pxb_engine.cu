@@ -46,7 +46,7 @@ struct ActorRec {
 static_assert(sizeof(ActorRec) == 128, "actor record layout");
 
 enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_COUNT = 16 };
-enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4 };
+enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8 };
 
 struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };
 
@@ -271,7 +271,7 @@ __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_
 __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
                               const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
                               float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
-                              uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce) {
+                              uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *nPairsP) return;
   const uint64_t key = pairKeys[i];
@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_BOX) np_sphere_box(tm0.p, d0.x, tm1, V3(d1.x, d1.y, d1.z), contactDist, out);
   else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CAPSULE) pcm_plane_capsule(tm0, tm1, d1.x, d1.y, contactDist, man, out);
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_CAPSULE) np_capsule_capsule(tm0, tm1, d0.x, d0.y, d1.x, d1.y, contactDist, out);
+  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // capsule-box (GJK/EPA family, a10): reported by fetchResults, never silently skipped
   if (man.dirty) manifold_store(man, rec); else if (usesManifold && man.n > 0) manifold_store_pens(man, rec);   // steady state: only the penetrations change
   if (flip && out.count) out.normal = -out.normal;
   cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
@@ -1216,6 +1217,7 @@ static int read_counters(PxbScene* s) {
   }
   if (s->hErr & E_PAIR_OVERFLOW) return fail(PXB_ERR_CAPACITY, "broadphase pair capacity (maxPairs) exceeded");
   if (s->hErr & (E_COLOUR_OVERFLOW | E_PARTITION_OVERFLOW)) return fail(PXB_ERR_CAPACITY, "more than 32 dynamic colours / 96 partitions needed");
+  if (s->hErr & E_UNSUPPORTED_PAIR) return fail(PXB_ERR_UNSUPPORTED, "a capsule-box pair came into contact range: that pair type needs the GJK/EPA narrowphase family, which is not built yet");
   return PXB_OK;
 }
 
@@ -1230,7 +1232,7 @@ static int enqueue_step(PxbScene* s, float dt) {
   const uint32_t* nP = s->nPairsDev + cur;
   const float contactDist = s->desc.contactOffset + s->desc.contactOffset;
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
-         s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce);
+         s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce, s->counters);
   SleepArgs SA; SA.threshold = s->sleepThreshold; SA.dt = dt; SA.wake = s->wake; SA.accLin = s->accLin; SA.accAng = s->accAng; SA.asleep = s->asleep; SA.nInter = s->nInter;
   if (s->sleepThreshold > 0.f) {   // island sleep / wake decisions for this step (needs this frame's touching pairs)
     uint32_t nA = s->nA;

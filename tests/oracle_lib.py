@@ -26,7 +26,7 @@ def lib():
         L.pxo_scene_destroy.argtypes = [vp]
         L.pxo_scene_step.argtypes = [vp, vp, u32]
         for f in ("pxo_scene_num_dynamic", "pxo_scene_num_actors", "pxo_scene_num_pairs", "pxo_scene_num_created",
-                  "pxo_scene_num_deleted", "pxo_scene_last_num_partitions", "pxo_scene_last_num_constraints"):
+                  "pxo_scene_num_deleted", "pxo_scene_last_num_partitions", "pxo_scene_last_num_constraints", "pxo_scene_unsupported_pairs"):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = u32
         for f in ("pxo_scene_get_states", "pxo_scene_set_states", "pxo_scene_get_bounds", "pxo_scene_set_bounds",
@@ -56,6 +56,10 @@ class OracleScene:
         if getattr(self, "h", None):
             self.L.pxo_scene_destroy(self.h)
             self.h = None
+
+    @property
+    def unsupported_pairs(self):
+        return int(self.L.pxo_scene_unsupported_pairs(self.h))
 
     def getSleep(self):
         """(wake counters f32[n_dyn], asleep flags u32[n_dyn]) -- PxRigidDynamic::getWakeCounter / isSleeping"""

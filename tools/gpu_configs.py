@@ -31,4 +31,4 @@ if which.startswith("pile"):
 else:
     n = max(4, int(round(128 * scale ** (1 / 3))))
     sc = scenes.falling_primitives(n, max(2, n // 2), n, relaxed_partitioning=relaxed)
-    run("config 3 shape: falling spheres/capsules/boxes", sc, 8 * len(sc.actors), 60, 50)
+    run("config 3 shape: falling spheres/boxes", sc, 8 * len(sc.actors), 60, 50)
