@@ -181,7 +181,7 @@ __device__ __forceinline__ void integrate_core_pgs(v3& p, q4& q, v3& linVel, v3&
   if (w != 0.0f) {
     w = sqrtf(w);
     const float v = dt * w * 0.5f;
-    float s = sinf(v); const float c = cosf(v);
+    float s, c; sincosf(v, &s, &c);
     s /= w;
     const v3 pqr = angularMotionVel * s;
     q4 res = qmul(Q4(pqr.x, pqr.y, pqr.z, 0.f), q);

@@ -68,7 +68,7 @@ PXB_D void integrate_core_step(v3 linVel, v3 angState, const m33& sqrtInvInertia
   if (w2 != 0.0f) {
     const float w = sqrtf(w2);
     const float v = dt * w * 0.5f;
-    float s = sinf(v); const float q = cosf(v);
+    float s, q; sincosf(v, &s, &q);   // PxSinCos: one shared range reduction; same values as sinf / cosf
     s /= w;
     const v3 pqr = w3 * s;
     q4 r = qmul(Q4(pqr.x, pqr.y, pqr.z, 0.f), deltaQ);
