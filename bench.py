@@ -141,7 +141,7 @@ def bench_ours(args):
     n_envs = args.envs
     solver = scenes.SOLVER_PGS if args.solver == "pgs" else scenes.SOLVER_TGS
     sc = scenes.env_grid_stacks(n_envs=n_envs, stacks_per_env=args.stacks, seed=1234 + rank, solver=solver)  # every rank owns its own envs (weak scaling)
-    scene = engine.Scene(sc, device=local)
+    scene = engine.Scene(sc, device=local, env_path=(args.path != "devicewide"))
     nb = scene.num_dynamic
     stream = torch.cuda.ExternalStream(scene.stream(), device=dev)
     gather = None
@@ -308,6 +308,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stacks", type=int, default=8, help="stacks of 8 boxes per environment (8 = config 2, 16 = the per-GPU shard of config 5)")
+    ap.add_argument("--path", default="auto", choices=["auto", "devicewide"], help="devicewide forces the path used by scenes without environment ids (comparison runs)")
     ap.add_argument("--solver", default="tgs", choices=["tgs", "pgs"], help="PxSolverType of the scene (headline metric: tgs)")
     args = ap.parse_args()
     if args.impl == "reference":

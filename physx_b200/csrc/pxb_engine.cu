@@ -10,8 +10,8 @@
 //   k_narrowphase       a8-a11 sphereNphase/boxBoxNphase/convexConvex... kernels               (oracle: CPU PCM)
 //   k_colour_partition  a13    PxgIncrementalPartition (host) -> here on device, first-fit in solver input order
 //   k_preintegrate      a12    preIntegrationLaunchTGS
-//   k_prep              a14    constraintContactBlockPrePrepLaunch + contactConstraintBlockPrepareParallelLaunchTGS
-//   k_solve             a15/a16 solveBlockUnified + propagateAverageSolverBodyVelocityTGS loop  (ONE cooperative launch)
+//   k_prep_rows         a14    constraintContactBlockPrePrepLaunch + contactConstraintBlockPrepareParallelLaunch[TGS]   (pxb_pgs.cuh)
+//   k_solve_tgs/_pgs    a15/a16 solveBlockUnified + propagateAverageSolverBodyVelocityTGS loop  (ONE cooperative launch)
 //   k_finalize          a17/a18 writebackBlocksTGS + integrateCoreParallelLaunchTGS
 //   k_rd_get/k_rd_set   a19    get/setRigidDynamic* (PxDirectGPUAPI)
 #include <cuda_runtime.h>
@@ -77,7 +77,7 @@ struct PxbScene {
   uint32_t *conB0 = 0, *conB1 = 0, *conPos0 = 0, *conPos1 = 0, *conColour = 0, *conDone = 0, *bodyList = 0, *ordered = 0;
   uint32_t *partCnt = 0, *partStart = 0, *partCursor = 0;
   // rows (solve order)
-  float4 *rowA = 0, *rowB = 0; uint4* rowC = 0; float4 *ptA = 0, *ptB = 0, *ptC = 0, *frA = 0, *frB = 0, *frC = 0, *frD = 0;
+  float4 *ptA = 0, *ptB = 0, *ptC = 0, *frA = 0, *frB = 0, *frC = 0, *frD = 0;
   uint32_t* counters = 0; uint32_t* hostCounters = 0;  // pinned mirror
   RadixSortTemp rsTmp; uint32_t* scanSums = 0;
   uint32_t launches = 0;
@@ -591,208 +591,8 @@ __device__ __forceinline__ m33 load_sym(const float4 A, const float4 B) {
   m33 m; m.c0 = V3(A.x, A.y, A.z); m.c1 = V3(A.y, A.w, B.x); m.c2 = V3(A.z, B.x, B.y); return m;
 }
 
-// a14: one constraint: friction-patch correlation + solver rows (createFinalizeSolverContactsStep, DyTGSContactPrep.cpp:1297-1490;
-// DyFrictionCorrelation.cpp:56-330).  `k` = row index (stride `cap`), `i` = pair index, b0/b1 = solver-body indices stored in the row.
+// a14 inputs of one constraint: body frames, inverse masses, pre-solver velocities, world sqrt(inverse inertia)
 struct PrepBodies { xf f0, f1; float invMass0, invMass1, pen0, pen1; v3 linVel0, linVel1, angVel0, angVel1; m33 sI0, sI1; };
-__device__ __forceinline__ void prep_constraint(uint32_t k, uint32_t cap, uint32_t i, uint32_t b0, uint32_t b1, const PrepBodies& B, const float4* __restrict__ cHdr,
-                                                const float4* __restrict__ cPts, float4* __restrict__ frec, const SolverParams& P,
-                                                float4* __restrict__ rowA, float4* __restrict__ rowB, uint4* __restrict__ rowC, float4* __restrict__ ptA, float4* __restrict__ ptB,
-                                                float4* __restrict__ ptC, float4* __restrict__ frA, float4* __restrict__ frB, float4* __restrict__ frC, float4* __restrict__ frD) {
-  Contacts con; const float4 h = cHdr[i]; con.normal = V3(h.x, h.y, h.z); con.count = __float_as_int(h.w);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { const float4 p = cPts[(size_t)i * 4 + j]; con.point[j] = V3(p.x, p.y, p.z); con.sep[j] = p.w; }
-  const xf& f0 = B.f0; const xf& f1 = B.f1;
-  FrictionPatch fp; friction_load(fp, frec);
-  friction_correlate(fp, con, f0, f1, P.staticFriction, P.dynamicFriction, P.restitution, P.correlationDistance, P.frictionOffsetThreshold + P.restDistance);
-  friction_store(fp, frec);
-  const float invMass0 = B.invMass0, invMass1 = B.invMass1;
-  const float maxPenBias = fmax_(B.pen0, B.pen1);
-  const v3 linVel0 = B.linVel0, linVel1 = B.linVel1, angVel0 = B.angVel0, angVel1 = B.angVel1;
-  const m33& sI0 = B.sI0; const m33& sI1 = B.sI1;
-  const float invMass0_dom0 = 1.f * invMass0, invMass1_dom1 = (-1.f) * invMass1;
-  const float scale = fmin_(0.8f, P.biasCoefficient);
-  const float invDtp8 = P.invStepDt * scale, frictionBiasScale = P.invStepDt * scale;
-  const v3 normal = con.normal;
-  const float normalLenSq = adot(normal, normal);
-  const float norVel0 = adot(linVel0, normal), norVel1 = adot(linVel1, normal);
-  const float imn0 = invMass0_dom0 * normalLenSq, imn1 = invMass1_dom1 * normalLenSq;
-  const bool haveFriction = fp.anchorCount != 0;
-  const uint32_t numFriction = haveFriction ? (uint32_t)fp.anchorCount * 2u : 0u;
-  rowA[k] = F4(normal, maxPenBias);
-  rowB[k] = make_float4(invMass0_dom0, -invMass1_dom1, P.staticFriction, P.dynamicFriction);
-  rowC[k] = make_uint4(b0, b1, (uint32_t)con.count | (numFriction << 8), i);
-  for (int j = 0; j < con.count; ++j) {
-    SPoint s; prep_point(s, con.point[j], con.sep[j], normal, f0.p, f1.p, sI0, sI1, angVel0, angVel1, norVel0, norVel1, imn0, imn1, P, invDtp8);
-    ptA[(size_t)j * cap + k] = F4(s.raXnI, s.velMultiplier); ptB[(size_t)j * cap + k] = F4(s.rbXnI, s.separation);
-    ptC[(size_t)j * cap + k] = make_float4(s.biasCoefficient, s.targetVelocity, s.recipResponse, 0.f);
-  }
-  if (haveFriction) {
-    const v3 linVrel = linVel0 - linVel1;
-    const v3 fb1 = V3(0.f, -normal.z, normal.y), fb2 = V3(-normal.y, normal.x, 0.f);
-    const v3 t0Fallback = (0.70710678f > fabsf(normal.x)) ? fb1 : fb2;
-    v3 t0 = linVrel - normal * adot(normal, linVrel);
-    t0 = (adot(t0, t0) > 0.0001f) ? t0 : t0Fallback;
-    t0 = anormalize(t0);
-    const v3 t1 = anormalize(cross(normal, t0));
-    const v3 relTr = f0.p - f1.p;
-    const float frictionScale = (fp.anchorCount == 2) ? 0.5f : 1.f;
-    for (int j = 0; j < fp.anchorCount; ++j) {
-      const v3 ra = aqrot(f0.q, fp.body0Anchors[j]), rb = aqrot(f1.q, fp.body1Anchors[j]);
-      const v3 error = (ra - rb) + relTr;
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        SFriction f; prep_friction_row(f, ra, rb, error, t == 0 ? t0 : t1, sI0, sI1, imn0, imn1, scale, frictionScale, frictionBiasScale);
-        const size_t o = (size_t)(j * 2 + t) * cap + k;
-        frA[o] = F4(f.normal, f.error); frB[o] = F4(f.raXnI, f.targetVel); frC[o] = F4(f.rbXnI, f.velMultiplier);
-        frD[o] = make_float4(0.f, f.frictionScale, f.biasScale, 0.f);
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(128) k_prep(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ ordered, const uint32_t* __restrict__ conPair, const uint32_t* __restrict__ pairSlots,
-                       const uint2* __restrict__ pairBodies, const uint32_t* __restrict__ geomFlags, const float4* __restrict__ cHdr, const float4* __restrict__ cPts,
-                       const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ linVel, const float4* __restrict__ sbOrigAng,
-                       const float4* __restrict__ invInertia, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, float4* __restrict__ frictions, SolverParams P, uint32_t cap,
-                       float4* __restrict__ rowA, float4* __restrict__ rowB, uint4* __restrict__ rowC, float4* __restrict__ ptA, float4* __restrict__ ptB, float4* __restrict__ ptC,
-                       float4* __restrict__ frA, float4* __restrict__ frB, float4* __restrict__ frC, float4* __restrict__ frD) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= counters[C_NCON]) return;
-  const uint32_t c = ordered[k]; const uint32_t i = conPair[c];
-  const uint2 bb = pairBodies[i]; const uint32_t b0 = bb.x, b1 = bb.y;
-  const bool dyn1 = (geomFlags[b1] & 0x100u) != 0;
-  if (__float_as_int(cHdr[i].w) == 0) {  // empty constraint kept only for the colouring (see k_flag_ordered)
-    rowA[k] = make_float4(0, 0, 0, 0); rowB[k] = make_float4(0, 0, 0, 0); rowC[k] = make_uint4(b0, dyn1 ? b1 : NONE32, 0u, i);
-    return;
-  }
-  PrepBodies B;
-  { const float4 p = pos[b0]; B.f0.p = V3(p.x, p.y, p.z); B.f0.q = Q4(quat[b0]); const float4 q = pos[b1]; B.f1.p = V3(q.x, q.y, q.z); B.f1.q = Q4(quat[b1]); }
-  B.invMass0 = pos[b0].w; B.invMass1 = dyn1 ? pos[b1].w : 0.f;
-  B.pen0 = -invInertia[b0].w; B.pen1 = dyn1 ? -invInertia[b1].w : -FLT_MAX;
-  B.linVel0 = V3(linVel[b0]); B.linVel1 = dyn1 ? V3(linVel[b1]) : V3(0, 0, 0);
-  B.angVel0 = V3(sbOrigAng[b0]); B.angVel1 = dyn1 ? V3(sbOrigAng[b1]) : V3(0, 0, 0);
-  B.sI0 = load_sym(sbIA[b0], sbIB[b0]);
-  if (dyn1) B.sI1 = load_sym(sbIA[b1], sbIB[b1]); else { B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
-  prep_constraint(k, cap, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, rowA, rowB, rowC, ptA, ptB, ptC, frA, frB, frC, frD);
-}
-
-// a15: one contact constraint (solveContact, DyTGSContactPrep.cpp:1581-1873)
-__device__ __forceinline__ void solve_constraint(uint32_t k, uint32_t cap, float minPen, float elapsedTime, const float4* __restrict__ rowA, const float4* __restrict__ rowB,
-                                                 const uint4* __restrict__ rowC, const float4* __restrict__ ptA, const float4* __restrict__ ptB, float4* __restrict__ ptC,
-                                                 const float4* __restrict__ frA, const float4* __restrict__ frB, const float4* __restrict__ frC, float4* __restrict__ frD,
-                                                 float4* __restrict__ sbLin, float4* __restrict__ sbAng, const float4* __restrict__ sbDLin, const float4* __restrict__ sbDAng,
-                                                 uint32_t* __restrict__ brokenFlags) {
-  const uint4 rc = rowC[k]; const uint32_t b0 = rc.x, b1 = rc.y;
-  const uint32_t numNormal = rc.z & 0xff, numFriction = (rc.z >> 8) & 0xff;
-  const float4 ra4 = rowA[k], rb4 = rowB[k];
-  const v3 n = V3(ra4.x, ra4.y, ra4.z); const float maxPenBias = ra4.w;
-  const float invMassA = rb4.x, invMassB = rb4.y;
-  v3 linVel0 = V3(sbLin[b0]), angState0 = V3(sbAng[b0]);
-  const v3 angMotion0 = V3(sbDAng[b0]); v3 relMotion = V3(sbDLin[b0]);
-  v3 linVel1 = V3(0, 0, 0), angState1 = V3(0, 0, 0), angMotion1 = V3(0, 0, 0);
-  if (b1 != NONE32) { linVel1 = V3(sbLin[b1]); angState1 = V3(sbAng[b1]); angMotion1 = V3(sbDAng[b1]); relMotion = relMotion - V3(sbDLin[b1]); }
-  float accum = 0.f;
-  {
-    const v3 nim0 = n * invMassA, nim1 = n * invMassB;
-    const float deltaV = adot(relMotion, n);
-    for (uint32_t j = 0; j < numNormal; ++j) {
-      const size_t o = (size_t)j * cap + k;
-      const float4 A = ptA[o], B = ptB[o]; float4 C = ptC[o];
-      const v3 raXnI = V3(A.x, A.y, A.z), rbXnI = V3(B.x, B.y, B.z);
-      const float deltaAng = adot(angMotion0, raXnI) - adot(angMotion1, rbXnI);
-      const float targetVel = C.y;
-      const float deltaBias = (deltaV + deltaAng) - targetVel * elapsedTime;
-      const float sep = fmax_(minPen, B.w + deltaBias);
-      const float bias = fmin_(-maxPenBias, C.x * sep);
-      const v3 dv = (vmul(linVel0, n) + vmul(angState0, raXnI)) - (vmul(linVel1, n) + vmul(angState1, rbXnI));
-      const float normalVel = (dv.x + dv.y) + dv.z;
-      const float biasNV = bias * C.z;
-      const float lambda = biasNV - (normalVel - targetVel) * A.w;
-      const float applied = C.w;
-      const float dF_ = fmax_(lambda, -applied);
-      const float newForce = fmin_(applied + dF_, FLT_MAX);
-      const float deltaF = newForce - applied;
-      linVel0 = scaleadd(nim0, deltaF, linVel0); linVel1 = negscalesub(nim1, deltaF, linVel1);
-      angState0 = scaleadd(raXnI, deltaF * 1.f, angState0); angState1 = negscalesub(rbXnI, deltaF * 1.f, angState1);
-      C.w = newForce; ptC[o] = C;
-      accum = accum + newForce;
-    }
-  }
-  if (numFriction) {
-    const float maxFrictionImpulse = rb4.z * accum, maxDynFrictionImpulse = rb4.w * accum;
-    bool broken = false;
-    for (uint32_t j = 0; j < numFriction; j += 2) {
-      const size_t o0 = (size_t)j * cap + k, o1 = (size_t)(j + 1) * cap + k;
-      const float4 A0 = frA[o0], B0 = frB[o0], C0 = frC[o0]; float4 D0 = frD[o0];
-      const float4 A1 = frA[o1], B1 = frB[o1], C1 = frC[o1]; float4 D1 = frD[o1];
-      const float frictionScale = D0.y, biasScale = D0.z;
-      const v3 normal0 = V3(A0.x, A0.y, A0.z), normal1 = V3(A1.x, A1.y, A1.z);
-      const v3 raXnI0 = V3(B0.x, B0.y, B0.z), rbXnI0 = V3(C0.x, C0.y, C0.z), raXnI1 = V3(B1.x, B1.y, B1.z), rbXnI1 = V3(C1.x, C1.y, C1.z);
-      const float applied0 = D0.x, applied1 = D1.x, targetVel0 = B0.w, targetVel1 = B1.w;
-      float deltaV0 = (adot(raXnI0, angMotion0) - adot(rbXnI0, angMotion1)) + adot(normal0, relMotion);
-      float deltaV1 = (adot(raXnI1, angMotion0) - adot(rbXnI1, angMotion1)) + adot(normal1, relMotion);
-      deltaV0 = deltaV0 - targetVel0 * elapsedTime; deltaV1 = deltaV1 - targetVel1 * elapsedTime;
-      const float bias0 = (A0.w + deltaV0) * biasScale, bias1 = (A1.w + deltaV1) * biasScale;
-      const float vm0 = C0.w, vm1 = C1.w;
-      const v3 d0 = (vmul(linVel0, normal0) + vmul(angState0, raXnI0)) - (vmul(linVel1, normal0) + vmul(angState1, rbXnI0));
-      const v3 d1 = (vmul(linVel0, normal1) + vmul(angState0, raXnI1)) - (vmul(linVel1, normal1) + vmul(angState1, rbXnI1));
-      const float normalVel0 = (d0.x + d0.y) + d0.z, normalVel1 = (d1.x + d1.y) + d1.z;
-      const float tmp10 = applied0 - (bias0 - targetVel0) * vm0, tmp11 = applied1 - (bias1 - targetVel1) * vm1;
-      const float total0 = tmp10 - normalVel0 * vm0, total1 = tmp11 - normalVel1 * vm1;
-      const float total = sqrtf(total0 * total0 + total1 * total1);
-      const bool clamp = total > (frictionScale * maxFrictionImpulse);
-      const float totalClamped = clamp ? fmin_(frictionScale * maxDynFrictionImpulse, total) : total;
-      const float ratio = (total > 0.f) ? (totalClamped / total) : 0.f;
-      const float new0 = total0 * ratio, new1 = total1 * ratio;
-      broken = broken || clamp;
-      const float dF0 = new0 - applied0, dF1 = new1 - applied1;
-      linVel0 = scaleadd(normal0 * invMassA, dF0, scaleadd(normal1 * invMassA, dF1, linVel0));
-      linVel1 = negscalesub(normal0 * invMassB, dF0, negscalesub(normal1 * invMassB, dF1, linVel1));
-      angState0 = scaleadd(raXnI0, dF0 * 1.f, scaleadd(raXnI1, dF1 * 1.f, angState0));
-      angState1 = negscalesub(rbXnI0, dF0 * 1.f, negscalesub(rbXnI1, dF1 * 1.f, angState1));
-      D0.x = new0; D1.x = new1; frD[o0] = D0; frD[o1] = D1;
-    }
-    brokenFlags[k] = broken ? 1u : 0u;  // hdr->broken is overwritten by every solve call (Store_From_BoolV)
-  }
-  sbLin[b0] = F4(linVel0, 0.f); sbAng[b0] = F4(angState0, 0.f);
-  if (b1 != NONE32) { sbLin[b1] = F4(linVel1, 0.f); sbAng[b1] = F4(angState1, 0.f); }
-}
-
-// a15/a16: the whole TGS iteration loop in ONE cooperative launch (iterativeSolveIsland, DyTGSDynamics.cpp:2515-2793):
-// position iterations = {solve every partition in order; integrate the sub-step}, then velocity iterations.
-__global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ partStart, uint32_t cap, uint32_t posIters, uint32_t velIters, float stepDt,
-                        const float4* __restrict__ rowA, const float4* __restrict__ rowB, const uint4* __restrict__ rowC, const float4* __restrict__ ptA, const float4* __restrict__ ptB,
-                        float4* __restrict__ ptC, const float4* __restrict__ frA, const float4* __restrict__ frB, const float4* __restrict__ frC, float4* __restrict__ frD,
-                        float4* __restrict__ sbLin, float4* __restrict__ sbAng, float4* __restrict__ sbDLin, float4* __restrict__ sbDAng, const float4* __restrict__ sbIA,
-                        const float4* __restrict__ sbIB, float4* __restrict__ sbP, float4* __restrict__ sbQ, const uint32_t* __restrict__ bodyHasCon, uint32_t nDyn,
-                        const uint32_t* __restrict__ dynActor, uint32_t* __restrict__ brokenFlags) {
-  cg::grid_group grid = cg::this_grid();
-  const uint32_t nPart = counters[C_NPART];
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-  if (nPart == 0) return;
-  float elapsed = 0.f;
-  for (uint32_t it = 0; it < posIters + velIters; ++it) {
-    const bool vel = it >= posIters;
-    const float minPen = vel ? 0.f : -FLT_MAX;
-    for (uint32_t p = 0; p < nPart; ++p) {
-      const uint32_t b = partStart[p], e = partStart[p + 1];
-      for (uint32_t k = b + gtid; k < e; k += gsize)
-        solve_constraint(k, cap, minPen, elapsed, rowA, rowB, rowC, ptA, ptB, ptC, frA, frB, frC, frD, sbLin, sbAng, sbDLin, sbDAng, brokenFlags);
-      grid.sync();
-    }
-    if (!vel) {
-      for (uint32_t d = gtid; d < nDyn; d += gsize) {
-        const uint32_t a = dynActor[d];
-        if (!bodyHasCon[a]) continue;
-        v3 p = V3(sbP[a]); q4 dq = Q4(sbQ[a]); v3 dl = V3(sbDLin[a]), da = V3(sbDAng[a]);
-        integrate_core_step(V3(sbLin[a]), V3(sbAng[a]), load_sym(sbIA[a], sbIB[a]), stepDt, p, dq, dl, da);
-        sbP[a] = F4(p, 0.f); sbQ[a] = F4(dq); sbDLin[a] = F4(dl, 0.f); sbDAng[a] = F4(da, 0.f);
-      }
-      elapsed += stepDt;
-      grid.sync();
-    }
-  }
-}
 
 // a17/a18: copyBackBodies (DyTGSDynamics.cpp:1549-1580); bodies without constraints take one full-dt step (:2573-2577)
 __global__ void k_finalize_bodies(uint32_t nDyn, const uint32_t* __restrict__ dynActor, float dt, float4* __restrict__ pos, float4* __restrict__ quat, float4* __restrict__ linVel,
@@ -814,16 +614,6 @@ __global__ void k_finalize_bodies(uint32_t nDyn, const uint32_t* __restrict__ dy
   linVel[a] = F4(lv, 0.f); angVel[a] = F4(mmul(sI, as), 0.f);
   if (S.threshold > 0.f) { const float invDt = 1.0f / dt; sleep_check_dev(S, a, q, invInertia[a], invMass, dl * invDt, mmul(sI, da * invDt)); }   // motionVel of copyBackBodies
 }
-// writeBackContact (DyTGSContactPrep.cpp:1875-1937): applied forces -> contact force stream, broken flag -> friction patch
-__global__ void k_writeback(const uint32_t* __restrict__ counters, uint32_t cap, const uint4* __restrict__ rowC, const float4* __restrict__ ptC, const uint32_t* __restrict__ brokenFlags,
-                            const uint32_t* __restrict__ pairSlots, float* __restrict__ cForce, float4* __restrict__ frictions) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= counters[C_NCON]) return;
-  const uint4 rc = rowC[k]; const uint32_t i = rc.w; const uint32_t numNormal = rc.z & 0xff, numFriction = (rc.z >> 8) & 0xff;
-  for (uint32_t j = 0; j < numNormal; ++j) cForce[(size_t)i * 4 + j] = ptC[(size_t)j * cap + k].w;
-  if (numFriction && brokenFlags[k]) frictions[(size_t)pairSlots[i] * PXB_FRICTION_F4 + 1].w = __int_as_float(1);
-}
-
 // a19: PxDirectGPUAPI get/set (gather/scatter by dynamic-body index)
 __global__ void k_rd_get(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, int type, const float4* __restrict__ pos, const float4* __restrict__ quat,
                          const float4* __restrict__ linVel, const float4* __restrict__ angVel, float* __restrict__ out) {
@@ -907,7 +697,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->conB0, Pn)); CK(dalloc(s->conB1, Pn)); CK(dalloc(s->conPos0, Pn)); CK(dalloc(s->conPos1, Pn)); CK(dalloc(s->conColour, Pn)); CK(dalloc(s->conDone, Pn));
   CK(dalloc(s->bodyList, Pn * 2)); CK(dalloc(s->ordered, Pn));
   CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
-  CK(dalloc(s->rowA, Pn)); CK(dalloc(s->rowB, Pn)); CK(dalloc(s->rowC, Pn)); CK(dalloc(s->ptA, Pn * 28)); s->ptB = s->ptA + Pn * 4; s->ptC = s->ptA + Pn * 8;   // one allocation: the environment path views it as 25 x Pn (pxb_env.cuh Rows)
+  CK(dalloc(s->ptA, Pn * 28)); s->ptB = s->ptA + Pn * 4; s->ptC = s->ptA + Pn * 8;   // one allocation: the environment path views it as 25 x Pn (pxb_env.cuh Rows)
   s->frA = s->ptA + Pn * 12; s->frB = s->ptA + Pn * 16; s->frC = s->ptA + Pn * 20; s->frD = s->ptA + Pn * 24;
   CK(dalloc(s->stage, A * 13 * 2)); CK(dalloc(s->stageIdx, A));   // staging: {get, set} x {pose 7, linear 3, angular 3} floats per actor
   CK(dalloc(s->counters, C_COUNT)); CK(cudaMallocHost((void**)&s->hostCounters, sizeof(uint32_t) * (C_COUNT + 2)));
@@ -949,7 +739,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   CK(cudaFuncSetAttribute(k_env_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sleep_islands, 256, 0)); s->coopBlocksSleep = std::max(1, std::min(occ, 2)) * s->numSMs;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_pgs, 256, 0)); s->coopBlocksSolvePgs = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_tgs, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
   s->capA = std::max(16u, desc->maxActors);
   s->capPairs = desc->maxPairs ? desc->maxPairs : std::max(1024u, 8u * s->capA);
   s->bitsA = bits_for(s->capA);
@@ -974,7 +764,7 @@ PXB_API void pxb_scene_release(PxbScene* s) {
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
-                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->rowA, s->rowB, s->rowC, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
+                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
                   s->envStart, s->envList, s->actorLocal, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
@@ -1297,31 +1087,30 @@ static int enqueue_step(PxbScene* s, float dt) {
          s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, pgs ? 1 : 0, SA);
   if (pgs) {   // PGS: rows in the 25-float4 record image, velocity-delta solver bodies (pxb_pgs.cuh)
     Rows R; R.f = s->ptA; R.broken = s->conDone; R.stride = s->capPairs;
-    LAUNCH(k_prep_pgs, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
+    LAUNCH(k_prep_rows<true>, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
            s->invInertia, s->sbIA, s->sbIB, s->frictions, P, R);
     MARK(4);
     uint32_t posIters = s->desc.posIters, velIters = s->desc.velIters, nDyn = s->nDyn;
     void* args[] = {&s->counters, &s->partStart, &posIters, &velIters, &R, &s->sbLin, &s->sbAng, &s->sbDLin, &s->sbDAng, &nDyn, &s->dynActorDev};
     CK(cudaLaunchCooperativeKernel((void*)k_solve_pgs, dim3(s->coopBlocksSolvePgs), dim3(256), args, 0, st)); s->launches++;
     MARK(5);
-    LAUNCH(k_writeback_pgs, gP, B, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions);
+    LAUNCH(k_writeback_rows, gP, B, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions);
     LAUNCH(k_finalize_bodies_pgs, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->invInertia, SA);
     MARK(6);
     CK(cudaGetLastError());
     return PXB_OK;
   }
-  LAUNCH(k_prep, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
-         s->invInertia, s->sbIA, s->sbIB, s->frictions, P, s->capPairs, s->rowA, s->rowB, s->rowC, s->ptA, s->ptB, s->ptC, s->frA, s->frB, s->frC, s->frD);
-  MARK(4);
-  {
-    uint32_t cap = s->capPairs, posIters = s->desc.posIters, velIters = s->desc.velIters; float stepDt = P.stepDt; uint32_t nDyn = s->nDyn; uint32_t* broken = s->conDone;
-    void* args[] = {&s->counters, &s->partStart, &cap, &posIters, &velIters, &stepDt, &s->rowA, &s->rowB, &s->rowC, &s->ptA, &s->ptB, &s->ptC, &s->frA, &s->frB, &s->frC, &s->frD,
-                    &s->sbLin, &s->sbAng, &s->sbDLin, &s->sbDAng, &s->sbIA, &s->sbIB, &s->sbP, &s->sbQ, &s->bodyHasCon, &nDyn, &s->dynActorDev, &broken};
-    CK(cudaMemsetAsync(s->conDone, 0, 4 * (size_t)s->capPairs, st));
-    CK(cudaLaunchCooperativeKernel((void*)k_solve, dim3(s->coopBlocksSolve), dim3(256), args, 0, st)); s->launches++;
+  {   // TGS: rows in the same 25-float4 record image as the environment path (pxb_env.cuh RegRows)
+    Rows R; R.f = s->ptA; R.broken = s->conDone; R.stride = s->capPairs;
+    LAUNCH(k_prep_rows<false>, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
+           s->invInertia, s->sbIA, s->sbIB, s->frictions, P, R);
+    MARK(4);
+    uint32_t posIters = s->desc.posIters, velIters = s->desc.velIters, nDyn = s->nDyn; float stepDt = P.stepDt;
+    void* args[] = {&s->counters, &s->partStart, &posIters, &velIters, &stepDt, &R, &s->sbLin, &s->sbAng, &s->sbDLin, &s->sbDAng, &s->sbIA, &s->sbIB, &s->sbP, &s->sbQ, &s->bodyHasCon, &nDyn, &s->dynActorDev};
+    CK(cudaLaunchCooperativeKernel((void*)k_solve_tgs, dim3(s->coopBlocksSolve), dim3(256), args, 0, st)); s->launches++;
+    MARK(5);
+    LAUNCH(k_writeback_rows, gP, B, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions);
   }
-  MARK(5);
-  LAUNCH(k_writeback, gP, B, s->counters, s->capPairs, s->rowC, s->ptC, s->conDone, s->pairSlots[cur], s->cForce, s->frictions);
   LAUNCH(k_finalize_bodies, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->bodyHasCon,
          s->sbDLin, s->sbDAng, s->invInertia, SA);
   MARK(6);

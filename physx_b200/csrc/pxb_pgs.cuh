@@ -193,8 +193,9 @@ __device__ __forceinline__ void integrate_core_pgs(v3& p, q4& q, v3& linVel, v3&
 }
 
 // ---------------------------------------------------------------------------------------------
-// device-wide PGS kernels (scenes without environment ids); rows live in the RegRows memory image (25 x cap float4)
-__global__ void __launch_bounds__(128) k_prep_pgs(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ ordered, const uint32_t* __restrict__ conPair, const uint32_t* __restrict__ pairSlots,
+// device-wide solver kernels, both solver types (scenes without environment ids); rows live in the RegRows memory image (25 x cap float4)
+template <bool PGS>
+__global__ void __launch_bounds__(128) k_prep_rows(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ ordered, const uint32_t* __restrict__ conPair, const uint32_t* __restrict__ pairSlots,
                        const uint2* __restrict__ pairBodies, const uint32_t* __restrict__ geomFlags, const float4* __restrict__ cHdr, const float4* __restrict__ cPts,
                        const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ linVel, const float4* __restrict__ sbOrigAng,
                        const float4* __restrict__ invInertia, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, float4* __restrict__ frictions, SolverParams P, Rows R) {
@@ -219,8 +220,47 @@ __global__ void __launch_bounds__(128) k_prep_pgs(const uint32_t* __restrict__ c
   B.angVel0 = V3(sbOrigAng[b0]); B.angVel1 = dyn1 ? V3(sbOrigAng[b1]) : V3(0, 0, 0);
   B.sI0 = load_sym(sbIA[b0], sbIB[b0]);
   if (dyn1) B.sI1 = load_sym(sbIA[b1], sbIB[b1]); else { B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
-  prep_constraint_pgs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P);
+  if (PGS) prep_constraint_pgs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P);
+  else prep_constraint_regs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P);
   rows_store(R, k, r);
+}
+
+// a15/a16: the whole TGS iteration loop in ONE cooperative launch (iterativeSolveIsland, DyTGSDynamics.cpp:2515-2793):
+// position iterations = {solve every partition in order; integrate the sub-step}, then velocity iterations.
+// Replaces solveBlockUnified x partitions x iterations + propagateAverageSolverBodyVelocityTGS (~65 launches in the reference).
+__global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve_tgs(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ partStart, uint32_t posIters, uint32_t velIters, float stepDt, Rows R,
+                            float4* __restrict__ sbLin, float4* __restrict__ sbAng, float4* __restrict__ sbDLin, float4* __restrict__ sbDAng, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB,
+                            float4* __restrict__ sbP, float4* __restrict__ sbQ, const uint32_t* __restrict__ bodyHasCon, uint32_t nDyn, const uint32_t* __restrict__ dynActor) {
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t nPart = counters[C_NPART];
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  if (nPart == 0) return;
+  float elapsed = 0.f;
+  for (uint32_t it = 0; it < posIters + velIters; ++it) {
+    const bool vel = it >= posIters;
+    const float minPen = vel ? 0.f : -FLT_MAX;
+    for (uint32_t p = 0; p < nPart; ++p) {
+      const uint32_t b = partStart[p], e = partStart[p + 1];
+      for (uint32_t k = b + gtid; k < e; k += gsize) {
+        RegRows r; rows_load(R, k, r);
+        if ((r.h2.z & 0xff) == 0) continue;   // empty constraint kept only for the colouring
+        solve_constraint_regs<false>(r, minPen, elapsed, sbLin, sbAng, sbDLin, sbDAng);
+        rows_store_state(R, k, r);
+      }
+      grid.sync();
+    }
+    if (!vel) {
+      for (uint32_t d = gtid; d < nDyn; d += gsize) {
+        const uint32_t a = dynActor[d];
+        if (!bodyHasCon[a]) continue;
+        v3 p = V3(sbP[a]); q4 dq = Q4(sbQ[a]); v3 dl = V3(sbDLin[a]), da = V3(sbDAng[a]);
+        integrate_core_step(V3(sbLin[a]), V3(sbAng[a]), load_sym(sbIA[a], sbIB[a]), stepDt, p, dq, dl, da);
+        sbP[a] = F4(p, 0.f); sbQ[a] = F4(dq); sbDLin[a] = F4(dl, 0.f); sbDAng[a] = F4(da, 0.f);
+      }
+      elapsed += stepDt;
+      grid.sync();
+    }
+  }
 }
 
 // the whole PGS iteration loop in ONE cooperative launch (solveV_Blocks, DySolverControl.cpp:163-405)
@@ -258,7 +298,8 @@ __global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve_pgs(const 
     }
 }
 
-__global__ void k_writeback_pgs(const uint32_t* __restrict__ counters, Rows R, const uint32_t* __restrict__ pairSlots, float* __restrict__ cForce, float4* __restrict__ frictions) {
+// a17: writeBackContact (DyTGSContactPrep.cpp:1875-1937 / DySolverConstraints.cpp:553-640): applied forces -> contact force stream, broken flag -> friction patch
+__global__ void k_writeback_rows(const uint32_t* __restrict__ counters, Rows R, const uint32_t* __restrict__ pairSlots, float* __restrict__ cForce, float4* __restrict__ frictions) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= counters[C_NCON]) return;
   const size_t s = R.stride;
