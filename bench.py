@@ -148,7 +148,7 @@ def bench_ours(args):
     if dist is not None:
         # one packed [n, 13] tensor (pose + linear + angular velocity) -> ONE NCCL all-gather per step, double-buffered on a
         # communication stream so that it overlaps the next step's kernels
-        gather = multi_gpu.PipelinedStateGather(dist, nb, 13, dev, scene_stream=stream)
+        gather, gather_kind = multi_gpu.make_state_gather(dist, nb, 13, dev, stream, kind=args.gather)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
 
     def one_step():
@@ -281,7 +281,7 @@ def bench_ours(args):
             "config": {"workload": f"config {2 if args.stacks == 8 else 5}: {n_envs} envs x {args.stacks * 8} boxes = {nb} bodies per GPU, shared ground plane, GPU broadphase + {args.solver.upper()} 4 pos/1 vel iterations, 60 Hz",
                        "bodies_total": total_bodies, "constraints_per_gpu": P, "partitions": scene.num_partitions, "path": "environment (pxb_env.cuh)" if scene.uses_env_path else "device-wide",
                        "timing": "CUDA events on the scene stream per step, max over ranks; L2 flushed (256 MiB memset) between timed steps",
-                       "multi_gpu": "env-partitioned, one scene per GPU, per-step NCCL all-gather of the packed pose+linear+angular velocity tensor (13 floats/body), double-buffered on a communication stream (overlaps the next step)" if world > 1 else "single scene"},
+                       "multi_gpu": ("env-partitioned, one scene per GPU, per-step all-gather of the packed pose+linear+angular velocity tensor (13 floats/body) by " + gather_kind + ", double-buffered on a communication stream (overlaps the next step)") if world > 1 else "single scene"},
             "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kernel_bytes, "kernel_ms": solve_ms,
                          "dram_frac": (traffic / (solve_ms / 1e3) / 1e9 / peak) if traffic else None, "note": note},
@@ -309,6 +309,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stacks", type=int, default=8, help="stacks of 8 boxes per environment (8 = config 2, 16 = the per-GPU shard of config 5)")
     ap.add_argument("--path", default="auto", choices=["auto", "devicewide"], help="devicewide forces the path used by scenes without environment ids (comparison runs)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"], help="multi-GPU state exchange: peer-memory copies or NCCL all-gather")
     ap.add_argument("--solver", default="tgs", choices=["tgs", "pgs"], help="PxSolverType of the scene (headline metric: tgs)")
     args = ap.parse_args()
     if args.impl == "reference":

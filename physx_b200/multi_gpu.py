@@ -138,6 +138,83 @@ class PipelinedStateGather:
                     (stream or self.scene_stream).wait_event(ev)
 
 
+class PeerStateGather:
+    """All-gather of the packed state over NVLink PEER MEMORY instead of an NCCL kernel: every rank's global tensor lives in
+    symmetric memory (torch.distributed._symmetric_memory), the engine's pack kernel writes this rank's block into its own copy
+    and the block is then pushed into every peer's copy with device-to-device peer copies (copy engines: no SM is taken away
+    from the next step's kernels, which the collective overlaps), followed by one symmetric-memory barrier.  Double-buffered
+    like PipelinedStateGather; same interface.  Raises at construction when symmetric memory is not available (callers fall
+    back to NCCL)."""
+
+    def __init__(self, dist, n_local: int, cols: int, device, scene_stream):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        self.torch, self.dist = torch, dist
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        cnt = torch.tensor([n_local], dtype=torch.int64, device=device)
+        allc = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(allc, cnt)
+        self.counts = [int(c.item()) for c in allc]
+        self.layout = gather_layout(self.counts)
+        total = sum(self.counts)
+        self.scene_stream = scene_stream
+        self.comm_stream = torch.cuda.Stream(device=device)
+        self.bufs, self.handles, self.peer_views = [], [], []
+        lo, hi = self.layout[self.rank]
+        for _ in range(2):
+            t = symm.empty((total, cols), dtype=torch.float32, device=device)
+            h = symm.rendezvous(t, dist.group.WORLD)
+            self.bufs.append(t)
+            self.handles.append(h)
+            self.peer_views.append([h.get_buffer(p, (total, cols), torch.float32)[lo:hi] for p in range(self.world)])
+        self.done = [None, None]
+        self.k = 0
+        dist.barrier()
+
+    def step(self, pack):
+        t = self.torch
+        b = self.k & 1
+        lo, hi = self.layout[self.rank]
+        local = self.bufs[b][lo:hi]
+        if self.done[b] is not None:
+            self.scene_stream.wait_event(self.done[b])          # exchange k-2 used this buffer
+        pack(local)                                             # engine pack kernel, stream-ordered on the scene stream
+        ready = t.cuda.Event()
+        ready.record(self.scene_stream)
+        self.comm_stream.wait_event(ready)
+        with t.cuda.stream(self.comm_stream):
+            for p in range(self.world):
+                if p != self.rank:
+                    self.peer_views[b][p].copy_(local, non_blocking=True)   # peer D2D copy over NVLink
+            self.handles[b].barrier(channel=b)                  # every rank's pushes into this buffer have landed
+            self.done[b] = t.cuda.Event()
+            self.done[b].record(self.comm_stream)
+        self.k += 1
+        return b
+
+    def latest(self):
+        return self.bufs[(self.k - 1) & 1]
+
+    def wait(self, stream=None):
+        for ev in self.done:
+            if ev is not None:
+                (stream or self.scene_stream).wait_event(ev)
+
+
+def make_state_gather(dist, n_local: int, cols: int, device, scene_stream, kind: str = "auto"):
+    """kind: 'peer' (symmetric-memory peer copies), 'nccl' (all_gather_into_tensor) or 'auto' (peer when available)."""
+    if kind in ("auto", "peer") and device.type == "cuda":
+        try:
+            return PeerStateGather(dist, n_local, cols, device, scene_stream), "peer-memory copies (symmetric memory, copy engines) + barrier"
+        except Exception as e:  # pragma: no cover - depends on the platform
+            if kind == "peer":
+                raise
+            reason = f" (peer memory unavailable: {type(e).__name__})"
+    else:
+        reason = ""
+    return PipelinedStateGather(dist, n_local, cols, device, scene_stream=scene_stream), "NCCL all_gather_into_tensor" + reason
+
+
 class EnvShardedScene:
     """One rank's scene of an env-partitioned job + the state all-gather."""
 
