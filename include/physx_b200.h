@@ -5,8 +5,8 @@
  * All functions return 0 (PXB_OK) on success or a negative PxbError; pxb_last_error() gives the text.
  * There is NO CPU fallback: without a CUDA device every compute entry point fails with PXB_ERR_NO_DEVICE.
  *
- * Pointers are HOST pointers unless the name says "_device"/"dev".  Actor records use the layout of
- * oracle/scene_format.h::PxbActorRec (128 bytes) so scenes are bit-identical on both sides of a test.
+ * Pointers are HOST pointers unless the name says "_device"/"dev".  Actor records are PxbActorRec below (128 bytes; the test
+ * oracle reads the same layout so scenes are bit-identical on both sides of a test).
  */
 #ifndef PHYSX_B200_H
 #define PHYSX_B200_H
@@ -60,6 +60,27 @@ enum { PXB_FLAG_NO_ENV_PATH = 1u,
  * device-wide path colours constraints with Jones-Plassmann rounds instead (a valid, deterministic partitioning that is NOT the
  * reference's first-fit, so trajectories are comparable to the reference only statistically).  Off by default. */
        PXB_FLAG_RELAXED_PARTITIONING = 2u };
+
+/* One actor = one rigid body (or static) with one shape, local shape pose = identity; 128 bytes, little endian.
+ * Planes: the actor pose carries the plane frame, normal = local +X (PxPlaneGeometry).  Mass properties are explicit
+ * (PxRigidBody::setMass / setMassSpaceInertiaTensor); the remaining fields are the PxRigidDynamic setters of the same name. */
+typedef struct {
+  uint32_t flags;       /* PXB_ACTOR_DYNAMIC or 0 (static) */
+  uint32_t geomType;    /* PXB_GEOM_* */
+  uint32_t envId;       /* PxActor::setEnvironmentID, 0xffffffff = none */
+  uint32_t hullIdx;     /* reserved for convex meshes */
+  float    pos[3];
+  float    quat[4];     /* x y z w, normalised */
+  float    dims[4];     /* sphere: r; capsule: r, halfHeight; box: hx hy hz */
+  float    linVel[3];
+  float    angVel[3];
+  float    mass;
+  float    inertia[3];  /* mass-space diagonal */
+  float    linDamping, angDamping;
+  float    maxLinVel, maxAngVel;
+  float    maxDepenetrationVel;
+  float    reserved[2];
+} PxbActorRec;
 
 typedef struct PxbScene PxbScene;
 

@@ -1317,18 +1317,18 @@ PXB_API int pxb_scene_get_states_device(PxbScene* s, float* devOut) {
 PXB_API int pxb_scene_get_states(PxbScene* s, float* out) {
   if (!s || !out) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;
-  cudaStream_t st = s->stream; float* d = nullptr; CK(cudaMalloc((void**)&d, 52 * (size_t)s->nDyn));
+  cudaStream_t st = s->stream; float* d = s->stage;   // persistent staging (26 floats per actor): no allocation per call
   LAUNCH(k_states_get, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, d);
-  CK(cudaMemcpyAsync(out, d, 52 * (size_t)s->nDyn, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); cudaFree(d);
+  CK(cudaMemcpyAsync(out, d, 52 * (size_t)s->nDyn, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
   return PXB_OK;
 }
 PXB_API int pxb_scene_set_states(PxbScene* s, const float* in) {
   if (!s || !in) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;
-  cudaStream_t st = s->stream; float* d = nullptr; CK(cudaMalloc((void**)&d, 52 * (size_t)s->nDyn));
+  cudaStream_t st = s->stream; float* d = s->stage + (size_t)s->capA * 13;
   CK(cudaMemcpyAsync(d, in, 52 * (size_t)s->nDyn, cudaMemcpyHostToDevice, st));
   LAUNCH(k_states_set, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, d, s->wake, s->asleep);
-  CK(cudaStreamSynchronize(st)); cudaFree(d);
+  CK(cudaStreamSynchronize(st));
   return PXB_OK;
 }
 

@@ -159,6 +159,7 @@ class PeerStateGather:
         total = sum(self.counts)
         self.scene_stream = scene_stream
         self.comm_stream = torch.cuda.Stream(device=device)
+        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(max(1, self.world - 1))]   # one per peer: concurrent copy engines
         self.bufs, self.handles, self.peer_views = [], [], []
         lo, hi = self.layout[self.rank]
         for _ in range(2):
@@ -181,11 +182,18 @@ class PeerStateGather:
         pack(local)                                             # engine pack kernel, stream-ordered on the scene stream
         ready = t.cuda.Event()
         ready.record(self.scene_stream)
+        j = 0
+        for p in range(self.world):                             # pushes to different peers run concurrently, one stream (copy engine) each
+            if p == self.rank:
+                continue
+            cs = self.copy_streams[j]; j += 1
+            cs.wait_event(ready)
+            with t.cuda.stream(cs):
+                self.peer_views[b][p].copy_(local, non_blocking=True)   # peer D2D copy over NVLink
+                ev = t.cuda.Event(); ev.record(cs)
+            self.comm_stream.wait_event(ev)
         self.comm_stream.wait_event(ready)
         with t.cuda.stream(self.comm_stream):
-            for p in range(self.world):
-                if p != self.rank:
-                    self.peer_views[b][p].copy_(local, non_blocking=True)   # peer D2D copy over NVLink
             self.handles[b].barrier(channel=b)                  # every rank's pushes into this buffer have landed
             self.done[b] = t.cuda.Event()
             self.done[b].record(self.comm_stream)

@@ -457,3 +457,22 @@ def test_unsupported_pair_type_is_reported_not_skipped(oracle):
             cpu.step()
             gpu.step()
     assert "capsule-box" in str(e.value) and cpu.unsupported_pairs > 0
+
+
+def test_cpp_host_mirror_snippet_hello_world():
+    """examples/snippet_hello_world.cpp (C++ host code over the C ABI, include/physx_b200.hpp) steps the SnippetHelloWorld scene
+    (BASELINE config 1) to the same state as the Python binding, bit for bit."""
+    import json, os, subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "snippet_hello_world")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-f", "examples/Makefile"], cwd=os.path.dirname(os.path.dirname(exe)), check=True)
+    for solver, arg in ((scenes.SOLVER_TGS, "tgs"), (scenes.SOLVER_PGS, "pgs")):
+        out = json.loads(subprocess.run([exe, "60", "10", "10", arg], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
+        g = engine.Scene(scenes.box_stacks(solver=solver))
+        for _ in range(60):
+            g.step()
+        st = g.getStates()
+        assert out["bodies"] == 100 and out["pairs"] == len(g.getPairs()) and out["constraints"] == g.num_constraints and out["partitions"] == g.num_partitions
+        assert np.float32(out["top_y"]) == st[-1, 1]   # %.9g round-trips a float32
+        assert abs(out["checksum"] - float(st[:, :7].astype(np.float64).sum())) < 1e-4
+        assert out["min_y"] > 0.49 and out["max_speed"] < 0.2
