@@ -475,4 +475,4 @@ def test_cpp_host_mirror_snippet_hello_world():
         assert out["bodies"] == 100 and out["pairs"] == len(g.getPairs()) and out["constraints"] == g.num_constraints and out["partitions"] == g.num_partitions
         assert np.float32(out["top_y"]) == st[-1, 1]   # %.9g round-trips a float32
         assert abs(out["checksum"] - float(st[:, :7].astype(np.float64).sum())) < 1e-4
-        assert out["min_y"] > 0.49 and out["max_speed"] < 0.2
+        assert out["min_y"] > 0.49 and out["max_speed"] < 0.5   # the stacks stand (PGS leaves a larger residual wobble than TGS)
