@@ -343,3 +343,23 @@ def falling_primitives(nx=128, ny=64, nz=128, pitch=0.6, seed=2, kinds=("sphere"
         else:
             set_box(a, idx, rng.uniform(0.1, 0.2, (len(idx), 3)).astype(np.float32))
     return Scene(default_header(**hdr), add_bin(a, half_size=float(max(nx, nz) * pitch / 2 + 1.0)))
+
+
+def env_piles(n_envs=3, nx=5, ny=4, nz=5, half_extent=0.25, gap=0.001, env_pitch=12.0, seed=4, **hdr):
+    """Environments that each hold a dense lattice pile of boxes (no walls): many more pairs and constraints per environment than
+    bodies, so the environment path runs with oversize constraint lists / rows streamed through global scratch."""
+    rng = np.random.RandomState(seed)
+    per = nx * ny * nz
+    a = _new_actors(n_envs * per)
+    he = np.float32(half_extent)
+    pitch = np.float32(2 * half_extent + gap)
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    for e in range(n_envs):
+        sl = slice(e * per, (e + 1) * per)
+        jit = rng.uniform(-gap * 0.4, gap * 0.4, size=(per, 2)).astype(np.float32)
+        a["pos"][sl, 0] = np.float32(e * env_pitch) + ix.ravel().astype(np.float32) * pitch + jit[:, 0]
+        a["pos"][sl, 1] = he + iy.ravel().astype(np.float32) * pitch + np.float32(gap)
+        a["pos"][sl, 2] = iz.ravel().astype(np.float32) * pitch + jit[:, 1]
+        a["envId"][sl] = e
+    set_box(a, np.arange(len(a)), np.array([he, he, he], dtype=np.float32))
+    return Scene(default_header(**hdr), add_ground_plane(a))

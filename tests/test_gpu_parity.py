@@ -199,7 +199,9 @@ def test_gpu_teacher_forced_steps_match_reference(name):
 def _env_scenes():
     return {"envs_16": (scenes.env_grid_stacks(n_envs=16, jitter=0.01), 40),
             "envs_37x3x5": (scenes.env_grid_stacks(n_envs=37, stacks_per_env=3, height=5, jitter=0.02), 40),
-            "ragged": (scenes.env_ragged(), 150)}
+            "ragged": (scenes.env_ragged(), 150),
+            "wide_200_bodies": (scenes.env_grid_stacks(n_envs=3, stacks_per_env=25, height=8, jitter=0.01), 25),   # 200 constraints per env: 256-thread CTAs
+            "piles_100": (scenes.env_piles(), 40)}   # ~300 constraints / ~650 pairs per env: rows and lists through global scratch
 
 
 @pytest.mark.parametrize("name", list(_env_scenes()))
@@ -207,7 +209,7 @@ def test_env_path_is_bit_identical_to_device_wide_path(name):
     """Environment path (one warp / CTA per environment, rows in shared memory) vs the device-wide path (grid broadphase,
     global colouring, cooperative solve): same pairs, events, contacts and states, bit for bit, every step."""
     sc, steps = _env_scenes()[name]
-    env, glob = engine.Scene(sc), engine.Scene(sc, env_path=False)
+    env, glob = engine.Scene(sc, max_pairs=16 * len(sc.actors)), engine.Scene(sc, max_pairs=16 * len(sc.actors), env_path=False)
     for t in range(steps):
         env.step()
         glob.step()
