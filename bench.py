@@ -148,7 +148,7 @@ def bench_ours(args):
     if dist is not None:
         # one packed [n, 13] tensor (pose + linear + angular velocity) -> ONE NCCL all-gather per step, double-buffered on a
         # communication stream so that it overlaps the next step's kernels
-        gather, gather_kind = multi_gpu.make_state_gather(dist, nb, 13, dev, stream, kind=args.gather)
+        gather, gather_kind = multi_gpu.make_state_gather(dist, nb, 13, dev, stream, kind=args.gather, scene=scene)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
 
     def one_step():
@@ -193,6 +193,15 @@ def bench_ours(args):
     torch.cuda.synchronize(dev)
     if dist is not None:
         dist.barrier()
+        # validity of the exchange (outside the timed region): the gathered tensor must equal a plain NCCL all-gather of every rank's packed state
+        mine = torch.empty((nb, 13), dtype=torch.float32, device=dev)
+        scene.getStatesDevice(mine.data_ptr())
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        ref = torch.empty((world * nb, 13), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(ref, mine)
+        torch.cuda.synchronize(dev)
+        if not torch.equal(ref, gather.latest()):
+            raise RuntimeError(f"rank {rank}: gathered state tensor differs from the NCCL reference all-gather")
     clocks = sampler.stop() if rank == 0 else None
     total_ms = float(sum(step_ms))
     # ---- per-stage device times (CUDA events inside the engine, direct launches) for the roofline of the
@@ -309,7 +318,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stacks", type=int, default=8, help="stacks of 8 boxes per environment (8 = config 2, 16 = the per-GPU shard of config 5)")
     ap.add_argument("--path", default="auto", choices=["auto", "devicewide"], help="devicewide forces the path used by scenes without environment ids (comparison runs)")
-    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"], help="multi-GPU state exchange: peer-memory copies or NCCL all-gather")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-copy", "nccl"], help="multi-GPU state exchange: peer-memory copies or NCCL all-gather")
     ap.add_argument("--solver", default="tgs", choices=["tgs", "pgs"], help="PxSolverType of the scene (headline metric: tgs)")
     args = ap.parse_args()
     if args.impl == "reference":

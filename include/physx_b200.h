@@ -131,6 +131,8 @@ PXB_API int  pxb_scene_get_states(PxbScene* scene, float* out);
 PXB_API int  pxb_scene_set_states(PxbScene* scene, const float* in);
 PXB_API int  pxb_scene_get_states_device(PxbScene* scene, float* devOut); /* same record, device pointer; stream-ordered on the scene stream (may follow pxb_scene_simulate
                                                                               without a fetch: it packs the state that step produces, e.g. into an NCCL send buffer) */
+/* Multi-GPU exchange helper: ONE kernel stores `bytes` from devSrc into nDst <= 8 peer-mapped device buffers over NVLink (P2P). */
+PXB_API int  pxb_scatter_to_peers(PxbScene* scene, void* cudaStream, const void* devSrc, size_t bytes, const uint64_t* devDstPtrs, uint32_t nDst, uint32_t ctas);
 PXB_API void* pxb_scene_state_device_ptr(PxbScene* scene, int which); /* 0 pos4, 1 quat4, 2 linVel4, 3 angVel4 (per ACTOR float4 arrays) */
 PXB_API void* pxb_scene_stream(PxbScene* scene);                        /* cudaStream_t */
 

@@ -649,6 +649,16 @@ __global__ void k_states_set(uint32_t nDyn, const uint32_t* __restrict__ dynActo
   const float w = pos[a].w;
   pos[a] = make_float4(o[0], o[1], o[2], w); quat[a] = make_float4(o[3], o[4], o[5], o[6]); linVel[a] = make_float4(o[7], o[8], o[9], 0.f); angVel[a] = make_float4(o[10], o[11], o[12], 0.f);
 }
+// Multi-GPU state exchange: one launch pushes a packed block into up to 8 peer buffers over NVLink (P2P stores to peer-mapped
+// addresses, e.g. torch symmetric memory); each 16-byte word is loaded once and stored to every destination.
+struct PeerPtrs { float4* p[8]; };
+__global__ void __launch_bounds__(256) k_scatter_to_peers(const float4* __restrict__ src, size_t n16, PeerPtrs dst, uint32_t nDst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (k < (int)nDst) dst.p[k][i] = v;
+  }
+}
 __global__ void k_init_freelist(uint32_t cap, uint32_t* __restrict__ freeList) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cap) freeList[i] = i;
@@ -1302,6 +1312,18 @@ PXB_API int pxb_set_rigid_dynamic_data(PxbScene* s, const void* data, const uint
 // pxb_scene_sync; a set takes effect for the next simulate, a get issued after pxb_scene_simulate returns that step's result.
 PXB_API int pxb_get_rigid_dynamic_data_async(PxbScene* s, void* pinned, int type, uint32_t nb) { return rd_host(s, pinned, nullptr, type, nb, false, true); }
 PXB_API int pxb_set_rigid_dynamic_data_async(PxbScene* s, const void* pinned, int type, uint32_t nb) { return rd_host(s, const_cast<void*>(pinned), nullptr, type, nb, true, true); }
+// Pushes `bytes` (multiple of 16) from `devSrc` into nDst <= 8 peer-mapped device buffers with ONE kernel on `stream`
+// (cudaStream_t; NULL = the scene stream).  Used by physx_b200/multi_gpu.py for the per-step all-gather of the state tensor.
+PXB_API int pxb_scatter_to_peers(PxbScene* s, void* stream, const void* devSrc, size_t bytes, const uint64_t* devDstPtrs, uint32_t nDst, uint32_t ctas) {
+  if (!s || !devSrc || !devDstPtrs) return fail(PXB_ERR_INVALID, "null argument");
+  if (nDst > 8 || (bytes & 15)) return fail(PXB_ERR_INVALID, "at most 8 destinations, size a multiple of 16 bytes");
+  if (!nDst || !bytes) return PXB_OK;
+  PeerPtrs P; for (uint32_t k = 0; k < 8; ++k) P.p[k] = k < nDst ? reinterpret_cast<float4*>(devDstPtrs[k]) : nullptr;
+  cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+  k_scatter_to_peers<<<ctas ? ctas : 32, 256, 0, st>>>((const float4*)devSrc, bytes / 16, P, nDst);
+  CK(cudaGetLastError());
+  return PXB_OK;
+}
 PXB_API int pxb_scene_sync(PxbScene* s) { if (!s) return fail(PXB_ERR_INVALID, "null scene"); CK(cudaStreamSynchronize(s->stream)); return PXB_OK; }
 
 // Packed 13-float state of every dynamic body written straight into a DEVICE buffer (e.g. this rank's slice of

@@ -29,7 +29,7 @@ EXPORTS = [
     "pxb_scene_num_created", "pxb_scene_num_deleted", "pxb_scene_get_created", "pxb_scene_get_deleted",
     "pxb_scene_get_contacts", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
-    "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync",
+    "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY = 0, 1, 2
@@ -93,6 +93,7 @@ def load_library():
     lib.pxb_get_rigid_dynamic_data_async.argtypes = [vp, vp, i32, u32]
     lib.pxb_set_rigid_dynamic_data_async.argtypes = [vp, vp, i32, u32]
     lib.pxb_scene_sync.argtypes = [vp]
+    lib.pxb_scatter_to_peers.argtypes = [vp, vp, vp, ctypes.c_size_t, vp, u32, u32]
     lib.pxb_scene_set_profiling.argtypes = [vp, i32]
     lib.pxb_scene_get_stage_times.argtypes = [vp, vp]
     lib.pxb_scene_state_device_ptr.argtypes = [vp, i32]
@@ -194,6 +195,11 @@ class Scene:
     def getStatesDevice(self, dev_ptr: int):
         """13 floats per dynamic body (pos3 quat4 linVel3 angVel3) into a device buffer, async on the scene stream."""
         _check(self._lib, self._lib.pxb_scene_get_states_device(self._h, dev_ptr))
+
+    def scatterToPeers(self, stream_ptr: int, src_ptr: int, nbytes: int, dst_ptrs, ctas: int = 32):
+        """One kernel that stores a device block into up to 8 peer-mapped buffers (multi-GPU state exchange)."""
+        arr = (ctypes.c_uint64 * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+        _check(self._lib, self._lib.pxb_scatter_to_peers(self._h, stream_ptr or None, src_ptr, nbytes, arr, len(dst_ptrs), ctas))
 
     def stream(self) -> int:
         return int(self._lib.pxb_scene_stream(self._h) or 0)

@@ -146,9 +146,10 @@ class PeerStateGather:
     like PipelinedStateGather; same interface.  Raises at construction when symmetric memory is not available (callers fall
     back to NCCL)."""
 
-    def __init__(self, dist, n_local: int, cols: int, device, scene_stream):
+    def __init__(self, dist, n_local: int, cols: int, device, scene_stream, scene=None, mode: str = "kernel"):
         import torch
         import torch.distributed._symmetric_memory as symm
+        self.scene, self.mode = scene, (mode if scene is not None else "copy")
         self.torch, self.dist = torch, dist
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         cnt = torch.tensor([n_local], dtype=torch.int64, device=device)
@@ -168,6 +169,9 @@ class PeerStateGather:
             self.bufs.append(t)
             self.handles.append(h)
             self.peer_views.append([h.get_buffer(p, (total, cols), torch.float32)[lo:hi] for p in range(self.world)])
+        self.row_bytes = cols * 4
+        if (n_local * self.row_bytes) % 16 or (lo * self.row_bytes) % 16 or self.world > 9:
+            self.mode = "copy"   # the scatter kernel moves 16-byte words to at most 8 peers
         self.done = [None, None]
         self.k = 0
         dist.barrier()
@@ -182,6 +186,17 @@ class PeerStateGather:
         pack(local)                                             # engine pack kernel, stream-ordered on the scene stream
         ready = t.cuda.Event()
         ready.record(self.scene_stream)
+        if self.mode == "kernel":
+            # ONE launch: the engine's scatter kernel stores this rank's block into every peer's buffer (P2P stores over NVLink)
+            self.comm_stream.wait_event(ready)
+            ptrs = [v.data_ptr() for p, v in enumerate(self.peer_views[b]) if p != self.rank]
+            self.scene.scatterToPeers(self.comm_stream.cuda_stream, local.data_ptr(), local.numel() * 4, ptrs)
+            with t.cuda.stream(self.comm_stream):
+                self.handles[b].barrier(channel=b)
+                self.done[b] = t.cuda.Event()
+                self.done[b].record(self.comm_stream)
+            self.k += 1
+            return b
         j = 0
         for p in range(self.world):                             # pushes to different peers run concurrently, one stream (copy engine) each
             if p == self.rank:
@@ -209,13 +224,16 @@ class PeerStateGather:
                 (stream or self.scene_stream).wait_event(ev)
 
 
-def make_state_gather(dist, n_local: int, cols: int, device, scene_stream, kind: str = "auto"):
-    """kind: 'peer' (symmetric-memory peer copies), 'nccl' (all_gather_into_tensor) or 'auto' (peer when available)."""
-    if kind in ("auto", "peer") and device.type == "cuda":
+def make_state_gather(dist, n_local: int, cols: int, device, scene_stream, kind: str = "auto", scene=None):
+    """kind: 'peer' (one scatter kernel with P2P stores into symmetric memory), 'peer-copy' (copy-engine peer copies), 'nccl'
+    (all_gather_into_tensor) or 'auto' (peer when available)."""
+    if kind in ("auto", "peer", "peer-copy") and device.type == "cuda":
         try:
-            return PeerStateGather(dist, n_local, cols, device, scene_stream), "peer-memory copies (symmetric memory, copy engines) + barrier"
+            mode = "copy" if kind == "peer-copy" else "kernel"
+            g = PeerStateGather(dist, n_local, cols, device, scene_stream, scene=scene, mode=mode)
+            return g, ("one scatter kernel with P2P stores into every peer's symmetric-memory buffer" if g.mode == "kernel" else "peer-memory copies (symmetric memory, copy engines)") + " + barrier"
         except Exception as e:  # pragma: no cover - depends on the platform
-            if kind == "peer":
+            if kind in ("peer", "peer-copy"):
                 raise
             reason = f" (peer memory unavailable: {type(e).__name__})"
     else:
