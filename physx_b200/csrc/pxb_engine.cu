@@ -516,7 +516,8 @@ __device__ __forceinline__ void sleep_check_dev(const SleepArgs& S, uint32_t a, 
 // islands = connected components over touching dynamic-dynamic pairs (min-label hooking + pointer jumping, cooperative)
 __global__ void __launch_bounds__(256) k_sleep_islands(uint32_t nA, const uint32_t* __restrict__ nPairsP, const uint2* __restrict__ pairBodies, const float4* __restrict__ cHdr,
                                                        const uint32_t* __restrict__ geomFlags, SleepArgs S, uint32_t* __restrict__ label, uint32_t* __restrict__ islandAwake,
-                                                       uint32_t* __restrict__ counters, float4* __restrict__ linVel, float4* __restrict__ angVel, uint32_t* __restrict__ conFlag) {
+                                                       uint32_t* __restrict__ counters, float4* __restrict__ linVel, float4* __restrict__ angVel, uint32_t* __restrict__ conFlag,
+                                                       const uint64_t* __restrict__ deletedKeys, uint32_t bitsA) {
   cg::grid_group grid = cg::this_grid();
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   const uint32_t nPairs = *nPairsP;
@@ -526,6 +527,11 @@ __global__ void __launch_bounds__(256) k_sleep_islands(uint32_t nA, const uint32
     const uint2 b = pairBodies[i];
     if (geomFlags[b.x] & 0x100u) atomicAdd(&S.nInter[b.x], 1u);
     if (geomFlags[b.y] & 0x100u) atomicAdd(&S.nInter[b.y], 1u);
+  }
+  for (uint32_t i = gtid; i < counters[C_NDELETED]; i += gsize) {   // pairs lost this frame still count: their interaction is destroyed after the solver
+    const uint64_t key = deletedKeys[i]; const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
+    if (geomFlags[lo] & 0x100u) atomicAdd(&S.nInter[lo], 1u);
+    if (geomFlags[hi] & 0x100u) atomicAdd(&S.nInter[hi], 1u);
   }
   for (;;) {
     if (gtid == 0) counters[C_REMAINING] = 0;
@@ -1036,7 +1042,7 @@ static int enqueue_step(PxbScene* s, float dt) {
   SleepArgs SA; SA.threshold = s->sleepThreshold; SA.dt = dt; SA.wake = s->wake; SA.accLin = s->accLin; SA.accAng = s->accAng; SA.asleep = s->asleep; SA.nInter = s->nInter;
   if (s->sleepThreshold > 0.f) {   // island sleep / wake decisions for this step (needs this frame's touching pairs)
     uint32_t nA = s->nA;
-    void* args[] = {&nA, &nP, &s->pairBodies, &s->cHdr, &s->geomFlags, &SA, &s->islandLabel, &s->islandAwake, &s->counters, &s->linVel, &s->angVel, &s->conFlag};
+    void* args[] = {&nA, &nP, &s->pairBodies, &s->cHdr, &s->geomFlags, &SA, &s->islandLabel, &s->islandAwake, &s->counters, &s->linVel, &s->angVel, &s->conFlag, &s->deletedKeys, &s->bitsA};
     CK(cudaLaunchCooperativeKernel((void*)k_sleep_islands, dim3(s->coopBlocksSleep), dim3(256), args, 0, st)); s->launches++;
   }
   MARK(2);

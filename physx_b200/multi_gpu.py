@@ -225,11 +225,11 @@ class PeerStateGather:
 
 
 def make_state_gather(dist, n_local: int, cols: int, device, scene_stream, kind: str = "auto", scene=None):
-    """kind: 'peer' (one scatter kernel with P2P stores into symmetric memory), 'peer-copy' (copy-engine peer copies), 'nccl'
-    (all_gather_into_tensor) or 'auto' (peer when available)."""
+    """kind: 'peer-copy' (concurrent copy-engine peer copies into symmetric memory), 'peer' (one scatter kernel with P2P stores),
+    'nccl' (all_gather_into_tensor) or 'auto' (peer-copy when symmetric memory is available, else NCCL)."""
     if kind in ("auto", "peer", "peer-copy") and device.type == "cuda":
         try:
-            mode = "copy" if kind == "peer-copy" else "kernel"
+            mode = "kernel" if kind == "peer" else "copy"   # auto: copy engines (measured faster at N=8: they take no SM from the next step)
             g = PeerStateGather(dist, n_local, cols, device, scene_stream, scene=scene, mode=mode)
             return g, ("one scatter kernel with P2P stores into every peer's symmetric-memory buffer" if g.mode == "kernel" else "peer-memory copies (symmetric memory, copy engines)") + " + barrier"
         except Exception as e:  # pragma: no cover - depends on the platform
