@@ -100,6 +100,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // kernels
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // a1: tight world AABB of one shape.  Formulas: Gu::computeBounds (geomutils/src/GuBounds.cpp:354-400, plane :210-260).
 __device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d, float* mn, float* mx) {
@@ -275,6 +276,9 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *nPairsP) return;
   const uint64_t key = pairKeys[i];
+#ifndef PXB_NO_PREFETCH
+  { const float4* r = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4; prefetch_l2(r); prefetch_l2(r + 8); }   // the record is needed two dependent loads later (types -> poses -> manifold)
+#endif
   if (key == ~0ull) { cHdr[i] = make_float4(0, 0, 0, __int_as_float(0)); conFlag[i] = 0u; pairBodies[i] = make_uint2(0, 0); return; }   // dropped segment (capacity error already flagged)
   const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
   uint32_t a0 = hi, a1 = lo;

@@ -508,6 +508,9 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
       f = touching;
       if (f && A.S.threshold > 0.f) { const uint2 bb = A.pairBodies[base + t]; if (A.S.asleep[bb.x] && (!(A.geomFlags[bb.y] & 0x100u) || A.S.asleep[bb.y])) f = false; }   // sleeping islands are not solved
       const uint32_t slot = A.pairSlots[base + t];
+#ifndef PXB_NO_PREFETCH
+      if (touching) { prefetch_l2(A.frictions + (size_t)slot * PXB_FRICTION_F4); prefetch_l2(A.cPts + (size_t)(base + t) * 4); }   // prep reads them after the colouring
+#endif
       prevCol = A.slotColour[slot];
       if (f != (prevCol != NONE32)) stale = 1;
       if (!touching) A.frictions[(size_t)slot * PXB_FRICTION_F4 + 2].w = __int_as_float(0);   // no contacts: the friction patch is dropped (a sleeping pair keeps its patch)
