@@ -27,7 +27,9 @@ typedef struct {
   PxoPgsFriction fr[4];
 } PxoPgsConstraint;
 
-static inline void pxo_pgs_body_data_init(PxoPgsBodyData* d, v3 lv, v3 av, float invMass, v3 invInertia, const xf* pose, float maxDepenVel) {
+static inline void pxo_pgs_body_data_init(PxoPgsBodyData* d, v3 lv, v3 av, float invMass, v3 invInertia, const xf* pose, float maxDepenVel, uint32_t lockFlags) {
+  /* copyToSolverBodyData :72-98: only the ANGULAR locks reach the data (the linear ones are written to data.linearVelocity before it is overwritten with `lin`) */
+  av = pxo_lock3(av, (lockFlags >> 3) & 7u);
   const m33 rot = am33fromq(pose->q);
   const v3 sqrtInvI = V3(invInertia.x == 0.f ? 0.f : sqrtf(invInertia.x), invInertia.y == 0.f ? 0.f : sqrtf(invInertia.y), invInertia.z == 0.f ? 0.f : sqrtf(invInertia.z));
   pxo_transform_inertia(sqrtInvI, &rot, &d->sqrtInvInertia);
@@ -181,7 +183,12 @@ static inline void pxo_pgs_conclude(PxoPgsConstraint* k) {   /* concludeContact 
 }
 
 /* integrateCore: pose from the motion velocity (state after the position iterations), velocity from the final state */
-static inline void pxo_pgs_integrate(PxoPgsBodyData* d, const PxoPgsBody* b, v3 motionLin, v3 motionAng, float dt) {
+static inline void pxo_pgs_integrate(PxoPgsBodyData* d, PxoPgsBody* b, v3 motionLin, v3 motionAng, float dt, uint32_t lockFlags, v3* outMotionLin, v3* outMotionAng) {
+  if (lockFlags) {   /* integrateCore :86-124 */
+    const uint32_t l = lockFlags & 7u, a = (lockFlags >> 3) & 7u;
+    motionLin = pxo_lock3(motionLin, l); b->linVel = pxo_lock3(b->linVel, l); d->linVel = pxo_lock3(d->linVel, l);
+    motionAng = pxo_lock3(motionAng, a); b->angState = pxo_lock3(b->angState, a);
+  }
   const v3 linearMotionVel = v3add(d->linVel, motionLin);
   d->body2World.p = v3add(d->body2World.p, v3scale(linearMotionVel, dt));
   const v3 angularMotionVel = v3add(d->angVel, m33mul(&d->sqrtInvInertia, motionAng));
@@ -197,6 +204,7 @@ static inline void pxo_pgs_integrate(PxoPgsBodyData* d, const PxoPgsBody* b, v3 
     result.x += d->body2World.q.x * q; result.y += d->body2World.q.y * q; result.z += d->body2World.q.z * q; result.w += d->body2World.q.w * q;
     d->body2World.q = q4normalized(result);
   }
+  *outMotionLin = linearMotionVel; *outMotionAng = angularMotionVel;   /* motionVelocityArray[i] after integrateCore (sleepCheck input) */
   d->linVel = v3add(d->linVel, b->linVel);
   d->angVel = v3add(d->angVel, m33mul(&d->sqrtInvInertia, b->angState));
 }

@@ -31,6 +31,7 @@ typedef struct {
   float invMass, penBiasClamp, maxContactImpulse;
   v3 origLinVel, origAngVel;
   int hasConstraints;
+  uint32_t lockFlags;       /* PxRigidDynamicLockFlag bits: linear x,y,z = 1,2,4; angular x,y,z = 8,16,32 */
 } PxoSolverBody;
 
 typedef struct { v3 raXnI, rbXnI; float velMultiplier, separation, biasCoefficient, targetVelocity, recipResponse, maxImpulse, appliedForce; } PxoSPoint;
@@ -76,7 +77,10 @@ static inline void pxo_unconstrained_velocity(v3 gravity, float dt, float linDam
 }
 
 /* DyTGSDynamics.cpp:154-243 (no gyroscopic forces, no lock flags) */
-static inline void pxo_solver_body_init(PxoSolverBody* b, v3 lv, v3 av, float invMass, v3 invInertia, const xf* pose, float maxDepenVel) {
+static inline v3 pxo_lock3(v3 v, uint32_t bits) { if (bits & 1u) v.x = 0.f; if (bits & 2u) v.y = 0.f; if (bits & 4u) v.z = 0.f; return v; }
+static inline void pxo_solver_body_init(PxoSolverBody* b, v3 lv, v3 av, float invMass, v3 invInertia, const xf* pose, float maxDepenVel, uint32_t lockFlags) {
+  lv = pxo_lock3(lv, lockFlags & 7u); av = pxo_lock3(av, (lockFlags >> 3) & 7u);   /* DyTGSDynamics.cpp:195-222 */
+  b->lockFlags = lockFlags;
   const m33 rot = am33fromq(pose->q); /* PxMat33Padded rotation(globalPose.q) */
   const v3 sqrtInvI = V3(invInertia.x == 0.f ? 0.f : sqrtf(invInertia.x), invInertia.y == 0.f ? 0.f : sqrtf(invInertia.y), invInertia.z == 0.f ? 0.f : sqrtf(invInertia.z));
   const v3 sqrtI = V3(sqrtInvI.x == 0.f ? 0.f : 1.0f / sqrtInvI.x, sqrtInvI.y == 0.f ? 0.f : 1.0f / sqrtInvI.y, sqrtInvI.z == 0.f ? 0.f : 1.0f / sqrtInvI.z);
@@ -95,6 +99,7 @@ static inline void pxo_static_body_init(PxoSolverBody* b) {
 
 /* DyTGSDynamics.cpp:1403-1476 */
 static inline void pxo_integrate_core_step(PxoSolverBody* b, float dt) {
+  if (b->lockFlags) { b->linVel = pxo_lock3(b->linVel, b->lockFlags & 7u); b->angState = pxo_lock3(b->angState, (b->lockFlags >> 3) & 7u); }   /* :1405-1422 (the angular lock acts on the sqrt-inertia-space state) */
   const v3 delta = v3scale(b->linVel, dt);
   const v3 unmolested = b->angState;
   const v3 angMotionVel = m33mul(&b->sqrtInvInertia, b->angState);

@@ -233,6 +233,7 @@ int main(int argc, char** argv) {
       d->setSolverIterationCounts(H.posIters, H.velIters);
       d->setSleepThreshold(H.sleepThreshold);
       if (H.sleepThreshold == 0.0f) d->setWakeCounter(1e9f);
+      d->setRigidDynamicLockFlags(PxRigidDynamicLockFlags(PxU8((r.flags >> 8) & 0x3f)));
       dyn.push_back(d);
     }
     actors[i] = a;

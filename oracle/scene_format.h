@@ -37,7 +37,7 @@ typedef struct {
 } PxbSceneHeader;
 
 typedef struct {
-  uint32_t flags;       /* PXB_ACTOR_DYNAMIC */
+  uint32_t flags;       /* PXB_ACTOR_DYNAMIC | PxRigidDynamicLockFlag bits << 8 */
   uint32_t geomType;
   uint32_t envId;       /* 0xffffffff = none */
   uint32_t hullIdx;

@@ -578,7 +578,7 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
                                float4* __restrict__ linVel, float4* __restrict__ angVel, const float4* __restrict__ invInertia, const float4* __restrict__ damp,
                                float gx, float gy, float gz, float dt, float4* __restrict__ sbLin, float4* __restrict__ sbAng, float4* __restrict__ sbDLin,
                                float4* __restrict__ sbDAng, float4* __restrict__ sbIA, float4* __restrict__ sbIB, float4* __restrict__ sbP, float4* __restrict__ sbQ,
-                               float4* __restrict__ sbOrigAng, int pgs, SleepArgs S) {
+                               float4* __restrict__ sbOrigAng, int pgs, SleepArgs S, const uint32_t* __restrict__ geomFlags) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
@@ -586,6 +586,9 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
   const float4 dm = damp[a]; const float4 ii = invInertia[a]; const float4 p4 = pos[a];
   v3 lv = V3(linVel[a]), av = V3(angVel[a]);
   if (!asleep) unconstrained_velocity(V3(gx, gy, gz), dt, dm.x, dm.y, dm.z, dm.w, lv, av);
+  // lock flags: TGS locks both velocities (copyToSolverBodyDataStep, DyTGSDynamics.cpp:195-222); PGS only the angular one (copyToSolverBodyData, DyRigidBodyToSolverBody.cpp:72-98)
+  const uint32_t lock = (geomFlags[a] >> 16) & 0x3fu;
+  if (lock && !asleep) { if (!pgs) lv = lock3(lv, lock & 7u); av = lock3(av, (lock >> 3) & 7u); }
   linVel[a] = F4(lv, 0.f); angVel[a] = F4(av, 0.f);
   const m33 rot = amfromq(Q4(quat[a]));
   const v3 sqrtInvI = V3(ii.x == 0.f ? 0.f : sqrtf(ii.x), ii.y == 0.f ? 0.f : sqrtf(ii.y), ii.z == 0.f ? 0.f : sqrtf(ii.z));
@@ -594,7 +597,7 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
   if (pgs) { sbLin[a] = make_float4(0, 0, 0, 0); sbAng[a] = make_float4(0, 0, 0, 0); }   // PGS solver bodies hold velocity deltas
   else { sbLin[a] = F4(lv, 0.f); sbAng[a] = F4(mmul(sInertia, av), 0.f); }
   sbDLin[a] = make_float4(0, 0, 0, 0); sbDAng[a] = make_float4(0, 0, 0, 0);
-  sbIA[a] = make_float4(sI.c0.x, sI.c0.y, sI.c0.z, sI.c1.y); sbIB[a] = make_float4(sI.c1.z, sI.c2.z, 0.f, 0.f);
+  sbIA[a] = make_float4(sI.c0.x, sI.c0.y, sI.c0.z, sI.c1.y); sbIB[a] = make_float4(sI.c1.z, sI.c2.z, __uint_as_float(lock), 0.f);
   sbP[a] = make_float4(p4.x, p4.y, p4.z, 0.f); sbQ[a] = make_float4(0, 0, 0, 1); sbOrigAng[a] = F4(av, 0.f);
 }
 __device__ __forceinline__ m33 load_sym(const float4 A, const float4 B) {
@@ -613,11 +616,12 @@ __global__ void k_finalize_bodies(uint32_t nDyn, const uint32_t* __restrict__ dy
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
   if (body_asleep(S, a)) return;
-  const m33 sI = load_sym(sbIA[a], sbIB[a]);
+  const float4 ib = sbIB[a];
+  const m33 sI = load_sym(sbIA[a], ib);
   v3 p = V3(sbP[a]); q4 dq = Q4(sbQ[a]);
-  const v3 lv = V3(sbLin[a]), as = V3(sbAng[a]);
+  v3 lv = V3(sbLin[a]), as = V3(sbAng[a]);
   v3 dl = V3(sbDLin[a]), da = V3(sbDAng[a]);
-  if (!bodyHasCon[a]) { dl = V3(0, 0, 0); da = V3(0, 0, 0); integrate_core_step(lv, as, sI, dt, p, dq, dl, da); }
+  if (!bodyHasCon[a]) { dl = V3(0, 0, 0); da = V3(0, 0, 0); integrate_core_step(lv, as, sI, dt, p, dq, dl, da, __float_as_uint(ib.z)); }
   const float invMass = pos[a].w;
   const q4 q = qnormalized(qmul(dq, Q4(quat[a])));
   pos[a] = make_float4(p.x, p.y, p.z, invMass); quat[a] = F4(q);
@@ -873,7 +877,7 @@ static void rebuild_grid(PxbScene* s) {
     const ActorRec& r = s->recs[a];
     const float d = shape_diameter(r);
     const bool global = !std::isfinite(d) || d > largeThresh || (usesEnv && r.envId == NONE32);
-    gf[a] = (r.geomType & 0xff) | ((r.flags & PXB_ACTOR_DYNAMIC) ? 0x100u : 0u) | (global ? 0x200u : 0u);
+    gf[a] = (r.geomType & 0xff) | ((r.flags & PXB_ACTOR_DYNAMIC) ? 0x100u : 0u) | (global ? 0x200u : 0u) | (((r.flags >> 8) & 0x3fu) << 16);   // bits 16..21: PxRigidDynamicLockFlags
     if (global) { s->largeHost.push_back(a); continue; }
     cell = std::max(cell, d);
     for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], r.pos[k]); mx[k] = std::max(mx[k], r.pos[k]); }
@@ -1104,7 +1108,7 @@ static int enqueue_step(PxbScene* s, float dt) {
   }
   MARK(3);
   LAUNCH(k_preintegrate, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, g[0], g[1], g[2], dt, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng,
-         s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, pgs ? 1 : 0, SA);
+         s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, pgs ? 1 : 0, SA, s->geomFlags);
   if (pgs) {   // PGS: rows in the 25-float4 record image, velocity-delta solver bodies (pxb_pgs.cuh)
     Rows R; R.f = s->ptA; R.broken = s->conDone; R.stride = s->capPairs;
     LAUNCH(k_prep_rows<true>, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,

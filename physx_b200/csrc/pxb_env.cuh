@@ -383,7 +383,10 @@ __device__ __forceinline__ void env_integrate_substep(uint32_t n, float stepDt, 
   for (uint32_t b = threadIdx.x; b < n; b += T) {
     if (!__float_as_uint(bP[b].w)) continue;
     v3 p = V3(bP[b]); q4 dq = Q4(bQ[b]); v3 dl = V3(bDLin[b]), da = V3(bDAng[b]);
-    integrate_core_step(V3(bLin[b]), V3(bAng[b]), load_sym(bIA[b], bIB[b]), stepDt, p, dq, dl, da);
+    const float4 ib = bIB[b]; const uint32_t lock = __float_as_uint(ib.z);
+    v3 lv = V3(bLin[b]), as = V3(bAng[b]);
+    integrate_core_step(lv, as, load_sym(bIA[b], ib), stepDt, p, dq, dl, da, lock);
+    if (lock) { bLin[b] = F4(lv, 0.f); bAng[b] = F4(as, 0.f); }
     bP[b] = F4(p, __uint_as_float(1u)); bQ[b] = F4(dq); bDLin[b] = F4(dl, 0.f); bDAng[b] = F4(da, 0.f);
   }
 }
@@ -477,10 +480,13 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   for (uint32_t b = tid; b < n; b += T) {
     const uint32_t a = list[b];
     bMask[b] = 0; bStat[b] = 0;
-    if (!(A.geomFlags[a] & 0x100u) || body_asleep(A.S, a)) { bP[b] = make_float4(0, 0, 0, 0); continue; }   // statics and sleeping bodies take no part
+    const uint32_t gf = A.geomFlags[a];
+    if (!(gf & 0x100u) || body_asleep(A.S, a)) { bP[b] = make_float4(0, 0, 0, 0); continue; }   // statics and sleeping bodies take no part
     const float4 dm = A.damp[a]; const float4 ii = A.invInertia[a]; const float4 p4 = A.pos[a];
     v3 lv = V3(A.linVel[a]), av = V3(A.angVel[a]);
     unconstrained_velocity(V3(A.gx, A.gy, A.gz), A.dt, dm.x, dm.y, dm.z, dm.w, lv, av);
+    const uint32_t lock = (gf >> 16) & 0x3fu;   // PxRigidDynamicLockFlags: TGS locks both velocities, PGS only the angular one (see k_preintegrate)
+    if (lock) { if (!PGS) lv = lock3(lv, lock & 7u); av = lock3(av, (lock >> 3) & 7u); }
     const m33 rot = amfromq(Q4(A.quat[a]));
     const v3 sqrtInvI = V3(ii.x == 0.f ? 0.f : sqrtf(ii.x), ii.y == 0.f ? 0.f : sqrtf(ii.y), ii.z == 0.f ? 0.f : sqrtf(ii.z));
     const v3 sqrtI = V3(sqrtInvI.x == 0.f ? 0.f : 1.0f / sqrtInvI.x, sqrtInvI.y == 0.f ? 0.f : 1.0f / sqrtInvI.y, sqrtInvI.z == 0.f ? 0.f : 1.0f / sqrtInvI.z);
@@ -490,7 +496,7 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
     } else {
       bLin[b] = F4(lv, 0.f); bAng[b] = F4(mmul(sInertia, av), 0.f); bDLin[b] = make_float4(0, 0, 0, 0); bDAng[b] = make_float4(0, 0, 0, 0);
     }
-    bIA[b] = make_float4(sI.c0.x, sI.c0.y, sI.c0.z, sI.c1.y); bIB[b] = make_float4(sI.c1.z, sI.c2.z, 0.f, 0.f);
+    bIA[b] = make_float4(sI.c0.x, sI.c0.y, sI.c0.z, sI.c1.y); bIB[b] = make_float4(sI.c1.z, sI.c2.z, __uint_as_float(lock), 0.f);
     bP[b] = make_float4(p4.x, p4.y, p4.z, __uint_as_float(0u)); bQ[b] = F4(av, 0.f);
   }
   for (uint32_t p = tid; p < MAX_PARTITIONS + 1; p += T) sPartCnt[p] = 0;
@@ -603,19 +609,20 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   for (uint32_t b = tid; b < n; b += T) {
     const uint32_t a = list[b];
     if (!(A.geomFlags[a] & 0x100u) || body_asleep(A.S, a)) continue;
-    const m33 sI = load_sym(bIA[b], bIB[b]);
+    const float4 ib = bIB[b]; const uint32_t lock = __float_as_uint(ib.z);
+    const m33 sI = load_sym(bIA[b], ib);
     if (PGS) {   // integrate (DyDynamics.cpp:1398-1423): every body, with or without constraints
       const float4 p4 = A.pos[a]; v3 p = V3(p4.x, p4.y, p4.z); q4 q = Q4(A.quat[a]); v3 lv = V3(bDLin[b]), av = V3(bDAng[b]);
-      const v3 motionLin = lv + V3(bP[b]), motionAng = av + mmul(sI, V3(bQ[b]));
-      integrate_core_pgs(p, q, lv, av, sI, V3(bP[b]), V3(bQ[b]), V3(bLin[b]), V3(bAng[b]), A.dt);
+      v3 motionLin, motionAng;
+      integrate_core_pgs(p, q, lv, av, sI, V3(bP[b]), V3(bQ[b]), V3(bLin[b]), V3(bAng[b]), A.dt, lock, motionLin, motionAng);
       A.pos[a] = make_float4(p.x, p.y, p.z, p4.w); A.quat[a] = F4(q); A.linVel[a] = F4(lv, 0.f); A.angVel[a] = F4(av, 0.f);
       if (A.S.threshold > 0.f) sleep_check_dev(A.S, a, q, A.invInertia[a], p4.w, motionLin, motionAng);
       continue;
     }
     v3 p = V3(bP[b]); q4 dq = Q4(bQ[b]);
-    const v3 lv = V3(bLin[b]), as = V3(bAng[b]);
+    v3 lv = V3(bLin[b]), as = V3(bAng[b]);
     v3 dl = V3(bDLin[b]), da = V3(bDAng[b]);
-    if (!__float_as_uint(bP[b].w)) { dl = V3(0, 0, 0); da = V3(0, 0, 0); integrate_core_step(lv, as, sI, A.dt, p, dq, dl, da); }
+    if (!__float_as_uint(bP[b].w)) { dl = V3(0, 0, 0); da = V3(0, 0, 0); integrate_core_step(lv, as, sI, A.dt, p, dq, dl, da, lock); }
     const float invMass = A.pos[a].w;
     const q4 q = qnormalized(qmul(dq, Q4(A.quat[a])));
     A.pos[a] = make_float4(p.x, p.y, p.z, invMass); A.quat[a] = F4(q);

@@ -173,7 +173,14 @@ __device__ __forceinline__ void conclude_constraint_pgs(RegRows& r, const FrView
 }
 
 // integrateCore: pose from the motion velocity (deltas after the position iterations), velocity from the final deltas
-__device__ __forceinline__ void integrate_core_pgs(v3& p, q4& q, v3& linVel, v3& angVel, const m33& sqrtInvInertia, v3 motionLin, v3 motionAng, v3 deltaLin, v3 deltaAng, float dt) {
+// (lock flags: DyBodyCoreIntegrator.h:86-124); outMotionLin / outMotionAng = motionVelocityArray after integrateCore (sleepCheck input)
+__device__ __forceinline__ void integrate_core_pgs(v3& p, q4& q, v3& linVel, v3& angVel, const m33& sqrtInvInertia, v3 motionLin, v3 motionAng, v3 deltaLin, v3 deltaAng, float dt,
+                                                   uint32_t lock, v3& outMotionLin, v3& outMotionAng) {
+  if (lock) {
+    const uint32_t l = lock & 7u, a = (lock >> 3) & 7u;
+    motionLin = lock3(motionLin, l); deltaLin = lock3(deltaLin, l); linVel = lock3(linVel, l);
+    motionAng = lock3(motionAng, a); deltaAng = lock3(deltaAng, a);
+  }
   const v3 linearMotionVel = linVel + motionLin;
   p = p + linearMotionVel * dt;
   const v3 angularMotionVel = angVel + mmul(sqrtInvInertia, motionAng);
@@ -188,6 +195,7 @@ __device__ __forceinline__ void integrate_core_pgs(v3& p, q4& q, v3& linVel, v3&
     res.x += q.x * c; res.y += q.y * c; res.z += q.z * c; res.w += q.w * c;
     q = qnormalized(res);
   }
+  outMotionLin = linearMotionVel; outMotionAng = angularMotionVel;
   linVel = linVel + deltaLin;
   angVel = angVel + mmul(sqrtInvInertia, deltaAng);
 }
@@ -254,7 +262,10 @@ __global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve_tgs(const 
         const uint32_t a = dynActor[d];
         if (!bodyHasCon[a]) continue;
         v3 p = V3(sbP[a]); q4 dq = Q4(sbQ[a]); v3 dl = V3(sbDLin[a]), da = V3(sbDAng[a]);
-        integrate_core_step(V3(sbLin[a]), V3(sbAng[a]), load_sym(sbIA[a], sbIB[a]), stepDt, p, dq, dl, da);
+        const float4 ib = sbIB[a]; const uint32_t lock = __float_as_uint(ib.z);
+        v3 lv = V3(sbLin[a]), as = V3(sbAng[a]);
+        integrate_core_step(lv, as, load_sym(sbIA[a], ib), stepDt, p, dq, dl, da, lock);
+        if (lock) { sbLin[a] = F4(lv, 0.f); sbAng[a] = F4(as, 0.f); }
         sbP[a] = F4(p, 0.f); sbQ[a] = F4(dq); sbDLin[a] = F4(dl, 0.f); sbDAng[a] = F4(da, 0.f);
       }
       elapsed += stepDt;
@@ -319,8 +330,8 @@ __global__ void k_finalize_bodies_pgs(uint32_t nDyn, const uint32_t* __restrict_
   if (body_asleep(S, a)) return;
   const float4 p4 = pos[a]; v3 p = V3(p4.x, p4.y, p4.z); q4 q = Q4(quat[a]); v3 lv = V3(linVel[a]), av = V3(angVel[a]);
   const m33 sI = load_sym(sbIA[a], sbIB[a]);
-  const v3 motionLin = lv + V3(sbDLin[a]), motionAng = av + mmul(sI, V3(sbDAng[a]));   // motionVelocityArray after integrateCore
-  integrate_core_pgs(p, q, lv, av, sI, V3(sbDLin[a]), V3(sbDAng[a]), V3(sbLin[a]), V3(sbAng[a]), dt);
+  v3 motionLin, motionAng;   // motionVelocityArray after integrateCore
+  integrate_core_pgs(p, q, lv, av, sI, V3(sbDLin[a]), V3(sbDAng[a]), V3(sbLin[a]), V3(sbAng[a]), dt, __float_as_uint(sbIB[a].z), motionLin, motionAng);
   pos[a] = make_float4(p.x, p.y, p.z, p4.w); quat[a] = F4(q); linVel[a] = F4(lv, 0.f); angVel[a] = F4(av, 0.f);
   if (S.threshold > 0.f) sleep_check_dev(S, a, q, invInertia[a], p4.w, motionLin, motionAng);
 }

@@ -8,7 +8,7 @@
 //   solve                   DyTGSContactPrep.cpp:1492-1873
 //   integration             DyTGSDynamics.cpp:1403-1476, :1549-1580
 // Scope: rigid dynamic vs rigid dynamic/static, one contact patch per pair (all primitive PCM pairs),
-// rigid (restitution >= 0) contacts, no dominance / kinematics / lock flags.
+// rigid (restitution >= 0) contacts, no dominance / kinematics.
 #pragma once
 #include "pxb_math.cuh"
 #include "pxb_np.cuh"
@@ -59,8 +59,11 @@ PXB_D void unconstrained_velocity(v3 gravity, float dt, float linDamping, float 
   lv = l; av = a;
 }
 
-// integrateCoreStep: returns updated (p, deltaQ, deltaLinDt, deltaAngDt)
-PXB_D void integrate_core_step(v3 linVel, v3 angState, const m33& sqrtInvInertia, float dt, v3& p, q4& deltaQ, v3& dLin, v3& dAng) {
+// PxRigidDynamicLockFlag bits (linear x,y,z = 1,2,4; angular x,y,z = 8,16,32) travel in the unused .z lane of the body's second inertia float4
+PXB_D v3 lock3(v3 v, uint32_t bits) { if (bits & 1u) v.x = 0.f; if (bits & 2u) v.y = 0.f; if (bits & 4u) v.z = 0.f; return v; }
+// integrateCoreStep: returns updated (p, deltaQ, deltaLinDt, deltaAngDt); lock flags zero the locked velocity components first (DyTGSDynamics.cpp:1405-1422)
+PXB_D void integrate_core_step(v3& linVel, v3& angState, const m33& sqrtInvInertia, float dt, v3& p, q4& deltaQ, v3& dLin, v3& dAng, uint32_t lock) {
+  if (lock) { linVel = lock3(linVel, lock & 7u); angState = lock3(angState, (lock >> 3) & 7u); }
   const v3 delta = linVel * dt;
   const v3 w3 = mmul(sqrtInvInertia, angState);
   const float w2 = lensq(w3);

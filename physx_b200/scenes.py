@@ -363,3 +363,30 @@ def env_piles(n_envs=3, nx=5, ny=4, nz=5, half_extent=0.25, gap=0.001, env_pitch
         a["envId"][sl] = e
     set_box(a, np.arange(len(a)), np.array([he, he, he], dtype=np.float32))
     return Scene(default_header(**hdr), add_ground_plane(a))
+
+
+LOCK_LINEAR_X, LOCK_LINEAR_Y, LOCK_LINEAR_Z, LOCK_ANGULAR_X, LOCK_ANGULAR_Y, LOCK_ANGULAR_Z = 1, 2, 4, 8, 16, 32   # PxRigidDynamicLockFlag
+
+
+def set_lock_flags(actors, idx, lock):
+    """PxRigidDynamic::setRigidDynamicLockFlags: the six lock bits live in bits 8..13 of the record's flags."""
+    actors["flags"][idx] = (actors["flags"][idx] & np.uint32(0xFF)) | (np.uint32(lock) << np.uint32(8))
+
+
+def locked_primitives(n=12, seed=3, kinds=("sphere", "capsule"), **hdr):
+    """Spheres / capsules dropped in a column with assorted PxRigidDynamicLockFlags (planar motion, no rotation, one free axis ...)."""
+    sc = mixed_primitives(n=n, seed=seed, kinds=kinds, **hdr)
+    sc.actors["angVel"][1:] = np.random.RandomState(seed).uniform(-2, 2, (n, 3)).astype(np.float32)
+    combos = [LOCK_LINEAR_Z | LOCK_ANGULAR_X | LOCK_ANGULAR_Y, LOCK_ANGULAR_X | LOCK_ANGULAR_Y | LOCK_ANGULAR_Z, LOCK_LINEAR_X, 0,
+              LOCK_LINEAR_X | LOCK_LINEAR_Z, LOCK_ANGULAR_Z, LOCK_LINEAR_Y | LOCK_ANGULAR_Y, 0]
+    for i in range(n):
+        set_lock_flags(sc.actors, 1 + i, combos[i % len(combos)])
+    return sc
+
+
+def locked_stacks(**hdr):
+    """Jittered box stacks in which some boxes may only move vertically / may not rotate."""
+    sc = box_stacks(n_stacks=3, height=5, half_extent=0.25, spacing=1.0, jitter=0.02, **hdr)
+    for i, lock in ((2, LOCK_LINEAR_X | LOCK_LINEAR_Z), (4, LOCK_ANGULAR_X | LOCK_ANGULAR_Y | LOCK_ANGULAR_Z), (7, LOCK_LINEAR_X), (9, LOCK_ANGULAR_Y), (12, LOCK_LINEAR_X | LOCK_LINEAR_Z | LOCK_ANGULAR_X | LOCK_ANGULAR_Z)):
+        set_lock_flags(sc.actors, i, lock)
+    return sc

@@ -78,6 +78,12 @@ def main():
     drop = scenes.box_stacks(n_stacks=1, height=3, half_extent=0.25, spacing=1.0, jitter=0.0, sleep_threshold=0.005)
     drop.actors["pos"][3, 1] = 4.0
     cases["sleep_drop"] = (drop, 80)
+    # PxRigidDynamicLockFlags (a18): boxes that may only move vertically / may not rotate inside jittered stacks (TGS and PGS),
+    # spheres / capsules with assorted locks dropped in a column (teacher-forced comparison: chaotic)
+    cases["lock_stacks"] = (scenes.locked_stacks(), 80)
+    cases["pgs_lock_stacks"] = (scenes.locked_stacks(solver=scenes.SOLVER_PGS), 80)
+    cases["lock_primitives"] = (scenes.locked_primitives(seed=4), 100)
+    cases["pgs_lock_primitives"] = (scenes.locked_primitives(seed=3, solver=scenes.SOLVER_PGS), 100)
     only = sys.argv[1:]
     if only:
         cases = {k: v for k, v in cases.items() if any(k.startswith(o) for o in only)}

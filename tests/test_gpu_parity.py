@@ -398,6 +398,50 @@ def test_sleeping_gpu_matches_reference_golden():
         assert np.array_equal(a, z["asleep"][t]) and np.abs(w - z["wake"][t]).max() < 1e-6, f"step {t}"
 
 
+def _lock_scenes():
+    env = scenes.env_grid_stacks(n_envs=6, stacks_per_env=3, height=5, jitter=0.01)
+    dyn = np.nonzero(env.actors["flags"] & 1)[0]
+    for k, lock in ((1, 5), (3, 56), (7, 1), (11, 16), (16, 61), (22, 2)):
+        scenes.set_lock_flags(env.actors, dyn[k], lock)
+    env_pgs = scenes.Scene(env.header, env.actors.copy()); env_pgs.header["solverType"] = scenes.SOLVER_PGS
+    return {
+        "lock_stacks": (scenes.locked_stacks(), 80),
+        "pgs_lock_stacks": (scenes.locked_stacks(solver=scenes.SOLVER_PGS), 80),
+        "lock_primitives": (scenes.locked_primitives(seed=4), 100),
+        "pgs_lock_primitives": (scenes.locked_primitives(seed=3, solver=scenes.SOLVER_PGS), 100),
+        "lock_envs": (env, 60),              # environment path
+        "pgs_lock_envs": (env_pgs, 60),
+    }
+
+
+@pytest.mark.parametrize("name", list(_lock_scenes()))
+def test_lock_flags_gpu_matches_oracle(oracle, name):
+    """PxRigidDynamicLockFlags on both paths and both solvers: same pairs / contacts, states within one-step rounding of the oracle."""
+    sc, steps = _lock_scenes()[name]
+    gpu, cpu = engine.Scene(sc, max_pairs=16 * len(sc.actors)), oracle.OracleScene(sc)
+    for t in range(steps):
+        gpu.step()
+        cpu.step()
+        assert gpu.uses_env_path == name.endswith("_envs")
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
+        assert np.array_equal(gpu.getContacts()[:, 0], cpu.getContacts()[:, 0]), f"contact counts, step {t}"
+        sg = gpu.getStates()
+        assert np.abs(sg - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
+        cpu.setStates(sg)
+
+
+@pytest.mark.parametrize("name", ["lock_stacks", "pgs_lock_stacks"])
+def test_lock_flags_gpu_matches_reference_golden(name):
+    z, sc = util.load_golden(name)
+    gpu = engine.Scene(sc)
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setConstraintOrder(util.golden_order(z, t))
+        gpu.step()
+        st, ref = gpu.getStates(), z["states"][t + 1]
+        assert util.rel_err(st[:, :3], ref[:, :3]) < TOL_POSE and util.rel_err(st[:, 3:7], ref[:, 3:7]) < TOL_POSE, f"pose, step {t}"
+        assert np.abs(st[:, 7:10] - ref[:, 7:10]).max() < TOL_LINVEL and np.abs(st[:, 10:] - ref[:, 10:]).max() < TOL_ANGVEL, f"velocity, step {t}"
+
+
 def test_stream_ordered_host_api_matches_blocking_api():
     """pxb_get/set_rigid_dynamic_data_async: enqueued around simulate with ONE host sync (fetchResults) per step, same results."""
     import ctypes
