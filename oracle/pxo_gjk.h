@@ -1,0 +1,603 @@
+/* pxo_gjk.h -- CPU restatement of the reference's GJK penetration query and the PCM pair functions built on it
+ * (SURVEY.md §8 a10).  TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg use it.
+ *   simplex solver:        physx/source/geomutils/src/gjk/GuGJKSimplex.h:50-448, GuGJKSimplex.cpp:38-213
+ *   barycentric coords:    physx/source/geomutils/src/common/GuBarycentricCoordinates.cpp:36-80
+ *   gjkPenetration:        physx/source/geomutils/src/gjk/GuGJKPenetration.h:89-311
+ *   support mappings:      gjk/GuVecCapsule.h:128-196 (CapsuleV), gjk/GuVecBox.h:56-68,148-205 (BoxV), convex/GuConvexSupportTable.cpp:33
+ *   capsule-box PCM:       pcm/GuPCMContactCapsuleBox.cpp:42-202, pcm/GuPCMContactGenSphereCapsule.cpp:43-420,
+ *                          pcm/GuPCMContactGenUtil.cpp:105-260, pcm/GuPCMShapeConvex.cpp:40-110 (PCMPolygonalBox)
+ *   manifold helpers:      pcm/GuPersistentContactManifold.h:227-241, .cpp:179-187,289-360,783-807,1177-1310
+ * Operation order follows the SSE2 vector layer (adot = (x+z)+y, exact _mm_div_ps reciprocals). */
+#ifndef PXO_GJK_H
+#define PXO_GJK_H
+#include "pxo_np.h"
+
+enum { PXO_CVX_CAPSULE = 0, PXO_CVX_BOX = 1 };
+enum { PXO_GJK_NON_INTERSECT = 0, PXO_GJK_CONTACT, PXO_GJK_UNDEFINED, PXO_GJK_DEGENERATE, PXO_EPA_CONTACT, PXO_EPA_DEGENERATE, PXO_EPA_FAIL };
+
+typedef struct {
+  int type;
+  v3 center;                /* ConvexV::center (getCenter) */
+  v3 p0, p1;                /* capsule segment */
+  v3 ext;                   /* box half extents */
+  float margin, minMargin;  /* ConvexV::margin / minMargin */
+  int marginIsRadius;
+} PxoConvex;
+
+typedef struct { v3 normal, closestA, closestB, searchDir; float penDep; } PxoGjkOutput;
+
+/* CapsuleV(center, v, radius): GuVecCapsule.h:74-85 */
+static inline PxoConvex pxo_cvx_capsule(v3 center, v3 v, float radius) {
+  PxoConvex c; memset(&c, 0, sizeof(c));
+  c.type = PXO_CVX_CAPSULE; c.center = center; c.p0 = v3add(center, v); c.p1 = v3sub(center, v);
+  c.margin = radius; c.minMargin = radius; c.marginIsRadius = 1;
+  return c;
+}
+/* BoxV(origin, extent) + CalculateBoxMargin: GuVecBox.h:56-68,112-117 */
+static inline PxoConvex pxo_cvx_box(v3 origin, v3 ext) {
+  PxoConvex c; memset(&c, 0, sizeof(c));
+  const float mn = fminf_(ext.x, fminf_(ext.y, ext.z));
+  c.type = PXO_CVX_BOX; c.center = origin; c.ext = ext; c.margin = mn * 0.15f; c.minMargin = mn * 0.05f; c.marginIsRadius = 0;
+  return c;
+}
+/* LocalConvex<T>::support(dir, index) = T::supportLocal(dir, index) */
+static inline v3 pxo_cvx_support(const PxoConvex* c, v3 dir, int* index) {
+  if (c->type == PXO_CVX_CAPSULE) {
+    const float d0 = adot(c->p0, dir), d1 = adot(c->p1, dir);
+    const int comp = d0 > d1;
+    *index = comp ? 1 : 0;
+    return comp ? c->p0 : c->p1;
+  }
+  const int bx = dir.x > 0.f, by = dir.y > 0.f, bz = dir.z > 0.f;
+  *index = bx | (by << 1) | (bz << 2);
+  return V3(bx ? c->ext.x : -c->ext.x, by ? c->ext.y : -c->ext.y, bz ? c->ext.z : -c->ext.z);
+}
+static inline v3 pxo_cvx_support_point(const PxoConvex* c, int index) {
+  if (c->type == PXO_CVX_CAPSULE) return index == 1 ? c->p0 : c->p1;   /* (&p0)[1-index] */
+  return V3((index & 1) ? c->ext.x : -c->ext.x, (index & 2) ? c->ext.y : -c->ext.y, (index & 4) ? c->ext.z : -c->ext.z);
+}
+
+/* ---------------- simplex solver ---------------- */
+static inline v3 pxo_v3div(v3 a, float s) { return V3(a.x / s, a.y / s, a.z / s); }   /* V3ScaleInv */
+
+/* GuBarycentricCoordinates.cpp:36-48 */
+static inline void pxo_bary2(v3 p, v3 a, v3 b, float* v) {
+  const v3 v0 = v3sub(a, p), v1 = v3sub(b, p), d = v3sub(v1, v0);
+  const float denominator = adot(d, d), numerator = adot(v3neg(v0), d);
+  const float denom = denominator > 0.f ? 1.0f / denominator : 0.f;
+  *v = numerator * denom;
+}
+/* GuBarycentricCoordinates.cpp:50-76 */
+static inline void pxo_bary3(v3 p, v3 a, v3 b, v3 c, float* v, float* w) {
+  const v3 ab = v3sub(b, a), ac = v3sub(c, a), n = v3cross(ab, ac);
+  const v3 ca = v3sub(a, p), cb = v3sub(b, p), cc = v3sub(c, p);
+  const v3 bCrossC = v3cross(cb, cc), cCrossA = v3cross(cc, ca), aCrossB = v3cross(ca, cb);
+  const float va = adot(n, bCrossC), vb = adot(n, cCrossA), vc = adot(n, aCrossB);
+  const float totalArea = va + (vb + vc);
+  const float denom = totalArea == 0.f ? 0.f : 1.0f / totalArea;
+  *v = vb * denom; *w = vc * denom;
+}
+
+/* GuGJKSimplex.h:91-118 */
+static inline v3 pxo_closest_segment(const v3* Q, uint32_t* size) {
+  const v3 a = Q[0], b = Q[1];
+  const v3 ab = v3sub(b, a);
+  const float denom = adot(ab, ab);
+  const v3 ap = v3neg(a);
+  const float nom = adot(ap, ab);
+  if (FLT_EPSILON >= denom) { *size = 1; return Q[0]; }
+  const float t = fmaxf_(fminf_(nom / denom, 1.f), 0.f);
+  return v3scaleadd(ab, t, a);
+}
+
+/* GuGJKSimplex.h:120-160 */
+static inline void pxo_gjk_closest_points(const v3* Q, const v3* A, const v3* B, v3 closest, v3* closestA, v3* closestB, uint32_t size) {
+  switch (size) {
+    case 1: *closestA = A[0]; *closestB = B[0]; break;
+    case 2: {
+      float v; pxo_bary2(closest, Q[0], Q[1], &v);
+      *closestA = v3scaleadd(v3sub(A[1], A[0]), v, A[0]);
+      *closestB = v3scaleadd(v3sub(B[1], B[0]), v, B[0]);
+      break;
+    }
+    case 3: {
+      float v, w; pxo_bary3(closest, Q[0], Q[1], Q[2], &v, &w);
+      const v3 av0 = v3sub(A[1], A[0]), av1 = v3sub(A[2], A[0]), bv0 = v3sub(B[1], B[0]), bv1 = v3sub(B[2], B[0]);
+      *closestA = v3add(A[0], v3add(v3scale(av0, v), v3scale(av1, w)));
+      *closestB = v3add(B[0], v3add(v3scale(bv0, v), v3scale(bv1, w)));
+      break;
+    }
+    default: break;
+  }
+}
+
+/* GuGJKSimplex.h:162-283: closest point of the origin on triangle abc, the sub-simplex that holds it in indices / size; returns the squared distance */
+static inline float pxo_closest_triangle_bary(v3 a, v3 b, v3 c, uint32_t* indices, uint32_t* size, v3* closestPt) {
+  *size = 3;
+  const float eps = FLT_EPSILON;
+  const v3 ab = v3sub(b, a), ac = v3sub(c, a);
+  const v3 n = v3cross(ab, ac);
+  const float nn = adot(n, n);
+  if (nn == 0.f) return FLT_MAX;
+  const v3 bCrossC = v3cross(b, c), cCrossA = v3cross(c, a), aCrossB = v3cross(a, b);
+  const float va = adot(n, bCrossC), vb = adot(n, cCrossA), vc = adot(n, aCrossB);
+  if (va >= 0.f && vb >= 0.f && vc >= 0.f) {
+    const float t = adot(n, a) / nn;
+    const v3 q = v3scale(n, t);
+    *closestPt = q; return adot(q, q);
+  }
+  const v3 ap = v3neg(a), bp = v3neg(b), cp = v3neg(c);
+  const float d1 = adot(ab, ap), d2 = adot(ac, ap), d3 = adot(ab, bp), d4 = adot(ac, bp), d5 = adot(ab, cp), d6 = adot(ac, cp);
+  const float unom = d4 - d3, udenom = d5 - d6;
+  *size = 2;
+  if (0.f >= vc && d1 >= 0.f && 0.f >= d3) {   /* edge AB */
+    const float toRecip = d1 - d3;
+    const float recip = fabsf(toRecip) > eps ? 1.0f / toRecip : 0.f;
+    const float t = d1 * recip;
+    const v3 q = v3scaleadd(ab, t, a);
+    *closestPt = q; return adot(q, q);
+  }
+  if (0.f >= va && d4 >= d3 && d5 >= d6) {   /* edge BC */
+    const v3 bc = v3sub(c, b);
+    const float toRecip = unom + udenom;
+    const float recip = fabsf(toRecip) > eps ? 1.0f / toRecip : 0.f;
+    const float t = unom * recip;
+    indices[0] = indices[1]; indices[1] = indices[2];
+    const v3 q = v3scaleadd(bc, t, b);
+    *closestPt = q; return adot(q, q);
+  }
+  if (0.f >= vb && d2 >= 0.f && 0.f >= d6) {   /* edge AC */
+    const float toRecip = d2 - d6;
+    const float recip = fabsf(toRecip) > eps ? 1.0f / toRecip : 0.f;
+    const float t = d2 * recip;
+    indices[1] = indices[2];
+    const v3 q = v3scaleadd(ac, t, a);
+    *closestPt = q; return adot(q, q);
+  }
+  *size = 1;
+  if (0.f >= d1 && 0.f >= d2) { *closestPt = a; return adot(a, a); }
+  if (d3 >= 0.f && d3 >= d4) { indices[0] = indices[1]; *closestPt = b; return adot(b, b); }
+  indices[0] = indices[2]; *closestPt = c; return adot(c, c);
+}
+
+/* GuGJKSimplex.h:329-378 (the index-carrying overload) */
+static inline v3 pxo_closest_triangle(v3* Q, v3* A, v3* B, int* aInd, int* bInd, uint32_t* size) {
+  *size = 3;
+  const float eps2 = FLT_EPSILON * FLT_EPSILON;
+  const v3 a = Q[0], b = Q[1], c = Q[2];
+  const v3 ab = v3sub(b, a), ac = v3sub(c, a);
+  const v3 signArea = v3cross(ab, ac);
+  const float area = adot(signArea, signArea);
+  if (eps2 >= area) { *size = 2; return pxo_closest_segment(Q, size); }
+  uint32_t _size; uint32_t indices[3] = {0, 1, 2};
+  v3 closestPt = V3(0, 0, 0);
+  pxo_closest_triangle_bary(a, b, c, indices, &_size, &closestPt);
+  if (_size != 3) {
+    const v3 q0 = Q[indices[0]], q1 = Q[indices[1]], a0 = A[indices[0]], a1 = A[indices[1]], b0 = B[indices[0]], b1 = B[indices[1]];
+    const int ai0 = aInd[indices[0]], ai1 = aInd[indices[1]], bi0 = bInd[indices[0]], bi1 = bInd[indices[1]];
+    Q[0] = q0; Q[1] = q1; A[0] = a0; A[1] = a1; B[0] = b0; B[1] = b1; aInd[0] = ai0; aInd[1] = ai1; bInd[0] = bi0; bInd[1] = bi1;
+    *size = _size;
+  }
+  return closestPt;
+}
+
+/* GuGJKSimplex.h:56-89: per face (abc, acd, adb, bdc) -- is the origin outside (on the other side than the fourth vertex)? */
+static inline void pxo_point_outside_of_plane4(v3 a, v3 b, v3 c, v3 d, int out[4]) {
+  const v3 ab = v3sub(b, a), ac = v3sub(c, a), ad = v3sub(d, a), bd = v3sub(d, b), bc = v3sub(c, b);
+  const v3 v0 = v3cross(ab, ac), v1 = v3cross(ac, ad), v2 = v3cross(ad, ab), v3_ = v3cross(bd, bc);
+  const float signa0 = adot(v0, a), signa1 = adot(v1, a), signa2 = adot(v2, a), signd3 = adot(v3_, a);
+  const float signd0 = adot(v0, d), signd1 = adot(v1, b), signd2 = adot(v2, c), signa3 = adot(v3_, b);
+  out[0] = signa0 * signd0 >= 0.f; out[1] = signa1 * signd1 >= 0.f; out[2] = signa2 * signd2 >= 0.f; out[3] = signa3 * signd3 >= 0.f;
+}
+
+/* GuGJKSimplex.cpp:38-121 */
+static inline v3 pxo_closest_of_faces(const v3* Q, const int outside[4], uint32_t* indices, uint32_t* size) {
+  float bestSqDist = FLT_MAX;
+  v3 closestPt = V3(0, 0, 0);
+  if (outside[0]) bestSqDist = pxo_closest_triangle_bary(Q[0], Q[1], Q[2], indices, size, &closestPt);
+  static const uint32_t faces[3][3] = {{0, 2, 3}, {0, 3, 1}, {1, 3, 2}};
+  for (int f = 0; f < 3; ++f) {
+    if (!outside[f + 1]) continue;
+    uint32_t _size = 3; uint32_t _indices[3] = {faces[f][0], faces[f][1], faces[f][2]};
+    v3 t = V3(0, 0, 0);
+    const float sqDist = pxo_closest_triangle_bary(Q[faces[f][0]], Q[faces[f][1]], Q[faces[f][2]], _indices, &_size, &t);
+    if (bestSqDist > sqDist) { closestPt = t; bestSqDist = sqDist; indices[0] = _indices[0]; indices[1] = _indices[1]; indices[2] = _indices[2]; *size = _size; }
+  }
+  return closestPt;
+}
+
+/* GuGJKSimplex.cpp:163-213 */
+static inline v3 pxo_closest_tetrahedron(v3* Q, v3* A, v3* B, int* aInd, int* bInd, uint32_t* size) {
+  const v3 a = Q[0], b = Q[1], c = Q[2], d = Q[3];
+  const v3 ab = v3sub(b, a), ac = v3sub(c, a);
+  const v3 n = anormalize(v3cross(ab, ac));
+  const float signDist = adot(n, v3sub(d, a));
+  if (1e-4f > fabsf(signDist)) { *size = 3; return pxo_closest_triangle(Q, A, B, aInd, bInd, size); }
+  int outside[4]; pxo_point_outside_of_plane4(a, b, c, d, outside);
+  if (!outside[0] && !outside[1] && !outside[2] && !outside[3]) return V3(0, 0, 0);   /* origin inside: size stays 4 */
+  uint32_t indices[3] = {0, 1, 2};
+  const v3 closest = pxo_closest_of_faces(Q, outside, indices, size);
+  const v3 q0 = Q[indices[0]], q1 = Q[indices[1]], q2 = Q[indices[2]], a0 = A[indices[0]], a1 = A[indices[1]], a2 = A[indices[2]];
+  const v3 b0 = B[indices[0]], b1 = B[indices[1]], b2 = B[indices[2]];
+  const int ai0 = aInd[indices[0]], ai1 = aInd[indices[1]], ai2 = aInd[indices[2]], bi0 = bInd[indices[0]], bi1 = bInd[indices[1]], bi2 = bInd[indices[2]];
+  Q[0] = q0; Q[1] = q1; Q[2] = q2; A[0] = a0; A[1] = a1; A[2] = a2; B[0] = b0; B[1] = b1; B[2] = b2;
+  aInd[0] = ai0; aInd[1] = ai1; aInd[2] = ai2; bInd[0] = bi0; bInd[1] = bi1; bInd[2] = bi2;
+  return closest;
+}
+
+/* GuGJKSimplex.h:413-443 */
+static inline v3 pxo_gjk_do_simplex(v3* Q, v3* A, v3* B, int* aInd, int* bInd, v3 support, uint32_t* size) {
+  switch (*size) {
+    case 1: return support;
+    case 2: return pxo_closest_segment(Q, size);
+    case 3: return pxo_closest_triangle(Q, A, B, aInd, bInd, size);
+    case 4: return pxo_closest_tetrahedron(Q, A, B, aInd, bInd, size);
+    default: return support;
+  }
+}
+
+/* ---------------- gjkPenetration: GuGJKPenetration.h:89-311 ----------------
+ * aIndices / bIndices / warmStartSize: the manifold's warm-start cache (mAIndice, mBIndice, mNumWarmStartPoints). */
+static inline int pxo_gjk_penetration(const PxoConvex* a, const PxoConvex* b, v3 initialSearchDir, float contactDist, int takeCoreShape,
+                                      uint8_t* aIndices, uint8_t* bIndices, uint8_t* warmStartSize, PxoGjkOutput* output) {
+  const float minMargin = fminf_(a->minMargin, b->minMargin);
+  const float eps = minMargin * 0.1f;
+  const float epsRel = 0.000225f, relDif = 1.0f - epsRel;
+  const float tMarginA = a->marginIsRadius ? a->margin : 0.f, tMarginB = b->marginIsRadius ? b->margin : 0.f;
+  const float sumMargin = tMarginA + tMarginB;
+  const float sumExpandedMargin = sumMargin + contactDist;
+  float dist = FLT_MAX, prevDist = dist;
+  v3 prevClos = V3(0, 0, 0);
+  int notTerminated = 1, notDegenerated = 1;
+  v3 closest, v;
+  v3 Q[4], A[4], B[4]; int aInd[4], bInd[4];
+  v3 supportA = V3(0, 0, 0), supportB = V3(0, 0, 0), support = V3(0, 0, 0);
+  uint32_t size = 0;
+#define PXO_ASSIGN_WARM(n) do { *warmStartSize = (uint8_t)(n); for (uint32_t i_ = 0; i_ < (uint32_t)(n); ++i_) { aIndices[i_] = (uint8_t)aInd[i_]; bIndices[i_] = (uint8_t)bInd[i_]; } } while (0)
+  if (*warmStartSize != 0) {
+    for (uint32_t i = 0; i < *warmStartSize; ++i) {
+      aInd[i] = aIndices[i]; bInd[i] = bIndices[i];
+      supportA = pxo_cvx_support_point(a, aIndices[i]); supportB = pxo_cvx_support_point(b, bIndices[i]);
+      support = v3sub(supportA, supportB);
+      A[size] = supportA; B[size] = supportB; Q[size++] = support;
+    }
+    closest = pxo_gjk_do_simplex(Q, A, B, aInd, bInd, support, &size);
+    dist = alen(closest);
+    v = pxo_v3div(closest, dist);
+    prevDist = dist; prevClos = closest;
+    notTerminated = dist > eps;
+  } else {
+    closest = adot(initialSearchDir, initialSearchDir) > 0.f ? initialSearchDir : V3(1, 0, 0);
+    v = anormalize(closest);
+  }
+  while (notTerminated) {
+    prevDist = dist; prevClos = closest;
+    supportA = pxo_cvx_support(a, v3neg(closest), &aInd[size]);
+    supportB = pxo_cvx_support(b, closest, &bInd[size]);
+    support = v3sub(supportA, supportB);
+    const float vw = adot(v, support);
+    if (vw > sumExpandedMargin) { PXO_ASSIGN_WARM(size); return PXO_GJK_NON_INTERSECT; }
+    if (vw > dist * relDif) {
+      PXO_ASSIGN_WARM(size);
+      output->normal = v;
+      v3 closA = V3(0, 0, 0), closB = V3(0, 0, 0);
+      pxo_gjk_closest_points(Q, A, B, closest, &closA, &closB, size);
+      if (takeCoreShape) { output->closestA = closA; output->closestB = closB; output->penDep = dist; }
+      else { output->closestA = v3negscalesub(v, tMarginA, closA); output->closestB = v3scaleadd(v, tMarginB, closB); output->penDep = dist - sumMargin; }
+      return PXO_GJK_CONTACT;
+    }
+    A[size] = supportA; B[size] = supportB; Q[size++] = support;
+    closest = pxo_gjk_do_simplex(Q, A, B, aInd, bInd, support, &size);
+    dist = alen(closest);
+    v = pxo_v3div(closest, dist);
+    notDegenerated = prevDist > dist;
+    notTerminated = (dist > eps) && notDegenerated;
+  }
+  if (!notDegenerated) {
+    PXO_ASSIGN_WARM(size - 1);
+    dist = prevDist; closest = prevClos;
+    v3 closA = V3(0, 0, 0), closB = V3(0, 0, 0);
+    pxo_gjk_closest_points(Q, A, B, closest, &closA, &closB, size);
+    const v3 n = pxo_v3div(prevClos, prevDist);
+    output->normal = n; output->searchDir = v;
+    if (takeCoreShape) { output->closestA = closA; output->closestB = closB; output->penDep = dist; }
+    else {
+      output->closestA = v3negscalesub(n, tMarginA, closA); output->closestB = v3scaleadd(n, tMarginB, closB); output->penDep = dist - sumMargin;
+      if (sumMargin >= dist) return PXO_GJK_CONTACT;
+    }
+    return PXO_GJK_DEGENERATE;
+  }
+  PXO_ASSIGN_WARM(size);
+  return PXO_EPA_CONTACT;
+#undef PXO_ASSIGN_WARM
+}
+
+/* ---------------- polygonal box: GuPCMShapeConvex.cpp:40-110 ---------------- */
+typedef struct { v3 n; float d; int minIndex; } PxoPoly;
+static const uint8_t pxo_box_poly_refs[24] = {0, 3, 2, 1, 1, 2, 6, 5, 5, 6, 7, 4, 4, 7, 3, 0, 3, 7, 6, 2, 4, 0, 1, 5};
+typedef struct { v3 verts[8]; PxoPoly polys[6]; } PxoPolyBox;
+static inline void pxo_poly_box(PxoPolyBox* pb, v3 h) {
+  const v3 mn = v3neg(h), mx = h;
+  pb->verts[0] = V3(mn.x, mn.y, mn.z); pb->verts[1] = V3(mx.x, mn.y, mn.z); pb->verts[2] = V3(mx.x, mx.y, mn.z); pb->verts[3] = V3(mn.x, mx.y, mn.z);
+  pb->verts[4] = V3(mn.x, mn.y, mx.z); pb->verts[5] = V3(mx.x, mn.y, mx.z); pb->verts[6] = V3(mx.x, mx.y, mx.z); pb->verts[7] = V3(mn.x, mx.y, mx.z);
+  pb->polys[1].n = V3(1, 0, 0);  pb->polys[1].d = -h.x; pb->polys[1].minIndex = 0;
+  pb->polys[3].n = V3(-1, 0, 0); pb->polys[3].d = -h.x; pb->polys[3].minIndex = 1;
+  pb->polys[4].n = V3(0, 1, 0);  pb->polys[4].d = -h.y; pb->polys[4].minIndex = 0;
+  pb->polys[5].n = V3(0, -1, 0); pb->polys[5].d = -h.y; pb->polys[5].minIndex = 2;
+  pb->polys[2].n = V3(0, 0, 1);  pb->polys[2].d = -h.z; pb->polys[2].minIndex = 0;
+  pb->polys[0].n = V3(0, 0, -1); pb->polys[0].d = -h.z; pb->polys[0].minIndex = 4;
+}
+
+/* GuPCMContactGenUtil.cpp:105-135: box polygonal data has no edges (mNbEdges = 0), so only the face loop runs */
+static inline int pxo_box_polygon_index(const PxoPolyBox* pb, v3 normal) {
+  const v3 n = normal;   /* vertex2Shape = identity */
+  float minProj = adot(n, pb->polys[0].n);
+  int closest = 0;
+  for (int i = 1; i < 6; ++i) { const float proj = adot(n, pb->polys[i].n); if (minProj > proj) { minProj = proj; closest = i; } }
+  return closest;
+}
+/* GuPCMContactGenUtil.cpp:204-260 (PxPlane::distance = n.dot(p) + d with PxVec3::dot = x+y+z order) */
+static inline int pxo_box_witness_polygon_index(const PxoPolyBox* pb, v3 normal, v3 closest, float tolerance) {
+  float pd[6];
+  const float eps = -tolerance;
+  float dist = v3dot(closest, pb->polys[0].n) + pb->polys[0].d;
+  float minDist = dist >= eps ? fabsf(dist) : FLT_MAX;
+  pd[0] = minDist;
+  float maxDist = dist; int maxFace = 0, closestFace = 0;
+  for (int i = 1; i < 6; ++i) {
+    dist = v3dot(closest, pb->polys[i].n) + pb->polys[i].d;
+    pd[i] = dist >= eps ? fabsf(dist) : FLT_MAX;
+    if (minDist > pd[i]) { minDist = pd[i]; closestFace = i; }
+    if (dist > maxDist) { maxDist = dist; maxFace = i; }
+  }
+  if (minDist == FLT_MAX) return maxFace;
+  float bestProj = adot(anormalize(pb->polys[closestFace].n), normal);
+  const int first = closestFace;
+  for (int i = 0; i < 6; ++i) {
+    if ((tolerance > (pd[i] - minDist)) && first != i) {
+      const float proj = adot(anormalize(pb->polys[i].n), normal);
+      if (bestProj > proj) { closestFace = i; bestProj = proj; }
+    }
+  }
+  return closestFace;
+}
+
+/* GuPersistentContactManifold.cpp:289-360 */
+static inline m33 pxo_rotation_from_z(v3 to) {
+  m33 m;
+  const float e = to.z, f = fabsf(e);
+  if (0.9999f > f) {
+    const float vx = -to.y, vy = to.x;
+    const float h = 1.0f / (1.0f + e);
+    const float hvx = h * vx, hvxy = hvx * vy;
+    m.c0 = V3(hvx * vx + e, hvxy, vy);
+    m.c1 = V3(hvxy, h * (vy * vy) + e, -vx);
+    m.c2 = V3(-vy, vx, e);
+  } else {
+    const v3 from = V3(0, 0, 1), absFrom = V3(0, 1, 0);
+    const v3 u = v3sub(absFrom, from), v = v3sub(absFrom, to);
+    const float dotU = adot(u, u), dotV = adot(v, v), dotUV = adot(u, v);
+    const float c1 = -(2.f / dotU), c2 = -(2.f / dotV), c3 = c1 * (c2 * dotUV);
+    const v3 c1u = v3scale(u, c1), c2v = v3scale(v, c2), c3v = v3scale(v, c3);
+    m.c0 = v3scaleadd(u, c1u.x, v3scaleadd(v, c2v.x, v3scale(u, c3v.x))); m.c0.x = m.c0.x + 1.0f;
+    m.c1 = v3scaleadd(u, c1u.y, v3scaleadd(v, c2v.y, v3scale(u, c3v.y))); m.c1.y = m.c1.y + 1.0f;
+    m.c2 = v3scaleadd(u, c1u.z, v3scaleadd(v, c2v.z, v3scale(u, c3v.z))); m.c2.z = m.c2.z + 1.0f;
+  }
+  return m;
+}
+
+/* ---------------- capsule vs polygonal box full manifold: GuPCMContactGenSphereCapsule.cpp ---------------- */
+/* :43-96 testPolyDataAxis (box: identity scaling) */
+static inline int pxo_capbox_test_poly_axis(const PxoConvex* cap, const PxoPolyBox* pb, float contactDist, float* minOverlap, v3* separatingAxis) {
+  float _minOverlap = FLT_MAX; v3 tempAxis = V3(0, 1, 0);
+  for (int i = 0; i < 6; ++i) {
+    const PxoPoly* poly = &pb->polys[i];
+    const v3 minVert = pb->verts[poly->minIndex];
+    const float magnitude = 1.0f / alen(poly->n);
+    const v3 planeN = v3scale(poly->n, magnitude);
+    const float min0 = adot(poly->n, minVert) * magnitude, max0 = (-poly->d) * magnitude;
+    const float tempMin = adot(cap->p0, planeN), tempMax = adot(cap->p1, planeN);
+    float min1 = fminf_(tempMin, tempMax), max1 = fmaxf_(tempMin, tempMax);
+    min1 = min1 - cap->margin; max1 = max1 + cap->margin;
+    if ((min1 > max0 + contactDist) || (min0 > max1 + contactDist)) return 0;
+    const float tempOverlap = max0 - min1;
+    if (_minOverlap > tempOverlap) { _minOverlap = tempOverlap; tempAxis = planeN; }
+  }
+  *separatingAxis = tempAxis; *minOverlap = _minOverlap;
+  return 1;
+}
+/* :154-219 testSATCapsulePoly; map->doSupport(normal,min,max) for a box = BoxV::supportLocal(dir,min,max) GuVecBox.h:171-177 */
+static inline int pxo_capbox_sat(const PxoConvex* cap, const PxoPolyBox* pb, v3 ext, float contactDist, float* minOverlap, v3* separatingAxis) {
+  float _minOverlap = FLT_MAX; v3 tempAxis = V3(0, 1, 0);
+  if (!pxo_capbox_test_poly_axis(cap, pb, contactDist, &_minOverlap, &tempAxis)) return 0;
+  const v3 capsuleAxis = v3sub(cap->p1, cap->p0);
+  for (int i = 0; i < 6; ++i) {
+    const uint8_t* inds = pxo_box_poly_refs + i * 4;
+    for (int lStart = 0, lEnd = 3; lStart < 4; lEnd = lStart++) {
+      const v3 p10 = pb->verts[inds[lStart]], p11 = pb->verts[inds[lEnd]];
+      const v3 shapeSpaceV = v3sub(p11, p10);
+      const v3 dir = v3cross(capsuleAxis, shapeSpaceV);
+      const float lenSq = adot(dir, dir);
+      if (FLT_EPSILON > lenSq) continue;
+      const v3 normal = pxo_v3div(dir, sqrtf(lenSq));
+      const v3 point = V3(normal.x > 0.f ? ext.x : -ext.x, normal.y > 0.f ? ext.y : -ext.y, normal.z > 0.f ? ext.z : -ext.z);
+      const float max0 = adot(normal, point), min0 = -max0;
+      const float tempMin = adot(cap->p0, normal), tempMax = adot(cap->p1, normal);
+      float min1 = fminf_(tempMin, tempMax), max1 = fmaxf_(tempMin, tempMax);
+      min1 = min1 - cap->margin; max1 = max1 + cap->margin;
+      if ((min1 > max0 + contactDist) || (min0 > max1 + contactDist)) return 0;
+      const float tempOverlap = max0 - min1;
+      if (_minOverlap > tempOverlap) { _minOverlap = tempOverlap; tempAxis = normal; }
+    }
+  }
+  *separatingAxis = tempAxis; *minOverlap = _minOverlap;
+  return 1;
+}
+/* :221-284 generatedCapsuleBoxFaceContacts */
+static inline void pxo_capbox_face_contacts(const PxoConvex* cap, const PxoPolyBox* pb, int ref, const mxf* aToB, PxoMPoint* mc, int* num, float contactDist, v3 normal) {
+  const float radius = cap->margin + contactDist;
+  const v3 planeNormal = anormalize(pb->polys[ref].n);
+  const uint8_t* inds = pxo_box_poly_refs + ref * 4;
+  const v3 a = pb->verts[inds[0]];
+  const float denom0 = adot(planeNormal, v3sub(cap->p0, a)), denom1 = adot(planeNormal, v3sub(cap->p1, a));
+  const float projPlaneN = adot(planeNormal, normal);
+  const float numer = projPlaneN > 0.f ? 1.0f / projPlaneN : 0.f;
+  const float t0 = denom0 * numer, t1 = denom1 * numer;
+  const int con0 = radius >= t0, con1 = radius >= t1;
+  if (con0 || con1) {
+    const m33 rot = pxo_rotation_from_z(planeNormal);
+    v3 pts[4]; v3 mn = V3(FLT_MAX, FLT_MAX, FLT_MAX), mx = v3neg(mn);
+    for (int i = 0; i < 4; ++i) { pts[i] = m33mul(&rot, pb->verts[inds[i]]); mn = v3min(mn, pts[i]); mx = v3max(mx, pts[i]); }
+    if (con0) {
+      const v3 proj = v3negscalesub(normal, t0, cap->p0);
+      const v3 point = m33mul(&rot, proj);
+      if (pxo_contains(pts, 4, point, mn, mx)) { mc[*num].a = amxftransforminv(aToB, cap->p0); mc[*num].b = proj; mc[*num].n = normal; mc[*num].pen = t0; (*num)++; }
+    }
+    if (con1) {
+      const v3 proj = v3negscalesub(normal, t1, cap->p1);
+      const v3 point = m33mul(&rot, proj);
+      if (pxo_contains(pts, 4, point, mn, mx)) { mc[*num].a = amxftransforminv(aToB, cap->p1); mc[*num].b = proj; mc[*num].n = normal; mc[*num].pen = t1; (*num)++; }
+    }
+  }
+}
+/* :312-359 generateEE */
+static inline void pxo_capbox_ee(v3 p, v3 q, v3 normal, v3 a, v3 b, const mxf* aToB, PxoMPoint* mc, int* num, float inflatedRadius) {
+  const float expandedRatio = 0.005f;
+  const v3 ab = v3sub(b, a);
+  const v3 n = v3cross(ab, normal);
+  const float d = adot(n, a), np = adot(n, p), nq = adot(n, q);
+  const float signP = np - d, signQ = nq - d;
+  if (signP * signQ > 0.f) return;
+  const v3 pq = v3sub(q, p);
+  const float npq = adot(n, pq);
+  if (npq == 0.f) return;
+  const float segT = (d - np) / npq;
+  const v3 localPointA = v3scaleadd(pq, segT, p);
+  const v3 perNormal = v3cross(normal, pq);
+  const v3 ap = v3sub(localPointA, a);
+  const float nom = adot(perNormal, ap), denom = adot(perNormal, ab);
+  const float tValue = nom / denom;
+  const float mx = 1.0f + expandedRatio, mn = 0.f - expandedRatio;
+  if (tValue > mx || mn > tValue) return;
+  const v3 v = v3negscalesub(ab, tValue, ap);
+  const float signedDist = adot(v, normal);
+  if (inflatedRadius >= signedDist) {
+    mc[*num].a = amxftransforminv(aToB, localPointA); mc[*num].b = v3sub(localPointA, v); mc[*num].n = normal; mc[*num].pen = signedDist; (*num)++;
+  }
+}
+/* :379-420 generateCapsuleBoxFullContactManifold (PCM_WITNESS_POINT_LOWER_EPS 1e-2, UPPER_EPS 5e-2: GuPCMContactGen.h) */
+static inline int pxo_capbox_full_manifold(const PxoConvex* cap, const PxoPolyBox* pb, v3 ext, const mxf* aToB, PxoMPoint* mc, int* num, float contactDist,
+                                           v3* normal, v3 closest, float margin, int doOverlapTest, float toleranceScale) {
+  const int original = *num;
+  int ref;
+  if (doOverlapTest) {
+    float minOverlap;
+    if (!pxo_capbox_sat(cap, pb, ext, contactDist, &minOverlap, normal)) return 0;
+    ref = pxo_box_polygon_index(pb, v3neg(*normal));
+  } else {
+    const float lowerEps = toleranceScale * 1e-2f, upperEps = toleranceScale * 5e-2f;
+    const float tolerance = fminf_(fmaxf_(margin, lowerEps), upperEps);   /* PxClamp */
+    ref = pxo_box_witness_polygon_index(pb, v3neg(*normal), closest, tolerance);
+  }
+  pxo_capbox_face_contacts(cap, pb, ref, aToB, mc, num, contactDist, *normal);
+  if (*num - original < 2) {
+    const uint8_t* inds = pxo_box_poly_refs + ref * 4;
+    const float inflatedRadius = cap->margin + contactDist;
+    for (int rStart = 0, rEnd = 3; rStart < 4; rEnd = rStart++)
+      pxo_capbox_ee(cap->p0, cap->p1, *normal, pb->verts[inds[rStart]], pb->verts[inds[rEnd]], aToB, mc, num, inflatedRadius);
+  }
+  return 1;
+}
+
+/* GuPersistentContactManifold.cpp:1177-1243 reduceBatchContacts2 + :1292-1310 addBatchManifoldContacts2 */
+static inline void pxo_add_batch2(PxoManifold* m, const PxoMPoint* p, int numPoints) {
+  if (numPoints <= 2) { for (int i = 0; i < numPoints; ++i) m->pts[i] = p[i]; m->n = numPoints; return; }
+  int chosen[64]; memset(chosen, 0, sizeof(chosen));
+  float maxDis = p[0].pen; int index = 0;
+  for (int i = 1; i < numPoints; ++i) if (maxDis > p[i].pen) { maxDis = p[i].pen; index = i; }
+  m->pts[0] = p[index]; chosen[index] = 1;
+  v3 v = v3sub(p[0].b, m->pts[0].b);
+  maxDis = adot(v, v); index = 0;
+  for (int i = 1; i < numPoints; ++i) { v = v3sub(p[i].b, m->pts[0].b); const float d = adot(v, v); if (d > maxDis) { maxDis = d; index = i; } }
+  m->pts[1] = p[index]; chosen[index] = 1;
+  int secondIndex = index;
+  const float maxDepth = p[index].pen;
+  for (int i = 0; i < numPoints; ++i) {
+    if (chosen[i]) continue;
+    const v3 d0 = v3sub(m->pts[0].b, p[i].b), d1 = v3sub(m->pts[1].b, p[i].b);
+    if (adot(d0, d0) > adot(d1, d1)) { if (maxDepth > p[i].pen) secondIndex = i; }
+  }
+  if (secondIndex != index) m->pts[1] = p[secondIndex];
+  m->n = 2;
+}
+
+/* GuPersistentContactManifold.h:227-241, thresholds .cpp:179,187 */
+static inline int pxo_invalidate_sphere_capsule(const PxoManifold* m, const xf* cur, float minMargin) {
+  static const float thr2[3] = {0.5f, 0.1f, 0.75f}, qthr2[3] = {0.9995f, 0.9999f, 0.9997f};
+  const float thresholdP = minMargin * thr2[m->n];
+  const float deltaP = pxo_max_pos_delta(m, cur->p);
+  const float deltaQ = adot4(cur->q, m->rel.q);
+  return (deltaP > thresholdP) || (qthr2[m->n] > deltaQ);
+}
+/* GuPersistentContactManifold.cpp:783-807 (sphere / capsule variant: points stored on the core segment) */
+static inline void pxo_manifold_to_contacts_radius(const PxoManifold* m, v3 normal, const xf* transf0, float radius, float contactOffset, PxoContacts* out) {
+  out->count = 0; out->normal = normal;
+  for (int i = 0; i < m->n; ++i) {
+    const float dist = m->pts[i].pen - radius;
+    if (contactOffset >= dist) { out->point[out->count] = v3negscalesub(normal, radius, axftransform(transf0, m->pts[i].a)); out->sep[out->count] = dist; out->count++; }
+  }
+}
+
+/* pcmContactCapsuleBox: GuPCMContactCapsuleBox.cpp:75-202 (shape0 = capsule, shape1 = box).
+ * Returns 0 normally; 1 when the reference would run EPA (segment inside the box), which is not restated yet -- the caller counts the pair as unsupported. */
+static inline int pxo_pcm_capsule_box(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, v3 boxExtents, float contactDist, float toleranceLength,
+                                      PxoManifold* manifold, PxoContacts* out) {
+  out->count = 0;
+  const xf curRTrans = axfinvmul(transf1, transf0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  const int initialContacts = manifold->n;
+  const float boxMargin = pxo_box_margin(boxExtents, toleranceLength);
+  const float minMargin = fminf_(boxMargin, capsuleRadius);
+  const float projectBreakingThreshold = minMargin * 0.8f;
+  pxo_refresh(manifold, &aToB, projectBreakingThreshold);
+  const int bLostContacts = manifold->n != initialContacts;
+  if (bLostContacts || pxo_invalidate_sphere_capsule(manifold, &curRTrans, minMargin)) {
+    manifold->rel = curRTrans;
+    const PxoConvex box = pxo_cvx_box(transf1->p, boxExtents);
+    const PxoConvex capsule = pxo_cvx_capsule(aToB.p, m33mul(&aToB.r, v3scale(V3(1, 0, 0), capsuleHalfHeight)), capsuleRadius);
+    PxoGjkOutput output; memset(&output, 0, sizeof(output));
+    const v3 initialSearchDir = v3sub(capsule.center, box.center);
+    int status = pxo_gjk_penetration(&capsule, &box, initialSearchDir, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+    PxoMPoint mc[64]; int numContacts = 0; int doOverlapTest = 0;
+    PxoPolyBox pb; pxo_poly_box(&pb, boxExtents);
+    v3 normal = output.normal;
+    if (status == PXO_GJK_NON_INTERSECT) return 0;
+    if (status == PXO_GJK_DEGENERATE) doOverlapTest = 1;
+    else {
+      if (status == PXO_GJK_CONTACT) {
+        mc[numContacts].a = amxftransforminv(&aToB, output.closestA); mc[numContacts].b = output.closestB; mc[numContacts].n = output.normal; mc[numContacts].pen = output.penDep; numContacts++;
+      } else return 1;   /* EPA_CONTACT: epaPenetration (GuEPA.cpp) not restated */
+      if (!(initialContacts == 0 || bLostContacts || doOverlapTest)) {
+        const float replaceBreakingThreshold = minMargin * 0.1f;
+        pxo_add_manifold_point2(manifold, aqrotinv(curRTrans.q, v3sub(output.closestA, curRTrans.p)), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+        const v3 n = aqrot(transf1->q, output.normal);
+        pxo_manifold_to_contacts_radius(manifold, n, transf0, capsuleRadius, contactDist, out);
+        return 0;
+      }
+    }
+    /* fullContactsGenerationCapsuleBox :42-73 */
+    const int origContacts = numContacts;
+    if (!pxo_capbox_full_manifold(&capsule, &pb, boxExtents, &aToB, mc, &numContacts, contactDist, &normal, output.closestB, box.margin, doOverlapTest, toleranceLength)) return 0;
+    const PxoMPoint* mcp = mc;
+    if (origContacts != 0 && numContacts != origContacts) { numContacts--; mcp++; }   /* new contacts replace the GJK one */
+    pxo_add_batch2(manifold, mcp, numContacts);
+    normal = aqrot(transf1->q, normal);
+    pxo_manifold_to_contacts_radius(manifold, normal, transf0, capsuleRadius, contactDist, out);
+    return 0;
+  } else if (manifold->n > 0) {
+    const v3 worldNormal = pxo_world_normal(manifold, transf1);
+    pxo_manifold_to_contacts_radius(manifold, worldNormal, transf0, capsuleRadius, contactDist, out);
+  }
+  return 0;
+}
+#endif

@@ -25,6 +25,7 @@ typedef struct {
   xf rel;           /* mRelativeTransform (p = FLT_MAX when invalid) */
   q4 quatA, quatB;  /* mQuatA / mQuatB */
   PxoMPoint pts[PXO_MANIFOLD_CACHE];
+  uint8_t aInd[4], bInd[4], nWarm;   /* mAIndice / mBIndice / mNumWarmStartPoints: GJK warm start (pxo_gjk.h) */
 } PxoManifold;
 
 typedef struct {

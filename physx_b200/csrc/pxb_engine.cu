@@ -26,6 +26,7 @@
 #include "../../include/physx_b200.h"
 #include "pxb_math.cuh"
 #include "pxb_np.cuh"
+#include "pxb_gjk.cuh"
 #include "pxb_solver.cuh"
 #include "pxb_sort.cuh"
 
@@ -45,8 +46,8 @@ struct ActorRec {
 };
 static_assert(sizeof(ActorRec) == 128, "actor record layout");
 
-enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_COUNT = 16 };
-enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8 };
+enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_NGJK, C_COUNT = 16 };
+enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8, E_EPA_PAIR = 16 };
 
 struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };
 
@@ -72,6 +73,7 @@ struct PxbScene {
   float4 *manifolds = 0, *frictions = 0;
   // per pair (this frame)
   float4 *cHdr = 0, *cPts = 0; uint2* pairBodies = 0; float* cForce = 0;
+  uint32_t* gjkList = 0; bool hasGjkPairs = false;   // a10: worklist of GJK-family pairs (filled by k_narrowphase)
   uint32_t *conFlag = 0, *conIdx = 0, *conPair = 0, *rankOfPair = 0; uint64_t *conSortKey = 0, *conSortKeyAlt = 0; uint32_t* conPairAlt = 0;
   uint64_t* orderKeys = 0; uint32_t nOrder = 0, capOrder = 0;
   uint32_t *conB0 = 0, *conB1 = 0, *conPos0 = 0, *conPos1 = 0, *conColour = 0, *conDone = 0, *bodyList = 0, *ordered = 0;
@@ -258,7 +260,7 @@ __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_
   newSlots[i] = slot;
   createdKeys[atomicAdd(&counters[C_NCREATED], 1u)] = k;
   float4* m = manifolds + (size_t)slot * PXB_MANIFOLD_F4;
-  m[0] = make_float4(__int_as_float(0), FLT_MAX, FLT_MAX, FLT_MAX); m[1] = make_float4(0, 0, 0, 1); m[2] = make_float4(0, 0, 0, 1); m[3] = make_float4(0, 0, 0, 1);
+  m[0] = make_float4(__int_as_float(0), FLT_MAX, FLT_MAX, FLT_MAX); m[1] = make_float4(0, 0, 0, 1); m[2] = make_float4(0, 0, 0, 1); m[3] = make_float4(0, 0, 0, 1); m[14] = make_float4(0, 0, 0, 0);
   float4* f = frictions + (size_t)slot * PXB_FRICTION_F4;
   f[0] = make_float4(0, 0, 0, __int_as_float(0)); f[1] = make_float4(0, 0, 0, __int_as_float(0)); f[2] = make_float4(0, 0, 0, __int_as_float(0));
 }
@@ -272,7 +274,7 @@ __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_
 __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
                               const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
                               float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
-                              uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters) {
+                              uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters, uint32_t* __restrict__ gjkList) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *nPairsP) return;
   const uint64_t key = pairKeys[i];
@@ -307,7 +309,8 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_BOX) np_sphere_box(tm0.p, d0.x, tm1, V3(d1.x, d1.y, d1.z), contactDist, out);
   else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CAPSULE) pcm_plane_capsule(tm0, tm1, d1.x, d1.y, contactDist, man, out);
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_CAPSULE) np_capsule_capsule(tm0, tm1, d0.x, d0.y, d1.x, d1.y, contactDist, out);
-  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // capsule-box (GJK/EPA family, a10): reported by fetchResults, never silently skipped
+  else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_BOX) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // GJK family (a10): k_narrowphase_gjk fills this pair's outputs
+  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // convex hulls (a10): reported by fetchResults, never silently skipped
   if (man.dirty) manifold_store(man, rec); else if (usesManifold && man.n > 0) manifold_store_pens(man, rec);   // steady state: only the penetrations change
   if (flip && out.count) out.normal = -out.normal;
   cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
@@ -315,6 +318,40 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   for (int k = 0; k < 4; ++k) { cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]); }   // (cForce: every pair with contacts is a constraint and gets its forces from write-back)
   pairBodies[i] = make_uint2(a0, a1);
   conFlag[i] = out.count > 0 ? 1u : 0u;
+}
+
+// a10: the GJK family (capsule-box), one thread per listed pair.  Kept out of k_narrowphase so that the box / sphere hot path keeps its register budget;
+// the list order is arbitrary (atomic append) but every pair writes only its own outputs, so the result is deterministic.
+__global__ void __launch_bounds__(128) k_narrowphase_gjk(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, uint32_t bitsA, const float4* __restrict__ pos, const float4* __restrict__ quat,
+                              const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags, float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr,
+                              float4* __restrict__ cPts, uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, uint32_t* __restrict__ counters, const uint32_t* __restrict__ gjkList) {
+  const uint32_t n = counters[C_NGJK];
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const uint32_t i = gjkList[w];
+    const uint64_t key = pairKeys[i];
+    const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
+    uint32_t a0 = hi, a1 = lo;
+    const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
+    if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
+    const uint32_t t0 = ((a0 == hi) ? gfHi : gfLo) & 0xff, t1 = ((a0 == hi) ? gfLo : gfHi) & 0xff;
+    const bool flip = t1 < t0;
+    const uint32_t s0 = flip ? a1 : a0, s1 = flip ? a0 : a1;   // s0 = capsule, s1 = box
+    const float4 p0 = pos[s0], p1 = pos[s1];
+    xf tm0, tm1; tm0.p = V3(p0.x, p0.y, p0.z); tm0.q = Q4(quat[s0]); tm1.p = V3(p1.x, p1.y, p1.z); tm1.q = Q4(quat[s1]);
+    const float4 d0 = dims[s0], d1 = dims[s1];
+    float4* rec = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4;
+    Manifold man; manifold_load(man, rec); manifold_load_warm(man, rec);
+    Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
+    for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
+    if (gjk_pcm_capsule_box(&tm0, &tm1, d0.x, d0.y, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out)) atomicOr(&counters[C_ERROR], (uint32_t)E_EPA_PAIR);
+    if (man.dirty) { manifold_store(man, rec); manifold_store_warm(man, rec); } else if (man.n > 0) manifold_store_pens(man, rec);
+    if (flip && out.count) out.normal = -out.normal;
+    cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]);
+    pairBodies[i] = make_uint2(a0, a1);
+    conFlag[i] = out.count > 0 ? 1u : 0u;
+  }
 }
 
 __global__ void k_compact(const uint32_t* __restrict__ nPairsP, const uint32_t* __restrict__ conFlag, const uint32_t* __restrict__ conIdx, uint32_t* __restrict__ conPair,
@@ -679,7 +716,7 @@ __global__ void k_init_freelist(uint32_t cap, uint32_t* __restrict__ freeList) {
 }
 
 __global__ void k_env_begin(uint32_t* __restrict__ counters) {   // per-step counter reset of the environment path
-  if (threadIdx.x == 0) { counters[C_NPAIRS_NEW] = 0; counters[C_NCREATED] = 0; counters[C_NDELETED] = 0; counters[C_NCON] = 0; counters[C_NPART] = 0; counters[C_MAXCONENV] = 0; counters[C_MAXPAIRENV] = 0;
+  if (threadIdx.x == 0) { counters[C_NPAIRS_NEW] = 0; counters[C_NCREATED] = 0; counters[C_NDELETED] = 0; counters[C_NCON] = 0; counters[C_NPART] = 0; counters[C_NGJK] = 0; counters[C_MAXCONENV] = 0; counters[C_MAXPAIRENV] = 0;
                           counters[C_FREE_SNAP] = counters[C_FREE_TAIL]; }
 }
 #include "pxb_env.cuh"
@@ -716,7 +753,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->createdKeys, Pn)); CK(dalloc(s->deletedKeys, Pn));
   CK(dalloc(s->manifolds, Pn * PXB_MANIFOLD_F4)); CK(dalloc(s->frictions, Pn * PXB_FRICTION_F4));
   CK(dalloc(s->cHdr, Pn)); CK(dalloc(s->cPts, Pn * 4)); CK(dalloc(s->pairBodies, Pn)); CK(dalloc(s->cForce, Pn * 4));
-  CK(dalloc(s->conFlag, Pn)); CK(dalloc(s->conIdx, Pn)); CK(dalloc(s->conPair, Pn)); CK(dalloc(s->rankOfPair, Pn)); CK(dalloc(s->conSortKey, Pn)); CK(dalloc(s->conSortKeyAlt, Pn));
+  CK(dalloc(s->gjkList, Pn)); CK(dalloc(s->conFlag, Pn)); CK(dalloc(s->conIdx, Pn)); CK(dalloc(s->conPair, Pn)); CK(dalloc(s->rankOfPair, Pn)); CK(dalloc(s->conSortKey, Pn)); CK(dalloc(s->conSortKeyAlt, Pn));
   CK(dalloc(s->conPairAlt, Pn));
   CK(dalloc(s->conB0, Pn)); CK(dalloc(s->conB1, Pn)); CK(dalloc(s->conPos0, Pn)); CK(dalloc(s->conPos1, Pn)); CK(dalloc(s->conColour, Pn)); CK(dalloc(s->conDone, Pn));
   CK(dalloc(s->bodyList, Pn * 2)); CK(dalloc(s->ordered, Pn));
@@ -786,7 +823,7 @@ PXB_API void pxb_scene_release(PxbScene* s) {
   void* ptrs[] = {s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
-                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->conFlag, s->conIdx,
+                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
                   s->envStart, s->envList, s->actorLocal, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
@@ -873,8 +910,10 @@ static void rebuild_grid(PxbScene* s) {
   float cell = 0.f; float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   s->largeHost.clear();
   std::vector<uint32_t> gf(s->nA);
+  bool anyCapsule = false, anyBox = false;
   for (uint32_t a = 0; a < s->nA; ++a) {
     const ActorRec& r = s->recs[a];
+    anyCapsule |= r.geomType == PXB_GEOM_CAPSULE; anyBox |= r.geomType == PXB_GEOM_BOX;
     const float d = shape_diameter(r);
     const bool global = !std::isfinite(d) || d > largeThresh || (usesEnv && r.envId == NONE32);
     gf[a] = (r.geomType & 0xff) | ((r.flags & PXB_ACTOR_DYNAMIC) ? 0x100u : 0u) | (global ? 0x200u : 0u) | (((r.flags >> 8) & 0x3fu) << 16);   // bits 16..21: PxRigidDynamicLockFlags
@@ -895,6 +934,7 @@ static void rebuild_grid(PxbScene* s) {
   // keep the key within 62 bits
   while ((long double)envCount * g.nx * g.ny * g.nz > 4.0e18L) { if (g.nx >= g.ny && g.nx >= g.nz) g.nx = (g.nx + 1) / 2; else if (g.ny >= g.nz) g.ny = (g.ny + 1) / 2; else g.nz = (g.nz + 1) / 2; }
   g.keyBits = bits_for((uint64_t)envCount * (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz + 1);
+  s->hasGjkPairs = anyCapsule && anyBox;
   s->grid = g; s->nLarge = (uint32_t)s->largeHost.size();
   s->desc.reserved[0] = (uint32_t)envCount;
   cudaMemcpyAsync(s->geomFlags, gf.data(), 4 * s->nA, cudaMemcpyHostToDevice, s->stream);
@@ -992,6 +1032,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     return PXB_OK;
   }
   CK(cudaMemsetAsync(s->counters + C_NPAIRS_NEW, 0, 4 * 3, st));  // NPAIRS_NEW, NCREATED, NDELETED
+  if (s->hasGjkPairs) CK(cudaMemsetAsync(s->counters + C_NGJK, 0, 4, st));
   LAUNCH(k_bounds, cdiv(nA, B), B, nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, externalTight ? 1 : 0, s->aabbMin, s->aabbMax, s->grid,
          s->desc.reserved[0], s->cellKey, s->cellVal);
   const int r = radix_sort_pairs(s->cellKey, s->cellVal, s->cellKeyAlt, s->cellValAlt, s->counters + C_NA, s->grid.keyBits, s->rsTmp, st);
@@ -1031,7 +1072,8 @@ static int read_counters(PxbScene* s) {
   }
   if (s->hErr & E_PAIR_OVERFLOW) return fail(PXB_ERR_CAPACITY, "broadphase pair capacity (maxPairs) exceeded");
   if (s->hErr & (E_COLOUR_OVERFLOW | E_PARTITION_OVERFLOW)) return fail(PXB_ERR_CAPACITY, "more than 32 dynamic colours / 96 partitions needed");
-  if (s->hErr & E_UNSUPPORTED_PAIR) return fail(PXB_ERR_UNSUPPORTED, "a capsule-box pair came into contact range: that pair type needs the GJK/EPA narrowphase family, which is not built yet");
+  if (s->hErr & E_UNSUPPORTED_PAIR) return fail(PXB_ERR_UNSUPPORTED, "a pair of an unsupported geometry type came into contact range");
+  if (s->hErr & E_EPA_PAIR) return fail(PXB_ERR_UNSUPPORTED, "a capsule's core segment penetrated a box: that case needs the EPA penetration query, which is not built yet");
   return PXB_OK;
 }
 
@@ -1046,7 +1088,9 @@ static int enqueue_step(PxbScene* s, float dt) {
   const uint32_t* nP = s->nPairsDev + cur;
   const float contactDist = s->desc.contactOffset + s->desc.contactOffset;
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
-         s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce, s->counters);
+         s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce, s->counters, s->gjkList);
+  if (s->hasGjkPairs) LAUNCH(k_narrowphase_gjk, 148 * 4, 128, s->pairKeys[cur], s->pairSlots[cur], s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds, s->cHdr, s->cPts,
+                             s->pairBodies, s->conFlag, s->counters, s->gjkList);
   SleepArgs SA; SA.threshold = s->sleepThreshold; SA.dt = dt; SA.wake = s->wake; SA.accLin = s->accLin; SA.accAng = s->accAng; SA.asleep = s->asleep; SA.nInter = s->nInter;
   if (s->sleepThreshold > 0.f) {   // island sleep / wake decisions for this step (needs this frame's touching pairs)
     uint32_t nA = s->nA;

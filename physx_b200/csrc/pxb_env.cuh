@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
       else slot = A.freeRing[h & A.ringMask];
       A.createdKeys[atomicAdd(&A.counters[C_NCREATED], 1u)] = k;
       float4* m = A.manifolds + (size_t)slot * PXB_MANIFOLD_F4;
-      m[0] = make_float4(__int_as_float(0), FLT_MAX, FLT_MAX, FLT_MAX); m[1] = make_float4(0, 0, 0, 1); m[2] = make_float4(0, 0, 0, 1); m[3] = make_float4(0, 0, 0, 1);
+      m[0] = make_float4(__int_as_float(0), FLT_MAX, FLT_MAX, FLT_MAX); m[1] = make_float4(0, 0, 0, 1); m[2] = make_float4(0, 0, 0, 1); m[3] = make_float4(0, 0, 0, 1); m[14] = make_float4(0, 0, 0, 0);
       float4* f = A.frictions + (size_t)slot * PXB_FRICTION_F4;
       f[0] = make_float4(0, 0, 0, __int_as_float(0)); f[1] = make_float4(0, 0, 0, __int_as_float(0)); f[2] = make_float4(0, 0, 0, __int_as_float(0));
       A.slotColour[slot] = NONE32;

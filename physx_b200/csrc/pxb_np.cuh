@@ -17,13 +17,25 @@
 #define PXB_MANIFOLD_F4 16   // float4 slots per persistent manifold record (14 used)
 
 struct MPoint { v3 a, b, n; float pen; };
-struct Manifold { int n; xf rel; q4 quatA, quatB; MPoint pts[PXB_MANIFOLD_CACHE]; int dirty; };   // dirty: points / frames regenerated this frame (else only pens changed)
+struct Manifold { int n; xf rel; q4 quatA, quatB; MPoint pts[PXB_MANIFOLD_CACHE]; int dirty; uint8_t aInd[4], bInd[4], nWarm; };   // aInd / bInd / nWarm: GJK warm start (mAIndice / mBIndice / mNumWarmStartPoints)   // dirty: points / frames regenerated this frame (else only pens changed)
 struct Contacts { int count; v3 normal; v3 point[PXB_MANIFOLD_CACHE]; float sep[PXB_MANIFOLD_CACHE]; };
 
 PXB_D void manifold_init(Manifold& m) {
   m.n = 0; m.rel.q = Q4(0, 0, 0, 1); m.rel.p = V3(FLT_MAX, FLT_MAX, FLT_MAX);
   m.quatA = Q4(0, 0, 0, 1); m.quatB = Q4(0, 0, 0, 1); m.dirty = 1;
-  for (int i = 0; i < PXB_MANIFOLD_CACHE; ++i) { m.pts[i].a = V3(0, 0, 0); m.pts[i].b = V3(0, 0, 0); m.pts[i].n = V3(0, 0, 0); m.pts[i].pen = 0.f; }
+  for (int i = 0; i < PXB_MANIFOLD_CACHE; ++i) { m.pts[i].a = V3(0, 0, 0); m.pts[i].b = V3(0, 0, 0); m.pts[i].n = V3(0, 0, 0); m.pts[i].pen = 0.f; m.aInd[i] = 0; m.bInd[i] = 0; }
+  m.nWarm = 0;
+}
+// GJK pair types keep their warm-start simplex in slot 14 of the record: (aInd packed, bInd packed, count)
+PXB_D void manifold_load_warm(Manifold& m, const float4* __restrict__ rec) {
+  const float4 w = rec[14]; const uint32_t a = __float_as_uint(w.x), b = __float_as_uint(w.y);
+  for (int i = 0; i < 4; ++i) { m.aInd[i] = (uint8_t)(a >> (8 * i)); m.bInd[i] = (uint8_t)(b >> (8 * i)); }
+  m.nWarm = (uint8_t)__float_as_uint(w.z);
+}
+PXB_D void manifold_store_warm(const Manifold& m, float4* __restrict__ rec) {
+  uint32_t a = 0, b = 0;
+  for (int i = 0; i < 4; ++i) { a |= (uint32_t)m.aInd[i] << (8 * i); b |= (uint32_t)m.bInd[i] << (8 * i); }
+  rec[14] = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float((uint32_t)m.nWarm), 0.f);
 }
 
 // record layout: [0]=(n, rel.p) [1]=rel.q [2]=quatA [3]=quatB [4]=pen of the 4 points [5..13]=4 points x 9 floats (a, b, n).

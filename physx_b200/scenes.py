@@ -42,13 +42,32 @@ def normalize_quat_f32(q):
     pose handed to createRigidStatic/Dynamic (physx/source/physx/src/NpPhysics.cpp); scene files carry
     quaternions that normalisation leaves unchanged so both sides start from identical bits."""
     q = np.asarray(q, dtype=np.float32)
-    for _ in range(8):
-        m = np.float32(np.sqrt(np.float32(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3])))
-        q2 = (q * (np.float32(1.0) / m)).astype(np.float32)
-        if (q2 == q).all():
-            break
-        q = q2
-    return q
+
+    def settle(q):
+        for _ in range(8):
+            m = np.float32(np.sqrt(np.float32(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3])))
+            q2 = (q * (np.float32(1.0) / m)).astype(np.float32)
+            if (q2 == q).all():
+                return q, True
+            q = q2
+        return q, False
+
+    q, ok = settle(q)
+    if ok:
+        return q
+    # normalisation can settle into a 2-cycle one ulp apart: re-solve the smallest non-zero component so that |q|^2 rounds to 1
+    k = int(np.argmin(np.where(q == 0, np.inf, np.abs(q))))
+    rest = float(np.sum(np.square(q.astype(np.float64)))) - float(q[k]) ** 2
+    base = q.copy()
+    base[k] = np.float32(np.sign(q[k]) * np.sqrt(max(0.0, 1.0 - rest)))
+    for off in range(0, 64):
+        for sgn in (1, -1):
+            c = base.copy()
+            c[k:k + 1].view(np.int32)[0] += sgn * off
+            c, ok = settle(c)
+            if ok:
+                return c
+    raise ValueError("no float32 normalisation fixed point found")
 
 
 # rotation taking local +X (PxPlaneGeometry normal) to world +Y: 90 deg about Z
@@ -390,3 +409,32 @@ def locked_stacks(**hdr):
     for i, lock in ((2, LOCK_LINEAR_X | LOCK_LINEAR_Z), (4, LOCK_ANGULAR_X | LOCK_ANGULAR_Y | LOCK_ANGULAR_Z), (7, LOCK_LINEAR_X), (9, LOCK_ANGULAR_Y), (12, LOCK_LINEAR_X | LOCK_LINEAR_Z | LOCK_ANGULAR_X | LOCK_ANGULAR_Z)):
         set_lock_flags(sc.actors, i, lock)
     return sc
+
+
+def capsules_on_boxes(n_boxes=6, per_box=3, seed=9, **hdr):
+    """Capsules (and a few spheres) dropped onto a row of boxes that never touch each other: every other box is static and tilted, the
+    rest are dynamic and rest flat on the ground.  Exercises the capsule-box GJK path (face, edge and corner contacts, manifold recycling)
+    without tumbling box-box pairs."""
+    rng = np.random.RandomState(seed)
+    nb = n_boxes
+    a = _new_actors(nb + nb * per_box)
+    for b in range(nb):
+        he = np.array([rng.uniform(0.25, 0.4), rng.uniform(0.12, 0.25), rng.uniform(0.25, 0.4)], dtype=np.float32)
+        set_box(a, np.array([b]), he)
+        a["pos"][b] = (1.6 * b, he[1], 0.0)
+        if b % 2 == 1:   # static, tilted
+            a["flags"][b] = 0
+            a["mass"][b] = 0; a["inertia"][b] = 0
+            ang = rng.uniform(-0.35, 0.35)
+            a["quat"][b] = normalize_quat_f32([0.0, 0.0, np.sin(ang / 2), np.cos(ang / 2)])
+            a["pos"][b, 1] = 0.45
+        for k in range(per_box):
+            i = nb + b * per_box + k
+            if k == per_box - 1 and b % 3 == 0:
+                set_sphere(a, i, rng.uniform(0.1, 0.18))
+            else:
+                set_capsule(a, i, rng.uniform(0.08, 0.15), rng.uniform(0.1, 0.3))
+            a["pos"][i] = (1.6 * b + rng.uniform(-0.2, 0.2), 1.0 + 0.5 * k, rng.uniform(-0.2, 0.2))
+            a["quat"][i] = random_unit_quats(rng, 1)[0]
+            a["angVel"][i] = rng.uniform(-2, 2, 3)
+    return Scene(default_header(**hdr), add_ground_plane(a))

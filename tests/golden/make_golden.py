@@ -84,6 +84,8 @@ def main():
     cases["pgs_lock_stacks"] = (scenes.locked_stacks(solver=scenes.SOLVER_PGS), 80)
     cases["lock_primitives"] = (scenes.locked_primitives(seed=4), 100)
     cases["pgs_lock_primitives"] = (scenes.locked_primitives(seed=3, solver=scenes.SOLVER_PGS), 100)
+    # a10 (GJK family): capsules and spheres dropped onto static tilted / dynamic resting boxes -- capsule-box face, edge and corner contacts
+    cases["capsules_on_boxes"] = (scenes.capsules_on_boxes(seed=3), 150)
     only = sys.argv[1:]
     if only:
         cases = {k: v for k, v in cases.items() if any(k.startswith(o) for o in only)}

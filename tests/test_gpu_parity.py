@@ -165,9 +165,13 @@ def test_reset_via_set_states_reproduces_trajectory():
     assert np.array_equal(b.getStates(), ref)
 
 
-@pytest.mark.parametrize("name", ["spheres_capsules", "capsule_row", "spheres_boxes"])
+@pytest.mark.parametrize("name", ["spheres_capsules", "capsule_row", "spheres_boxes", "capsules_on_boxes", "capsules_on_boxes_4", "capsules_boxes_tumbling", "all_primitives"])
 def test_gpu_matches_oracle_primitives(oracle, name):
     sc = {"spheres_capsules": scenes.mixed_primitives(n=14, seed=3, kinds=("sphere", "capsule")),
+          "capsules_on_boxes": scenes.capsules_on_boxes(seed=3),                                   # a10: capsule-box through GJK (k_narrowphase_gjk)
+          "capsules_on_boxes_4": scenes.capsules_on_boxes(n_boxes=8, per_box=4, seed=4),
+          "capsules_boxes_tumbling": scenes.mixed_primitives(n=14, seed=5, kinds=("capsule", "box")),
+          "all_primitives": scenes.mixed_primitives(n=18, seed=3),
           "capsule_row": scenes.mixed_primitives(n=6, seed=5, kinds=("capsule",), spread=0.05),
           "spheres_boxes": scenes.mixed_primitives(n=24, seed=11, kinds=("sphere", "box", "box", "sphere"))}[name]
     gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
@@ -182,7 +186,7 @@ def test_gpu_matches_oracle_primitives(oracle, name):
         cpu.setStates(sg)
 
 
-@pytest.mark.parametrize("name", ["capsule_row", "spheres_capsules_14"])
+@pytest.mark.parametrize("name", ["capsule_row", "spheres_capsules_14", "capsules_on_boxes"])
 def test_gpu_teacher_forced_steps_match_reference(name):
     z, sc = util.load_golden(name)
     gpu = engine.Scene(sc)
@@ -495,14 +499,15 @@ def test_env_path_pair_capacity_overflow_is_reported():
 
 
 def test_unsupported_pair_type_is_reported_not_skipped(oracle):
-    """capsule-box needs the GJK/EPA family (not built yet): the step fails loudly once such a pair is in range."""
-    sc = scenes.mixed_primitives(n=6, seed=2, kinds=("capsule", "box"), spread=0.05)
+    """A capsule whose core segment lies inside a box needs the EPA penetration query (not built yet): the step fails loudly."""
+    sc = scenes.capsules_on_boxes(n_boxes=2, per_box=1, seed=1)
+    assert sc.actors["geomType"][4] == scenes.GEOM_CAPSULE and sc.actors["geomType"][2] == scenes.GEOM_BOX
+    sc.actors["pos"][4] = sc.actors["pos"][2]   # the capsule at the centre of the static box
     gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    cpu.step()
     with pytest.raises(engine.PhysxB200Error) as e:
-        for _ in range(120):
-            cpu.step()
-            gpu.step()
-    assert "capsule-box" in str(e.value) and cpu.unsupported_pairs > 0
+        gpu.step()
+    assert "EPA" in str(e.value) and cpu.unsupported_pairs > 0
 
 
 def test_cpp_host_mirror_snippet_hello_world():
