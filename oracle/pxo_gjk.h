@@ -312,6 +312,229 @@ static inline int pxo_gjk_penetration(const PxoConvex* a, const PxoConvex* b, v3
 #undef PXO_ASSIGN_WARM
 }
 
+
+/* ---------------- epaPenetration: GuEPA.cpp:70-623, GuEPAFacet.h:61-301 ----------------
+ * Expanding polytope over the Minkowski difference, started from the GJK simplex (warm-start indices).  Facets live in a pool of 64
+ * (Cm::InlineDeferredIDPool, CmIDPool.h:40-191), the open facets in a binary heap keyed by plane distance (CmPriorityQueue.h:77-118). */
+#define PXO_EPA_MAX_FACETS 64
+#define PXO_EPA_MAX_EDGES 32
+#define PXO_EPA_MAX_SUPPORT 64
+typedef struct { v3 n; float d; int8_t adjF[3], adjE[3], idx[3]; uint8_t obsolete, inHeap; } PxoFacet;
+typedef struct {
+  v3 aBuf[PXO_EPA_MAX_SUPPORT], bBuf[PXO_EPA_MAX_SUPPORT];
+  PxoFacet f[PXO_EPA_MAX_FACETS];
+  uint8_t heap[PXO_EPA_MAX_FACETS]; uint32_t heapSize;
+  uint8_t edgeF[PXO_EPA_MAX_EDGES], edgeI[PXO_EPA_MAX_EDGES]; uint32_t edgeSize; int edgeOverflow;
+  uint32_t curId, nFree, nDeferred; uint8_t freeIds[PXO_EPA_MAX_FACETS], deferred[PXO_EPA_MAX_FACETS];
+} PxoEpa;
+
+static inline void pxo_epa_heap_push(PxoEpa* e, uint8_t id) {
+  uint32_t newIndex, parentIndex = (e->heapSize - 1) >> 1;
+  for (newIndex = e->heapSize; newIndex > 0 && e->f[id].d < e->f[e->heap[parentIndex]].d; newIndex = parentIndex, parentIndex = (newIndex - 1) >> 1) e->heap[newIndex] = e->heap[parentIndex];
+  e->heap[newIndex] = id; e->heapSize++;
+}
+static inline uint8_t pxo_epa_heap_pop(PxoEpa* e) {
+  uint32_t i, child; const uint32_t tempHs = e->heapSize - 1;
+  e->heapSize = tempHs;
+  const uint8_t mn = e->heap[0], last = e->heap[tempHs];
+  for (i = 0; (child = (i << 1) + 1) < tempHs; i = child) {
+    const uint32_t rightChild = child + 1;
+    child += ((rightChild < tempHs) && (e->f[e->heap[rightChild]].d < e->f[e->heap[child]].d)) ? 1 : 0;
+    if (e->f[last].d < e->f[e->heap[child]].d) break;
+    e->heap[i] = e->heap[child];
+  }
+  e->heap[i] = last;
+  return mn;
+}
+static inline uint32_t pxo_epa_new_id(PxoEpa* e) { if (e->nFree) return e->freeIds[--e->nFree]; return e->curId++; }
+static inline void pxo_epa_free_id(PxoEpa* e, uint32_t id) { if (id == e->curId - 1) --e->curId; else e->freeIds[e->nFree++] = (uint8_t)id; }
+static inline void pxo_epa_process_deferred(PxoEpa* e) { for (uint32_t a = 0; a < e->nDeferred; ++a) pxo_epa_free_id(e, e->deferred[a]); e->nDeferred = 0; }
+static inline uint32_t pxo_epa_remaining_ids(const PxoEpa* e) { return PXO_EPA_MAX_FACETS - (e->curId - e->nFree); }
+
+/* Facet::isValid2 GuEPA.cpp:137-172 + EPA::addFacet :174-199 */
+static inline int pxo_epa_add_facet(PxoEpa* e, uint32_t i0, uint32_t i1, uint32_t i2, float upper) {
+  const uint32_t id = pxo_epa_new_id(e);
+  PxoFacet* f = &e->f[id];
+  f->obsolete = 0; f->inHeap = 0; f->idx[0] = (int8_t)i0; f->idx[1] = (int8_t)i1; f->idx[2] = (int8_t)i2;
+  f->adjF[0] = f->adjF[1] = f->adjF[2] = -1; f->adjE[0] = f->adjE[1] = f->adjE[2] = -1;
+  const v3 p0 = v3sub(e->aBuf[i0], e->bBuf[i0]), p1 = v3sub(e->aBuf[i1], e->bBuf[i1]), p2 = v3sub(e->aBuf[i2], e->bBuf[i2]);
+  const v3 v0 = v3sub(p1, p0), v1 = v3sub(p2, p0);
+  const v3 denormalizedNormal = v3cross(v0, v1);
+  float norValue = adot(denormalizedNormal, denormalizedNormal);
+  const int con = norValue > FLT_EPSILON;
+  norValue = con ? norValue : 1.0f;
+  const v3 planeNormal = v3scale(denormalizedNormal, 1.0f / sqrtf(norValue));
+  const float planeDist = adot(planeNormal, p0);
+  f->n = planeNormal; f->d = planeDist;
+  if (con && upper >= planeDist) { pxo_epa_heap_push(e, (uint8_t)id); f->inHeap = 1; }
+  return (int)id;
+}
+/* Facet::link GuEPAFacet.h:290-298 */
+static inline void pxo_epa_link(PxoEpa* e, int f0, uint32_t edge0, int f1, uint32_t edge1) {
+  e->f[f0].adjF[edge0] = (int8_t)f1; e->f[f0].adjE[edge0] = (int8_t)edge1; e->f[f1].adjF[edge1] = (int8_t)f0; e->f[f1].adjE[edge1] = (int8_t)edge0;
+}
+static inline float pxo_epa_plane_dist(const PxoEpa* e, const PxoFacet* f, v3 p) {
+  const v3 p0 = v3sub(e->aBuf[f->idx[0]], e->bBuf[f->idx[0]]);
+  return adot(f->n, v3sub(p, p0));
+}
+/* Facet::silhouette(index, w, ...) GuEPA.cpp:201-240 */
+static inline void pxo_epa_silhouette_edge(PxoEpa* e, int facet, uint32_t _index, v3 w) {
+  int stackF[PXO_EPA_MAX_FACETS]; uint32_t stackI[PXO_EPA_MAX_FACETS];
+  stackF[0] = facet; stackI[0] = _index;
+  int size = 1;
+  while (size--) {
+    PxoFacet* f = &e->f[stackF[size]]; const uint32_t index = stackI[size]; const int fid = stackF[size];
+    if (!f->obsolete) {
+      const float pointPlaneDist = pxo_epa_plane_dist(e, f, w);
+      if (0.f > pointPlaneDist) {
+        if (e->edgeSize < PXO_EPA_MAX_EDGES) { e->edgeF[e->edgeSize] = (uint8_t)fid; e->edgeI[e->edgeSize] = (uint8_t)index; e->edgeSize++; }
+        else { e->edgeOverflow = 1; return; }
+      } else {
+        f->obsolete = 1;
+        const uint32_t next = (index + 1) % 3, next2 = (next + 1) % 3;
+        stackF[size] = f->adjF[next2]; stackI[size] = (uint32_t)f->adjE[next2]; size++;
+        stackF[size] = f->adjF[next]; stackI[size] = (uint32_t)f->adjE[next]; size++;
+        if (!f->inHeap) e->deferred[e->nDeferred++] = (uint8_t)fid;
+      }
+    }
+  }
+}
+/* Facet::getClosestPoint GuEPAFacet.h:252-288 + calculateContactInformation GuEPA.cpp:306-337 */
+static inline void pxo_epa_contact_info(const PxoEpa* e, const PxoFacet* f, const PxoConvex* a, const PxoConvex* b, int takeCoreShape, PxoGjkOutput* out) {
+  const v3 pa0 = e->aBuf[f->idx[0]], pa1 = e->aBuf[f->idx[1]], pa2 = e->aBuf[f->idx[2]], pb0 = e->bBuf[f->idx[0]], pb1 = e->bBuf[f->idx[1]], pb2 = e->bBuf[f->idx[2]];
+  const v3 p0 = v3sub(pa0, pb0), p1 = v3sub(pa1, pb1), p2 = v3sub(pa2, pb2);
+  const v3 v0 = v3sub(p1, p0), v1 = v3sub(p2, p0);
+  const v3 closestP = v3scale(f->n, f->d);
+  const v3 v2 = v3sub(closestP, p0);
+  const float d00 = adot(v0, v0), d01 = adot(v0, v1), d11 = adot(v1, v1), d20 = adot(v2, v0), d21 = adot(v2, v1);
+  const float det = d00 * d11 - d01 * d01;
+  const float recip = det > FLT_EPSILON ? 1.0f / det : 0.f;
+  const float lambda1 = (d11 * d20 - d01 * d21) * recip, lambda2 = (d00 * d21 - d01 * d20) * recip;
+  const float u = 1.0f - (lambda1 + lambda2);
+  const v3 _pa = v3scaleadd(pa0, u, v3scaleadd(pa1, lambda1, v3scale(pa2, lambda2)));
+  const v3 _pb = v3scaleadd(pb0, u, v3scaleadd(pb1, lambda1, v3scale(pb2, lambda2)));
+  const float dist = fabsf(f->d);
+  const v3 planeNormal = v3neg(f->n);
+  if (takeCoreShape) { out->closestA = _pa; out->closestB = _pb; out->normal = planeNormal; out->penDep = -dist; }
+  else {
+    const float marginA = a->marginIsRadius ? a->margin : 0.f, marginB = b->marginIsRadius ? b->margin : 0.f;
+    const float sumMargin = marginA + marginB;
+    out->closestA = v3negscalesub(planeNormal, marginA, _pa); out->closestB = v3scaleadd(planeNormal, marginB, _pb); out->normal = planeNormal; out->penDep = -(dist + sumMargin);
+  }
+}
+static inline v3 pxo_cvx_support_noidx(const PxoConvex* c, v3 dir) { int i; return pxo_cvx_support(c, dir, &i); }
+/* EPA::expandTriangle :293-304 */
+static inline int pxo_epa_expand_triangle(PxoEpa* e, int* numVerts, float upper) {
+  *numVerts = 3;
+  const int f0 = pxo_epa_add_facet(e, 0, 1, 2, upper), f1 = pxo_epa_add_facet(e, 1, 0, 2, upper);
+  if (e->heapSize == 0) return 0;
+  pxo_epa_link(e, f0, 0, f1, 0); pxo_epa_link(e, f0, 1, f1, 2); pxo_epa_link(e, f0, 2, f1, 1);
+  return 1;
+}
+/* EPA::expandSegment :257-291 */
+static inline int pxo_epa_expand_segment(PxoEpa* e, const PxoConvex* a, const PxoConvex* b, int* numVerts, float upper) {
+  const v3 q0 = v3sub(e->aBuf[0], e->bBuf[0]), q1 = v3sub(e->aBuf[1], e->bBuf[1]);
+  const v3 v = v3sub(q1, q0), absV = v3abs(v);
+  v3 axis = V3(1, 0, 0);
+  if (absV.x > absV.y && absV.z > absV.y) axis = V3(0, 1, 0);
+  else if (absV.x > absV.z) axis = V3(0, 0, 1);
+  const v3 n = anormalize(v3cross(axis, v));
+  e->aBuf[2] = pxo_cvx_support_noidx(a, v3neg(n)); e->bBuf[2] = pxo_cvx_support_noidx(b, n);   /* doSupport :83-90 */
+  return pxo_epa_expand_triangle(e, numVerts, upper);
+}
+/* EPA::expandPoint :242-255 */
+static inline int pxo_epa_expand_point(PxoEpa* e, const PxoConvex* a, const PxoConvex* b, int* numVerts, float upper) {
+  const v3 x = V3(1, 0, 0);
+  const v3 q0 = v3sub(e->aBuf[0], e->bBuf[0]);
+  e->aBuf[1] = pxo_cvx_support_noidx(a, v3neg(x)); e->bBuf[1] = pxo_cvx_support_noidx(b, x);
+  const v3 q1 = v3sub(e->aBuf[1], e->bBuf[1]);
+  if (q0.x == q1.x && q0.y == q1.y && q0.z == q1.z) return 0;
+  return pxo_epa_expand_segment(e, a, b, numVerts, upper);
+}
+/* epaPenetration (index overload) :92-110 + EPA::PenetrationDepth :339-621 */
+static uint32_t pxo_epa_calls = 0;   /* coverage counter for the tests */
+static inline int pxo_epa_penetration(const PxoConvex* a, const PxoConvex* b, const uint8_t* aInd, const uint8_t* bInd, uint8_t size, int takeCoreShape, float toleranceLength, PxoGjkOutput* output) {
+  static PxoEpa epa_;   /* ~4 KB of scratch; the oracle is single-threaded */
+  PxoEpa* e = &epa_;
+  pxo_epa_calls++;
+  e->heapSize = 0; e->edgeSize = 0; e->edgeOverflow = 0; e->curId = 0; e->nFree = 0; e->nDeferred = 0;
+  for (int i = 0; i < 4; ++i) { e->aBuf[i] = V3(0, 0, 0); e->bBuf[i] = V3(0, 0, 0); }
+  for (uint32_t i = 0; i < size; ++i) { e->aBuf[i] = pxo_cvx_support_point(a, aInd[i]); e->bBuf[i] = pxo_cvx_support_point(b, bInd[i]); }
+  float upper_bound = FLT_MAX;
+  int numVertsLocal = 0;
+  switch (size) {
+    case 1: if (!pxo_epa_expand_point(e, a, b, &numVertsLocal, upper_bound)) return PXO_EPA_FAIL; break;
+    case 2: if (!pxo_epa_expand_segment(e, a, b, &numVertsLocal, upper_bound)) return PXO_EPA_FAIL; break;
+    case 3: if (!pxo_epa_expand_triangle(e, &numVertsLocal, upper_bound)) return PXO_EPA_FAIL; break;
+    case 4: {
+      const v3 p0 = v3sub(e->aBuf[0], e->bBuf[0]), p1 = v3sub(e->aBuf[1], e->bBuf[1]), p2 = v3sub(e->aBuf[2], e->bBuf[2]), p3 = v3sub(e->aBuf[3], e->bBuf[3]);
+      const v3 v1 = v3sub(p1, p0), v2 = v3sub(p2, p0);
+      const v3 planeNormal = anormalize(v3cross(v1, v2));
+      const float signDist = adot(planeNormal, v3sub(p3, p0));
+      if (signDist > 0.f) { const v3 ta = e->aBuf[2], tb = e->bBuf[2]; e->aBuf[2] = e->aBuf[1]; e->bBuf[2] = e->bBuf[1]; e->aBuf[1] = ta; e->bBuf[1] = tb; }
+      const int f0 = pxo_epa_add_facet(e, 0, 1, 2, upper_bound), f1 = pxo_epa_add_facet(e, 0, 3, 1, upper_bound), f2 = pxo_epa_add_facet(e, 0, 2, 3, upper_bound), f3 = pxo_epa_add_facet(e, 1, 3, 2, upper_bound);
+      if (e->heapSize == 0) return PXO_EPA_FAIL;
+      pxo_epa_link(e, f0, 0, f1, 2); pxo_epa_link(e, f0, 1, f3, 2); pxo_epa_link(e, f0, 2, f2, 0); pxo_epa_link(e, f1, 0, f2, 2); pxo_epa_link(e, f1, 1, f3, 0); pxo_epa_link(e, f2, 1, f3, 1);
+      numVertsLocal = 4;
+      break;
+    }
+    default: return PXO_EPA_FAIL;
+  }
+  const float minMargin = fminf_(a->minMargin, b->minMargin);
+  const float eps = minMargin * 0.1f;
+  int facetId = -1;
+  do {
+    pxo_epa_process_deferred(e);
+    facetId = pxo_epa_heap_pop(e);
+    PxoFacet* facet = &e->f[facetId];
+    facet->inHeap = 0;
+    if (!facet->obsolete) {
+      const v3 planeNormal = facet->n; const float planeDist = facet->d;
+      const v3 tempa = pxo_cvx_support_noidx(a, planeNormal), tempb = pxo_cvx_support_noidx(b, v3neg(planeNormal));
+      const v3 q = v3sub(tempa, tempb);
+      const float dist = adot(q, planeNormal);
+      if (eps >= fabsf(dist - planeDist)) {
+        pxo_epa_contact_info(e, facet, a, b, takeCoreShape, output);
+        if (takeCoreShape) {
+          const float toleranceEps = 1e-3f * toleranceLength;
+          const v3 dif = v3sub(output->closestA, output->closestB);
+          const float pen = fabsf(output->penDep) + toleranceEps;
+          const float sqDif = adot(dif, dif);
+          const float length = sqDif > 0.f ? sqrtf(sqDif) : 0.f;
+          if (length > pen) return PXO_EPA_DEGENERATE;
+        }
+        return PXO_EPA_CONTACT;
+      }
+      upper_bound = fminf_(upper_bound, dist);
+      e->aBuf[numVertsLocal] = tempa; e->bBuf[numVertsLocal] = tempb;
+      const uint32_t index = (uint32_t)numVertsLocal++;
+      e->edgeSize = 0; e->edgeOverflow = 0;
+      facet->obsolete = 1;   /* Facet::silhouette(w, ...) :242-250 */
+      for (uint32_t k = 0; k < 3; ++k) pxo_epa_silhouette_edge(e, facet->adjF[k], (uint32_t)facet->adjE[k], q);
+      if (!(e->edgeSize > 0 && !e->edgeOverflow)) { pxo_epa_contact_info(e, facet, a, b, takeCoreShape, output); return PXO_EPA_DEGENERATE; }
+      const uint32_t bufferSize = e->edgeSize;
+      if (bufferSize > pxo_epa_remaining_ids(e)) { pxo_epa_contact_info(e, facet, a, b, takeCoreShape, output); return PXO_EPA_DEGENERATE; }
+#define PXO_EDGE_SRC(k) ((uint32_t)e->f[e->edgeF[k]].idx[e->edgeI[k]])
+#define PXO_EDGE_TGT(k) ((uint32_t)e->f[e->edgeF[k]].idx[(e->edgeI[k] + 1) % 3])
+      const int firstFacet = pxo_epa_add_facet(e, PXO_EDGE_TGT(0), PXO_EDGE_SRC(0), index, upper_bound);
+      pxo_epa_link(e, firstFacet, 0, e->edgeF[0], e->edgeI[0]);
+      int lastFacet = firstFacet;
+      for (uint32_t i = 1; i < bufferSize; ++i) {
+        const int newFacet = pxo_epa_add_facet(e, PXO_EDGE_TGT(i), PXO_EDGE_SRC(i), index, upper_bound);
+        pxo_epa_link(e, newFacet, 0, e->edgeF[i], e->edgeI[i]);
+        pxo_epa_link(e, newFacet, 2, lastFacet, 1);
+        lastFacet = newFacet;
+      }
+#undef PXO_EDGE_SRC
+#undef PXO_EDGE_TGT
+      pxo_epa_link(e, firstFacet, 2, lastFacet, 1);
+    }
+    pxo_epa_free_id(e, (uint32_t)facetId);
+  } while (e->heapSize > 0 && upper_bound > e->f[e->heap[0]].d && numVertsLocal != PXO_EPA_MAX_SUPPORT);
+  pxo_epa_contact_info(e, &e->f[facetId], a, b, takeCoreShape, output);
+  return PXO_EPA_DEGENERATE;
+}
+
 /* ---------------- polygonal box: GuPCMShapeConvex.cpp:40-110 ---------------- */
 typedef struct { v3 n; float d; int minIndex; } PxoPoly;
 static const uint8_t pxo_box_poly_refs[24] = {0, 3, 2, 1, 1, 2, 6, 5, 5, 6, 7, 4, 4, 7, 3, 0, 3, 7, 6, 2, 4, 0, 1, 5};
@@ -549,7 +772,7 @@ static inline void pxo_manifold_to_contacts_radius(const PxoManifold* m, v3 norm
 }
 
 /* pcmContactCapsuleBox: GuPCMContactCapsuleBox.cpp:75-202 (shape0 = capsule, shape1 = box).
- * Returns 0 normally; 1 when the reference would run EPA (segment inside the box), which is not restated yet -- the caller counts the pair as unsupported. */
+ * Always returns 0 (no unsupported case left). */
 static inline int pxo_pcm_capsule_box(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, v3 boxExtents, float contactDist, float toleranceLength,
                                       PxoManifold* manifold, PxoContacts* out) {
   out->count = 0;
@@ -576,7 +799,13 @@ static inline int pxo_pcm_capsule_box(const xf* transf0, const xf* transf1, floa
     else {
       if (status == PXO_GJK_CONTACT) {
         mc[numContacts].a = amxftransforminv(&aToB, output.closestA); mc[numContacts].b = output.closestB; mc[numContacts].n = output.normal; mc[numContacts].pen = output.penDep; numContacts++;
-      } else return 1;   /* EPA_CONTACT: epaPenetration (GuEPA.cpp) not restated */
+      } else {   /* EPA_CONTACT: the core segment overlaps the box */
+        status = pxo_epa_penetration(&capsule, &box, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+        if (status == PXO_EPA_CONTACT) {
+          mc[numContacts].a = amxftransforminv(&aToB, output.closestA); mc[numContacts].b = output.closestB; mc[numContacts].n = output.normal; mc[numContacts].pen = output.penDep; numContacts++;
+        } else doOverlapTest = 1;
+        normal = output.normal;
+      }
       if (!(initialContacts == 0 || bLostContacts || doOverlapTest)) {
         const float replaceBreakingThreshold = minMargin * 0.1f;
         pxo_add_manifold_point2(manifold, aqrotinv(curRTrans.q, v3sub(output.closestA, curRTrans.p)), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);

@@ -47,7 +47,7 @@ struct ActorRec {
 static_assert(sizeof(ActorRec) == 128, "actor record layout");
 
 enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_NGJK, C_COUNT = 16 };
-enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8, E_EPA_PAIR = 16 };
+enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8 };
 
 struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };
 
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(128) k_narrowphase_gjk(const uint64_t* __restr
     Manifold man; manifold_load(man, rec); manifold_load_warm(man, rec);
     Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
     for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
-    if (gjk_pcm_capsule_box(&tm0, &tm1, d0.x, d0.y, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out)) atomicOr(&counters[C_ERROR], (uint32_t)E_EPA_PAIR);
+    gjk_pcm_capsule_box(&tm0, &tm1, d0.x, d0.y, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
     if (man.dirty) { manifold_store(man, rec); manifold_store_warm(man, rec); } else if (man.n > 0) manifold_store_pens(man, rec);
     if (flip && out.count) out.normal = -out.normal;
     cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
@@ -1073,7 +1073,6 @@ static int read_counters(PxbScene* s) {
   if (s->hErr & E_PAIR_OVERFLOW) return fail(PXB_ERR_CAPACITY, "broadphase pair capacity (maxPairs) exceeded");
   if (s->hErr & (E_COLOUR_OVERFLOW | E_PARTITION_OVERFLOW)) return fail(PXB_ERR_CAPACITY, "more than 32 dynamic colours / 96 partitions needed");
   if (s->hErr & E_UNSUPPORTED_PAIR) return fail(PXB_ERR_UNSUPPORTED, "a pair of an unsupported geometry type came into contact range");
-  if (s->hErr & E_EPA_PAIR) return fail(PXB_ERR_UNSUPPORTED, "a capsule's core segment penetrated a box: that case needs the EPA penetration query, which is not built yet");
   return PXB_OK;
 }
 

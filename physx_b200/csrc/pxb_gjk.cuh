@@ -1,7 +1,7 @@
 // pxb_gjk.cuh -- GJK penetration query and the PCM pair functions built on it, one thread per pair.
 // Follows the reference's CPU PCM path so that contacts match it bit for bit (same operation order as its SSE2 vector layer, FMA contraction off):
 //   simplex solver   physx/source/geomutils/src/gjk/GuGJKSimplex.h:50-448, GuGJKSimplex.cpp:38-213; barycentric coords common/GuBarycentricCoordinates.cpp:36-80
-//   gjkPenetration   gjk/GuGJKPenetration.h:89-311; supports gjk/GuVecCapsule.h:128-196, gjk/GuVecBox.h:56-68,148-205
+//   gjkPenetration   gjk/GuGJKPenetration.h:89-311; epaPenetration gjk/GuEPA.cpp:70-623, gjk/GuEPAFacet.h:61-301; supports gjk/GuVecCapsule.h:128-196, gjk/GuVecBox.h:56-68,148-205
 //   capsule-box      pcm/GuPCMContactCapsuleBox.cpp:42-202, pcm/GuPCMContactGenSphereCapsule.cpp:43-420, pcm/GuPCMContactGenUtil.cpp:105-260, pcm/GuPCMShapeConvex.cpp:40-110
 //   manifold helpers pcm/GuPersistentContactManifold.h:227-241, .cpp:179-187,289-360,783-807,1177-1310
 // (replaces convexConvexNphase_stage1/2Kernel + gjk.cuh / epa.cuh of the reference GPU path for these pair types)
@@ -12,6 +12,7 @@
 PXB_D v3 v3add(v3 a, v3 b) { return a + b; }
 PXB_D v3 v3sub(v3 a, v3 b) { return a - b; }
 PXB_D v3 v3neg(v3 a) { return -a; }
+PXB_D v3 v3abs(v3 a) { return vabs(a); }
 PXB_D v3 v3scale(v3 a, float s) { return a * s; }
 PXB_D v3 v3cross(v3 a, v3 b) { return cross(a, b); }
 PXB_D float v3dot(v3 a, v3 b) { return dot(a, b); }
@@ -325,6 +326,226 @@ PXB_D int gjk_penetration(const GjkConvex* a, const GjkConvex* b, v3 initialSear
 #undef GJK_ASSIGN_WARM
 }
 
+/* ---------------- epaPenetration: GuEPA.cpp:70-623, GuEPAFacet.h:61-301 ----------------
+ * Expanding polytope over the Minkowski difference, started from the GJK simplex (warm-start indices).  Facets live in a pool of 64
+ * (Cm::InlineDeferredIDPool, CmIDPool.h:40-191), the open facets in a binary heap keyed by plane distance (CmPriorityQueue.h:77-118). */
+#define EPA_MAX_FACETS 64
+#define EPA_MAX_EDGES 32
+#define EPA_MAX_SUPPORT 64
+typedef struct { v3 n; float d; int8_t adjF[3], adjE[3], idx[3]; uint8_t obsolete, inHeap; } EpaFacet;
+typedef struct {
+  v3 aBuf[EPA_MAX_SUPPORT], bBuf[EPA_MAX_SUPPORT];
+  EpaFacet f[EPA_MAX_FACETS];
+  uint8_t heap[EPA_MAX_FACETS]; uint32_t heapSize;
+  uint8_t edgeF[EPA_MAX_EDGES], edgeI[EPA_MAX_EDGES]; uint32_t edgeSize; int edgeOverflow;
+  uint32_t curId, nFree, nDeferred; uint8_t freeIds[EPA_MAX_FACETS], deferred[EPA_MAX_FACETS];
+} EpaScratch;
+
+PXB_D void gjk_epa_heap_push(EpaScratch* e, uint8_t id) {
+  uint32_t newIndex, parentIndex = (e->heapSize - 1) >> 1;
+  for (newIndex = e->heapSize; newIndex > 0 && e->f[id].d < e->f[e->heap[parentIndex]].d; newIndex = parentIndex, parentIndex = (newIndex - 1) >> 1) e->heap[newIndex] = e->heap[parentIndex];
+  e->heap[newIndex] = id; e->heapSize++;
+}
+PXB_D uint8_t gjk_epa_heap_pop(EpaScratch* e) {
+  uint32_t i, child; const uint32_t tempHs = e->heapSize - 1;
+  e->heapSize = tempHs;
+  const uint8_t mn = e->heap[0], last = e->heap[tempHs];
+  for (i = 0; (child = (i << 1) + 1) < tempHs; i = child) {
+    const uint32_t rightChild = child + 1;
+    child += ((rightChild < tempHs) && (e->f[e->heap[rightChild]].d < e->f[e->heap[child]].d)) ? 1 : 0;
+    if (e->f[last].d < e->f[e->heap[child]].d) break;
+    e->heap[i] = e->heap[child];
+  }
+  e->heap[i] = last;
+  return mn;
+}
+PXB_D uint32_t gjk_epa_new_id(EpaScratch* e) { if (e->nFree) return e->freeIds[--e->nFree]; return e->curId++; }
+PXB_D void gjk_epa_free_id(EpaScratch* e, uint32_t id) { if (id == e->curId - 1) --e->curId; else e->freeIds[e->nFree++] = (uint8_t)id; }
+PXB_D void gjk_epa_process_deferred(EpaScratch* e) { for (uint32_t a = 0; a < e->nDeferred; ++a) gjk_epa_free_id(e, e->deferred[a]); e->nDeferred = 0; }
+PXB_D uint32_t gjk_epa_remaining_ids(const EpaScratch* e) { return EPA_MAX_FACETS - (e->curId - e->nFree); }
+
+/* Facet::isValid2 GuEPA.cpp:137-172 + EPA::addFacet :174-199 */
+PXB_D int gjk_epa_add_facet(EpaScratch* e, uint32_t i0, uint32_t i1, uint32_t i2, float upper) {
+  const uint32_t id = gjk_epa_new_id(e);
+  EpaFacet* f = &e->f[id];
+  f->obsolete = 0; f->inHeap = 0; f->idx[0] = (int8_t)i0; f->idx[1] = (int8_t)i1; f->idx[2] = (int8_t)i2;
+  f->adjF[0] = f->adjF[1] = f->adjF[2] = -1; f->adjE[0] = f->adjE[1] = f->adjE[2] = -1;
+  const v3 p0 = v3sub(e->aBuf[i0], e->bBuf[i0]), p1 = v3sub(e->aBuf[i1], e->bBuf[i1]), p2 = v3sub(e->aBuf[i2], e->bBuf[i2]);
+  const v3 v0 = v3sub(p1, p0), v1 = v3sub(p2, p0);
+  const v3 denormalizedNormal = v3cross(v0, v1);
+  float norValue = adot(denormalizedNormal, denormalizedNormal);
+  const int con = norValue > FLT_EPSILON;
+  norValue = con ? norValue : 1.0f;
+  const v3 planeNormal = v3scale(denormalizedNormal, 1.0f / sqrtf(norValue));
+  const float planeDist = adot(planeNormal, p0);
+  f->n = planeNormal; f->d = planeDist;
+  if (con && upper >= planeDist) { gjk_epa_heap_push(e, (uint8_t)id); f->inHeap = 1; }
+  return (int)id;
+}
+/* Facet::link GuEPAFacet.h:290-298 */
+PXB_D void gjk_epa_link(EpaScratch* e, int f0, uint32_t edge0, int f1, uint32_t edge1) {
+  e->f[f0].adjF[edge0] = (int8_t)f1; e->f[f0].adjE[edge0] = (int8_t)edge1; e->f[f1].adjF[edge1] = (int8_t)f0; e->f[f1].adjE[edge1] = (int8_t)edge0;
+}
+PXB_D float gjk_epa_plane_dist(const EpaScratch* e, const EpaFacet* f, v3 p) {
+  const v3 p0 = v3sub(e->aBuf[f->idx[0]], e->bBuf[f->idx[0]]);
+  return adot(f->n, v3sub(p, p0));
+}
+/* Facet::silhouette(index, w, ...) GuEPA.cpp:201-240 */
+PXB_D void gjk_epa_silhouette_edge(EpaScratch* e, int facet, uint32_t _index, v3 w) {
+  int stackF[EPA_MAX_FACETS]; uint32_t stackI[EPA_MAX_FACETS];
+  stackF[0] = facet; stackI[0] = _index;
+  int size = 1;
+  while (size--) {
+    EpaFacet* f = &e->f[stackF[size]]; const uint32_t index = stackI[size]; const int fid = stackF[size];
+    if (!f->obsolete) {
+      const float pointPlaneDist = gjk_epa_plane_dist(e, f, w);
+      if (0.f > pointPlaneDist) {
+        if (e->edgeSize < EPA_MAX_EDGES) { e->edgeF[e->edgeSize] = (uint8_t)fid; e->edgeI[e->edgeSize] = (uint8_t)index; e->edgeSize++; }
+        else { e->edgeOverflow = 1; return; }
+      } else {
+        f->obsolete = 1;
+        const uint32_t next = (index + 1) % 3, next2 = (next + 1) % 3;
+        stackF[size] = f->adjF[next2]; stackI[size] = (uint32_t)f->adjE[next2]; size++;
+        stackF[size] = f->adjF[next]; stackI[size] = (uint32_t)f->adjE[next]; size++;
+        if (!f->inHeap) e->deferred[e->nDeferred++] = (uint8_t)fid;
+      }
+    }
+  }
+}
+/* Facet::getClosestPoint GuEPAFacet.h:252-288 + calculateContactInformation GuEPA.cpp:306-337 */
+PXB_D void gjk_epa_contact_info(const EpaScratch* e, const EpaFacet* f, const GjkConvex* a, const GjkConvex* b, int takeCoreShape, GjkOutput* out) {
+  const v3 pa0 = e->aBuf[f->idx[0]], pa1 = e->aBuf[f->idx[1]], pa2 = e->aBuf[f->idx[2]], pb0 = e->bBuf[f->idx[0]], pb1 = e->bBuf[f->idx[1]], pb2 = e->bBuf[f->idx[2]];
+  const v3 p0 = v3sub(pa0, pb0), p1 = v3sub(pa1, pb1), p2 = v3sub(pa2, pb2);
+  const v3 v0 = v3sub(p1, p0), v1 = v3sub(p2, p0);
+  const v3 closestP = v3scale(f->n, f->d);
+  const v3 v2 = v3sub(closestP, p0);
+  const float d00 = adot(v0, v0), d01 = adot(v0, v1), d11 = adot(v1, v1), d20 = adot(v2, v0), d21 = adot(v2, v1);
+  const float det = d00 * d11 - d01 * d01;
+  const float recip = det > FLT_EPSILON ? 1.0f / det : 0.f;
+  const float lambda1 = (d11 * d20 - d01 * d21) * recip, lambda2 = (d00 * d21 - d01 * d20) * recip;
+  const float u = 1.0f - (lambda1 + lambda2);
+  const v3 _pa = v3scaleadd(pa0, u, v3scaleadd(pa1, lambda1, v3scale(pa2, lambda2)));
+  const v3 _pb = v3scaleadd(pb0, u, v3scaleadd(pb1, lambda1, v3scale(pb2, lambda2)));
+  const float dist = fabsf(f->d);
+  const v3 planeNormal = v3neg(f->n);
+  if (takeCoreShape) { out->closestA = _pa; out->closestB = _pb; out->normal = planeNormal; out->penDep = -dist; }
+  else {
+    const float marginA = a->marginIsRadius ? a->margin : 0.f, marginB = b->marginIsRadius ? b->margin : 0.f;
+    const float sumMargin = marginA + marginB;
+    out->closestA = v3negscalesub(planeNormal, marginA, _pa); out->closestB = v3scaleadd(planeNormal, marginB, _pb); out->normal = planeNormal; out->penDep = -(dist + sumMargin);
+  }
+}
+PXB_D v3 gjk_cvx_support_noidx(const GjkConvex* c, v3 dir) { int i; return gjk_cvx_support(c, dir, &i); }
+/* EPA::expandTriangle :293-304 */
+PXB_D int gjk_epa_expand_triangle(EpaScratch* e, int* numVerts, float upper) {
+  *numVerts = 3;
+  const int f0 = gjk_epa_add_facet(e, 0, 1, 2, upper), f1 = gjk_epa_add_facet(e, 1, 0, 2, upper);
+  if (e->heapSize == 0) return 0;
+  gjk_epa_link(e, f0, 0, f1, 0); gjk_epa_link(e, f0, 1, f1, 2); gjk_epa_link(e, f0, 2, f1, 1);
+  return 1;
+}
+/* EPA::expandSegment :257-291 */
+PXB_D int gjk_epa_expand_segment(EpaScratch* e, const GjkConvex* a, const GjkConvex* b, int* numVerts, float upper) {
+  const v3 q0 = v3sub(e->aBuf[0], e->bBuf[0]), q1 = v3sub(e->aBuf[1], e->bBuf[1]);
+  const v3 v = v3sub(q1, q0), absV = v3abs(v);
+  v3 axis = V3(1, 0, 0);
+  if (absV.x > absV.y && absV.z > absV.y) axis = V3(0, 1, 0);
+  else if (absV.x > absV.z) axis = V3(0, 0, 1);
+  const v3 n = anormalize(v3cross(axis, v));
+  e->aBuf[2] = gjk_cvx_support_noidx(a, v3neg(n)); e->bBuf[2] = gjk_cvx_support_noidx(b, n);   /* doSupport :83-90 */
+  return gjk_epa_expand_triangle(e, numVerts, upper);
+}
+/* EPA::expandPoint :242-255 */
+PXB_D int gjk_epa_expand_point(EpaScratch* e, const GjkConvex* a, const GjkConvex* b, int* numVerts, float upper) {
+  const v3 x = V3(1, 0, 0);
+  const v3 q0 = v3sub(e->aBuf[0], e->bBuf[0]);
+  e->aBuf[1] = gjk_cvx_support_noidx(a, v3neg(x)); e->bBuf[1] = gjk_cvx_support_noidx(b, x);
+  const v3 q1 = v3sub(e->aBuf[1], e->bBuf[1]);
+  if (q0.x == q1.x && q0.y == q1.y && q0.z == q1.z) return 0;
+  return gjk_epa_expand_segment(e, a, b, numVerts, upper);
+}
+/* epaPenetration (index overload) :92-110 + EPA::PenetrationDepth :339-621 */
+PXB_D int gjk_epa_penetration(const GjkConvex* a, const GjkConvex* b, const uint8_t* aInd, const uint8_t* bInd, uint8_t size, int takeCoreShape, float toleranceLength, GjkOutput* output) {
+  EpaScratch epa_;   // ~4 KB of per-thread local memory, touched only by the (rare) pairs that reach EPA
+  EpaScratch* e = &epa_;
+  e->heapSize = 0; e->edgeSize = 0; e->edgeOverflow = 0; e->curId = 0; e->nFree = 0; e->nDeferred = 0;
+  for (int i = 0; i < 4; ++i) { e->aBuf[i] = V3(0, 0, 0); e->bBuf[i] = V3(0, 0, 0); }
+  for (uint32_t i = 0; i < size; ++i) { e->aBuf[i] = gjk_cvx_support_point(a, aInd[i]); e->bBuf[i] = gjk_cvx_support_point(b, bInd[i]); }
+  float upper_bound = FLT_MAX;
+  int numVertsLocal = 0;
+  switch (size) {
+    case 1: if (!gjk_epa_expand_point(e, a, b, &numVertsLocal, upper_bound)) return EPA_FAIL; break;
+    case 2: if (!gjk_epa_expand_segment(e, a, b, &numVertsLocal, upper_bound)) return EPA_FAIL; break;
+    case 3: if (!gjk_epa_expand_triangle(e, &numVertsLocal, upper_bound)) return EPA_FAIL; break;
+    case 4: {
+      const v3 p0 = v3sub(e->aBuf[0], e->bBuf[0]), p1 = v3sub(e->aBuf[1], e->bBuf[1]), p2 = v3sub(e->aBuf[2], e->bBuf[2]), p3 = v3sub(e->aBuf[3], e->bBuf[3]);
+      const v3 v1 = v3sub(p1, p0), v2 = v3sub(p2, p0);
+      const v3 planeNormal = anormalize(v3cross(v1, v2));
+      const float signDist = adot(planeNormal, v3sub(p3, p0));
+      if (signDist > 0.f) { const v3 ta = e->aBuf[2], tb = e->bBuf[2]; e->aBuf[2] = e->aBuf[1]; e->bBuf[2] = e->bBuf[1]; e->aBuf[1] = ta; e->bBuf[1] = tb; }
+      const int f0 = gjk_epa_add_facet(e, 0, 1, 2, upper_bound), f1 = gjk_epa_add_facet(e, 0, 3, 1, upper_bound), f2 = gjk_epa_add_facet(e, 0, 2, 3, upper_bound), f3 = gjk_epa_add_facet(e, 1, 3, 2, upper_bound);
+      if (e->heapSize == 0) return EPA_FAIL;
+      gjk_epa_link(e, f0, 0, f1, 2); gjk_epa_link(e, f0, 1, f3, 2); gjk_epa_link(e, f0, 2, f2, 0); gjk_epa_link(e, f1, 0, f2, 2); gjk_epa_link(e, f1, 1, f3, 0); gjk_epa_link(e, f2, 1, f3, 1);
+      numVertsLocal = 4;
+      break;
+    }
+    default: return EPA_FAIL;
+  }
+  const float minMargin = fmin_(a->minMargin, b->minMargin);
+  const float eps = minMargin * 0.1f;
+  int facetId = -1;
+  do {
+    gjk_epa_process_deferred(e);
+    facetId = gjk_epa_heap_pop(e);
+    EpaFacet* facet = &e->f[facetId];
+    facet->inHeap = 0;
+    if (!facet->obsolete) {
+      const v3 planeNormal = facet->n; const float planeDist = facet->d;
+      const v3 tempa = gjk_cvx_support_noidx(a, planeNormal), tempb = gjk_cvx_support_noidx(b, v3neg(planeNormal));
+      const v3 q = v3sub(tempa, tempb);
+      const float dist = adot(q, planeNormal);
+      if (eps >= fabsf(dist - planeDist)) {
+        gjk_epa_contact_info(e, facet, a, b, takeCoreShape, output);
+        if (takeCoreShape) {
+          const float toleranceEps = 1e-3f * toleranceLength;
+          const v3 dif = v3sub(output->closestA, output->closestB);
+          const float pen = fabsf(output->penDep) + toleranceEps;
+          const float sqDif = adot(dif, dif);
+          const float length = sqDif > 0.f ? sqrtf(sqDif) : 0.f;
+          if (length > pen) return EPA_DEGENERATE;
+        }
+        return EPA_CONTACT;
+      }
+      upper_bound = fmin_(upper_bound, dist);
+      e->aBuf[numVertsLocal] = tempa; e->bBuf[numVertsLocal] = tempb;
+      const uint32_t index = (uint32_t)numVertsLocal++;
+      e->edgeSize = 0; e->edgeOverflow = 0;
+      facet->obsolete = 1;   /* Facet::silhouette(w, ...) :242-250 */
+      for (uint32_t k = 0; k < 3; ++k) gjk_epa_silhouette_edge(e, facet->adjF[k], (uint32_t)facet->adjE[k], q);
+      if (!(e->edgeSize > 0 && !e->edgeOverflow)) { gjk_epa_contact_info(e, facet, a, b, takeCoreShape, output); return EPA_DEGENERATE; }
+      const uint32_t bufferSize = e->edgeSize;
+      if (bufferSize > gjk_epa_remaining_ids(e)) { gjk_epa_contact_info(e, facet, a, b, takeCoreShape, output); return EPA_DEGENERATE; }
+#define EPA_EDGE_SRC(k) ((uint32_t)e->f[e->edgeF[k]].idx[e->edgeI[k]])
+#define EPA_EDGE_TGT(k) ((uint32_t)e->f[e->edgeF[k]].idx[(e->edgeI[k] + 1) % 3])
+      const int firstFacet = gjk_epa_add_facet(e, EPA_EDGE_TGT(0), EPA_EDGE_SRC(0), index, upper_bound);
+      gjk_epa_link(e, firstFacet, 0, e->edgeF[0], e->edgeI[0]);
+      int lastFacet = firstFacet;
+      for (uint32_t i = 1; i < bufferSize; ++i) {
+        const int newFacet = gjk_epa_add_facet(e, EPA_EDGE_TGT(i), EPA_EDGE_SRC(i), index, upper_bound);
+        gjk_epa_link(e, newFacet, 0, e->edgeF[i], e->edgeI[i]);
+        gjk_epa_link(e, newFacet, 2, lastFacet, 1);
+        lastFacet = newFacet;
+      }
+#undef EPA_EDGE_SRC
+#undef EPA_EDGE_TGT
+      gjk_epa_link(e, firstFacet, 2, lastFacet, 1);
+    }
+    gjk_epa_free_id(e, (uint32_t)facetId);
+  } while (e->heapSize > 0 && upper_bound > e->f[e->heap[0]].d && numVertsLocal != EPA_MAX_SUPPORT);
+  gjk_epa_contact_info(e, &e->f[facetId], a, b, takeCoreShape, output);
+  return EPA_DEGENERATE;
+}
+
 /* ---------------- polygonal box: GuPCMShapeConvex.cpp:40-110 ---------------- */
 typedef struct { v3 n; float d; int minIndex; } Poly;
 __device__ const uint8_t gjk_box_poly_refs[24] = {0, 3, 2, 1, 1, 2, 6, 5, 5, 6, 7, 4, 4, 7, 3, 0, 3, 7, 6, 2, 4, 0, 1, 5};
@@ -589,7 +810,13 @@ PXB_D int gjk_pcm_capsule_box(const xf* transf0, const xf* transf1, float capsul
     else {
       if (status == GJK_CONTACT) {
         mc[numContacts].a = amxftransforminv(&aToB, output.closestA); mc[numContacts].b = output.closestB; mc[numContacts].n = output.normal; mc[numContacts].pen = output.penDep; numContacts++;
-      } else return 1;   /* EPA_CONTACT: epaPenetration (GuEPA.cpp) not restated */
+      } else {   /* EPA_CONTACT: the core segment overlaps the box */
+        status = gjk_epa_penetration(&capsule, &box, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+        if (status == EPA_CONTACT) {
+          mc[numContacts].a = amxftransforminv(&aToB, output.closestA); mc[numContacts].b = output.closestB; mc[numContacts].n = output.normal; mc[numContacts].pen = output.penDep; numContacts++;
+        } else doOverlapTest = 1;
+        normal = output.normal;
+      }
       if (!(initialContacts == 0 || bLostContacts || doOverlapTest)) {
         const float replaceBreakingThreshold = minMargin * 0.1f;
         add_manifold_point2(*manifold, aqrotinv(curRTrans.q, v3sub(output.closestA, curRTrans.p)), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);

@@ -438,3 +438,15 @@ def capsules_on_boxes(n_boxes=6, per_box=3, seed=9, **hdr):
             a["quat"][i] = random_unit_quats(rng, 1)[0]
             a["angVel"][i] = rng.uniform(-2, 2, 3)
     return Scene(default_header(**hdr), add_ground_plane(a))
+
+
+def capsules_into_boxes(seed=2, speed=14.0, **hdr):
+    """capsules_on_boxes with the capsules fired downwards at `speed` m/s and a few spawned overlapping their box: the core segment ends up
+    inside the box, which sends pcmContactCapsuleBox through the EPA penetration query."""
+    sc = capsules_on_boxes(seed=seed, **hdr)
+    cap = np.nonzero(sc.actors["geomType"] == GEOM_CAPSULE)[0]
+    sc.actors["linVel"][cap, 1] = -np.float32(speed)
+    for j, i in enumerate(cap[::4]):
+        b = 1 + (i - 1 - 6) // 3          # the box under this capsule (capsules_on_boxes layout: 6 boxes, 3 droppers per box)
+        sc.actors["pos"][i] = sc.actors["pos"][b] + np.array([0.05 * j, 0.1, -0.03 * j], dtype=np.float32)
+    return sc

@@ -86,6 +86,7 @@ def main():
     cases["pgs_lock_primitives"] = (scenes.locked_primitives(seed=3, solver=scenes.SOLVER_PGS), 100)
     # a10 (GJK family): capsules and spheres dropped onto static tilted / dynamic resting boxes -- capsule-box face, edge and corner contacts
     cases["capsules_on_boxes"] = (scenes.capsules_on_boxes(seed=3), 150)
+    cases["capsules_into_boxes"] = (scenes.capsules_into_boxes(seed=3), 60)   # deep penetration: the EPA query
     only = sys.argv[1:]
     if only:
         cases = {k: v for k, v in cases.items() if any(k.startswith(o) for o in only)}

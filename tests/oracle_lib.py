@@ -32,6 +32,7 @@ def lib():
         for f in ("pxo_scene_get_states", "pxo_scene_set_states", "pxo_scene_get_bounds", "pxo_scene_set_bounds",
                   "pxo_scene_get_pairs", "pxo_scene_get_created", "pxo_scene_get_deleted", "pxo_scene_get_contacts"):
             getattr(L, f).argtypes = [vp, vp]
+        L.pxo_debug_epa_calls.restype = u32
         L.pxo_scene_get_sleep.argtypes = [vp, vp, vp]
         L.pxo_scene_compute_bounds.argtypes = [vp]
         L.pxo_scene_broadphase.argtypes = [vp]
@@ -41,6 +42,11 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def epa_calls():
+    """number of EPA penetration queries run so far in this process (coverage check for the a10 tests)"""
+    return int(lib().pxo_debug_epa_calls())
 
 
 class OracleScene:

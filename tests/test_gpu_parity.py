@@ -165,13 +165,14 @@ def test_reset_via_set_states_reproduces_trajectory():
     assert np.array_equal(b.getStates(), ref)
 
 
-@pytest.mark.parametrize("name", ["spheres_capsules", "capsule_row", "spheres_boxes", "capsules_on_boxes", "capsules_on_boxes_4", "capsules_boxes_tumbling", "all_primitives"])
+@pytest.mark.parametrize("name", ["spheres_capsules", "capsule_row", "spheres_boxes", "capsules_on_boxes", "capsules_on_boxes_4", "capsules_boxes_tumbling", "all_primitives", "capsules_into_boxes"])
 def test_gpu_matches_oracle_primitives(oracle, name):
     sc = {"spheres_capsules": scenes.mixed_primitives(n=14, seed=3, kinds=("sphere", "capsule")),
           "capsules_on_boxes": scenes.capsules_on_boxes(seed=3),                                   # a10: capsule-box through GJK (k_narrowphase_gjk)
           "capsules_on_boxes_4": scenes.capsules_on_boxes(n_boxes=8, per_box=4, seed=4),
           "capsules_boxes_tumbling": scenes.mixed_primitives(n=14, seed=5, kinds=("capsule", "box")),
           "all_primitives": scenes.mixed_primitives(n=18, seed=3),
+          "capsules_into_boxes": scenes.capsules_into_boxes(seed=2),                              # deep penetration: EPA on the device
           "capsule_row": scenes.mixed_primitives(n=6, seed=5, kinds=("capsule",), spread=0.05),
           "spheres_boxes": scenes.mixed_primitives(n=24, seed=11, kinds=("sphere", "box", "box", "sphere"))}[name]
     gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
@@ -498,16 +499,12 @@ def test_env_path_pair_capacity_overflow_is_reported():
     assert "capacity" in str(e.value)
 
 
-def test_unsupported_pair_type_is_reported_not_skipped(oracle):
-    """A capsule whose core segment lies inside a box needs the EPA penetration query (not built yet): the step fails loudly."""
+def test_unsupported_geometry_is_rejected_not_skipped():
+    """Convex hulls (the rest of SURVEY 8a row a10) are not built yet: a scene that contains one is refused when its actors are added."""
     sc = scenes.capsules_on_boxes(n_boxes=2, per_box=1, seed=1)
-    assert sc.actors["geomType"][4] == scenes.GEOM_CAPSULE and sc.actors["geomType"][2] == scenes.GEOM_BOX
-    sc.actors["pos"][4] = sc.actors["pos"][2]   # the capsule at the centre of the static box
-    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
-    cpu.step()
-    with pytest.raises(engine.PhysxB200Error) as e:
-        gpu.step()
-    assert "EPA" in str(e.value) and cpu.unsupported_pairs > 0
+    sc.actors["geomType"][4] = scenes.GEOM_CONVEX
+    with pytest.raises(engine.PhysxB200Error):
+        engine.Scene(sc)
 
 
 def test_cpp_host_mirror_snippet_hello_world():
