@@ -22,6 +22,8 @@ typedef struct {
   v3 ext;                   /* box half extents */
   float margin, minMargin;  /* ConvexV::margin / minMargin */
   int marginIsRadius;
+  int relative;             /* RelativeConvex<T> (GuGJKType.h:110-150): the shape lives in A's frame, supports are returned in B's */
+  mxf aToB; m33 aToBT;      /* mAToB and the precomputed transpose of its rotation */
 } PxoConvex;
 
 typedef struct { v3 normal, closestA, closestB, searchDir; float penDep; } PxoGjkOutput;
@@ -40,8 +42,16 @@ static inline PxoConvex pxo_cvx_box(v3 origin, v3 ext) {
   c.type = PXO_CVX_BOX; c.center = origin; c.ext = ext; c.margin = mn * 0.15f; c.minMargin = mn * 0.05f; c.marginIsRadius = 0;
   return c;
 }
-/* LocalConvex<T>::support(dir, index) = T::supportLocal(dir, index) */
+static inline void pxo_cvx_make_relative(PxoConvex* c, const mxf* aToB) { c->relative = 1; c->aToB = *aToB; c->aToBT = m33transpose(&aToB->r); }
+/* LocalConvex<T>::support(dir, index) = T::supportLocal(dir, index); RelativeConvex<T>::support = T::supportRelative (GuVecBox.h:186-204) */
+static inline v3 pxo_cvx_support_local(const PxoConvex* c, v3 dir, int* index);
 static inline v3 pxo_cvx_support(const PxoConvex* c, v3 dir, int* index) {
+  if (!c->relative) return pxo_cvx_support_local(c, dir, index);
+  const v3 _dir = m33mul(&c->aToBT, dir);
+  const v3 p = pxo_cvx_support_local(c, _dir, index);
+  return amxftransform(&c->aToB, p);
+}
+static inline v3 pxo_cvx_support_local(const PxoConvex* c, v3 dir, int* index) {
   if (c->type == PXO_CVX_CAPSULE) {
     const float d0 = adot(c->p0, dir), d1 = adot(c->p1, dir);
     const int comp = d0 > d1;
@@ -52,9 +62,13 @@ static inline v3 pxo_cvx_support(const PxoConvex* c, v3 dir, int* index) {
   *index = bx | (by << 1) | (bz << 2);
   return V3(bx ? c->ext.x : -c->ext.x, by ? c->ext.y : -c->ext.y, bz ? c->ext.z : -c->ext.z);
 }
-static inline v3 pxo_cvx_support_point(const PxoConvex* c, int index) {
+static inline v3 pxo_cvx_support_point_local(const PxoConvex* c, int index) {
   if (c->type == PXO_CVX_CAPSULE) return index == 1 ? c->p0 : c->p1;   /* (&p0)[1-index] */
   return V3((index & 1) ? c->ext.x : -c->ext.x, (index & 2) ? c->ext.y : -c->ext.y, (index & 4) ? c->ext.z : -c->ext.z);
+}
+static inline v3 pxo_cvx_support_point(const PxoConvex* c, int index) {
+  const v3 p = pxo_cvx_support_point_local(c, index);
+  return c->relative ? amxftransform(&c->aToB, p) : p;
 }
 
 /* ---------------- simplex solver ---------------- */
@@ -533,6 +547,94 @@ static inline int pxo_epa_penetration(const PxoConvex* a, const PxoConvex* b, co
   } while (e->heapSize > 0 && upper_bound > e->f[e->heap[0]].d && numVertsLocal != PXO_EPA_MAX_SUPPORT);
   pxo_epa_contact_info(e, &e->f[facetId], a, b, takeCoreShape, output);
   return PXO_EPA_DEGENERATE;
+}
+
+
+/* ---------------- box-box: the GJK / EPA single-point fallback of pcmContactBoxBox ----------------
+ * GuPersistentContactManifold.cpp:43-60 */
+static inline float pxo_dist_point_segment_sq_local(v3 a, v3 b, v3 p) {
+  const v3 ap = v3sub(p, a), ab = v3sub(b, a);
+  const float nom = adot(ap, ab), denom = adot(ab, ab);
+  const float tValue = fmaxf_(fminf_(nom / denom, 1.f), 0.f);
+  const float t = denom == 0.f ? 0.f : tValue;
+  const v3 v = v3negscalesub(ab, t, ap);
+  return adot(v, v);
+}
+/* GuPersistentContactManifold.cpp:61-170 */
+static inline float pxo_dist_point_triangle_sq_local(v3 p, v3 a, v3 b, v3 c) {
+  const v3 ab = v3sub(b, a), ac = v3sub(c, a), bc = v3sub(c, b), ap = v3sub(p, a), bp = v3sub(p, b), cp = v3sub(p, c);
+  const float d1 = adot(ab, ap), d2 = adot(ac, ap), d3 = adot(ab, bp), d4 = adot(ac, bp), d5 = adot(ab, cp), d6 = adot(ac, cp);
+  const float unom = d4 - d3, udenom = d5 - d6;
+  if (0.f > d1 && 0.f > d2) { const v3 vv = v3sub(p, a); return adot(vv, vv); }
+  if (d3 >= 0.f && d3 >= d4) { const v3 vv = v3sub(p, b); return adot(vv, vv); }
+  if (d6 >= 0.f && d6 >= d5) { const v3 vv = v3sub(p, c); return adot(vv, vv); }
+  const float vc = d1 * d4 - d3 * d2;
+  if (0.f > vc && d1 >= 0.f && 0.f > d3) { const float sScale = d1 / (d1 - d3); const v3 vv = v3sub(p, v3scaleadd(ab, sScale, a)); return adot(vv, vv); }
+  const float va = d3 * d6 - d5 * d4;
+  if (0.f > va && d4 >= d3 && d5 >= d6) { const float uScale = unom / (unom + udenom); const v3 vv = v3sub(p, v3scaleadd(bc, uScale, b)); return adot(vv, vv); }
+  const float vb = d5 * d2 - d1 * d6;
+  if (0.f > vb && d2 >= 0.f && 0.f > d6) { const float tScale = d2 / (d2 - d6); const v3 vv = v3sub(p, v3scaleadd(ac, tScale, a)); return adot(vv, vv); }
+  const v3 n = v3cross(ab, ac);
+  const float nn = adot(n, n);
+  const float t = nn > 0.f ? adot(n, v3sub(a, p)) / nn : 0.f;
+  const v3 closest6 = v3add(p, v3scale(n, t));
+  const v3 vv = v3sub(p, closest6);
+  return adot(vv, vv);
+}
+/* PersistentContactManifold::addManifoldPoint (.cpp:1246-1266) -> replaceManifoldPoint (:552-576) / reduceContactsForPCM (:603-737) */
+static inline void pxo_add_manifold_point(PxoManifold* m, v3 la, v3 lb, v3 n, float pen, float replaceBreakingThreshold) {
+  const float shortest = replaceBreakingThreshold * replaceBreakingThreshold;
+  for (int i = 0; i < m->n; ++i) {
+    const v3 dB = v3sub(m->pts[i].b, lb), dA = v3sub(m->pts[i].a, la);
+    if (shortest > fminf_(adot(dB, dB), adot(dA, dA))) { m->pts[i].a = la; m->pts[i].b = lb; m->pts[i].n = n; m->pts[i].pen = pen; return; }
+  }
+  if (m->n < 4) { m->pts[m->n].a = la; m->pts[m->n].b = lb; m->pts[m->n].n = n; m->pts[m->n].pen = pen; m->n++; return; }
+  int chosen[5] = {0, 0, 0, 0, 0};
+  PxoMPoint temp[5];
+  for (int i = 0; i < 4; ++i) temp[i] = m->pts[i];
+  temp[4].a = la; temp[4].b = lb; temp[4].n = n; temp[4].pen = pen;
+  float maxDist = pen; int index = 4;
+  for (int i = 0; i < 4; ++i) if (maxDist > temp[i].pen) { maxDist = temp[i].pen; index = i; }
+  chosen[index] = 1; m->pts[0] = temp[index];
+  v3 dir = v3sub(temp[0].b, m->pts[0].b);
+  maxDist = adot(dir, dir); index = 0;
+  for (int i = 1; i < 5; ++i) if (!chosen[i]) { dir = v3sub(temp[i].b, m->pts[0].b); const float d = adot(dir, dir); if (d > maxDist) { maxDist = d; index = i; } }
+  chosen[index] = 1; m->pts[1] = temp[index];
+  maxDist = -FLT_MAX;
+  for (int i = 0; i < 5; ++i) if (!chosen[i]) { const float sq = pxo_dist_point_segment_sq_local(m->pts[0].b, m->pts[1].b, temp[i].b); if (sq > maxDist) { maxDist = sq; index = i; } }
+  chosen[index] = 1; m->pts[2] = temp[index];
+  maxDist = -FLT_MAX;
+  for (int i = 0; i < 5; ++i) if (!chosen[i]) { const float sq = pxo_dist_point_triangle_sq_local(temp[i].b, m->pts[0].b, m->pts[1].b, m->pts[2].b); if (sq > maxDist) { maxDist = sq; index = i; } }
+  if (chosen[index]) { m->n = 3; return; }
+  chosen[index] = 1; m->pts[3] = temp[index];
+  int notChosen = 0;
+  for (int a = 0; a < 5; ++a) if (!chosen[a]) { notChosen = a; break; }
+  float closest = FLT_MAX; index = 0;
+  for (int a = 0; a < 4; ++a) { const v3 dif = v3sub(m->pts[a].a, temp[notChosen].a); const float d2 = adot(dif, dif); if (closest > d2) { closest = d2; index = a; } }
+  if (m->pts[index].pen > temp[notChosen].pen) m->pts[index] = temp[notChosen];
+}
+/* GuPCMContactBoxBox.cpp:918-958: the SAT passed but face clipping produced no point (edge-edge / corner configurations):
+ * one GJK (or EPA) point is merged into whatever the manifold still holds.  manifold->rel / quatA / quatB were already updated by the caller. */
+static inline void pxo_boxbox_gjk_fallback(const xf* tm0, const xf* tm1, v3 ext0, v3 ext1, float contactDist, float toleranceLength, PxoManifold* manifold, PxoContacts* out) {
+  const xf curRTrans = axfinvmul(tm1, tm0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  const float minMargin = fminf_(pxo_box_margin(ext0, toleranceLength), pxo_box_margin(ext1, toleranceLength));
+  PxoConvex box0 = pxo_cvx_box(V3(0, 0, 0), ext0); pxo_cvx_make_relative(&box0, &aToB);
+  const PxoConvex box1 = pxo_cvx_box(V3(0, 0, 0), ext1);
+  manifold->nWarm = 0;
+  PxoGjkOutput output; memset(&output, 0, sizeof(output));
+  int status = pxo_gjk_penetration(&box0, &box1, aToB.p, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+  if (status == PXO_EPA_CONTACT) status = pxo_epa_penetration(&box0, &box1, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+  out->count = 0;
+  if (status == PXO_GJK_CONTACT || status == PXO_EPA_CONTACT) {
+    const float replaceBreakingThreshold = minMargin * 0.05f;
+    pxo_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+    out->normal = anormalize(aqrot(tm1->q, output.normal));
+    for (int i = 0; i < manifold->n; ++i) {   /* addManifoldContactsToContactBuffer(buffer, normal, transf1, contactOffset) .cpp:739-759 */
+      const float dist = manifold->pts[i].pen;
+      if (contactDist >= dist) { out->point[out->count] = axftransform(tm1, manifold->pts[i].b); out->sep[out->count] = dist; out->count++; }
+    }
+  }
 }
 
 /* ---------------- polygonal box: GuPCMShapeConvex.cpp:40-110 ---------------- */

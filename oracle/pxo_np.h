@@ -3,9 +3,8 @@
  *   persistent manifold:  physx/source/geomutils/src/pcm/GuPersistentContactManifold.{h,cpp}
  *   plane-box:            physx/source/geomutils/src/pcm/GuPCMContactPlaneBox.cpp:36-209
  *   box-box:              physx/source/geomutils/src/pcm/GuPCMContactBoxBox.cpp:42-971
- * Deviation (documented in DESIGN.md): the GJK/EPA single-point fallback of pcmContactBoxBox
- * (GuPCMContactBoxBox.cpp:922-958, taken only when the SAT passes but face clipping yields no point)
- * is not restated; such a pair reports no contact this frame.
+ * The GJK/EPA single-point fallback of pcmContactBoxBox (GuPCMContactBoxBox.cpp:918-958, taken when the SAT passes but face
+ * clipping yields no point) lives in pxo_gjk.h (pxo_boxbox_gjk_fallback); pxo_pcm_box_box returns 2 to ask for it.
  * The reference's V3RecipFast (_mm_rcp_ps, 12-bit) in intersectSegmentAABB is restated as an exact
  * reciprocal; contact points produced by edge clipping therefore agree to ~4e-4 relative, not bitwise. */
 #ifndef PXO_NP_H
@@ -520,7 +519,7 @@ static inline int pxo_pcm_box_box(const xf* tm0, const xf* tm1, v3 ext0, v3 ext1
         }
         return 1;
       }
-      /* GJK/EPA single point fallback not restated (see header) */
+      return 2;   /* SAT passed, clipping found no point: the caller runs the GJK / EPA single-point fallback (pxo_gjk.h: pxo_boxbox_gjk_fallback) */
     }
     return 0;
   } else if (manifold->n > 0) {

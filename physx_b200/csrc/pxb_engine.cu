@@ -302,7 +302,13 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
   for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
   if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_BOX) pcm_plane_box(tm0, tm1, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
-  else if (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX) pcm_box_box(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
+  else if (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX) {
+    if (pcm_box_box(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out)) {   // edge-edge / corner configuration (rare)
+      manifold_load_warm(man, rec);
+      gjk_boxbox_gjk_fallback(&tm0, &tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
+      manifold_store_warm(man, rec);
+    }
+  }
   else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_SPHERE) np_sphere_sphere(tm0.p, tm1.p, d0.x, d1.x, contactDist, out);
   else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_PLANE) np_sphere_plane(tm0.p, d0.x, tm1, contactDist, out);
   else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_CAPSULE) np_sphere_capsule(tm0.p, d0.x, tm1, d1.x, d1.y, contactDist, out);

@@ -7,9 +7,9 @@
 //       physx/source/geomutils/src/pcm/GuPersistentContactManifold.cpp:739-1174
 //   plane vs box   physx/source/geomutils/src/pcm/GuPCMContactPlaneBox.cpp:36-209
 //   box vs box     physx/source/geomutils/src/pcm/GuPCMContactBoxBox.cpp:42-971
-// Known deviations: (1) the reference's _mm_rcp_ps in the segment/AABB clip is an exact reciprocal
-// here; (2) the GJK/EPA single-point fallback of box-box (taken only when the SAT passes and face
-// clipping produces no point) is not implemented yet -- such a pair reports no contact that frame.
+// Known deviation: the reference's _mm_rcp_ps in the segment/AABB clip is an exact reciprocal here.
+// The GJK/EPA single-point fallback of box-box (taken when the SAT passes and face clipping produces
+// no point) is gjk_boxbox_gjk_fallback in pxb_gjk.cuh.
 #pragma once
 #include "pxb_math.cuh"
 
@@ -481,7 +481,8 @@ PXB_D bool boxbox_generate(v3 e0, v3 e1, const mxf& t0, const mxf& t1, float con
 }
 
 // GuPCMContactBoxBox.cpp:848-971
-PXB_D void pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contactDist, float toleranceLength, Manifold& man, Contacts& out) {
+// returns true when the SAT passed but clipping found no point: the caller then runs the GJK / EPA single-point fallback (pxb_gjk.cuh)
+PXB_D bool pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contactDist, float toleranceLength, Manifold& man, Contacts& out) {
   const xf cur = axfinvmul(tm1, tm0);  // A into B
   const mxf aToB = amxffromxf(cur);
   const float minMargin = fmin_(box_margin(e0, toleranceLength), box_margin(e1, toleranceLength));
@@ -502,7 +503,7 @@ PXB_D void pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contact
         else { reduce_batch(man, mc, num, toleranceLength); man.n = PXB_MANIFOLD_CACHE; }
         out.normal = anormalize(mmul(tv1.r, man.pts[0].n));
         for (int i = 0; i < man.n; ++i) { out.point[out.count] = amxftransform(tv1, man.pts[i].b); out.sep[out.count] = man.pts[i].pen; out.count++; }
-      }
+      } else return true;
     }
   } else if (man.n > 0) {
     out.normal = manifold_world_normal(man, tm1);
@@ -511,6 +512,7 @@ PXB_D void pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contact
       if (contactDist >= dist) { out.point[out.count] = axftransform(tm1, man.pts[i].b); out.sep[out.count] = dist; out.count++; }
     }
   }
+  return false;
 }
 
 // ---------------- sphere / capsule family (reference GPU kernel: sphereNphase_Kernel) ----------------
