@@ -73,6 +73,7 @@ struct PxbScene {
   float4 *manifolds = 0, *frictions = 0;
   // per pair (this frame)
   float4 *cHdr = 0, *cPts = 0; uint2* pairBodies = 0; float* cForce = 0;
+  uint32_t *pairOrder = 0, *npClassCount = 0; uint8_t* npClass = 0; bool binPairs = false;   // mixed-type scenes: pairs binned by type pair before the narrowphase
   uint32_t* gjkList = 0; bool hasGjkPairs = false;   // a10: worklist of GJK-family pairs (filled by k_narrowphase)
   uint32_t *conFlag = 0, *conIdx = 0, *conPair = 0, *rankOfPair = 0; uint64_t *conSortKey = 0, *conSortKeyAlt = 0; uint32_t* conPairAlt = 0;
   uint64_t* orderKeys = 0; uint32_t nOrder = 0, capOrder = 0;
@@ -265,6 +266,45 @@ __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_
   f[0] = make_float4(0, 0, 0, __int_as_float(0)); f[1] = make_float4(0, 0, 0, __int_as_float(0)); f[2] = make_float4(0, 0, 0, __int_as_float(0));
 }
 
+// Scenes that mix geometry types: pairs are binned by (type0, type1) before the narrowphase so that a warp runs ONE contact function
+// (in pair-key order the types alternate at random: ncu measured 4.5 of 32 threads active per instruction on BASELINE config 3).
+// Counting sort in two passes (histogram, then scatter with warp-aggregated cursors); the order inside a bin is arbitrary, every pair
+// writes only its own outputs, so the result does not depend on it.
+#define NP_CLASSES 37   // 6 x 6 geometry types + 1 bin for dropped keys
+__device__ __forceinline__ uint32_t np_pair_class(uint64_t key, uint32_t bitsA, const uint32_t* __restrict__ geomFlags) {
+  if (key == ~0ull) return NP_CLASSES - 1;
+  const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
+  const uint32_t a = geomFlags[lo] & 0xff, b = geomFlags[hi] & 0xff;
+  return a < b ? a * 6 + b : b * 6 + a;
+}
+__global__ void k_np_class_count(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ nPairsP, uint32_t bitsA, const uint32_t* __restrict__ geomFlags, uint8_t* __restrict__ cls,
+                                 uint32_t* __restrict__ classCount) {
+  __shared__ uint32_t hist[NP_CLASSES];
+  if (threadIdx.x < NP_CLASSES) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *nPairsP) { const uint32_t c = np_pair_class(pairKeys[i], bitsA, geomFlags); cls[i] = (uint8_t)c; atomicAdd(&hist[c], 1u); }
+  __syncthreads();
+  if (threadIdx.x < NP_CLASSES && hist[threadIdx.x]) atomicAdd(&classCount[threadIdx.x], hist[threadIdx.x]);
+}
+__global__ void k_np_class_scatter(const uint32_t* __restrict__ nPairsP, const uint8_t* __restrict__ cls, const uint32_t* __restrict__ classCount, uint32_t* __restrict__ classCursor,
+                                   uint32_t* __restrict__ pairOrder) {
+  __shared__ uint32_t base[NP_CLASSES];
+  if (threadIdx.x == 0) { uint32_t acc = 0; for (int c = 0; c < NP_CLASSES; ++c) { base[c] = acc; acc += classCount[c]; } }
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < *nPairsP;
+  const uint32_t c = valid ? cls[i] : 0xffu;
+  const uint32_t active = __activemask();
+  const uint32_t peers = __match_any_sync(active, c);
+  if (!valid) return;
+  const uint32_t lane = threadIdx.x & 31, leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+  uint32_t start = 0;
+  if (lane == leader) start = atomicAdd(&classCursor[c], (uint32_t)__popc(peers));
+  start = __shfl_sync(peers, start, leader);
+  pairOrder[base[c] + start + rank] = i;
+}
+
 // a8-a11: one thread per pair.  Driver logic of PxcNpBatch.cpp:364-498: body0 is the dynamic actor (for
 // two dynamics the later-created one, ScNPhaseCore.cpp:182-252), shapes are ordered by geometry type for
 // the contact function and the normal is flipped back afterwards (flipContacts).
@@ -274,9 +314,11 @@ __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_
 __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
                               const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
                               float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
-                              uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters, uint32_t* __restrict__ gjkList) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *nPairsP) return;
+                              uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters, uint32_t* __restrict__ gjkList,
+                              const uint32_t* __restrict__ pairOrder) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *nPairsP) return;
+  const uint32_t i = pairOrder ? pairOrder[t] : t;   // mixed-type scenes: pairs binned by type pair (k_np_class_*)
   const uint64_t key = pairKeys[i];
 #ifndef PXB_NO_PREFETCH
   { const float4* r = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4; prefetch_l2(r); prefetch_l2(r + 8); }   // the record is needed two dependent loads later (types -> poses -> manifold)
@@ -759,7 +801,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->createdKeys, Pn)); CK(dalloc(s->deletedKeys, Pn));
   CK(dalloc(s->manifolds, Pn * PXB_MANIFOLD_F4)); CK(dalloc(s->frictions, Pn * PXB_FRICTION_F4));
   CK(dalloc(s->cHdr, Pn)); CK(dalloc(s->cPts, Pn * 4)); CK(dalloc(s->pairBodies, Pn)); CK(dalloc(s->cForce, Pn * 4));
-  CK(dalloc(s->gjkList, Pn)); CK(dalloc(s->conFlag, Pn)); CK(dalloc(s->conIdx, Pn)); CK(dalloc(s->conPair, Pn)); CK(dalloc(s->rankOfPair, Pn)); CK(dalloc(s->conSortKey, Pn)); CK(dalloc(s->conSortKeyAlt, Pn));
+  CK(dalloc(s->gjkList, Pn)); CK(dalloc(s->pairOrder, Pn)); CK(dalloc(s->npClass, Pn)); CK(dalloc(s->npClassCount, 2 * NP_CLASSES)); CK(dalloc(s->conFlag, Pn)); CK(dalloc(s->conIdx, Pn)); CK(dalloc(s->conPair, Pn)); CK(dalloc(s->rankOfPair, Pn)); CK(dalloc(s->conSortKey, Pn)); CK(dalloc(s->conSortKeyAlt, Pn));
   CK(dalloc(s->conPairAlt, Pn));
   CK(dalloc(s->conB0, Pn)); CK(dalloc(s->conB1, Pn)); CK(dalloc(s->conPos0, Pn)); CK(dalloc(s->conPos1, Pn)); CK(dalloc(s->conColour, Pn)); CK(dalloc(s->conDone, Pn));
   CK(dalloc(s->bodyList, Pn * 2)); CK(dalloc(s->ordered, Pn));
@@ -829,7 +871,7 @@ PXB_API void pxb_scene_release(PxbScene* s) {
   void* ptrs[] = {s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
-                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->conFlag, s->conIdx,
+                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
                   s->envStart, s->envList, s->actorLocal, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
@@ -916,10 +958,11 @@ static void rebuild_grid(PxbScene* s) {
   float cell = 0.f; float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   s->largeHost.clear();
   std::vector<uint32_t> gf(s->nA);
-  bool anyCapsule = false, anyBox = false;
+  bool anyCapsule = false, anyBox = false; uint32_t typeMask = 0;
   for (uint32_t a = 0; a < s->nA; ++a) {
     const ActorRec& r = s->recs[a];
     anyCapsule |= r.geomType == PXB_GEOM_CAPSULE; anyBox |= r.geomType == PXB_GEOM_BOX;
+    if (r.geomType != PXB_GEOM_PLANE) typeMask |= 1u << (r.geomType & 31);
     const float d = shape_diameter(r);
     const bool global = !std::isfinite(d) || d > largeThresh || (usesEnv && r.envId == NONE32);
     gf[a] = (r.geomType & 0xff) | ((r.flags & PXB_ACTOR_DYNAMIC) ? 0x100u : 0u) | (global ? 0x200u : 0u) | (((r.flags >> 8) & 0x3fu) << 16);   // bits 16..21: PxRigidDynamicLockFlags
@@ -941,6 +984,7 @@ static void rebuild_grid(PxbScene* s) {
   while ((long double)envCount * g.nx * g.ny * g.nz > 4.0e18L) { if (g.nx >= g.ny && g.nx >= g.nz) g.nx = (g.nx + 1) / 2; else if (g.ny >= g.nz) g.ny = (g.ny + 1) / 2; else g.nz = (g.nz + 1) / 2; }
   g.keyBits = bits_for((uint64_t)envCount * (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz + 1);
   s->hasGjkPairs = anyCapsule && anyBox;
+  s->binPairs = __builtin_popcount(typeMask) >= 2 && !getenv("PXB_NO_PAIR_BINS");
   s->grid = g; s->nLarge = (uint32_t)s->largeHost.size();
   s->desc.reserved[0] = (uint32_t)envCount;
   cudaMemcpyAsync(s->geomFlags, gf.data(), 4 * s->nA, cudaMemcpyHostToDevice, s->stream);
@@ -1092,8 +1136,13 @@ static int enqueue_step(PxbScene* s, float dt) {
   const int cur = s->cur; const uint32_t gP = cdiv(s->capPairs, B);
   const uint32_t* nP = s->nPairsDev + cur;
   const float contactDist = s->desc.contactOffset + s->desc.contactOffset;
+  if (s->binPairs) {   // several geometry types: counting sort of the pairs by type pair, so that warps do not diverge across contact functions
+    CK(cudaMemsetAsync(s->npClassCount, 0, 4 * 2 * NP_CLASSES, st));
+    LAUNCH(k_np_class_count, gP, B, s->pairKeys[cur], nP, s->bitsA, s->geomFlags, s->npClass, s->npClassCount);
+    LAUNCH(k_np_class_scatter, gP, B, nP, s->npClass, s->npClassCount, s->npClassCount + NP_CLASSES, s->pairOrder);
+  }
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
-         s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce, s->counters, s->gjkList);
+         s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce, s->counters, s->gjkList, s->binPairs ? s->pairOrder : (const uint32_t*)nullptr);
   if (s->hasGjkPairs) LAUNCH(k_narrowphase_gjk, 148 * 4, 128, s->pairKeys[cur], s->pairSlots[cur], s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds, s->cHdr, s->cPts,
                              s->pairBodies, s->conFlag, s->counters, s->gjkList);
   SleepArgs SA; SA.threshold = s->sleepThreshold; SA.dt = dt; SA.wake = s->wake; SA.accLin = s->accLin; SA.accAng = s->accAng; SA.asleep = s->asleep; SA.nInter = s->nInter;

@@ -340,8 +340,8 @@ def box_pile(nx=100, ny=20, nz=100, half_extent=0.25, gap=0.001, seed=1, **hdr):
 
 def falling_primitives(nx=128, ny=64, nz=128, pitch=0.6, seed=2, kinds=("sphere", "box"), **hdr):
     """BASELINE config 3 shape (broadphase + narrowphase stress): nx*ny*nz mixed primitives with random orientations dropped
-    from a lattice into a walled bin.  (Config 3 is spheres / capsules / convex hulls; until the GJK/EPA family (a10: convex hulls,
-    capsule-box) lands this runs spheres + boxes -- the bin walls are boxes, so capsules cannot take part.)"""
+    from a lattice into a walled bin.  (Config 3 is spheres / capsules / convex hulls; boxes stand in for the hulls until the
+    hull half of a10 lands: kinds=("sphere", "capsule", "box") runs every primitive pair type incl. capsule-box through GJK / EPA.)"""
     rng = np.random.RandomState(seed)
     n = nx * ny * nz
     a = _new_actors(n)
