@@ -113,10 +113,12 @@ PXB_API int  pxb_scene_fetch_results(PxbScene* scene, int block);
 PXB_API int  pxb_scene_set_constraint_order(PxbScene* scene, const uint32_t* pairs, uint32_t n);
 
 /* ---- PxDirectGPUAPI mirror (physx/include/PxDirectGPUAPI.h:311-463; kernels updateBodiesAndShapes.cu:999-1253).
- *      dataType: 0 = global pose (7 floats q.xyzw,p.xyz = PxTransform), 1 = linear velocity, 2 = angular velocity.
+ *      dataType: 0 = global pose (7 floats q.xyzw,p.xyz = PxTransform), 1 = linear velocity, 2 = angular velocity,
+ *      3 = force, 4 = torque (writes only).
  *      `indices` are dynamic-body indices (PxRigidDynamicGPUIndex analogue), NULL = 0..nb-1.
  *      *_device variants take device pointers and run on the scene stream without synchronising. ---- */
-enum { PXB_RD_GLOBAL_POSE = 0, PXB_RD_LINEAR_VELOCITY = 1, PXB_RD_ANGULAR_VELOCITY = 2 };
+enum { PXB_RD_GLOBAL_POSE = 0, PXB_RD_LINEAR_VELOCITY = 1, PXB_RD_ANGULAR_VELOCITY = 2,
+       PXB_RD_FORCE = 3, PXB_RD_TORQUE = 4 /* set only (PxRigidDynamicGPUAPIWriteType::eFORCE / eTORQUE, PxDirectGPUAPI.h:60-72): 3 floats per body, world frame, applied at the centre of mass by the next simulate only */ };
 PXB_API int  pxb_get_rigid_dynamic_data(PxbScene* scene, void* data, const uint32_t* indices, int dataType, uint32_t nb);
 PXB_API int  pxb_set_rigid_dynamic_data(PxbScene* scene, const void* data, const uint32_t* indices, int dataType, uint32_t nb);
 /* stream-ordered host variants: PINNED host buffers, no index list, no synchronisation; complete at the next

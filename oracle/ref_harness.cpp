@@ -121,7 +121,7 @@ int main(int argc, char** argv) {
   }
   const char* scenePath = argv[2];
   int steps = 100, threads = 1, warmup = 0;
-  const char *statesPath = nullptr, *bpPath = nullptr, *contactsPath = nullptr, *hullsPath = nullptr, *orderPath = nullptr, *sleepPath = nullptr;
+  const char *statesPath = nullptr, *bpPath = nullptr, *contactsPath = nullptr, *hullsPath = nullptr, *orderPath = nullptr, *sleepPath = nullptr, *forcesPath = nullptr;
   for (int i = 3; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--steps") steps = atoi(argv[++i]);
@@ -132,6 +132,7 @@ int main(int argc, char** argv) {
     else if (a == "--contacts") contactsPath = argv[++i];
     else if (a == "--hulls") hullsPath = argv[++i];
     else if (a == "--order") orderPath = argv[++i];
+    else if (a == "--forces") forcesPath = argv[++i];   // f32[blocks][nDyn][6] = force xyz, torque xyz: block s (mod blocks) is applied with addForce / addTorque(eFORCE) before step s
     else if (a == "--sleep") sleepPath = argv[++i];   // per step, per dynamic actor: f32 wakeCounter, u32 isSleeping
   }
   gWantContacts = contactsPath != nullptr;
@@ -319,12 +320,22 @@ int main(int argc, char** argv) {
     for (auto& p : d) { fwrite(&p.first, 4, 1, fb); fwrite(&p.second, 4, 1, fb); }
   };
 
+  std::vector<float> forces;
+  if (forcesPath) { std::vector<uint8_t> fb_ = readFile(forcesPath); forces.resize(fb_.size() / 4); memcpy(forces.data(), fb_.data(), forces.size() * 4); }
   inlineDispatcher.hook = [](void*) { sDump(); };
   dumpStates();
   double totalMs = 0; std::vector<double> stepMs;
   for (int s = 0; s < steps + warmup; s++) {
     bpStep(s == 0);
     gContacts.pairs.clear();
+    if (!forces.empty()) {   // PxRigidBody::addForce / addTorque (PxForceMode::eFORCE): the CPU-side equivalent of PxDirectGPUAPI eFORCE / eTORQUE writes
+      const size_t blocks = forces.size() / (dyn.size() * 6); const float* f = forces.data() + (size_t(s) % blocks) * dyn.size() * 6;
+      for (size_t i = 0; i < dyn.size(); i++) {
+        const PxVec3 F(f[i * 6], f[i * 6 + 1], f[i * 6 + 2]), T(f[i * 6 + 3], f[i * 6 + 4], f[i * 6 + 5]);
+        if (!F.isZero()) dyn[i]->addForce(F, PxForceMode::eFORCE);
+        if (!T.isZero()) dyn[i]->addTorque(T, PxForceMode::eFORCE);
+      }
+    }
     auto t0 = std::chrono::steady_clock::now();
     scene->simulate(H.dt);
     scene->fetchResults(true);

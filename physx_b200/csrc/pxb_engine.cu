@@ -74,7 +74,8 @@ struct PxbScene {
   // per pair (this frame)
   float4 *cHdr = 0, *cPts = 0; uint2* pairBodies = 0; float* cForce = 0;
   uint32_t *pairOrder = 0, *npClassCount = 0; uint8_t* npClass = 0; bool binPairs = false;   // mixed-type scenes: pairs binned by type pair before the narrowphase
-  uint32_t* gjkList = 0; bool hasGjkPairs = false;   // a10: worklist of GJK-family pairs (filled by k_narrowphase)
+  uint32_t* gjkList = 0; bool hasGjkPairs = false, anyLocks = false;
+  float4 *extForce = 0, *extTorque = 0; bool forcesUsed = false;   // PxDirectGPUAPI eFORCE / eTORQUE writes pending for the next step   // a10: worklist of GJK-family pairs (filled by k_narrowphase)
   uint32_t *conFlag = 0, *conIdx = 0, *conPair = 0, *rankOfPair = 0; uint64_t *conSortKey = 0, *conSortKeyAlt = 0; uint32_t* conPairAlt = 0;
   uint64_t* orderKeys = 0; uint32_t nOrder = 0, capOrder = 0;
   uint32_t *conB0 = 0, *conB1 = 0, *conPos0 = 0, *conPos1 = 0, *conColour = 0, *conDone = 0, *bodyList = 0, *ordered = 0;
@@ -345,9 +346,11 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
   if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_BOX) pcm_plane_box(tm0, tm1, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
   else if (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX) {
-    if (pcm_box_box(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out)) {   // edge-edge / corner configuration (rare)
+    if (pcm_box_box(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out)) {
+      // edge-edge / corner configuration (rare): the SAT passed but clipping found no point -> GJK / EPA single-point fallback, called out of
+      // line so that this kernel keeps its register budget (measured: cheaper than handing the pair to a second, usually empty, launch).
       manifold_load_warm(man, rec);
-      gjk_boxbox_gjk_fallback(&tm0, &tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
+      gjk_boxbox_gjk_fallback_outofline(&tm0, &tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
       manifold_store_warm(man, rec);
     }
   }
@@ -663,13 +666,20 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
                                float4* __restrict__ linVel, float4* __restrict__ angVel, const float4* __restrict__ invInertia, const float4* __restrict__ damp,
                                float gx, float gy, float gz, float dt, float4* __restrict__ sbLin, float4* __restrict__ sbAng, float4* __restrict__ sbDLin,
                                float4* __restrict__ sbDAng, float4* __restrict__ sbIA, float4* __restrict__ sbIB, float4* __restrict__ sbP, float4* __restrict__ sbQ,
-                               float4* __restrict__ sbOrigAng, int pgs, SleepArgs S, const uint32_t* __restrict__ geomFlags) {
+                               float4* __restrict__ sbOrigAng, int pgs, SleepArgs S, const uint32_t* __restrict__ geomFlags, float4* __restrict__ extForce, float4* __restrict__ extTorque) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
   const bool asleep = body_asleep(S, a);
   const float4 dm = damp[a]; const float4 ii = invInertia[a]; const float4 p4 = pos[a];
   v3 lv = V3(linVel[a]), av = V3(angVel[a]);
+  if (extForce) {   // pending eFORCE / eTORQUE writes: consumed by this step
+    const float4 F = extForce[a], T = extTorque[a];
+    if (F.x != 0.f || F.y != 0.f || F.z != 0.f || T.x != 0.f || T.y != 0.f || T.z != 0.f) {
+      if (!asleep) apply_external_force(V3(F), V3(T), p4.w, ii, Q4(quat[a]), dt, lv, av);
+      extForce[a] = make_float4(0, 0, 0, 0); extTorque[a] = make_float4(0, 0, 0, 0);
+    }
+  }
   if (!asleep) unconstrained_velocity(V3(gx, gy, gz), dt, dm.x, dm.y, dm.z, dm.w, lv, av);
   // lock flags: TGS locks both velocities (copyToSolverBodyDataStep, DyTGSDynamics.cpp:195-222); PGS only the angular one (copyToSolverBodyData, DyRigidBodyToSolverBody.cpp:72-98)
   const uint32_t lock = (geomFlags[a] >> 16) & 0x3fu;
@@ -723,10 +733,17 @@ __global__ void k_rd_get(uint32_t nb, const uint32_t* __restrict__ idx, const ui
   else { const float4 v = type == PXB_RD_LINEAR_VELOCITY ? linVel[a] : angVel[a]; float* o = out + (size_t)i * 3; o[0] = v.x; o[1] = v.y; o[2] = v.z; }
 }
 __global__ void k_rd_set(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, int type, float4* __restrict__ pos, float4* __restrict__ quat,
-                         float4* __restrict__ linVel, float4* __restrict__ angVel, const float* __restrict__ in, float* __restrict__ wake, uint32_t* __restrict__ asleep) {
+                         float4* __restrict__ linVel, float4* __restrict__ angVel, const float* __restrict__ in, float* __restrict__ wake, uint32_t* __restrict__ asleep,
+                         float4* __restrict__ extForce, float4* __restrict__ extTorque) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nb) return;
   const uint32_t a = dynActor[idx ? idx[i] : i];
+  if (type == PXB_RD_FORCE || type == PXB_RD_TORQUE) {   // applied by the next step only; a non-zero force wakes the body (autowake)
+    const float* o = in + (size_t)i * 3; const float4 v = make_float4(o[0], o[1], o[2], 0.f);
+    if (type == PXB_RD_FORCE) extForce[a] = v; else extTorque[a] = v;
+    if (v.x != 0.f || v.y != 0.f || v.z != 0.f) { if (wake[a] < 20.0f * 0.02f) wake[a] = 20.0f * 0.02f; asleep[a] = 0u; }
+    return;
+  }
   wake[a] = 20.0f * 0.02f; asleep[a] = 0u;   // setting pose / velocity wakes the body (PxRigidDynamic autowake, wakeCounterResetValue)
   if (type == PXB_RD_GLOBAL_POSE) { const float* o = in + (size_t)i * 7; quat[a] = make_float4(o[0], o[1], o[2], o[3]); const float w = pos[a].w; pos[a] = make_float4(o[4], o[5], o[6], w); }
   else { const float* o = in + (size_t)i * 3; const float4 v = make_float4(o[0], o[1], o[2], 0.f); if (type == PXB_RD_LINEAR_VELOCITY) linVel[a] = v; else angVel[a] = v; }
@@ -808,7 +825,8 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
   CK(dalloc(s->ptA, Pn * 28)); s->ptB = s->ptA + Pn * 4; s->ptC = s->ptA + Pn * 8;   // one allocation: the environment path views it as 25 x Pn (pxb_env.cuh Rows)
   s->frA = s->ptA + Pn * 12; s->frB = s->ptA + Pn * 16; s->frC = s->ptA + Pn * 20; s->frD = s->ptA + Pn * 24;
-  CK(dalloc(s->stage, A * 13 * 2)); CK(dalloc(s->stageIdx, A));   // staging: {get, set} x {pose 7, linear 3, angular 3} floats per actor
+  CK(dalloc(s->stage, A * 32)); CK(dalloc(s->stageIdx, A));   // staging: {get, set} x {pose 7, linear 3, angular 3} + set {force 3, torque 3} floats per actor
+  CK(dalloc(s->extForce, A)); CK(dalloc(s->extTorque, A)); CK(cudaMemsetAsync(s->extForce, 0, sizeof(float4) * A, s->stream)); CK(cudaMemsetAsync(s->extTorque, 0, sizeof(float4) * A, s->stream));
   CK(dalloc(s->counters, C_COUNT)); CK(cudaMallocHost((void**)&s->hostCounters, sizeof(uint32_t) * (C_COUNT + 2)));
   CK(dalloc(s->rsTmp.blockHist, RS_MAX_CTAS * 256)); CK(dalloc(s->rsTmp.digitTotals, 256)); CK(dalloc(s->scanSums, RS_MAX_CTAS));
   CK(cudaMemsetAsync(s->counters, 0, sizeof(uint32_t) * C_COUNT, s->stream)); CK(cudaMemsetAsync(s->nPairsDev, 0, 8, s->stream));
@@ -841,8 +859,10 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->numSMs = prop.multiProcessorCount;
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_colour_partition, 256, 0)); s->coopBlocksColour = std::max(1, std::min(occ, 4)) * s->numSMs;
-#define ENV_ATTR(T) do { CK(cudaFuncSetAttribute(k_env_solve<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); \
-                         CK(cudaFuncSetAttribute(k_env_solve<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); } while (0)
+#define ENV_ATTR(T) do { CK(cudaFuncSetAttribute(k_env_solve<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); \
+                         CK(cudaFuncSetAttribute(k_env_solve<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); \
+                         CK(cudaFuncSetAttribute(k_env_solve<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); \
+                         CK(cudaFuncSetAttribute(k_env_solve<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); } while (0)
   ENV_ATTR(32); ENV_ATTR(64); ENV_ATTR(128); ENV_ATTR(256);
 #undef ENV_ATTR
   CK(cudaFuncSetAttribute(k_env_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
@@ -873,7 +893,7 @@ PXB_API void pxb_scene_release(PxbScene* s) {
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
-                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx,
+                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque,
                   s->envStart, s->envList, s->actorLocal, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
@@ -958,11 +978,12 @@ static void rebuild_grid(PxbScene* s) {
   float cell = 0.f; float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   s->largeHost.clear();
   std::vector<uint32_t> gf(s->nA);
-  bool anyCapsule = false, anyBox = false; uint32_t typeMask = 0;
+  bool anyCapsule = false, anyBox = false, anyLocks = false; uint32_t typeMask = 0;
   for (uint32_t a = 0; a < s->nA; ++a) {
     const ActorRec& r = s->recs[a];
     anyCapsule |= r.geomType == PXB_GEOM_CAPSULE; anyBox |= r.geomType == PXB_GEOM_BOX;
     if (r.geomType != PXB_GEOM_PLANE) typeMask |= 1u << (r.geomType & 31);
+    anyLocks |= ((r.flags >> 8) & 0x3fu) != 0;
     const float d = shape_diameter(r);
     const bool global = !std::isfinite(d) || d > largeThresh || (usesEnv && r.envId == NONE32);
     gf[a] = (r.geomType & 0xff) | ((r.flags & PXB_ACTOR_DYNAMIC) ? 0x100u : 0u) | (global ? 0x200u : 0u) | (((r.flags >> 8) & 0x3fu) << 16);   // bits 16..21: PxRigidDynamicLockFlags
@@ -983,7 +1004,8 @@ static void rebuild_grid(PxbScene* s) {
   // keep the key within 62 bits
   while ((long double)envCount * g.nx * g.ny * g.nz > 4.0e18L) { if (g.nx >= g.ny && g.nx >= g.nz) g.nx = (g.nx + 1) / 2; else if (g.ny >= g.nz) g.ny = (g.ny + 1) / 2; else g.nz = (g.nz + 1) / 2; }
   g.keyBits = bits_for((uint64_t)envCount * (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz + 1);
-  s->hasGjkPairs = anyCapsule && anyBox;
+  s->anyLocks = anyLocks;
+  s->hasGjkPairs = anyCapsule && anyBox;   // k_narrowphase_gjk: capsule-box pairs
   s->binPairs = __builtin_popcount(typeMask) >= 2 && !getenv("PXB_NO_PAIR_BINS");
   s->grid = g; s->nLarge = (uint32_t)s->largeHost.size();
   s->desc.reserved[0] = (uint32_t)envCount;
@@ -1165,13 +1187,15 @@ static int enqueue_step(PxbScene* s, float dt) {
     A.nEnv = s->nEnv; A.maxList = s->envMaxList; A.conCap = s->envConCap; A.cap = s->capPairs; A.posIters = s->desc.posIters; A.velIters = s->desc.velIters;
     A.dt = dt; A.gx = g[0]; A.gy = g[1]; A.gz = g[2]; A.P = P;
     A.envStart = s->envStart; A.envList = s->envList; A.actorLocal = s->actorLocal; A.seg = s->envSeg[cur];
-    A.pos = s->pos; A.quat = s->quat; A.linVel = s->linVel; A.angVel = s->angVel; A.invInertia = s->invInertia; A.damp = s->damp; A.geomFlags = s->geomFlags;
+    A.pos = s->pos; A.quat = s->quat; A.linVel = s->linVel; A.angVel = s->angVel; A.invInertia = s->invInertia; A.damp = s->damp; A.geomFlags = s->geomFlags; A.anyLocks = s->anyLocks ? 1u : 0u; A.extForce = s->forcesUsed ? s->extForce : nullptr; A.extTorque = s->forcesUsed ? s->extTorque : nullptr;
     A.pairSlots = s->pairSlots[cur]; A.pairBodies = s->pairBodies; A.cHdr = s->cHdr; A.cPts = s->cPts; A.cForce = s->cForce; A.frictions = s->frictions;
     A.conPair = s->conPair; A.conB0 = s->conB0; A.conB1 = s->conB1; A.conColour = s->conColour; A.ordered = s->ordered; A.broken = s->conDone;
     A.rowScratch = s->ptA;   // ptA|ptB|ptC|frA|frB|frC|frD are ONE allocation of 28 x cap float4 (scene_alloc); the environment path uses 25 of them
     A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour; A.S = SA;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
-#define ENV_LAUNCH(T) do { if (pgs) k_env_solve<T, true><<<s->nEnv, T, smem, st>>>(A); else k_env_solve<T, false><<<s->nEnv, T, smem, st>>>(A); } while (0)
+    const bool ext = s->anyLocks || s->forcesUsed;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
+#define ENV_LAUNCH(T) do { if (pgs) { if (ext) k_env_solve<T, true, true><<<s->nEnv, T, smem, st>>>(A); else k_env_solve<T, true, false><<<s->nEnv, T, smem, st>>>(A); } \
+                           else { if (ext) k_env_solve<T, false, true><<<s->nEnv, T, smem, st>>>(A); else k_env_solve<T, false, false><<<s->nEnv, T, smem, st>>>(A); } } while (0)
     if (s->envSolveThreads == 32) ENV_LAUNCH(32); else if (s->envSolveThreads == 64) ENV_LAUNCH(64); else if (s->envSolveThreads == 128) ENV_LAUNCH(128); else ENV_LAUNCH(256);
 #undef ENV_LAUNCH
     s->launches++;
@@ -1206,7 +1230,7 @@ static int enqueue_step(PxbScene* s, float dt) {
   }
   MARK(3);
   LAUNCH(k_preintegrate, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, g[0], g[1], g[2], dt, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng,
-         s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, pgs ? 1 : 0, SA, s->geomFlags);
+         s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, pgs ? 1 : 0, SA, s->geomFlags, s->forcesUsed ? s->extForce : (float4*)nullptr, s->forcesUsed ? s->extTorque : (float4*)nullptr);
   if (pgs) {   // PGS: rows in the 25-float4 record image, velocity-delta solver bodies (pxb_pgs.cuh)
     Rows R; R.f = s->ptA; R.broken = s->conDone; R.stride = s->capPairs;
     LAUNCH(k_prep_rows<true>, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
@@ -1380,11 +1404,12 @@ extern "C" PXB_API int pxb_debug_env_timing(PxbScene* s, unsigned long long* out
 #endif
 
 static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb, bool set) {
-  if (type < 0 || type > 2) return fail(PXB_ERR_INVALID, "bad dataType");
+  if (type < 0 || type > (set ? PXB_RD_TORQUE : PXB_RD_ANGULAR_VELOCITY)) return fail(PXB_ERR_INVALID, "bad dataType");
+  if (type >= PXB_RD_FORCE && !s->forcesUsed) { s->forcesUsed = true; drop_graphs(s); }   // the step kernels read the force arrays from now on
   if (!devIdx && nb > s->nDyn) return fail(PXB_ERR_INVALID, "nb exceeds the number of dynamic bodies");
   cudaStream_t st = s->stream;
   if (!nb) return PXB_OK;
-  if (set) LAUNCH(k_rd_set, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (const float*)devData, s->wake, s->asleep);
+  if (set) LAUNCH(k_rd_set, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (const float*)devData, s->wake, s->asleep, s->extForce, s->extTorque);
   else LAUNCH(k_rd_get, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (float*)devData);
   CK(cudaGetLastError());
   return PXB_OK;
@@ -1401,14 +1426,14 @@ PXB_API int pxb_set_rigid_dynamic_data_device(PxbScene* s, const void* devData, 
 }
 static int rd_host(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb, bool set, bool async) {
   if (!s || !data) return fail(PXB_ERR_INVALID, "null argument");
-  if (type < 0 || type > 2) return fail(PXB_ERR_INVALID, "bad dataType");
+  if (type < 0 || type > (set ? PXB_RD_TORQUE : PXB_RD_ANGULAR_VELOCITY)) return fail(PXB_ERR_INVALID, "bad dataType");
   if (s->stepping && !async) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
   if (async && idx) return fail(PXB_ERR_INVALID, "the stream-ordered host variants take no index list");
   if (!nb) return PXB_OK;
   const size_t bytes = (size_t)nb * (type == 0 ? 28 : 12);
   if (nb > s->capA) return fail(PXB_ERR_INVALID, "nb exceeds the actor capacity");
   // persistent staging, one region per (direction, data type): no allocation on the per-step path and stream-ordered calls never share a buffer
-  float* d = s->stage + (size_t)s->capA * ((set ? 13 : 0) + (type == 0 ? 0 : (type == 1 ? 7 : 10))); uint32_t* di = nullptr;
+  float* d = s->stage + (size_t)s->capA * (type >= PXB_RD_FORCE ? 26 + 3 * (type - PXB_RD_FORCE) : (set ? 13 : 0) + (type == 0 ? 0 : (type == 1 ? 7 : 10))); uint32_t* di = nullptr;
   if (idx) { for (uint32_t i = 0; i < nb; ++i) if (idx[i] >= s->nDyn) return fail(PXB_ERR_INVALID, "index out of range");
              di = s->stageIdx; CK(cudaMemcpyAsync(di, idx, 4 * (size_t)nb, cudaMemcpyHostToDevice, s->stream)); }
   if (set) CK(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, s->stream));

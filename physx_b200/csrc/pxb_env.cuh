@@ -149,6 +149,8 @@ struct EnvSolveArgs {
   uint32_t* slotColour;   // per persistent pair slot: partition of the pair's constraint last frame (NONE32 = no contacts)
   float4* rowScratch;   // 25 x cap float4, field-major: memory image of RegRows for environments with more constraints than threads
   uint32_t* counters; unsigned long long* timing; SleepArgs S;
+  uint32_t anyLocks;   // some actor carries PxRigidDynamicLockFlags (uniform fast path otherwise)
+  float4 *extForce, *extTorque;   // pending eFORCE / eTORQUE writes (NULL until the application uses them)
 };
 #ifdef PXB_ENV_TIMING
 #define ENV_T(i) do { __syncthreads(); if (threadIdx.x == 0) { const long long c_ = clock64(); A.timing[(size_t)blockIdx.x * 16 + (i)] = (unsigned long long)(c_ - t_prev); t_prev = c_; } } while (0)
@@ -378,15 +380,15 @@ __device__ __forceinline__ void env_writeback_one(const EnvSolveArgs& A, const R
   for (int j = 0; j < 4; ++j) if (j < numNormal) A.cForce[(size_t)i * 4 + j] = f4get(r.ap, j);
   if (numFriction && r.broken) A.frictions[(size_t)A.pairSlots[i] * PXB_FRICTION_F4 + 1].w = __int_as_float(1);
 }
-template <int T>
+template <int T, bool EXT>
 __device__ __forceinline__ void env_integrate_substep(uint32_t n, float stepDt, float4* bLin, float4* bAng, float4* bDLin, float4* bDAng, const float4* bIA, const float4* bIB, float4* bP, float4* bQ) {
   for (uint32_t b = threadIdx.x; b < n; b += T) {
     if (!__float_as_uint(bP[b].w)) continue;
     v3 p = V3(bP[b]); q4 dq = Q4(bQ[b]); v3 dl = V3(bDLin[b]), da = V3(bDAng[b]);
-    const float4 ib = bIB[b]; const uint32_t lock = __float_as_uint(ib.z);
+    const float4 ib = bIB[b]; const uint32_t lock = EXT ? __float_as_uint(ib.z) : 0u;   // PxRigidDynamicLockFlags only in the EXT instantiation
     v3 lv = V3(bLin[b]), as = V3(bAng[b]);
     integrate_core_step(lv, as, load_sym(bIA[b], ib), stepDt, p, dq, dl, da, lock);
-    if (lock) { bLin[b] = F4(lv, 0.f); bAng[b] = F4(as, 0.f); }
+    if (EXT && lock) { bLin[b] = F4(lv, 0.f); bAng[b] = F4(as, 0.f); }
     bP[b] = F4(p, __uint_as_float(1u)); bQ[b] = F4(dq); bDLin[b] = F4(dl, 0.f); bDAng[b] = F4(da, 0.f);
   }
 }
@@ -394,7 +396,7 @@ __device__ __forceinline__ void env_integrate_substep(uint32_t n, float stepDt, 
 // prep + all TGS iterations + write-back of one environment (iterativeSolveIsland, DyTGSDynamics.cpp:2515-2793, with CTA
 // barriers between partitions).  REG: every thread owns exactly one constraint (nCon <= T) and keeps its rows in registers
 // for the whole solve; otherwise rows stream through the memory image R (global scratch, L2 resident).
-template <int T, bool REG, bool PGS>
+template <int T, bool REG, bool PGS, bool EXT>
 __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows R, const ConLists L, const uint32_t base, const uint32_t nCon, const uint32_t n,
                                                float4* bLin, float4* bAng, float4* bDLin, float4* bDAng, float4* bIA, float4* bIB, float4* bP, float4* bQ,
                                                const uint32_t* sPartStart, const uint32_t nPart, float4* sFr, long long& t_prev) {
@@ -443,7 +445,7 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
         __syncthreads();
       }
       if (!vel) {
-        env_integrate_substep<T>(n, stepDt, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ);
+        env_integrate_substep<T, EXT>(n, stepDt, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ);
         elapsed += stepDt;
         __syncthreads();
       }
@@ -460,7 +462,7 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
 #ifndef PXB_ENV_CTAS64
 #define PXB_ENV_CTAS64 8
 #endif
-template <int T, bool PGS>
+template <int T, bool PGS, bool EXT>   // EXT: scenes that use PxRigidDynamicLockFlags or eFORCE / eTORQUE writes (the plain instantiation carries none of that code)
 __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB_ENV_CTAS64 / 2 : 1))) k_env_solve(const EnvSolveArgs A) {
   extern __shared__ float4 envSmem[];
   __shared__ uint32_t sPartCnt[MAX_PARTITIONS + 1], sPartStart[MAX_PARTITIONS + 1], sWarp[T / 32 + 1], sMisc[4];
@@ -484,9 +486,16 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
     if (!(gf & 0x100u) || body_asleep(A.S, a)) { bP[b] = make_float4(0, 0, 0, 0); continue; }   // statics and sleeping bodies take no part
     const float4 dm = A.damp[a]; const float4 ii = A.invInertia[a]; const float4 p4 = A.pos[a];
     v3 lv = V3(A.linVel[a]), av = V3(A.angVel[a]);
+    if (EXT && A.extForce) {   // pending eFORCE / eTORQUE writes: consumed by this step
+      const float4 F = A.extForce[a], Tq = A.extTorque[a];
+      if (F.x != 0.f || F.y != 0.f || F.z != 0.f || Tq.x != 0.f || Tq.y != 0.f || Tq.z != 0.f) {
+        apply_external_force(V3(F), V3(Tq), p4.w, ii, Q4(A.quat[a]), A.dt, lv, av);
+        A.extForce[a] = make_float4(0, 0, 0, 0); A.extTorque[a] = make_float4(0, 0, 0, 0);
+      }
+    }
     unconstrained_velocity(V3(A.gx, A.gy, A.gz), A.dt, dm.x, dm.y, dm.z, dm.w, lv, av);
-    const uint32_t lock = (gf >> 16) & 0x3fu;   // PxRigidDynamicLockFlags: TGS locks both velocities, PGS only the angular one (see k_preintegrate)
-    if (lock) { if (!PGS) lv = lock3(lv, lock & 7u); av = lock3(av, (lock >> 3) & 7u); }
+    const uint32_t lock = EXT ? (gf >> 16) & 0x3fu : 0u;   // PxRigidDynamicLockFlags: TGS locks both velocities, PGS only the angular one (see k_preintegrate)
+    if (EXT && lock) { if (!PGS) lv = lock3(lv, lock & 7u); av = lock3(av, (lock >> 3) & 7u); }
     const m33 rot = amfromq(Q4(A.quat[a]));
     const v3 sqrtInvI = V3(ii.x == 0.f ? 0.f : sqrtf(ii.x), ii.y == 0.f ? 0.f : sqrtf(ii.y), ii.z == 0.f ? 0.f : sqrtf(ii.z));
     const v3 sqrtI = V3(sqrtInvI.x == 0.f ? 0.f : 1.0f / sqrtInvI.x, sqrtInvI.y == 0.f ? 0.f : 1.0f / sqrtInvI.y, sqrtInvI.z == 0.f ? 0.f : 1.0f / sqrtInvI.z);
@@ -598,8 +607,8 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   ENV_T(3);
   if (nCon) {
     Rows R; R.f = A.rowScratch + base; R.broken = A.broken + base; R.stride = A.cap;
-    if (nCon <= T) env_solve_body<T, true, PGS>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, sFr, t_prev);
-    else env_solve_body<T, false, PGS>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, sFr, t_prev);
+    if (nCon <= T) env_solve_body<T, true, PGS, EXT>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, sFr, t_prev);
+    else env_solve_body<T, false, PGS, EXT>(A, R, L, base, nCon, n, bLin, bAng, bDLin, bDAng, bIA, bIB, bP, bQ, sPartStart, nPart, sFr, t_prev);
   } else {
     for (uint32_t b = tid; b < n; b += T) { if (PGS) { bP[b] = make_float4(0, 0, 0, 0); bQ[b] = make_float4(0, 0, 0, 0); } else bQ[b] = make_float4(0, 0, 0, 1); }
   }
@@ -609,7 +618,7 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   for (uint32_t b = tid; b < n; b += T) {
     const uint32_t a = list[b];
     if (!(A.geomFlags[a] & 0x100u) || body_asleep(A.S, a)) continue;
-    const float4 ib = bIB[b]; const uint32_t lock = __float_as_uint(ib.z);
+    const float4 ib = bIB[b]; const uint32_t lock = EXT ? __float_as_uint(ib.z) : 0u;
     const m33 sI = load_sym(bIA[b], ib);
     if (PGS) {   // integrate (DyDynamics.cpp:1398-1423): every body, with or without constraints
       const float4 p4 = A.pos[a]; v3 p = V3(p4.x, p4.y, p4.z); q4 q = Q4(A.quat[a]); v3 lv = V3(bDLin[b]), av = V3(bDAng[b]);

@@ -627,7 +627,7 @@ PXB_D void gjk_add_manifold_point(Manifold* m, v3 la, v3 lb, v3 n, float pen, fl
 }
 /* GuPCMContactBoxBox.cpp:918-958: the SAT passed but face clipping produced no point (edge-edge / corner configurations):
  * one GJK (or EPA) point is merged into whatever the manifold still holds.  manifold->rel / quatA / quatB were already updated by the caller. */
-__device__ __noinline__ void gjk_boxbox_gjk_fallback(const xf* tm0, const xf* tm1, v3 ext0, v3 ext1, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
+PXB_D void gjk_boxbox_gjk_fallback(const xf* tm0, const xf* tm1, v3 ext0, v3 ext1, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
   const xf curRTrans = axfinvmul(tm1, tm0);
   const mxf aToB = amxffromxf(&curRTrans);
   const float minMargin = fmin_(box_margin(ext0, toleranceLength), box_margin(ext1, toleranceLength));
@@ -647,6 +647,10 @@ __device__ __noinline__ void gjk_boxbox_gjk_fallback(const xf* tm0, const xf* tm
       if (contactDist >= dist) { out->point[out->count] = axftransform(tm1, manifold->pts[i].b); out->sep[out->count] = dist; out->count++; }
     }
   }
+}
+
+__device__ __noinline__ void gjk_boxbox_gjk_fallback_outofline(const xf* tm0, const xf* tm1, v3 ext0, v3 ext1, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
+  gjk_boxbox_gjk_fallback(tm0, tm1, ext0, ext1, contactDist, toleranceLength, manifold, out);
 }
 
 /* ---------------- polygonal box: GuPCMShapeConvex.cpp:40-110 ---------------- */

@@ -61,6 +61,18 @@ PXB_D void unconstrained_velocity(v3 gravity, float dt, float linDamping, float 
 
 // PxRigidDynamicLockFlag bits (linear x,y,z = 1,2,4; angular x,y,z = 8,16,32) travel in the unused .z lane of the body's second inertia float4
 PXB_D v3 lock3(v3 v, uint32_t bits) { if (bits & 1u) v.x = 0.f; if (bits & 2u) v.y = 0.f; if (bits & 4u) v.z = 0.f; return v; }
+// External force / torque for this step (PxDirectGPUAPI eFORCE / eTORQUE = PxRigidBody::addForce / addTorque(eFORCE)):
+// NpRigidBodyTemplate.h:507-528 (linAcc = F * invMass, angAcc = world inverse inertia * T, inertia as in :315-320) and
+// Sc::BodySim::updateForces ScBodySim.cpp:656-720 (v += acc * dt before the unconstrained-velocity pass).
+__device__ __noinline__ void apply_external_force(v3 F, v3 T, float invMass, float4 invI, q4 q, float dt, v3& lv, v3& av) {   // rare path: out of line, the solve kernels are register bound
+  if (F.x != 0.f || F.y != 0.f || F.z != 0.f) { const v3 linAcc = F * invMass; lv = lv + (V3(0, 0, 0) + linAcc * dt); }
+  if (T.x != 0.f || T.y != 0.f || T.z != 0.f) {
+    const m33 rot = amfromq(q);
+    m33 invIW; transform_inertia(V3(invI.x, invI.y, invI.z), rot, invIW);
+    const v3 angAcc = mmul(invIW, T);
+    av = av + (V3(0, 0, 0) + angAcc * dt);
+  }
+}
 // integrateCoreStep: returns updated (p, deltaQ, deltaLinDt, deltaAngDt); lock flags zero the locked velocity components first (DyTGSDynamics.cpp:1405-1422)
 PXB_D void integrate_core_step(v3& linVel, v3& angState, const m33& sqrtInvInertia, float dt, v3& p, q4& deltaQ, v3& dLin, v3& dAng, uint32_t lock) {
   if (lock) { linVel = lock3(linVel, lock & 7u); angState = lock3(angState, (lock >> 3) & 7u); }

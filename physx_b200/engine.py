@@ -32,7 +32,7 @@ EXPORTS = [
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
 ]
 
-RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY = 0, 1, 2
+RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
 
 
 class PhysxB200Error(RuntimeError):
@@ -185,6 +185,13 @@ class Scene:
         d = np.ascontiguousarray(data, dtype=np.float32)
         idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.uint32)
         _check(self._lib, self._lib.pxb_set_rigid_dynamic_data(self._h, _ptr(d), _ptr(idx), data_type, len(d)))
+
+    def setForces(self, forces=None, torques=None):
+        """PxDirectGPUAPI::setRigidDynamicData(eFORCE / eTORQUE) for every dynamic body: applied by the next simulate only."""
+        if forces is not None:
+            self.setRigidDynamicData(RD_FORCE, forces)
+        if torques is not None:
+            self.setRigidDynamicData(RD_TORQUE, torques)
 
     def getRigidDynamicDataDevice(self, data_type: int, dev_ptr: int, nb: int, dev_indices: int = 0):
         _check(self._lib, self._lib.pxb_get_rigid_dynamic_data_device(self._h, dev_ptr, dev_indices or None, data_type, nb))

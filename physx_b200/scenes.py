@@ -450,3 +450,14 @@ def capsules_into_boxes(seed=2, speed=14.0, **hdr):
         b = 1 + (i - 1 - 6) // 3          # the box under this capsule (capsules_on_boxes layout: 6 boxes, 3 droppers per box)
         sc.actors["pos"][i] = sc.actors["pos"][b] + np.array([0.05 * j, 0.1, -0.03 * j], dtype=np.float32)
     return sc
+
+
+def test_forces(n_dynamic, seed=1, blocks=7):
+    """(blocks, n_dynamic, 6) force xyz + torque xyz cycle for the eFORCE / eTORQUE tests: every third body and one block stay force-free."""
+    rng = np.random.RandomState(seed)
+    f = np.zeros((blocks, n_dynamic, 6), np.float32)
+    f[:, :, :3] = rng.uniform(-3, 3, (blocks, n_dynamic, 3))
+    f[:, :, 3:] = rng.uniform(-0.3, 0.3, (blocks, n_dynamic, 3))
+    f[:, ::3] = 0
+    f[2] = 0
+    return f

@@ -19,12 +19,16 @@ from physx_b200 import scenes  # noqa: E402
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 
-def run_reference(scene, steps, threads=1):
+def run_reference(scene, steps, threads=1, forces=None):
     with tempfile.TemporaryDirectory() as d:
         sp = os.path.join(d, "s.bin")
         scene.save(sp)
+        extra = []
+        if forces is not None:   # (blocks, n_dyn, 6) force xyz + torque xyz: block t % blocks is applied before step t
+            np.ascontiguousarray(forces, dtype="<f4").tofile(d + "/forces")
+            extra = ["--forces", d + "/forces"]
         subprocess.run([HARNESS, "run", sp, "--steps", str(steps), "--threads", str(threads), "--states", d + "/st", "--order", d + "/ord",
-                        "--bp", d + "/bp", "--contacts", d + "/con", "--sleep", d + "/sl"], check=True, capture_output=True)
+                        "--bp", d + "/bp", "--contacts", d + "/con", "--sleep", d + "/sl"] + extra, check=True, capture_output=True)
         sl = np.fromfile(d + "/sl", dtype=[("wc", "<f4"), ("s", "<u4")]).reshape(steps, scene.n_dynamic)
         nd, na = scene.n_dynamic, len(scene.actors)
         states = np.fromfile(d + "/st", "<f4").reshape(steps + 1, nd, 13)
@@ -50,7 +54,7 @@ def run_reference(scene, steps, threads=1):
                 con_pts.append(np.frombuffer(cb, "<f4", k * 10, off).reshape(k, 10)[:, :7]); off += k * 40
                 pt_off.append(pt_off[-1] + k)
             con_off.append(con_off[-1] + n)
-        return dict(scene=np.frombuffer(scene.tobytes(), np.uint8), states=states, wake=sl["wc"].copy(), asleep=sl["s"].copy(),
+        return dict(scene=np.frombuffer(scene.tobytes(), np.uint8), forces=(np.zeros((0, nd, 6), np.float32) if forces is None else np.asarray(forces, np.float32)), states=states, wake=sl["wc"].copy(), asleep=sl["s"].copy(),
                     order=np.concatenate(order_flat) if order_flat else np.zeros((0, 2), np.uint32), order_off=np.array(order_off),
                     bounds=np.stack(bounds), created=np.concatenate(cr), created_off=np.array(cro), deleted=np.concatenate(de) if de else np.zeros((0, 2), np.uint32),
                     deleted_off=np.array(deo), con_pairs=np.array(con_pairs, np.uint32).reshape(-1, 3), con_off=np.array(con_off),
@@ -87,9 +91,19 @@ def main():
     # a10 (GJK family): capsules and spheres dropped onto static tilted / dynamic resting boxes -- capsule-box face, edge and corner contacts
     cases["capsules_on_boxes"] = (scenes.capsules_on_boxes(seed=3), 150)
     cases["capsules_into_boxes"] = (scenes.capsules_into_boxes(seed=3), 60)   # deep penetration: the EPA query
+    # a19: PxDirectGPUAPI eFORCE / eTORQUE writes (= addForce / addTorque(eFORCE) before every step), a 7-step cycle of per-body forces
+    forced = {"forces_stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01),
+              "pgs_forces_stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01, solver=scenes.SOLVER_PGS),
+              "forces_primitives": scenes.mixed_primitives(n=12, seed=3, kinds=("sphere", "capsule"))}
     only = sys.argv[1:]
     if only:
         cases = {k: v for k, v in cases.items() if any(k.startswith(o) for o in only)}
+    for name, sc in forced.items():
+        if only and not any(name.startswith(o) for o in only):
+            continue
+        data = run_reference(sc, 80, forces=scenes.test_forces(sc.n_dynamic))
+        np.savez_compressed(os.path.join(out, name + ".npz"), **data)
+        print(name, "bodies", sc.n_dynamic, "steps", 80, "bytes", os.path.getsize(os.path.join(out, name + ".npz")))
     for name, (sc, steps) in cases.items():
         data = run_reference(sc, steps)
         np.savez_compressed(os.path.join(out, name + ".npz"), **data)

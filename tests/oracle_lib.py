@@ -34,6 +34,7 @@ def lib():
             getattr(L, f).argtypes = [vp, vp]
         L.pxo_debug_epa_calls.restype = u32
         L.pxo_scene_get_sleep.argtypes = [vp, vp, vp]
+        L.pxo_scene_set_forces.argtypes = [vp, vp, vp]
         L.pxo_scene_compute_bounds.argtypes = [vp]
         L.pxo_scene_broadphase.argtypes = [vp]
         _LIB = L
@@ -72,6 +73,12 @@ class OracleScene:
         w, a = np.zeros(self.num_dynamic, np.float32), np.zeros(self.num_dynamic, np.uint32)
         self.L.pxo_scene_get_sleep(self.h, _p(w), _p(a))
         return w, a
+
+    def setForces(self, forces=None, torques=None):
+        """PxDirectGPUAPI::setRigidDynamicData(eFORCE / eTORQUE): (n_dyn, 3) arrays applied at the next step only"""
+        f = None if forces is None else np.ascontiguousarray(forces, dtype=np.float32)
+        t = None if torques is None else np.ascontiguousarray(torques, dtype=np.float32)
+        self.L.pxo_scene_set_forces(self.h, _p(f), _p(t))
 
     def step(self, order=None):
         if order is None or len(order) == 0:

@@ -447,6 +447,42 @@ def test_lock_flags_gpu_matches_reference_golden(name):
         assert np.abs(st[:, 7:10] - ref[:, 7:10]).max() < TOL_LINVEL and np.abs(st[:, 10:] - ref[:, 10:]).max() < TOL_ANGVEL, f"velocity, step {t}"
 
 
+@pytest.mark.parametrize("name", ["stacks", "pgs_stacks", "envs", "pgs_envs", "primitives"])
+def test_external_forces_gpu_matches_oracle(oracle, name):
+    """PxDirectGPUAPI eFORCE / eTORQUE writes on both paths and both solvers: bit-level agreement with the oracle every step; forces last one step."""
+    sc = {"stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01),
+          "pgs_stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01, solver=scenes.SOLVER_PGS),
+          "envs": scenes.env_grid_stacks(n_envs=5, stacks_per_env=3, height=4, jitter=0.01),
+          "pgs_envs": scenes.env_grid_stacks(n_envs=5, stacks_per_env=3, height=4, jitter=0.01, solver=scenes.SOLVER_PGS),
+          "primitives": scenes.mixed_primitives(n=12, seed=3, kinds=("sphere", "capsule"))}[name]
+    F = scenes.test_forces(sc.n_dynamic)
+    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    for t in range(60):
+        if t % 9 != 8:   # every ninth step nothing is written: the previous step's forces must not persist
+            gpu.setForces(F[t % len(F), :, :3], F[t % len(F), :, 3:])
+            cpu.setForces(F[t % len(F), :, :3], F[t % len(F), :, 3:])
+        gpu.step()
+        cpu.step()
+        assert gpu.uses_env_path == name.endswith("envs")
+        sg = gpu.getStates()
+        assert np.abs(sg - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
+        cpu.setStates(sg)
+
+
+@pytest.mark.parametrize("name", ["forces_stacks", "pgs_forces_stacks"])
+def test_external_forces_gpu_matches_reference_golden(name):
+    z, sc = util.load_golden(name)
+    F = z["forces"]
+    gpu = engine.Scene(sc)
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setForces(F[t % len(F), :, :3], F[t % len(F), :, 3:])
+        gpu.setConstraintOrder(util.golden_order(z, t))
+        gpu.step()
+        st, ref = gpu.getStates(), z["states"][t + 1]
+        assert util.rel_err(st[:, :3], ref[:, :3]) < TOL_POSE and util.rel_err(st[:, 3:7], ref[:, 3:7]) < TOL_POSE, f"pose, step {t}"
+        assert np.abs(st[:, 7:10] - ref[:, 7:10]).max() < TOL_LINVEL and np.abs(st[:, 10:] - ref[:, 10:]).max() < TOL_ANGVEL, f"velocity, step {t}"
+
+
 def test_stream_ordered_host_api_matches_blocking_api():
     """pxb_get/set_rigid_dynamic_data_async: enqueued around simulate with ONE host sync (fetchResults) per step, same results."""
     import ctypes
