@@ -11,6 +11,7 @@
 #ifndef PXO_GJK_H
 #define PXO_GJK_H
 #include "pxo_np.h"
+#include "scene_format.h"
 
 enum { PXO_CVX_CAPSULE = 0, PXO_CVX_BOX = 1 };
 enum { PXO_GJK_NON_INTERSECT = 0, PXO_GJK_CONTACT, PXO_GJK_UNDEFINED, PXO_GJK_DEGENERATE, PXO_EPA_CONTACT, PXO_EPA_DEGENERATE, PXO_EPA_FAIL };
@@ -634,6 +635,84 @@ static inline void pxo_boxbox_gjk_fallback(const xf* tm0, const xf* tm1, v3 ext0
       const float dist = manifold->pts[i].pen;
       if (contactDist >= dist) { out->point[out->count] = axftransform(tm1, manifold->pts[i].b); out->sep[out->count] = dist; out->count++; }
     }
+  }
+}
+
+
+/* ---------------- convex hulls (cooked: Gu::ConvexHullData, see scene_format.h) ---------------- */
+typedef struct {
+  uint32_t nVerts, nPolys, nEdges, nIdx;
+  v3 centerOfMass, boundsCenter, boundsExtents, internalExtents; float internalRadius;
+  const float* verts;              /* [nVerts][3] */
+  const PxbCookedPoly* polys;      /* plane, vref, nbVerts, minIndex */
+  const uint8_t* vertexRefs;       /* getVertexData8 */
+  const uint8_t* facesByEdges;     /* getFacesByEdges8 */
+} PxoHull;
+static inline v3 pxo_hull_vert(const PxoHull* h, uint32_t i) { return V3(h->verts[i * 3], h->verts[i * 3 + 1], h->verts[i * 3 + 2]); }
+static inline v3 pxo_hull_plane_n(const PxoHull* h, uint32_t p) { return V3(h->polys[p].plane[0], h->polys[p].plane[1], h->polys[p].plane[2]); }
+/* CalculatePCMConvexMargin GuVecConvexHull.h:55-65 (identity scale) */
+static inline float pxo_hull_pcm_margin(const PxoHull* h, float toleranceLength) {
+  const float mn = fminf_(h->internalExtents.x, fminf_(h->internalExtents.y, h->internalExtents.z));
+  return fminf_(mn * 0.25f, toleranceLength * 0.05f);
+}
+
+/* pcmContactPlaneConvex: GuPCMContactPlaneConvex.cpp:36-227 (shape0 = plane, shape1 = convex mesh, identity mesh scale).
+ * Note the reference's vertex loop visits mPolygons[closestFaceIndex] on BOTH passes (the second pass was meant for polyIndex2):
+ * restated as is, the duplicated points are merged by the manifold reduction. */
+static inline void pxo_pcm_plane_convex(const xf* planeTm, const xf* convexTm, const PxoHull* hull, float contactDist, float toleranceLength, PxoManifold* manifold, PxoContacts* out) {
+  const xf* transf0 = convexTm; const xf* transf1 = planeTm;
+  const xf curTransf = axfinvmul(transf1, transf0);
+  const float convexMargin = pxo_hull_pcm_margin(hull, toleranceLength);
+  const v3 planeNormal = anormalize(aqbasis0(transf1->q));
+  const v3 negPlaneNormal = v3neg(planeNormal);
+  const float projectBreakingThreshold = convexMargin * 0.2f;
+  const int initialContacts = manifold->n;
+  const mxf aToB = amxffromxf(&curTransf);
+  pxo_refresh(manifold, &aToB, projectBreakingThreshold);
+  const int bLostContacts = manifold->n != initialContacts;
+  if (bLostContacts || pxo_invalidate_plane(manifold, &curTransf, convexMargin, 0.2f)) {
+    const v3 localNormal = V3(1, 0, 0);
+    manifold->n = 0; manifold->rel = curTransf;
+    const v3 n = anormalize(amxfrotateinv(&aToB, localNormal));   /* vertex2Shape = identity: M33MulV3(I, v) = v */
+    const v3 nnormal = v3neg(n);
+    PxoMPoint mc[64]; int numContacts = 0;
+    float minProj = FLT_MAX; uint32_t closestFaceIndex = 0, polyIndex2 = 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < hull->nPolys; ++i) { const float proj = adot(n, pxo_hull_plane_n(hull, i)); if (minProj > proj) { minProj = proj; closestFaceIndex = i; } }
+    uint32_t closestEdge = 0xffffffffu;
+    minProj = minProj - 5e-4f;
+    float maxDpSq = minProj * minProj;
+    for (uint32_t i = 0; i < hull->nEdges; ++i) {
+      const uint8_t f0 = hull->facesByEdges[i * 2], f1 = hull->facesByEdges[i * 2 + 1];
+      const v3 edgeNormal = v3add(pxo_hull_plane_n(hull, f0), pxo_hull_plane_n(hull, f1));
+      const float enMagSq = adot(edgeNormal, edgeNormal), dp = adot(edgeNormal, nnormal), sqDp = dp * dp;
+      if (dp >= 0.f && sqDp > maxDpSq * enMagSq) { maxDpSq = sqDp / enMagSq; closestEdge = i; }
+    }
+    if (closestEdge != 0xffffffffu) {
+      const uint32_t f0 = hull->facesByEdges[closestEdge * 2], f1 = hull->facesByEdges[closestEdge * 2 + 1];
+      const float dp0 = adot(pxo_hull_plane_n(hull, f0), nnormal), dp1 = adot(pxo_hull_plane_n(hull, f1), nnormal);
+      if (dp0 > dp1) { closestFaceIndex = f0; polyIndex2 = f1; } else { closestFaceIndex = f1; polyIndex2 = f0; }
+    }
+    for (uint32_t index = closestFaceIndex; index != 0xFFFFFFFFu; index = polyIndex2, polyIndex2 = 0xFFFFFFFFu) {
+      const PxbCookedPoly* face = &hull->polys[closestFaceIndex];
+      const uint8_t* vertInds = hull->vertexRefs + face->vref;
+      for (uint32_t i = 0; i < face->nbVerts; ++i) {
+        const v3 pInVertexSpace = pxo_hull_vert(hull, vertInds[i]);
+        const v3 pInPlaneSpace = amxftransform(&aToB, pInVertexSpace);   /* aToBVertexSpace = (aToB.p, aToB.rot * I) */
+        const float signDist = pInPlaneSpace.x;
+        if (contactDist > signDist) {
+          mc[numContacts].a = pInVertexSpace; mc[numContacts].b = v3negscalesub(localNormal, signDist, pInPlaneSpace); mc[numContacts].n = localNormal; mc[numContacts].pen = signDist; numContacts++;
+          if (numContacts == 64) { pxo_reduce_cluster(manifold, mc, numContacts); numContacts = PXO_MANIFOLD_CACHE; for (int c = 0; c < PXO_MANIFOLD_CACHE; ++c) mc[c] = manifold->pts[c]; }
+        }
+      }
+    }
+    /* addBatchManifoldContacts .cpp:812-831 */
+    if (numContacts <= PXO_MANIFOLD_CACHE) { for (int i = 0; i < numContacts; ++i) manifold->pts[i] = mc[i]; manifold->n = numContacts; }
+    else { pxo_reduce_batch(manifold, mc, numContacts, toleranceLength); manifold->n = PXO_MANIFOLD_CACHE; }
+  }
+  out->count = 0; out->normal = negPlaneNormal;
+  for (int i = 0; i < manifold->n; ++i) {   /* addManifoldContactsToContactBuffer(buffer, normal, transf1, contactOffset) .cpp:739-759 */
+    const float dist = manifold->pts[i].pen;
+    if (contactDist >= dist) { out->point[out->count] = axftransform(transf1, manifold->pts[i].b); out->sep[out->count] = dist; out->count++; }
   }
 }
 

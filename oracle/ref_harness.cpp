@@ -41,6 +41,7 @@
 #undef private
 #undef protected
 #include "scene_format.h"
+#include "GuConvexMesh.h"
 
 using namespace physx;
 
@@ -115,7 +116,9 @@ static std::vector<uint8_t> readFile(const char* path) {
 struct Hull { std::vector<PxVec3> verts; PxConvexMesh* mesh = nullptr; };
 
 int main(int argc, char** argv) {
-  if (argc < 3 || strcmp(argv[1], "run") != 0) {
+  const char* cookOut = nullptr;
+  if (argc == 4 && strcmp(argv[1], "cook") == 0) { cookOut = argv[3]; argc = 3; }
+  else if (argc < 3 || strcmp(argv[1], "run") != 0) {
     fprintf(stderr, "usage: ref_harness run <scene.bin> --steps N [--threads T] [--states f] [--bp f] [--contacts f] [--warmup W] [--hulls f]\n");
     return 2;
   }
@@ -160,6 +163,33 @@ int main(int argc, char** argv) {
     PxCookingParams cp(scale); cp.buildGPUData = true;
     hulls[h].mesh = PxCreateConvexMesh(cp, d, physics->getPhysicsInsertionCallback());
     if (!hulls[h].mesh) { fprintf(stderr, "hull cook failed\n"); return 3; }
+  }
+  if (cookOut) {   // `ref_harness cook scene.bin out.bin`: the cooked section of the scene format (scene_format.h) from Gu::ConvexHullData
+    FILE* f = fopen(cookOut, "wb");
+    for (auto& h : hulls) {
+      const Gu::ConvexHullData& hd = static_cast<Gu::ConvexMesh*>(h.mesh)->getHull();
+      PxbCookedHullHeader ch; memset(&ch, 0, sizeof(ch));
+      ch.nVerts = hd.mNbHullVertices; ch.nPolys = hd.mNbPolygons; ch.nEdges = PxU32(PxU16(hd.mNbEdges));
+      uint32_t nIdx = 0; for (uint32_t p = 0; p < ch.nPolys; p++) nIdx = PxMax(nIdx, uint32_t(hd.mPolygons[p].mVRef8) + hd.mPolygons[p].mNbVerts);
+      ch.nIdx = nIdx;
+      memcpy(ch.centerOfMass, &hd.mCenterOfMass, 12); memcpy(ch.boundsCenter, &hd.mAABB.mCenter, 12); memcpy(ch.boundsExtents, &hd.mAABB.mExtents, 12);
+      ch.internalRadius = hd.mInternal.mInternalRadius; memcpy(ch.internalExtents, &hd.mInternal.mInternalExtents, 12);
+      PxReal mass; PxMat33 inertia; PxVec3 com; h.mesh->getMassInformation(mass, inertia, com);
+      ch.unitMass = mass; ch.unitInertiaDiag[0] = inertia.column0.x; ch.unitInertiaDiag[1] = inertia.column1.y; ch.unitInertiaDiag[2] = inertia.column2.z; memcpy(ch.unitCom, &com, 12);
+      fwrite(&ch, sizeof(ch), 1, f);
+      fwrite(hd.getHullVertices(), 12, ch.nVerts, f);
+      for (uint32_t p = 0; p < ch.nPolys; p++) {
+        const Gu::HullPolygonData& pd = hd.mPolygons[p];
+        PxbCookedPoly cp_; cp_.plane[0] = pd.mPlane.n.x; cp_.plane[1] = pd.mPlane.n.y; cp_.plane[2] = pd.mPlane.n.z; cp_.plane[3] = pd.mPlane.d;
+        cp_.vref = pd.mVRef8; cp_.nbVerts = pd.mNbVerts; cp_.minIndex = pd.mMinIndex; cp_.pad = 0;
+        fwrite(&cp_, sizeof(cp_), 1, f);
+      }
+      const uint8_t zero[4] = {0, 0, 0, 0};
+      fwrite(hd.getVertexData8(), 1, nIdx, f); fwrite(zero, 1, (4 - nIdx % 4) % 4, f);
+      fwrite(hd.getFacesByEdges8(), 1, 2 * ch.nEdges, f); fwrite(zero, 1, (4 - (2 * ch.nEdges) % 4) % 4, f);
+    }
+    fclose(f);
+    return 0;
   }
   if (hullsPath) {
     // cooked hull dump: per hull: u32 nVerts, u32 nPolys, verts xyz, per poly: plane(nx ny nz d), u32 nIdx, u32 idx[nIdx]

@@ -1,6 +1,10 @@
 /* Scene interchange format shared by the oracle tools (test infrastructure).
  *
  * A scene file is:  SceneHeader | ActorRec[nActors] | for each hull: u32 nVerts, float xyz[nVerts]
+ *                   | (when header.reserved[1] == PXB_COOKED_MAGIC) for each hull: PxbCookedHullHeader + arrays (see below)
+ * The cooked section is what PxCreateConvexMesh makes of the point cloud (Gu::ConvexHullData): convex cooking is host-side work in PhysX
+ * too (the GPU pipeline receives cooked hulls through PxsSimulationController::addPxgShape), so cooked hulls are an INPUT of the hot path.
+ * `ref_harness cook scene.bin out.bin` writes the section from the unmodified reference cooking code.
  * All little-endian, 4-byte fields, no padding.  Python mirror: physx_b200/scenes.py (numpy dtypes).
  * One shape per actor, shape local pose = identity (planes: actor pose carries the plane frame,
  * normal = local +X as in PxPlaneGeometry, physx/include/geometry/PxPlaneGeometry.h).
@@ -53,6 +57,19 @@ typedef struct {
   float    maxDepenetrationVel;
   float    reserved[2];
 } PxbActorRec;
+
+#define PXB_COOKED_MAGIC 0x43485850u /* "PXHC" */
+/* followed by: float verts[nVerts][3]; PxbCookedPoly polys[nPolys]; uint8_t vertexRefs[nIdx] (padded to 4);
+ * uint8_t facesByEdges[2 * nEdges] (padded to 4)   -- Gu::ConvexHullData, physx/source/geomutils/src/convex/GuConvexMeshData.h:47-175 */
+typedef struct {
+  uint32_t nVerts, nPolys, nEdges, nIdx;
+  float centerOfMass[3];          /* mCenterOfMass */
+  float boundsCenter[3], boundsExtents[3];   /* mAABB (local bounds) */
+  float internalRadius, internalExtents[3];  /* mInternal */
+  float unitMass, unitInertiaDiag[3], unitCom[3];   /* PxConvexMesh::getMassInformation at density 1 (diagonal of the inertia tensor) */
+  uint32_t reserved[1];
+} PxbCookedHullHeader;            /* 25 words = 100 bytes */
+typedef struct { float plane[4]; uint32_t vref, nbVerts, minIndex, pad; } PxbCookedPoly;   /* HullPolygonData */
 
 /* Per-step state record written by ref_harness / oracle tools: for every DYNAMIC actor, in actor
  * order: pos[3] quat[4] linVel[3] angVel[3] = 13 floats. */

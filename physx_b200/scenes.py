@@ -125,11 +125,37 @@ def add_ground_plane(actors):
     return np.concatenate([p, actors])
 
 
+COOKED_MAGIC = 0x43485850   # "PXHC": header.reserved[1] when the cooked-hull section is present (oracle/scene_format.h)
+COOKED_HDR_DTYPE = np.dtype([
+    ("nVerts", "<u4"), ("nPolys", "<u4"), ("nEdges", "<u4"), ("nIdx", "<u4"),
+    ("centerOfMass", "<f4", 3), ("boundsCenter", "<f4", 3), ("boundsExtents", "<f4", 3),
+    ("internalRadius", "<f4"), ("internalExtents", "<f4", 3),
+    ("unitMass", "<f4"), ("unitInertiaDiag", "<f4", 3), ("unitCom", "<f4", 3), ("reserved", "<u4", 1),
+])
+COOKED_POLY_DTYPE = np.dtype([("plane", "<f4", 4), ("vref", "<u4"), ("nbVerts", "<u4"), ("minIndex", "<u4"), ("pad", "<u4")])
+assert COOKED_HDR_DTYPE.itemsize == 100 and COOKED_POLY_DTYPE.itemsize == 32
+
+
+def parse_cooked(buf, n_hulls, off=0):
+    """cooked-hull section -> list of dicts (hdr, verts, polys, vertexRefs, facesByEdges); returns (list, end offset)"""
+    out = []
+    for _ in range(n_hulls):
+        hdr = np.frombuffer(buf, COOKED_HDR_DTYPE, 1, off)[0].copy(); off += COOKED_HDR_DTYPE.itemsize
+        nv, npoly, ne, ni = int(hdr["nVerts"]), int(hdr["nPolys"]), int(hdr["nEdges"]), int(hdr["nIdx"])
+        verts = np.frombuffer(buf, "<f4", nv * 3, off).reshape(nv, 3).copy(); off += nv * 12
+        polys = np.frombuffer(buf, COOKED_POLY_DTYPE, npoly, off).copy(); off += npoly * COOKED_POLY_DTYPE.itemsize
+        refs = np.frombuffer(buf, np.uint8, ni, off).copy(); off += (ni + 3) // 4 * 4
+        fbe = np.frombuffer(buf, np.uint8, 2 * ne, off).copy(); off += (2 * ne + 3) // 4 * 4
+        out.append(dict(hdr=hdr, verts=verts, polys=polys, vertexRefs=refs, facesByEdges=fbe))
+    return out, off
+
+
 class Scene:
-    def __init__(self, header, actors, hulls=()):
+    def __init__(self, header, actors, hulls=(), cooked=b""):
         self.header = header.copy()
         self.actors = actors
         self.hulls = list(hulls)
+        self.cooked = bytes(cooked)   # cooked-hull section (reference cooking output, see cook_hulls); empty = not cooked
         self.header["nActors"] = len(actors)
         self.header["nHulls"] = len(self.hulls)
 
@@ -138,11 +164,14 @@ class Scene:
         return int(np.count_nonzero(self.actors["flags"] & ACTOR_DYNAMIC))
 
     def tobytes(self):
-        out = [self.header.tobytes(), self.actors.tobytes()]
-        for h in self.hulls:
-            h = np.asarray(h, dtype="<f4").reshape(-1, 3)
-            out.append(np.uint32(len(h)).tobytes())
-            out.append(h.tobytes())
+        h = self.header.copy()
+        h["reserved"][1] = COOKED_MAGIC if self.cooked else 0
+        out = [h.tobytes(), self.actors.tobytes()]
+        for hl in self.hulls:
+            hl = np.asarray(hl, dtype="<f4").reshape(-1, 3)
+            out.append(np.uint32(len(hl)).tobytes())
+            out.append(hl.tobytes())
+        out.append(self.cooked)
         return b"".join(out)
 
     def save(self, path):
@@ -160,7 +189,63 @@ class Scene:
         for _ in range(int(h["nHulls"])):
             nv = int(np.frombuffer(buf, "<u4", 1, off)[0]); off += 4
             hulls.append(np.frombuffer(buf, "<f4", nv * 3, off).reshape(nv, 3).copy()); off += nv * 12
-        return Scene(h, a, hulls)
+        cooked = buf[off:] if int(h["reserved"][1]) == COOKED_MAGIC else b""
+        return Scene(h, a, hulls, cooked)
+
+    def cooked_hulls(self):
+        return parse_cooked(self.cooked, len(self.hulls))[0] if self.cooked else []
+
+
+def cook_hulls(scene, density=10.0):
+    """Runs the reference's convex cooking (oracle/_ref/ref_harness cook: PxCreateConvexMesh, unmodified) over the scene's hull point clouds,
+    attaches the cooked section and fills mass / inertia of the convex actors from the cooked mass information (mass = density * volume,
+    diagonal of the inertia tensor, centre-of-mass frame = actor frame: both sides get the same explicit values).  Needs the build container
+    (/root/reference); fixtures under tests/golden carry the cooked bytes so that the GPU box never cooks."""
+    import os, subprocess, tempfile
+    harness = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_harness")
+    with tempfile.TemporaryDirectory() as d:
+        scene.cooked = b""
+        scene.save(d + "/s.bin")
+        subprocess.run([harness, "cook", d + "/s.bin", d + "/c.bin"], check=True, capture_output=True)
+        scene.cooked = open(d + "/c.bin", "rb").read()
+    ch = scene.cooked_hulls()
+    for i in np.nonzero(scene.actors["geomType"] == GEOM_CONVEX)[0]:
+        hdr = ch[int(scene.actors["hullIdx"][i])]["hdr"]
+        if scene.actors["flags"][i] & ACTOR_DYNAMIC:
+            scene.actors["mass"][i] = np.float32(density) * hdr["unitMass"]
+            scene.actors["inertia"][i] = np.float32(density) * hdr["unitInertiaDiag"]
+    return scene
+
+
+def random_hull_points(rng, n_points=16, radius=0.2):
+    """points on a jittered sphere (12-20 vertex hulls, r ~ 0.2), centred on their mean"""
+    p = rng.normal(size=(n_points, 3))
+    p /= np.linalg.norm(p, axis=1, keepdims=True)
+    p *= radius * rng.uniform(0.75, 1.0, (n_points, 1))
+    p -= p.mean(axis=0, keepdims=True)
+    return p.astype(np.float32)
+
+
+def set_convex(a, idx, hull_idx):
+    a["geomType"][idx] = GEOM_CONVEX
+    a["flags"][idx] = ACTOR_DYNAMIC
+    a["hullIdx"][idx] = hull_idx
+    a["mass"][idx] = 1.0          # placeholders until cook_hulls fills them from the cooked mass information
+    a["inertia"][idx] = 0.01
+
+
+def hulls_on_plane(n=8, n_hulls=3, seed=6, **hdr):
+    """Convex hulls (12-20 vertices) with random orientations and spins dropped onto the ground plane, spaced so that they never touch
+    each other: exercises convex bounds and pcmContactPlaneConvex."""
+    rng = np.random.RandomState(seed)
+    hulls = [random_hull_points(rng, int(rng.randint(12, 21)), 0.25) for _ in range(n_hulls)]
+    a = _new_actors(n)
+    for i in range(n):
+        set_convex(a, i, i % n_hulls)
+        a["pos"][i] = (1.5 * (i % 4), 0.6 + 0.25 * (i // 4), 1.5 * (i // 4))
+        a["angVel"][i] = rng.uniform(-2, 2, 3)
+    a["quat"] = random_unit_quats(rng, n)
+    return cook_hulls(Scene(default_header(**hdr), add_ground_plane(a), hulls))
 
 
 def box_stacks(n_stacks=10, height=10, half_extent=0.5, spacing=4.0, jitter=0.0, seed=1234, **hdr):
