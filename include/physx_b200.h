@@ -95,6 +95,21 @@ PXB_API int  pxb_device_count(void);
 /* PxsSimulationController::addDynamics / addPxgShape + Bp::AABBManagerBase::addBounds
  * (lowlevel/software/include/PxsSimulationController.h:122-354, lowlevelaabb/include/BpAABBManagerBase.h:175-330).
  * `recs` = nb records of 128 bytes (PxbActorRec layout).  Actor index = order of addition. */
+/* ---- cooked convex hulls.  Replaces: PxsSimulationController::addPxgShape + the hull upload of PxgShapeManager (the reference GPU pipeline
+ *      receives Gu::ConvexHullData cooked on the host, S/gpunarrowphase/include/PxgConvexConvexShape.h:50-65, S/geomutils/src/convex/GuConvexMeshData.h:47-175).
+ *      `cooked` = nHulls records, each: PxbCookedHullHeader, float verts[nVerts][3], PxbCookedPoly polys[nPolys],
+ *      uint8_t vertexRefs[nIdx] (getVertexData8, padded to 4 bytes), uint8_t facesByEdges[2 * nEdges] (getFacesByEdges8, padded to 4 bytes).
+ *      Call once, before adding the actors whose PxbActorRec::hullIdx refer to it.  Supported hull pairs so far: plane-convex. ---- */
+typedef struct {
+  uint32_t nVerts, nPolys, nEdges, nIdx;
+  float centerOfMass[3];
+  float boundsCenter[3], boundsExtents[3];
+  float internalRadius, internalExtents[3];
+  float unitMass, unitInertiaDiag[3], unitCom[3];
+  uint32_t reserved[1];
+} PxbCookedHullHeader;
+typedef struct { float plane[4]; uint32_t vref, nbVerts, minIndex, pad; } PxbCookedPoly;
+PXB_API int  pxb_scene_set_convex_meshes(PxbScene* scene, const void* cooked, size_t bytes, uint32_t nHulls);
 PXB_API int  pxb_scene_add_actors(PxbScene* scene, const void* recs, uint32_t nb);
 PXB_API uint32_t pxb_scene_num_actors(const PxbScene* scene);
 PXB_API uint32_t pxb_scene_num_dynamic(const PxbScene* scene);

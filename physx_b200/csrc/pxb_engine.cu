@@ -74,8 +74,9 @@ struct PxbScene {
   // per pair (this frame)
   float4 *cHdr = 0, *cPts = 0; uint2* pairBodies = 0; float* cForce = 0;
   uint32_t *pairOrder = 0, *npClassCount = 0; uint8_t* npClass = 0; bool binPairs = false;   // mixed-type scenes: pairs binned by type pair before the narrowphase
-  uint32_t* gjkList = 0; bool hasGjkPairs = false, anyLocks = false;
-  float4 *extForce = 0, *extTorque = 0; bool forcesUsed = false;   // PxDirectGPUAPI eFORCE / eTORQUE writes pending for the next step   // a10: worklist of GJK-family pairs (filled by k_narrowphase)
+  uint32_t* gjkList = 0; bool hasGjkPairs = false, anyLocks = false, anyConvex = false;
+  float4 *extForce = 0, *extTorque = 0; bool forcesUsed = false;
+  uint4* hullMeta = 0; float4 *hullVerts = 0, *hullPolys = 0; uint8_t *hullRefs = 0, *hullEdges = 0; uint32_t nHulls = 0; std::vector<float> hullDiam;   // cooked convex hulls (pxb_scene_set_convex_meshes)   // PxDirectGPUAPI eFORCE / eTORQUE writes pending for the next step   // a10: worklist of GJK-family pairs (filled by k_narrowphase)
   uint32_t *conFlag = 0, *conIdx = 0, *conPair = 0, *rankOfPair = 0; uint64_t *conSortKey = 0, *conSortKeyAlt = 0; uint32_t* conPairAlt = 0;
   uint64_t* orderKeys = 0; uint32_t nOrder = 0, capOrder = 0;
   uint32_t *conB0 = 0, *conB1 = 0, *conPos0 = 0, *conPos1 = 0, *conColour = 0, *conDone = 0, *bodyList = 0, *ordered = 0;
@@ -98,6 +99,7 @@ struct PxbScene {
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static HullArrays hull_arrays(const PxbScene* s) { HullArrays H; H.meta = s->hullMeta; H.verts = s->hullVerts; H.polys = s->hullPolys; H.refs = s->hullRefs; H.edges = s->hullEdges; return H; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (s) s->abort = true; return fail(PXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
 
 // ---------------------------------------------------------------------------------------------
@@ -107,7 +109,21 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterp
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // a1: tight world AABB of one shape.  Formulas: Gu::computeBounds (geomutils/src/GuBounds.cpp:354-400, plane :210-260).
-__device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d, float* mn, float* mx) {
+__device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d, float* mn, float* mx, const HullArrays* hulls = nullptr) {
+  if (type == PXB_GEOM_CONVEXMESH && hulls) {   // Gu::computeTightBounds (GuBounds.cpp:301-352; PxConvexMeshGeometry defaults to eTIGHT_BOUNDS): rotated vertices, last vertex first
+    const DevHull h = load_hull(*hulls, __float_as_uint(d.x));
+    const m33 b = amfromq(q);
+    v3 lo = V3(0, 0, 0), hi = V3(0, 0, 0);
+    for (uint32_t k = 0; k < h.nVerts; ++k) {
+      const v3 v = h.vert(k == 0 ? h.nVerts - 1 : k - 1);
+      const v3 w = (b.c0 * v.x + b.c1 * v.y) + b.c2 * v.z;
+      if (k == 0) { lo = w; hi = w; } else { lo = vmin(lo, w); hi = vmax(hi, w); }
+    }
+    hi = hi + p; lo = lo + p;
+    const v3 c = (hi + lo) * 0.5f, e = (hi - lo) * 0.5f;
+    mn[0] = c.x - e.x; mn[1] = c.y - e.y; mn[2] = c.z - e.z; mx[0] = c.x + e.x; mx[1] = c.y + e.y; mx[2] = c.z + e.z;
+    return;
+  }
   v3 e = V3(0, 0, 0); bool plane = false;
   if (type == PXB_GEOM_SPHERE) e = V3(d.x, d.x, d.x);
   else if (type == PXB_GEOM_CAPSULE) { const v3 dd = qbasis0(q) * d.y; e = V3(fabsf(dd.x) + d.x, fabsf(dd.y) + d.x, fabsf(dd.z) + d.x); }
@@ -131,7 +147,7 @@ __device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d
 __global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims,
                          const uint32_t* __restrict__ geomFlags, const uint32_t* __restrict__ envId, float contactOffset, float* __restrict__ tight,
                          int externalTight, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax, GridParams g, uint32_t envCount,
-                         uint64_t* __restrict__ cellKey, uint32_t* __restrict__ cellVal) {
+                         uint64_t* __restrict__ cellKey, uint32_t* __restrict__ cellVal, HullArrays hulls) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nA) return;
   const uint32_t gf = geomFlags[a];
@@ -139,7 +155,7 @@ __global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const floa
   if (externalTight) { for (int k = 0; k < 3; ++k) { mn[k] = tight[a * 6 + k]; mx[k] = tight[a * 6 + 3 + k]; } }
   else {
     const float4 p4 = pos[a];
-    tight_bounds(gf & 0xff, V3(p4.x, p4.y, p4.z), Q4(quat[a]), dims[a], mn, mx);
+    tight_bounds(gf & 0xff, V3(p4.x, p4.y, p4.z), Q4(quat[a]), dims[a], mn, mx, &hulls);
     for (int k = 0; k < 3; ++k) { tight[a * 6 + k] = mn[k]; tight[a * 6 + 3 + k] = mx[k]; }
   }
   const float co = contactOffset;
@@ -339,7 +355,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   const float4 d0 = dims[s0], d1 = dims[s1];
   float4* rec = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4;
   // only the PCM pair types keep a persistent manifold (plane-box, box-box, plane-capsule); the closed-form sphere family does not
-  const bool usesManifold = (ty0 == PXB_GEOM_PLANE && (ty1 == PXB_GEOM_BOX || ty1 == PXB_GEOM_CAPSULE)) || (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX);
+  const bool usesManifold = (ty0 == PXB_GEOM_PLANE && (ty1 == PXB_GEOM_BOX || ty1 == PXB_GEOM_CAPSULE)) || (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX);   // (GJK-family pairs load theirs in k_narrowphase_gjk)
   Manifold man;
   if (usesManifold) manifold_load(man, rec); else { man.n = 0; man.dirty = 0; }
   Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
@@ -361,7 +377,8 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CAPSULE) pcm_plane_capsule(tm0, tm1, d1.x, d1.y, contactDist, man, out);
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_CAPSULE) np_capsule_capsule(tm0, tm1, d0.x, d0.y, d1.x, d1.y, contactDist, out);
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_BOX) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // GJK family (a10): k_narrowphase_gjk fills this pair's outputs
-  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // convex hulls (a10): reported by fetchResults, never silently skipped
+  else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CONVEXMESH) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // hull pairs also go through k_narrowphase_gjk
+  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // hull vs sphere / capsule / box / hull (a10): reported by fetchResults, never silently skipped
   if (man.dirty) manifold_store(man, rec); else if (usesManifold && man.n > 0) manifold_store_pens(man, rec);   // steady state: only the penetrations change
   if (flip && out.count) out.normal = -out.normal;
   cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
@@ -375,7 +392,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
 // the list order is arbitrary (atomic append) but every pair writes only its own outputs, so the result is deterministic.
 __global__ void __launch_bounds__(128) k_narrowphase_gjk(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, uint32_t bitsA, const float4* __restrict__ pos, const float4* __restrict__ quat,
                               const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags, float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr,
-                              float4* __restrict__ cPts, uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, uint32_t* __restrict__ counters, const uint32_t* __restrict__ gjkList) {
+                              float4* __restrict__ cPts, uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, uint32_t* __restrict__ counters, const uint32_t* __restrict__ gjkList, HullArrays hulls) {
   const uint32_t n = counters[C_NGJK];
   for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
     const uint32_t i = gjkList[w];
@@ -394,7 +411,9 @@ __global__ void __launch_bounds__(128) k_narrowphase_gjk(const uint64_t* __restr
     Manifold man; manifold_load(man, rec); manifold_load_warm(man, rec);
     Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
     for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
-    gjk_pcm_capsule_box(&tm0, &tm1, d0.x, d0.y, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
+    const uint32_t ty1 = flip ? t0 : t1;
+    if (ty1 == PXB_GEOM_CONVEXMESH) { const DevHull h = load_hull(hulls, __float_as_uint(d1.x)); gjk_pcm_plane_convex(&tm0, &tm1, h, contactDist, toleranceLength, &man, &out); }   // s0 = plane, s1 = hull
+    else gjk_pcm_capsule_box(&tm0, &tm1, d0.x, d0.y, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
     if (man.dirty) { manifold_store(man, rec); manifold_store_warm(man, rec); } else if (man.n > 0) manifold_store_pens(man, rec);
     if (flip && out.count) out.normal = -out.normal;
     cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
@@ -893,7 +912,7 @@ PXB_API void pxb_scene_release(PxbScene* s) {
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
-                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque,
+                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
                   s->envStart, s->envList, s->actorLocal, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
@@ -915,6 +934,7 @@ static float shape_diameter(const ActorRec& r) {
     case PXB_GEOM_SPHERE: return 2.f * r.dims[0];
     case PXB_GEOM_CAPSULE: return 2.f * (r.dims[0] + r.dims[1]);
     case PXB_GEOM_BOX: return 2.f * std::sqrt(r.dims[0] * r.dims[0] + r.dims[1] * r.dims[1] + r.dims[2] * r.dims[2]);
+    case PXB_GEOM_CONVEXMESH: return r.dims[3] > 0.f ? r.dims[3] : INFINITY;   // dims[3] = hull diameter, filled by pxb_scene_add_actors
     default: return INFINITY;
   }
 }
@@ -927,6 +947,7 @@ static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
   s->envEligible = false;
   const char* em = getenv("PXB_ENV_MODE");
   if (!usesEnv || s->envDisabled || (em && em[0] == '0')) return;
+  for (auto& r : s->recs) if (r.geomType == PXB_GEOM_CONVEXMESH) return;   // hull bounds are not in k_env_bp yet: scenes with hulls run device-wide
   if (maxEnv >= s->capA) return;   // sparse environment ids: stay on the device-wide path
   std::vector<uint32_t> globals; const uint32_t nEnv = maxEnv + 1;
   std::vector<uint32_t> cnt(nEnv, 0);
@@ -978,10 +999,10 @@ static void rebuild_grid(PxbScene* s) {
   float cell = 0.f; float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   s->largeHost.clear();
   std::vector<uint32_t> gf(s->nA);
-  bool anyCapsule = false, anyBox = false, anyLocks = false; uint32_t typeMask = 0;
+  bool anyCapsule = false, anyBox = false, anyLocks = false, anyConvex = false; uint32_t typeMask = 0;
   for (uint32_t a = 0; a < s->nA; ++a) {
     const ActorRec& r = s->recs[a];
-    anyCapsule |= r.geomType == PXB_GEOM_CAPSULE; anyBox |= r.geomType == PXB_GEOM_BOX;
+    anyCapsule |= r.geomType == PXB_GEOM_CAPSULE; anyBox |= r.geomType == PXB_GEOM_BOX; anyConvex |= r.geomType == PXB_GEOM_CONVEXMESH;
     if (r.geomType != PXB_GEOM_PLANE) typeMask |= 1u << (r.geomType & 31);
     anyLocks |= ((r.flags >> 8) & 0x3fu) != 0;
     const float d = shape_diameter(r);
@@ -1005,7 +1026,8 @@ static void rebuild_grid(PxbScene* s) {
   while ((long double)envCount * g.nx * g.ny * g.nz > 4.0e18L) { if (g.nx >= g.ny && g.nx >= g.nz) g.nx = (g.nx + 1) / 2; else if (g.ny >= g.nz) g.ny = (g.ny + 1) / 2; else g.nz = (g.nz + 1) / 2; }
   g.keyBits = bits_for((uint64_t)envCount * (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz + 1);
   s->anyLocks = anyLocks;
-  s->hasGjkPairs = anyCapsule && anyBox;   // k_narrowphase_gjk: capsule-box pairs
+  s->hasGjkPairs = (anyCapsule && anyBox) || anyConvex;   // k_narrowphase_gjk: capsule-box and hull pairs
+  s->anyConvex = anyConvex;
   s->binPairs = __builtin_popcount(typeMask) >= 2 && !getenv("PXB_NO_PAIR_BINS");
   s->grid = g; s->nLarge = (uint32_t)s->largeHost.size();
   s->desc.reserved[0] = (uint32_t)envCount;
@@ -1014,6 +1036,44 @@ static void rebuild_grid(PxbScene* s) {
   cudaStreamSynchronize(s->stream);
   s->gridDirty = false;
   rebuild_env(s, usesEnv, maxEnv);
+}
+
+// Cooked convex hulls (Gu::ConvexHullData as produced by the host's PxCreateConvexMesh; the reference uploads the same data per shape through
+// PxsSimulationController::addPxgShape -> PxgShape::hullOrMeshPtr, PxgConvexConvexShape.h:50-65).  Layout: include/physx_b200.h.
+PXB_API int pxb_scene_set_convex_meshes(PxbScene* s, const void* cooked, size_t bytes, uint32_t nHulls) {
+  if (!s || (!cooked && nHulls)) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->nHulls) return fail(PXB_ERR_INVALID, "convex meshes are set once per scene, before the actors that use them");
+  const uint8_t* q = (const uint8_t*)cooked; const uint8_t* end = q + bytes;
+  std::vector<uint4> meta; std::vector<float4> verts, polys; std::vector<uint8_t> refs, edges;
+  for (uint32_t h = 0; h < nHulls; ++h) {
+    if (q + sizeof(PxbCookedHullHeader) > end) return fail(PXB_ERR_INVALID, "cooked hull data truncated");
+    PxbCookedHullHeader ch; memcpy(&ch, q, sizeof(ch)); q += sizeof(ch);
+    const size_t need = (size_t)ch.nVerts * 12 + (size_t)ch.nPolys * sizeof(PxbCookedPoly) + (ch.nIdx + 3) / 4 * 4 + (2 * (size_t)ch.nEdges + 3) / 4 * 4;
+    if (q + need > end || ch.nVerts > 255 || ch.nPolys > 255) return fail(PXB_ERR_INVALID, "cooked hull data truncated or out of range");
+    meta.push_back(make_uint4((uint32_t)verts.size(), (uint32_t)(polys.size() / 2), (uint32_t)refs.size(), (uint32_t)edges.size()));
+    meta.push_back(make_uint4(ch.nVerts, ch.nPolys, ch.nEdges, ch.nIdx));
+    uint4 m2; memcpy(&m2.x, &ch.internalExtents[0], 4); memcpy(&m2.y, &ch.internalExtents[1], 4); memcpy(&m2.z, &ch.internalExtents[2], 4); memcpy(&m2.w, &ch.internalRadius, 4);
+    meta.push_back(m2);
+    s->hullDiam.push_back(2.f * (std::sqrt(ch.boundsCenter[0] * ch.boundsCenter[0] + ch.boundsCenter[1] * ch.boundsCenter[1] + ch.boundsCenter[2] * ch.boundsCenter[2]) +
+                                 std::sqrt(ch.boundsExtents[0] * ch.boundsExtents[0] + ch.boundsExtents[1] * ch.boundsExtents[1] + ch.boundsExtents[2] * ch.boundsExtents[2])));
+    const float* v = (const float*)q; for (uint32_t i = 0; i < ch.nVerts; ++i) verts.push_back(make_float4(v[i * 3], v[i * 3 + 1], v[i * 3 + 2], 0.f));
+    q += (size_t)ch.nVerts * 12;
+    for (uint32_t p = 0; p < ch.nPolys; ++p) {
+      PxbCookedPoly cp; memcpy(&cp, q, sizeof(cp)); q += sizeof(cp);
+      polys.push_back(make_float4(cp.plane[0], cp.plane[1], cp.plane[2], cp.plane[3]));
+      float4 m; memcpy(&m.x, &cp.vref, 4); memcpy(&m.y, &cp.nbVerts, 4); memcpy(&m.z, &cp.minIndex, 4); m.w = 0.f; polys.push_back(m);
+    }
+    refs.insert(refs.end(), q, q + ch.nIdx); q += (ch.nIdx + 3) / 4 * 4;
+    edges.insert(edges.end(), q, q + 2 * (size_t)ch.nEdges); q += (2 * (size_t)ch.nEdges + 3) / 4 * 4;
+  }
+  if (!nHulls) { s->hullDiam.clear(); return PXB_OK; }
+  CK(dalloc(s->hullMeta, meta.size())); CK(dalloc(s->hullVerts, verts.size())); CK(dalloc(s->hullPolys, polys.size())); CK(dalloc(s->hullRefs, refs.size() + 4)); CK(dalloc(s->hullEdges, edges.size() + 4));
+  CK(cudaMemcpyAsync(s->hullMeta, meta.data(), 16 * meta.size(), cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->hullVerts, verts.data(), 16 * verts.size(), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->hullPolys, polys.data(), 16 * polys.size(), cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->hullRefs, refs.data(), refs.size(), cudaMemcpyHostToDevice, s->stream));
+  if (!edges.empty()) CK(cudaMemcpyAsync(s->hullEdges, edges.data(), edges.size(), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  s->nHulls = nHulls;
+  return PXB_OK;
 }
 
 PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
@@ -1025,10 +1085,12 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
   std::vector<float4> pos(nb), quat(nb), lin(nb), ang(nb), inv(nb), dmp(nb), dims(nb); std::vector<uint32_t> env(nb);
   for (uint32_t i = 0; i < nb; ++i) {
     const ActorRec& r = in[i];
-    if (r.geomType != PXB_GEOM_BOX && r.geomType != PXB_GEOM_PLANE && r.geomType != PXB_GEOM_SPHERE && r.geomType != PXB_GEOM_CAPSULE)
+    if (r.geomType == PXB_GEOM_CONVEXMESH) { if (r.hullIdx >= s->nHulls) return fail(PXB_ERR_UNSUPPORTED, "convex actor without a cooked hull: call pxb_scene_set_convex_meshes first"); }
+    else if (r.geomType != PXB_GEOM_BOX && r.geomType != PXB_GEOM_PLANE && r.geomType != PXB_GEOM_SPHERE && r.geomType != PXB_GEOM_CAPSULE)
       return fail(PXB_ERR_UNSUPPORTED, "geometry type not supported yet");
     const bool dyn = r.flags & PXB_ACTOR_DYNAMIC;
     s->recs.push_back(r);
+    if (r.geomType == PXB_GEOM_CONVEXMESH) s->recs.back().dims[3] = s->hullDiam[r.hullIdx];   // bounding diameter for the broadphase grid
     if (dyn) { s->dynIndex.push_back((int)s->nDyn); s->dynActor.push_back(base + i); s->nDyn++; } else s->dynIndex.push_back(-1);
     const float invMass = (dyn && r.mass > 0.f) ? 1.0f / r.mass : 0.f;
     pos[i] = make_float4(r.pos[0], r.pos[1], r.pos[2], invMass); quat[i] = make_float4(r.quat[0], r.quat[1], r.quat[2], r.quat[3]);
@@ -1036,6 +1098,7 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
     inv[i] = make_float4(dyn && r.inertia[0] > 0.f ? 1.0f / r.inertia[0] : 0.f, dyn && r.inertia[1] > 0.f ? 1.0f / r.inertia[1] : 0.f, dyn && r.inertia[2] > 0.f ? 1.0f / r.inertia[2] : 0.f, r.maxDepenetrationVel);
     dmp[i] = make_float4(r.linDamping, r.angDamping, r.maxLinVel * r.maxLinVel, r.maxAngVel * r.maxAngVel);
     dims[i] = make_float4(r.dims[0], r.dims[1], r.dims[2], r.dims[3]); env[i] = r.envId;
+    if (r.geomType == PXB_GEOM_CONVEXMESH) memcpy(&dims[i].x, &r.hullIdx, 4);   // convex actors carry their hull index where the primitives carry their size
   }
   s->nA += nb;
   CK(cudaMemcpyAsync(s->pos + base, pos.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->quat + base, quat.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream));
@@ -1106,7 +1169,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
   CK(cudaMemsetAsync(s->counters + C_NPAIRS_NEW, 0, 4 * 3, st));  // NPAIRS_NEW, NCREATED, NDELETED
   if (s->hasGjkPairs) CK(cudaMemsetAsync(s->counters + C_NGJK, 0, 4, st));
   LAUNCH(k_bounds, cdiv(nA, B), B, nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, externalTight ? 1 : 0, s->aabbMin, s->aabbMax, s->grid,
-         s->desc.reserved[0], s->cellKey, s->cellVal);
+         s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s));
   const int r = radix_sort_pairs(s->cellKey, s->cellVal, s->cellKeyAlt, s->cellValAlt, s->counters + C_NA, s->grid.keyBits, s->rsTmp, st);
   s->launches += 3 * ((s->grid.keyBits + 7) / 8);
   const uint64_t* sk = r ? s->cellKeyAlt : s->cellKey; const uint32_t* sv = r ? s->cellValAlt : s->cellVal;
@@ -1166,7 +1229,7 @@ static int enqueue_step(PxbScene* s, float dt) {
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
          s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce, s->counters, s->gjkList, s->binPairs ? s->pairOrder : (const uint32_t*)nullptr);
   if (s->hasGjkPairs) LAUNCH(k_narrowphase_gjk, 148 * 4, 128, s->pairKeys[cur], s->pairSlots[cur], s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds, s->cHdr, s->cPts,
-                             s->pairBodies, s->conFlag, s->counters, s->gjkList);
+                             s->pairBodies, s->conFlag, s->counters, s->gjkList, hull_arrays(s));
   SleepArgs SA; SA.threshold = s->sleepThreshold; SA.dt = dt; SA.wake = s->wake; SA.accLin = s->accLin; SA.accAng = s->accAng; SA.asleep = s->asleep; SA.nInter = s->nInter;
   if (s->sleepThreshold > 0.f) {   // island sleep / wake decisions for this step (needs this frame's touching pairs)
     uint32_t nA = s->nA;
@@ -1333,7 +1396,7 @@ PXB_API int pxb_scene_compute_bounds(PxbScene* s) {
   if (!s) return fail(PXB_ERR_INVALID, "null scene");
   cudaStream_t st = s->stream;
   if (s->gridDirty) rebuild_grid(s);
-  LAUNCH(k_bounds, cdiv(s->nA, 256), 256, s->nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, 0, s->aabbMin, s->aabbMax, s->grid, s->desc.reserved[0], s->cellKey, s->cellVal);
+  LAUNCH(k_bounds, cdiv(s->nA, 256), 256, s->nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, 0, s->aabbMin, s->aabbMax, s->grid, s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s));
   CK(cudaStreamSynchronize(st));
   return PXB_OK;
 }

@@ -653,6 +653,88 @@ __device__ __noinline__ void gjk_boxbox_gjk_fallback_outofline(const xf* tm0, co
   gjk_boxbox_gjk_fallback(tm0, tm1, ext0, ext1, contactDist, toleranceLength, manifold, out);
 }
 
+/* ---------------- convex hulls: cooked Gu::ConvexHullData in device memory (uploaded by pxb_scene_set_convex_meshes) ---------------- */
+struct HullArrays { const uint4* meta; const float4* verts; const float4* polys; const uint8_t* refs; const uint8_t* edges; };   // meta: 3 x 16 B per hull
+struct DevHull {
+  uint32_t nVerts, nPolys, nEdges; v3 internalExtents;
+  const float4* verts; const float4* polys; const uint8_t* vertexRefs; const uint8_t* facesByEdges;
+  PXB_D v3 vert(uint32_t i) const { return V3(verts[i]); }
+  PXB_D v3 plane_n(uint32_t p) const { return V3(polys[2 * p]); }
+  PXB_D uint4 poly_meta(uint32_t p) const { const float4 m = polys[2 * p + 1]; return make_uint4(__float_as_uint(m.x), __float_as_uint(m.y), __float_as_uint(m.z), 0u); }   // (vref, nbVerts, minIndex)
+};
+PXB_D DevHull load_hull(const HullArrays& H, uint32_t hullIdx) {
+  const uint4 m0 = H.meta[3 * hullIdx], m1 = H.meta[3 * hullIdx + 1], m2 = H.meta[3 * hullIdx + 2];
+  DevHull h; h.nVerts = m1.x; h.nPolys = m1.y; h.nEdges = m1.z;
+  h.internalExtents = V3(__uint_as_float(m2.x), __uint_as_float(m2.y), __uint_as_float(m2.z));
+  h.verts = H.verts + m0.x; h.polys = H.polys + 2 * m0.y; h.vertexRefs = H.refs + m0.z; h.facesByEdges = H.edges + m0.w;
+  return h;
+}
+/* CalculatePCMConvexMargin GuVecConvexHull.h:55-65 (identity scale) */
+PXB_D float gjk_hull_pcm_margin(const DevHull& h, float toleranceLength) {
+  const float mn = fmin_(h.internalExtents.x, fmin_(h.internalExtents.y, h.internalExtents.z));
+  return fmin_(mn * 0.25f, toleranceLength * 0.05f);
+}
+
+/* pcmContactPlaneConvex: GuPCMContactPlaneConvex.cpp:36-227 (shape0 = plane, shape1 = convex mesh, identity mesh scale).
+ * Note the reference's vertex loop visits mPolygons[closestFaceIndex] on BOTH passes (the second pass was meant for polyIndex2):
+ * restated as is, the duplicated points are merged by the manifold reduction. */
+PXB_D void gjk_pcm_plane_convex(const xf* planeTm, const xf* convexTm, const DevHull& hull, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
+  const xf* transf0 = convexTm; const xf* transf1 = planeTm;
+  const xf curTransf = axfinvmul(transf1, transf0);
+  const float convexMargin = gjk_hull_pcm_margin(hull, toleranceLength);
+  const v3 planeNormal = anormalize(aqbasis0(transf1->q));
+  const v3 negPlaneNormal = v3neg(planeNormal);
+  const float projectBreakingThreshold = convexMargin * 0.2f;
+  const int initialContacts = manifold->n;
+  const mxf aToB = amxffromxf(&curTransf);
+  manifold_refresh(*manifold, aToB, projectBreakingThreshold);
+  const int bLostContacts = manifold->n != initialContacts;
+  if (bLostContacts || invalidate_plane(*manifold, curTransf, convexMargin, 0.2f)) {
+    const v3 localNormal = V3(1, 0, 0);
+    manifold->n = 0; manifold->rel = curTransf; manifold->dirty = 1;
+    const v3 n = anormalize(amtmul(aToB.r, localNormal));   /* vertex2Shape = identity: M33MulV3(I, v) = v */
+    const v3 nnormal = v3neg(n);
+    MPoint mc[64]; int numContacts = 0;
+    float minProj = FLT_MAX; uint32_t closestFaceIndex = 0, polyIndex2 = 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < hull.nPolys; ++i) { const float proj = adot(n, hull.plane_n(i)); if (minProj > proj) { minProj = proj; closestFaceIndex = i; } }
+    uint32_t closestEdge = 0xffffffffu;
+    minProj = minProj - 5e-4f;
+    float maxDpSq = minProj * minProj;
+    for (uint32_t i = 0; i < hull.nEdges; ++i) {
+      const uint8_t f0 = hull.facesByEdges[i * 2], f1 = hull.facesByEdges[i * 2 + 1];
+      const v3 edgeNormal = v3add(hull.plane_n(f0), hull.plane_n(f1));
+      const float enMagSq = adot(edgeNormal, edgeNormal), dp = adot(edgeNormal, nnormal), sqDp = dp * dp;
+      if (dp >= 0.f && sqDp > maxDpSq * enMagSq) { maxDpSq = sqDp / enMagSq; closestEdge = i; }
+    }
+    if (closestEdge != 0xffffffffu) {
+      const uint32_t f0 = hull.facesByEdges[closestEdge * 2], f1 = hull.facesByEdges[closestEdge * 2 + 1];
+      const float dp0 = adot(hull.plane_n(f0), nnormal), dp1 = adot(hull.plane_n(f1), nnormal);
+      if (dp0 > dp1) { closestFaceIndex = f0; polyIndex2 = f1; } else { closestFaceIndex = f1; polyIndex2 = f0; }
+    }
+    for (uint32_t index = closestFaceIndex; index != 0xFFFFFFFFu; index = polyIndex2, polyIndex2 = 0xFFFFFFFFu) {
+      const uint4 face = hull.poly_meta(closestFaceIndex);
+      const uint8_t* vertInds = hull.vertexRefs + face.x;
+      for (uint32_t i = 0; i < face.y; ++i) {
+        const v3 pInVertexSpace = hull.vert(vertInds[i]);
+        const v3 pInPlaneSpace = amxftransform(&aToB, pInVertexSpace);   /* aToBVertexSpace = (aToB.p, aToB.rot * I) */
+        const float signDist = pInPlaneSpace.x;
+        if (contactDist > signDist) {
+          mc[numContacts].a = pInVertexSpace; mc[numContacts].b = v3negscalesub(localNormal, signDist, pInPlaneSpace); mc[numContacts].n = localNormal; mc[numContacts].pen = signDist; numContacts++;
+          if (numContacts == 64) { reduce_cluster(*manifold, mc, numContacts); numContacts = PXB_MANIFOLD_CACHE; for (int c = 0; c < PXB_MANIFOLD_CACHE; ++c) mc[c] = manifold->pts[c]; }
+        }
+      }
+    }
+    /* addBatchManifoldContacts .cpp:812-831 */
+    if (numContacts <= PXB_MANIFOLD_CACHE) { for (int i = 0; i < numContacts; ++i) manifold->pts[i] = mc[i]; manifold->n = numContacts; }
+    else { reduce_batch(*manifold, mc, numContacts, toleranceLength); manifold->n = PXB_MANIFOLD_CACHE; }
+  }
+  out->count = 0; out->normal = negPlaneNormal;
+  for (int i = 0; i < manifold->n; ++i) {   /* addManifoldContactsToContactBuffer(buffer, normal, transf1, contactOffset) .cpp:739-759 */
+    const float dist = manifold->pts[i].pen;
+    if (contactDist >= dist) { out->point[out->count] = axftransform(transf1, manifold->pts[i].b); out->sep[out->count] = dist; out->count++; }
+  }
+}
+
 /* ---------------- polygonal box: GuPCMShapeConvex.cpp:40-110 ---------------- */
 typedef struct { v3 n; float d; int minIndex; } Poly;
 __device__ const uint8_t gjk_box_poly_refs[24] = {0, 3, 2, 1, 1, 2, 6, 5, 5, 6, 7, 4, 4, 7, 3, 0, 3, 7, 6, 2, 4, 0, 1, 5};

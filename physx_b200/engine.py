@@ -20,7 +20,7 @@ _lib = None
 
 # every symbol include/physx_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "pxb_scene_create", "pxb_scene_release", "pxb_last_error", "pxb_device_count", "pxb_scene_add_actors",
+    "pxb_scene_create", "pxb_scene_release", "pxb_last_error", "pxb_device_count", "pxb_scene_add_actors", "pxb_scene_set_convex_meshes",
     "pxb_scene_num_actors", "pxb_scene_num_dynamic", "pxb_scene_simulate", "pxb_scene_fetch_results",
     "pxb_scene_set_constraint_order", "pxb_get_rigid_dynamic_data", "pxb_set_rigid_dynamic_data",
     "pxb_get_rigid_dynamic_data_device", "pxb_set_rigid_dynamic_data_device", "pxb_scene_get_states",
@@ -68,6 +68,7 @@ def load_library():
     lib = ctypes.CDLL(path)
     vp, u32, i32, f32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_float
     lib.pxb_scene_create.argtypes = [ctypes.POINTER(SceneDesc), ctypes.POINTER(vp)]
+    lib.pxb_scene_set_convex_meshes.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, u32]
     lib.pxb_scene_release.argtypes = [vp]
     lib.pxb_scene_release.restype = None
     lib.pxb_last_error.restype = ctypes.c_char_p
@@ -142,6 +143,8 @@ class Scene:
         self.dt = float(h["dt"])
         self._h = ctypes.c_void_p()
         _check(lib, lib.pxb_scene_create(ctypes.byref(d), ctypes.byref(self._h)))
+        if scene.cooked:   # cooked convex hulls (reference cooking output carried by the scene) go in before the actors that use them
+            _check(lib, lib.pxb_scene_set_convex_meshes(self._h, scene.cooked, len(scene.cooked), len(scene.hulls)))
         recs = np.ascontiguousarray(scene.actors)
         _check(lib, lib.pxb_scene_add_actors(self._h, _ptr(recs), len(recs)))
         self.num_actors = int(lib.pxb_scene_num_actors(self._h))

@@ -187,7 +187,7 @@ def test_gpu_matches_oracle_primitives(oracle, name):
         cpu.setStates(sg)
 
 
-@pytest.mark.parametrize("name", ["capsule_row", "spheres_capsules_14", "capsules_on_boxes"])
+@pytest.mark.parametrize("name", ["capsule_row", "spheres_capsules_14", "capsules_on_boxes", "hulls_on_plane"])
 def test_gpu_teacher_forced_steps_match_reference(name):
     z, sc = util.load_golden(name)
     gpu = engine.Scene(sc)
@@ -535,12 +535,38 @@ def test_env_path_pair_capacity_overflow_is_reported():
     assert "capacity" in str(e.value)
 
 
-def test_unsupported_geometry_is_rejected_not_skipped():
-    """Convex hulls (the rest of SURVEY 8a row a10) are not built yet: a scene that contains one is refused when its actors are added."""
-    sc = scenes.capsules_on_boxes(n_boxes=2, per_box=1, seed=1)
-    sc.actors["geomType"][4] = scenes.GEOM_CONVEX
+def test_convex_hulls_gpu_matches_oracle_and_reference(oracle):
+    """Cooked convex hulls through pxb_scene_set_convex_meshes: tight bounds bit-identical to the reference's, broadphase events equal, plane-hull
+    contacts and states equal to the oracle every step (the hull fixture carries the reference's cooking output; nothing is cooked here)."""
+    z, sc = util.load_golden("hulls_on_plane")
+    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setStates(z["states"][t])
+        assert np.array_equal(gpu.computeBounds(), z["bounds"][t]), f"bounds, step {t}"
+        cpu.setStates(z["states"][t])
+        gpu.setConstraintOrder(util.golden_order(z, t))
+        gpu.step()
+        cpu.step(util.golden_order(z, t))
+        assert not gpu.uses_env_path
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
+        cg, cc = gpu.getContacts(), cpu.getContacts()
+        assert np.array_equal(cg[:, 0], cc[:, 0]) and np.abs(cg[:, :4 + 5 * 4] - cc[:, :4 + 5 * 4])[:, [0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12]].max(initial=0) < 1e-6, f"contacts, step {t}"
+        assert np.abs(gpu.getStates() - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
+
+
+def test_unsupported_hull_pair_is_reported_not_skipped():
+    """Hull vs sphere / capsule / box / hull pairs (the rest of SURVEY 8a row a10) are not built yet: a convex actor without cooked data is
+    refused when it is added, and a hull pair other than plane-hull fails the step loudly once it comes into contact range."""
+    z, sc = util.load_golden("hulls_on_plane")
+    bare = scenes.Scene(sc.header, sc.actors.copy(), sc.hulls)      # hull point clouds only, no cooked section
     with pytest.raises(engine.PhysxB200Error):
-        engine.Scene(sc)
+        engine.Scene(bare)
+    a = sc.actors.copy()
+    a["pos"][2] = a["pos"][1] + np.array([0.1, 0.05, 0.0], np.float32)   # two hulls overlapping
+    gpu = engine.Scene(scenes.Scene(sc.header, a, sc.hulls, sc.cooked))
+    with pytest.raises(engine.PhysxB200Error) as e:
+        gpu.step()
+    assert "unsupported" in str(e.value)
 
 
 def test_cpp_host_mirror_snippet_hello_world():
