@@ -13,7 +13,8 @@
 #include "pxo_np.h"
 #include "scene_format.h"
 
-enum { PXO_CVX_CAPSULE = 0, PXO_CVX_BOX = 1 };
+enum { PXO_CVX_CAPSULE = 0, PXO_CVX_BOX = 1, PXO_CVX_HULL = 2 };
+struct PxoHull_;
 enum { PXO_GJK_NON_INTERSECT = 0, PXO_GJK_CONTACT, PXO_GJK_UNDEFINED, PXO_GJK_DEGENERATE, PXO_EPA_CONTACT, PXO_EPA_DEGENERATE, PXO_EPA_FAIL };
 
 typedef struct {
@@ -23,9 +24,22 @@ typedef struct {
   v3 ext;                   /* box half extents */
   float margin, minMargin;  /* ConvexV::margin / minMargin */
   int marginIsRadius;
+  const struct PxoHull_* hull;   /* PXO_CVX_HULL: cooked hull (ConvexHullNoScaleV: identity mesh scale) */
   int relative;             /* RelativeConvex<T> (GuGJKType.h:110-150): the shape lives in A's frame, supports are returned in B's */
   mxf aToB; m33 aToBT;      /* mAToB and the precomputed transpose of its rotation */
 } PxoConvex;
+
+/* ---------------- convex hulls (cooked: Gu::ConvexHullData, see scene_format.h) ---------------- */
+typedef struct PxoHull_ {
+  uint32_t nVerts, nPolys, nEdges, nIdx;
+  v3 centerOfMass, boundsCenter, boundsExtents, internalExtents; float internalRadius;
+  const float* verts;              /* [nVerts][3] */
+  const PxbCookedPoly* polys;      /* plane, vref, nbVerts, minIndex */
+  const uint8_t* vertexRefs;       /* getVertexData8 */
+  const uint8_t* facesByEdges;     /* getFacesByEdges8 */
+} PxoHull;
+static inline v3 pxo_hull_vert(const PxoHull* h, uint32_t i) { return V3(h->verts[i * 3], h->verts[i * 3 + 1], h->verts[i * 3 + 2]); }
+static inline v3 pxo_hull_plane_n(const PxoHull* h, uint32_t p) { return V3(h->polys[p].plane[0], h->polys[p].plane[1], h->polys[p].plane[2]); }
 
 typedef struct { v3 normal, closestA, closestB, searchDir; float penDep; } PxoGjkOutput;
 
@@ -43,6 +57,13 @@ static inline PxoConvex pxo_cvx_box(v3 origin, v3 ext) {
   c.type = PXO_CVX_BOX; c.center = origin; c.ext = ext; c.margin = mn * 0.15f; c.minMargin = mn * 0.05f; c.marginIsRadius = 0;
   return c;
 }
+/* ConvexHullV(hullData, centerOfMass, scale = 1, ...): GuVecConvexHull.h:202-215, CalculateConvexMargin :77-94 */
+static inline PxoConvex pxo_cvx_hull(const PxoHull* h) {
+  PxoConvex c; memset(&c, 0, sizeof(c));
+  const float mn = fminf_(h->internalExtents.x, fminf_(h->internalExtents.y, h->internalExtents.z));
+  c.type = PXO_CVX_HULL; c.hull = h; c.center = h->centerOfMass; c.margin = mn * 0.1f; c.minMargin = mn * 0.05f; c.marginIsRadius = 0;
+  return c;
+}
 static inline void pxo_cvx_make_relative(PxoConvex* c, const mxf* aToB) { c->relative = 1; c->aToB = *aToB; c->aToBT = m33transpose(&aToB->r); }
 /* LocalConvex<T>::support(dir, index) = T::supportLocal(dir, index); RelativeConvex<T>::support = T::supportRelative (GuVecBox.h:186-204) */
 static inline v3 pxo_cvx_support_local(const PxoConvex* c, v3 dir, int* index);
@@ -53,6 +74,13 @@ static inline v3 pxo_cvx_support(const PxoConvex* c, v3 dir, int* index) {
   return amxftransform(&c->aToB, p);
 }
 static inline v3 pxo_cvx_support_local(const PxoConvex* c, v3 dir, int* index) {
+  if (c->type == PXO_CVX_HULL) {   /* ConvexHullV::bruteForceSearch GuVecConvexHull.h:377-397 (hulls of <= 32 vertices carry no hill-climbing data) */
+    const PxoHull* h = c->hull;
+    float mx = v3dot(pxo_hull_vert(h, 0), dir); uint32_t mi = 0;
+    for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(pxo_hull_vert(h, i), dir); if (d > mx) { mx = d; mi = i; } }
+    *index = (int)mi;
+    return pxo_hull_vert(h, mi);
+  }
   if (c->type == PXO_CVX_CAPSULE) {
     const float d0 = adot(c->p0, dir), d1 = adot(c->p1, dir);
     const int comp = d0 > d1;
@@ -64,6 +92,7 @@ static inline v3 pxo_cvx_support_local(const PxoConvex* c, v3 dir, int* index) {
   return V3(bx ? c->ext.x : -c->ext.x, by ? c->ext.y : -c->ext.y, bz ? c->ext.z : -c->ext.z);
 }
 static inline v3 pxo_cvx_support_point_local(const PxoConvex* c, int index) {
+  if (c->type == PXO_CVX_HULL) return pxo_hull_vert(c->hull, (uint32_t)index);
   if (c->type == PXO_CVX_CAPSULE) return index == 1 ? c->p0 : c->p1;   /* (&p0)[1-index] */
   return V3((index & 1) ? c->ext.x : -c->ext.x, (index & 2) ? c->ext.y : -c->ext.y, (index & 4) ? c->ext.z : -c->ext.z);
 }
@@ -639,17 +668,6 @@ static inline void pxo_boxbox_gjk_fallback(const xf* tm0, const xf* tm1, v3 ext0
 }
 
 
-/* ---------------- convex hulls (cooked: Gu::ConvexHullData, see scene_format.h) ---------------- */
-typedef struct {
-  uint32_t nVerts, nPolys, nEdges, nIdx;
-  v3 centerOfMass, boundsCenter, boundsExtents, internalExtents; float internalRadius;
-  const float* verts;              /* [nVerts][3] */
-  const PxbCookedPoly* polys;      /* plane, vref, nbVerts, minIndex */
-  const uint8_t* vertexRefs;       /* getVertexData8 */
-  const uint8_t* facesByEdges;     /* getFacesByEdges8 */
-} PxoHull;
-static inline v3 pxo_hull_vert(const PxoHull* h, uint32_t i) { return V3(h->verts[i * 3], h->verts[i * 3 + 1], h->verts[i * 3 + 2]); }
-static inline v3 pxo_hull_plane_n(const PxoHull* h, uint32_t p) { return V3(h->polys[p].plane[0], h->polys[p].plane[1], h->polys[p].plane[2]); }
 /* CalculatePCMConvexMargin GuVecConvexHull.h:55-65 (identity scale) */
 static inline float pxo_hull_pcm_margin(const PxoHull* h, float toleranceLength) {
   const float mn = fminf_(h->internalExtents.x, fminf_(h->internalExtents.y, h->internalExtents.z));
@@ -715,6 +733,7 @@ static inline void pxo_pcm_plane_convex(const xf* planeTm, const xf* convexTm, c
     if (contactDist >= dist) { out->point[out->count] = axftransform(transf1, manifold->pts[i].b); out->sep[out->count] = dist; out->count++; }
   }
 }
+
 
 /* ---------------- polygonal box: GuPCMShapeConvex.cpp:40-110 ---------------- */
 typedef struct { v3 n; float d; int minIndex; } PxoPoly;
@@ -1010,4 +1029,88 @@ static inline int pxo_pcm_capsule_box(const xf* transf0, const xf* transf1, floa
   }
   return 0;
 }
+/* ---------------- sphere vs convex hull: GuPCMContactSphereConvex.cpp:47-246, GuPCMContactGenSphereCapsule.cpp:43-152,470-497 ---------------- */
+/* testPolyDataAxis :43-96 over a hull (identity scaling) */
+static inline int pxo_hull_test_poly_axis(const PxoConvex* cap, const PxoHull* h, float contactDist, float* minOverlap, v3* separatingAxis) {
+  float _minOverlap = FLT_MAX; v3 tempAxis = V3(0, 1, 0);
+  for (uint32_t i = 0; i < h->nPolys; ++i) {
+    const v3 pn = pxo_hull_plane_n(h, i);
+    const v3 minVert = pxo_hull_vert(h, h->polys[i].minIndex);
+    const float magnitude = 1.0f / alen(pn);
+    const v3 planeN = v3scale(pn, magnitude);
+    const float min0 = adot(pn, minVert) * magnitude, max0 = (-h->polys[i].plane[3]) * magnitude;
+    const float tempMin = adot(cap->p0, planeN), tempMax = adot(cap->p1, planeN);
+    float min1 = fminf_(tempMin, tempMax), max1 = fmaxf_(tempMin, tempMax);
+    min1 = min1 - cap->margin; max1 = max1 + cap->margin;
+    if ((min1 > max0 + contactDist) || (min0 > max1 + contactDist)) return 0;
+    const float tempOverlap = max0 - min1;
+    if (_minOverlap > tempOverlap) { _minOverlap = tempOverlap; tempAxis = planeN; }
+  }
+  *separatingAxis = tempAxis; *minOverlap = _minOverlap;
+  return 1;
+}
+/* intersectRayPolyhedron :98-152 */
+static inline int pxo_hull_ray(v3 a, v3 dir, const PxoHull* h, float* tEnter, float* tExit) {
+  float tFirst = 0.f, tLast = FLT_MAX;
+  for (uint32_t k = 0; k < h->nPolys; ++k) {
+    const v3 n = pxo_hull_plane_n(h, k); const float d = h->polys[k].plane[3];
+    const float denominator = adot(n, dir), distToPlane = adot(n, a) + d;
+    if (1e-7f > fabsf(denominator)) { if (distToPlane > 0.f) return 0; }
+    else {
+      const float tTemp = -(distToPlane / denominator);
+      const int con = 0.f > denominator;
+      if (con && tTemp > tFirst) tFirst = tTemp;
+      if (!con && tLast > tTemp) tLast = tTemp;
+    }
+    if (tFirst > tLast) return 0;
+  }
+  *tEnter = tFirst; *tExit = tLast;
+  return 1;
+}
+static inline void pxo_pcm_sphere_convex(const xf* transf0, const xf* transf1, float sphereRadius, const PxoHull* hull, float contactDist, float toleranceLength, PxoManifold* manifold, PxoContacts* out) {
+  out->count = 0;
+  const xf curRTrans = axfinvmul(transf1, transf0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  const float convexMargin = pxo_hull_pcm_margin(hull, toleranceLength);
+  const int initialContacts = manifold->n;
+  const float minMargin = fminf_(convexMargin, sphereRadius);
+  pxo_refresh(manifold, &aToB, minMargin * 0.05f);
+  const int bLostContacts = manifold->n != initialContacts;
+  if (bLostContacts || pxo_invalidate_sphere_capsule(manifold, &curRTrans, minMargin)) {
+    manifold->rel = curRTrans;
+    const PxoConvex convexHull = pxo_cvx_hull(hull);
+    const PxoConvex capsule = pxo_cvx_capsule(aToB.p, V3(0, 0, 0), sphereRadius);   /* CapsuleV(p, radius): p0 = p1 = p */
+    PxoGjkOutput output; memset(&output, 0, sizeof(output));
+    const v3 initialSearchDir = v3sub(capsule.center, convexHull.center);
+    int status = pxo_gjk_penetration(&capsule, &convexHull, initialSearchDir, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+    if (status == PXO_GJK_NON_INTERSECT) return;
+    if (status == PXO_EPA_CONTACT) {
+      status = pxo_epa_penetration(&capsule, &convexHull, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+      if (status != PXO_EPA_CONTACT) status = PXO_GJK_DEGENERATE;   /* EPA failed: full contact generation with the overlap test, like a degenerate GJK */
+      else status = PXO_GJK_CONTACT;
+    }
+    if (status == PXO_GJK_CONTACT) {
+      manifold->pts[0].a = V3(0, 0, 0); manifold->pts[0].b = output.closestB; manifold->pts[0].n = output.normal; manifold->pts[0].pen = output.penDep; manifold->n = 1;
+      const v3 worldNormal = aqrot(transf1->q, output.normal);
+      out->normal = worldNormal; out->point[0] = v3negscalesub(worldNormal, sphereRadius, transf0->p); out->sep[0] = output.penDep - sphereRadius; out->count = 1;
+      return;
+    }
+    if (status == PXO_GJK_DEGENERATE) {   /* fullContactsGenerationSphereConvex :47-82 with doOverlapTest = true */
+      v3 normal = output.normal; float minOverlap;
+      if (!pxo_hull_test_poly_axis(&capsule, hull, contactDist, &minOverlap, &normal)) return;
+      float tEnter = 0.f, tExit = 0.f;
+      const float inflatedRadius = sphereRadius + contactDist;
+      const v3 dir = v3neg(normal);
+      if (pxo_hull_ray(capsule.p0, dir, hull, &tEnter, &tExit) && inflatedRadius >= tEnter) {
+        manifold->pts[0].a = V3(0, 0, 0); manifold->pts[0].b = v3scaleadd(dir, tEnter, capsule.p0); manifold->pts[0].n = normal; manifold->pts[0].pen = tEnter; manifold->n = 1;
+        const v3 worldNormal = aqrot(transf1->q, normal);
+        out->normal = worldNormal; out->point[0] = v3negscalesub(worldNormal, sphereRadius, transf0->p); out->sep[0] = tEnter - sphereRadius; out->count = 1;
+      }
+    }
+  } else if (manifold->n > 0) {
+    const v3 worldNormal = aqrot(transf1->q, manifold->pts[0].n);
+    out->normal = worldNormal; out->point[0] = v3negscalesub(worldNormal, sphereRadius, transf0->p); out->sep[0] = manifold->pts[0].pen - sphereRadius; out->count = 1;
+  }
+}
+
 #endif

@@ -377,8 +377,8 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CAPSULE) pcm_plane_capsule(tm0, tm1, d1.x, d1.y, contactDist, man, out);
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_CAPSULE) np_capsule_capsule(tm0, tm1, d0.x, d0.y, d1.x, d1.y, contactDist, out);
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_BOX) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // GJK family (a10): k_narrowphase_gjk fills this pair's outputs
-  else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CONVEXMESH) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // hull pairs also go through k_narrowphase_gjk
-  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // hull vs sphere / capsule / box / hull (a10): reported by fetchResults, never silently skipped
+  else if ((ty0 == PXB_GEOM_PLANE || ty0 == PXB_GEOM_SPHERE) && ty1 == PXB_GEOM_CONVEXMESH) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // hull pairs also go through k_narrowphase_gjk
+  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // hull vs capsule / box / hull (a10): reported by fetchResults, never silently skipped
   if (man.dirty) manifold_store(man, rec); else if (usesManifold && man.n > 0) manifold_store_pens(man, rec);   // steady state: only the penetrations change
   if (flip && out.count) out.normal = -out.normal;
   cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
@@ -412,7 +412,12 @@ __global__ void __launch_bounds__(128) k_narrowphase_gjk(const uint64_t* __restr
     Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
     for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
     const uint32_t ty1 = flip ? t0 : t1;
-    if (ty1 == PXB_GEOM_CONVEXMESH) { const DevHull h = load_hull(hulls, __float_as_uint(d1.x)); gjk_pcm_plane_convex(&tm0, &tm1, h, contactDist, toleranceLength, &man, &out); }   // s0 = plane, s1 = hull
+    const uint32_t ty0 = flip ? t1 : t0;
+    if (ty1 == PXB_GEOM_CONVEXMESH) {   // s1 = hull, s0 = plane or sphere
+      const DevHull h = load_hull(hulls, __float_as_uint(d1.x));
+      if (ty0 == PXB_GEOM_PLANE) gjk_pcm_plane_convex(&tm0, &tm1, h, contactDist, toleranceLength, &man, &out);
+      else gjk_pcm_sphere_convex(&tm0, &tm1, d0.x, &h, contactDist, toleranceLength, &man, &out);
+    }
     else gjk_pcm_capsule_box(&tm0, &tm1, d0.x, d0.y, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
     if (man.dirty) { manifold_store(man, rec); manifold_store_warm(man, rec); } else if (man.n > 0) manifold_store_pens(man, rec);
     if (flip && out.count) out.normal = -out.normal;
@@ -1050,10 +1055,12 @@ PXB_API int pxb_scene_set_convex_meshes(PxbScene* s, const void* cooked, size_t 
     PxbCookedHullHeader ch; memcpy(&ch, q, sizeof(ch)); q += sizeof(ch);
     const size_t need = (size_t)ch.nVerts * 12 + (size_t)ch.nPolys * sizeof(PxbCookedPoly) + (ch.nIdx + 3) / 4 * 4 + (2 * (size_t)ch.nEdges + 3) / 4 * 4;
     if (q + need > end || ch.nVerts > 255 || ch.nPolys > 255) return fail(PXB_ERR_INVALID, "cooked hull data truncated or out of range");
+    if (ch.nVerts > 32) return fail(PXB_ERR_UNSUPPORTED, "hulls of more than 32 vertices use the reference's hill-climbing support (BigConvexData), which is not built yet");
     meta.push_back(make_uint4((uint32_t)verts.size(), (uint32_t)(polys.size() / 2), (uint32_t)refs.size(), (uint32_t)edges.size()));
     meta.push_back(make_uint4(ch.nVerts, ch.nPolys, ch.nEdges, ch.nIdx));
     uint4 m2; memcpy(&m2.x, &ch.internalExtents[0], 4); memcpy(&m2.y, &ch.internalExtents[1], 4); memcpy(&m2.z, &ch.internalExtents[2], 4); memcpy(&m2.w, &ch.internalRadius, 4);
     meta.push_back(m2);
+    uint4 m3; memcpy(&m3.x, &ch.centerOfMass[0], 4); memcpy(&m3.y, &ch.centerOfMass[1], 4); memcpy(&m3.z, &ch.centerOfMass[2], 4); m3.w = 0; meta.push_back(m3);
     s->hullDiam.push_back(2.f * (std::sqrt(ch.boundsCenter[0] * ch.boundsCenter[0] + ch.boundsCenter[1] * ch.boundsCenter[1] + ch.boundsCenter[2] * ch.boundsCenter[2]) +
                                  std::sqrt(ch.boundsExtents[0] * ch.boundsExtents[0] + ch.boundsExtents[1] * ch.boundsExtents[1] + ch.boundsExtents[2] * ch.boundsExtents[2])));
     const float* v = (const float*)q; for (uint32_t i = 0; i < ch.nVerts; ++i) verts.push_back(make_float4(v[i * 3], v[i * 3 + 1], v[i * 3 + 2], 0.f));

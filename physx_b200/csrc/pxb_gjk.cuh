@@ -28,7 +28,25 @@ PXB_D mxf amxffromxf(const xf* t) { return amxffromxf(*t); }
 PXB_D xf axfinvmul(const xf* a, const xf* b) { return axfinvmul(*a, *b); }
 PXB_D v3 axftransform(const xf* t, v3 v) { return axftransform(*t, v); }
 
-enum { GJK_CVX_CAPSULE = 0, GJK_CVX_BOX = 1 };
+/* ---------------- convex hulls: cooked Gu::ConvexHullData in device memory (uploaded by pxb_scene_set_convex_meshes) ---------------- */
+struct HullArrays { const uint4* meta; const float4* verts; const float4* polys; const uint8_t* refs; const uint8_t* edges; };   // meta: 4 x 16 B per hull
+struct DevHull {
+  uint32_t nVerts, nPolys, nEdges; v3 internalExtents, centerOfMass;
+  const float4* verts; const float4* polys; const uint8_t* vertexRefs; const uint8_t* facesByEdges;
+  PXB_D v3 vert(uint32_t i) const { return V3(verts[i]); }
+  PXB_D v3 plane_n(uint32_t p) const { return V3(polys[2 * p]); }
+  PXB_D float plane_d(uint32_t p) const { return polys[2 * p].w; }
+  PXB_D uint4 poly_meta(uint32_t p) const { const float4 m = polys[2 * p + 1]; return make_uint4(__float_as_uint(m.x), __float_as_uint(m.y), __float_as_uint(m.z), 0u); }   // (vref, nbVerts, minIndex)
+};
+PXB_D DevHull load_hull(const HullArrays& H, uint32_t hullIdx) {
+  const uint4 m0 = H.meta[4 * hullIdx], m1 = H.meta[4 * hullIdx + 1], m2 = H.meta[4 * hullIdx + 2], m3 = H.meta[4 * hullIdx + 3];
+  DevHull h; h.nVerts = m1.x; h.nPolys = m1.y; h.nEdges = m1.z;
+  h.internalExtents = V3(__uint_as_float(m2.x), __uint_as_float(m2.y), __uint_as_float(m2.z)); h.centerOfMass = V3(__uint_as_float(m3.x), __uint_as_float(m3.y), __uint_as_float(m3.z));
+  h.verts = H.verts + m0.x; h.polys = H.polys + 2 * m0.y; h.vertexRefs = H.refs + m0.z; h.facesByEdges = H.edges + m0.w;
+  return h;
+}
+
+enum { GJK_CVX_CAPSULE = 0, GJK_CVX_BOX = 1, GJK_CVX_HULL = 2 };
 enum { GJK_NON_INTERSECT = 0, GJK_CONTACT, GJK_UNDEFINED, GJK_DEGENERATE, EPA_CONTACT, EPA_DEGENERATE, EPA_FAIL };
 
 typedef struct {
@@ -38,6 +56,7 @@ typedef struct {
   v3 ext;                   /* box half extents */
   float margin, minMargin;  /* ConvexV::margin / minMargin */
   int marginIsRadius;
+  const DevHull* hull;      /* GJK_CVX_HULL: cooked hull (ConvexHullNoScaleV: identity mesh scale) */
   int relative;             /* RelativeConvex<T> (GuGJKType.h:110-150): the shape lives in A's frame, supports are returned in B's */
   mxf aToB; m33 aToBT;      /* mAToB and the precomputed transpose of its rotation */
 } GjkConvex;
@@ -46,16 +65,23 @@ typedef struct { v3 normal, closestA, closestB, searchDir; float penDep; } GjkOu
 
 /* CapsuleV(center, v, radius): GuVecCapsule.h:74-85 */
 PXB_D GjkConvex gjk_cvx_capsule(v3 center, v3 v, float radius) {
-  GjkConvex c; c.center = V3(0, 0, 0); c.p0 = c.p1 = c.ext = V3(0, 0, 0); c.relative = 0;
+  GjkConvex c; c.center = V3(0, 0, 0); c.p0 = c.p1 = c.ext = V3(0, 0, 0); c.relative = 0; c.hull = nullptr;
   c.type = GJK_CVX_CAPSULE; c.center = center; c.p0 = v3add(center, v); c.p1 = v3sub(center, v);
   c.margin = radius; c.minMargin = radius; c.marginIsRadius = 1;
   return c;
 }
 /* BoxV(origin, extent) + CalculateBoxMargin: GuVecBox.h:56-68,112-117 */
 PXB_D GjkConvex gjk_cvx_box(v3 origin, v3 ext) {
-  GjkConvex c; c.center = V3(0, 0, 0); c.p0 = c.p1 = c.ext = V3(0, 0, 0); c.relative = 0;
+  GjkConvex c; c.center = V3(0, 0, 0); c.p0 = c.p1 = c.ext = V3(0, 0, 0); c.relative = 0; c.hull = nullptr;
   const float mn = fmin_(ext.x, fmin_(ext.y, ext.z));
   c.type = GJK_CVX_BOX; c.center = origin; c.ext = ext; c.margin = mn * 0.15f; c.minMargin = mn * 0.05f; c.marginIsRadius = 0;
+  return c;
+}
+/* ConvexHullV(hullData, centerOfMass, scale = 1, ...): GuVecConvexHull.h:202-215, CalculateConvexMargin :77-94 */
+PXB_D GjkConvex gjk_cvx_hull(const DevHull* h) {
+  GjkConvex c; c.center = V3(0, 0, 0); c.p0 = c.p1 = c.ext = V3(0, 0, 0); c.relative = 0; c.hull = nullptr;
+  const float mn = fmin_(h->internalExtents.x, fmin_(h->internalExtents.y, h->internalExtents.z));
+  c.type = GJK_CVX_HULL; c.hull = h; c.center = h->centerOfMass; c.margin = mn * 0.1f; c.minMargin = mn * 0.05f; c.marginIsRadius = 0;
   return c;
 }
 PXB_D void gjk_cvx_make_relative(GjkConvex* c, const mxf* aToB) { c->relative = 1; c->aToB = *aToB; c->aToBT = m33transpose(&aToB->r); }
@@ -68,6 +94,13 @@ PXB_D v3 gjk_cvx_support(const GjkConvex* c, v3 dir, int* index) {
   return amxftransform(&c->aToB, p);
 }
 PXB_D v3 gjk_cvx_support_local(const GjkConvex* c, v3 dir, int* index) {
+  if (c->type == GJK_CVX_HULL) {   /* ConvexHullV::bruteForceSearch GuVecConvexHull.h:377-397 (hulls of <= 32 vertices carry no hill-climbing data) */
+    const DevHull* h = c->hull;
+    float mx = v3dot(h->vert(0), dir); uint32_t mi = 0;
+    for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(h->vert(i), dir); if (d > mx) { mx = d; mi = i; } }
+    *index = (int)mi;
+    return h->vert(mi);
+  }
   if (c->type == GJK_CVX_CAPSULE) {
     const float d0 = adot(c->p0, dir), d1 = adot(c->p1, dir);
     const int comp = d0 > d1;
@@ -79,6 +112,7 @@ PXB_D v3 gjk_cvx_support_local(const GjkConvex* c, v3 dir, int* index) {
   return V3(bx ? c->ext.x : -c->ext.x, by ? c->ext.y : -c->ext.y, bz ? c->ext.z : -c->ext.z);
 }
 PXB_D v3 gjk_cvx_support_point_local(const GjkConvex* c, int index) {
+  if (c->type == GJK_CVX_HULL) return c->hull->vert((uint32_t)index);
   if (c->type == GJK_CVX_CAPSULE) return index == 1 ? c->p0 : c->p1;   /* (&p0)[1-index] */
   return V3((index & 1) ? c->ext.x : -c->ext.x, (index & 2) ? c->ext.y : -c->ext.y, (index & 4) ? c->ext.z : -c->ext.z);
 }
@@ -653,23 +687,9 @@ __device__ __noinline__ void gjk_boxbox_gjk_fallback_outofline(const xf* tm0, co
   gjk_boxbox_gjk_fallback(tm0, tm1, ext0, ext1, contactDist, toleranceLength, manifold, out);
 }
 
-/* ---------------- convex hulls: cooked Gu::ConvexHullData in device memory (uploaded by pxb_scene_set_convex_meshes) ---------------- */
-struct HullArrays { const uint4* meta; const float4* verts; const float4* polys; const uint8_t* refs; const uint8_t* edges; };   // meta: 3 x 16 B per hull
-struct DevHull {
-  uint32_t nVerts, nPolys, nEdges; v3 internalExtents;
-  const float4* verts; const float4* polys; const uint8_t* vertexRefs; const uint8_t* facesByEdges;
-  PXB_D v3 vert(uint32_t i) const { return V3(verts[i]); }
-  PXB_D v3 plane_n(uint32_t p) const { return V3(polys[2 * p]); }
-  PXB_D uint4 poly_meta(uint32_t p) const { const float4 m = polys[2 * p + 1]; return make_uint4(__float_as_uint(m.x), __float_as_uint(m.y), __float_as_uint(m.z), 0u); }   // (vref, nbVerts, minIndex)
-};
-PXB_D DevHull load_hull(const HullArrays& H, uint32_t hullIdx) {
-  const uint4 m0 = H.meta[3 * hullIdx], m1 = H.meta[3 * hullIdx + 1], m2 = H.meta[3 * hullIdx + 2];
-  DevHull h; h.nVerts = m1.x; h.nPolys = m1.y; h.nEdges = m1.z;
-  h.internalExtents = V3(__uint_as_float(m2.x), __uint_as_float(m2.y), __uint_as_float(m2.z));
-  h.verts = H.verts + m0.x; h.polys = H.polys + 2 * m0.y; h.vertexRefs = H.refs + m0.z; h.facesByEdges = H.edges + m0.w;
-  return h;
-}
 /* CalculatePCMConvexMargin GuVecConvexHull.h:55-65 (identity scale) */
+PXB_D float gjk_hull_pcm_margin(const DevHull& h, float toleranceLength);
+PXB_D float gjk_hull_pcm_margin(const DevHull* h, float toleranceLength) { return gjk_hull_pcm_margin(*h, toleranceLength); }
 PXB_D float gjk_hull_pcm_margin(const DevHull& h, float toleranceLength) {
   const float mn = fmin_(h.internalExtents.x, fmin_(h.internalExtents.y, h.internalExtents.z));
   return fmin_(mn * 0.25f, toleranceLength * 0.05f);
@@ -1029,3 +1049,88 @@ PXB_D int gjk_pcm_capsule_box(const xf* transf0, const xf* transf1, float capsul
   }
   return 0;
 }
+
+/* ---------------- sphere vs convex hull: GuPCMContactSphereConvex.cpp:47-246, GuPCMContactGenSphereCapsule.cpp:43-152,470-497 ---------------- */
+/* testPolyDataAxis :43-96 over a hull (identity scaling) */
+PXB_D int gjk_hull_test_poly_axis(const GjkConvex* cap, const DevHull* h, float contactDist, float* minOverlap, v3* separatingAxis) {
+  float _minOverlap = FLT_MAX; v3 tempAxis = V3(0, 1, 0);
+  for (uint32_t i = 0; i < h->nPolys; ++i) {
+    const v3 pn = h->plane_n(i);
+    const v3 minVert = h->vert(h->poly_meta(i).z);
+    const float magnitude = 1.0f / alen(pn);
+    const v3 planeN = v3scale(pn, magnitude);
+    const float min0 = adot(pn, minVert) * magnitude, max0 = (-h->plane_d(i)) * magnitude;
+    const float tempMin = adot(cap->p0, planeN), tempMax = adot(cap->p1, planeN);
+    float min1 = fmin_(tempMin, tempMax), max1 = fmax_(tempMin, tempMax);
+    min1 = min1 - cap->margin; max1 = max1 + cap->margin;
+    if ((min1 > max0 + contactDist) || (min0 > max1 + contactDist)) return 0;
+    const float tempOverlap = max0 - min1;
+    if (_minOverlap > tempOverlap) { _minOverlap = tempOverlap; tempAxis = planeN; }
+  }
+  *separatingAxis = tempAxis; *minOverlap = _minOverlap;
+  return 1;
+}
+/* intersectRayPolyhedron :98-152 */
+PXB_D int gjk_hull_ray(v3 a, v3 dir, const DevHull* h, float* tEnter, float* tExit) {
+  float tFirst = 0.f, tLast = FLT_MAX;
+  for (uint32_t k = 0; k < h->nPolys; ++k) {
+    const v3 n = h->plane_n(k); const float d = h->plane_d(k);
+    const float denominator = adot(n, dir), distToPlane = adot(n, a) + d;
+    if (1e-7f > fabsf(denominator)) { if (distToPlane > 0.f) return 0; }
+    else {
+      const float tTemp = -(distToPlane / denominator);
+      const int con = 0.f > denominator;
+      if (con && tTemp > tFirst) tFirst = tTemp;
+      if (!con && tLast > tTemp) tLast = tTemp;
+    }
+    if (tFirst > tLast) return 0;
+  }
+  *tEnter = tFirst; *tExit = tLast;
+  return 1;
+}
+PXB_D void gjk_pcm_sphere_convex(const xf* transf0, const xf* transf1, float sphereRadius, const DevHull* hull, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
+  out->count = 0;
+  const xf curRTrans = axfinvmul(transf1, transf0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  const float convexMargin = gjk_hull_pcm_margin(hull, toleranceLength);
+  const int initialContacts = manifold->n;
+  const float minMargin = fmin_(convexMargin, sphereRadius);
+  manifold_refresh(*manifold, aToB, minMargin * 0.05f);
+  const int bLostContacts = manifold->n != initialContacts;
+  if (bLostContacts || gjk_invalidate_sphere_capsule(manifold, &curRTrans, minMargin)) {
+    manifold->rel = curRTrans; manifold->dirty = 1;
+    const GjkConvex convexHull = gjk_cvx_hull(hull);
+    const GjkConvex capsule = gjk_cvx_capsule(aToB.p, V3(0, 0, 0), sphereRadius);   /* CapsuleV(p, radius): p0 = p1 = p */
+    GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
+    const v3 initialSearchDir = v3sub(capsule.center, convexHull.center);
+    int status = gjk_penetration(&capsule, &convexHull, initialSearchDir, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+    if (status == GJK_NON_INTERSECT) return;
+    if (status == EPA_CONTACT) {
+      status = gjk_epa_penetration(&capsule, &convexHull, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+      if (status != EPA_CONTACT) status = GJK_DEGENERATE;   /* EPA failed: full contact generation with the overlap test, like a degenerate GJK */
+      else status = GJK_CONTACT;
+    }
+    if (status == GJK_CONTACT) {
+      manifold->pts[0].a = V3(0, 0, 0); manifold->pts[0].b = output.closestB; manifold->pts[0].n = output.normal; manifold->pts[0].pen = output.penDep; manifold->n = 1;
+      const v3 worldNormal = aqrot(transf1->q, output.normal);
+      out->normal = worldNormal; out->point[0] = v3negscalesub(worldNormal, sphereRadius, transf0->p); out->sep[0] = output.penDep - sphereRadius; out->count = 1;
+      return;
+    }
+    if (status == GJK_DEGENERATE) {   /* fullContactsGenerationSphereConvex :47-82 with doOverlapTest = true */
+      v3 normal = output.normal; float minOverlap;
+      if (!gjk_hull_test_poly_axis(&capsule, hull, contactDist, &minOverlap, &normal)) return;
+      float tEnter = 0.f, tExit = 0.f;
+      const float inflatedRadius = sphereRadius + contactDist;
+      const v3 dir = v3neg(normal);
+      if (gjk_hull_ray(capsule.p0, dir, hull, &tEnter, &tExit) && inflatedRadius >= tEnter) {
+        manifold->pts[0].a = V3(0, 0, 0); manifold->pts[0].b = v3scaleadd(dir, tEnter, capsule.p0); manifold->pts[0].n = normal; manifold->pts[0].pen = tEnter; manifold->n = 1;
+        const v3 worldNormal = aqrot(transf1->q, normal);
+        out->normal = worldNormal; out->point[0] = v3negscalesub(worldNormal, sphereRadius, transf0->p); out->sep[0] = tEnter - sphereRadius; out->count = 1;
+      }
+    }
+  } else if (manifold->n > 0) {
+    const v3 worldNormal = aqrot(transf1->q, manifold->pts[0].n);
+    out->normal = worldNormal; out->point[0] = v3negscalesub(worldNormal, sphereRadius, transf0->p); out->sep[0] = manifold->pts[0].pen - sphereRadius; out->count = 1;
+  }
+}
+

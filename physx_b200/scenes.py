@@ -546,3 +546,32 @@ def test_forces(n_dynamic, seed=1, blocks=7):
     f[:, ::3] = 0
     f[2] = 0
     return f
+
+
+def hulls_and_spheres(n=10, n_hulls=3, seed=11, **hdr):
+    """Spheres dropped onto convex hulls that rest on the ground plane (hulls spaced apart so that no hull touches another hull):
+    exercises pcmContactSphereConvex (GJK with the hull support mapping) next to plane-convex and sphere-plane."""
+    rng = np.random.RandomState(seed)
+    hulls = [random_hull_points(rng, int(rng.randint(12, 21)), 0.3) for _ in range(n_hulls)]
+    nh = n // 2
+    a = _new_actors(n)
+    for i in range(nh):
+        set_convex(a, i, i % n_hulls)
+        a["pos"][i] = (1.6 * i, 0.35, 0.0)
+    a["quat"][:nh] = random_unit_quats(rng, nh)
+    for k in range(n - nh):
+        i = nh + k
+        set_sphere(a, i, rng.uniform(0.08, 0.16))
+        a["pos"][i] = (1.6 * (k % nh) + rng.uniform(-0.12, 0.12), 0.9 + 0.4 * (k // nh), rng.uniform(-0.12, 0.12))
+        a["linVel"][i] = (0.0, -rng.uniform(0.0, 3.0), 0.0)
+    return cook_hulls(Scene(default_header(**hdr), add_ground_plane(a), hulls))
+
+
+def spheres_into_hulls(seed=11, speed=14.0, **hdr):
+    """hulls_and_spheres with the spheres fired downwards and a few spawned inside a hull: pcmContactSphereConvex through EPA."""
+    sc = hulls_and_spheres(seed=seed, n=12, **hdr)
+    sph = np.nonzero(sc.actors["geomType"] == GEOM_SPHERE)[0]
+    sc.actors["linVel"][sph, 1] = -np.float32(speed)
+    inside = sph[::3]
+    sc.actors["pos"][inside] = sc.actors["pos"][1 + (np.arange(len(inside)) % 6)] + np.array([0.02, 0.05, 0.01], np.float32)
+    return sc

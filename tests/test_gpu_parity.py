@@ -187,7 +187,7 @@ def test_gpu_matches_oracle_primitives(oracle, name):
         cpu.setStates(sg)
 
 
-@pytest.mark.parametrize("name", ["capsule_row", "spheres_capsules_14", "capsules_on_boxes", "hulls_on_plane"])
+@pytest.mark.parametrize("name", ["capsule_row", "spheres_capsules_14", "capsules_on_boxes", "hulls_on_plane", "hulls_and_spheres"])
 def test_gpu_teacher_forced_steps_match_reference(name):
     z, sc = util.load_golden(name)
     gpu = engine.Scene(sc)
@@ -551,6 +551,23 @@ def test_convex_hulls_gpu_matches_oracle_and_reference(oracle):
         assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
         cg, cc = gpu.getContacts(), cpu.getContacts()
         assert np.array_equal(cg[:, 0], cc[:, 0]) and np.abs(cg[:, :4 + 5 * 4] - cc[:, :4 + 5 * 4])[:, [0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12]].max(initial=0) < 1e-6, f"contacts, step {t}"
+        assert np.abs(gpu.getStates() - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
+
+
+@pytest.mark.parametrize("name", ["hulls_and_spheres", "spheres_into_hulls"])
+def test_sphere_convex_gpu_matches_oracle(oracle, name):
+    """pcmContactSphereConvex on the device (hull support mapping, GJK, EPA) against the oracle, teacher-forced from the golden states."""
+    z, sc = util.load_golden(name)
+    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setStates(z["states"][t]); cpu.setStates(z["states"][t])
+        gpu.setConstraintOrder(util.golden_order(z, t))
+        gpu.step()
+        cpu.step(util.golden_order(z, t))
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
+        cg, cc = gpu.getContacts(), cpu.getContacts()
+        assert np.array_equal(cg[:, 0], cc[:, 0]), f"contact counts, step {t}"
+        assert np.abs(cg[:, 1:8] - cc[:, 1:8]).max(initial=0) < 1e-6, f"first contact, step {t}"
         assert np.abs(gpu.getStates() - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
 
 
