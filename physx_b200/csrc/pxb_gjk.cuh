@@ -1134,3 +1134,168 @@ PXB_D void gjk_pcm_sphere_convex(const xf* transf0, const xf* transf1, float sph
   }
 }
 
+
+/* ---------------- capsule vs convex hull: GuPCMContactCapsuleConvex.cpp:42-262, GuPCMContactGenSphereCapsule.cpp:154-468, GuPCMContactGenUtil.cpp:105-260 ---------------- */
+/* ConvexHullNoScaleV::bruteForceSearchMinMax GuVecConvexHull.h:410-429 (SupportLocalImpl::doSupport) */
+PXB_D void gjk_hull_support_minmax(const DevHull* h, v3 dir, float* mn, float* mx) {
+  float _max = v3dot(h->vert(0), dir), _min = _max;
+  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(h->vert(i), dir); _max = d > _max ? d : _max; _min = d < _min ? d : _min; }   /* PxMax / PxMin */
+  *mn = _min; *mx = _max;
+}
+/* testSATCapsulePoly :154-219 */
+PXB_D int gjk_hull_sat_capsule(const GjkConvex* cap, const DevHull* h, float contactDist, float* minOverlap, v3* separatingAxis) {
+  float _minOverlap = FLT_MAX; v3 tempAxis = V3(0, 1, 0);
+  if (!gjk_hull_test_poly_axis(cap, h, contactDist, &_minOverlap, &tempAxis)) return 0;
+  const v3 capsuleAxis = v3sub(cap->p1, cap->p0);
+  for (uint32_t i = 0; i < h->nPolys; ++i) {
+    const uint8_t* inds = h->vertexRefs + h->poly_meta(i).x; const uint32_t nb = h->poly_meta(i).y;
+    for (uint32_t lStart = 0, lEnd = nb - 1; lStart < nb; lEnd = lStart++) {
+      const v3 p10 = h->vert(inds[lStart]), p11 = h->vert(inds[lEnd]);
+      const v3 dir = v3cross(capsuleAxis, v3sub(p11, p10));
+      const float lenSq = adot(dir, dir);
+      if (FLT_EPSILON > lenSq) continue;
+      const v3 normal = gjk_v3div(dir, sqrtf(lenSq));
+      float min0, max0; gjk_hull_support_minmax(h, normal, &min0, &max0);
+      const float tempMin = adot(cap->p0, normal), tempMax = adot(cap->p1, normal);
+      float min1 = fmin_(tempMin, tempMax), max1 = fmax_(tempMin, tempMax);
+      min1 = min1 - cap->margin; max1 = max1 + cap->margin;
+      if ((min1 > max0 + contactDist) || (min0 > max1 + contactDist)) return 0;
+      const float tempOverlap = max0 - min1;
+      if (_minOverlap > tempOverlap) { _minOverlap = tempOverlap; tempAxis = normal; }
+    }
+  }
+  *separatingAxis = tempAxis; *minOverlap = _minOverlap;
+  return 1;
+}
+/* generatedFaceContacts :286-310 */
+PXB_D void gjk_hull_capsule_face_contacts(const GjkConvex* cap, const DevHull* h, const mxf* aToB, MPoint* mc, int* num, float contactDist, v3 normal) {
+  float tEnter = 0.f, tExit = 0.f;
+  const float inflatedRadius = cap->margin + contactDist;
+  const v3 dir = v3neg(normal);
+  if (gjk_hull_ray(cap->p0, dir, h, &tEnter, &tExit) && inflatedRadius >= tEnter) { mc[*num].a = amxftransforminv(aToB, cap->p0); mc[*num].b = v3scaleadd(dir, tEnter, cap->p0); mc[*num].n = normal; mc[*num].pen = tEnter; (*num)++; }
+  if (gjk_hull_ray(cap->p1, dir, h, &tEnter, &tExit) && inflatedRadius >= tEnter) { mc[*num].a = amxftransforminv(aToB, cap->p1); mc[*num].b = v3scaleadd(dir, tEnter, cap->p1); mc[*num].n = normal; mc[*num].pen = tEnter; (*num)++; }
+}
+/* getPolygonIndex GuPCMContactGenUtil.cpp:105-202 (identity scaling; hulls carry their edge -> faces table) */
+PXB_D int gjk_hull_polygon_index(const DevHull* h, v3 normal) {
+  const v3 n = normal, nnormal = v3neg(n);
+  float minProj = adot(n, h->plane_n(0));
+  int closestFaceIndex = 0;
+  for (uint32_t i = 1; i < h->nPolys; ++i) { const float proj = adot(n, h->plane_n(i)); if (minProj > proj) { minProj = proj; closestFaceIndex = (int)i; } }
+  uint32_t closestEdge = 0xffffffffu;
+  float maxDpSq = minProj * minProj;
+  for (uint32_t i = 0; i < h->nEdges; ++i) {
+    const uint8_t f0 = h->facesByEdges[i * 2], f1 = h->facesByEdges[i * 2 + 1];
+    const v3 edgeNormal = v3add(h->plane_n(f0), h->plane_n(f1));
+    const float enMagSq = adot(edgeNormal, edgeNormal), dp = adot(edgeNormal, nnormal), sqDp = dp * dp;
+    if (dp >= 0.f && sqDp > maxDpSq * enMagSq) { maxDpSq = sqDp / enMagSq; closestEdge = i; }
+  }
+  if (closestEdge != 0xffffffffu) {
+    const uint32_t f0 = h->facesByEdges[closestEdge * 2], f1 = h->facesByEdges[closestEdge * 2 + 1];
+    const float dp0 = adot(h->plane_n(f0), nnormal), dp1 = adot(h->plane_n(f1), nnormal);
+    closestFaceIndex = dp0 > dp1 ? (int)f0 : (int)f1;
+  }
+  return closestFaceIndex;
+}
+/* getWitnessPolygonIndex GuPCMContactGenUtil.cpp:204-260 */
+PXB_D int gjk_hull_witness_polygon_index(const DevHull* h, v3 normal, v3 closest, float tolerance) {
+  float pd[64];   // hulls of <= 32 vertices have <= 60 polygons (pxb_scene_set_convex_meshes enforces the vertex limit)
+  const float eps = -tolerance;
+  float dist = v3dot(closest, h->plane_n(0)) + h->plane_d(0);
+  float minDist = dist >= eps ? fabsf(dist) : FLT_MAX;
+  pd[0] = minDist;
+  float maxDist = dist; int maxFace = 0, closestFace = 0;
+  for (uint32_t i = 1; i < h->nPolys; ++i) {
+    dist = v3dot(closest, h->plane_n(i)) + h->plane_d(i);
+    pd[i] = dist >= eps ? fabsf(dist) : FLT_MAX;
+    if (minDist > pd[i]) { minDist = pd[i]; closestFace = (int)i; }
+    if (dist > maxDist) { maxDist = dist; maxFace = (int)i; }
+  }
+  if (minDist == FLT_MAX) return maxFace;
+  float bestProj = adot(anormalize(h->plane_n(closestFace)), normal);
+  const int first = closestFace;
+  for (uint32_t i = 0; i < h->nPolys; ++i) {
+    if ((tolerance > (pd[i] - minDist)) && first != (int)i) {
+      const float proj = adot(anormalize(h->plane_n(i)), normal);
+      if (bestProj > proj) { closestFace = (int)i; bestProj = proj; }
+    }
+  }
+  return closestFace;
+}
+/* generatedContactsEEContacts :361-377 */
+PXB_D void gjk_hull_capsule_ee_contacts(const GjkConvex* cap, const DevHull* h, int ref, const mxf* aToB, MPoint* mc, int* num, float contactDist, v3 normal) {
+  const uint8_t* inds = h->vertexRefs + h->poly_meta(ref).x; const uint32_t nb = h->poly_meta(ref).y;
+  const float inflatedRadius = cap->margin + contactDist;
+  for (uint32_t rStart = 0, rEnd = nb - 1; rStart < nb; rEnd = rStart++)
+    gjk_capbox_ee(cap->p0, cap->p1, normal, h->vert(inds[rStart]), h->vert(inds[rEnd]), aToB, mc, num, inflatedRadius);
+}
+/* generateFullContactManifold(capsule, polyData, ...) :423-468 */
+PXB_D int gjk_hull_capsule_full_manifold(const GjkConvex* cap, const DevHull* h, const mxf* aToB, MPoint* mc, int* num, float contactDist, v3* normal, v3 closest, float margin,
+                                                 int doOverlapTest, float toleranceLength) {
+  const int original = *num;
+  v3 tNormal = *normal;
+  if (doOverlapTest) {
+    float minOverlap;
+    if (!gjk_hull_sat_capsule(cap, h, contactDist, &minOverlap, &tNormal)) return 0;
+    gjk_hull_capsule_face_contacts(cap, h, aToB, mc, num, contactDist, tNormal);
+    if (*num - original < 2) gjk_hull_capsule_ee_contacts(cap, h, gjk_hull_polygon_index(h, v3neg(tNormal)), aToB, mc, num, contactDist, tNormal);
+  } else {
+    gjk_hull_capsule_face_contacts(cap, h, aToB, mc, num, contactDist, tNormal);
+    if (*num - original < 2) {
+      const float lowerEps = toleranceLength * 1e-2f, upperEps = toleranceLength * 5e-2f;
+      const float tolerance = fmin_(fmax_(margin, lowerEps), upperEps);
+      gjk_hull_capsule_ee_contacts(cap, h, gjk_hull_witness_polygon_index(h, v3neg(tNormal), closest, tolerance), aToB, mc, num, contactDist, tNormal);
+    }
+  }
+  *normal = tNormal;
+  return 1;
+}
+/* pcmContactCapsuleConvex :80-262 (shape0 = capsule, shape1 = convex mesh, identity mesh scale) */
+PXB_D void gjk_pcm_capsule_convex(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, const DevHull* hull, float contactDist, float toleranceLength,
+                                          Manifold* manifold, Contacts* out) {
+  out->count = 0;
+  const xf curRTrans = axfinvmul(transf1, transf0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  const float convexMargin = gjk_hull_pcm_margin(hull, toleranceLength);
+  const float minMargin = fmin_(convexMargin, capsuleRadius * 0.05f);   /* CalculateCapsuleMinMargin GuVecCapsule.h:42-47 */
+  const int initialContacts = manifold->n;
+  manifold_refresh(*manifold, aToB, minMargin * 1.25f);
+  const int bLostContacts = manifold->n != initialContacts;
+  if (bLostContacts || gjk_invalidate_sphere_capsule(manifold, &curRTrans, minMargin)) {
+    manifold->rel = curRTrans; manifold->dirty = 1;
+    const GjkConvex convexHull = gjk_cvx_hull(hull);
+    const GjkConvex capsule = gjk_cvx_capsule(aToB.p, m33mul(&aToB.r, v3scale(V3(1, 0, 0), capsuleHalfHeight)), capsuleRadius);
+    GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
+    const v3 initialSearchDir = v3sub(capsule.center, convexHull.center);
+    int status = gjk_penetration(&capsule, &convexHull, initialSearchDir, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+    MPoint mc[16]; int numContacts = 0; int doOverlapTest = 0;   // <= 2 face points + one edge-edge point per polygon edge that the segment crosses (2 for a convex polygon)
+    if (status == GJK_NON_INTERSECT) return;
+    if (status == GJK_DEGENERATE) doOverlapTest = 1;
+    else {
+      const float replaceBreakingThreshold = minMargin * 0.05f;
+      if (status == EPA_CONTACT) {
+        status = gjk_epa_penetration(&capsule, &convexHull, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+        if (status != EPA_CONTACT) doOverlapTest = 1;
+      }
+      if (!doOverlapTest) add_manifold_point2(*manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+      if (!(initialContacts == 0 || bLostContacts || doOverlapTest)) {
+        const v3 n = aqrot(transf1->q, output.normal);
+        gjk_manifold_to_contacts_radius(manifold, n, transf0, capsuleRadius, contactDist, out);
+        return;
+      }
+    }
+    /* fullContactsGenerationCapsuleConvex :42-78 */
+    v3 normal = output.normal;
+    if (!gjk_hull_capsule_full_manifold(&capsule, hull, &aToB, mc, &numContacts, contactDist, &normal, output.closestB, convexHull.margin, doOverlapTest, toleranceLength)) return;
+    if (numContacts > 0) {
+      gjk_add_batch2(manifold, mc, numContacts);
+      normal = aqrot(transf1->q, normal);
+      gjk_manifold_to_contacts_radius(manifold, normal, transf0, capsuleRadius, contactDist, out);
+    } else if (!doOverlapTest) {
+      normal = aqrot(transf1->q, normal);
+      gjk_manifold_to_contacts_radius(manifold, normal, transf0, capsuleRadius, contactDist, out);
+    }
+  } else if (manifold->n > 0) {
+    const v3 worldNormal = manifold_world_normal(*manifold, *transf1);
+    gjk_manifold_to_contacts_radius(manifold, worldNormal, transf0, capsuleRadius, contactDist, out);
+  }
+}

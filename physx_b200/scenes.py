@@ -575,3 +575,23 @@ def spheres_into_hulls(seed=11, speed=14.0, **hdr):
     inside = sph[::3]
     sc.actors["pos"][inside] = sc.actors["pos"][1 + (np.arange(len(inside)) % 6)] + np.array([0.02, 0.05, 0.01], np.float32)
     return sc
+
+
+def hulls_and_capsules(n=12, n_hulls=3, seed=21, speed=0.0, **hdr):
+    """Capsules dropped onto convex hulls resting on the ground plane (hulls spaced apart): pcmContactCapsuleConvex -- GJK over the hull
+    support mapping, face (ray) and edge-edge contacts against the witness polygon.  speed > 0 fires the capsules downwards (EPA)."""
+    rng = np.random.RandomState(seed)
+    hulls = [random_hull_points(rng, int(rng.randint(12, 21)), 0.3) for _ in range(n_hulls)]
+    nh = n // 2
+    a = _new_actors(n)
+    for i in range(nh):
+        set_convex(a, i, i % n_hulls)
+        a["pos"][i] = (1.6 * i, 0.35, 0.0)
+    a["quat"] = random_unit_quats(rng, n)
+    for k in range(n - nh):
+        i = nh + k
+        set_capsule(a, i, rng.uniform(0.06, 0.12), rng.uniform(0.1, 0.25))
+        a["pos"][i] = (1.6 * (k % nh) + rng.uniform(-0.1, 0.1), 0.9 + 0.45 * (k // nh), rng.uniform(-0.1, 0.1))
+        a["angVel"][i] = rng.uniform(-2, 2, 3)
+        a["linVel"][i] = (0.0, -speed, 0.0)
+    return cook_hulls(Scene(default_header(**hdr), add_ground_plane(a), hulls))

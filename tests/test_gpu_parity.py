@@ -187,7 +187,7 @@ def test_gpu_matches_oracle_primitives(oracle, name):
         cpu.setStates(sg)
 
 
-@pytest.mark.parametrize("name", ["capsule_row", "spheres_capsules_14", "capsules_on_boxes", "hulls_on_plane", "hulls_and_spheres"])
+@pytest.mark.parametrize("name", ["capsule_row", "spheres_capsules_14", "capsules_on_boxes", "hulls_on_plane", "hulls_and_spheres", "hulls_and_capsules"])
 def test_gpu_teacher_forced_steps_match_reference(name):
     z, sc = util.load_golden(name)
     gpu = engine.Scene(sc)
@@ -554,9 +554,10 @@ def test_convex_hulls_gpu_matches_oracle_and_reference(oracle):
         assert np.abs(gpu.getStates() - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
 
 
-@pytest.mark.parametrize("name", ["hulls_and_spheres", "spheres_into_hulls"])
+@pytest.mark.parametrize("name", ["hulls_and_spheres", "spheres_into_hulls", "hulls_and_capsules", "capsules_into_hulls"])
 def test_sphere_convex_gpu_matches_oracle(oracle, name):
-    """pcmContactSphereConvex on the device (hull support mapping, GJK, EPA) against the oracle, teacher-forced from the golden states."""
+    """pcmContactSphereConvex / pcmContactCapsuleConvex on the device (hull support mapping, GJK, EPA, face + edge-edge contacts) against the
+    oracle, teacher-forced from the golden states (hull-hull pairs of the *_into_* scenes excepted: they stop the step, see below)."""
     z, sc = util.load_golden(name)
     gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
     for t in range(z["states"].shape[0] - 1):
