@@ -1278,4 +1278,195 @@ static inline void pxo_pcm_capsule_convex(const xf* transf0, const xf* transf1, 
     pxo_manifold_to_contacts_radius(manifold, worldNormal, transf0, capsuleRadius, contactDist, out);
   }
 }
+
+/* ---------------- polygonal pairs: box vs hull, hull vs hull ----------------
+ * GuPCMContactGenBoxConvex.cpp:331-530 (generatedContacts), :532-665 (generateFullContactManifold, witness-polygon branch), :668-720 (addGJKEPAContacts),
+ * GuPCMContactBoxConvex.cpp:47-256, GuPCMContactConvexConvex.cpp:42-276.
+ * NOT restated yet: the SAT branch of generateFullContactManifold (testFaceNormal / testEdgeNormal / buildPartialHull, :56-328), taken when GJK
+ * degenerates away from the centre line or EPA fails -- such a pair is counted as unsupported by the caller. */
+typedef struct { float verts[24]; PxbCookedPoly polys[6]; PxoHull view; } PxoBoxAsHull;
+static inline const PxoHull* pxo_box_as_hull(PxoBoxAsHull* b, v3 ext) {   /* PCMPolygonalBox as the same polygonal view the hulls use */
+  PxoPolyBox pb; pxo_poly_box(&pb, ext);
+  for (int i = 0; i < 8; ++i) { b->verts[i * 3] = pb.verts[i].x; b->verts[i * 3 + 1] = pb.verts[i].y; b->verts[i * 3 + 2] = pb.verts[i].z; }
+  for (int i = 0; i < 6; ++i) { b->polys[i].plane[0] = pb.polys[i].n.x; b->polys[i].plane[1] = pb.polys[i].n.y; b->polys[i].plane[2] = pb.polys[i].n.z; b->polys[i].plane[3] = pb.polys[i].d;
+                                b->polys[i].vref = (uint32_t)i * 4; b->polys[i].nbVerts = 4; b->polys[i].minIndex = (uint32_t)pb.polys[i].minIndex; b->polys[i].pad = 0; }
+  memset(&b->view, 0, sizeof(b->view));
+  b->view.nVerts = 8; b->view.nPolys = 6; b->view.nEdges = 0; b->view.nIdx = 24; b->view.verts = b->verts; b->view.polys = b->polys; b->view.vertexRefs = pxo_box_poly_refs; b->view.facesByEdges = NULL;
+  b->view.internalExtents = ext;
+  return &b->view;
+}
+static inline float pxo_signed_2d_tri_area(v3 a, v3 b, v3 c) { const v3 ca = v3sub(a, c), cb = v3sub(b, c); return ca.x * cb.y - ca.y * cb.x; }   /* GuPCMContactGenUtil.h:56-66 */
+#define PXO_POLY_MAX_CONTACTS 256
+/* generatedContacts :331-530: incident polygon (of poly1) clipped against the reference polygon (of poly0) in the reference polygon's plane */
+static inline void pxo_poly_generated_contacts(const PxoHull* poly0, const PxoHull* poly1, int refIdx, int incIdx, const mxf* transform0To1, PxoMPoint* mc, int* numContacts, float contactDist) {
+  const PxbCookedPoly* referencePolygon = &poly0->polys[refIdx]; const PxbCookedPoly* incidentPolygon = &poly1->polys[incIdx];
+  const uint8_t* inds0 = poly0->vertexRefs + referencePolygon->vref; const uint8_t* inds1 = poly1->vertexRefs + incidentPolygon->vref;
+  const uint32_t nRef = referencePolygon->nbVerts, nInc = incidentPolygon->nbVerts;
+  const v3 contactNormal = anormalize(pxo_hull_plane_n(poly0, (uint32_t)refIdx));
+  const m33 rot = pxo_rotation_from_z(contactNormal);
+  v3 points0In0[64], points1In0[64]; int pen1[64]; float tval1[64];
+  for (uint32_t i = 0; i < nRef; ++i) points0In0[i] = pxo_hull_vert(poly0, inds0[i]);
+  for (uint32_t i = 0; i < nInc; ++i) points1In0[i] = pxo_hull_vert(poly1, inds1[i]);
+  const v3 sPoint = points1In0[0];
+  const float eps = FLT_EPSILON;
+  v3 rMin = V3(FLT_MAX, FLT_MAX, FLT_MAX), rMax = V3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+  for (uint32_t i = 0; i < nRef; ++i) { points0In0[i] = m33mul(&rot, points0In0[i]); rMin = v3min(rMin, points0In0[i]); rMax = v3max(rMax, points0In0[i]); }
+  rMin = v3sub(rMin, V3(eps, eps, eps)); rMax = v3add(rMax, V3(eps, eps, eps));
+  const float d = points0In0[0].z, rd = d + contactDist;
+  v3 iMin = V3(FLT_MAX, FLT_MAX, FLT_MAX), iMax = V3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+  uint32_t inside = 0;
+  for (uint32_t i = 0; i < nInc; ++i) {
+    const v3 vert1 = points1In0[i];
+    const v3 a = amxftransforminv(transform0To1, vert1);
+    points1In0[i] = m33mul(&rot, a);
+    const float z = points1In0[i].z;
+    tval1[i] = z - d;
+    points1In0[i].z = d;
+    iMin = v3min(iMin, points1In0[i]); iMax = v3max(iMax, points1In0[i]);
+    if (rd > z) {
+      pen1[i] = 1;
+      if (pxo_contains(points0In0, (int)nRef, points1In0[i], rMin, rMax)) {
+        inside++;
+        if (*numContacts == PXO_POLY_MAX_CONTACTS) return;
+        mc[*numContacts].a = vert1; mc[*numContacts].b = am33tmul(&rot, points1In0[i]); mc[*numContacts].n = contactNormal; mc[*numContacts].pen = tval1[i]; (*numContacts)++;
+      }
+    } else pen1[i] = 0;
+  }
+  if (inside == nInc) return;
+  inside = 0;
+  iMin = v3sub(iMin, V3(eps, eps, eps)); iMax = v3add(iMax, V3(eps, eps, eps));
+  const v3 incidentNormal = anormalize(pxo_hull_plane_n(poly1, (uint32_t)incIdx));
+  const v3 contactNormalIn1 = m33mul(&transform0To1->r, contactNormal);
+  for (uint32_t i = 0; i < nRef; ++i) {
+    if (pxo_contains(points1In0, (int)nInc, points0In0[i], iMin, iMax)) {
+      const v3 vert0 = am33tmul(&rot, points0In0[i]);
+      const v3 a = amxftransform(transform0To1, vert0);
+      const float nom = adot(incidentNormal, v3sub(sPoint, a)), denom = adot(incidentNormal, contactNormalIn1);
+      const float t = nom / denom;
+      if (t > contactDist) continue;
+      inside++;
+      if (*numContacts == PXO_POLY_MAX_CONTACTS) return;
+      mc[*numContacts].a = v3scaleadd(contactNormalIn1, t, a); mc[*numContacts].b = vert0; mc[*numContacts].n = contactNormal; mc[*numContacts].pen = t; (*numContacts)++;
+    }
+  }
+  if (inside == nRef) return;
+  for (uint32_t iStart = 0, iEnd = nInc - 1; iStart < nInc; iEnd = iStart++) {
+    if (!pen1[iStart] && !pen1[iEnd]) continue;
+    const v3 ipA = points1In0[iStart], ipB = points1In0[iEnd];
+    v3 ipAOri = points1In0[iStart]; ipAOri.z = tval1[iStart] + d;
+    v3 ipBOri = points1In0[iEnd]; ipBOri.z = tval1[iEnd] + d;
+    const v3 sMin = v3min(ipA, ipB), sMax = v3max(ipA, ipB);
+    for (uint32_t rStart = 0, rEnd = nRef - 1; rStart < nRef; rEnd = rStart++) {
+      const v3 rpA = points0In0[rStart], rpB = points0In0[rEnd];
+      const v3 qMin = v3min(rpA, rpB), qMax = v3max(rpA, rpB);
+      if ((sMin.x > qMax.x) || (qMin.x > sMax.x) || (sMin.y > qMax.y) || (qMin.y > sMax.y)) continue;
+      const float a1 = pxo_signed_2d_tri_area(rpA, rpB, ipA), a2 = pxo_signed_2d_tri_area(rpA, rpB, ipB);
+      if (0.f > a1 * a2) {
+        const float a3 = pxo_signed_2d_tri_area(ipA, ipB, rpA), a4 = pxo_signed_2d_tri_area(ipA, ipB, rpB);
+        if (0.f > a3 * a4) {
+          const float t = a1 / (a2 - a1);
+          const v3 pBB = v3negscalesub(v3sub(ipBOri, ipAOri), t, ipAOri);
+          v3 pAA = pBB; pAA.z = d;
+          const v3 pA = am33tmul(&rot, pAA);
+          const v3 pB = amxftransform(transform0To1, am33tmul(&rot, pBB));
+          const float pen = pBB.z - pAA.z;
+          if (pen > contactDist) continue;
+          if (*numContacts == PXO_POLY_MAX_CONTACTS) return;
+          mc[*numContacts].a = pB; mc[*numContacts].b = pA; mc[*numContacts].n = contactNormal; mc[*numContacts].pen = pen; (*numContacts)++;
+        }
+      }
+    }
+  }
+}
+/* generateFullContactManifold :532-665, doOverlapTest == false (witness polygons of the GJK / EPA closest points).  map0 / map1 = world transforms of the two shapes. */
+static inline void pxo_poly_full_manifold(const PxoHull* poly0, const PxoHull* poly1, const mxf* map0, const mxf* map1, PxoMPoint* mc, int* numContacts, float contactDist,
+                                          v3 normal, v3 closestA, v3 closestB, float marginA, float marginB, float toleranceLength) {
+  const mxf transform1To0 = amxfinvmul(map0, map1), transform0To1 = amxfinvmul(map1, map0);
+  const float lowerEps = toleranceLength * 1e-2f, upperEps = toleranceLength * 5e-2f;
+  const float toleranceA = fminf_(fmaxf_(marginA, lowerEps), upperEps), toleranceB = fminf_(fmaxf_(marginB, lowerEps), upperEps);
+  const v3 negNormal = v3neg(normal);
+  const v3 normalIn0 = am33tmul(&transform0To1.r, normal);
+  const int faceIndex1 = pxo_hull_witness_polygon_index(poly1, negNormal, closestB, toleranceB);
+  const int faceIndex0 = pxo_hull_witness_polygon_index(poly0, normalIn0, amxftransforminv(&transform0To1, closestA), toleranceA);
+  const v3 referenceNormal = anormalize(pxo_hull_plane_n(poly1, (uint32_t)faceIndex1)), incidentNormal = anormalize(pxo_hull_plane_n(poly0, (uint32_t)faceIndex0));
+  const float referenceProject = fabsf(adot(referenceNormal, negNormal)), incidentProject = fabsf(adot(incidentNormal, normalIn0));
+  if (referenceProject >= incidentProject) pxo_poly_generated_contacts(poly1, poly0, faceIndex1, faceIndex0, &transform1To0, mc, numContacts, contactDist);
+  else {
+    pxo_poly_generated_contacts(poly0, poly1, faceIndex0, faceIndex1, &transform0To1, mc, numContacts, contactDist);
+    if (*numContacts > 0) {
+      const v3 n = m33mul(&transform0To1.r, incidentNormal), nn = v3neg(n);
+      for (int i = 0; i < *numContacts; ++i) { const v3 lb = mc[i].b; mc[i].b = mc[i].a; mc[i].a = lb; mc[i].n = nn; }
+    }
+  }
+}
+static inline v3 pxo_manifold_local_normal(const PxoManifold* m) { v3 n = m->pts[0].n; for (int i = 1; i < m->n; ++i) n = v3add(n, m->pts[i].n); return anormalize(n); }   /* getLocalNormal .h:710-718 */
+static inline void pxo_manifold_to_contacts(const PxoManifold* m, v3 worldNormal, const xf* transf1, float contactDist, PxoContacts* out) {   /* .cpp:739-759 */
+  out->count = 0; out->normal = worldNormal;
+  for (int i = 0; i < m->n; ++i) { const float dist = m->pts[i].pen; if (contactDist >= dist) { out->point[out->count] = axftransform(transf1, m->pts[i].b); out->sep[out->count] = dist; out->count++; } }
+}
+/* pcmContactBoxConvex / pcmContactConvexConvex: shape A (box or hull) relative to hull B.  convexA must already be relative (aToB).
+ * Returns 1 when the reference would run the SAT branch (not restated), 0 otherwise. */
+static inline int pxo_pcm_poly_convex(const xf* transf0, const xf* transf1, PxoConvex* convexA, const PxoHull* polyA, float marginPcmA, float radiusA, const PxoHull* hullB,
+                                      float contactDist, float toleranceLength, PxoManifold* manifold, PxoContacts* out) {
+  out->count = 0;
+  const xf curRTrans = axfinvmul(transf1, transf0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  const float convexMarginB = pxo_hull_pcm_margin(hullB, toleranceLength);
+  const float minMargin = fminf_(marginPcmA, convexMarginB);
+  const int initialContacts = manifold->n;
+  pxo_refresh(manifold, &aToB, minMargin * 0.8f);
+  const int bLostContacts = manifold->n != initialContacts;
+  const float radiusB = alen(hullB->internalExtents);
+  if (bLostContacts || pxo_invalidate_boxconvex(manifold, &curRTrans, transf0->q, transf1->q, minMargin, radiusA, radiusB)) {
+    manifold->rel = curRTrans; manifold->quatA = transf0->q; manifold->quatB = transf1->q;
+    pxo_cvx_make_relative(convexA, &aToB);
+    const PxoConvex convexB = pxo_cvx_hull(hullB);
+    PxoGjkOutput output; memset(&output, 0, sizeof(output));
+    int status = pxo_gjk_penetration(convexA, &convexB, aToB.p, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+    if (status == PXO_GJK_NON_INTERSECT) return 0;
+    /* generateOrProcessContacts* + addGJKEPAContacts */
+    const v3 localNor = manifold->n ? pxo_manifold_local_normal(manifold) : V3(0, 0, 0);
+    const float replaceBreakingThreshold = minMargin * 0.05f;
+    int doOverlapTest = 0;
+    if (status == PXO_GJK_DEGENERATE) {
+      const float costheta = adot(output.searchDir, output.normal);
+      if (costheta > 0.9999f) {
+        const v3 centreA = amxftransform(&aToB, convexA->center), centreB = convexB.center;
+        const v3 dir = anormalize(v3sub(centreA, centreB));
+        if (adot(dir, output.normal) > 0.707f) pxo_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+        else doOverlapTest = 1;
+      } else doOverlapTest = 1;
+    } else if (status == PXO_GJK_CONTACT) pxo_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+    else {
+      status = pxo_epa_penetration(convexA, &convexB, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+      if (status == PXO_EPA_CONTACT) pxo_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+      else doOverlapTest = 1;
+    }
+    if (doOverlapTest) return 1;   /* SAT branch: not restated */
+    const int fullContactGen = (0.707106781f > adot(localNor, output.normal)) || (manifold->n < initialContacts);
+    if (fullContactGen) {
+      static PxoMPoint mc[PXO_POLY_MAX_CONTACTS]; int numContacts = 0;
+      const mxf map0 = amxffromxf(transf0), map1 = amxffromxf(transf1);
+      pxo_poly_full_manifold(polyA, hullB, &map0, &map1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
+      if (numContacts > 0) {
+        if (numContacts <= PXO_MANIFOLD_CACHE) { for (int i = 0; i < numContacts; ++i) manifold->pts[i] = mc[i]; manifold->n = numContacts; }
+        else { pxo_reduce_batch(manifold, mc, numContacts, toleranceLength); manifold->n = PXO_MANIFOLD_CACHE; }
+      }
+      pxo_manifold_to_contacts(manifold, pxo_world_normal(manifold, transf1), transf1, contactDist, out);
+    } else {
+      const v3 newLocalNor = v3add(localNor, output.normal);
+      pxo_manifold_to_contacts(manifold, anormalize(aqrot(transf1->q, newLocalNor)), transf1, contactDist, out);
+    }
+  } else if (manifold->n > 0) pxo_manifold_to_contacts(manifold, pxo_world_normal(manifold, transf1), transf1, contactDist, out);
+  return 0;
+}
+static inline int pxo_pcm_box_convex(const xf* transf0, const xf* transf1, v3 boxExtents, const PxoHull* hull, float contactDist, float toleranceLength, PxoManifold* manifold, PxoContacts* out) {
+  PxoBoxAsHull bh; const PxoHull* polyA = pxo_box_as_hull(&bh, boxExtents);
+  PxoConvex box = pxo_cvx_box(V3(0, 0, 0), boxExtents);
+  return pxo_pcm_poly_convex(transf0, transf1, &box, polyA, pxo_box_margin(boxExtents, toleranceLength), alen(boxExtents), hull, contactDist, toleranceLength, manifold, out);
+}
+static inline int pxo_pcm_convex_convex(const xf* transf0, const xf* transf1, const PxoHull* hull0, const PxoHull* hull1, float contactDist, float toleranceLength, PxoManifold* manifold, PxoContacts* out) {
+  PxoConvex c0 = pxo_cvx_hull(hull0);
+  return pxo_pcm_poly_convex(transf0, transf1, &c0, hull0, pxo_hull_pcm_margin(hull0, toleranceLength), alen(hull0->internalExtents), hull1, contactDist, toleranceLength, manifold, out);
+}
 #endif

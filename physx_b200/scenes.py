@@ -55,18 +55,25 @@ def normalize_quat_f32(q):
     q, ok = settle(q)
     if ok:
         return q
-    # normalisation can settle into a 2-cycle one ulp apart: re-solve the smallest non-zero component so that |q|^2 rounds to 1
-    k = int(np.argmin(np.where(q == 0, np.inf, np.abs(q))))
-    rest = float(np.sum(np.square(q.astype(np.float64)))) - float(q[k]) ** 2
-    base = q.copy()
-    base[k] = np.float32(np.sign(q[k]) * np.sqrt(max(0.0, 1.0 - rest)))
-    for off in range(0, 64):
-        for sgn in (1, -1):
-            c = base.copy()
-            c[k:k + 1].view(np.int32)[0] += sgn * off
-            c, ok = settle(c)
-            if ok:
-                return c
+    # normalisation can settle into a 2-cycle one ulp apart: re-solve one component so that the float32 norm is exactly 1 (then 1/m = 1 and
+    # the quaternion is a fixed point), trying the components from the smallest to the largest and a window of ulps around the exact solution
+    def norm_is_one(c):
+        return np.float32(np.sqrt(np.float32(c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + c[3] * c[3]))) == np.float32(1.0)
+
+    for k in np.argsort(np.where(q == 0, np.inf, np.abs(q))):
+        if q[k] == 0:
+            continue
+        rest = float(np.sum(np.square(q.astype(np.float64)))) - float(q[k]) ** 2
+        base = q.copy()
+        base[k] = np.float32(np.sign(q[k]) * np.sqrt(max(0.0, 1.0 - rest)))
+        for off in range(0, 4096):
+            for sgn in (1, -1):
+                c = base.copy()
+                c[k:k + 1].view(np.int32)[0] += sgn * off
+                if norm_is_one(c):
+                    c2, ok = settle(c)
+                    if ok:
+                        return c2
     raise ValueError("no float32 normalisation fixed point found")
 
 
@@ -594,4 +601,27 @@ def hulls_and_capsules(n=12, n_hulls=3, seed=21, speed=0.0, **hdr):
         a["pos"][i] = (1.6 * (k % nh) + rng.uniform(-0.1, 0.1), 0.9 + 0.45 * (k // nh), rng.uniform(-0.1, 0.1))
         a["angVel"][i] = rng.uniform(-2, 2, 3)
         a["linVel"][i] = (0.0, -speed, 0.0)
+    return cook_hulls(Scene(default_header(**hdr), add_ground_plane(a), hulls))
+
+
+def hull_pile(n=10, n_hulls=3, seed=31, kinds=("convex",), spread=0.35, **hdr):
+    """Convex hulls (optionally mixed with boxes / spheres / capsules) dropped in a loose column onto the ground plane: hull-hull and
+    box-hull contacts (GJK / EPA point + polygon clipping of the witness faces), BASELINE config 3's pair types at small size."""
+    rng = np.random.RandomState(seed)
+    hulls = [random_hull_points(rng, int(rng.randint(12, 21)), 0.25) for _ in range(n_hulls)]
+    a = _new_actors(n)
+    a["pos"][:, 0] = rng.uniform(-spread, spread, n)
+    a["pos"][:, 1] = 0.5 + 0.5 * np.arange(n)
+    a["pos"][:, 2] = rng.uniform(-spread, spread, n)
+    a["quat"] = random_unit_quats(rng, n)
+    for i in range(n):
+        k = kinds[i % len(kinds)]
+        if k == "convex":
+            set_convex(a, i, i % n_hulls)
+        elif k == "box":
+            set_box(a, np.array([i]), np.array([rng.uniform(0.12, 0.25), rng.uniform(0.12, 0.25), rng.uniform(0.12, 0.25)], dtype=np.float32))
+        elif k == "sphere":
+            set_sphere(a, i, rng.uniform(0.1, 0.2))
+        else:
+            set_capsule(a, i, rng.uniform(0.08, 0.15), rng.uniform(0.1, 0.3))
     return cook_hulls(Scene(default_header(**hdr), add_ground_plane(a), hulls))

@@ -95,6 +95,8 @@ def main():
     cases["spheres_into_hulls"] = (scenes.spheres_into_hulls(seed=13), 60)  # ... through EPA
     cases["hulls_and_capsules"] = (scenes.hulls_and_capsules(seed=21), 150)            # pcmContactCapsuleConvex
     cases["capsules_into_hulls"] = (scenes.hulls_and_capsules(seed=23, speed=14.0), 60)   # ... through EPA (a seed whose hulls never come near each other)
+    cases["hull_pile"] = (scenes.hull_pile(seed=32), 150)                                   # pcmContactConvexConvex: GJK / EPA + polygon clipping
+    cases["box_hull_pile"] = (scenes.hull_pile(seed=33, kinds=("convex", "box")), 150)     # pcmContactBoxConvex
     cases["capsules_into_boxes"] = (scenes.capsules_into_boxes(seed=3), 60)   # deep penetration: the EPA query
     # a19: PxDirectGPUAPI eFORCE / eTORQUE writes (= addForce / addTorque(eFORCE) before every step), a 7-step cycle of per-body forces
     forced = {"forces_stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01),
