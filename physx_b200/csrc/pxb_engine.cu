@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CAPSULE) pcm_plane_capsule(tm0, tm1, d1.x, d1.y, contactDist, man, out);
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_CAPSULE) np_capsule_capsule(tm0, tm1, d0.x, d0.y, d1.x, d1.y, contactDist, out);
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_BOX) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // GJK family (a10): k_narrowphase_gjk fills this pair's outputs
-  else if ((ty0 == PXB_GEOM_PLANE || ty0 == PXB_GEOM_SPHERE || ty0 == PXB_GEOM_CAPSULE) && ty1 == PXB_GEOM_CONVEXMESH) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // hull pairs also go through k_narrowphase_gjk
+  else if (ty1 == PXB_GEOM_CONVEXMESH) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // hull pairs also go through k_narrowphase_gjk
   else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // hull vs box / hull (a10): reported by fetchResults, never silently skipped
   if (man.dirty) manifold_store(man, rec); else if (usesManifold && man.n > 0) manifold_store_pens(man, rec);   // steady state: only the penetrations change
   if (flip && out.count) out.normal = -out.normal;
@@ -413,11 +413,17 @@ __global__ void __launch_bounds__(128) k_narrowphase_gjk(const uint64_t* __restr
     for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
     const uint32_t ty1 = flip ? t0 : t1;
     const uint32_t ty0 = flip ? t1 : t0;
-    if (ty1 == PXB_GEOM_CONVEXMESH) {   // s1 = hull, s0 = plane, sphere or capsule
+    if (ty1 == PXB_GEOM_CONVEXMESH) {   // s1 = hull, s0 = plane, sphere, capsule, box or hull
       const DevHull h = load_hull(hulls, __float_as_uint(d1.x));
       if (ty0 == PXB_GEOM_PLANE) gjk_pcm_plane_convex(&tm0, &tm1, h, contactDist, toleranceLength, &man, &out);
       else if (ty0 == PXB_GEOM_SPHERE) gjk_pcm_sphere_convex(&tm0, &tm1, d0.x, &h, contactDist, toleranceLength, &man, &out);
-      else gjk_pcm_capsule_convex(&tm0, &tm1, d0.x, d0.y, &h, contactDist, toleranceLength, &man, &out);
+      else if (ty0 == PXB_GEOM_CAPSULE) gjk_pcm_capsule_convex(&tm0, &tm1, d0.x, d0.y, &h, contactDist, toleranceLength, &man, &out);
+      else {   // box-hull / hull-hull: a pair that needs the SAT branch of generateFullContactManifold (not built) is reported, never skipped
+        int sat;
+        if (ty0 == PXB_GEOM_BOX) sat = gjk_pcm_box_convex(&tm0, &tm1, V3(d0.x, d0.y, d0.z), &h, contactDist, toleranceLength, &man, &out);
+        else { const DevHull h0 = load_hull(hulls, __float_as_uint(d0.x)); sat = gjk_pcm_convex_convex(&tm0, &tm1, &h0, &h, contactDist, toleranceLength, &man, &out); }
+        if (sat) atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);
+      }
     }
     else gjk_pcm_capsule_box(&tm0, &tm1, d0.x, d0.y, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
     if (man.dirty) { manifold_store(man, rec); manifold_store_warm(man, rec); } else if (man.n > 0) manifold_store_pens(man, rec);

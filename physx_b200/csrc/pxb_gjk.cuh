@@ -22,6 +22,8 @@ PXB_D v3 v3min(v3 a, v3 b) { return vmin(a, b); }
 PXB_D v3 v3max(v3 a, v3 b) { return vmax(a, b); }
 PXB_D v3 m33mul(const m33* m, v3 v) { return mmul(*m, v); }
 PXB_D m33 m33transpose(const m33* m) { return mtranspose(*m); }
+PXB_D v3 am33tmul(const m33* m, v3 v) { return amtmul(*m, v); }
+PXB_D mxf amxfinvmul(const mxf* a, const mxf* b) { return amxfinvmul(*a, *b); }
 PXB_D v3 amxftransform(const mxf* t, v3 v) { return amxftransform(*t, v); }
 PXB_D v3 amxftransforminv(const mxf* t, v3 v) { return amtmul(t->r, v - t->p); }
 PXB_D mxf amxffromxf(const xf* t) { return amxffromxf(*t); }
@@ -1298,4 +1300,209 @@ PXB_D void gjk_pcm_capsule_convex(const xf* transf0, const xf* transf1, float ca
     const v3 worldNormal = manifold_world_normal(*manifold, *transf1);
     gjk_manifold_to_contacts_radius(manifold, worldNormal, transf0, capsuleRadius, contactDist, out);
   }
+}
+
+/* ---------------- polygonal pairs: box vs hull, hull vs hull (GuPCMContactGenBoxConvex.cpp:331-720, GuPCMContactBoxConvex.cpp, GuPCMContactConvexConvex.cpp) ---------------- */
+// Gu::contains GuPCMContactGenUtil.cpp:35-103 for an n-vertex polygon (poly_contains in pxb_np.cuh is the 4-vertex instance)
+PXB_D bool gjk_poly_contains_n(const v3* verts, int numVerts, v3 p, v3 mn, v3 mx) {
+  if ((mn.x > p.x) || (p.x > mx.x) || (mn.y > p.y) || (p.y > mx.y)) return false;
+  const float tx = p.x, ty = p.y; const float eps = FLT_EPSILON;
+  int inter = 0;
+  for (int i = 0, j = numVerts - 1; i < numVerts; j = i++) {
+    const float jy = verts[j].y, iy = verts[i].y, jx = verts[j].x, ix = verts[i].x;
+    if ((tx == jx && ty == jy) || (tx == ix && ty == iy)) return true;
+    const bool yflag0 = jy > ty, yflag1 = iy > ty;
+    if (yflag0 != yflag1) {
+      const float jix = ix - jx, jiy = iy - jy, jty = ty - jy;
+      const float part1 = jty * jix, part2 = (jx + eps) * jiy, part3 = tx * jiy;
+      const bool comp = jiy > 0.f;
+      const float tmp = part1 + part2;
+      const float comp1 = comp ? tmp : part3, comp2 = comp ? part3 : tmp;
+      if (comp1 >= comp2) { if (inter == 1) return false; inter++; }
+    }
+  }
+  return inter > 0;
+}
+PXB_D float gjk_signed_2d_tri_area(v3 a, v3 b, v3 c) { const v3 ca = v3sub(a, c), cb = v3sub(b, c); return ca.x * cb.y - ca.y * cb.x; }   /* GuPCMContactGenUtil.h:56-66 */
+#define GJK_POLY_MAX_CONTACTS 32   // per-thread buffer; a pair of <= 32-vertex hull polygons stays far below it (the reference's buffer holds 256)
+/* generatedContacts :331-530: incident polygon (of poly1) clipped against the reference polygon (of poly0) in the reference polygon's plane */
+PXB_D void gjk_poly_generated_contacts(const DevHull* poly0, const DevHull* poly1, int refIdx, int incIdx, const mxf* transform0To1, MPoint* mc, int* numContacts, float contactDist) {
+  const uint4 referencePolygon = poly0->poly_meta((uint32_t)refIdx), incidentPolygon = poly1->poly_meta((uint32_t)incIdx);
+  const uint8_t* inds0 = poly0->vertexRefs + referencePolygon.x; const uint8_t* inds1 = poly1->vertexRefs + incidentPolygon.x;
+  const uint32_t nRef = min(referencePolygon.y, 32u), nInc = min(incidentPolygon.y, 32u);
+  const v3 contactNormal = anormalize(poly0->plane_n((uint32_t)refIdx));
+  const m33 rot = gjk_rotation_from_z(contactNormal);
+  v3 points0In0[32], points1In0[32]; int pen1[32]; float tval1[32];
+  for (uint32_t i = 0; i < nRef; ++i) points0In0[i] = poly0->vert(inds0[i]);
+  for (uint32_t i = 0; i < nInc; ++i) points1In0[i] = poly1->vert(inds1[i]);
+  const v3 sPoint = points1In0[0];
+  const float eps = FLT_EPSILON;
+  v3 rMin = V3(FLT_MAX, FLT_MAX, FLT_MAX), rMax = V3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+  for (uint32_t i = 0; i < nRef; ++i) { points0In0[i] = m33mul(&rot, points0In0[i]); rMin = v3min(rMin, points0In0[i]); rMax = v3max(rMax, points0In0[i]); }
+  rMin = v3sub(rMin, V3(eps, eps, eps)); rMax = v3add(rMax, V3(eps, eps, eps));
+  const float d = points0In0[0].z, rd = d + contactDist;
+  v3 iMin = V3(FLT_MAX, FLT_MAX, FLT_MAX), iMax = V3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+  uint32_t inside = 0;
+  for (uint32_t i = 0; i < nInc; ++i) {
+    const v3 vert1 = points1In0[i];
+    const v3 a = amxftransforminv(transform0To1, vert1);
+    points1In0[i] = m33mul(&rot, a);
+    const float z = points1In0[i].z;
+    tval1[i] = z - d;
+    points1In0[i].z = d;
+    iMin = v3min(iMin, points1In0[i]); iMax = v3max(iMax, points1In0[i]);
+    if (rd > z) {
+      pen1[i] = 1;
+      if (gjk_poly_contains_n(points0In0, (int)nRef, points1In0[i], rMin, rMax)) {
+        inside++;
+        if (*numContacts == GJK_POLY_MAX_CONTACTS) return;
+        mc[*numContacts].a = vert1; mc[*numContacts].b = am33tmul(&rot, points1In0[i]); mc[*numContacts].n = contactNormal; mc[*numContacts].pen = tval1[i]; (*numContacts)++;
+      }
+    } else pen1[i] = 0;
+  }
+  if (inside == nInc) return;
+  inside = 0;
+  iMin = v3sub(iMin, V3(eps, eps, eps)); iMax = v3add(iMax, V3(eps, eps, eps));
+  const v3 incidentNormal = anormalize(poly1->plane_n((uint32_t)incIdx));
+  const v3 contactNormalIn1 = m33mul(&transform0To1->r, contactNormal);
+  for (uint32_t i = 0; i < nRef; ++i) {
+    if (gjk_poly_contains_n(points1In0, (int)nInc, points0In0[i], iMin, iMax)) {
+      const v3 vert0 = am33tmul(&rot, points0In0[i]);
+      const v3 a = amxftransform(transform0To1, vert0);
+      const float nom = adot(incidentNormal, v3sub(sPoint, a)), denom = adot(incidentNormal, contactNormalIn1);
+      const float t = nom / denom;
+      if (t > contactDist) continue;
+      inside++;
+      if (*numContacts == GJK_POLY_MAX_CONTACTS) return;
+      mc[*numContacts].a = v3scaleadd(contactNormalIn1, t, a); mc[*numContacts].b = vert0; mc[*numContacts].n = contactNormal; mc[*numContacts].pen = t; (*numContacts)++;
+    }
+  }
+  if (inside == nRef) return;
+  for (uint32_t iStart = 0, iEnd = nInc - 1; iStart < nInc; iEnd = iStart++) {
+    if (!pen1[iStart] && !pen1[iEnd]) continue;
+    const v3 ipA = points1In0[iStart], ipB = points1In0[iEnd];
+    v3 ipAOri = points1In0[iStart]; ipAOri.z = tval1[iStart] + d;
+    v3 ipBOri = points1In0[iEnd]; ipBOri.z = tval1[iEnd] + d;
+    const v3 sMin = v3min(ipA, ipB), sMax = v3max(ipA, ipB);
+    for (uint32_t rStart = 0, rEnd = nRef - 1; rStart < nRef; rEnd = rStart++) {
+      const v3 rpA = points0In0[rStart], rpB = points0In0[rEnd];
+      const v3 qMin = v3min(rpA, rpB), qMax = v3max(rpA, rpB);
+      if ((sMin.x > qMax.x) || (qMin.x > sMax.x) || (sMin.y > qMax.y) || (qMin.y > sMax.y)) continue;
+      const float a1 = gjk_signed_2d_tri_area(rpA, rpB, ipA), a2 = gjk_signed_2d_tri_area(rpA, rpB, ipB);
+      if (0.f > a1 * a2) {
+        const float a3 = gjk_signed_2d_tri_area(ipA, ipB, rpA), a4 = gjk_signed_2d_tri_area(ipA, ipB, rpB);
+        if (0.f > a3 * a4) {
+          const float t = a1 / (a2 - a1);
+          const v3 pBB = v3negscalesub(v3sub(ipBOri, ipAOri), t, ipAOri);
+          v3 pAA = pBB; pAA.z = d;
+          const v3 pA = am33tmul(&rot, pAA);
+          const v3 pB = amxftransform(transform0To1, am33tmul(&rot, pBB));
+          const float pen = pBB.z - pAA.z;
+          if (pen > contactDist) continue;
+          if (*numContacts == GJK_POLY_MAX_CONTACTS) return;
+          mc[*numContacts].a = pB; mc[*numContacts].b = pA; mc[*numContacts].n = contactNormal; mc[*numContacts].pen = pen; (*numContacts)++;
+        }
+      }
+    }
+  }
+}
+/* generateFullContactManifold :532-665, doOverlapTest == false (witness polygons of the GJK / EPA closest points).  map0 / map1 = world transforms of the two shapes. */
+PXB_D void gjk_poly_full_manifold(const DevHull* poly0, const DevHull* poly1, const mxf* map0, const mxf* map1, MPoint* mc, int* numContacts, float contactDist,
+                                          v3 normal, v3 closestA, v3 closestB, float marginA, float marginB, float toleranceLength) {
+  const mxf transform1To0 = amxfinvmul(map0, map1), transform0To1 = amxfinvmul(map1, map0);
+  const float lowerEps = toleranceLength * 1e-2f, upperEps = toleranceLength * 5e-2f;
+  const float toleranceA = fmin_(fmax_(marginA, lowerEps), upperEps), toleranceB = fmin_(fmax_(marginB, lowerEps), upperEps);
+  const v3 negNormal = v3neg(normal);
+  const v3 normalIn0 = am33tmul(&transform0To1.r, normal);
+  const int faceIndex1 = gjk_hull_witness_polygon_index(poly1, negNormal, closestB, toleranceB);
+  const int faceIndex0 = gjk_hull_witness_polygon_index(poly0, normalIn0, amxftransforminv(&transform0To1, closestA), toleranceA);
+  const v3 referenceNormal = anormalize(poly1->plane_n((uint32_t)faceIndex1)), incidentNormal = anormalize(poly0->plane_n((uint32_t)faceIndex0));
+  const float referenceProject = fabsf(adot(referenceNormal, negNormal)), incidentProject = fabsf(adot(incidentNormal, normalIn0));
+  if (referenceProject >= incidentProject) gjk_poly_generated_contacts(poly1, poly0, faceIndex1, faceIndex0, &transform1To0, mc, numContacts, contactDist);
+  else {
+    gjk_poly_generated_contacts(poly0, poly1, faceIndex0, faceIndex1, &transform0To1, mc, numContacts, contactDist);
+    if (*numContacts > 0) {
+      const v3 n = m33mul(&transform0To1.r, incidentNormal), nn = v3neg(n);
+      for (int i = 0; i < *numContacts; ++i) { const v3 lb = mc[i].b; mc[i].b = mc[i].a; mc[i].a = lb; mc[i].n = nn; }
+    }
+  }
+}
+PXB_D v3 gjk_manifold_local_normal(const Manifold* m) { v3 n = m->pts[0].n; for (int i = 1; i < m->n; ++i) n = v3add(n, m->pts[i].n); return anormalize(n); }   /* getLocalNormal .h:710-718 */
+PXB_D void gjk_manifold_to_contacts(const Manifold* m, v3 worldNormal, const xf* transf1, float contactDist, Contacts* out) {   /* .cpp:739-759 */
+  out->count = 0; out->normal = worldNormal;
+  for (int i = 0; i < m->n; ++i) { const float dist = m->pts[i].pen; if (contactDist >= dist) { out->point[out->count] = axftransform(transf1, m->pts[i].b); out->sep[out->count] = dist; out->count++; } }
+}
+/* pcmContactBoxConvex / pcmContactConvexConvex: shape A (box or hull) relative to hull B.  convexA must already be relative (aToB).
+ * Returns 1 when the reference would run the SAT branch (not restated), 0 otherwise. */
+PXB_D int gjk_pcm_poly_convex(const xf* transf0, const xf* transf1, GjkConvex* convexA, const DevHull* polyA, float marginPcmA, float radiusA, const DevHull* hullB,
+                                      float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
+  out->count = 0;
+  const xf curRTrans = axfinvmul(transf1, transf0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  const float convexMarginB = gjk_hull_pcm_margin(hullB, toleranceLength);
+  const float minMargin = fmin_(marginPcmA, convexMarginB);
+  const int initialContacts = manifold->n;
+  manifold_refresh(*manifold, aToB, minMargin * 0.8f);
+  const int bLostContacts = manifold->n != initialContacts;
+  const float radiusB = alen(hullB->internalExtents);
+  if (bLostContacts || invalidate_boxconvex(*manifold, curRTrans, transf0->q, transf1->q, minMargin, radiusA, radiusB)) {
+    manifold->rel = curRTrans; manifold->quatA = transf0->q; manifold->quatB = transf1->q; manifold->dirty = 1;
+    gjk_cvx_make_relative(convexA, &aToB);
+    const GjkConvex convexB = gjk_cvx_hull(hullB);
+    GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
+    int status = gjk_penetration(convexA, &convexB, aToB.p, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+    if (status == GJK_NON_INTERSECT) return 0;
+    /* generateOrProcessContacts* + addGJKEPAContacts */
+    const v3 localNor = manifold->n ? gjk_manifold_local_normal(manifold) : V3(0, 0, 0);
+    const float replaceBreakingThreshold = minMargin * 0.05f;
+    int doOverlapTest = 0;
+    if (status == GJK_DEGENERATE) {
+      const float costheta = adot(output.searchDir, output.normal);
+      if (costheta > 0.9999f) {
+        const v3 centreA = amxftransform(&aToB, convexA->center), centreB = convexB.center;
+        const v3 dir = anormalize(v3sub(centreA, centreB));
+        if (adot(dir, output.normal) > 0.707f) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+        else doOverlapTest = 1;
+      } else doOverlapTest = 1;
+    } else if (status == GJK_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+    else {
+      status = gjk_epa_penetration(convexA, &convexB, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+      if (status == EPA_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+      else doOverlapTest = 1;
+    }
+    if (doOverlapTest) return 1;   /* SAT branch: not restated */
+    const int fullContactGen = (0.707106781f > adot(localNor, output.normal)) || (manifold->n < initialContacts);
+    if (fullContactGen) {
+      MPoint mc[GJK_POLY_MAX_CONTACTS]; int numContacts = 0;
+      const mxf map0 = amxffromxf(transf0), map1 = amxffromxf(transf1);
+      gjk_poly_full_manifold(polyA, hullB, &map0, &map1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
+      if (numContacts > 0) {
+        if (numContacts <= PXB_MANIFOLD_CACHE) { for (int i = 0; i < numContacts; ++i) manifold->pts[i] = mc[i]; manifold->n = numContacts; }
+        else { reduce_batch(*manifold, mc, numContacts, toleranceLength); manifold->n = PXB_MANIFOLD_CACHE; }
+      }
+      gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
+    } else {
+      const v3 newLocalNor = v3add(localNor, output.normal);
+      gjk_manifold_to_contacts(manifold, anormalize(aqrot(transf1->q, newLocalNor)), transf1, contactDist, out);
+    }
+  } else if (manifold->n > 0) gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
+  return 0;
+}
+struct BoxAsHull { float4 verts[8]; float4 polys[12]; DevHull view; };
+PXB_D const DevHull* gjk_box_as_hull(BoxAsHull* b, v3 ext) {   // PCMPolygonalBox as the polygonal view the hulls use (per-thread arrays)
+  PolyBox pb; gjk_poly_box(&pb, ext);
+  for (int i = 0; i < 8; ++i) b->verts[i] = F4(pb.verts[i], 0.f);
+  for (int i = 0; i < 6; ++i) { b->polys[2 * i] = F4(pb.polys[i].n, pb.polys[i].d); b->polys[2 * i + 1] = make_float4(__uint_as_float((uint32_t)i * 4), __uint_as_float(4u), __uint_as_float((uint32_t)pb.polys[i].minIndex), 0.f); }
+  b->view.nVerts = 8; b->view.nPolys = 6; b->view.nEdges = 0; b->view.internalExtents = ext; b->view.centerOfMass = V3(0, 0, 0);
+  b->view.verts = b->verts; b->view.polys = b->polys; b->view.vertexRefs = gjk_box_poly_refs; b->view.facesByEdges = nullptr;
+  return &b->view;
+}
+PXB_D int gjk_pcm_box_convex(const xf* transf0, const xf* transf1, v3 boxExtents, const DevHull* hull, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
+  BoxAsHull bh; const DevHull* polyA = gjk_box_as_hull(&bh, boxExtents);
+  GjkConvex box = gjk_cvx_box(V3(0, 0, 0), boxExtents);
+  return gjk_pcm_poly_convex(transf0, transf1, &box, polyA, box_margin(boxExtents, toleranceLength), alen(boxExtents), hull, contactDist, toleranceLength, manifold, out);
+}
+PXB_D int gjk_pcm_convex_convex(const xf* transf0, const xf* transf1, const DevHull* hull0, const DevHull* hull1, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
+  GjkConvex c0 = gjk_cvx_hull(hull0);
+  return gjk_pcm_poly_convex(transf0, transf1, &c0, hull0, gjk_hull_pcm_margin(hull0, toleranceLength), alen(hull0->internalExtents), hull1, contactDist, toleranceLength, manifold, out);
 }

@@ -554,7 +554,7 @@ def test_convex_hulls_gpu_matches_oracle_and_reference(oracle):
         assert np.abs(gpu.getStates() - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
 
 
-@pytest.mark.parametrize("name", ["hulls_and_spheres", "spheres_into_hulls", "hulls_and_capsules", "capsules_into_hulls"])
+@pytest.mark.parametrize("name", ["hulls_and_spheres", "spheres_into_hulls", "hulls_and_capsules", "capsules_into_hulls", "hull_pile", "box_hull_pile"])
 def test_sphere_convex_gpu_matches_oracle(oracle, name):
     """pcmContactSphereConvex / pcmContactCapsuleConvex on the device (hull support mapping, GJK, EPA, face + edge-edge contacts) against the
     oracle, teacher-forced from the golden states (hull-hull pairs of the *_into_* scenes excepted: they stop the step, see below)."""
@@ -568,23 +568,34 @@ def test_sphere_convex_gpu_matches_oracle(oracle, name):
         assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
         cg, cc = gpu.getContacts(), cpu.getContacts()
         assert np.array_equal(cg[:, 0], cc[:, 0]), f"contact counts, step {t}"
-        assert np.abs(cg[:, 1:8] - cc[:, 1:8]).max(initial=0) < 1e-6, f"first contact, step {t}"
+        assert np.abs(cg[:, 1:8] - cc[:, 1:8]).max(initial=0) < 1e-6, f"first contact, step {t}"   # (hull_pile / box_hull_pile: pcmContactConvexConvex / BoxConvex)
         assert np.abs(gpu.getStates() - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
 
 
-def test_unsupported_hull_pair_is_reported_not_skipped():
-    """Hull vs sphere / capsule / box / hull pairs (the rest of SURVEY 8a row a10) are not built yet: a convex actor without cooked data is
-    refused when it is added, and a hull pair other than plane-hull fails the step loudly once it comes into contact range."""
+def test_hull_without_cooked_data_is_rejected():
+    """A convex actor whose hull was not uploaded (pxb_scene_set_convex_meshes) is refused when it is added -- nothing is silently skipped."""
     z, sc = util.load_golden("hulls_on_plane")
     bare = scenes.Scene(sc.header, sc.actors.copy(), sc.hulls)      # hull point clouds only, no cooked section
     with pytest.raises(engine.PhysxB200Error):
         engine.Scene(bare)
+
+
+def test_all_geometry_types_free_running_gpu_matches_oracle(oracle):
+    """Spheres, capsules, boxes and hulls in one pile (BASELINE config 3's pair types): GPU and oracle agree step by step, free running."""
+    z, sc = util.load_golden("box_hull_pile")
+    rng = np.random.RandomState(3)
     a = sc.actors.copy()
-    a["pos"][2] = a["pos"][1] + np.array([0.1, 0.05, 0.0], np.float32)   # two hulls overlapping
-    gpu = engine.Scene(scenes.Scene(sc.header, a, sc.hulls, sc.cooked))
-    with pytest.raises(engine.PhysxB200Error) as e:
-        gpu.step()
-    assert "unsupported" in str(e.value)
+    scenes.set_sphere(a, 3, 0.15); scenes.set_capsule(a, 6, 0.1, 0.2)       # turn two of the pile's bodies into a sphere and a capsule
+    mixed = scenes.Scene(sc.header, a, sc.hulls, sc.cooked)
+    gpu, cpu = engine.Scene(mixed), oracle.OracleScene(mixed)
+    for t in range(120):
+        gpu.step(); cpu.step()
+        assert cpu.unsupported_pairs == 0
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
+        assert np.array_equal(gpu.getContacts()[:, 0], cpu.getContacts()[:, 0]), f"contact counts, step {t}"
+        sg = gpu.getStates()
+        assert np.abs(sg - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
+        cpu.setStates(sg)
 
 
 def test_cpp_host_mirror_snippet_hello_world():
