@@ -1282,8 +1282,8 @@ static inline void pxo_pcm_capsule_convex(const xf* transf0, const xf* transf1, 
 /* ---------------- polygonal pairs: box vs hull, hull vs hull ----------------
  * GuPCMContactGenBoxConvex.cpp:331-530 (generatedContacts), :532-665 (generateFullContactManifold, witness-polygon branch), :668-720 (addGJKEPAContacts),
  * GuPCMContactBoxConvex.cpp:47-256, GuPCMContactConvexConvex.cpp:42-276.
- * NOT restated yet: the SAT branch of generateFullContactManifold (testFaceNormal / testEdgeNormal / buildPartialHull, :56-328), taken when GJK
- * degenerates away from the centre line or EPA fails -- such a pair is counted as unsupported by the caller. */
+ * The SAT branch of generateFullContactManifold (testFaceNormal / testEdgeNormal / buildPartialHull, :56-328; taken when GJK degenerates away
+ * from the centre line or EPA fails) is pxo_poly_full_manifold_sat above. */
 typedef struct { float verts[24]; PxbCookedPoly polys[6]; PxoHull view; } PxoBoxAsHull;
 static inline const PxoHull* pxo_box_as_hull(PxoBoxAsHull* b, v3 ext) {   /* PCMPolygonalBox as the same polygonal view the hulls use */
   PxoPolyBox pb; pxo_poly_box(&pb, ext);
@@ -1295,6 +1295,157 @@ static inline const PxoHull* pxo_box_as_hull(PxoBoxAsHull* b, v3 ext) {   /* PCM
   b->view.internalExtents = ext;
   return &b->view;
 }
+
+/* ---------------- SAT branch of generateFullContactManifold: GuPCMContactGenBoxConvex.cpp:56-328, :537-603 (PCM_USE_INTERNAL_OBJECT = 1) ---------------- */
+#define PXO_SAT_MAX_AXES 256   /* SEP_AXIS_FIXED_MEMORY, GuSeparatingAxes.h:40 */
+/* SupportLocalImpl::doSupport(dir, min, max) / doSupport(dir): hull = brute force (GuVecConvexHull.h:377-429), box = sign select (GuVecBox.h:165-177) */
+static inline void pxo_poly_support_minmax(const PxoHull* h, int isBox, v3 dir, float* mn, float* mx) {
+  if (isBox) { const v3 e = h->internalExtents; const v3 pt = V3(dir.x > 0.f ? e.x : -e.x, dir.y > 0.f ? e.y : -e.y, dir.z > 0.f ? e.z : -e.z); *mx = adot(dir, pt); *mn = -*mx; return; }
+  pxo_hull_support_minmax(h, dir, mn, mx);
+}
+static inline v3 pxo_poly_support(const PxoHull* h, int isBox, v3 dir) {
+  if (isBox) { const v3 e = h->internalExtents; return V3(dir.x > 0.f ? e.x : -e.x, dir.y > 0.f ? e.y : -e.y, dir.z > 0.f ? e.z : -e.z); }
+  float mx = v3dot(pxo_hull_vert(h, 0), dir); uint32_t mi = 0;
+  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(pxo_hull_vert(h, i), dir); if (d > mx) { mx = d; mi = i; } }
+  return pxo_hull_vert(h, mi);
+}
+typedef struct { const PxoHull* h; int isBox; v3 center; float internalRadius; v3 internalExtents; } PxoPolyData;   /* PolygonalData: mCenter, mInternal */
+static inline PxoPolyData pxo_poly_data(const PxoHull* h, int isBox) {
+  PxoPolyData p; p.h = h; p.isBox = isBox;
+  p.center = isBox ? V3(0, 0, 0) : h->centerOfMass; p.internalRadius = isBox ? 0.f : h->internalRadius; p.internalExtents = h->internalExtents;
+  return p;
+}
+/* testFaceNormal :56-156 */
+static inline int pxo_sat_face_normal(const PxoPolyData* p0, const PxoPolyData* p1, const mxf* transform0To1, const mxf* transform1To0, float contactDist,
+                                      float* minOverlap, uint32_t* feature, v3* faceNormal, int faceStatus, int* status) {
+  float _minOverlap = FLT_MAX; uint32_t _feature = 0; v3 _faceNormal = *faceNormal;
+  const v3 center1To0 = transform1To0->p;
+  const v3 internalCenter1In0 = amxftransform(transform1To0, p1->center);
+  const v3 ie1 = p1->internalExtents;
+  for (uint32_t i = 0; i < p0->h->nPolys; ++i) {
+    const v3 pn = pxo_hull_plane_n(p0->h, i);
+    const v3 minVert = pxo_hull_vert(p0->h, p0->h->polys[i].minIndex);
+    const float magnitude = 1.0f / alen(pn);
+    const float min0 = adot(pn, minVert) * magnitude, max0 = (-p0->h->polys[i].plane[3]) * magnitude;
+    const v3 n0 = v3scale(pn, magnitude);
+    const v3 n1 = m33mul(&transform0To1->r, n0);
+    const v3 proj = V3(n1.x > 0.f ? ie1.x : -ie1.x, n1.y > 0.f ? ie1.y : -ie1.y, n1.z > 0.f ? ie1.z : -ie1.z);
+    const float radius = fmaxf_(adot(n1, proj), p1->internalRadius);
+    const float internalTrans = adot(internalCenter1In0, n0);
+    const float _min1 = internalTrans - radius, _max1 = internalTrans + radius;
+    const float _min = fmaxf_(min0, _min1), _max = fminf_(max0, _max1);
+    if ((_max - _min) > _minOverlap) continue;
+    const float translate = adot(center1To0, n0);
+    float min1, max1; pxo_poly_support_minmax(p1->h, p1->isBox, n1, &min1, &max1);
+    min1 = translate + min1; max1 = translate + max1;
+    if ((min1 > max0 + contactDist) || (min0 > max1 + contactDist)) return 0;
+    const float tempOverlap = max0 - min1;
+    if (_minOverlap > tempOverlap) { _minOverlap = tempOverlap; _feature = i; _faceNormal = n0; }
+  }
+  if (*minOverlap > _minOverlap) { *faceNormal = _faceNormal; *minOverlap = _minOverlap; *status = faceStatus; }
+  *feature = _feature;
+  return 1;
+}
+/* buildPartialHull :159-193 + SeparatingAxes::addAxis GuSeparatingAxes.cpp:33-57 */
+static inline void pxo_sat_partial_hull(const PxoHull* h, v3* axes, uint32_t* nAxes, v3 planeP, v3 planeDir) {
+  const v3 dir = anormalize(planeDir);
+  for (uint32_t i = 0; i < h->nPolys; ++i) {
+    const uint8_t* inds = h->vertexRefs + h->polys[i].vref; const uint32_t nb = h->polys[i].nbVerts;
+    v3 v0 = pxo_hull_vert(h, inds[nb - 1]);
+    float dist0 = adot(dir, v3sub(v0, planeP));
+    for (uint32_t k = 0; k < nb; ++k) {
+      const v3 v1 = pxo_hull_vert(h, inds[k]);
+      const float dist1 = adot(dir, v3sub(v1, planeP));
+      if (dist0 > 0.f || dist1 > 0.f) {
+        const v3 t = v3sub(v0, v1);
+        const float m = t.x * t.x + t.y * t.y + t.z * t.z;                       /* PxVec3::getNormalized */
+        const v3 axis = m > 0.f ? v3scale(t, 1.0f / sqrtf(m)) : V3(0, 0, 0);
+        int dup = 0;
+        for (uint32_t a = 0; a < *nAxes; ++a) if (fabsf(v3dot(axis, axes[a])) > 0.9999f) { dup = 1; break; }
+        if (!dup && *nAxes < PXO_SAT_MAX_AXES) axes[(*nAxes)++] = axis;
+      }
+      v0 = v1; dist0 = dist1;
+    }
+  }
+}
+/* testEdgeNormal :195-328 */
+static inline int pxo_sat_edge_normal(const PxoPolyData* p0, const PxoPolyData* p1, const mxf* transform0To1, const mxf* transform1To0, float contactDist,
+                                      float* minOverlap, v3* edgeNormalIn0, int edgeStatus, int* status) {
+  float overlap = *minOverlap;
+  const v3 internalCenter1In0 = v3sub(amxftransform(transform1To0, p1->center), p0->center);
+  const v3 ie1 = p1->internalExtents, ie0 = p0->internalExtents;
+  const v3 center1To0 = transform1To0->p;
+  const v3 dir0 = v3sub(amxftransform(transform1To0, p1->center), p0->center);
+  const v3 support0 = pxo_poly_support(p0->h, p0->isBox, dir0);
+  const v3 dir1 = m33mul(&transform0To1->r, v3neg(dir0));
+  const v3 support1 = pxo_poly_support(p1->h, p1->isBox, dir1);
+  const v3 support0In1 = amxftransform(transform0To1, support0), support1In0 = amxftransform(transform1To0, support1);
+  static v3 axe0[PXO_SAT_MAX_AXES], axe1[PXO_SAT_MAX_AXES]; uint32_t numAxe0 = 0, numAxe1 = 0;
+  pxo_sat_partial_hull(p0->h, axe0, &numAxe0, support1In0, dir0);
+  pxo_sat_partial_hull(p1->h, axe1, &numAxe1, support0In1, dir1);
+  for (uint32_t i = 0; i < numAxe0; ++i) {
+    const v3 v0 = axe0[i];
+    for (uint32_t j = 0; j < numAxe1; ++j) {
+      const v3 dir = v3cross(v0, m33mul(&transform1To0->r, axe1[j]));
+      const float lenSq = adot(dir, dir);
+      if (FLT_EPSILON > lenSq) continue;
+      const v3 n0 = v3scale(dir, 1.0f / sqrtf(lenSq));
+      const v3 n1 = m33mul(&transform0To1->r, n0);
+      const v3 proj = V3(n1.x > 0.f ? ie1.x : -ie1.x, n1.y > 0.f ? ie1.y : -ie1.y, n1.z > 0.f ? ie1.z : -ie1.z);
+      const float radius = fmaxf_(adot(n1, proj), p1->internalRadius);
+      const float internalTrans = adot(internalCenter1In0, n0);
+      const float _min1 = internalTrans - radius, _max1 = internalTrans + radius;
+      const v3 proj0 = V3(n0.x > 0.f ? ie0.x : -ie0.x, n0.y > 0.f ? ie0.y : -ie0.y, n0.z > 0.f ? ie0.z : -ie0.z);
+      const float radius0 = fmaxf_(adot(n0, proj0), p0->internalRadius);
+      const float _min = fmaxf_(-radius0, _min1), _max = fminf_(radius0, _max1);
+      if ((_max - _min) > overlap) continue;
+      float min0, max0, min1, max1;
+      pxo_poly_support_minmax(p0->h, p0->isBox, n0, &min0, &max0);
+      const float translate = adot(center1To0, n0);
+      pxo_poly_support_minmax(p1->h, p1->isBox, n1, &min1, &max1);
+      min1 = translate + min1; max1 = translate + max1;
+      if ((min1 > max0 + contactDist) || (min0 > max1 + contactDist)) return 0;
+      const float tempOverlap = max0 - min1;
+      if (overlap > tempOverlap) { overlap = tempOverlap; *edgeNormalIn0 = n0; *status = edgeStatus; }
+    }
+  }
+  *minOverlap = overlap;
+  return 1;
+}
+/* generateFullContactManifold, doOverlapTest == true (:537-603).  Returns 0 when a separating axis was found. */
+enum { PXO_FS_POLYDATA0 = 0, PXO_FS_POLYDATA1 = 1, PXO_FS_EDGE = 2 };
+static inline void pxo_poly_generated_contacts(const PxoHull* poly0, const PxoHull* poly1, int refIdx, int incIdx, const mxf* transform0To1, PxoMPoint* mc, int* numContacts, float contactDist);
+static inline int pxo_poly_full_manifold_sat(const PxoHull* poly0, int isBox0, const PxoHull* poly1, const mxf* map0, const mxf* map1, PxoMPoint* mc, int* numContacts, float contactDist) {
+  const mxf transform1To0 = amxfinvmul(map0, map1), transform0To1 = amxfinvmul(map1, map0);
+  const PxoPolyData p0 = pxo_poly_data(poly0, isBox0), p1 = pxo_poly_data(poly1, 0);
+  int status = PXO_FS_POLYDATA0;
+  float minOverlap = FLT_MAX; v3 minNormal = V3(0, 0, 0);
+  uint32_t feature0, feature1;
+  if (!pxo_sat_face_normal(&p0, &p1, &transform0To1, &transform1To0, contactDist, &minOverlap, &feature0, &minNormal, PXO_FS_POLYDATA0, &status)) return 0;
+  if (!pxo_sat_face_normal(&p1, &p0, &transform1To0, &transform0To1, contactDist, &minOverlap, &feature1, &minNormal, PXO_FS_POLYDATA1, &status)) return 0;
+  int doEdgeTest = 0;
+  for (;;) {
+    if (doEdgeTest) {
+      if (!pxo_sat_edge_normal(&p0, &p1, &transform0To1, &transform1To0, contactDist, &minOverlap, &minNormal, PXO_FS_EDGE, &status)) return 0;
+      if (status != PXO_FS_EDGE) return 1;
+    }
+    if (status == PXO_FS_POLYDATA0) {
+      const v3 n = m33mul(&transform0To1.r, minNormal);
+      pxo_poly_generated_contacts(poly0, poly1, (int)feature0, pxo_hull_polygon_index(poly1, n), &transform0To1, mc, numContacts, contactDist);
+      if (*numContacts > 0) { const v3 nn = v3neg(n); for (int i = 0; i < *numContacts; ++i) { const v3 lb = mc[i].b; mc[i].b = mc[i].a; mc[i].a = lb; mc[i].n = nn; } }
+    } else if (status == PXO_FS_POLYDATA1) {
+      pxo_poly_generated_contacts(poly1, poly0, (int)feature1, pxo_hull_polygon_index(poly0, m33mul(&transform1To0.r, minNormal)), &transform1To0, mc, numContacts, contactDist);
+    } else {
+      const int incident = pxo_hull_polygon_index(poly0, v3neg(minNormal));
+      const int reference = pxo_hull_polygon_index(poly1, m33mul(&transform0To1.r, minNormal));
+      pxo_poly_generated_contacts(poly1, poly0, reference, incident, &transform1To0, mc, numContacts, contactDist);
+    }
+    if (*numContacts == 0 && !doEdgeTest) { doEdgeTest = 1; continue; }
+    break;
+  }
+  return 1;
+}
+
 static inline float pxo_signed_2d_tri_area(v3 a, v3 b, v3 c) { const v3 ca = v3sub(a, c), cb = v3sub(b, c); return ca.x * cb.y - ca.y * cb.x; }   /* GuPCMContactGenUtil.h:56-66 */
 #define PXO_POLY_MAX_CONTACTS 256
 /* generatedContacts :331-530: incident polygon (of poly1) clipped against the reference polygon (of poly0) in the reference polygon's plane */
@@ -1405,7 +1556,7 @@ static inline void pxo_manifold_to_contacts(const PxoManifold* m, v3 worldNormal
   for (int i = 0; i < m->n; ++i) { const float dist = m->pts[i].pen; if (contactDist >= dist) { out->point[out->count] = axftransform(transf1, m->pts[i].b); out->sep[out->count] = dist; out->count++; } }
 }
 /* pcmContactBoxConvex / pcmContactConvexConvex: shape A (box or hull) relative to hull B.  convexA must already be relative (aToB).
- * Returns 1 when the reference would run the SAT branch (not restated), 0 otherwise. */
+ * Always returns 0 (kept for the callers' unsupported-pair accounting). */
 static inline int pxo_pcm_poly_convex(const xf* transf0, const xf* transf1, PxoConvex* convexA, const PxoHull* polyA, float marginPcmA, float radiusA, const PxoHull* hullB,
                                       float contactDist, float toleranceLength, PxoManifold* manifold, PxoContacts* out) {
   out->count = 0;
@@ -1442,17 +1593,17 @@ static inline int pxo_pcm_poly_convex(const xf* transf0, const xf* transf1, PxoC
       if (status == PXO_EPA_CONTACT) pxo_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
       else doOverlapTest = 1;
     }
-    if (doOverlapTest) return 1;   /* SAT branch: not restated */
     const int fullContactGen = (0.707106781f > adot(localNor, output.normal)) || (manifold->n < initialContacts);
-    if (fullContactGen) {
+    if (fullContactGen || doOverlapTest) {   /* fullContactsGenerationBoxConvex / ConvexConvex */
       static PxoMPoint mc[PXO_POLY_MAX_CONTACTS]; int numContacts = 0;
       const mxf map0 = amxffromxf(transf0), map1 = amxffromxf(transf1);
-      pxo_poly_full_manifold(polyA, hullB, &map0, &map1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
+      if (doOverlapTest) { if (!pxo_poly_full_manifold_sat(polyA, convexA->type == PXO_CVX_BOX, hullB, &map0, &map1, mc, &numContacts, contactDist)) return 0; }
+      else pxo_poly_full_manifold(polyA, hullB, &map0, &map1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
       if (numContacts > 0) {
         if (numContacts <= PXO_MANIFOLD_CACHE) { for (int i = 0; i < numContacts; ++i) manifold->pts[i] = mc[i]; manifold->n = numContacts; }
         else { pxo_reduce_batch(manifold, mc, numContacts, toleranceLength); manifold->n = PXO_MANIFOLD_CACHE; }
-      }
-      pxo_manifold_to_contacts(manifold, pxo_world_normal(manifold, transf1), transf1, contactDist, out);
+        pxo_manifold_to_contacts(manifold, pxo_world_normal(manifold, transf1), transf1, contactDist, out);
+      } else if (!doOverlapTest) pxo_manifold_to_contacts(manifold, pxo_world_normal(manifold, transf1), transf1, contactDist, out);
     } else {
       const v3 newLocalNor = v3add(localNor, output.normal);
       pxo_manifold_to_contacts(manifold, anormalize(aqrot(transf1->q, newLocalNor)), transf1, contactDist, out);

@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_CAPSULE) np_capsule_capsule(tm0, tm1, d0.x, d0.y, d1.x, d1.y, contactDist, out);
   else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_BOX) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // GJK family (a10): k_narrowphase_gjk fills this pair's outputs
   else if (ty1 == PXB_GEOM_CONVEXMESH) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // hull pairs also go through k_narrowphase_gjk
-  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // hull vs box / hull (a10): reported by fetchResults, never silently skipped
+  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // unknown geometry type: reported by fetchResults, never silently skipped
   if (man.dirty) manifold_store(man, rec); else if (usesManifold && man.n > 0) manifold_store_pens(man, rec);   // steady state: only the penetrations change
   if (flip && out.count) out.normal = -out.normal;
   cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(128) k_narrowphase_gjk(const uint64_t* __restr
       if (ty0 == PXB_GEOM_PLANE) gjk_pcm_plane_convex(&tm0, &tm1, h, contactDist, toleranceLength, &man, &out);
       else if (ty0 == PXB_GEOM_SPHERE) gjk_pcm_sphere_convex(&tm0, &tm1, d0.x, &h, contactDist, toleranceLength, &man, &out);
       else if (ty0 == PXB_GEOM_CAPSULE) gjk_pcm_capsule_convex(&tm0, &tm1, d0.x, d0.y, &h, contactDist, toleranceLength, &man, &out);
-      else {   // box-hull / hull-hull: a pair that needs the SAT branch of generateFullContactManifold (not built) is reported, never skipped
+      else {   // box-hull / hull-hull
         int sat;
         if (ty0 == PXB_GEOM_BOX) sat = gjk_pcm_box_convex(&tm0, &tm1, V3(d0.x, d0.y, d0.z), &h, contactDist, toleranceLength, &man, &out);
         else { const DevHull h0 = load_hull(hulls, __float_as_uint(d0.x)); sat = gjk_pcm_convex_convex(&tm0, &tm1, &h0, &h, contactDist, toleranceLength, &man, &out); }
@@ -1242,7 +1242,7 @@ static int enqueue_step(PxbScene* s, float dt) {
   }
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
          s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce, s->counters, s->gjkList, s->binPairs ? s->pairOrder : (const uint32_t*)nullptr);
-  if (s->hasGjkPairs) LAUNCH(k_narrowphase_gjk, 148 * 4, 128, s->pairKeys[cur], s->pairSlots[cur], s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds, s->cHdr, s->cPts,
+  if (s->hasGjkPairs) LAUNCH(k_narrowphase_gjk, std::max(148u * 4u, std::min(cdiv(s->capPairs, 128), 148u * 64u)), 128, s->pairKeys[cur], s->pairSlots[cur], s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds, s->cHdr, s->cPts,
                              s->pairBodies, s->conFlag, s->counters, s->gjkList, hull_arrays(s));
   SleepArgs SA; SA.threshold = s->sleepThreshold; SA.dt = dt; SA.wake = s->wake; SA.accLin = s->accLin; SA.accAng = s->accAng; SA.asleep = s->asleep; SA.nInter = s->nInter;
   if (s->sleepThreshold > 0.f) {   // island sleep / wake decisions for this step (needs this frame's touching pairs)

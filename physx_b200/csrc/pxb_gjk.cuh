@@ -33,7 +33,7 @@ PXB_D v3 axftransform(const xf* t, v3 v) { return axftransform(*t, v); }
 /* ---------------- convex hulls: cooked Gu::ConvexHullData in device memory (uploaded by pxb_scene_set_convex_meshes) ---------------- */
 struct HullArrays { const uint4* meta; const float4* verts; const float4* polys; const uint8_t* refs; const uint8_t* edges; };   // meta: 4 x 16 B per hull
 struct DevHull {
-  uint32_t nVerts, nPolys, nEdges; v3 internalExtents, centerOfMass;
+  uint32_t nVerts, nPolys, nEdges; v3 internalExtents, centerOfMass; float internalRadius;
   const float4* verts; const float4* polys; const uint8_t* vertexRefs; const uint8_t* facesByEdges;
   PXB_D v3 vert(uint32_t i) const { return V3(verts[i]); }
   PXB_D v3 plane_n(uint32_t p) const { return V3(polys[2 * p]); }
@@ -43,7 +43,7 @@ struct DevHull {
 PXB_D DevHull load_hull(const HullArrays& H, uint32_t hullIdx) {
   const uint4 m0 = H.meta[4 * hullIdx], m1 = H.meta[4 * hullIdx + 1], m2 = H.meta[4 * hullIdx + 2], m3 = H.meta[4 * hullIdx + 3];
   DevHull h; h.nVerts = m1.x; h.nPolys = m1.y; h.nEdges = m1.z;
-  h.internalExtents = V3(__uint_as_float(m2.x), __uint_as_float(m2.y), __uint_as_float(m2.z)); h.centerOfMass = V3(__uint_as_float(m3.x), __uint_as_float(m3.y), __uint_as_float(m3.z));
+  h.internalExtents = V3(__uint_as_float(m2.x), __uint_as_float(m2.y), __uint_as_float(m2.z)); h.centerOfMass = V3(__uint_as_float(m3.x), __uint_as_float(m3.y), __uint_as_float(m3.z)); h.internalRadius = __uint_as_float(m2.w);
   h.verts = H.verts + m0.x; h.polys = H.polys + 2 * m0.y; h.vertexRefs = H.refs + m0.z; h.facesByEdges = H.edges + m0.w;
   return h;
 }
@@ -1323,6 +1323,157 @@ PXB_D bool gjk_poly_contains_n(const v3* verts, int numVerts, v3 p, v3 mn, v3 mx
   }
   return inter > 0;
 }
+/* ---------------- SAT branch of generateFullContactManifold: GuPCMContactGenBoxConvex.cpp:56-328, :537-603 (PCM_USE_INTERNAL_OBJECT = 1) ---------------- */
+#define GJK_SAT_MAX_AXES 96   // per-thread; a hull of <= 32 vertices has <= 90 edges (the reference's SEP_AXIS_FIXED_MEMORY is 256)
+/* SupportLocalImpl::doSupport(dir, min, max) / doSupport(dir): hull = brute force (GuVecConvexHull.h:377-429), box = sign select (GuVecBox.h:165-177) */
+PXB_D void gjk_poly_support_minmax(const DevHull* h, int isBox, v3 dir, float* mn, float* mx) {
+  if (isBox) { const v3 e = h->internalExtents; const v3 pt = V3(dir.x > 0.f ? e.x : -e.x, dir.y > 0.f ? e.y : -e.y, dir.z > 0.f ? e.z : -e.z); *mx = adot(dir, pt); *mn = -*mx; return; }
+  gjk_hull_support_minmax(h, dir, mn, mx);
+}
+PXB_D v3 gjk_poly_support(const DevHull* h, int isBox, v3 dir) {
+  if (isBox) { const v3 e = h->internalExtents; return V3(dir.x > 0.f ? e.x : -e.x, dir.y > 0.f ? e.y : -e.y, dir.z > 0.f ? e.z : -e.z); }
+  float mx = v3dot(h->vert(0), dir); uint32_t mi = 0;
+  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(h->vert(i), dir); if (d > mx) { mx = d; mi = i; } }
+  return h->vert(mi);
+}
+typedef struct { const DevHull* h; int isBox; v3 center; float internalRadius; v3 internalExtents; } GjkPolyData;   /* PolygonalData: mCenter, mInternal */
+PXB_D GjkPolyData gjk_poly_data(const DevHull* h, int isBox) {
+  GjkPolyData p; p.h = h; p.isBox = isBox;
+  p.center = isBox ? V3(0, 0, 0) : h->centerOfMass; p.internalRadius = isBox ? 0.f : h->internalRadius; p.internalExtents = h->internalExtents;
+  return p;
+}
+/* testFaceNormal :56-156 */
+PXB_D int gjk_sat_face_normal(const GjkPolyData* p0, const GjkPolyData* p1, const mxf* transform0To1, const mxf* transform1To0, float contactDist,
+                                      float* minOverlap, uint32_t* feature, v3* faceNormal, int faceStatus, int* status) {
+  float _minOverlap = FLT_MAX; uint32_t _feature = 0; v3 _faceNormal = *faceNormal;
+  const v3 center1To0 = transform1To0->p;
+  const v3 internalCenter1In0 = amxftransform(transform1To0, p1->center);
+  const v3 ie1 = p1->internalExtents;
+  for (uint32_t i = 0; i < p0->h->nPolys; ++i) {
+    const v3 pn = p0->h->plane_n(i);
+    const v3 minVert = p0->h->vert(p0->h->poly_meta(i).z);
+    const float magnitude = 1.0f / alen(pn);
+    const float min0 = adot(pn, minVert) * magnitude, max0 = (-p0->h->plane_d(i)) * magnitude;
+    const v3 n0 = v3scale(pn, magnitude);
+    const v3 n1 = m33mul(&transform0To1->r, n0);
+    const v3 proj = V3(n1.x > 0.f ? ie1.x : -ie1.x, n1.y > 0.f ? ie1.y : -ie1.y, n1.z > 0.f ? ie1.z : -ie1.z);
+    const float radius = fmax_(adot(n1, proj), p1->internalRadius);
+    const float internalTrans = adot(internalCenter1In0, n0);
+    const float _min1 = internalTrans - radius, _max1 = internalTrans + radius;
+    const float _min = fmax_(min0, _min1), _max = fmin_(max0, _max1);
+    if ((_max - _min) > _minOverlap) continue;
+    const float translate = adot(center1To0, n0);
+    float min1, max1; gjk_poly_support_minmax(p1->h, p1->isBox, n1, &min1, &max1);
+    min1 = translate + min1; max1 = translate + max1;
+    if ((min1 > max0 + contactDist) || (min0 > max1 + contactDist)) return 0;
+    const float tempOverlap = max0 - min1;
+    if (_minOverlap > tempOverlap) { _minOverlap = tempOverlap; _feature = i; _faceNormal = n0; }
+  }
+  if (*minOverlap > _minOverlap) { *faceNormal = _faceNormal; *minOverlap = _minOverlap; *status = faceStatus; }
+  *feature = _feature;
+  return 1;
+}
+/* buildPartialHull :159-193 + SeparatingAxes::addAxis GuSeparatingAxes.cpp:33-57 */
+PXB_D void gjk_sat_partial_hull(const DevHull* h, v3* axes, uint32_t* nAxes, v3 planeP, v3 planeDir) {
+  const v3 dir = anormalize(planeDir);
+  for (uint32_t i = 0; i < h->nPolys; ++i) {
+    const uint8_t* inds = h->vertexRefs + h->poly_meta(i).x; const uint32_t nb = h->poly_meta(i).y;
+    v3 v0 = h->vert(inds[nb - 1]);
+    float dist0 = adot(dir, v3sub(v0, planeP));
+    for (uint32_t k = 0; k < nb; ++k) {
+      const v3 v1 = h->vert(inds[k]);
+      const float dist1 = adot(dir, v3sub(v1, planeP));
+      if (dist0 > 0.f || dist1 > 0.f) {
+        const v3 t = v3sub(v0, v1);
+        const float m = t.x * t.x + t.y * t.y + t.z * t.z;                       /* PxVec3::getNormalized */
+        const v3 axis = m > 0.f ? v3scale(t, 1.0f / sqrtf(m)) : V3(0, 0, 0);
+        int dup = 0;
+        for (uint32_t a = 0; a < *nAxes; ++a) if (fabsf(v3dot(axis, axes[a])) > 0.9999f) { dup = 1; break; }
+        if (!dup && *nAxes < GJK_SAT_MAX_AXES) axes[(*nAxes)++] = axis;
+      }
+      v0 = v1; dist0 = dist1;
+    }
+  }
+}
+/* testEdgeNormal :195-328 */
+PXB_D int gjk_sat_edge_normal(const GjkPolyData* p0, const GjkPolyData* p1, const mxf* transform0To1, const mxf* transform1To0, float contactDist,
+                                      float* minOverlap, v3* edgeNormalIn0, int edgeStatus, int* status) {
+  float overlap = *minOverlap;
+  const v3 internalCenter1In0 = v3sub(amxftransform(transform1To0, p1->center), p0->center);
+  const v3 ie1 = p1->internalExtents, ie0 = p0->internalExtents;
+  const v3 center1To0 = transform1To0->p;
+  const v3 dir0 = v3sub(amxftransform(transform1To0, p1->center), p0->center);
+  const v3 support0 = gjk_poly_support(p0->h, p0->isBox, dir0);
+  const v3 dir1 = m33mul(&transform0To1->r, v3neg(dir0));
+  const v3 support1 = gjk_poly_support(p1->h, p1->isBox, dir1);
+  const v3 support0In1 = amxftransform(transform0To1, support0), support1In0 = amxftransform(transform1To0, support1);
+  v3 axe0[GJK_SAT_MAX_AXES], axe1[GJK_SAT_MAX_AXES]; uint32_t numAxe0 = 0, numAxe1 = 0;
+  gjk_sat_partial_hull(p0->h, axe0, &numAxe0, support1In0, dir0);
+  gjk_sat_partial_hull(p1->h, axe1, &numAxe1, support0In1, dir1);
+  for (uint32_t i = 0; i < numAxe0; ++i) {
+    const v3 v0 = axe0[i];
+    for (uint32_t j = 0; j < numAxe1; ++j) {
+      const v3 dir = v3cross(v0, m33mul(&transform1To0->r, axe1[j]));
+      const float lenSq = adot(dir, dir);
+      if (FLT_EPSILON > lenSq) continue;
+      const v3 n0 = v3scale(dir, 1.0f / sqrtf(lenSq));
+      const v3 n1 = m33mul(&transform0To1->r, n0);
+      const v3 proj = V3(n1.x > 0.f ? ie1.x : -ie1.x, n1.y > 0.f ? ie1.y : -ie1.y, n1.z > 0.f ? ie1.z : -ie1.z);
+      const float radius = fmax_(adot(n1, proj), p1->internalRadius);
+      const float internalTrans = adot(internalCenter1In0, n0);
+      const float _min1 = internalTrans - radius, _max1 = internalTrans + radius;
+      const v3 proj0 = V3(n0.x > 0.f ? ie0.x : -ie0.x, n0.y > 0.f ? ie0.y : -ie0.y, n0.z > 0.f ? ie0.z : -ie0.z);
+      const float radius0 = fmax_(adot(n0, proj0), p0->internalRadius);
+      const float _min = fmax_(-radius0, _min1), _max = fmin_(radius0, _max1);
+      if ((_max - _min) > overlap) continue;
+      float min0, max0, min1, max1;
+      gjk_poly_support_minmax(p0->h, p0->isBox, n0, &min0, &max0);
+      const float translate = adot(center1To0, n0);
+      gjk_poly_support_minmax(p1->h, p1->isBox, n1, &min1, &max1);
+      min1 = translate + min1; max1 = translate + max1;
+      if ((min1 > max0 + contactDist) || (min0 > max1 + contactDist)) return 0;
+      const float tempOverlap = max0 - min1;
+      if (overlap > tempOverlap) { overlap = tempOverlap; *edgeNormalIn0 = n0; *status = edgeStatus; }
+    }
+  }
+  *minOverlap = overlap;
+  return 1;
+}
+/* generateFullContactManifold, doOverlapTest == true (:537-603).  Returns 0 when a separating axis was found. */
+enum { GJK_FS_POLYDATA0 = 0, GJK_FS_POLYDATA1 = 1, GJK_FS_EDGE = 2 };
+PXB_D void gjk_poly_generated_contacts(const DevHull* poly0, const DevHull* poly1, int refIdx, int incIdx, const mxf* transform0To1, MPoint* mc, int* numContacts, float contactDist);
+PXB_D int gjk_poly_full_manifold_sat(const DevHull* poly0, int isBox0, const DevHull* poly1, const mxf* map0, const mxf* map1, MPoint* mc, int* numContacts, float contactDist) {
+  const mxf transform1To0 = amxfinvmul(map0, map1), transform0To1 = amxfinvmul(map1, map0);
+  const GjkPolyData p0 = gjk_poly_data(poly0, isBox0), p1 = gjk_poly_data(poly1, 0);
+  int status = GJK_FS_POLYDATA0;
+  float minOverlap = FLT_MAX; v3 minNormal = V3(0, 0, 0);
+  uint32_t feature0, feature1;
+  if (!gjk_sat_face_normal(&p0, &p1, &transform0To1, &transform1To0, contactDist, &minOverlap, &feature0, &minNormal, GJK_FS_POLYDATA0, &status)) return 0;
+  if (!gjk_sat_face_normal(&p1, &p0, &transform1To0, &transform0To1, contactDist, &minOverlap, &feature1, &minNormal, GJK_FS_POLYDATA1, &status)) return 0;
+  int doEdgeTest = 0;
+  for (;;) {
+    if (doEdgeTest) {
+      if (!gjk_sat_edge_normal(&p0, &p1, &transform0To1, &transform1To0, contactDist, &minOverlap, &minNormal, GJK_FS_EDGE, &status)) return 0;
+      if (status != GJK_FS_EDGE) return 1;
+    }
+    if (status == GJK_FS_POLYDATA0) {
+      const v3 n = m33mul(&transform0To1.r, minNormal);
+      gjk_poly_generated_contacts(poly0, poly1, (int)feature0, gjk_hull_polygon_index(poly1, n), &transform0To1, mc, numContacts, contactDist);
+      if (*numContacts > 0) { const v3 nn = v3neg(n); for (int i = 0; i < *numContacts; ++i) { const v3 lb = mc[i].b; mc[i].b = mc[i].a; mc[i].a = lb; mc[i].n = nn; } }
+    } else if (status == GJK_FS_POLYDATA1) {
+      gjk_poly_generated_contacts(poly1, poly0, (int)feature1, gjk_hull_polygon_index(poly0, m33mul(&transform1To0.r, minNormal)), &transform1To0, mc, numContacts, contactDist);
+    } else {
+      const int incident = gjk_hull_polygon_index(poly0, v3neg(minNormal));
+      const int reference = gjk_hull_polygon_index(poly1, m33mul(&transform0To1.r, minNormal));
+      gjk_poly_generated_contacts(poly1, poly0, reference, incident, &transform1To0, mc, numContacts, contactDist);
+    }
+    if (*numContacts == 0 && !doEdgeTest) { doEdgeTest = 1; continue; }
+    break;
+  }
+  return 1;
+}
+
+
 PXB_D float gjk_signed_2d_tri_area(v3 a, v3 b, v3 c) { const v3 ca = v3sub(a, c), cb = v3sub(b, c); return ca.x * cb.y - ca.y * cb.x; }   /* GuPCMContactGenUtil.h:56-66 */
 #define GJK_POLY_MAX_CONTACTS 32   // per-thread buffer; a pair of <= 32-vertex hull polygons stays far below it (the reference's buffer holds 256)
 /* generatedContacts :331-530: incident polygon (of poly1) clipped against the reference polygon (of poly0) in the reference polygon's plane */
@@ -1470,17 +1621,17 @@ PXB_D int gjk_pcm_poly_convex(const xf* transf0, const xf* transf1, GjkConvex* c
       if (status == EPA_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
       else doOverlapTest = 1;
     }
-    if (doOverlapTest) return 1;   /* SAT branch: not restated */
     const int fullContactGen = (0.707106781f > adot(localNor, output.normal)) || (manifold->n < initialContacts);
-    if (fullContactGen) {
+    if (fullContactGen || doOverlapTest) {   /* fullContactsGenerationBoxConvex / ConvexConvex */
       MPoint mc[GJK_POLY_MAX_CONTACTS]; int numContacts = 0;
       const mxf map0 = amxffromxf(transf0), map1 = amxffromxf(transf1);
-      gjk_poly_full_manifold(polyA, hullB, &map0, &map1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
+      if (doOverlapTest) { if (!gjk_poly_full_manifold_sat(polyA, convexA->type == GJK_CVX_BOX, hullB, &map0, &map1, mc, &numContacts, contactDist)) return 0; }
+      else gjk_poly_full_manifold(polyA, hullB, &map0, &map1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
       if (numContacts > 0) {
         if (numContacts <= PXB_MANIFOLD_CACHE) { for (int i = 0; i < numContacts; ++i) manifold->pts[i] = mc[i]; manifold->n = numContacts; }
         else { reduce_batch(*manifold, mc, numContacts, toleranceLength); manifold->n = PXB_MANIFOLD_CACHE; }
-      }
-      gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
+        gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
+      } else if (!doOverlapTest) gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
     } else {
       const v3 newLocalNor = v3add(localNor, output.normal);
       gjk_manifold_to_contacts(manifold, anormalize(aqrot(transf1->q, newLocalNor)), transf1, contactDist, out);
@@ -1493,7 +1644,7 @@ PXB_D const DevHull* gjk_box_as_hull(BoxAsHull* b, v3 ext) {   // PCMPolygonalBo
   PolyBox pb; gjk_poly_box(&pb, ext);
   for (int i = 0; i < 8; ++i) b->verts[i] = F4(pb.verts[i], 0.f);
   for (int i = 0; i < 6; ++i) { b->polys[2 * i] = F4(pb.polys[i].n, pb.polys[i].d); b->polys[2 * i + 1] = make_float4(__uint_as_float((uint32_t)i * 4), __uint_as_float(4u), __uint_as_float((uint32_t)pb.polys[i].minIndex), 0.f); }
-  b->view.nVerts = 8; b->view.nPolys = 6; b->view.nEdges = 0; b->view.internalExtents = ext; b->view.centerOfMass = V3(0, 0, 0);
+  b->view.nVerts = 8; b->view.nPolys = 6; b->view.nEdges = 0; b->view.internalExtents = ext; b->view.centerOfMass = V3(0, 0, 0); b->view.internalRadius = 0.f;
   b->view.verts = b->verts; b->view.polys = b->polys; b->view.vertexRefs = gjk_box_poly_refs; b->view.facesByEdges = nullptr;
   return &b->view;
 }

@@ -430,6 +430,15 @@ def box_pile(nx=100, ny=20, nz=100, half_extent=0.25, gap=0.001, seed=1, **hdr):
     return Scene(default_header(**hdr), add_bin(a, half_size=float(max(nx, nz) * pitch / 2 + 0.5)))
 
 
+def load_hull_library():
+    """16 cooked convex hulls (12-20 input points, r ~ 0.2; cooked once by the reference's PxCreateConvexMesh and committed as
+    tests/golden/hull_library.npz together with its generator in the git history) -> (point clouds, cooked bytes, unit masses, unit inertias).
+    Lets full-size scenes use hulls on the GPU box, where the reference (and its cooking) does not exist."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "hull_library.npz"), allow_pickle=True)
+    return [np.asarray(c, np.float32) for c in z["clouds"]], z["cooked"].tobytes(), z["unitMass"], z["unitInertiaDiag"]
+
+
 def falling_primitives(nx=128, ny=64, nz=128, pitch=0.6, seed=2, kinds=("sphere", "box"), **hdr):
     """BASELINE config 3 shape (broadphase + narrowphase stress): nx*ny*nz mixed primitives with random orientations dropped
     from a lattice into a walled bin.  (Config 3 is spheres / capsules / convex hulls; boxes stand in for the hulls until the
@@ -451,8 +460,16 @@ def falling_primitives(nx=128, ny=64, nz=128, pitch=0.6, seed=2, kinds=("sphere"
             set_sphere(a, idx, rng.uniform(0.1, 0.2, len(idx)).astype(np.float32))
         elif k == "capsule":
             set_capsule(a, idx, rng.uniform(0.08, 0.15, len(idx)).astype(np.float32), rng.uniform(0.1, 0.3, len(idx)).astype(np.float32))
+        elif k == "convex":   # the 16 library hulls, round robin; mass / inertia from the cooked mass information at density 10
+            clouds, cooked, unit_mass, unit_inertia = load_hull_library()
+            hi = (np.arange(len(idx)) % len(clouds)).astype(np.uint32)
+            a["geomType"][idx] = GEOM_CONVEX; a["flags"][idx] = ACTOR_DYNAMIC; a["hullIdx"][idx] = hi
+            a["mass"][idx] = np.float32(10.0) * unit_mass[hi]; a["inertia"][idx] = np.float32(10.0) * unit_inertia[hi]
         else:
             set_box(a, idx, rng.uniform(0.1, 0.2, (len(idx), 3)).astype(np.float32))
+    if "convex" in kinds:
+        clouds, cooked, _, _ = load_hull_library()
+        return Scene(default_header(**hdr), add_bin(a, half_size=float(max(nx, nz) * pitch / 2 + 1.0)), clouds, cooked)
     return Scene(default_header(**hdr), add_bin(a, half_size=float(max(nx, nz) * pitch / 2 + 1.0)))
 
 

@@ -572,6 +572,21 @@ def test_sphere_convex_gpu_matches_oracle(oracle, name):
         assert np.abs(gpu.getStates() - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
 
 
+def test_config3_shape_with_hulls_gpu_matches_oracle(oracle):
+    """BASELINE config 3 at small size (spheres / capsules / library hulls falling into a walled bin, relaxed partitioning): every pair type of
+    a10 incl. the SAT branch of the hull-hull manifold generation; GPU and oracle agree step by step."""
+    sc = scenes.falling_primitives(6, 4, 6, kinds=("sphere", "capsule", "convex"), relaxed_partitioning=True)
+    gpu, cpu = engine.Scene(sc, max_pairs=32 * len(sc.actors)), oracle.OracleScene(sc)
+    for t in range(100):
+        gpu.step(); cpu.step()
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
+        assert np.array_equal(gpu.getContacts()[:, 0], cpu.getContacts()[:, 0]), f"contact counts, step {t}"
+        sg = gpu.getStates()
+        assert np.abs(sg - cpu.getStates()).max() < 5e-5, f"state, step {t}"
+        cpu.setStates(sg)
+    assert cpu.unsupported_pairs == 0 and sg[:, 1].min() > 0.0
+
+
 def test_hull_without_cooked_data_is_rejected():
     """A convex actor whose hull was not uploaded (pxb_scene_set_convex_meshes) is refused when it is added -- nothing is silently skipped."""
     z, sc = util.load_golden("hulls_on_plane")

@@ -1,5 +1,5 @@
 """BASELINE configs 3 and 4 (device-wide path: no environment ids) at full size on the GPU: ms/step and per-stage times.
-usage: python tools/gpu_configs.py [pile|fall|fall_sb|pile_pgs] [scale] [exact]   (scale 1.0 = full size; default = PXB_FLAG_RELAXED_PARTITIONING)"""
+usage: python tools/gpu_configs.py [pile|fall|fall_hulls|fall_sb|pile_pgs] [scale] [exact]   (scale 1.0 = full size; default = PXB_FLAG_RELAXED_PARTITIONING)"""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -30,6 +30,6 @@ if which.startswith("pile"):
     run("config 4: dense box pile " + ("PGS" if which.endswith("pgs") else "TGS"), sc, 16 * len(sc.actors), 30, 50)
 else:
     n = max(4, int(round(128 * scale ** (1 / 3))))
-    kinds = ("sphere", "capsule", "box") if which == "fall" else ("sphere", "box")   # fall_sb: the old sphere / box mix
+    kinds = {"fall": ("sphere", "capsule", "box"), "fall_hulls": ("sphere", "capsule", "convex"), "fall_sb": ("sphere", "box")}[which]   # fall_hulls = BASELINE config 3 proper
     sc = scenes.falling_primitives(n, max(2, n // 2), n, kinds=kinds, relaxed_partitioning=relaxed)
     run("config 3 shape: falling " + "/".join(kinds), sc, 8 * len(sc.actors), 60, 50)
