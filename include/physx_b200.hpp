@@ -62,6 +62,8 @@ class Scene {
   ~Scene() { if (h_) pxb_scene_release(h_); }
   Scene(const Scene&) = delete; Scene& operator=(const Scene&) = delete;
 
+  // cooked convex hulls (what the host's PxCreateConvexMesh produced; layout in physx_b200.h): once, before the actors that refer to them by hullIdx
+  void setConvexMeshes(const void* cooked, size_t bytes, uint32_t nHulls) { check(pxb_scene_set_convex_meshes(h_, cooked, bytes, nHulls)); }
   void addActors(const std::vector<PxbActorRec>& recs) { if (!recs.empty()) check(pxb_scene_add_actors(h_, recs.data(), (uint32_t)recs.size())); }
   uint32_t getNbActors() const { return pxb_scene_num_actors(h_); }
   uint32_t getNbDynamics() const { return pxb_scene_num_dynamic(h_); }

@@ -203,25 +203,9 @@ class Scene:
         return parse_cooked(self.cooked, len(self.hulls))[0] if self.cooked else []
 
 
-def cook_hulls(scene, density=10.0):
-    """Runs the reference's convex cooking (oracle/_ref/ref_harness cook: PxCreateConvexMesh, unmodified) over the scene's hull point clouds,
-    attaches the cooked section and fills mass / inertia of the convex actors from the cooked mass information (mass = density * volume,
-    diagonal of the inertia tensor, centre-of-mass frame = actor frame: both sides get the same explicit values).  Needs the build container
-    (/root/reference); fixtures under tests/golden carry the cooked bytes so that the GPU box never cooks."""
-    import os, subprocess, tempfile
-    harness = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_harness")
-    with tempfile.TemporaryDirectory() as d:
-        scene.cooked = b""
-        scene.save(d + "/s.bin")
-        subprocess.run([harness, "cook", d + "/s.bin", d + "/c.bin"], check=True, capture_output=True)
-        scene.cooked = open(d + "/c.bin", "rb").read()
-    ch = scene.cooked_hulls()
-    for i in np.nonzero(scene.actors["geomType"] == GEOM_CONVEX)[0]:
-        hdr = ch[int(scene.actors["hullIdx"][i])]["hdr"]
-        if scene.actors["flags"][i] & ACTOR_DYNAMIC:
-            scene.actors["mass"][i] = np.float32(density) * hdr["unitMass"]
-            scene.actors["inertia"][i] = np.float32(density) * hdr["unitInertiaDiag"]
-    return scene
+# Convex cooking is the host SDK's job (PxCreateConvexMesh); the test infrastructure cooks with the unmodified reference
+# (tests/golden/cooking.py: cook_hulls) and scene fixtures / physx_b200/data/hull_library.npz carry the cooked bytes.  The builders below that
+# create new hull point clouds take that function as `cook`; without it they return the scene uncooked (hull clouds only).
 
 
 def random_hull_points(rng, n_points=16, radius=0.2):
@@ -241,7 +225,7 @@ def set_convex(a, idx, hull_idx):
     a["inertia"][idx] = 0.01
 
 
-def hulls_on_plane(n=8, n_hulls=3, seed=6, **hdr):
+def hulls_on_plane(n=8, n_hulls=3, seed=6, cook=None, **hdr):
     """Convex hulls (12-20 vertices) with random orientations and spins dropped onto the ground plane, spaced so that they never touch
     each other: exercises convex bounds and pcmContactPlaneConvex."""
     rng = np.random.RandomState(seed)
@@ -252,7 +236,8 @@ def hulls_on_plane(n=8, n_hulls=3, seed=6, **hdr):
         a["pos"][i] = (1.5 * (i % 4), 0.6 + 0.25 * (i // 4), 1.5 * (i // 4))
         a["angVel"][i] = rng.uniform(-2, 2, 3)
     a["quat"] = random_unit_quats(rng, n)
-    return cook_hulls(Scene(default_header(**hdr), add_ground_plane(a), hulls))
+    sc = Scene(default_header(**hdr), add_ground_plane(a), hulls)
+    return cook(sc) if cook else sc
 
 
 def box_stacks(n_stacks=10, height=10, half_extent=0.5, spacing=4.0, jitter=0.0, seed=1234, **hdr):
@@ -431,11 +416,11 @@ def box_pile(nx=100, ny=20, nz=100, half_extent=0.25, gap=0.001, seed=1, **hdr):
 
 
 def load_hull_library():
-    """16 cooked convex hulls (12-20 input points, r ~ 0.2; cooked once by the reference's PxCreateConvexMesh and committed as
-    tests/golden/hull_library.npz together with its generator in the git history) -> (point clouds, cooked bytes, unit masses, unit inertias).
+    """16 cooked convex hulls (12-20 input points, r ~ 0.2; cooked once by the reference's PxCreateConvexMesh with tests/golden/cooking.py
+    and committed as physx_b200/data/hull_library.npz) -> (point clouds, cooked bytes, unit masses, unit inertias).
     Lets full-size scenes use hulls on the GPU box, where the reference (and its cooking) does not exist."""
     import os
-    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "hull_library.npz"), allow_pickle=True)
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "hull_library.npz"), allow_pickle=True)
     return [np.asarray(c, np.float32) for c in z["clouds"]], z["cooked"].tobytes(), z["unitMass"], z["unitInertiaDiag"]
 
 
@@ -572,7 +557,7 @@ def test_forces(n_dynamic, seed=1, blocks=7):
     return f
 
 
-def hulls_and_spheres(n=10, n_hulls=3, seed=11, **hdr):
+def hulls_and_spheres(n=10, n_hulls=3, seed=11, cook=None, **hdr):
     """Spheres dropped onto convex hulls that rest on the ground plane (hulls spaced apart so that no hull touches another hull):
     exercises pcmContactSphereConvex (GJK with the hull support mapping) next to plane-convex and sphere-plane."""
     rng = np.random.RandomState(seed)
@@ -588,12 +573,13 @@ def hulls_and_spheres(n=10, n_hulls=3, seed=11, **hdr):
         set_sphere(a, i, rng.uniform(0.08, 0.16))
         a["pos"][i] = (1.6 * (k % nh) + rng.uniform(-0.12, 0.12), 0.9 + 0.4 * (k // nh), rng.uniform(-0.12, 0.12))
         a["linVel"][i] = (0.0, -rng.uniform(0.0, 3.0), 0.0)
-    return cook_hulls(Scene(default_header(**hdr), add_ground_plane(a), hulls))
+    sc = Scene(default_header(**hdr), add_ground_plane(a), hulls)
+    return cook(sc) if cook else sc
 
 
-def spheres_into_hulls(seed=11, speed=14.0, **hdr):
+def spheres_into_hulls(seed=11, speed=14.0, cook=None, **hdr):
     """hulls_and_spheres with the spheres fired downwards and a few spawned inside a hull: pcmContactSphereConvex through EPA."""
-    sc = hulls_and_spheres(seed=seed, n=12, **hdr)
+    sc = hulls_and_spheres(seed=seed, n=12, cook=cook, **hdr)
     sph = np.nonzero(sc.actors["geomType"] == GEOM_SPHERE)[0]
     sc.actors["linVel"][sph, 1] = -np.float32(speed)
     inside = sph[::3]
@@ -601,7 +587,7 @@ def spheres_into_hulls(seed=11, speed=14.0, **hdr):
     return sc
 
 
-def hulls_and_capsules(n=12, n_hulls=3, seed=21, speed=0.0, **hdr):
+def hulls_and_capsules(n=12, n_hulls=3, seed=21, speed=0.0, cook=None, **hdr):
     """Capsules dropped onto convex hulls resting on the ground plane (hulls spaced apart): pcmContactCapsuleConvex -- GJK over the hull
     support mapping, face (ray) and edge-edge contacts against the witness polygon.  speed > 0 fires the capsules downwards (EPA)."""
     rng = np.random.RandomState(seed)
@@ -618,10 +604,11 @@ def hulls_and_capsules(n=12, n_hulls=3, seed=21, speed=0.0, **hdr):
         a["pos"][i] = (1.6 * (k % nh) + rng.uniform(-0.1, 0.1), 0.9 + 0.45 * (k // nh), rng.uniform(-0.1, 0.1))
         a["angVel"][i] = rng.uniform(-2, 2, 3)
         a["linVel"][i] = (0.0, -speed, 0.0)
-    return cook_hulls(Scene(default_header(**hdr), add_ground_plane(a), hulls))
+    sc = Scene(default_header(**hdr), add_ground_plane(a), hulls)
+    return cook(sc) if cook else sc
 
 
-def hull_pile(n=10, n_hulls=3, seed=31, kinds=("convex",), spread=0.35, **hdr):
+def hull_pile(n=10, n_hulls=3, seed=31, kinds=("convex",), spread=0.35, cook=None, **hdr):
     """Convex hulls (optionally mixed with boxes / spheres / capsules) dropped in a loose column onto the ground plane: hull-hull and
     box-hull contacts (GJK / EPA point + polygon clipping of the witness faces), BASELINE config 3's pair types at small size."""
     rng = np.random.RandomState(seed)
@@ -641,4 +628,5 @@ def hull_pile(n=10, n_hulls=3, seed=31, kinds=("convex",), spread=0.35, **hdr):
             set_sphere(a, i, rng.uniform(0.1, 0.2))
         else:
             set_capsule(a, i, rng.uniform(0.08, 0.15), rng.uniform(0.1, 0.3))
-    return cook_hulls(Scene(default_header(**hdr), add_ground_plane(a), hulls))
+    sc = Scene(default_header(**hdr), add_ground_plane(a), hulls)
+    return cook(sc) if cook else sc

@@ -15,6 +15,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from physx_b200 import scenes  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from cooking import cook_hulls  # noqa: E402
 
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
@@ -90,13 +92,13 @@ def main():
     cases["pgs_lock_primitives"] = (scenes.locked_primitives(seed=3, solver=scenes.SOLVER_PGS), 100)
     # a10 (GJK family): capsules and spheres dropped onto static tilted / dynamic resting boxes -- capsule-box face, edge and corner contacts
     cases["capsules_on_boxes"] = (scenes.capsules_on_boxes(seed=3), 150)
-    cases["hulls_on_plane"] = (scenes.hulls_on_plane(seed=6), 150)   # convex hulls (cooked by the reference): tight bounds + pcmContactPlaneConvex
-    cases["hulls_and_spheres"] = (scenes.hulls_and_spheres(seed=11), 150)   # pcmContactSphereConvex: GJK with the hull support mapping
-    cases["spheres_into_hulls"] = (scenes.spheres_into_hulls(seed=13), 60)  # ... through EPA
-    cases["hulls_and_capsules"] = (scenes.hulls_and_capsules(seed=21), 150)            # pcmContactCapsuleConvex
-    cases["capsules_into_hulls"] = (scenes.hulls_and_capsules(seed=23, speed=14.0), 60)   # ... through EPA (a seed whose hulls never come near each other)
-    cases["hull_pile"] = (scenes.hull_pile(seed=32), 150)                                   # pcmContactConvexConvex: GJK / EPA + polygon clipping
-    cases["box_hull_pile"] = (scenes.hull_pile(seed=33, kinds=("convex", "box")), 150)     # pcmContactBoxConvex
+    cases["hulls_on_plane"] = (scenes.hulls_on_plane(seed=6, cook=cook_hulls), 150)   # convex hulls (cooked by the reference): tight bounds + pcmContactPlaneConvex
+    cases["hulls_and_spheres"] = (scenes.hulls_and_spheres(seed=11, cook=cook_hulls), 150)   # pcmContactSphereConvex: GJK with the hull support mapping
+    cases["spheres_into_hulls"] = (scenes.spheres_into_hulls(seed=13, cook=cook_hulls), 60)  # ... through EPA
+    cases["hulls_and_capsules"] = (scenes.hulls_and_capsules(seed=21, cook=cook_hulls), 150)            # pcmContactCapsuleConvex
+    cases["capsules_into_hulls"] = (scenes.hulls_and_capsules(seed=23, speed=14.0, cook=cook_hulls), 60)   # ... through EPA (a seed whose hulls never come near each other)
+    cases["hull_pile"] = (scenes.hull_pile(seed=32, cook=cook_hulls), 150)                                   # pcmContactConvexConvex: GJK / EPA + polygon clipping
+    cases["box_hull_pile"] = (scenes.hull_pile(seed=33, kinds=("convex", "box"), cook=cook_hulls), 150)     # pcmContactBoxConvex
     cases["capsules_into_boxes"] = (scenes.capsules_into_boxes(seed=3), 60)   # deep penetration: the EPA query
     # a19: PxDirectGPUAPI eFORCE / eTORQUE writes (= addForce / addTorque(eFORCE) before every step), a 7-step cycle of per-body forces
     forced = {"forces_stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01),
