@@ -287,20 +287,23 @@ __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_
 // (in pair-key order the types alternate at random: ncu measured 4.5 of 32 threads active per instruction on BASELINE config 3).
 // Counting sort in two passes (histogram, then scatter with warp-aggregated cursors); the order inside a bin is arbitrary, every pair
 // writes only its own outputs, so the result does not depend on it.
-#define NP_CLASSES 37   // 6 x 6 geometry types + 1 bin for dropped keys
-__device__ __forceinline__ uint32_t np_pair_class(uint64_t key, uint32_t bitsA, const uint32_t* __restrict__ geomFlags) {
+#define NP_CLASSES 75   // 6 x 6 geometry types x {no contacts last frame, contacts last frame} + 1 bin for dropped keys (+ padding)
+// The second key bit -- did the pair's persistent manifold hold contacts last frame -- separates the (cheap) separated pairs from the touching
+// ones that run the full contact generation, so warps are uniform in work as well as in code path.
+__device__ __forceinline__ uint32_t np_pair_class(uint64_t key, uint32_t bitsA, const uint32_t* __restrict__ geomFlags, uint32_t slot, const float4* __restrict__ manifolds) {
   if (key == ~0ull) return NP_CLASSES - 1;
   const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
   const uint32_t a = geomFlags[lo] & 0xff, b = geomFlags[hi] & 0xff;
-  return a < b ? a * 6 + b : b * 6 + a;
+  const uint32_t touching = __float_as_int(manifolds[(size_t)slot * PXB_MANIFOLD_F4].x) > 0 ? 1u : 0u;
+  return 2u * (a < b ? a * 6 + b : b * 6 + a) + touching;
 }
 __global__ void k_np_class_count(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ nPairsP, uint32_t bitsA, const uint32_t* __restrict__ geomFlags, uint8_t* __restrict__ cls,
-                                 uint32_t* __restrict__ classCount) {
+                                 uint32_t* __restrict__ classCount, const uint32_t* __restrict__ pairSlots, const float4* __restrict__ manifolds) {
   __shared__ uint32_t hist[NP_CLASSES];
   if (threadIdx.x < NP_CLASSES) hist[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < *nPairsP) { const uint32_t c = np_pair_class(pairKeys[i], bitsA, geomFlags); cls[i] = (uint8_t)c; atomicAdd(&hist[c], 1u); }
+  if (i < *nPairsP) { const uint32_t c = np_pair_class(pairKeys[i], bitsA, geomFlags, pairSlots[i], manifolds); cls[i] = (uint8_t)c; atomicAdd(&hist[c], 1u); }
   __syncthreads();
   if (threadIdx.x < NP_CLASSES && hist[threadIdx.x]) atomicAdd(&classCount[threadIdx.x], hist[threadIdx.x]);
 }
@@ -1237,7 +1240,7 @@ static int enqueue_step(PxbScene* s, float dt) {
   const float contactDist = s->desc.contactOffset + s->desc.contactOffset;
   if (s->binPairs) {   // several geometry types: counting sort of the pairs by type pair, so that warps do not diverge across contact functions
     CK(cudaMemsetAsync(s->npClassCount, 0, 4 * 2 * NP_CLASSES, st));
-    LAUNCH(k_np_class_count, gP, B, s->pairKeys[cur], nP, s->bitsA, s->geomFlags, s->npClass, s->npClassCount);
+    LAUNCH(k_np_class_count, gP, B, s->pairKeys[cur], nP, s->bitsA, s->geomFlags, s->npClass, s->npClassCount, s->pairSlots[cur], s->manifolds);
     LAUNCH(k_np_class_scatter, gP, B, nP, s->npClass, s->npClassCount, s->npClassCount + NP_CLASSES, s->pairOrder);
   }
   LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
