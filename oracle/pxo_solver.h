@@ -368,17 +368,17 @@ static inline void pxo_solve_contact(PxoConstraint* k, PxoSolverBody* b0, PxoSol
 /* First-fit colouring in input order: DyConstraintPartition.cpp:460-568 for dynamic-dynamic constraints;
  * static constraints go to partition maxNormalProgress(body)+k (:203-262).  colour[] receives the
  * partition index of every constraint; returns the number of partitions.  bodyMask/bodyMaxDyn/bodyStatic
- * are scratch arrays of nBodies entries.  (Single 32-colour pass; overflow returns -1.) */
-static inline int pxo_colour(const int* body0, const int* body1, int n, int nBodies, int* colour, uint32_t* bodyMask, int* bodyMaxDyn, int* bodyStatic) {
-  memset(bodyMask, 0, sizeof(uint32_t) * nBodies); memset(bodyMaxDyn, 0, sizeof(int) * nBodies); memset(bodyStatic, 0, sizeof(int) * nBodies);
+ * are scratch arrays of nBodies entries.  (64 colours; overflow returns -1.) */
+static inline int pxo_colour(const int* body0, const int* body1, int n, int nBodies, int* colour, uint64_t* bodyMask, int* bodyMaxDyn, int* bodyStatic) {
+  memset(bodyMask, 0, sizeof(uint64_t) * nBodies); memset(bodyMaxDyn, 0, sizeof(int) * nBodies); memset(bodyStatic, 0, sizeof(int) * nBodies);
   int nPart = 0;
   for (int i = 0; i < n; ++i) {
     const int a = body0[i], b = body1[i];
     if (a >= 0 && b >= 0) {
-      const uint32_t comb = ~bodyMask[a] & ~bodyMask[b];
+      const uint64_t comb = ~bodyMask[a] & ~bodyMask[b];   /* 64 colours = two of the reference's 32-colour rounds (:520-552): overflow constraints see only each other's colours */
       if (comb == 0) return -1;
       int p = 0; while (!((comb >> p) & 1u)) p++;
-      bodyMask[a] |= 1u << p; bodyMask[b] |= 1u << p;
+      bodyMask[a] |= 1ull << p; bodyMask[b] |= 1ull << p;
       if (p + 1 > bodyMaxDyn[a]) bodyMaxDyn[a] = p + 1;
       if (p + 1 > bodyMaxDyn[b]) bodyMaxDyn[b] = p + 1;
       colour[i] = p;
@@ -394,8 +394,8 @@ static inline int pxo_colour(const int* body0, const int* body1, int n, int nBod
 /* PXB_FLAG_RELAXED_PARTITIONING (include/physx_b200.h): the same Jones-Plassmann rounds as k_colour_partition's relaxed branch
  * (physx_b200/csrc/pxb_engine.cu), run sequentially.  Not a reference algorithm: it exists so the relaxed GPU mode stays testable
  * bit for bit.  Static contacts are placed exactly as in pxo_colour. */
-static inline int pxo_colour_relaxed(const int* body0, const int* body1, int n, int nBodies, int* colour, uint32_t* bodyMask, int* bodyMaxDyn, int* bodyStatic) {
-  memset(bodyMask, 0, sizeof(uint32_t) * nBodies); memset(bodyMaxDyn, 0, sizeof(int) * nBodies); memset(bodyStatic, 0, sizeof(int) * nBodies);
+static inline int pxo_colour_relaxed(const int* body0, const int* body1, int n, int nBodies, int* colour, uint64_t* bodyMask, int* bodyMaxDyn, int* bodyStatic) {
+  memset(bodyMask, 0, sizeof(uint64_t) * nBodies); memset(bodyMaxDyn, 0, sizeof(int) * nBodies); memset(bodyStatic, 0, sizeof(int) * nBodies);
   uint64_t* best = (uint64_t*)calloc(nBodies ? nBodies : 1, sizeof(uint64_t));
   int remaining = 0;
   for (int i = 0; i < n; ++i) { colour[i] = -1; if (body0[i] >= 0 && body1[i] >= 0) remaining++; }
@@ -411,10 +411,10 @@ static inline int pxo_colour_relaxed(const int* body0, const int* body1, int n, 
       const uint64_t bid = ((uint64_t)round << 32) | ((uint32_t)i * 2654435761u + 1u);
       const int a = body0[i], b = body1[i];
       if (best[a] != bid || best[b] != bid) continue;
-      const uint32_t comb = ~bodyMask[a] & ~bodyMask[b];
+      const uint64_t comb = ~bodyMask[a] & ~bodyMask[b];
       if (comb == 0) { free(best); return -1; }
       int p = 0; while (!((comb >> p) & 1u)) p++;
-      bodyMask[a] |= 1u << p; bodyMask[b] |= 1u << p;
+      bodyMask[a] |= 1ull << p; bodyMask[b] |= 1ull << p;
       colour[i] = p; remaining--;
     }
   }
@@ -423,7 +423,7 @@ static inline int pxo_colour_relaxed(const int* body0, const int* body1, int n, 
   for (int i = 0; i < n; ++i) {
     const int a = body0[i], b = body1[i];
     if (!(a >= 0 && b >= 0)) {
-      const int d = a >= 0 ? a : b; const uint32_t m = bodyMask[d]; int mx = 0; while (mx < 32 && (m >> mx)) mx++;
+      const int d = a >= 0 ? a : b; const uint64_t m = bodyMask[d]; int mx = 0; while (mx < 64 && (m >> mx)) mx++;
       colour[i] = mx + bodyStatic[d]++;
     }
     if (colour[i] + 1 > nPart) nPart = colour[i] + 1;

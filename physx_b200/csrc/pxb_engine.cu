@@ -33,7 +33,7 @@
 namespace cg = cooperative_groups;
 
 #define NONE32 0xffffffffu
-#define MAX_PARTITIONS 96
+#define MAX_PARTITIONS 160   // 64 dynamic colours (two rounds of the reference's 32, DyConstraintPartition.cpp:520-552) + static slots
 #ifndef PXB_SOLVE_CTAS_PER_SM
 #define PXB_SOLVE_CTAS_PER_SM 2   // measured on B200: 3 CTAs/SM (80 regs, spills, wider grid.sync) is 20% slower than 2
 #endif
@@ -63,7 +63,7 @@ struct PxbScene {
   float* tight = 0;
   // solver body state (per actor)
   float4 *sbLin = 0, *sbAng = 0, *sbDLin = 0, *sbDAng = 0, *sbIA = 0, *sbIB = 0, *sbP = 0, *sbQ = 0, *sbOrigAng = 0;
-  uint32_t *bodyCnt = 0, *bodyStart = 0, *bodyCursor = 0, *bodyNext = 0, *bodyMask = 0, *bodyHasCon = 0;
+  uint32_t *bodyCnt = 0, *bodyStart = 0, *bodyCursor = 0, *bodyNext = 0, *bodyHasCon = 0; unsigned long long* bodyMask = 0;   // bodyMask: the 64 dynamic colours a body's constraints hold
   // broadphase
   uint64_t *cellKey = 0, *cellKeyAlt = 0; uint32_t *cellVal = 0, *cellValAlt = 0; float4 *sMin = 0, *sMax = 0;
   uint64_t* pairKeys[2] = {0, 0}; uint32_t* pairSlots[2] = {0, 0}; uint64_t* pairKeyAlt = 0; uint32_t *pairValTmp = 0, *pairValAlt = 0;
@@ -106,6 +106,8 @@ static HullArrays hull_arrays(const PxbScene* s) { HullArrays H; H.meta = s->hul
 // kernels
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+__device__ __forceinline__ unsigned long long ld_volatile64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ void st_volatile64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // a1: tight world AABB of one shape.  Formulas: Gu::computeBounds (geomutils/src/GuBounds.cpp:354-400, plane :210-260).
@@ -492,7 +494,7 @@ __global__ void k_con_fill(const uint32_t* __restrict__ counters, const uint32_t
 // dynamic (resp. static) constraints
 __global__ void k_body_lists(uint32_t nA, const uint32_t* __restrict__ bodyStart, const uint32_t* __restrict__ bodyCnt, uint32_t* __restrict__ bodyList,
                              const uint32_t* __restrict__ conB0, const uint32_t* __restrict__ conB1, uint32_t* __restrict__ conPos0, uint32_t* __restrict__ conPos1,
-                             uint32_t* __restrict__ bodyNext, uint32_t* __restrict__ bodyMask, uint32_t* __restrict__ bodyHasCon) {
+                             uint32_t* __restrict__ bodyNext, unsigned long long* __restrict__ bodyMask, uint32_t* __restrict__ bodyHasCon) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nA) return;
   const uint32_t n = bodyCnt[a]; uint32_t* l = bodyList + bodyStart[a];
@@ -503,7 +505,7 @@ __global__ void k_body_lists(uint32_t nA, const uint32_t* __restrict__ bodyStart
     if (conB0[c] == a) conPos0[c] = isStatic ? spos : dpos; else conPos1[c] = dpos;
     if (isStatic) spos++; else dpos++;
   }
-  bodyNext[a] = 0; bodyMask[a] = 0; bodyHasCon[a] = n > 0 ? 1u : 0u;
+  bodyNext[a] = 0; bodyMask[a] = 0ull; bodyHasCon[a] = n > 0 ? 1u : 0u;
 }
 // a13 (3/3): first-fit colouring in solver input order, identical to the sequential
 // classifyConstraintDesc (DyConstraintPartition.cpp:475-568): a constraint takes the lowest colour free on
@@ -511,7 +513,7 @@ __global__ void k_body_lists(uint32_t nA, const uint32_t* __restrict__ bodyStart
 // partitions maxDynamicColour(body)+k (:203-262).  Then partition-major ordering of the constraints.
 __global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__ counters, const uint32_t* __restrict__ conB0, const uint32_t* __restrict__ conB1,
                                    const uint32_t* __restrict__ conPos0, const uint32_t* __restrict__ conPos1, uint32_t* __restrict__ conColour, uint32_t* __restrict__ conDone,
-                                   uint32_t* __restrict__ bodyNext, uint32_t* __restrict__ bodyMask, uint32_t* __restrict__ partCnt, uint32_t* __restrict__ partStart,
+                                   uint32_t* __restrict__ bodyNext, unsigned long long* __restrict__ bodyMask, uint32_t* __restrict__ partCnt, uint32_t* __restrict__ partStart,
                                    uint32_t* __restrict__ partCursor, uint32_t* __restrict__ ordered, unsigned long long* __restrict__ bodyBest, int relaxed) {
   cg::grid_group grid = cg::this_grid();
   const uint32_t nCon = counters[C_NCON];
@@ -540,10 +542,10 @@ __global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__
         const unsigned long long bid = ((unsigned long long)round << 32) | (c * 2654435761u + 1u);
         const uint32_t a = conB0[c], b = conB1[c];
         if (bodyBest[a] != bid || bodyBest[b] != bid) continue;
-        const uint32_t ma = bodyMask[a], mb = bodyMask[b]; const uint32_t comb = ~ma & ~mb;
-        uint32_t col = 31;
-        if (comb) col = __ffs(comb) - 1; else atomicOr(&counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
-        conColour[c] = col; conDone[c] = 1u; bodyMask[a] = ma | (1u << col); bodyMask[b] = mb | (1u << col);
+        const unsigned long long ma = bodyMask[a], mb = bodyMask[b]; const unsigned long long comb = ~ma & ~mb;
+        uint32_t col = 63;
+        if (comb) col = __ffsll((long long)comb) - 1; else atomicOr(&counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
+        conColour[c] = col; conDone[c] = 1u; bodyMask[a] = ma | (1ull << col); bodyMask[b] = mb | (1ull << col);
         ++won;
       }
       if (won) atomicSub(&counters[C_REMAINING], won);
@@ -565,12 +567,12 @@ __global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__
         const uint32_t a = conB0[c], b = conB1[c];
         if (ld_volatile(&bodyNext[a]) != conPos0[c] || ld_volatile(&bodyNext[b]) != conPos1[c]) continue;
         __threadfence();
-        const uint32_t ma = ld_volatile(&bodyMask[a]), mb = ld_volatile(&bodyMask[b]);
-        const uint32_t comb = ~ma & ~mb;
-        uint32_t col = 31;
-        if (comb) col = __ffs(comb) - 1; else atomicOr(&counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
+        const unsigned long long ma = ld_volatile64(&bodyMask[a]), mb = ld_volatile64(&bodyMask[b]);
+        const unsigned long long comb = ~ma & ~mb;   // first fit over 64 colours = the reference's second 32-colour round for the constraints that overflow the first
+        uint32_t col = 63;
+        if (comb) col = __ffsll((long long)comb) - 1; else atomicOr(&counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
         conColour[c] = col; conDone[c] = 1u;
-        st_volatile(&bodyMask[a], ma | (1u << col)); st_volatile(&bodyMask[b], mb | (1u << col));
+        st_volatile64(&bodyMask[a], ma | (1ull << col)); st_volatile64(&bodyMask[b], mb | (1ull << col));
         __threadfence();
         st_volatile(&bodyNext[a], conPos0[c] + 1); st_volatile(&bodyNext[b], conPos1[c] + 1);
         atomicSub(&counters[C_REMAINING], 1u);
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__
   __syncthreads();
   for (uint32_t c = cb + threadIdx.x; c < ce; c += blockDim.x) {
     uint32_t col;
-    if (conB1[c] == NONE32) { const uint32_t m = bodyMask[conB0[c]]; col = (m ? 32u - __clz(m) : 0u) + conPos0[c]; }
+    if (conB1[c] == NONE32) { const unsigned long long m = bodyMask[conB0[c]]; col = (m ? 64u - __clzll((long long)m) : 0u) + conPos0[c]; }
     else col = conColour[c];
     if (col >= MAX_PARTITIONS) { col = MAX_PARTITIONS - 1; atomicOr(&counters[C_ERROR], (uint32_t)E_PARTITION_OVERFLOW); }
     conColour[c] = col;
@@ -1223,7 +1225,7 @@ static int read_counters(PxbScene* s) {
     }
   }
   if (s->hErr & E_PAIR_OVERFLOW) return fail(PXB_ERR_CAPACITY, "broadphase pair capacity (maxPairs) exceeded");
-  if (s->hErr & (E_COLOUR_OVERFLOW | E_PARTITION_OVERFLOW)) return fail(PXB_ERR_CAPACITY, "more than 32 dynamic colours / 96 partitions needed");
+  if (s->hErr & (E_COLOUR_OVERFLOW | E_PARTITION_OVERFLOW)) return fail(PXB_ERR_CAPACITY, "more than 64 dynamic colours / 160 partitions needed");
   if (s->hErr & E_UNSUPPORTED_PAIR) return fail(PXB_ERR_UNSUPPORTED, "a pair of an unsupported geometry type came into contact range");
   return PXB_OK;
 }
