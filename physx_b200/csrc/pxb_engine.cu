@@ -111,21 +111,23 @@ __device__ __forceinline__ void st_volatile64(unsigned long long* p, unsigned lo
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // a1: tight world AABB of one shape.  Formulas: Gu::computeBounds (geomutils/src/GuBounds.cpp:354-400, plane :210-260).
-__device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d, float* mn, float* mx, const HullArrays* hulls = nullptr) {
-  if (type == PXB_GEOM_CONVEXMESH && hulls) {   // Gu::computeTightBounds (GuBounds.cpp:301-352; PxConvexMeshGeometry defaults to eTIGHT_BOUNDS): rotated vertices, last vertex first
-    const DevHull h = load_hull(*hulls, __float_as_uint(d.x));
-    const m33 b = amfromq(q);
-    v3 lo = V3(0, 0, 0), hi = V3(0, 0, 0);
-    for (uint32_t k = 0; k < h.nVerts; ++k) {
-      const v3 v = h.vert(k == 0 ? h.nVerts - 1 : k - 1);
-      const v3 w = (b.c0 * v.x + b.c1 * v.y) + b.c2 * v.z;
-      if (k == 0) { lo = w; hi = w; } else { lo = vmin(lo, w); hi = vmax(hi, w); }
-    }
-    hi = hi + p; lo = lo + p;
-    const v3 c = (hi + lo) * 0.5f, e = (hi - lo) * 0.5f;
-    mn[0] = c.x - e.x; mn[1] = c.y - e.y; mn[2] = c.z - e.z; mx[0] = c.x + e.x; mx[1] = c.y + e.y; mx[2] = c.z + e.z;
-    return;
+// Gu::computeTightBounds (GuBounds.cpp:301-352; PxConvexMeshGeometry defaults to eTIGHT_BOUNDS): rotated vertices, last vertex first.  Out of line:
+// the bounds kernels of box / sphere scenes keep their register budget.
+__device__ __noinline__ void hull_tight_bounds(const HullArrays* hulls, uint32_t hullIdx, v3 p, q4 q, float* mn, float* mx) {
+  const DevHull h = load_hull(*hulls, hullIdx);
+  const m33 b = amfromq(q);
+  v3 lo = V3(0, 0, 0), hi = V3(0, 0, 0);
+  for (uint32_t k = 0; k < h.nVerts; ++k) {
+    const v3 v = h.vert(k == 0 ? h.nVerts - 1 : k - 1);
+    const v3 w = (b.c0 * v.x + b.c1 * v.y) + b.c2 * v.z;
+    if (k == 0) { lo = w; hi = w; } else { lo = vmin(lo, w); hi = vmax(hi, w); }
   }
+  hi = hi + p; lo = lo + p;
+  const v3 c = (hi + lo) * 0.5f, e = (hi - lo) * 0.5f;
+  mn[0] = c.x - e.x; mn[1] = c.y - e.y; mn[2] = c.z - e.z; mx[0] = c.x + e.x; mx[1] = c.y + e.y; mx[2] = c.z + e.z;
+}
+__device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d, float* mn, float* mx, const HullArrays* hulls = nullptr) {
+  if (hulls && type == PXB_GEOM_CONVEXMESH) { hull_tight_bounds(hulls, __float_as_uint(d.x), p, q, mn, mx); return; }
   v3 e = V3(0, 0, 0); bool plane = false;
   if (type == PXB_GEOM_SPHERE) e = V3(d.x, d.x, d.x);
   else if (type == PXB_GEOM_CAPSULE) { const v3 dd = qbasis0(q) * d.y; e = V3(fabsf(dd.x) + d.x, fabsf(dd.y) + d.x, fabsf(dd.z) + d.x); }
@@ -901,7 +903,8 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
                          CK(cudaFuncSetAttribute(k_env_solve<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); } while (0)
   ENV_ATTR(32); ENV_ATTR(64); ENV_ATTR(128); ENV_ATTR(256);
 #undef ENV_ATTR
-  CK(cudaFuncSetAttribute(k_env_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
+  CK(cudaFuncSetAttribute(k_env_bp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
+  CK(cudaFuncSetAttribute(k_env_bp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sleep_islands, 256, 0)); s->coopBlocksSleep = std::max(1, std::min(occ, 2)) * s->numSMs;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_pgs, 256, 0)); s->coopBlocksSolvePgs = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_tgs, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
@@ -964,7 +967,6 @@ static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
   s->envEligible = false;
   const char* em = getenv("PXB_ENV_MODE");
   if (!usesEnv || s->envDisabled || (em && em[0] == '0')) return;
-  for (auto& r : s->recs) if (r.geomType == PXB_GEOM_CONVEXMESH) return;   // hull bounds are not in k_env_bp yet: scenes with hulls run device-wide
   if (maxEnv >= s->capA) return;   // sparse environment ids: stay on the device-wide path
   std::vector<uint32_t> globals; const uint32_t nEnv = maxEnv + 1;
   std::vector<uint32_t> cnt(nEnv, 0);
@@ -1177,11 +1179,12 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     LAUNCH(k_env_begin, 1, 32, s->counters);
     EnvBpArgs A;
     A.nEnv = s->nEnv; A.maxList = s->envMaxList; A.bitsA = s->bitsA; A.cap = s->capPairs; A.ringMask = s->ringMask; A.externalTight = externalTight ? 1 : 0; A.contactOffset = s->desc.contactOffset;
-    A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight;
+    A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight; A.hulls = hull_arrays(s);
     A.oldKeys = s->pairKeys[prev]; A.oldSlots = s->pairSlots[prev]; A.oldSeg = s->envSeg[prev]; A.newKeys = s->pairKeys[cur]; A.newSlots = s->pairSlots[cur]; A.newSeg = s->envSeg[cur];
     A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions; A.slotColour = s->slotColour;
     const size_t smem = (size_t)ENV_BP_WARPS * (s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t)) + ENV_BP_STAGE * sizeof(uint64_t));
-    k_env_bp<<<cdiv(s->nEnv, ENV_BP_WARPS), 32 * ENV_BP_WARPS, smem, st>>>(A); s->launches++;
+    if (s->anyConvex) k_env_bp<true><<<cdiv(s->nEnv, ENV_BP_WARPS), 32 * ENV_BP_WARPS, smem, st>>>(A); else k_env_bp<false><<<cdiv(s->nEnv, ENV_BP_WARPS), 32 * ENV_BP_WARPS, smem, st>>>(A);
+    s->launches++;
     LAUNCH(k_clamp_count, 1, 32, s->counters, s->capPairs, s->nPairsDev + cur);
     return PXB_OK;
   }

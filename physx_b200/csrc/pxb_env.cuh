@@ -23,7 +23,7 @@
 struct EnvBpArgs {
   uint32_t nEnv, maxList, bitsA, cap, ringMask; int externalTight; float contactOffset;
   const uint32_t *envStart, *envList;
-  const float4 *pos, *quat, *dims; const uint32_t *geomFlags, *envId; float* tight;
+  const float4 *pos, *quat, *dims; const uint32_t *geomFlags, *envId; float* tight; HullArrays hulls;
   const uint64_t* oldKeys; const uint32_t* oldSlots; const uint2* oldSeg;
   uint64_t* newKeys; uint32_t* newSlots; uint2* newSeg;
   uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions;
@@ -39,6 +39,7 @@ __device__ __forceinline__ bool env_bp_test(const float4& amin, const float4& am
   return !sep & (((__float_as_uint(amax.w) | __float_as_uint(bmax.w)) & 0x100u) != 0);
 }
 
+template <bool HULLS>   // HULLS: the scene holds convex meshes (the plain instantiation carries no hull-bounds code)
 __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A) {
   extern __shared__ float4 envBpSmem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
     if (A.externalTight) { for (int c = 0; c < 3; ++c) { mn[c] = A.tight[a * 6 + c]; mx[c] = A.tight[a * 6 + 3 + c]; } }
     else {
       const float4 p4 = A.pos[a];
-      tight_bounds(gf & 0xff, V3(p4.x, p4.y, p4.z), Q4(A.quat[a]), A.dims[a], mn, mx);
+      tight_bounds(gf & 0xff, V3(p4.x, p4.y, p4.z), Q4(A.quat[a]), A.dims[a], mn, mx, HULLS ? &A.hulls : nullptr);
       if (env == e || e == 0) for (int c = 0; c < 3; ++c) { A.tight[a * 6 + c] = mn[c]; A.tight[a * 6 + 3 + c] = mx[c]; }
     }
     const float co = A.contactOffset;

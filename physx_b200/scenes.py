@@ -630,3 +630,28 @@ def hull_pile(n=10, n_hulls=3, seed=31, kinds=("convex",), spread=0.35, cook=Non
             set_capsule(a, i, rng.uniform(0.08, 0.15), rng.uniform(0.1, 0.3))
     sc = Scene(default_header(**hdr), add_ground_plane(a), hulls)
     return cook(sc) if cook else sc
+
+
+def env_hulls(n_envs=6, per_env=7, seed=8, env_pitch=6.0, **hdr):
+    """Environments that each hold a small heap of library hulls, spheres, capsules and boxes (environment ids set, shared ground plane):
+    every pair type of a10 on the environment path."""
+    rng = np.random.RandomState(seed)
+    clouds, cooked, unit_mass, unit_inertia = load_hull_library()
+    a = _new_actors(n_envs * per_env)
+    for e in range(n_envs):
+        ex, ez = (e % 3) * env_pitch, (e // 3) * env_pitch
+        for k in range(per_env):
+            i = e * per_env + k
+            kind = (e + k) % 4
+            if kind in (0, 2):
+                hi = int(rng.randint(0, len(clouds)))
+                set_convex(a, i, hi)
+                a["mass"][i] = np.float32(10.0) * unit_mass[hi]; a["inertia"][i] = np.float32(10.0) * unit_inertia[hi]
+            elif kind == 1:
+                set_sphere(a, i, rng.uniform(0.1, 0.18))
+            else:
+                set_capsule(a, i, rng.uniform(0.07, 0.12), rng.uniform(0.1, 0.25)) if k % 2 else set_box(a, np.array([i]), np.array([0.15, 0.12, 0.2], dtype=np.float32))
+            a["pos"][i] = (ex + rng.uniform(-0.25, 0.25), 0.4 + 0.45 * k, ez + rng.uniform(-0.25, 0.25))
+            a["envId"][i] = e
+    a["quat"] = random_unit_quats(rng, len(a))
+    return Scene(default_header(**hdr), add_ground_plane(a), clouds, cooked)

@@ -206,7 +206,8 @@ def _env_scenes():
             "envs_37x3x5": (scenes.env_grid_stacks(n_envs=37, stacks_per_env=3, height=5, jitter=0.02), 40),
             "ragged": (scenes.env_ragged(), 150),
             "wide_200_bodies": (scenes.env_grid_stacks(n_envs=3, stacks_per_env=25, height=8, jitter=0.01), 25),   # 200 constraints per env: 256-thread CTAs
-            "piles_100": (scenes.env_piles(), 40)}   # ~300 constraints / ~650 pairs per env: rows and lists through global scratch
+            "piles_100": (scenes.env_piles(), 40),   # ~300 constraints / ~650 pairs per env: rows and lists through global scratch
+            "env_hulls": (scenes.env_hulls(), 120)}  # library hulls + spheres + capsules + boxes per environment: hull bounds in k_env_bp, every a10 pair type
 
 
 @pytest.mark.parametrize("name", list(_env_scenes()))
