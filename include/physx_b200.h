@@ -99,7 +99,9 @@ PXB_API int  pxb_device_count(void);
  *      receives Gu::ConvexHullData cooked on the host, S/gpunarrowphase/include/PxgConvexConvexShape.h:50-65, S/geomutils/src/convex/GuConvexMeshData.h:47-175).
  *      `cooked` = nHulls records, each: PxbCookedHullHeader, float verts[nVerts][3], PxbCookedPoly polys[nPolys],
  *      uint8_t vertexRefs[nIdx] (getVertexData8, padded to 4 bytes), uint8_t facesByEdges[2 * nEdges] (getFacesByEdges8, padded to 4 bytes).
- *      Call once, before adding the actors whose PxbActorRec::hullIdx refer to it.  Supported hull pairs so far: plane-convex. ---- */
+ *      Call once, before adding the actors whose PxbActorRec::hullIdx refer to it.  Hulls of at most 32 vertices (the reference's brute-force
+ *      support mapping; larger hulls use its hill-climbing data, not built yet -> PXB_ERR_UNSUPPORTED), identity mesh scale.  Every hull pair type
+ *      is supported: plane / sphere / capsule / box / hull vs hull. ---- */
 typedef struct {
   uint32_t nVerts, nPolys, nEdges, nIdx;
   float centerOfMass[3];
