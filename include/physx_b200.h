@@ -99,9 +99,12 @@ PXB_API int  pxb_device_count(void);
  *      receives Gu::ConvexHullData cooked on the host, S/gpunarrowphase/include/PxgConvexConvexShape.h:50-65, S/geomutils/src/convex/GuConvexMeshData.h:47-175).
  *      `cooked` = nHulls records, each: PxbCookedHullHeader, float verts[nVerts][3], PxbCookedPoly polys[nPolys],
  *      uint8_t vertexRefs[nIdx] (getVertexData8, padded to 4 bytes), uint8_t facesByEdges[2 * nEdges] (getFacesByEdges8, padded to 4 bytes).
- *      Call once, before adding the actors whose PxbActorRec::hullIdx refer to it.  Hulls of at most 32 vertices (the reference's brute-force
- *      support mapping; larger hulls use its hill-climbing data, not built yet -> PXB_ERR_UNSUPPORTED), identity mesh scale.  Every hull pair type
- *      is supported: plane / sphere / capsule / box / hull vs hull. ---- */
+ *      A hull of more than 32 vertices also carries its hill-climbing data (Gu::BigConvexRawData, S/geomutils/src/convex/GuBigConvexData.h:54-75):
+ *      PxbCookedHullHeader::reserved[0] = mSubdiv | mNbAdjVerts << 16 (0 = none), and after facesByEdges: uint8_t samples[6 * subdiv^2] (padded
+ *      to 4), uint16_t valencies[nVerts][2] ({mCount, mOffset}), uint8_t adjacentVerts[nAdj] (padded to 4).
+ *      Call once, before adding the actors whose PxbActorRec::hullIdx refer to it.  Limits: the reference's GPU-compatible hulls -- at most 64
+ *      vertices and 64 polygons (include/cooking/PxConvexMeshDesc.h:139), at most 32 vertices per polygon; larger -> PXB_ERR_UNSUPPORTED.
+ *      Identity mesh scale.  Every hull pair type is supported: plane / sphere / capsule / box / hull vs hull. ---- */
 typedef struct {
   uint32_t nVerts, nPolys, nEdges, nIdx;
   float centerOfMass[3];

@@ -37,9 +37,55 @@ typedef struct PxoHull_ {
   const PxbCookedPoly* polys;      /* plane, vref, nbVerts, minIndex */
   const uint8_t* vertexRefs;       /* getVertexData8 */
   const uint8_t* facesByEdges;     /* getFacesByEdges8 */
+  /* Gu::BigConvexRawData (GuBigConvexData.h:54-75): only hulls of more than 32 vertices carry it; bigSubdiv == 0 otherwise */
+  uint32_t bigSubdiv; const uint8_t* samples; const uint16_t* valencies; const uint8_t* adjacentVerts;
 } PxoHull;
 static inline v3 pxo_hull_vert(const PxoHull* h, uint32_t i) { return V3(h->verts[i * 3], h->verts[i * 3 + 1], h->verts[i * 3 + 2]); }
 static inline v3 pxo_hull_plane_n(const PxoHull* h, uint32_t p) { return V3(h->polys[p].plane[0], h->polys[p].plane[1], h->polys[p].plane[2]); }
+
+/* ComputeCubemapNearestOffset + CubemapLookup, GuCubeIndex.h:101-150: the cube-map texel a direction falls into */
+static inline uint32_t pxo_cubemap_nearest_offset(v3 dir, uint32_t subdiv) {
+  const float d[3] = { dir.x, dir.y, dir.z };
+  const float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);   /* the reference compares the sign-stripped bit patterns: the same order for finite floats */
+  uint32_t i1 = 0, i2 = 1, i3 = 2;
+  if ((ay > ax) & (ay > az)) { i2 = 2; i3 = 0; i1 = 1; }
+  else if (az > ax) { i2 = 0; i3 = 1; i1 = 2; }
+  const float c = 1.0f / fabsf(d[i1]);
+  float u = d[i2] * c, v = d[i3] * c;
+  uint32_t bits; memcpy(&bits, &d[i1], 4);
+  const uint32_t ci = (bits >> 31) | (i1 + i1);
+  const float coeff = 0.5f * (float)(subdiv - 1);
+  u += 1.0f; u *= coeff; v += 1.0f; v *= coeff;
+  return ci * (subdiv * subdiv) + (uint32_t)(u + 0.5f) * subdiv + (uint32_t)(v + 0.5f);
+}
+/* ConvexHullV::hillClimbing GuVecConvexHull.h:321-375: start at the cube-map sample, walk to a better neighbour until none improves.
+ * A neighbour is taken once only (the visited bits), and the start vertex is not marked -- both as in the reference. */
+static inline uint32_t pxo_hull_hill_climb(const PxoHull* h, v3 dir) {
+  uint32_t visited[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  uint32_t index = h->samples[pxo_cubemap_nearest_offset(dir, h->bigSubdiv)];
+  float mx = adot(pxo_hull_vert(h, index), dir);
+  uint32_t initialIndex;
+  do {
+    initialIndex = index;
+    const uint32_t numNeighbours = h->valencies[2 * index], offset = h->valencies[2 * index + 1];
+    for (uint32_t a = 0; a < numNeighbours; ++a) {
+      const uint32_t nb = h->adjacentVerts[offset + a];
+      const float dist = adot(pxo_hull_vert(h, nb), dir);
+      if (dist > mx) {
+        const uint32_t ind = nb >> 5, mask = 1u << (nb & 31);
+        if ((visited[ind] & mask) == 0) { visited[ind] |= mask; mx = dist; index = nb; }
+      }
+    }
+  } while (index != initialIndex);
+  return index;
+}
+/* ConvexHullV::supportVertexIndex GuVecConvexHull.h:399-406: hill climbing when the hull has the data, else bruteForceSearch :377-397 */
+static inline uint32_t pxo_hull_support_index(const PxoHull* h, v3 dir) {
+  if (h->bigSubdiv) return pxo_hull_hill_climb(h, dir);
+  float mx = v3dot(pxo_hull_vert(h, 0), dir); uint32_t mi = 0;
+  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(pxo_hull_vert(h, i), dir); if (d > mx) { mx = d; mi = i; } }
+  return mi;
+}
 
 typedef struct { v3 normal, closestA, closestB, searchDir; float penDep; } PxoGjkOutput;
 
@@ -74,10 +120,9 @@ static inline v3 pxo_cvx_support(const PxoConvex* c, v3 dir, int* index) {
   return amxftransform(&c->aToB, p);
 }
 static inline v3 pxo_cvx_support_local(const PxoConvex* c, v3 dir, int* index) {
-  if (c->type == PXO_CVX_HULL) {   /* ConvexHullV::bruteForceSearch GuVecConvexHull.h:377-397 (hulls of <= 32 vertices carry no hill-climbing data) */
+  if (c->type == PXO_CVX_HULL) {   /* ConvexHullNoScaleV::supportLocal GuVecConvexHullNoScale.h:91-102 */
     const PxoHull* h = c->hull;
-    float mx = v3dot(pxo_hull_vert(h, 0), dir); uint32_t mi = 0;
-    for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(pxo_hull_vert(h, i), dir); if (d > mx) { mx = d; mi = i; } }
+    const uint32_t mi = pxo_hull_support_index(h, dir);
     *index = (int)mi;
     return pxo_hull_vert(h, mi);
   }
@@ -1115,10 +1160,15 @@ static inline void pxo_pcm_sphere_convex(const xf* transf0, const xf* transf1, f
 
 
 /* ---------------- capsule vs convex hull: GuPCMContactCapsuleConvex.cpp:42-262, GuPCMContactGenSphereCapsule.cpp:154-468, GuPCMContactGenUtil.cpp:105-260 ---------------- */
-/* ConvexHullNoScaleV::bruteForceSearchMinMax GuVecConvexHull.h:410-429 (SupportLocalImpl::doSupport) */
+/* ConvexHullNoScaleV::bruteForceSearchMinMax GuVecConvexHullNoScale.h:116-136 (SupportLocalImpl::doSupport) */
 static inline void pxo_hull_support_minmax(const PxoHull* h, v3 dir, float* mn, float* mx) {
-  float _max = v3dot(pxo_hull_vert(h, 0), dir), _min = _max;
-  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(pxo_hull_vert(h, i), dir); _max = d > _max ? d : _max; _min = d < _min ? d : _min; }   /* PxMax / PxMin */
+  if (h->bigSubdiv) {   /* ConvexHullNoScaleV::supportVertexMinMax GuVecConvexHullNoScale.h:139-155: two hill climbs */
+    const uint32_t maxIndex = pxo_hull_hill_climb(h, dir), minIndex = pxo_hull_hill_climb(h, v3neg(dir));
+    *mn = adot(dir, pxo_hull_vert(h, minIndex)); *mx = adot(dir, pxo_hull_vert(h, maxIndex));
+    return;
+  }
+  float _max = adot(pxo_hull_vert(h, 0), dir), _min = _max;
+  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = adot(pxo_hull_vert(h, i), dir); _max = d > _max ? d : _max; _min = d < _min ? d : _min; }   /* FMax / FMin */
   *mn = _min; *mx = _max;
 }
 /* testSATCapsulePoly :154-219 */
@@ -1305,9 +1355,7 @@ static inline void pxo_poly_support_minmax(const PxoHull* h, int isBox, v3 dir, 
 }
 static inline v3 pxo_poly_support(const PxoHull* h, int isBox, v3 dir) {
   if (isBox) { const v3 e = h->internalExtents; return V3(dir.x > 0.f ? e.x : -e.x, dir.y > 0.f ? e.y : -e.y, dir.z > 0.f ? e.z : -e.z); }
-  float mx = v3dot(pxo_hull_vert(h, 0), dir); uint32_t mi = 0;
-  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(pxo_hull_vert(h, i), dir); if (d > mx) { mx = d; mi = i; } }
-  return pxo_hull_vert(h, mi);
+  return pxo_hull_vert(h, pxo_hull_support_index(h, dir));
 }
 typedef struct { const PxoHull* h; int isBox; v3 center; float internalRadius; v3 internalExtents; } PxoPolyData;   /* PolygonalData: mCenter, mInternal */
 static inline PxoPolyData pxo_poly_data(const PxoHull* h, int isBox) {

@@ -42,6 +42,7 @@
 #undef protected
 #include "scene_format.h"
 #include "GuConvexMesh.h"
+#include "GuBigConvexData.h"
 
 using namespace physx;
 
@@ -174,6 +175,8 @@ int main(int argc, char** argv) {
       ch.nIdx = nIdx;
       memcpy(ch.centerOfMass, &hd.mCenterOfMass, 12); memcpy(ch.boundsCenter, &hd.mAABB.mCenter, 12); memcpy(ch.boundsExtents, &hd.mAABB.mExtents, 12);
       ch.internalRadius = hd.mInternal.mInternalRadius; memcpy(ch.internalExtents, &hd.mInternal.mInternalExtents, 12);
+      const Gu::BigConvexRawData* big = hd.mBigConvexRawData;   // hill-climbing data: only hulls of more than 32 vertices carry it
+      if (big) ch.reserved[0] = PxU32(big->mSubdiv) | (big->mNbAdjVerts << 16);
       PxReal mass; PxMat33 inertia; PxVec3 com; h.mesh->getMassInformation(mass, inertia, com);
       ch.unitMass = mass; ch.unitInertiaDiag[0] = inertia.column0.x; ch.unitInertiaDiag[1] = inertia.column1.y; ch.unitInertiaDiag[2] = inertia.column2.z; memcpy(ch.unitCom, &com, 12);
       fwrite(&ch, sizeof(ch), 1, f);
@@ -187,6 +190,12 @@ int main(int argc, char** argv) {
       const uint8_t zero[4] = {0, 0, 0, 0};
       fwrite(hd.getVertexData8(), 1, nIdx, f); fwrite(zero, 1, (4 - nIdx % 4) % 4, f);
       fwrite(hd.getFacesByEdges8(), 1, 2 * ch.nEdges, f); fwrite(zero, 1, (4 - (2 * ch.nEdges) % 4) % 4, f);
+      if (big) {
+        const uint32_t ns = 6u * big->mSubdiv * big->mSubdiv;   // mSamples: one vertex index per cube-map texel
+        fwrite(big->mSamples, 1, ns, f); fwrite(zero, 1, (4 - ns % 4) % 4, f);
+        fwrite(big->mValencies, 4, ch.nVerts, f);               // Gu::Valency {u16 mCount, u16 mOffset}
+        fwrite(big->mAdjacentVerts, 1, big->mNbAdjVerts, f); fwrite(zero, 1, (4 - big->mNbAdjVerts % 4) % 4, f);
+      }
     }
     fclose(f);
     return 0;

@@ -60,7 +60,10 @@ typedef struct {
 
 #define PXB_COOKED_MAGIC 0x43485850u /* "PXHC" */
 /* followed by: float verts[nVerts][3]; PxbCookedPoly polys[nPolys]; uint8_t vertexRefs[nIdx] (padded to 4);
- * uint8_t facesByEdges[2 * nEdges] (padded to 4)   -- Gu::ConvexHullData, physx/source/geomutils/src/convex/GuConvexMeshData.h:47-175 */
+ * uint8_t facesByEdges[2 * nEdges] (padded to 4)   -- Gu::ConvexHullData, physx/source/geomutils/src/convex/GuConvexMeshData.h:47-175;
+ * and, when reserved[0] != 0 (hulls of more than 32 vertices; subdiv = reserved[0] & 0xffff, nAdj = reserved[0] >> 16), the hill-climbing
+ * data Gu::BigConvexRawData (GuBigConvexData.h:54-75): uint8_t samples[6 * subdiv^2] (padded to 4); uint16_t valencies[nVerts][2]
+ * ({mCount, mOffset}); uint8_t adjacentVerts[nAdj] (padded to 4) */
 typedef struct {
   uint32_t nVerts, nPolys, nEdges, nIdx;
   float centerOfMass[3];          /* mCenterOfMass */

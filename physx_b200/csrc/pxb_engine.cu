@@ -1069,23 +1069,36 @@ PXB_API int pxb_scene_set_convex_meshes(PxbScene* s, const void* cooked, size_t 
     PxbCookedHullHeader ch; memcpy(&ch, q, sizeof(ch)); q += sizeof(ch);
     const size_t need = (size_t)ch.nVerts * 12 + (size_t)ch.nPolys * sizeof(PxbCookedPoly) + (ch.nIdx + 3) / 4 * 4 + (2 * (size_t)ch.nEdges + 3) / 4 * 4;
     if (q + need > end || ch.nVerts > 255 || ch.nPolys > 255) return fail(PXB_ERR_INVALID, "cooked hull data truncated or out of range");
-    if (ch.nVerts > 32) return fail(PXB_ERR_UNSUPPORTED, "hulls of more than 32 vertices use the reference's hill-climbing support (BigConvexData), which is not built yet");
+    // the reference's GPU pipeline takes hulls of <= 64 vertices and <= 64 polygons (PxConvexMeshDesc.h:139, cooking with buildGPUData); larger ones fall back to its CPU narrowphase
+    if (ch.nVerts > 64 || ch.nPolys > 64) return fail(PXB_ERR_UNSUPPORTED, "convex hulls are limited to 64 vertices and 64 polygons (the reference's GPU-compatible limit)");
+    const uint32_t bigSubdiv = ch.reserved[0] & 0xffffu, bigAdj = ch.reserved[0] >> 16;   // Gu::BigConvexRawData: hulls of more than 32 vertices
+    const size_t bigBytes = bigSubdiv ? (6 * (size_t)bigSubdiv * bigSubdiv + 3) / 4 * 4 + (size_t)ch.nVerts * 4 + (bigAdj + 3) / 4 * 4 : 0;
+    if (q + need + bigBytes > end) return fail(PXB_ERR_INVALID, "cooked hull data truncated");
+    if (ch.nVerts > 32 && !bigSubdiv) return fail(PXB_ERR_INVALID, "a hull of more than 32 vertices needs its hill-climbing data (Gu::BigConvexRawData)");
     meta.push_back(make_uint4((uint32_t)verts.size(), (uint32_t)(polys.size() / 2), (uint32_t)refs.size(), (uint32_t)edges.size()));
     meta.push_back(make_uint4(ch.nVerts, ch.nPolys, ch.nEdges, ch.nIdx));
     uint4 m2; memcpy(&m2.x, &ch.internalExtents[0], 4); memcpy(&m2.y, &ch.internalExtents[1], 4); memcpy(&m2.z, &ch.internalExtents[2], 4); memcpy(&m2.w, &ch.internalRadius, 4);
     meta.push_back(m2);
-    uint4 m3; memcpy(&m3.x, &ch.centerOfMass[0], 4); memcpy(&m3.y, &ch.centerOfMass[1], 4); memcpy(&m3.z, &ch.centerOfMass[2], 4); m3.w = 0; meta.push_back(m3);
+    uint4 m3; memcpy(&m3.x, &ch.centerOfMass[0], 4); memcpy(&m3.y, &ch.centerOfMass[1], 4); memcpy(&m3.z, &ch.centerOfMass[2], 4); m3.w = bigSubdiv; meta.push_back(m3);
     s->hullDiam.push_back(2.f * (std::sqrt(ch.boundsCenter[0] * ch.boundsCenter[0] + ch.boundsCenter[1] * ch.boundsCenter[1] + ch.boundsCenter[2] * ch.boundsCenter[2]) +
                                  std::sqrt(ch.boundsExtents[0] * ch.boundsExtents[0] + ch.boundsExtents[1] * ch.boundsExtents[1] + ch.boundsExtents[2] * ch.boundsExtents[2])));
     const float* v = (const float*)q; for (uint32_t i = 0; i < ch.nVerts; ++i) verts.push_back(make_float4(v[i * 3], v[i * 3 + 1], v[i * 3 + 2], 0.f));
     q += (size_t)ch.nVerts * 12;
     for (uint32_t p = 0; p < ch.nPolys; ++p) {
       PxbCookedPoly cp; memcpy(&cp, q, sizeof(cp)); q += sizeof(cp);
+      if (cp.nbVerts < 3 || cp.nbVerts > 32 || cp.vref + cp.nbVerts > ch.nIdx) return fail(PXB_ERR_INVALID, "hull polygon out of range (3..32 vertices per polygon)");
       polys.push_back(make_float4(cp.plane[0], cp.plane[1], cp.plane[2], cp.plane[3]));
       float4 m; memcpy(&m.x, &cp.vref, 4); memcpy(&m.y, &cp.nbVerts, 4); memcpy(&m.z, &cp.minIndex, 4); m.w = 0.f; polys.push_back(m);
     }
     refs.insert(refs.end(), q, q + ch.nIdx); q += (ch.nIdx + 3) / 4 * 4;
-    edges.insert(edges.end(), q, q + 2 * (size_t)ch.nEdges); q += (2 * (size_t)ch.nEdges + 3) / 4 * 4;
+    edges.insert(edges.end(), q, q + (2 * (size_t)ch.nEdges + 3) / 4 * 4); q += (2 * (size_t)ch.nEdges + 3) / 4 * 4;   // padded: every hull starts 4-byte aligned
+    if (bigSubdiv) {   // samples | valencies | adjacent vertices, as they lie in the cooked section (load_hull / gjk_hull_hill_climb)
+      const uint8_t* val = q + (6 * (size_t)bigSubdiv * bigSubdiv + 3) / 4 * 4; const uint8_t* adj = val + (size_t)ch.nVerts * 4;
+      for (uint32_t i = 0; i < 6 * bigSubdiv * bigSubdiv; ++i) if (q[i] >= ch.nVerts) return fail(PXB_ERR_INVALID, "hill-climbing sample out of range");
+      for (uint32_t i = 0; i < ch.nVerts; ++i) { uint16_t v2[2]; memcpy(v2, val + 4 * i, 4); if ((uint32_t)v2[0] + v2[1] > bigAdj) return fail(PXB_ERR_INVALID, "hill-climbing valency out of range"); }
+      for (uint32_t i = 0; i < bigAdj; ++i) if (adj[i] >= ch.nVerts) return fail(PXB_ERR_INVALID, "hill-climbing neighbour out of range");
+      edges.insert(edges.end(), q, q + bigBytes); q += bigBytes;
+    }
   }
   if (!nHulls) { s->hullDiam.clear(); return PXB_OK; }
   CK(dalloc(s->hullMeta, meta.size())); CK(dalloc(s->hullVerts, verts.size())); CK(dalloc(s->hullPolys, polys.size())); CK(dalloc(s->hullRefs, refs.size() + 4)); CK(dalloc(s->hullEdges, edges.size() + 4));

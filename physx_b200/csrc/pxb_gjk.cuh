@@ -35,6 +35,7 @@ struct HullArrays { const uint4* meta; const float4* verts; const float4* polys;
 struct DevHull {
   uint32_t nVerts, nPolys, nEdges; v3 internalExtents, centerOfMass; float internalRadius;
   const float4* verts; const float4* polys; const uint8_t* vertexRefs; const uint8_t* facesByEdges;
+  uint32_t bigSubdiv; const uint8_t* big;   // Gu::BigConvexRawData of hulls with more than 32 vertices: samples[6 * subdiv^2] | u16 valencies[nVerts][2] | adjacentVerts (bigSubdiv == 0: none)
   PXB_D v3 vert(uint32_t i) const { return V3(verts[i]); }
   PXB_D v3 plane_n(uint32_t p) const { return V3(polys[2 * p]); }
   PXB_D float plane_d(uint32_t p) const { return polys[2 * p].w; }
@@ -45,7 +46,51 @@ PXB_D DevHull load_hull(const HullArrays& H, uint32_t hullIdx) {
   DevHull h; h.nVerts = m1.x; h.nPolys = m1.y; h.nEdges = m1.z;
   h.internalExtents = V3(__uint_as_float(m2.x), __uint_as_float(m2.y), __uint_as_float(m2.z)); h.centerOfMass = V3(__uint_as_float(m3.x), __uint_as_float(m3.y), __uint_as_float(m3.z)); h.internalRadius = __uint_as_float(m2.w);
   h.verts = H.verts + m0.x; h.polys = H.polys + 2 * m0.y; h.vertexRefs = H.refs + m0.z; h.facesByEdges = H.edges + m0.w;
+  h.bigSubdiv = m3.w; h.big = h.facesByEdges + ((2 * m1.z + 3) & ~3u);   // the hill-climbing data follows the hull's edge bytes (4-byte aligned)
   return h;
+}
+/* ComputeCubemapNearestOffset + CubemapLookup, GuCubeIndex.h:101-150: the cube-map texel a direction falls into */
+PXB_D uint32_t gjk_cubemap_nearest_offset(v3 dir, uint32_t subdiv) {
+  const float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);   // the reference compares the sign-stripped bit patterns: the same order for finite floats
+  float d1 = dir.x, d2 = dir.y, d3 = dir.z; uint32_t i1 = 0;
+  if ((ay > ax) & (ay > az)) { d1 = dir.y; d2 = dir.z; d3 = dir.x; i1 = 1; }
+  else if (az > ax) { d1 = dir.z; d2 = dir.x; d3 = dir.y; i1 = 2; }
+  const float c = __fdiv_rn(1.0f, fabsf(d1));
+  float u = __fmul_rn(d2, c), v = __fmul_rn(d3, c);
+  const uint32_t ci = (__float_as_uint(d1) >> 31) | (i1 + i1);
+  const float coeff = __fmul_rn(0.5f, (float)(subdiv - 1));
+  u = __fmul_rn(__fadd_rn(u, 1.0f), coeff); v = __fmul_rn(__fadd_rn(v, 1.0f), coeff);
+  return ci * (subdiv * subdiv) + (uint32_t)__fadd_rn(u, 0.5f) * subdiv + (uint32_t)__fadd_rn(v, 0.5f);
+}
+/* ConvexHullV::hillClimbing GuVecConvexHull.h:321-375: start at the cube-map sample, walk to a better neighbour until none improves.
+ * A neighbour is taken once only (the visited bits; <= 64 vertices on the GPU, PxConvexMeshDesc.h:139), and the start vertex is not marked -- both as in the reference. */
+PXB_D uint32_t gjk_hull_hill_climb(const DevHull* h, v3 dir) {
+  unsigned long long visited = 0ull;
+  const uint16_t* valencies = (const uint16_t*)(h->big + ((6u * h->bigSubdiv * h->bigSubdiv + 3u) & ~3u));
+  const uint8_t* adjacentVerts = (const uint8_t*)(valencies + 2 * h->nVerts);
+  uint32_t index = h->big[gjk_cubemap_nearest_offset(dir, h->bigSubdiv)];
+  float mx = adot(h->vert(index), dir);
+  uint32_t initialIndex;
+  do {
+    initialIndex = index;
+    const uint32_t numNeighbours = valencies[2 * index], offset = valencies[2 * index + 1];
+    for (uint32_t a = 0; a < numNeighbours; ++a) {
+      const uint32_t nb = adjacentVerts[offset + a];
+      const float dist = adot(h->vert(nb), dir);
+      if (dist > mx) {
+        const unsigned long long mask = 1ull << nb;
+        if ((visited & mask) == 0ull) { visited |= mask; mx = dist; index = nb; }
+      }
+    }
+  } while (index != initialIndex);
+  return index;
+}
+/* ConvexHullV::supportVertexIndex GuVecConvexHull.h:399-406: hill climbing when the hull has the data, else bruteForceSearch :377-397 */
+PXB_D uint32_t gjk_hull_support_index(const DevHull* h, v3 dir) {
+  if (h->bigSubdiv) return gjk_hull_hill_climb(h, dir);
+  float mx = v3dot(h->vert(0), dir); uint32_t mi = 0;
+  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(h->vert(i), dir); if (d > mx) { mx = d; mi = i; } }
+  return mi;
 }
 
 enum { GJK_CVX_CAPSULE = 0, GJK_CVX_BOX = 1, GJK_CVX_HULL = 2 };
@@ -96,10 +141,9 @@ PXB_D v3 gjk_cvx_support(const GjkConvex* c, v3 dir, int* index) {
   return amxftransform(&c->aToB, p);
 }
 PXB_D v3 gjk_cvx_support_local(const GjkConvex* c, v3 dir, int* index) {
-  if (c->type == GJK_CVX_HULL) {   /* ConvexHullV::bruteForceSearch GuVecConvexHull.h:377-397 (hulls of <= 32 vertices carry no hill-climbing data) */
+  if (c->type == GJK_CVX_HULL) {   /* ConvexHullNoScaleV::supportLocal GuVecConvexHullNoScale.h:91-102 */
     const DevHull* h = c->hull;
-    float mx = v3dot(h->vert(0), dir); uint32_t mi = 0;
-    for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(h->vert(i), dir); if (d > mx) { mx = d; mi = i; } }
+    const uint32_t mi = gjk_hull_support_index(h, dir);
     *index = (int)mi;
     return h->vert(mi);
   }
@@ -1138,10 +1182,15 @@ PXB_D void gjk_pcm_sphere_convex(const xf* transf0, const xf* transf1, float sph
 
 
 /* ---------------- capsule vs convex hull: GuPCMContactCapsuleConvex.cpp:42-262, GuPCMContactGenSphereCapsule.cpp:154-468, GuPCMContactGenUtil.cpp:105-260 ---------------- */
-/* ConvexHullNoScaleV::bruteForceSearchMinMax GuVecConvexHull.h:410-429 (SupportLocalImpl::doSupport) */
+/* ConvexHullNoScaleV::bruteForceSearchMinMax GuVecConvexHullNoScale.h:116-136 (SupportLocalImpl::doSupport) */
 PXB_D void gjk_hull_support_minmax(const DevHull* h, v3 dir, float* mn, float* mx) {
-  float _max = v3dot(h->vert(0), dir), _min = _max;
-  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(h->vert(i), dir); _max = d > _max ? d : _max; _min = d < _min ? d : _min; }   /* PxMax / PxMin */
+  if (h->bigSubdiv) {   /* ConvexHullNoScaleV::supportVertexMinMax GuVecConvexHullNoScale.h:139-155: two hill climbs */
+    const uint32_t maxIndex = gjk_hull_hill_climb(h, dir), minIndex = gjk_hull_hill_climb(h, v3neg(dir));
+    *mn = adot(dir, h->vert(minIndex)); *mx = adot(dir, h->vert(maxIndex));
+    return;
+  }
+  float _max = adot(h->vert(0), dir), _min = _max;
+  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = adot(h->vert(i), dir); _max = d > _max ? d : _max; _min = d < _min ? d : _min; }   /* FMax / FMin */
   *mn = _min; *mx = _max;
 }
 /* testSATCapsulePoly :154-219 */
@@ -1200,7 +1249,7 @@ PXB_D int gjk_hull_polygon_index(const DevHull* h, v3 normal) {
 }
 /* getWitnessPolygonIndex GuPCMContactGenUtil.cpp:204-260 */
 PXB_D int gjk_hull_witness_polygon_index(const DevHull* h, v3 normal, v3 closest, float tolerance) {
-  float pd[64];   // hulls of <= 32 vertices have <= 60 polygons (pxb_scene_set_convex_meshes enforces the vertex limit)
+  float pd[64];   // GPU-compatible hulls have <= 64 polygons (pxb_scene_set_convex_meshes enforces the limit)
   const float eps = -tolerance;
   float dist = v3dot(closest, h->plane_n(0)) + h->plane_d(0);
   float minDist = dist >= eps ? fabsf(dist) : FLT_MAX;
@@ -1324,7 +1373,7 @@ PXB_D bool gjk_poly_contains_n(const v3* verts, int numVerts, v3 p, v3 mn, v3 mx
   return inter > 0;
 }
 /* ---------------- SAT branch of generateFullContactManifold: GuPCMContactGenBoxConvex.cpp:56-328, :537-603 (PCM_USE_INTERNAL_OBJECT = 1) ---------------- */
-#define GJK_SAT_MAX_AXES 96   // per-thread; a hull of <= 32 vertices has <= 90 edges (the reference's SEP_AXIS_FIXED_MEMORY is 256)
+#define GJK_SAT_MAX_AXES 128   // per-thread; a GPU-compatible hull (<= 64 vertices, <= 64 polygons) has <= 126 edges (the reference's SEP_AXIS_FIXED_MEMORY is 256)
 /* SupportLocalImpl::doSupport(dir, min, max) / doSupport(dir): hull = brute force (GuVecConvexHull.h:377-429), box = sign select (GuVecBox.h:165-177) */
 PXB_D void gjk_poly_support_minmax(const DevHull* h, int isBox, v3 dir, float* mn, float* mx) {
   if (isBox) { const v3 e = h->internalExtents; const v3 pt = V3(dir.x > 0.f ? e.x : -e.x, dir.y > 0.f ? e.y : -e.y, dir.z > 0.f ? e.z : -e.z); *mx = adot(dir, pt); *mn = -*mx; return; }
@@ -1332,9 +1381,7 @@ PXB_D void gjk_poly_support_minmax(const DevHull* h, int isBox, v3 dir, float* m
 }
 PXB_D v3 gjk_poly_support(const DevHull* h, int isBox, v3 dir) {
   if (isBox) { const v3 e = h->internalExtents; return V3(dir.x > 0.f ? e.x : -e.x, dir.y > 0.f ? e.y : -e.y, dir.z > 0.f ? e.z : -e.z); }
-  float mx = v3dot(h->vert(0), dir); uint32_t mi = 0;
-  for (uint32_t i = 1; i < h->nVerts; ++i) { const float d = v3dot(h->vert(i), dir); if (d > mx) { mx = d; mi = i; } }
-  return h->vert(mi);
+  return h->vert(gjk_hull_support_index(h, dir));
 }
 typedef struct { const DevHull* h; int isBox; v3 center; float internalRadius; v3 internalExtents; } GjkPolyData;   /* PolygonalData: mCenter, mInternal */
 PXB_D GjkPolyData gjk_poly_data(const DevHull* h, int isBox) {

@@ -144,7 +144,7 @@ assert COOKED_HDR_DTYPE.itemsize == 100 and COOKED_POLY_DTYPE.itemsize == 32
 
 
 def parse_cooked(buf, n_hulls, off=0):
-    """cooked-hull section -> list of dicts (hdr, verts, polys, vertexRefs, facesByEdges); returns (list, end offset)"""
+    """cooked-hull section -> list of dicts (hdr, verts, polys, vertexRefs, facesByEdges [, samples, valencies, adjacentVerts]); returns (list, end offset)"""
     out = []
     for _ in range(n_hulls):
         hdr = np.frombuffer(buf, COOKED_HDR_DTYPE, 1, off)[0].copy(); off += COOKED_HDR_DTYPE.itemsize
@@ -153,7 +153,15 @@ def parse_cooked(buf, n_hulls, off=0):
         polys = np.frombuffer(buf, COOKED_POLY_DTYPE, npoly, off).copy(); off += npoly * COOKED_POLY_DTYPE.itemsize
         refs = np.frombuffer(buf, np.uint8, ni, off).copy(); off += (ni + 3) // 4 * 4
         fbe = np.frombuffer(buf, np.uint8, 2 * ne, off).copy(); off += (2 * ne + 3) // 4 * 4
-        out.append(dict(hdr=hdr, verts=verts, polys=polys, vertexRefs=refs, facesByEdges=fbe))
+        rec = dict(hdr=hdr, verts=verts, polys=polys, vertexRefs=refs, facesByEdges=fbe)
+        big = int(hdr["reserved"][0])   # hill-climbing data of hulls with more than 32 vertices (Gu::BigConvexRawData): subdiv | nAdj << 16
+        if big:
+            subdiv, n_adj = big & 0xffff, big >> 16
+            ns = 6 * subdiv * subdiv
+            rec["samples"] = np.frombuffer(buf, np.uint8, ns, off).copy(); off += (ns + 3) // 4 * 4
+            rec["valencies"] = np.frombuffer(buf, "<u2", 2 * nv, off).reshape(nv, 2).copy(); off += 4 * nv
+            rec["adjacentVerts"] = np.frombuffer(buf, np.uint8, n_adj, off).copy(); off += (n_adj + 3) // 4 * 4
+        out.append(rec)
     return out, off
 
 
@@ -608,11 +616,11 @@ def hulls_and_capsules(n=12, n_hulls=3, seed=21, speed=0.0, cook=None, **hdr):
     return cook(sc) if cook else sc
 
 
-def hull_pile(n=10, n_hulls=3, seed=31, kinds=("convex",), spread=0.35, cook=None, **hdr):
+def hull_pile(n=10, n_hulls=3, seed=31, kinds=("convex",), spread=0.35, cook=None, hull_points=(12, 21), **hdr):
     """Convex hulls (optionally mixed with boxes / spheres / capsules) dropped in a loose column onto the ground plane: hull-hull and
     box-hull contacts (GJK / EPA point + polygon clipping of the witness faces), BASELINE config 3's pair types at small size."""
     rng = np.random.RandomState(seed)
-    hulls = [random_hull_points(rng, int(rng.randint(12, 21)), 0.25) for _ in range(n_hulls)]
+    hulls = [random_hull_points(rng, int(rng.randint(*hull_points)), 0.25) for _ in range(n_hulls)]
     a = _new_actors(n)
     a["pos"][:, 0] = rng.uniform(-spread, spread, n)
     a["pos"][:, 1] = 0.5 + 0.5 * np.arange(n)

@@ -555,7 +555,7 @@ def test_convex_hulls_gpu_matches_oracle_and_reference(oracle):
         assert np.abs(gpu.getStates() - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
 
 
-@pytest.mark.parametrize("name", ["hulls_and_spheres", "spheres_into_hulls", "hulls_and_capsules", "capsules_into_hulls", "hull_pile", "box_hull_pile"])
+@pytest.mark.parametrize("name", ["hulls_and_spheres", "spheres_into_hulls", "hulls_and_capsules", "capsules_into_hulls", "hull_pile", "box_hull_pile", "big_hull_pile"])
 def test_sphere_convex_gpu_matches_oracle(oracle, name):
     """pcmContactSphereConvex / pcmContactCapsuleConvex on the device (hull support mapping, GJK, EPA, face + edge-edge contacts) against the
     oracle, teacher-forced from the golden states (hull-hull pairs of the *_into_* scenes excepted: they stop the step, see below)."""
@@ -586,6 +586,29 @@ def test_config3_shape_with_hulls_gpu_matches_oracle(oracle):
         assert np.abs(sg - cpu.getStates()).max() < 5e-5, f"state, step {t}"
         cpu.setStates(sg)
     assert cpu.unsupported_pairs == 0 and sg[:, 1].min() > 0.0
+
+
+def test_big_hulls_free_running_gpu_matches_oracle(oracle):
+    """Hulls of more than 32 vertices (hill-climbing support over Gu::BigConvexRawData: cube-map start sample + vertex adjacency) mixed with
+    boxes, spheres and capsules: GPU and oracle agree step by step, free running, on the device-wide path and (environment ids set) on the
+    fused environment path."""
+    z, sc = util.load_golden("big_hull_pile")
+    assert sum("samples" in h for h in sc.cooked_hulls()) >= 2
+    for env in (False, True):
+        a = sc.actors.copy()
+        if env:
+            a["envId"][a["flags"] & scenes.ACTOR_DYNAMIC != 0] = 0
+        scn = scenes.Scene(sc.header, a, sc.hulls, sc.cooked)
+        gpu, cpu = engine.Scene(scn), oracle.OracleScene(scn)
+        for t in range(120):
+            gpu.step(); cpu.step()
+            assert gpu.uses_env_path == env
+            assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
+            assert np.array_equal(gpu.getContacts()[:, 0], cpu.getContacts()[:, 0]), f"contact counts, step {t}"
+            sg = gpu.getStates()
+            assert np.abs(sg - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
+            cpu.setStates(sg)
+        assert cpu.unsupported_pairs == 0
 
 
 def test_hull_without_cooked_data_is_rejected():
