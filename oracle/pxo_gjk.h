@@ -1463,8 +1463,10 @@ static inline int pxo_sat_edge_normal(const PxoPolyData* p0, const PxoPolyData* 
 /* generateFullContactManifold, doOverlapTest == true (:537-603).  Returns 0 when a separating axis was found. */
 enum { PXO_FS_POLYDATA0 = 0, PXO_FS_POLYDATA1 = 1, PXO_FS_EDGE = 2 };
 static inline void pxo_poly_generated_contacts(const PxoHull* poly0, const PxoHull* poly1, int refIdx, int incIdx, const mxf* transform0To1, PxoMPoint* mc, int* numContacts, float contactDist);
-static inline int pxo_poly_full_manifold_sat(const PxoHull* poly0, int isBox0, const PxoHull* poly1, const mxf* map0, const mxf* map1, PxoMPoint* mc, int* numContacts, float contactDist) {
-  const mxf transform1To0 = amxfinvmul(map0, map1), transform0To1 = amxfinvmul(map1, map0);
+static inline int pxo_poly_full_manifold_sat(const PxoHull* poly0, int isBox0, const PxoHull* poly1, const xf* map0, const xf* map1, PxoMPoint* mc, int* numContacts, float contactDist) {
+  /* SupportLocal::transform is a PxTransformV (GuConvexSupportTable.h:55): quaternion transformInv, then the conversion PxMatTransformV(PxTransformV) */
+  const xf t10 = axfinvmul(map0, map1), t01 = axfinvmul(map1, map0);
+  const mxf transform1To0 = amxffromxf(&t10), transform0To1 = amxffromxf(&t01);
   const PxoPolyData p0 = pxo_poly_data(poly0, isBox0), p1 = pxo_poly_data(poly1, 0);
   int status = PXO_FS_POLYDATA0;
   float minOverlap = FLT_MAX; v3 minNormal = V3(0, 0, 0);
@@ -1578,9 +1580,10 @@ static inline void pxo_poly_generated_contacts(const PxoHull* poly0, const PxoHu
   }
 }
 /* generateFullContactManifold :532-665, doOverlapTest == false (witness polygons of the GJK / EPA closest points).  map0 / map1 = world transforms of the two shapes. */
-static inline void pxo_poly_full_manifold(const PxoHull* poly0, const PxoHull* poly1, const mxf* map0, const mxf* map1, PxoMPoint* mc, int* numContacts, float contactDist,
+static inline void pxo_poly_full_manifold(const PxoHull* poly0, const PxoHull* poly1, const xf* map0, const xf* map1, PxoMPoint* mc, int* numContacts, float contactDist,
                                           v3 normal, v3 closestA, v3 closestB, float marginA, float marginB, float toleranceLength) {
-  const mxf transform1To0 = amxfinvmul(map0, map1), transform0To1 = amxfinvmul(map1, map0);
+  const xf t10 = axfinvmul(map0, map1), t01 = axfinvmul(map1, map0);   /* PxTransformV::transformInv, then PxMatTransformV(PxTransformV) */
+  const mxf transform1To0 = amxffromxf(&t10), transform0To1 = amxffromxf(&t01);
   const float lowerEps = toleranceLength * 1e-2f, upperEps = toleranceLength * 5e-2f;
   const float toleranceA = fminf_(fmaxf_(marginA, lowerEps), upperEps), toleranceB = fminf_(fmaxf_(marginB, lowerEps), upperEps);
   const v3 negNormal = v3neg(normal);
@@ -1644,9 +1647,8 @@ static inline int pxo_pcm_poly_convex(const xf* transf0, const xf* transf1, PxoC
     const int fullContactGen = (0.707106781f > adot(localNor, output.normal)) || (manifold->n < initialContacts);
     if (fullContactGen || doOverlapTest) {   /* fullContactsGenerationBoxConvex / ConvexConvex */
       static PxoMPoint mc[PXO_POLY_MAX_CONTACTS]; int numContacts = 0;
-      const mxf map0 = amxffromxf(transf0), map1 = amxffromxf(transf1);
-      if (doOverlapTest) { if (!pxo_poly_full_manifold_sat(polyA, convexA->type == PXO_CVX_BOX, hullB, &map0, &map1, mc, &numContacts, contactDist)) return 0; }
-      else pxo_poly_full_manifold(polyA, hullB, &map0, &map1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
+      if (doOverlapTest) { if (!pxo_poly_full_manifold_sat(polyA, convexA->type == PXO_CVX_BOX, hullB, transf0, transf1, mc, &numContacts, contactDist)) return 0; }
+      else pxo_poly_full_manifold(polyA, hullB, transf0, transf1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
       if (numContacts > 0) {
         if (numContacts <= PXO_MANIFOLD_CACHE) { for (int i = 0; i < numContacts; ++i) manifold->pts[i] = mc[i]; manifold->n = numContacts; }
         else { pxo_reduce_batch(manifold, mc, numContacts, toleranceLength); manifold->n = PXO_MANIFOLD_CACHE; }

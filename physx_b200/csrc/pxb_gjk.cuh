@@ -1489,8 +1489,10 @@ PXB_D int gjk_sat_edge_normal(const GjkPolyData* p0, const GjkPolyData* p1, cons
 /* generateFullContactManifold, doOverlapTest == true (:537-603).  Returns 0 when a separating axis was found. */
 enum { GJK_FS_POLYDATA0 = 0, GJK_FS_POLYDATA1 = 1, GJK_FS_EDGE = 2 };
 PXB_D void gjk_poly_generated_contacts(const DevHull* poly0, const DevHull* poly1, int refIdx, int incIdx, const mxf* transform0To1, MPoint* mc, int* numContacts, float contactDist);
-PXB_D int gjk_poly_full_manifold_sat(const DevHull* poly0, int isBox0, const DevHull* poly1, const mxf* map0, const mxf* map1, MPoint* mc, int* numContacts, float contactDist) {
-  const mxf transform1To0 = amxfinvmul(map0, map1), transform0To1 = amxfinvmul(map1, map0);
+PXB_D int gjk_poly_full_manifold_sat(const DevHull* poly0, int isBox0, const DevHull* poly1, const xf* map0, const xf* map1, MPoint* mc, int* numContacts, float contactDist) {
+  /* SupportLocal::transform is a PxTransformV (GuConvexSupportTable.h:55): quaternion transformInv, then the conversion PxMatTransformV(PxTransformV) */
+  const xf t10 = axfinvmul(map0, map1), t01 = axfinvmul(map1, map0);
+  const mxf transform1To0 = amxffromxf(&t10), transform0To1 = amxffromxf(&t01);
   const GjkPolyData p0 = gjk_poly_data(poly0, isBox0), p1 = gjk_poly_data(poly1, 0);
   int status = GJK_FS_POLYDATA0;
   float minOverlap = FLT_MAX; v3 minNormal = V3(0, 0, 0);
@@ -1605,9 +1607,10 @@ PXB_D void gjk_poly_generated_contacts(const DevHull* poly0, const DevHull* poly
   }
 }
 /* generateFullContactManifold :532-665, doOverlapTest == false (witness polygons of the GJK / EPA closest points).  map0 / map1 = world transforms of the two shapes. */
-PXB_D void gjk_poly_full_manifold(const DevHull* poly0, const DevHull* poly1, const mxf* map0, const mxf* map1, MPoint* mc, int* numContacts, float contactDist,
+PXB_D void gjk_poly_full_manifold(const DevHull* poly0, const DevHull* poly1, const xf* map0, const xf* map1, MPoint* mc, int* numContacts, float contactDist,
                                           v3 normal, v3 closestA, v3 closestB, float marginA, float marginB, float toleranceLength) {
-  const mxf transform1To0 = amxfinvmul(map0, map1), transform0To1 = amxfinvmul(map1, map0);
+  const xf t10 = axfinvmul(map0, map1), t01 = axfinvmul(map1, map0);   /* PxTransformV::transformInv, then PxMatTransformV(PxTransformV) */
+  const mxf transform1To0 = amxffromxf(&t10), transform0To1 = amxffromxf(&t01);
   const float lowerEps = toleranceLength * 1e-2f, upperEps = toleranceLength * 5e-2f;
   const float toleranceA = fmin_(fmax_(marginA, lowerEps), upperEps), toleranceB = fmin_(fmax_(marginB, lowerEps), upperEps);
   const v3 negNormal = v3neg(normal);
@@ -1671,9 +1674,8 @@ PXB_D int gjk_pcm_poly_convex(const xf* transf0, const xf* transf1, GjkConvex* c
     const int fullContactGen = (0.707106781f > adot(localNor, output.normal)) || (manifold->n < initialContacts);
     if (fullContactGen || doOverlapTest) {   /* fullContactsGenerationBoxConvex / ConvexConvex */
       MPoint mc[GJK_POLY_MAX_CONTACTS]; int numContacts = 0;
-      const mxf map0 = amxffromxf(transf0), map1 = amxffromxf(transf1);
-      if (doOverlapTest) { if (!gjk_poly_full_manifold_sat(polyA, convexA->type == GJK_CVX_BOX, hullB, &map0, &map1, mc, &numContacts, contactDist)) return 0; }
-      else gjk_poly_full_manifold(polyA, hullB, &map0, &map1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
+      if (doOverlapTest) { if (!gjk_poly_full_manifold_sat(polyA, convexA->type == GJK_CVX_BOX, hullB, transf0, transf1, mc, &numContacts, contactDist)) return 0; }
+      else gjk_poly_full_manifold(polyA, hullB, transf0, transf1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
       if (numContacts > 0) {
         if (numContacts <= PXB_MANIFOLD_CACHE) { for (int i = 0; i < numContacts; ++i) manifold->pts[i] = mc[i]; manifold->n = numContacts; }
         else { reduce_batch(*manifold, mc, numContacts, toleranceLength); manifold->n = PXB_MANIFOLD_CACHE; }

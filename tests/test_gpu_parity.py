@@ -555,7 +555,7 @@ def test_convex_hulls_gpu_matches_oracle_and_reference(oracle):
         assert np.abs(gpu.getStates() - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
 
 
-@pytest.mark.parametrize("name", ["hulls_and_spheres", "spheres_into_hulls", "hulls_and_capsules", "capsules_into_hulls", "hull_pile", "box_hull_pile", "big_hull_pile"])
+@pytest.mark.parametrize("name", ["hulls_and_spheres", "spheres_into_hulls", "hulls_and_capsules", "capsules_into_hulls", "hull_pile", "box_hull_pile", "big_hull_pile", "config3_small"])
 def test_sphere_convex_gpu_matches_oracle(oracle, name):
     """pcmContactSphereConvex / pcmContactCapsuleConvex on the device (hull support mapping, GJK, EPA, face + edge-edge contacts) against the
     oracle, teacher-forced from the golden states (hull-hull pairs of the *_into_* scenes excepted: they stop the step, see below)."""
