@@ -397,7 +397,10 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
 
 // a10: the GJK family (capsule-box), one thread per listed pair.  Kept out of k_narrowphase so that the box / sphere hot path keeps its register budget;
 // the list order is arbitrary (atomic append) but every pair writes only its own outputs, so the result is deterministic.
-__global__ void __launch_bounds__(128) k_narrowphase_gjk(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, uint32_t bitsA, const float4* __restrict__ pos, const float4* __restrict__ quat,
+#ifndef PXB_GJK_CTAS
+#define PXB_GJK_CTAS 3   // 168 registers.  Measured on config 3 with hulls: 4 CTAs/SM (128 registers, +240 B of spills) is slower, 10.15 vs 10.0 ms/step -- the kernel is divergence bound (5 of 32 threads active), not residency bound
+#endif
+__global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, uint32_t bitsA, const float4* __restrict__ pos, const float4* __restrict__ quat,
                               const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags, float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr,
                               float4* __restrict__ cPts, uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, uint32_t* __restrict__ counters, const uint32_t* __restrict__ gjkList, HullArrays hulls) {
   const uint32_t n = counters[C_NGJK];
