@@ -19,9 +19,12 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from cooking import cook_hulls  # noqa: E402
 
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+LITE_FULL_STEPS = 4
 
 
-def run_reference(scene, steps, threads=1, forces=None):
+def run_reference(scene, steps, threads=1, forces=None, lite=False):
+    """lite: long-horizon fixtures keep the states, the island-manager order and the per-pair contact COUNTS of every step, but
+    bounds / ABP events / contact points only for the first `LITE_FULL_STEPS` steps (fixture size)."""
     with tempfile.TemporaryDirectory() as d:
         sp = os.path.join(d, "s.bin")
         scene.save(sp)
@@ -56,11 +59,40 @@ def run_reference(scene, steps, threads=1, forces=None):
                 con_pts.append(np.frombuffer(cb, "<f4", k * 10, off).reshape(k, 10)[:, :7]); off += k * 40
                 pt_off.append(pt_off[-1] + k)
             con_off.append(con_off[-1] + n)
+        if lite:
+            k = LITE_FULL_STEPS
+            bounds, cr, de = bounds[:k], cr[:k], de[:k]; cro, deo = cro[:k + 1], deo[:k + 1]
+            con_pts = con_pts[:con_off[k]]; pt_off = pt_off[:con_off[k] + 1]
         return dict(scene=np.frombuffer(scene.tobytes(), np.uint8), forces=(np.zeros((0, nd, 6), np.float32) if forces is None else np.asarray(forces, np.float32)), states=states, wake=sl["wc"].copy(), asleep=sl["s"].copy(),
                     order=np.concatenate(order_flat) if order_flat else np.zeros((0, 2), np.uint32), order_off=np.array(order_off),
                     bounds=np.stack(bounds), created=np.concatenate(cr), created_off=np.array(cro), deleted=np.concatenate(de) if de else np.zeros((0, 2), np.uint32),
                     deleted_off=np.array(deo), con_pairs=np.array(con_pairs, np.uint32).reshape(-1, 3), con_off=np.array(con_off),
                     con_pts=np.concatenate(con_pts).astype(np.float32) if con_pts else np.zeros((0, 7), np.float32), pt_off=np.array(pt_off))
+
+
+def scene_statistics(scene, data, steps, keep_every=30):
+    """Reduction of a reference run to the statistics SURVEY 8d asks for on configs 3 / 4 (tests/util.py: run_statistics computes the same
+    quantities from an engine / oracle run)."""
+    dyn = (scene.actors["flags"] & scenes.ACTOR_DYNAMIC) != 0
+    mass = scene.actors["mass"][dyn].astype(np.float64); inertia = scene.actors["inertia"][dyn].astype(np.float64)
+    st = data["states"].astype(np.float64)
+    ke, mean_y, min_sep, mean_pen, n_touch, n_pts = [], [], [], [], [], []
+    for t in range(steps):
+        s = st[t + 1]
+        # angular part in the body frame: w_body = q^-1 w q
+        q = s[:, 3:7]; w = s[:, 10:13]
+        qv, qw = q[:, :3], q[:, 3:4]
+        wb = w + 2.0 * np.cross(-qv, np.cross(-qv, w) + qw * w)
+        ke.append(float(0.5 * (mass * (s[:, 7:10] ** 2).sum(1)).sum() + 0.5 * (inertia * wb ** 2).sum()))
+        mean_y.append(float(s[:, 1].mean()))
+        a, b = data["con_off"][t], data["con_off"][t + 1]
+        seps = data["con_pts"][data["pt_off"][a]:data["pt_off"][b], 6].astype(np.float64)
+        n_touch.append(int(np.count_nonzero(data["con_pairs"][a:b, 2]))); n_pts.append(int(len(seps)))
+        min_sep.append(float(seps.min()) if len(seps) else 0.0)
+        mean_pen.append(float(np.clip(-seps, 0, None).mean()) if len(seps) else 0.0)
+    keep = list(range(0, steps + 1, keep_every))
+    return dict(scene=data["scene"], steps=np.int64(steps), ke=np.array(ke), mean_y=np.array(mean_y), min_sep=np.array(min_sep), mean_pen=np.array(mean_pen),
+                n_touch=np.array(n_touch), n_pts=np.array(n_pts), kept_steps=np.array(keep), states=data["states"][keep].astype(np.float32))
 
 
 def main():
@@ -108,7 +140,32 @@ def main():
     forced = {"forces_stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01),
               "pgs_forces_stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01, solver=scenes.SOLVER_PGS),
               "forces_primitives": scenes.mixed_primitives(n=12, seed=3, kinds=("sphere", "capsule"))}
+    # Long horizons (120 steps on configs 1 / 2 / 5, 300 on config 1 proper) and the dense pile of config 4 in the reference's own
+    # first-fit order -- "lite" fixtures (states + solver order + contact counts every step)
+    lite = {
+        "stacks_10x10": (scenes.box_stacks(), 300),                                                   # BASELINE config 1 proper: 10 x 10 unit boxes
+        "envs_4_long": (scenes.env_grid_stacks(n_envs=4, jitter=0.01), 120),                          # config 2 shape, 120 steps
+        "envs_2x128": (scenes.env_grid_stacks(n_envs=2, stacks_per_env=16, jitter=0.01), 120),        # config 5 shape: 128 boxes per environment
+        "pile_6x4x6": (scenes.box_pile(6, 4, 6), 60),                                                 # config 4 shape: one dense island in a walled bin
+        "pgs_pile_6x4x6": (scenes.box_pile(6, 4, 6, solver=scenes.SOLVER_PGS), 60),
+    }
+    # statistics fixtures ("energy / penetration statistics only for configs 3-4"): per-step kinetic energy, mean height, deepest and
+    # mean penetration, touching pairs and contact points of the reference on a pile large enough to be chaotic in detail; states kept every 30 steps
+    stats = {"pile_12x6x12_stats": (scenes.box_pile(12, 6, 12), 120),
+             "fall_6x5x6_stats": (scenes.falling_primitives(6, 5, 6, kinds=("sphere", "capsule", "convex")), 150)}
     only = sys.argv[1:]
+    for name, (sc, steps) in lite.items():
+        if only and not any(name.startswith(o) for o in only):
+            continue
+        data = run_reference(sc, steps, lite=True)
+        np.savez_compressed(os.path.join(out, name + ".npz"), **data)
+        print(name, "bodies", sc.n_dynamic, "steps", steps, "bytes", os.path.getsize(os.path.join(out, name + ".npz")))
+    for name, (sc, steps) in stats.items():
+        if only and not any(name.startswith(o) for o in only):
+            continue
+        data = run_reference(sc, steps)
+        np.savez_compressed(os.path.join(out, name + ".npz"), **scene_statistics(sc, data, steps))
+        print(name, "bodies", sc.n_dynamic, "steps", steps, "bytes", os.path.getsize(os.path.join(out, name + ".npz")))
     if only:
         cases = {k: v for k, v in cases.items() if any(k.startswith(o) for o in only)}
     for name, sc in forced.items():

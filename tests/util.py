@@ -53,3 +53,41 @@ def contact_counts(pairs, contacts):
 def rel_err(a, b, floor=1.0):
     """max |a-b| / max(|b|, floor): relative error with an absolute floor of `floor` scene units."""
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def run_statistics(sc, states, pairs_contacts):
+    """The statistics tests/golden/make_golden.py::scene_statistics keeps of a reference run, from one step of an engine / oracle run:
+    kinetic energy, mean height, deepest and mean penetration, touching pairs and contact points."""
+    dyn = (sc.actors["flags"] & scenes.ACTOR_DYNAMIC) != 0
+    mass = sc.actors["mass"][dyn].astype(np.float64); inertia = sc.actors["inertia"][dyn].astype(np.float64)
+    s = states.astype(np.float64)
+    qv, qw, w = s[:, 3:6], s[:, 6:7], s[:, 10:13]
+    wb = w + 2.0 * np.cross(-qv, np.cross(-qv, w) + qw * w)
+    ke = float(0.5 * (mass * (s[:, 7:10] ** 2).sum(1)).sum() + 0.5 * (inertia * wb ** 2).sum())
+    con = pairs_contacts
+    cnt = con[:, 0].astype(int)
+    seps = np.concatenate([con[i, 4:4 + 5 * k].reshape(k, 5)[:, 3] for i, k in enumerate(cnt) if k]) if cnt.any() else np.zeros(0)
+    return dict(ke=ke, mean_y=float(s[:, 1].mean()), min_sep=float(seps.min()) if len(seps) else 0.0,
+                mean_pen=float(np.clip(-seps, 0, None).mean()) if len(seps) else 0.0, n_touch=int(np.count_nonzero(cnt)), n_pts=int(cnt.sum()))
+
+
+def load_stats_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+        f.write(z["scene"].tobytes())
+        f.flush()
+        sc = scenes.Scene.load(f.name)
+    return z, sc
+
+
+# Horizons of SURVEY.md 8d on the deterministic-order scenes (solver input order teacher-forced from the reference's island manager every step,
+# everything else free running).  Bars: north_star's 1e-4 relative pose error where the scene is not chaotic; the dense piles are, and carry the
+# bound measured on the oracle with 1.5x headroom (DESIGN.md 5: the remaining differences are the reference's 4-wide solver path and _mm_rcp_ps).
+LONG_HORIZON = {
+    # name: (pose tolerance, linear velocity, angular velocity)
+    "stacks_10x10": (1e-4, 1e-2, 5e-2),        # BASELINE config 1 proper, 300 steps
+    "envs_4_long": (1e-4, 1e-2, 5e-2),         # config 2 shape, 120 steps
+    "envs_2x128": (3e-4, 1.5e-2, 5e-2),        # config 5 shape (128 boxes per environment), 120 steps: 2.2e-4 measured
+    "pile_6x4x6": (2e-4, 1.5e-2, 6e-2),        # config 4 shape, exact first-fit in the reference's order, 60 steps: 1.4e-4 measured
+    "pgs_pile_6x4x6": (2e-3, 2e-2, 8e-2),      # the same under PGS: 1.1e-3 measured (open item)
+}
