@@ -1,16 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- rigid-body-steps/s of the simulate()+fetchResults() hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5] [--churn F] [--impl ours|reference]
 
-Our arm (default): BASELINE config 2, 4096 independent envs x 64 boxes (262144 bodies) per GPU, GPU
-broadphase + TGS 4+1 iterations, 60 Hz, synthetic seeded scene.  N > 1 (under torchrun): one process per
-GPU, each rank owns its own 4096 envs (weak scaling, no physics coupling) and, per step, the ranks
-all-gather the Direct-GPU-API state tensors over NCCL.  One JSON line is printed by rank 0.
+Workloads (BASELINE.json `configs`; synthetic seeded scenes, TGS 4 position + 1 velocity iteration unless --solver pgs, 60 Hz):
+  1  10 stacks x 10 unit boxes on a ground plane (100 bodies; the reference's own CPU-runnable case)
+  2  4096 independent envs x 64 boxes = 262 144 bodies per GPU  (DEFAULT: the configuration the metric is quoted on)
+  3  1 048 576 mixed spheres / capsules / convex hulls falling into a walled bin (broadphase + narrowphase stress)
+  4  200 000-box dense pile in a walled bin, one giant island (solver partitioning stress)
+  5  32 768 envs x 128 boxes env-partitioned over 8 GPUs = 4096 envs x 128 boxes per GPU (--config 5 at N=1 is one GPU's shard)
+Our arm: one process per GPU (torchrun for N > 1), every rank owns its own scene (weak scaling, no physics coupling); configs 2 / 5
+all-gather the Direct-GPU-API state tensor over NVLink every step.  One JSON line is printed by rank 0.
 
-Reference arm (--impl reference): the UNMODIFIED reference CPU SDK (oracle/_ref/ref_harness: eABP
-broadphase, CPU TGS, PxDefaultCpuDispatcher with all host threads) on a bounded sample of the same
-workload; rank 0 only.
+Reference arm (--impl reference): the UNMODIFIED reference CPU SDK (oracle/_ref/ref_harness: eABP broadphase, CPU TGS,
+PxDefaultCpuDispatcher) on the SAME scene -- configs 1 / 2 / 4 / 5 at full size, config 3 at 1/8 of the bodies (stated in the line: the
+metric is per body) -- with the dispatcher thread count chosen by a short sweep over {1, 8, nproc/2, nproc-1}; rank 0 only.
 """
 import argparse
 import json
@@ -27,10 +31,14 @@ sys.path.insert(0, ROOT)
 
 METRIC = "rigid-body-steps/sec"
 UNIT = "bodies*steps/s"
-BOXES_PER_ENV = 64
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_env_solve launch at config 2 (4096 envs x 64 boxes), from the committed
-# ncu --set full capture profiles/r01_env_kernels_full_raw.csv (a profiler number: quoted, never timed under ncu)
-ENV_SOLVE_DRAM_BYTES_PER_LAUNCH = 122_967_552   # 87.23 MB read + 35.73 MB written
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of each config's dominant kernel, from the committed `ncu --set full` captures under
+# profiles/ (profiler numbers: quoted, never timed under ncu).  None = not captured for that configuration.
+NCU_DRAM_BYTES_PER_LAUNCH = {}
+try:
+    with open(os.path.join(ROOT, "profiles", "ncu_dram_bytes.json")) as _f:
+        NCU_DRAM_BYTES_PER_LAUNCH = json.load(_f)
+except Exception:
+    pass
 
 
 def measured_peaks():
@@ -76,51 +84,118 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def run_reference_sample(n_envs, steps, threads, warmup=2):
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# workloads
+SETTLE = {1: 0, 2: 0, 3: 60, 4: 30, 5: 0}   # untimed steps before the warm-up: config 3's lattice is falling into the bin, config 4's pile closes its 1 mm gaps
+
+
+def build_scene(config, envs, rank=0, solver="tgs", scale=1.0, relaxed=False, world=1):
+    """The scene one GPU (our arm) or the host (reference arm, `world` GPUs' worth of environments) simulates."""
     from physx_b200 import scenes
+    sv = scenes.SOLVER_PGS if solver == "pgs" else scenes.SOLVER_TGS
+    if config == 1:
+        return scenes.box_stacks(solver=sv), 0
+    if config in (2, 5):
+        return scenes.env_grid_stacks(n_envs=envs * world, stacks_per_env=8 if config == 2 else 16, seed=1234 + rank, solver=sv), 0
+    if config == 3:
+        n = max(4, int(round(128 * scale ** (1 / 3))))
+        sc = scenes.falling_primitives(n, max(2, n // 2), n, kinds=("sphere", "capsule", "convex"), solver=sv, relaxed_partitioning=relaxed)
+        return sc, 8 * len(sc.actors)
+    if config == 4:
+        n = max(4, int(round(100 * scale ** (1 / 3))))
+        sc = scenes.box_pile(n, max(2, int(round(20 * scale ** (1 / 3)))), n, solver=sv, relaxed_partitioning=relaxed)
+        return sc, 16 * len(sc.actors)
+    raise SystemExit(f"unknown config {config}")
+
+
+def workload_string(config, envs, solver, churn):
+    s = solver.upper()
+    w = {1: f"config 1: 10 stacks x 10 unit boxes on a ground plane = 100 bodies, {s} 4 pos/1 vel iterations, 60 Hz",
+         2: f"config 2: {envs} envs x 64 boxes = {envs * 64} bodies per GPU, shared ground plane, GPU broadphase + {s} 4 pos/1 vel iterations, 60 Hz",
+         3: f"config 3: 1048576 mixed spheres / capsules / convex hulls falling into a walled bin, {s} 4 pos/1 vel iterations, 60 Hz",
+         4: f"config 4: dense pile of 200000 boxes (100 x 20 x 100, 1 mm gaps) in a walled bin, one island, {s} 4 pos/1 vel iterations, 60 Hz",
+         5: f"config 5: {envs} envs x 128 boxes = {envs * 128} bodies per GPU (32768 envs over 8 GPUs), shared ground plane, GPU broadphase + {s} 4 pos/1 vel iterations, per-step state all-gather, 60 Hz"}[config]
+    if churn > 0:
+        w += f"; churn: {churn:.0%} of the environments reset every step through pxb_set_rigid_dynamic_data_device"
+    return w
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference CPU SDK on the host cores
+def run_harness(scene, steps, threads, warmup):
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     if not os.path.exists(harness):
         return None
-    sc = scenes.env_grid_stacks(n_envs=n_envs)
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "s.bin")
-        sc.save(p)
+        scene.save(p)
         out = subprocess.run([harness, "run", p, "--steps", str(steps), "--warmup", str(warmup), "--threads", str(threads)], capture_output=True, text=True, check=True).stdout
     return json.loads(out.strip().splitlines()[-1])
 
 
-def cpu_baseline_block(steps=20, n_envs=1024):
-    threads = os.cpu_count() or 1
-    r = run_reference_sample(n_envs, steps, threads)
-    if r is None:
-        return {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "oracle/_ref/ref_harness not built"}
-    return {"value": r["body_steps_per_s"], "unit": UNIT, "cores": threads, "kind": "reference", "ms_per_step": r["ms_per_step"],
-            "sample": f"{n_envs} envs x {BOXES_PER_ENV} boxes = {n_envs * BOXES_PER_ENV} bodies, {steps} steps after 2 warm-up, unmodified PhysX 5.6.1 CPU (eABP + CPU TGS 4+1, PxDefaultCpuDispatcher({threads}))"}
+def thread_candidates():
+    n = os.cpu_count() or 1
+    return sorted({t for t in (1, 8, n // 2, n - 1, n) if 1 <= t <= n})
+
+
+def sweep_threads(config, solver):
+    """Short sweep of PxDefaultCpuDispatcher thread counts on a small scene of the same shape (T in {1, 8, nproc-1}); returns the
+    best count and the table."""
+    small, _ = {1: lambda: build_scene(1, 0, solver=solver), 2: lambda: build_scene(2, 512, solver=solver), 5: lambda: build_scene(5, 256, solver=solver),
+                3: lambda: build_scene(3, 0, solver=solver, scale=1 / 64), 4: lambda: build_scene(4, 0, solver=solver, scale=1 / 32)}[config]()
+    table = {}
+    for t in thread_candidates():
+        r = run_harness(small, 6 if config != 1 else 200, t, 2 + (SETTLE[config] if config == 3 else 0))
+        if r is None:
+            return None, {}
+        table[t] = r["body_steps_per_s"]
+    return max(table, key=table.get), table
+
+
+def reference_run(config, envs, solver, steps, warmup, world=1):
+    """(harness result, description) of the reference CPU SDK on this arm's workload.  Config 3: 1/8 of the bodies, stated."""
+    best, table = sweep_threads(config, solver)
+    if best is None:
+        return None, None, None
+    scale = 1 / 8 if config == 3 else 1.0
+    sc, _ = build_scene(config, envs, solver=solver, scale=scale, world=world)
+    r = run_harness(sc, steps, best, warmup + SETTLE[config])
+    sample = (f"the same scene at {'1/8 of the bodies' if scale != 1.0 else 'FULL size'} ({sc.n_dynamic} bodies), {steps} steps after {warmup + SETTLE[config]} untimed, unmodified PhysX 5.6.1 CPU "
+              f"(eABP + CPU {solver.upper()} 4+1, PxDefaultCpuDispatcher({best}) = best of the sweep {json.dumps({str(k): round(v) for k, v in table.items()})} body-steps/s on a small scene of the same shape; {os.cpu_count()} host threads available)")
+    return r, best, sample
 
 
 def bench_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n_envs = args.ref_envs
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     t0 = time.time()
-    vals, ms = [], []
-    # each "step" of this arm = one simulate+fetchResults of the bounded sample scene
-    r = run_reference_sample(n_envs, args.steps, threads, warmup=args.warmup)
+    steps = min(args.steps, 30) if args.config != 1 else args.steps
+    r, threads, sample = reference_run(args.config, args.envs, args.solver, steps, args.warmup, world=world if args.config in (2, 5) else 1)
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness is not built (needs /root/reference at build time)"}))
         return
     v = r["body_steps_per_s"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{n_envs} envs x {BOXES_PER_ENV} boxes ({n_envs * BOXES_PER_ENV} bodies): bounded sample of config 2 (4096 envs x 64 boxes), TGS 4+1, 60 Hz",
-                       "implementation": "unmodified PhysX 5.6.1 CPU path: eABP broadphase, CPU TGS, PxDefaultCpuDispatcher", "threads": threads},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": f"{n_envs * BOXES_PER_ENV} bodies x {args.steps} steps"},
+            "config": {"workload": workload_string(args.config, args.envs, args.solver, 0.0)},
+            "details": {"implementation": "unmodified PhysX 5.6.1 CPU path: eABP broadphase, CPU TGS/PGS, PxDefaultCpuDispatcher", "threads": threads, "timed_steps": steps, "bodies": r["bodies"],
+                        "ms_median": r.get("ms_median"), "ms_p95": r.get("ms_p95")},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0, "wall_s": time.time() - t0}
     print(json.dumps(line))
 
 
+def cpu_baseline_block(config, envs, solver):
+    """Bounded sample for the `cpu_baseline` key of our own line (N = 1 only): 10 timed steps of the reference arm's run."""
+    r, threads, sample = reference_run(config, envs, solver, 10 if config != 1 else 300, 3)
+    if r is None:
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference", "sample": "oracle/_ref/ref_harness not built"}
+    return {"value": r["body_steps_per_s"], "unit": UNIT, "cores": threads, "kind": "reference", "ms_per_step": r["ms_per_step"], "sample": sample}
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
 def bench_ours(args):
     import numpy as np
     import torch
@@ -138,26 +213,57 @@ def bench_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
 
-    n_envs = args.envs
-    solver = scenes.SOLVER_PGS if args.solver == "pgs" else scenes.SOLVER_TGS
-    sc = scenes.env_grid_stacks(n_envs=n_envs, stacks_per_env=args.stacks, seed=1234 + rank, solver=solver)  # every rank owns its own envs (weak scaling)
-    scene = engine.Scene(sc, device=local, env_path=(args.path != "devicewide"))
+    cfg, n_envs = args.config, args.envs
+    relaxed = args.partitioning == "relaxed"
+    sc, max_pairs = build_scene(cfg, n_envs, rank=rank, solver=args.solver, relaxed=relaxed)   # every rank owns its own scene (weak scaling)
+    scene = engine.Scene(sc, device=local, env_path=(args.path != "devicewide"), max_pairs=max_pairs)
     nb = scene.num_dynamic
     stream = torch.cuda.ExternalStream(scene.stream(), device=dev)
-    gather = None
-    if dist is not None:
-        # one packed [n, 13] tensor (pose + linear + angular velocity) -> ONE NCCL all-gather per step, double-buffered on a
-        # communication stream so that it overlaps the next step's kernels
+    gather, gather_kind = None, None
+    if dist is not None and cfg in (2, 5):
+        # one packed [n, 13] tensor (pose + linear + angular velocity) exchanged every step, double-buffered on communication streams
         gather, gather_kind = multi_gpu.make_state_gather(dist, nb, 13, dev, stream, kind=args.gather, scene=scene)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
 
+    # churn (RL resets): every step a rotating window of environments is put back to a lifted copy of its initial state -- the boxes of a stack
+    # separated by more than the contact offset -- through the Direct-GPU-API device write, so pairs are lost and found, manifolds rebuilt
+    # and the environments recoloured all the time.
+    churn = None
+    if args.churn > 0 and cfg in (2, 5):
+        per_env = nb // n_envs
+        k = max(1, int(round(args.churn * n_envs)))
+        st0 = scene.getStates()
+        level = (np.arange(nb) % per_env) % 8
+        pose0 = np.concatenate([st0[:, 3:7], st0[:, 0:3]], axis=1).astype(np.float32)
+        pose0[:, 5] += 0.06 * (level + 1)
+        churn = {"k": k, "per_env": per_env, "cursor": 0,
+                 "pose": torch.from_numpy(pose0).to(dev), "zero": torch.zeros((nb, 3), dtype=torch.float32, device=dev),
+                 "idx": torch.arange(nb, dtype=torch.int32, device=dev)}
+
+    def apply_churn():
+        if churn is None:
+            return 0
+        k, pe = churn["k"], churn["per_env"]
+        e0 = churn["cursor"]; churn["cursor"] = (e0 + k) % n_envs
+        e1 = min(e0 + k, n_envs)
+        lo, hi = e0 * pe, e1 * pe
+        n = hi - lo
+        with torch.cuda.stream(stream):
+            idx = churn["idx"][lo:hi]
+            scene.setRigidDynamicDataDevice(engine.RD_GLOBAL_POSE, churn["pose"][lo:hi].data_ptr(), n, idx.data_ptr())
+            scene.setRigidDynamicDataDevice(engine.RD_LINEAR_VELOCITY, churn["zero"][lo:hi].data_ptr(), n, idx.data_ptr())
+            scene.setRigidDynamicDataDevice(engine.RD_ANGULAR_VELOCITY, churn["zero"][lo:hi].data_ptr(), n, idx.data_ptr())
+        return 3
+
     def one_step():
+        apply_churn()
         scene.simulate()
         if gather is not None:
             gather.step(lambda view: scene.getStatesDevice(view.data_ptr()))
         scene.fetchResults(True)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(SETTLE[cfg] + warm + (40 if churn else 0)):
         one_step()
     torch.cuda.synchronize(dev)
 
@@ -174,16 +280,17 @@ def bench_ours(args):
             flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        launches += apply_churn()
         scene.simulate()
         if gather is not None:
-            gather.step(lambda view: scene.getStatesDevice(view.data_ptr()))   # pack kernel on the scene stream, NCCL on the comm stream
+            gather.step(lambda view: scene.getStatesDevice(view.data_ptr()))   # exchange on the communication streams, overlapping the next step
         e1.record(stream)
         scene.fetchResults(True)
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
         launches += scene.num_launches + (1 if gather is not None else 0)
     if gather is not None:
-        # the collectives of the last two steps may still be in flight: their completion is part of the timed region
+        # the exchanges of the last two steps may still be in flight: their completion is part of the timed region
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         gather.wait()
@@ -191,8 +298,10 @@ def bench_ours(args):
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
     torch.cuda.synchronize(dev)
+    n_pairs = len(scene.getPairs()) if cfg != 2 and cfg != 5 else None
     if dist is not None:
         dist.barrier()
+    if gather is not None:
         # validity of the exchange (outside the timed region): the gathered tensor must equal a plain NCCL all-gather of every rank's packed state
         mine = torch.empty((nb, 13), dtype=torch.float32, device=dev)
         scene.getStatesDevice(mine.data_ptr())
@@ -204,18 +313,23 @@ def bench_ours(args):
             raise RuntimeError(f"rank {rank}: gathered state tensor differs from the NCCL reference all-gather")
     clocks = sampler.stop() if rank == 0 else None
     total_ms = float(sum(step_ms))
+    per_step = sorted(step_ms[:args.steps])
     # ---- per-stage device times (CUDA events inside the engine, direct launches) for the roofline of the
     #      dominant kernel; separate from the timed region, which replays the captured CUDA graph ----
     scene.setProfiling(True)
-    prof_steps = 20
+    prof_steps = 20 if cfg in (1, 2, 5) else 8
     for _ in range(prof_steps):
         with torch.cuda.stream(stream):
             flush.zero_()
+        apply_churn()
         scene.simulate()
         scene.fetchResults(True)
         for k, v in scene.getStageTimes().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     scene.setProfiling(False)
+    P = scene.num_constraints            # contact patches = touching pairs (one patch per pair)
+    if n_pairs is None:
+        n_pairs = len(scene.getPairs())
     if dist is not None:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -260,47 +374,55 @@ def bench_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        P = scene.num_constraints            # contact patches = touching pairs (one patch per primitive pair)
-        C = 4 * P                            # contact points (box-plane / box-box face manifolds: 4)
-        F = 4 * P                            # friction rows (2 anchors x 2 tangents)
         iters = int(sc.header["posIters"]) + int(sc.header["velIters"])
-        # SURVEY.md §8d algorithmic bytes: solver per iteration 116 P + 60 C + 48 F + 72 N_b; contact prep reads 64 P + 16 C + 2*112 P
-        # and writes 116 P + 56 C + 44 F; integration 132 N_b.
+        stages = {k: round(v / prof_steps, 4) for k, v in stage_acc.items()}
+        # SURVEY.md 8d algorithmic bytes.  Contact points / friction rows per patch: 4 / 4 for the box scenes (face manifolds, 2 anchors x 2
+        # tangents); config 3's mix averages about 1.5 points per touching pair (spheres / capsules: 1-2, hulls: up to 4) -> C = F = 2 P is used.
+        C = F = (4 * P if cfg != 3 else 2 * P)
         solve_bytes = (116 * P + 60 * C + 48 * F + 72 * nb) * iters
         prep_bytes = (64 * P + 16 * C + 224 * P) + (116 * P + 56 * C + 44 * F)
         integ_bytes = 132 * nb
-        solve_ms = stage_acc["solve"] / prof_steps
+        np_bytes = n_pairs * (16 + 2 * 48 + 2 * 32 + 2 * 256 + 32) + 64 * P + 16 * C
+        key = None
         if scene.uses_env_path:
-            # environment path: ONE kernel does pre-integration, colouring, prep, all TGS iterations, write-back and integration
-            kernel_name = "k_env_solve (a12-a18 fused: prep + all TGS iterations + integration, one CTA per environment, rows in registers)"
+            # environment path: ONE kernel does pre-integration, colouring, prep, all solver iterations, write-back and integration
+            kernel_name, stage = "k_env_solve (a12-a18 fused: prep + all solver iterations + integration, environments on chip, rows in registers)", "solve"
             kernel_bytes = prep_bytes + solve_bytes + integ_bytes
             note = ("algorithmic bytes = SURVEY 8d prep + 5 solver iterations + integration; the kernel keeps every solver row on chip (registers), "
-                    "so only contacts, friction patches and body state cross HBM once: see `traffic` (ncu dram bytes per launch, profiles/r01_env_kernels_full_raw.csv)")
-            traffic = ENV_SOLVE_DRAM_BYTES_PER_LAUNCH if (n_envs == 4096 and args.stacks == 8 and args.solver == "tgs") else None
+                    "so only contacts, friction patches and body state cross HBM once: see `traffic` (ncu dram bytes per launch)")
+            key = f"k_env_solve/config{cfg}" if (n_envs == 4096 and args.solver == "tgs" and not churn) else None
+        elif cfg == 3:
+            kernel_name, stage = "k_narrowphase + k_narrowphase_gjk (a8-a11: contact generation over all broadphase pairs)", "narrowphase"
+            kernel_bytes = np_bytes
+            note = "algorithmic bytes = SURVEY 8d narrowphase: per pair 16 + 2*48 + 2*32 read, 2*256 manifold r/w, 32 + 64 P + 16 C written"
+            key = "k_narrowphase_gjk/config3"
         else:
-            kernel_name = "k_solve (all TGS iterations, one cooperative launch)"
+            kernel_name, stage = "k_solve_tgs / k_solve_pgs (all solver iterations, one cooperative launch)", "solve"
             kernel_bytes = solve_bytes
             note = "device-wide path: rows re-streamed from HBM every iteration"
-            traffic = None
-        achieved = kernel_bytes / (solve_ms / 1e3) / 1e9
-        stages = {k: round(v / prof_steps, 4) for k, v in stage_acc.items()}
+            key = f"k_solve/config{cfg}"
+        kernel_ms = stage_acc[stage] / prof_steps
+        traffic = NCU_DRAM_BYTES_PER_LAUNCH.get(key) if key else None
+        achieved = kernel_bytes / (kernel_ms / 1e3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config {2 if args.stacks == 8 else 5}: {n_envs} envs x {args.stacks * 8} boxes = {nb} bodies per GPU, shared ground plane, GPU broadphase + {args.solver.upper()} 4 pos/1 vel iterations, 60 Hz",
-                       "bodies_total": total_bodies, "constraints_per_gpu": P, "partitions": scene.num_partitions, "path": "environment (pxb_env.cuh)" if scene.uses_env_path else "device-wide",
-                       "timing": "CUDA events on the scene stream per step, max over ranks; L2 flushed (256 MiB memset) between timed steps",
-                       "multi_gpu": ("env-partitioned, one scene per GPU, per-step all-gather of the packed pose+linear+angular velocity tensor (13 floats/body) by " + gather_kind + ", double-buffered on a communication stream (overlaps the next step)") if world > 1 else "single scene"},
+            "config": {"workload": workload_string(cfg, n_envs, args.solver, args.churn if churn else 0.0)},
+            "details": {"bodies_total": total_bodies, "pairs_per_gpu": n_pairs, "constraints_per_gpu": P, "partitions": scene.num_partitions, "path": "environment (pxb_env.cuh)" if scene.uses_env_path else "device-wide",
+                        "partitioning": ("relaxed (Jones-Plassmann rounds)" if relaxed else "exact first-fit (the reference's order-preserving greedy colouring)") if not scene.uses_env_path else "exact first-fit per environment",
+                        "settle_steps": SETTLE[cfg], "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_p95": per_step[min(len(per_step) - 1, int(len(per_step) * 0.95))],
+                        "timing": "CUDA events on the scene stream per step, max over ranks; L2 flushed (256 MiB memset) between timed steps",
+                        "multi_gpu": ("env-partitioned, one scene per GPU, per-step all-gather of the packed pose+linear+angular velocity tensor (13 floats/body) by " + str(gather_kind) + ", double-buffered on communication streams (overlaps the next step)") if gather is not None else ("independent replicas" if world > 1 else "single scene")},
             "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kernel_bytes, "kernel_ms": solve_ms,
-                         "dram_frac": (traffic / (solve_ms / 1e3) / 1e9 / peak) if traffic else None, "note": note},
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kernel_bytes, "kernel_ms": kernel_ms,
+                         "dram_frac": (traffic / (kernel_ms / 1e3) / 1e9 / peak) if traffic else None, "note": note},
             "stage_ms": stages,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nb * 24), "d2h_bytes_per_step": int(nb * (28 + 24)), "steps": e2e_steps,
                     "api": "pxb_set_rigid_dynamic_data_async(lin,ang) -> pxb_scene_simulate -> pxb_get_rigid_dynamic_data_async(pose,lin,ang) -> pxb_scene_fetch_results (one host sync per step), pinned host buffers"},
             "gpu_launches": launches, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_block()
+            line["cpu_baseline"] = cpu_baseline_block(cfg, n_envs, args.solver)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -310,17 +432,21 @@ def bench_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
-    ap.add_argument("--ref-envs", type=int, default=1024, help="environments in the reference arm's bounded sample")
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json workload (2 = the configuration the metric is quoted on)")
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU (configs 2 / 5)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stacks", type=int, default=8, help="stacks of 8 boxes per environment (8 = config 2, 16 = the per-GPU shard of config 5)")
+    ap.add_argument("--stacks", type=int, default=0, help="deprecated: --stacks 16 = --config 5")
+    ap.add_argument("--churn", type=float, default=0.0, help="fraction of the environments reset every step (configs 2 / 5)")
+    ap.add_argument("--partitioning", default="exact", choices=["exact", "relaxed"], help="configs 3 / 4: the reference's first-fit (default) or PXB_FLAG_RELAXED_PARTITIONING")
     ap.add_argument("--path", default="auto", choices=["auto", "devicewide"], help="devicewide forces the path used by scenes without environment ids (comparison runs)")
-    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-copy", "nccl"], help="multi-GPU state exchange: peer-memory copies or NCCL all-gather")
+    ap.add_argument("--gather", default="auto", choices=["auto", "fused", "peer", "peer-copy", "nccl"], help="multi-GPU state exchange")
     ap.add_argument("--solver", default="tgs", choices=["tgs", "pgs"], help="PxSolverType of the scene (headline metric: tgs)")
     args = ap.parse_args()
+    if args.stacks == 16:
+        args.config = 5
     if args.impl == "reference":
         bench_reference(args)
     else:
