@@ -1,0 +1,133 @@
+// pxb_common.cuh -- device helpers and constants shared by every translation unit of libphysx_b200.so (pxb_engine.cu: host side + small
+// kernels; pxb_narrowphase.cu; pxb_env.cu; pxb_solve.cu).  Everything here is inline device code or plain data.
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include "../../include/physx_b200.h"
+#include "pxb_math.cuh"
+#include "pxb_np.cuh"
+#include "pxb_gjk.cuh"
+#include "pxb_solver.cuh"
+
+namespace cg = cooperative_groups;
+
+#define NONE32 0xffffffffu
+#define MAX_PARTITIONS 160   // 64 dynamic colours (two rounds of the reference's 32, DyConstraintPartition.cpp:520-552) + static slots
+#ifndef PXB_SOLVE_CTAS_PER_SM
+#define PXB_SOLVE_CTAS_PER_SM 2   // measured on B200: 3 CTAs/SM (80 regs, spills, wider grid.sync) is 20% slower than 2
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// host-side record (layout of oracle/scene_format.h::PxbActorRec, 128 bytes)
+struct ActorRec {
+  uint32_t flags, geomType, envId, hullIdx;
+  float pos[3], quat[4], dims[4], linVel[3], angVel[3], mass, inertia[3], linDamping, angDamping, maxLinVel, maxAngVel, maxDepenetrationVel, reserved[2];
+};
+static_assert(sizeof(ActorRec) == 128, "actor record layout");
+
+enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_NGJK, C_COUNT = 16 };
+enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8 };
+
+struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+__device__ __forceinline__ unsigned long long ld_volatile64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ void st_volatile64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// a1: tight world AABB of one shape.  Formulas: Gu::computeBounds (geomutils/src/GuBounds.cpp:354-400, plane :210-260).
+// Gu::computeTightBounds (GuBounds.cpp:301-352; PxConvexMeshGeometry defaults to eTIGHT_BOUNDS): rotated vertices, last vertex first.  Out of line:
+// the bounds kernels of box / sphere scenes keep their register budget.
+static __device__ __noinline__ void hull_tight_bounds(const HullArrays* hulls, uint32_t hullIdx, v3 p, q4 q, float* mn, float* mx) {
+  const DevHull h = load_hull(*hulls, hullIdx);
+  const m33 b = amfromq(q);
+  v3 lo = V3(0, 0, 0), hi = V3(0, 0, 0);
+  for (uint32_t k = 0; k < h.nVerts; ++k) {
+    const v3 v = h.vert(k == 0 ? h.nVerts - 1 : k - 1);
+    const v3 w = (b.c0 * v.x + b.c1 * v.y) + b.c2 * v.z;
+    if (k == 0) { lo = w; hi = w; } else { lo = vmin(lo, w); hi = vmax(hi, w); }
+  }
+  hi = hi + p; lo = lo + p;
+  const v3 c = (hi + lo) * 0.5f, e = (hi - lo) * 0.5f;
+  mn[0] = c.x - e.x; mn[1] = c.y - e.y; mn[2] = c.z - e.z; mx[0] = c.x + e.x; mx[1] = c.y + e.y; mx[2] = c.z + e.z;
+}
+__device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d, float* mn, float* mx, const HullArrays* hulls = nullptr) {
+  if (hulls && type == PXB_GEOM_CONVEXMESH) { hull_tight_bounds(hulls, __float_as_uint(d.x), p, q, mn, mx); return; }
+  v3 e = V3(0, 0, 0); bool plane = false;
+  if (type == PXB_GEOM_SPHERE) e = V3(d.x, d.x, d.x);
+  else if (type == PXB_GEOM_CAPSULE) { const v3 dd = qbasis0(q) * d.y; e = V3(fabsf(dd.x) + d.x, fabsf(dd.y) + d.x, fabsf(dd.z) + d.x); }
+  else if (type == PXB_GEOM_BOX) {
+    const m33 b = amfromq(q);
+    const v3 c0 = b.c0 * d.x, c1 = b.c1 * d.y, c2 = b.c2 * d.z;
+    e = V3((fabsf(c0.x) + fabsf(c1.x)) + fabsf(c2.x), (fabsf(c0.y) + fabsf(c1.y)) + fabsf(c2.y), (fabsf(c0.z) + fabsf(c1.z)) + fabsf(c2.z));
+  } else if (type == PXB_GEOM_PLANE) plane = true;
+  if (!plane) { mn[0] = p.x - e.x; mn[1] = p.y - e.y; mn[2] = p.z - e.z; mx[0] = p.x + e.x; mx[1] = p.y + e.y; mx[2] = p.z + e.z; }
+  else {
+    const float big = FLT_MAX * 0.25f;
+    mn[0] = mn[1] = mn[2] = -big; mx[0] = mx[1] = mx[2] = big;
+    const v3 n = qbasis0(q); const float dd = -dot(p, n);
+    const float nx = fabsf(n.x), ny = fabsf(n.y), nz = fabsf(n.z); const float eps = 1e-6f, ome = 1.0f - eps;
+    if (nx > ome && ny < eps && nz < eps) { if (n.x > 0.f) mx[0] = -dd; else mn[0] = dd; }
+    else if (nx < eps && ny > ome && nz < eps) { if (n.y > 0.f) mx[1] = -dd; else mn[1] = dd; }
+    else if (nx < eps && ny < eps && nz > ome) { if (n.z > 0.f) mx[2] = -dd; else mn[2] = dd; }
+  }
+}
+// pair filter: closed-interval overlap on all axes (PxgIntegerAABB::intersects / ABP intersect2D semantics),
+// at least one dynamic actor (BpFiltering.h:99-114 groups), equal-or-invalid environment ids (broadphase.cu:62-80)
+__device__ __forceinline__ bool bp_test(const float4& amin, const float4& amax, const float4& bmin, const float4& bmax) {
+  if (amin.x > bmax.x || bmin.x > amax.x || amin.y > bmax.y || bmin.y > amax.y || amin.z > bmax.z || bmin.z > amax.z) return false;
+  const uint32_t fa = __float_as_uint(amax.w), fb = __float_as_uint(bmax.w);
+  if (!((fa | fb) & 0x100u)) return false;
+  const uint32_t ea = __float_as_uint(amin.w), eb = __float_as_uint(bmin.w);
+  if (ea != NONE32 && eb != NONE32 && ea != eb) return false;
+  return true;
+}
+__device__ __forceinline__ void bp_emit(uint32_t a, uint32_t b, uint32_t bitsA, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt, uint32_t cap, uint32_t* __restrict__ err) {
+  const uint32_t lo = min(a, b), hi = max(a, b);
+  const uint32_t idx = atomicAdd(cnt, 1u);
+  if (idx < cap) keys[idx] = ((uint64_t)lo << bitsA) | hi; else atomicOr(err, (uint32_t)E_PAIR_OVERFLOW);
+}
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__ k, uint32_t n, uint64_t v) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (k[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// a18 sleeping.  Per body: Dy::sleepCheck / updateWakeCounter, non-stabilised branch (lowleveldynamics/src/DySleep.cpp:169-236;
+// GPU reference: sleepCheck / updateWakeCounter in gpusolver integration.cuh:40-435).  Per island (the host island manager's
+// job in the reference pipeline, IG::IslandSim): k_sleep_islands puts an island to sleep once every body in it is ready and
+// wakes sleeping bodies that touch an awake island.  Disabled (threshold 0) for throughput runs, SURVEY.md 8d.
+struct SleepArgs { float threshold, dt; float* wake; float4 *accLin, *accAng; uint32_t *asleep, *nInter; };
+__device__ __forceinline__ bool body_asleep(const SleepArgs& S, uint32_t a) { return S.threshold > 0.f && S.asleep[a] != 0u; }
+__device__ __forceinline__ void sleep_check_dev(const SleepArgs& S, uint32_t a, q4 q, float4 invInertia, float invMassIn, v3 motionLin, v3 motionAng) {
+  const float wakeCounterResetTime = 20.0f * 0.02f;
+  float wc = S.wake[a];
+  if (wc < wakeCounterResetTime * 0.5f || wc < S.dt) {
+    const v3 inertia = V3(invInertia.x > 0.f ? 1.0f / invInertia.x : 1.0f, invInertia.y > 0.f ? 1.0f / invInertia.y : 1.0f, invInertia.z > 0.f ? 1.0f / invInertia.z : 1.0f);
+    const v3 accL = V3(S.accLin[a]) + motionLin, accA = V3(S.accAng[a]) + qrotinv(q, motionAng);
+    const float invMass = invMassIn == 0.0f ? 1.0f : invMassIn;
+    const float angular = dot(vmul(accA, accA), inertia) * invMass, linear = lensq(accL);
+    const float normalizedEnergy = 0.5f * (angular + linear);
+    const float clusterFactor = (float)(1u + S.nInter[a]);
+    const float threshold = clusterFactor * S.threshold;
+    if (normalizedEnergy >= threshold) {
+      S.accLin[a] = make_float4(0, 0, 0, 0); S.accAng[a] = make_float4(0, 0, 0, 0);   // resetSleepFilter
+      const float ratio = normalizedEnergy / threshold;
+      const float factor = threshold == 0.0f ? 2.0f : (ratio < 2.0f ? ratio : 2.0f);
+      S.wake[a] = factor * 0.5f * wakeCounterResetTime + S.dt * (clusterFactor - 1.0f);
+      return;
+    }
+    S.accLin[a] = F4(accL, 0.f); S.accAng[a] = F4(accA, 0.f);
+  }
+  wc = wc - S.dt; if (!(wc > 0.0f)) wc = 0.0f;
+  S.wake[a] = wc;
+  if (wc == 0.0f) { S.accLin[a] = make_float4(0, 0, 0, 0); S.accAng[a] = make_float4(0, 0, 0, 0); }
+}
+__device__ __forceinline__ m33 load_sym(const float4 A, const float4 B) {
+  m33 m; m.c0 = V3(A.x, A.y, A.z); m.c1 = V3(A.y, A.w, B.x); m.c2 = V3(A.z, B.x, B.y); return m;
+}
+
+// a14 inputs of one constraint: body frames, inverse masses, pre-solver velocities, world sqrt(inverse inertia)
+struct PrepBodies { xf f0, f1; float invMass0, invMass1, pen0, pen1; v3 linVel0, linVel1, angVel0, angVel1; m33 sI0, sI1; };
+

@@ -14,8 +14,6 @@
 //   k_solve_tgs/_pgs    a15/a16 solveBlockUnified + propagateAverageSolverBodyVelocityTGS loop  (ONE cooperative launch)
 //   k_finalize          a17/a18 writebackBlocksTGS + integrateCoreParallelLaunchTGS
 //   k_rd_get/k_rd_set   a19    get/setRigidDynamic* (PxDirectGPUAPI)
-#include <cuda_runtime.h>
-#include <cooperative_groups.h>
 #include <vector>
 #include <string>
 #include <algorithm>
@@ -23,36 +21,13 @@
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
-#include "../../include/physx_b200.h"
-#include "pxb_math.cuh"
-#include "pxb_np.cuh"
-#include "pxb_gjk.cuh"
-#include "pxb_solver.cuh"
+#include "pxb_launch.h"
 #include "pxb_sort.cuh"
 
-namespace cg = cooperative_groups;
 
-#define NONE32 0xffffffffu
-#define MAX_PARTITIONS 160   // 64 dynamic colours (two rounds of the reference's 32, DyConstraintPartition.cpp:520-552) + static slots
-#ifndef PXB_SOLVE_CTAS_PER_SM
-#define PXB_SOLVE_CTAS_PER_SM 2   // measured on B200: 3 CTAs/SM (80 regs, spills, wider grid.sync) is 20% slower than 2
-#endif
-
-// ---------------------------------------------------------------------------------------------
-// host-side record (layout of oracle/scene_format.h::PxbActorRec, 128 bytes)
-struct ActorRec {
-  uint32_t flags, geomType, envId, hullIdx;
-  float pos[3], quat[4], dims[4], linVel[3], angVel[3], mass, inertia[3], linDamping, angDamping, maxLinVel, maxAngVel, maxDepenetrationVel, reserved[2];
-};
-static_assert(sizeof(ActorRec) == 128, "actor record layout");
-
-enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_NGJK, C_COUNT = 16 };
-enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8 };
-
-struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };
 
 struct PxbScene {
-  PxbSceneDesc desc; cudaStream_t stream = nullptr; bool abort = false; bool stepping = false;
+  PxbSceneDesc desc; int device = 0; cudaStream_t stream = nullptr; bool abort = false; bool stepping = false;
   uint32_t nA = 0, nDyn = 0, capA = 0, capPairs = 0, bitsA = 1, nLarge = 0;
   std::vector<ActorRec> recs; std::vector<int> dynIndex; std::vector<uint32_t> dynActor; std::vector<uint32_t> largeHost;
   GridParams grid; bool gridDirty = true;
@@ -98,55 +73,20 @@ struct PxbScene {
 };
 
 static thread_local std::string g_err;
+// Every entry point runs with the scene's device current and restores the caller's on return: scenes on different GPUs can be driven from
+// one thread, and torch / other libraries may change the current device between calls.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur != device) { if (cudaSetDevice(device) == cudaSuccess) prev = cur; } else if (cur < 0) cudaGetLastError(); }
+  explicit DeviceGuard(const PxbScene* s) : DeviceGuard(s ? s->device : 0) {}
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 static HullArrays hull_arrays(const PxbScene* s) { HullArrays H; H.meta = s->hullMeta; H.verts = s->hullVerts; H.polys = s->hullPolys; H.refs = s->hullRefs; H.edges = s->hullEdges; return H; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (s) s->abort = true; return fail(PXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // kernels
-__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
-__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
-__device__ __forceinline__ unsigned long long ld_volatile64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
-__device__ __forceinline__ void st_volatile64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// a1: tight world AABB of one shape.  Formulas: Gu::computeBounds (geomutils/src/GuBounds.cpp:354-400, plane :210-260).
-// Gu::computeTightBounds (GuBounds.cpp:301-352; PxConvexMeshGeometry defaults to eTIGHT_BOUNDS): rotated vertices, last vertex first.  Out of line:
-// the bounds kernels of box / sphere scenes keep their register budget.
-__device__ __noinline__ void hull_tight_bounds(const HullArrays* hulls, uint32_t hullIdx, v3 p, q4 q, float* mn, float* mx) {
-  const DevHull h = load_hull(*hulls, hullIdx);
-  const m33 b = amfromq(q);
-  v3 lo = V3(0, 0, 0), hi = V3(0, 0, 0);
-  for (uint32_t k = 0; k < h.nVerts; ++k) {
-    const v3 v = h.vert(k == 0 ? h.nVerts - 1 : k - 1);
-    const v3 w = (b.c0 * v.x + b.c1 * v.y) + b.c2 * v.z;
-    if (k == 0) { lo = w; hi = w; } else { lo = vmin(lo, w); hi = vmax(hi, w); }
-  }
-  hi = hi + p; lo = lo + p;
-  const v3 c = (hi + lo) * 0.5f, e = (hi - lo) * 0.5f;
-  mn[0] = c.x - e.x; mn[1] = c.y - e.y; mn[2] = c.z - e.z; mx[0] = c.x + e.x; mx[1] = c.y + e.y; mx[2] = c.z + e.z;
-}
-__device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d, float* mn, float* mx, const HullArrays* hulls = nullptr) {
-  if (hulls && type == PXB_GEOM_CONVEXMESH) { hull_tight_bounds(hulls, __float_as_uint(d.x), p, q, mn, mx); return; }
-  v3 e = V3(0, 0, 0); bool plane = false;
-  if (type == PXB_GEOM_SPHERE) e = V3(d.x, d.x, d.x);
-  else if (type == PXB_GEOM_CAPSULE) { const v3 dd = qbasis0(q) * d.y; e = V3(fabsf(dd.x) + d.x, fabsf(dd.y) + d.x, fabsf(dd.z) + d.x); }
-  else if (type == PXB_GEOM_BOX) {
-    const m33 b = amfromq(q);
-    const v3 c0 = b.c0 * d.x, c1 = b.c1 * d.y, c2 = b.c2 * d.z;
-    e = V3((fabsf(c0.x) + fabsf(c1.x)) + fabsf(c2.x), (fabsf(c0.y) + fabsf(c1.y)) + fabsf(c2.y), (fabsf(c0.z) + fabsf(c1.z)) + fabsf(c2.z));
-  } else if (type == PXB_GEOM_PLANE) plane = true;
-  if (!plane) { mn[0] = p.x - e.x; mn[1] = p.y - e.y; mn[2] = p.z - e.z; mx[0] = p.x + e.x; mx[1] = p.y + e.y; mx[2] = p.z + e.z; }
-  else {
-    const float big = FLT_MAX * 0.25f;
-    mn[0] = mn[1] = mn[2] = -big; mx[0] = mx[1] = mx[2] = big;
-    const v3 n = qbasis0(q); const float dd = -dot(p, n);
-    const float nx = fabsf(n.x), ny = fabsf(n.y), nz = fabsf(n.z); const float eps = 1e-6f, ome = 1.0f - eps;
-    if (nx > ome && ny < eps && nz < eps) { if (n.x > 0.f) mx[0] = -dd; else mn[0] = dd; }
-    else if (nx < eps && ny > ome && nz < eps) { if (n.y > 0.f) mx[1] = -dd; else mn[1] = dd; }
-    else if (nx < eps && ny < eps && nz > ome) { if (n.z > 0.f) mx[2] = -dd; else mn[2] = dd; }
-  }
-}
 // a1/a2: world AABB of every actor (tight, then inflated by the contact offset, BpBroadPhaseABP.cpp:1187-1197) + grid cell key.
 __global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims,
                          const uint32_t* __restrict__ geomFlags, const uint32_t* __restrict__ envId, float contactOffset, float* __restrict__ tight,
@@ -182,27 +122,6 @@ __global__ void k_bp_gather(uint32_t nA, const uint32_t* __restrict__ sortedActo
   if (i >= nA) return;
   const uint32_t a = sortedActor[i];
   sMin[i] = aabbMin[a]; sMax[i] = aabbMax[a];
-}
-
-// pair filter: closed-interval overlap on all axes (PxgIntegerAABB::intersects / ABP intersect2D semantics),
-// at least one dynamic actor (BpFiltering.h:99-114 groups), equal-or-invalid environment ids (broadphase.cu:62-80)
-__device__ __forceinline__ bool bp_test(const float4& amin, const float4& amax, const float4& bmin, const float4& bmax) {
-  if (amin.x > bmax.x || bmin.x > amax.x || amin.y > bmax.y || bmin.y > amax.y || amin.z > bmax.z || bmin.z > amax.z) return false;
-  const uint32_t fa = __float_as_uint(amax.w), fb = __float_as_uint(bmax.w);
-  if (!((fa | fb) & 0x100u)) return false;
-  const uint32_t ea = __float_as_uint(amin.w), eb = __float_as_uint(bmin.w);
-  if (ea != NONE32 && eb != NONE32 && ea != eb) return false;
-  return true;
-}
-__device__ __forceinline__ void bp_emit(uint32_t a, uint32_t b, uint32_t bitsA, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt, uint32_t cap, uint32_t* __restrict__ err) {
-  const uint32_t lo = min(a, b), hi = max(a, b);
-  const uint32_t idx = atomicAdd(cnt, 1u);
-  if (idx < cap) keys[idx] = ((uint64_t)lo << bitsA) | hi; else atomicOr(err, (uint32_t)E_PAIR_OVERFLOW);
-}
-__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__ k, uint32_t n, uint64_t v) {
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (k[mid] < v) lo = mid + 1; else hi = mid; }
-  return lo;
 }
 
 // a4/a5: every grid object looks "forward" in (env, cz, cy, cx) order: its own row from itself on, and the
@@ -327,123 +246,6 @@ __global__ void k_np_class_scatter(const uint32_t* __restrict__ nPairsP, const u
   if (lane == leader) start = atomicAdd(&classCursor[c], (uint32_t)__popc(peers));
   start = __shfl_sync(peers, start, leader);
   pairOrder[base[c] + start + rank] = i;
-}
-
-// a8-a11: one thread per pair.  Driver logic of PxcNpBatch.cpp:364-498: body0 is the dynamic actor (for
-// two dynamics the later-created one, ScNPhaseCore.cpp:182-252), shapes are ordered by geometry type for
-// the contact function and the normal is flipped back afterwards (flipContacts).
-#ifndef PXB_NP_CTAS
-#define PXB_NP_CTAS 5
-#endif
-__global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
-                              const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
-                              float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
-                              uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters, uint32_t* __restrict__ gjkList,
-                              const uint32_t* __restrict__ pairOrder) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= *nPairsP) return;
-  const uint32_t i = pairOrder ? pairOrder[t] : t;   // mixed-type scenes: pairs binned by type pair (k_np_class_*)
-  const uint64_t key = pairKeys[i];
-#ifndef PXB_NO_PREFETCH
-  { const float4* r = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4; prefetch_l2(r); prefetch_l2(r + 8); }   // the record is needed two dependent loads later (types -> poses -> manifold)
-#endif
-  if (key == ~0ull) { cHdr[i] = make_float4(0, 0, 0, __int_as_float(0)); conFlag[i] = 0u; pairBodies[i] = make_uint2(0, 0); return; }   // dropped segment (capacity error already flagged)
-  const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
-  uint32_t a0 = hi, a1 = lo;
-  const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
-  if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
-  const uint32_t g0 = (a0 == hi) ? gfHi : gfLo, g1 = (a0 == hi) ? gfLo : gfHi;
-  const uint32_t t0 = g0 & 0xff, t1 = g1 & 0xff;
-  const bool flip = t1 < t0;
-  const uint32_t s0 = flip ? a1 : a0, s1 = flip ? a0 : a1;
-  const uint32_t ty0 = flip ? t1 : t0, ty1 = flip ? t0 : t1;
-  const float4 p0 = pos[s0], p1 = pos[s1];
-  xf tm0, tm1; tm0.p = V3(p0.x, p0.y, p0.z); tm0.q = Q4(quat[s0]); tm1.p = V3(p1.x, p1.y, p1.z); tm1.q = Q4(quat[s1]);
-  const float4 d0 = dims[s0], d1 = dims[s1];
-  float4* rec = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4;
-  // only the PCM pair types keep a persistent manifold (plane-box, box-box, plane-capsule); the closed-form sphere family does not
-  const bool usesManifold = (ty0 == PXB_GEOM_PLANE && (ty1 == PXB_GEOM_BOX || ty1 == PXB_GEOM_CAPSULE)) || (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX);   // (GJK-family pairs load theirs in k_narrowphase_gjk)
-  Manifold man;
-  if (usesManifold) manifold_load(man, rec); else { man.n = 0; man.dirty = 0; }
-  Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
-  for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
-  if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_BOX) pcm_plane_box(tm0, tm1, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
-  else if (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX) {
-    if (pcm_box_box(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out)) {
-      // edge-edge / corner configuration (rare): the SAT passed but clipping found no point -> GJK / EPA single-point fallback, called out of
-      // line so that this kernel keeps its register budget (measured: cheaper than handing the pair to a second, usually empty, launch).
-      manifold_load_warm(man, rec);
-      gjk_boxbox_gjk_fallback_outofline(&tm0, &tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
-      manifold_store_warm(man, rec);
-    }
-  }
-  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_SPHERE) np_sphere_sphere(tm0.p, tm1.p, d0.x, d1.x, contactDist, out);
-  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_PLANE) np_sphere_plane(tm0.p, d0.x, tm1, contactDist, out);
-  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_CAPSULE) np_sphere_capsule(tm0.p, d0.x, tm1, d1.x, d1.y, contactDist, out);
-  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_BOX) np_sphere_box(tm0.p, d0.x, tm1, V3(d1.x, d1.y, d1.z), contactDist, out);
-  else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CAPSULE) pcm_plane_capsule(tm0, tm1, d1.x, d1.y, contactDist, man, out);
-  else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_CAPSULE) np_capsule_capsule(tm0, tm1, d0.x, d0.y, d1.x, d1.y, contactDist, out);
-  else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_BOX) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // GJK family (a10): k_narrowphase_gjk fills this pair's outputs
-  else if (ty1 == PXB_GEOM_CONVEXMESH) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // hull pairs also go through k_narrowphase_gjk
-  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // unknown geometry type: reported by fetchResults, never silently skipped
-  if (man.dirty) manifold_store(man, rec); else if (usesManifold && man.n > 0) manifold_store_pens(man, rec);   // steady state: only the penetrations change
-  if (flip && out.count) out.normal = -out.normal;
-  cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]); }   // (cForce: every pair with contacts is a constraint and gets its forces from write-back)
-  pairBodies[i] = make_uint2(a0, a1);
-  conFlag[i] = out.count > 0 ? 1u : 0u;
-}
-
-// a10: the GJK family (capsule-box), one thread per listed pair.  Kept out of k_narrowphase so that the box / sphere hot path keeps its register budget;
-// the list order is arbitrary (atomic append) but every pair writes only its own outputs, so the result is deterministic.
-#ifndef PXB_GJK_CTAS
-#define PXB_GJK_CTAS 3   // 168 registers.  Measured on config 3 with hulls: 4 CTAs/SM (128 registers, +240 B of spills) is slower, 10.15 vs 10.0 ms/step -- the kernel is divergence bound (5 of 32 threads active), not residency bound
-#endif
-__global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, uint32_t bitsA, const float4* __restrict__ pos, const float4* __restrict__ quat,
-                              const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags, float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr,
-                              float4* __restrict__ cPts, uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, uint32_t* __restrict__ counters, const uint32_t* __restrict__ gjkList, HullArrays hulls) {
-  const uint32_t n = counters[C_NGJK];
-  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
-    const uint32_t i = gjkList[w];
-    const uint64_t key = pairKeys[i];
-    const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
-    uint32_t a0 = hi, a1 = lo;
-    const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
-    if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
-    const uint32_t t0 = ((a0 == hi) ? gfHi : gfLo) & 0xff, t1 = ((a0 == hi) ? gfLo : gfHi) & 0xff;
-    const bool flip = t1 < t0;
-    const uint32_t s0 = flip ? a1 : a0, s1 = flip ? a0 : a1;   // s0 = capsule, s1 = box
-    const float4 p0 = pos[s0], p1 = pos[s1];
-    xf tm0, tm1; tm0.p = V3(p0.x, p0.y, p0.z); tm0.q = Q4(quat[s0]); tm1.p = V3(p1.x, p1.y, p1.z); tm1.q = Q4(quat[s1]);
-    const float4 d0 = dims[s0], d1 = dims[s1];
-    float4* rec = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4;
-    Manifold man; manifold_load(man, rec); manifold_load_warm(man, rec);
-    Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
-    for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
-    const uint32_t ty1 = flip ? t0 : t1;
-    const uint32_t ty0 = flip ? t1 : t0;
-    if (ty1 == PXB_GEOM_CONVEXMESH) {   // s1 = hull, s0 = plane, sphere, capsule, box or hull
-      const DevHull h = load_hull(hulls, __float_as_uint(d1.x));
-      if (ty0 == PXB_GEOM_PLANE) gjk_pcm_plane_convex(&tm0, &tm1, h, contactDist, toleranceLength, &man, &out);
-      else if (ty0 == PXB_GEOM_SPHERE) gjk_pcm_sphere_convex(&tm0, &tm1, d0.x, &h, contactDist, toleranceLength, &man, &out);
-      else if (ty0 == PXB_GEOM_CAPSULE) gjk_pcm_capsule_convex(&tm0, &tm1, d0.x, d0.y, &h, contactDist, toleranceLength, &man, &out);
-      else {   // box-hull / hull-hull
-        int sat;
-        if (ty0 == PXB_GEOM_BOX) sat = gjk_pcm_box_convex(&tm0, &tm1, V3(d0.x, d0.y, d0.z), &h, contactDist, toleranceLength, &man, &out);
-        else { const DevHull h0 = load_hull(hulls, __float_as_uint(d0.x)); sat = gjk_pcm_convex_convex(&tm0, &tm1, &h0, &h, contactDist, toleranceLength, &man, &out); }
-        if (sat) atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);
-      }
-    }
-    else gjk_pcm_capsule_box(&tm0, &tm1, d0.x, d0.y, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
-    if (man.dirty) { manifold_store(man, rec); manifold_store_warm(man, rec); } else if (man.n > 0) manifold_store_pens(man, rec);
-    if (flip && out.count) out.normal = -out.normal;
-    cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]);
-    pairBodies[i] = make_uint2(a0, a1);
-    conFlag[i] = out.count > 0 ? 1u : 0u;
-  }
 }
 
 __global__ void k_compact(const uint32_t* __restrict__ nPairsP, const uint32_t* __restrict__ conFlag, const uint32_t* __restrict__ conIdx, uint32_t* __restrict__ conPair,
@@ -616,36 +418,6 @@ __global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// a18 sleeping.  Per body: Dy::sleepCheck / updateWakeCounter, non-stabilised branch (lowleveldynamics/src/DySleep.cpp:169-236;
-// GPU reference: sleepCheck / updateWakeCounter in gpusolver integration.cuh:40-435).  Per island (the host island manager's
-// job in the reference pipeline, IG::IslandSim): k_sleep_islands puts an island to sleep once every body in it is ready and
-// wakes sleeping bodies that touch an awake island.  Disabled (threshold 0) for throughput runs, SURVEY.md 8d.
-struct SleepArgs { float threshold, dt; float* wake; float4 *accLin, *accAng; uint32_t *asleep, *nInter; };
-__device__ __forceinline__ bool body_asleep(const SleepArgs& S, uint32_t a) { return S.threshold > 0.f && S.asleep[a] != 0u; }
-__device__ __forceinline__ void sleep_check_dev(const SleepArgs& S, uint32_t a, q4 q, float4 invInertia, float invMassIn, v3 motionLin, v3 motionAng) {
-  const float wakeCounterResetTime = 20.0f * 0.02f;
-  float wc = S.wake[a];
-  if (wc < wakeCounterResetTime * 0.5f || wc < S.dt) {
-    const v3 inertia = V3(invInertia.x > 0.f ? 1.0f / invInertia.x : 1.0f, invInertia.y > 0.f ? 1.0f / invInertia.y : 1.0f, invInertia.z > 0.f ? 1.0f / invInertia.z : 1.0f);
-    const v3 accL = V3(S.accLin[a]) + motionLin, accA = V3(S.accAng[a]) + qrotinv(q, motionAng);
-    const float invMass = invMassIn == 0.0f ? 1.0f : invMassIn;
-    const float angular = dot(vmul(accA, accA), inertia) * invMass, linear = lensq(accL);
-    const float normalizedEnergy = 0.5f * (angular + linear);
-    const float clusterFactor = (float)(1u + S.nInter[a]);
-    const float threshold = clusterFactor * S.threshold;
-    if (normalizedEnergy >= threshold) {
-      S.accLin[a] = make_float4(0, 0, 0, 0); S.accAng[a] = make_float4(0, 0, 0, 0);   // resetSleepFilter
-      const float ratio = normalizedEnergy / threshold;
-      const float factor = threshold == 0.0f ? 2.0f : (ratio < 2.0f ? ratio : 2.0f);
-      S.wake[a] = factor * 0.5f * wakeCounterResetTime + S.dt * (clusterFactor - 1.0f);
-      return;
-    }
-    S.accLin[a] = F4(accL, 0.f); S.accAng[a] = F4(accA, 0.f);
-  }
-  wc = wc - S.dt; if (!(wc > 0.0f)) wc = 0.0f;
-  S.wake[a] = wc;
-  if (wc == 0.0f) { S.accLin[a] = make_float4(0, 0, 0, 0); S.accAng[a] = make_float4(0, 0, 0, 0); }
-}
 // islands = connected components over touching dynamic-dynamic pairs (min-label hooking + pointer jumping, cooperative)
 __global__ void __launch_bounds__(256) k_sleep_islands(uint32_t nA, const uint32_t* __restrict__ nPairsP, const uint2* __restrict__ pairBodies, const float4* __restrict__ cHdr,
                                                        const uint32_t* __restrict__ geomFlags, SleepArgs S, uint32_t* __restrict__ label, uint32_t* __restrict__ islandAwake,
@@ -736,13 +508,6 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
   sbIA[a] = make_float4(sI.c0.x, sI.c0.y, sI.c0.z, sI.c1.y); sbIB[a] = make_float4(sI.c1.z, sI.c2.z, __uint_as_float(lock), 0.f);
   sbP[a] = make_float4(p4.x, p4.y, p4.z, 0.f); sbQ[a] = make_float4(0, 0, 0, 1); sbOrigAng[a] = F4(av, 0.f);
 }
-__device__ __forceinline__ m33 load_sym(const float4 A, const float4 B) {
-  m33 m; m.c0 = V3(A.x, A.y, A.z); m.c1 = V3(A.y, A.w, B.x); m.c2 = V3(A.z, B.x, B.y); return m;
-}
-
-// a14 inputs of one constraint: body frames, inverse masses, pre-solver velocities, world sqrt(inverse inertia)
-struct PrepBodies { xf f0, f1; float invMass0, invMass1, pen0, pen1; v3 linVel0, linVel1, angVel0, angVel1; m33 sI0, sI1; };
-
 // a17/a18: copyBackBodies (DyTGSDynamics.cpp:1549-1580); bodies without constraints take one full-dt step (:2573-2577)
 __global__ void k_finalize_bodies(uint32_t nDyn, const uint32_t* __restrict__ dynActor, float dt, float4* __restrict__ pos, float4* __restrict__ quat, float4* __restrict__ linVel,
                                   float4* __restrict__ angVel, const float4* __restrict__ sbLin, const float4* __restrict__ sbAng, const float4* __restrict__ sbIA,
@@ -825,7 +590,6 @@ __global__ void k_env_begin(uint32_t* __restrict__ counters) {   // per-step cou
   if (threadIdx.x == 0) { counters[C_NPAIRS_NEW] = 0; counters[C_NCREATED] = 0; counters[C_NDELETED] = 0; counters[C_NCON] = 0; counters[C_NPART] = 0; counters[C_NGJK] = 0; counters[C_MAXCONENV] = 0; counters[C_MAXPAIRENV] = 0;
                           counters[C_FREE_SNAP] = counters[C_FREE_TAIL]; }
 }
-#include "pxb_env.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -893,24 +657,17 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PXB_ERR_NO_DEVICE, "no CUDA device: physx_b200 has no CPU fallback"); }
   if (desc->solverType != PXB_SOLVER_TGS && desc->solverType != PXB_SOLVER_PGS) return fail(PXB_ERR_INVALID, "unknown solver type");
   if (desc->device < 0 || desc->device >= ndev) return fail(PXB_ERR_INVALID, "bad device ordinal");
-  s = new PxbScene(); s->desc = *desc;
-  CK(cudaSetDevice(desc->device));
+  DeviceGuard dg_(desc->device);
+  s = new PxbScene(); s->desc = *desc; s->device = desc->device;
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, desc->device));
   s->numSMs = prop.multiProcessorCount;
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_colour_partition, 256, 0)); s->coopBlocksColour = std::max(1, std::min(occ, 4)) * s->numSMs;
-#define ENV_ATTR(T) do { CK(cudaFuncSetAttribute(k_env_solve<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); \
-                         CK(cudaFuncSetAttribute(k_env_solve<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); \
-                         CK(cudaFuncSetAttribute(k_env_solve<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); \
-                         CK(cudaFuncSetAttribute(k_env_solve<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENV_SMEM_MAX)); } while (0)
-  ENV_ATTR(32); ENV_ATTR(64); ENV_ATTR(128); ENV_ATTR(256);
-#undef ENV_ATTR
-  CK(cudaFuncSetAttribute(k_env_bp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
-  CK(cudaFuncSetAttribute(k_env_bp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
+  CK(pxb_env_set_attributes((int)ENV_SMEM_MAX, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sleep_islands, 256, 0)); s->coopBlocksSleep = std::max(1, std::min(occ, 2)) * s->numSMs;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_pgs, 256, 0)); s->coopBlocksSolvePgs = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_tgs, 256, 0)); s->coopBlocksSolve = std::max(1, std::min(occ, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs;
+  { int occT = 0, occP = 0; CK(pxb_solve_occupancy(&occT, &occP));
+    s->coopBlocksSolvePgs = std::max(1, std::min(occP, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs; s->coopBlocksSolve = std::max(1, std::min(occT, PXB_SOLVE_CTAS_PER_SM)) * s->numSMs; }
   s->capA = std::max(16u, desc->maxActors);
   s->capPairs = desc->maxPairs ? desc->maxPairs : std::max(1024u, 8u * s->capA);
   s->bitsA = bits_for(s->capA);
@@ -926,7 +683,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   return PXB_OK;
 }
 
-PXB_API void pxb_scene_release(PxbScene* s) {
+PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
   if (!s) return;
   cudaStreamSynchronize(s->stream);
   drop_graphs(s);
@@ -945,8 +702,8 @@ PXB_API void pxb_scene_release(PxbScene* s) {
 
 PXB_API uint32_t pxb_scene_num_actors(const PxbScene* s) { return s ? s->nA : 0; }
 PXB_API uint32_t pxb_scene_num_dynamic(const PxbScene* s) { return s ? s->nDyn : 0; }
-PXB_API void* pxb_scene_stream(PxbScene* s) { return s ? (void*)s->stream : nullptr; }
-PXB_API void* pxb_scene_state_device_ptr(PxbScene* s, int which) {
+PXB_API void* pxb_scene_stream(PxbScene* s) { DeviceGuard dg_(s); return s ? (void*)s->stream : nullptr; }
+PXB_API void* pxb_scene_state_device_ptr(PxbScene* s, int which) { DeviceGuard dg_(s);
   if (!s) return nullptr;
   switch (which) { case 0: return s->pos; case 1: return s->quat; case 2: return s->linVel; case 3: return s->angVel; default: return nullptr; }
 }
@@ -1062,39 +819,44 @@ static void rebuild_grid(PxbScene* s) {
 
 // Cooked convex hulls (Gu::ConvexHullData as produced by the host's PxCreateConvexMesh; the reference uploads the same data per shape through
 // PxsSimulationController::addPxgShape -> PxgShape::hullOrMeshPtr, PxgConvexConvexShape.h:50-65).  Layout: include/physx_b200.h.
-PXB_API int pxb_scene_set_convex_meshes(PxbScene* s, const void* cooked, size_t bytes, uint32_t nHulls) {
+PXB_API int pxb_scene_set_convex_meshes(PxbScene* s, const void* cooked, size_t bytes, uint32_t nHulls) { DeviceGuard dg_(s);
   if (!s || (!cooked && nHulls)) return fail(PXB_ERR_INVALID, "null argument");
   if (s->nHulls) return fail(PXB_ERR_INVALID, "convex meshes are set once per scene, before the actors that use them");
   const uint8_t* q = (const uint8_t*)cooked; const uint8_t* end = q + bytes;
-  std::vector<uint4> meta; std::vector<float4> verts, polys; std::vector<uint8_t> refs, edges;
+  std::vector<uint4> meta; std::vector<float4> verts, polys; std::vector<uint8_t> refs, edges; std::vector<float> diam;   // host state is committed only after the whole blob is validated
   for (uint32_t h = 0; h < nHulls; ++h) {
-    if (q + sizeof(PxbCookedHullHeader) > end) return fail(PXB_ERR_INVALID, "cooked hull data truncated");
+    if ((size_t)(end - q) < sizeof(PxbCookedHullHeader)) return fail(PXB_ERR_INVALID, "cooked hull data truncated");
     PxbCookedHullHeader ch; memcpy(&ch, q, sizeof(ch)); q += sizeof(ch);
-    const size_t need = (size_t)ch.nVerts * 12 + (size_t)ch.nPolys * sizeof(PxbCookedPoly) + (ch.nIdx + 3) / 4 * 4 + (2 * (size_t)ch.nEdges + 3) / 4 * 4;
-    if (q + need > end || ch.nVerts > 255 || ch.nPolys > 255) return fail(PXB_ERR_INVALID, "cooked hull data truncated or out of range");
+    // sizes in size_t with every count bounded first (a hull of <= 255 vertices / polygons has at most 3 * 255 edges and 255 * 32 vertex references)
+    if (ch.nVerts > 255 || ch.nPolys > 255 || ch.nEdges > 3u * 255u || ch.nIdx > 255u * 32u) return fail(PXB_ERR_INVALID, "cooked hull data out of range");
+    const size_t idxBytes = ((size_t)ch.nIdx + 3) / 4 * 4, edgeBytes = (2 * (size_t)ch.nEdges + 3) / 4 * 4;
+    const size_t need = (size_t)ch.nVerts * 12 + (size_t)ch.nPolys * sizeof(PxbCookedPoly) + idxBytes + edgeBytes;
+    if ((size_t)(end - q) < need) return fail(PXB_ERR_INVALID, "cooked hull data truncated or out of range");
     // the reference's GPU pipeline takes hulls of <= 64 vertices and <= 64 polygons (PxConvexMeshDesc.h:139, cooking with buildGPUData); larger ones fall back to its CPU narrowphase
     if (ch.nVerts > 64 || ch.nPolys > 64) return fail(PXB_ERR_UNSUPPORTED, "convex hulls are limited to 64 vertices and 64 polygons (the reference's GPU-compatible limit)");
     const uint32_t bigSubdiv = ch.reserved[0] & 0xffffu, bigAdj = ch.reserved[0] >> 16;   // Gu::BigConvexRawData: hulls of more than 32 vertices
     const size_t bigBytes = bigSubdiv ? (6 * (size_t)bigSubdiv * bigSubdiv + 3) / 4 * 4 + (size_t)ch.nVerts * 4 + (bigAdj + 3) / 4 * 4 : 0;
-    if (q + need + bigBytes > end) return fail(PXB_ERR_INVALID, "cooked hull data truncated");
+    if ((size_t)(end - q) < need + bigBytes) return fail(PXB_ERR_INVALID, "cooked hull data truncated");
     if (ch.nVerts > 32 && !bigSubdiv) return fail(PXB_ERR_INVALID, "a hull of more than 32 vertices needs its hill-climbing data (Gu::BigConvexRawData)");
     meta.push_back(make_uint4((uint32_t)verts.size(), (uint32_t)(polys.size() / 2), (uint32_t)refs.size(), (uint32_t)edges.size()));
     meta.push_back(make_uint4(ch.nVerts, ch.nPolys, ch.nEdges, ch.nIdx));
     uint4 m2; memcpy(&m2.x, &ch.internalExtents[0], 4); memcpy(&m2.y, &ch.internalExtents[1], 4); memcpy(&m2.z, &ch.internalExtents[2], 4); memcpy(&m2.w, &ch.internalRadius, 4);
     meta.push_back(m2);
     uint4 m3; memcpy(&m3.x, &ch.centerOfMass[0], 4); memcpy(&m3.y, &ch.centerOfMass[1], 4); memcpy(&m3.z, &ch.centerOfMass[2], 4); m3.w = bigSubdiv; meta.push_back(m3);
-    s->hullDiam.push_back(2.f * (std::sqrt(ch.boundsCenter[0] * ch.boundsCenter[0] + ch.boundsCenter[1] * ch.boundsCenter[1] + ch.boundsCenter[2] * ch.boundsCenter[2]) +
+    diam.push_back(2.f * (std::sqrt(ch.boundsCenter[0] * ch.boundsCenter[0] + ch.boundsCenter[1] * ch.boundsCenter[1] + ch.boundsCenter[2] * ch.boundsCenter[2]) +
                                  std::sqrt(ch.boundsExtents[0] * ch.boundsExtents[0] + ch.boundsExtents[1] * ch.boundsExtents[1] + ch.boundsExtents[2] * ch.boundsExtents[2])));
     const float* v = (const float*)q; for (uint32_t i = 0; i < ch.nVerts; ++i) verts.push_back(make_float4(v[i * 3], v[i * 3 + 1], v[i * 3 + 2], 0.f));
     q += (size_t)ch.nVerts * 12;
     for (uint32_t p = 0; p < ch.nPolys; ++p) {
       PxbCookedPoly cp; memcpy(&cp, q, sizeof(cp)); q += sizeof(cp);
-      if (cp.nbVerts < 3 || cp.nbVerts > 32 || cp.vref + cp.nbVerts > ch.nIdx) return fail(PXB_ERR_INVALID, "hull polygon out of range (3..32 vertices per polygon)");
+      if (cp.nbVerts < 3 || cp.nbVerts > 32 || (size_t)cp.vref + cp.nbVerts > ch.nIdx || cp.minIndex >= ch.nVerts) return fail(PXB_ERR_INVALID, "hull polygon out of range (3..32 vertices per polygon)");
       polys.push_back(make_float4(cp.plane[0], cp.plane[1], cp.plane[2], cp.plane[3]));
       float4 m; memcpy(&m.x, &cp.vref, 4); memcpy(&m.y, &cp.nbVerts, 4); memcpy(&m.z, &cp.minIndex, 4); m.w = 0.f; polys.push_back(m);
     }
-    refs.insert(refs.end(), q, q + ch.nIdx); q += (ch.nIdx + 3) / 4 * 4;
-    edges.insert(edges.end(), q, q + (2 * (size_t)ch.nEdges + 3) / 4 * 4); q += (2 * (size_t)ch.nEdges + 3) / 4 * 4;   // padded: every hull starts 4-byte aligned
+    for (uint32_t i = 0; i < ch.nIdx; ++i) if (q[i] >= ch.nVerts) return fail(PXB_ERR_INVALID, "hull vertex reference out of range");
+    refs.insert(refs.end(), q, q + ch.nIdx); q += idxBytes;
+    for (uint32_t i = 0; i < 2 * ch.nEdges; ++i) if (q[i] >= ch.nPolys) return fail(PXB_ERR_INVALID, "hull edge face out of range");
+    edges.insert(edges.end(), q, q + edgeBytes); q += edgeBytes;   // padded: every hull starts 4-byte aligned
     if (bigSubdiv) {   // samples | valencies | adjacent vertices, as they lie in the cooked section (load_hull / gjk_hull_hill_climb)
       const uint8_t* val = q + (6 * (size_t)bigSubdiv * bigSubdiv + 3) / 4 * 4; const uint8_t* adj = val + (size_t)ch.nVerts * 4;
       for (uint32_t i = 0; i < 6 * bigSubdiv * bigSubdiv; ++i) if (q[i] >= ch.nVerts) return fail(PXB_ERR_INVALID, "hill-climbing sample out of range");
@@ -1104,6 +866,7 @@ PXB_API int pxb_scene_set_convex_meshes(PxbScene* s, const void* cooked, size_t 
     }
   }
   if (!nHulls) { s->hullDiam.clear(); return PXB_OK; }
+  s->hullDiam = diam;
   CK(dalloc(s->hullMeta, meta.size())); CK(dalloc(s->hullVerts, verts.size())); CK(dalloc(s->hullPolys, polys.size())); CK(dalloc(s->hullRefs, refs.size() + 4)); CK(dalloc(s->hullEdges, edges.size() + 4));
   CK(cudaMemcpyAsync(s->hullMeta, meta.data(), 16 * meta.size(), cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->hullVerts, verts.data(), 16 * verts.size(), cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->hullPolys, polys.data(), 16 * polys.size(), cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->hullRefs, refs.data(), refs.size(), cudaMemcpyHostToDevice, s->stream));
@@ -1113,18 +876,21 @@ PXB_API int pxb_scene_set_convex_meshes(PxbScene* s, const void* cooked, size_t 
   return PXB_OK;
 }
 
-PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
+PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) { DeviceGuard dg_(s);
   if (!s || !recsIn) return fail(PXB_ERR_INVALID, "null argument");
   if (s->abort) return fail(PXB_ERR_CUDA, "scene is in abort mode");
   if (s->nA + nb > s->capA) return fail(PXB_ERR_CAPACITY, "maxActors exceeded");
   const ActorRec* in = (const ActorRec*)recsIn;
   const uint32_t base = s->nA;
   std::vector<float4> pos(nb), quat(nb), lin(nb), ang(nb), inv(nb), dmp(nb), dims(nb); std::vector<uint32_t> env(nb);
-  for (uint32_t i = 0; i < nb; ++i) {
+  for (uint32_t i = 0; i < nb; ++i) {   // first pass: every record is checked before any host state changes (a rejected batch leaves the scene untouched)
     const ActorRec& r = in[i];
     if (r.geomType == PXB_GEOM_CONVEXMESH) { if (r.hullIdx >= s->nHulls) return fail(PXB_ERR_UNSUPPORTED, "convex actor without a cooked hull: call pxb_scene_set_convex_meshes first"); }
     else if (r.geomType != PXB_GEOM_BOX && r.geomType != PXB_GEOM_PLANE && r.geomType != PXB_GEOM_SPHERE && r.geomType != PXB_GEOM_CAPSULE)
       return fail(PXB_ERR_UNSUPPORTED, "geometry type not supported yet");
+  }
+  for (uint32_t i = 0; i < nb; ++i) {
+    const ActorRec& r = in[i];
     const bool dyn = r.flags & PXB_ACTOR_DYNAMIC;
     s->recs.push_back(r);
     if (r.geomType == PXB_GEOM_CONVEXMESH) s->recs.back().dims[3] = s->hullDiam[r.hullIdx];   // bounding diameter for the broadphase grid
@@ -1149,7 +915,7 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
   return PXB_OK;
 }
 
-PXB_API int pxb_scene_set_constraint_order(PxbScene* s, const uint32_t* pairs, uint32_t n) {
+PXB_API int pxb_scene_set_constraint_order(PxbScene* s, const uint32_t* pairs, uint32_t n) { DeviceGuard dg_(s);
   if (!s) return fail(PXB_ERR_INVALID, "null scene");
   s->nOrder = 0;
   if (!n) return PXB_OK;
@@ -1199,7 +965,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     A.oldKeys = s->pairKeys[prev]; A.oldSlots = s->pairSlots[prev]; A.oldSeg = s->envSeg[prev]; A.newKeys = s->pairKeys[cur]; A.newSlots = s->pairSlots[cur]; A.newSeg = s->envSeg[cur];
     A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions; A.slotColour = s->slotColour;
     const size_t smem = (size_t)ENV_BP_WARPS * (s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t)) + ENV_BP_STAGE * sizeof(uint64_t));
-    if (s->anyConvex) k_env_bp<true><<<cdiv(s->nEnv, ENV_BP_WARPS), 32 * ENV_BP_WARPS, smem, st>>>(A); else k_env_bp<false><<<cdiv(s->nEnv, ENV_BP_WARPS), 32 * ENV_BP_WARPS, smem, st>>>(A);
+    pxb_launch_env_bp(st, A, s->anyConvex, smem);
     s->launches++;
     LAUNCH(k_clamp_count, 1, 32, s->counters, s->capPairs, s->nPairsDev + cur);
     return PXB_OK;
@@ -1243,6 +1009,7 @@ static int read_counters(PxbScene* s) {
       if (s->hMaxPairEnv > s->envConCap ? want != s->envConCap : want * 2 <= s->envConCap) { s->envConCap = want; drop_graphs(s); }
     }
   }
+  if (s->hErr) CK(cudaMemsetAsync(s->counters + C_ERROR, 0, 4, s->stream));   // an error is reported by the fetchResults of the step that raised it, not by every later one
   if (s->hErr & E_PAIR_OVERFLOW) return fail(PXB_ERR_CAPACITY, "broadphase pair capacity (maxPairs) exceeded");
   if (s->hErr & (E_COLOUR_OVERFLOW | E_PARTITION_OVERFLOW)) return fail(PXB_ERR_CAPACITY, "more than 64 dynamic colours / 160 partitions needed");
   if (s->hErr & E_UNSUPPORTED_PAIR) return fail(PXB_ERR_UNSUPPORTED, "a pair of an unsupported geometry type came into contact range");
@@ -1264,10 +1031,12 @@ static int enqueue_step(PxbScene* s, float dt) {
     LAUNCH(k_np_class_count, gP, B, s->pairKeys[cur], nP, s->bitsA, s->geomFlags, s->npClass, s->npClassCount, s->pairSlots[cur], s->manifolds);
     LAUNCH(k_np_class_scatter, gP, B, nP, s->npClass, s->npClassCount, s->npClassCount + NP_CLASSES, s->pairOrder);
   }
-  LAUNCH(k_narrowphase, cdiv(s->capPairs, 128), 128, s->pairKeys[cur], s->pairSlots[cur], nP, s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds,
-         s->cHdr, s->cPts, s->pairBodies, s->conFlag, s->cForce, s->counters, s->gjkList, s->binPairs ? s->pairOrder : (const uint32_t*)nullptr);
-  if (s->hasGjkPairs) LAUNCH(k_narrowphase_gjk, std::max(148u * 4u, std::min(cdiv(s->capPairs, 128), 148u * 64u)), 128, s->pairKeys[cur], s->pairSlots[cur], s->bitsA, s->pos, s->quat, s->dims, s->geomFlags, contactDist, s->desc.toleranceLength, s->manifolds, s->cHdr, s->cPts,
-                             s->pairBodies, s->conFlag, s->counters, s->gjkList, hull_arrays(s));
+  NpArgs NA;
+  NA.pairKeys = s->pairKeys[cur]; NA.pairSlots = s->pairSlots[cur]; NA.nPairsP = nP; NA.bitsA = s->bitsA; NA.pos = s->pos; NA.quat = s->quat; NA.dims = s->dims; NA.geomFlags = s->geomFlags;
+  NA.contactDist = contactDist; NA.toleranceLength = s->desc.toleranceLength; NA.manifolds = s->manifolds; NA.cHdr = s->cHdr; NA.cPts = s->cPts; NA.pairBodies = s->pairBodies; NA.conFlag = s->conFlag;
+  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s);
+  pxb_launch_narrowphase(st, s->capPairs, NA); s->launches++;
+  if (s->hasGjkPairs) { pxb_launch_narrowphase_gjk(st, std::max(148u * 4u, std::min(cdiv(s->capPairs, 128), 148u * 64u)), NA); s->launches++; }
   SleepArgs SA; SA.threshold = s->sleepThreshold; SA.dt = dt; SA.wake = s->wake; SA.accLin = s->accLin; SA.accAng = s->accAng; SA.asleep = s->asleep; SA.nInter = s->nInter;
   if (s->sleepThreshold > 0.f) {   // island sleep / wake decisions for this step (needs this frame's touching pairs)
     uint32_t nA = s->nA;
@@ -1295,10 +1064,7 @@ static int enqueue_step(PxbScene* s, float dt) {
     A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour; A.S = SA;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
     const bool ext = s->anyLocks || s->forcesUsed;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
-#define ENV_LAUNCH(T) do { if (pgs) { if (ext) k_env_solve<T, true, true><<<s->nEnv, T, smem, st>>>(A); else k_env_solve<T, true, false><<<s->nEnv, T, smem, st>>>(A); } \
-                           else { if (ext) k_env_solve<T, false, true><<<s->nEnv, T, smem, st>>>(A); else k_env_solve<T, false, false><<<s->nEnv, T, smem, st>>>(A); } } while (0)
-    if (s->envSolveThreads == 32) ENV_LAUNCH(32); else if (s->envSolveThreads == 64) ENV_LAUNCH(64); else if (s->envSolveThreads == 128) ENV_LAUNCH(128); else ENV_LAUNCH(256);
-#undef ENV_LAUNCH
+    pxb_launch_env_solve(st, A, s->envSolveThreads, pgs, ext, smem);
     s->launches++;
     MARK(5); MARK(6);
     CK(cudaGetLastError());
@@ -1332,31 +1098,26 @@ static int enqueue_step(PxbScene* s, float dt) {
   MARK(3);
   LAUNCH(k_preintegrate, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, g[0], g[1], g[2], dt, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng,
          s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, pgs ? 1 : 0, SA, s->geomFlags, s->forcesUsed ? s->extForce : (float4*)nullptr, s->forcesUsed ? s->extTorque : (float4*)nullptr);
-  if (pgs) {   // PGS: rows in the 25-float4 record image, velocity-delta solver bodies (pxb_pgs.cuh)
+  {   // rows in the same 25-float4 record image as the environment path (pxb_env.cuh RegRows); PGS: velocity-delta solver bodies (pxb_pgs.cuh)
     Rows R; R.f = s->ptA; R.broken = s->conDone; R.stride = s->capPairs;
-    LAUNCH(k_prep_rows<true>, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
-           s->invInertia, s->sbIA, s->sbIB, s->frictions, P, R);
+    PrepArgs PA;
+    PA.counters = s->counters; PA.ordered = s->ordered; PA.conPair = s->conPair; PA.pairSlots = s->pairSlots[cur]; PA.pairBodies = s->pairBodies; PA.geomFlags = s->geomFlags; PA.cHdr = s->cHdr; PA.cPts = s->cPts;
+    PA.pos = s->pos; PA.quat = s->quat; PA.linVel = s->linVel; PA.sbOrigAng = s->sbOrigAng; PA.invInertia = s->invInertia; PA.sbIA = s->sbIA; PA.sbIB = s->sbIB; PA.frictions = s->frictions; PA.P = P; PA.R = R;
+    pxb_launch_prep_rows(st, pgs, s->capPairs, PA); s->launches++;
     MARK(4);
-    uint32_t posIters = s->desc.posIters, velIters = s->desc.velIters, nDyn = s->nDyn;
-    void* args[] = {&s->counters, &s->partStart, &posIters, &velIters, &R, &s->sbLin, &s->sbAng, &s->sbDLin, &s->sbDAng, &nDyn, &s->dynActorDev};
-    CK(cudaLaunchCooperativeKernel((void*)k_solve_pgs, dim3(s->coopBlocksSolvePgs), dim3(256), args, 0, st)); s->launches++;
+    SolveArgs VA;
+    VA.counters = s->counters; VA.partStart = s->partStart; VA.posIters = s->desc.posIters; VA.velIters = s->desc.velIters; VA.stepDt = P.stepDt; VA.R = R;
+    VA.sbLin = s->sbLin; VA.sbAng = s->sbAng; VA.sbDLin = s->sbDLin; VA.sbDAng = s->sbDAng; VA.sbIA = s->sbIA; VA.sbIB = s->sbIB; VA.sbP = s->sbP; VA.sbQ = s->sbQ; VA.bodyHasCon = s->bodyHasCon;
+    VA.nDyn = s->nDyn; VA.dynActor = s->dynActorDev;
+    CK(pxb_launch_solve(st, pgs, pgs ? s->coopBlocksSolvePgs : s->coopBlocksSolve, VA)); s->launches++;
     MARK(5);
-    LAUNCH(k_writeback_rows, gP, B, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions);
-    LAUNCH(k_finalize_bodies_pgs, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->invInertia, SA);
-    MARK(6);
-    CK(cudaGetLastError());
-    return PXB_OK;
-  }
-  {   // TGS: rows in the same 25-float4 record image as the environment path (pxb_env.cuh RegRows)
-    Rows R; R.f = s->ptA; R.broken = s->conDone; R.stride = s->capPairs;
-    LAUNCH(k_prep_rows<false>, cdiv(s->capPairs, 128), 128, s->counters, s->ordered, s->conPair, s->pairSlots[cur], s->pairBodies, s->geomFlags, s->cHdr, s->cPts, s->pos, s->quat, s->linVel, s->sbOrigAng,
-           s->invInertia, s->sbIA, s->sbIB, s->frictions, P, R);
-    MARK(4);
-    uint32_t posIters = s->desc.posIters, velIters = s->desc.velIters, nDyn = s->nDyn; float stepDt = P.stepDt;
-    void* args[] = {&s->counters, &s->partStart, &posIters, &velIters, &stepDt, &R, &s->sbLin, &s->sbAng, &s->sbDLin, &s->sbDAng, &s->sbIA, &s->sbIB, &s->sbP, &s->sbQ, &s->bodyHasCon, &nDyn, &s->dynActorDev};
-    CK(cudaLaunchCooperativeKernel((void*)k_solve_tgs, dim3(s->coopBlocksSolve), dim3(256), args, 0, st)); s->launches++;
-    MARK(5);
-    LAUNCH(k_writeback_rows, gP, B, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions);
+    pxb_launch_writeback_rows(st, s->capPairs, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions); s->launches++;
+    if (pgs) {
+      pxb_launch_finalize_bodies_pgs(st, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->invInertia, SA); s->launches++;
+      MARK(6);
+      CK(cudaGetLastError());
+      return PXB_OK;
+    }
   }
   LAUNCH(k_finalize_bodies, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->bodyHasCon,
          s->sbDLin, s->sbDAng, s->invInertia, SA);
@@ -1372,7 +1133,7 @@ static void drop_graphs(PxbScene* s) {
 // The launch sequence of a step depends only on the buffer parity (all counts live in device memory), so it is
 // captured once per parity into a CUDA graph and replayed: ~55 kernel launches become one graph launch.
 // Teacher-forced constraint order, stage profiling and PXB_NO_GRAPH=1 use direct launches.
-PXB_API int pxb_scene_simulate(PxbScene* s, float dt) {
+PXB_API int pxb_scene_simulate(PxbScene* s, float dt) { DeviceGuard dg_(s);
   if (!s) return fail(PXB_ERR_INVALID, "null scene");
   if (s->abort) return fail(PXB_ERR_CUDA, "scene is in abort mode");
   if (s->nA == 0) return PXB_OK;
@@ -1408,13 +1169,13 @@ PXB_API int pxb_scene_simulate(PxbScene* s, float dt) {
 // Per-stage device times of the last completed step (CUDA events on the scene stream), in ms:
 // [0] bounds+broadphase+pair lifecycle, [1] narrowphase, [2] constraint ordering+colouring, [3] preintegrate+prep,
 // [4] solve (the cooperative k_solve launch), [5] writeback+integration, [6] whole step.
-PXB_API int pxb_scene_set_profiling(PxbScene* s, int enable) {
+PXB_API int pxb_scene_set_profiling(PxbScene* s, int enable) { DeviceGuard dg_(s);
   if (!s) return fail(PXB_ERR_INVALID, "null scene");
   if (enable && !s->ev[0]) for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&s->ev[i]));
   s->profiling = enable != 0;
   return PXB_OK;
 }
-PXB_API int pxb_scene_get_stage_times(PxbScene* s, float* ms7) {
+PXB_API int pxb_scene_get_stage_times(PxbScene* s, float* ms7) { DeviceGuard dg_(s);
   if (!s || !ms7) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->profiling) return fail(PXB_ERR_INVALID, "profiling is off");
   CK(cudaEventSynchronize(s->ev[6]));
@@ -1423,14 +1184,14 @@ PXB_API int pxb_scene_get_stage_times(PxbScene* s, float* ms7) {
   return PXB_OK;
 }
 
-PXB_API int pxb_scene_fetch_results(PxbScene* s, int block) {
+PXB_API int pxb_scene_fetch_results(PxbScene* s, int block) { DeviceGuard dg_(s);
   if (!s) return fail(PXB_ERR_INVALID, "null scene");
   if (!block) { const cudaError_t e = cudaStreamQuery(s->stream); if (e == cudaErrorNotReady) return 1; }
   s->stepping = false;
   return read_counters(s);
 }
 
-PXB_API int pxb_scene_compute_bounds(PxbScene* s) {
+PXB_API int pxb_scene_compute_bounds(PxbScene* s) { DeviceGuard dg_(s);
   if (!s) return fail(PXB_ERR_INVALID, "null scene");
   cudaStream_t st = s->stream;
   if (s->gridDirty) rebuild_grid(s);
@@ -1438,12 +1199,12 @@ PXB_API int pxb_scene_compute_bounds(PxbScene* s) {
   CK(cudaStreamSynchronize(st));
   return PXB_OK;
 }
-PXB_API int pxb_scene_get_bounds(PxbScene* s, float* out6) {
+PXB_API int pxb_scene_get_bounds(PxbScene* s, float* out6) { DeviceGuard dg_(s);
   if (!s || !out6) return fail(PXB_ERR_INVALID, "null argument");
   CK(cudaMemcpyAsync(out6, s->tight, 24 * (size_t)s->nA, cudaMemcpyDeviceToHost, s->stream)); CK(cudaStreamSynchronize(s->stream));
   return PXB_OK;
 }
-PXB_API int pxb_scene_broadphase(PxbScene* s, const float* tightBounds) {
+PXB_API int pxb_scene_broadphase(PxbScene* s, const float* tightBounds) { DeviceGuard dg_(s);
   if (!s) return fail(PXB_ERR_INVALID, "null scene");
   if (s->abort) return fail(PXB_ERR_CUDA, "scene is in abort mode");
   s->launches = 0;
@@ -1461,13 +1222,13 @@ static int copy_pairs(PxbScene* s, const uint64_t* dev, uint32_t n, uint32_t* ou
   for (uint32_t i = 0; i < n; ++i) { out[2 * i] = (uint32_t)(k[i] >> s->bitsA); out[2 * i + 1] = (uint32_t)(k[i] & ((1ull << s->bitsA) - 1ull)); }
   return PXB_OK;
 }
-PXB_API uint32_t pxb_scene_num_pairs(PxbScene* s) { return s ? s->hNPairs : 0; }
-PXB_API uint32_t pxb_scene_num_created(PxbScene* s) { return s ? s->hNCreated : 0; }
-PXB_API uint32_t pxb_scene_num_deleted(PxbScene* s) { return s ? s->hNDeleted : 0; }
-PXB_API int pxb_scene_get_pairs(PxbScene* s, uint32_t* out) { if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->pairKeys[s->cur], s->hNPairs, out, s->envActive); }
-PXB_API int pxb_scene_get_created(PxbScene* s, uint32_t* out) { if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->createdKeys, s->hNCreated, out, true); }
-PXB_API int pxb_scene_get_deleted(PxbScene* s, uint32_t* out) { if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->deletedKeys, s->hNDeleted, out, true); }
-PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) {
+PXB_API uint32_t pxb_scene_num_pairs(PxbScene* s) { DeviceGuard dg_(s); return s ? s->hNPairs : 0; }
+PXB_API uint32_t pxb_scene_num_created(PxbScene* s) { DeviceGuard dg_(s); return s ? s->hNCreated : 0; }
+PXB_API uint32_t pxb_scene_num_deleted(PxbScene* s) { DeviceGuard dg_(s); return s ? s->hNDeleted : 0; }
+PXB_API int pxb_scene_get_pairs(PxbScene* s, uint32_t* out) { DeviceGuard dg_(s); if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->pairKeys[s->cur], s->hNPairs, out, s->envActive); }
+PXB_API int pxb_scene_get_created(PxbScene* s, uint32_t* out) { DeviceGuard dg_(s); if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->createdKeys, s->hNCreated, out, true); }
+PXB_API int pxb_scene_get_deleted(PxbScene* s, uint32_t* out) { DeviceGuard dg_(s); if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->deletedKeys, s->hNDeleted, out, true); }
+PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) { DeviceGuard dg_(s);
   if (!s || !out24) return fail(PXB_ERR_INVALID, "null argument");
   const uint32_t n = s->hNPairs; if (!n) return PXB_OK;
   std::vector<float4> h(n), p((size_t)n * 4); std::vector<float> f((size_t)n * 4);
@@ -1488,11 +1249,11 @@ PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) {
   }
   return PXB_OK;
 }
-PXB_API uint32_t pxb_scene_last_num_partitions(PxbScene* s) { return s ? s->hNPart : 0; }
-PXB_API uint32_t pxb_scene_last_num_constraints(PxbScene* s) { return s ? s->hNCon : 0; }
-PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* s) { return s ? s->launches : 0; }
-PXB_API int pxb_scene_uses_env_path(PxbScene* s) { return s && s->envActive ? 1 : 0; }
-PXB_API int pxb_scene_get_sleep_data(PxbScene* s, float* wakeCounters, uint32_t* asleep) {
+PXB_API uint32_t pxb_scene_last_num_partitions(PxbScene* s) { DeviceGuard dg_(s); return s ? s->hNPart : 0; }
+PXB_API uint32_t pxb_scene_last_num_constraints(PxbScene* s) { DeviceGuard dg_(s); return s ? s->hNCon : 0; }
+PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* s) { DeviceGuard dg_(s); return s ? s->launches : 0; }
+PXB_API int pxb_scene_uses_env_path(PxbScene* s) { DeviceGuard dg_(s); return s && s->envActive ? 1 : 0; }
+PXB_API int pxb_scene_get_sleep_data(PxbScene* s, float* wakeCounters, uint32_t* asleep) { DeviceGuard dg_(s);
   if (!s || !wakeCounters || !asleep) return fail(PXB_ERR_INVALID, "null argument");
   std::vector<float> w(s->nA); std::vector<uint32_t> f(s->nA);
   CK(cudaMemcpyAsync(w.data(), s->wake, 4 * (size_t)s->nA, cudaMemcpyDeviceToHost, s->stream)); CK(cudaMemcpyAsync(f.data(), s->asleep, 4 * (size_t)s->nA, cudaMemcpyDeviceToHost, s->stream));
@@ -1501,7 +1262,7 @@ PXB_API int pxb_scene_get_sleep_data(PxbScene* s, float* wakeCounters, uint32_t*
   return PXB_OK;
 }
 #ifdef PXB_ENV_TIMING
-extern "C" PXB_API int pxb_debug_env_timing(PxbScene* s, unsigned long long* out) { cudaStreamSynchronize(s->stream); cudaMemcpy(out, s->envTiming, (size_t)s->nEnv * 16 * 8, cudaMemcpyDeviceToHost); return (int)s->nEnv; }
+extern "C" PXB_API int pxb_debug_env_timing(PxbScene* s, unsigned long long* out) { DeviceGuard dg_(s); cudaStreamSynchronize(s->stream); cudaMemcpy(out, s->envTiming, (size_t)s->nEnv * 16 * 8, cudaMemcpyDeviceToHost); return (int)s->nEnv; }
 #endif
 
 static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb, bool set) {
@@ -1515,12 +1276,12 @@ static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int typ
   CK(cudaGetLastError());
   return PXB_OK;
 }
-PXB_API int pxb_get_rigid_dynamic_data_device(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb) {
+PXB_API int pxb_get_rigid_dynamic_data_device(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb) { DeviceGuard dg_(s);
   if (!s || !devData) return fail(PXB_ERR_INVALID, "null argument");
   if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
   return rd_common(s, devData, devIdx, type, nb, false);
 }
-PXB_API int pxb_set_rigid_dynamic_data_device(PxbScene* s, const void* devData, const uint32_t* devIdx, int type, uint32_t nb) {
+PXB_API int pxb_set_rigid_dynamic_data_device(PxbScene* s, const void* devData, const uint32_t* devIdx, int type, uint32_t nb) { DeviceGuard dg_(s);
   if (!s || !devData) return fail(PXB_ERR_INVALID, "null argument");
   if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
   return rd_common(s, const_cast<void*>(devData), devIdx, type, nb, true);
@@ -1543,16 +1304,16 @@ static int rd_host(PxbScene* s, void* data, const uint32_t* idx, int type, uint3
   if (!async) CK(cudaStreamSynchronize(s->stream));
   return rc;
 }
-PXB_API int pxb_get_rigid_dynamic_data(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, data, idx, type, nb, false, false); }
-PXB_API int pxb_set_rigid_dynamic_data(PxbScene* s, const void* data, const uint32_t* idx, int type, uint32_t nb) { return rd_host(s, const_cast<void*>(data), idx, type, nb, true, false); }
+PXB_API int pxb_get_rigid_dynamic_data(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb) { DeviceGuard dg_(s); return rd_host(s, data, idx, type, nb, false, false); }
+PXB_API int pxb_set_rigid_dynamic_data(PxbScene* s, const void* data, const uint32_t* idx, int type, uint32_t nb) { DeviceGuard dg_(s); return rd_host(s, const_cast<void*>(data), idx, type, nb, true, false); }
 // Stream-ordered host variants (the PxDirectGPUAPI calls are asynchronous too: they take start / finish CUevents,
 // PxDirectGPUAPI.h:311-463).  `data` must be PINNED host memory that stays valid until the next pxb_scene_fetch_results /
 // pxb_scene_sync; a set takes effect for the next simulate, a get issued after pxb_scene_simulate returns that step's result.
-PXB_API int pxb_get_rigid_dynamic_data_async(PxbScene* s, void* pinned, int type, uint32_t nb) { return rd_host(s, pinned, nullptr, type, nb, false, true); }
-PXB_API int pxb_set_rigid_dynamic_data_async(PxbScene* s, const void* pinned, int type, uint32_t nb) { return rd_host(s, const_cast<void*>(pinned), nullptr, type, nb, true, true); }
+PXB_API int pxb_get_rigid_dynamic_data_async(PxbScene* s, void* pinned, int type, uint32_t nb) { DeviceGuard dg_(s); return rd_host(s, pinned, nullptr, type, nb, false, true); }
+PXB_API int pxb_set_rigid_dynamic_data_async(PxbScene* s, const void* pinned, int type, uint32_t nb) { DeviceGuard dg_(s); return rd_host(s, const_cast<void*>(pinned), nullptr, type, nb, true, true); }
 // Pushes `bytes` (multiple of 16) from `devSrc` into nDst <= 8 peer-mapped device buffers with ONE kernel on `stream`
 // (cudaStream_t; NULL = the scene stream).  Used by physx_b200/multi_gpu.py for the per-step all-gather of the state tensor.
-PXB_API int pxb_scatter_to_peers(PxbScene* s, void* stream, const void* devSrc, size_t bytes, const uint64_t* devDstPtrs, uint32_t nDst, uint32_t ctas) {
+PXB_API int pxb_scatter_to_peers(PxbScene* s, void* stream, const void* devSrc, size_t bytes, const uint64_t* devDstPtrs, uint32_t nDst, uint32_t ctas) { DeviceGuard dg_(s);
   if (!s || !devSrc || !devDstPtrs) return fail(PXB_ERR_INVALID, "null argument");
   if (nDst > 8 || (bytes & 15)) return fail(PXB_ERR_INVALID, "at most 8 destinations, size a multiple of 16 bytes");
   if (!nDst || !bytes) return PXB_OK;
@@ -1562,11 +1323,11 @@ PXB_API int pxb_scatter_to_peers(PxbScene* s, void* stream, const void* devSrc, 
   CK(cudaGetLastError());
   return PXB_OK;
 }
-PXB_API int pxb_scene_sync(PxbScene* s) { if (!s) return fail(PXB_ERR_INVALID, "null scene"); CK(cudaStreamSynchronize(s->stream)); return PXB_OK; }
+PXB_API int pxb_scene_sync(PxbScene* s) { DeviceGuard dg_(s); if (!s) return fail(PXB_ERR_INVALID, "null scene"); CK(cudaStreamSynchronize(s->stream)); return PXB_OK; }
 
 // Packed 13-float state of every dynamic body written straight into a DEVICE buffer (e.g. this rank's slice of
 // the NCCL all-gather receive tensor); asynchronous on the scene stream.
-PXB_API int pxb_scene_get_states_device(PxbScene* s, float* devOut) {
+PXB_API int pxb_scene_get_states_device(PxbScene* s, float* devOut) { DeviceGuard dg_(s);
   if (!s || !devOut) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;   // stream-ordered: legal right after pxb_scene_simulate, it reads the state that step produces
   cudaStream_t st = s->stream;
@@ -1574,7 +1335,7 @@ PXB_API int pxb_scene_get_states_device(PxbScene* s, float* devOut) {
   CK(cudaGetLastError());
   return PXB_OK;
 }
-PXB_API int pxb_scene_get_states(PxbScene* s, float* out) {
+PXB_API int pxb_scene_get_states(PxbScene* s, float* out) { DeviceGuard dg_(s);
   if (!s || !out) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;
   cudaStream_t st = s->stream; float* d = s->stage;   // persistent staging (26 floats per actor): no allocation per call
@@ -1582,7 +1343,7 @@ PXB_API int pxb_scene_get_states(PxbScene* s, float* out) {
   CK(cudaMemcpyAsync(out, d, 52 * (size_t)s->nDyn, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
   return PXB_OK;
 }
-PXB_API int pxb_scene_set_states(PxbScene* s, const float* in) {
+PXB_API int pxb_scene_set_states(PxbScene* s, const float* in) { DeviceGuard dg_(s);
   if (!s || !in) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;
   cudaStream_t st = s->stream; float* d = s->stage + (size_t)s->capA * 13;

@@ -1,0 +1,25 @@
+// pxb_env.cu -- instantiations and launchers of the environment path's kernels (pxb_env.cuh: k_env_bp, k_env_solve).
+#include "pxb_launch.h"
+
+cudaError_t pxb_env_set_attributes(int solveSmemMax, int bpSmemMax) {
+  cudaError_t e = cudaSuccess;
+#define ENV_ATTR(T) do { if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_solve<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, solveSmemMax); \
+                         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_solve<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, solveSmemMax); \
+                         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_solve<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, solveSmemMax); \
+                         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_solve<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, solveSmemMax); } while (0)
+  ENV_ATTR(32); ENV_ATTR(64); ENV_ATTR(128); ENV_ATTR(256);
+#undef ENV_ATTR
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_bp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bpSmemMax);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_bp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bpSmemMax);
+  return e;
+}
+void pxb_launch_env_bp(cudaStream_t st, const EnvBpArgs& A, bool hulls, size_t smem) {
+  const uint32_t grid = (A.nEnv + ENV_BP_WARPS - 1) / ENV_BP_WARPS;
+  if (hulls) k_env_bp<true><<<grid, 32 * ENV_BP_WARPS, smem, st>>>(A); else k_env_bp<false><<<grid, 32 * ENV_BP_WARPS, smem, st>>>(A);
+}
+void pxb_launch_env_solve(cudaStream_t st, const EnvSolveArgs& A, uint32_t threads, bool pgs, bool ext, size_t smem) {
+#define ENV_LAUNCH(T) do { if (pgs) { if (ext) k_env_solve<T, true, true><<<A.nEnv, T, smem, st>>>(A); else k_env_solve<T, true, false><<<A.nEnv, T, smem, st>>>(A); } \
+                           else { if (ext) k_env_solve<T, false, true><<<A.nEnv, T, smem, st>>>(A); else k_env_solve<T, false, false><<<A.nEnv, T, smem, st>>>(A); } } while (0)
+  if (threads == 32) ENV_LAUNCH(32); else if (threads == 64) ENV_LAUNCH(64); else if (threads == 128) ENV_LAUNCH(128); else ENV_LAUNCH(256);
+#undef ENV_LAUNCH
+}

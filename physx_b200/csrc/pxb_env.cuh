@@ -13,8 +13,9 @@
 //                        of the reference's "re-stream every row per iteration" traffic are served on chip.
 // Both produce bit-identical results to the device-wide path (same arithmetic, same Gauss-Seidel order inside
 // every island); tests/test_gpu_parity.py checks env path == global path == oracle.
-// Included by pxb_engine.cu after the shared helpers (bp_test, lower_bound_u64, solve_constraint, ...).
+// Instantiated by pxb_env.cu; shared helpers (tight_bounds, lower_bound_u64, sleep_check_dev, ...) come from pxb_common.cuh.
 #pragma once
+#include "pxb_common.cuh"
 
 #define ENV_BP_WARPS 4
 #define ENV_MAX_LIST 288        // actors per environment incl. the shared env-less statics (eligibility limit)

@@ -729,7 +729,7 @@ PXB_D void gjk_boxbox_gjk_fallback(const xf* tm0, const xf* tm1, v3 ext0, v3 ext
   }
 }
 
-__device__ __noinline__ void gjk_boxbox_gjk_fallback_outofline(const xf* tm0, const xf* tm1, v3 ext0, v3 ext1, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
+static __device__ __noinline__ void gjk_boxbox_gjk_fallback_outofline(const xf* tm0, const xf* tm1, v3 ext0, v3 ext1, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
   gjk_boxbox_gjk_fallback(tm0, tm1, ext0, ext1, contactDist, toleranceLength, manifold, out);
 }
 

@@ -1,0 +1,129 @@
+// pxb_narrowphase.cu -- a8-a11: the contact-generation kernels (k_narrowphase: sphere family, plane-box, box-box PCM; k_narrowphase_gjk: the GJK /
+// EPA family over a device-side worklist) in their own translation unit.
+#include "pxb_launch.h"
+
+// a8-a11: one thread per pair.  Driver logic of PxcNpBatch.cpp:364-498: body0 is the dynamic actor (for
+// two dynamics the later-created one, ScNPhaseCore.cpp:182-252), shapes are ordered by geometry type for
+// the contact function and the normal is flipped back afterwards (flipContacts).
+#ifndef PXB_NP_CTAS
+#define PXB_NP_CTAS 5
+#endif
+__global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
+                              const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
+                              float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
+                              uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters, uint32_t* __restrict__ gjkList,
+                              const uint32_t* __restrict__ pairOrder) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *nPairsP) return;
+  const uint32_t i = pairOrder ? pairOrder[t] : t;   // mixed-type scenes: pairs binned by type pair (k_np_class_*)
+  const uint64_t key = pairKeys[i];
+#ifndef PXB_NO_PREFETCH
+  { const float4* r = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4; prefetch_l2(r); prefetch_l2(r + 8); }   // the record is needed two dependent loads later (types -> poses -> manifold)
+#endif
+  if (key == ~0ull) { cHdr[i] = make_float4(0, 0, 0, __int_as_float(0)); conFlag[i] = 0u; pairBodies[i] = make_uint2(0, 0); return; }   // dropped segment (capacity error already flagged)
+  const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
+  uint32_t a0 = hi, a1 = lo;
+  const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
+  if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
+  const uint32_t g0 = (a0 == hi) ? gfHi : gfLo, g1 = (a0 == hi) ? gfLo : gfHi;
+  const uint32_t t0 = g0 & 0xff, t1 = g1 & 0xff;
+  const bool flip = t1 < t0;
+  const uint32_t s0 = flip ? a1 : a0, s1 = flip ? a0 : a1;
+  const uint32_t ty0 = flip ? t1 : t0, ty1 = flip ? t0 : t1;
+  const float4 p0 = pos[s0], p1 = pos[s1];
+  xf tm0, tm1; tm0.p = V3(p0.x, p0.y, p0.z); tm0.q = Q4(quat[s0]); tm1.p = V3(p1.x, p1.y, p1.z); tm1.q = Q4(quat[s1]);
+  const float4 d0 = dims[s0], d1 = dims[s1];
+  float4* rec = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4;
+  // only the PCM pair types keep a persistent manifold (plane-box, box-box, plane-capsule); the closed-form sphere family does not
+  const bool usesManifold = (ty0 == PXB_GEOM_PLANE && (ty1 == PXB_GEOM_BOX || ty1 == PXB_GEOM_CAPSULE)) || (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX);   // (GJK-family pairs load theirs in k_narrowphase_gjk)
+  Manifold man;
+  if (usesManifold) manifold_load(man, rec); else { man.n = 0; man.dirty = 0; }
+  Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
+  for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
+  if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_BOX) pcm_plane_box(tm0, tm1, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
+  else if (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX) {
+    if (pcm_box_box(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out)) {
+      // edge-edge / corner configuration (rare): the SAT passed but clipping found no point -> GJK / EPA single-point fallback, called out of
+      // line so that this kernel keeps its register budget (measured: cheaper than handing the pair to a second, usually empty, launch).
+      manifold_load_warm(man, rec);
+      gjk_boxbox_gjk_fallback_outofline(&tm0, &tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
+      manifold_store_warm(man, rec);
+    }
+  }
+  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_SPHERE) np_sphere_sphere(tm0.p, tm1.p, d0.x, d1.x, contactDist, out);
+  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_PLANE) np_sphere_plane(tm0.p, d0.x, tm1, contactDist, out);
+  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_CAPSULE) np_sphere_capsule(tm0.p, d0.x, tm1, d1.x, d1.y, contactDist, out);
+  else if (ty0 == PXB_GEOM_SPHERE && ty1 == PXB_GEOM_BOX) np_sphere_box(tm0.p, d0.x, tm1, V3(d1.x, d1.y, d1.z), contactDist, out);
+  else if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_CAPSULE) pcm_plane_capsule(tm0, tm1, d1.x, d1.y, contactDist, man, out);
+  else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_CAPSULE) np_capsule_capsule(tm0, tm1, d0.x, d0.y, d1.x, d1.y, contactDist, out);
+  else if (ty0 == PXB_GEOM_CAPSULE && ty1 == PXB_GEOM_BOX) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // GJK family (a10): k_narrowphase_gjk fills this pair's outputs
+  else if (ty1 == PXB_GEOM_CONVEXMESH) { gjkList[atomicAdd(&counters[C_NGJK], 1u)] = i; return; }   // hull pairs also go through k_narrowphase_gjk
+  else atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);   // unknown geometry type: reported by fetchResults, never silently skipped
+  if (man.dirty) manifold_store(man, rec); else if (usesManifold && man.n > 0) manifold_store_pens(man, rec);   // steady state: only the penetrations change
+  if (flip && out.count) out.normal = -out.normal;
+  cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]); }   // (cForce: every pair with contacts is a constraint and gets its forces from write-back)
+  pairBodies[i] = make_uint2(a0, a1);
+  conFlag[i] = out.count > 0 ? 1u : 0u;
+}
+
+// a10: the GJK family (capsule-box), one thread per listed pair.  Kept out of k_narrowphase so that the box / sphere hot path keeps its register budget;
+// the list order is arbitrary (atomic append) but every pair writes only its own outputs, so the result is deterministic.
+#ifndef PXB_GJK_CTAS
+#define PXB_GJK_CTAS 3   // 168 registers.  Measured on config 3 with hulls: 4 CTAs/SM (128 registers, +240 B of spills) is slower, 10.15 vs 10.0 ms/step -- the kernel is divergence bound (5 of 32 threads active), not residency bound
+#endif
+__global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, uint32_t bitsA, const float4* __restrict__ pos, const float4* __restrict__ quat,
+                              const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags, float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr,
+                              float4* __restrict__ cPts, uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, uint32_t* __restrict__ counters, const uint32_t* __restrict__ gjkList, HullArrays hulls) {
+  const uint32_t n = counters[C_NGJK];
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const uint32_t i = gjkList[w];
+    const uint64_t key = pairKeys[i];
+    const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
+    uint32_t a0 = hi, a1 = lo;
+    const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
+    if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
+    const uint32_t t0 = ((a0 == hi) ? gfHi : gfLo) & 0xff, t1 = ((a0 == hi) ? gfLo : gfHi) & 0xff;
+    const bool flip = t1 < t0;
+    const uint32_t s0 = flip ? a1 : a0, s1 = flip ? a0 : a1;   // s0 = capsule, s1 = box
+    const float4 p0 = pos[s0], p1 = pos[s1];
+    xf tm0, tm1; tm0.p = V3(p0.x, p0.y, p0.z); tm0.q = Q4(quat[s0]); tm1.p = V3(p1.x, p1.y, p1.z); tm1.q = Q4(quat[s1]);
+    const float4 d0 = dims[s0], d1 = dims[s1];
+    float4* rec = manifolds + (size_t)pairSlots[i] * PXB_MANIFOLD_F4;
+    Manifold man; manifold_load(man, rec); manifold_load_warm(man, rec);
+    Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
+    for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
+    const uint32_t ty1 = flip ? t0 : t1;
+    const uint32_t ty0 = flip ? t1 : t0;
+    if (ty1 == PXB_GEOM_CONVEXMESH) {   // s1 = hull, s0 = plane, sphere, capsule, box or hull
+      const DevHull h = load_hull(hulls, __float_as_uint(d1.x));
+      if (ty0 == PXB_GEOM_PLANE) gjk_pcm_plane_convex(&tm0, &tm1, h, contactDist, toleranceLength, &man, &out);
+      else if (ty0 == PXB_GEOM_SPHERE) gjk_pcm_sphere_convex(&tm0, &tm1, d0.x, &h, contactDist, toleranceLength, &man, &out);
+      else if (ty0 == PXB_GEOM_CAPSULE) gjk_pcm_capsule_convex(&tm0, &tm1, d0.x, d0.y, &h, contactDist, toleranceLength, &man, &out);
+      else {   // box-hull / hull-hull
+        int sat;
+        if (ty0 == PXB_GEOM_BOX) sat = gjk_pcm_box_convex(&tm0, &tm1, V3(d0.x, d0.y, d0.z), &h, contactDist, toleranceLength, &man, &out);
+        else { const DevHull h0 = load_hull(hulls, __float_as_uint(d0.x)); sat = gjk_pcm_convex_convex(&tm0, &tm1, &h0, &h, contactDist, toleranceLength, &man, &out); }
+        if (sat) atomicOr(&counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);
+      }
+    }
+    else gjk_pcm_capsule_box(&tm0, &tm1, d0.x, d0.y, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, &man, &out);
+    if (man.dirty) { manifold_store(man, rec); manifold_store_warm(man, rec); } else if (man.n > 0) manifold_store_pens(man, rec);
+    if (flip && out.count) out.normal = -out.normal;
+    cHdr[i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]);
+    pairBodies[i] = make_uint2(a0, a1);
+    conFlag[i] = out.count > 0 ? 1u : 0u;
+  }
+}
+
+void pxb_launch_narrowphase(cudaStream_t st, uint32_t capPairs, const NpArgs& A) {
+  k_narrowphase<<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies,
+                                                         A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder);
+}
+void pxb_launch_narrowphase_gjk(cudaStream_t st, uint32_t ctas, const NpArgs& A) {
+  k_narrowphase_gjk<<<ctas, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies, A.conFlag, A.counters,
+                                          A.gjkList, A.hulls);
+}

@@ -200,6 +200,7 @@ __device__ __forceinline__ void integrate_core_pgs(v3& p, q4& q, v3& linVel, v3&
   angVel = angVel + mmul(sqrtInvInertia, deltaAng);
 }
 
+#ifdef PXB_SOLVE_KERNELS   // compiled by pxb_solve.cu only
 // ---------------------------------------------------------------------------------------------
 // device-wide solver kernels, both solver types (scenes without environment ids); rows live in the RegRows memory image (25 x cap float4)
 template <bool PGS>
@@ -335,3 +336,4 @@ __global__ void k_finalize_bodies_pgs(uint32_t nDyn, const uint32_t* __restrict_
   pos[a] = make_float4(p.x, p.y, p.z, p4.w); quat[a] = F4(q); linVel[a] = F4(lv, 0.f); angVel[a] = F4(av, 0.f);
   if (S.threshold > 0.f) sleep_check_dev(S, a, q, invInertia[a], p4.w, motionLin, motionAng);
 }
+#endif

@@ -64,7 +64,7 @@ PXB_D v3 lock3(v3 v, uint32_t bits) { if (bits & 1u) v.x = 0.f; if (bits & 2u) v
 // External force / torque for this step (PxDirectGPUAPI eFORCE / eTORQUE = PxRigidBody::addForce / addTorque(eFORCE)):
 // NpRigidBodyTemplate.h:507-528 (linAcc = F * invMass, angAcc = world inverse inertia * T, inertia as in :315-320) and
 // Sc::BodySim::updateForces ScBodySim.cpp:656-720 (v += acc * dt before the unconstrained-velocity pass).
-__device__ __noinline__ void apply_external_force(v3 F, v3 T, float invMass, float4 invI, q4 q, float dt, v3& lv, v3& av) {   // rare path: out of line, the solve kernels are register bound
+static __device__ __noinline__ void apply_external_force(v3 F, v3 T, float invMass, float4 invI, q4 q, float dt, v3& lv, v3& av) {   // rare path: out of line, the solve kernels are register bound
   if (F.x != 0.f || F.y != 0.f || F.z != 0.f) { const v3 linAcc = F * invMass; lv = lv + (V3(0, 0, 0) + linAcc * dt); }
   if (T.x != 0.f || T.y != 0.f || T.z != 0.f) {
     const m33 rot = amfromq(q);

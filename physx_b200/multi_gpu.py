@@ -28,12 +28,17 @@ def env_range(n_envs: int, world_size: int, rank: int):
 
 def shard_scene(scene: _scenes.Scene, world_size: int, rank: int) -> _scenes.Scene:
     """Sub-scene with the actors of this rank's environments plus every env-less (shared) actor, e.g. the
-    ground plane.  Actor order is preserved, so local dynamic-body order = global order restricted to the shard."""
+    ground plane.  Actor order is preserved, so local dynamic-body order = global order restricted to the shard.
+    Environment ids are rebased to start at 0 on every rank (the engine builds one CTA / warp per id up to the largest one),
+    and the convex hulls travel with the shard (point clouds and the cooked section; hull indices are unchanged)."""
     env = scene.actors["envId"]
     n_envs = int(env[env != _scenes.NO_ENV].max()) + 1 if np.any(env != _scenes.NO_ENV) else 0
     lo, hi = env_range(n_envs, world_size, rank)
     keep = (env == _scenes.NO_ENV) | ((env >= lo) & (env < hi))
-    return _scenes.Scene(scene.header, scene.actors[keep].copy(), scene.hulls)
+    actors = scene.actors[keep].copy()
+    own = actors["envId"] != _scenes.NO_ENV
+    actors["envId"][own] -= np.uint32(lo)
+    return _scenes.Scene(scene.header, actors, scene.hulls, scene.cooked)
 
 
 def gather_layout(counts):

@@ -26,12 +26,37 @@ def test_shard_scene_keeps_shared_actors_and_order():
     seen = []
     for r in range(4):
         sh = multi_gpu.shard_scene(sc, 4, r)
+        lo, hi = multi_gpu.env_range(6, 4, r)
         assert sh.actors[0]["geomType"] == scenes.GEOM_PLANE           # the shared ground plane is in every shard
         env = sh.actors["envId"][1:]
         assert np.all(np.diff(env.astype(np.int64)) >= 0)
-        seen.extend(np.unique(env).tolist())
+        assert env.min() == 0 and env.max() == hi - lo - 1              # environment ids are rebased to 0 on every rank
+        seen.extend((np.unique(env) + lo).tolist())
         assert sh.n_dynamic == len(env)
+        # same bodies as the global scene's slice, in the same order
+        glob = sc.actors[(sc.actors["envId"] >= lo) & (sc.actors["envId"] < hi)]
+        assert np.array_equal(glob["pos"], sh.actors["pos"][1:])
     assert sorted(seen) == list(range(6))
+
+
+def test_shard_scene_carries_the_cooked_hulls():
+    """A hull scene shards with its cooked section (the shard used to drop it, so every convex actor was refused)."""
+    sc = scenes.env_hulls()
+    assert len(sc.cooked) > 0
+    for r in range(2):
+        sh = multi_gpu.shard_scene(sc, 2, r)
+        assert sh.cooked == sc.cooked and len(sh.hulls) == len(sc.hulls)
+        assert sh.actors["hullIdx"][sh.actors["geomType"] == scenes.GEOM_CONVEX].max() < len(sh.hulls)
+        rt = scenes.Scene.load(_save_tmp(sh))
+        assert rt.cooked == sc.cooked and np.array_equal(rt.actors, sh.actors)
+
+
+def _save_tmp(sc):
+    import tempfile
+    f = tempfile.NamedTemporaryFile(suffix=".bin", delete=False)
+    f.write(sc.tobytes())
+    f.close()
+    return f.name
 
 
 def _free_port():
