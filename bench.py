@@ -235,7 +235,7 @@ def bench_ours(args):
         st0 = scene.getStates()
         level = (np.arange(nb) % per_env) % 8
         pose0 = np.concatenate([st0[:, 3:7], st0[:, 0:3]], axis=1).astype(np.float32)
-        pose0[:, 5] += 0.06 * (level + 1)
+        pose0[:, 5] += 0.045 * (level + 1)
         churn = {"k": k, "per_env": per_env, "cursor": 0,
                  "pose": torch.from_numpy(pose0).to(dev), "zero": torch.zeros((nb, 3), dtype=torch.float32, device=dev),
                  "idx": torch.arange(nb, dtype=torch.int32, device=dev)}
@@ -298,7 +298,8 @@ def bench_ours(args):
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
     torch.cuda.synchronize(dev)
-    n_pairs = len(scene.getPairs()) if cfg != 2 and cfg != 5 else None
+    n_pairs = len(scene.getPairs())
+    churn_stats = {"pairs_created_last_timed_step": len(scene.getCreatedPairs()), "pairs_deleted_last_timed_step": len(scene.getDeletedPairs()), "constraints_last_timed_step": scene.num_constraints}
     if dist is not None:
         dist.barrier()
     if gather is not None:
@@ -328,8 +329,6 @@ def bench_ours(args):
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     scene.setProfiling(False)
     P = scene.num_constraints            # contact patches = touching pairs (one patch per pair)
-    if n_pairs is None:
-        n_pairs = len(scene.getPairs())
     if dist is not None:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -356,6 +355,7 @@ def bench_ours(args):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         # stream-ordered calls on pinned host buffers, ONE host synchronisation per step (fetchResults), as with PxDirectGPUAPI's events
+        apply_churn()
         lib.pxb_set_rigid_dynamic_data_async(h, lin_h.data_ptr(), engine.RD_LINEAR_VELOCITY, nb)   # H2D (identity action: values just read back)
         lib.pxb_set_rigid_dynamic_data_async(h, ang_h.data_ptr(), engine.RD_ANGULAR_VELOCITY, nb)
         scene.simulate()
@@ -410,6 +410,7 @@ def bench_ours(args):
             "config": {"workload": workload_string(cfg, n_envs, args.solver, args.churn if churn else 0.0)},
             "details": {"bodies_total": total_bodies, "pairs_per_gpu": n_pairs, "constraints_per_gpu": P, "partitions": scene.num_partitions, "path": "environment (pxb_env.cuh)" if scene.uses_env_path else "device-wide",
                         "partitioning": ("relaxed (Jones-Plassmann rounds)" if relaxed else "exact first-fit (the reference's order-preserving greedy colouring)") if not scene.uses_env_path else "exact first-fit per environment",
+                        **churn_stats,
                         "settle_steps": SETTLE[cfg], "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_p95": per_step[min(len(per_step) - 1, int(len(per_step) * 0.95))],
                         "timing": "CUDA events on the scene stream per step, max over ranks; L2 flushed (256 MiB memset) between timed steps",
                         "multi_gpu": ("env-partitioned, one scene per GPU, per-step all-gather of the packed pose+linear+angular velocity tensor (13 floats/body) by " + str(gather_kind) + ", double-buffered on communication streams (overlaps the next step)") if gather is not None else ("independent replicas" if world > 1 else "single scene")},

@@ -55,7 +55,7 @@ struct PxbScene {
   uint32_t *conFlag = 0, *conIdx = 0, *conPair = 0, *rankOfPair = 0; uint64_t *conSortKey = 0, *conSortKeyAlt = 0; uint32_t* conPairAlt = 0;
   uint64_t* orderKeys = 0; uint32_t nOrder = 0, capOrder = 0;
   uint32_t *conB0 = 0, *conB1 = 0, *conPos0 = 0, *conPos1 = 0, *conColour = 0, *conDone = 0, *bodyList = 0, *ordered = 0;
-  uint32_t *partCnt = 0, *partStart = 0, *partCursor = 0;
+  uint32_t *partCnt = 0, *partStart = 0, *partCursor = 0, *colourTicket = 0; bool colourLegacy = false; uint32_t colourBackoffNs = 0;
   // rows (solve order)
   float4 *ptA = 0, *ptB = 0, *ptC = 0, *frA = 0, *frB = 0, *frC = 0, *frD = 0;
   uint32_t* counters = 0; uint32_t* hostCounters = 0;  // pinned mirror
@@ -314,6 +314,43 @@ __global__ void k_body_lists(uint32_t nA, const uint32_t* __restrict__ bodyStart
   }
   bodyNext[a] = 0; bodyMask[a] = 0ull; bodyHasCon[a] = n > 0 ? 1u : 0u;
 }
+// a13 (3/3, exact): the reference's sequential first-fit (classifyConstraintDesc, DyConstraintPartition.cpp:475-568) as a DATAFLOW over the
+// constraint list instead of grid-wide rounds.  One thread per constraint; a dynamic constraint may take its colour once every earlier
+// constraint of both its bodies has one.  Colours on a body are distinct, so popcount(bodyMask[body]) IS the number of the body's coloured
+// dynamic constraints: a single 64-bit word per body carries readiness and data, and one volatile load per body is the whole handshake (no
+// fence, no atomic: the only thread allowed to write a body's mask is the one whose turn it is).  Blocks take a ticket for their position in
+// the list, so every constraint a thread waits for belongs to a block that has already started -- the wait cannot deadlock.  The length
+// of the longest dependency chain (2 091 links on BASELINE config 4's 2.4 M constraints) times one L2 round trip bounds the time, instead
+// of chain length x grid barrier + list sweep (405 ms -> a few ms on config 4).
+__global__ void __launch_bounds__(128) k_colour_firstfit(uint32_t* __restrict__ counters, const uint32_t* __restrict__ conB0, const uint32_t* __restrict__ conB1, const uint32_t* __restrict__ conPos0,
+                                                         const uint32_t* __restrict__ conPos1, uint32_t* __restrict__ conColour, unsigned long long* __restrict__ bodyMask, uint32_t* __restrict__ ticket,
+                                                         uint32_t backoffNs) {
+  __shared__ uint32_t sBlock;
+  if (threadIdx.x == 0) sBlock = atomicAdd(&ticket[0], 1u);
+  __syncthreads();
+  const uint32_t c = sBlock * blockDim.x + threadIdx.x;
+  if (c >= counters[C_NCON]) return;
+  const uint32_t b = conB1[c];
+  if (b == NONE32) return;   // static contacts take their partition after the dynamic colours are known (k_colour_partition's ordering pass)
+  const uint32_t a = conB0[c], pa = conPos0[c], pb = conPos1[c];
+  uint32_t spins = 0;
+  for (;;) {   // the colour is published INSIDE the loop body: no thread of the warp ever waits for code after a divergent loop exit
+    const unsigned long long ma = ld_volatile64(&bodyMask[a]);
+    if ((uint32_t)__popcll(ma) == pa) {
+      const unsigned long long mb = ld_volatile64(&bodyMask[b]);
+      if ((uint32_t)__popcll(mb) == pb) {
+        const unsigned long long comb = ~ma & ~mb;   // first fit over 64 colours = the reference's second 32-colour round for the constraints that overflow the first
+        if (!comb) { atomicOr(&counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW); st_volatile(&ticket[1], 1u); conColour[c] = 63; return; }   // reported by fetchResults; everybody stops waiting
+        const uint32_t col = __ffsll((long long)comb) - 1;
+        conColour[c] = col;
+        st_volatile64(&bodyMask[a], ma | (1ull << col)); st_volatile64(&bodyMask[b], mb | (1ull << col));
+        return;
+      }
+    }
+    if ((++spins & 63u) == 0 && ld_volatile(&ticket[1])) return;
+    if (backoffNs && spins > 2) __nanosleep(backoffNs);
+  }
+}
 // a13 (3/3): first-fit colouring in solver input order, identical to the sequential
 // classifyConstraintDesc (DyConstraintPartition.cpp:475-568): a constraint takes the lowest colour free on
 // both bodies once every earlier constraint of both bodies is coloured.  Static contacts of a body go to
@@ -328,7 +365,8 @@ __global__ void __launch_bounds__(256) k_colour_partition(uint32_t* __restrict__
   for (uint32_t p = gtid; p < MAX_PARTITIONS + 1; p += gsize) { partCnt[p] = 0; }
   const uint32_t perCta = (nCon + gridDim.x - 1) / gridDim.x;
   const uint32_t cb = min(nCon, blockIdx.x * perCta), ce = min(nCon, cb + perCta);
-  if (relaxed) {
+  if (relaxed == 2) {   // colours already assigned by k_colour_firstfit
+  } else if (relaxed) {
     // PXB_FLAG_RELAXED_PARTITIONING: Jones-Plassmann style rounds.  Every uncoloured constraint bids its priority (a fixed
     // bijective hash of its index) on both bodies; the constraint that holds the highest bid on BOTH bodies takes the lowest
     // colour free on both.  Winners of a round are body-disjoint, the result is a valid partitioning that depends only on the
@@ -595,7 +633,7 @@ __global__ void k_env_begin(uint32_t* __restrict__ counters) {   // per-step cou
 // host side
 static const size_t ENV_SMEM_MAX = 227 * 1024 - 2048;   // dynamic shared memory budget of k_env_solve (static part: partition tables)
 static const size_t ENV_CON_BYTES = 5 * sizeof(uint32_t);   // 5 u32 lists per pair slot (rows live in registers)
-static size_t env_solve_smem(uint32_t maxList, uint32_t conCap, uint32_t threads = 256) { return (size_t)maxList * (8 * sizeof(float4) + 3 * sizeof(uint32_t)) + (size_t)conCap * ENV_CON_BYTES + 16 + (size_t)threads * 12 * sizeof(float4); }
+static size_t env_solve_smem(uint32_t maxList, uint32_t conCap, uint32_t threads = 256) { return (size_t)maxList * (8 * sizeof(float4) + 4 * sizeof(uint32_t)) + (size_t)conCap * ENV_CON_BYTES + 16 + (size_t)threads * 12 * sizeof(float4); }
 static uint32_t env_con_cap_limit(uint32_t maxList) { return (uint32_t)((ENV_SMEM_MAX - env_solve_smem(maxList, 0)) / ENV_CON_BYTES); }
 template <typename T> static cudaError_t dalloc(T*& p, size_t n) { return cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)); }
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -627,7 +665,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->conPairAlt, Pn));
   CK(dalloc(s->conB0, Pn)); CK(dalloc(s->conB1, Pn)); CK(dalloc(s->conPos0, Pn)); CK(dalloc(s->conPos1, Pn)); CK(dalloc(s->conColour, Pn)); CK(dalloc(s->conDone, Pn));
   CK(dalloc(s->bodyList, Pn * 2)); CK(dalloc(s->ordered, Pn));
-  CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
+  CK(dalloc(s->colourTicket, 2)); CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
   CK(dalloc(s->ptA, Pn * 28)); s->ptB = s->ptA + Pn * 4; s->ptC = s->ptA + Pn * 8;   // one allocation: the environment path views it as 25 x Pn (pxb_env.cuh Rows)
   s->frA = s->ptA + Pn * 12; s->frB = s->ptA + Pn * 16; s->frC = s->ptA + Pn * 20; s->frD = s->ptA + Pn * 24;
   CK(dalloc(s->stage, A * 32)); CK(dalloc(s->stageIdx, A));   // staging: {get, set} x {pose 7, linear 3, angular 3} + set {force 3, torque 3} floats per actor
@@ -673,6 +711,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->bitsA = bits_for(s->capA);
   s->rsTmp.ctas = std::min<uint32_t>(RS_MAX_CTAS, (uint32_t)s->numSMs * 2);
   { const char* ng = getenv("PXB_NO_GRAPH"); if (ng && ng[0] == '1') s->useGraph = false; }
+  { const char* cl = getenv("PXB_COLOUR_LEGACY"); if (cl && cl[0] == '1') s->colourLegacy = true; const char* cb = getenv("PXB_COLOUR_BACKOFF_NS"); if (cb) s->colourBackoffNs = (uint32_t)atoi(cb); }   // A/B hooks of the exact colouring
   if (desc->reserved[1] & PXB_FLAG_NO_ENV_PATH) s->envDisabled = true;
   if (desc->reserved[1] & PXB_FLAG_RELAXED_PARTITIONING) { s->relaxedPartitioning = true; s->envDisabled = true; }
   s->envConCapForced = desc->reserved[2]; s->envThreadsForced = desc->reserved[3];
@@ -692,7 +731,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
-                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
+                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
                   s->envStart, s->envList, s->actorLocal, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
@@ -726,14 +765,20 @@ static float shape_diameter(const ActorRec& r) {
 static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
   s->envEligible = false;
   const char* em = getenv("PXB_ENV_MODE");
-  if (!usesEnv || s->envDisabled || (em && em[0] == '0')) return;
+  if (s->envDisabled || (em && em[0] == '0')) return;
+  // A small scene without environment ids (BASELINE config 1: 100 boxes) is ONE environment: the whole step then runs on one SM in 5 launches
+  // instead of ~36, which is what bounds a scene of that size.
+  const bool single = !usesEnv && s->nA > 0 && s->nA <= ENV_MAX_LIST;
+  if (!usesEnv && !single) return;
+  if (single) maxEnv = 0;
   if (maxEnv >= s->capA) return;   // sparse environment ids: stay on the device-wide path
   std::vector<uint32_t> globals; const uint32_t nEnv = maxEnv + 1;
   std::vector<uint32_t> cnt(nEnv, 0);
+  auto envOf = [&](uint32_t a) { return single ? 0u : s->recs[a].envId; };
   for (uint32_t a = 0; a < s->nA; ++a) {
     const ActorRec& r = s->recs[a];
-    if (r.envId == NONE32) { if (r.flags & PXB_ACTOR_DYNAMIC) return; globals.push_back(a); if (globals.size() > ENV_MAX_GLOBALS) return; }
-    else cnt[r.envId]++;
+    if (envOf(a) == NONE32) { if (r.flags & PXB_ACTOR_DYNAMIC) return; globals.push_back(a); if (globals.size() > ENV_MAX_GLOBALS) return; }
+    else cnt[envOf(a)]++;
   }
   const uint32_t G = (uint32_t)globals.size();
   uint32_t maxList = 0;
@@ -743,7 +788,7 @@ static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
   for (uint32_t e = 0; e < nEnv; ++e) start[e + 1] = start[e] + cnt[e] + G;
   std::vector<uint32_t> list(start[nEnv]), cur(start.begin(), start.end() - 1), gi(nEnv, 0);
   for (uint32_t a = 0; a < s->nA; ++a) {   // ascending a: merge the env-less statics in by index
-    const uint32_t e = s->recs[a].envId;
+    const uint32_t e = envOf(a);
     if (e == NONE32) continue;
     while (gi[e] < G && globals[gi[e]] < a) list[cur[e]++] = globals[gi[e]++];
     local[a] = cur[e] - start[e]; list[cur[e]++] = a;
@@ -1091,6 +1136,11 @@ static int enqueue_step(PxbScene* s, float dt) {
   {
     int relaxed = (s->relaxedPartitioning && s->nOrder == 0) ? 1 : 0;   // a host-provided solver order always gets the exact first-fit
     if (relaxed) CK(cudaMemsetAsync(s->bodyBest, 0, 8 * (size_t)s->nA, st));
+    else if (!s->colourLegacy) {   // exact first-fit as a dataflow (k_colour_firstfit); the cooperative kernel below then only orders the constraints partition-major
+      CK(cudaMemsetAsync(s->colourTicket, 0, 8, st));
+      LAUNCH(k_colour_firstfit, cdiv(s->capPairs, 128), 128, s->counters, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->bodyMask, s->colourTicket, s->colourBackoffNs);
+      relaxed = 2;
+    }
     void* args[] = {&s->counters, &s->conB0, &s->conB1, &s->conPos0, &s->conPos1, &s->conColour, &s->conDone, &s->bodyNext, &s->bodyMask, &s->partCnt, &s->partStart, &s->partCursor, &s->ordered,
                     &s->bodyBest, &relaxed};
     CK(cudaLaunchCooperativeKernel((void*)k_colour_partition, dim3(s->coopBlocksColour), dim3(256), args, 0, st)); s->launches++;

@@ -459,7 +459,7 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
 }
 
 // dynamic shared memory of k_env_solve (host mirror: env_solve_smem in pxb_engine.cu):
-//   8 x maxList float4 body state | u32: 3 x maxList body masks, 5 x conCap constraint lists (padded to 16 B) | 12 x T float4 friction rows
+//   8 x maxList float4 body state | u32: 4 x maxList (64-bit colour masks, first-in-line, static counts), 5 x conCap constraint lists (padded to 16 B) | 12 x T float4 friction rows
 // conCap = list capacity (pairs of the environment); environments with more pairs keep their lists in global scratch.
 #ifndef PXB_ENV_CTAS64
 #define PXB_ENV_CTAS64 8
@@ -473,9 +473,10 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   const uint2 sg = A.seg[e]; const uint32_t base = sg.x, m = sg.y & 0x7fffffffu; const bool sameSeg = (sg.y >> 31) != 0;
   const uint32_t nb = A.maxList, lc = A.conCap;
   float4 *bLin = envSmem, *bAng = bLin + nb, *bDLin = bAng + nb, *bDAng = bDLin + nb, *bIA = bDAng + nb, *bIB = bIA + nb, *bP = bIB + nb, *bQ = bP + nb;
-  uint32_t* bMask = reinterpret_cast<uint32_t*>(bQ + nb); uint32_t* bFirst = bMask + nb; uint32_t* bStat = bFirst + nb;
+  unsigned long long* bMask = reinterpret_cast<unsigned long long*>(bQ + nb);   // the 64 dynamic colours a body's constraints hold (as on the device-wide path)
+  uint32_t* bFirst = reinterpret_cast<uint32_t*>(bMask + nb); uint32_t* bStat = bFirst + nb;
   uint32_t* sLists = bStat + nb;
-  float4* sFr = reinterpret_cast<float4*>(sLists + 5 * lc + ((4 - ((3 * nb + 5 * lc) & 3)) & 3));   // 12 x T float4: friction half of the register rows
+  float4* sFr = reinterpret_cast<float4*>(sLists + 5 * lc + ((4 - ((4 * nb + 5 * lc) & 3)) & 3));   // 12 x T float4: friction half of the register rows
   ConLists L;
   if (m <= lc) { L.conPair = sLists; L.b0 = sLists + lc; L.b1 = sLists + 2 * lc; L.colour = sLists + 3 * lc; L.ordered = sLists + 4 * lc; }
   else { L.conPair = A.conPair + base; L.b0 = A.conB0 + base; L.b1 = A.conB1 + base; L.colour = A.conColour + base; L.ordered = A.ordered + base; }
@@ -572,10 +573,10 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
       if (l1 == NONE32 || L.colour[k] != NONE32) continue;
       const uint32_t l0 = L.b0[k];
       if (bFirst[l0] != k || bFirst[l1] != k) continue;
-      const uint32_t ma = bMask[l0], mb = bMask[l1]; const uint32_t comb = ~ma & ~mb;
-      uint32_t col = 31;
-      if (comb) col = __ffs(comb) - 1; else atomicOr(&A.counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
-      L.colour[k] = col; bMask[l0] = ma | (1u << col); bMask[l1] = mb | (1u << col);
+      const unsigned long long ma = bMask[l0], mb = bMask[l1]; const unsigned long long comb = ~ma & ~mb;
+      uint32_t col = 63;
+      if (comb) col = __ffsll((long long)comb) - 1; else atomicOr(&A.counters[C_ERROR], (uint32_t)E_COLOUR_OVERFLOW);
+      L.colour[k] = col; bMask[l0] = ma | (1ull << col); bMask[l1] = mb | (1ull << col);
     }
     __syncthreads();
   }
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
     if (L.b1[k] == NONE32) {
       const uint32_t l0 = L.b0[k]; uint32_t rank = 0;
       if (bStat[l0] > 1) for (uint32_t kk = 0; kk < k; ++kk) if (L.b1[kk] == NONE32 && L.b0[kk] == l0) ++rank;
-      const uint32_t mk = bMask[l0]; col = (mk ? 32u - __clz(mk) : 0u) + rank;
+      const unsigned long long mk = bMask[l0]; col = (mk ? 64u - __clzll((long long)mk) : 0u) + rank;
       if (col >= MAX_PARTITIONS) { col = MAX_PARTITIONS - 1; atomicOr(&A.counters[C_ERROR], (uint32_t)E_PARTITION_OVERFLOW); }
       L.colour[k] = col;
     } else col = L.colour[k];

@@ -2,15 +2,8 @@
 // the host side in pxb_engine.cu.  Splitting the library into four units keeps a kernel edit from recompiling the GJK / EPA family.
 #pragma once
 #include "pxb_common.cuh"
+#include "pxb_np_launch.h"
 #include "pxb_env.cuh"   // EnvBpArgs / EnvSolveArgs / Rows (plain structs; the kernels in there are templates instantiated by pxb_env.cu only)
-
-struct NpArgs {
-  const uint64_t* pairKeys; const uint32_t* pairSlots; const uint32_t* nPairsP; uint32_t bitsA;
-  const float4 *pos, *quat, *dims; const uint32_t* geomFlags; float contactDist, toleranceLength;
-  float4 *manifolds, *cHdr, *cPts; uint2* pairBodies; uint32_t* conFlag; float* cForce; uint32_t *counters, *gjkList; const uint32_t* pairOrder; HullArrays hulls;
-};
-void pxb_launch_narrowphase(cudaStream_t st, uint32_t capPairs, const NpArgs& A);
-void pxb_launch_narrowphase_gjk(cudaStream_t st, uint32_t ctas, const NpArgs& A);
 
 cudaError_t pxb_env_set_attributes(int solveSmemMax, int bpSmemMax);
 void pxb_launch_env_bp(cudaStream_t st, const EnvBpArgs& A, bool hulls, size_t smem);

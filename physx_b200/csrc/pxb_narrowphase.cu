@@ -1,6 +1,6 @@
 // pxb_narrowphase.cu -- a8-a11: the contact-generation kernels (k_narrowphase: sphere family, plane-box, box-box PCM; k_narrowphase_gjk: the GJK /
 // EPA family over a device-side worklist) in their own translation unit.
-#include "pxb_launch.h"
+#include "pxb_np_launch.h"
 
 // a8-a11: one thread per pair.  Driver logic of PxcNpBatch.cpp:364-498: body0 is the dynamic actor (for
 // two dynamics the later-created one, ScNPhaseCore.cpp:182-252), shapes are ordered by geometry type for

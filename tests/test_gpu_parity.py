@@ -33,10 +33,14 @@ def _free_fall():
     return s
 
 
+@pytest.mark.parametrize("path", ["auto", "devicewide"])
 @pytest.mark.parametrize("name", list(_scenes_small()))
-def test_gpu_matches_oracle(oracle, name):
+def test_gpu_matches_oracle(oracle, name, path):
+    """path auto: scenes of at most 288 actors without environment ids run as ONE environment on the fused environment path, larger ones and
+    environment scenes as before; devicewide: the device-wide path forced (PXB_FLAG_NO_ENV_PATH)."""
     sc, steps = _scenes_small()[name]
-    gpu, cpu = engine.Scene(sc, max_pairs=16 * len(sc.actors)), oracle.OracleScene(sc)
+    gpu, cpu = engine.Scene(sc, max_pairs=16 * len(sc.actors), env_path=(path == "auto")), oracle.OracleScene(sc)
+    assert path == "auto" or not gpu.uses_env_path
     exact = True
     for t in range(steps):
         gpu.step()
@@ -282,7 +286,7 @@ def _pgs_scenes():
 @pytest.mark.parametrize("name", list(_pgs_scenes()))
 def test_pgs_gpu_matches_oracle(oracle, name):
     sc, steps, env = _pgs_scenes()[name]
-    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    gpu, cpu = engine.Scene(sc, env_path=env), oracle.OracleScene(sc)
     glob = engine.Scene(sc, env_path=False) if env else None
     for t in range(steps):
         gpu.step()
@@ -368,7 +372,7 @@ def test_sleeping_gpu_matches_oracle(oracle, name):
     """Wake counters, asleep flags and states against the oracle (itself pinned against the reference's getWakeCounter /
     isSleeping, tests/test_oracle_vs_reference.py): islands fall asleep and wake on the same step; no resynchronisation."""
     sc, steps, env = _sleep_scenes()[name]
-    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    gpu, cpu = engine.Scene(sc, env_path=env), oracle.OracleScene(sc)
     ever_slept = woke = False
     prev = None
     for t in range(steps):
@@ -424,7 +428,7 @@ def _lock_scenes():
 def test_lock_flags_gpu_matches_oracle(oracle, name):
     """PxRigidDynamicLockFlags on both paths and both solvers: same pairs / contacts, states within one-step rounding of the oracle."""
     sc, steps = _lock_scenes()[name]
-    gpu, cpu = engine.Scene(sc, max_pairs=16 * len(sc.actors)), oracle.OracleScene(sc)
+    gpu, cpu = engine.Scene(sc, max_pairs=16 * len(sc.actors), env_path=name.endswith("_envs")), oracle.OracleScene(sc)
     for t in range(steps):
         gpu.step()
         cpu.step()
@@ -457,7 +461,7 @@ def test_external_forces_gpu_matches_oracle(oracle, name):
           "pgs_envs": scenes.env_grid_stacks(n_envs=5, stacks_per_env=3, height=4, jitter=0.01, solver=scenes.SOLVER_PGS),
           "primitives": scenes.mixed_primitives(n=12, seed=3, kinds=("sphere", "capsule"))}[name]
     F = scenes.test_forces(sc.n_dynamic)
-    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    gpu, cpu = engine.Scene(sc, env_path=name.endswith("envs")), oracle.OracleScene(sc)
     for t in range(60):
         if t % 9 != 8:   # every ninth step nothing is written: the previous step's forces must not persist
             gpu.setForces(F[t % len(F), :, :3], F[t % len(F), :, 3:])
@@ -540,7 +544,7 @@ def test_convex_hulls_gpu_matches_oracle_and_reference(oracle):
     """Cooked convex hulls through pxb_scene_set_convex_meshes: tight bounds bit-identical to the reference's, broadphase events equal, plane-hull
     contacts and states equal to the oracle every step (the hull fixture carries the reference's cooking output; nothing is cooked here)."""
     z, sc = util.load_golden("hulls_on_plane")
-    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    gpu, cpu = engine.Scene(sc, env_path=False), oracle.OracleScene(sc)
     for t in range(z["states"].shape[0] - 1):
         gpu.setStates(z["states"][t])
         assert np.array_equal(gpu.computeBounds(), z["bounds"][t]), f"bounds, step {t}"
@@ -599,7 +603,7 @@ def test_big_hulls_free_running_gpu_matches_oracle(oracle):
         if env:
             a["envId"][a["flags"] & scenes.ACTOR_DYNAMIC != 0] = 0
         scn = scenes.Scene(sc.header, a, sc.hulls, sc.cooked)
-        gpu, cpu = engine.Scene(scn), oracle.OracleScene(scn)
+        gpu, cpu = engine.Scene(scn, env_path=env), oracle.OracleScene(scn)
         for t in range(120):
             gpu.step(); cpu.step()
             assert gpu.uses_env_path == env
