@@ -257,6 +257,8 @@ def bench_ours(args):
 
     def one_step():
         apply_churn()
+        if gather is not None:
+            gather.pre_step()
         scene.simulate()
         if gather is not None:
             gather.step(lambda view: scene.getStatesDevice(view.data_ptr()))
@@ -281,9 +283,11 @@ def bench_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         launches += apply_churn()
+        if gather is not None:
+            gather.pre_step()
         scene.simulate()
         if gather is not None:
-            gather.step(lambda view: scene.getStatesDevice(view.data_ptr()))   # exchange on the communication streams, overlapping the next step
+            gather.step(lambda view: scene.getStatesDevice(view.data_ptr()))   # fused: only raises this rank's flag; copy-based kinds: exchange on communication streams
         e1.record(stream)
         scene.fetchResults(True)
         e1.synchronize()
@@ -340,15 +344,27 @@ def bench_ours(args):
         total_bodies = nb
     value = total_bodies * args.steps / (total_ms / 1e3)
 
-    # ---- end-to-end through the public API with HOST buffers (pinned): per step H2D of the velocity "action"
-    #      tensors, simulate+fetchResults, D2H of pose + velocities ----
-    pose_h = torch.empty((nb, 7), dtype=torch.float32).pin_memory()
+    if gather is not None and hasattr(gather, "close"):
+        gather.close()
+    # ---- end-to-end through the public API with HOST buffers (pinned): per step H2D of the velocity "action" tensors (stream-ordered
+    #      pxb_set_rigid_dynamic_data_async: the copy overlaps bounds / broadphase / narrowphase), simulate + fetchResults, and the step's packed
+    #      state block (pose + velocities, 52 bytes per body) stored by the step itself into MAPPED PINNED host memory (pxb_scene_set_state_export):
+    #      the device-to-host transfer overlaps the solve instead of following it. ----
+    state_h = torch.empty((nb, 13), dtype=torch.float32).pin_memory()
     lin_h = torch.empty((nb, 3), dtype=torch.float32).pin_memory()
     ang_h = torch.empty((nb, 3), dtype=torch.float32).pin_memory()
     lib, h = scene._lib, scene._h
     lib.pxb_get_rigid_dynamic_data(h, lin_h.data_ptr(), None, engine.RD_LINEAR_VELOCITY, nb)
     lib.pxb_get_rigid_dynamic_data(h, ang_h.data_ptr(), None, engine.RD_ANGULAR_VELOCITY, nb)
     e2e_steps = max(5, min(args.steps, 50))
+    e2e_api = "pxb_set_rigid_dynamic_data_async(lin,ang) -> pxb_scene_simulate (state export into mapped pinned host memory) -> pxb_scene_fetch_results (one host sync per step), pinned host buffers"
+    if args.e2e == "copy":
+        pose_h = torch.empty((nb, 7), dtype=torch.float32).pin_memory()
+        e2e_api = "pxb_set_rigid_dynamic_data_async(lin,ang) -> pxb_scene_simulate -> pxb_get_rigid_dynamic_data_async(pose,lin,ang) -> pxb_scene_fetch_results (one host sync per step), pinned host buffers"
+    else:
+        scene.setStateExport([state_h.data_ptr()], 0)
+    for _ in range(3):   # untimed: graph capture of the export variant of the step
+        scene.simulate(); scene.fetchResults(True)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -356,21 +372,34 @@ def bench_ours(args):
     for _ in range(e2e_steps):
         # stream-ordered calls on pinned host buffers, ONE host synchronisation per step (fetchResults), as with PxDirectGPUAPI's events
         apply_churn()
-        lib.pxb_set_rigid_dynamic_data_async(h, lin_h.data_ptr(), engine.RD_LINEAR_VELOCITY, nb)   # H2D (identity action: values just read back)
+        lib.pxb_set_rigid_dynamic_data_async(h, lin_h.data_ptr(), engine.RD_LINEAR_VELOCITY, nb)   # H2D of the action tensors (export leg: the resting velocities read before the loop; copy leg: the values read back last step)
         lib.pxb_set_rigid_dynamic_data_async(h, ang_h.data_ptr(), engine.RD_ANGULAR_VELOCITY, nb)
         scene.simulate()
-        lib.pxb_get_rigid_dynamic_data_async(h, pose_h.data_ptr(), engine.RD_GLOBAL_POSE, nb)      # D2H
-        lib.pxb_get_rigid_dynamic_data_async(h, lin_h.data_ptr(), engine.RD_LINEAR_VELOCITY, nb)
-        lib.pxb_get_rigid_dynamic_data_async(h, ang_h.data_ptr(), engine.RD_ANGULAR_VELOCITY, nb)
-        scene.fetchResults(True)                                                                   # waits for the step and the copies
+        if args.e2e == "copy":
+            lib.pxb_get_rigid_dynamic_data_async(h, pose_h.data_ptr(), engine.RD_GLOBAL_POSE, nb)      # D2H
+            lib.pxb_get_rigid_dynamic_data_async(h, lin_h.data_ptr(), engine.RD_LINEAR_VELOCITY, nb)
+            lib.pxb_get_rigid_dynamic_data_async(h, ang_h.data_ptr(), engine.RD_ANGULAR_VELOCITY, nb)
+        scene.fetchResults(True)                                                                   # waits for the step (and the copies)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    e2e_stage = {}
+    scene.setProfiling(True)
+    for _ in range(10):   # per-stage device times of the step as the end-to-end leg runs it (export on): how much the in-kernel transfer costs the solve
+        scene.simulate(); scene.fetchResults(True)
+        for k, v in scene.getStageTimes().items():
+            e2e_stage[k] = e2e_stage.get(k, 0.0) + v / 10
+    scene.setProfiling(False)
+    if args.e2e != "copy":
+        chk = scene.getStates()
+        if not np.array_equal(chk, state_h.numpy()):
+            raise RuntimeError("exported host state differs from pxb_scene_get_states")
+        scene.setStateExport(())
     if dist is not None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = total_bodies * e2e_steps / e2e_s
-    assert np.isfinite(pose_h.numpy()).all()
+    assert np.isfinite(state_h.numpy() if args.e2e != "copy" else pose_h.numpy()).all()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -419,7 +448,7 @@ def bench_ours(args):
                          "dram_frac": (traffic / (kernel_ms / 1e3) / 1e9 / peak) if traffic else None, "note": note},
             "stage_ms": stages,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nb * 24), "d2h_bytes_per_step": int(nb * (28 + 24)), "steps": e2e_steps,
-                    "api": "pxb_set_rigid_dynamic_data_async(lin,ang) -> pxb_scene_simulate -> pxb_get_rigid_dynamic_data_async(pose,lin,ang) -> pxb_scene_fetch_results (one host sync per step), pinned host buffers"},
+                    "api": e2e_api, "ms_per_step": e2e_s / e2e_steps * 1e3, "stage_ms": {k: round(v, 4) for k, v in e2e_stage.items()}},
             "gpu_launches": launches, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -444,6 +473,7 @@ def main():
     ap.add_argument("--partitioning", default="exact", choices=["exact", "relaxed"], help="configs 3 / 4: the reference's first-fit (default) or PXB_FLAG_RELAXED_PARTITIONING")
     ap.add_argument("--path", default="auto", choices=["auto", "devicewide"], help="devicewide forces the path used by scenes without environment ids (comparison runs)")
     ap.add_argument("--gather", default="auto", choices=["auto", "fused", "peer", "peer-copy", "nccl"], help="multi-GPU state exchange")
+    ap.add_argument("--e2e", default="export", choices=["export", "copy"], help="end-to-end leg: state export into mapped pinned host memory (default) or explicit D2H copies after the step")
     ap.add_argument("--solver", default="tgs", choices=["tgs", "pgs"], help="PxSolverType of the scene (headline metric: tgs)")
     args = ap.parse_args()
     if args.stacks == 16:

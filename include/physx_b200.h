@@ -155,6 +155,19 @@ PXB_API int  pxb_scene_get_states_device(PxbScene* scene, float* devOut); /* sam
                                                                               without a fetch: it packs the state that step produces, e.g. into an NCCL send buffer) */
 /* Multi-GPU exchange helper: ONE kernel stores `bytes` from devSrc into nDst <= 8 peer-mapped device buffers over NVLink (P2P). */
 PXB_API int  pxb_scatter_to_peers(PxbScene* scene, void* cudaStream, const void* devSrc, size_t bytes, const uint64_t* devDstPtrs, uint32_t nDst, uint32_t ctas);
+/* Fused state export.  From the next pxb_scene_simulate on, the step's integration epilogue stores every dynamic body's packed state record
+ * (13 floats, dynamic-body order, as pxb_scene_get_states) into each of nDst <= 9 device-accessible buffers at row `rowOffset`: memory of this
+ * GPU, PEER-MAPPED memory of other GPUs (P2P stores over NVLink, e.g. a symmetric-memory tensor: the per-step all-gather of the many-environment
+ * layout then needs no pack kernel and no copy) or MAPPED PINNED HOST memory (the device-to-host transfer overlaps the step instead of following
+ * it).  Stands in for PxDirectGPUAPI::getRigidDynamicData (PxDirectGPUAPI.h:311-360; getRigidDynamicGlobalPose / LinearVelocity / AngularVelocity
+ * kernels, updateBodiesAndShapes.cu:999-1253) when the consumer reads every body every step.  The targets may change every call (double
+ * buffering); nDst = 0 switches the export off.  Data is complete when the step is (pxb_scene_fetch_results, or stream order on pxb_scene_stream). */
+PXB_API int  pxb_scene_set_state_export(PxbScene* scene, void* const* dst, uint32_t nDst, uint32_t rowOffset);
+/* Cross-GPU flags for exchanges built on the export: pxb_peer_signal stores `value` into n <= 9 (peer-mapped) 32-bit flags with ONE kernel on
+ * `cudaStream` (NULL = the scene stream), ordered after everything enqueued before it at system scope; pxb_peer_wait makes the stream wait until
+ * n <= 32 consecutive LOCAL flags have all reached `value` (wrap-around compare). */
+PXB_API int  pxb_peer_signal(PxbScene* scene, void* cudaStream, const uint64_t* flagPtrs, uint32_t n, uint32_t value);
+PXB_API int  pxb_peer_wait(PxbScene* scene, void* cudaStream, const void* devFlags, uint32_t n, uint32_t value);
 PXB_API void* pxb_scene_state_device_ptr(PxbScene* scene, int which); /* 0 pos4, 1 quat4, 2 linVel4, 3 angVel4 (per ACTOR float4 arrays) */
 PXB_API void* pxb_scene_stream(PxbScene* scene);                        /* cudaStream_t */
 

@@ -20,13 +20,23 @@ MODULES  := foundation task common geomutils lowlevel lowlevelaabb lowleveldynam
             simulationcontroller physx physxextensions scenequery pvd physxcooking \
             immediatemode physxmetadata physxcharacterkinematic
 
+# GPU=1: the same host SDK with PX_SUPPORT_GPU_PHYSX on (no -DDISABLE_CUDA_PHYSX, + physx/src/gpu: the PhysXGpu module loader), into oracle/_ref_gpu/.
+# Still CPU code only -- it is the unmodified HOST the plugin shim (plugin/) is loaded into by ref_harness_gpu.
+ifeq ($(GPU),1)
+OUT      := oracle/_ref_gpu
+OBJ      := $(OUT)/obj
+EXCL     := /windows/|/omnipvd/|/device/windows|/mac/|/switch/|/android/
+CUDADEF  :=
+else
 EXCL     := /windows/|/gpu/|/omnipvd/|/device/windows|/mac/|/switch/|/android/
+CUDADEF  := -DDISABLE_CUDA_PHYSX
+endif
 SRCS     := $(shell find $(addprefix $(S)/,$(MODULES)) -name '*.cpp' | grep -Ev '$(EXCL)')
-INCDIRS  := $(shell find $(S) -type d | grep -Ev '$(EXCL)|/CUDA|/gpu[a-z]*|cudamanager/src|physxgpu/src|compiler|/physxvehicle')
+INCDIRS  := $(shell find $(S) -type d | grep -Ev '$(EXCL)|/gpu/|/CUDA|/gpu[a-z]*|cudamanager/src|physxgpu/src|compiler|/physxvehicle')
 INCS     := -I$(PX)/include $(addprefix -I,$(INCDIRS)) -I$(PX)/pvdruntime/include
 
 DEFS     := -DNDEBUG -DPX_SUPPORT_PVD=0 -DPX_SUPPORT_OMNI_PVD=0 -DPX_PHYSX_STATIC_LIB \
-            -DPX_PUBLIC_RELEASE=1 -DDISABLE_CUDA_PHYSX -DPX_NVTX=0
+            -DPX_PUBLIC_RELEASE=1 $(CUDADEF) -DPX_NVTX=0
 CXXFLAGS := -O3 -std=c++14 -fno-rtti -fno-exceptions -fno-strict-aliasing -ffunction-sections \
             -fdata-sections -fPIC -w $(DEFS)
 

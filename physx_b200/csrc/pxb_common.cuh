@@ -131,3 +131,37 @@ __device__ __forceinline__ m33 load_sym(const float4 A, const float4 B) {
 // a14 inputs of one constraint: body frames, inverse masses, pre-solver velocities, world sqrt(inverse inertia)
 struct PrepBodies { xf f0, f1; float invMass0, invMass1, pen0, pen1; v3 linVel0, linVel1, angVel0, angVel1; m33 sI0, sI1; };
 
+
+// Fused state export (pxb_scene_set_state_export): the table lives in device memory so that the captured step graph stays valid while the
+// targets alternate (double buffering); n = 0 switches the export off.  Targets are device-accessible buffers of packed 13-float records
+// (pos3 quat4 linVel3 angVel3, dynamic-body order): this GPU's memory, peer-mapped memory (P2P stores over NVLink) or mapped pinned host memory.
+#define PXB_MAX_EXPORT 9
+struct ExportTable { float* dst[PXB_MAX_EXPORT]; uint32_t n, rowOffset; };
+// One field of a body's packed record, read back from the per-actor float4 arrays (pos.w / vel.w are not part of the record).
+__device__ __forceinline__ float packed_state_field(const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ linVel, const float4* __restrict__ angVel, uint32_t a, uint32_t f) {
+  const float* src = f < 3 ? reinterpret_cast<const float*>(pos + a) + f : (f < 7 ? reinterpret_cast<const float*>(quat + a) + (f - 3)
+                   : (f < 10 ? reinterpret_cast<const float*>(linVel + a) + (f - 7) : reinterpret_cast<const float*>(angVel + a) + (f - 10)));
+  return *reinterpret_cast<const volatile float*>(src);   // volatile: the values were stored by other threads of this CTA (or an earlier kernel) a moment ago
+}
+// Coalesced export of the dynamic bodies [d0, d0 + nd): consecutive threads store consecutive floats of the packed block (full 128-byte
+// lines per warp instruction) into every target.
+__device__ __forceinline__ void export_packed_range(const ExportTable* __restrict__ tab, uint32_t nT, const uint32_t* __restrict__ dynActor, uint32_t d0, uint32_t nd, const float4* pos, const float4* quat,
+                                                    const float4* linVel, const float4* angVel, uint32_t tid, uint32_t nThreads) {
+  const uint32_t rowOffset = tab->rowOffset;
+  const size_t base = (size_t)(rowOffset + d0) * 13u; const uint32_t nf = nd * 13u;
+  if (((base | nf) & 3u) == 0) {   // 16-byte aligned block (e.g. 64-body environments): one float4 store per lane, 512 contiguous bytes per warp instruction
+    for (uint32_t i4 = tid; i4 < nf / 4u; i4 += nThreads) {
+      float v[4];
+#pragma unroll
+      for (uint32_t c = 0; c < 4; ++c) { const uint32_t i = i4 * 4u + c, j = i / 13u; v[c] = packed_state_field(pos, quat, linVel, angVel, dynActor[d0 + j], i - j * 13u); }
+      const float4 w = make_float4(v[0], v[1], v[2], v[3]);
+      for (uint32_t t = 0; t < nT; ++t) reinterpret_cast<float4*>(tab->dst[t] + base)[i4] = w;
+    }
+    return;
+  }
+  for (uint32_t i = tid; i < nf; i += nThreads) {
+    const uint32_t j = i / 13u, f = i - j * 13u;
+    const float v = packed_state_field(pos, quat, linVel, angVel, dynActor[d0 + j], f);
+    for (uint32_t t = 0; t < nT; ++t) tab->dst[t][base + i] = v;
+  }
+}

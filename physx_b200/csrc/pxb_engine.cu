@@ -62,13 +62,17 @@ struct PxbScene {
   RadixSortTemp rsTmp; uint32_t* scanSums = 0;
   uint32_t launches = 0;
   float* stage = 0; uint32_t* stageIdx = 0;
-  bool useGraph = true; cudaGraphExec_t graphExec[2] = {0, 0}; float graphDt = 0.f; uint32_t graphLaunches[2] = {0, 0};
+  // [parity][0 = whole step, 1 = bounds + broadphase + narrowphase, 2 = the rest]: the split pair is replayed when a stream-ordered velocity
+  // write is pending on the copy stream, so that its host-to-device copy overlaps the first part (which reads poses only)
+  bool useGraph = true; cudaGraphExec_t graphExec[2][3] = {{0, 0, 0}, {0, 0, 0}}; float graphDt = 0.f; uint32_t graphLaunches[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  cudaStream_t copyStream = nullptr; cudaEvent_t velEvent = nullptr, orderEvent = nullptr; bool velPending = false;
   bool profiling = false; cudaEvent_t ev[8] = {0, 0, 0, 0, 0, 0, 0, 0}; float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
   uint32_t hNPairs = 0, hNCreated = 0, hNDeleted = 0, hNCon = 0, hNPart = 0, hErr = 0;
   // environment-partitioned path (pxb_env.cuh)
   bool envEligible = false, envActive = false, envDisabled = false, everStepped = false; uint32_t ringMask = 0;
   uint32_t nEnv = 0, envMaxList = 0, envConCap = 0, envConCapForced = 0, envThreadsForced = 0, hMaxConEnv = 0, hMaxPairEnv = 0, envSolveThreads = 64;
   uint32_t *envStart = 0, *envList = 0, *actorLocal = 0, *slotColour = 0; unsigned long long* bodyBest = 0; bool relaxedPartitioning = false;
+  ExportTable* exportTab = 0; uint2* envDyn = 0; bool exportOn = false, envDynContiguous = false;   // fused state export (pxb_scene_set_state_export)
   float sleepThreshold = 0.f; float* wake = 0; float4 *accLin = 0, *accAng = 0; uint32_t *asleep = 0, *nInter = 0, *islandLabel = 0, *islandAwake = 0; int coopBlocksSleep = 0; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
 };
 
@@ -619,6 +623,26 @@ __global__ void __launch_bounds__(256) k_scatter_to_peers(const float4* __restri
     for (int k = 0; k < 8; ++k) if (k < (int)nDst) dst.p[k][i] = v;
   }
 }
+// a19: packed state export for scenes whose step does not end in k_env_solve (device-wide path; environments whose dynamic bodies are not
+// contiguous in dynamic-body order): one CTA per 256 bodies, coalesced stores into every target.
+__global__ void __launch_bounds__(256) k_states_export(uint32_t nDyn, const uint32_t* __restrict__ dynActor, const float4* pos, const float4* quat, const float4* linVel, const float4* angVel,
+                                                       const ExportTable* __restrict__ tab) {
+  const uint32_t nT = tab->n;
+  if (!nT) return;
+  const uint32_t d0 = blockIdx.x * 256u;
+  export_packed_range(tab, nT, dynActor, d0, min(256u, nDyn - d0), pos, quat, linVel, angVel, threadIdx.x, 256u);
+}
+__global__ void k_set_export(ExportTable* __restrict__ tab, ExportTable v) { if (threadIdx.x == 0 && blockIdx.x == 0) *tab = v; }
+// Cross-GPU flags for the exchange built on the export (physx_b200/multi_gpu.py FusedStateGather): a rank raises its flag in every peer's
+// signal pad after its step (the step's P2P stores are complete at the kernel boundary; the fence orders them before the flag at system
+// scope), consumers spin on their own pad.
+struct FlagPtrs { uint32_t* f[PXB_MAX_EXPORT]; };
+__global__ void k_peer_signal(FlagPtrs p, uint32_t n, uint32_t value) {
+  if (threadIdx.x < n) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(p.f[threadIdx.x]) = value; }
+}
+__global__ void k_peer_wait(const uint32_t* __restrict__ flags, uint32_t n, uint32_t value) {
+  if (threadIdx.x < n) { while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(flags + threadIdx.x) - value) < 0) __nanosleep(64); __threadfence_system(); }
+}
 __global__ void k_init_freelist(uint32_t cap, uint32_t* __restrict__ freeList) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cap) freeList[i] = i;
@@ -683,6 +707,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->wake, A)); CK(dalloc(s->accLin, A)); CK(dalloc(s->accAng, A)); CK(dalloc(s->asleep, A)); CK(dalloc(s->nInter, A)); CK(dalloc(s->islandLabel, A)); CK(dalloc(s->islandAwake, A));
   CK(cudaMemsetAsync(s->accLin, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->accAng, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->asleep, 0, 4 * A, s->stream)); CK(cudaMemsetAsync(s->nInter, 0, 4 * A, s->stream));
   { std::vector<float> w(A, 20.0f * 0.02f); CK(cudaMemcpyAsync(s->wake, w.data(), 4 * A, cudaMemcpyHostToDevice, s->stream)); CK(cudaStreamSynchronize(s->stream)); }   // PxRigidDynamic default wake counter
+  CK(dalloc(s->exportTab, 1)); CK(cudaMemsetAsync(s->exportTab, 0, sizeof(ExportTable), s->stream)); CK(dalloc(s->envDyn, A));
   CK(dalloc(s->bodyBest, A)); CK(dalloc(s->actorLocal, A)); CK(dalloc(s->slotColour, Pn)); CK(cudaMemsetAsync(s->slotColour, 0xff, 4 * Pn, s->stream)); for (int k = 0; k < 2; ++k) { CK(dalloc(s->envSeg[k], A)); CK(cudaMemsetAsync(s->envSeg[k], 0, sizeof(uint2) * A, s->stream)); }
   CK(cudaStreamSynchronize(s->stream));
   return PXB_OK;
@@ -697,7 +722,8 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   if (desc->device < 0 || desc->device >= ndev) return fail(PXB_ERR_INVALID, "bad device ordinal");
   DeviceGuard dg_(desc->device);
   s = new PxbScene(); s->desc = *desc; s->device = desc->device;
-  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&s->velEvent, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->orderEvent, cudaEventDisableTiming));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, desc->device));
   s->numSMs = prop.multiProcessorCount;
   int occ = 0;
@@ -732,10 +758,10 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
-                  s->envStart, s->envList, s->actorLocal, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
+                  s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
-  cudaStreamDestroy(s->stream);
+  cudaStreamDestroy(s->stream); if (s->copyStream) cudaStreamDestroy(s->copyStream); if (s->velEvent) cudaEventDestroy(s->velEvent); if (s->orderEvent) cudaEventDestroy(s->orderEvent);
   delete s;
 }
 
@@ -800,6 +826,18 @@ static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
   cudaMemcpyAsync(s->envList, list.data(), 4 * list.size(), cudaMemcpyHostToDevice, s->stream);
   cudaMemcpyAsync(s->actorLocal, local.data(), 4 * s->nA, cudaMemcpyHostToDevice, s->stream);
   cudaStreamSynchronize(s->stream);
+  {   // per environment: the range its dynamic bodies occupy in dynamic-body order (the fused state export writes whole blocks; contiguous in every
+      // scene whose actors are added environment by environment)
+    std::vector<uint2> ed(nEnv, make_uint2(0, 0)); bool contiguous = true;
+    for (uint32_t e = 0; e < nEnv; ++e) {
+      int first = -1, last = -1; uint32_t nd = 0;
+      for (uint32_t k = start[e]; k < start[e + 1]; ++k) { const int d = s->dynIndex[list[k]]; if (d < 0 || envOf(list[k]) == NONE32) continue; if (first < 0) first = d; last = d; ++nd; }
+      if (nd && (uint32_t)(last - first + 1) != nd) contiguous = false;
+      ed[e] = make_uint2(first < 0 ? 0u : (uint32_t)first, nd);
+    }
+    cudaMemcpyAsync(s->envDyn, ed.data(), sizeof(uint2) * nEnv, cudaMemcpyHostToDevice, s->stream); cudaStreamSynchronize(s->stream);
+    s->envDynContiguous = contiguous;
+  }
   s->nEnv = nEnv; s->envMaxList = maxList; s->envEligible = true;
 #ifdef PXB_ENV_TIMING
   if (s->envTiming) cudaFree(s->envTiming); cudaMalloc((void**)&s->envTiming, (size_t)nEnv * 16 * 8); cudaMemset(s->envTiming, 0, (size_t)nEnv * 16 * 8);
@@ -1061,16 +1099,20 @@ static int read_counters(PxbScene* s) {
   return PXB_OK;
 }
 
-static int enqueue_step(PxbScene* s, float dt) {
+// phase 0: the whole step; 1: bounds + broadphase + narrowphase (+ island sleep decisions) only; 2: the rest (s->cur already switched by phase 1)
+static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
   cudaStream_t st = s->stream; const uint32_t B = 256;
   s->launches = 0;
 #define MARK(i) do { if (s->profiling) CK(cudaEventRecord(s->ev[i], st)); } while (0)
-  MARK(0);
-  int rc = run_broadphase(s, false); if (rc) return rc;
-  MARK(1);
+  if (phase != 2) {
+    MARK(0);
+    int rc = run_broadphase(s, false); if (rc) return rc;
+    MARK(1);
+  }
   const int cur = s->cur; const uint32_t gP = cdiv(s->capPairs, B);
   const uint32_t* nP = s->nPairsDev + cur;
   const float contactDist = s->desc.contactOffset + s->desc.contactOffset;
+  if (phase != 2) {
   if (s->binPairs) {   // several geometry types: counting sort of the pairs by type pair, so that warps do not diverge across contact functions
     CK(cudaMemsetAsync(s->npClassCount, 0, 4 * 2 * NP_CLASSES, st));
     LAUNCH(k_np_class_count, gP, B, s->pairKeys[cur], nP, s->bitsA, s->geomFlags, s->npClass, s->npClassCount, s->pairSlots[cur], s->manifolds);
@@ -1082,12 +1124,14 @@ static int enqueue_step(PxbScene* s, float dt) {
   NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s);
   pxb_launch_narrowphase(st, s->capPairs, NA); s->launches++;
   if (s->hasGjkPairs) { pxb_launch_narrowphase_gjk(st, std::max(148u * 4u, std::min(cdiv(s->capPairs, 128), 148u * 64u)), NA); s->launches++; }
+  }
   SleepArgs SA; SA.threshold = s->sleepThreshold; SA.dt = dt; SA.wake = s->wake; SA.accLin = s->accLin; SA.accAng = s->accAng; SA.asleep = s->asleep; SA.nInter = s->nInter;
-  if (s->sleepThreshold > 0.f) {   // island sleep / wake decisions for this step (needs this frame's touching pairs)
+  if (phase != 2 && s->sleepThreshold > 0.f) {   // island sleep / wake decisions for this step (needs this frame's touching pairs)
     uint32_t nA = s->nA;
     void* args[] = {&nA, &nP, &s->pairBodies, &s->cHdr, &s->geomFlags, &SA, &s->islandLabel, &s->islandAwake, &s->counters, &s->linVel, &s->angVel, &s->conFlag, &s->deletedKeys, &s->bitsA};
     CK(cudaLaunchCooperativeKernel((void*)k_sleep_islands, dim3(s->coopBlocksSleep), dim3(256), args, 0, st)); s->launches++;
   }
+  if (phase == 1) { CK(cudaGetLastError()); return PXB_OK; }
   MARK(2);
   const float* g = s->desc.gravity; const bool pgs = s->desc.solverType == PXB_SOLVER_PGS;
   SolverParams P;
@@ -1107,10 +1151,13 @@ static int enqueue_step(PxbScene* s, float dt) {
     A.conPair = s->conPair; A.conB0 = s->conB0; A.conB1 = s->conB1; A.conColour = s->conColour; A.ordered = s->ordered; A.broken = s->conDone;
     A.rowScratch = s->ptA;   // ptA|ptB|ptC|frA|frB|frC|frD are ONE allocation of 28 x cap float4 (scene_alloc); the environment path uses 25 of them
     A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour; A.S = SA;
+    const bool fusedExport = s->exportOn && s->envDynContiguous;
+    A.exportTab = fusedExport ? s->exportTab : nullptr; A.envDyn = s->envDyn; A.dynActor = s->dynActorDev;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
     const bool ext = s->anyLocks || s->forcesUsed;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
     pxb_launch_env_solve(st, A, s->envSolveThreads, pgs, ext, smem);
     s->launches++;
+    if (s->exportOn && !fusedExport) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
     MARK(5); MARK(6);
     CK(cudaGetLastError());
     return PXB_OK;
@@ -1164,6 +1211,7 @@ static int enqueue_step(PxbScene* s, float dt) {
     pxb_launch_writeback_rows(st, s->capPairs, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions); s->launches++;
     if (pgs) {
       pxb_launch_finalize_bodies_pgs(st, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->invInertia, SA); s->launches++;
+      if (s->exportOn) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
       MARK(6);
       CK(cudaGetLastError());
       return PXB_OK;
@@ -1171,13 +1219,33 @@ static int enqueue_step(PxbScene* s, float dt) {
   }
   LAUNCH(k_finalize_bodies, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->bodyHasCon,
          s->sbDLin, s->sbDAng, s->invInertia, SA);
+  if (s->exportOn) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
   MARK(6);
   CK(cudaGetLastError());
   return PXB_OK;
 }
 
 static void drop_graphs(PxbScene* s) {
-  for (int k = 0; k < 2; ++k) if (s->graphExec[k]) { cudaGraphExecDestroy(s->graphExec[k]); s->graphExec[k] = 0; }
+  for (int k = 0; k < 2; ++k) for (int j = 0; j < 3; ++j) if (s->graphExec[k][j]) { cudaGraphExecDestroy(s->graphExec[k][j]); s->graphExec[k][j] = 0; }
+}
+
+// Captures one replayable piece of the step for buffer parity `par` (kind as enqueue_step's phase).  Returns false when capture is not possible.
+static bool capture_graph(PxbScene* s, float dt, int par, int kind) {
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+  const int curBefore = s->cur;
+  if (kind == 2) s->cur = par;   // the second part runs with the parity the first part switched to
+  const int rc = enqueue_step(s, dt, kind);
+  const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+  s->cur = curBefore;
+  if (rc != PXB_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&s->graphExec[par][kind], graph, 0) != cudaSuccess) {
+    cudaGetLastError(); if (graph) cudaGraphDestroy(graph);
+    s->graphExec[par][kind] = 0; s->abort = false;
+    return false;
+  }
+  cudaGraphDestroy(graph);
+  s->graphLaunches[par][kind] = s->launches;
+  return true;
 }
 
 // The launch sequence of a step depends only on the buffer parity (all counts live in device memory), so it is
@@ -1192,26 +1260,25 @@ PXB_API int pxb_scene_simulate(PxbScene* s, float dt) { DeviceGuard dg_(s);
   if (int rc = select_path(s)) return rc;
   if (!s->envActive) s->everStepped = true;
   const bool graphOk = s->useGraph && s->nOrder == 0 && !s->profiling;
-  if (!graphOk) { const int rc = enqueue_step(s, dt); if (rc) return rc; s->stepping = true; return PXB_OK; }
+  if (!graphOk) {
+    if (s->velPending) { CK(cudaStreamWaitEvent(s->stream, s->velEvent, 0)); s->velPending = false; }
+    const int rc = enqueue_step(s, dt); if (rc) return rc; s->stepping = true; return PXB_OK;
+  }
   if (s->graphDt != dt) { drop_graphs(s); s->graphDt = dt; }
   const int par = s->cur ^ 1;   // parity this step runs with
-  if (!s->graphExec[par]) {
-    cudaGraph_t graph = nullptr;
-    if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); s->useGraph = false; return pxb_scene_simulate(s, dt); }
-    const int curBefore = s->cur;
-    const int rc = enqueue_step(s, dt);
-    const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
-    s->cur = curBefore;
-    if (rc != PXB_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&s->graphExec[par], graph, 0) != cudaSuccess) {
-      cudaGetLastError(); if (graph) cudaGraphDestroy(graph);
-      s->graphExec[par] = 0; s->useGraph = false; s->abort = false;   // capture not possible here: direct launches from now on
-      return pxb_scene_simulate(s, dt);
-    }
-    cudaGraphDestroy(graph);
-    s->graphLaunches[par] = s->launches;
+  if (s->velPending) {
+    // a velocity write is in flight on the copy stream: replay the step in two pieces and join it between them (poses only before the join)
+    if ((!s->graphExec[par][1] && !capture_graph(s, dt, par, 1)) || (!s->graphExec[par][2] && !capture_graph(s, dt, par, 2))) { s->useGraph = false; return pxb_scene_simulate(s, dt); }
+    CK(cudaGraphLaunch(s->graphExec[par][1], s->stream));
+    CK(cudaStreamWaitEvent(s->stream, s->velEvent, 0)); s->velPending = false;
+    s->cur = par; s->launches = s->graphLaunches[par][1] + s->graphLaunches[par][2];
+    CK(cudaGraphLaunch(s->graphExec[par][2], s->stream));
+    s->stepping = true;
+    return PXB_OK;
   }
-  s->cur = par; s->launches = s->graphLaunches[par];
-  CK(cudaGraphLaunch(s->graphExec[par], s->stream));
+  if (!s->graphExec[par][0] && !capture_graph(s, dt, par, 0)) { s->useGraph = false; return pxb_scene_simulate(s, dt); }   // capture not possible here: direct launches from now on
+  s->cur = par; s->launches = s->graphLaunches[par][0];
+  CK(cudaGraphLaunch(s->graphExec[par][0], s->stream));
   s->stepping = true;
   return PXB_OK;
 }
@@ -1315,12 +1382,15 @@ PXB_API int pxb_scene_get_sleep_data(PxbScene* s, float* wakeCounters, uint32_t*
 extern "C" PXB_API int pxb_debug_env_timing(PxbScene* s, unsigned long long* out) { DeviceGuard dg_(s); cudaStreamSynchronize(s->stream); cudaMemcpy(out, s->envTiming, (size_t)s->nEnv * 16 * 8, cudaMemcpyDeviceToHost); return (int)s->nEnv; }
 #endif
 
+// any other access to the body state is ordered after a velocity write still in flight on the copy stream
+static int join_pending(PxbScene* s) { if (s->velPending) { CK(cudaStreamWaitEvent(s->stream, s->velEvent, 0)); s->velPending = false; } return PXB_OK; }
 static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb, bool set) {
   if (type < 0 || type > (set ? PXB_RD_TORQUE : PXB_RD_ANGULAR_VELOCITY)) return fail(PXB_ERR_INVALID, "bad dataType");
   if (type >= PXB_RD_FORCE && !s->forcesUsed) { s->forcesUsed = true; drop_graphs(s); }   // the step kernels read the force arrays from now on
   if (!devIdx && nb > s->nDyn) return fail(PXB_ERR_INVALID, "nb exceeds the number of dynamic bodies");
   cudaStream_t st = s->stream;
   if (!nb) return PXB_OK;
+  if (int rc = join_pending(s)) return rc;
   if (set) LAUNCH(k_rd_set, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (const float*)devData, s->wake, s->asleep, s->extForce, s->extTorque);
   else LAUNCH(k_rd_get, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (float*)devData);
   CK(cudaGetLastError());
@@ -1348,6 +1418,17 @@ static int rd_host(PxbScene* s, void* data, const uint32_t* idx, int type, uint3
   float* d = s->stage + (size_t)s->capA * (type >= PXB_RD_FORCE ? 26 + 3 * (type - PXB_RD_FORCE) : (set ? 13 : 0) + (type == 0 ? 0 : (type == 1 ? 7 : 10))); uint32_t* di = nullptr;
   if (idx) { for (uint32_t i = 0; i < nb; ++i) if (idx[i] >= s->nDyn) return fail(PXB_ERR_INVALID, "index out of range");
              di = s->stageIdx; CK(cudaMemcpyAsync(di, idx, 4 * (size_t)nb, cudaMemcpyHostToDevice, s->stream)); }
+  if (set && async && (type == PXB_RD_LINEAR_VELOCITY || type == PXB_RD_ANGULAR_VELOCITY) && s->sleepThreshold == 0.f && !s->stepping && s->copyStream && nb <= s->nDyn) {
+    // Stream-ordered velocity write: copy + scatter run on the copy stream, ordered after everything already enqueued on the scene stream; the next
+    // pxb_scene_simulate joins them right before the solver, so the host-to-device copy overlaps bounds / broadphase / narrowphase (which read
+    // poses only).  With sleeping enabled the write also wakes bodies, which the island pass of the first part reads: no overlap then.
+    if (!s->velPending) { CK(cudaEventRecord(s->orderEvent, s->stream)); CK(cudaStreamWaitEvent(s->copyStream, s->orderEvent, 0)); }
+    CK(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, s->copyStream));
+    k_rd_set<<<cdiv(nb, 256), 256, 0, s->copyStream>>>(nb, nullptr, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (const float*)d, s->wake, s->asleep, s->extForce, s->extTorque);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s->velEvent, s->copyStream)); s->velPending = true;
+    return PXB_OK;
+  }
   if (set) CK(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, s->stream));
   int rc = rd_common(s, d, di, type, nb, set);
   if (!rc && !set) CK(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -1373,11 +1454,48 @@ PXB_API int pxb_scatter_to_peers(PxbScene* s, void* stream, const void* devSrc, 
   CK(cudaGetLastError());
   return PXB_OK;
 }
+// Fused state export (include/physx_b200.h).  The table is written by a one-thread kernel that takes it by value: stream-ordered before the
+// next step, no host buffer has to outlive the call, and the captured step graph (which reads the table from device memory) stays valid.
+PXB_API int pxb_scene_set_state_export(PxbScene* s, void* const* dst, uint32_t nDst, uint32_t rowOffset) { DeviceGuard dg_(s);
+  if (!s || (nDst && !dst)) return fail(PXB_ERR_INVALID, "null argument");
+  if (nDst > PXB_MAX_EXPORT) return fail(PXB_ERR_INVALID, "at most 9 export targets");
+  ExportTable t; memset(&t, 0, sizeof(t));
+  for (uint32_t k = 0; k < nDst; ++k) {
+    if (!dst[k] || ((uintptr_t)dst[k] & 15u)) return fail(PXB_ERR_INVALID, "export targets must be non-null and 16-byte aligned");
+    cudaPointerAttributes at; memset(&at, 0, sizeof(at));
+    if (cudaPointerGetAttributes(&at, dst[k]) != cudaSuccess) { cudaGetLastError(); return fail(PXB_ERR_INVALID, "export target is not a CUDA-accessible pointer"); }
+    if (at.type == cudaMemoryTypeUnregistered) return fail(PXB_ERR_INVALID, "export target is pageable host memory: pass device, peer-mapped or pinned (mapped) host memory");
+    t.dst[k] = (float*)(at.type == cudaMemoryTypeHost && at.devicePointer ? at.devicePointer : dst[k]);   // mapped pinned host memory: the device-side alias
+  }
+  t.n = nDst; t.rowOffset = rowOffset;
+  if ((nDst != 0) != s->exportOn) { s->exportOn = nDst != 0; drop_graphs(s); }   // the launch sequence gains / loses the export
+  k_set_export<<<1, 32, 0, s->stream>>>(s->exportTab, t);
+  CK(cudaGetLastError());
+  return PXB_OK;
+}
+PXB_API int pxb_peer_signal(PxbScene* s, void* stream, const uint64_t* flagPtrs, uint32_t n, uint32_t value) { DeviceGuard dg_(s);
+  if (!s || (n && !flagPtrs)) return fail(PXB_ERR_INVALID, "null argument");
+  if (n > PXB_MAX_EXPORT) return fail(PXB_ERR_INVALID, "at most 9 flags");
+  if (!n) return PXB_OK;
+  FlagPtrs P; for (uint32_t k = 0; k < PXB_MAX_EXPORT; ++k) P.f[k] = k < n ? reinterpret_cast<uint32_t*>(flagPtrs[k]) : nullptr;
+  k_peer_signal<<<1, 32, 0, stream ? (cudaStream_t)stream : s->stream>>>(P, n, value);
+  CK(cudaGetLastError());
+  return PXB_OK;
+}
+PXB_API int pxb_peer_wait(PxbScene* s, void* stream, const void* devFlags, uint32_t n, uint32_t value) { DeviceGuard dg_(s);
+  if (!s || (n && !devFlags)) return fail(PXB_ERR_INVALID, "null argument");
+  if (n > 32) return fail(PXB_ERR_INVALID, "at most 32 flags");
+  if (!n) return PXB_OK;
+  k_peer_wait<<<1, 32, 0, stream ? (cudaStream_t)stream : s->stream>>>((const uint32_t*)devFlags, n, value);
+  CK(cudaGetLastError());
+  return PXB_OK;
+}
 PXB_API int pxb_scene_sync(PxbScene* s) { DeviceGuard dg_(s); if (!s) return fail(PXB_ERR_INVALID, "null scene"); CK(cudaStreamSynchronize(s->stream)); return PXB_OK; }
 
 // Packed 13-float state of every dynamic body written straight into a DEVICE buffer (e.g. this rank's slice of
 // the NCCL all-gather receive tensor); asynchronous on the scene stream.
 PXB_API int pxb_scene_get_states_device(PxbScene* s, float* devOut) { DeviceGuard dg_(s);
+  if (s) { if (int rc = join_pending(s)) return rc; }
   if (!s || !devOut) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;   // stream-ordered: legal right after pxb_scene_simulate, it reads the state that step produces
   cudaStream_t st = s->stream;
@@ -1386,6 +1504,7 @@ PXB_API int pxb_scene_get_states_device(PxbScene* s, float* devOut) { DeviceGuar
   return PXB_OK;
 }
 PXB_API int pxb_scene_get_states(PxbScene* s, float* out) { DeviceGuard dg_(s);
+  if (s) { if (int rc = join_pending(s)) return rc; }
   if (!s || !out) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;
   cudaStream_t st = s->stream; float* d = s->stage;   // persistent staging (26 floats per actor): no allocation per call
@@ -1394,6 +1513,7 @@ PXB_API int pxb_scene_get_states(PxbScene* s, float* out) { DeviceGuard dg_(s);
   return PXB_OK;
 }
 PXB_API int pxb_scene_set_states(PxbScene* s, const float* in) { DeviceGuard dg_(s);
+  if (s) { if (int rc = join_pending(s)) return rc; }
   if (!s || !in) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;
   cudaStream_t st = s->stream; float* d = s->stage + (size_t)s->capA * 13;

@@ -153,6 +153,7 @@ struct EnvSolveArgs {
   uint32_t* counters; unsigned long long* timing; SleepArgs S;
   uint32_t anyLocks;   // some actor carries PxRigidDynamicLockFlags (uniform fast path otherwise)
   float4 *extForce, *extTorque;   // pending eFORCE / eTORQUE writes (NULL until the application uses them)
+  const ExportTable* exportTab; const uint2* envDyn; const uint32_t* dynActor;   // fused state export: targets, per environment {first dynamic-body index, count}
 };
 #ifdef PXB_ENV_TIMING
 #define ENV_T(i) do { __syncthreads(); if (threadIdx.x == 0) { const long long c_ = clock64(); A.timing[(size_t)blockIdx.x * 16 + (i)] = (unsigned long long)(c_ - t_prev); t_prev = c_; } } while (0)
@@ -640,6 +641,16 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
     A.pos[a] = make_float4(p.x, p.y, p.z, invMass); A.quat[a] = F4(q);
     A.linVel[a] = F4(lv, 0.f); A.angVel[a] = F4(mmul(sI, as), 0.f);
     if (A.S.threshold > 0.f) { const float invDt = 1.0f / A.dt; sleep_check_dev(A.S, a, q, A.invInertia[a], invMass, dl * invDt, mmul(sI, da * invDt)); }
+  }
+  // a19 fused into the step: this environment's packed state block goes straight into every registered export target (the learner's tensor
+  // on every peer GPU over NVLink, or mapped pinned host memory), so no pack kernel and no copy follow the step.
+  if (A.exportTab) {
+    const uint32_t nT = A.exportTab->n;
+    if (nT) {
+      __syncthreads();   // the final states above were written by other threads of this CTA
+      const uint2 dr = A.envDyn[e];
+      export_packed_range(A.exportTab, nT, A.dynActor, dr.x, dr.y, A.pos, A.quat, A.linVel, A.angVel, tid, T);
+    }
   }
   ENV_T(7);
 }

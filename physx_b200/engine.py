@@ -30,6 +30,7 @@ EXPORTS = [
     "pxb_scene_get_contacts", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
+    "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
@@ -95,6 +96,9 @@ def load_library():
     lib.pxb_set_rigid_dynamic_data_async.argtypes = [vp, vp, i32, u32]
     lib.pxb_scene_sync.argtypes = [vp]
     lib.pxb_scatter_to_peers.argtypes = [vp, vp, vp, ctypes.c_size_t, vp, u32, u32]
+    lib.pxb_scene_set_state_export.argtypes = [vp, vp, u32, u32]
+    lib.pxb_peer_signal.argtypes = [vp, vp, vp, u32, u32]
+    lib.pxb_peer_wait.argtypes = [vp, vp, vp, u32, u32]
     lib.pxb_scene_set_profiling.argtypes = [vp, i32]
     lib.pxb_scene_get_stage_times.argtypes = [vp, vp]
     lib.pxb_scene_state_device_ptr.argtypes = [vp, i32]
@@ -210,6 +214,19 @@ class Scene:
         """One kernel that stores a device block into up to 8 peer-mapped buffers (multi-GPU state exchange)."""
         arr = (ctypes.c_uint64 * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
         _check(self._lib, self._lib.pxb_scatter_to_peers(self._h, stream_ptr or None, src_ptr, nbytes, arr, len(dst_ptrs), ctas))
+
+    def setStateExport(self, dst_ptrs=(), row_offset: int = 0):
+        """Fused state export: from the next simulate on, the step itself stores the packed [n_dyn, 13] state block at row `row_offset` of every
+        buffer in `dst_ptrs` (own / peer-mapped device memory, or mapped pinned host memory).  Empty = off."""
+        arr = (ctypes.c_void_p * max(1, len(dst_ptrs)))(*[int(p) for p in dst_ptrs])
+        _check(self._lib, self._lib.pxb_scene_set_state_export(self._h, arr, len(dst_ptrs), int(row_offset)))
+
+    def peerSignal(self, stream_ptr: int, flag_ptrs, value: int):
+        arr = (ctypes.c_uint64 * max(1, len(flag_ptrs)))(*[int(p) for p in flag_ptrs])
+        _check(self._lib, self._lib.pxb_peer_signal(self._h, stream_ptr or None, arr, len(flag_ptrs), int(value) & 0xFFFFFFFF))
+
+    def peerWait(self, stream_ptr: int, flags_ptr: int, n: int, value: int):
+        _check(self._lib, self._lib.pxb_peer_wait(self._h, stream_ptr or None, flags_ptr, int(n), int(value) & 0xFFFFFFFF))
 
     def stream(self) -> int:
         return int(self._lib.pxb_scene_stream(self._h) or 0)

@@ -131,6 +131,9 @@ class PipelinedStateGather:
         self.k += 1
         return b
 
+    def pre_step(self, consumer_stream=None):
+        """Nothing to prepare: the exchange is enqueued by step() after the simulate call."""
+
     def latest(self):
         """Global tensor of the most recent step (caller must `wait()` or order its stream after `done`)."""
         return self.bufs[(self.k - 1) & 1].global_tensor
@@ -220,6 +223,16 @@ class PeerStateGather:
         self.k += 1
         return b
 
+    def pre_step(self, consumer_stream=None):
+        """Consumer release: a peer may push step k into the buffer this rank last read for step k-2 only after every rank has
+        ENTERED step k-1, i.e. finished with it.  One symmetric-memory barrier on the communication stream, before this step's pushes."""
+        t = self.torch
+        ev = t.cuda.Event()
+        ev.record(consumer_stream if consumer_stream is not None else self.scene_stream)
+        self.comm_stream.wait_event(ev)
+        with t.cuda.stream(self.comm_stream):
+            self.handles[self.k & 1].barrier(channel=2 + (self.k & 1))
+
     def latest(self):
         return self.bufs[(self.k - 1) & 1]
 
@@ -229,10 +242,94 @@ class PeerStateGather:
                 (stream or self.scene_stream).wait_event(ev)
 
 
+class FusedStateGather:
+    """The all-gather FUSED INTO THE STEP: every rank's global [sum(n), 13] tensor lives in symmetric memory, and the engine's integration
+    epilogue (pxb_scene_set_state_export) stores each environment's packed block straight into this rank's rows of EVERY rank's tensor with P2P
+    stores over NVLink -- no pack kernel, no copies, no collective call; the transfer overlaps the solve environment by environment.
+    Synchronisation is two flags per rank in a symmetric signal pad, written with pxb_peer_signal (one tiny kernel) and awaited with
+    pxb_peer_wait:
+      * data[r]    = k  once rank r's block of step k has landed everywhere (raised right after r's step on its scene stream);
+      * release[r] = k  once rank r has ENTERED step k, i.e. is done reading the tensor of step k-1.
+    Buffers rotate over `nbuf` slots; a rank may start writing step k (slot k % nbuf) only when every release flag has reached k - nbuf + 1, so
+    a peer can never overwrite a tensor this rank is still reading (the consumer-release handshake the copy-based exchange lacked).
+    Usage per step:  pre_step() -> scene.simulate() -> step()  [-> wait() / latest() by the consumer]."""
+
+    def __init__(self, dist, n_local: int, cols: int, device, scene_stream, scene, nbuf: int = 2):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        assert cols == 13, "the fused export writes the packed 13-float state record"
+        self.torch, self.dist, self.scene, self.scene_stream, self.nbuf = torch, dist, scene, scene_stream, nbuf
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if self.world > 9:
+            raise RuntimeError("at most 9 export targets")
+        cnt = torch.tensor([n_local], dtype=torch.int64, device=device)
+        allc = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(allc, cnt)
+        self.counts = [int(c.item()) for c in allc]
+        self.layout = gather_layout(self.counts)
+        total = sum(self.counts)
+        self.bufs, self.handles, self.ptrs = [], [], []
+        for _ in range(nbuf):
+            t = symm.empty((total, cols), dtype=torch.float32, device=device)
+            h = symm.rendezvous(t, dist.group.WORLD)
+            self.bufs.append(t)
+            self.handles.append(h)
+            self.ptrs.append([h.get_buffer(p, (total, cols), torch.float32).data_ptr() for p in range(self.world)])
+        self.flags = symm.empty((2 * self.world,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.fh = symm.rendezvous(self.flags, dist.group.WORLD)
+        peer_flags = [self.fh.get_buffer(p, (2 * self.world,), torch.int32).data_ptr() for p in range(self.world)]
+        self.data_flag_ptrs = [f + 4 * self.rank for f in peer_flags]                      # my slot in everybody's pad
+        self.release_flag_ptrs = [f + 4 * (self.world + self.rank) for f in peer_flags]
+        self.k = 0
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    def pre_step(self, consumer_stream=None):
+        """Before scene.simulate(): announce that this rank is done with the previous tensor, wait until the slot of this step is free on every
+        rank, and point the step's export at it."""
+        k = self.k + 1
+        st = self.scene_stream
+        if consumer_stream is not None:
+            ev = self.torch.cuda.Event()
+            ev.record(consumer_stream)
+            st.wait_event(ev)
+        self.scene.peerSignal(st.cuda_stream, self.release_flag_ptrs, k)
+        self.scene.peerWait(st.cuda_stream, self.flags.data_ptr() + 4 * self.world, self.world, k - self.nbuf + 1)
+        self.scene.setStateExport(self.ptrs[k % self.nbuf], self.layout[self.rank][0])
+
+    def step(self, pack=None):
+        """After scene.simulate(): raise this rank's data flag on every rank (the step's P2P stores are complete at its kernel boundary)."""
+        self.k += 1
+        self.scene.peerSignal(self.scene_stream.cuda_stream, self.data_flag_ptrs, self.k)
+        return self.k % self.nbuf
+
+    def close(self):
+        """Stops exporting (the scene keeps stepping without writing into the exchange buffers)."""
+        self.scene.setStateExport(())
+
+    def latest(self):
+        return self.bufs[self.k % self.nbuf]
+
+    def wait(self, stream=None):
+        """Orders `stream` (default: the scene stream) after the arrival of every rank's block of the latest step."""
+        st = stream or self.scene_stream
+        self.scene.peerWait(st.cuda_stream, self.flags.data_ptr(), self.world, self.k)
+
+
 def make_state_gather(dist, n_local: int, cols: int, device, scene_stream, kind: str = "auto", scene=None):
-    """kind: 'peer-copy' (concurrent copy-engine peer copies into symmetric memory), 'peer' (one scatter kernel with P2P stores),
-    'nccl' (all_gather_into_tensor) or 'auto' (peer-copy when symmetric memory is available, else NCCL)."""
-    if kind in ("auto", "peer", "peer-copy") and device.type == "cuda":
+    """kind: 'fused' (the step's integration epilogue stores into every rank's symmetric-memory tensor: FusedStateGather), 'peer-copy'
+    (concurrent copy-engine peer copies into symmetric memory), 'peer' (one scatter kernel with P2P stores), 'nccl' (all_gather_into_tensor)
+    or 'auto' (fused when symmetric memory is available, else NCCL)."""
+    if kind in ("auto", "fused") and device.type == "cuda" and scene is not None and cols == 13:
+        try:
+            g = FusedStateGather(dist, n_local, cols, device, scene_stream, scene)
+            return g, "P2P stores from the step's integration epilogue into every rank's symmetric-memory tensor (fused export) + per-rank flags"
+        except Exception as e:  # pragma: no cover - depends on the platform
+            if kind == "fused":
+                raise
+            kind = "auto-copy"
+    if kind in ("auto", "auto-copy", "peer", "peer-copy") and device.type == "cuda":
         try:
             mode = "kernel" if kind == "peer" else "copy"   # auto: copy engines (measured faster at N=8: they take no SM from the next step)
             g = PeerStateGather(dist, n_local, cols, device, scene_stream, scene=scene, mode=mode)

@@ -735,3 +735,63 @@ def test_gpu_hull_contacts_match_reference_golden_all_points(name, types, bar):
             assert nrm <= max(bar, 1e-6), f"normal, pair {k}, step {t}"
             checked += 1
     assert checked >= 30
+
+
+# ---- fused state export / stream-ordered velocity writes (a19) ----
+@pytest.mark.parametrize("kind", ["envs", "envs_ragged", "devicewide", "pgs_devicewide"])
+def test_state_export_matches_get_states(kind):
+    """pxb_scene_set_state_export: the step itself stores the packed state block into device memory (at a row offset) and into mapped pinned host
+    memory; both equal pxb_scene_get_states after every step, on the environment path (fused into k_env_solve), on environments whose bodies
+    are not contiguous in dynamic-body order (k_states_export) and on the device-wide path."""
+    import torch
+    if kind == "envs":
+        sc = scenes.env_grid_stacks(n_envs=9, jitter=0.01)
+    elif kind == "envs_ragged":
+        sc = scenes.env_grid_stacks(n_envs=6, stacks_per_env=2, height=3, jitter=0.01)
+        perm = np.concatenate([[0], 1 + np.random.RandomState(1).permutation(len(sc.actors) - 1)])    # interleave the environments' bodies
+        sc = scenes.Scene(sc.header, sc.actors[perm].copy())
+    else:
+        sc = scenes.box_stacks(n_stacks=3, height=5, half_extent=0.25, spacing=1.0, jitter=0.01, solver=scenes.SOLVER_PGS if kind.startswith("pgs") else scenes.SOLVER_TGS)
+    gpu = engine.Scene(sc, env_path=not kind.endswith("devicewide"))
+    n = gpu.num_dynamic
+    dev = torch.zeros((n + 7, 13), dtype=torch.float32, device="cuda")
+    host = torch.zeros((n, 13), dtype=torch.float32).pin_memory()
+    gpu.step()                                    # one step without export first: the launch sequence changes when it is switched on
+    gpu.setStateExport([dev.data_ptr(), host.data_ptr()], 0)
+    for t in range(12):
+        if t == 6:
+            gpu.setStateExport([dev.data_ptr()], 5)    # targets and row offset may change between steps
+        gpu.step()
+        st = gpu.getStates()
+        assert gpu.uses_env_path == kind.startswith("envs")
+        off = 0 if t < 6 else 5
+        assert np.array_equal(dev[off:off + n].cpu().numpy(), st), f"device target, step {t}"
+        if t < 6:
+            assert np.array_equal(host.numpy(), st), f"pinned host target, step {t}"
+    gpu.setStateExport(())
+    before = dev.clone()
+    gpu.step()
+    assert torch.equal(dev, before), "export switched off"
+    with pytest.raises(engine.PhysxB200Error):
+        gpu.setStateExport([np.zeros(4, np.float32).ctypes.data])   # pageable host memory is refused
+
+
+def test_stream_ordered_velocity_write_overlaps_and_matches_the_synchronous_one():
+    """pxb_set_rigid_dynamic_data_async on velocities runs on the copy stream and is joined between the narrowphase and the solver (split step
+    graph): same result as the synchronous write, bit for bit, step after step."""
+    import torch
+    sc = scenes.env_grid_stacks(n_envs=16, jitter=0.01)
+    a, b = engine.Scene(sc), engine.Scene(sc)
+    n = a.num_dynamic
+    rng = np.random.RandomState(0)
+    lin = torch.zeros((n, 3), dtype=torch.float32).pin_memory(); ang = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
+    for t in range(10):
+        v = (0.05 * rng.standard_normal((n, 3))).astype(np.float32); w = (0.1 * rng.standard_normal((n, 3))).astype(np.float32)
+        lin.numpy()[:] = v; ang.numpy()[:] = w
+        engine._check(a._lib, a._lib.pxb_set_rigid_dynamic_data_async(a._h, lin.data_ptr(), engine.RD_LINEAR_VELOCITY, n))
+        engine._check(a._lib, a._lib.pxb_set_rigid_dynamic_data_async(a._h, ang.data_ptr(), engine.RD_ANGULAR_VELOCITY, n))
+        b.setRigidDynamicData(engine.RD_LINEAR_VELOCITY, v); b.setRigidDynamicData(engine.RD_ANGULAR_VELOCITY, w)
+        if t == 4:   # a read between the write and the step is ordered after the write
+            assert np.array_equal(a.getRigidDynamicData(engine.RD_LINEAR_VELOCITY), v)
+        a.step(); b.step()
+        assert np.array_equal(a.getStates(), b.getStates()), f"step {t}"
