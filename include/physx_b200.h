@@ -204,6 +204,20 @@ PXB_API int  pxb_scene_get_sleep_data(PxbScene* scene, float* wakeCounters, uint
 /* 1 if the last step ran on the environment path, 0 for the device-wide path */
 PXB_API int  pxb_scene_uses_env_path(PxbScene* scene);
 
+/* ---- standalone broadphase object: a2-a6 behind the reference's own Bp::BroadPhase interface (lowlevelaabb/include/BpBroadPhase.h:98-222).
+ *      The plugin shim's Bp::BroadPhase subclass (plugin/PxgB200BroadPhase.cpp) forwards Bp::BroadPhaseUpdateData (BpBroadPhaseUpdate.h:48-140)
+ *      to pxb_bp_update and serves getCreatedPairs / getDeletedPairs from pxb_bp_fetch.  Objects are slots of the host arrays: bounds6 = PxBounds3
+ *      per slot (tight), contactDist, groups = Bp::FilterGroup values (3-bit Bp::FilterType in the low bits), envIds or NULL, lut49 = the 7 x 7
+ *      BpFilter table (BpFiltering.h:116-128) as bytes.  Pair semantics of the reference: closed-interval overlap of the bounds inflated by the
+ *      contact distance, groups differ, type table, equal-or-invalid environment ids; created = new overlaps, deleted = lost overlaps between
+ *      objects that are still in the broadphase (BpBroadPhase.h:160-192).  Pairs are (a, b) with a < b, sorted. ---- */
+typedef struct PxbBroadPhase PxbBroadPhase;
+PXB_API int  pxb_bp_create(uint32_t maxObjects, uint32_t maxPairs, int device, PxbBroadPhase** out);
+PXB_API void pxb_bp_release(PxbBroadPhase* bp);
+PXB_API int  pxb_bp_update(PxbBroadPhase* bp, const float* bounds6, const float* contactDist, const uint32_t* groups, const uint32_t* envIds, uint32_t capacity, const uint8_t* lut49,
+                           const uint32_t* created, uint32_t nCreated, const uint32_t* updated, uint32_t nUpdated, const uint32_t* removed, uint32_t nRemoved);
+PXB_API int  pxb_bp_fetch(PxbBroadPhase* bp, const uint32_t** createdPairs, uint32_t* nCreated, const uint32_t** deletedPairs, uint32_t* nDeleted);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,6 +125,7 @@ int main(int argc, char** argv) {
   }
   const char* scenePath = argv[2];
   int steps = 100, threads = 1, warmup = 0;
+  const char* gpuPlugin = nullptr; bool gpuBp = false, gpuDynamics = false;
   const char *statesPath = nullptr, *bpPath = nullptr, *contactsPath = nullptr, *hullsPath = nullptr, *orderPath = nullptr, *sleepPath = nullptr, *forcesPath = nullptr;
   for (int i = 3; i < argc; i++) {
     std::string a = argv[i];
@@ -137,6 +138,9 @@ int main(int argc, char** argv) {
     else if (a == "--hulls") hullsPath = argv[++i];
     else if (a == "--order") orderPath = argv[++i];
     else if (a == "--forces") forcesPath = argv[++i];   // f32[blocks][nDyn][6] = force xyz, torque xyz: block s (mod blocks) is applied with addForce / addTorque(eFORCE) before step s
+    else if (a == "--gpu-plugin") gpuPlugin = argv[++i];   // (GPU-enabled host build only) path of a libPhysXGpu_64.so to load through PxSetPhysXGpuLoadHook
+    else if (a == "--gpu-bp") gpuBp = true;                // PxBroadPhaseType::eGPU (CPU dynamics)
+    else if (a == "--gpu-dynamics") gpuDynamics = true;    // + PxSceneFlag::eENABLE_GPU_DYNAMICS
     else if (a == "--sleep") sleepPath = argv[++i];   // per step, per dynamic actor: f32 wakeCounter, u32 isSleeping
   }
   gWantContacts = contactsPath != nullptr;
@@ -227,6 +231,26 @@ int main(int argc, char** argv) {
   sd.filterShaderData = &wantContactsFlag;
   sd.filterShaderDataSize = sizeof(int);
   sd.broadPhaseType = PxBroadPhaseType::eABP;
+#if PX_SUPPORT_GPU_PHYSX
+  // The UNMODIFIED host SDK with a PhysXGpu plugin loaded through its own loader (PxPhysXGpuModuleLoader.cpp): used to run the repo's
+  // libPhysXGpu_64.so (plugin/) inside the reference -- the scene is created exactly as an application would.
+  struct LoadHook : public PxGpuLoadHook { const char* name; const char* getPhysXGpuDllName() const override { return name; } };
+  static LoadHook hook;
+  PxCudaContextManager* cudaMgr = nullptr;
+  if (gpuBp || gpuDynamics) {
+    if (gpuPlugin) { hook.name = gpuPlugin; PxSetPhysXGpuLoadHook(&hook); }
+    PxCudaContextManagerDesc cd;
+    cudaMgr = PxCreateCudaContextManager(*foundation, cd, nullptr);
+    if (!cudaMgr || !cudaMgr->contextIsValid()) { fprintf(stderr, "no CUDA context manager (plugin not loaded or no GPU)\n"); return 4; }
+    sd.cudaContextManager = cudaMgr;
+    sd.broadPhaseType = PxBroadPhaseType::eGPU;
+    if (gpuDynamics) sd.flags |= PxSceneFlag::eENABLE_GPU_DYNAMICS;
+    sd.gpuDynamicsConfig.foundLostPairsCapacity = PxMax(1u << 20, 8u * H.nActors);
+    fprintf(stderr, "GPU plugin: %s on %s\n", gpuPlugin ? gpuPlugin : "(default libPhysXGpu_64.so)", cudaMgr->getDeviceName());
+  }
+#else
+  if (gpuBp || gpuDynamics || gpuPlugin) { fprintf(stderr, "this ref_harness was built without PX_SUPPORT_GPU_PHYSX: use oracle/_ref_gpu/ref_harness\n"); return 2; }
+#endif
   sd.solverType = H.solverType == PXB_SOLVER_TGS ? PxSolverType::eTGS : PxSolverType::ePGS;
   sd.flags |= PxSceneFlag::eENABLE_PCM;
   sd.bounceThresholdVelocity = H.bounceThreshold;
@@ -411,6 +435,9 @@ int main(int argc, char** argv) {
   scene->release();
   dispatcher->release();
   physics->release();
+#if PX_SUPPORT_GPU_PHYSX
+  if (cudaMgr) cudaMgr->release();
+#endif
   foundation->release();
   return 0;
 }

@@ -131,8 +131,28 @@ __global__ void k_bp_gather(uint32_t nA, const uint32_t* __restrict__ sortedActo
 // a4/a5: every grid object looks "forward" in (env, cz, cy, cx) order: its own row from itself on, and the
 // 4 following neighbour rows; because the cell edge is >= every object extent, overlapping objects differ
 // by at most one cell per axis, so each unordered pair is visited exactly once.
+// Pair filters.  EngineFilter: the scene engine's (bp_test: at least one dynamic actor, environment ids).  GroupFilter: the reference's
+// Bp::FilterGroup semantics for the standalone broadphase object behind Bp::BroadPhase (groupFiltering, BpFiltering.h:99-114: equal groups never
+// pair, otherwise the 7 x 7 BpFilter table indexed by the 3-bit type in the group's low bits -- passed as a 49-bit mask; environment ids as in
+// broadphase.cu:62-80): amin.w = environment id, amax.w = filter group.
+struct EngineFilter {
+  __device__ __forceinline__ bool operator()(const float4& amin, const float4& amax, const float4& bmin, const float4& bmax) const { return bp_test(amin, amax, bmin, bmax); }
+  __device__ __forceinline__ bool isLarge(const float4& amax, uint32_t) const { return (__float_as_uint(amax.w) & 0x200u) != 0; }
+};
+struct GroupFilter {
+  unsigned long long lut; const uint32_t* large;
+  __device__ __forceinline__ bool operator()(const float4& amin, const float4& amax, const float4& bmin, const float4& bmax) const {
+    if (amin.x > bmax.x || bmin.x > amax.x || amin.y > bmax.y || bmin.y > amax.y || amin.z > bmax.z || bmin.z > amax.z) return false;
+    const uint32_t ga = __float_as_uint(amax.w), gb = __float_as_uint(bmax.w);
+    if (ga == gb || !((lut >> ((ga & 7u) * 7u + (gb & 7u))) & 1ull)) return false;
+    const uint32_t ea = __float_as_uint(amin.w), eb = __float_as_uint(bmin.w);
+    return ea == NONE32 || eb == NONE32 || ea == eb;
+  }
+  __device__ __forceinline__ bool isLarge(const float4&, uint32_t a) const { return large[a] != 0u; }
+};
+template <class F>
 __global__ void k_bp_pairs(uint32_t nA, const uint64_t* __restrict__ key, const uint32_t* __restrict__ sortedActor, const float4* __restrict__ sMin,
-                           const float4* __restrict__ sMax, GridParams g, uint32_t bitsA, uint64_t* __restrict__ pairKeys, uint32_t* __restrict__ counters, uint32_t cap) {
+                           const float4* __restrict__ sMax, GridParams g, uint32_t bitsA, uint64_t* __restrict__ pairKeys, uint32_t* __restrict__ counters, uint32_t cap, const F filter) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nA) return;
   const uint64_t k = key[i];
@@ -145,7 +165,7 @@ __global__ void k_bp_pairs(uint32_t nA, const uint64_t* __restrict__ key, const 
   {  // own row, forward
     const uint64_t last = r1 * nx + (uint64_t)x1;
     for (uint32_t j = i + 1; j < nA && key[j] <= last; ++j)
-      if (bp_test(amin, amax, sMin[j], sMax[j])) bp_emit(a, sortedActor[j], bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
+      if (filter(amin, amax, sMin[j], sMax[j])) bp_emit(a, sortedActor[j], bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
   }
   const int dzs[4] = {0, 1, 1, 1}, dys[4] = {1, -1, 0, 1};
 #pragma unroll
@@ -155,20 +175,21 @@ __global__ void k_bp_pairs(uint32_t nA, const uint64_t* __restrict__ key, const 
     const uint64_t rowBase = ((e * nz + (uint64_t)zz) * ny + (uint64_t)yy) * nx;
     const uint64_t first = rowBase + (uint64_t)x0, last = rowBase + (uint64_t)x1;
     for (uint32_t j = lower_bound_u64(key, nA, first); j < nA && key[j] <= last; ++j)
-      if (bp_test(amin, amax, sMin[j], sMax[j])) bp_emit(a, sortedActor[j], bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
+      if (filter(amin, amax, sMin[j], sMax[j])) bp_emit(a, sortedActor[j], bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
   }
 }
 // global / oversize objects (planes, shapes larger than a cell, env-less actors in env scenes) against everything
+template <class F>
 __global__ void k_bp_large(uint32_t nA, uint32_t nLarge, const uint32_t* __restrict__ largeList, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax,
-                           uint32_t bitsA, uint64_t* __restrict__ pairKeys, uint32_t* __restrict__ counters, uint32_t cap) {
+                           uint32_t bitsA, uint64_t* __restrict__ pairKeys, uint32_t* __restrict__ counters, uint32_t cap, const F filter) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nA) return;
   const float4 amin = aabbMin[a], amax = aabbMax[a];
-  const bool aLarge = (__float_as_uint(amax.w) & 0x200u) != 0;
+  const bool aLarge = filter.isLarge(amax, a);
   for (uint32_t l = 0; l < nLarge; ++l) {
     const uint32_t b = largeList[l];
     if (b == a || (aLarge && a > b)) continue;
-    if (bp_test(amin, amax, aabbMin[b], aabbMax[b])) bp_emit(a, b, bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
+    if (filter(amin, amax, aabbMin[b], aabbMax[b])) bp_emit(a, b, bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
   }
 }
 __global__ void k_clamp_count(uint32_t* __restrict__ counters, uint32_t cap, uint32_t* __restrict__ nPairsCur) {
@@ -1066,8 +1087,8 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
   const bool oddPasses = (((2 * s->bitsA + 7) / 8) & 1u) != 0;
   uint64_t* emit = oddPasses ? s->pairKeyAlt : s->pairKeys[cur];
   uint64_t* other = oddPasses ? s->pairKeys[cur] : s->pairKeyAlt;
-  LAUNCH(k_bp_pairs, cdiv(nA, 128), 128, nA, sk, sv, s->sMin, s->sMax, s->grid, s->bitsA, emit, s->counters, s->capPairs);
-  if (s->nLarge) LAUNCH(k_bp_large, cdiv(nA, B), B, nA, s->nLarge, s->largeList, s->aabbMin, s->aabbMax, s->bitsA, emit, s->counters, s->capPairs);
+  LAUNCH(k_bp_pairs<EngineFilter>, cdiv(nA, 128), 128, nA, sk, sv, s->sMin, s->sMax, s->grid, s->bitsA, emit, s->counters, s->capPairs, EngineFilter());
+  if (s->nLarge) LAUNCH(k_bp_large<EngineFilter>, cdiv(nA, B), B, nA, s->nLarge, s->largeList, s->aabbMin, s->aabbMax, s->bitsA, emit, s->counters, s->capPairs, EngineFilter());
   LAUNCH(k_clamp_count, 1, 32, s->counters, s->capPairs, s->nPairsDev + cur);
   radix_sort_pairs(emit, s->pairValTmp, other, s->pairValAlt, s->nPairsDev + cur, 2 * s->bitsA, s->rsTmp, st);
   s->launches += 3 * ((2 * s->bitsA + 7) / 8);
@@ -1490,6 +1511,190 @@ PXB_API int pxb_peer_wait(PxbScene* s, void* stream, const void* devFlags, uint3
   CK(cudaGetLastError());
   return PXB_OK;
 }
+// ---------------------------------------------------------------------------------------------
+// Standalone broadphase object (include/physx_b200.h pxb_bp_*): a2-a6 behind the reference's own Bp::BroadPhase interface.  The plugin shim's
+// Bp::BroadPhase subclass (plugin/) forwards BroadPhaseUpdateData to pxb_bp_update and reads created / deleted pairs back with pxb_bp_fetch.
+// Same kernels as the scene engine's device-wide broadphase (uniform grid keyed (env, cz, cy, cx), 8-bit LSD radix sorts, forward sweep,
+// large objects against everything), with the reference's group / type-table / environment filter (GroupFilter).
+struct PxbBroadPhase {
+  int device = 0; cudaStream_t stream = nullptr; uint32_t cap = 0, capPairs = 0, bitsA = 1, nSlots = 0;
+  float* bounds6 = 0; float* dist = 0; uint32_t *groups = 0, *envs = 0, *largeFlag = 0, *largeList = 0, *counters = 0, *cellVal = 0, *cellValAlt = 0, *valTmp = 0, *valAlt = 0;
+  float4 *aabbMin = 0, *aabbMax = 0, *sMin = 0, *sMax = 0; uint64_t *cellKey = 0, *cellKeyAlt = 0, *keys[2] = {0, 0}, *keyAlt = 0, *created = 0, *deleted = 0;
+  uint32_t* nPairsDev = 0; int cur = 0; uint32_t* hostCounters = 0; RadixSortTemp rs; GridParams grid; bool gridValid = false; uint32_t nLarge = 0, envCount = 1;
+  std::vector<uint8_t> active; std::vector<uint32_t> outCreated, outDeleted; std::vector<uint64_t> tmpKeys; bool pending = false;
+};
+enum { BC_NPAIRS = 0, BC_NCREATED = 1, BC_NDELETED = 2, BC_N = 3, BC_ERROR = 4 /* = C_ERROR: bp_emit flags overflow there */, BC_COUNT = 8 };
+__global__ void k_bpo_prepare(uint32_t n, const float* __restrict__ bounds6, const float* __restrict__ dist, const uint32_t* __restrict__ groups, const uint32_t* __restrict__ envs,
+                              const uint32_t* __restrict__ largeFlag, GridParams g, uint32_t envCount, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax, uint64_t* __restrict__ cellKey,
+                              uint32_t* __restrict__ cellVal) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const uint32_t grp = groups[a]; const uint32_t env = envs ? envs[a] : NONE32;
+  const float d = dist[a];   // inflation by the contact distance in float, as the reference's ABP does (BpBroadPhaseABP.cpp:1187-1197)
+  const float mn0 = bounds6[a * 6 + 0] - d, mn1 = bounds6[a * 6 + 1] - d, mn2 = bounds6[a * 6 + 2] - d, mx0 = bounds6[a * 6 + 3] + d, mx1 = bounds6[a * 6 + 4] + d, mx2 = bounds6[a * 6 + 5] + d;
+  aabbMin[a] = make_float4(mn0, mn1, mn2, __uint_as_float(env)); aabbMax[a] = make_float4(mx0, mx1, mx2, __uint_as_float(grp));
+  uint64_t key = ~0ull;
+  if (grp != NONE32 && !largeFlag[a]) {
+    int cx = (int)floorf((mn0 - g.ox) * g.invCell), cy = (int)floorf((mn1 - g.oy) * g.invCell), cz = (int)floorf((mn2 - g.oz) * g.invCell);
+    cx = max(0, min(g.nx - 1, cx)); cy = max(0, min(g.ny - 1, cy)); cz = max(0, min(g.nz - 1, cz));
+    const uint64_t e = (env == NONE32) ? 0ull : (uint64_t)min(env, envCount - 1);
+    key = ((e * (uint64_t)g.nz + (uint64_t)cz) * (uint64_t)g.ny + (uint64_t)cy) * (uint64_t)g.nx + (uint64_t)cx;
+  }
+  cellKey[a] = key; cellVal[a] = a;
+}
+__global__ void k_bpo_clamp(uint32_t* __restrict__ counters, uint32_t cap, uint32_t* __restrict__ nCur) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { if (counters[BC_NPAIRS] > cap) { counters[BC_ERROR] = 1u; counters[BC_NPAIRS] = cap; } *nCur = counters[BC_NPAIRS]; }
+}
+// created = new \ old; deleted = old \ new restricted to pairs whose two objects are still in the broadphase (lost overlaps caused by a
+// removal are not reported, BpBroadPhase.h:181-192)
+__global__ void k_bpo_diff(const uint64_t* __restrict__ a, const uint32_t* __restrict__ nAP, const uint64_t* __restrict__ b, const uint32_t* __restrict__ nBP, uint64_t* __restrict__ out,
+                           uint32_t* __restrict__ outCount, const uint32_t* __restrict__ groups, uint32_t bitsA, int requireActive) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nA = *nAP, nB = *nBP;
+  if (i >= nA) return;
+  const uint64_t k = a[i];
+  const uint32_t p = lower_bound_u64(b, nB, k);
+  if (p < nB && b[p] == k) return;
+  if (requireActive) { const uint32_t lo = (uint32_t)(k >> bitsA), hi = (uint32_t)(k & ((1ull << bitsA) - 1ull)); if (groups[lo] == NONE32 || groups[hi] == NONE32) return; }
+  out[atomicAdd(outCount, 1u)] = k;
+}
+#define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(PXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+static void bpo_free(PxbBroadPhase* b) {
+  void* ptrs[] = {b->bounds6, b->dist, b->groups, b->envs, b->largeFlag, b->largeList, b->counters, b->cellVal, b->cellValAlt, b->valTmp, b->valAlt, b->aabbMin, b->aabbMax, b->sMin, b->sMax, b->cellKey, b->cellKeyAlt,
+                  b->keys[0], b->keys[1], b->keyAlt, b->created, b->deleted, b->nPairsDev, b->rs.blockHist, b->rs.digitTotals};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (b->hostCounters) cudaFreeHost(b->hostCounters);
+  if (b->stream) cudaStreamDestroy(b->stream);
+}
+PXB_API int pxb_bp_create(uint32_t maxObjects, uint32_t maxPairs, int device, PxbBroadPhase** out) {
+  if (!out) return fail(PXB_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PXB_ERR_NO_DEVICE, "no CUDA device: physx_b200 has no CPU fallback"); }
+  if (device < 0 || device >= ndev) return fail(PXB_ERR_INVALID, "bad device ordinal");
+  DeviceGuard dg_(device);
+  PxbBroadPhase* b = new PxbBroadPhase(); b->device = device;
+  b->cap = std::max(64u, maxObjects); b->capPairs = maxPairs ? maxPairs : std::max(1024u, 8u * b->cap); b->bitsA = bits_for(b->cap);
+  const size_t A = b->cap, P = b->capPairs;
+  cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+  auto A_ = [&](auto*& p, size_t n) { if (e == cudaSuccess) e = dalloc(p, n); };
+  A_(b->bounds6, A * 6); A_(b->dist, A); A_(b->groups, A); A_(b->envs, A); A_(b->largeFlag, A); A_(b->largeList, A); A_(b->counters, BC_COUNT); A_(b->cellVal, A); A_(b->cellValAlt, A); A_(b->valTmp, P); A_(b->valAlt, P);
+  A_(b->aabbMin, A); A_(b->aabbMax, A); A_(b->sMin, A); A_(b->sMax, A); A_(b->cellKey, A); A_(b->cellKeyAlt, A); A_(b->keys[0], P); A_(b->keys[1], P); A_(b->keyAlt, P); A_(b->created, P); A_(b->deleted, P);
+  A_(b->nPairsDev, 2); A_(b->rs.blockHist, RS_MAX_CTAS * 256); A_(b->rs.digitTotals, 256);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&b->hostCounters, 4 * (BC_COUNT + 2));
+  cudaDeviceProp prop; if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { bpo_free(b); delete b; cudaGetLastError(); return fail(PXB_ERR_CUDA, std::string("pxb_bp_create: ") + cudaGetErrorString(e)); }
+  b->rs.ctas = std::min<uint32_t>(RS_MAX_CTAS, (uint32_t)prop.multiProcessorCount * 2);
+  cudaMemsetAsync(b->groups, 0xff, 4 * A, b->stream); cudaMemsetAsync(b->envs, 0xff, 4 * A, b->stream); cudaMemsetAsync(b->largeFlag, 0, 4 * A, b->stream); cudaMemsetAsync(b->nPairsDev, 0, 8, b->stream);
+  cudaMemsetAsync(b->counters, 0, 4 * BC_COUNT, b->stream); cudaMemsetAsync(b->bounds6, 0, 24 * A, b->stream); cudaMemsetAsync(b->dist, 0, 4 * A, b->stream);
+  cudaStreamSynchronize(b->stream);
+  b->active.assign(A, 0);
+  *out = b;
+  return PXB_OK;
+}
+PXB_API void pxb_bp_release(PxbBroadPhase* b) { if (!b) return; DeviceGuard dg_(b->device); cudaStreamSynchronize(b->stream); bpo_free(b); delete b; }
+// Grid for the objects currently in the broadphase: cell edge = the largest inflated extent among regular objects (x 1.02), objects more than
+// 8 x the median extent (and unbounded ones: planes) are "large" and tested against everything.  Rebuilt on frames that add objects and when an
+// updated object has grown past the cell; objects that wander outside are clamped to the border cells (still exact, only slower).
+static int bpo_rebuild_grid(PxbBroadPhase* b, const float* bounds6, const float* dist, const uint32_t* envIds) {
+  std::vector<float> ext; ext.reserve(b->nSlots);
+  auto extent = [&](uint32_t a) { const float* q = bounds6 + 6 * (size_t)a; return std::max(q[3] - q[0], std::max(q[4] - q[1], q[5] - q[2])) + 2.f * dist[a]; };
+  for (uint32_t a = 0; a < b->nSlots; ++a) if (b->active[a]) { const float x = extent(a); if (std::isfinite(x) && x < 1e18f) ext.push_back(x); }
+  float med = 1.f;
+  if (!ext.empty()) { std::nth_element(ext.begin(), ext.begin() + ext.size() / 2, ext.end()); med = ext[ext.size() / 2]; }
+  const float largeThresh = 8.f * med;
+  std::vector<uint32_t> lf(b->nSlots, 0), ll; float cell = 0.f; float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}; uint32_t maxEnv = 0; bool anyEnv = false;
+  for (uint32_t a = 0; a < b->nSlots; ++a) {
+    if (!b->active[a]) continue;
+    const float x = extent(a);
+    if (!(std::isfinite(x) && x < 1e18f) || x > largeThresh) { lf[a] = 1; ll.push_back(a); continue; }
+    cell = std::max(cell, x);
+    for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], bounds6[6 * (size_t)a + k]); mx[k] = std::max(mx[k], bounds6[6 * (size_t)a + k]); }
+    if (envIds && envIds[a] != NONE32) { anyEnv = true; maxEnv = std::max(maxEnv, envIds[a]); }
+  }
+  cell *= 1.02f; if (!(cell > 0.f)) cell = 1.f;
+  GridParams g; g.invCell = 1.0f / cell; int n[3];
+  for (int k = 0; k < 3; ++k) { if (!std::isfinite(mn[k])) { mn[k] = 0.f; mx[k] = 0.f; } n[k] = std::max(4, (int)std::ceil(((mx[k] - mn[k]) + 16.f * cell) / cell) + 1); }
+  g.ox = mn[0] - 8.f * cell; g.oy = mn[1] - 8.f * cell; g.oz = mn[2] - 8.f * cell; g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
+  const uint64_t envCount = anyEnv ? (uint64_t)maxEnv + 1 : 1;
+  while ((long double)envCount * g.nx * g.ny * g.nz > 4.0e18L) { if (g.nx >= g.ny && g.nx >= g.nz) g.nx = (g.nx + 1) / 2; else if (g.ny >= g.nz) g.ny = (g.ny + 1) / 2; else g.nz = (g.nz + 1) / 2; }
+  g.keyBits = bits_for((uint64_t)envCount * (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz + 1);
+  b->grid = g; b->envCount = (uint32_t)envCount; b->nLarge = (uint32_t)ll.size(); b->gridValid = true;
+  CKB(cudaMemcpyAsync(b->largeFlag, lf.data(), 4 * (size_t)b->nSlots, cudaMemcpyHostToDevice, b->stream));
+  if (b->nLarge) CKB(cudaMemcpyAsync(b->largeList, ll.data(), 4 * (size_t)b->nLarge, cudaMemcpyHostToDevice, b->stream));
+  CKB(cudaStreamSynchronize(b->stream));   // lf / ll are locals
+  return PXB_OK;
+}
+PXB_API int pxb_bp_update(PxbBroadPhase* b, const float* bounds6, const float* contactDist, const uint32_t* groups, const uint32_t* envIds, uint32_t capacity, const uint8_t* lut49,
+                          const uint32_t* created, uint32_t nCreated, const uint32_t* updated, uint32_t nUpdated, const uint32_t* removed, uint32_t nRemoved) {
+  if (!b || !bounds6 || !contactDist || !groups || !lut49) return fail(PXB_ERR_INVALID, "null argument");
+  if (capacity > b->cap) return fail(PXB_ERR_CAPACITY, "more broadphase objects than pxb_bp_create was sized for");
+  DeviceGuard dg_(b->device);
+  cudaStream_t st = b->stream;
+  for (uint32_t i = 0; i < nRemoved; ++i) { if (removed[i] >= capacity) return fail(PXB_ERR_INVALID, "removed handle out of range"); b->active[removed[i]] = 0; }
+  for (uint32_t i = 0; i < nCreated; ++i) { if (created[i] >= capacity) return fail(PXB_ERR_INVALID, "created handle out of range"); b->active[created[i]] = 1; b->nSlots = std::max(b->nSlots, created[i] + 1); }
+  const uint32_t n = b->nSlots;
+  // device copies of the host arrays (the shim hands over pinned memory: Bp::BoundsArray and the AABB manager's arrays are allocated through the
+  // plugin's host allocator).  Removed / never-added slots carry group eINVALID on the device whatever the host array holds.
+  std::vector<uint32_t> g(n);
+  for (uint32_t a = 0; a < n; ++a) g[a] = b->active[a] ? groups[a] : NONE32;
+  bool needGrid = !b->gridValid || nCreated > 0;
+  if (!needGrid) {   // an updated regular object that outgrew the cell edge would be missed by the one-cell neighbourhood
+    const float cell = 1.0f / b->grid.invCell;
+    for (uint32_t i = 0; i < nUpdated && !needGrid; ++i) { const uint32_t a = updated[i]; if (a < n && b->active[a]) { const float* q = bounds6 + 6 * (size_t)a; if (std::max(q[3] - q[0], std::max(q[4] - q[1], q[5] - q[2])) + 2.f * contactDist[a] > cell) needGrid = true; } }
+  }
+  if (needGrid) { if (int rc = bpo_rebuild_grid(b, bounds6, contactDist, envIds)) return rc; }
+  if (!n) { b->pending = true; return PXB_OK; }
+  CKB(cudaMemcpyAsync(b->bounds6, bounds6, 24 * (size_t)n, cudaMemcpyHostToDevice, st)); CKB(cudaMemcpyAsync(b->dist, contactDist, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  CKB(cudaMemcpyAsync(b->groups, g.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  if (envIds) CKB(cudaMemcpyAsync(b->envs, envIds, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  CKB(cudaStreamSynchronize(st));   // g is a local; the host arrays may change as soon as update() returns
+  unsigned long long lut = 0; for (int i = 0; i < 49; ++i) if (lut49[i]) lut |= 1ull << i;
+  const int prev = b->cur; b->cur ^= 1; const int cur = b->cur;
+  CKB(cudaMemsetAsync(b->counters, 0, 4 * BC_COUNT, st));
+  CKB(cudaMemcpyAsync(b->counters + BC_N, &n, 4, cudaMemcpyHostToDevice, st));
+  k_bpo_prepare<<<cdiv(n, 256), 256, 0, st>>>(n, b->bounds6, b->dist, b->groups, envIds ? b->envs : nullptr, b->largeFlag, b->grid, b->envCount, b->aabbMin, b->aabbMax, b->cellKey, b->cellVal);
+  const int r = radix_sort_pairs(b->cellKey, b->cellVal, b->cellKeyAlt, b->cellValAlt, b->counters + BC_N, b->grid.keyBits, b->rs, st);
+  const uint64_t* sk = r ? b->cellKeyAlt : b->cellKey; const uint32_t* sv = r ? b->cellValAlt : b->cellVal;
+  k_bp_gather<<<cdiv(n, 256), 256, 0, st>>>(n, sv, b->aabbMin, b->aabbMax, b->sMin, b->sMax);
+  const bool oddPasses = (((2 * b->bitsA + 7) / 8) & 1u) != 0;
+  uint64_t* emit = oddPasses ? b->keyAlt : b->keys[cur]; uint64_t* other = oddPasses ? b->keys[cur] : b->keyAlt;
+  GroupFilter F; F.lut = lut; F.large = b->largeFlag;
+  // the pair kernels count into counters[C_NPAIRS_NEW] and flag counters[C_ERROR]: the same slots as BC_NPAIRS / BC_ERROR
+  k_bp_pairs<GroupFilter><<<cdiv(n, 128), 128, 0, st>>>(n, sk, sv, b->sMin, b->sMax, b->grid, b->bitsA, emit, b->counters, b->capPairs, F);
+  if (b->nLarge) k_bp_large<GroupFilter><<<cdiv(n, 256), 256, 0, st>>>(n, b->nLarge, b->largeList, b->aabbMin, b->aabbMax, b->bitsA, emit, b->counters, b->capPairs, F);
+  k_bpo_clamp<<<1, 32, 0, st>>>(b->counters, b->capPairs, b->nPairsDev + cur);
+  radix_sort_pairs(emit, b->valTmp, other, b->valAlt, b->nPairsDev + cur, 2 * b->bitsA, b->rs, st);
+  const uint32_t gP = cdiv(b->capPairs, 256);
+  k_bpo_diff<<<gP, 256, 0, st>>>(b->keys[cur], b->nPairsDev + cur, b->keys[prev], b->nPairsDev + prev, b->created, b->counters + BC_NCREATED, b->groups, b->bitsA, 0);
+  k_bpo_diff<<<gP, 256, 0, st>>>(b->keys[prev], b->nPairsDev + prev, b->keys[cur], b->nPairsDev + cur, b->deleted, b->counters + BC_NDELETED, b->groups, b->bitsA, 1);
+  CKB(cudaMemcpyAsync(b->hostCounters, b->counters, 4 * BC_COUNT, cudaMemcpyDeviceToHost, st));
+  CKB(cudaGetLastError());
+  b->pending = true;
+  return PXB_OK;
+}
+PXB_API int pxb_bp_fetch(PxbBroadPhase* b, const uint32_t** createdPairs, uint32_t* nCreated, const uint32_t** deletedPairs, uint32_t* nDeleted) {
+  if (!b || !createdPairs || !nCreated || !deletedPairs || !nDeleted) return fail(PXB_ERR_INVALID, "null argument");
+  DeviceGuard dg_(b->device);
+  b->outCreated.clear(); b->outDeleted.clear();
+  if (b->pending && b->nSlots) {
+    CKB(cudaStreamSynchronize(b->stream));
+    if (b->hostCounters[BC_ERROR]) return fail(PXB_ERR_CAPACITY, "broadphase pair capacity (maxPairs) exceeded");
+    auto pull = [&](const uint64_t* dev, uint32_t n, std::vector<uint32_t>& out) -> int {
+      b->tmpKeys.resize(n);
+      if (n) { CKB(cudaMemcpyAsync(b->tmpKeys.data(), dev, 8 * (size_t)n, cudaMemcpyDeviceToHost, b->stream)); CKB(cudaStreamSynchronize(b->stream)); }
+      std::sort(b->tmpKeys.begin(), b->tmpKeys.end());
+      out.resize(2 * (size_t)n);
+      for (uint32_t i = 0; i < n; ++i) { out[2 * i] = (uint32_t)(b->tmpKeys[i] >> b->bitsA); out[2 * i + 1] = (uint32_t)(b->tmpKeys[i] & ((1ull << b->bitsA) - 1ull)); }
+      return PXB_OK;
+    };
+    if (int rc = pull(b->created, b->hostCounters[BC_NCREATED], b->outCreated)) return rc;
+    if (int rc = pull(b->deleted, b->hostCounters[BC_NDELETED], b->outDeleted)) return rc;
+  }
+  b->pending = false;
+  *createdPairs = b->outCreated.data(); *nCreated = (uint32_t)(b->outCreated.size() / 2); *deletedPairs = b->outDeleted.data(); *nDeleted = (uint32_t)(b->outDeleted.size() / 2);
+  return PXB_OK;
+}
+
 PXB_API int pxb_scene_sync(PxbScene* s) { DeviceGuard dg_(s); if (!s) return fail(PXB_ERR_INVALID, "null scene"); CK(cudaStreamSynchronize(s->stream)); return PXB_OK; }
 
 // Packed 13-float state of every dynamic body written straight into a DEVICE buffer (e.g. this rank's slice of

@@ -30,7 +30,7 @@ EXPORTS = [
     "pxb_scene_get_contacts", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
-    "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait",
+    "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait", "pxb_bp_create", "pxb_bp_release", "pxb_bp_update", "pxb_bp_fetch",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
@@ -99,6 +99,11 @@ def load_library():
     lib.pxb_scene_set_state_export.argtypes = [vp, vp, u32, u32]
     lib.pxb_peer_signal.argtypes = [vp, vp, vp, u32, u32]
     lib.pxb_peer_wait.argtypes = [vp, vp, vp, u32, u32]
+    lib.pxb_bp_create.argtypes = [u32, u32, i32, ctypes.POINTER(vp)]
+    lib.pxb_bp_release.argtypes = [vp]
+    lib.pxb_bp_release.restype = None
+    lib.pxb_bp_update.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, u32, vp, u32, vp, u32]
+    lib.pxb_bp_fetch.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u32), ctypes.POINTER(vp), ctypes.POINTER(u32)]
     lib.pxb_scene_set_profiling.argtypes = [vp, i32]
     lib.pxb_scene_get_stage_times.argtypes = [vp, vp]
     lib.pxb_scene_state_device_ptr.argtypes = [vp, i32]
@@ -311,3 +316,37 @@ class Scene:
     @property
     def num_launches(self):
         return int(self._lib.pxb_scene_last_num_launches(self._h))
+
+
+class BroadPhase:
+    """Standalone broadphase object (pxb_bp_*): what the plugin shim's Bp::BroadPhase forwards to.  Host-side mirror for the parity tests:
+    update(bounds, dist, groups, envs, created, updated, removed) + fetch() -> (created pairs, deleted pairs)."""
+    # Bp::BpFilter table for the default pair filtering modes (BpFiltering.cpp): statics never pair with statics, everything else may
+    LUT_DEFAULT = np.ones((7, 7), np.uint8)
+    LUT_DEFAULT[0, 0] = 0
+
+    def __init__(self, max_objects: int, max_pairs: int = 0, device: int = 0):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        _check(self._lib, self._lib.pxb_bp_create(int(max_objects), int(max_pairs), int(device), ctypes.byref(self._h)))
+
+    def release(self):
+        if getattr(self, "_h", None):
+            self._lib.pxb_bp_release(self._h)
+            self._h = None
+
+    __del__ = release
+
+    def update(self, bounds6, dist, groups, envs=None, created=(), updated=(), removed=(), lut=None):
+        b = np.ascontiguousarray(bounds6, np.float32); d = np.ascontiguousarray(dist, np.float32); g = np.ascontiguousarray(groups, np.uint32)
+        e = None if envs is None else np.ascontiguousarray(envs, np.uint32)
+        l = np.ascontiguousarray(self.LUT_DEFAULT if lut is None else lut, np.uint8)
+        c, u, r = (np.ascontiguousarray(x, np.uint32) for x in (created, updated, removed))
+        _check(self._lib, self._lib.pxb_bp_update(self._h, _ptr(b), _ptr(d), _ptr(g), _ptr(e), len(g), _ptr(l), _ptr(c), len(c), _ptr(u), len(u), _ptr(r), len(r)))
+
+    def fetch(self):
+        cp, dp, nc, nd = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint32(), ctypes.c_uint32()
+        _check(self._lib, self._lib.pxb_bp_fetch(self._h, ctypes.byref(cp), ctypes.byref(nc), ctypes.byref(dp), ctypes.byref(nd)))
+        def arr(p, n):
+            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint32)), (n.value, 2)).copy() if n.value else np.zeros((0, 2), np.uint32)
+        return arr(cp, nc), arr(dp, nd)

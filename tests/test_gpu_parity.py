@@ -795,3 +795,60 @@ def test_stream_ordered_velocity_write_overlaps_and_matches_the_synchronous_one(
             assert np.array_equal(a.getRigidDynamicData(engine.RD_LINEAR_VELOCITY), v)
         a.step(); b.step()
         assert np.array_equal(a.getStates(), b.getStates()), f"step {t}"
+
+
+# ---- standalone broadphase object (pxb_bp_*: what the plugin shim's Bp::BroadPhase forwards to) ----
+def _bp_groups(sc):
+    dyn = (sc.actors["flags"] & scenes.ACTOR_DYNAMIC) != 0
+    ids = np.arange(len(sc.actors), dtype=np.uint32)
+    return np.where(dyn, ((ids + 1) << 3) | 2, 0).astype(np.uint32), dyn     # Bp::getFilterGroup_Dynamics / eSTATICS (BpFiltering.h:79-95)
+
+
+@pytest.mark.parametrize("name", ["stacks_4x8_jitter", "tumble_12", "envs_4", "hulls_on_plane", "capsules_on_boxes"])
+def test_broadphase_object_matches_abp_bit_exact(name):
+    """pxb_bp_update / pxb_bp_fetch driven the way Bp::AABBManager drives a Bp::BroadPhase (created list on the first update, updated list of the
+    dynamic objects afterwards, tight bounds + contact distance + filter groups): created / deleted pair lists identical to the reference's ABP
+    (PxBroadPhase(eABP) + PxAABBManager, golden) at every step."""
+    z, sc = util.load_golden(name)
+    groups, dyn = _bp_groups(sc)
+    n = len(sc.actors)
+    dist = np.full(n, float(sc.header["contactOffset"]), np.float32)
+    bp = engine.BroadPhase(n)
+    for t in range(z["bounds"].shape[0]):
+        if t == 0:
+            bp.update(z["bounds"][t], dist, groups, created=np.arange(n))
+        else:
+            bp.update(z["bounds"][t], dist, groups, updated=np.nonzero(dyn)[0])
+        created, deleted = bp.fetch()
+        assert np.array_equal(created, util.golden_created(z, t)), f"created, step {t}"
+        assert np.array_equal(deleted, util.golden_deleted(z, t)), f"deleted, step {t}"
+
+
+def test_broadphase_object_removal_and_environment_filter():
+    """Lost overlaps caused by a removal are not reported (BpBroadPhase.h:181-192), a re-added object finds its overlaps again, equal groups never
+    pair, different environment ids never pair."""
+    b = np.array([[0, 0, 0, 1, 1, 1], [0.5, 0, 0, 1.5, 1, 1], [0.9, 0, 0, 1.9, 1, 1], [5, 5, 5, 6, 6, 6]], np.float32)
+    d = np.zeros(4, np.float32)
+    g = np.array([(1 << 3) | 2, (2 << 3) | 2, (3 << 3) | 2, 0], np.uint32)
+    bp = engine.BroadPhase(16)
+    bp.update(b, d, g, created=[0, 1, 2, 3])
+    c, dl = bp.fetch()
+    assert c.tolist() == [[0, 1], [0, 2], [1, 2]] and len(dl) == 0
+    bp.update(b, d, g, removed=[1])
+    c, dl = bp.fetch()
+    assert len(c) == 0 and len(dl) == 0
+    bp.update(b, d, g, created=[1])
+    c, dl = bp.fetch()
+    assert c.tolist() == [[0, 1], [1, 2]] and len(dl) == 0
+    b2 = b.copy(); b2[2, [0, 3]] += 5.0
+    bp.update(b2, d, g, updated=[2])
+    c, dl = bp.fetch()
+    assert len(c) == 0 and dl.tolist() == [[0, 2], [1, 2]]
+    # equal groups (shapes of one actor) and different environments
+    bp2 = engine.BroadPhase(16)
+    g2 = np.array([(1 << 3) | 2, (1 << 3) | 2, (2 << 3) | 2, (3 << 3) | 2], np.uint32)
+    b3 = np.array([[0, 0, 0, 1, 1, 1]] * 4, np.float32)
+    env = np.array([0, 0, 0, 1], np.uint32)
+    bp2.update(b3, d, g2, envs=env, created=[0, 1, 2, 3])
+    c, dl = bp2.fetch()
+    assert c.tolist() == [[0, 2], [1, 2]]
