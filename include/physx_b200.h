@@ -184,6 +184,13 @@ PXB_API uint32_t pxb_scene_num_created(PxbScene* scene);
 PXB_API uint32_t pxb_scene_num_deleted(PxbScene* scene);
 PXB_API int  pxb_scene_get_created(PxbScene* scene, uint32_t* outPairs);     /* sorted */
 PXB_API int  pxb_scene_get_deleted(PxbScene* scene, uint32_t* outPairs);     /* sorted */
+/* Touch events of the last step (a7: prepareLostFoundPairs_Stage1 / 2, gpunarrowphase/src/CUDA/cudaGJKEPA.cu:1468,1532 -> the found / lost patch
+ * lists PxgNphaseImplementationContext hands to the island manager and to contact reports): pairs that started / stopped producing contacts,
+ * incl. touching pairs that left the broadphase.  (a,b) actor indices with a<b, sorted.  One patch per pair, so "patch count changed" = these. */
+PXB_API uint32_t pxb_scene_num_touch_found(PxbScene* scene);
+PXB_API uint32_t pxb_scene_num_touch_lost(PxbScene* scene);
+PXB_API int  pxb_scene_get_touch_found(PxbScene* scene, uint32_t* outPairs);
+PXB_API int  pxb_scene_get_touch_lost(PxbScene* scene, uint32_t* outPairs);
 /* Contacts of the last step, one 24-float record per pair in pair order:
  * [count, nx, ny, nz, 4 x (px, py, pz, separation, appliedForce)]; normal points body1 -> body0
  * (PxsContactManagerOutput / PxContactPatch + PxContact stream analogue, physx/include/PxContact.h:57-148). */

@@ -26,7 +26,7 @@ struct ActorRec {
 };
 static_assert(sizeof(ActorRec) == 128, "actor record layout");
 
-enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_NGJK, C_COUNT = 16 };
+enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_NGJK, C_NTOUCH_FOUND, C_NTOUCH_LOST, C_COUNT = 24 };
 enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8 };
 
 struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };
@@ -164,4 +164,15 @@ __device__ __forceinline__ void export_packed_range(const ExportTable* __restric
     const float v = packed_state_field(pos, quat, linVel, angVel, dynActor[d0 + j], f);
     for (uint32_t t = 0; t < nT; ++t) tab->dst[t][base + i] = v;
   }
+}
+
+// a7 touch events (prepareLostFoundPairs_Stage1 / 2, gpunarrowphase/src/CUDA/cudaGJKEPA.cu:1468,1532; consumed on the host by the island manager
+// and the contact-report code): per persistent pair slot the narrowphase keeps whether the pair produced contacts last frame and appends the
+// pair key to the touch-found / touch-lost list when that changes.  One patch per pair here, so "patch count changed" is the same event.
+struct TouchLists { uint32_t* state; uint64_t *found, *lost; };
+__device__ __forceinline__ void touch_event(const TouchLists& T, uint32_t* __restrict__ counters, uint32_t slot, uint64_t key, bool touching) {
+  const uint32_t prev = T.state[slot];
+  if ((prev != 0u) == touching) return;
+  T.state[slot] = touching ? 1u : 0u;
+  if (touching) T.found[atomicAdd(&counters[C_NTOUCH_FOUND], 1u)] = key; else T.lost[atomicAdd(&counters[C_NTOUCH_LOST], 1u)] = key;
 }

@@ -72,6 +72,7 @@ struct PxbScene {
   bool envEligible = false, envActive = false, envDisabled = false, everStepped = false; uint32_t ringMask = 0;
   uint32_t nEnv = 0, envMaxList = 0, envConCap = 0, envConCapForced = 0, envThreadsForced = 0, hMaxConEnv = 0, hMaxPairEnv = 0, envSolveThreads = 64;
   uint32_t *envStart = 0, *envList = 0, *actorLocal = 0, *slotColour = 0; unsigned long long* bodyBest = 0; bool relaxedPartitioning = false;
+  uint32_t* touchState = 0; uint64_t *touchFound = 0, *touchLost = 0; uint32_t hNTouchFound = 0, hNTouchLost = 0;   // a7 touch found / lost events
   ExportTable* exportTab = 0; uint2* envDyn = 0; bool exportOn = false, envDynContiguous = false;   // fused state export (pxb_scene_set_state_export)
   float sleepThreshold = 0.f; float* wake = 0; float4 *accLin = 0, *accAng = 0; uint32_t *asleep = 0, *nInter = 0, *islandLabel = 0, *islandAwake = 0; int coopBlocksSleep = 0; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
 };
@@ -86,6 +87,7 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static TouchLists touch_lists(const PxbScene* s) { TouchLists T; T.state = s->touchState; T.found = s->touchFound; T.lost = s->touchLost; return T; }
 static HullArrays hull_arrays(const PxbScene* s) { HullArrays H; H.meta = s->hullMeta; H.verts = s->hullVerts; H.polys = s->hullPolys; H.refs = s->hullRefs; H.edges = s->hullEdges; return H; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (s) s->abort = true; return fail(PXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
 
@@ -200,7 +202,7 @@ __global__ void k_clamp_count(uint32_t* __restrict__ counters, uint32_t cap, uin
 // take one from the free list and start with an empty manifold (PersistentContactManifold::initialize).
 __global__ void k_pair_lost(const uint64_t* __restrict__ oldKeys, const uint32_t* __restrict__ oldSlots, const uint32_t* __restrict__ nOldP,
                             const uint64_t* __restrict__ newKeys, const uint32_t* __restrict__ nNewP, uint32_t* __restrict__ freeList, uint32_t ringMask,
-                            uint64_t* __restrict__ deletedKeys, uint32_t* __restrict__ counters) {
+                            uint64_t* __restrict__ deletedKeys, uint32_t* __restrict__ counters, const TouchLists touch) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nOld = *nOldP, nNew = *nNewP;
   if (j >= nOld) return;
@@ -209,11 +211,12 @@ __global__ void k_pair_lost(const uint64_t* __restrict__ oldKeys, const uint32_t
   if (p < nNew && newKeys[p] == k) return;
   freeList[atomicAdd(&counters[C_FREE_TAIL], 1u) & ringMask] = oldSlots[j];
   deletedKeys[atomicAdd(&counters[C_NDELETED], 1u)] = k;
+  touch_event(touch, counters, oldSlots[j], k, false);   // a pair that leaves the broadphase while touching loses its touch
 }
 __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_t* __restrict__ oldSlots, const uint32_t* __restrict__ nOldP,
                              const uint64_t* __restrict__ newKeys, uint32_t* __restrict__ newSlots, const uint32_t* __restrict__ nNewP,
                              const uint32_t* __restrict__ freeList, uint32_t ringMask, uint64_t* __restrict__ createdKeys, uint32_t* __restrict__ counters,
-                             float4* __restrict__ manifolds, float4* __restrict__ frictions) {
+                             float4* __restrict__ manifolds, float4* __restrict__ frictions, uint32_t* __restrict__ touchState) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nOld = *nOldP, nNew = *nNewP;
   if (i >= nNew) return;
@@ -229,6 +232,7 @@ __global__ void k_pair_found(const uint64_t* __restrict__ oldKeys, const uint32_
   m[0] = make_float4(__int_as_float(0), FLT_MAX, FLT_MAX, FLT_MAX); m[1] = make_float4(0, 0, 0, 1); m[2] = make_float4(0, 0, 0, 1); m[3] = make_float4(0, 0, 0, 1); m[14] = make_float4(0, 0, 0, 0);
   float4* f = frictions + (size_t)slot * PXB_FRICTION_F4;
   f[0] = make_float4(0, 0, 0, __int_as_float(0)); f[1] = make_float4(0, 0, 0, __int_as_float(0)); f[2] = make_float4(0, 0, 0, __int_as_float(0));
+  touchState[slot] = 0u;
 }
 
 // Scenes that mix geometry types: pairs are binned by (type0, type1) before the narrowphase so that a warp runs ONE contact function
@@ -670,7 +674,7 @@ __global__ void k_init_freelist(uint32_t cap, uint32_t* __restrict__ freeList) {
 }
 
 __global__ void k_env_begin(uint32_t* __restrict__ counters) {   // per-step counter reset of the environment path
-  if (threadIdx.x == 0) { counters[C_NPAIRS_NEW] = 0; counters[C_NCREATED] = 0; counters[C_NDELETED] = 0; counters[C_NCON] = 0; counters[C_NPART] = 0; counters[C_NGJK] = 0; counters[C_MAXCONENV] = 0; counters[C_MAXPAIRENV] = 0;
+  if (threadIdx.x == 0) { counters[C_NPAIRS_NEW] = 0; counters[C_NCREATED] = 0; counters[C_NDELETED] = 0; counters[C_NCON] = 0; counters[C_NPART] = 0; counters[C_NGJK] = 0; counters[C_MAXCONENV] = 0; counters[C_MAXPAIRENV] = 0; counters[C_NTOUCH_FOUND] = 0; counters[C_NTOUCH_LOST] = 0;
                           counters[C_FREE_SNAP] = counters[C_FREE_TAIL]; }
 }
 
@@ -728,6 +732,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->wake, A)); CK(dalloc(s->accLin, A)); CK(dalloc(s->accAng, A)); CK(dalloc(s->asleep, A)); CK(dalloc(s->nInter, A)); CK(dalloc(s->islandLabel, A)); CK(dalloc(s->islandAwake, A));
   CK(cudaMemsetAsync(s->accLin, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->accAng, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->asleep, 0, 4 * A, s->stream)); CK(cudaMemsetAsync(s->nInter, 0, 4 * A, s->stream));
   { std::vector<float> w(A, 20.0f * 0.02f); CK(cudaMemcpyAsync(s->wake, w.data(), 4 * A, cudaMemcpyHostToDevice, s->stream)); CK(cudaStreamSynchronize(s->stream)); }   // PxRigidDynamic default wake counter
+  CK(dalloc(s->touchState, Pn)); CK(cudaMemsetAsync(s->touchState, 0, 4 * Pn, s->stream)); CK(dalloc(s->touchFound, Pn)); CK(dalloc(s->touchLost, Pn));
   CK(dalloc(s->exportTab, 1)); CK(cudaMemsetAsync(s->exportTab, 0, sizeof(ExportTable), s->stream)); CK(dalloc(s->envDyn, A));
   CK(dalloc(s->bodyBest, A)); CK(dalloc(s->actorLocal, A)); CK(dalloc(s->slotColour, Pn)); CK(cudaMemsetAsync(s->slotColour, 0xff, 4 * Pn, s->stream)); for (int k = 0; k < 2; ++k) { CK(dalloc(s->envSeg[k], A)); CK(cudaMemsetAsync(s->envSeg[k], 0, sizeof(uint2) * A, s->stream)); }
   CK(cudaStreamSynchronize(s->stream));
@@ -779,7 +784,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
-                  s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
+                  s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->touchState, s->touchFound, s->touchLost, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
   cudaStreamDestroy(s->stream); if (s->copyStream) cudaStreamDestroy(s->copyStream); if (s->velEvent) cudaEventDestroy(s->velEvent); if (s->orderEvent) cudaEventDestroy(s->orderEvent);
@@ -1067,7 +1072,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     A.nEnv = s->nEnv; A.maxList = s->envMaxList; A.bitsA = s->bitsA; A.cap = s->capPairs; A.ringMask = s->ringMask; A.externalTight = externalTight ? 1 : 0; A.contactOffset = s->desc.contactOffset;
     A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight; A.hulls = hull_arrays(s);
     A.oldKeys = s->pairKeys[prev]; A.oldSlots = s->pairSlots[prev]; A.oldSeg = s->envSeg[prev]; A.newKeys = s->pairKeys[cur]; A.newSlots = s->pairSlots[cur]; A.newSeg = s->envSeg[cur];
-    A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions; A.slotColour = s->slotColour;
+    A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions; A.slotColour = s->slotColour; A.touch = touch_lists(s);
     const size_t smem = (size_t)ENV_BP_WARPS * (s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t)) + ENV_BP_STAGE * sizeof(uint64_t));
     pxb_launch_env_bp(st, A, s->anyConvex, smem);
     s->launches++;
@@ -1075,6 +1080,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     return PXB_OK;
   }
   CK(cudaMemsetAsync(s->counters + C_NPAIRS_NEW, 0, 4 * 3, st));  // NPAIRS_NEW, NCREATED, NDELETED
+  CK(cudaMemsetAsync(s->counters + C_NTOUCH_FOUND, 0, 4 * 2, st));
   if (s->hasGjkPairs) CK(cudaMemsetAsync(s->counters + C_NGJK, 0, 4, st));
   LAUNCH(k_bounds, cdiv(nA, B), B, nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, externalTight ? 1 : 0, s->aabbMin, s->aabbMax, s->grid,
          s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s));
@@ -1093,9 +1099,9 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
   radix_sort_pairs(emit, s->pairValTmp, other, s->pairValAlt, s->nPairsDev + cur, 2 * s->bitsA, s->rsTmp, st);
   s->launches += 3 * ((2 * s->bitsA + 7) / 8);
   const uint32_t gP = cdiv(s->capPairs, B);
-  LAUNCH(k_pair_lost, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->nPairsDev + cur, s->freeList, s->ringMask, s->deletedKeys, s->counters);
+  LAUNCH(k_pair_lost, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->nPairsDev + cur, s->freeList, s->ringMask, s->deletedKeys, s->counters, touch_lists(s));
   LAUNCH(k_pair_found, gP, B, s->pairKeys[prev], s->pairSlots[prev], s->nPairsDev + prev, s->pairKeys[cur], s->pairSlots[cur], s->nPairsDev + cur, s->freeList, s->ringMask, s->createdKeys, s->counters,
-         s->manifolds, s->frictions);
+         s->manifolds, s->frictions, s->touchState);
   return PXB_OK;
 }
 
@@ -1105,6 +1111,7 @@ static int read_counters(PxbScene* s) {
   CK(cudaStreamSynchronize(s->stream));
   s->hNPairs = s->hostCounters[C_COUNT + s->cur]; s->hNCreated = s->hostCounters[C_NCREATED]; s->hNDeleted = s->hostCounters[C_NDELETED];
   s->hNCon = s->hostCounters[C_NCON]; s->hNPart = s->hostCounters[C_NPART]; s->hErr = s->hostCounters[C_ERROR];
+  s->hNTouchFound = s->hostCounters[C_NTOUCH_FOUND]; s->hNTouchLost = s->hostCounters[C_NTOUCH_LOST];
   if (s->envActive) {   // fit k_env_solve to the largest environment seen: one thread per constraint (rows in registers), lists in shared memory
     s->hMaxConEnv = s->hostCounters[C_MAXCONENV]; s->hMaxPairEnv = s->hostCounters[C_MAXPAIRENV];
     if (!s->envThreadsForced) { const uint32_t t = env_threads_for(s->hMaxConEnv); if (t != s->envSolveThreads && s->hMaxConEnv) { s->envSolveThreads = t; drop_graphs(s); } }
@@ -1142,7 +1149,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
   NpArgs NA;
   NA.pairKeys = s->pairKeys[cur]; NA.pairSlots = s->pairSlots[cur]; NA.nPairsP = nP; NA.bitsA = s->bitsA; NA.pos = s->pos; NA.quat = s->quat; NA.dims = s->dims; NA.geomFlags = s->geomFlags;
   NA.contactDist = contactDist; NA.toleranceLength = s->desc.toleranceLength; NA.manifolds = s->manifolds; NA.cHdr = s->cHdr; NA.cPts = s->cPts; NA.pairBodies = s->pairBodies; NA.conFlag = s->conFlag;
-  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s);
+  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s); NA.touch = touch_lists(s);
   pxb_launch_narrowphase(st, s->capPairs, NA); s->launches++;
   if (s->hasGjkPairs) { pxb_launch_narrowphase_gjk(st, std::max(148u * 4u, std::min(cdiv(s->capPairs, 128), 148u * 64u)), NA); s->launches++; }
   }
@@ -1387,6 +1394,10 @@ PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) { DeviceGuard dg_(
   }
   return PXB_OK;
 }
+PXB_API uint32_t pxb_scene_num_touch_found(PxbScene* s) { return s ? s->hNTouchFound : 0; }
+PXB_API uint32_t pxb_scene_num_touch_lost(PxbScene* s) { return s ? s->hNTouchLost : 0; }
+PXB_API int pxb_scene_get_touch_found(PxbScene* s, uint32_t* out) { DeviceGuard dg_(s); if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->touchFound, s->hNTouchFound, out, true); }
+PXB_API int pxb_scene_get_touch_lost(PxbScene* s, uint32_t* out) { DeviceGuard dg_(s); if (!s || !out) return fail(PXB_ERR_INVALID, "null argument"); return copy_pairs(s, s->touchLost, s->hNTouchLost, out, true); }
 PXB_API uint32_t pxb_scene_last_num_partitions(PxbScene* s) { DeviceGuard dg_(s); return s ? s->hNPart : 0; }
 PXB_API uint32_t pxb_scene_last_num_constraints(PxbScene* s) { DeviceGuard dg_(s); return s ? s->hNCon : 0; }
 PXB_API uint32_t pxb_scene_last_num_launches(PxbScene* s) { DeviceGuard dg_(s); return s ? s->launches : 0; }

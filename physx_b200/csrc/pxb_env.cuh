@@ -27,7 +27,7 @@ struct EnvBpArgs {
   const float4 *pos, *quat, *dims; const uint32_t *geomFlags, *envId; float* tight; HullArrays hulls;
   const uint64_t* oldKeys; const uint32_t* oldSlots; const uint2* oldSeg;
   uint64_t* newKeys; uint32_t* newSlots; uint2* newSeg;
-  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions;
+  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions; TouchLists touch;
 };
 
 #define ENV_BP_STAGE 256   // pair keys staged per warp in shared memory before the segment base is known
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
       m[0] = make_float4(__int_as_float(0), FLT_MAX, FLT_MAX, FLT_MAX); m[1] = make_float4(0, 0, 0, 1); m[2] = make_float4(0, 0, 0, 1); m[3] = make_float4(0, 0, 0, 1); m[14] = make_float4(0, 0, 0, 0);
       float4* f = A.frictions + (size_t)slot * PXB_FRICTION_F4;
       f[0] = make_float4(0, 0, 0, __int_as_float(0)); f[1] = make_float4(0, 0, 0, __int_as_float(0)); f[2] = make_float4(0, 0, 0, __int_as_float(0));
-      A.slotColour[slot] = NONE32;
+      A.slotColour[slot] = NONE32; A.touch.state[slot] = 0u;
     }
     A.newSlots[base + t] = slot;
   }
@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
     if (p < cnt && A.newKeys[base + p] == k) continue;
     A.freeRing[atomicAdd(&A.counters[C_FREE_TAIL], 1u) & A.ringMask] = A.oldSlots[ob + t];
     A.deletedKeys[atomicAdd(&A.counters[C_NDELETED], 1u)] = k;
+    touch_event(A.touch, A.counters, A.oldSlots[ob + t], k, false);
   }
   same = __all_sync(0xffffffffu, same);
   if (lane == 0) A.newSeg[e] = make_uint2(base, cnt | (same ? 0x80000000u : 0u));

@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
                               const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
                               float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
                               uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters, uint32_t* __restrict__ gjkList,
-                              const uint32_t* __restrict__ pairOrder) {
+                              const uint32_t* __restrict__ pairOrder, const TouchLists touch) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *nPairsP) return;
   const uint32_t i = pairOrder ? pairOrder[t] : t;   // mixed-type scenes: pairs binned by type pair (k_np_class_*)
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   for (int k = 0; k < 4; ++k) { cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]); }   // (cForce: every pair with contacts is a constraint and gets its forces from write-back)
   pairBodies[i] = make_uint2(a0, a1);
   conFlag[i] = out.count > 0 ? 1u : 0u;
+  touch_event(touch, counters, pairSlots[i], key, out.count > 0);
 }
 
 // a10: the GJK family (capsule-box), one thread per listed pair.  Kept out of k_narrowphase so that the box / sphere hot path keeps its register budget;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
 #endif
 __global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, uint32_t bitsA, const float4* __restrict__ pos, const float4* __restrict__ quat,
                               const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags, float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr,
-                              float4* __restrict__ cPts, uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, uint32_t* __restrict__ counters, const uint32_t* __restrict__ gjkList, HullArrays hulls) {
+                              float4* __restrict__ cPts, uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, uint32_t* __restrict__ counters, const uint32_t* __restrict__ gjkList, HullArrays hulls, const TouchLists touch) {
   const uint32_t n = counters[C_NGJK];
   for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
     const uint32_t i = gjkList[w];
@@ -116,14 +117,15 @@ __global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uin
     for (int k = 0; k < 4; ++k) cPts[(size_t)i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]);
     pairBodies[i] = make_uint2(a0, a1);
     conFlag[i] = out.count > 0 ? 1u : 0u;
+    touch_event(touch, counters, pairSlots[i], key, out.count > 0);
   }
 }
 
 void pxb_launch_narrowphase(cudaStream_t st, uint32_t capPairs, const NpArgs& A) {
   k_narrowphase<<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies,
-                                                         A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder);
+                                                         A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch);
 }
 void pxb_launch_narrowphase_gjk(cudaStream_t st, uint32_t ctas, const NpArgs& A) {
   k_narrowphase_gjk<<<ctas, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies, A.conFlag, A.counters,
-                                          A.gjkList, A.hulls);
+                                          A.gjkList, A.hulls, A.touch);
 }

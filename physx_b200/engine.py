@@ -31,6 +31,7 @@ EXPORTS = [
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
     "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait", "pxb_bp_create", "pxb_bp_release", "pxb_bp_update", "pxb_bp_fetch",
+    "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
@@ -76,7 +77,7 @@ def load_library():
     lib.pxb_scene_add_actors.argtypes = [vp, vp, u32]
     for f in ("pxb_scene_num_actors", "pxb_scene_num_dynamic", "pxb_scene_num_pairs", "pxb_scene_num_created",
               "pxb_scene_num_deleted", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
-              "pxb_scene_last_num_launches"):
+              "pxb_scene_last_num_launches", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost"):
         getattr(lib, f).argtypes = [vp]
         getattr(lib, f).restype = u32
     lib.pxb_scene_simulate.argtypes = [vp, f32]
@@ -86,7 +87,7 @@ def load_library():
               "pxb_set_rigid_dynamic_data_device"):
         getattr(lib, f).argtypes = [vp, vp, vp, i32, u32]
     for f in ("pxb_scene_get_states", "pxb_scene_set_states", "pxb_scene_get_bounds", "pxb_scene_broadphase",
-              "pxb_scene_get_pairs", "pxb_scene_get_created", "pxb_scene_get_deleted", "pxb_scene_get_contacts"):
+              "pxb_scene_get_pairs", "pxb_scene_get_created", "pxb_scene_get_deleted", "pxb_scene_get_contacts", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost"):
         getattr(lib, f).argtypes = [vp, vp]
     lib.pxb_scene_compute_bounds.argtypes = [vp]
     lib.pxb_scene_get_states_device.argtypes = [vp, vp]
@@ -277,6 +278,14 @@ class Scene:
 
     def getDeletedPairs(self):
         return self._pairs(self._lib.pxb_scene_num_deleted, self._lib.pxb_scene_get_deleted)
+
+    def getTouchFound(self):
+        """pairs that started producing contacts in the last step (touch-found events)"""
+        return self._pairs(self._lib.pxb_scene_num_touch_found, self._lib.pxb_scene_get_touch_found)
+
+    def getTouchLost(self):
+        """pairs that stopped producing contacts in the last step, incl. touching pairs that left the broadphase"""
+        return self._pairs(self._lib.pxb_scene_num_touch_lost, self._lib.pxb_scene_get_touch_lost)
 
     def getContacts(self):
         n = int(self._lib.pxb_scene_num_pairs(self._h))

@@ -852,3 +852,39 @@ def test_broadphase_object_removal_and_environment_filter():
     bp2.update(b3, d, g2, envs=env, created=[0, 1, 2, 3])
     c, dl = bp2.fetch()
     assert c.tolist() == [[0, 2], [1, 2]]
+
+
+# ---- a7: touch found / lost event lists ----
+@pytest.mark.parametrize("kind", ["tumble_devicewide", "tumble_env", "envs_ragged", "fall_mixed"])
+def test_touch_events_are_the_changes_of_the_touching_pair_set(kind):
+    """pxb_scene_get_touch_found / _lost: exactly the pairs whose contact state changed in the step -- incl. touching pairs that left the
+    broadphase -- on both paths and for the GJK-family pairs (their events are raised by k_narrowphase_gjk)."""
+    sc = {"tumble_devicewide": scenes.tumbling_boxes(n=12, seed=7), "tumble_env": scenes.tumbling_boxes(n=12, seed=7), "envs_ragged": scenes.env_ragged(),
+          "fall_mixed": scenes.falling_primitives(4, 3, 4, kinds=("sphere", "capsule", "box"))}[kind]
+    gpu = engine.Scene(sc, max_pairs=32 * len(sc.actors), env_path=(kind != "tumble_devicewide"))
+    prev, events = set(), 0
+    for t in range(150):
+        gpu.step()
+        cur = {(int(a), int(b)) for (a, b), c in zip(gpu.getPairs(), gpu.getContacts()) if c[0] > 0}
+        found = {(int(a), int(b)) for a, b in gpu.getTouchFound()}; lost = {(int(a), int(b)) for a, b in gpu.getTouchLost()}
+        assert found == cur - prev, f"touch found, step {t}"
+        assert lost == prev - cur, f"touch lost, step {t}"
+        events += len(found) + len(lost)
+        prev = cur
+    assert events > 20
+
+
+def test_touch_events_match_the_reference_contact_reports():
+    """Teacher-forced from the golden states: the touch-found / touch-lost events equal the changes of the reference's own touching pair set
+    (its contact reports carry every touching pair of the step: eNOTIFY_TOUCH_FOUND | eNOTIFY_TOUCH_PERSISTS)."""
+    z, sc = util.load_golden("tumble_12")
+    gpu = engine.Scene(sc, env_path=False)
+    prev = set()
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setStates(z["states"][t])
+        gpu.setConstraintOrder(util.golden_order(z, t))
+        gpu.step()
+        cur = set(util.golden_contact_counts(z, t))
+        assert {(int(a), int(b)) for a, b in gpu.getTouchFound()} == cur - prev, f"touch found, step {t}"
+        assert {(int(a), int(b)) for a, b in gpu.getTouchLost()} == prev - cur, f"touch lost, step {t}"
+        prev = cur
