@@ -472,7 +472,7 @@ def main():
     ap.add_argument("--churn", type=float, default=0.0, help="fraction of the environments reset every step (configs 2 / 5)")
     ap.add_argument("--partitioning", default="exact", choices=["exact", "relaxed"], help="configs 3 / 4: the reference's first-fit (default) or PXB_FLAG_RELAXED_PARTITIONING")
     ap.add_argument("--path", default="auto", choices=["auto", "devicewide"], help="devicewide forces the path used by scenes without environment ids (comparison runs)")
-    ap.add_argument("--gather", default="auto", choices=["auto", "fused", "peer", "peer-copy", "nccl"], help="multi-GPU state exchange")
+    ap.add_argument("--gather", default="auto", choices=["auto", "graph", "fused", "peer", "peer-copy", "nccl"], help="multi-GPU state exchange")
     ap.add_argument("--e2e", default="export", choices=["export", "copy"], help="end-to-end leg: state export into mapped pinned host memory (default) or explicit D2H copies after the step")
     ap.add_argument("--solver", default="tgs", choices=["tgs", "pgs"], help="PxSolverType of the scene (headline metric: tgs)")
     args = ap.parse_args()

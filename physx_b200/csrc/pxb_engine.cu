@@ -55,7 +55,7 @@ struct PxbScene {
   uint32_t *conFlag = 0, *conIdx = 0, *conPair = 0, *rankOfPair = 0; uint64_t *conSortKey = 0, *conSortKeyAlt = 0; uint32_t* conPairAlt = 0;
   uint64_t* orderKeys = 0; uint32_t nOrder = 0, capOrder = 0;
   uint32_t *conB0 = 0, *conB1 = 0, *conPos0 = 0, *conPos1 = 0, *conColour = 0, *conDone = 0, *bodyList = 0, *ordered = 0;
-  uint32_t *partCnt = 0, *partStart = 0, *partCursor = 0, *colourTicket = 0; bool colourLegacy = false; uint32_t colourBackoffNs = 0;
+  uint32_t *partCnt = 0, *partStart = 0, *partCursor = 0, *colourTicket = 0, *prevB0 = 0, *prevB1 = 0, *prevColour = 0, *prevNCon = 0; bool colourLegacy = false, colourPrefix = true; uint32_t colourBackoffNs = 100;
   // rows (solve order)
   float4 *ptA = 0, *ptB = 0, *ptC = 0, *frA = 0, *frB = 0, *frC = 0, *frD = 0;
   uint32_t* counters = 0; uint32_t* hostCounters = 0;  // pinned mirror
@@ -343,6 +343,29 @@ __global__ void k_body_lists(uint32_t nA, const uint32_t* __restrict__ bodyStart
   }
   bodyNext[a] = 0; bodyMask[a] = 0ull; bodyHasCon[a] = n > 0 ? 1u : 0u;
 }
+// a13 prefix reuse.  First fit is sequential in solver input order, so a constraint's colour depends only on the constraints BEFORE it: when this
+// frame's constraint list agrees with last frame's up to index F, the first F colours are last frame's.  k_colour_prefix_find computes F (first
+// difference), k_colour_prefix_apply re-installs those colours and the body masks they imply, and the dataflow below only runs for c >= F.  A pile
+// at rest keeps its list, so its colouring costs two light passes (BASELINE config 4: 3.6 ms -> ~0.1 ms once settled).
+__global__ void k_colour_prefix_find(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ conB0, const uint32_t* __restrict__ conB1, const uint32_t* __restrict__ prevB0,
+                                     const uint32_t* __restrict__ prevB1, const uint32_t* __restrict__ prevN, uint32_t* __restrict__ ticket) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = min(counters[C_NCON], *prevN);
+  if (c == 0) atomicMin(&ticket[2], n);
+  if (c >= n) return;
+  if (conB0[c] != prevB0[c] || conB1[c] != prevB1[c]) atomicMin(&ticket[2], c);
+}
+__global__ void k_colour_prefix_apply(const uint32_t* __restrict__ conB0, const uint32_t* __restrict__ conB1, const uint32_t* __restrict__ prevColour, uint32_t* __restrict__ conColour,
+                                      unsigned long long* __restrict__ bodyMask, const uint32_t* __restrict__ ticket) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ticket[2]) return;
+  const uint32_t b = conB1[c];
+  if (b == NONE32) return;
+  const uint32_t col = prevColour[c];
+  conColour[c] = col;
+  atomicOr(&bodyMask[conB0[c]], 1ull << col); atomicOr(&bodyMask[b], 1ull << col);
+}
+__global__ void k_colour_remember(const uint32_t* __restrict__ counters, uint32_t* __restrict__ prevN) { if (threadIdx.x == 0 && blockIdx.x == 0) *prevN = (counters[C_ERROR] & E_COLOUR_OVERFLOW) ? 0u : counters[C_NCON]; }
 // a13 (3/3, exact): the reference's sequential first-fit (classifyConstraintDesc, DyConstraintPartition.cpp:475-568) as a DATAFLOW over the
 // constraint list instead of grid-wide rounds.  One thread per constraint; a dynamic constraint may take its colour once every earlier
 // constraint of both its bodies has one.  Colours on a body are distinct, so popcount(bodyMask[body]) IS the number of the body's coloured
@@ -358,7 +381,7 @@ __global__ void __launch_bounds__(128) k_colour_firstfit(uint32_t* __restrict__ 
   if (threadIdx.x == 0) sBlock = atomicAdd(&ticket[0], 1u);
   __syncthreads();
   const uint32_t c = sBlock * blockDim.x + threadIdx.x;
-  if (c >= counters[C_NCON]) return;
+  if (c >= counters[C_NCON] || c < ticket[2]) return;   // ticket[2]: constraints before it kept last frame's colours (k_colour_prefix_*)
   const uint32_t b = conB1[c];
   if (b == NONE32) return;   // static contacts take their partition after the dynamic colours are known (k_colour_partition's ordering pass)
   const uint32_t a = conB0[c], pa = conPos0[c], pb = conPos1[c];
@@ -714,7 +737,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->conPairAlt, Pn));
   CK(dalloc(s->conB0, Pn)); CK(dalloc(s->conB1, Pn)); CK(dalloc(s->conPos0, Pn)); CK(dalloc(s->conPos1, Pn)); CK(dalloc(s->conColour, Pn)); CK(dalloc(s->conDone, Pn));
   CK(dalloc(s->bodyList, Pn * 2)); CK(dalloc(s->ordered, Pn));
-  CK(dalloc(s->colourTicket, 2)); CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
+  CK(dalloc(s->colourTicket, 4)); CK(dalloc(s->prevB0, Pn)); CK(dalloc(s->prevB1, Pn)); CK(dalloc(s->prevColour, Pn)); CK(dalloc(s->prevNCon, 1)); CK(cudaMemsetAsync(s->prevNCon, 0, 4, s->stream)); CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
   CK(dalloc(s->ptA, Pn * 28)); s->ptB = s->ptA + Pn * 4; s->ptC = s->ptA + Pn * 8;   // one allocation: the environment path views it as 25 x Pn (pxb_env.cuh Rows)
   s->frA = s->ptA + Pn * 12; s->frB = s->ptA + Pn * 16; s->frC = s->ptA + Pn * 20; s->frD = s->ptA + Pn * 24;
   CK(dalloc(s->stage, A * 32)); CK(dalloc(s->stageIdx, A));   // staging: {get, set} x {pose 7, linear 3, angular 3} + set {force 3, torque 3} floats per actor
@@ -763,7 +786,8 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->bitsA = bits_for(s->capA);
   s->rsTmp.ctas = std::min<uint32_t>(RS_MAX_CTAS, (uint32_t)s->numSMs * 2);
   { const char* ng = getenv("PXB_NO_GRAPH"); if (ng && ng[0] == '1') s->useGraph = false; }
-  { const char* cl = getenv("PXB_COLOUR_LEGACY"); if (cl && cl[0] == '1') s->colourLegacy = true; const char* cb = getenv("PXB_COLOUR_BACKOFF_NS"); if (cb) s->colourBackoffNs = (uint32_t)atoi(cb); }   // A/B hooks of the exact colouring
+  { const char* cl = getenv("PXB_COLOUR_LEGACY"); if (cl && cl[0] == '1') s->colourLegacy = true; const char* cb = getenv("PXB_COLOUR_BACKOFF_NS"); if (cb) s->colourBackoffNs = (uint32_t)atoi(cb);
+    const char* cp = getenv("PXB_COLOUR_PREFIX"); if (cp && cp[0] == '0') s->colourPrefix = false; }   // A/B hooks of the exact colouring
   if (desc->reserved[1] & PXB_FLAG_NO_ENV_PATH) s->envDisabled = true;
   if (desc->reserved[1] & PXB_FLAG_RELAXED_PARTITIONING) { s->relaxedPartitioning = true; s->envDisabled = true; }
   s->envConCapForced = desc->reserved[2]; s->envThreadsForced = desc->reserved[3];
@@ -783,7 +807,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
-                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
+                  s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->prevB0, s->prevB1, s->prevColour, s->prevNCon, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
                   s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->touchState, s->touchFound, s->touchLost, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
@@ -1212,13 +1236,22 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     int relaxed = (s->relaxedPartitioning && s->nOrder == 0) ? 1 : 0;   // a host-provided solver order always gets the exact first-fit
     if (relaxed) CK(cudaMemsetAsync(s->bodyBest, 0, 8 * (size_t)s->nA, st));
     else if (!s->colourLegacy) {   // exact first-fit as a dataflow (k_colour_firstfit); the cooperative kernel below then only orders the constraints partition-major
-      CK(cudaMemsetAsync(s->colourTicket, 0, 8, st));
+      CK(cudaMemsetAsync(s->colourTicket, 0, 8, st)); CK(cudaMemsetAsync(s->colourTicket + 2, s->colourPrefix ? 0xff : 0, 4, st));
+      if (s->colourPrefix) {
+        LAUNCH(k_colour_prefix_find, gP, B, s->counters, s->conB0, s->conB1, s->prevB0, s->prevB1, s->prevNCon, s->colourTicket);
+        LAUNCH(k_colour_prefix_apply, gP, B, s->conB0, s->conB1, s->prevColour, s->conColour, s->bodyMask, s->colourTicket);
+      }
       LAUNCH(k_colour_firstfit, cdiv(s->capPairs, 128), 128, s->counters, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->bodyMask, s->colourTicket, s->colourBackoffNs);
       relaxed = 2;
     }
     void* args[] = {&s->counters, &s->conB0, &s->conB1, &s->conPos0, &s->conPos1, &s->conColour, &s->conDone, &s->bodyNext, &s->bodyMask, &s->partCnt, &s->partStart, &s->partCursor, &s->ordered,
                     &s->bodyBest, &relaxed};
     CK(cudaLaunchCooperativeKernel((void*)k_colour_partition, dim3(s->coopBlocksColour), dim3(256), args, 0, st)); s->launches++;
+    if (relaxed == 2 && s->colourPrefix) {   // remember this frame's list and colours for the next frame's prefix reuse
+      CK(cudaMemcpyAsync(s->prevB0, s->conB0, 4 * (size_t)s->capPairs, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(s->prevB1, s->conB1, 4 * (size_t)s->capPairs, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(s->prevColour, s->conColour, 4 * (size_t)s->capPairs, cudaMemcpyDeviceToDevice, st));
+      LAUNCH(k_colour_remember, 1, 32, s->counters, s->prevNCon);
+    }
   }
   MARK(3);
   LAUNCH(k_preintegrate, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, g[0], g[1], g[2], dt, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng,

@@ -317,10 +317,109 @@ class FusedStateGather:
         self.scene.peerWait(st.cuda_stream, self.flags.data_ptr(), self.world, self.k)
 
 
+class GraphPeerGather:
+    """The per-step all-gather as ONE CUDA-graph replay per step and no pack kernel:
+      * the step's integration epilogue writes this rank's packed block into its rows of its OWN symmetric-memory tensor
+        (pxb_scene_set_state_export with one local target: nothing crosses NVLink from the solve kernel);
+      * the pushes into the peers (one copy-engine peer copy per peer, concurrent) and the closing symmetric-memory barrier are captured once
+        per buffer into a CUDA graph on the communication stream and replayed: the host enqueues a step's exchange with three calls instead
+        of ~10 per peer (at N = 8 the Python-side enqueue of the copy-based exchange took about as long as the step itself).
+    Consumer release: graph launches are serialised on the communication stream, so the pushes of exchange k+2 (same buffer as k) start only
+    after the barrier of exchange k+1 has passed, i.e. after EVERY rank has finished step k+1 -- and a rank starts step k+1 only after its
+    consumer is done with the tensor of step k (program / stream order).  No peer can overwrite a tensor that is still being read."""
+
+    def __init__(self, dist, n_local: int, cols: int, device, scene_stream, scene):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        assert cols == 13
+        self.torch, self.dist, self.scene, self.scene_stream = torch, dist, scene, scene_stream
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        cnt = torch.tensor([n_local], dtype=torch.int64, device=device)
+        allc = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(allc, cnt)
+        self.counts = [int(c.item()) for c in allc]
+        self.layout = gather_layout(self.counts)
+        total = sum(self.counts)
+        lo, hi = self.layout[self.rank]
+        self.comm_stream = torch.cuda.Stream(device=device)
+        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(max(1, self.world - 1))]
+        self.bufs, self.handles, self.peer_views, self.graphs = [], [], [], [None, None]
+        for _ in range(2):
+            t = symm.empty((total, cols), dtype=torch.float32, device=device)
+            h = symm.rendezvous(t, dist.group.WORLD)
+            self.bufs.append(t)
+            self.handles.append(h)
+            self.peer_views.append([h.get_buffer(p, (total, cols), torch.float32)[lo:hi] for p in range(self.world)])
+        self.done = [None, None]
+        self.k = 0
+        dist.barrier()
+        for b in range(2):      # one eager exchange per buffer (lazy initialisation inside the barrier / copy paths), then capture
+            with torch.cuda.stream(self.comm_stream):
+                self._exchange(b)
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        for b in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.comm_stream, capture_error_mode="thread_local"):
+                self._exchange(b)
+            self.graphs[b] = g
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    def _exchange(self, b):
+        """pushes of this rank's block into every peer's copy of buffer b (fork over the copy streams) + barrier; runs on / is captured from the communication stream"""
+        t = self.torch
+        lo, hi = self.layout[self.rank]
+        local = self.bufs[b][lo:hi]
+        j = 0
+        for p in range(self.world):
+            if p == self.rank:
+                continue
+            cs = self.copy_streams[j]; j += 1
+            cs.wait_stream(self.comm_stream)
+            with t.cuda.stream(cs):
+                self.peer_views[b][p].copy_(local, non_blocking=True)
+            self.comm_stream.wait_stream(cs)
+        self.handles[b].barrier(channel=b)
+
+    def pre_step(self, consumer_stream=None):
+        b = self.k & 1
+        if consumer_stream is not None:
+            self.scene_stream.wait_stream(consumer_stream)
+        if self.done[b] is not None:
+            self.scene_stream.wait_event(self.done[b])          # exchange k-2 has finished reading this rank's rows of buffer b
+        self.scene.setStateExport([self.bufs[b].data_ptr()], self.layout[self.rank][0])
+
+    def step(self, pack=None):
+        t = self.torch
+        b = self.k & 1
+        ready = t.cuda.Event()
+        ready.record(self.scene_stream)
+        self.comm_stream.wait_event(ready)
+        with t.cuda.stream(self.comm_stream):
+            self.graphs[b].replay()
+            self.done[b] = t.cuda.Event()
+            self.done[b].record(self.comm_stream)
+        self.k += 1
+        return b
+
+    def close(self):
+        self.scene.setStateExport(())
+
+    def latest(self):
+        return self.bufs[(self.k - 1) & 1]
+
+    def wait(self, stream=None):
+        for ev in self.done:
+            if ev is not None:
+                (stream or self.scene_stream).wait_event(ev)
+
+
 def make_state_gather(dist, n_local: int, cols: int, device, scene_stream, kind: str = "auto", scene=None):
     """kind: 'fused' (the step's integration epilogue stores into every rank's symmetric-memory tensor: FusedStateGather), 'peer-copy'
     (concurrent copy-engine peer copies into symmetric memory), 'peer' (one scatter kernel with P2P stores), 'nccl' (all_gather_into_tensor)
-    or 'auto' (peer-copy when symmetric memory is available, else NCCL)."""
+    'graph' (GraphPeerGather: local export + one CUDA-graph replay of the peer pushes and the barrier) or 'auto' (graph, else peer-copy when symmetric
+    memory is available, else NCCL)."""
     # measured at N = 2 (config 2 per GPU): copy engines 0.3115 ms/step, NCCL 0.3161, fused export 0.3418 (its P2P stores and flag kernels sit on
     # the step's critical path; the copy engines do not) -> 'auto' stays with the copy engines, 'fused' is opt-in
     if kind == "fused" and device.type == "cuda" and scene is not None and cols == 13:
@@ -329,6 +428,14 @@ def make_state_gather(dist, n_local: int, cols: int, device, scene_stream, kind:
             return g, "P2P stores from the step's integration epilogue into every rank's symmetric-memory tensor (fused export) + per-rank flags"
         except Exception as e:  # pragma: no cover - depends on the platform
             if kind == "fused":
+                raise
+            kind = "auto-copy"
+    if kind in ("auto", "graph") and device.type == "cuda" and scene is not None and cols == 13:
+        try:
+            g = GraphPeerGather(dist, n_local, cols, device, scene_stream, scene)
+            return g, "state export into the local symmetric-memory tensor by the step itself + one CUDA-graph replay per step (concurrent copy-engine peer pushes + barrier)"
+        except Exception as e:  # pragma: no cover - depends on the platform
+            if kind == "graph":
                 raise
             kind = "auto-copy"
     if kind in ("auto", "auto-copy", "peer", "peer-copy") and device.type == "cuda":
