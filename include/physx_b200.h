@@ -79,7 +79,8 @@ typedef struct {
   float    linDamping, angDamping;
   float    maxLinVel, maxAngVel;
   float    maxDepenetrationVel;
-  float    reserved[2];
+  uint32_t materialIndex; /* index into the table of pxb_scene_set_materials (ignored while no table is set) */
+  float    reserved1;
 } PxbActorRec;
 
 typedef struct PxbScene PxbScene;
@@ -115,6 +116,15 @@ typedef struct {
 } PxbCookedHullHeader;
 typedef struct { float plane[4]; uint32_t vref, nbVerts, minIndex, pad; } PxbCookedPoly;
 PXB_API int  pxb_scene_set_convex_meshes(PxbScene* scene, const void* cooked, size_t bytes, uint32_t nHulls);
+/* Material table (a11: materialCombiner.cuh:35 / PxsCombineMaterials, lowlevel/software/include/PxsMaterialCombiner.h:69-175).  Each actor's shape
+ * refers to one entry (PxbActorRec::materialIndex); a pair's friction coefficients and restitution are combined from its two materials with the
+ * larger of their PxCombineMode values (average, min, multiply, max), static friction is raised to the dynamic one, and
+ * PxMaterialFlag::eDISABLE_FRICTION on either side removes the friction rows.  bits = frictionCombineMode | restitutionCombineMode << 4 |
+ * flags << 8 (bit 0: eDISABLE_FRICTION).  Without a table every pair uses PxbSceneDesc's staticFriction / dynamicFriction / restitution.
+ * Compliant contacts (negative restitution), eDISABLE_STRONG_FRICTION, eIMPROVED_PATCH_FRICTION -> PXB_ERR_UNSUPPORTED.  Call before the
+ * first simulate. */
+typedef struct { float staticFriction, dynamicFriction, restitution; uint32_t bits; } PxbMaterial;
+PXB_API int  pxb_scene_set_materials(PxbScene* scene, const PxbMaterial* materials, uint32_t nb);
 PXB_API int  pxb_scene_add_actors(PxbScene* scene, const void* recs, uint32_t nb);
 PXB_API uint32_t pxb_scene_num_actors(const PxbScene* scene);
 PXB_API uint32_t pxb_scene_num_dynamic(const PxbScene* scene);

@@ -95,6 +95,7 @@ struct InlineDispatcher : public PxCpuDispatcher {
 };
 
 static bool gWantContacts = false;
+static PxMaterial* gDefaultMat = nullptr;
 static PxFilterFlags filterShader(PxFilterObjectAttributes a0, PxFilterData, PxFilterObjectAttributes a1, PxFilterData,
                                   PxPairFlags& pairFlags, const void* cb, PxU32) {
   PX_UNUSED(a0); PX_UNUSED(a1);
@@ -150,7 +151,8 @@ int main(int argc, char** argv) {
   const PxbSceneHeader& H = *reinterpret_cast<const PxbSceneHeader*>(buf.data());
   if (H.magic != PXB_SCENE_MAGIC) { fprintf(stderr, "bad magic\n"); return 2; }
   const PxbActorRec* recs = reinterpret_cast<const PxbActorRec*>(buf.data() + sizeof(PxbSceneHeader));
-  const uint8_t* hp = reinterpret_cast<const uint8_t*>(recs + H.nActors);
+  const PxbMaterialRec* matRecs = reinterpret_cast<const PxbMaterialRec*>(recs + H.nActors);   // material table (may be empty)
+  const uint8_t* hp = reinterpret_cast<const uint8_t*>(matRecs + H.reserved[2]);
 
   PxFoundation* foundation = PxCreateFoundation(PX_PHYSICS_VERSION, gAllocator, gErrorCallback);
   PxTolerancesScale scale; scale.length = H.toleranceLength; scale.speed = 10.0f * H.toleranceLength;
@@ -260,6 +262,13 @@ int main(int argc, char** argv) {
   if (gWantContacts) sd.simulationEventCallback = &cb;
   PxScene* scene = physics->createScene(sd);
   PxMaterial* mat = physics->createMaterial(H.staticFriction, H.dynamicFriction, H.restitution);
+  gDefaultMat = mat;
+  std::vector<PxMaterial*> mats(H.reserved[2]);
+  for (uint32_t m = 0; m < H.reserved[2]; m++) {   // PxMaterial per table entry: coefficients, combine modes, eDISABLE_FRICTION
+    mats[m] = physics->createMaterial(matRecs[m].staticFriction, matRecs[m].dynamicFriction, matRecs[m].restitution);
+    mats[m]->setFrictionCombineMode(PxCombineMode::Enum(matRecs[m].bits & 15u)); mats[m]->setRestitutionCombineMode(PxCombineMode::Enum((matRecs[m].bits >> 4) & 15u));
+    if ((matRecs[m].bits >> 8) & 1u) mats[m]->setFlag(PxMaterialFlag::eDISABLE_FRICTION, true);
+  }
 
   std::vector<PxRigidActor*> actors(H.nActors);
   std::vector<PxRigidDynamic*> dyn;
@@ -268,6 +277,7 @@ int main(int argc, char** argv) {
     const PxbActorRec& r = recs[i];
     PxTransform pose(PxVec3(r.pos[0], r.pos[1], r.pos[2]), PxQuat(r.quat[0], r.quat[1], r.quat[2], r.quat[3]));
     PxRigidActor* a;
+    PxMaterial* mat = mats.empty() ? ::gDefaultMat : mats[r.materialIndex < mats.size() ? r.materialIndex : 0];
     if (r.flags & PXB_ACTOR_DYNAMIC) a = physics->createRigidDynamic(pose); else a = physics->createRigidStatic(pose);
     PxShape* s = nullptr;
     switch (r.geomType) {

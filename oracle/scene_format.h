@@ -1,6 +1,7 @@
 /* Scene interchange format shared by the oracle tools (test infrastructure).
  *
- * A scene file is:  SceneHeader | ActorRec[nActors] | for each hull: u32 nVerts, float xyz[nVerts]
+ * A scene file is:  SceneHeader | ActorRec[nActors] | PxbMaterialRec[header.reserved[2]] (material table, may be empty)
+ *                   | for each hull: u32 nVerts, float xyz[nVerts]
  *                   | (when header.reserved[1] == PXB_COOKED_MAGIC) for each hull: PxbCookedHullHeader + arrays (see below)
  * The cooked section is what PxCreateConvexMesh makes of the point cloud (Gu::ConvexHullData): convex cooking is host-side work in PhysX
  * too (the GPU pipeline receives cooked hulls through PxsSimulationController::addPxgShape), so cooked hulls are an INPUT of the hot path.
@@ -55,8 +56,14 @@ typedef struct {
   float    linDamping, angDamping;
   float    maxLinVel, maxAngVel;
   float    maxDepenetrationVel;
-  float    reserved[2];
+  uint32_t materialIndex; /* index into the scene's material table (ignored when the table is empty: the header's material applies) */
+  float    reserved1;
 } PxbActorRec;
+
+/* One PxMaterial (physx/include/PxMaterial.h): bits = frictionCombineMode | restitutionCombineMode << 4 (PxCombineMode: 0 average, 1 min,
+ * 2 multiply, 3 max) | flags << 8 (bit 0 = PxMaterialFlag::eDISABLE_FRICTION).  Pairs combine as PxsCombineMaterials does
+ * (lowlevel/software/include/PxsMaterialCombiner.h:69-175, rigid non-compliant branch). */
+typedef struct { float staticFriction, dynamicFriction, restitution; uint32_t bits; } PxbMaterialRec;
 
 #define PXB_COOKED_MAGIC 0x43485850u /* "PXHC" */
 /* followed by: float verts[nVerts][3]; PxbCookedPoly polys[nPolys]; uint8_t vertexRefs[nIdx] (padded to 4);

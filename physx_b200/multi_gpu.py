@@ -38,7 +38,7 @@ def shard_scene(scene: _scenes.Scene, world_size: int, rank: int) -> _scenes.Sce
     actors = scene.actors[keep].copy()
     own = actors["envId"] != _scenes.NO_ENV
     actors["envId"][own] -= np.uint32(lo)
-    return _scenes.Scene(scene.header, actors, scene.hulls, scene.cooked)
+    return _scenes.Scene(scene.header, actors, scene.hulls, scene.cooked, scene.materials)
 
 
 def gather_layout(counts):
@@ -418,7 +418,7 @@ class GraphPeerGather:
 def make_state_gather(dist, n_local: int, cols: int, device, scene_stream, kind: str = "auto", scene=None):
     """kind: 'fused' (the step's integration epilogue stores into every rank's symmetric-memory tensor: FusedStateGather), 'peer-copy'
     (concurrent copy-engine peer copies into symmetric memory), 'peer' (one scatter kernel with P2P stores), 'nccl' (all_gather_into_tensor)
-    'graph' (GraphPeerGather: local export + one CUDA-graph replay of the peer pushes and the barrier) or 'auto' (graph, else peer-copy when symmetric
+    'graph' (GraphPeerGather: local export + one CUDA-graph replay of the peer pushes and the barrier) or 'auto' (peer-copy when symmetric
     memory is available, else NCCL)."""
     # measured at N = 2 (config 2 per GPU): copy engines 0.3115 ms/step, NCCL 0.3161, fused export 0.3418 (its P2P stores and flag kernels sit on
     # the step's critical path; the copy engines do not) -> 'auto' stays with the copy engines, 'fused' is opt-in
@@ -430,7 +430,9 @@ def make_state_gather(dist, n_local: int, cols: int, device, scene_stream, kind:
             if kind == "fused":
                 raise
             kind = "auto-copy"
-    if kind in ("auto", "graph") and device.type == "cuda" and scene is not None and cols == 13:
+    # measured (config 2 per GPU): N = 2: copy engines 0.3157 ms/step, graph 0.3257; N = 8: copy engines 0.3281, graph 0.4168 (the captured
+    # peer copies no longer run concurrently on the copy engines) -> 'auto' stays with the eager copy-engine exchange, 'graph' is opt-in
+    if kind == "graph" and device.type == "cuda" and scene is not None and cols == 13:
         try:
             g = GraphPeerGather(dist, n_local, cols, device, scene_stream, scene)
             return g, "state export into the local symmetric-memory tensor by the step itself + one CUDA-graph replay per step (concurrent copy-engine peer pushes + barrier)"

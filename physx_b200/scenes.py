@@ -31,8 +31,20 @@ ACTOR_DTYPE = np.dtype([
     ("pos", "<f4", 3), ("quat", "<f4", 4), ("dims", "<f4", 4),
     ("linVel", "<f4", 3), ("angVel", "<f4", 3), ("mass", "<f4"), ("inertia", "<f4", 3),
     ("linDamping", "<f4"), ("angDamping", "<f4"), ("maxLinVel", "<f4"), ("maxAngVel", "<f4"),
-    ("maxDepenetrationVel", "<f4"), ("reserved", "<f4", 2),
+    ("maxDepenetrationVel", "<f4"), ("materialIndex", "<u4"), ("reserved1", "<f4"),
 ])
+MATERIAL_DTYPE = np.dtype([("staticFriction", "<f4"), ("dynamicFriction", "<f4"), ("restitution", "<f4"), ("bits", "<u4")])
+COMBINE_AVERAGE, COMBINE_MIN, COMBINE_MULTIPLY, COMBINE_MAX = 0, 1, 2, 3
+MATERIAL_DISABLE_FRICTION = 1 << 8
+
+
+def make_materials(entries):
+    """entries: (staticFriction, dynamicFriction, restitution, frictionCombineMode, restitutionCombineMode[, disableFriction]) tuples"""
+    m = np.zeros(len(entries), MATERIAL_DTYPE)
+    for i, e in enumerate(entries):
+        m[i] = (e[0], e[1], e[2], int(e[3]) | int(e[4]) << 4 | (MATERIAL_DISABLE_FRICTION if len(e) > 5 and e[5] else 0))
+    return m
+
 assert HEADER_DTYPE.itemsize == 96 and ACTOR_DTYPE.itemsize == 128
 
 STATE_FLOATS = 13  # pos3 quat4 linVel3 angVel3
@@ -166,9 +178,11 @@ def parse_cooked(buf, n_hulls, off=0):
 
 
 class Scene:
-    def __init__(self, header, actors, hulls=(), cooked=b""):
+    def __init__(self, header, actors, hulls=(), cooked=b"", materials=None):
         self.header = header.copy()
         self.actors = actors
+        self.materials = np.zeros(0, MATERIAL_DTYPE) if materials is None else np.asarray(materials, MATERIAL_DTYPE)   # material table (empty: the header's material)
+        self.header["reserved"][2] = len(self.materials)
         self.hulls = list(hulls)
         self.cooked = bytes(cooked)   # cooked-hull section (reference cooking output, see cook_hulls); empty = not cooked
         self.header["nActors"] = len(actors)
@@ -181,7 +195,7 @@ class Scene:
     def tobytes(self):
         h = self.header.copy()
         h["reserved"][1] = COOKED_MAGIC if self.cooked else 0
-        out = [h.tobytes(), self.actors.tobytes()]
+        out = [h.tobytes(), self.actors.tobytes(), self.materials.tobytes()]
         for hl in self.hulls:
             hl = np.asarray(hl, dtype="<f4").reshape(-1, 3)
             out.append(np.uint32(len(hl)).tobytes())
@@ -200,12 +214,14 @@ class Scene:
         off = HEADER_DTYPE.itemsize
         a = np.frombuffer(buf, dtype=ACTOR_DTYPE, count=int(h["nActors"]), offset=off).copy()
         off += a.nbytes
+        mats = np.frombuffer(buf, dtype=MATERIAL_DTYPE, count=int(h["reserved"][2]), offset=off).copy()
+        off += mats.nbytes
         hulls = []
         for _ in range(int(h["nHulls"])):
             nv = int(np.frombuffer(buf, "<u4", 1, off)[0]); off += 4
             hulls.append(np.frombuffer(buf, "<f4", nv * 3, off).reshape(nv, 3).copy()); off += nv * 12
         cooked = buf[off:] if int(h["reserved"][1]) == COOKED_MAGIC else b""
-        return Scene(h, a, hulls, cooked)
+        return Scene(h, a, hulls, cooked, mats)
 
     def cooked_hulls(self):
         return parse_cooked(self.cooked, len(self.hulls))[0] if self.cooked else []
