@@ -22,7 +22,7 @@ namespace cg = cooperative_groups;
 // host-side record (layout of oracle/scene_format.h::PxbActorRec, 128 bytes)
 struct ActorRec {
   uint32_t flags, geomType, envId, hullIdx;
-  float pos[3], quat[4], dims[4], linVel[3], angVel[3], mass, inertia[3], linDamping, angDamping, maxLinVel, maxAngVel, maxDepenetrationVel, reserved[2];
+  float pos[3], quat[4], dims[4], linVel[3], angVel[3], mass, inertia[3], linDamping, angDamping, maxLinVel, maxAngVel, maxDepenetrationVel; uint32_t materialIndex; float reserved1;
 };
 static_assert(sizeof(ActorRec) == 128, "actor record layout");
 
@@ -175,4 +175,21 @@ __device__ __forceinline__ void touch_event(const TouchLists& T, uint32_t* __res
   if ((prev != 0u) == touching) return;
   T.state[slot] = touching ? 1u : 0u;
   if (touching) T.found[atomicAdd(&counters[C_NTOUCH_FOUND], 1u)] = key; else T.lost[atomicAdd(&counters[C_NTOUCH_LOST], 1u)] = key;
+}
+
+// a11: PxsCombineMaterials (lowlevel/software/include/PxsMaterialCombiner.h:69-175; GPU: gpunarrowphase/src/CUDA/materialCombiner.cuh:35), rigid
+// non-compliant branch.  matTab: one float4 per material (staticFriction, dynamicFriction, restitution, bits = frictionCombineMode |
+// restitutionCombineMode << 4 | flags << 8); returns true when eDISABLE_FRICTION on either side removes the friction rows.
+struct MaterialArgs { const uint32_t* actorMat; const float4* matTab; };
+__device__ __forceinline__ float combine_scalars(float a, float b, uint32_t mode) { return mode == 0u ? 0.5f * (a + b) : (mode == 1u ? fminf(a, b) : (mode == 2u ? a * b : fmaxf(a, b))); }
+__device__ __forceinline__ bool pair_material(const MaterialArgs& M, uint32_t actor0, uint32_t actor1, SolverParams& P) {
+  const float4 m0 = M.matTab[M.actorMat[actor0]], m1 = M.matTab[M.actorMat[actor1]];
+  const uint32_t b0 = __float_as_uint(m0.w), b1 = __float_as_uint(m1.w);
+  P.restitution = combine_scalars(m0.z, m1.z, max((b0 >> 4) & 15u, (b1 >> 4) & 15u));
+  if (((b0 | b1) >> 8) & 1u) { P.staticFriction = 0.f; P.dynamicFriction = 0.f; return true; }
+  const uint32_t fm = max(b0 & 15u, b1 & 15u);
+  const float dyn = combine_scalars(m0.y, m1.y, fm), sta = combine_scalars(m0.x, m1.x, fm);
+  const float fDyn = fmaxf(dyn, 0.f);
+  P.dynamicFriction = fDyn; P.staticFriction = (sta - fDyn) >= 0.f ? sta : fDyn;
+  return false;
 }

@@ -72,6 +72,7 @@ struct PxbScene {
   bool envEligible = false, envActive = false, envDisabled = false, everStepped = false; uint32_t ringMask = 0;
   uint32_t nEnv = 0, envMaxList = 0, envConCap = 0, envConCapForced = 0, envThreadsForced = 0, hMaxConEnv = 0, hMaxPairEnv = 0, envSolveThreads = 64;
   uint32_t *envStart = 0, *envList = 0, *actorLocal = 0, *slotColour = 0; unsigned long long* bodyBest = 0; bool relaxedPartitioning = false;
+  uint32_t* actorMat = 0; float4* matTab = 0; uint32_t nMaterials = 0;   // a11 material table (pxb_scene_set_materials)
   uint32_t* touchState = 0; uint64_t *touchFound = 0, *touchLost = 0; uint32_t hNTouchFound = 0, hNTouchLost = 0;   // a7 touch found / lost events
   ExportTable* exportTab = 0; uint2* envDyn = 0; bool exportOn = false, envDynContiguous = false;   // fused state export (pxb_scene_set_state_export)
   float sleepThreshold = 0.f; float* wake = 0; float4 *accLin = 0, *accAng = 0; uint32_t *asleep = 0, *nInter = 0, *islandLabel = 0, *islandAwake = 0; int coopBlocksSleep = 0; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
@@ -87,6 +88,7 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static MaterialArgs material_args(const PxbScene* s) { MaterialArgs M; M.actorMat = s->actorMat; M.matTab = s->nMaterials ? s->matTab : nullptr; return M; }
 static TouchLists touch_lists(const PxbScene* s) { TouchLists T; T.state = s->touchState; T.found = s->touchFound; T.lost = s->touchLost; return T; }
 static HullArrays hull_arrays(const PxbScene* s) { HullArrays H; H.meta = s->hullMeta; H.verts = s->hullVerts; H.polys = s->hullPolys; H.refs = s->hullRefs; H.edges = s->hullEdges; return H; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (s) s->abort = true; return fail(PXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
@@ -755,6 +757,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->wake, A)); CK(dalloc(s->accLin, A)); CK(dalloc(s->accAng, A)); CK(dalloc(s->asleep, A)); CK(dalloc(s->nInter, A)); CK(dalloc(s->islandLabel, A)); CK(dalloc(s->islandAwake, A));
   CK(cudaMemsetAsync(s->accLin, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->accAng, 0, 16 * A, s->stream)); CK(cudaMemsetAsync(s->asleep, 0, 4 * A, s->stream)); CK(cudaMemsetAsync(s->nInter, 0, 4 * A, s->stream));
   { std::vector<float> w(A, 20.0f * 0.02f); CK(cudaMemcpyAsync(s->wake, w.data(), 4 * A, cudaMemcpyHostToDevice, s->stream)); CK(cudaStreamSynchronize(s->stream)); }   // PxRigidDynamic default wake counter
+  CK(dalloc(s->actorMat, A)); CK(cudaMemsetAsync(s->actorMat, 0, 4 * A, s->stream));
   CK(dalloc(s->touchState, Pn)); CK(cudaMemsetAsync(s->touchState, 0, 4 * Pn, s->stream)); CK(dalloc(s->touchFound, Pn)); CK(dalloc(s->touchLost, Pn));
   CK(dalloc(s->exportTab, 1)); CK(cudaMemsetAsync(s->exportTab, 0, sizeof(ExportTable), s->stream)); CK(dalloc(s->envDyn, A));
   CK(dalloc(s->bodyBest, A)); CK(dalloc(s->actorLocal, A)); CK(dalloc(s->slotColour, Pn)); CK(cudaMemsetAsync(s->slotColour, 0xff, 4 * Pn, s->stream)); for (int k = 0; k < 2; ++k) { CK(dalloc(s->envSeg[k], A)); CK(cudaMemsetAsync(s->envSeg[k], 0, sizeof(uint2) * A, s->stream)); }
@@ -808,7 +811,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->prevB0, s->prevB1, s->prevColour, s->prevNCon, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
-                  s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->touchState, s->touchFound, s->touchLost, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
+                  s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->actorMat, s->matTab, s->touchState, s->touchFound, s->touchLost, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->hostCounters) cudaFreeHost(s->hostCounters);
   cudaStreamDestroy(s->stream); if (s->copyStream) cudaStreamDestroy(s->copyStream); if (s->velEvent) cudaEventDestroy(s->velEvent); if (s->orderEvent) cudaEventDestroy(s->orderEvent);
@@ -1009,13 +1012,29 @@ PXB_API int pxb_scene_set_convex_meshes(PxbScene* s, const void* cooked, size_t 
   return PXB_OK;
 }
 
+PXB_API int pxb_scene_set_materials(PxbScene* s, const PxbMaterial* m, uint32_t nb) { DeviceGuard dg_(s);
+  if (!s || (nb && !m)) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->nA) return fail(PXB_ERR_INVALID, "the material table is set before the actors that refer to it");
+  std::vector<float4> tab(nb);
+  for (uint32_t i = 0; i < nb; ++i) {
+    if (m[i].restitution < 0.f) return fail(PXB_ERR_UNSUPPORTED, "compliant contacts (negative restitution) are not supported");
+    if ((m[i].bits & 15u) > 3u || ((m[i].bits >> 4) & 15u) > 3u || (m[i].bits >> 9)) return fail(PXB_ERR_UNSUPPORTED, "unknown combine mode or unsupported material flag (only eDISABLE_FRICTION)");
+    float w; memcpy(&w, &m[i].bits, 4); tab[i] = make_float4(m[i].staticFriction, m[i].dynamicFriction, m[i].restitution, w);
+  }
+  if (s->matTab) { cudaFree(s->matTab); s->matTab = nullptr; }
+  s->nMaterials = 0;
+  if (!nb) return PXB_OK;
+  CK(dalloc(s->matTab, nb)); CK(cudaMemcpyAsync(s->matTab, tab.data(), 16 * (size_t)nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaStreamSynchronize(s->stream));
+  s->nMaterials = nb; drop_graphs(s);
+  return PXB_OK;
+}
 PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) { DeviceGuard dg_(s);
   if (!s || !recsIn) return fail(PXB_ERR_INVALID, "null argument");
   if (s->abort) return fail(PXB_ERR_CUDA, "scene is in abort mode");
   if (s->nA + nb > s->capA) return fail(PXB_ERR_CAPACITY, "maxActors exceeded");
   const ActorRec* in = (const ActorRec*)recsIn;
   const uint32_t base = s->nA;
-  std::vector<float4> pos(nb), quat(nb), lin(nb), ang(nb), inv(nb), dmp(nb), dims(nb); std::vector<uint32_t> env(nb);
+  std::vector<float4> pos(nb), quat(nb), lin(nb), ang(nb), inv(nb), dmp(nb), dims(nb); std::vector<uint32_t> env(nb), mat(nb);
   for (uint32_t i = 0; i < nb; ++i) {   // first pass: every record is checked before any host state changes (a rejected batch leaves the scene untouched)
     const ActorRec& r = in[i];
     if (r.geomType == PXB_GEOM_CONVEXMESH) { if (r.hullIdx >= s->nHulls) return fail(PXB_ERR_UNSUPPORTED, "convex actor without a cooked hull: call pxb_scene_set_convex_meshes first"); }
@@ -1033,14 +1052,14 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
     lin[i] = make_float4(r.linVel[0], r.linVel[1], r.linVel[2], 0.f); ang[i] = make_float4(r.angVel[0], r.angVel[1], r.angVel[2], 0.f);
     inv[i] = make_float4(dyn && r.inertia[0] > 0.f ? 1.0f / r.inertia[0] : 0.f, dyn && r.inertia[1] > 0.f ? 1.0f / r.inertia[1] : 0.f, dyn && r.inertia[2] > 0.f ? 1.0f / r.inertia[2] : 0.f, r.maxDepenetrationVel);
     dmp[i] = make_float4(r.linDamping, r.angDamping, r.maxLinVel * r.maxLinVel, r.maxAngVel * r.maxAngVel);
-    dims[i] = make_float4(r.dims[0], r.dims[1], r.dims[2], r.dims[3]); env[i] = r.envId;
+    dims[i] = make_float4(r.dims[0], r.dims[1], r.dims[2], r.dims[3]); env[i] = r.envId; mat[i] = (s->nMaterials && r.materialIndex < s->nMaterials) ? r.materialIndex : 0u;
     if (r.geomType == PXB_GEOM_CONVEXMESH) memcpy(&dims[i].x, &r.hullIdx, 4);   // convex actors carry their hull index where the primitives carry their size
   }
   s->nA += nb;
   CK(cudaMemcpyAsync(s->pos + base, pos.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->quat + base, quat.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->linVel + base, lin.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->angVel + base, ang.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->invInertia + base, inv.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->damp + base, dmp.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream));
-  CK(cudaMemcpyAsync(s->dims + base, dims.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->envId + base, env.data(), 4 * nb, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->dims + base, dims.data(), 16 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->envId + base, env.data(), 4 * nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->actorMat + base, mat.data(), 4 * nb, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->dynActorDev, s->dynActor.data(), 4 * s->nDyn, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->counters + C_NA, &s->nA, 4, cudaMemcpyHostToDevice, s->stream));
   CK(cudaStreamSynchronize(s->stream));
@@ -1206,7 +1225,8 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     const bool fusedExport = s->exportOn && s->envDynContiguous;
     A.exportTab = fusedExport ? s->exportTab : nullptr; A.envDyn = s->envDyn; A.dynActor = s->dynActorDev;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
-    const bool ext = s->anyLocks || s->forcesUsed;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
+    A.M = material_args(s);
+    const bool ext = s->anyLocks || s->forcesUsed || s->nMaterials != 0;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
     pxb_launch_env_solve(st, A, s->envSolveThreads, pgs, ext, smem);
     s->launches++;
     if (s->exportOn && !fusedExport) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
@@ -1260,7 +1280,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     Rows R; R.f = s->ptA; R.broken = s->conDone; R.stride = s->capPairs;
     PrepArgs PA;
     PA.counters = s->counters; PA.ordered = s->ordered; PA.conPair = s->conPair; PA.pairSlots = s->pairSlots[cur]; PA.pairBodies = s->pairBodies; PA.geomFlags = s->geomFlags; PA.cHdr = s->cHdr; PA.cPts = s->cPts;
-    PA.pos = s->pos; PA.quat = s->quat; PA.linVel = s->linVel; PA.sbOrigAng = s->sbOrigAng; PA.invInertia = s->invInertia; PA.sbIA = s->sbIA; PA.sbIB = s->sbIB; PA.frictions = s->frictions; PA.P = P; PA.R = R;
+    PA.pos = s->pos; PA.quat = s->quat; PA.linVel = s->linVel; PA.sbOrigAng = s->sbOrigAng; PA.invInertia = s->invInertia; PA.sbIA = s->sbIA; PA.sbIB = s->sbIB; PA.frictions = s->frictions; PA.P = P; PA.R = R; PA.M = material_args(s);
     pxb_launch_prep_rows(st, pgs, s->capPairs, PA); s->launches++;
     MARK(4);
     SolveArgs VA;

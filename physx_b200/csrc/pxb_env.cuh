@@ -154,6 +154,7 @@ struct EnvSolveArgs {
   uint32_t* counters; unsigned long long* timing; SleepArgs S;
   uint32_t anyLocks;   // some actor carries PxRigidDynamicLockFlags (uniform fast path otherwise)
   float4 *extForce, *extTorque;   // pending eFORCE / eTORQUE writes (NULL until the application uses them)
+  MaterialArgs M;   // material table (matTab NULL: the scene's single material in P)
   const ExportTable* exportTab; const uint2* envDyn; const uint32_t* dynActor;   // fused state export: targets, per environment {first dynamic-body index, count}
 };
 #ifdef PXB_ENV_TIMING
@@ -183,13 +184,14 @@ PXB_D void f4set(float4& v, int j, float x) { if (j == 0) v.x = x; else if (j ==
 // a14 into registers: same arithmetic as prep_constraint (createFinalizeSolverContactsStep, DyTGSContactPrep.cpp:1297-1490;
 // friction correlation DyFrictionCorrelation.cpp:56-330).
 __device__ __forceinline__ void prep_constraint_regs(RegRows& r, uint32_t i, uint32_t b0, uint32_t b1, const PrepBodies& B, const float4* __restrict__ cHdr,
-                                                     const float4* __restrict__ cPts, float4* __restrict__ frec, const SolverParams& P) {
+                                                     const float4* __restrict__ cPts, float4* __restrict__ frec, const SolverParams& P, const bool noFriction = false) {
   Contacts con; const float4 h = cHdr[i]; con.normal = V3(h.x, h.y, h.z); con.count = __float_as_int(h.w);
 #pragma unroll
   for (int j = 0; j < 4; ++j) { const float4 p = cPts[(size_t)i * 4 + j]; con.point[j] = V3(p.x, p.y, p.z); con.sep[j] = p.w; }
   const xf& f0 = B.f0; const xf& f1 = B.f1;
   FrictionPatch fp; friction_load(fp, frec);
   friction_correlate(fp, con, f0, f1, P.staticFriction, P.dynamicFriction, P.restitution, P.correlationDistance, P.frictionOffsetThreshold + P.restDistance);
+  if (noFriction) fp.anchorCount = 0;   // PxMaterialFlag::eDISABLE_FRICTION: no friction rows (haveFriction = !disableStrongFriction && anchorCount != 0)
   friction_store(fp, frec);
   const float maxPenBias = fmax_(B.pen0, B.pen1);
   const v3 linVel0 = B.linVel0, linVel1 = B.linVel1, angVel0 = B.angVel0, angVel1 = B.angVel1;
@@ -361,7 +363,7 @@ PXB_D void rows_store_state(const Rows& R, uint32_t k, const RegRows& r) { const
 struct ConLists { uint32_t *conPair, *b0, *b1, *colour, *ordered; };   // per-constraint scratch of one environment (shared memory, or global when it does not fit)
 
 // vLin / vAng: per-body pre-solver (unconstrained) linear and world angular velocity
-template <bool PGS>
+template <bool PGS, bool EXT>
 __device__ __forceinline__ void env_prep_one(const EnvSolveArgs& A, const ConLists& L, uint32_t base, uint32_t pos, const float4* vLin, const float4* bIA, const float4* bIB, const float4* vAng, RegRows& r) {
   const uint32_t k = L.ordered[pos]; const uint32_t i = base + L.conPair[k];
   const uint32_t l0 = L.b0[k], l1 = L.b1[k];
@@ -374,6 +376,12 @@ __device__ __forceinline__ void env_prep_one(const EnvSolveArgs& A, const ConLis
   B.linVel0 = V3(vLin[l0]); B.angVel0 = V3(vAng[l0]); B.sI0 = load_sym(bIA[l0], bIB[l0]);
   if (dyn1) { B.linVel1 = V3(vLin[l1]); B.angVel1 = V3(vAng[l1]); B.sI1 = load_sym(bIA[l1], bIB[l1]); }
   else { B.linVel1 = V3(0, 0, 0); B.angVel1 = V3(0, 0, 0); B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
+  if (EXT && A.M.matTab) {   // material table: this pair's combined coefficients (the plain instantiation carries none of this)
+    SolverParams Pm = A.P; const bool noFriction = pair_material(A.M, bb.x, bb.y, Pm);
+    if (PGS) prep_constraint_pgs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, Pm, noFriction);
+    else prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, Pm, noFriction);
+    return;
+  }
   if (PGS) prep_constraint_pgs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.P);
   else prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.P);
 }
@@ -408,8 +416,8 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
   RegRows mine;
   const float4* vLin = PGS ? bDLin : bLin; const float4* vAng = PGS ? bDAng : bQ;
   const FrView fr = {sFr + tid, T};
-  if (REG) { if (tid < nCon) { env_prep_one<PGS>(A, L, base, tid, vLin, bIA, bIB, vAng, mine); fr_spill(fr, mine); } }
-  else for (uint32_t pos = tid; pos < nCon; pos += T) { RegRows r; env_prep_one<PGS>(A, L, base, pos, vLin, bIA, bIB, vAng, r); rows_store(R, pos, r); }
+  if (REG) { if (tid < nCon) { env_prep_one<PGS, EXT>(A, L, base, tid, vLin, bIA, bIB, vAng, mine); fr_spill(fr, mine); } }
+  else for (uint32_t pos = tid; pos < nCon; pos += T) { RegRows r; env_prep_one<PGS, EXT>(A, L, base, pos, vLin, bIA, bIB, vAng, r); rows_store(R, pos, r); }
   __syncthreads();
   ENV_T(4);
   if (PGS) {

@@ -11,7 +11,7 @@ void pxb_launch_env_solve(cudaStream_t st, const EnvSolveArgs& A, uint32_t threa
 
 struct PrepArgs {
   const uint32_t *counters, *ordered, *conPair, *pairSlots; const uint2* pairBodies; const uint32_t* geomFlags; const float4 *cHdr, *cPts, *pos, *quat, *linVel, *sbOrigAng, *invInertia, *sbIA, *sbIB;
-  float4* frictions; SolverParams P; Rows R;
+  float4* frictions; SolverParams P; Rows R; MaterialArgs M;
 };
 struct SolveArgs {
   uint32_t *counters, *partStart; uint32_t posIters, velIters; float stepDt; Rows R;

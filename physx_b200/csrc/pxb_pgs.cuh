@@ -16,13 +16,14 @@
 #pragma once
 
 __device__ __forceinline__ void prep_constraint_pgs(RegRows& r, uint32_t i, uint32_t b0, uint32_t b1, const PrepBodies& B, const float4* __restrict__ cHdr,
-                                                    const float4* __restrict__ cPts, float4* __restrict__ frec, const SolverParams& P) {
+                                                    const float4* __restrict__ cPts, float4* __restrict__ frec, const SolverParams& P, const bool noFriction = false) {
   Contacts con; const float4 h = cHdr[i]; con.normal = V3(h.x, h.y, h.z); con.count = __float_as_int(h.w);
 #pragma unroll
   for (int j = 0; j < 4; ++j) { const float4 p = cPts[(size_t)i * 4 + j]; con.point[j] = V3(p.x, p.y, p.z); con.sep[j] = p.w; }
   const xf& f0 = B.f0; const xf& f1 = B.f1;
   FrictionPatch fp; friction_load(fp, frec);
   friction_correlate(fp, con, f0, f1, P.staticFriction, P.dynamicFriction, P.restitution, P.correlationDistance, P.frictionOffsetThreshold + P.restDistance);
+  if (noFriction) fp.anchorCount = 0;   // PxMaterialFlag::eDISABLE_FRICTION
   friction_store(fp, frec);
   const float maxPenBias = fmax_(B.pen0, B.pen1);
   const v3 linVel0 = B.linVel0, linVel1 = B.linVel1, angVel0 = B.angVel0, angVel1 = B.angVel1;
@@ -207,7 +208,7 @@ template <bool PGS>
 __global__ void __launch_bounds__(128) k_prep_rows(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ ordered, const uint32_t* __restrict__ conPair, const uint32_t* __restrict__ pairSlots,
                        const uint2* __restrict__ pairBodies, const uint32_t* __restrict__ geomFlags, const float4* __restrict__ cHdr, const float4* __restrict__ cPts,
                        const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ linVel, const float4* __restrict__ sbOrigAng,
-                       const float4* __restrict__ invInertia, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, float4* __restrict__ frictions, SolverParams P, Rows R) {
+                       const float4* __restrict__ invInertia, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, float4* __restrict__ frictions, SolverParams P, Rows R, const MaterialArgs M) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= counters[C_NCON]) return;
   const uint32_t c = ordered[k]; const uint32_t i = conPair[c];
@@ -229,8 +230,10 @@ __global__ void __launch_bounds__(128) k_prep_rows(const uint32_t* __restrict__ 
   B.angVel0 = V3(sbOrigAng[b0]); B.angVel1 = dyn1 ? V3(sbOrigAng[b1]) : V3(0, 0, 0);
   B.sI0 = load_sym(sbIA[b0], sbIB[b0]);
   if (dyn1) B.sI1 = load_sym(sbIA[b1], sbIB[b1]); else { B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
-  if (PGS) prep_constraint_pgs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P);
-  else prep_constraint_regs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P);
+  bool noFriction = false;
+  if (M.matTab) noFriction = pair_material(M, b0, b1, P);   // material table: this pair's combined coefficients (P is this thread's copy)
+  if (PGS) prep_constraint_pgs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, noFriction);
+  else prep_constraint_regs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, noFriction);
   rows_store(R, k, r);
 }
 

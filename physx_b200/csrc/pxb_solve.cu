@@ -10,8 +10,8 @@ cudaError_t pxb_solve_occupancy(int* tgs, int* pgs) {
 }
 void pxb_launch_prep_rows(cudaStream_t st, bool pgs, uint32_t capPairs, const PrepArgs& A) {
   const uint32_t grid = (capPairs + 127) / 128;
-  if (pgs) k_prep_rows<true><<<grid, 128, 0, st>>>(A.counters, A.ordered, A.conPair, A.pairSlots, A.pairBodies, A.geomFlags, A.cHdr, A.cPts, A.pos, A.quat, A.linVel, A.sbOrigAng, A.invInertia, A.sbIA, A.sbIB, A.frictions, A.P, A.R);
-  else k_prep_rows<false><<<grid, 128, 0, st>>>(A.counters, A.ordered, A.conPair, A.pairSlots, A.pairBodies, A.geomFlags, A.cHdr, A.cPts, A.pos, A.quat, A.linVel, A.sbOrigAng, A.invInertia, A.sbIA, A.sbIB, A.frictions, A.P, A.R);
+  if (pgs) k_prep_rows<true><<<grid, 128, 0, st>>>(A.counters, A.ordered, A.conPair, A.pairSlots, A.pairBodies, A.geomFlags, A.cHdr, A.cPts, A.pos, A.quat, A.linVel, A.sbOrigAng, A.invInertia, A.sbIA, A.sbIB, A.frictions, A.P, A.R, A.M);
+  else k_prep_rows<false><<<grid, 128, 0, st>>>(A.counters, A.ordered, A.conPair, A.pairSlots, A.pairBodies, A.geomFlags, A.cHdr, A.cPts, A.pos, A.quat, A.linVel, A.sbOrigAng, A.invInertia, A.sbIA, A.sbIB, A.frictions, A.P, A.R, A.M);
 }
 cudaError_t pxb_launch_solve(cudaStream_t st, bool pgs, int blocks, SolveArgs& A) {
   if (pgs) {

@@ -31,7 +31,7 @@ EXPORTS = [
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
     "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait", "pxb_bp_create", "pxb_bp_release", "pxb_bp_update", "pxb_bp_fetch",
-    "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost",
+    "pxb_scene_set_materials", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
@@ -75,6 +75,7 @@ def load_library():
     lib.pxb_scene_release.restype = None
     lib.pxb_last_error.restype = ctypes.c_char_p
     lib.pxb_scene_add_actors.argtypes = [vp, vp, u32]
+    lib.pxb_scene_set_materials.argtypes = [vp, vp, u32]
     for f in ("pxb_scene_num_actors", "pxb_scene_num_dynamic", "pxb_scene_num_pairs", "pxb_scene_num_created",
               "pxb_scene_num_deleted", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
               "pxb_scene_last_num_launches", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost"):
@@ -155,6 +156,10 @@ class Scene:
         _check(lib, lib.pxb_scene_create(ctypes.byref(d), ctypes.byref(self._h)))
         if scene.cooked:   # cooked convex hulls (reference cooking output carried by the scene) go in before the actors that use them
             _check(lib, lib.pxb_scene_set_convex_meshes(self._h, scene.cooked, len(scene.cooked), len(scene.hulls)))
+        mats = getattr(scene, "materials", None)
+        if mats is not None and len(mats):   # material table (PxMaterial per shape): before the actors that refer to it
+            mm = np.ascontiguousarray(mats)
+            _check(lib, lib.pxb_scene_set_materials(self._h, _ptr(mm), len(mm)))
         recs = np.ascontiguousarray(scene.actors)
         _check(lib, lib.pxb_scene_add_actors(self._h, _ptr(recs), len(recs)))
         self.num_actors = int(lib.pxb_scene_num_actors(self._h))

@@ -679,3 +679,29 @@ def env_hulls(n_envs=6, per_env=7, seed=8, env_pitch=6.0, **hdr):
             a["envId"][i] = e
     a["quat"] = random_unit_quats(rng, len(a))
     return Scene(default_header(**hdr), add_ground_plane(a), clouds, cooked)
+
+
+def material_mix(n_boxes=12, n_spheres=8, seed=5, **hdr):
+    """a11: a material table with every combine mode and eDISABLE_FRICTION.  Boxes slide on the ground plane with an initial lateral velocity
+    (combined friction decides where they stop), pairs of stacked boxes carry different materials, spheres are dropped from 1.5 m (combined
+    restitution decides the bounce).  Bodies are far enough apart to be independent islands."""
+    rng = np.random.RandomState(seed)
+    mats = make_materials([(0.5, 0.5, 0.6, COMBINE_AVERAGE, COMBINE_AVERAGE), (0.9, 0.8, 0.1, COMBINE_MAX, COMBINE_MIN), (0.2, 0.1, 0.0, COMBINE_MULTIPLY, COMBINE_MULTIPLY),
+                           (0.6, 0.4, 0.3, COMBINE_MIN, COMBINE_MAX, True), (0.3, 0.7, 0.9, COMBINE_AVERAGE, COMBINE_MAX)])
+    n = 2 * n_boxes + n_spheres
+    a = _new_actors(n)
+    he = np.float32(0.25)
+    for i in range(n_boxes):          # lower box slides, upper box rides on it
+        x = np.float32(3.0 * i)
+        a["pos"][2 * i] = (x, he, 0.0); a["pos"][2 * i + 1] = (x, 3 * he, 0.0)
+        a["linVel"][2 * i] = (1.5, 0.0, 0.8); a["linVel"][2 * i + 1] = (1.5, 0.0, 0.8)
+        a["materialIndex"][2 * i] = i % len(mats); a["materialIndex"][2 * i + 1] = (i // 2 + 1) % len(mats)
+    set_box(a, np.arange(2 * n_boxes), np.array([he, he, he], dtype=np.float32))
+    for k in range(n_spheres):
+        j = 2 * n_boxes + k
+        a["pos"][j] = (np.float32(3.0 * k), 1.5, 4.0)
+        a["materialIndex"][j] = (k * 2 + 1) % len(mats)
+    set_sphere(a, np.arange(2 * n_boxes, n), np.float32(0.2))
+    sc = Scene(default_header(**hdr), add_ground_plane(a), materials=mats)
+    sc.actors["materialIndex"][0] = 4     # the plane has its own material
+    return sc

@@ -135,6 +135,9 @@ def main():
     cases["big_hull_pile"] = (scenes.hull_pile(n=12, seed=35, kinds=("convex", "convex", "box", "convex", "sphere", "capsule"), hull_points=(40, 64), cook=cook_hulls), 150)
     # BASELINE config 3 at small size (spheres / capsules / library hulls falling into a walled bin): every hull pair type in one scene
     cases["config3_small"] = (scenes.falling_primitives(4, 3, 4, kinds=("sphere", "capsule", "convex")), 110)
+    # a11: material table (every PxCombineMode, eDISABLE_FRICTION): sliding / stacked boxes and bouncing spheres, TGS and PGS
+    cases["materials_mix"] = (scenes.material_mix(), 90)
+    cases["pgs_materials_mix"] = (scenes.material_mix(solver=scenes.SOLVER_PGS), 90)
     cases["capsules_into_boxes"] = (scenes.capsules_into_boxes(seed=3), 60)   # deep penetration: the EPA query
     # a19: PxDirectGPUAPI eFORCE / eTORQUE writes (= addForce / addTorque(eFORCE) before every step), a 7-step cycle of per-body forces
     forced = {"forces_stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01),

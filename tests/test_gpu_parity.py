@@ -888,3 +888,42 @@ def test_touch_events_match_the_reference_contact_reports():
         assert {(int(a), int(b)) for a, b in gpu.getTouchFound()} == cur - prev, f"touch found, step {t}"
         assert {(int(a), int(b)) for a, b in gpu.getTouchLost()} == prev - cur, f"touch lost, step {t}"
         prev = cur
+
+
+# ---- a11: material table / combine modes ----
+@pytest.mark.parametrize("solver", ["tgs", "pgs"])
+@pytest.mark.parametrize("path", ["auto", "devicewide"])
+def test_material_table_gpu_matches_oracle(oracle, solver, path):
+    """pxb_scene_set_materials: per-pair combined friction / restitution (every PxCombineMode, eDISABLE_FRICTION) on both paths and both solvers,
+    step by step against the oracle (itself pinned against the reference: test_material_table_matches_reference)."""
+    sc = scenes.material_mix(solver=scenes.SOLVER_PGS if solver == "pgs" else scenes.SOLVER_TGS)
+    gpu, cpu = engine.Scene(sc, env_path=(path == "auto")), oracle.OracleScene(sc)
+    for t in range(90):
+        gpu.step(); cpu.step()
+        assert gpu.uses_env_path == (path == "auto")
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pair set, step {t}"
+        cg, cc = gpu.getContacts(), cpu.getContacts()
+        assert np.array_equal(cg[:, 0], cc[:, 0]) and np.abs(cg - cc).max(initial=0) < 1e-4, f"contacts / applied forces, step {t}"
+        sg = gpu.getStates()
+        assert np.abs(sg - cpu.getStates()).max() < TOL_STEP, f"state, step {t}"
+        cpu.setStates(sg)
+
+
+def test_material_table_gpu_matches_reference_golden():
+    z, sc = util.load_golden("materials_mix")
+    gpu = engine.Scene(sc, env_path=False)
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setStates(z["states"][t])
+        gpu.setConstraintOrder(util.golden_order(z, t))
+        gpu.step()
+        st, ref = gpu.getStates(), z["states"][t + 1]
+        assert np.abs(st[:, :7] - ref[:, :7]).max() < 2e-5, f"pose, step {t}"
+        assert np.abs(st[:, 7:10] - ref[:, 7:10]).max() < 2e-4 and np.abs(st[:, 10:] - ref[:, 10:]).max() < 2e-3, f"velocity, step {t}"
+        assert util.contact_counts(gpu.getPairs(), gpu.getContacts()) == util.golden_contact_counts(z, t), f"manifolds, step {t}"
+
+
+def test_material_table_rejects_unsupported_entries():
+    sc = scenes.material_mix()
+    bad = sc.materials.copy(); bad["restitution"][1] = -100.0     # compliant contact
+    with pytest.raises(engine.PhysxB200Error):
+        engine.Scene(scenes.Scene(sc.header, sc.actors, materials=bad))
