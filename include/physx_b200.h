@@ -163,6 +163,17 @@ PXB_API int  pxb_scene_get_states(PxbScene* scene, float* out);
 PXB_API int  pxb_scene_set_states(PxbScene* scene, const float* in);
 PXB_API int  pxb_scene_get_states_device(PxbScene* scene, float* devOut); /* same record, device pointer; stream-ordered on the scene stream (may follow pxb_scene_simulate
                                                                               without a fetch: it packs the state that step produces, e.g. into an NCCL send buffer) */
+/* ---- tensor front end: device tensors in the wire formats of the reference's ovphysx bindings
+ *      (ovphysx/include/ovphysx/ovphysx.h, python/ovphysx/types.py TensorType; same enum values).  Rows follow dynamic-body order or `devIdx`.
+ *      Stream-ordered on the scene stream (no synchronisation); DLPack producers hand over the device pointer (physx_b200/tensor_api.py). ---- */
+enum { PXB_TENSOR_RIGID_BODY_POSE = 1,      /* [N,7] (p.xyz, q.xyzw), read / write */
+       PXB_TENSOR_RIGID_BODY_VELOCITY = 2,  /* [N,6] (linear, angular), read / write */
+       PXB_TENSOR_RIGID_BODY_MASS = 3,      /* [N] read */
+       PXB_TENSOR_RIGID_BODY_INV_MASS = 7,  /* [N] read */
+       PXB_TENSOR_RIGID_BODY_FORCE = 50,    /* [N,3] world-frame force at the centre of mass, write: applied by the next simulate only */
+       PXB_TENSOR_RIGID_BODY_WRENCH = 51 }; /* [N,9] (force, torque, application point in the world frame), write */
+PXB_API int  pxb_tensor_read_device(PxbScene* scene, int tensorType, void* devOut, const uint32_t* devIdx, uint32_t nb);
+PXB_API int  pxb_tensor_write_device(PxbScene* scene, int tensorType, const void* devIn, const uint32_t* devIdx, uint32_t nb);
 /* Multi-GPU exchange helper: ONE kernel stores `bytes` from devSrc into nDst <= 8 peer-mapped device buffers over NVLink (P2P). */
 PXB_API int  pxb_scatter_to_peers(PxbScene* scene, void* cudaStream, const void* devSrc, size_t bytes, const uint64_t* devDstPtrs, uint32_t nDst, uint32_t ctas);
 /* Fused state export.  From the next pxb_scene_simulate on, the step's integration epilogue stores every dynamic body's packed state record

@@ -646,6 +646,35 @@ __global__ void k_rd_set(uint32_t nb, const uint32_t* __restrict__ idx, const ui
   if (type == PXB_RD_GLOBAL_POSE) { const float* o = in + (size_t)i * 7; quat[a] = make_float4(o[0], o[1], o[2], o[3]); const float w = pos[a].w; pos[a] = make_float4(o[4], o[5], o[6], w); }
   else { const float* o = in + (size_t)i * 3; const float4 v = make_float4(o[0], o[1], o[2], 0.f); if (type == PXB_RD_LINEAR_VELOCITY) linVel[a] = v; else angVel[a] = v; }
 }
+// f3: tensor front end in the reference's ovphysx wire formats (ovphysx/python/ovphysx/types.py TensorType): pose [N,7] = (p.xyz, q.xyzw), velocity
+// [N,6] = (linear, angular), mass / inverse mass [N], force [N,3], wrench [N,9] = (force, torque, application point in the world frame).
+__global__ void k_tensor_read(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, int type, const float4* __restrict__ pos, const float4* __restrict__ quat,
+                              const float4* __restrict__ linVel, const float4* __restrict__ angVel, float* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const uint32_t a = dynActor[idx ? idx[i] : i];
+  if (type == PXB_TENSOR_RIGID_BODY_POSE) { const float4 q = quat[a], p = pos[a]; float* o = out + (size_t)i * 7; o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = q.x; o[4] = q.y; o[5] = q.z; o[6] = q.w; }
+  else if (type == PXB_TENSOR_RIGID_BODY_VELOCITY) { const float4 v = linVel[a], w = angVel[a]; float* o = out + (size_t)i * 6; o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = w.x; o[4] = w.y; o[5] = w.z; }
+  else { const float im = pos[a].w; out[i] = type == PXB_TENSOR_RIGID_BODY_INV_MASS ? im : (im > 0.f ? 1.0f / im : 0.f); }
+}
+__global__ void k_tensor_write(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, int type, float4* __restrict__ pos, float4* __restrict__ quat,
+                               float4* __restrict__ linVel, float4* __restrict__ angVel, const float* __restrict__ in, float* __restrict__ wake, uint32_t* __restrict__ asleep,
+                               float4* __restrict__ extForce, float4* __restrict__ extTorque) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const uint32_t a = dynActor[idx ? idx[i] : i];
+  if (type == PXB_TENSOR_RIGID_BODY_FORCE || type == PXB_TENSOR_RIGID_BODY_WRENCH) {   // applied by the next step only (PxRigidBody::addForce / addTorque, eFORCE)
+    const float* o = in + (size_t)i * (type == PXB_TENSOR_RIGID_BODY_FORCE ? 3 : 9);
+    const v3 F = V3(o[0], o[1], o[2]); v3 T = V3(0, 0, 0);
+    if (type == PXB_TENSOR_RIGID_BODY_WRENCH) { const float4 p = pos[a]; T = V3(o[3], o[4], o[5]) + cross(V3(o[6], o[7], o[8]) - V3(p.x, p.y, p.z), F); extTorque[a] = F4(T, 0.f); }
+    extForce[a] = F4(F, 0.f);
+    if (F.x != 0.f || F.y != 0.f || F.z != 0.f || T.x != 0.f || T.y != 0.f || T.z != 0.f) { if (wake[a] < 20.0f * 0.02f) wake[a] = 20.0f * 0.02f; asleep[a] = 0u; }
+    return;
+  }
+  wake[a] = 20.0f * 0.02f; asleep[a] = 0u;
+  if (type == PXB_TENSOR_RIGID_BODY_POSE) { const float* o = in + (size_t)i * 7; const float w = pos[a].w; pos[a] = make_float4(o[0], o[1], o[2], w); quat[a] = make_float4(o[3], o[4], o[5], o[6]); }
+  else { const float* o = in + (size_t)i * 6; linVel[a] = make_float4(o[0], o[1], o[2], 0.f); angVel[a] = make_float4(o[3], o[4], o[5], 0.f); }
+}
 __global__ void k_states_get(uint32_t nDyn, const uint32_t* __restrict__ dynActor, const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ linVel,
                              const float4* __restrict__ angVel, float* __restrict__ out) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1759,6 +1788,32 @@ PXB_API int pxb_bp_fetch(PxbBroadPhase* b, const uint32_t** createdPairs, uint32
   return PXB_OK;
 }
 
+// f3 tensor front end (include/physx_b200.h): device tensors in the ovphysx wire formats, stream-ordered on the scene stream.
+PXB_API int pxb_tensor_read_device(PxbScene* s, int tensorType, void* devOut, const uint32_t* devIdx, uint32_t nb) { DeviceGuard dg_(s);
+  if (!s || !devOut) return fail(PXB_ERR_INVALID, "null argument");
+  if (tensorType != PXB_TENSOR_RIGID_BODY_POSE && tensorType != PXB_TENSOR_RIGID_BODY_VELOCITY && tensorType != PXB_TENSOR_RIGID_BODY_MASS && tensorType != PXB_TENSOR_RIGID_BODY_INV_MASS)
+    return fail(PXB_ERR_INVALID, "tensor type is not readable");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running");
+  if (!devIdx && nb > s->nDyn) return fail(PXB_ERR_INVALID, "nb exceeds the number of dynamic bodies");
+  if (!nb) return PXB_OK;
+  if (int rc = join_pending(s)) return rc;
+  k_tensor_read<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, devIdx, s->dynActorDev, tensorType, s->pos, s->quat, s->linVel, s->angVel, (float*)devOut);
+  CK(cudaGetLastError());
+  return PXB_OK;
+}
+PXB_API int pxb_tensor_write_device(PxbScene* s, int tensorType, const void* devIn, const uint32_t* devIdx, uint32_t nb) { DeviceGuard dg_(s);
+  if (!s || !devIn) return fail(PXB_ERR_INVALID, "null argument");
+  if (tensorType != PXB_TENSOR_RIGID_BODY_POSE && tensorType != PXB_TENSOR_RIGID_BODY_VELOCITY && tensorType != PXB_TENSOR_RIGID_BODY_FORCE && tensorType != PXB_TENSOR_RIGID_BODY_WRENCH)
+    return fail(PXB_ERR_INVALID, "tensor type is not writable");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running");
+  if (!devIdx && nb > s->nDyn) return fail(PXB_ERR_INVALID, "nb exceeds the number of dynamic bodies");
+  if (!nb) return PXB_OK;
+  if ((tensorType == PXB_TENSOR_RIGID_BODY_FORCE || tensorType == PXB_TENSOR_RIGID_BODY_WRENCH) && !s->forcesUsed) { s->forcesUsed = true; drop_graphs(s); }
+  if (int rc = join_pending(s)) return rc;
+  k_tensor_write<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, devIdx, s->dynActorDev, tensorType, s->pos, s->quat, s->linVel, s->angVel, (const float*)devIn, s->wake, s->asleep, s->extForce, s->extTorque);
+  CK(cudaGetLastError());
+  return PXB_OK;
+}
 PXB_API int pxb_scene_sync(PxbScene* s) { DeviceGuard dg_(s); if (!s) return fail(PXB_ERR_INVALID, "null scene"); CK(cudaStreamSynchronize(s->stream)); return PXB_OK; }
 
 // Packed 13-float state of every dynamic body written straight into a DEVICE buffer (e.g. this rank's slice of

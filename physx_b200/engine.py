@@ -31,7 +31,7 @@ EXPORTS = [
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
     "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait", "pxb_bp_create", "pxb_bp_release", "pxb_bp_update", "pxb_bp_fetch",
-    "pxb_scene_set_materials", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost",
+    "pxb_scene_set_materials", "pxb_tensor_read_device", "pxb_tensor_write_device", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
@@ -76,6 +76,8 @@ def load_library():
     lib.pxb_last_error.restype = ctypes.c_char_p
     lib.pxb_scene_add_actors.argtypes = [vp, vp, u32]
     lib.pxb_scene_set_materials.argtypes = [vp, vp, u32]
+    lib.pxb_tensor_read_device.argtypes = [vp, i32, vp, vp, u32]
+    lib.pxb_tensor_write_device.argtypes = [vp, i32, vp, vp, u32]
     for f in ("pxb_scene_num_actors", "pxb_scene_num_dynamic", "pxb_scene_num_pairs", "pxb_scene_num_created",
               "pxb_scene_num_deleted", "pxb_scene_last_num_partitions", "pxb_scene_last_num_constraints",
               "pxb_scene_last_num_launches", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost"):
@@ -152,6 +154,7 @@ class Scene:
         d.reserved[4] = int(np.float32(h["sleepThreshold"]).view(np.uint32))   # sleep threshold as float bits (0 = sleeping off)
         d.reserved[3] = int(env_threads)
         self.dt = float(h["dt"])
+        self.device_index = int(device)
         self._h = ctypes.c_void_p()
         _check(lib, lib.pxb_scene_create(ctypes.byref(d), ctypes.byref(self._h)))
         if scene.cooked:   # cooked convex hulls (reference cooking output carried by the scene) go in before the actors that use them

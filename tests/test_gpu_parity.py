@@ -927,3 +927,45 @@ def test_material_table_rejects_unsupported_entries():
     bad = sc.materials.copy(); bad["restitution"][1] = -100.0     # compliant contact
     with pytest.raises(engine.PhysxB200Error):
         engine.Scene(scenes.Scene(sc.header, sc.actors, materials=bad))
+
+
+# ---- f3: tensor front end (ovphysx-style TensorBinding over DLPack / torch tensors) ----
+def test_tensor_binding_reads_and_writes_device_and_host_tensors():
+    import torch
+    from physx_b200 import tensor_api as ta
+    sc = scenes.env_grid_stacks(n_envs=8, jitter=0.01)
+    gpu = engine.Scene(sc)
+    for _ in range(3):
+        gpu.step()
+    st = gpu.getStates()
+    n = gpu.num_dynamic
+    pose = ta.TensorBinding(gpu, ta.TensorType.RIGID_BODY_POSE); vel = ta.TensorBinding(gpu, ta.TensorType.RIGID_BODY_VELOCITY)
+    assert pose.shape == (n, 7) and vel.shape == (n, 6) and pose.count == n
+    p = torch.empty((n, 7), dtype=torch.float32, device="cuda"); v = np.empty((n, 6), np.float32)
+    pose.read(p); vel.read(v)                                   # CUDA tensor and host array
+    assert np.array_equal(p.cpu().numpy(), st[:, :7]) and np.array_equal(v, st[:, 7:13])       # (p, q) and (lin, ang): the packed state's own order
+    m = torch.empty(n, dtype=torch.float32, device="cuda"); ta.TensorBinding(gpu, ta.TensorType.RIGID_BODY_MASS).read(m)
+    assert np.allclose(m.cpu().numpy(), sc.actors["mass"][1:], rtol=1e-6)
+    # write through DLPack with indices and with a mask
+    idx = torch.tensor([5, 1, 40], dtype=torch.int64)
+    newv = torch.arange(18, dtype=torch.float32, device="cuda").reshape(3, 6)
+    vel.write(torch.utils.dlpack.to_dlpack(newv) if False else newv, indices=idx)
+    vel.read(v)
+    assert np.array_equal(v[[5, 1, 40]], newv.cpu().numpy())
+    mask = np.zeros(n, bool); mask[[2, 7]] = True
+    newp = st[[2, 7], :7].copy(); newp[:, 1] += 1.0
+    pose.write(newp, mask=mask)
+    pose.read(p)
+    assert np.array_equal(p.cpu().numpy()[[2, 7]], newp)
+    with pytest.raises(ValueError):
+        pose.read(torch.empty((n, 6), dtype=torch.float32, device="cuda"))
+    with pytest.raises(ValueError):
+        ta.TensorBinding(gpu, ta.TensorType.RIGID_BODY_FORCE).read(p)
+    # forces: same effect as PXB_RD_FORCE on a twin scene
+    a, b = engine.Scene(sc), engine.Scene(sc)
+    F = np.zeros((n, 3), np.float32); F[:, 0] = 3.0
+    ta.TensorBinding(a, ta.TensorType.RIGID_BODY_FORCE).write(F); b.setForces(forces=F)
+    a.step(); b.step()
+    assert np.array_equal(a.getStates(), b.getStates())
+    rep = ta.get_contact_report(a)
+    assert len(rep["actor0"]) == a.num_constraints and rep["counts"].sum() == len(rep["positions"]) and np.all(rep["impulses"] >= 0)
