@@ -113,11 +113,8 @@ class TensorBinding:
         st = self._scene_stream()
         st.wait_stream(torch.cuda.current_stream(self._device()))
         _engine._check(self.scene._lib, self.scene._lib.pxb_tensor_write_device(self.scene._h, int(self.tensor_type), dev.data_ptr(), idx.data_ptr() if idx is not None else None, rows))
-        torch.cuda.current_stream(self._device()).wait_stream(st)
-        if dev is not t or idx is not None:
-            dev.record_stream(st)
-            if idx is not None:
-                idx.record_stream(st)
+        torch.cuda.current_stream(self._device()).wait_stream(st)   # staging / index tensors are freed in current-stream order, i.e. after the kernel
+                                                                    # (no record_stream on the scene's stream: it may be destroyed before the tensors are)
 
 
 def get_contact_report(scene: _engine.Scene) -> dict:
