@@ -55,7 +55,7 @@ struct PxbScene {
   uint32_t *conFlag = 0, *conIdx = 0, *conPair = 0, *rankOfPair = 0; uint64_t *conSortKey = 0, *conSortKeyAlt = 0; uint32_t* conPairAlt = 0;
   uint64_t* orderKeys = 0; uint32_t nOrder = 0, capOrder = 0;
   uint32_t *conB0 = 0, *conB1 = 0, *conPos0 = 0, *conPos1 = 0, *conColour = 0, *conDone = 0, *bodyList = 0, *ordered = 0;
-  uint32_t *partCnt = 0, *partStart = 0, *partCursor = 0, *colourTicket = 0, *prevB0 = 0, *prevB1 = 0, *prevColour = 0, *prevNCon = 0; bool colourLegacy = false, colourPrefix = true; uint32_t colourBackoffNs = 100;
+  uint32_t *partCnt = 0, *partStart = 0, *partCursor = 0, *colourTicket = 0, *prevB0 = 0, *prevB1 = 0, *prevColour = 0, *prevNCon = 0; bool colourLegacy = false, colourPrefix = true; uint32_t colourBackoffNs = 400, colourWindow = 0;
   // rows (solve order)
   float4 *ptA = 0, *ptB = 0, *ptC = 0, *frA = 0, *frB = 0, *frC = 0, *frD = 0;
   uint32_t* counters = 0; uint32_t* hostCounters = 0;  // pinned mirror
@@ -809,6 +809,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->numSMs = prop.multiProcessorCount;
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_colour_partition, 256, 0)); s->coopBlocksColour = std::max(1, std::min(occ, 4)) * s->numSMs;
+  CK(cudaFuncSetAttribute(k_colour_firstfit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(pxb_env_set_attributes((int)ENV_SMEM_MAX, (int)(ENV_BP_WARPS * (ENV_MAX_LIST * 36 + ENV_BP_STAGE * 8))));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sleep_islands, 256, 0)); s->coopBlocksSleep = std::max(1, std::min(occ, 2)) * s->numSMs;
   { int occT = 0, occP = 0; CK(pxb_solve_occupancy(&occT, &occP));
@@ -819,7 +820,8 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   s->rsTmp.ctas = std::min<uint32_t>(RS_MAX_CTAS, (uint32_t)s->numSMs * 2);
   { const char* ng = getenv("PXB_NO_GRAPH"); if (ng && ng[0] == '1') s->useGraph = false; }
   { const char* cl = getenv("PXB_COLOUR_LEGACY"); if (cl && cl[0] == '1') s->colourLegacy = true; const char* cb = getenv("PXB_COLOUR_BACKOFF_NS"); if (cb) s->colourBackoffNs = (uint32_t)atoi(cb);
-    const char* cp = getenv("PXB_COLOUR_PREFIX"); if (cp && cp[0] == '0') s->colourPrefix = false; }   // A/B hooks of the exact colouring
+    const char* cp = getenv("PXB_COLOUR_PREFIX"); if (cp && cp[0] == '0') s->colourPrefix = false;
+    const char* cw = getenv("PXB_COLOUR_WINDOW"); if (cw) s->colourWindow = (uint32_t)atoi(cw); }   // A/B hooks of the exact colouring
   if (desc->reserved[1] & PXB_FLAG_NO_ENV_PATH) s->envDisabled = true;
   if (desc->reserved[1] & PXB_FLAG_RELAXED_PARTITIONING) { s->relaxedPartitioning = true; s->envDisabled = true; }
   s->envConCapForced = desc->reserved[2]; s->envThreadsForced = desc->reserved[3];
@@ -1290,7 +1292,10 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
         LAUNCH(k_colour_prefix_find, gP, B, s->counters, s->conB0, s->conB1, s->prevB0, s->prevB1, s->prevNCon, s->colourTicket);
         LAUNCH(k_colour_prefix_apply, gP, B, s->conB0, s->conB1, s->prevColour, s->conColour, s->bodyMask, s->colourTicket);
       }
-      LAUNCH(k_colour_firstfit, cdiv(s->capPairs, 128), 128, s->counters, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->bodyMask, s->colourTicket, s->colourBackoffNs);
+      // resident window: every resident thread polls L2 while it waits, so the number of resident CTAs is capped with a dynamic shared-memory
+      // request (colourWindow CTAs per SM); blocks behind the window wait in the hardware queue without polling
+      k_colour_firstfit<<<cdiv(s->capPairs, 128), 128, s->colourWindow ? (size_t)(200 * 1024) / s->colourWindow : 0, st>>>(s->counters, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->bodyMask,
+                                                                                                                              s->colourTicket, s->colourBackoffNs); s->launches++;
       relaxed = 2;
     }
     void* args[] = {&s->counters, &s->conB0, &s->conB1, &s->conPos0, &s->conPos1, &s->conColour, &s->conDone, &s->bodyNext, &s->bodyMask, &s->partCnt, &s->partStart, &s->partCursor, &s->ordered,
