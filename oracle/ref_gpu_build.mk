@@ -15,7 +15,7 @@ EXCL     := /windows/
 CU       := $(shell find $(addprefix $(S)/,$(GPUMODS)) -name '*.cu' | grep -Ev '$(EXCL)')
 CPP      := $(shell find $(addprefix $(S)/,$(GPUMODS)) -name '*.cpp' | grep -Ev '$(EXCL)')
 INCDIRS  := $(shell find $(S) -type d | grep -Ev '/windows|/omnipvd|/mac/|/switch/|/android/|compiler|/physxvehicle')
-INCS     := -I$(PX)/include $(addprefix -I,$(INCDIRS)) -I$(PX)/pvdruntime/include -I/usr/local/cuda/include
+INCS     := -I$(PX)/include $(addprefix -I,$(INCDIRS)) -I$(PX)/pvdruntime/include -I/usr/local/cuda/include -Ioracle/stubs
 DEFS     := -DNDEBUG -DPX_SUPPORT_PVD=0 -DPX_SUPPORT_OMNI_PVD=0 -DPX_PHYSX_STATIC_LIB -DPX_PHYSX_GPU_EXPORTS -DPX_PUBLIC_RELEASE=1 -DPX_NVTX=0 -D_CONSOLE
 CXXFLAGS := -O3 -std=c++14 -fno-rtti -fno-exceptions -fno-strict-aliasing -ffunction-sections -fdata-sections -fvisibility=hidden -fPIC -w $(DEFS)
 NVFLAGS  := -gencode arch=compute_100,code=sm_100 -O3 -std=c++14 -use_fast_math -ftz=true -prec-div=false -prec-sqrt=false -w $(DEFS) \

@@ -248,6 +248,13 @@ int main(int argc, char** argv) {
     sd.broadPhaseType = PxBroadPhaseType::eGPU;
     if (gpuDynamics) sd.flags |= PxSceneFlag::eENABLE_GPU_DYNAMICS;
     sd.gpuDynamicsConfig.foundLostPairsCapacity = PxMax(1u << 20, 8u * H.nActors);
+    if (gpuDynamics) {   // PxGpuDynamicsMemoryConfig sized for the scene (contacts >= 8 M, patches >= 2 M at BASELINE sizes)
+      sd.gpuDynamicsConfig.maxRigidContactCount = PxMax(1u << 20, 16u * H.nActors);
+      sd.gpuDynamicsConfig.maxRigidPatchCount = PxMax(1u << 18, 8u * H.nActors);
+      sd.gpuDynamicsConfig.tempBufferCapacity = PxMax(16u << 20, 256u * H.nActors);
+      sd.gpuDynamicsConfig.heapCapacity = PxMax(64u << 20, 1024u * H.nActors);
+      sd.gpuMaxNumPartitions = 8;
+    }
     fprintf(stderr, "GPU plugin: %s on %s\n", gpuPlugin ? gpuPlugin : "(default libPhysXGpu_64.so)", cudaMgr->getDeviceName());
   }
 #else
