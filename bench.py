@@ -187,6 +187,32 @@ def bench_reference(args):
     print(json.dumps(line))
 
 
+def second_baseline_block(config, envs, solver):
+    """SURVEY 8d "second baseline": the reference's OWN GPU plugin (built for sm_100 from its sources by oracle/ref_gpu_build.mk) inside the unmodified
+    host SDK on this GPU -- PxBroadPhaseType::eGPU + PxSceneFlag::eENABLE_GPU_DYNAMICS through the public PxScene API, simulate + fetchResults wall
+    time on the same scene.  Reported next to `cpu_baseline`; None when the binaries are not there or the config is not one it is run on."""
+    harness = os.path.join(ROOT, "oracle", "_ref_gpu", "ref_harness")
+    plugin = os.path.join(ROOT, "oracle", "_ref_gpu", "reference_plugin", "libPhysXGpu_64.so")
+    if config not in (1, 2, 5) or not (os.path.exists(harness) and os.path.exists(plugin)):
+        return None
+    sc, _ = build_scene(config, envs, solver=solver)
+    threads = min(8, os.cpu_count() or 1)
+    steps = 20 if config != 1 else 200
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            p = os.path.join(d, "s.bin")
+            sc.save(p)
+            r = subprocess.run([harness, "run", p, "--steps", str(steps), "--warmup", "5", "--threads", str(threads), "--gpu-plugin", plugin, "--gpu-bp", "--gpu-dynamics"],
+                               capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            return {"value": None, "error": r.stderr[-300:]}
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"value": j["body_steps_per_s"], "unit": UNIT, "ms_per_step": j["ms_per_step"], "kind": "reference GPU plugin (PhysX 5.6.1 libPhysXGpu_64.so, sm_100 build) in the unmodified host SDK",
+                "sample": f"the same scene at full size ({j['bodies']} bodies), {steps} steps after 5 untimed, eGPU broadphase + eENABLE_GPU_DYNAMICS, PxDefaultCpuDispatcher({threads}), state read back to the host by the SDK every step"}
+    except Exception as e:   # pragma: no cover
+        return {"value": None, "error": repr(e)[:300]}
+
+
 def cpu_baseline_block(config, envs, solver):
     """Bounded sample for the `cpu_baseline` key of our own line (N = 1 only): 10 timed steps of the reference arm's run."""
     r, threads, sample = reference_run(config, envs, solver, 10 if config != 1 else 300, 3)
@@ -453,6 +479,9 @@ def bench_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_block(cfg, n_envs, args.solver)
+            sb = second_baseline_block(cfg, n_envs, args.solver)
+            if sb is not None:
+                line["second_baseline"] = sb
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
