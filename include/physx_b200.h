@@ -126,6 +126,9 @@ PXB_API int  pxb_scene_set_convex_meshes(PxbScene* scene, const void* cooked, si
 typedef struct { float staticFriction, dynamicFriction, restitution; uint32_t bits; } PxbMaterial;
 PXB_API int  pxb_scene_set_materials(PxbScene* scene, const PxbMaterial* materials, uint32_t nb);
 PXB_API int  pxb_scene_add_actors(PxbScene* scene, const void* recs, uint32_t nb);
+/* Bp::AABBManagerBase::removeBounds (BpAABBManagerBase.h:191) + PxsSimulationController::removeDynamic: the listed actors leave the simulation at
+ * the next step (their pairs are reported deleted / touch-lost, they are no longer integrated); actor and dynamic-body indices stay valid. */
+PXB_API int  pxb_scene_remove_actors(PxbScene* scene, const uint32_t* actorIndices, uint32_t nb);
 PXB_API uint32_t pxb_scene_num_actors(const PxbScene* scene);
 PXB_API uint32_t pxb_scene_num_dynamic(const PxbScene* scene);
 

@@ -78,6 +78,7 @@ struct PxbScene {
   float sleepThreshold = 0.f; float* wake = 0; float4 *accLin = 0, *accAng = 0; uint32_t *asleep = 0, *nInter = 0, *islandLabel = 0, *islandAwake = 0; int coopBlocksSleep = 0; uint2* envSeg[2] = {0, 0}; unsigned long long* envTiming = 0;
 };
 
+#define ACTOR_REMOVED 0x80000000u   // host-side bit of ActorRec::flags: the actor was taken out by pxb_scene_remove_actors (its index stays)
 static thread_local std::string g_err;
 // Every entry point runs with the scene's device current and restores the caller's on return: scenes on different GPUs can be driven from
 // one thread, and torch / other libraries may change the current device between calls.
@@ -103,6 +104,11 @@ __global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const floa
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nA) return;
   const uint32_t gf = geomFlags[a];
+  if (gf & 0x400u) {   // removed actor (pxb_scene_remove_actors): empty bounds, in no grid cell -- its pairs are reported deleted by this step's lifecycle
+    aabbMin[a] = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, __uint_as_float(NONE32)); aabbMax[a] = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, __uint_as_float(gf));
+    cellKey[a] = ~0ull; cellVal[a] = a;
+    return;
+  }
   float mn[3], mx[3];
   if (externalTight) { for (int k = 0; k < 3; ++k) { mn[k] = tight[a * 6 + k]; mx[k] = tight[a * 6 + 3 + k]; } }
   else {
@@ -575,6 +581,7 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
+  if (!(geomFlags[a] & 0x100u)) return;   // removed actor
   const bool asleep = body_asleep(S, a);
   const float4 dm = damp[a]; const float4 ii = invInertia[a]; const float4 p4 = pos[a];
   v3 lv = V3(linVel[a]), av = V3(angVel[a]);
@@ -604,11 +611,11 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
 __global__ void k_finalize_bodies(uint32_t nDyn, const uint32_t* __restrict__ dynActor, float dt, float4* __restrict__ pos, float4* __restrict__ quat, float4* __restrict__ linVel,
                                   float4* __restrict__ angVel, const float4* __restrict__ sbLin, const float4* __restrict__ sbAng, const float4* __restrict__ sbIA,
                                   const float4* __restrict__ sbIB, const float4* __restrict__ sbP, const float4* __restrict__ sbQ, const uint32_t* __restrict__ bodyHasCon,
-                                  const float4* __restrict__ sbDLin, const float4* __restrict__ sbDAng, const float4* __restrict__ invInertia, SleepArgs S) {
+                                  const float4* __restrict__ sbDLin, const float4* __restrict__ sbDAng, const float4* __restrict__ invInertia, SleepArgs S, const uint32_t* __restrict__ geomFlags) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
-  if (body_asleep(S, a)) return;
+  if (body_asleep(S, a) || !(geomFlags[a] & 0x100u)) return;   // (removed actors lose their dynamic bit)
   const float4 ib = sbIB[a];
   const m33 sI = load_sym(sbIA[a], ib);
   v3 p = V3(sbP[a]); q4 dq = Q4(sbQ[a]);
@@ -887,6 +894,7 @@ static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
   auto envOf = [&](uint32_t a) { return single ? 0u : s->recs[a].envId; };
   for (uint32_t a = 0; a < s->nA; ++a) {
     const ActorRec& r = s->recs[a];
+    if (r.flags & ACTOR_REMOVED) continue;
     if (envOf(a) == NONE32) { if (r.flags & PXB_ACTOR_DYNAMIC) return; globals.push_back(a); if (globals.size() > ENV_MAX_GLOBALS) return; }
     else cnt[envOf(a)]++;
   }
@@ -899,7 +907,7 @@ static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
   std::vector<uint32_t> list(start[nEnv]), cur(start.begin(), start.end() - 1), gi(nEnv, 0);
   for (uint32_t a = 0; a < s->nA; ++a) {   // ascending a: merge the env-less statics in by index
     const uint32_t e = envOf(a);
-    if (e == NONE32) continue;
+    if (e == NONE32 || (s->recs[a].flags & ACTOR_REMOVED)) continue;
     while (gi[e] < G && globals[gi[e]] < a) list[cur[e]++] = globals[gi[e]++];
     local[a] = cur[e] - start[e]; list[cur[e]++] = a;
   }
@@ -936,18 +944,19 @@ static void rebuild_grid(PxbScene* s) {
   // cell edge = largest rotation-independent extent among regular shapes (+ inflation, + 2% slack); shapes more
   // than 8x the median are classified "large" (tested against everything) so they do not blow the cell up.
   std::vector<float> diam; diam.reserve(s->nA);
-  for (auto& r : s->recs) { const float d = shape_diameter(r); if (std::isfinite(d)) diam.push_back(d); }
+  for (auto& r : s->recs) { if (r.flags & ACTOR_REMOVED) continue; const float d = shape_diameter(r); if (std::isfinite(d)) diam.push_back(d); }
   float med = 1.f;
   if (!diam.empty()) { std::vector<float> t = diam; std::nth_element(t.begin(), t.begin() + t.size() / 2, t.end()); med = t[t.size() / 2]; }
   const float largeThresh = 8.f * med;
   bool usesEnv = false; uint32_t maxEnv = 0;
-  for (auto& r : s->recs) if (r.envId != NONE32) { usesEnv = true; maxEnv = std::max(maxEnv, r.envId); }
+  for (auto& r : s->recs) if (r.envId != NONE32 && !(r.flags & ACTOR_REMOVED)) { usesEnv = true; maxEnv = std::max(maxEnv, r.envId); }
   float cell = 0.f; float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   s->largeHost.clear();
   std::vector<uint32_t> gf(s->nA);
   bool anyCapsule = false, anyBox = false, anyLocks = false, anyConvex = false; uint32_t typeMask = 0;
   for (uint32_t a = 0; a < s->nA; ++a) {
     const ActorRec& r = s->recs[a];
+    if (r.flags & ACTOR_REMOVED) { gf[a] = (r.geomType & 0xff) | 0x400u; continue; }   // no dynamic bit, not in the grid, not in the large list
     anyCapsule |= r.geomType == PXB_GEOM_CAPSULE; anyBox |= r.geomType == PXB_GEOM_BOX; anyConvex |= r.geomType == PXB_GEOM_CONVEXMESH;
     if (r.geomType != PXB_GEOM_PLANE) typeMask |= 1u << (r.geomType & 31);
     anyLocks |= ((r.flags >> 8) & 0x3fu) != 0;
@@ -1098,6 +1107,17 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
   return PXB_OK;
 }
 
+// Bp::AABBManagerBase::removeBounds + PxsSimulationController::removeDynamic (BpAABBManagerBase.h:191): the actors leave the simulation at the next
+// step -- their pairs are reported deleted (and touch-lost), they are no longer integrated -- while every actor / dynamic-body index stays valid
+// (PxRigidDynamicGPUIndex values are stable node indices in the reference too).  Their last state remains readable.
+PXB_API int pxb_scene_remove_actors(PxbScene* s, const uint32_t* actors, uint32_t nb) { DeviceGuard dg_(s);
+  if (!s || (nb && !actors)) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running");
+  for (uint32_t i = 0; i < nb; ++i) if (actors[i] >= s->nA) return fail(PXB_ERR_INVALID, "actor index out of range");
+  for (uint32_t i = 0; i < nb; ++i) s->recs[actors[i]].flags |= ACTOR_REMOVED;
+  if (nb) { s->gridDirty = true; drop_graphs(s); }
+  return PXB_OK;
+}
 PXB_API int pxb_scene_set_constraint_order(PxbScene* s, const uint32_t* pairs, uint32_t n) { DeviceGuard dg_(s);
   if (!s) return fail(PXB_ERR_INVALID, "null scene");
   s->nOrder = 0;
@@ -1325,7 +1345,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     MARK(5);
     pxb_launch_writeback_rows(st, s->capPairs, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions); s->launches++;
     if (pgs) {
-      pxb_launch_finalize_bodies_pgs(st, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->invInertia, SA); s->launches++;
+      pxb_launch_finalize_bodies_pgs(st, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->invInertia, SA, s->geomFlags); s->launches++;
       if (s->exportOn) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
       MARK(6);
       CK(cudaGetLastError());
@@ -1333,7 +1353,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     }
   }
   LAUNCH(k_finalize_bodies, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->bodyHasCon,
-         s->sbDLin, s->sbDAng, s->invInertia, SA);
+         s->sbDLin, s->sbDAng, s->invInertia, SA, s->geomFlags);
   if (s->exportOn) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
   MARK(6);
   CK(cudaGetLastError());

@@ -327,11 +327,12 @@ __global__ void k_writeback_rows(const uint32_t* __restrict__ counters, Rows R, 
 
 __global__ void k_finalize_bodies_pgs(uint32_t nDyn, const uint32_t* __restrict__ dynActor, float dt, float4* __restrict__ pos, float4* __restrict__ quat, float4* __restrict__ linVel,
                                       float4* __restrict__ angVel, const float4* __restrict__ sbLin, const float4* __restrict__ sbAng, const float4* __restrict__ sbDLin,
-                                      const float4* __restrict__ sbDAng, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, const float4* __restrict__ invInertia, SleepArgs S) {
+                                      const float4* __restrict__ sbDAng, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, const float4* __restrict__ invInertia, SleepArgs S,
+                                      const uint32_t* __restrict__ geomFlags) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
-  if (body_asleep(S, a)) return;
+  if (body_asleep(S, a) || !(geomFlags[a] & 0x100u)) return;   // (removed actors lose their dynamic bit)
   const float4 p4 = pos[a]; v3 p = V3(p4.x, p4.y, p4.z); q4 q = Q4(quat[a]); v3 lv = V3(linVel[a]), av = V3(angVel[a]);
   const m33 sI = load_sym(sbIA[a], sbIB[a]);
   v3 motionLin, motionAng;   // motionVelocityArray after integrateCore

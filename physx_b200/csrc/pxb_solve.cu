@@ -25,6 +25,6 @@ void pxb_launch_writeback_rows(cudaStream_t st, uint32_t capPairs, const uint32_
   k_writeback_rows<<<(capPairs + 255) / 256, 256, 0, st>>>(counters, R, pairSlots, cForce, frictions);
 }
 void pxb_launch_finalize_bodies_pgs(cudaStream_t st, uint32_t nDyn, const uint32_t* dynActor, float dt, float4* pos, float4* quat, float4* linVel, float4* angVel, const float4* sbLin, const float4* sbAng,
-                                    const float4* sbDLin, const float4* sbDAng, const float4* sbIA, const float4* sbIB, const float4* invInertia, SleepArgs S) {
-  k_finalize_bodies_pgs<<<(nDyn + 255) / 256, 256, 0, st>>>(nDyn, dynActor, dt, pos, quat, linVel, angVel, sbLin, sbAng, sbDLin, sbDAng, sbIA, sbIB, invInertia, S);
+                                    const float4* sbDLin, const float4* sbDAng, const float4* sbIA, const float4* sbIB, const float4* invInertia, SleepArgs S, const uint32_t* geomFlags) {
+  k_finalize_bodies_pgs<<<(nDyn + 255) / 256, 256, 0, st>>>(nDyn, dynActor, dt, pos, quat, linVel, angVel, sbLin, sbAng, sbDLin, sbDAng, sbIA, sbIB, invInertia, S, geomFlags);
 }

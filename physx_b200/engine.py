@@ -31,7 +31,7 @@ EXPORTS = [
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
     "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait", "pxb_bp_create", "pxb_bp_release", "pxb_bp_update", "pxb_bp_fetch",
-    "pxb_scene_set_materials", "pxb_tensor_read_device", "pxb_tensor_write_device", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost",
+    "pxb_scene_set_materials", "pxb_scene_remove_actors", "pxb_tensor_read_device", "pxb_tensor_write_device", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
@@ -76,6 +76,7 @@ def load_library():
     lib.pxb_last_error.restype = ctypes.c_char_p
     lib.pxb_scene_add_actors.argtypes = [vp, vp, u32]
     lib.pxb_scene_set_materials.argtypes = [vp, vp, u32]
+    lib.pxb_scene_remove_actors.argtypes = [vp, vp, u32]
     lib.pxb_tensor_read_device.argtypes = [vp, i32, vp, vp, u32]
     lib.pxb_tensor_write_device.argtypes = [vp, i32, vp, vp, u32]
     for f in ("pxb_scene_num_actors", "pxb_scene_num_dynamic", "pxb_scene_num_pairs", "pxb_scene_num_created",
@@ -174,6 +175,11 @@ class Scene:
             self._h = None
 
     __del__ = release
+
+    def removeActors(self, actor_indices):
+        """PxScene::removeActor for the listed actor indices: they leave the simulation at the next step; indices stay valid."""
+        idx = np.ascontiguousarray(actor_indices, dtype=np.uint32)
+        _check(self._lib, self._lib.pxb_scene_remove_actors(self._h, _ptr(idx), len(idx)))
 
     # ---- PxScene ----
     def simulate(self, dt: float | None = None):

@@ -969,3 +969,36 @@ def test_tensor_binding_reads_and_writes_device_and_host_tensors():
     assert np.array_equal(a.getStates(), b.getStates())
     rep = ta.get_contact_report(a)
     assert len(rep["actor0"]) == a.num_constraints and rep["counts"].sum() == len(rep["positions"]) and np.all(rep["impulses"] >= 0)
+
+
+# ---- actor removal (Bp::AABBManagerBase::removeBounds / removeDynamic) ----
+@pytest.mark.parametrize("path", ["auto", "devicewide"])
+def test_removed_actor_leaves_the_simulation_and_the_rest_continues(oracle, path):
+    """pxb_scene_remove_actors: the middle box of a stack is taken out after 10 steps.  Its pairs are reported deleted and touch-lost in the next
+    step, it is no longer integrated (state frozen, indices unchanged), and every other body continues exactly like a scene that never had
+    it (oracle scene built without the actor, started from the same states)."""
+    sc = scenes.box_stacks(n_stacks=2, height=3, half_extent=0.25, spacing=1.0, jitter=0.01)      # actors: plane 0 | stack 0: 1 2 3 | stack 1: 4 5 6
+    gpu = engine.Scene(sc, env_path=(path == "auto"))
+    for _ in range(10):
+        gpu.step()
+    st10 = gpu.getStates()
+    gpu.removeActors([2])
+    keep = [0, 1, 3, 4, 5, 6]
+    cpu = oracle.OracleScene(scenes.Scene(sc.header, sc.actors[keep].copy()))
+    dyn_keep = [0, 2, 3, 4, 5]
+    cpu.setStates(st10[dyn_keep])
+    remap = {a: i for i, a in enumerate(keep)}
+    for t in range(40):
+        gpu.step(); cpu.step()
+        if t == 0:
+            assert {(1, 2), (2, 3)} <= {(int(a), int(b)) for a, b in gpu.getDeletedPairs()}
+            assert {(1, 2), (2, 3)} <= {(int(a), int(b)) for a, b in gpu.getTouchLost()}
+        pg = gpu.getPairs()
+        assert 2 not in pg
+        assert {(remap[int(a)], remap[int(b)]) for a, b in pg} == {(int(a), int(b)) for a, b in cpu.getPairs()}, f"pair set, step {t}"
+        sg = gpu.getStates()
+        assert np.array_equal(sg[1], st10[1]), "the removed body keeps its last state"
+        assert np.abs(sg[dyn_keep] - cpu.getStates()).max() < 2e-4, f"state, step {t}"
+    assert gpu.num_dynamic == 6 and sg[2, 1] < st10[2, 1] - 0.2, "the box above fell onto the bottom box"
+    with pytest.raises(engine.PhysxB200Error):
+        gpu.removeActors([99])
