@@ -998,7 +998,8 @@ def test_removed_actor_leaves_the_simulation_and_the_rest_continues(oracle, path
         assert {(remap[int(a)], remap[int(b)]) for a, b in pg} == {(int(a), int(b)) for a, b in cpu.getPairs()}, f"pair set, step {t}"
         sg = gpu.getStates()
         assert np.array_equal(sg[1], st10[1]), "the removed body keeps its last state"
-        assert np.abs(sg[dyn_keep] - cpu.getStates()).max() < 2e-4, f"state, step {t}"
+        d = np.abs(sg[dyn_keep] - cpu.getStates())     # the oracle scene starts with cold manifolds / friction patches, the GPU scene keeps its warm ones
+        assert d[:, :7].max() < 1e-4 and d[:, 7:].max() < 5e-3, f"state, step {t}"
     assert gpu.num_dynamic == 6 and sg[2, 1] < st10[2, 1] - 0.2, "the box above fell onto the bottom box"
     with pytest.raises(engine.PhysxB200Error):
         gpu.removeActors([99])
