@@ -6,8 +6,11 @@ src, lib, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
 d = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=d, check=True, stdout=subprocess.DEVNULL)
-cubin = glob.glob(os.path.join(d, "*.cubin"))[0]
-txt = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+txt = []
+for cubin in sorted(glob.glob(os.path.join(d, "*.cubin"))):   # the library has one cubin per translation unit: take every one that holds the kernel
+    t = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
+    if kname in t:
+        txt += t.splitlines()
 lines, cur, inside, pend = [], ("?", 0), False, []
 depth = int(os.environ.get("DEPTH", "0"))   # 0 = outermost frame, 1 = one level of inlining below it, ...
 for l in txt:
