@@ -1300,9 +1300,14 @@ PXB_D int gjk_hull_capsule_full_manifold(const GjkConvex* cap, const DevHull* h,
   *normal = tNormal;
   return 1;
 }
-/* pcmContactCapsuleConvex :80-262 (shape0 = capsule, shape1 = convex mesh, identity mesh scale) */
-PXB_D void gjk_pcm_capsule_convex(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, const DevHull* hull, float contactDist, float toleranceLength,
-                                          Manifold* manifold, Contacts* out) {
+/* pcmContactCapsuleConvex :80-262 (shape0 = capsule, shape1 = convex mesh, identity mesh scale), in the three phases the kernels run separately
+ * (k_gjk_refresh -> k_gjk_query -> k_gjk_manifold: every phase's warps hold only pairs that need that phase):
+ *   refresh  manifold refresh + invalidation test; a manifold that stays valid emits its cached points and the pair is finished
+ *   query    GJK (+ EPA) on the invalidated pairs; separated pairs and pairs that only add the GJK point are finished
+ *   manifold fullContactsGenerationCapsuleConvex for the rest
+ * What a later phase needs from an earlier one travels in GjkCarry (+ the manifold record itself). */
+struct GjkCarry { v3 normal, closestA, closestB; int doOverlapTest; };
+PXB_D int gjk_capsule_convex_refresh(const xf* transf0, const xf* transf1, float capsuleRadius, const DevHull* hull, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out, int* flags) {
   out->count = 0;
   const xf curRTrans = axfinvmul(transf1, transf0);
   const mxf aToB = amxffromxf(&curRTrans);
@@ -1313,42 +1318,72 @@ PXB_D void gjk_pcm_capsule_convex(const xf* transf0, const xf* transf1, float ca
   const int bLostContacts = manifold->n != initialContacts;
   if (bLostContacts || gjk_invalidate_sphere_capsule(manifold, &curRTrans, minMargin)) {
     manifold->rel = curRTrans; manifold->dirty = 1;
-    const GjkConvex convexHull = gjk_cvx_hull(hull);
-    const GjkConvex capsule = gjk_cvx_capsule(aToB.p, m33mul(&aToB.r, v3scale(V3(1, 0, 0), capsuleHalfHeight)), capsuleRadius);
-    GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
-    const v3 initialSearchDir = v3sub(capsule.center, convexHull.center);
-    int status = gjk_penetration(&capsule, &convexHull, initialSearchDir, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
-    MPoint mc[16]; int numContacts = 0; int doOverlapTest = 0;   // <= 2 face points + one edge-edge point per polygon edge that the segment crosses (2 for a convex polygon)
-    if (status == GJK_NON_INTERSECT) return;
-    if (status == GJK_DEGENERATE) doOverlapTest = 1;
-    else {
-      const float replaceBreakingThreshold = minMargin * 0.05f;
-      if (status == EPA_CONTACT) {
-        status = gjk_epa_penetration(&capsule, &convexHull, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
-        if (status != EPA_CONTACT) doOverlapTest = 1;
-      }
-      if (!doOverlapTest) add_manifold_point2(*manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
-      if (!(initialContacts == 0 || bLostContacts || doOverlapTest)) {
-        const v3 n = aqrot(transf1->q, output.normal);
-        gjk_manifold_to_contacts_radius(manifold, n, transf0, capsuleRadius, contactDist, out);
-        return;
-      }
-    }
-    /* fullContactsGenerationCapsuleConvex :42-78 */
-    v3 normal = output.normal;
-    if (!gjk_hull_capsule_full_manifold(&capsule, hull, &aToB, mc, &numContacts, contactDist, &normal, output.closestB, convexHull.margin, doOverlapTest, toleranceLength)) return;
-    if (numContacts > 0) {
-      gjk_add_batch2(manifold, mc, numContacts);
-      normal = aqrot(transf1->q, normal);
-      gjk_manifold_to_contacts_radius(manifold, normal, transf0, capsuleRadius, contactDist, out);
-    } else if (!doOverlapTest) {
-      normal = aqrot(transf1->q, normal);
-      gjk_manifold_to_contacts_radius(manifold, normal, transf0, capsuleRadius, contactDist, out);
-    }
-  } else if (manifold->n > 0) {
+    *flags = initialContacts | (bLostContacts << 8);
+    return 1;
+  }
+  if (manifold->n > 0) {
     const v3 worldNormal = manifold_world_normal(*manifold, *transf1);
     gjk_manifold_to_contacts_radius(manifold, worldNormal, transf0, capsuleRadius, contactDist, out);
   }
+  return 0;
+}
+PXB_D int gjk_capsule_convex_query(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, const DevHull* hull, float contactDist, float toleranceLength, int flags,
+                                   Manifold* manifold, Contacts* out, GjkCarry* carry) {
+  out->count = 0;
+  const int initialContacts = flags & 0xff, bLostContacts = flags >> 8;
+  const xf curRTrans = axfinvmul(transf1, transf0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  const float minMargin = fmin_(gjk_hull_pcm_margin(hull, toleranceLength), capsuleRadius * 0.05f);
+  const GjkConvex convexHull = gjk_cvx_hull(hull);
+  const GjkConvex capsule = gjk_cvx_capsule(aToB.p, m33mul(&aToB.r, v3scale(V3(1, 0, 0), capsuleHalfHeight)), capsuleRadius);
+  GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
+  const v3 initialSearchDir = v3sub(capsule.center, convexHull.center);
+  int status = gjk_penetration(&capsule, &convexHull, initialSearchDir, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+  int doOverlapTest = 0;
+  if (status == GJK_NON_INTERSECT) return 0;
+  if (status == GJK_DEGENERATE) doOverlapTest = 1;
+  else {
+    const float replaceBreakingThreshold = minMargin * 0.05f;
+    if (status == EPA_CONTACT) {
+      status = gjk_epa_penetration(&capsule, &convexHull, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+      if (status != EPA_CONTACT) doOverlapTest = 1;
+    }
+    if (!doOverlapTest) add_manifold_point2(*manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+    if (!(initialContacts == 0 || bLostContacts || doOverlapTest)) {
+      const v3 n = aqrot(transf1->q, output.normal);
+      gjk_manifold_to_contacts_radius(manifold, n, transf0, capsuleRadius, contactDist, out);
+      return 0;
+    }
+  }
+  carry->normal = output.normal; carry->closestA = output.closestA; carry->closestB = output.closestB; carry->doOverlapTest = doOverlapTest;
+  return 1;
+}
+/* fullContactsGenerationCapsuleConvex :42-78 */
+PXB_D void gjk_capsule_convex_manifold(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, const DevHull* hull, float contactDist, float toleranceLength,
+                                       const GjkCarry* carry, Manifold* manifold, Contacts* out) {
+  out->count = 0;
+  const xf curRTrans = axfinvmul(transf1, transf0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  const GjkConvex convexHull = gjk_cvx_hull(hull);
+  const GjkConvex capsule = gjk_cvx_capsule(aToB.p, m33mul(&aToB.r, v3scale(V3(1, 0, 0), capsuleHalfHeight)), capsuleRadius);
+  MPoint mc[16]; int numContacts = 0; const int doOverlapTest = carry->doOverlapTest;   // <= 2 face points + one edge-edge point per polygon edge that the segment crosses (2 for a convex polygon)
+  v3 normal = carry->normal;
+  if (!gjk_hull_capsule_full_manifold(&capsule, hull, &aToB, mc, &numContacts, contactDist, &normal, carry->closestB, convexHull.margin, doOverlapTest, toleranceLength)) return;
+  if (numContacts > 0) {
+    gjk_add_batch2(manifold, mc, numContacts);
+    normal = aqrot(transf1->q, normal);
+    gjk_manifold_to_contacts_radius(manifold, normal, transf0, capsuleRadius, contactDist, out);
+  } else if (!doOverlapTest) {
+    normal = aqrot(transf1->q, normal);
+    gjk_manifold_to_contacts_radius(manifold, normal, transf0, capsuleRadius, contactDist, out);
+  }
+}
+PXB_D void gjk_pcm_capsule_convex(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, const DevHull* hull, float contactDist, float toleranceLength,
+                                          Manifold* manifold, Contacts* out) {   // the three phases back to back (single-kernel variant)
+  int flags; GjkCarry carry;
+  if (!gjk_capsule_convex_refresh(transf0, transf1, capsuleRadius, hull, contactDist, toleranceLength, manifold, out, &flags)) return;
+  if (!gjk_capsule_convex_query(transf0, transf1, capsuleRadius, capsuleHalfHeight, hull, contactDist, toleranceLength, flags, manifold, out, &carry)) return;
+  gjk_capsule_convex_manifold(transf0, transf1, capsuleRadius, capsuleHalfHeight, hull, contactDist, toleranceLength, &carry, manifold, out);
 }
 
 /* ---------------- polygonal pairs: box vs hull, hull vs hull (GuPCMContactGenBoxConvex.cpp:331-720, GuPCMContactBoxConvex.cpp, GuPCMContactConvexConvex.cpp) ---------------- */
@@ -1633,10 +1668,9 @@ PXB_D void gjk_manifold_to_contacts(const Manifold* m, v3 worldNormal, const xf*
   out->count = 0; out->normal = worldNormal;
   for (int i = 0; i < m->n; ++i) { const float dist = m->pts[i].pen; if (contactDist >= dist) { out->point[out->count] = axftransform(transf1, m->pts[i].b); out->sep[out->count] = dist; out->count++; } }
 }
-/* pcmContactBoxConvex / pcmContactConvexConvex: shape A (box or hull) relative to hull B.  convexA must already be relative (aToB).
- * Returns 1 when the reference would run the SAT branch (not restated), 0 otherwise. */
-PXB_D int gjk_pcm_poly_convex(const xf* transf0, const xf* transf1, GjkConvex* convexA, const DevHull* polyA, float marginPcmA, float radiusA, const DevHull* hullB,
-                                      float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {
+/* pcmContactBoxConvex / pcmContactConvexConvex: shape A (box or hull) relative to hull B, in the same three phases as the capsule (see GjkCarry).
+ * The manifold phase returns 1 when the reference would run the SAT branch (not restated), 0 otherwise. */
+PXB_D int gjk_poly_convex_refresh(const xf* transf0, const xf* transf1, float marginPcmA, float radiusA, const DevHull* hullB, float contactDist, float toleranceLength, Manifold* manifold, Contacts* out, int* flags) {
   out->count = 0;
   const xf curRTrans = axfinvmul(transf1, transf0);
   const mxf aToB = amxffromxf(&curRTrans);
@@ -1648,45 +1682,72 @@ PXB_D int gjk_pcm_poly_convex(const xf* transf0, const xf* transf1, GjkConvex* c
   const float radiusB = alen(hullB->internalExtents);
   if (bLostContacts || invalidate_boxconvex(*manifold, curRTrans, transf0->q, transf1->q, minMargin, radiusA, radiusB)) {
     manifold->rel = curRTrans; manifold->quatA = transf0->q; manifold->quatB = transf1->q; manifold->dirty = 1;
-    gjk_cvx_make_relative(convexA, &aToB);
-    const GjkConvex convexB = gjk_cvx_hull(hullB);
-    GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
-    int status = gjk_penetration(convexA, &convexB, aToB.p, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
-    if (status == GJK_NON_INTERSECT) return 0;
-    /* generateOrProcessContacts* + addGJKEPAContacts */
-    const v3 localNor = manifold->n ? gjk_manifold_local_normal(manifold) : V3(0, 0, 0);
-    const float replaceBreakingThreshold = minMargin * 0.05f;
-    int doOverlapTest = 0;
-    if (status == GJK_DEGENERATE) {
-      const float costheta = adot(output.searchDir, output.normal);
-      if (costheta > 0.9999f) {
-        const v3 centreA = amxftransform(&aToB, convexA->center), centreB = convexB.center;
-        const v3 dir = anormalize(v3sub(centreA, centreB));
-        if (adot(dir, output.normal) > 0.707f) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
-        else doOverlapTest = 1;
-      } else doOverlapTest = 1;
-    } else if (status == GJK_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
-    else {
-      status = gjk_epa_penetration(convexA, &convexB, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
-      if (status == EPA_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
-      else doOverlapTest = 1;
-    }
-    const int fullContactGen = (0.707106781f > adot(localNor, output.normal)) || (manifold->n < initialContacts);
-    if (fullContactGen || doOverlapTest) {   /* fullContactsGenerationBoxConvex / ConvexConvex */
-      MPoint mc[GJK_POLY_MAX_CONTACTS]; int numContacts = 0;
-      if (doOverlapTest) { if (!gjk_poly_full_manifold_sat(polyA, convexA->type == GJK_CVX_BOX, hullB, transf0, transf1, mc, &numContacts, contactDist)) return 0; }
-      else gjk_poly_full_manifold(polyA, hullB, transf0, transf1, mc, &numContacts, contactDist, output.normal, output.closestA, output.closestB, convexA->margin, convexB.margin, toleranceLength);
-      if (numContacts > 0) {
-        if (numContacts <= PXB_MANIFOLD_CACHE) { for (int i = 0; i < numContacts; ++i) manifold->pts[i] = mc[i]; manifold->n = numContacts; }
-        else { reduce_batch(*manifold, mc, numContacts, toleranceLength); manifold->n = PXB_MANIFOLD_CACHE; }
-        gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
-      } else if (!doOverlapTest) gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
-    } else {
-      const v3 newLocalNor = v3add(localNor, output.normal);
-      gjk_manifold_to_contacts(manifold, anormalize(aqrot(transf1->q, newLocalNor)), transf1, contactDist, out);
-    }
-  } else if (manifold->n > 0) gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
+    *flags = initialContacts | (bLostContacts << 8);
+    return 1;
+  }
+  if (manifold->n > 0) gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
   return 0;
+}
+PXB_D int gjk_poly_convex_query(const xf* transf0, const xf* transf1, GjkConvex* convexA, float marginPcmA, const DevHull* hullB, float contactDist, float toleranceLength, int flags,
+                                Manifold* manifold, Contacts* out, GjkCarry* carry) {
+  out->count = 0;
+  const int initialContacts = flags & 0xff;
+  const xf curRTrans = axfinvmul(transf1, transf0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  const float minMargin = fmin_(marginPcmA, gjk_hull_pcm_margin(hullB, toleranceLength));
+  gjk_cvx_make_relative(convexA, &aToB);
+  const GjkConvex convexB = gjk_cvx_hull(hullB);
+  GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
+  int status = gjk_penetration(convexA, &convexB, aToB.p, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+  if (status == GJK_NON_INTERSECT) return 0;
+  /* generateOrProcessContacts* + addGJKEPAContacts */
+  const v3 localNor = manifold->n ? gjk_manifold_local_normal(manifold) : V3(0, 0, 0);
+  const float replaceBreakingThreshold = minMargin * 0.05f;
+  int doOverlapTest = 0;
+  if (status == GJK_DEGENERATE) {
+    const float costheta = adot(output.searchDir, output.normal);
+    if (costheta > 0.9999f) {
+      const v3 centreA = amxftransform(&aToB, convexA->center), centreB = convexB.center;
+      const v3 dir = anormalize(v3sub(centreA, centreB));
+      if (adot(dir, output.normal) > 0.707f) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+      else doOverlapTest = 1;
+    } else doOverlapTest = 1;
+  } else if (status == GJK_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+  else {
+    status = gjk_epa_penetration(convexA, &convexB, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+    if (status == EPA_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+    else doOverlapTest = 1;
+  }
+  const int fullContactGen = (0.707106781f > adot(localNor, output.normal)) || (manifold->n < initialContacts);
+  if (fullContactGen || doOverlapTest) {
+    carry->normal = output.normal; carry->closestA = output.closestA; carry->closestB = output.closestB; carry->doOverlapTest = doOverlapTest;
+    return 1;
+  }
+  const v3 newLocalNor = v3add(localNor, output.normal);
+  gjk_manifold_to_contacts(manifold, anormalize(aqrot(transf1->q, newLocalNor)), transf1, contactDist, out);
+  return 0;
+}
+/* fullContactsGenerationBoxConvex / ConvexConvex */
+PXB_D int gjk_poly_convex_manifold(const xf* transf0, const xf* transf1, const GjkConvex* convexA, const DevHull* polyA, const DevHull* hullB, float contactDist, float toleranceLength, const GjkCarry* carry,
+                                   Manifold* manifold, Contacts* out) {
+  out->count = 0;
+  const GjkConvex convexB = gjk_cvx_hull(hullB);
+  MPoint mc[GJK_POLY_MAX_CONTACTS]; int numContacts = 0; const int doOverlapTest = carry->doOverlapTest;
+  if (doOverlapTest) { if (!gjk_poly_full_manifold_sat(polyA, convexA->type == GJK_CVX_BOX, hullB, transf0, transf1, mc, &numContacts, contactDist)) return 0; }
+  else gjk_poly_full_manifold(polyA, hullB, transf0, transf1, mc, &numContacts, contactDist, carry->normal, carry->closestA, carry->closestB, convexA->margin, convexB.margin, toleranceLength);
+  if (numContacts > 0) {
+    if (numContacts <= PXB_MANIFOLD_CACHE) { for (int i = 0; i < numContacts; ++i) manifold->pts[i] = mc[i]; manifold->n = numContacts; }
+    else { reduce_batch(*manifold, mc, numContacts, toleranceLength); manifold->n = PXB_MANIFOLD_CACHE; }
+    gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
+  } else if (!doOverlapTest) gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
+  return 0;
+}
+PXB_D int gjk_pcm_poly_convex(const xf* transf0, const xf* transf1, GjkConvex* convexA, const DevHull* polyA, float marginPcmA, float radiusA, const DevHull* hullB,
+                                      float contactDist, float toleranceLength, Manifold* manifold, Contacts* out) {   // the three phases back to back (single-kernel variant)
+  int flags; GjkCarry carry;
+  if (!gjk_poly_convex_refresh(transf0, transf1, marginPcmA, radiusA, hullB, contactDist, toleranceLength, manifold, out, &flags)) return 0;
+  if (!gjk_poly_convex_query(transf0, transf1, convexA, marginPcmA, hullB, contactDist, toleranceLength, flags, manifold, out, &carry)) return 0;
+  return gjk_poly_convex_manifold(transf0, transf1, convexA, polyA, hullB, contactDist, toleranceLength, &carry, manifold, out);
 }
 struct BoxAsHull { float4 verts[8]; float4 polys[12]; DevHull view; };
 PXB_D const DevHull* gjk_box_as_hull(BoxAsHull* b, v3 ext) {   // PCMPolygonalBox as the polygonal view the hulls use (per-thread arrays)

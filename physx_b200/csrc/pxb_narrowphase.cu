@@ -121,6 +121,141 @@ __global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uin
   }
 }
 
+// ---- a10 in three phases -------------------------------------------------------------------------------------------------------------
+// A persistent-manifold pair does one of three very different amounts of work per step: its manifold is still valid (refresh only), it is
+// invalidated and GJK finds it separated or only adds the GJK point, or it regenerates the full manifold (polygon clipping / SAT).  One thread
+// per pair through all of that left 5 of 32 lanes active (ncu, BASELINE config 3).  Here every phase is its own kernel over a compacted
+// worklist, so a warp holds 32 pairs that all need that phase; what a pair carries between phases is its manifold record (stored by the
+// phase that changed it) plus a few words parked in the pair's own, not yet written, output slots (conFlag: refresh flags, cPts: GjkCarry).
+// The arithmetic per pair is the single-kernel variant's (same device functions, same order), so the contacts are bit-identical.
+struct GjkPair { uint32_t i, a0, a1, ty0, ty1, slot; bool flip; uint64_t key; xf tm0, tm1; float4 d0, d1; float4* rec; };
+__device__ __forceinline__ void gjk_pair_setup(const NpArgs& A, uint32_t i, GjkPair& P) {
+  P.i = i; P.key = A.pairKeys[i];
+  const uint32_t lo = (uint32_t)(P.key >> A.bitsA), hi = (uint32_t)(P.key & ((1ull << A.bitsA) - 1ull));
+  P.a0 = hi; P.a1 = lo;
+  const uint32_t gfHi = A.geomFlags[hi], gfLo = A.geomFlags[lo];
+  if (!(gfHi & 0x100u)) { P.a0 = lo; P.a1 = hi; }
+  const uint32_t t0 = ((P.a0 == hi) ? gfHi : gfLo) & 0xff, t1 = ((P.a0 == hi) ? gfLo : gfHi) & 0xff;
+  P.flip = t1 < t0;
+  const uint32_t s0 = P.flip ? P.a1 : P.a0, s1 = P.flip ? P.a0 : P.a1;
+  const float4 p0 = A.pos[s0], p1 = A.pos[s1];
+  P.tm0.p = V3(p0.x, p0.y, p0.z); P.tm0.q = Q4(A.quat[s0]); P.tm1.p = V3(p1.x, p1.y, p1.z); P.tm1.q = Q4(A.quat[s1]);
+  P.d0 = A.dims[s0]; P.d1 = A.dims[s1];
+  P.slot = A.pairSlots[i]; P.rec = A.manifolds + (size_t)P.slot * PXB_MANIFOLD_F4;
+  P.ty1 = P.flip ? t0 : t1; P.ty0 = P.flip ? t1 : t0;
+}
+__device__ __forceinline__ void gjk_pair_finish(const NpArgs& A, const GjkPair& P, const Manifold& man, Contacts& out) {
+  if (man.dirty) { manifold_store(man, P.rec); manifold_store_warm(man, P.rec); } else if (man.n > 0) manifold_store_pens(man, P.rec);
+  if (P.flip && out.count) out.normal = -out.normal;
+  A.cHdr[P.i] = make_float4(out.normal.x, out.normal.y, out.normal.z, __int_as_float(out.count));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) A.cPts[(size_t)P.i * 4 + k] = make_float4(out.point[k].x, out.point[k].y, out.point[k].z, out.sep[k]);
+  A.pairBodies[P.i] = make_uint2(P.a0, P.a1);
+  A.conFlag[P.i] = out.count > 0 ? 1u : 0u;
+  touch_event(A.touch, A.counters, P.slot, P.key, out.count > 0);
+}
+__device__ __forceinline__ void gjk_contacts_clear(Contacts& out) { out.count = 0; out.normal = V3(0, 0, 0); for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; } }
+// all 32 lanes call: the lanes with `need` append `v` to the list in lane order behind one atomic
+__device__ __forceinline__ void gjk_warp_append(bool need, uint32_t v, uint32_t* __restrict__ list, uint32_t* counter) {
+  const uint32_t m = __ballot_sync(0xffffffffu, need);
+  if (!m) return;
+  const uint32_t lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (need) list[base + __popc(m & ((1u << lane) - 1u))] = v;
+}
+#define GJK_PHASE_LOOP(nExpr) const uint32_t n = (nExpr); const uint32_t lane = threadIdx.x & 31; \
+  for (uint32_t w0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; w0 < n; w0 += gridDim.x * blockDim.x)
+
+// phase 1: every GJK-family pair.  Plane / sphere vs hull and capsule-box (cheap, no second phase worth a launch) run to completion.
+__global__ void __launch_bounds__(128, 4) k_gjk_refresh(const NpArgs A) {
+  GJK_PHASE_LOOP(A.counters[C_NGJK]) {
+    const uint32_t w = w0 + lane; bool need = false; uint32_t i = 0;
+    if (w < n) {
+      i = A.gjkList[w];
+      GjkPair P; gjk_pair_setup(A, i, P);
+      Manifold man; manifold_load(man, P.rec); manifold_load_warm(man, P.rec);
+      Contacts out; gjk_contacts_clear(out);
+      int flags = 0;
+      if (P.ty1 == PXB_GEOM_CONVEXMESH) {
+        const DevHull h = load_hull(A.hulls, __float_as_uint(P.d1.x));
+        if (P.ty0 == PXB_GEOM_PLANE) gjk_pcm_plane_convex(&P.tm0, &P.tm1, h, A.contactDist, A.toleranceLength, &man, &out);
+        else if (P.ty0 == PXB_GEOM_SPHERE) gjk_pcm_sphere_convex(&P.tm0, &P.tm1, P.d0.x, &h, A.contactDist, A.toleranceLength, &man, &out);
+        else if (P.ty0 == PXB_GEOM_CAPSULE) need = gjk_capsule_convex_refresh(&P.tm0, &P.tm1, P.d0.x, &h, A.contactDist, A.toleranceLength, &man, &out, &flags);
+        else if (P.ty0 == PXB_GEOM_BOX) { const v3 e = V3(P.d0.x, P.d0.y, P.d0.z); need = gjk_poly_convex_refresh(&P.tm0, &P.tm1, box_margin(e, A.toleranceLength), alen(e), &h, A.contactDist, A.toleranceLength, &man, &out, &flags); }
+        else {
+          const DevHull h0 = load_hull(A.hulls, __float_as_uint(P.d0.x));
+          need = gjk_poly_convex_refresh(&P.tm0, &P.tm1, gjk_hull_pcm_margin(&h0, A.toleranceLength), alen(h0.internalExtents), &h, A.contactDist, A.toleranceLength, &man, &out, &flags);
+        }
+      }
+      else gjk_pcm_capsule_box(&P.tm0, &P.tm1, P.d0.x, P.d0.y, V3(P.d1.x, P.d1.y, P.d1.z), A.contactDist, A.toleranceLength, &man, &out);
+      if (need) { manifold_store(man, P.rec); A.conFlag[i] = (uint32_t)flags; }   // the refreshed manifold and the new relative frame; the warm-start simplex is untouched
+      else gjk_pair_finish(A, P, man, out);
+    }
+    gjk_warp_append(need, i, A.gjkQuery, &A.counters[C_NGJK_QUERY]);
+  }
+}
+// phase 2: GJK / EPA for the pairs whose manifold was invalidated
+__global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_gjk_query(const NpArgs A) {
+  GJK_PHASE_LOOP(A.counters[C_NGJK_QUERY]) {
+    const uint32_t w = w0 + lane; bool need = false; uint32_t i = 0;
+    if (w < n) {
+      i = A.gjkQuery[w];
+      GjkPair P; gjk_pair_setup(A, i, P);
+      Manifold man; manifold_load(man, P.rec); manifold_load_warm(man, P.rec); man.dirty = 1;
+      Contacts out; gjk_contacts_clear(out);
+      const int flags = (int)A.conFlag[i];
+      GjkCarry carry; carry.normal = carry.closestA = carry.closestB = V3(0, 0, 0); carry.doOverlapTest = 0;
+      const DevHull h = load_hull(A.hulls, __float_as_uint(P.d1.x));
+      if (P.ty0 == PXB_GEOM_CAPSULE) need = gjk_capsule_convex_query(&P.tm0, &P.tm1, P.d0.x, P.d0.y, &h, A.contactDist, A.toleranceLength, flags, &man, &out, &carry);
+      else if (P.ty0 == PXB_GEOM_BOX) {
+        const v3 e = V3(P.d0.x, P.d0.y, P.d0.z); GjkConvex box = gjk_cvx_box(V3(0, 0, 0), e);
+        need = gjk_poly_convex_query(&P.tm0, &P.tm1, &box, box_margin(e, A.toleranceLength), &h, A.contactDist, A.toleranceLength, flags, &man, &out, &carry);
+      } else {
+        const DevHull h0 = load_hull(A.hulls, __float_as_uint(P.d0.x)); GjkConvex c0 = gjk_cvx_hull(&h0);
+        need = gjk_poly_convex_query(&P.tm0, &P.tm1, &c0, gjk_hull_pcm_margin(&h0, A.toleranceLength), &h, A.contactDist, A.toleranceLength, flags, &man, &out, &carry);
+      }
+      if (need) {
+        manifold_store(man, P.rec); manifold_store_warm(man, P.rec);
+        float4* c = A.cPts + (size_t)i * 4;
+        c[0] = make_float4(carry.normal.x, carry.normal.y, carry.normal.z, __int_as_float(carry.doOverlapTest));
+        c[1] = make_float4(carry.closestA.x, carry.closestA.y, carry.closestA.z, 0.f); c[2] = make_float4(carry.closestB.x, carry.closestB.y, carry.closestB.z, 0.f);
+      } else gjk_pair_finish(A, P, man, out);
+    }
+    gjk_warp_append(need, i, A.gjkFull, &A.counters[C_NGJK_FULL]);
+  }
+}
+// phase 3: full manifold generation
+__global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_gjk_manifold(const NpArgs A) {
+  GJK_PHASE_LOOP(A.counters[C_NGJK_FULL]) {
+    const uint32_t w = w0 + lane;
+    if (w < n) {
+      const uint32_t i = A.gjkFull[w];
+      GjkPair P; gjk_pair_setup(A, i, P);
+      Manifold man; manifold_load(man, P.rec); manifold_load_warm(man, P.rec); man.dirty = 1;
+      Contacts out; gjk_contacts_clear(out);
+      GjkCarry carry;
+      { const float4* c = A.cPts + (size_t)i * 4; const float4 c0 = c[0], c1 = c[1], c2 = c[2];
+        carry.normal = V3(c0.x, c0.y, c0.z); carry.doOverlapTest = __float_as_int(c0.w); carry.closestA = V3(c1.x, c1.y, c1.z); carry.closestB = V3(c2.x, c2.y, c2.z); }
+      const DevHull h = load_hull(A.hulls, __float_as_uint(P.d1.x));
+      if (P.ty0 == PXB_GEOM_CAPSULE) gjk_capsule_convex_manifold(&P.tm0, &P.tm1, P.d0.x, P.d0.y, &h, A.contactDist, A.toleranceLength, &carry, &man, &out);
+      else {
+        int sat;
+        if (P.ty0 == PXB_GEOM_BOX) {
+          const v3 e = V3(P.d0.x, P.d0.y, P.d0.z); BoxAsHull bh; const DevHull* polyA = gjk_box_as_hull(&bh, e); const GjkConvex box = gjk_cvx_box(V3(0, 0, 0), e);
+          sat = gjk_poly_convex_manifold(&P.tm0, &P.tm1, &box, polyA, &h, A.contactDist, A.toleranceLength, &carry, &man, &out);
+        } else {
+          const DevHull h0 = load_hull(A.hulls, __float_as_uint(P.d0.x)); const GjkConvex c0 = gjk_cvx_hull(&h0);
+          sat = gjk_poly_convex_manifold(&P.tm0, &P.tm1, &c0, &h0, &h, A.contactDist, A.toleranceLength, &carry, &man, &out);
+        }
+        if (sat) atomicOr(&A.counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);
+      }
+      gjk_pair_finish(A, P, man, out);
+    }
+  }
+}
+
 void pxb_launch_narrowphase(cudaStream_t st, uint32_t capPairs, const NpArgs& A) {
   k_narrowphase<<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies,
                                                          A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch);
@@ -128,4 +263,9 @@ void pxb_launch_narrowphase(cudaStream_t st, uint32_t capPairs, const NpArgs& A)
 void pxb_launch_narrowphase_gjk(cudaStream_t st, uint32_t ctas, const NpArgs& A) {
   k_narrowphase_gjk<<<ctas, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies, A.conFlag, A.counters,
                                           A.gjkList, A.hulls, A.touch);
+}
+void pxb_launch_narrowphase_gjk_phases(cudaStream_t st, uint32_t ctas, const NpArgs& A) {
+  k_gjk_refresh<<<ctas, 128, 0, st>>>(A);
+  k_gjk_query<<<ctas, 128, 0, st>>>(A);
+  k_gjk_manifold<<<ctas, 128, 0, st>>>(A);
 }
