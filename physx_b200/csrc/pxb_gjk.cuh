@@ -1327,36 +1327,46 @@ PXB_D int gjk_capsule_convex_refresh(const xf* transf0, const xf* transf1, float
   }
   return 0;
 }
-PXB_D int gjk_capsule_convex_query(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, const DevHull* hull, float contactDist, float toleranceLength, int flags,
-                                   Manifold* manifold, Contacts* out, GjkCarry* carry) {
-  out->count = 0;
-  const int initialContacts = flags & 0xff, bLostContacts = flags >> 8;
+/* the two GJK shapes of the pair (capsule in the hull's frame) and the initial search direction */
+PXB_D void gjk_capsule_convex_shapes(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, const DevHull* hull, GjkConvex* capsule, GjkConvex* convexHull, mxf* aToB, v3* initialSearchDir) {
   const xf curRTrans = axfinvmul(transf1, transf0);
-  const mxf aToB = amxffromxf(&curRTrans);
+  *aToB = amxffromxf(&curRTrans);
+  *convexHull = gjk_cvx_hull(hull);
+  *capsule = gjk_cvx_capsule(aToB->p, m33mul(&aToB->r, v3scale(V3(1, 0, 0), capsuleHalfHeight)), capsuleRadius);
+  *initialSearchDir = v3sub(capsule->center, convexHull->center);
+}
+/* what pcmContactCapsuleConvex does with the query's answer.  status: gjk_penetration's (never GJK_NON_INTERSECT here); epaStatus: gjk_epa_penetration's when
+ * status == EPA_CONTACT.  Returns 1 when the full manifold generation has to run (carry filled), 0 when the pair is finished. */
+PXB_D int gjk_capsule_convex_post(const xf* transf0, const xf* transf1, float capsuleRadius, const DevHull* hull, float contactDist, float toleranceLength, int flags, int status, int epaStatus,
+                                  const GjkOutput* output, const mxf* aToB, Manifold* manifold, Contacts* out, GjkCarry* carry) {
+  const int initialContacts = flags & 0xff, bLostContacts = flags >> 8;
   const float minMargin = fmin_(gjk_hull_pcm_margin(hull, toleranceLength), capsuleRadius * 0.05f);
-  const GjkConvex convexHull = gjk_cvx_hull(hull);
-  const GjkConvex capsule = gjk_cvx_capsule(aToB.p, m33mul(&aToB.r, v3scale(V3(1, 0, 0), capsuleHalfHeight)), capsuleRadius);
-  GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
-  const v3 initialSearchDir = v3sub(capsule.center, convexHull.center);
-  int status = gjk_penetration(&capsule, &convexHull, initialSearchDir, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
   int doOverlapTest = 0;
-  if (status == GJK_NON_INTERSECT) return 0;
   if (status == GJK_DEGENERATE) doOverlapTest = 1;
   else {
     const float replaceBreakingThreshold = minMargin * 0.05f;
-    if (status == EPA_CONTACT) {
-      status = gjk_epa_penetration(&capsule, &convexHull, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
-      if (status != EPA_CONTACT) doOverlapTest = 1;
-    }
-    if (!doOverlapTest) add_manifold_point2(*manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+    if (status == EPA_CONTACT && epaStatus != EPA_CONTACT) doOverlapTest = 1;
+    if (!doOverlapTest) add_manifold_point2(*manifold, amxftransforminv(aToB, output->closestA), output->closestB, output->normal, output->penDep, replaceBreakingThreshold);
     if (!(initialContacts == 0 || bLostContacts || doOverlapTest)) {
-      const v3 n = aqrot(transf1->q, output.normal);
+      const v3 n = aqrot(transf1->q, output->normal);
       gjk_manifold_to_contacts_radius(manifold, n, transf0, capsuleRadius, contactDist, out);
       return 0;
     }
   }
-  carry->normal = output.normal; carry->closestA = output.closestA; carry->closestB = output.closestB; carry->doOverlapTest = doOverlapTest;
+  carry->normal = output->normal; carry->closestA = output->closestA; carry->closestB = output->closestB; carry->doOverlapTest = doOverlapTest;
   return 1;
+}
+PXB_D int gjk_capsule_convex_query(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, const DevHull* hull, float contactDist, float toleranceLength, int flags,
+                                   Manifold* manifold, Contacts* out, GjkCarry* carry) {
+  out->count = 0;
+  GjkConvex capsule, convexHull; mxf aToB; v3 initialSearchDir;
+  gjk_capsule_convex_shapes(transf0, transf1, capsuleRadius, capsuleHalfHeight, hull, &capsule, &convexHull, &aToB, &initialSearchDir);
+  GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
+  const int status = gjk_penetration(&capsule, &convexHull, initialSearchDir, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+  if (status == GJK_NON_INTERSECT) return 0;
+  int epaStatus = 0;
+  if (status == EPA_CONTACT) epaStatus = gjk_epa_penetration(&capsule, &convexHull, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+  return gjk_capsule_convex_post(transf0, transf1, capsuleRadius, hull, contactDist, toleranceLength, flags, status, epaStatus, &output, &aToB, manifold, out, carry);
 }
 /* fullContactsGenerationCapsuleConvex :42-78 */
 PXB_D void gjk_capsule_convex_manifold(const xf* transf0, const xf* transf1, float capsuleRadius, float capsuleHalfHeight, const DevHull* hull, float contactDist, float toleranceLength,
@@ -1688,44 +1698,50 @@ PXB_D int gjk_poly_convex_refresh(const xf* transf0, const xf* transf1, float ma
   if (manifold->n > 0) gjk_manifold_to_contacts(manifold, manifold_world_normal(*manifold, *transf1), transf1, contactDist, out);
   return 0;
 }
-PXB_D int gjk_poly_convex_query(const xf* transf0, const xf* transf1, GjkConvex* convexA, float marginPcmA, const DevHull* hullB, float contactDist, float toleranceLength, int flags,
-                                Manifold* manifold, Contacts* out, GjkCarry* carry) {
-  out->count = 0;
+/* generateOrProcessContacts* + addGJKEPAContacts: what pcmContactBoxConvex / ConvexConvex do with the query's answer (status / epaStatus as for the capsule).
+ * centreA: convexA's centre in its own frame.  Returns 1 when the full manifold generation has to run. */
+PXB_D int gjk_poly_convex_post(const xf* transf1, v3 centreALocal, v3 centreB, float marginPcmA, const DevHull* hullB, float contactDist, float toleranceLength, int flags, int status, int epaStatus,
+                               const GjkOutput* output, const mxf* aToB, Manifold* manifold, Contacts* out, GjkCarry* carry) {
   const int initialContacts = flags & 0xff;
-  const xf curRTrans = axfinvmul(transf1, transf0);
-  const mxf aToB = amxffromxf(&curRTrans);
   const float minMargin = fmin_(marginPcmA, gjk_hull_pcm_margin(hullB, toleranceLength));
-  gjk_cvx_make_relative(convexA, &aToB);
-  const GjkConvex convexB = gjk_cvx_hull(hullB);
-  GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
-  int status = gjk_penetration(convexA, &convexB, aToB.p, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
-  if (status == GJK_NON_INTERSECT) return 0;
-  /* generateOrProcessContacts* + addGJKEPAContacts */
   const v3 localNor = manifold->n ? gjk_manifold_local_normal(manifold) : V3(0, 0, 0);
   const float replaceBreakingThreshold = minMargin * 0.05f;
   int doOverlapTest = 0;
   if (status == GJK_DEGENERATE) {
-    const float costheta = adot(output.searchDir, output.normal);
+    const float costheta = adot(output->searchDir, output->normal);
     if (costheta > 0.9999f) {
-      const v3 centreA = amxftransform(&aToB, convexA->center), centreB = convexB.center;
+      const v3 centreA = amxftransform(aToB, centreALocal);
       const v3 dir = anormalize(v3sub(centreA, centreB));
-      if (adot(dir, output.normal) > 0.707f) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+      if (adot(dir, output->normal) > 0.707f) gjk_add_manifold_point(manifold, amxftransforminv(aToB, output->closestA), output->closestB, output->normal, output->penDep, replaceBreakingThreshold);
       else doOverlapTest = 1;
     } else doOverlapTest = 1;
-  } else if (status == GJK_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+  } else if (status == GJK_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(aToB, output->closestA), output->closestB, output->normal, output->penDep, replaceBreakingThreshold);
   else {
-    status = gjk_epa_penetration(convexA, &convexB, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
-    if (status == EPA_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(&aToB, output.closestA), output.closestB, output.normal, output.penDep, replaceBreakingThreshold);
+    if (epaStatus == EPA_CONTACT) gjk_add_manifold_point(manifold, amxftransforminv(aToB, output->closestA), output->closestB, output->normal, output->penDep, replaceBreakingThreshold);
     else doOverlapTest = 1;
   }
-  const int fullContactGen = (0.707106781f > adot(localNor, output.normal)) || (manifold->n < initialContacts);
+  const int fullContactGen = (0.707106781f > adot(localNor, output->normal)) || (manifold->n < initialContacts);
   if (fullContactGen || doOverlapTest) {
-    carry->normal = output.normal; carry->closestA = output.closestA; carry->closestB = output.closestB; carry->doOverlapTest = doOverlapTest;
+    carry->normal = output->normal; carry->closestA = output->closestA; carry->closestB = output->closestB; carry->doOverlapTest = doOverlapTest;
     return 1;
   }
-  const v3 newLocalNor = v3add(localNor, output.normal);
+  const v3 newLocalNor = v3add(localNor, output->normal);
   gjk_manifold_to_contacts(manifold, anormalize(aqrot(transf1->q, newLocalNor)), transf1, contactDist, out);
   return 0;
+}
+PXB_D int gjk_poly_convex_query(const xf* transf0, const xf* transf1, GjkConvex* convexA, float marginPcmA, const DevHull* hullB, float contactDist, float toleranceLength, int flags,
+                                Manifold* manifold, Contacts* out, GjkCarry* carry) {
+  out->count = 0;
+  const xf curRTrans = axfinvmul(transf1, transf0);
+  const mxf aToB = amxffromxf(&curRTrans);
+  gjk_cvx_make_relative(convexA, &aToB);
+  const GjkConvex convexB = gjk_cvx_hull(hullB);
+  GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
+  const int status = gjk_penetration(convexA, &convexB, aToB.p, contactDist, 1, manifold->aInd, manifold->bInd, &manifold->nWarm, &output);
+  if (status == GJK_NON_INTERSECT) return 0;
+  int epaStatus = 0;
+  if (status != GJK_DEGENERATE && status != GJK_CONTACT) epaStatus = gjk_epa_penetration(convexA, &convexB, manifold->aInd, manifold->bInd, manifold->nWarm, 1, toleranceLength, &output);
+  return gjk_poly_convex_post(transf1, convexA->center, convexB.center, marginPcmA, hullB, contactDist, toleranceLength, flags, status, epaStatus, &output, &aToB, manifold, out, carry);
 }
 /* fullContactsGenerationBoxConvex / ConvexConvex */
 PXB_D int gjk_poly_convex_manifold(const xf* transf0, const xf* transf1, const GjkConvex* convexA, const DevHull* polyA, const DevHull* hullB, float contactDist, float toleranceLength, const GjkCarry* carry,

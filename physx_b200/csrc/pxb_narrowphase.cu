@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uin
   }
 }
 
-// ---- a10 in three phases -------------------------------------------------------------------------------------------------------------
-// A persistent-manifold pair does one of three very different amounts of work per step: its manifold is still valid (refresh only), it is
-// invalidated and GJK finds it separated or only adds the GJK point, or it regenerates the full manifold (polygon clipping / SAT).  One thread
+// ---- a10 in four phases -------------------------------------------------------------------------------------------------------------
+// A persistent-manifold pair does one of four very different amounts of work per step: its manifold is still valid (refresh only), it is
+// invalidated and GJK finds it separated or only adds the GJK point, it is deep enough for EPA, or it regenerates the full manifold (polygon clipping / SAT).  One thread
 // per pair through all of that left 5 of 32 lanes active (ncu, BASELINE config 3).  Here every phase is its own kernel over a compacted
 // worklist, so a warp holds 32 pairs that all need that phase; what a pair carries between phases is its manifold record (stored by the
 // phase that changed it) plus a few words parked in the pair's own, not yet written, output slots (conFlag: refresh flags, cPts: GjkCarry).
@@ -196,34 +196,76 @@ __global__ void __launch_bounds__(128, 4) k_gjk_refresh(const NpArgs A) {
     gjk_warp_append(need, i, A.gjkQuery, &A.counters[C_NGJK_QUERY]);
   }
 }
-// phase 2: GJK / EPA for the pairs whose manifold was invalidated
-__global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_gjk_query(const NpArgs A) {
+// The shapes of an invalidated pair as the GJK / EPA query sees them: convexA = capsule (already in B's frame), box or hull (relative), convexB = hull.
+struct GjkShapes { GjkConvex a, b; DevHull hA, hB; mxf aToB; v3 dir; float marginPcmA; };
+__device__ __forceinline__ void gjk_pair_shapes(const NpArgs& A, const GjkPair& P, GjkShapes& S) {
+  S.hB = load_hull(A.hulls, __float_as_uint(P.d1.x)); S.marginPcmA = 0.f;
+  if (P.ty0 == PXB_GEOM_CAPSULE) gjk_capsule_convex_shapes(&P.tm0, &P.tm1, P.d0.x, P.d0.y, &S.hB, &S.a, &S.b, &S.aToB, &S.dir);
+  else {
+    const xf curRTrans = axfinvmul(&P.tm1, &P.tm0);
+    S.aToB = amxffromxf(&curRTrans); S.dir = S.aToB.p; S.b = gjk_cvx_hull(&S.hB);
+    if (P.ty0 == PXB_GEOM_BOX) { const v3 e = V3(P.d0.x, P.d0.y, P.d0.z); S.a = gjk_cvx_box(V3(0, 0, 0), e); S.marginPcmA = box_margin(e, A.toleranceLength); }
+    else { S.hA = load_hull(A.hulls, __float_as_uint(P.d0.x)); S.a = gjk_cvx_hull(&S.hA); S.marginPcmA = gjk_hull_pcm_margin(&S.hA, A.toleranceLength); }
+    gjk_cvx_make_relative(&S.a, &S.aToB);
+  }
+}
+__device__ __forceinline__ bool gjk_pair_post(const NpArgs& A, const GjkPair& P, const GjkShapes& S, int flags, int status, int epaStatus, const GjkOutput& output, Manifold& man, Contacts& out) {
+  GjkCarry carry; int need;
+  if (P.ty0 == PXB_GEOM_CAPSULE) need = gjk_capsule_convex_post(&P.tm0, &P.tm1, P.d0.x, &S.hB, A.contactDist, A.toleranceLength, flags, status, epaStatus, &output, &S.aToB, &man, &out, &carry);
+  else need = gjk_poly_convex_post(&P.tm1, S.a.center, S.b.center, S.marginPcmA, &S.hB, A.contactDist, A.toleranceLength, flags, status, epaStatus, &output, &S.aToB, &man, &out, &carry);
+  if (need) {
+    manifold_store(man, P.rec); manifold_store_warm(man, P.rec);
+    float4* c = A.cPts + (size_t)P.i * 4;
+    c[0] = make_float4(carry.normal.x, carry.normal.y, carry.normal.z, __int_as_float(carry.doOverlapTest));
+    c[1] = make_float4(carry.closestA.x, carry.closestA.y, carry.closestA.z, 0.f); c[2] = make_float4(carry.closestB.x, carry.closestB.y, carry.closestB.z, 0.f);
+  } else gjk_pair_finish(A, P, man, out);
+  return need != 0;
+}
+// phase 2: GJK for the pairs whose manifold was invalidated -- ONE call site for every shape pair, so a warp that mixes capsule-hull, box-hull and hull-hull
+// pairs still iterates together (the shapes differ only inside the support mapping).  Deep pairs (EPA_CONTACT) go on to k_gjk_epa.
+__global__ void __launch_bounds__(128, 4) k_gjk_query(const NpArgs A) {
   GJK_PHASE_LOOP(A.counters[C_NGJK_QUERY]) {
-    const uint32_t w = w0 + lane; bool need = false; uint32_t i = 0;
+    const uint32_t w = w0 + lane; bool needFull = false, needEpa = false; uint32_t i = 0;
     if (w < n) {
       i = A.gjkQuery[w];
       GjkPair P; gjk_pair_setup(A, i, P);
       Manifold man; manifold_load(man, P.rec); manifold_load_warm(man, P.rec); man.dirty = 1;
       Contacts out; gjk_contacts_clear(out);
       const int flags = (int)A.conFlag[i];
-      GjkCarry carry; carry.normal = carry.closestA = carry.closestB = V3(0, 0, 0); carry.doOverlapTest = 0;
-      const DevHull h = load_hull(A.hulls, __float_as_uint(P.d1.x));
-      if (P.ty0 == PXB_GEOM_CAPSULE) need = gjk_capsule_convex_query(&P.tm0, &P.tm1, P.d0.x, P.d0.y, &h, A.contactDist, A.toleranceLength, flags, &man, &out, &carry);
-      else if (P.ty0 == PXB_GEOM_BOX) {
-        const v3 e = V3(P.d0.x, P.d0.y, P.d0.z); GjkConvex box = gjk_cvx_box(V3(0, 0, 0), e);
-        need = gjk_poly_convex_query(&P.tm0, &P.tm1, &box, box_margin(e, A.toleranceLength), &h, A.contactDist, A.toleranceLength, flags, &man, &out, &carry);
-      } else {
-        const DevHull h0 = load_hull(A.hulls, __float_as_uint(P.d0.x)); GjkConvex c0 = gjk_cvx_hull(&h0);
-        need = gjk_poly_convex_query(&P.tm0, &P.tm1, &c0, gjk_hull_pcm_margin(&h0, A.toleranceLength), &h, A.contactDist, A.toleranceLength, flags, &man, &out, &carry);
-      }
-      if (need) {
-        manifold_store(man, P.rec); manifold_store_warm(man, P.rec);
+      GjkShapes S; gjk_pair_shapes(A, P, S);
+      GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
+      const int status = gjk_penetration(&S.a, &S.b, S.dir, A.contactDist, 1, man.aInd, man.bInd, &man.nWarm, &output);
+      if (status == GJK_NON_INTERSECT) gjk_pair_finish(A, P, man, out);
+      else if (status == EPA_CONTACT) {   // the GJK answer (EPA starts from the warm-start simplex and may leave parts of it in place) travels in the pair's output slots
+        needEpa = true; manifold_store_warm(man, P.rec);
         float4* c = A.cPts + (size_t)i * 4;
-        c[0] = make_float4(carry.normal.x, carry.normal.y, carry.normal.z, __int_as_float(carry.doOverlapTest));
-        c[1] = make_float4(carry.closestA.x, carry.closestA.y, carry.closestA.z, 0.f); c[2] = make_float4(carry.closestB.x, carry.closestB.y, carry.closestB.z, 0.f);
-      } else gjk_pair_finish(A, P, man, out);
+        c[0] = make_float4(output.normal.x, output.normal.y, output.normal.z, output.penDep); c[1] = make_float4(output.closestA.x, output.closestA.y, output.closestA.z, 0.f);
+        c[2] = make_float4(output.closestB.x, output.closestB.y, output.closestB.z, 0.f); c[3] = make_float4(output.searchDir.x, output.searchDir.y, output.searchDir.z, 0.f);
+      }
+      else needFull = gjk_pair_post(A, P, S, flags, status, 0, output, man, out);
     }
-    gjk_warp_append(need, i, A.gjkFull, &A.counters[C_NGJK_FULL]);
+    gjk_warp_append(needEpa, i, A.gjkEpa, &A.counters[C_NGJK_EPA]);
+    gjk_warp_append(needFull, i, A.gjkFull, &A.counters[C_NGJK_FULL]);
+  }
+}
+// phase 2b: EPA for the deep pairs
+__global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_gjk_epa(const NpArgs A) {
+  GJK_PHASE_LOOP(A.counters[C_NGJK_EPA]) {
+    const uint32_t w = w0 + lane; bool needFull = false; uint32_t i = 0;
+    if (w < n) {
+      i = A.gjkEpa[w];
+      GjkPair P; gjk_pair_setup(A, i, P);
+      Manifold man; manifold_load(man, P.rec); manifold_load_warm(man, P.rec); man.dirty = 1;
+      Contacts out; gjk_contacts_clear(out);
+      const int flags = (int)A.conFlag[i];
+      GjkShapes S; gjk_pair_shapes(A, P, S);
+      GjkOutput output;
+      { const float4* c = A.cPts + (size_t)i * 4; const float4 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+        output.normal = V3(c0.x, c0.y, c0.z); output.penDep = c0.w; output.closestA = V3(c1.x, c1.y, c1.z); output.closestB = V3(c2.x, c2.y, c2.z); output.searchDir = V3(c3.x, c3.y, c3.z); }
+      const int epaStatus = gjk_epa_penetration(&S.a, &S.b, man.aInd, man.bInd, man.nWarm, 1, A.toleranceLength, &output);
+      needFull = gjk_pair_post(A, P, S, flags, EPA_CONTACT, epaStatus, output, man, out);
+    }
+    gjk_warp_append(needFull, i, A.gjkFull, &A.counters[C_NGJK_FULL]);
   }
 }
 // phase 3: full manifold generation
@@ -267,5 +309,6 @@ void pxb_launch_narrowphase_gjk(cudaStream_t st, uint32_t ctas, const NpArgs& A)
 void pxb_launch_narrowphase_gjk_phases(cudaStream_t st, uint32_t ctas, const NpArgs& A) {
   k_gjk_refresh<<<ctas, 128, 0, st>>>(A);
   k_gjk_query<<<ctas, 128, 0, st>>>(A);
+  k_gjk_epa<<<ctas, 128, 0, st>>>(A);
   k_gjk_manifold<<<ctas, 128, 0, st>>>(A);
 }
