@@ -445,17 +445,17 @@ def bench_ours(args):
             kernel_bytes = prep_bytes + solve_bytes + integ_bytes
             note = ("algorithmic bytes = SURVEY 8d prep + 5 solver iterations + integration; the kernel keeps every solver row on chip (registers), "
                     "so only contacts, friction patches and body state cross HBM once: see `traffic` (ncu dram bytes per launch)")
-            key = f"k_env_solve/config{cfg}" if (n_envs == 4096 and args.solver == "tgs" and not churn) else None
+            key = f"k_env_solve/config{cfg}" if ((n_envs == 4096 or cfg == 1) and args.solver == "tgs" and not churn) else None
         elif cfg == 3:
-            kernel_name, stage = "k_narrowphase + k_narrowphase_gjk (a8-a11: contact generation over all broadphase pairs)", "narrowphase"
+            kernel_name, stage = "k_narrowphase + k_gjk_refresh / k_gjk_query / k_gjk_epa / k_gjk_manifold (a8-a11: contact generation over all broadphase pairs)", "narrowphase"
             kernel_bytes = np_bytes
             note = "algorithmic bytes = SURVEY 8d narrowphase: per pair 16 + 2*48 + 2*32 read, 2*256 manifold r/w, 32 + 64 P + 16 C written"
-            key = "k_narrowphase_gjk/config3"
+            key = "narrowphase/config3" if args.partitioning == "exact" else None
         else:
             kernel_name, stage = "k_solve_tgs / k_solve_pgs (all solver iterations, one cooperative launch)", "solve"
             kernel_bytes = solve_bytes
             note = "device-wide path: rows re-streamed from HBM every iteration"
-            key = f"k_solve/config{cfg}"
+            key = f"k_solve/config{cfg}" if args.solver == "tgs" else None
         kernel_ms = stage_acc[stage] / prof_steps
         traffic = NCU_DRAM_BYTES_PER_LAUNCH.get(key) if key else None
         achieved = kernel_bytes / (kernel_ms / 1e3) / 1e9
