@@ -26,7 +26,7 @@ struct ActorRec {
 };
 static_assert(sizeof(ActorRec) == 128, "actor record layout");
 
-enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_NGJK, C_NTOUCH_FOUND, C_NTOUCH_LOST, C_NGJK_QUERY, C_NGJK_FULL, C_NGJK_EPA, C_COUNT = 24 };
+enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_NGJK, C_NTOUCH_FOUND, C_NTOUCH_LOST, C_NGJK_QUERY, C_NGJK_FULL, C_NGJK_EPA, C_NBOXGEN, C_COUNT = 24 };
 enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8 };
 
 struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };

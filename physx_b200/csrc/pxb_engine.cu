@@ -49,7 +49,7 @@ struct PxbScene {
   // per pair (this frame)
   float4 *cHdr = 0, *cPts = 0; uint2* pairBodies = 0; float* cForce = 0;
   uint32_t *pairOrder = 0, *npClassCount = 0; uint8_t* npClass = 0; bool binPairs = false;   // mixed-type scenes: pairs binned by type pair before the narrowphase
-  uint32_t *gjkList = 0, *gjkQuery = 0, *gjkFull = 0, *gjkEpa = 0; bool gjkPhases = true; bool hasGjkPairs = false, anyLocks = false, anyConvex = false;
+  uint32_t *gjkList = 0, *gjkQuery = 0, *gjkFull = 0, *gjkEpa = 0, *boxList = 0; bool boxPhases = true; bool gjkPhases = true; bool hasGjkPairs = false, anyLocks = false, anyConvex = false;
   float4 *extForce = 0, *extTorque = 0; bool forcesUsed = false;
   uint4* hullMeta = 0; float4 *hullVerts = 0, *hullPolys = 0; uint8_t *hullRefs = 0, *hullEdges = 0; uint32_t nHulls = 0; std::vector<float> hullDiam;   // cooked convex hulls (pxb_scene_set_convex_meshes)   // PxDirectGPUAPI eFORCE / eTORQUE writes pending for the next step   // a10: worklist of GJK-family pairs (filled by k_narrowphase)
   uint32_t *conFlag = 0, *conIdx = 0, *conPair = 0, *rankOfPair = 0; uint64_t *conSortKey = 0, *conSortKeyAlt = 0; uint32_t* conPairAlt = 0;
@@ -735,7 +735,7 @@ __global__ void k_init_freelist(uint32_t cap, uint32_t* __restrict__ freeList) {
 }
 
 __global__ void k_env_begin(uint32_t* __restrict__ counters) {   // per-step counter reset of the environment path
-  if (threadIdx.x == 0) { counters[C_NPAIRS_NEW] = 0; counters[C_NCREATED] = 0; counters[C_NDELETED] = 0; counters[C_NCON] = 0; counters[C_NPART] = 0; counters[C_NGJK] = 0; counters[C_NGJK_QUERY] = 0; counters[C_NGJK_FULL] = 0; counters[C_NGJK_EPA] = 0; counters[C_MAXCONENV] = 0; counters[C_MAXPAIRENV] = 0; counters[C_NTOUCH_FOUND] = 0; counters[C_NTOUCH_LOST] = 0;
+  if (threadIdx.x == 0) { counters[C_NPAIRS_NEW] = 0; counters[C_NCREATED] = 0; counters[C_NDELETED] = 0; counters[C_NCON] = 0; counters[C_NPART] = 0; counters[C_NGJK] = 0; counters[C_NGJK_QUERY] = 0; counters[C_NGJK_FULL] = 0; counters[C_NGJK_EPA] = 0; counters[C_NBOXGEN] = 0; counters[C_MAXCONENV] = 0; counters[C_MAXPAIRENV] = 0; counters[C_NTOUCH_FOUND] = 0; counters[C_NTOUCH_LOST] = 0;
                           counters[C_FREE_SNAP] = counters[C_FREE_TAIL]; }
 }
 
@@ -771,7 +771,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->createdKeys, Pn)); CK(dalloc(s->deletedKeys, Pn));
   CK(dalloc(s->manifolds, Pn * PXB_MANIFOLD_F4)); CK(dalloc(s->frictions, Pn * PXB_FRICTION_F4));
   CK(dalloc(s->cHdr, Pn)); CK(dalloc(s->cPts, Pn * 4)); CK(dalloc(s->pairBodies, Pn)); CK(dalloc(s->cForce, Pn * 4));
-  CK(dalloc(s->gjkList, Pn)); CK(dalloc(s->gjkQuery, Pn)); CK(dalloc(s->gjkFull, Pn)); CK(dalloc(s->gjkEpa, Pn)); CK(dalloc(s->pairOrder, Pn)); CK(dalloc(s->npClass, Pn)); CK(dalloc(s->npClassCount, 2 * NP_CLASSES)); CK(dalloc(s->conFlag, Pn)); CK(dalloc(s->conIdx, Pn)); CK(dalloc(s->conPair, Pn)); CK(dalloc(s->rankOfPair, Pn)); CK(dalloc(s->conSortKey, Pn)); CK(dalloc(s->conSortKeyAlt, Pn));
+  CK(dalloc(s->gjkList, Pn)); CK(dalloc(s->gjkQuery, Pn)); CK(dalloc(s->gjkFull, Pn)); CK(dalloc(s->gjkEpa, Pn)); CK(dalloc(s->boxList, Pn)); CK(dalloc(s->pairOrder, Pn)); CK(dalloc(s->npClass, Pn)); CK(dalloc(s->npClassCount, 2 * NP_CLASSES)); CK(dalloc(s->conFlag, Pn)); CK(dalloc(s->conIdx, Pn)); CK(dalloc(s->conPair, Pn)); CK(dalloc(s->rankOfPair, Pn)); CK(dalloc(s->conSortKey, Pn)); CK(dalloc(s->conSortKeyAlt, Pn));
   CK(dalloc(s->conPairAlt, Pn));
   CK(dalloc(s->conB0, Pn)); CK(dalloc(s->conB1, Pn)); CK(dalloc(s->conPos0, Pn)); CK(dalloc(s->conPos1, Pn)); CK(dalloc(s->conColour, Pn)); CK(dalloc(s->conDone, Pn));
   CK(dalloc(s->bodyList, Pn * 2)); CK(dalloc(s->ordered, Pn));
@@ -829,6 +829,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   { const char* cl = getenv("PXB_COLOUR_LEGACY"); if (cl && cl[0] == '1') s->colourLegacy = true; const char* cb = getenv("PXB_COLOUR_BACKOFF_NS"); if (cb) s->colourBackoffNs = (uint32_t)atoi(cb);
     const char* cp = getenv("PXB_COLOUR_PREFIX"); if (cp && cp[0] == '0') s->colourPrefix = false;
     const char* cw = getenv("PXB_COLOUR_WINDOW"); if (cw) s->colourWindow = (uint32_t)atoi(cw);
+    const char* bp_ = getenv("PXB_BOX_PHASES"); if (bp_ && bp_[0] == '0') s->boxPhases = false;
     const char* gp = getenv("PXB_GJK_PHASES"); if (gp && gp[0] == '0') s->gjkPhases = false; }   // A/B hooks of the exact colouring
   if (desc->reserved[1] & PXB_FLAG_NO_ENV_PATH) s->envDisabled = true;
   if (desc->reserved[1] & PXB_FLAG_RELAXED_PARTITIONING) { s->relaxedPartitioning = true; s->envDisabled = true; }
@@ -847,7 +848,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
   void* ptrs[] = {s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
-                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
+                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->prevB0, s->prevB1, s->prevColour, s->prevNCon, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
                   s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->actorMat, s->matTab, s->touchState, s->touchFound, s->touchLost, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
@@ -1175,7 +1176,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     return PXB_OK;
   }
   CK(cudaMemsetAsync(s->counters + C_NPAIRS_NEW, 0, 4 * 3, st));  // NPAIRS_NEW, NCREATED, NDELETED
-  CK(cudaMemsetAsync(s->counters + C_NTOUCH_FOUND, 0, 4 * 5, st));   // NTOUCH_FOUND, NTOUCH_LOST, NGJK_QUERY, NGJK_FULL, NGJK_EPA
+  CK(cudaMemsetAsync(s->counters + C_NTOUCH_FOUND, 0, 4 * 6, st));   // NTOUCH_FOUND, NTOUCH_LOST, NGJK_QUERY, NGJK_FULL, NGJK_EPA, NBOXGEN
   if (s->hasGjkPairs) CK(cudaMemsetAsync(s->counters + C_NGJK, 0, 4, st));
   LAUNCH(k_bounds, cdiv(nA, B), B, nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, externalTight ? 1 : 0, s->aabbMin, s->aabbMax, s->grid,
          s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s));
@@ -1244,8 +1245,8 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
   NpArgs NA;
   NA.pairKeys = s->pairKeys[cur]; NA.pairSlots = s->pairSlots[cur]; NA.nPairsP = nP; NA.bitsA = s->bitsA; NA.pos = s->pos; NA.quat = s->quat; NA.dims = s->dims; NA.geomFlags = s->geomFlags;
   NA.contactDist = contactDist; NA.toleranceLength = s->desc.toleranceLength; NA.manifolds = s->manifolds; NA.cHdr = s->cHdr; NA.cPts = s->cPts; NA.pairBodies = s->pairBodies; NA.conFlag = s->conFlag;
-  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.gjkQuery = s->gjkQuery; NA.gjkFull = s->gjkFull; NA.gjkEpa = s->gjkEpa; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s); NA.touch = touch_lists(s);
-  pxb_launch_narrowphase(st, s->capPairs, NA); s->launches++;
+  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.gjkQuery = s->gjkQuery; NA.gjkFull = s->gjkFull; NA.gjkEpa = s->gjkEpa; NA.boxList = (s->boxPhases && !s->envActive) ? s->boxList : nullptr; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s); NA.touch = touch_lists(s);
+  pxb_launch_narrowphase(st, s->capPairs, NA); s->launches += NA.boxList ? 2 : 1;
   if (s->hasGjkPairs) {
     const uint32_t ctas = std::max(148u * 4u, std::min(cdiv(s->capPairs, 128), 148u * 64u));
     if (s->anyConvex && s->gjkPhases) { pxb_launch_narrowphase_gjk_phases(st, ctas, NA); s->launches += 4; }   // hull scenes: refresh -> query -> EPA -> manifold over compacted worklists

@@ -1,6 +1,7 @@
 // pxb_narrowphase.cu -- a8-a11: the contact-generation kernels (k_narrowphase: sphere family, plane-box, box-box PCM; k_narrowphase_gjk: the GJK /
 // EPA family over a device-side worklist) in their own translation unit.
 #include "pxb_np_launch.h"
+#include <algorithm>
 
 // a8-a11: one thread per pair.  Driver logic of PxcNpBatch.cpp:364-498: body0 is the dynamic actor (for
 // two dynamics the later-created one, ScNPhaseCore.cpp:182-252), shapes are ordered by geometry type for
@@ -12,7 +13,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
                               const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
                               float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
                               uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters, uint32_t* __restrict__ gjkList,
-                              const uint32_t* __restrict__ pairOrder, const TouchLists touch) {
+                              const uint32_t* __restrict__ pairOrder, const TouchLists touch, uint32_t* __restrict__ boxList) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *nPairsP) return;
   const uint32_t i = pairOrder ? pairOrder[t] : t;   // mixed-type scenes: pairs binned by type pair (k_np_class_*)
@@ -41,6 +42,11 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
   for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
   if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_BOX) pcm_plane_box(tm0, tm1, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
+  else if (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX && boxList) {   // device-wide path: only the refresh here, regeneration over a compacted worklist (k_boxbox_generate)
+    if (pcm_box_box_refresh(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out)) {
+      manifold_store(man, rec); boxList[atomicAdd(&counters[C_NBOXGEN], 1u)] = i; return;
+    }
+  }
   else if (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX) {
     if (pcm_box_box(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out)) {
       // edge-edge / corner configuration (rare): the SAT passed but clipping found no point -> GJK / EPA single-point fallback, called out of
@@ -298,9 +304,27 @@ __global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_gjk_manifold(const NpArgs
   }
 }
 
+// box-box manifold regeneration (SAT + clipping + reduction, the GJK / EPA single-point fallback when clipping finds nothing) for the pairs whose
+// manifold k_narrowphase found invalid: a dense pile regenerates a minority of its manifolds per step, and next to the cached majority those
+// lanes ran alone (11 of 32 lanes active in k_narrowphase on BASELINE config 4).
+__global__ void __launch_bounds__(128, PXB_NP_CTAS) k_boxbox_generate(const NpArgs A) {
+  const uint32_t n = A.counters[C_NBOXGEN];
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const uint32_t i = A.boxList[w];
+    GjkPair P; gjk_pair_setup(A, i, P);
+    Manifold man; manifold_load(man, P.rec); manifold_load_warm(man, P.rec); man.dirty = 1;
+    Contacts out; gjk_contacts_clear(out);
+    const v3 e0 = V3(P.d0.x, P.d0.y, P.d0.z), e1 = V3(P.d1.x, P.d1.y, P.d1.z);
+    if (pcm_box_box_generate(P.tm0, P.tm1, e0, e1, A.contactDist, A.toleranceLength, man, out))
+      gjk_boxbox_gjk_fallback_outofline(&P.tm0, &P.tm1, e0, e1, A.contactDist, A.toleranceLength, &man, &out);
+    gjk_pair_finish(A, P, man, out);
+  }
+}
+
 void pxb_launch_narrowphase(cudaStream_t st, uint32_t capPairs, const NpArgs& A) {
   k_narrowphase<<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies,
-                                                         A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch);
+                                                         A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch, A.boxList);
+  if (A.boxList) k_boxbox_generate<<<std::max(148u * 4u, std::min((capPairs + 127) / 128, 148u * 64u)), 128, 0, st>>>(A);
 }
 void pxb_launch_narrowphase_gjk(cudaStream_t st, uint32_t ctas, const NpArgs& A) {
   k_narrowphase_gjk<<<ctas, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies, A.conFlag, A.counters,

@@ -480,9 +480,9 @@ PXB_D bool boxbox_generate(v3 e0, v3 e1, const mxf& t0, const mxf& t1, float con
   return true;
 }
 
-// GuPCMContactBoxBox.cpp:848-971
-// returns true when the SAT passed but clipping found no point: the caller then runs the GJK / EPA single-point fallback (pxb_gjk.cuh)
-PXB_D bool pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contactDist, float toleranceLength, Manifold& man, Contacts& out) {
+// GuPCMContactBoxBox.cpp:848-971, in two parts so that the device-wide path can run the (expensive, divergent) regeneration over a compacted worklist:
+// pcm_box_box_refresh: manifold refresh + invalidation test; returns true when the manifold has to be regenerated (frames already updated), else emits the cached points.
+PXB_D bool pcm_box_box_refresh(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contactDist, float toleranceLength, Manifold& man, Contacts& out) {
   const xf cur = axfinvmul(tm1, tm0);  // A into B
   const mxf aToB = amxffromxf(cur);
   const float minMargin = fmin_(box_margin(e0, toleranceLength), box_margin(e1, toleranceLength));
@@ -493,19 +493,9 @@ PXB_D bool pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contact
   out.count = 0; out.normal = V3(0, 0, 0);
   if (lost || invalidate_boxconvex(man, cur, tm0.q, tm1.q, minMargin, radiusA, radiusB)) {
     man.rel = cur; man.quatA = tm0.q; man.quatB = tm1.q; man.dirty = 1;
-    mxf tv0 = amxffromxf(tm0), tv1 = amxffromxf(tm1);
-    tv0.r.c0 = anormalize(tv0.r.c0); tv0.r.c1 = anormalize(tv0.r.c1); tv0.r.c2 = anormalize(tv0.r.c2);
-    tv1.r.c0 = anormalize(tv1.r.c0); tv1.r.c1 = anormalize(tv1.r.c1); tv1.r.c2 = anormalize(tv1.r.c2);
-    MPoint mc[16]; int num = 0;
-    if (boxbox_generate(e0, e1, tv0, tv1, contactDist, mc, num)) {
-      if (num > 0) {
-        if (num <= PXB_MANIFOLD_CACHE) { for (int i = 0; i < num; ++i) man.pts[i] = mc[i]; man.n = num; }
-        else { reduce_batch(man, mc, num, toleranceLength); man.n = PXB_MANIFOLD_CACHE; }
-        out.normal = anormalize(mmul(tv1.r, man.pts[0].n));
-        for (int i = 0; i < man.n; ++i) { out.point[out.count] = amxftransform(tv1, man.pts[i].b); out.sep[out.count] = man.pts[i].pen; out.count++; }
-      } else return true;
-    }
-  } else if (man.n > 0) {
+    return true;
+  }
+  if (man.n > 0) {
     out.normal = manifold_world_normal(man, tm1);
     for (int i = 0; i < man.n; ++i) {
       const float dist = man.pts[i].pen;
@@ -513,6 +503,27 @@ PXB_D bool pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contact
     }
   }
   return false;
+}
+// pcm_box_box_generate: SAT + clipping + reduction.  Returns true when the SAT passed but clipping found no point: the caller then runs the GJK / EPA single-point fallback (pxb_gjk.cuh)
+PXB_D bool pcm_box_box_generate(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contactDist, float toleranceLength, Manifold& man, Contacts& out) {
+  out.count = 0; out.normal = V3(0, 0, 0);
+  mxf tv0 = amxffromxf(tm0), tv1 = amxffromxf(tm1);
+  tv0.r.c0 = anormalize(tv0.r.c0); tv0.r.c1 = anormalize(tv0.r.c1); tv0.r.c2 = anormalize(tv0.r.c2);
+  tv1.r.c0 = anormalize(tv1.r.c0); tv1.r.c1 = anormalize(tv1.r.c1); tv1.r.c2 = anormalize(tv1.r.c2);
+  MPoint mc[16]; int num = 0;
+  if (boxbox_generate(e0, e1, tv0, tv1, contactDist, mc, num)) {
+    if (num > 0) {
+      if (num <= PXB_MANIFOLD_CACHE) { for (int i = 0; i < num; ++i) man.pts[i] = mc[i]; man.n = num; }
+      else { reduce_batch(man, mc, num, toleranceLength); man.n = PXB_MANIFOLD_CACHE; }
+      out.normal = anormalize(mmul(tv1.r, man.pts[0].n));
+      for (int i = 0; i < man.n; ++i) { out.point[out.count] = amxftransform(tv1, man.pts[i].b); out.sep[out.count] = man.pts[i].pen; out.count++; }
+    } else return true;
+  }
+  return false;
+}
+PXB_D bool pcm_box_box(const xf& tm0, const xf& tm1, v3 e0, v3 e1, float contactDist, float toleranceLength, Manifold& man, Contacts& out) {
+  if (!pcm_box_box_refresh(tm0, tm1, e0, e1, contactDist, toleranceLength, man, out)) return false;
+  return pcm_box_box_generate(tm0, tm1, e0, e1, contactDist, toleranceLength, man, out);
 }
 
 // ---------------- sphere / capsule family (reference GPU kernel: sphereNphase_Kernel) ----------------
