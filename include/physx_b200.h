@@ -219,6 +219,26 @@ PXB_API int  pxb_scene_get_touch_lost(PxbScene* scene, uint32_t* outPairs);
  * [count, nx, ny, nz, 4 x (px, py, pz, separation, appliedForce)]; normal points body1 -> body0
  * (PxsContactManagerOutput / PxContactPatch + PxContact stream analogue, physx/include/PxContact.h:57-148). */
 PXB_API int  pxb_scene_get_contacts(PxbScene* scene, float* out24);
+/* PxDirectGPUAPI::copyContactData (physx/include/PxDirectGPUAPI.h:388-401; reference kernels compressContactStage1 / 2,
+ * gpunarrowphase/src/CUDA/compressOutputContacts.cu:48-275): one PxGpuContactPair record (physx/include/PxContact.h:818-833, 80 bytes, same field
+ * layout) per pair that produced contacts in the last step, in pair order, written to DEVICE memory `data` (maxPairs records); the device word
+ * `nbContactPairs` receives the number of touching pairs (it can exceed maxPairs: only maxPairs records are written).  The pointers inside a record
+ * point into streams owned by the scene and stay valid until the next simulate: contactPatches -> one PxContactPatch (64 B: normal, combined
+ * restitution / dynamic / static friction, nbContacts, material indices), contactPoints -> nbContacts PxContact (point, separation), contactForces ->
+ * nbContacts applied normal impulses, frictionPatches -> one PxFrictionPatch (52 B: world anchor positions, anchor impulses, anchor count; the
+ * reference's writeBackContactBlockFriction, gpusolver/src/CUDA/solverBlockCommon.cuh:33-66).  transformCacheRef0/1 = actor indices (one shape per
+ * actor), nodeIndex0/1 = PxNodeIndex with mID = PxRigidDynamicGPUIndex (0xffffffff for a static actor), actor0/1 = the actor index as a handle.
+ * Stream-ordered on the scene stream (read `data` after pxb_scene_sync or on that stream).  The friction write-back costs a few loads per
+ * constraint, so it is off by default: pxb_scene_enable_contact_data(scene, 1) BEFORE the step whose contacts are wanted. */
+typedef struct PxbGpuContactPair {
+  uint8_t* contactPatches; uint8_t* contactPoints; float* contactForces; uint8_t* frictionPatches;
+  uint32_t transformCacheRef0, transformCacheRef1;
+  uint64_t nodeIndex0, nodeIndex1;
+  uint64_t actor0, actor1;
+  uint16_t nbContacts, nbPatches; uint32_t pad;
+} PxbGpuContactPair;
+PXB_API int  pxb_scene_enable_contact_data(PxbScene* scene, int enable);
+PXB_API int  pxb_scene_copy_contact_data(PxbScene* scene, void* data, uint32_t* nbContactPairs, uint32_t maxPairs);
 /* Solver statistics of the last step (PxSimulationStatistics::mNbPartitions analogue). */
 PXB_API uint32_t pxb_scene_last_num_partitions(PxbScene* scene);
 PXB_API uint32_t pxb_scene_last_num_constraints(PxbScene* scene);

@@ -49,6 +49,7 @@ struct PxbScene {
   // per pair (this frame)
   float4 *cHdr = 0, *cPts = 0; uint2* pairBodies = 0; float* cForce = 0;
   uint32_t *pairOrder = 0, *npClassCount = 0; uint8_t* npClass = 0; bool binPairs = false;   // mixed-type scenes: pairs binned by type pair before the narrowphase
+  float4* frReport = 0; uint32_t *ccIdx = 0, *ccOff = 0, *ccCount = 0, *ccTotal = 0, *actorDyn = 0; uint8_t *ccPatches = 0, *ccPoints = 0, *ccFriction = 0; float* ccForces = 0; bool contactData = false;
   uint32_t *gjkList = 0, *gjkQuery = 0, *gjkFull = 0, *gjkEpa = 0, *boxList = 0; bool boxPhases = true; bool gjkPhases = true; bool hasGjkPairs = false, anyLocks = false, anyConvex = false;
   float4 *extForce = 0, *extTorque = 0; bool forcesUsed = false;
   uint4* hullMeta = 0; float4 *hullVerts = 0, *hullPolys = 0; uint8_t *hullRefs = 0, *hullEdges = 0; uint32_t nHulls = 0; std::vector<float> hullDiam;   // cooked convex hulls (pxb_scene_set_convex_meshes)   // PxDirectGPUAPI eFORCE / eTORQUE writes pending for the next step   // a10: worklist of GJK-family pairs (filled by k_narrowphase)
@@ -848,7 +849,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
   void* ptrs[] = {s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
-                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
+                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->prevB0, s->prevB1, s->prevColour, s->prevNCon, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
                   s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->actorMat, s->matTab, s->touchState, s->touchFound, s->touchLost, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
@@ -1275,7 +1276,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     A.dt = dt; A.gx = g[0]; A.gy = g[1]; A.gz = g[2]; A.P = P;
     A.envStart = s->envStart; A.envList = s->envList; A.actorLocal = s->actorLocal; A.seg = s->envSeg[cur];
     A.pos = s->pos; A.quat = s->quat; A.linVel = s->linVel; A.angVel = s->angVel; A.invInertia = s->invInertia; A.damp = s->damp; A.geomFlags = s->geomFlags; A.anyLocks = s->anyLocks ? 1u : 0u; A.extForce = s->forcesUsed ? s->extForce : nullptr; A.extTorque = s->forcesUsed ? s->extTorque : nullptr;
-    A.pairSlots = s->pairSlots[cur]; A.pairBodies = s->pairBodies; A.cHdr = s->cHdr; A.cPts = s->cPts; A.cForce = s->cForce; A.frictions = s->frictions;
+    A.pairSlots = s->pairSlots[cur]; A.pairBodies = s->pairBodies; A.cHdr = s->cHdr; A.cPts = s->cPts; A.cForce = s->cForce; A.frictions = s->frictions; A.frReport = s->contactData ? s->frReport : nullptr;
     A.conPair = s->conPair; A.conB0 = s->conB0; A.conB1 = s->conB1; A.conColour = s->conColour; A.ordered = s->ordered; A.broken = s->conDone;
     A.rowScratch = s->ptA;   // ptA|ptB|ptC|frA|frB|frC|frD are ONE allocation of 28 x cap float4 (scene_alloc); the environment path uses 25 of them
     A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour; A.S = SA;
@@ -1349,7 +1350,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     VA.nDyn = s->nDyn; VA.dynActor = s->dynActorDev;
     CK(pxb_launch_solve(st, pgs, pgs ? s->coopBlocksSolvePgs : s->coopBlocksSolve, VA)); s->launches++;
     MARK(5);
-    pxb_launch_writeback_rows(st, s->capPairs, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions); s->launches++;
+    pxb_launch_writeback_rows(st, s->capPairs, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions, s->contactData ? s->frReport : nullptr, s->pairBodies, s->pos, s->quat); s->launches++;
     if (pgs) {
       pxb_launch_finalize_bodies_pgs(st, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->invInertia, SA, s->geomFlags); s->launches++;
       if (s->exportOn) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
@@ -1505,6 +1506,80 @@ PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) { DeviceGuard dg_(
     if (cnt) { o[1] = h[i].x; o[2] = h[i].y; o[3] = h[i].z; }
     for (int k = 0; k < cnt && k < 4; ++k) { const float4 q = p[(size_t)i * 4 + k]; float* r = o + 4 + k * 5; r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; r[4] = f[(size_t)i * 4 + k]; }
   }
+  return PXB_OK;
+}
+// ---- f3: PxDirectGPUAPI::copyContactData (PxDirectGPUAPI.h:388-401; the reference's compressContactStage1/2, gpunarrowphase/src/CUDA/compressOutputContacts.cu) ----
+// One PxGpuContactPair record per pair that has contacts, in pair order (stable compaction by two exclusive scans: touching flags -> record index, contact counts ->
+// offset into the point / force streams), pointing into PxContactPatch / PxContact / force / PxFrictionPatch streams owned by the scene.
+struct ContactPairRec { unsigned long long contactPatches, contactPoints, contactForces, frictionPatches; uint32_t ref0, ref1; unsigned long long node0, node1, actor0, actor1; uint16_t nbContacts, nbPatches; uint32_t pad; };
+static_assert(sizeof(ContactPairRec) == 80 && sizeof(ContactPairRec) == sizeof(PxbGpuContactPair), "PxGpuContactPair layout");
+__global__ void k_cc_counts(const uint32_t* __restrict__ nPairsP, const float4* __restrict__ cHdr, uint32_t* __restrict__ cnt) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *nPairsP) cnt[i] = (uint32_t)__float_as_int(cHdr[i].w);
+}
+__global__ void k_cc_actor_dyn(uint32_t nDyn, const uint32_t* __restrict__ dynActor, uint32_t* __restrict__ actorDyn) { const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; if (d < nDyn) actorDyn[dynActor[d]] = d; }
+__global__ void k_cc_write(const uint32_t* __restrict__ nPairsP, const float4* __restrict__ cHdr, const float4* __restrict__ cPts, const float* __restrict__ cForce, const uint2* __restrict__ pairBodies,
+                           const uint32_t* __restrict__ pairSlots, const float4* __restrict__ frictions, const float4* __restrict__ frReport, const uint32_t* __restrict__ actorMat,
+                           const uint32_t* __restrict__ actorDyn, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ off, uint8_t* __restrict__ patches, uint8_t* __restrict__ points,
+                           float* __restrict__ forces, uint8_t* __restrict__ fric, ContactPairRec* __restrict__ out, uint32_t maxPairs) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *nPairsP) return;
+  const float4 h = cHdr[i]; const int n = __float_as_int(h.w);
+  if (n <= 0) return;
+  const uint32_t r = idx[i], o = off[i];
+  const uint2 bb = pairBodies[i];
+  const float4* fr = frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4;
+  // PxContactPatch (PxContact.h:56-137, 64 bytes): mass modification 1,1,1,1 | normal, restitution | dynamic friction, static friction, damping, (startContactIndex u16, nbContacts u8,
+  // materialFlags u8) | (internalFlags u16, materialIndex0 u16), (materialIndex1 u16, pad) ...
+  float4* P = reinterpret_cast<float4*>(patches + (size_t)r * 64);
+  P[0] = make_float4(1.f, 1.f, 1.f, 1.f);
+  P[1] = make_float4(h.x, h.y, h.z, fr[5].w);
+  P[2] = make_float4(fr[4].w, fr[3].w, 0.f, __uint_as_float(((uint32_t)n & 0xffu) << 16));
+  const uint32_t m0 = actorMat ? actorMat[bb.x] : 0u, m1 = actorMat ? actorMat[bb.y] : 0u;
+  P[3] = make_float4(__uint_as_float((m0 & 0xffffu) << 16), __uint_as_float(m1 & 0xffffu), 0.f, 0.f);
+  float4* C = reinterpret_cast<float4*>(points) + o;   // PxContact: point, separation
+  for (int k = 0; k < n; ++k) { C[k] = cPts[(size_t)i * 4 + k]; forces[o + k] = cForce[(size_t)i * 4 + k]; }
+  // PxFrictionPatch (PxContact.h:635-658, 52 bytes): anchorPositions[2], anchorImpulses[2], anchorCount
+  float* F = reinterpret_cast<float*>(fric + (size_t)r * 52);
+  const float4 q0 = frReport[(size_t)i * 4], q1 = frReport[(size_t)i * 4 + 1], w0 = frReport[(size_t)i * 4 + 2], w1 = frReport[(size_t)i * 4 + 3];
+  F[0] = w0.x; F[1] = w0.y; F[2] = w0.z; F[3] = w1.x; F[4] = w1.y; F[5] = w1.z; F[6] = q0.x; F[7] = q0.y; F[8] = q0.z; F[9] = q1.x; F[10] = q1.y; F[11] = q1.z; F[12] = q0.w;
+  if (r >= maxPairs) return;
+  ContactPairRec c;
+  c.contactPatches = (unsigned long long)(patches + (size_t)r * 64); c.contactPoints = (unsigned long long)(C); c.contactForces = (unsigned long long)(forces + o);
+  c.frictionPatches = (unsigned long long)(fric + (size_t)r * 52); c.ref0 = bb.x; c.ref1 = bb.y;
+  c.node0 = actorDyn[bb.x]; c.node1 = actorDyn[bb.y];   // PxNodeIndex: mID in the low word (0xffffffff = static actor), mLinkID 0
+  c.actor0 = bb.x; c.actor1 = bb.y; c.nbContacts = (uint16_t)n; c.nbPatches = 1; c.pad = 0;
+  out[r] = c;
+}
+PXB_API int pxb_scene_enable_contact_data(PxbScene* s, int enable) { DeviceGuard dg_(s);
+  if (!s) return fail(PXB_ERR_INVALID, "null argument");
+  if ((enable != 0) == s->contactData) return PXB_OK;
+  CK(cudaStreamSynchronize(s->stream));
+  if (enable) {
+    const size_t Pn = s->capPairs;
+    if (!s->frReport) {
+      CK(dalloc(s->frReport, Pn * 4)); CK(dalloc(s->ccIdx, Pn)); CK(dalloc(s->ccOff, Pn)); CK(dalloc(s->ccCount, Pn)); CK(dalloc(s->ccTotal, 4)); CK(dalloc(s->actorDyn, std::max<size_t>(s->capA, 1)));
+      CK(dalloc(s->ccPatches, Pn * 64)); CK(dalloc(s->ccPoints, Pn * 64)); CK(dalloc(s->ccFriction, Pn * 52)); CK(dalloc(s->ccForces, Pn * 4));
+      CK(cudaMemsetAsync(s->frReport, 0, Pn * 64, s->stream));
+    }
+  }
+  s->contactData = enable != 0;
+  drop_graphs(s);   // the write-back kernels gain / lose the friction report
+  return PXB_OK;
+}
+PXB_API int pxb_scene_copy_contact_data(PxbScene* s, void* data, uint32_t* nbContactPairs, uint32_t maxPairs) { DeviceGuard dg_(s);
+  if (!s || !nbContactPairs || (maxPairs && !data)) return fail(PXB_ERR_INVALID, "null argument");
+  if (!s->contactData) return fail(PXB_ERR_INVALID, "contact data is off: call pxb_scene_enable_contact_data before the step");
+  cudaStream_t st = s->stream; const uint32_t B = 256; const uint32_t gP = cdiv(s->capPairs, B);
+  const uint32_t* nP = s->nPairsDev + s->cur;
+  CK(cudaMemsetAsync(s->actorDyn, 0xff, 4 * (size_t)std::max<uint32_t>(s->nA, 1), st));
+  if (s->nDyn) k_cc_actor_dyn<<<cdiv(s->nDyn, B), B, 0, st>>>(s->nDyn, s->dynActorDev, s->actorDyn);
+  k_cc_counts<<<gP, B, 0, st>>>(nP, s->cHdr, s->ccCount);
+  exclusive_scan_u32(s->conFlag, s->ccIdx, nP, nbContactPairs, s->scanSums, s->rsTmp.ctas, st);
+  exclusive_scan_u32(s->ccCount, s->ccOff, nP, s->ccTotal, s->scanSums, s->rsTmp.ctas, st);
+  k_cc_write<<<gP, B, 0, st>>>(nP, s->cHdr, s->cPts, s->cForce, s->pairBodies, s->pairSlots[s->cur], s->frictions, s->frReport, s->matTab ? s->actorMat : (const uint32_t*)nullptr, s->actorDyn, s->ccIdx, s->ccOff,
+                              s->ccPatches, s->ccPoints, s->ccForces, s->ccFriction, (ContactPairRec*)data, maxPairs);
+  CK(cudaGetLastError());
   return PXB_OK;
 }
 PXB_API uint32_t pxb_scene_num_touch_found(PxbScene* s) { return s ? s->hNTouchFound : 0; }

@@ -147,7 +147,7 @@ struct EnvSolveArgs {
   uint32_t nEnv, maxList, conCap, cap, posIters, velIters; float dt, gx, gy, gz; SolverParams P;
   const uint32_t *envStart, *envList, *actorLocal; const uint2* seg;
   float4 *pos, *quat, *linVel, *angVel; const float4 *invInertia, *damp; const uint32_t* geomFlags;
-  const uint32_t* pairSlots; const uint2* pairBodies; const float4 *cHdr, *cPts; float* cForce; float4* frictions;
+  const uint32_t* pairSlots; const uint2* pairBodies; const float4 *cHdr, *cPts; float* cForce; float4* frictions; float4* frReport;
   uint32_t *conPair, *conB0, *conB1, *conColour, *ordered, *broken;   // per-pair-index scratch (global, L2 resident)
   uint32_t* slotColour;   // per persistent pair slot: partition of the pair's constraint last frame (NONE32 = no contacts)
   float4* rowScratch;   // 25 x cap float4, field-major: memory image of RegRows for environments with more constraints than threads
@@ -386,11 +386,16 @@ __device__ __forceinline__ void env_prep_one(const EnvSolveArgs& A, const ConLis
   else prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.P);
 }
 // a17: writeBackContact (DyTGSContactPrep.cpp:1875-1937)
-__device__ __forceinline__ void env_writeback_one(const EnvSolveArgs& A, const RegRows& r) {
+__device__ __forceinline__ void env_writeback_one(const EnvSolveArgs& A, const RegRows& r, const FrView fr = FrView()) {
   const uint32_t i = r.h2.w; const int numNormal = (int)(r.h2.z & 0xff), numFriction = (int)((r.h2.z >> 8) & 0xff);
 #pragma unroll
   for (int j = 0; j < 4; ++j) if (j < numNormal) A.cForce[(size_t)i * 4 + j] = f4get(r.ap, j);
   if (numFriction && r.broken) A.frictions[(size_t)A.pairSlots[i] * PXB_FRICTION_F4 + 1].w = __int_as_float(1);
+  if (A.frReport) {   // contact reports on: friction impulses + world anchors (the body poses in global memory are still the start-of-step ones here)
+    const uint32_t a0 = A.pairBodies[i].x;
+    friction_report_store(A.frReport, i, numFriction, fr.p ? fr.p[0] : r.t0, fr.p ? fr.p[fr.stride] : r.t1, fr.p ? fr.p[10 * fr.stride] : r.fap,
+                          A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.pos[a0], A.quat[a0]);
+  }
 }
 template <int T, bool EXT>
 __device__ __forceinline__ void env_integrate_substep(uint32_t n, float stepDt, float4* bLin, float4* bAng, float4* bDLin, float4* bDAng, const float4* bIA, const float4* bIB, float4* bP, float4* bQ) {
@@ -464,7 +469,7 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
     }
   }
   ENV_T(5);
-  if (REG) { if (tid < nCon) env_writeback_one(A, mine); }
+  if (REG) { if (tid < nCon) env_writeback_one(A, mine, fr); }
   else for (uint32_t pos = tid; pos < nCon; pos += T) { RegRows r; rows_load(R, pos, r); env_writeback_one(A, r); }
 }
 

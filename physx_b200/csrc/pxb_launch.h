@@ -20,6 +20,7 @@ struct SolveArgs {
 cudaError_t pxb_solve_occupancy(int* tgsCtasPerSm, int* pgsCtasPerSm);
 void pxb_launch_prep_rows(cudaStream_t st, bool pgs, uint32_t capPairs, const PrepArgs& A);
 cudaError_t pxb_launch_solve(cudaStream_t st, bool pgs, int blocks, SolveArgs& A);   // ONE cooperative launch: every solver iteration
-void pxb_launch_writeback_rows(cudaStream_t st, uint32_t capPairs, const uint32_t* counters, Rows R, const uint32_t* pairSlots, float* cForce, float4* frictions);
+void pxb_launch_writeback_rows(cudaStream_t st, uint32_t capPairs, const uint32_t* counters, Rows R, const uint32_t* pairSlots, float* cForce, float4* frictions, float4* frReport, const uint2* pairBodies,
+                               const float4* pos, const float4* quat);   // frReport: null unless contact reports are enabled (pxb_scene_enable_contact_data)
 void pxb_launch_finalize_bodies_pgs(cudaStream_t st, uint32_t nDyn, const uint32_t* dynActor, float dt, float4* pos, float4* quat, float4* linVel, float4* angVel, const float4* sbLin, const float4* sbAng,
                                     const float4* sbDLin, const float4* sbDAng, const float4* sbIA, const float4* sbIB, const float4* invInertia, SleepArgs S, const uint32_t* geomFlags);

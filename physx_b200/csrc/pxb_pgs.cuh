@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve_pgs(const 
 }
 
 // a17: writeBackContact (DyTGSContactPrep.cpp:1875-1937 / DySolverConstraints.cpp:553-640): applied forces -> contact force stream, broken flag -> friction patch
-__global__ void k_writeback_rows(const uint32_t* __restrict__ counters, Rows R, const uint32_t* __restrict__ pairSlots, float* __restrict__ cForce, float4* __restrict__ frictions) {
+__global__ void k_writeback_rows(const uint32_t* __restrict__ counters, Rows R, const uint32_t* __restrict__ pairSlots, float* __restrict__ cForce, float4* __restrict__ frictions,
+                                 float4* __restrict__ frReport, const uint2* __restrict__ pairBodies, const float4* __restrict__ pos, const float4* __restrict__ quat) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= counters[C_NCON]) return;
   const size_t s = R.stride;
@@ -323,6 +324,7 @@ __global__ void k_writeback_rows(const uint32_t* __restrict__ counters, Rows R, 
   const float4 ap = R.f[13 * s + k];
   for (int j = 0; j < numNormal; ++j) cForce[(size_t)i * 4 + j] = f4get(ap, j);
   if (numFriction && R.broken[k]) frictions[(size_t)pairSlots[i] * PXB_FRICTION_F4 + 1].w = __int_as_float(1);
+  if (frReport) { const uint32_t a0 = pairBodies[i].x; friction_report_store(frReport, i, numFriction, R.f[14 * s + k], R.f[15 * s + k], R.f[24 * s + k], frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, pos[a0], quat[a0]); }
 }
 
 __global__ void k_finalize_bodies_pgs(uint32_t nDyn, const uint32_t* __restrict__ dynActor, float dt, float4* __restrict__ pos, float4* __restrict__ quat, float4* __restrict__ linVel,

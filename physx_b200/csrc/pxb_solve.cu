@@ -21,8 +21,9 @@ cudaError_t pxb_launch_solve(cudaStream_t st, bool pgs, int blocks, SolveArgs& A
   void* args[] = {&A.counters, &A.partStart, &A.posIters, &A.velIters, &A.stepDt, &A.R, &A.sbLin, &A.sbAng, &A.sbDLin, &A.sbDAng, &A.sbIA, &A.sbIB, &A.sbP, &A.sbQ, &A.bodyHasCon, &A.nDyn, &A.dynActor};
   return cudaLaunchCooperativeKernel((void*)k_solve_tgs, dim3(blocks), dim3(256), args, 0, st);
 }
-void pxb_launch_writeback_rows(cudaStream_t st, uint32_t capPairs, const uint32_t* counters, Rows R, const uint32_t* pairSlots, float* cForce, float4* frictions) {
-  k_writeback_rows<<<(capPairs + 255) / 256, 256, 0, st>>>(counters, R, pairSlots, cForce, frictions);
+void pxb_launch_writeback_rows(cudaStream_t st, uint32_t capPairs, const uint32_t* counters, Rows R, const uint32_t* pairSlots, float* cForce, float4* frictions, float4* frReport, const uint2* pairBodies,
+                               const float4* pos, const float4* quat) {
+  k_writeback_rows<<<(capPairs + 255) / 256, 256, 0, st>>>(counters, R, pairSlots, cForce, frictions, frReport, pairBodies, pos, quat);
 }
 void pxb_launch_finalize_bodies_pgs(cudaStream_t st, uint32_t nDyn, const uint32_t* dynActor, float dt, float4* pos, float4* quat, float4* linVel, float4* angVel, const float4* sbLin, const float4* sbAng,
                                     const float4* sbDLin, const float4* sbDAng, const float4* sbIA, const float4* sbIB, const float4* invInertia, SleepArgs S, const uint32_t* geomFlags) {

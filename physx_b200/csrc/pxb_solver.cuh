@@ -35,6 +35,20 @@ PXB_D void friction_store(const FrictionPatch& f, float4* __restrict__ r) {
   r[4] = F4(f.body1Anchors[0], f.df); r[5] = F4(f.body1Anchors[1], f.rest); r[6] = F4(f.relativeQuat);
 }
 
+// PxFrictionPatch write-back for PxDirectGPUAPI::copyContactData (the reference's writeBackContactBlockFriction, gpusolver/src/CUDA/solverBlockCommon.cuh:33-66):
+// per pair 4 float4 = impulse at anchor 0 (w: anchor count), impulse at anchor 1, world anchor 0, world anchor 1.  impulse[k] = t0 * applied[2k] + t1 * applied[2k+1];
+// the anchors are body 0's local anchors of the pair's friction patch in body 0's start-of-step frame (what contact prep solved with).
+PXB_D void friction_report_store(float4* __restrict__ out, uint32_t i, int numFriction, float4 t0, float4 t1, float4 fap, const float4* __restrict__ frRec, float4 p0, float4 q0) {
+  float4* o = out + (size_t)i * 4;
+  const int anchors = numFriction >> 1;
+  const v3 T0 = V3(t0.x, t0.y, t0.z), T1 = V3(t1.x, t1.y, t1.z);
+  const v3 i0 = anchors >= 1 ? T0 * fap.x + T1 * fap.y : V3(0, 0, 0), i1 = anchors >= 2 ? T0 * fap.z + T1 * fap.w : V3(0, 0, 0);
+  xf tm; tm.p = V3(p0.x, p0.y, p0.z); tm.q = Q4(q0);
+  const float4 a0 = frRec[2], a1 = frRec[3];
+  const v3 w0 = anchors >= 1 ? axftransform(tm, V3(a0.x, a0.y, a0.z)) : V3(0, 0, 0), w1 = anchors >= 2 ? axftransform(tm, V3(a1.x, a1.y, a1.z)) : V3(0, 0, 0);
+  o[0] = F4(i0, __int_as_float(anchors)); o[1] = F4(i1, 0.f); o[2] = F4(w0, 0.f); o[3] = F4(w1, 0.f);
+}
+
 PXB_D void transform_inertia(v3 d, const m33& M, m33& out) {  // Cm::transformInertiaTensor, M(r,c) = column c row r
   const float axx = d.x * M.c0.x, axy = d.x * M.c0.y, axz = d.x * M.c0.z;
   const float byx = d.y * M.c1.x, byy = d.y * M.c1.y, byz = d.y * M.c1.z;

@@ -31,7 +31,7 @@ EXPORTS = [
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
     "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait", "pxb_bp_create", "pxb_bp_release", "pxb_bp_update", "pxb_bp_fetch",
-    "pxb_scene_set_materials", "pxb_scene_remove_actors", "pxb_tensor_read_device", "pxb_tensor_write_device", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost",
+    "pxb_scene_set_materials", "pxb_scene_remove_actors", "pxb_tensor_read_device", "pxb_tensor_write_device", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost", "pxb_scene_enable_contact_data", "pxb_scene_copy_contact_data",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
@@ -94,6 +94,8 @@ def load_library():
               "pxb_scene_get_pairs", "pxb_scene_get_created", "pxb_scene_get_deleted", "pxb_scene_get_contacts", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost"):
         getattr(lib, f).argtypes = [vp, vp]
     lib.pxb_scene_compute_bounds.argtypes = [vp]
+    lib.pxb_scene_enable_contact_data.argtypes = [vp, i32]
+    lib.pxb_scene_copy_contact_data.argtypes = [vp, vp, vp, u32]
     lib.pxb_scene_get_states_device.argtypes = [vp, vp]
     lib.pxb_scene_uses_env_path.argtypes = [vp]
     lib.pxb_scene_get_sleep_data.argtypes = [vp, vp, vp]
@@ -300,6 +302,22 @@ class Scene:
     def getTouchLost(self):
         """pairs that stopped producing contacts in the last step, incl. touching pairs that left the broadphase"""
         return self._pairs(self._lib.pxb_scene_num_touch_lost, self._lib.pxb_scene_get_touch_lost)
+
+    GPU_CONTACT_PAIR_DTYPE = np.dtype([("contactPatches", "<u8"), ("contactPoints", "<u8"), ("contactForces", "<u8"), ("frictionPatches", "<u8"), ("transformCacheRef0", "<u4"),
+                                       ("transformCacheRef1", "<u4"), ("nodeIndex0", "<u8"), ("nodeIndex1", "<u8"), ("actor0", "<u8"), ("actor1", "<u8"), ("nbContacts", "<u2"),
+                                       ("nbPatches", "<u2"), ("pad", "<u4")])   # PxGpuContactPair, PxContact.h:818-833
+
+    def sync(self):
+        """wait for everything queued on the scene stream"""
+        _check(self._lib, self._lib.pxb_scene_sync(self._h))
+
+    def enableContactData(self, on=True):
+        """PxDirectGPUAPI::copyContactData needs the friction write-back of the step: switch it on BEFORE the step whose contacts are wanted"""
+        _check(self._lib, self._lib.pxb_scene_enable_contact_data(self._h, 1 if on else 0))
+
+    def copyContactData(self, data_ptr, count_ptr, max_pairs):
+        """PxDirectGPUAPI::copyContactData: PxGpuContactPair records into device memory `data_ptr`, their number into the device word `count_ptr` (stream-ordered)"""
+        _check(self._lib, self._lib.pxb_scene_copy_contact_data(self._h, ctypes.c_void_p(int(data_ptr)), ctypes.c_void_p(int(count_ptr)), int(max_pairs)))
 
     def getContacts(self):
         n = int(self._lib.pxb_scene_num_pairs(self._h))

@@ -129,3 +129,56 @@ def get_contact_report(scene: _engine.Scene) -> dict:
     return {"actor0": pairs[keep, 0], "actor1": pairs[keep, 1], "normals": con[keep, 1:4], "counts": counts,
             "start_indices": np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int32) if len(counts) else np.zeros(0, np.int32),
             "positions": pts[:, :3], "separations": pts[:, 3], "impulses": pts[:, 4]}
+
+
+class GpuContactData:
+    """PxDirectGPUAPI::copyContactData through the C ABI (pxb_scene_copy_contact_data): the PxGpuContactPair records stay in a device tensor
+    (`records`, uint8 [max_pairs, 80]; `count`, int32 [1]); `to_host()` follows the record pointers into the scene-owned PxContactPatch / PxContact /
+    force / PxFrictionPatch streams and returns numpy views of everything (for tests and debugging: a learner reads the device memory directly).
+
+        scene.enableContactData()                # before the step
+        scene.step()
+        cd = GpuContactData(scene, max_pairs)    # after fetchResults
+        host = cd.to_host()
+    """
+
+    PATCH_DTYPE = np.dtype([("massModification", "<f4", 4), ("normal", "<f4", 3), ("restitution", "<f4"), ("dynamicFriction", "<f4"), ("staticFriction", "<f4"), ("damping", "<f4"),
+                            ("startContactIndex", "<u2"), ("nbContacts", "u1"), ("materialFlags", "u1"), ("internalFlags", "<u2"), ("materialIndex0", "<u2"), ("materialIndex1", "<u2"),
+                            ("pad", "<u2", 5)])   # PxContactPatch, PxContact.h:56-137
+    FRICTION_DTYPE = np.dtype([("anchorPositions", "<f4", (2, 3)), ("anchorImpulses", "<f4", (2, 3)), ("anchorCount", "<u4")])   # PxFrictionPatch, PxContact.h:635-658
+
+    def __init__(self, scene: _engine.Scene, max_pairs: int):
+        import torch
+        assert self.PATCH_DTYPE.itemsize == 64 and self.FRICTION_DTYPE.itemsize == 52 and _engine.Scene.GPU_CONTACT_PAIR_DTYPE.itemsize == 80
+        dev = torch.device("cuda", scene.device_index)
+        self.scene, self.max_pairs = scene, int(max_pairs)
+        self.records = torch.zeros((self.max_pairs, 80), dtype=torch.uint8, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int32, device=dev)
+        scene.copyContactData(self.records.data_ptr(), self.count.data_ptr(), self.max_pairs)
+        scene.sync()
+
+    @staticmethod
+    def _read(ptr: int, nbytes: int) -> bytes:
+        from cuda.bindings import runtime as cudart
+        buf = np.empty(max(nbytes, 1), np.uint8)
+        if nbytes:
+            err, = cudart.cudaMemcpy(buf.ctypes.data, int(ptr), nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+            if int(err) != 0:
+                raise RuntimeError(f"cudaMemcpy failed: {err}")
+        return buf[:nbytes].tobytes()
+
+    def to_host(self) -> dict:
+        n_total = int(self.count.cpu()[0])
+        n = min(n_total, self.max_pairs)
+        rec = self.records[:n].cpu().numpy().reshape(-1).view(_engine.Scene.GPU_CONTACT_PAIR_DTYPE).copy()
+        out = {"total_pairs": n_total, "records": rec}
+        if n == 0:
+            return out
+        nc = int(rec["nbContacts"].astype(np.int64).sum())
+        # the streams are compact and in record order, so one copy per stream starting at the first record's pointer covers all records
+        out["patches"] = np.frombuffer(self._read(rec["contactPatches"][0], 64 * n), self.PATCH_DTYPE)
+        out["points"] = np.frombuffer(self._read(rec["contactPoints"][0], 16 * nc), np.float32).reshape(nc, 4)
+        out["forces"] = np.frombuffer(self._read(rec["contactForces"][0], 4 * nc), np.float32)
+        out["friction"] = np.frombuffer(self._read(rec["frictionPatches"][0], 52 * n), self.FRICTION_DTYPE)
+        out["start_indices"] = ((rec["contactPoints"] - rec["contactPoints"][0]) // 16).astype(np.int64)
+        return out

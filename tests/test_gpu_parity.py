@@ -1003,3 +1003,103 @@ def test_removed_actor_leaves_the_simulation_and_the_rest_continues(oracle, path
     assert gpu.num_dynamic == 6 and sg[2, 1] < st10[2, 1] - 0.2, "the box above fell onto the bottom box"
     with pytest.raises(engine.PhysxB200Error):
         gpu.removeActors([99])
+
+
+# ---- f3: PxDirectGPUAPI::copyContactData (PxGpuContactPair records + PxContactPatch / PxContact / force / PxFrictionPatch streams in device memory) ----
+def _combine(a, b, mode):
+    return {0: 0.5 * (a + b), 1: min(a, b), 2: a * b, 3: max(a, b)}[int(mode)]
+
+
+def _check_contact_data(gpu, sc, host):
+    pairs, con = gpu.getPairs(), gpu.getContacts()
+    touching = con[:, 0] > 0
+    rec = host["records"]
+    assert host["total_pairs"] == int(touching.sum()) == len(rec)
+    # the environment path keeps its pairs per environment, the host getters report them key-sorted: compare as sets keyed by the actor pair
+    key = lambda a, b: (min(int(a), int(b)), max(int(a), int(b)))
+    ref = {key(*pairs[i]): con[i] for i in np.nonzero(touching)[0]}
+    dyn_of = {int(a): d for d, a in enumerate(np.nonzero(sc.actors["flags"] & 1)[0])}     # PxRigidDynamicGPUIndex = position among the dynamic actors
+    mats = sc.materials
+    for r, (rc, pt, fr, s0) in enumerate(zip(rec, host["patches"], host["friction"], host["start_indices"])):
+        c = ref[key(rc["transformCacheRef0"], rc["transformCacheRef1"])]
+        k = int(rc["nbContacts"])
+        assert k == int(c[0]) == int(pt["nbContacts"]) and rc["nbPatches"] == 1 and pt["startContactIndex"] == 0
+        assert np.array_equal(pt["normal"], c[1:4])                                        # normal (body1 -> body0), bit for bit
+        pts = c[4:4 + 5 * k].reshape(k, 5)
+        assert np.array_equal(host["points"][s0:s0 + k], pts[:, :4])                       # PxContact: point + separation
+        assert np.array_equal(host["forces"][s0:s0 + k], pts[:, 4])                        # applied normal impulses
+        assert np.array_equal(pt["massModification"], np.ones(4, np.float32)) and pt["damping"] == 0
+        a0, a1 = int(rc["transformCacheRef0"]), int(rc["transformCacheRef1"])
+        assert rc["actor0"] == a0 and rc["actor1"] == a1
+        for a, node in ((a0, rc["nodeIndex0"]), (a1, rc["nodeIndex1"])):
+            assert int(node) == (dyn_of[a] if a in dyn_of else 0xffffffff)
+        if mats is not None and len(mats):
+            m0, m1 = mats[sc.actors["materialIndex"][a0]], mats[sc.actors["materialIndex"][a1]]
+            assert pt["materialIndex0"] == sc.actors["materialIndex"][a0] and pt["materialIndex1"] == sc.actors["materialIndex"][a1]
+            b0, b1 = int(m0["bits"]), int(m1["bits"])
+            rest = _combine(m0["restitution"], m1["restitution"], max((b0 >> 4) & 15, (b1 >> 4) & 15))
+            assert abs(float(pt["restitution"]) - rest) < 1e-6
+            if ((b0 | b1) >> 8) & 1:
+                assert pt["staticFriction"] == 0 and pt["dynamicFriction"] == 0 and fr["anchorCount"] == 0
+            else:
+                fm = max(b0 & 15, b1 & 15)
+                dynf = max(_combine(m0["dynamicFriction"], m1["dynamicFriction"], fm), 0.0)
+                assert abs(float(pt["dynamicFriction"]) - dynf) < 1e-6
+        # friction patch: anchors of the pair's friction patch in world space lie in the contact area, impulses are tangential and inside the friction cone
+        na = int(fr["anchorCount"])
+        assert na in (0, 1, 2)
+        n = pt["normal"].astype(np.float64)
+        lo, hi = pts[:, :3].min(0) - 0.05, pts[:, :3].max(0) + 0.05
+        total_normal = float(pts[:, 4].sum())
+        for j in range(na):
+            assert np.all(fr["anchorPositions"][j] >= lo - 0.3) and np.all(fr["anchorPositions"][j] <= hi + 0.3)
+            imp = fr["anchorImpulses"][j].astype(np.float64)
+            assert abs(imp @ n) <= 1e-4 * (1.0 + np.linalg.norm(imp))
+            assert np.linalg.norm(imp) <= float(pt["staticFriction"]) * total_normal * 1.001 + 1e-5
+        for j in range(na, 2):
+            assert not fr["anchorImpulses"][j].any() and not fr["anchorPositions"][j].any()
+    return rec
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_path", [True, False])
+def test_copy_contact_data_matches_host_contacts(env_path):
+    from physx_b200 import tensor_api as ta
+    sc = scenes.material_mix()
+    gpu = engine.Scene(sc, env_path=env_path)
+    with pytest.raises(RuntimeError):                      # contact data has to be switched on before the step
+        ta.GpuContactData(gpu, 16)
+    gpu.enableContactData()
+    for _ in range(25):
+        gpu.step()
+    cd = ta.GpuContactData(gpu, 4096)
+    host = cd.to_host()
+    assert host["total_pairs"] > 20
+    _check_contact_data(gpu, sc, host)
+    assert (host["friction"]["anchorCount"] > 0).any() and np.abs(host["friction"]["anchorImpulses"]).max() > 1e-4   # the sliding boxes carry friction impulses
+    # fewer records than pairs: the count still reports all of them, only max_pairs records are written
+    small = ta.GpuContactData(gpu, 5).to_host()
+    assert small["total_pairs"] == host["total_pairs"] and len(small["records"]) == 5
+    assert np.array_equal(small["records"]["transformCacheRef0"], host["records"]["transformCacheRef0"][:5])
+
+
+@pytest.mark.gpu
+def test_copy_contact_data_same_on_both_paths():
+    from physx_b200 import tensor_api as ta
+    sc = scenes.env_grid_stacks(n_envs=6, jitter=0.01)
+    out = []
+    for env_path in (True, False):
+        gpu = engine.Scene(sc, env_path=env_path)
+        gpu.enableContactData()
+        for _ in range(12):
+            gpu.step()
+        h = ta.GpuContactData(gpu, 8192).to_host()
+        _check_contact_data(gpu, sc, h)
+        order = np.lexsort((h["records"]["transformCacheRef1"], h["records"]["transformCacheRef0"]))
+        out.append((h, order))
+    (a, oa), (b, ob) = out
+    assert a["total_pairs"] == b["total_pairs"]
+    for f in ("transformCacheRef0", "transformCacheRef1", "nbContacts", "nodeIndex0", "nodeIndex1"):
+        assert np.array_equal(a["records"][f][oa], b["records"][f][ob])
+    assert np.array_equal(a["patches"][oa], b["patches"][ob])
+    assert np.array_equal(a["friction"][oa], b["friction"][ob])          # friction anchors and impulses bit-identical across the two paths
