@@ -230,6 +230,12 @@ PXB_API int  pxb_scene_get_contacts(PxbScene* scene, float* out24);
  * actor), nodeIndex0/1 = PxNodeIndex with mID = PxRigidDynamicGPUIndex (0xffffffff for a static actor), actor0/1 = the actor index as a handle.
  * Stream-ordered on the scene stream (read `data` after pxb_scene_sync or on that stream).  The friction write-back costs a few loads per
  * constraint, so it is off by default: pxb_scene_enable_contact_data(scene, 1) BEFORE the step whose contacts are wanted. */
+/* Local poses (a1: PxgShapeSim.shape2Actor, PxsBodyCore.body2Actor): PxShape::setLocalPose and PxRigidBody::setCMassLocalPose for actors [firstActor, firstActor + n),
+ * 7 floats each (p.xyz, q.xyzw; stored normalised like the reference).  The actor keeps its pose (Sc::BodyCore::setCMassLocalPose, ScBodyCore.cpp:98-108); the body
+ * frame the solver integrates becomes actorPose * body2Actor, the shape's world pose in the transform cache body2World * (body2Actor^-1 * shape2Actor)
+ * (Sc::ShapeSimBase::getAbsPoseAligned, ScShapeSimBase.cpp:214-249 / updateCacheAndBound.cuh:67-160).  Every pose the API reports or accepts stays the ACTOR pose
+ * (PxRigidActor::getGlobalPose); PxbActorRec.inertia is in the body frame.  Not combinable with pxb_scene_set_state_export when a body2Actor is not the identity. */
+PXB_API int  pxb_scene_set_local_poses(PxbScene* scene, uint32_t firstActor, uint32_t n, const float* shape2Actor, const float* body2Actor);
 typedef struct PxbGpuContactPair {
   uint8_t* contactPatches; uint8_t* contactPoints; float* contactForces; uint8_t* frictionPatches;
   uint32_t transformCacheRef0, transformCacheRef1;

@@ -158,6 +158,31 @@ static inline xf axfinvmul(const xf* a, const xf* b) { /* PxTransformV::transfor
   r.q = aqmul(qinv, b->q);
   return r;
 }
+/* Cm::getStaticGlobalPoseAligned / getDynamicGlobalPoseAligned (common/src/CmTransformUtils.h:40-133): the shape's world pose as the transform cache holds it.
+ * atransform_fast(a, b) = a * b, atransform_inv_fast(a, b) = a^-1 * b, in the aos operation order of transformFast / transformInvFast. */
+static inline xf atransform_fast(const xf* a, const xf* b) {
+  const float wa = a->q.w, wb = b->q.w; const v3 va = V3(a->q.x, a->q.y, a->q.z), vb = V3(b->q.x, b->q.y, b->q.z);
+  const float wo = wa * wb - adot(va, vb);
+  const v3 vo = v3scaleadd(va, wb, v3scaleadd(vb, wa, v3cross(va, vb)));
+  const v3 t1 = v3scale(b->p, wa * wa + (-0.5f));
+  const v3 t2 = v3scaleadd(v3cross(va, b->p), wa, t1);
+  const v3 t3 = v3scaleadd(va, adot(va, b->p), t2);
+  xf o; o.p = v3scaleadd(t3, 2.f, a->p); o.q = Q4(vo.x, vo.y, vo.z, wo); return o;
+}
+static inline xf atransform_inv_fast(const xf* a, const xf* b) {
+  const float wa = a->q.w, wb = b->q.w; const v3 va = V3(a->q.x, a->q.y, a->q.z), vb = V3(b->q.x, b->q.y, b->q.z);
+  const float wo = wa * wb + adot(va, vb);
+  const v3 vo = v3negscalesub(va, wb, v3scaleadd(vb, wa, v3cross(vb, va)));
+  const v3 pt = v3sub(b->p, a->p);
+  const v3 t1 = v3scale(pt, wa * wa + (-0.5f));
+  const v3 t2 = v3scaleadd(v3cross(pt, va), wa, t1);
+  const v3 t3 = v3scaleadd(va, adot(va, pt), t2);
+  xf o; o.p = v3add(t3, t3); o.q = Q4(vo.x, vo.y, vo.z, wo); return o;
+}
+/* scalar PxTransform algebra of the API layer (foundation/PxTransform.h): a * b = (a.q.rotate(b.p) + a.p, a.q * b.q), getInverse = (q.rotateInv(-p), q*), getNormalized */
+static inline xf xfmul(const xf* a, const xf* b) { xf o; o.p = v3add(q4rot(a->q, b->p), a->p); o.q = q4mul(a->q, b->q); return o; }
+static inline xf xfinverse(const xf* a) { xf o; o.p = q4rotinv(a->q, v3neg(a->p)); o.q = q4conj(a->q); return o; }
+static inline xf xfnormalized(const xf* a) { const float s = 1.0f / sqrtf(a->q.x * a->q.x + a->q.y * a->q.y + a->q.z * a->q.z + a->q.w * a->q.w); xf o; o.p = a->p; o.q = Q4(a->q.x * s, a->q.y * s, a->q.z * s, a->q.w * s); return o; }
 static inline v3 am33tmul(const m33* m, v3 v) { return V3(adot(m->c0, v), adot(m->c1, v), adot(m->c2, v)); }
 static inline v3 amxftransform(const mxf* t, v3 v) { return v3add(t->p, m33mul(&t->r, v)); }
 static inline v3 amxftransforminv(const mxf* t, v3 v) { return am33tmul(&t->r, v3sub(v, t->p)); }

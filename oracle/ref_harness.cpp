@@ -152,7 +152,8 @@ int main(int argc, char** argv) {
   if (H.magic != PXB_SCENE_MAGIC) { fprintf(stderr, "bad magic\n"); return 2; }
   const PxbActorRec* recs = reinterpret_cast<const PxbActorRec*>(buf.data() + sizeof(PxbSceneHeader));
   const PxbMaterialRec* matRecs = reinterpret_cast<const PxbMaterialRec*>(recs + H.nActors);   // material table (may be empty)
-  const uint8_t* hp = reinterpret_cast<const uint8_t*>(matRecs + H.reserved[2]);
+  const PxbLocalPoseRec* localPoses = H.reserved[3] == PXB_LOCAL_POSE_MAGIC ? reinterpret_cast<const PxbLocalPoseRec*>(matRecs + H.reserved[2]) : nullptr;   // PxShape::setLocalPose / setCMassLocalPose per actor
+  const uint8_t* hp = reinterpret_cast<const uint8_t*>(matRecs + H.reserved[2]) + (localPoses ? sizeof(PxbLocalPoseRec) * size_t(H.nActors) : 0);
 
   PxFoundation* foundation = PxCreateFoundation(PX_PHYSICS_VERSION, gAllocator, gErrorCallback);
   PxTolerancesScale scale; scale.length = H.toleranceLength; scale.speed = 10.0f * H.toleranceLength;
@@ -297,13 +298,15 @@ int main(int argc, char** argv) {
     }
     s->setContactOffset(H.contactOffset);
     s->setRestOffset(H.restOffset);
+    if (localPoses) { const PxbLocalPoseRec& l = localPoses[i]; s->setLocalPose(PxTransform(PxVec3(l.shapeP[0], l.shapeP[1], l.shapeP[2]), PxQuat(l.shapeQ[0], l.shapeQ[1], l.shapeQ[2], l.shapeQ[3]))); }
     shapes[i] = s;
     a->userData = reinterpret_cast<void*>(size_t(i));
     if (r.flags & PXB_ACTOR_DYNAMIC) {
       PxRigidDynamic* d = static_cast<PxRigidDynamic*>(a);
       d->setMass(r.mass);
       d->setMassSpaceInertiaTensor(PxVec3(r.inertia[0], r.inertia[1], r.inertia[2]));
-      d->setCMassLocalPose(PxTransform(PxIdentity));
+      if (localPoses) { const PxbLocalPoseRec& l = localPoses[i]; d->setCMassLocalPose(PxTransform(PxVec3(l.bodyP[0], l.bodyP[1], l.bodyP[2]), PxQuat(l.bodyQ[0], l.bodyQ[1], l.bodyQ[2], l.bodyQ[3]))); }
+      else d->setCMassLocalPose(PxTransform(PxIdentity));
       d->setLinearVelocity(PxVec3(r.linVel[0], r.linVel[1], r.linVel[2]));
       d->setAngularVelocity(PxVec3(r.angVel[0], r.angVel[1], r.angVel[2]));
       d->setLinearDamping(r.linDamping);

@@ -1,14 +1,17 @@
 /* Scene interchange format shared by the oracle tools (test infrastructure).
  *
  * A scene file is:  SceneHeader | ActorRec[nActors] | PxbMaterialRec[header.reserved[2]] (material table, may be empty)
+ *                   | (when header.reserved[3] == PXB_LOCAL_POSE_MAGIC) PxbLocalPoseRec[nActors]
  *                   | for each hull: u32 nVerts, float xyz[nVerts]
  *                   | (when header.reserved[1] == PXB_COOKED_MAGIC) for each hull: PxbCookedHullHeader + arrays (see below)
  * The cooked section is what PxCreateConvexMesh makes of the point cloud (Gu::ConvexHullData): convex cooking is host-side work in PhysX
  * too (the GPU pipeline receives cooked hulls through PxsSimulationController::addPxgShape), so cooked hulls are an INPUT of the hot path.
  * `ref_harness cook scene.bin out.bin` writes the section from the unmodified reference cooking code.
  * All little-endian, 4-byte fields, no padding.  Python mirror: physx_b200/scenes.py (numpy dtypes).
- * One shape per actor, shape local pose = identity (planes: actor pose carries the plane frame,
- * normal = local +X as in PxPlaneGeometry, physx/include/geometry/PxPlaneGeometry.h).
+ * One shape per actor; without the local-pose section the shape local pose and the centre-of-mass pose are identity (planes: the
+ * actor pose carries the plane frame, normal = local +X as in PxPlaneGeometry, physx/include/geometry/PxPlaneGeometry.h).  With it
+ * ActorRec.pos / quat are the ACTOR pose (PxRigidActor::getGlobalPose), the shape sits at shape2Actor (PxShape::setLocalPose) and the
+ * body frame the solver integrates is actor pose * body2Actor (PxRigidBody::setCMassLocalPose); states are reported as actor poses.
  *
  * geomType values follow PxGeometryType (physx/include/geometry/PxGeometry.h:48-62):
  *   0 sphere, 1 plane, 2 capsule, 3 box, 5 convex mesh.
@@ -80,6 +83,10 @@ typedef struct {
   uint32_t reserved[1];
 } PxbCookedHullHeader;            /* 25 words = 100 bytes */
 typedef struct { float plane[4]; uint32_t vref, nbVerts, minIndex, pad; } PxbCookedPoly;   /* HullPolygonData */
+
+/* local poses: shape2Actor (p, q.xyzw), body2Actor (p, q.xyzw) */
+#define PXB_LOCAL_POSE_MAGIC 0x504c5850u /* "PXLP" */
+typedef struct { float shapeP[3], shapeQ[4], bodyP[3], bodyQ[4], pad[2]; } PxbLocalPoseRec;   /* 64 bytes */
 
 /* Per-step state record written by ref_harness / oracle tools: for every DYNAMIC actor, in actor
  * order: pos[3] quat[4] linVel[3] angVel[3] = 13 floats. */

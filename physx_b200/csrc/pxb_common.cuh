@@ -98,6 +98,28 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__
 // GPU reference: sleepCheck / updateWakeCounter in gpusolver integration.cuh:40-435).  Per island (the host island manager's
 // job in the reference pipeline, IG::IslandSim): k_sleep_islands puts an island to sleep once every body in it is ready and
 // wakes sleeping bodies that touch an awake island.  Disabled (threshold 0) for throughput runs, SURVEY.md 8d.
+// a1, transform cache with local poses (PxShape::setLocalPose / PxRigidBody::setCMassLocalPose).  pos / quat hold body2World (the centre-of-mass frame the solver
+// integrates); the shape's world pose is body2World * shape2Body with shape2Body = body2Actor^-1 * shape2Actor precomputed on the host, composed in the aos operation
+// order of Cm::getDynamicGlobalPoseAligned / getStaticGlobalPoseAligned (common/src/CmTransformUtils.h:40-133, transformFast).  The narrowphase reads the cache.
+struct LocalPoses { const float4 *s2bP, *s2bQ; float4 *tcPos, *tcQuat; };   // s2bP == nullptr: no local poses, shapes sit at pos / quat
+__device__ __forceinline__ xf atransform_fast(const xf& a, const xf& b) {
+  const float wa = a.q.w, wb = b.q.w; const v3 va = V3(a.q.x, a.q.y, a.q.z), vb = V3(b.q.x, b.q.y, b.q.z);
+  const float wo = wa * wb - adot(va, vb);
+  const v3 vo = scaleadd(va, wb, scaleadd(vb, wa, cross(va, vb)));
+  const v3 t1 = b.p * (wa * wa + (-0.5f));
+  const v3 t2 = scaleadd(cross(va, b.p), wa, t1);
+  const v3 t3 = scaleadd(va, adot(va, b.p), t2);
+  xf o; o.p = scaleadd(t3, 2.f, a.p); o.q = Q4(vo.x, vo.y, vo.z, wo); return o;
+}
+__device__ __forceinline__ xf shape_world_pose(const LocalPoses& L, uint32_t a, float4 p4, float4 q4_, bool writeCache = true) {
+  xf t; t.p = V3(p4.x, p4.y, p4.z); t.q = Q4(q4_);
+  if (!L.s2bP) return t;
+  xf l; { const float4 lp = L.s2bP[a]; l.p = V3(lp.x, lp.y, lp.z); l.q = Q4(L.s2bQ[a]); }
+  const xf w = atransform_fast(t, l);
+  if (writeCache) { L.tcPos[a] = F4(w.p, p4.w); L.tcQuat[a] = F4(w.q); }
+  return w;
+}
+
 struct SleepArgs { float threshold, dt; float* wake; float4 *accLin, *accAng; uint32_t *asleep, *nInter; };
 __device__ __forceinline__ bool body_asleep(const SleepArgs& S, uint32_t a) { return S.threshold > 0.f && S.asleep[a] != 0u; }
 __device__ __forceinline__ void sleep_check_dev(const SleepArgs& S, uint32_t a, q4 q, float4 invInertia, float invMassIn, v3 motionLin, v3 motionAng) {

@@ -49,6 +49,8 @@ struct PxbScene {
   // per pair (this frame)
   float4 *cHdr = 0, *cPts = 0; uint2* pairBodies = 0; float* cForce = 0;
   uint32_t *pairOrder = 0, *npClassCount = 0; uint8_t* npClass = 0; bool binPairs = false;   // mixed-type scenes: pairs binned by type pair before the narrowphase
+  float4 *tcPos = 0, *tcQuat = 0, *s2bP = 0, *s2bQ = 0, *b2aP = 0, *b2aQ = 0, *actorPos = 0, *actorQuat = 0; bool hasLocal = false, hasCom = false;   // local poses (pxb_scene_set_local_poses)
+  std::vector<float4> hS2aP, hS2aQ, hB2aP, hB2aQ;
   float4* frReport = 0; uint32_t *ccIdx = 0, *ccOff = 0, *ccCount = 0, *ccTotal = 0, *actorDyn = 0; uint8_t *ccPatches = 0, *ccPoints = 0, *ccFriction = 0; float* ccForces = 0; bool contactData = false;
   uint32_t *gjkList = 0, *gjkQuery = 0, *gjkFull = 0, *gjkEpa = 0, *boxList = 0; bool boxPhases = true; bool gjkPhases = true; bool hasGjkPairs = false, anyLocks = false, anyConvex = false;
   float4 *extForce = 0, *extTorque = 0; bool forcesUsed = false;
@@ -90,6 +92,7 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static LocalPoses local_poses(const PxbScene* s) { LocalPoses L; L.s2bP = s->hasLocal ? s->s2bP : nullptr; L.s2bQ = s->s2bQ; L.tcPos = s->tcPos; L.tcQuat = s->tcQuat; return L; }
 static MaterialArgs material_args(const PxbScene* s) { MaterialArgs M; M.actorMat = s->actorMat; M.matTab = s->nMaterials ? s->matTab : nullptr; return M; }
 static TouchLists touch_lists(const PxbScene* s) { TouchLists T; T.state = s->touchState; T.found = s->touchFound; T.lost = s->touchLost; return T; }
 static HullArrays hull_arrays(const PxbScene* s) { HullArrays H; H.meta = s->hullMeta; H.verts = s->hullVerts; H.polys = s->hullPolys; H.refs = s->hullRefs; H.edges = s->hullEdges; return H; }
@@ -101,7 +104,7 @@ static HullArrays hull_arrays(const PxbScene* s) { HullArrays H; H.meta = s->hul
 __global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims,
                          const uint32_t* __restrict__ geomFlags, const uint32_t* __restrict__ envId, float contactOffset, float* __restrict__ tight,
                          int externalTight, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax, GridParams g, uint32_t envCount,
-                         uint64_t* __restrict__ cellKey, uint32_t* __restrict__ cellVal, HullArrays hulls) {
+                         uint64_t* __restrict__ cellKey, uint32_t* __restrict__ cellVal, HullArrays hulls, LocalPoses L) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nA) return;
   const uint32_t gf = geomFlags[a];
@@ -111,10 +114,10 @@ __global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const floa
     return;
   }
   float mn[3], mx[3];
+  const xf shape = shape_world_pose(L, a, pos[a], quat[a]);   // (also refreshes the transform cache the narrowphase reads when the scene has local poses)
   if (externalTight) { for (int k = 0; k < 3; ++k) { mn[k] = tight[a * 6 + k]; mx[k] = tight[a * 6 + 3 + k]; } }
   else {
-    const float4 p4 = pos[a];
-    tight_bounds(gf & 0xff, V3(p4.x, p4.y, p4.z), Q4(quat[a]), dims[a], mn, mx, &hulls);
+    tight_bounds(gf & 0xff, shape.p, shape.q, dims[a], mn, mx, &hulls);
     for (int k = 0; k < 3; ++k) { tight[a * 6 + k] = mn[k]; tight[a * 6 + 3 + k] = mx[k]; }
   }
   const float co = contactOffset;
@@ -849,7 +852,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
   void* ptrs[] = {s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
-                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
+                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->tcPos, s->tcQuat, s->s2bP, s->s2bQ, s->b2aP, s->b2aQ, s->actorPos, s->actorQuat, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->prevB0, s->prevB1, s->prevColour, s->prevNCon, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
                   s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->actorMat, s->matTab, s->touchState, s->touchFound, s->touchLost, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
@@ -1091,7 +1094,9 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
     if (r.geomType == PXB_GEOM_CONVEXMESH) s->recs.back().dims[3] = s->hullDiam[r.hullIdx];   // bounding diameter for the broadphase grid
     if (dyn) { s->dynIndex.push_back((int)s->nDyn); s->dynActor.push_back(base + i); s->nDyn++; } else s->dynIndex.push_back(-1);
     const float invMass = (dyn && r.mass > 0.f) ? 1.0f / r.mass : 0.f;
-    pos[i] = make_float4(r.pos[0], r.pos[1], r.pos[2], invMass); quat[i] = make_float4(r.quat[0], r.quat[1], r.quat[2], r.quat[3]);
+    pos[i] = make_float4(r.pos[0], r.pos[1], r.pos[2], invMass);
+    { const float sN = 1.0f / sqrtf(r.quat[0] * r.quat[0] + r.quat[1] * r.quat[1] + r.quat[2] * r.quat[2] + r.quat[3] * r.quat[3]);   // NpPhysics::createRigidDynamic / createRigidStatic store globalPose.getNormalized()
+      quat[i] = make_float4(r.quat[0] * sN, r.quat[1] * sN, r.quat[2] * sN, r.quat[3] * sN); }
     lin[i] = make_float4(r.linVel[0], r.linVel[1], r.linVel[2], 0.f); ang[i] = make_float4(r.angVel[0], r.angVel[1], r.angVel[2], 0.f);
     inv[i] = make_float4(dyn && r.inertia[0] > 0.f ? 1.0f / r.inertia[0] : 0.f, dyn && r.inertia[1] > 0.f ? 1.0f / r.inertia[1] : 0.f, dyn && r.inertia[2] > 0.f ? 1.0f / r.inertia[2] : 0.f, r.maxDepenetrationVel);
     dmp[i] = make_float4(r.linDamping, r.angDamping, r.maxLinVel * r.maxLinVel, r.maxAngVel * r.maxAngVel);
@@ -1167,7 +1172,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     LAUNCH(k_env_begin, 1, 32, s->counters);
     EnvBpArgs A;
     A.nEnv = s->nEnv; A.maxList = s->envMaxList; A.bitsA = s->bitsA; A.cap = s->capPairs; A.ringMask = s->ringMask; A.externalTight = externalTight ? 1 : 0; A.contactOffset = s->desc.contactOffset;
-    A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight; A.hulls = hull_arrays(s);
+    A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight; A.hulls = hull_arrays(s); A.L = local_poses(s);
     A.oldKeys = s->pairKeys[prev]; A.oldSlots = s->pairSlots[prev]; A.oldSeg = s->envSeg[prev]; A.newKeys = s->pairKeys[cur]; A.newSlots = s->pairSlots[cur]; A.newSeg = s->envSeg[cur];
     A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions; A.slotColour = s->slotColour; A.touch = touch_lists(s);
     const size_t smem = (size_t)ENV_BP_WARPS * (s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t)) + ENV_BP_STAGE * sizeof(uint64_t));
@@ -1180,7 +1185,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
   CK(cudaMemsetAsync(s->counters + C_NTOUCH_FOUND, 0, 4 * 6, st));   // NTOUCH_FOUND, NTOUCH_LOST, NGJK_QUERY, NGJK_FULL, NGJK_EPA, NBOXGEN
   if (s->hasGjkPairs) CK(cudaMemsetAsync(s->counters + C_NGJK, 0, 4, st));
   LAUNCH(k_bounds, cdiv(nA, B), B, nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, externalTight ? 1 : 0, s->aabbMin, s->aabbMax, s->grid,
-         s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s));
+         s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s), local_poses(s));
   const int r = radix_sort_pairs(s->cellKey, s->cellVal, s->cellKeyAlt, s->cellValAlt, s->counters + C_NA, s->grid.keyBits, s->rsTmp, st);
   s->launches += 3 * ((s->grid.keyBits + 7) / 8);
   const uint64_t* sk = r ? s->cellKeyAlt : s->cellKey; const uint32_t* sv = r ? s->cellValAlt : s->cellVal;
@@ -1244,7 +1249,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     LAUNCH(k_np_class_scatter, gP, B, nP, s->npClass, s->npClassCount, s->npClassCount + NP_CLASSES, s->pairOrder);
   }
   NpArgs NA;
-  NA.pairKeys = s->pairKeys[cur]; NA.pairSlots = s->pairSlots[cur]; NA.nPairsP = nP; NA.bitsA = s->bitsA; NA.pos = s->pos; NA.quat = s->quat; NA.dims = s->dims; NA.geomFlags = s->geomFlags;
+  NA.pairKeys = s->pairKeys[cur]; NA.pairSlots = s->pairSlots[cur]; NA.nPairsP = nP; NA.bitsA = s->bitsA; NA.pos = s->hasLocal ? s->tcPos : s->pos; NA.quat = s->hasLocal ? s->tcQuat : s->quat; /* shape world poses: the transform cache when the scene has local poses */ NA.dims = s->dims; NA.geomFlags = s->geomFlags;
   NA.contactDist = contactDist; NA.toleranceLength = s->desc.toleranceLength; NA.manifolds = s->manifolds; NA.cHdr = s->cHdr; NA.cPts = s->cPts; NA.pairBodies = s->pairBodies; NA.conFlag = s->conFlag;
   NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.gjkQuery = s->gjkQuery; NA.gjkFull = s->gjkFull; NA.gjkEpa = s->gjkEpa; NA.boxList = (s->boxPhases && !s->envActive) ? s->boxList : nullptr; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s); NA.touch = touch_lists(s);
   pxb_launch_narrowphase(st, s->capPairs, NA); s->launches += NA.boxList ? 2 : 1;
@@ -1454,7 +1459,7 @@ PXB_API int pxb_scene_compute_bounds(PxbScene* s) { DeviceGuard dg_(s);
   if (!s) return fail(PXB_ERR_INVALID, "null scene");
   cudaStream_t st = s->stream;
   if (s->gridDirty) rebuild_grid(s);
-  LAUNCH(k_bounds, cdiv(s->nA, 256), 256, s->nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, 0, s->aabbMin, s->aabbMax, s->grid, s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s));
+  LAUNCH(k_bounds, cdiv(s->nA, 256), 256, s->nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, 0, s->aabbMin, s->aabbMax, s->grid, s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s), local_poses(s));
   CK(cudaStreamSynchronize(st));
   return PXB_OK;
 }
@@ -1508,6 +1513,106 @@ PXB_API int pxb_scene_get_contacts(PxbScene* s, float* out24) { DeviceGuard dg_(
   }
   return PXB_OK;
 }
+// ---- a1: local poses (PxShape::setLocalPose, PxRigidBody::setCMassLocalPose) ----
+// Host restatement of the scalar PxTransform algebra the API layer uses (foundation/PxTransform.h: a * b, getInverse, getNormalized) and of transformInvFast
+// (CmTransformUtils.h:56-69) for the constant shape2Body = body2Actor^-1 * shape2Actor.  x86-64 host code without FMA, like the reference build.
+namespace lp {
+struct Q { float x, y, z, w; }; struct V { float x, y, z; }; struct T { V p; Q q; };
+static inline V rot(Q q, V v) { const float vx = 2.0f * v.x, vy = 2.0f * v.y, vz = 2.0f * v.z; const float w2 = q.w * q.w - 0.5f; const float d2 = (q.x * vx + q.y * vy + q.z * vz);
+  return V{(vx * w2 + (q.y * vz - q.z * vy) * q.w + q.x * d2), (vy * w2 + (q.z * vx - q.x * vz) * q.w + q.y * d2), (vz * w2 + (q.x * vy - q.y * vx) * q.w + q.z * d2)}; }
+static inline V rotinv(Q q, V v) { const float vx = 2.0f * v.x, vy = 2.0f * v.y, vz = 2.0f * v.z; const float w2 = q.w * q.w - 0.5f; const float d2 = (q.x * vx + q.y * vy + q.z * vz);
+  return V{(vx * w2 - (q.y * vz - q.z * vy) * q.w + q.x * d2), (vy * w2 - (q.z * vx - q.x * vz) * q.w + q.y * d2), (vz * w2 - (q.x * vy - q.y * vx) * q.w + q.z * d2)}; }
+static inline Q qmul(Q a, Q b) { return Q{a.w * b.x + b.w * a.x + a.y * b.z - b.y * a.z, a.w * b.y + b.w * a.y + a.z * b.x - b.z * a.x, a.w * b.z + b.w * a.z + a.x * b.y - b.x * a.y, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z}; }
+static inline T mul(const T& a, const T& b) { const V r = rot(a.q, b.p); return T{V{r.x + a.p.x, r.y + a.p.y, r.z + a.p.z}, qmul(a.q, b.q)}; }
+static inline T inverse(const T& a) { return T{rotinv(a.q, V{-a.p.x, -a.p.y, -a.p.z}), Q{-a.q.x, -a.q.y, -a.q.z, a.q.w}}; }
+static inline T normalized(const T& a) { const float s = 1.0f / sqrtf(a.q.x * a.q.x + a.q.y * a.q.y + a.q.z * a.q.z + a.q.w * a.q.w); return T{a.p, Q{a.q.x * s, a.q.y * s, a.q.z * s, a.q.w * s}}; }
+static inline bool identity(const T& a) { return a.p.x == 0.f && a.p.y == 0.f && a.p.z == 0.f && a.q.x == 0.f && a.q.y == 0.f && a.q.z == 0.f && a.q.w == 1.f; }
+static inline float adot(V a, V b) { return (a.x * b.x + a.z * b.z) + (a.y * b.y); }
+static inline V cross(V a, V b) { return V{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+static inline V scaleadd(V a, float s, V b) { return V{a.x * s + b.x, a.y * s + b.y, a.z * s + b.z}; }
+static inline T inv_fast(const T& a, const T& b) {   // a^-1 * b, aos operation order
+  const float wa = a.q.w, wb = b.q.w; const V va{a.q.x, a.q.y, a.q.z}, vb{b.q.x, b.q.y, b.q.z};
+  const float wo = wa * wb + adot(va, vb);
+  const V c = scaleadd(vb, wa, cross(vb, va)); const V vo{c.x - va.x * wb, c.y - va.y * wb, c.z - va.z * wb};
+  const V pt{b.p.x - a.p.x, b.p.y - a.p.y, b.p.z - a.p.z};
+  const float k = wa * wa + (-0.5f); const V t1{pt.x * k, pt.y * k, pt.z * k};
+  const V t2 = scaleadd(cross(pt, va), wa, t1);
+  const V t3 = scaleadd(va, adot(va, pt), t2);
+  return T{V{t3.x + t3.x, t3.y + t3.y, t3.z + t3.z}, Q{vo.x, vo.y, vo.z, wo}};
+}
+}  // namespace lp
+// actor pose = body2World * body2Actor^-1 (NpRigidDynamic::getGlobalPoseFast), body2World = actor pose * body2Actor (NpRigidDynamic::setGlobalPose), scalar PxTransform algebra
+__global__ void k_actor_poses(uint32_t nA, const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ b2aP, const float4* __restrict__ b2aQ, float4* __restrict__ actorPos,
+                              float4* __restrict__ actorQuat) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nA) return;
+  const float4 p = pos[a], q = quat[a], bp = b2aP[a];
+  if (bp.w == 0.f) { actorPos[a] = p; actorQuat[a] = q; return; }   // w of the body2Actor position: 1 = not the identity
+  const q4 bq = Q4(b2aQ[a]);
+  const v3 ip = qrotinv(bq, V3(-bp.x, -bp.y, -bp.z)); const q4 iq = conj(bq);
+  const q4 Qw = Q4(q);
+  actorPos[a] = F4(qrot(Qw, ip) + V3(p.x, p.y, p.z), p.w); actorQuat[a] = F4(qmul(Qw, iq));
+}
+__global__ void k_actor_to_body(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, float4* __restrict__ pos, float4* __restrict__ quat, const float4* __restrict__ b2aP,
+                                const float4* __restrict__ b2aQ) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb) return;
+  const uint32_t a = dynActor[idx ? idx[t] : t];
+  const float4 bp = b2aP[a];
+  if (bp.w == 0.f) return;
+  const float4 p = pos[a]; const q4 Qa = Q4(quat[a]);
+  pos[a] = F4(qrot(Qa, V3(bp.x, bp.y, bp.z)) + V3(p.x, p.y, p.z), p.w); quat[a] = F4(qmul(Qa, Q4(b2aQ[a])));
+}
+// Poses handed out by the getters are ACTOR poses: with centre-of-mass local poses they are derived from the body frames first.
+static int refresh_actor_poses(PxbScene* s, cudaStream_t st) {
+  if (!s->hasCom || !s->nA) return PXB_OK;
+  k_actor_poses<<<cdiv(s->nA, 256), 256, 0, st>>>(s->nA, s->pos, s->quat, s->b2aP, s->b2aQ, s->actorPos, s->actorQuat);
+  CK(cudaGetLastError());
+  return PXB_OK;
+}
+PXB_API int pxb_scene_set_local_poses(PxbScene* s, uint32_t firstActor, uint32_t n, const float* shape2Actor, const float* body2Actor) { DeviceGuard dg_(s);
+  if (!s || (n && (!shape2Actor || !body2Actor))) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running");
+  if ((uint64_t)firstActor + n > s->nA) return fail(PXB_ERR_INVALID, "actor range out of bounds");
+  if (s->exportOn) return fail(PXB_ERR_UNSUPPORTED, "the fused state export reports body frames: switch it off before setting local poses");
+  if (!n) return PXB_OK;
+  CK(cudaStreamSynchronize(s->stream));
+  const size_t A = std::max<size_t>(s->capA, 1);
+  if (!s->tcPos) {
+    CK(dalloc(s->tcPos, A)); CK(dalloc(s->tcQuat, A)); CK(dalloc(s->s2bP, A)); CK(dalloc(s->s2bQ, A)); CK(dalloc(s->b2aP, A)); CK(dalloc(s->b2aQ, A)); CK(dalloc(s->actorPos, A)); CK(dalloc(s->actorQuat, A));
+    s->hS2aP.assign(A, make_float4(0, 0, 0, 0)); s->hS2aQ.assign(A, make_float4(0, 0, 0, 1)); s->hB2aP.assign(A, make_float4(0, 0, 0, 0)); s->hB2aQ.assign(A, make_float4(0, 0, 0, 1));
+    CK(cudaMemcpy(s->s2bP, s->hS2aP.data(), 16 * A, cudaMemcpyHostToDevice)); CK(cudaMemcpy(s->s2bQ, s->hS2aQ.data(), 16 * A, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->b2aP, s->hB2aP.data(), 16 * A, cudaMemcpyHostToDevice)); CK(cudaMemcpy(s->b2aQ, s->hB2aQ.data(), 16 * A, cudaMemcpyHostToDevice));
+  }
+  std::vector<float4> pos(n), quat(n), s2bP(n), s2bQ(n);
+  CK(cudaMemcpy(pos.data(), s->pos + firstActor, 16 * (size_t)n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(quat.data(), s->quat + firstActor, 16 * (size_t)n, cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t a = firstActor + i; const bool dyn = s->recs[a].flags & PXB_ACTOR_DYNAMIC;
+    const float* sa = shape2Actor + 7 * (size_t)i; const float* ba = body2Actor + 7 * (size_t)i;
+    const lp::T s2a = lp::normalized(lp::T{lp::V{sa[0], sa[1], sa[2]}, lp::Q{sa[3], sa[4], sa[5], sa[6]}});   // NpShape::setLocalPose / NpRigidDynamic::setCMassLocalPose keep the normalised transform
+    lp::T b2a = lp::normalized(lp::T{lp::V{ba[0], ba[1], ba[2]}, lp::Q{ba[3], ba[4], ba[5], ba[6]}});
+    if (!dyn) b2a = lp::T{lp::V{0, 0, 0}, lp::Q{0, 0, 0, 1}};
+    const lp::T oldB2a{lp::V{s->hB2aP[a].x, s->hB2aP[a].y, s->hB2aP[a].z}, lp::Q{s->hB2aQ[a].x, s->hB2aQ[a].y, s->hB2aQ[a].z, s->hB2aQ[a].w}};
+    lp::T b2w{lp::V{pos[i].x, pos[i].y, pos[i].z}, lp::Q{quat[i].x, quat[i].y, quat[i].z, quat[i].w}};
+    if (dyn && !(lp::identity(oldB2a) && lp::identity(b2a))) {   // Sc::BodyCore::setCMassLocalPose (ScBodyCore.cpp:98-108): the actor keeps its pose
+      const lp::T a2w = lp::mul(b2w, lp::inverse(oldB2a));
+      b2w = lp::mul(a2w, b2a);
+    }
+    pos[i] = make_float4(b2w.p.x, b2w.p.y, b2w.p.z, pos[i].w); quat[i] = make_float4(b2w.q.x, b2w.q.y, b2w.q.z, b2w.q.w);
+    const lp::T s2b = (dyn && !lp::identity(b2a)) ? lp::inv_fast(b2a, s2a) : s2a;   // Cm::getDynamicGlobalPoseAligned's first product, constant per shape
+    s2bP[i] = make_float4(s2b.p.x, s2b.p.y, s2b.p.z, 0.f); s2bQ[i] = make_float4(s2b.q.x, s2b.q.y, s2b.q.z, s2b.q.w);
+    s->hS2aP[a] = make_float4(s2a.p.x, s2a.p.y, s2a.p.z, 0.f); s->hS2aQ[a] = make_float4(s2a.q.x, s2a.q.y, s2a.q.z, s2a.q.w);
+    s->hB2aP[a] = make_float4(b2a.p.x, b2a.p.y, b2a.p.z, lp::identity(b2a) ? 0.f : 1.f); s->hB2aQ[a] = make_float4(b2a.q.x, b2a.q.y, b2a.q.z, b2a.q.w);
+  }
+  CK(cudaMemcpy(s->pos + firstActor, pos.data(), 16 * (size_t)n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(s->quat + firstActor, quat.data(), 16 * (size_t)n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->s2bP + firstActor, s2bP.data(), 16 * (size_t)n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(s->s2bQ + firstActor, s2bQ.data(), 16 * (size_t)n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->b2aP + firstActor, s->hB2aP.data() + firstActor, 16 * (size_t)n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(s->b2aQ + firstActor, s->hB2aQ.data() + firstActor, 16 * (size_t)n, cudaMemcpyHostToDevice));
+  s->hasLocal = true;
+  s->hasCom = false; for (uint32_t a = 0; a < s->nA; ++a) if (s->hB2aP[a].w != 0.f) { s->hasCom = true; break; }
+  drop_graphs(s);   // the narrowphase now reads the transform cache
+  return PXB_OK;
+}
+
 // ---- f3: PxDirectGPUAPI::copyContactData (PxDirectGPUAPI.h:388-401; the reference's compressContactStage1/2, gpunarrowphase/src/CUDA/compressOutputContacts.cu) ----
 // One PxGpuContactPair record per pair that has contacts, in pair order (stable compaction by two exclusive scans: touching flags -> record index, contact counts ->
 // offset into the point / force streams), pointing into PxContactPatch / PxContact / force / PxFrictionPatch streams owned by the scene.
@@ -1611,8 +1716,14 @@ static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int typ
   cudaStream_t st = s->stream;
   if (!nb) return PXB_OK;
   if (int rc = join_pending(s)) return rc;
-  if (set) LAUNCH(k_rd_set, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (const float*)devData, s->wake, s->asleep, s->extForce, s->extTorque);
-  else LAUNCH(k_rd_get, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (float*)devData);
+  const bool poseIO = s->hasCom && type == PXB_RD_GLOBAL_POSE;   // PxRigidDynamic poses are ACTOR poses; the engine integrates body (centre-of-mass) frames
+  if (set) {
+    LAUNCH(k_rd_set, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, s->pos, s->quat, s->linVel, s->angVel, (const float*)devData, s->wake, s->asleep, s->extForce, s->extTorque);
+    if (poseIO) LAUNCH(k_actor_to_body, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, s->pos, s->quat, s->b2aP, s->b2aQ);
+  } else {
+    if (poseIO) { if (int rc = refresh_actor_poses(s, st)) return rc; }
+    LAUNCH(k_rd_get, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, poseIO ? s->actorPos : s->pos, poseIO ? s->actorQuat : s->quat, s->linVel, s->angVel, (float*)devData);
+  }
   CK(cudaGetLastError());
   return PXB_OK;
 }
@@ -1679,6 +1790,7 @@ PXB_API int pxb_scatter_to_peers(PxbScene* s, void* stream, const void* devSrc, 
 PXB_API int pxb_scene_set_state_export(PxbScene* s, void* const* dst, uint32_t nDst, uint32_t rowOffset) { DeviceGuard dg_(s);
   if (!s || (nDst && !dst)) return fail(PXB_ERR_INVALID, "null argument");
   if (nDst > PXB_MAX_EXPORT) return fail(PXB_ERR_INVALID, "at most 9 export targets");
+  if (nDst && s->hasCom) return fail(PXB_ERR_UNSUPPORTED, "the fused state export reports body frames: not available with centre-of-mass local poses (use pxb_scene_get_states_device)");
   ExportTable t; memset(&t, 0, sizeof(t));
   for (uint32_t k = 0; k < nDst; ++k) {
     if (!dst[k] || ((uintptr_t)dst[k] & 15u)) return fail(PXB_ERR_INVALID, "export targets must be non-null and 16-byte aligned");
@@ -1903,7 +2015,9 @@ PXB_API int pxb_tensor_read_device(PxbScene* s, int tensorType, void* devOut, co
   if (!devIdx && nb > s->nDyn) return fail(PXB_ERR_INVALID, "nb exceeds the number of dynamic bodies");
   if (!nb) return PXB_OK;
   if (int rc = join_pending(s)) return rc;
-  k_tensor_read<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, devIdx, s->dynActorDev, tensorType, s->pos, s->quat, s->linVel, s->angVel, (float*)devOut);
+  const bool poseIO = s->hasCom && tensorType == PXB_TENSOR_RIGID_BODY_POSE;
+  if (poseIO) { if (int rc = refresh_actor_poses(s, s->stream)) return rc; }
+  k_tensor_read<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, devIdx, s->dynActorDev, tensorType, poseIO ? s->actorPos : s->pos, poseIO ? s->actorQuat : s->quat, s->linVel, s->angVel, (float*)devOut);
   CK(cudaGetLastError());
   return PXB_OK;
 }
@@ -1917,6 +2031,7 @@ PXB_API int pxb_tensor_write_device(PxbScene* s, int tensorType, const void* dev
   if ((tensorType == PXB_TENSOR_RIGID_BODY_FORCE || tensorType == PXB_TENSOR_RIGID_BODY_WRENCH) && !s->forcesUsed) { s->forcesUsed = true; drop_graphs(s); }
   if (int rc = join_pending(s)) return rc;
   k_tensor_write<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, devIdx, s->dynActorDev, tensorType, s->pos, s->quat, s->linVel, s->angVel, (const float*)devIn, s->wake, s->asleep, s->extForce, s->extTorque);
+  if (s->hasCom && tensorType == PXB_TENSOR_RIGID_BODY_POSE) k_actor_to_body<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, devIdx, s->dynActorDev, s->pos, s->quat, s->b2aP, s->b2aQ);
   CK(cudaGetLastError());
   return PXB_OK;
 }
@@ -1929,7 +2044,8 @@ PXB_API int pxb_scene_get_states_device(PxbScene* s, float* devOut) { DeviceGuar
   if (!s || !devOut) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;   // stream-ordered: legal right after pxb_scene_simulate, it reads the state that step produces
   cudaStream_t st = s->stream;
-  LAUNCH(k_states_get, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, devOut);
+  if (int rc = refresh_actor_poses(s, st)) return rc;
+  LAUNCH(k_states_get, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->hasCom ? s->actorPos : s->pos, s->hasCom ? s->actorQuat : s->quat, s->linVel, s->angVel, devOut);
   CK(cudaGetLastError());
   return PXB_OK;
 }
@@ -1938,7 +2054,8 @@ PXB_API int pxb_scene_get_states(PxbScene* s, float* out) { DeviceGuard dg_(s);
   if (!s || !out) return fail(PXB_ERR_INVALID, "null argument");
   if (!s->nDyn) return PXB_OK;
   cudaStream_t st = s->stream; float* d = s->stage;   // persistent staging (26 floats per actor): no allocation per call
-  LAUNCH(k_states_get, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, d);
+  if (int rc = refresh_actor_poses(s, st)) return rc;
+  LAUNCH(k_states_get, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->hasCom ? s->actorPos : s->pos, s->hasCom ? s->actorQuat : s->quat, s->linVel, s->angVel, d);
   CK(cudaMemcpyAsync(out, d, 52 * (size_t)s->nDyn, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
   return PXB_OK;
 }
@@ -1949,6 +2066,7 @@ PXB_API int pxb_scene_set_states(PxbScene* s, const float* in) { DeviceGuard dg_
   cudaStream_t st = s->stream; float* d = s->stage + (size_t)s->capA * 13;
   CK(cudaMemcpyAsync(d, in, 52 * (size_t)s->nDyn, cudaMemcpyHostToDevice, st));
   LAUNCH(k_states_set, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, d, s->wake, s->asleep);
+  if (s->hasCom) LAUNCH(k_actor_to_body, cdiv(s->nDyn, 256), 256, s->nDyn, (const uint32_t*)nullptr, s->dynActorDev, s->pos, s->quat, s->b2aP, s->b2aQ);
   CK(cudaStreamSynchronize(st));
   return PXB_OK;
 }

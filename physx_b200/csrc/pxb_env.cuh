@@ -27,7 +27,7 @@ struct EnvBpArgs {
   const float4 *pos, *quat, *dims; const uint32_t *geomFlags, *envId; float* tight; HullArrays hulls;
   const uint64_t* oldKeys; const uint32_t* oldSlots; const uint2* oldSeg;
   uint64_t* newKeys; uint32_t* newSlots; uint2* newSeg;
-  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions; TouchLists touch;
+  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions; TouchLists touch; LocalPoses L;
 };
 
 #define ENV_BP_STAGE 256   // pair keys staged per warp in shared memory before the segment base is known
@@ -54,11 +54,13 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
   for (uint32_t k = lane; k < n; k += 32) {
     const uint32_t a = A.envList[ls + k]; const uint32_t gf = A.geomFlags[a], env = A.envId[a];
     float mn[3], mx[3];
+    const bool own = env == e || e == 0;   // the shared env-less statics are in every environment's list: environment 0 writes their bounds and their transform-cache entry
+    xf shape; shape.p = V3(0, 0, 0); shape.q = Q4(0, 0, 0, 1);
+    if (A.L.s2bP || !A.externalTight) shape = shape_world_pose(A.L, a, A.pos[a], A.quat[a], own);
     if (A.externalTight) { for (int c = 0; c < 3; ++c) { mn[c] = A.tight[a * 6 + c]; mx[c] = A.tight[a * 6 + 3 + c]; } }
     else {
-      const float4 p4 = A.pos[a];
-      tight_bounds(gf & 0xff, V3(p4.x, p4.y, p4.z), Q4(A.quat[a]), A.dims[a], mn, mx, HULLS ? &A.hulls : nullptr);
-      if (env == e || e == 0) for (int c = 0; c < 3; ++c) { A.tight[a * 6 + c] = mn[c]; A.tight[a * 6 + 3 + c] = mx[c]; }
+      tight_bounds(gf & 0xff, shape.p, shape.q, A.dims[a], mn, mx, HULLS ? &A.hulls : nullptr);
+      if (own) for (int c = 0; c < 3; ++c) { A.tight[a * 6 + c] = mn[c]; A.tight[a * 6 + 3 + c] = mx[c]; }
     }
     const float co = A.contactOffset;
     sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(env));

@@ -177,10 +177,27 @@ def parse_cooked(buf, n_hulls, off=0):
     return out, off
 
 
+# Local poses (PxgShapeSim.shape2Actor + PxsBodyCore.body2Actor): per actor the shape's pose in the actor frame (PxShape::setLocalPose)
+# and the centre-of-mass frame in the actor frame (PxRigidBody::setCMassLocalPose).  ActorRec.pos / quat stay the ACTOR pose (PxRigidActor::getGlobalPose).
+LOCAL_POSE_DTYPE = np.dtype([("shapeP", "<f4", 3), ("shapeQ", "<f4", 4), ("bodyP", "<f4", 3), ("bodyQ", "<f4", 4), ("pad", "<f4", 2)])
+LOCAL_POSE_MAGIC = 0x504c5850   # "PXLP": header.reserved[3] when the local-pose section (one record per actor, after the material table) is present
+assert LOCAL_POSE_DTYPE.itemsize == 64
+
+
+def identity_local_poses(n):
+    lp = np.zeros(n, LOCAL_POSE_DTYPE)
+    lp["shapeQ"][:, 3] = 1.0
+    lp["bodyQ"][:, 3] = 1.0
+    return lp
+
+
 class Scene:
-    def __init__(self, header, actors, hulls=(), cooked=b"", materials=None):
+    def __init__(self, header, actors, hulls=(), cooked=b"", materials=None, local_poses=None):
         self.header = header.copy()
         self.actors = actors
+        self.local_poses = None if local_poses is None else np.asarray(local_poses, LOCAL_POSE_DTYPE)
+        assert self.local_poses is None or len(self.local_poses) == len(actors)
+        self.header["reserved"][3] = LOCAL_POSE_MAGIC if self.local_poses is not None else 0
         self.materials = np.zeros(0, MATERIAL_DTYPE) if materials is None else np.asarray(materials, MATERIAL_DTYPE)   # material table (empty: the header's material)
         self.header["reserved"][2] = len(self.materials)
         self.hulls = list(hulls)
@@ -196,6 +213,8 @@ class Scene:
         h = self.header.copy()
         h["reserved"][1] = COOKED_MAGIC if self.cooked else 0
         out = [h.tobytes(), self.actors.tobytes(), self.materials.tobytes()]
+        if self.local_poses is not None:
+            out.append(self.local_poses.tobytes())
         for hl in self.hulls:
             hl = np.asarray(hl, dtype="<f4").reshape(-1, 3)
             out.append(np.uint32(len(hl)).tobytes())
@@ -216,12 +235,16 @@ class Scene:
         off += a.nbytes
         mats = np.frombuffer(buf, dtype=MATERIAL_DTYPE, count=int(h["reserved"][2]), offset=off).copy()
         off += mats.nbytes
+        lp = None
+        if int(h["reserved"][3]) == LOCAL_POSE_MAGIC:
+            lp = np.frombuffer(buf, dtype=LOCAL_POSE_DTYPE, count=int(h["nActors"]), offset=off).copy()
+            off += lp.nbytes
         hulls = []
         for _ in range(int(h["nHulls"])):
             nv = int(np.frombuffer(buf, "<u4", 1, off)[0]); off += 4
             hulls.append(np.frombuffer(buf, "<f4", nv * 3, off).reshape(nv, 3).copy()); off += nv * 12
         cooked = buf[off:] if int(h["reserved"][1]) == COOKED_MAGIC else b""
-        return Scene(h, a, hulls, cooked, mats)
+        return Scene(h, a, hulls, cooked, mats, lp)
 
     def cooked_hulls(self):
         return parse_cooked(self.cooked, len(self.hulls))[0] if self.cooked else []
@@ -705,3 +728,69 @@ def material_mix(n_boxes=12, n_spheres=8, seed=5, **hdr):
     sc = Scene(default_header(**hdr), add_ground_plane(a), materials=mats)
     sc.actors["materialIndex"][0] = 4     # the plane has its own material
     return sc
+
+
+def _rand_quat(rng, n=None):
+    q = rng.normal(size=(4,) if n is None else (n, 4))
+    return (q / np.linalg.norm(q, axis=-1, keepdims=True)).astype(np.float32)
+
+
+def _qmul(a, b):   # float64 helpers for BUILDING scenes (inputs, not parity arithmetic)
+    ax, ay, az, aw = a; bx, by, bz, bw = b
+    return np.array([aw * bx + bw * ax + ay * bz - by * az, aw * by + bw * ay + az * bx - bz * ax, aw * bz + bw * az + ax * by - bx * ay, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _qrot(q, v):
+    qv, qw = np.asarray(q[:3], np.float64), float(q[3])
+    return v + 2.0 * np.cross(qv, np.cross(qv, v) + qw * v)
+
+
+def local_pose_mix(n_stacks=4, height=3, n_loose=10, seed=9, **hdr):
+    """a1 with local poses (PxShape::setLocalPose, PxRigidBody::setCMassLocalPose): stacks of boxes whose SHAPES line up while the actor frames and the
+    centre-of-mass frames are offset and rotated per body (so the stacks lean and topple: pairs come and go), spheres / capsules with offset shapes
+    dropped next to them, one static box with a shape offset.  Inertia tensors are given in the body (centre-of-mass) frame."""
+    rng = np.random.RandomState(seed)
+    nb = n_stacks * height
+    n = nb + n_loose + 1
+    a = _new_actors(n)
+    lp = identity_local_poses(n)
+    he = np.float32(0.25)
+    set_box(a, np.arange(nb), np.array([he, he * 0.8, he * 1.2], dtype=np.float32))
+    kinds = []
+    for k in range(n_loose):
+        j = nb + k
+        if k % 2:
+            set_capsule(a, j, 0.12, 0.2); kinds.append("capsule")
+        else:
+            set_sphere(a, j, 0.18); kinds.append("sphere")
+    shape_world = []
+    for i in range(nb):
+        s, l = divmod(i, height)
+        shape_world.append((np.array([1.5 * s, he * 0.8 * (2 * l + 1) + 0.002 * l, 0.0]), np.array([0, 0, 0, 1.0])))
+    for k in range(n_loose):
+        shape_world.append((np.array([1.5 * (k % n_stacks) + 0.6, 1.0 + 0.45 * (k // n_stacks), 0.5 * ((k % 3) - 1)]), _rand_quat(rng).astype(np.float64)))
+    for i, (wp, wq) in enumerate(shape_world):
+        # shape2Actor: offset up to 15 cm, any rotation (every third body keeps an identity shape pose, every fourth an identity CoM pose)
+        sp = rng.uniform(-0.15, 0.15, 3) if i % 3 else np.zeros(3)
+        sq = _rand_quat(rng).astype(np.float64) if i % 3 else np.array([0, 0, 0, 1.0])
+        # actor pose = shape world pose * shape2Actor^-1
+        sq_inv = np.array([-sq[0], -sq[1], -sq[2], sq[3]])
+        aq = _qmul(wq, sq_inv)
+        ap = wp - _qrot(aq, sp)
+        a["pos"][i] = ap.astype(np.float32); a["quat"][i] = (aq / np.linalg.norm(aq)).astype(np.float32)
+        lp["shapeP"][i] = sp.astype(np.float32); lp["shapeQ"][i] = sq.astype(np.float32)
+        if i % 4:
+            lp["bodyP"][i] = (sp + rng.uniform(-0.06, 0.06, 3)).astype(np.float32)   # centre of mass near the shape centre, not at it
+            lp["bodyQ"][i] = _rand_quat(rng) if i % 2 else np.array([0, 0, 0, 1], np.float32)
+            a["inertia"][i] *= np.array([1.0, 1.3, 0.8], np.float32)                   # distinct principal moments (body frame)
+        a["angVel"][i] = rng.uniform(-0.5, 0.5, 3).astype(np.float32) if i >= nb else 0.0
+    # static box with an offset shape: a ledge some loose bodies land on
+    j = n - 1
+    set_box(a, j, np.array([0.6, 0.1, 0.6], dtype=np.float32))
+    a["flags"][j] = 0; a["mass"][j] = 0; a["inertia"][j] = 0
+    a["pos"][j] = (2.0, 0.3, 1.2)
+    lp["shapeP"][j] = (0.3, 0.1, -0.2); lp["shapeQ"][j] = _rand_quat(np.random.RandomState(seed + 1)) * np.float32(1.0)
+    lp["shapeQ"][j] = np.array([0.0, 0.0, 0.08715574, 0.9961947], np.float32)   # 10 degrees about z
+    actors = add_ground_plane(a)
+    lp = np.concatenate([identity_local_poses(1), lp])
+    return Scene(default_header(**hdr), actors, local_poses=lp)

@@ -138,6 +138,9 @@ def main():
     # a11: material table (every PxCombineMode, eDISABLE_FRICTION): sliding / stacked boxes and bouncing spheres, TGS and PGS
     cases["materials_mix"] = (scenes.material_mix(), 90)
     cases["pgs_materials_mix"] = (scenes.material_mix(solver=scenes.SOLVER_PGS), 90)
+    # a1 with local poses: PxShape::setLocalPose + PxRigidBody::setCMassLocalPose per body (offset / rotated shape and centre-of-mass frames), TGS and PGS
+    cases["local_poses_mix"] = (scenes.local_pose_mix(), 90)
+    cases["pgs_local_poses_mix"] = (scenes.local_pose_mix(solver=scenes.SOLVER_PGS), 90)
     cases["capsules_into_boxes"] = (scenes.capsules_into_boxes(seed=3), 60)   # deep penetration: the EPA query
     # a19: PxDirectGPUAPI eFORCE / eTORQUE writes (= addForce / addTorque(eFORCE) before every step), a 7-step cycle of per-body forces
     forced = {"forces_stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01),

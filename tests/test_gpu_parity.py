@@ -1103,3 +1103,59 @@ def test_copy_contact_data_same_on_both_paths():
         assert np.array_equal(a["records"][f][oa], b["records"][f][ob])
     assert np.array_equal(a["patches"][oa], b["patches"][ob])
     assert np.array_equal(a["friction"][oa], b["friction"][ob])          # friction anchors and impulses bit-identical across the two paths
+
+
+# ---- a1 with local poses: PxShape::setLocalPose + PxRigidBody::setCMassLocalPose (transform cache, actor-pose I/O) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["local_poses_mix", "pgs_local_poses_mix"])
+@pytest.mark.parametrize("env_path", [True, False])
+def test_local_poses_gpu_matches_oracle_and_reference(name, env_path):
+    """Shape frame, actor frame and centre-of-mass frame all different per body.  The engine integrates body frames, composes the shapes' world poses
+    into the transform cache in the reference's operation order and reports actor poses: initial actor poses (through setCMassLocalPose and back)
+    bit-identical to the reference; 30 free-running steps bit-identical to the oracle with TGS (1e-5 with PGS) and within 1e-5 (pose) of the reference."""
+    z, sc = util.load_golden(name)
+    gpu = engine.Scene(sc, env_path=env_path); cpu = oracle_lib.OracleScene(sc)
+    assert np.array_equal(gpu.getStates(), z["states"][0])
+    pgs = name.startswith("pgs")
+    for t in range(30):
+        gpu.setConstraintOrder(util.golden_order(z, t)); gpu.step(); cpu.step(util.golden_order(z, t))
+        a, b, ref = gpu.getStates(), cpu.getStates(), z["states"][t + 1]
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()), f"pairs, step {t}"
+        if pgs:
+            assert np.abs(a - b).max() < 1e-5, f"gpu vs oracle, step {t}"
+        else:
+            assert np.array_equal(a, b), f"gpu vs oracle, step {t}"
+            assert np.array_equal(gpu.getContacts(), cpu.getContacts()), f"contacts, step {t}"
+        assert np.abs(a[:, :7] - ref[:, :7]).max() < 1e-5 and np.abs(a[:, 7:] - ref[:, 7:]).max() < 5e-4, f"gpu vs reference, step {t}"
+
+
+@pytest.mark.gpu
+def test_local_poses_pose_io_is_in_actor_frames():
+    import torch
+    from physx_b200 import tensor_api as ta
+    sc = scenes.local_pose_mix()
+    gpu = engine.Scene(sc)
+    for _ in range(5):
+        gpu.step()
+    st = gpu.getStates()
+    n = gpu.num_dynamic
+    pose = gpu.getRigidDynamicData(engine.RD_GLOBAL_POSE)                       # PxDirectGPUAPI pose wire format: q.xyzw, p.xyz
+    assert np.array_equal(pose[:, 4:7], st[:, 0:3]) and np.array_equal(pose[:, 0:4], st[:, 3:7])
+    t = torch.empty((n, 7), dtype=torch.float32, device="cuda"); ta.TensorBinding(gpu, ta.TensorType.RIGID_BODY_POSE).read(t)
+    assert np.array_equal(t.cpu().numpy(), st[:, :7])
+    # writing the actor poses back re-derives the body frames: one step later the result is the same to rounding (body2World = pose * body2Actor is not exactly invertible)
+    ref = engine.Scene(sc)
+    for _ in range(5):
+        ref.step()
+    gpu.setRigidDynamicData(engine.RD_GLOBAL_POSE, pose)
+    back = gpu.getStates()
+    assert np.abs(back[:, :7] - st[:, :7]).max() < 1e-6 and np.array_equal(back[:, 7:], st[:, 7:])
+    gpu.step(); ref.step()
+    assert np.abs(gpu.getStates() - ref.getStates()).max() < 1e-4
+    # a moved actor really moves (shape and body frame follow)
+    moved = pose.copy(); moved[3, 5] += 2.0
+    gpu.setRigidDynamicData(engine.RD_GLOBAL_POSE, moved)
+    assert abs(gpu.getStates()[3, 1] - (back[3, 1] + 2.0)) < 1e-5
+    with pytest.raises(RuntimeError):      # the fused export reports body frames
+        buf = torch.zeros((n, 13), dtype=torch.float32, device="cuda")
+        gpu.setStateExport((buf.data_ptr(),))

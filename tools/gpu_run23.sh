@@ -1,4 +1,4 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-python -m pytest tests -x -q -m gpu > $O/r23_tests.log 2>&1; tail -30 $O/r23_tests.log
+python -m pytest tests -x -q -m gpu > $O/r23_tests.log 2>&1; tail -40 $O/r23_tests.log
