@@ -786,7 +786,7 @@ def local_pose_mix(n_stacks=4, height=3, n_loose=10, seed=9, **hdr):
         a["angVel"][i] = rng.uniform(-0.5, 0.5, 3).astype(np.float32) if i >= nb else 0.0
     # static box with an offset shape: a ledge some loose bodies land on
     j = n - 1
-    set_box(a, j, np.array([0.6, 0.1, 0.6], dtype=np.float32))
+    set_box(a, np.arange(j, j + 1), np.array([0.6, 0.1, 0.6], dtype=np.float32))
     a["flags"][j] = 0; a["mass"][j] = 0; a["inertia"][j] = 0
     a["pos"][j] = (2.0, 0.3, 1.2)
     lp["shapeP"][j] = (0.3, 0.1, -0.2); lp["shapeQ"][j] = _rand_quat(np.random.RandomState(seed + 1)) * np.float32(1.0)

@@ -1109,12 +1109,12 @@ def test_copy_contact_data_same_on_both_paths():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["local_poses_mix", "pgs_local_poses_mix"])
 @pytest.mark.parametrize("env_path", [True, False])
-def test_local_poses_gpu_matches_oracle_and_reference(name, env_path):
+def test_local_poses_gpu_matches_oracle_and_reference(oracle, name, env_path):
     """Shape frame, actor frame and centre-of-mass frame all different per body.  The engine integrates body frames, composes the shapes' world poses
     into the transform cache in the reference's operation order and reports actor poses: initial actor poses (through setCMassLocalPose and back)
     bit-identical to the reference; 30 free-running steps bit-identical to the oracle with TGS (1e-5 with PGS) and within 1e-5 (pose) of the reference."""
     z, sc = util.load_golden(name)
-    gpu = engine.Scene(sc, env_path=env_path); cpu = oracle_lib.OracleScene(sc)
+    gpu = engine.Scene(sc, env_path=env_path); cpu = oracle.OracleScene(sc)
     assert np.array_equal(gpu.getStates(), z["states"][0])
     pgs = name.startswith("pgs")
     for t in range(30):
