@@ -78,6 +78,21 @@ class Scene {
     wakeCounters.resize(getNbDynamics()); asleep.resize(getNbDynamics());
     if (!asleep.empty()) check(pxb_scene_get_sleep_data(h_, wakeCounters.data(), asleep.data()));
   }
+  // PxMaterial table (PxMaterial::setFrictionCombineMode / setRestitutionCombineMode / eDISABLE_FRICTION per entry; PxbActorRec.materialIndex refers to it): before the actors
+  void setMaterials(const std::vector<PxbMaterial>& table) { if (!table.empty()) check(pxb_scene_set_materials(h_, table.data(), (uint32_t)table.size())); }
+  // PxShape::setLocalPose / PxRigidBody::setCMassLocalPose for actors [first, first + n): 7 floats each (p.xyz, q.xyzw); poses in and out of the API stay actor poses
+  void setLocalPoses(uint32_t first, uint32_t n, const float* shape2Actor, const float* body2Actor) { check(pxb_scene_set_local_poses(h_, first, n, shape2Actor, body2Actor)); }
+  // PxScene::removeActor: the actors leave the simulation at the next step, indices stay valid
+  void removeActors(const std::vector<uint32_t>& actors) { if (!actors.empty()) check(pxb_scene_remove_actors(h_, actors.data(), (uint32_t)actors.size())); }
+  // contact reports of the last step: pairs that started / stopped touching (eNOTIFY_TOUCH_FOUND / eNOTIFY_TOUCH_LOST), (a, b) actor indices with a < b
+  std::vector<uint32_t> getTouchFound() { std::vector<uint32_t> p(2 * (size_t)pxb_scene_num_touch_found(h_)); if (!p.empty()) check(pxb_scene_get_touch_found(h_, p.data())); return p; }
+  std::vector<uint32_t> getTouchLost() { std::vector<uint32_t> p(2 * (size_t)pxb_scene_num_touch_lost(h_)); if (!p.empty()) check(pxb_scene_get_touch_lost(h_, p.data())); return p; }
+  // PxDirectGPUAPI::copyContactData: PxGpuContactPair records into DEVICE memory (enable before the step whose contacts are wanted)
+  void enableContactData(bool on = true) { check(pxb_scene_enable_contact_data(h_, on ? 1 : 0)); }
+  void copyContactData(void* deviceData, uint32_t* deviceNbContactPairs, uint32_t maxPairs) { check(pxb_scene_copy_contact_data(h_, deviceData, deviceNbContactPairs, maxPairs)); }
+  // fused state export: the step stores the packed State block of every dynamic body into the given device / peer-mapped / mapped pinned host buffers
+  void setStateExport(const std::vector<void*>& targets, uint32_t rowOffset = 0) { check(pxb_scene_set_state_export(h_, targets.empty() ? nullptr : targets.data(), (uint32_t)targets.size(), rowOffset)); }
+  void sync() { check(pxb_scene_sync(h_)); }
   uint32_t getNbPairs() { return pxb_scene_num_pairs(h_); }
   uint32_t getNbConstraints() { return pxb_scene_last_num_constraints(h_); }
   uint32_t getNbPartitions() { return pxb_scene_last_num_partitions(h_); }
