@@ -1159,3 +1159,110 @@ def test_local_poses_pose_io_is_in_actor_frames():
     with pytest.raises(RuntimeError):      # the fused export reports body frames
         buf = torch.zeros((n, 13), dtype=torch.float32, device="cuda")
         gpu.setStateExport((buf.data_ptr(),))
+
+
+# ---- BASELINE.json's full sizes through size-independent properties (configs 3, 4, 5; config 2: test_config2_full_size_properties) ----
+def _fast_stats(sc, st, con):
+    """kinetic energy (linear part), deepest separation and mean penetration of a large run, vectorised"""
+    dyn = (sc.actors["flags"] & scenes.ACTOR_DYNAMIC) != 0
+    mass = sc.actors["mass"][dyn].astype(np.float64)
+    ke = float(0.5 * (mass * (st[:, 7:10].astype(np.float64) ** 2).sum(1)).sum())
+    cnt = con[:, 0].astype(np.int64)
+    seps = con[:, 4:24].reshape(-1, 4, 5)[:, :, 3]
+    valid = np.arange(4)[None, :] < cnt[:, None]
+    s = seps[valid].astype(np.float64)
+    return dict(ke=ke, min_sep=float(s.min()) if len(s) else 0.0, mean_pen=float(np.clip(-s, 0, None).mean()) if len(s) else 0.0)
+
+
+def _pair_set_properties(sc, gpu):
+    pairs = gpu.getPairs()
+    keys = pairs[:, 0].astype(np.int64) << 32 | pairs[:, 1]
+    assert np.all(np.diff(keys) > 0), "pair list sorted and unique"
+    dyn = (sc.actors["flags"] & scenes.ACTOR_DYNAMIC) != 0
+    assert np.all(dyn[pairs[:, 0]] | dyn[pairs[:, 1]]), "every pair has a dynamic actor"
+    return pairs
+
+
+@pytest.mark.gpu
+def test_config4_full_size_properties():
+    """200 000 boxes in one island (BASELINE config 4), exact first-fit colouring: the run is bitwise deterministic, the pile neither explodes nor sinks
+    (kinetic energy decays, penetration stays at the contact-offset scale), every touching pair is a constraint, and the box-box regeneration worklist
+    (k_boxbox_generate) gives the same result as regeneration inside k_narrowphase."""
+    import os
+    sc = scenes.box_pile(100, 20, 100)
+    assert sc.n_dynamic == 200000
+    runs = []
+    for phases in ("1", "0", "1"):
+        os.environ["PXB_BOX_PHASES"] = phases
+        try:
+            gpu = engine.Scene(sc, max_pairs=16 * len(sc.actors))
+        finally:
+            del os.environ["PXB_BOX_PHASES"]
+        assert not gpu.uses_env_path
+        ke = []
+        for t in range(24):
+            gpu.step()
+            if t in (3, 23):
+                ke.append(_fast_stats(sc, gpu.getStates(), gpu.getContacts()))
+        runs.append((gpu.getStates(), gpu.getPairs(), ke))
+        if phases == "1" and len(runs) == 1:
+            pairs = _pair_set_properties(sc, gpu)
+            con = gpu.getContacts()
+            assert gpu.num_constraints == int(np.count_nonzero(con[:, 0])) > 2.0e6
+            assert gpu.num_partitions <= 64
+    (s0, p0, k0), (s1, p1, k1), (s2, p2, k2) = runs
+    assert np.isfinite(s0).all() and np.abs(np.linalg.norm(s0[:, 3:7], axis=1) - 1).max() < 1e-5
+    assert np.array_equal(s0, s2) and np.array_equal(p0, p2), "bitwise deterministic"
+    assert np.array_equal(s0, s1) and np.array_equal(p0, p1), "worklist regeneration == in-kernel regeneration"
+    assert k0[1]["ke"] < k0[0]["ke"] * 1.5 and k0[1]["min_sep"] > -0.05 and k0[1]["mean_pen"] < 5e-3
+    assert s0[:, 1].min() > 0.2 and s0[:, 1].max() < 11.0      # nobody fell through the floor or got shot out of the bin
+
+
+@pytest.mark.gpu
+def test_config3_full_size_properties():
+    """1 048 576 spheres / capsules / convex hulls falling into a walled bin (BASELINE config 3): bitwise deterministic, no unsupported pair, finite,
+    and the four-phase GJK family gives exactly what the single kernel gives (states and pair sets after 70 steps of the fall)."""
+    import os
+    sc = scenes.falling_primitives(128, 64, 128, kinds=("sphere", "capsule", "convex"))
+    assert sc.n_dynamic == 1048576
+    out = []
+    for phases in ("1", "0"):
+        os.environ["PXB_GJK_PHASES"] = phases
+        try:
+            gpu = engine.Scene(sc, max_pairs=16 * len(sc.actors))
+        finally:
+            del os.environ["PXB_GJK_PHASES"]
+        for t in range(70):
+            gpu.step()          # fetchResults raises on E_UNSUPPORTED_PAIR / capacity errors
+        st = gpu.getStates()
+        assert np.isfinite(st).all()
+        out.append((st, _pair_set_properties(sc, gpu), gpu.num_constraints))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2] > 1.0e6
+    assert out[0][0][:, 1].min() > 0.0
+
+
+@pytest.mark.gpu
+def test_config5_shard_full_size_properties():
+    """one GPU's shard of BASELINE config 5: 4096 envs x 128 boxes = 524 288 bodies.  No cross-environment pair, every environment's result equals the
+    result of the same environment simulated alone (environments never interact), stacks stay standing."""
+    sc = scenes.env_grid_stacks(n_envs=4096, stacks_per_env=16)
+    assert sc.n_dynamic == 524288
+    gpu = engine.Scene(sc)
+    assert gpu.uses_env_path
+    for _ in range(20):
+        gpu.step()
+    pairs = _pair_set_properties(sc, gpu)
+    env = sc.actors["envId"]
+    e0, e1 = env[pairs[:, 0]], env[pairs[:, 1]]
+    assert np.all((e0 == e1) | (e0 == scenes.NO_ENV) | (e1 == scenes.NO_ENV)), "no cross-environment pair"
+    st = gpu.getStates()
+    assert np.isfinite(st).all()
+    dyn_env = env[(sc.actors["flags"] & scenes.ACTOR_DYNAMIC) != 0]
+    for e in (0, 1777, 4095):                      # the same environment alone (plus the shared ground plane): bit-identical trajectories
+        keep = (env == e) | (env == scenes.NO_ENV)
+        sub_actors = sc.actors[keep].copy()
+        sub_actors["envId"][sub_actors["envId"] == e] = 0
+        alone = engine.Scene(scenes.Scene(sc.header, sub_actors))
+        for _ in range(20):
+            alone.step()
+        assert np.array_equal(alone.getStates(), st[dyn_env == e]), f"environment {e}"
