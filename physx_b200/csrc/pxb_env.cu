@@ -1,6 +1,10 @@
 // pxb_env.cu -- instantiations and launchers of the environment path's kernels (pxb_env.cuh: k_env_bp, k_env_solve).
 #include "pxb_launch.h"
 
+#ifndef PXB_ENV_BP_CTA_MAX_ENVS
+#define PXB_ENV_BP_CTA_MAX_ENVS 148   // up to one CTA per SM; beyond that a warp per environment keeps more environments in flight
+#endif
+
 cudaError_t pxb_env_set_attributes(int solveSmemMax, int bpSmemMax) {
   cudaError_t e = cudaSuccess;
 #define ENV_ATTR(T) do { if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_solve<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, solveSmemMax); \
@@ -11,9 +15,16 @@ cudaError_t pxb_env_set_attributes(int solveSmemMax, int bpSmemMax) {
 #undef ENV_ATTR
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_bp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bpSmemMax);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_bp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bpSmemMax);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_bp_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bpSmemMax);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_env_bp_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bpSmemMax);
   return e;
 }
 void pxb_launch_env_bp(cudaStream_t st, const EnvBpArgs& A, bool hulls, size_t smem) {
+  if (A.nEnv <= PXB_ENV_BP_CTA_MAX_ENVS) {   // few environments: a CTA per environment (the warps share the rows), else the step is one warp's latency
+    const size_t ctaSmem = (size_t)A.maxList * (2 * sizeof(float4) + 2 * sizeof(uint32_t));
+    if (hulls) k_env_bp_cta<true><<<A.nEnv, ENV_BP_CTA_THREADS, ctaSmem, st>>>(A); else k_env_bp_cta<false><<<A.nEnv, ENV_BP_CTA_THREADS, ctaSmem, st>>>(A);
+    return;
+  }
   const uint32_t grid = (A.nEnv + ENV_BP_WARPS - 1) / ENV_BP_WARPS;
   if (hulls) k_env_bp<true><<<grid, 32 * ENV_BP_WARPS, smem, st>>>(A); else k_env_bp<false><<<grid, 32 * ENV_BP_WARPS, smem, st>>>(A);
 }

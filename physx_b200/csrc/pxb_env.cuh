@@ -40,6 +40,43 @@ __device__ __forceinline__ bool env_bp_test(const float4& amin, const float4& am
   return !sep & (((__float_as_uint(amax.w) | __float_as_uint(bmax.w)) & 0x100u) != 0);
 }
 
+// a7: pair lifecycle of one environment against last frame's segment of the same environment (both sorted); `tid` of `stride` cooperating threads.
+// Returns false when this thread saw a key that was not at the same position last frame (segment changed).
+__device__ __forceinline__ bool env_bp_lifecycle(const EnvBpArgs& A, uint32_t e, uint32_t base, uint32_t cnt, uint32_t tid, uint32_t stride) {
+  const uint2 os = A.oldSeg[e]; const uint32_t ob = os.x, oc = os.y & 0x7fffffffu;
+  bool same = cnt == oc;   // segment identical to last frame's (steady state): k_env_solve may reuse last frame's colouring
+  for (uint32_t t = tid; t < cnt; t += stride) {
+    const uint64_t k = A.newKeys[base + t];
+    uint32_t slot = NONE32;
+    if (t < oc && A.oldKeys[ob + t] == k) slot = A.oldSlots[ob + t];
+    else {
+      same = false; const uint32_t p = lower_bound_u64(A.oldKeys + ob, oc, k); if (p < oc && A.oldKeys[ob + p] == k) slot = A.oldSlots[ob + p]; }
+    if (slot == NONE32) {
+      // pops only consume ring entries that existed when the step began (C_FREE_SNAP), pushes of this step land behind them
+      const uint32_t h = atomicAdd(&A.counters[C_FREE_HEAD], 1u);
+      if ((int32_t)(A.counters[C_FREE_SNAP] - h) <= 0) { atomicOr(&A.counters[C_ERROR], (uint32_t)E_PAIR_OVERFLOW); slot = 0; }
+      else slot = A.freeRing[h & A.ringMask];
+      A.createdKeys[atomicAdd(&A.counters[C_NCREATED], 1u)] = k;
+      float4* m = A.manifolds + (size_t)slot * PXB_MANIFOLD_F4;
+      m[0] = make_float4(__int_as_float(0), FLT_MAX, FLT_MAX, FLT_MAX); m[1] = make_float4(0, 0, 0, 1); m[2] = make_float4(0, 0, 0, 1); m[3] = make_float4(0, 0, 0, 1); m[14] = make_float4(0, 0, 0, 0);
+      float4* f = A.frictions + (size_t)slot * PXB_FRICTION_F4;
+      f[0] = make_float4(0, 0, 0, __int_as_float(0)); f[1] = make_float4(0, 0, 0, __int_as_float(0)); f[2] = make_float4(0, 0, 0, __int_as_float(0));
+      A.slotColour[slot] = NONE32; A.touch.state[slot] = 0u;
+    }
+    A.newSlots[base + t] = slot;
+  }
+  for (uint32_t t = tid; t < oc; t += stride) {
+    const uint64_t k = A.oldKeys[ob + t];
+    if (t < cnt && A.newKeys[base + t] == k) continue;
+    const uint32_t p = lower_bound_u64(A.newKeys + base, cnt, k);
+    if (p < cnt && A.newKeys[base + p] == k) continue;
+    A.freeRing[atomicAdd(&A.counters[C_FREE_TAIL], 1u) & A.ringMask] = A.oldSlots[ob + t];
+    A.deletedKeys[atomicAdd(&A.counters[C_NDELETED], 1u)] = k;
+    touch_event(A.touch, A.counters, A.oldSlots[ob + t], k, false);
+  }
+  return same;
+}
+
 template <bool HULLS>   // HULLS: the scene holds convex meshes (the plain instantiation carries no hull-bounds code)
 __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A) {
   extern __shared__ float4 envBpSmem[];
@@ -108,40 +145,84 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
     }
   }
   __syncwarp();
-  // a7: pair lifecycle against last frame's segment of the same environment (both sorted)
-  const uint2 os = A.oldSeg[e]; const uint32_t ob = os.x, oc = os.y & 0x7fffffffu;
-  bool same = cnt == oc;   // segment identical to last frame's (steady state): k_env_solve may reuse last frame's colouring
-  for (uint32_t t = lane; t < cnt; t += 32) {
-    const uint64_t k = A.newKeys[base + t];
-    uint32_t slot = NONE32;
-    if (t < oc && A.oldKeys[ob + t] == k) slot = A.oldSlots[ob + t];
-    else {
-      same = false; const uint32_t p = lower_bound_u64(A.oldKeys + ob, oc, k); if (p < oc && A.oldKeys[ob + p] == k) slot = A.oldSlots[ob + p]; }
-    if (slot == NONE32) {
-      // pops only consume ring entries that existed when the step began (C_FREE_SNAP), pushes of this step land behind them
-      const uint32_t h = atomicAdd(&A.counters[C_FREE_HEAD], 1u);
-      if ((int32_t)(A.counters[C_FREE_SNAP] - h) <= 0) { atomicOr(&A.counters[C_ERROR], (uint32_t)E_PAIR_OVERFLOW); slot = 0; }
-      else slot = A.freeRing[h & A.ringMask];
-      A.createdKeys[atomicAdd(&A.counters[C_NCREATED], 1u)] = k;
-      float4* m = A.manifolds + (size_t)slot * PXB_MANIFOLD_F4;
-      m[0] = make_float4(__int_as_float(0), FLT_MAX, FLT_MAX, FLT_MAX); m[1] = make_float4(0, 0, 0, 1); m[2] = make_float4(0, 0, 0, 1); m[3] = make_float4(0, 0, 0, 1); m[14] = make_float4(0, 0, 0, 0);
-      float4* f = A.frictions + (size_t)slot * PXB_FRICTION_F4;
-      f[0] = make_float4(0, 0, 0, __int_as_float(0)); f[1] = make_float4(0, 0, 0, __int_as_float(0)); f[2] = make_float4(0, 0, 0, __int_as_float(0));
-      A.slotColour[slot] = NONE32; A.touch.state[slot] = 0u;
-    }
-    A.newSlots[base + t] = slot;
-  }
-  for (uint32_t t = lane; t < oc; t += 32) {
-    const uint64_t k = A.oldKeys[ob + t];
-    if (t < cnt && A.newKeys[base + t] == k) continue;
-    const uint32_t p = lower_bound_u64(A.newKeys + base, cnt, k);
-    if (p < cnt && A.newKeys[base + p] == k) continue;
-    A.freeRing[atomicAdd(&A.counters[C_FREE_TAIL], 1u) & A.ringMask] = A.oldSlots[ob + t];
-    A.deletedKeys[atomicAdd(&A.counters[C_NDELETED], 1u)] = k;
-    touch_event(A.touch, A.counters, A.oldSlots[ob + t], k, false);
-  }
+  bool same = env_bp_lifecycle(A, e, base, cnt, lane, 32u);
   same = __all_sync(0xffffffffu, same);
   if (lane == 0) A.newSeg[e] = make_uint2(base, cnt | (same ? 0x80000000u : 0u));
+}
+
+// The same stage with a whole CTA per environment, for scenes of FEW environments (BASELINE config 1 is one environment of 101 actors): with one warp the
+// step is that warp's latency (46 us for 100 boxes); here the rows of the all-pairs enumeration are dealt to the CTA's warps.  Two passes keep the key order:
+// pass 1 counts the hits of every row, a scan gives each row its offset in the environment's segment, pass 2 enumerates again and writes the keys in place.
+#define ENV_BP_CTA_THREADS 256
+template <bool HULLS>
+__global__ void __launch_bounds__(ENV_BP_CTA_THREADS) k_env_bp_cta(const EnvBpArgs A) {
+  extern __shared__ float4 envBpSmem[];
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, W = ENV_BP_CTA_THREADS / 32;
+  const uint32_t e = blockIdx.x;
+  float4* sMin = envBpSmem; float4* sMax = sMin + A.maxList;
+  uint32_t* sAct = reinterpret_cast<uint32_t*>(sMax + A.maxList); uint32_t* sRow = sAct + A.maxList;   // sRow: hits per row, then the row's offset
+  __shared__ uint32_t sBase, sCnt;
+  const uint32_t ls = A.envStart[e], n = A.envStart[e + 1] - ls;
+  for (uint32_t k = tid; k < n; k += ENV_BP_CTA_THREADS) {   // a1 / a2 as in k_env_bp
+    const uint32_t a = A.envList[ls + k]; const uint32_t gf = A.geomFlags[a], env = A.envId[a];
+    float mn[3], mx[3];
+    const bool own = env == e || e == 0;
+    xf shape; shape.p = V3(0, 0, 0); shape.q = Q4(0, 0, 0, 1);
+    if (A.L.s2bP || !A.externalTight) shape = shape_world_pose(A.L, a, A.pos[a], A.quat[a], own);
+    if (A.externalTight) { for (int c = 0; c < 3; ++c) { mn[c] = A.tight[a * 6 + c]; mx[c] = A.tight[a * 6 + 3 + c]; } }
+    else {
+      tight_bounds(gf & 0xff, shape.p, shape.q, A.dims[a], mn, mx, HULLS ? &A.hulls : nullptr);
+      if (own) for (int c = 0; c < 3; ++c) { A.tight[a * 6 + c] = mn[c]; A.tight[a * 6 + 3 + c] = mx[c]; }
+    }
+    const float co = A.contactOffset;
+    sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(env));
+    sMax[k] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf));
+    sAct[k] = a;
+  }
+  __syncthreads();
+  for (uint32_t i = warp; i < n; i += W) {   // pass 1: hits per row (the last row has none)
+    uint32_t c = 0;
+    if (i + 1 < n) {
+      const float4 amin = sMin[i], amax = sMax[i];
+      for (uint32_t j0 = i + 1; j0 < n; j0 += 32) { const uint32_t j = j0 + lane; c += __popc(__ballot_sync(0xffffffffu, j < n && env_bp_test(amin, amax, sMin[j], sMax[j]))); }
+    }
+    if (lane == 0) sRow[i] = c;
+  }
+  __syncthreads();
+  if (warp == 0) {   // exclusive scan of the row counts: every lane takes a run of consecutive rows
+    const uint32_t per = (n + 31) / 32, r0 = lane * per, r1 = min(n, r0 + per);
+    uint32_t sum = 0; for (uint32_t i = r0; i < r1; ++i) sum += sRow[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
+    uint32_t run = incl - sum;
+    for (uint32_t i = r0; i < r1; ++i) { const uint32_t c = sRow[i]; sRow[i] = run; run += c; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) { sCnt = total; sBase = total ? atomicAdd(&A.counters[C_NPAIRS_NEW], total) : 0u; }
+  }
+  __syncthreads();
+  const uint32_t base = sBase; uint32_t cnt = sCnt;
+  if (base + cnt > A.cap) {   // capacity exceeded: report, keep the flat list crash-free (sentinel keys), drop the segment
+    if (tid == 0) atomicOr(&A.counters[C_ERROR], (uint32_t)E_PAIR_OVERFLOW);
+    for (uint32_t t = base + tid; t < min(base + cnt, A.cap); t += ENV_BP_CTA_THREADS) { A.newKeys[t] = ~0ull; A.newSlots[t] = 0; }
+    cnt = 0;
+  } else {
+    for (uint32_t i = warp; i + 1 < n; i += W) {   // pass 2: the same enumeration, keys written at their final position
+      const float4 amin = sMin[i], amax = sMax[i]; const uint64_t hiKey = (uint64_t)sAct[i] << A.bitsA;
+      uint32_t w = sRow[i];
+      for (uint32_t j0 = i + 1; j0 < n; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool hit = j < n && env_bp_test(amin, amax, sMin[j], sMax[j]);
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (hit) A.newKeys[base + w + __popc(m & ((1u << lane) - 1u))] = hiKey | sAct[j];
+        w += __popc(m);
+      }
+    }
+  }
+  __syncthreads();   // the segment's keys are read back by other threads of the CTA below
+  const bool same = env_bp_lifecycle(A, e, base, cnt, tid, ENV_BP_CTA_THREADS);
+  const int allSame = __syncthreads_and(same ? 1 : 0);
+  if (tid == 0) A.newSeg[e] = make_uint2(base, cnt | (allSame ? 0x80000000u : 0u));
 }
 
 // ---------------------------------------------------------------------------------------------

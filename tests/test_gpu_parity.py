@@ -1237,7 +1237,7 @@ def test_config3_full_size_properties():
         st = gpu.getStates()
         assert np.isfinite(st).all()
         out.append((st, _pair_set_properties(sc, gpu), gpu.num_constraints))
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2] > 1.0e6
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2] > 5.0e5
     assert out[0][0][:, 1].min() > 0.0
 
 
