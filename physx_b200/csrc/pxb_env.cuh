@@ -77,7 +77,7 @@ __device__ __forceinline__ bool env_bp_lifecycle(const EnvBpArgs& A, uint32_t e,
   return same;
 }
 
-template <bool HULLS>   // HULLS: the scene holds convex meshes (the plain instantiation carries no hull-bounds code)
+template <bool HULLS, bool LOCAL>   // HULLS: the scene holds convex meshes; LOCAL: it has local poses (the plain instantiation carries neither code)
 __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A) {
   extern __shared__ float4 envBpSmem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
     float mn[3], mx[3];
     const bool own = env == e || e == 0;   // the shared env-less statics are in every environment's list: environment 0 writes their bounds and their transform-cache entry
     xf shape; shape.p = V3(0, 0, 0); shape.q = Q4(0, 0, 0, 1);
-    if (A.L.s2bP || !A.externalTight) shape = shape_world_pose(A.L, a, A.pos[a], A.quat[a], own);
+    if (LOCAL) shape = shape_world_pose(A.L, a, A.pos[a], A.quat[a], own);
+    else if (!A.externalTight) { const float4 p4 = A.pos[a]; shape.p = V3(p4.x, p4.y, p4.z); shape.q = Q4(A.quat[a]); }
     if (A.externalTight) { for (int c = 0; c < 3; ++c) { mn[c] = A.tight[a * 6 + c]; mx[c] = A.tight[a * 6 + 3 + c]; } }
     else {
       tight_bounds(gf & 0xff, shape.p, shape.q, A.dims[a], mn, mx, HULLS ? &A.hulls : nullptr);
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
 // step is that warp's latency (46 us for 100 boxes); here the rows of the all-pairs enumeration are dealt to the CTA's warps.  Two passes keep the key order:
 // pass 1 counts the hits of every row, a scan gives each row its offset in the environment's segment, pass 2 enumerates again and writes the keys in place.
 #define ENV_BP_CTA_THREADS 256
-template <bool HULLS>
+template <bool HULLS, bool LOCAL>
 __global__ void __launch_bounds__(ENV_BP_CTA_THREADS) k_env_bp_cta(const EnvBpArgs A) {
   extern __shared__ float4 envBpSmem[];
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, W = ENV_BP_CTA_THREADS / 32;
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(ENV_BP_CTA_THREADS) k_env_bp_cta(const EnvBpAr
     float mn[3], mx[3];
     const bool own = env == e || e == 0;
     xf shape; shape.p = V3(0, 0, 0); shape.q = Q4(0, 0, 0, 1);
-    if (A.L.s2bP || !A.externalTight) shape = shape_world_pose(A.L, a, A.pos[a], A.quat[a], own);
+    if (LOCAL) shape = shape_world_pose(A.L, a, A.pos[a], A.quat[a], own);
+    else if (!A.externalTight) { const float4 p4 = A.pos[a]; shape.p = V3(p4.x, p4.y, p4.z); shape.q = Q4(A.quat[a]); }
     if (A.externalTight) { for (int c = 0; c < 3; ++c) { mn[c] = A.tight[a * 6 + c]; mx[c] = A.tight[a * 6 + 3 + c]; } }
     else {
       tight_bounds(gf & 0xff, shape.p, shape.q, A.dims[a], mn, mx, HULLS ? &A.hulls : nullptr);

@@ -9,6 +9,7 @@
 #ifndef PXB_NP_CTAS
 #define PXB_NP_CTAS 5
 #endif
+template <bool BOXW>   // BOXW: box-box manifolds are only refreshed here, the invalidated ones go to k_boxbox_generate's worklist (device-wide path)
 __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
                               const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
                               float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   Contacts out; out.count = 0; out.normal = V3(0, 0, 0);
   for (int k = 0; k < 4; ++k) { out.point[k] = V3(0, 0, 0); out.sep[k] = 0.f; }
   if (ty0 == PXB_GEOM_PLANE && ty1 == PXB_GEOM_BOX) pcm_plane_box(tm0, tm1, V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out);
-  else if (ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX && boxList) {   // device-wide path: only the refresh here, regeneration over a compacted worklist (k_boxbox_generate)
+  else if (BOXW && ty0 == PXB_GEOM_BOX && ty1 == PXB_GEOM_BOX) {   // device-wide path: only the refresh here, regeneration over a compacted worklist (k_boxbox_generate)
     if (pcm_box_box_refresh(tm0, tm1, V3(d0.x, d0.y, d0.z), V3(d1.x, d1.y, d1.z), contactDist, toleranceLength, man, out)) {
       manifold_store(man, rec); boxList[atomicAdd(&counters[C_NBOXGEN], 1u)] = i; return;
     }
@@ -322,8 +323,10 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_boxbox_generate(const NpAr
 }
 
 void pxb_launch_narrowphase(cudaStream_t st, uint32_t capPairs, const NpArgs& A) {
-  k_narrowphase<<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies,
-                                                         A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch, A.boxList);
+  if (A.boxList) k_narrowphase<true><<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts,
+                                                                            A.pairBodies, A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch, A.boxList);
+  else k_narrowphase<false><<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies,
+                                                                    A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch, A.boxList);
   if (A.boxList) k_boxbox_generate<<<std::max(148u * 4u, std::min((capPairs + 127) / 128, 148u * 64u)), 128, 0, st>>>(A);
 }
 void pxb_launch_narrowphase_gjk(cudaStream_t st, uint32_t ctas, const NpArgs& A) {

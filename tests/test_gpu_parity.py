@@ -1248,9 +1248,9 @@ def test_config5_shard_full_size_properties():
     sc = scenes.env_grid_stacks(n_envs=4096, stacks_per_env=16)
     assert sc.n_dynamic == 524288
     gpu = engine.Scene(sc)
-    assert gpu.uses_env_path
     for _ in range(20):
         gpu.step()
+    assert gpu.uses_env_path
     pairs = _pair_set_properties(sc, gpu)
     env = sc.actors["envId"]
     e0, e1 = env[pairs[:, 0]], env[pairs[:, 1]]
