@@ -52,7 +52,7 @@ struct PxbScene {
   float4 *tcPos = 0, *tcQuat = 0, *s2bP = 0, *s2bQ = 0, *b2aP = 0, *b2aQ = 0, *actorPos = 0, *actorQuat = 0; bool hasLocal = false, hasCom = false;   // local poses (pxb_scene_set_local_poses)
   std::vector<float4> hS2aP, hS2aQ, hB2aP, hB2aQ;
   float4* frReport = 0; uint32_t *ccIdx = 0, *ccOff = 0, *ccCount = 0, *ccTotal = 0, *actorDyn = 0; uint8_t *ccPatches = 0, *ccPoints = 0, *ccFriction = 0; float* ccForces = 0; bool contactData = false;
-  uint32_t *gjkList = 0, *gjkQuery = 0, *gjkFull = 0, *gjkEpa = 0, *boxList = 0; bool boxPhases = true; bool gjkPhases = true; bool hasGjkPairs = false, anyLocks = false, anyConvex = false;
+  uint32_t *gjkList = 0, *gjkQuery = 0, *gjkFull = 0, *gjkEpa = 0, *boxList = 0; bool boxPhases = true, boxPhasesEnv = false; bool gjkPhases = true; bool hasGjkPairs = false, anyLocks = false, anyConvex = false;
   float4 *extForce = 0, *extTorque = 0; bool forcesUsed = false;
   uint4* hullMeta = 0; float4 *hullVerts = 0, *hullPolys = 0; uint8_t *hullRefs = 0, *hullEdges = 0; uint32_t nHulls = 0; std::vector<float> hullDiam;   // cooked convex hulls (pxb_scene_set_convex_meshes)   // PxDirectGPUAPI eFORCE / eTORQUE writes pending for the next step   // a10: worklist of GJK-family pairs (filled by k_narrowphase)
   uint32_t *conFlag = 0, *conIdx = 0, *conPair = 0, *rankOfPair = 0; uint64_t *conSortKey = 0, *conSortKeyAlt = 0; uint32_t* conPairAlt = 0;
@@ -833,7 +833,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
   { const char* cl = getenv("PXB_COLOUR_LEGACY"); if (cl && cl[0] == '1') s->colourLegacy = true; const char* cb = getenv("PXB_COLOUR_BACKOFF_NS"); if (cb) s->colourBackoffNs = (uint32_t)atoi(cb);
     const char* cp = getenv("PXB_COLOUR_PREFIX"); if (cp && cp[0] == '0') s->colourPrefix = false;
     const char* cw = getenv("PXB_COLOUR_WINDOW"); if (cw) s->colourWindow = (uint32_t)atoi(cw);
-    const char* bp_ = getenv("PXB_BOX_PHASES"); if (bp_ && bp_[0] == '0') s->boxPhases = false;
+    const char* bp_ = getenv("PXB_BOX_PHASES"); if (bp_ && bp_[0] == '0') s->boxPhases = false; if (bp_ && bp_[0] == '2') s->boxPhasesEnv = true;   // 2: also on the environment path (A/B)
     const char* gp = getenv("PXB_GJK_PHASES"); if (gp && gp[0] == '0') s->gjkPhases = false; }   // A/B hooks of the exact colouring
   if (desc->reserved[1] & PXB_FLAG_NO_ENV_PATH) s->envDisabled = true;
   if (desc->reserved[1] & PXB_FLAG_RELAXED_PARTITIONING) { s->relaxedPartitioning = true; s->envDisabled = true; }
@@ -1251,7 +1251,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
   NpArgs NA;
   NA.pairKeys = s->pairKeys[cur]; NA.pairSlots = s->pairSlots[cur]; NA.nPairsP = nP; NA.bitsA = s->bitsA; NA.pos = s->hasLocal ? s->tcPos : s->pos; NA.quat = s->hasLocal ? s->tcQuat : s->quat; /* shape world poses: the transform cache when the scene has local poses */ NA.dims = s->dims; NA.geomFlags = s->geomFlags;
   NA.contactDist = contactDist; NA.toleranceLength = s->desc.toleranceLength; NA.manifolds = s->manifolds; NA.cHdr = s->cHdr; NA.cPts = s->cPts; NA.pairBodies = s->pairBodies; NA.conFlag = s->conFlag;
-  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.gjkQuery = s->gjkQuery; NA.gjkFull = s->gjkFull; NA.gjkEpa = s->gjkEpa; NA.boxList = (s->boxPhases && !s->envActive) ? s->boxList : nullptr; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s); NA.touch = touch_lists(s);
+  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.gjkQuery = s->gjkQuery; NA.gjkFull = s->gjkFull; NA.gjkEpa = s->gjkEpa; NA.boxList = (s->boxPhases && (!s->envActive || s->boxPhasesEnv)) ? s->boxList : nullptr; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s); NA.touch = touch_lists(s);
   pxb_launch_narrowphase(st, s->capPairs, NA); s->launches += NA.boxList ? 2 : 1;
   if (s->hasGjkPairs) {
     const uint32_t ctas = std::max(148u * 4u, std::min(cdiv(s->capPairs, 128), 148u * 64u));
