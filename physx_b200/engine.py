@@ -55,7 +55,8 @@ class SceneDesc(ctypes.Structure):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    # PXB_LIB: another build of the same library (A/B experiments with compile-time parameters; tools/gpu_run30.sh)
+    return os.environ.get("PXB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 def load_library():
