@@ -199,16 +199,23 @@ def second_baseline_block(config, envs, solver):
     threads = min(8, os.cpu_count() or 1)
     steps = 20 if config != 1 else 200
     try:
+        out = {}
         with tempfile.TemporaryDirectory() as d:
             p = os.path.join(d, "s.bin")
             sc.save(p)
-            r = subprocess.run([harness, "run", p, "--steps", str(steps), "--warmup", "5", "--threads", str(threads), "--gpu-plugin", plugin, "--gpu-bp", "--gpu-dynamics"],
-                               capture_output=True, text=True, timeout=600)
-        if r.returncode != 0:
-            return {"value": None, "error": r.stderr[-300:]}
-        j = json.loads(r.stdout.strip().splitlines()[-1])
-        return {"value": j["body_steps_per_s"], "unit": UNIT, "ms_per_step": j["ms_per_step"], "kind": "reference GPU plugin (PhysX 5.6.1 libPhysXGpu_64.so, sm_100 build) in the unmodified host SDK",
-                "sample": f"the same scene at full size ({j['bodies']} bodies), {steps} steps after 5 untimed, eGPU broadphase + eENABLE_GPU_DYNAMICS, PxDefaultCpuDispatcher({threads}), state read back to the host by the SDK every step"}
+            # two of the reference's modes: the SDK reads the state back to its host objects every step (what `e2e` is compared with), and
+            # PxSceneFlag::eENABLE_DIRECT_GPU_API, where the state stays on the device (what `value` is compared with)
+            for key, extra in (("host_readback", []), ("direct_gpu_api", ["--direct-gpu-api"])):
+                r = subprocess.run([harness, "run", p, "--steps", str(steps), "--warmup", "5", "--threads", str(threads), "--gpu-plugin", plugin, "--gpu-bp", "--gpu-dynamics"] + extra,
+                                   capture_output=True, text=True, timeout=600)
+                if r.returncode != 0:
+                    return {"value": None, "error": r.stderr[-300:]}
+                out[key] = json.loads(r.stdout.strip().splitlines()[-1])
+        j, jd = out["host_readback"], out["direct_gpu_api"]
+        return {"value": jd["body_steps_per_s"], "unit": UNIT, "ms_per_step": jd["ms_per_step"], "kind": "reference GPU plugin (PhysX 5.6.1 libPhysXGpu_64.so, sm_100 build) in the unmodified host SDK",
+                "with_host_readback": {"value": j["body_steps_per_s"], "ms_per_step": j["ms_per_step"]},
+                "sample": f"the same scene at full size ({j['bodies']} bodies), {steps} steps after 5 untimed, eGPU broadphase (default PxGpuBroadPhaseDesc) + eENABLE_GPU_DYNAMICS, "
+                          f"PxDefaultCpuDispatcher({threads}); value: with eENABLE_DIRECT_GPU_API (state stays on the device), with_host_readback: the SDK updates its host objects every step"}
     except Exception as e:   # pragma: no cover
         return {"value": None, "error": repr(e)[:300]}
 

@@ -126,7 +126,7 @@ int main(int argc, char** argv) {
   }
   const char* scenePath = argv[2];
   int steps = 100, threads = 1, warmup = 0;
-  const char* gpuPlugin = nullptr; bool gpuBp = false, gpuDynamics = false;
+  const char* gpuPlugin = nullptr; bool gpuBp = false, gpuDynamics = false, directGpuApi = false; int gpuBpShift = -1;
   const char *statesPath = nullptr, *bpPath = nullptr, *contactsPath = nullptr, *hullsPath = nullptr, *orderPath = nullptr, *sleepPath = nullptr, *forcesPath = nullptr;
   for (int i = 3; i < argc; i++) {
     std::string a = argv[i];
@@ -142,6 +142,8 @@ int main(int argc, char** argv) {
     else if (a == "--gpu-plugin") gpuPlugin = argv[++i];   // (GPU-enabled host build only) path of a libPhysXGpu_64.so to load through PxSetPhysXGpuLoadHook
     else if (a == "--gpu-bp") gpuBp = true;                // PxBroadPhaseType::eGPU (CPU dynamics)
     else if (a == "--gpu-dynamics") gpuDynamics = true;    // + PxSceneFlag::eENABLE_GPU_DYNAMICS
+    else if (a == "--direct-gpu-api") directGpuApi = true; // + PxSceneFlag::eENABLE_DIRECT_GPU_API (no state read-back to the host objects: timing runs only)
+    else if (a == "--gpu-bp-shift") gpuBpShift = atoi(argv[++i]);   // PxGpuBroadPhaseDesc::gpuBroadPhaseNbBitsShiftX/Y/Z (default 4; SURVEY 8d asks for the shift-0 variant too)
     else if (a == "--sleep") sleepPath = argv[++i];   // per step, per dynamic actor: f32 wakeCounter, u32 isSleeping
   }
   gWantContacts = contactsPath != nullptr;
@@ -248,6 +250,9 @@ int main(int argc, char** argv) {
     sd.cudaContextManager = cudaMgr;
     sd.broadPhaseType = PxBroadPhaseType::eGPU;
     if (gpuDynamics) sd.flags |= PxSceneFlag::eENABLE_GPU_DYNAMICS;
+    if (gpuDynamics && directGpuApi) sd.flags |= PxSceneFlag::eENABLE_DIRECT_GPU_API;
+    static PxGpuBroadPhaseDesc bpDesc;
+    if (gpuBpShift >= 0) { bpDesc.gpuBroadPhaseNbBitsShiftX = bpDesc.gpuBroadPhaseNbBitsShiftY = bpDesc.gpuBroadPhaseNbBitsShiftZ = PxU8(gpuBpShift); sd.gpuBroadPhaseDesc = &bpDesc; }
     sd.gpuDynamicsConfig.foundLostPairsCapacity = PxMax(1u << 20, 8u * H.nActors);
     if (gpuDynamics) {   // PxGpuDynamicsMemoryConfig sized for the scene (contacts >= 8 M, patches >= 2 M at BASELINE sizes)
       sd.gpuDynamicsConfig.maxRigidContactCount = PxMax(1u << 20, 16u * H.nActors);

@@ -14,14 +14,19 @@ for name, sc, steps in (("config 1: 10x10 unit boxes", scenes.box_stacks(), 200)
     with tempfile.TemporaryDirectory() as d:
         p = d + "/s.bin"; sc.save(p)
         for label, extra in (("reference CPU (eABP + CPU TGS)", []), ("reference GPU plugin: eGPU broadphase + eENABLE_GPU_DYNAMICS", ["--gpu-plugin", REFP, "--gpu-bp", "--gpu-dynamics"]),
+                             ("reference GPU plugin: eGPU broadphase (shift 0) + eENABLE_GPU_DYNAMICS", ["--gpu-plugin", REFP, "--gpu-bp", "--gpu-dynamics", "--gpu-bp-shift", "0"]),
+                             ("reference GPU plugin: eGPU broadphase + eENABLE_GPU_DYNAMICS + eENABLE_DIRECT_GPU_API", ["--gpu-plugin", REFP, "--gpu-bp", "--gpu-dynamics", "--direct-gpu-api"]),
+                             ("reference GPU plugin: eGPU broadphase (shift 0) + eENABLE_GPU_DYNAMICS + eENABLE_DIRECT_GPU_API", ["--gpu-plugin", REFP, "--gpu-bp", "--gpu-dynamics", "--direct-gpu-api", "--gpu-bp-shift", "0"]),
                              ("reference GPU plugin: eGPU broadphase, CPU dynamics", ["--gpu-plugin", REFP, "--gpu-bp"]), ("our plugin: eGPU broadphase, CPU dynamics", ["--gpu-plugin", OURP, "--gpu-bp"])):
-            r = subprocess.run([H, "run", p, "--steps", str(steps), "--warmup", "5", "--threads", str(threads), "--states", d + "/st"] + extra, capture_output=True, text=True)
+            direct = "--direct-gpu-api" in extra   # with the direct GPU API the host objects are not updated: no state dump
+            r = subprocess.run([H, "run", p, "--steps", str(steps), "--warmup", "5", "--threads", str(threads)] + ([] if direct else ["--states", d + "/st"]) + extra, capture_output=True, text=True)
             rec = {"scene": name, "arm": label, "rc": r.returncode}
             if r.returncode == 0:
                 j = json.loads(r.stdout.strip().splitlines()[-1]); rec.update(ms_per_step=j["ms_per_step"], ms_median=j["ms_median"], body_steps_per_s=j["body_steps_per_s"], bodies=j["bodies"], threads=threads)
-                import numpy as np
-                st = np.fromfile(d + "/st", "<f4").reshape(-1, sc.n_dynamic, 13)
-                rec["finite"] = bool(np.isfinite(st).all()); rec["max_drop_m"] = float((st[0, :, 1] - st[-1, :, 1]).max())
+                if not direct:
+                    import numpy as np
+                    st = np.fromfile(d + "/st", "<f4").reshape(-1, sc.n_dynamic, 13)
+                    rec["finite"] = bool(np.isfinite(st).all()); rec["max_drop_m"] = float((st[0, :, 1] - st[-1, :, 1]).max())
             else:
                 rec["stderr"] = r.stderr[-600:]
             print(json.dumps(rec), flush=True); out.append(rec)
