@@ -230,6 +230,14 @@ PXB_API int  pxb_scene_get_contacts(PxbScene* scene, float* out24);
  * actor), nodeIndex0/1 = PxNodeIndex with mID = PxRigidDynamicGPUIndex (0xffffffff for a static actor), actor0/1 = the actor index as a handle.
  * Stream-ordered on the scene stream (read `data` after pxb_scene_sync or on that stream).  The friction write-back costs a few loads per
  * constraint, so it is off by default: pxb_scene_enable_contact_data(scene, 1) BEFORE the step whose contacts are wanted. */
+/* f1: the default simulation filter shader on the device (PxDefaultSimulationFilterShader, physxextensions/src/ExtDefaultSimulationFilterShader.cpp:238-280, without
+ * the trigger branch).  Config = the extension's global state: collisionTable[g] bit h = PxGetGroupCollisionFlag(g, h); ops[3] = PxSetFilterOps (PxFilterOp: 0 AND,
+ * 1 OR, 2 XOR, 3 NAND, 4 NOR, 5 NXOR, 6 SWAP_AND); filterBool = PxSetFilterBool; constants = PxSetFilterConstants (K0 word2, K0 word3, K1 word2, K1 word3).  Filter
+ * data = the shape's PxFilterData (word0 = collision group 0..31, word2 / word3 = PxGroupsMask), 4 words per actor.  A pair the shader answers eSUPPRESS for stays a
+ * broadphase pair (created / deleted lists unchanged) and generates no contacts, as in the reference (no contact manager).  NULL config = filtering off. */
+typedef struct PxbFilterShaderConfig { uint32_t collisionTable[32]; uint32_t ops[3]; uint32_t filterBool; uint32_t constants[4]; } PxbFilterShaderConfig;
+PXB_API int  pxb_scene_set_filter_shader(PxbScene* scene, const PxbFilterShaderConfig* config);
+PXB_API int  pxb_scene_set_filter_data(PxbScene* scene, uint32_t firstActor, uint32_t n, const uint32_t* data4);
 /* Local poses (a1: PxgShapeSim.shape2Actor, PxsBodyCore.body2Actor): PxShape::setLocalPose and PxRigidBody::setCMassLocalPose for actors [firstActor, firstActor + n),
  * 7 floats each (p.xyz, q.xyzw; stored normalised like the reference).  The actor keeps its pose (Sc::BodyCore::setCMassLocalPose, ScBodyCore.cpp:98-108); the body
  * frame the solver integrates becomes actorPose * body2Actor, the shape's world pose in the transform cache body2World * (body2Actor^-1 * shape2Actor)

@@ -82,6 +82,10 @@ class Scene {
   void setMaterials(const std::vector<PxbMaterial>& table) { if (!table.empty()) check(pxb_scene_set_materials(h_, table.data(), (uint32_t)table.size())); }
   // PxShape::setLocalPose / PxRigidBody::setCMassLocalPose for actors [first, first + n): 7 floats each (p.xyz, q.xyzw); poses in and out of the API stay actor poses
   void setLocalPoses(uint32_t first, uint32_t n, const float* shape2Actor, const float* body2Actor) { check(pxb_scene_set_local_poses(h_, first, n, shape2Actor, body2Actor)); }
+  // PxDefaultSimulationFilterShader on the device: the extension's global state (PxSetGroupCollisionFlag / PxSetFilterOps / PxSetFilterBool / PxSetFilterConstants)
+  // and the shapes' PxFilterData (4 words per actor); suppressed pairs stay broadphase pairs and generate no contacts
+  void setFilterShader(const PxbFilterShaderConfig* config) { check(pxb_scene_set_filter_shader(h_, config)); }
+  void setFilterData(uint32_t first, uint32_t n, const uint32_t* data4) { check(pxb_scene_set_filter_data(h_, first, n, data4)); }
   // PxScene::removeActor: the actors leave the simulation at the next step, indices stay valid
   void removeActors(const std::vector<uint32_t>& actors) { if (!actors.empty()) check(pxb_scene_remove_actors(h_, actors.data(), (uint32_t)actors.size())); }
   // contact reports of the last step: pairs that started / stopped touching (eNOTIFY_TOUCH_FOUND / eNOTIFY_TOUCH_LOST), (a, b) actor indices with a < b

@@ -96,9 +96,13 @@ struct InlineDispatcher : public PxCpuDispatcher {
 
 static bool gWantContacts = false;
 static PxMaterial* gDefaultMat = nullptr;
-static PxFilterFlags filterShader(PxFilterObjectAttributes a0, PxFilterData, PxFilterObjectAttributes a1, PxFilterData,
+static bool gUseDefaultFilter = false;   // scene file carries a filter section: the pair goes through the extension's PxDefaultSimulationFilterShader first
+static PxFilterFlags filterShader(PxFilterObjectAttributes a0, PxFilterData fd0, PxFilterObjectAttributes a1, PxFilterData fd1,
                                   PxPairFlags& pairFlags, const void* cb, PxU32) {
-  PX_UNUSED(a0); PX_UNUSED(a1);
+  if (gUseDefaultFilter) {
+    const PxFilterFlags f = PxDefaultSimulationFilterShader(a0, fd0, a1, fd1, pairFlags, nullptr, 0);
+    if (f & PxFilterFlag::eSUPPRESS) return f;
+  }
   pairFlags = PxPairFlag::eCONTACT_DEFAULT;
   if (cb && *reinterpret_cast<const int*>(cb))
     pairFlags |= PxPairFlag::eNOTIFY_TOUCH_FOUND | PxPairFlag::eNOTIFY_TOUCH_PERSISTS | PxPairFlag::eNOTIFY_CONTACT_POINTS;
@@ -155,7 +159,20 @@ int main(int argc, char** argv) {
   const PxbActorRec* recs = reinterpret_cast<const PxbActorRec*>(buf.data() + sizeof(PxbSceneHeader));
   const PxbMaterialRec* matRecs = reinterpret_cast<const PxbMaterialRec*>(recs + H.nActors);   // material table (may be empty)
   const PxbLocalPoseRec* localPoses = H.reserved[3] == PXB_LOCAL_POSE_MAGIC ? reinterpret_cast<const PxbLocalPoseRec*>(matRecs + H.reserved[2]) : nullptr;   // PxShape::setLocalPose / setCMassLocalPose per actor
-  const uint8_t* hp = reinterpret_cast<const uint8_t*>(matRecs + H.reserved[2]) + (localPoses ? sizeof(PxbLocalPoseRec) * size_t(H.nActors) : 0);
+  const uint8_t* afterLocal = reinterpret_cast<const uint8_t*>(matRecs + H.reserved[2]) + (localPoses ? sizeof(PxbLocalPoseRec) * size_t(H.nActors) : 0);
+  const PxbFilterShaderConfig* filterCfg = (H.reserved[0] & PXB_FLAG_FILTER_SECTION) ? reinterpret_cast<const PxbFilterShaderConfig*>(afterLocal) : nullptr;
+  const uint32_t* filterData = filterCfg ? reinterpret_cast<const uint32_t*>(filterCfg + 1) : nullptr;
+  const uint8_t* hp = afterLocal + (filterCfg ? sizeof(PxbFilterShaderConfig) + 16 * size_t(H.nActors) : 0);
+  if (filterCfg) {   // the extension's global filter state, through its public setters
+    gUseDefaultFilter = true;
+    for (PxU16 g = 0; g < 32; g++) for (PxU16 h = 0; h < 32; h++) PxSetGroupCollisionFlag(g, h, ((filterCfg->collisionTable[g] >> h) & 1u) != 0);
+    PxSetFilterOps(PxFilterOp::Enum(filterCfg->ops[0]), PxFilterOp::Enum(filterCfg->ops[1]), PxFilterOp::Enum(filterCfg->ops[2]));
+    PxSetFilterBool(filterCfg->filterBool != 0);
+    PxGroupsMask k0, k1;
+    k0.bits0 = PxU16(filterCfg->constants[0] & 0xffff); k0.bits1 = PxU16(filterCfg->constants[0] >> 16); k0.bits2 = PxU16(filterCfg->constants[1] & 0xffff); k0.bits3 = PxU16(filterCfg->constants[1] >> 16);
+    k1.bits0 = PxU16(filterCfg->constants[2] & 0xffff); k1.bits1 = PxU16(filterCfg->constants[2] >> 16); k1.bits2 = PxU16(filterCfg->constants[3] & 0xffff); k1.bits3 = PxU16(filterCfg->constants[3] >> 16);
+    PxSetFilterConstants(k0, k1);
+  }
 
   PxFoundation* foundation = PxCreateFoundation(PX_PHYSICS_VERSION, gAllocator, gErrorCallback);
   PxTolerancesScale scale; scale.length = H.toleranceLength; scale.speed = 10.0f * H.toleranceLength;
@@ -303,6 +320,7 @@ int main(int argc, char** argv) {
     }
     s->setContactOffset(H.contactOffset);
     s->setRestOffset(H.restOffset);
+    if (filterData) s->setSimulationFilterData(PxFilterData(filterData[4 * i], filterData[4 * i + 1], filterData[4 * i + 2], filterData[4 * i + 3]));
     if (localPoses) { const PxbLocalPoseRec& l = localPoses[i]; s->setLocalPose(PxTransform(PxVec3(l.shapeP[0], l.shapeP[1], l.shapeP[2]), PxQuat(l.shapeQ[0], l.shapeQ[1], l.shapeQ[2], l.shapeQ[3]))); }
     shapes[i] = s;
     a->userData = reinterpret_cast<void*>(size_t(i));

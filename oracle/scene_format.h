@@ -2,6 +2,7 @@
  *
  * A scene file is:  SceneHeader | ActorRec[nActors] | PxbMaterialRec[header.reserved[2]] (material table, may be empty)
  *                   | (when header.reserved[3] == PXB_LOCAL_POSE_MAGIC) PxbLocalPoseRec[nActors]
+ *                   | (when header.reserved[0] & PXB_FLAG_FILTER_SECTION) PxbFilterShaderConfig, then uint32 filterData[nActors][4] (PxFilterData word0..3 per shape)
  *                   | for each hull: u32 nVerts, float xyz[nVerts]
  *                   | (when header.reserved[1] == PXB_COOKED_MAGIC) for each hull: PxbCookedHullHeader + arrays (see below)
  * The cooked section is what PxCreateConvexMesh makes of the point cloud (Gu::ConvexHullData): convex cooking is host-side work in PhysX
@@ -83,6 +84,13 @@ typedef struct {
   uint32_t reserved[1];
 } PxbCookedHullHeader;            /* 25 words = 100 bytes */
 typedef struct { float plane[4]; uint32_t vref, nbVerts, minIndex, pad; } PxbCookedPoly;   /* HullPolygonData */
+
+/* f1: the default simulation filter shader (PxDefaultSimulationFilterShader, physxextensions/src/ExtDefaultSimulationFilterShader.cpp:238-280) and its global state:
+ * PxSetGroupCollisionFlag (collisionTable[g] bit h = groups g and h collide; all ones by default), PxSetFilterOps (ops[3]: 0 AND, 1 OR, 2 XOR, 3 NAND, 4 NOR, 5 NXOR,
+ * 6 SWAP_AND), PxSetFilterBool, PxSetFilterConstants (constants[0..1] = K0 as PxFilterData word2 / word3, [2..3] = K1).  Per actor: the shape's PxFilterData
+ * (word0 = collision group 0..31, word2 / word3 = PxGroupsMask).  A pair the shader answers eSUPPRESS for stays a broadphase pair and generates no contacts. */
+#define PXB_FLAG_FILTER_SECTION 2u   /* header.reserved[0] bit 1 */
+typedef struct { uint32_t collisionTable[32]; uint32_t ops[3]; uint32_t filterBool; uint32_t constants[4]; } PxbFilterShaderConfig;   /* 160 bytes */
 
 /* local poses: shape2Actor (p, q.xyzw), body2Actor (p, q.xyzw) */
 #define PXB_LOCAL_POSE_MAGIC 0x504c5850u /* "PXLP" */

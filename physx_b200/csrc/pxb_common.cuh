@@ -120,6 +120,27 @@ __device__ __forceinline__ xf shape_world_pose(const LocalPoses& L, uint32_t a, 
   return w;
 }
 
+// f1: PxDefaultSimulationFilterShader on the device (physxextensions/src/ExtDefaultSimulationFilterShader.cpp:238-280, without the trigger branch): collision-group
+// table (PxSetGroupCollisionFlag), groups masks with PxSetFilterOps / PxSetFilterConstants / PxSetFilterBool.  data: PxFilterData (word0..3) per actor.
+struct FilterConfig { uint32_t collisionTable[32]; uint32_t ops[3]; uint32_t filterBool; uint32_t constants[4]; };
+struct FilterArgs { const uint4* data; FilterConfig cfg; };
+__device__ __forceinline__ uint32_t filter_op16x2(uint32_t op, uint32_t x, uint32_t y) {   // two PxGroupsMask halves at once (16-bit lanes; the NOT forms stay inside 32 bits)
+  return op == 1u ? (x | y) : (op == 2u ? (x ^ y) : (op == 3u ? ~(x & y) : (op == 4u ? ~(x | y) : (op == 5u ? ~(x ^ y) : (x & y)))));
+}
+__device__ __forceinline__ void filter_op(uint32_t op, uint32_t a2, uint32_t a3, uint32_t b2, uint32_t b3, uint32_t& r2, uint32_t& r3) {
+  if (op == 6u) { const uint32_t t = b2; b2 = b3; b3 = t; }   // SWAP_AND: bits0 & bits2, bits1 & bits3, bits2 & bits0, bits3 & bits1 (word2 = bits0 | bits1 << 16, word3 = bits2 | bits3 << 16)
+  r2 = filter_op16x2(op, a2, b2); r3 = filter_op16x2(op, a3, b3);
+}
+__device__ __forceinline__ bool filter_suppressed(const FilterArgs& F, uint32_t actor0, uint32_t actor1) {
+  const uint4 f0 = F.data[actor0], f1 = F.data[actor1];
+  if (!((F.cfg.collisionTable[f0.x & 31u] >> (f1.x & 31u)) & 1u)) return true;
+  uint32_t a2, a3, b2, b3, r2, r3;
+  filter_op(F.cfg.ops[0], f0.z, f0.w, F.cfg.constants[0], F.cfg.constants[1], a2, a3);
+  filter_op(F.cfg.ops[1], f1.z, f1.w, F.cfg.constants[2], F.cfg.constants[3], b2, b3);
+  filter_op(F.cfg.ops[2], a2, a3, b2, b3, r2, r3);
+  return ((r2 | r3) != 0u) != (F.cfg.filterBool != 0u);
+}
+
 struct SleepArgs { float threshold, dt; float* wake; float4 *accLin, *accAng; uint32_t *asleep, *nInter; };
 __device__ __forceinline__ bool body_asleep(const SleepArgs& S, uint32_t a) { return S.threshold > 0.f && S.asleep[a] != 0u; }
 __device__ __forceinline__ void sleep_check_dev(const SleepArgs& S, uint32_t a, q4 q, float4 invInertia, float invMassIn, v3 motionLin, v3 motionAng) {

@@ -51,6 +51,7 @@ struct PxbScene {
   uint32_t *pairOrder = 0, *npClassCount = 0; uint8_t* npClass = 0; bool binPairs = false;   // mixed-type scenes: pairs binned by type pair before the narrowphase
   float4 *tcPos = 0, *tcQuat = 0, *s2bP = 0, *s2bQ = 0, *b2aP = 0, *b2aQ = 0, *actorPos = 0, *actorQuat = 0; bool hasLocal = false, hasCom = false;   // local poses (pxb_scene_set_local_poses)
   std::vector<float4> hS2aP, hS2aQ, hB2aP, hB2aQ;
+  uint4* filterData = 0; FilterConfig filterCfg; bool hasFilter = false;   // f1: default simulation filter shader (pxb_scene_set_filter_shader / _data)
   float4* frReport = 0; uint32_t *ccIdx = 0, *ccOff = 0, *ccCount = 0, *ccTotal = 0, *actorDyn = 0; uint8_t *ccPatches = 0, *ccPoints = 0, *ccFriction = 0; float* ccForces = 0; bool contactData = false;
   uint32_t *gjkList = 0, *gjkQuery = 0, *gjkFull = 0, *gjkEpa = 0, *boxList = 0; bool boxPhases = true, boxPhasesEnv = false; bool gjkPhases = true; bool hasGjkPairs = false, anyLocks = false, anyConvex = false;
   float4 *extForce = 0, *extTorque = 0; bool forcesUsed = false;
@@ -852,7 +853,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
   void* ptrs[] = {s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
-                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->tcPos, s->tcQuat, s->s2bP, s->s2bQ, s->b2aP, s->b2aQ, s->actorPos, s->actorQuat, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
+                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->filterData, s->tcPos, s->tcQuat, s->s2bP, s->s2bQ, s->b2aP, s->b2aQ, s->actorPos, s->actorQuat, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->prevB0, s->prevB1, s->prevColour, s->prevNCon, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
                   s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->actorMat, s->matTab, s->touchState, s->touchFound, s->touchLost, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
@@ -1251,7 +1252,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
   NpArgs NA;
   NA.pairKeys = s->pairKeys[cur]; NA.pairSlots = s->pairSlots[cur]; NA.nPairsP = nP; NA.bitsA = s->bitsA; NA.pos = s->hasLocal ? s->tcPos : s->pos; NA.quat = s->hasLocal ? s->tcQuat : s->quat; /* shape world poses: the transform cache when the scene has local poses */ NA.dims = s->dims; NA.geomFlags = s->geomFlags;
   NA.contactDist = contactDist; NA.toleranceLength = s->desc.toleranceLength; NA.manifolds = s->manifolds; NA.cHdr = s->cHdr; NA.cPts = s->cPts; NA.pairBodies = s->pairBodies; NA.conFlag = s->conFlag;
-  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.gjkQuery = s->gjkQuery; NA.gjkFull = s->gjkFull; NA.gjkEpa = s->gjkEpa; NA.boxList = (s->boxPhases && (!s->envActive || s->boxPhasesEnv)) ? s->boxList : nullptr; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s); NA.touch = touch_lists(s);
+  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.gjkQuery = s->gjkQuery; NA.gjkFull = s->gjkFull; NA.gjkEpa = s->gjkEpa; NA.boxList = (s->boxPhases && (!s->envActive || s->boxPhasesEnv)) ? s->boxList : nullptr; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s); NA.touch = touch_lists(s); NA.filter.data = s->hasFilter ? s->filterData : nullptr; NA.filter.cfg = s->filterCfg;
   pxb_launch_narrowphase(st, s->capPairs, NA); s->launches += NA.boxList ? 2 : 1;
   if (s->hasGjkPairs) {
     const uint32_t ctas = std::max(148u * 4u, std::min(cdiv(s->capPairs, 128), 148u * 64u));
@@ -1610,6 +1611,28 @@ PXB_API int pxb_scene_set_local_poses(PxbScene* s, uint32_t firstActor, uint32_t
   s->hasLocal = true;
   s->hasCom = false; for (uint32_t a = 0; a < s->nA; ++a) if (s->hB2aP[a].w != 0.f) { s->hasCom = true; break; }
   drop_graphs(s);   // the narrowphase now reads the transform cache
+  return PXB_OK;
+}
+
+// ---- f1: the default simulation filter shader on the device ----
+PXB_API int pxb_scene_set_filter_shader(PxbScene* s, const PxbFilterShaderConfig* cfg) { DeviceGuard dg_(s);
+  if (!s) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running");
+  if (cfg) { for (int k = 0; k < 3; ++k) if (cfg->ops[k] > 6u) return fail(PXB_ERR_INVALID, "filter op out of range (PxFilterOp: 0..6)"); }
+  CK(cudaStreamSynchronize(s->stream));
+  if (cfg && !s->filterData) { const size_t A = std::max<size_t>(s->capA, 1); CK(dalloc(s->filterData, A)); CK(cudaMemset(s->filterData, 0, 16 * A)); }
+  if (cfg) { static_assert(sizeof(FilterConfig) == sizeof(PxbFilterShaderConfig), "filter config layout"); memcpy(&s->filterCfg, cfg, sizeof(FilterConfig)); }
+  if ((cfg != nullptr) != s->hasFilter) { s->hasFilter = cfg != nullptr; }
+  drop_graphs(s);   // the configuration travels in the kernel arguments
+  return PXB_OK;
+}
+PXB_API int pxb_scene_set_filter_data(PxbScene* s, uint32_t firstActor, uint32_t n, const uint32_t* data4) { DeviceGuard dg_(s);
+  if (!s || (n && !data4)) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running");
+  if (!s->filterData) return fail(PXB_ERR_INVALID, "call pxb_scene_set_filter_shader first");
+  if ((uint64_t)firstActor + n > s->capA) return fail(PXB_ERR_INVALID, "actor range out of bounds");
+  if (!n) return PXB_OK;
+  CK(cudaMemcpyAsync(s->filterData + firstActor, data4, 16 * (size_t)n, cudaMemcpyHostToDevice, s->stream)); CK(cudaStreamSynchronize(s->stream));
   return PXB_OK;
 }
 

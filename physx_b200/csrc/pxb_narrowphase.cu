@@ -9,12 +9,12 @@
 #ifndef PXB_NP_CTAS
 #define PXB_NP_CTAS 5
 #endif
-template <bool BOXW>   // BOXW: box-box manifolds are only refreshed here, the invalidated ones go to k_boxbox_generate's worklist (device-wide path)
+template <bool BOXW, bool FILT>   // BOXW: box-box manifolds are only refreshed here, the invalidated ones go to k_boxbox_generate's worklist (device-wide path); FILT: default filter shader
 __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
                               const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
                               float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
                               uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters, uint32_t* __restrict__ gjkList,
-                              const uint32_t* __restrict__ pairOrder, const TouchLists touch, uint32_t* __restrict__ boxList) {
+                              const uint32_t* __restrict__ pairOrder, const TouchLists touch, uint32_t* __restrict__ boxList, const FilterArgs F) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *nPairsP) return;
   const uint32_t i = pairOrder ? pairOrder[t] : t;   // mixed-type scenes: pairs binned by type pair (k_np_class_*)
@@ -27,6 +27,11 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   uint32_t a0 = hi, a1 = lo;
   const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
   if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
+  if (FILT && filter_suppressed(F, a0, a1)) {   // eSUPPRESS: the pair stays a broadphase pair, there is no contact manager behind it
+    cHdr[i] = make_float4(0, 0, 0, __int_as_float(0)); conFlag[i] = 0u; pairBodies[i] = make_uint2(a0, a1);
+    touch_event(touch, counters, pairSlots[i], key, false);
+    return;
+  }
   const uint32_t g0 = (a0 == hi) ? gfHi : gfLo, g1 = (a0 == hi) ? gfLo : gfHi;
   const uint32_t t0 = g0 & 0xff, t1 = g1 & 0xff;
   const bool flip = t1 < t0;
@@ -323,10 +328,11 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_boxbox_generate(const NpAr
 }
 
 void pxb_launch_narrowphase(cudaStream_t st, uint32_t capPairs, const NpArgs& A) {
-  if (A.boxList) k_narrowphase<true><<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts,
-                                                                            A.pairBodies, A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch, A.boxList);
-  else k_narrowphase<false><<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies,
-                                                                    A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch, A.boxList);
+#define NP_LAUNCH(B, F) k_narrowphase<B, F><<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, \
+                                                                                A.cHdr, A.cPts, A.pairBodies, A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch, A.boxList, A.filter)
+  if (A.filter.data) { if (A.boxList) NP_LAUNCH(true, true); else NP_LAUNCH(false, true); }
+  else { if (A.boxList) NP_LAUNCH(true, false); else NP_LAUNCH(false, false); }
+#undef NP_LAUNCH
   if (A.boxList) k_boxbox_generate<<<std::max(148u * 4u, std::min((capPairs + 127) / 128, 148u * 64u)), 128, 0, st>>>(A);
 }
 void pxb_launch_narrowphase_gjk(cudaStream_t st, uint32_t ctas, const NpArgs& A) {

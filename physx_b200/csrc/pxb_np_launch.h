@@ -6,7 +6,7 @@
 struct NpArgs {
   const uint64_t* pairKeys; const uint32_t* pairSlots; const uint32_t* nPairsP; uint32_t bitsA;
   const float4 *pos, *quat, *dims; const uint32_t* geomFlags; float contactDist, toleranceLength;
-  float4 *manifolds, *cHdr, *cPts; uint2* pairBodies; uint32_t* conFlag; float* cForce; uint32_t *counters, *gjkList, *gjkQuery, *gjkFull, *gjkEpa, *boxList /* null = box-box regeneration inside k_narrowphase (environment path) */; const uint32_t* pairOrder; HullArrays hulls; TouchLists touch;
+  float4 *manifolds, *cHdr, *cPts; uint2* pairBodies; uint32_t* conFlag; float* cForce; uint32_t *counters, *gjkList, *gjkQuery, *gjkFull, *gjkEpa, *boxList /* null = box-box regeneration inside k_narrowphase (environment path) */; const uint32_t* pairOrder; HullArrays hulls; TouchLists touch; FilterArgs filter /* data == null: no filter shader */;
 };
 void pxb_launch_narrowphase(cudaStream_t st, uint32_t capPairs, const NpArgs& A);
 void pxb_launch_narrowphase_gjk(cudaStream_t st, uint32_t ctas, const NpArgs& A);

@@ -184,6 +184,28 @@ LOCAL_POSE_MAGIC = 0x504c5850   # "PXLP": header.reserved[3] when the local-pose
 assert LOCAL_POSE_DTYPE.itemsize == 64
 
 
+# f1: PxDefaultSimulationFilterShader state (oracle/scene_format.h PxbFilterShaderConfig) + PxFilterData per actor
+FILTER_CONFIG_DTYPE = np.dtype([("collisionTable", "<u4", 32), ("ops", "<u4", 3), ("filterBool", "<u4"), ("constants", "<u4", 4)])
+FLAG_FILTER_SECTION = 2
+FILTER_AND, FILTER_OR, FILTER_XOR, FILTER_NAND, FILTER_NOR, FILTER_NXOR, FILTER_SWAP_AND = range(7)
+assert FILTER_CONFIG_DTYPE.itemsize == 160
+
+
+def default_filter_config():
+    """the extension's initial state: every group collides with every group, ops AND / AND / AND, constants 0, filterBool false"""
+    c = np.zeros((), FILTER_CONFIG_DTYPE)
+    c["collisionTable"][:] = 0xffffffff
+    return c
+
+
+def set_group_collision_flag(cfg, g1, g2, enable):   # PxSetGroupCollisionFlag
+    for a, b in ((g1, g2), (g2, g1)):
+        if enable:
+            cfg["collisionTable"][a] |= np.uint32(1 << b)
+        else:
+            cfg["collisionTable"][a] &= np.uint32(~(1 << b) & 0xffffffff)
+
+
 def identity_local_poses(n):
     lp = np.zeros(n, LOCAL_POSE_DTYPE)
     lp["shapeQ"][:, 3] = 1.0
@@ -192,9 +214,14 @@ def identity_local_poses(n):
 
 
 class Scene:
-    def __init__(self, header, actors, hulls=(), cooked=b"", materials=None, local_poses=None):
+    def __init__(self, header, actors, hulls=(), cooked=b"", materials=None, local_poses=None, filter_config=None, filter_data=None):
         self.header = header.copy()
         self.actors = actors
+        # default simulation filter shader: global state + PxFilterData (word0..3) per actor
+        self.filter_config = None if filter_config is None else np.asarray(filter_config, FILTER_CONFIG_DTYPE).reshape(())
+        self.filter_data = None if filter_data is None else np.ascontiguousarray(filter_data, dtype="<u4").reshape(len(actors), 4)
+        assert (self.filter_config is None) == (self.filter_data is None)
+        self.header["reserved"][0] = (int(self.header["reserved"][0]) & ~FLAG_FILTER_SECTION) | (FLAG_FILTER_SECTION if self.filter_config is not None else 0)
         self.local_poses = None if local_poses is None else np.asarray(local_poses, LOCAL_POSE_DTYPE)
         assert self.local_poses is None or len(self.local_poses) == len(actors)
         self.header["reserved"][3] = LOCAL_POSE_MAGIC if self.local_poses is not None else 0
@@ -215,6 +242,8 @@ class Scene:
         out = [h.tobytes(), self.actors.tobytes(), self.materials.tobytes()]
         if self.local_poses is not None:
             out.append(self.local_poses.tobytes())
+        if self.filter_config is not None:
+            out.append(self.filter_config.tobytes()); out.append(self.filter_data.tobytes())
         for hl in self.hulls:
             hl = np.asarray(hl, dtype="<f4").reshape(-1, 3)
             out.append(np.uint32(len(hl)).tobytes())
@@ -239,12 +268,16 @@ class Scene:
         if int(h["reserved"][3]) == LOCAL_POSE_MAGIC:
             lp = np.frombuffer(buf, dtype=LOCAL_POSE_DTYPE, count=int(h["nActors"]), offset=off).copy()
             off += lp.nbytes
+        fc = fd = None
+        if int(h["reserved"][0]) & FLAG_FILTER_SECTION:
+            fc = np.frombuffer(buf, dtype=FILTER_CONFIG_DTYPE, count=1, offset=off)[0].copy(); off += FILTER_CONFIG_DTYPE.itemsize
+            fd = np.frombuffer(buf, dtype="<u4", count=4 * int(h["nActors"]), offset=off).reshape(-1, 4).copy(); off += fd.nbytes
         hulls = []
         for _ in range(int(h["nHulls"])):
             nv = int(np.frombuffer(buf, "<u4", 1, off)[0]); off += 4
             hulls.append(np.frombuffer(buf, "<f4", nv * 3, off).reshape(nv, 3).copy()); off += nv * 12
         cooked = buf[off:] if int(h["reserved"][1]) == COOKED_MAGIC else b""
-        return Scene(h, a, hulls, cooked, mats, lp)
+        return Scene(h, a, hulls, cooked, mats, lp, fc, fd)
 
     def cooked_hulls(self):
         return parse_cooked(self.cooked, len(self.hulls))[0] if self.cooked else []
@@ -794,3 +827,31 @@ def local_pose_mix(n_stacks=4, height=3, n_loose=10, seed=9, **hdr):
     actors = add_ground_plane(a)
     lp = np.concatenate([identity_local_poses(1), lp])
     return Scene(default_header(**hdr), actors, local_poses=lp)
+
+
+def filter_groups_mix(n=6, seed=17, **hdr):
+    """f1: PxDefaultSimulationFilterShader.  Collision groups (PxSetGroupCollisionFlag): "ghost" boxes (group 2) are dropped onto resting "solid" boxes (group 1)
+    with the 1-2 flag cleared -- they fall through the solids and land on the ground (group 0).  Groups masks (PxSetFilterOps AND / AND / AND, constants all ones,
+    PxSetFilterBool(true): a pair collides only when the two masks share a bit): spheres with mask 1 are dropped onto spheres with mask 2 and pass through them,
+    both kinds collide with the boxes and the ground (mask 3)."""
+    rng = np.random.RandomState(seed)
+    nb = 2 * n
+    a = _new_actors(nb + 2 * n)
+    he = np.float32(0.25)
+    set_box(a, np.arange(nb), np.array([he, he, he], dtype=np.float32))
+    set_sphere(a, np.arange(nb, nb + 2 * n), np.float32(0.15))
+    fd = np.zeros((nb + 2 * n + 1, 4), np.uint32)   # row 0: the ground plane
+    fd[0] = (0, 0, 3, 0)
+    for i in range(n):
+        x = np.float32(1.2 * i)
+        a["pos"][i] = (x, he, 0.0)                                   # solid, resting
+        a["pos"][n + i] = (x + np.float32(rng.uniform(-0.05, 0.05)), 1.0 + 0.1 * i, np.float32(rng.uniform(-0.05, 0.05)))   # ghost, dropped on it
+        fd[1 + i] = (1, 0, 3, 0); fd[1 + n + i] = (2, 0, 3, 0)
+        a["pos"][nb + i] = (x, 0.15, 1.5)                            # sphere with mask 2 resting on the ground
+        a["pos"][nb + n + i] = (x + np.float32(rng.uniform(-0.02, 0.02)), 0.9 + 0.15 * i, 1.5 + np.float32(rng.uniform(-0.02, 0.02)))   # sphere with mask 1 dropped on it
+        fd[1 + nb + i] = (0, 0, 2, 0); fd[1 + nb + n + i] = (0, 0, 1, 0)
+    # two more solids stacked on the first two solids: same group, they do collide
+    cfg = default_filter_config()
+    set_group_collision_flag(cfg, 1, 2, False)
+    cfg["ops"][:] = (FILTER_AND, FILTER_AND, FILTER_AND); cfg["filterBool"] = 1; cfg["constants"][:] = 0xffffffff
+    return Scene(default_header(**hdr), add_ground_plane(a), filter_config=cfg, filter_data=fd)

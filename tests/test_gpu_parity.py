@@ -1266,3 +1266,43 @@ def test_config5_shard_full_size_properties():
         for _ in range(20):
             alone.step()
         assert np.array_equal(alone.getStates(), st[dyn_env == e]), f"environment {e}"
+
+
+# ---- f1: the default simulation filter shader on the device ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_path", [True, False])
+def test_default_filter_shader_gpu_matches_oracle_and_reference(oracle, env_path):
+    """collision groups + groups masks (PxDefaultSimulationFilterShader): suppressed pairs stay in the pair lists and generate no contacts.  GPU == oracle bit for bit
+    over 90 free-running steps (pairs, created / deleted, contacts, states); within 1e-4 of the reference's poses."""
+    z, sc = util.load_golden("filter_groups_mix")
+    gpu, cpu = engine.Scene(sc, env_path=env_path), oracle.OracleScene(sc)
+    for t in range(90):
+        gpu.setConstraintOrder(util.golden_order(z, t)); gpu.step(); cpu.step(util.golden_order(z, t))
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()) and np.array_equal(gpu.getCreatedPairs(), cpu.getCreatedPairs()) and np.array_equal(gpu.getDeletedPairs(), cpu.getDeletedPairs()), f"pairs, step {t}"
+        assert np.array_equal(gpu.getContacts(), cpu.getContacts()), f"contacts, step {t}"
+        assert np.array_equal(gpu.getStates(), cpu.getStates()), f"states, step {t}"
+    assert np.abs(gpu.getStates()[:, :7] - z["states"][90][:, :7]).max() < 1e-4
+    # the same scene without the filter section ends somewhere else (the ghosts rest on the solids)
+    plain = engine.Scene(scenes.Scene(sc.header, sc.actors.copy()), env_path=env_path)
+    for _ in range(90):
+        plain.step()
+    assert plain.getStates()[6, 1] > 0.7 > gpu.getStates()[6, 1]
+
+
+@pytest.mark.gpu
+def test_filter_shader_api_errors():
+    sc = scenes.box_stacks(n_stacks=2, height=2)
+    gpu = engine.Scene(sc)
+    lib = gpu._lib
+    fd = np.zeros((len(sc.actors), 4), np.uint32)
+    assert lib.pxb_scene_set_filter_data(gpu._h, 0, len(fd), fd.ctypes.data) < 0          # before a filter shader is configured
+    cfg = scenes.default_filter_config().reshape(1).copy()
+    cfg["ops"][0][0] = 9
+    assert lib.pxb_scene_set_filter_shader(gpu._h, cfg.ctypes.data) < 0                  # PxFilterOp out of range
+    cfg["ops"][0][0] = 0
+    assert lib.pxb_scene_set_filter_shader(gpu._h, cfg.ctypes.data) == 0
+    assert lib.pxb_scene_set_filter_data(gpu._h, 0, len(fd), fd.ctypes.data) == 0
+    ref = engine.Scene(sc)
+    for _ in range(10):
+        gpu.step(); ref.step()
+    assert np.array_equal(gpu.getStates(), ref.getStates())                               # the extension's default state filters nothing
