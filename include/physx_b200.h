@@ -238,6 +238,10 @@ PXB_API int  pxb_scene_get_contacts(PxbScene* scene, float* out24);
 typedef struct PxbFilterShaderConfig { uint32_t collisionTable[32]; uint32_t ops[3]; uint32_t filterBool; uint32_t constants[4]; } PxbFilterShaderConfig;
 PXB_API int  pxb_scene_set_filter_shader(PxbScene* scene, const PxbFilterShaderConfig* config);
 PXB_API int  pxb_scene_set_filter_data(PxbScene* scene, uint32_t firstActor, uint32_t n, const uint32_t* data4);
+/* PxShape::setContactOffset / setRestOffset per shape, for actors [firstActor, firstActor + n): 2 floats each (contactOffset, restOffset).  Without this call every
+ * shape has PxbSceneDesc's contactOffset / restOffset.  The broadphase inflates every bound by its own shape's contact offset (Bp contact distances,
+ * BpBroadPhaseABP.cpp:1187-1197), a pair's contact distance is the sum of the two contact offsets and its rest distance the sum of the two rest offsets (PxcNpWorkUnit). */
+PXB_API int  pxb_scene_set_shape_offsets(PxbScene* scene, uint32_t firstActor, uint32_t n, const float* contactRest2);
 /* Local poses (a1: PxgShapeSim.shape2Actor, PxsBodyCore.body2Actor): PxShape::setLocalPose and PxRigidBody::setCMassLocalPose for actors [firstActor, firstActor + n),
  * 7 floats each (p.xyz, q.xyzw; stored normalised like the reference).  The actor keeps its pose (Sc::BodyCore::setCMassLocalPose, ScBodyCore.cpp:98-108); the body
  * frame the solver integrates becomes actorPose * body2Actor, the shape's world pose in the transform cache body2World * (body2Actor^-1 * shape2Actor)

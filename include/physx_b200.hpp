@@ -86,6 +86,8 @@ class Scene {
   // and the shapes' PxFilterData (4 words per actor); suppressed pairs stay broadphase pairs and generate no contacts
   void setFilterShader(const PxbFilterShaderConfig* config) { check(pxb_scene_set_filter_shader(h_, config)); }
   void setFilterData(uint32_t first, uint32_t n, const uint32_t* data4) { check(pxb_scene_set_filter_data(h_, first, n, data4)); }
+  // PxShape::setContactOffset / setRestOffset per shape: 2 floats per actor (contactOffset, restOffset)
+  void setShapeOffsets(uint32_t first, uint32_t n, const float* contactRest2) { check(pxb_scene_set_shape_offsets(h_, first, n, contactRest2)); }
   // PxScene::removeActor: the actors leave the simulation at the next step, indices stay valid
   void removeActors(const std::vector<uint32_t>& actors) { if (!actors.empty()) check(pxb_scene_remove_actors(h_, actors.data(), (uint32_t)actors.size())); }
   // contact reports of the last step: pairs that started / stopped touching (eNOTIFY_TOUCH_FOUND / eNOTIFY_TOUCH_LOST), (a, b) actor indices with a < b

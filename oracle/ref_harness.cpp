@@ -162,7 +162,9 @@ int main(int argc, char** argv) {
   const uint8_t* afterLocal = reinterpret_cast<const uint8_t*>(matRecs + H.reserved[2]) + (localPoses ? sizeof(PxbLocalPoseRec) * size_t(H.nActors) : 0);
   const PxbFilterShaderConfig* filterCfg = (H.reserved[0] & PXB_FLAG_FILTER_SECTION) ? reinterpret_cast<const PxbFilterShaderConfig*>(afterLocal) : nullptr;
   const uint32_t* filterData = filterCfg ? reinterpret_cast<const uint32_t*>(filterCfg + 1) : nullptr;
-  const uint8_t* hp = afterLocal + (filterCfg ? sizeof(PxbFilterShaderConfig) + 16 * size_t(H.nActors) : 0);
+  const uint8_t* afterFilter = afterLocal + (filterCfg ? sizeof(PxbFilterShaderConfig) + 16 * size_t(H.nActors) : 0);
+  const float* shapeOffsets = (H.reserved[0] & PXB_FLAG_SHAPE_OFFSETS) ? reinterpret_cast<const float*>(afterFilter) : nullptr;   // per shape: contactOffset, restOffset
+  const uint8_t* hp = afterFilter + (shapeOffsets ? 8 * size_t(H.nActors) : 0);
   if (filterCfg) {   // the extension's global filter state, through its public setters
     gUseDefaultFilter = true;
     for (PxU16 g = 0; g < 32; g++) for (PxU16 h = 0; h < 32; h++) PxSetGroupCollisionFlag(g, h, ((filterCfg->collisionTable[g] >> h) & 1u) != 0);
@@ -318,8 +320,8 @@ int main(int argc, char** argv) {
       case PXB_GEOM_CONVEX: s = PxRigidActorExt::createExclusiveShape(*a, PxConvexMeshGeometry(hulls[r.hullIdx].mesh), *mat); break;
       default: fprintf(stderr, "bad geom %u\n", r.geomType); return 2;
     }
-    s->setContactOffset(H.contactOffset);
-    s->setRestOffset(H.restOffset);
+    s->setContactOffset(shapeOffsets ? shapeOffsets[2 * i] : H.contactOffset);
+    s->setRestOffset(shapeOffsets ? shapeOffsets[2 * i + 1] : H.restOffset);
     if (filterData) s->setSimulationFilterData(PxFilterData(filterData[4 * i], filterData[4 * i + 1], filterData[4 * i + 2], filterData[4 * i + 3]));
     if (localPoses) { const PxbLocalPoseRec& l = localPoses[i]; s->setLocalPose(PxTransform(PxVec3(l.shapeP[0], l.shapeP[1], l.shapeP[2]), PxQuat(l.shapeQ[0], l.shapeQ[1], l.shapeQ[2], l.shapeQ[3]))); }
     shapes[i] = s;
@@ -405,7 +407,7 @@ int main(int argc, char** argv) {
       const bool isDyn = recs[i].flags & PXB_ACTOR_DYNAMIC;
       if (first) {
         PxBpFilterGroup g = isDyn ? PxGetBroadPhaseDynamicFilterGroup(i) : PxGetBroadPhaseStaticFilterGroup();
-        aabb->addObject(i, b, g, H.contactOffset);
+        aabb->addObject(i, b, g, shapeOffsets ? shapeOffsets[2 * i] : H.contactOffset);   // contact distance of the object = its shape's contact offset
       } else if (isDyn) {
         aabb->updateObject(i, &b, nullptr);
       }

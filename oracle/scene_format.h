@@ -3,6 +3,8 @@
  * A scene file is:  SceneHeader | ActorRec[nActors] | PxbMaterialRec[header.reserved[2]] (material table, may be empty)
  *                   | (when header.reserved[3] == PXB_LOCAL_POSE_MAGIC) PxbLocalPoseRec[nActors]
  *                   | (when header.reserved[0] & PXB_FLAG_FILTER_SECTION) PxbFilterShaderConfig, then uint32 filterData[nActors][4] (PxFilterData word0..3 per shape)
+ *                   | (when header.reserved[0] & PXB_FLAG_SHAPE_OFFSETS) float shapeOffsets[nActors][2] = PxShape::setContactOffset / setRestOffset per shape
+ *                     (without the section every shape has the header's contactOffset / restOffset)
  *                   | for each hull: u32 nVerts, float xyz[nVerts]
  *                   | (when header.reserved[1] == PXB_COOKED_MAGIC) for each hull: PxbCookedHullHeader + arrays (see below)
  * The cooked section is what PxCreateConvexMesh makes of the point cloud (Gu::ConvexHullData): convex cooking is host-side work in PhysX
@@ -90,6 +92,7 @@ typedef struct { float plane[4]; uint32_t vref, nbVerts, minIndex, pad; } PxbCoo
  * 6 SWAP_AND), PxSetFilterBool, PxSetFilterConstants (constants[0..1] = K0 as PxFilterData word2 / word3, [2..3] = K1).  Per actor: the shape's PxFilterData
  * (word0 = collision group 0..31, word2 / word3 = PxGroupsMask).  A pair the shader answers eSUPPRESS for stays a broadphase pair and generates no contacts. */
 #define PXB_FLAG_FILTER_SECTION 2u   /* header.reserved[0] bit 1 */
+#define PXB_FLAG_SHAPE_OFFSETS 4u    /* header.reserved[0] bit 2 */
 typedef struct { uint32_t collisionTable[32]; uint32_t ops[3]; uint32_t filterBool; uint32_t constants[4]; } PxbFilterShaderConfig;   /* 160 bytes */
 
 /* local poses: shape2Actor (p, q.xyzw), body2Actor (p, q.xyzw) */

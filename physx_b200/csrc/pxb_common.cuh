@@ -123,7 +123,7 @@ __device__ __forceinline__ xf shape_world_pose(const LocalPoses& L, uint32_t a, 
 // f1: PxDefaultSimulationFilterShader on the device (physxextensions/src/ExtDefaultSimulationFilterShader.cpp:238-280, without the trigger branch): collision-group
 // table (PxSetGroupCollisionFlag), groups masks with PxSetFilterOps / PxSetFilterConstants / PxSetFilterBool.  data: PxFilterData (word0..3) per actor.
 struct FilterConfig { uint32_t collisionTable[32]; uint32_t ops[3]; uint32_t filterBool; uint32_t constants[4]; };
-struct FilterArgs { const uint4* data; FilterConfig cfg; };
+struct FilterArgs { const uint4* data; FilterConfig cfg; const float2* shapeOff; };   // shapeOff: per-actor (contactOffset, restOffset) for the pair's contact distance, or null
 __device__ __forceinline__ uint32_t filter_op16x2(uint32_t op, uint32_t x, uint32_t y) {   // two PxGroupsMask halves at once (16-bit lanes; the NOT forms stay inside 32 bits)
   return op == 1u ? (x | y) : (op == 2u ? (x ^ y) : (op == 3u ? ~(x & y) : (op == 4u ? ~(x | y) : (op == 5u ? ~(x ^ y) : (x & y)))));
 }
@@ -223,7 +223,7 @@ __device__ __forceinline__ void touch_event(const TouchLists& T, uint32_t* __res
 // a11: PxsCombineMaterials (lowlevel/software/include/PxsMaterialCombiner.h:69-175; GPU: gpunarrowphase/src/CUDA/materialCombiner.cuh:35), rigid
 // non-compliant branch.  matTab: one float4 per material (staticFriction, dynamicFriction, restitution, bits = frictionCombineMode |
 // restitutionCombineMode << 4 | flags << 8); returns true when eDISABLE_FRICTION on either side removes the friction rows.
-struct MaterialArgs { const uint32_t* actorMat; const float4* matTab; };
+struct MaterialArgs { const uint32_t* actorMat; const float4* matTab; const float2* shapeOff; };   // shapeOff: per-actor (contactOffset, restOffset), null = the scene's uniform values
 __device__ __forceinline__ float combine_scalars(float a, float b, uint32_t mode) { return mode == 0u ? 0.5f * (a + b) : (mode == 1u ? fminf(a, b) : (mode == 2u ? a * b : fmaxf(a, b))); }
 __device__ __forceinline__ bool pair_material(const MaterialArgs& M, uint32_t actor0, uint32_t actor1, SolverParams& P) {
   const float4 m0 = M.matTab[M.actorMat[actor0]], m1 = M.matTab[M.actorMat[actor1]];

@@ -51,7 +51,8 @@ struct PxbScene {
   uint32_t *pairOrder = 0, *npClassCount = 0; uint8_t* npClass = 0; bool binPairs = false;   // mixed-type scenes: pairs binned by type pair before the narrowphase
   float4 *tcPos = 0, *tcQuat = 0, *s2bP = 0, *s2bQ = 0, *b2aP = 0, *b2aQ = 0, *actorPos = 0, *actorQuat = 0; bool hasLocal = false, hasCom = false;   // local poses (pxb_scene_set_local_poses)
   std::vector<float4> hS2aP, hS2aQ, hB2aP, hB2aQ;
-  uint4* filterData = 0; FilterConfig filterCfg; bool hasFilter = false;   // f1: default simulation filter shader (pxb_scene_set_filter_shader / _data)
+  uint4* filterData = 0; FilterConfig filterCfg; bool hasFilter = false;
+  float2* shapeOff = 0; bool hasShapeOff = false; float maxContactOffset = 0.f;   // PxShape::setContactOffset / setRestOffset per actor (pxb_scene_set_shape_offsets)   // f1: default simulation filter shader (pxb_scene_set_filter_shader / _data)
   float4* frReport = 0; uint32_t *ccIdx = 0, *ccOff = 0, *ccCount = 0, *ccTotal = 0, *actorDyn = 0; uint8_t *ccPatches = 0, *ccPoints = 0, *ccFriction = 0; float* ccForces = 0; bool contactData = false;
   uint32_t *gjkList = 0, *gjkQuery = 0, *gjkFull = 0, *gjkEpa = 0, *boxList = 0; bool boxPhases = true, boxPhasesEnv = false; bool gjkPhases = true; bool hasGjkPairs = false, anyLocks = false, anyConvex = false;
   float4 *extForce = 0, *extTorque = 0; bool forcesUsed = false;
@@ -94,7 +95,7 @@ struct DeviceGuard {
 };
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 static LocalPoses local_poses(const PxbScene* s) { LocalPoses L; L.s2bP = s->hasLocal ? s->s2bP : nullptr; L.s2bQ = s->s2bQ; L.tcPos = s->tcPos; L.tcQuat = s->tcQuat; return L; }
-static MaterialArgs material_args(const PxbScene* s) { MaterialArgs M; M.actorMat = s->actorMat; M.matTab = s->nMaterials ? s->matTab : nullptr; return M; }
+static MaterialArgs material_args(const PxbScene* s) { MaterialArgs M; M.actorMat = s->actorMat; M.matTab = s->nMaterials ? s->matTab : nullptr; M.shapeOff = s->hasShapeOff ? s->shapeOff : nullptr; return M; }
 static TouchLists touch_lists(const PxbScene* s) { TouchLists T; T.state = s->touchState; T.found = s->touchFound; T.lost = s->touchLost; return T; }
 static HullArrays hull_arrays(const PxbScene* s) { HullArrays H; H.meta = s->hullMeta; H.verts = s->hullVerts; H.polys = s->hullPolys; H.refs = s->hullRefs; H.edges = s->hullEdges; return H; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (s) s->abort = true; return fail(PXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
@@ -105,7 +106,7 @@ static HullArrays hull_arrays(const PxbScene* s) { HullArrays H; H.meta = s->hul
 __global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims,
                          const uint32_t* __restrict__ geomFlags, const uint32_t* __restrict__ envId, float contactOffset, float* __restrict__ tight,
                          int externalTight, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax, GridParams g, uint32_t envCount,
-                         uint64_t* __restrict__ cellKey, uint32_t* __restrict__ cellVal, HullArrays hulls, LocalPoses L) {
+                         uint64_t* __restrict__ cellKey, uint32_t* __restrict__ cellVal, HullArrays hulls, LocalPoses L, const float2* __restrict__ shapeOff) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nA) return;
   const uint32_t gf = geomFlags[a];
@@ -121,7 +122,7 @@ __global__ void k_bounds(uint32_t nA, const float4* __restrict__ pos, const floa
     tight_bounds(gf & 0xff, shape.p, shape.q, dims[a], mn, mx, &hulls);
     for (int k = 0; k < 3; ++k) { tight[a * 6 + k] = mn[k]; tight[a * 6 + 3 + k] = mx[k]; }
   }
-  const float co = contactOffset;
+  const float co = shapeOff ? shapeOff[a].x : contactOffset;   // every bound is inflated by its own shape's contact offset
   const uint32_t env = envId[a];
   aabbMin[a] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(env));
   aabbMax[a] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf));
@@ -853,7 +854,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
   void* ptrs[] = {s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
-                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->filterData, s->tcPos, s->tcQuat, s->s2bP, s->s2bQ, s->b2aP, s->b2aQ, s->actorPos, s->actorQuat, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
+                  s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->filterData, s->shapeOff, s->tcPos, s->tcQuat, s->s2bP, s->s2bQ, s->b2aP, s->b2aQ, s->actorPos, s->actorQuat, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
                   s->conPair, s->rankOfPair, s->conSortKey, s->conSortKeyAlt, s->conPairAlt, s->orderKeys, s->conB0, s->conB1, s->conPos0, s->conPos1, s->conColour, s->conDone, s->bodyList,
                   s->ordered, s->partCnt, s->partStart, s->partCursor, s->colourTicket, s->prevB0, s->prevB1, s->prevColour, s->prevNCon, s->ptA, s->counters, s->rsTmp.blockHist, s->rsTmp.digitTotals, s->scanSums, s->stage, s->stageIdx, s->extForce, s->extTorque, s->hullMeta, s->hullVerts, s->hullPolys, s->hullRefs, s->hullEdges,
                   s->envStart, s->envList, s->actorLocal, s->exportTab, s->envDyn, s->actorMat, s->matTab, s->touchState, s->touchFound, s->touchLost, s->slotColour, s->bodyBest, s->wake, s->accLin, s->accAng, s->asleep, s->nInter, s->islandLabel, s->islandAwake, s->envSeg[0], s->envSeg[1]};
@@ -974,7 +975,7 @@ static void rebuild_grid(PxbScene* s) {
     cell = std::max(cell, d);
     for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], r.pos[k]); mx[k] = std::max(mx[k], r.pos[k]); }
   }
-  cell = (cell + 2.f * s->desc.contactOffset) * 1.02f; if (!(cell > 0.f)) cell = 1.f;
+  cell = (cell + 2.f * std::max(s->desc.contactOffset, s->maxContactOffset)) * 1.02f; if (!(cell > 0.f)) cell = 1.f;
   GridParams g; g.invCell = 1.0f / cell;
   int n[3];
   for (int k = 0; k < 3; ++k) {
@@ -1173,7 +1174,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     LAUNCH(k_env_begin, 1, 32, s->counters);
     EnvBpArgs A;
     A.nEnv = s->nEnv; A.maxList = s->envMaxList; A.bitsA = s->bitsA; A.cap = s->capPairs; A.ringMask = s->ringMask; A.externalTight = externalTight ? 1 : 0; A.contactOffset = s->desc.contactOffset;
-    A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight; A.hulls = hull_arrays(s); A.L = local_poses(s);
+    A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight; A.hulls = hull_arrays(s); A.L = local_poses(s); A.shapeOff = s->hasShapeOff ? s->shapeOff : nullptr;
     A.oldKeys = s->pairKeys[prev]; A.oldSlots = s->pairSlots[prev]; A.oldSeg = s->envSeg[prev]; A.newKeys = s->pairKeys[cur]; A.newSlots = s->pairSlots[cur]; A.newSeg = s->envSeg[cur];
     A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions; A.slotColour = s->slotColour; A.touch = touch_lists(s);
     const size_t smem = (size_t)ENV_BP_WARPS * (s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t)) + ENV_BP_STAGE * sizeof(uint64_t));
@@ -1186,7 +1187,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
   CK(cudaMemsetAsync(s->counters + C_NTOUCH_FOUND, 0, 4 * 6, st));   // NTOUCH_FOUND, NTOUCH_LOST, NGJK_QUERY, NGJK_FULL, NGJK_EPA, NBOXGEN
   if (s->hasGjkPairs) CK(cudaMemsetAsync(s->counters + C_NGJK, 0, 4, st));
   LAUNCH(k_bounds, cdiv(nA, B), B, nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, externalTight ? 1 : 0, s->aabbMin, s->aabbMax, s->grid,
-         s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s), local_poses(s));
+         s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s), local_poses(s), s->hasShapeOff ? s->shapeOff : (const float2*)nullptr);
   const int r = radix_sort_pairs(s->cellKey, s->cellVal, s->cellKeyAlt, s->cellValAlt, s->counters + C_NA, s->grid.keyBits, s->rsTmp, st);
   s->launches += 3 * ((s->grid.keyBits + 7) / 8);
   const uint64_t* sk = r ? s->cellKeyAlt : s->cellKey; const uint32_t* sv = r ? s->cellValAlt : s->cellVal;
@@ -1252,7 +1253,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
   NpArgs NA;
   NA.pairKeys = s->pairKeys[cur]; NA.pairSlots = s->pairSlots[cur]; NA.nPairsP = nP; NA.bitsA = s->bitsA; NA.pos = s->hasLocal ? s->tcPos : s->pos; NA.quat = s->hasLocal ? s->tcQuat : s->quat; /* shape world poses: the transform cache when the scene has local poses */ NA.dims = s->dims; NA.geomFlags = s->geomFlags;
   NA.contactDist = contactDist; NA.toleranceLength = s->desc.toleranceLength; NA.manifolds = s->manifolds; NA.cHdr = s->cHdr; NA.cPts = s->cPts; NA.pairBodies = s->pairBodies; NA.conFlag = s->conFlag;
-  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.gjkQuery = s->gjkQuery; NA.gjkFull = s->gjkFull; NA.gjkEpa = s->gjkEpa; NA.boxList = (s->boxPhases && (!s->envActive || s->boxPhasesEnv)) ? s->boxList : nullptr; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s); NA.touch = touch_lists(s); NA.filter.data = s->hasFilter ? s->filterData : nullptr; NA.filter.cfg = s->filterCfg;
+  NA.cForce = s->cForce; NA.counters = s->counters; NA.gjkList = s->gjkList; NA.gjkQuery = s->gjkQuery; NA.gjkFull = s->gjkFull; NA.gjkEpa = s->gjkEpa; NA.boxList = (s->boxPhases && (!s->envActive || s->boxPhasesEnv)) ? s->boxList : nullptr; NA.pairOrder = s->binPairs ? s->pairOrder : (const uint32_t*)nullptr; NA.hulls = hull_arrays(s); NA.touch = touch_lists(s); NA.filter.data = s->hasFilter ? s->filterData : nullptr; NA.filter.cfg = s->filterCfg; NA.filter.shapeOff = s->hasShapeOff ? s->shapeOff : nullptr;
   pxb_launch_narrowphase(st, s->capPairs, NA); s->launches += NA.boxList ? 2 : 1;
   if (s->hasGjkPairs) {
     const uint32_t ctas = std::max(148u * 4u, std::min(cdiv(s->capPairs, 128), 148u * 64u));
@@ -1290,7 +1291,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     A.exportTab = fusedExport ? s->exportTab : nullptr; A.envDyn = s->envDyn; A.dynActor = s->dynActorDev;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
     A.M = material_args(s);
-    const bool ext = s->anyLocks || s->forcesUsed || s->nMaterials != 0;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
+    const bool ext = s->anyLocks || s->forcesUsed || s->nMaterials != 0 || s->hasShapeOff;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
     pxb_launch_env_solve(st, A, s->envSolveThreads, pgs, ext, smem);
     s->launches++;
     if (s->exportOn && !fusedExport) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
@@ -1460,7 +1461,7 @@ PXB_API int pxb_scene_compute_bounds(PxbScene* s) { DeviceGuard dg_(s);
   if (!s) return fail(PXB_ERR_INVALID, "null scene");
   cudaStream_t st = s->stream;
   if (s->gridDirty) rebuild_grid(s);
-  LAUNCH(k_bounds, cdiv(s->nA, 256), 256, s->nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, 0, s->aabbMin, s->aabbMax, s->grid, s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s), local_poses(s));
+  LAUNCH(k_bounds, cdiv(s->nA, 256), 256, s->nA, s->pos, s->quat, s->dims, s->geomFlags, s->envId, s->desc.contactOffset, s->tight, 0, s->aabbMin, s->aabbMax, s->grid, s->desc.reserved[0], s->cellKey, s->cellVal, hull_arrays(s), local_poses(s), s->hasShapeOff ? s->shapeOff : (const float2*)nullptr);
   CK(cudaStreamSynchronize(st));
   return PXB_OK;
 }
@@ -1633,6 +1634,30 @@ PXB_API int pxb_scene_set_filter_data(PxbScene* s, uint32_t firstActor, uint32_t
   if ((uint64_t)firstActor + n > s->capA) return fail(PXB_ERR_INVALID, "actor range out of bounds");
   if (!n) return PXB_OK;
   CK(cudaMemcpyAsync(s->filterData + firstActor, data4, 16 * (size_t)n, cudaMemcpyHostToDevice, s->stream)); CK(cudaStreamSynchronize(s->stream));
+  return PXB_OK;
+}
+
+// ---- PxShape::setContactOffset / setRestOffset per shape ----
+PXB_API int pxb_scene_set_shape_offsets(PxbScene* s, uint32_t firstActor, uint32_t n, const float* contactRest2) { DeviceGuard dg_(s);
+  if (!s || (n && !contactRest2)) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running");
+  if ((uint64_t)firstActor + n > s->capA) return fail(PXB_ERR_INVALID, "actor range out of bounds");
+  for (uint32_t i = 0; i < n; ++i) {   // PxShape::setContactOffset / setRestOffset: contactOffset >= 0, contactOffset > restOffset (NpShape.cpp)
+    const float c = contactRest2[2 * i], r = contactRest2[2 * i + 1];
+    if (!(c >= 0.f) || !(c > r) || !std::isfinite(c) || !std::isfinite(r)) return fail(PXB_ERR_INVALID, "contactOffset must be >= 0 and larger than restOffset");
+  }
+  if (!n) return PXB_OK;
+  CK(cudaStreamSynchronize(s->stream));
+  if (!s->shapeOff) {
+    const size_t A = std::max<size_t>(s->capA, 1);
+    CK(dalloc(s->shapeOff, A));
+    std::vector<float2> init(A, make_float2(s->desc.contactOffset, s->desc.restOffset));
+    CK(cudaMemcpy(s->shapeOff, init.data(), 8 * A, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpy(s->shapeOff + firstActor, contactRest2, 8 * (size_t)n, cudaMemcpyHostToDevice));
+  for (uint32_t i = 0; i < n; ++i) s->maxContactOffset = std::max(s->maxContactOffset, contactRest2[2 * i]);
+  s->hasShapeOff = true; s->gridDirty = true;
+  drop_graphs(s);
   return PXB_OK;
 }
 

@@ -27,7 +27,7 @@ struct EnvBpArgs {
   const float4 *pos, *quat, *dims; const uint32_t *geomFlags, *envId; float* tight; HullArrays hulls;
   const uint64_t* oldKeys; const uint32_t* oldSlots; const uint2* oldSeg;
   uint64_t* newKeys; uint32_t* newSlots; uint2* newSeg;
-  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions; TouchLists touch; LocalPoses L;
+  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions; TouchLists touch; LocalPoses L; const float2* shapeOff;   // shapeOff: per-actor (contactOffset, restOffset), LOCAL instantiation only
 };
 
 #define ENV_BP_STAGE 256   // pair keys staged per warp in shared memory before the segment base is known
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
       tight_bounds(gf & 0xff, shape.p, shape.q, A.dims[a], mn, mx, HULLS ? &A.hulls : nullptr);
       if (own) for (int c = 0; c < 3; ++c) { A.tight[a * 6 + c] = mn[c]; A.tight[a * 6 + 3 + c] = mx[c]; }
     }
-    const float co = A.contactOffset;
+    const float co = (LOCAL && A.shapeOff) ? A.shapeOff[a].x : A.contactOffset;   // every bound is inflated by its own shape's contact offset
     sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(env));
     sMax[k] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf));
     sAct[k] = a;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(ENV_BP_CTA_THREADS) k_env_bp_cta(const EnvBpAr
       tight_bounds(gf & 0xff, shape.p, shape.q, A.dims[a], mn, mx, HULLS ? &A.hulls : nullptr);
       if (own) for (int c = 0; c < 3; ++c) { A.tight[a * 6 + c] = mn[c]; A.tight[a * 6 + 3 + c] = mx[c]; }
     }
-    const float co = A.contactOffset;
+    const float co = (LOCAL && A.shapeOff) ? A.shapeOff[a].x : A.contactOffset;   // every bound is inflated by its own shape's contact offset
     sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(env));
     sMax[k] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf));
     sAct[k] = a;
@@ -461,8 +461,9 @@ __device__ __forceinline__ void env_prep_one(const EnvSolveArgs& A, const ConLis
   B.linVel0 = V3(vLin[l0]); B.angVel0 = V3(vAng[l0]); B.sI0 = load_sym(bIA[l0], bIB[l0]);
   if (dyn1) { B.linVel1 = V3(vLin[l1]); B.angVel1 = V3(vAng[l1]); B.sI1 = load_sym(bIA[l1], bIB[l1]); }
   else { B.linVel1 = V3(0, 0, 0); B.angVel1 = V3(0, 0, 0); B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
-  if (EXT && A.M.matTab) {   // material table: this pair's combined coefficients (the plain instantiation carries none of this)
-    SolverParams Pm = A.P; const bool noFriction = pair_material(A.M, bb.x, bb.y, Pm);
+  if (EXT && (A.M.matTab || A.M.shapeOff)) {   // material table / per-shape rest offsets: this pair's own parameters (the plain instantiation carries none of this)
+    SolverParams Pm = A.P; const bool noFriction = A.M.matTab ? pair_material(A.M, bb.x, bb.y, Pm) : false;
+    if (A.M.shapeOff) Pm.restDistance = A.M.shapeOff[bb.x].y + A.M.shapeOff[bb.y].y;
     if (PGS) prep_constraint_pgs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, Pm, noFriction);
     else prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, Pm, noFriction);
     return;

@@ -12,7 +12,7 @@
 template <bool BOXW, bool FILT>   // BOXW: box-box manifolds are only refreshed here, the invalidated ones go to k_boxbox_generate's worklist (device-wide path); FILT: default filter shader
 __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, const uint32_t* __restrict__ nPairsP, uint32_t bitsA,
                               const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags,
-                              float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
+                              float contactDistScene, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr, float4* __restrict__ cPts,
                               uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, float* __restrict__ cForce, uint32_t* __restrict__ counters, uint32_t* __restrict__ gjkList,
                               const uint32_t* __restrict__ pairOrder, const TouchLists touch, uint32_t* __restrict__ boxList, const FilterArgs F) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   uint32_t a0 = hi, a1 = lo;
   const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
   if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
-  if (FILT && filter_suppressed(F, a0, a1)) {   // eSUPPRESS: the pair stays a broadphase pair, there is no contact manager behind it
+  const float contactDist = (FILT && F.shapeOff) ? F.shapeOff[a0].x + F.shapeOff[a1].x : contactDistScene;   // sum of the two shapes' contact offsets
+  if (FILT && F.data && filter_suppressed(F, a0, a1)) {   // eSUPPRESS: the pair stays a broadphase pair, there is no contact manager behind it
     cHdr[i] = make_float4(0, 0, 0, __int_as_float(0)); conFlag[i] = 0u; pairBodies[i] = make_uint2(a0, a1);
     touch_event(touch, counters, pairSlots[i], key, false);
     return;
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
 #define PXB_GJK_CTAS 3   // 168 registers.  Measured on config 3 with hulls: 4 CTAs/SM (128 registers, +240 B of spills) is slower, 10.15 vs 10.0 ms/step -- the kernel is divergence bound (5 of 32 threads active), not residency bound
 #endif
 __global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uint64_t* __restrict__ pairKeys, const uint32_t* __restrict__ pairSlots, uint32_t bitsA, const float4* __restrict__ pos, const float4* __restrict__ quat,
-                              const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags, float contactDist, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr,
-                              float4* __restrict__ cPts, uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, uint32_t* __restrict__ counters, const uint32_t* __restrict__ gjkList, HullArrays hulls, const TouchLists touch) {
+                              const float4* __restrict__ dims, const uint32_t* __restrict__ geomFlags, float contactDistScene, float toleranceLength, float4* __restrict__ manifolds, float4* __restrict__ cHdr,
+                              float4* __restrict__ cPts, uint2* __restrict__ pairBodies, uint32_t* __restrict__ conFlag, uint32_t* __restrict__ counters, const uint32_t* __restrict__ gjkList, HullArrays hulls, const TouchLists touch, const float2* __restrict__ shapeOff) {
   const uint32_t n = counters[C_NGJK];
   for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
     const uint32_t i = gjkList[w];
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uin
     const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
     if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
     const uint32_t t0 = ((a0 == hi) ? gfHi : gfLo) & 0xff, t1 = ((a0 == hi) ? gfLo : gfHi) & 0xff;
+    const float contactDist = shapeOff ? shapeOff[a0].x + shapeOff[a1].x : contactDistScene;
     const bool flip = t1 < t0;
     const uint32_t s0 = flip ? a1 : a0, s1 = flip ? a0 : a1;   // s0 = capsule, s1 = box
     const float4 p0 = pos[s0], p1 = pos[s1];
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uin
 // worklist, so a warp holds 32 pairs that all need that phase; what a pair carries between phases is its manifold record (stored by the
 // phase that changed it) plus a few words parked in the pair's own, not yet written, output slots (conFlag: refresh flags, cPts: GjkCarry).
 // The arithmetic per pair is the single-kernel variant's (same device functions, same order), so the contacts are bit-identical.
-struct GjkPair { uint32_t i, a0, a1, ty0, ty1, slot; bool flip; uint64_t key; xf tm0, tm1; float4 d0, d1; float4* rec; };
+struct GjkPair { uint32_t i, a0, a1, ty0, ty1, slot; bool flip; uint64_t key; xf tm0, tm1; float4 d0, d1; float4* rec; float cd; };   // cd: the pair's contact distance
 __device__ __forceinline__ void gjk_pair_setup(const NpArgs& A, uint32_t i, GjkPair& P) {
   P.i = i; P.key = A.pairKeys[i];
   const uint32_t lo = (uint32_t)(P.key >> A.bitsA), hi = (uint32_t)(P.key & ((1ull << A.bitsA) - 1ull));
@@ -155,6 +157,7 @@ __device__ __forceinline__ void gjk_pair_setup(const NpArgs& A, uint32_t i, GjkP
   P.d0 = A.dims[s0]; P.d1 = A.dims[s1];
   P.slot = A.pairSlots[i]; P.rec = A.manifolds + (size_t)P.slot * PXB_MANIFOLD_F4;
   P.ty1 = P.flip ? t0 : t1; P.ty0 = P.flip ? t1 : t0;
+  P.cd = A.filter.shapeOff ? A.filter.shapeOff[P.a0].x + A.filter.shapeOff[P.a1].x : A.contactDist;
 }
 __device__ __forceinline__ void gjk_pair_finish(const NpArgs& A, const GjkPair& P, const Manifold& man, Contacts& out) {
   if (man.dirty) { manifold_store(man, P.rec); manifold_store_warm(man, P.rec); } else if (man.n > 0) manifold_store_pens(man, P.rec);
@@ -192,16 +195,16 @@ __global__ void __launch_bounds__(128, 4) k_gjk_refresh(const NpArgs A) {
       int flags = 0;
       if (P.ty1 == PXB_GEOM_CONVEXMESH) {
         const DevHull h = load_hull(A.hulls, __float_as_uint(P.d1.x));
-        if (P.ty0 == PXB_GEOM_PLANE) gjk_pcm_plane_convex(&P.tm0, &P.tm1, h, A.contactDist, A.toleranceLength, &man, &out);
-        else if (P.ty0 == PXB_GEOM_SPHERE) gjk_pcm_sphere_convex(&P.tm0, &P.tm1, P.d0.x, &h, A.contactDist, A.toleranceLength, &man, &out);
-        else if (P.ty0 == PXB_GEOM_CAPSULE) need = gjk_capsule_convex_refresh(&P.tm0, &P.tm1, P.d0.x, &h, A.contactDist, A.toleranceLength, &man, &out, &flags);
-        else if (P.ty0 == PXB_GEOM_BOX) { const v3 e = V3(P.d0.x, P.d0.y, P.d0.z); need = gjk_poly_convex_refresh(&P.tm0, &P.tm1, box_margin(e, A.toleranceLength), alen(e), &h, A.contactDist, A.toleranceLength, &man, &out, &flags); }
+        if (P.ty0 == PXB_GEOM_PLANE) gjk_pcm_plane_convex(&P.tm0, &P.tm1, h, P.cd, A.toleranceLength, &man, &out);
+        else if (P.ty0 == PXB_GEOM_SPHERE) gjk_pcm_sphere_convex(&P.tm0, &P.tm1, P.d0.x, &h, P.cd, A.toleranceLength, &man, &out);
+        else if (P.ty0 == PXB_GEOM_CAPSULE) need = gjk_capsule_convex_refresh(&P.tm0, &P.tm1, P.d0.x, &h, P.cd, A.toleranceLength, &man, &out, &flags);
+        else if (P.ty0 == PXB_GEOM_BOX) { const v3 e = V3(P.d0.x, P.d0.y, P.d0.z); need = gjk_poly_convex_refresh(&P.tm0, &P.tm1, box_margin(e, A.toleranceLength), alen(e), &h, P.cd, A.toleranceLength, &man, &out, &flags); }
         else {
           const DevHull h0 = load_hull(A.hulls, __float_as_uint(P.d0.x));
-          need = gjk_poly_convex_refresh(&P.tm0, &P.tm1, gjk_hull_pcm_margin(&h0, A.toleranceLength), alen(h0.internalExtents), &h, A.contactDist, A.toleranceLength, &man, &out, &flags);
+          need = gjk_poly_convex_refresh(&P.tm0, &P.tm1, gjk_hull_pcm_margin(&h0, A.toleranceLength), alen(h0.internalExtents), &h, P.cd, A.toleranceLength, &man, &out, &flags);
         }
       }
-      else gjk_pcm_capsule_box(&P.tm0, &P.tm1, P.d0.x, P.d0.y, V3(P.d1.x, P.d1.y, P.d1.z), A.contactDist, A.toleranceLength, &man, &out);
+      else gjk_pcm_capsule_box(&P.tm0, &P.tm1, P.d0.x, P.d0.y, V3(P.d1.x, P.d1.y, P.d1.z), P.cd, A.toleranceLength, &man, &out);
       if (need) { manifold_store(man, P.rec); A.conFlag[i] = (uint32_t)flags; }   // the refreshed manifold and the new relative frame; the warm-start simplex is untouched
       else gjk_pair_finish(A, P, man, out);
     }
@@ -223,8 +226,8 @@ __device__ __forceinline__ void gjk_pair_shapes(const NpArgs& A, const GjkPair& 
 }
 __device__ __forceinline__ bool gjk_pair_post(const NpArgs& A, const GjkPair& P, const GjkShapes& S, int flags, int status, int epaStatus, const GjkOutput& output, Manifold& man, Contacts& out) {
   GjkCarry carry; int need;
-  if (P.ty0 == PXB_GEOM_CAPSULE) need = gjk_capsule_convex_post(&P.tm0, &P.tm1, P.d0.x, &S.hB, A.contactDist, A.toleranceLength, flags, status, epaStatus, &output, &S.aToB, &man, &out, &carry);
-  else need = gjk_poly_convex_post(&P.tm1, S.a.center, S.b.center, S.marginPcmA, &S.hB, A.contactDist, A.toleranceLength, flags, status, epaStatus, &output, &S.aToB, &man, &out, &carry);
+  if (P.ty0 == PXB_GEOM_CAPSULE) need = gjk_capsule_convex_post(&P.tm0, &P.tm1, P.d0.x, &S.hB, P.cd, A.toleranceLength, flags, status, epaStatus, &output, &S.aToB, &man, &out, &carry);
+  else need = gjk_poly_convex_post(&P.tm1, S.a.center, S.b.center, S.marginPcmA, &S.hB, P.cd, A.toleranceLength, flags, status, epaStatus, &output, &S.aToB, &man, &out, &carry);
   if (need) {
     manifold_store(man, P.rec); manifold_store_warm(man, P.rec);
     float4* c = A.cPts + (size_t)P.i * 4;
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(128, 4) k_gjk_query(const NpArgs A) {
       const int flags = (int)A.conFlag[i];
       GjkShapes S; gjk_pair_shapes(A, P, S);
       GjkOutput output; output.normal = output.closestA = output.closestB = output.searchDir = V3(0, 0, 0); output.penDep = 0.f;
-      const int status = gjk_penetration(&S.a, &S.b, S.dir, A.contactDist, 1, man.aInd, man.bInd, &man.nWarm, &output);
+      const int status = gjk_penetration(&S.a, &S.b, S.dir, P.cd, 1, man.aInd, man.bInd, &man.nWarm, &output);
       if (status == GJK_NON_INTERSECT) gjk_pair_finish(A, P, man, out);
       else if (status == EPA_CONTACT) {   // the GJK answer (EPA starts from the warm-start simplex and may leave parts of it in place) travels in the pair's output slots
         needEpa = true; manifold_store_warm(man, P.rec);
@@ -293,15 +296,15 @@ __global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_gjk_manifold(const NpArgs
       { const float4* c = A.cPts + (size_t)i * 4; const float4 c0 = c[0], c1 = c[1], c2 = c[2];
         carry.normal = V3(c0.x, c0.y, c0.z); carry.doOverlapTest = __float_as_int(c0.w); carry.closestA = V3(c1.x, c1.y, c1.z); carry.closestB = V3(c2.x, c2.y, c2.z); }
       const DevHull h = load_hull(A.hulls, __float_as_uint(P.d1.x));
-      if (P.ty0 == PXB_GEOM_CAPSULE) gjk_capsule_convex_manifold(&P.tm0, &P.tm1, P.d0.x, P.d0.y, &h, A.contactDist, A.toleranceLength, &carry, &man, &out);
+      if (P.ty0 == PXB_GEOM_CAPSULE) gjk_capsule_convex_manifold(&P.tm0, &P.tm1, P.d0.x, P.d0.y, &h, P.cd, A.toleranceLength, &carry, &man, &out);
       else {
         int sat;
         if (P.ty0 == PXB_GEOM_BOX) {
           const v3 e = V3(P.d0.x, P.d0.y, P.d0.z); BoxAsHull bh; const DevHull* polyA = gjk_box_as_hull(&bh, e); const GjkConvex box = gjk_cvx_box(V3(0, 0, 0), e);
-          sat = gjk_poly_convex_manifold(&P.tm0, &P.tm1, &box, polyA, &h, A.contactDist, A.toleranceLength, &carry, &man, &out);
+          sat = gjk_poly_convex_manifold(&P.tm0, &P.tm1, &box, polyA, &h, P.cd, A.toleranceLength, &carry, &man, &out);
         } else {
           const DevHull h0 = load_hull(A.hulls, __float_as_uint(P.d0.x)); const GjkConvex c0 = gjk_cvx_hull(&h0);
-          sat = gjk_poly_convex_manifold(&P.tm0, &P.tm1, &c0, &h0, &h, A.contactDist, A.toleranceLength, &carry, &man, &out);
+          sat = gjk_poly_convex_manifold(&P.tm0, &P.tm1, &c0, &h0, &h, P.cd, A.toleranceLength, &carry, &man, &out);
         }
         if (sat) atomicOr(&A.counters[C_ERROR], (uint32_t)E_UNSUPPORTED_PAIR);
       }
@@ -321,8 +324,8 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_boxbox_generate(const NpAr
     Manifold man; manifold_load(man, P.rec); manifold_load_warm(man, P.rec); man.dirty = 1;
     Contacts out; gjk_contacts_clear(out);
     const v3 e0 = V3(P.d0.x, P.d0.y, P.d0.z), e1 = V3(P.d1.x, P.d1.y, P.d1.z);
-    if (pcm_box_box_generate(P.tm0, P.tm1, e0, e1, A.contactDist, A.toleranceLength, man, out))
-      gjk_boxbox_gjk_fallback_outofline(&P.tm0, &P.tm1, e0, e1, A.contactDist, A.toleranceLength, &man, &out);
+    if (pcm_box_box_generate(P.tm0, P.tm1, e0, e1, P.cd, A.toleranceLength, man, out))
+      gjk_boxbox_gjk_fallback_outofline(&P.tm0, &P.tm1, e0, e1, P.cd, A.toleranceLength, &man, &out);
     gjk_pair_finish(A, P, man, out);
   }
 }
@@ -330,14 +333,14 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_boxbox_generate(const NpAr
 void pxb_launch_narrowphase(cudaStream_t st, uint32_t capPairs, const NpArgs& A) {
 #define NP_LAUNCH(B, F) k_narrowphase<B, F><<<(capPairs + 127) / 128, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.nPairsP, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, \
                                                                                 A.cHdr, A.cPts, A.pairBodies, A.conFlag, A.cForce, A.counters, A.gjkList, A.pairOrder, A.touch, A.boxList, A.filter)
-  if (A.filter.data) { if (A.boxList) NP_LAUNCH(true, true); else NP_LAUNCH(false, true); }
+  if (A.filter.data || A.filter.shapeOff) { if (A.boxList) NP_LAUNCH(true, true); else NP_LAUNCH(false, true); }
   else { if (A.boxList) NP_LAUNCH(true, false); else NP_LAUNCH(false, false); }
 #undef NP_LAUNCH
   if (A.boxList) k_boxbox_generate<<<std::max(148u * 4u, std::min((capPairs + 127) / 128, 148u * 64u)), 128, 0, st>>>(A);
 }
 void pxb_launch_narrowphase_gjk(cudaStream_t st, uint32_t ctas, const NpArgs& A) {
   k_narrowphase_gjk<<<ctas, 128, 0, st>>>(A.pairKeys, A.pairSlots, A.bitsA, A.pos, A.quat, A.dims, A.geomFlags, A.contactDist, A.toleranceLength, A.manifolds, A.cHdr, A.cPts, A.pairBodies, A.conFlag, A.counters,
-                                          A.gjkList, A.hulls, A.touch);
+                                          A.gjkList, A.hulls, A.touch, A.filter.shapeOff);
 }
 void pxb_launch_narrowphase_gjk_phases(cudaStream_t st, uint32_t ctas, const NpArgs& A) {
   k_gjk_refresh<<<ctas, 128, 0, st>>>(A);

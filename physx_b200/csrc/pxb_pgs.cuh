@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(128) k_prep_rows(const uint32_t* __restrict__ 
   if (dyn1) B.sI1 = load_sym(sbIA[b1], sbIB[b1]); else { B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
   bool noFriction = false;
   if (M.matTab) noFriction = pair_material(M, b0, b1, P);   // material table: this pair's combined coefficients (P is this thread's copy)
+  if (M.shapeOff) P.restDistance = M.shapeOff[b0].y + M.shapeOff[b1].y;   // per-shape rest offsets: the pair's rest distance is their sum (PxcNpWorkUnit::restDistance)
   if (PGS) prep_constraint_pgs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, noFriction);
   else prep_constraint_regs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, noFriction);
   rows_store(R, k, r);

@@ -31,7 +31,7 @@ EXPORTS = [
     "pxb_scene_last_num_launches", "pxb_scene_set_profiling", "pxb_scene_get_stage_times",
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
     "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait", "pxb_bp_create", "pxb_bp_release", "pxb_bp_update", "pxb_bp_fetch",
-    "pxb_scene_set_materials", "pxb_scene_remove_actors", "pxb_tensor_read_device", "pxb_tensor_write_device", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost", "pxb_scene_enable_contact_data", "pxb_scene_copy_contact_data", "pxb_scene_set_local_poses", "pxb_scene_set_filter_shader", "pxb_scene_set_filter_data",
+    "pxb_scene_set_materials", "pxb_scene_remove_actors", "pxb_tensor_read_device", "pxb_tensor_write_device", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost", "pxb_scene_enable_contact_data", "pxb_scene_copy_contact_data", "pxb_scene_set_local_poses", "pxb_scene_set_filter_shader", "pxb_scene_set_filter_data", "pxb_scene_set_shape_offsets",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
@@ -99,6 +99,7 @@ def load_library():
     lib.pxb_scene_set_local_poses.argtypes = [vp, u32, u32, vp, vp]
     lib.pxb_scene_set_filter_shader.argtypes = [vp, vp]
     lib.pxb_scene_set_filter_data.argtypes = [vp, u32, u32, vp]
+    lib.pxb_scene_set_shape_offsets.argtypes = [vp, u32, u32, vp]
     lib.pxb_scene_copy_contact_data.argtypes = [vp, vp, vp, u32]
     lib.pxb_scene_get_states_device.argtypes = [vp, vp]
     lib.pxb_scene_uses_env_path.argtypes = [vp]
@@ -180,6 +181,10 @@ class Scene:
             _check(lib, lib.pxb_scene_set_filter_shader(self._h, _ptr(cfg)))
             fd = np.ascontiguousarray(scene.filter_data, dtype=np.uint32)
             _check(lib, lib.pxb_scene_set_filter_data(self._h, 0, len(fd), _ptr(fd)))
+        so = getattr(scene, "shape_offsets", None)
+        if so is not None:   # PxShape::setContactOffset / setRestOffset per shape
+            so = np.ascontiguousarray(so, dtype=np.float32)
+            _check(lib, lib.pxb_scene_set_shape_offsets(self._h, 0, len(so), _ptr(so)))
         lp = getattr(scene, "local_poses", None)
         if lp is not None:   # PxShape::setLocalPose / PxRigidBody::setCMassLocalPose per actor
             self.setLocalPoses(0, np.concatenate([lp["shapeP"], lp["shapeQ"]], axis=1), np.concatenate([lp["bodyP"], lp["bodyQ"]], axis=1))

@@ -187,6 +187,7 @@ assert LOCAL_POSE_DTYPE.itemsize == 64
 # f1: PxDefaultSimulationFilterShader state (oracle/scene_format.h PxbFilterShaderConfig) + PxFilterData per actor
 FILTER_CONFIG_DTYPE = np.dtype([("collisionTable", "<u4", 32), ("ops", "<u4", 3), ("filterBool", "<u4"), ("constants", "<u4", 4)])
 FLAG_FILTER_SECTION = 2
+FLAG_SHAPE_OFFSETS = 4   # header.reserved[0] bit 2: per-shape (contactOffset, restOffset) section
 FILTER_AND, FILTER_OR, FILTER_XOR, FILTER_NAND, FILTER_NOR, FILTER_NXOR, FILTER_SWAP_AND = range(7)
 assert FILTER_CONFIG_DTYPE.itemsize == 160
 
@@ -214,9 +215,12 @@ def identity_local_poses(n):
 
 
 class Scene:
-    def __init__(self, header, actors, hulls=(), cooked=b"", materials=None, local_poses=None, filter_config=None, filter_data=None):
+    def __init__(self, header, actors, hulls=(), cooked=b"", materials=None, local_poses=None, filter_config=None, filter_data=None, shape_offsets=None):
         self.header = header.copy()
         self.actors = actors
+        # PxShape::setContactOffset / setRestOffset per shape: (n, 2) float32, or None = the header's values for every shape
+        self.shape_offsets = None if shape_offsets is None else np.ascontiguousarray(shape_offsets, dtype="<f4").reshape(len(actors), 2)
+        self.header["reserved"][0] = (int(self.header["reserved"][0]) & ~FLAG_SHAPE_OFFSETS) | (FLAG_SHAPE_OFFSETS if self.shape_offsets is not None else 0)
         # default simulation filter shader: global state + PxFilterData (word0..3) per actor
         self.filter_config = None if filter_config is None else np.asarray(filter_config, FILTER_CONFIG_DTYPE).reshape(())
         self.filter_data = None if filter_data is None else np.ascontiguousarray(filter_data, dtype="<u4").reshape(len(actors), 4)
@@ -244,6 +248,8 @@ class Scene:
             out.append(self.local_poses.tobytes())
         if self.filter_config is not None:
             out.append(self.filter_config.tobytes()); out.append(self.filter_data.tobytes())
+        if self.shape_offsets is not None:
+            out.append(self.shape_offsets.tobytes())
         for hl in self.hulls:
             hl = np.asarray(hl, dtype="<f4").reshape(-1, 3)
             out.append(np.uint32(len(hl)).tobytes())
@@ -272,12 +278,15 @@ class Scene:
         if int(h["reserved"][0]) & FLAG_FILTER_SECTION:
             fc = np.frombuffer(buf, dtype=FILTER_CONFIG_DTYPE, count=1, offset=off)[0].copy(); off += FILTER_CONFIG_DTYPE.itemsize
             fd = np.frombuffer(buf, dtype="<u4", count=4 * int(h["nActors"]), offset=off).reshape(-1, 4).copy(); off += fd.nbytes
+        so = None
+        if int(h["reserved"][0]) & FLAG_SHAPE_OFFSETS:
+            so = np.frombuffer(buf, dtype="<f4", count=2 * int(h["nActors"]), offset=off).reshape(-1, 2).copy(); off += so.nbytes
         hulls = []
         for _ in range(int(h["nHulls"])):
             nv = int(np.frombuffer(buf, "<u4", 1, off)[0]); off += 4
             hulls.append(np.frombuffer(buf, "<f4", nv * 3, off).reshape(nv, 3).copy()); off += nv * 12
         cooked = buf[off:] if int(h["reserved"][1]) == COOKED_MAGIC else b""
-        return Scene(h, a, hulls, cooked, mats, lp, fc, fd)
+        return Scene(h, a, hulls, cooked, mats, lp, fc, fd, so)
 
     def cooked_hulls(self):
         return parse_cooked(self.cooked, len(self.hulls))[0] if self.cooked else []
@@ -855,3 +864,15 @@ def filter_groups_mix(n=6, seed=17, **hdr):
     set_group_collision_flag(cfg, 1, 2, False)
     cfg["ops"][:] = (FILTER_AND, FILTER_AND, FILTER_AND); cfg["filterBool"] = 1; cfg["constants"][:] = 0xffffffff
     return Scene(default_header(**hdr), add_ground_plane(a), filter_config=cfg, filter_data=fd)
+
+
+def shape_offsets_mix(seed=29, **hdr):
+    """PxShape::setContactOffset / setRestOffset per shape: stacks and loose primitives whose shapes carry different contact offsets (0.01 .. 0.06: pairs enter the
+    narrowphase at different distances) and rest offsets (-0.01 .. 0.03: bodies come to rest hovering above / sunk into each other by the sum of the two rest offsets)."""
+    rng = np.random.RandomState(seed)
+    sc = mixed_primitives(n=14, seed=seed, kinds=("box", "sphere", "capsule", "box"), **hdr)
+    n = len(sc.actors)
+    so = np.zeros((n, 2), np.float32)
+    so[:, 0] = rng.uniform(0.03, 0.06, n); so[:, 1] = rng.uniform(-0.01, 0.025, n)
+    so[0] = (0.02, 0.01)   # the ground plane
+    return Scene(sc.header, sc.actors, shape_offsets=so)

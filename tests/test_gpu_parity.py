@@ -1306,3 +1306,30 @@ def test_filter_shader_api_errors():
     for _ in range(10):
         gpu.step(); ref.step()
     assert np.array_equal(gpu.getStates(), ref.getStates())                               # the extension's default state filters nothing
+
+
+# ---- PxShape::setContactOffset / setRestOffset per shape ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["shape_offsets_mix", "pgs_shape_offsets_mix"])
+@pytest.mark.parametrize("env_path", [True, False])
+def test_shape_offsets_gpu_matches_oracle_and_reference(oracle, name, env_path):
+    """Every shape with its own contact / rest offset: bounds inflated per shape in the broadphase, contact distance and rest distance per pair.  GPU vs oracle over 120
+    steps (oracle re-synchronised to the GPU state every step): pair sets, created / deleted reports and contact counts identical, states within TOL_STEP (bit-identical for the
+    first 40 steps with TGS); within 2e-4 (pose; PGS 2e-3) of the reference at step 40."""
+    z, sc = util.load_golden(name)
+    gpu, cpu = engine.Scene(sc, env_path=env_path), oracle.OracleScene(sc)
+    pgs = name.startswith("pgs")
+    for t in range(120):
+        gpu.setConstraintOrder(util.golden_order(z, t)); gpu.step(); cpu.step(util.golden_order(z, t))
+        assert np.array_equal(gpu.getPairs(), cpu.getPairs()) and np.array_equal(gpu.getCreatedPairs(), cpu.getCreatedPairs()) and np.array_equal(gpu.getDeletedPairs(), cpu.getDeletedPairs()), f"pairs, step {t}"
+        a, b = gpu.getStates(), cpu.getStates()
+        assert np.array_equal(gpu.getContacts()[:, 0], cpu.getContacts()[:, 0]), f"contact counts, step {t}"
+        assert np.abs(a - b).max() < TOL_STEP, f"states, step {t}"      # tumbling primitives: the oracle is re-synchronised every step (as in test_gpu_matches_oracle_primitives)
+        if t < 40 and not pgs:
+            assert np.array_equal(a, b), f"bit-identical while nothing tumbles, step {t}"
+        cpu.setStates(a)
+        if t == 39:
+            assert np.abs(a[:, :7] - z["states"][40][:, :7]).max() < (2e-3 if pgs else 2e-4)   # PGS: the block-solver difference (DESIGN 5)
+    lib = gpu._lib
+    bad = np.array([[0.01, 0.02]], np.float32)      # contactOffset must exceed restOffset
+    assert lib.pxb_scene_set_shape_offsets(gpu._h, 1, 1, bad.ctypes.data) < 0
