@@ -286,6 +286,17 @@ PXB_D void incident_polygon(v3* pts, v3& faceNormal, v3 axis, const mxf& t, v3 e
 
 PXB_D float comp(v3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 
+// The reference's V3RecipFast = x86 RCPSS / RCPPS, a 12-bit table approximation: where box-box edge clipping puts its points -- and so which of them sit just inside
+// the friction-offset threshold -- depends on it (an exact reciprocal moves tumbling boxes by up to 3e-2 per step against the reference: friction anchors from other
+// points).  The instruction is restated through the pinning host's table (pxb_rcp_table.h, tools/make_rcp_table.c): its result depends only on sign, exponent and the
+// top 11 mantissa bits and scales exactly with the exponent.
+#include "pxb_rcp_table.h"
+PXB_D float rcp_fast(float x) {
+  const uint32_t b = __float_as_uint(x); const uint32_t e = (b >> 23) & 0xffu;
+  if (e == 0u || e >= 253u) return 1.0f / x;   // zero, denormals, huge, inf, nan: outside the table's domain (results the clipping code does not use)
+  const uint32_t r = PXB_RCP_TABLE[(b >> 12) & 0x7ffu];
+  return __uint_as_float((b & 0x80000000u) | ((((r >> 23) & 0xffu) - (e - 127u)) << 23) | (r & 0x7fffffu));
+}
 PXB_D bool seg_aabb(v3 p0, v3 d, v3 mx, v3 mn, float& tmin, float& tmax) {  // :121-165
   const float eps = 1e-6f;
   bool par[3];
@@ -298,7 +309,7 @@ PXB_D bool seg_aabb(v3 p0, v3 d, v3 mx, v3 mn, float& tmin, float& tmax) {  // :
   float ft1 = -FLT_MAX, ft2 = FLT_MAX;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const float odd = 1.0f / comp(d, k);  // reference: V3RecipFast (approximate)
+    const float odd = rcp_fast(comp(d, k));  // reference: V3RecipFast
     const float t1 = par[k] ? 0.f : (comp(mn, k) - comp(p0, k)) * odd;
     const float t2 = par[k] ? FLT_MAX : (comp(mx, k) - comp(p0, k)) * odd;
     ft1 = fmax_(ft1, fmin_(t1, t2)); ft2 = fmin_(ft2, fmax_(t1, t2));

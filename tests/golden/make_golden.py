@@ -145,6 +145,8 @@ def main():
     cases["filter_groups_mix"] = (scenes.filter_groups_mix(), 90)
     cases["shape_offsets_mix"] = (scenes.shape_offsets_mix(), 120)   # PxShape::setContactOffset / setRestOffset per shape (TGS)
     cases["pgs_shape_offsets_mix"] = (scenes.shape_offsets_mix(solver=scenes.SOLVER_PGS), 120)
+    # tumbling boxes next to spheres / capsules: energetic multi-body impacts with friction (teacher-forced comparison; pins the reference's reciprocal table in the edge clipping)
+    cases["tumble_mixed_14"] = (scenes.mixed_primitives(n=14, seed=24, kinds=("box", "sphere", "capsule", "box")), 120)
     cases["capsules_into_boxes"] = (scenes.capsules_into_boxes(seed=3), 60)   # deep penetration: the EPA query
     # a19: PxDirectGPUAPI eFORCE / eTORQUE writes (= addForce / addTorque(eFORCE) before every step), a 7-step cycle of per-body forces
     forced = {"forces_stacks": scenes.box_stacks(n_stacks=3, height=4, half_extent=0.25, spacing=1.0, jitter=0.01),

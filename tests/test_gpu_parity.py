@@ -191,7 +191,7 @@ def test_gpu_matches_oracle_primitives(oracle, name):
         cpu.setStates(sg)
 
 
-@pytest.mark.parametrize("name", ["capsule_row", "spheres_capsules_14", "capsules_on_boxes", "hulls_on_plane", "hulls_and_spheres", "hulls_and_capsules"])
+@pytest.mark.parametrize("name", ["capsule_row", "spheres_capsules_14", "capsules_on_boxes", "hulls_on_plane", "hulls_and_spheres", "hulls_and_capsules", "tumble_12", "tumble_mixed_14"])
 def test_gpu_teacher_forced_steps_match_reference(name):
     z, sc = util.load_golden(name)
     gpu = engine.Scene(sc)
