@@ -59,7 +59,10 @@ enum { PXB_FLAG_NO_ENV_PATH = 1u,
  * solver input order (DyConstraintPartition.cpp:475-568) whose dependency chains grow with the island; with this flag the
  * device-wide path colours constraints with Jones-Plassmann rounds instead (a valid, deterministic partitioning that is NOT the
  * reference's first-fit, so trajectories are comparable to the reference only statistically).  Off by default. */
-       PXB_FLAG_RELAXED_PARTITIONING = 2u };
+       PXB_FLAG_RELAXED_PARTITIONING = 2u,
+/* PxSceneFlag::eENABLE_BODY_ACCELERATIONS (PxSceneDesc.h): the step keeps the velocities it started from (integrationTGS.cu:124-131,
+ * mBodySimPrevVelocitiesBufferDeviceData) so that PXB_RD_LINEAR_ACCELERATION / PXB_RD_ANGULAR_ACCELERATION can be read.  Off by default (two copies of 16 B per actor and step). */
+       PXB_FLAG_BODY_ACCELERATIONS = 4u };
 
 /* One actor = one rigid body (or static) with one shape, local shape pose = identity; 128 bytes, little endian.
  * Planes: the actor pose carries the plane frame, normal = local +X (PxPlaneGeometry).  Mass properties are explicit
@@ -151,7 +154,9 @@ PXB_API int  pxb_scene_set_constraint_order(PxbScene* scene, const uint32_t* pai
  *      `indices` are dynamic-body indices (PxRigidDynamicGPUIndex analogue), NULL = 0..nb-1.
  *      *_device variants take device pointers and run on the scene stream without synchronising. ---- */
 enum { PXB_RD_GLOBAL_POSE = 0, PXB_RD_LINEAR_VELOCITY = 1, PXB_RD_ANGULAR_VELOCITY = 2,
-       PXB_RD_FORCE = 3, PXB_RD_TORQUE = 4 /* set only (PxRigidDynamicGPUAPIWriteType::eFORCE / eTORQUE, PxDirectGPUAPI.h:60-72): 3 floats per body, world frame, applied at the centre of mass by the next simulate only */ };
+       PXB_RD_FORCE = 3, PXB_RD_TORQUE = 4, /* set only (PxRigidDynamicGPUAPIWriteType::eFORCE / eTORQUE, PxDirectGPUAPI.h:60-72): 3 floats per body, world frame, applied at the centre of mass by the next simulate only */
+       PXB_RD_LINEAR_ACCELERATION = 5, PXB_RD_ANGULAR_ACCELERATION = 6 /* get only (PxRigidDynamicGPUAPIReadType::eLINEAR_ACCELERATION / eANGULAR_ACCELERATION; kernels getRigidDynamicLinearAcceleration /
+                                                                          AngularAcceleration, updateBodiesAndShapes.cu:1063-1106): (velocity - velocity the last step started from) * (1 / dt), 3 floats; needs PXB_FLAG_BODY_ACCELERATIONS */ };
 PXB_API int  pxb_get_rigid_dynamic_data(PxbScene* scene, void* data, const uint32_t* indices, int dataType, uint32_t nb);
 PXB_API int  pxb_set_rigid_dynamic_data(PxbScene* scene, const void* data, const uint32_t* indices, int dataType, uint32_t nb);
 /* stream-ordered host variants: PINNED host buffers, no index list, no synchronisation; complete at the next
@@ -161,6 +166,10 @@ PXB_API int  pxb_set_rigid_dynamic_data_async(PxbScene* scene, const void* pinne
 PXB_API int  pxb_scene_sync(PxbScene* scene);
 PXB_API int  pxb_get_rigid_dynamic_data_device(PxbScene* scene, void* devData, const uint32_t* devIndices, int dataType, uint32_t nb);
 PXB_API int  pxb_set_rigid_dynamic_data_device(PxbScene* scene, const void* devData, const uint32_t* devIndices, int dataType, uint32_t nb);
+/* The same two calls with the start / finish events of PxDirectGPUAPI::getRigidDynamicData / setRigidDynamicData (PxDirectGPUAPI.h:311-370; CUevent = cudaEvent_t):
+ * the work waits for `startEvent` (NULL = none) and records `finishEvent` once done; without a finish event the call synchronises, as the reference does (PxgSimulationCore.cpp:2736-2850). */
+PXB_API int  pxb_get_rigid_dynamic_data_device_ev(PxbScene* scene, void* devData, const uint32_t* devIndices, int dataType, uint32_t nb, void* startEvent, void* finishEvent);
+PXB_API int  pxb_set_rigid_dynamic_data_device_ev(PxbScene* scene, const void* devData, const uint32_t* devIndices, int dataType, uint32_t nb, void* startEvent, void* finishEvent);
 /* Packed state convenience: 13 floats per dynamic body (pos3 quat4 linVel3 angVel3), dynamic-body order. */
 PXB_API int  pxb_scene_get_states(PxbScene* scene, float* out);
 PXB_API int  pxb_scene_set_states(PxbScene* scene, const float* in);

@@ -72,6 +72,9 @@ class Scene {
   bool fetchResults(bool block = true) { const int rc = pxb_scene_fetch_results(h_, block ? 1 : 0); check(rc); return rc == 0; }
   // PxDirectGPUAPI (host buffers; *_device / *_async variants are in the C header)
   void getRigidDynamicData(void* data, int dataType, uint32_t nb, const uint32_t* indices = nullptr) { check(pxb_get_rigid_dynamic_data(h_, data, indices, dataType, nb)); }
+  // PxDirectGPUAPI::getRigidDynamicData(data, gpuIndices, dataType, nbElements, startEvent, finishEvent) on device memory (PxDirectGPUAPI.h:311-340)
+  void getRigidDynamicDataDevice(void* devData, const uint32_t* devIndices, int dataType, uint32_t nb, void* startEvent = nullptr, void* finishEvent = nullptr) { check(pxb_get_rigid_dynamic_data_device_ev(h_, devData, devIndices, dataType, nb, startEvent, finishEvent)); }
+  void setRigidDynamicDataDevice(const void* devData, const uint32_t* devIndices, int dataType, uint32_t nb, void* startEvent = nullptr, void* finishEvent = nullptr) { check(pxb_set_rigid_dynamic_data_device_ev(h_, devData, devIndices, dataType, nb, startEvent, finishEvent)); }
   void setRigidDynamicData(const void* data, int dataType, uint32_t nb, const uint32_t* indices = nullptr) { check(pxb_set_rigid_dynamic_data(h_, data, indices, dataType, nb)); }
   std::vector<State> getStates() { std::vector<State> s(getNbDynamics()); if (!s.empty()) check(pxb_scene_get_states(h_, &s[0].p[0])); return s; }
   void getSleepData(std::vector<float>& wakeCounters, std::vector<uint32_t>& asleep) {

@@ -71,6 +71,7 @@ struct PxbScene {
   // write is pending on the copy stream, so that its host-to-device copy overlaps the first part (which reads poses only)
   bool useGraph = true; cudaGraphExec_t graphExec[2][3] = {{0, 0, 0}, {0, 0, 0}}; float graphDt = 0.f; uint32_t graphLaunches[2][3] = {{0, 0, 0}, {0, 0, 0}};
   cudaStream_t copyStream = nullptr; cudaEvent_t velEvent = nullptr, orderEvent = nullptr; bool velPending = false;
+  bool bodyAccel = false; float4 *prevLin = 0, *prevAng = 0; float accelInvDt = 0.f;   // PxSceneFlag::eENABLE_BODY_ACCELERATIONS: velocities the last step started from
   bool profiling = false; cudaEvent_t ev[8] = {0, 0, 0, 0, 0, 0, 0, 0}; float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
   uint32_t hNPairs = 0, hNCreated = 0, hNDeleted = 0, hNCon = 0, hNPart = 0, hErr = 0;
   // environment-partitioned path (pxb_env.cuh)
@@ -643,6 +644,15 @@ __global__ void k_rd_get(uint32_t nb, const uint32_t* __restrict__ idx, const ui
   if (type == PXB_RD_GLOBAL_POSE) { const float4 q = quat[a], p = pos[a]; float* o = out + (size_t)i * 7; o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; o[4] = p.x; o[5] = p.y; o[6] = p.z; }
   else { const float4 v = type == PXB_RD_LINEAR_VELOCITY ? linVel[a] : angVel[a]; float* o = out + (size_t)i * 3; o[0] = v.x; o[1] = v.y; o[2] = v.z; }
 }
+// getRigidDynamicLinearAcceleration / AngularAcceleration (updateBodiesAndShapes.cu:1063-1106): (velocity now - velocity the step started from) * (1 / dt),
+// computed for the requested bodies only, as the reference does (the CPU path has the same expression, NpSceneFetchResults.cpp:170-186)
+__global__ void k_rd_get_accel(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, const float4* __restrict__ vel, const float4* __restrict__ prev,
+                               float oneOverDt, float* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= nb) return;
+  const uint32_t a = dynActor[idx ? idx[i] : i];
+  const float4 v = vel[a], p = prev[a]; float* o = out + (size_t)i * 3;
+  o[0] = __fmul_rn(__fsub_rn(v.x, p.x), oneOverDt); o[1] = __fmul_rn(__fsub_rn(v.y, p.y), oneOverDt); o[2] = __fmul_rn(__fsub_rn(v.z, p.z), oneOverDt);
+}
 __global__ void k_rd_set(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, int type, float4* __restrict__ pos, float4* __restrict__ quat,
                          float4* __restrict__ linVel, float4* __restrict__ angVel, const float* __restrict__ in, float* __restrict__ wake, uint32_t* __restrict__ asleep,
                          float4* __restrict__ extForce, float4* __restrict__ extTorque) {
@@ -767,6 +777,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->pos, A)); CK(dalloc(s->quat, A)); CK(dalloc(s->linVel, A)); CK(dalloc(s->angVel, A)); CK(dalloc(s->invInertia, A)); CK(dalloc(s->damp, A));
   CK(dalloc(s->dims, A)); CK(dalloc(s->aabbMin, A)); CK(dalloc(s->aabbMax, A)); CK(dalloc(s->geomFlags, A)); CK(dalloc(s->envId, A)); CK(dalloc(s->dynActorDev, A));
   CK(dalloc(s->largeList, A)); CK(dalloc(s->tight, A * 6));
+  if (s->bodyAccel) { CK(dalloc(s->prevLin, A)); CK(dalloc(s->prevAng, A)); CK(cudaMemset(s->prevLin, 0, 16 * A)); CK(cudaMemset(s->prevAng, 0, 16 * A)); }
   CK(dalloc(s->sbLin, A)); CK(dalloc(s->sbAng, A)); CK(dalloc(s->sbDLin, A)); CK(dalloc(s->sbDAng, A)); CK(dalloc(s->sbIA, A)); CK(dalloc(s->sbIB, A)); CK(dalloc(s->sbP, A));
   CK(dalloc(s->sbQ, A)); CK(dalloc(s->sbOrigAng, A));
   CK(dalloc(s->bodyCnt, A)); CK(dalloc(s->bodyStart, A)); CK(dalloc(s->bodyCursor, A)); CK(dalloc(s->bodyNext, A)); CK(dalloc(s->bodyMask, A)); CK(dalloc(s->bodyHasCon, A));
@@ -784,7 +795,7 @@ static int scene_alloc(PxbScene* s) {
   CK(dalloc(s->colourTicket, 4)); CK(dalloc(s->prevB0, Pn)); CK(dalloc(s->prevB1, Pn)); CK(dalloc(s->prevColour, Pn)); CK(dalloc(s->prevNCon, 1)); CK(cudaMemsetAsync(s->prevNCon, 0, 4, s->stream)); CK(dalloc(s->partCnt, MAX_PARTITIONS + 1)); CK(dalloc(s->partStart, MAX_PARTITIONS + 1)); CK(dalloc(s->partCursor, MAX_PARTITIONS + 1));
   CK(dalloc(s->ptA, Pn * 28)); s->ptB = s->ptA + Pn * 4; s->ptC = s->ptA + Pn * 8;   // one allocation: the environment path views it as 25 x Pn (pxb_env.cuh Rows)
   s->frA = s->ptA + Pn * 12; s->frB = s->ptA + Pn * 16; s->frC = s->ptA + Pn * 20; s->frD = s->ptA + Pn * 24;
-  CK(dalloc(s->stage, A * 32)); CK(dalloc(s->stageIdx, A));   // staging: {get, set} x {pose 7, linear 3, angular 3} + set {force 3, torque 3} floats per actor
+  CK(dalloc(s->stage, A * 38)); CK(dalloc(s->stageIdx, A));   // staging: {get, set} x {pose 7, linear 3, angular 3} + set {force 3, torque 3} + get {linear, angular acceleration 3} floats per actor
   CK(dalloc(s->extForce, A)); CK(dalloc(s->extTorque, A)); CK(cudaMemsetAsync(s->extForce, 0, sizeof(float4) * A, s->stream)); CK(cudaMemsetAsync(s->extTorque, 0, sizeof(float4) * A, s->stream));
   CK(dalloc(s->counters, C_COUNT)); CK(cudaMallocHost((void**)&s->hostCounters, sizeof(uint32_t) * (C_COUNT + 2)));
   CK(dalloc(s->rsTmp.blockHist, RS_MAX_CTAS * 256)); CK(dalloc(s->rsTmp.digitTotals, 256)); CK(dalloc(s->scanSums, RS_MAX_CTAS));
@@ -839,6 +850,7 @@ PXB_API int pxb_scene_create(const PxbSceneDesc* desc, PxbScene** out) {
     const char* gp = getenv("PXB_GJK_PHASES"); if (gp && gp[0] == '0') s->gjkPhases = false; }   // A/B hooks of the exact colouring
   if (desc->reserved[1] & PXB_FLAG_NO_ENV_PATH) s->envDisabled = true;
   if (desc->reserved[1] & PXB_FLAG_RELAXED_PARTITIONING) { s->relaxedPartitioning = true; s->envDisabled = true; }
+  if (desc->reserved[1] & PXB_FLAG_BODY_ACCELERATIONS) s->bodyAccel = true;
   s->envConCapForced = desc->reserved[2]; s->envThreadsForced = desc->reserved[3];
   memcpy(&s->sleepThreshold, &desc->reserved[4], 4); if (!(s->sleepThreshold > 0.f)) s->sleepThreshold = 0.f;
   const int rc = scene_alloc(s);
@@ -851,7 +863,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
   if (!s) return;
   cudaStreamSynchronize(s->stream);
   drop_graphs(s);
-  void* ptrs[] = {s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
+  void* ptrs[] = {s->prevLin, s->prevAng, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->filterData, s->shapeOff, s->tcPos, s->tcQuat, s->s2bP, s->s2bQ, s->b2aP, s->b2aQ, s->actorPos, s->actorQuat, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
@@ -1236,6 +1248,9 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
   cudaStream_t st = s->stream; const uint32_t B = 256;
   s->launches = 0;
 #define MARK(i) do { if (s->profiling) CK(cudaEventRecord(s->ev[i], st)); } while (0)
+  if (s->bodyAccel && phase != 1) {   // velocities this step starts from (integrationTGS.cu:124-131 keeps them in mBodySimPrevVelocities); after the join of a stream-ordered velocity write
+    CK(cudaMemcpyAsync(s->prevLin, s->linVel, 16 * (size_t)s->nA, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(s->prevAng, s->angVel, 16 * (size_t)s->nA, cudaMemcpyDeviceToDevice, st));
+  }
   if (phase != 2) {
     MARK(0);
     int rc = run_broadphase(s, false); if (rc) return rc;
@@ -1408,6 +1423,7 @@ PXB_API int pxb_scene_simulate(PxbScene* s, float dt) { DeviceGuard dg_(s);
   if (s->gridDirty) { rebuild_grid(s); drop_graphs(s); }
   if (int rc = select_path(s)) return rc;
   if (!s->envActive) s->everStepped = true;
+  if (s->bodyAccel) s->accelInvDt = 1.0f / dt;
   const bool graphOk = s->useGraph && s->nOrder == 0 && !s->profiling;
   if (!graphOk) {
     if (s->velPending) { CK(cudaStreamWaitEvent(s->stream, s->velEvent, 0)); s->velPending = false; }
@@ -1758,8 +1774,10 @@ extern "C" PXB_API int pxb_debug_env_timing(PxbScene* s, unsigned long long* out
 // any other access to the body state is ordered after a velocity write still in flight on the copy stream
 static int join_pending(PxbScene* s) { if (s->velPending) { CK(cudaStreamWaitEvent(s->stream, s->velEvent, 0)); s->velPending = false; } return PXB_OK; }
 static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb, bool set) {
-  if (type < 0 || type > (set ? PXB_RD_TORQUE : PXB_RD_ANGULAR_VELOCITY)) return fail(PXB_ERR_INVALID, "bad dataType");
-  if (type >= PXB_RD_FORCE && !s->forcesUsed) { s->forcesUsed = true; drop_graphs(s); }   // the step kernels read the force arrays from now on
+  const bool accel = !set && (type == PXB_RD_LINEAR_ACCELERATION || type == PXB_RD_ANGULAR_ACCELERATION);
+  if (!accel && (type < 0 || type > (set ? PXB_RD_TORQUE : PXB_RD_ANGULAR_VELOCITY))) return fail(PXB_ERR_INVALID, "bad dataType");
+  if (accel && !s->bodyAccel) return fail(PXB_ERR_INVALID, "acceleration getters need PXB_FLAG_BODY_ACCELERATIONS (PxSceneFlag::eENABLE_BODY_ACCELERATIONS)");
+  if (set && type >= PXB_RD_FORCE && !s->forcesUsed) { s->forcesUsed = true; drop_graphs(s); }   // the step kernels read the force arrays from now on
   if (!devIdx && nb > s->nDyn) return fail(PXB_ERR_INVALID, "nb exceeds the number of dynamic bodies");
   cudaStream_t st = s->stream;
   if (!nb) return PXB_OK;
@@ -1770,7 +1788,8 @@ static int rd_common(PxbScene* s, void* devData, const uint32_t* devIdx, int typ
     if (poseIO) LAUNCH(k_actor_to_body, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, s->pos, s->quat, s->b2aP, s->b2aQ);
   } else {
     if (poseIO) { if (int rc = refresh_actor_poses(s, st)) return rc; }
-    LAUNCH(k_rd_get, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, poseIO ? s->actorPos : s->pos, poseIO ? s->actorQuat : s->quat, s->linVel, s->angVel, (float*)devData);
+    if (accel) LAUNCH(k_rd_get_accel, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type == PXB_RD_LINEAR_ACCELERATION ? s->linVel : s->angVel, type == PXB_RD_LINEAR_ACCELERATION ? s->prevLin : s->prevAng, s->accelInvDt, (float*)devData);
+    else LAUNCH(k_rd_get, cdiv(nb, 256), 256, nb, devIdx, s->dynActorDev, type, poseIO ? s->actorPos : s->pos, poseIO ? s->actorQuat : s->quat, s->linVel, s->angVel, (float*)devData);
   }
   CK(cudaGetLastError());
   return PXB_OK;
@@ -1785,16 +1804,31 @@ PXB_API int pxb_set_rigid_dynamic_data_device(PxbScene* s, const void* devData, 
   if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
   return rd_common(s, const_cast<void*>(devData), devIdx, type, nb, true);
 }
+// start / finish events of the PxDirectGPUAPI calls (PxgSimulationCore.cpp:2736-2850): wait for the start event on the scene stream, record the finish event
+// after the kernel, synchronise when the caller gave none
+static int rd_events(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb, bool set, void* startEvent, void* finishEvent) {
+  if (!s || !devData) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
+  if (startEvent) CK(cudaStreamWaitEvent(s->stream, (cudaEvent_t)startEvent, 0));
+  if (int rc = rd_common(s, devData, devIdx, type, nb, set)) return rc;
+  if (finishEvent) CK(cudaEventRecord((cudaEvent_t)finishEvent, s->stream)); else CK(cudaStreamSynchronize(s->stream));
+  return PXB_OK;
+}
+PXB_API int pxb_get_rigid_dynamic_data_device_ev(PxbScene* s, void* devData, const uint32_t* devIdx, int type, uint32_t nb, void* startEvent, void* finishEvent) { DeviceGuard dg_(s);
+  return rd_events(s, devData, devIdx, type, nb, false, startEvent, finishEvent); }
+PXB_API int pxb_set_rigid_dynamic_data_device_ev(PxbScene* s, const void* devData, const uint32_t* devIdx, int type, uint32_t nb, void* startEvent, void* finishEvent) { DeviceGuard dg_(s);
+  return rd_events(s, const_cast<void*>(devData), devIdx, type, nb, true, startEvent, finishEvent); }
 static int rd_host(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb, bool set, bool async) {
   if (!s || !data) return fail(PXB_ERR_INVALID, "null argument");
-  if (type < 0 || type > (set ? PXB_RD_TORQUE : PXB_RD_ANGULAR_VELOCITY)) return fail(PXB_ERR_INVALID, "bad dataType");
+  const bool accel = !set && (type == PXB_RD_LINEAR_ACCELERATION || type == PXB_RD_ANGULAR_ACCELERATION);
+  if (!accel && (type < 0 || type > (set ? PXB_RD_TORQUE : PXB_RD_ANGULAR_VELOCITY))) return fail(PXB_ERR_INVALID, "bad dataType");
   if (s->stepping && !async) return fail(PXB_ERR_INVALID, "illegal while the simulation is running (NpDirectGPUAPI.cpp:63-78)");
   if (async && idx) return fail(PXB_ERR_INVALID, "the stream-ordered host variants take no index list");
   if (!nb) return PXB_OK;
   const size_t bytes = (size_t)nb * (type == 0 ? 28 : 12);
   if (nb > s->capA) return fail(PXB_ERR_INVALID, "nb exceeds the actor capacity");
   // persistent staging, one region per (direction, data type): no allocation on the per-step path and stream-ordered calls never share a buffer
-  float* d = s->stage + (size_t)s->capA * (type >= PXB_RD_FORCE ? 26 + 3 * (type - PXB_RD_FORCE) : (set ? 13 : 0) + (type == 0 ? 0 : (type == 1 ? 7 : 10))); uint32_t* di = nullptr;
+  float* d = s->stage + (size_t)s->capA * (accel ? 32 + 3 * (type - PXB_RD_LINEAR_ACCELERATION) : type >= PXB_RD_FORCE ? 26 + 3 * (type - PXB_RD_FORCE) : (set ? 13 : 0) + (type == 0 ? 0 : (type == 1 ? 7 : 10))); uint32_t* di = nullptr;
   if (idx) { for (uint32_t i = 0; i < nb; ++i) if (idx[i] >= s->nDyn) return fail(PXB_ERR_INVALID, "index out of range");
              di = s->stageIdx; CK(cudaMemcpyAsync(di, idx, 4 * (size_t)nb, cudaMemcpyHostToDevice, s->stream)); }
   if (set && async && (type == PXB_RD_LINEAR_VELOCITY || type == PXB_RD_ANGULAR_VELOCITY) && s->sleepThreshold == 0.f && !s->stepping && s->copyStream && nb <= s->nDyn) {

@@ -32,9 +32,11 @@ EXPORTS = [
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
     "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait", "pxb_bp_create", "pxb_bp_release", "pxb_bp_update", "pxb_bp_fetch",
     "pxb_scene_set_materials", "pxb_scene_remove_actors", "pxb_tensor_read_device", "pxb_tensor_write_device", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost", "pxb_scene_enable_contact_data", "pxb_scene_copy_contact_data", "pxb_scene_set_local_poses", "pxb_scene_set_filter_shader", "pxb_scene_set_filter_data", "pxb_scene_set_shape_offsets",
+    "pxb_get_rigid_dynamic_data_device_ev", "pxb_set_rigid_dynamic_data_device_ev",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
+RD_LINEAR_ACCELERATION, RD_ANGULAR_ACCELERATION = 5, 6   # read only; scenes created with body_accelerations=True (PxSceneFlag::eENABLE_BODY_ACCELERATIONS)
 
 
 class PhysxB200Error(RuntimeError):
@@ -91,6 +93,8 @@ def load_library():
     for f in ("pxb_get_rigid_dynamic_data", "pxb_set_rigid_dynamic_data", "pxb_get_rigid_dynamic_data_device",
               "pxb_set_rigid_dynamic_data_device"):
         getattr(lib, f).argtypes = [vp, vp, vp, i32, u32]
+    for f in ("pxb_get_rigid_dynamic_data_device_ev", "pxb_set_rigid_dynamic_data_device_ev"):
+        getattr(lib, f).argtypes = [vp, vp, vp, i32, u32, vp, vp]
     for f in ("pxb_scene_get_states", "pxb_scene_set_states", "pxb_scene_get_bounds", "pxb_scene_broadphase",
               "pxb_scene_get_pairs", "pxb_scene_get_created", "pxb_scene_get_deleted", "pxb_scene_get_contacts", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost"):
         getattr(lib, f).argtypes = [vp, vp]
@@ -139,7 +143,8 @@ def _ptr(a):
 class Scene:
     """One simulation scene resident on one GPU (one PxScene <-> one device, ScScene.cpp:718)."""
 
-    def __init__(self, scene: _scenes.Scene, device: int = 0, max_pairs: int = 0, max_actors: int = 0, env_path: bool = True, env_row_cap: int = 0, env_threads: int = 0):
+    def __init__(self, scene: _scenes.Scene, device: int = 0, max_pairs: int = 0, max_actors: int = 0, env_path: bool = True, env_row_cap: int = 0, env_threads: int = 0,
+                 body_accelerations: bool = False):
         lib = load_library()
         self._lib = lib
         h = scene.header
@@ -157,7 +162,7 @@ class Scene:
         d.maxPairs = int(max_pairs)
         d.device = int(device)
         relaxed = bool(int(h["reserved"][0]) & 1)   # scene header reserved[0] bit 0: PXB_FLAG_RELAXED_PARTITIONING (shared with the oracle)
-        d.reserved[1] = (0 if env_path else 1) | (2 if relaxed else 0)   # PXB_FLAG_NO_ENV_PATH | PXB_FLAG_RELAXED_PARTITIONING
+        d.reserved[1] = (0 if env_path else 1) | (2 if relaxed else 0) | (4 if body_accelerations else 0)   # PXB_FLAG_NO_ENV_PATH | PXB_FLAG_RELAXED_PARTITIONING | PXB_FLAG_BODY_ACCELERATIONS
         d.reserved[2] = int(env_row_cap)
         d.reserved[4] = int(np.float32(h["sleepThreshold"]).view(np.uint32))   # sleep threshold as float bits (0 = sleeping off)
         d.reserved[3] = int(env_threads)
@@ -251,6 +256,13 @@ class Scene:
 
     def setRigidDynamicDataDevice(self, data_type: int, dev_ptr: int, nb: int, dev_indices: int = 0):
         _check(self._lib, self._lib.pxb_set_rigid_dynamic_data_device(self._h, dev_ptr, dev_indices or None, data_type, nb))
+
+    def getRigidDynamicDataDeviceEv(self, data_type: int, dev_ptr: int, nb: int, dev_indices: int = 0, start_event: int = 0, finish_event: int = 0):
+        """PxDirectGPUAPI::getRigidDynamicData with its startEvent / finishEvent arguments (cudaEvent_t handles; 0 = none, no finish event = synchronous)."""
+        _check(self._lib, self._lib.pxb_get_rigid_dynamic_data_device_ev(self._h, dev_ptr, dev_indices or None, data_type, nb, start_event or None, finish_event or None))
+
+    def setRigidDynamicDataDeviceEv(self, data_type: int, dev_ptr: int, nb: int, dev_indices: int = 0, start_event: int = 0, finish_event: int = 0):
+        _check(self._lib, self._lib.pxb_set_rigid_dynamic_data_device_ev(self._h, dev_ptr, dev_indices or None, data_type, nb, start_event or None, finish_event or None))
 
     def getStatesDevice(self, dev_ptr: int):
         """13 floats per dynamic body (pos3 quat4 linVel3 angVel3) into a device buffer, async on the scene stream."""

@@ -1333,3 +1333,48 @@ def test_shape_offsets_gpu_matches_oracle_and_reference(oracle, name, env_path):
     lib = gpu._lib
     bad = np.array([[0.01, 0.02]], np.float32)      # contactOffset must exceed restOffset
     assert lib.pxb_scene_set_shape_offsets(gpu._h, 1, 1, bad.ctypes.data) < 0
+
+
+# ---- PxSceneFlag::eENABLE_BODY_ACCELERATIONS: PxDirectGPUAPI acceleration getters, start / finish events ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_path", [True, False])
+def test_acceleration_getters_and_events(env_path):
+    """eLINEAR_ACCELERATION / eANGULAR_ACCELERATION = (velocity - velocity the step started from) * (1 / dt), the expression of the reference's getter kernels
+    (updateBodiesAndShapes.cu:1063-1106) and of its CPU path (NpSceneFetchResults.cpp:170-186): bit-exact against the velocities read through the same API, with a user
+    velocity write between steps counted as the new start velocity (NpRigidDynamic.cpp:245-252).  The *_device_ev variants take PxDirectGPUAPI's start / finish events."""
+    import torch
+    sc = scenes.env_grid_stacks(n_envs=8)
+    with pytest.raises(engine.PhysxB200Error):
+        engine.Scene(sc, env_path=env_path).getRigidDynamicData(engine.RD_LINEAR_ACCELERATION)      # flag off: the reference reports an error as well
+    gpu, plain = engine.Scene(sc, env_path=env_path, body_accelerations=True), engine.Scene(sc, env_path=env_path)
+    nb = gpu.num_dynamic
+    inv_dt = np.float32(1.0) / np.float32(gpu.dt)
+    assert not gpu.getRigidDynamicData(engine.RD_LINEAR_ACCELERATION).any()                          # nothing stepped yet
+    rng = np.random.RandomState(3)
+    for t in range(6):
+        if t == 3:                                                                                    # a velocity write is the velocity the next step starts from
+            kick = rng.uniform(-0.5, 0.5, (nb, 3)).astype(np.float32)
+            gpu.setRigidDynamicData(engine.RD_LINEAR_VELOCITY, kick); plain.setRigidDynamicData(engine.RD_LINEAR_VELOCITY, kick)
+        l0, a0 = gpu.getRigidDynamicData(engine.RD_LINEAR_VELOCITY), gpu.getRigidDynamicData(engine.RD_ANGULAR_VELOCITY)
+        gpu.step(); plain.step()
+        l1, a1 = gpu.getRigidDynamicData(engine.RD_LINEAR_VELOCITY), gpu.getRigidDynamicData(engine.RD_ANGULAR_VELOCITY)
+        assert np.array_equal(gpu.getRigidDynamicData(engine.RD_LINEAR_ACCELERATION), (l1 - l0) * inv_dt), f"step {t}"
+        assert np.array_equal(gpu.getRigidDynamicData(engine.RD_ANGULAR_ACCELERATION), (a1 - a0) * inv_dt), f"step {t}"
+        assert np.array_equal(gpu.getStates(), plain.getStates())                                    # the flag changes nothing else
+    assert np.abs(gpu.getRigidDynamicData(engine.RD_LINEAR_ACCELERATION)[:, 2]).max() < 12.0         # resting stacks: far below free fall over one step
+    idx = np.array([7, 2, 40], np.uint32)
+    assert np.array_equal(gpu.getRigidDynamicData(engine.RD_LINEAR_ACCELERATION, idx), ((l1 - l0) * inv_dt)[idx])
+    # start / finish events (CUevent arguments of PxDirectGPUAPI::getRigidDynamicData / setRigidDynamicData)
+    other = torch.cuda.Stream()
+    src = torch.zeros((nb, 3), dtype=torch.float32, device="cuda"); dst = torch.empty_like(src)
+    start, finish, done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+    for e in (start, finish, done):
+        e.record()                                                                                  # torch creates the cudaEvent_t lazily, at the first record
+    with torch.cuda.stream(other):
+        src.fill_(0.25); start.record(other)                                                         # producer on another stream: the set must wait for it
+    gpu.setRigidDynamicDataDeviceEv(engine.RD_LINEAR_VELOCITY, src.data_ptr(), nb, start_event=start.cuda_event, finish_event=finish.cuda_event)
+    gpu.getRigidDynamicDataDeviceEv(engine.RD_LINEAR_VELOCITY, dst.data_ptr(), nb, start_event=finish.cuda_event, finish_event=done.cuda_event)
+    done.synchronize()
+    assert bool((dst == 0.25).all())
+    gpu.getRigidDynamicDataDeviceEv(engine.RD_ANGULAR_VELOCITY, dst.data_ptr(), nb)                  # no finish event: synchronous
+    assert np.array_equal(dst.cpu().numpy(), gpu.getRigidDynamicData(engine.RD_ANGULAR_VELOCITY))
