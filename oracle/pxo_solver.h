@@ -31,6 +31,7 @@ typedef struct {
   float invMass, penBiasClamp, maxContactImpulse;
   v3 origLinVel, origAngVel;
   int hasConstraints;
+  int isKinematic;          /* PxTGSSolverBodyVel::isKinematic: zero solver velocity, the body's velocity enters the rows' target velocities */
   uint32_t lockFlags;       /* PxRigidDynamicLockFlag bits: linear x,y,z = 1,2,4; angular x,y,z = 8,16,32 */
 } PxoSolverBody;
 
@@ -90,7 +91,14 @@ static inline void pxo_solver_body_init(PxoSolverBody* b, v3 lv, v3 av, float in
   b->linVel = lv; b->angState = m33mul(&sqrtInertia, av);
   b->deltaLinDt = V3(0, 0, 0); b->deltaAngDt = V3(0, 0, 0);
   b->invMass = invMass; b->penBiasClamp = -maxDepenVel; b->maxContactImpulse = FLT_MAX;
-  b->origLinVel = lv; b->origAngVel = av;
+  b->origLinVel = lv; b->origAngVel = av; b->isKinematic = 0;
+}
+/* copyToSolverBodyDataStepKinematic, DyTGSDynamics.cpp:245-274 */
+static inline void pxo_kinematic_body_init(PxoSolverBody* b, v3 lv, v3 av, const xf* pose, float maxDepenVel) {
+  memset(b, 0, sizeof(*b));
+  b->body2WorldP = pose->p; b->deltaQ = Q4(0, 0, 0, 1);
+  b->invMass = 0.f; b->penBiasClamp = -maxDepenVel; b->maxContactImpulse = FLT_MAX;
+  b->origLinVel = lv; b->origAngVel = av; b->isKinematic = 1;
 }
 
 static inline void pxo_static_body_init(PxoSolverBody* b) {
@@ -234,6 +242,8 @@ static inline void pxo_prep_contact(PxoConstraint* k, const PxoContacts* c, cons
     float totalError = penetration;
     float targetVelocity = cTargetVel + (isGreater2 ? ((-vrel) * restitution) : 0.f);
     totalError = targetVelocity * ratio + totalError;
+    if (b0->isKinematic) targetVelocity = targetVelocity - vrel1;   /* DyTGSContactPrep.cpp:406-409 */
+    if (b1->isKinematic) targetVelocity = targetVelocity + vrel2;
     s->raXnI = raXnI; s->rbXnI = rbXnI; s->velMultiplier = velMultiplier; s->separation = totalError;
     s->biasCoefficient = biasCoeff; s->targetVelocity = targetVelocity; s->recipResponse = recipResponse;
     s->maxImpulse = FLT_MAX; s->appliedForce = 0.f;
@@ -249,6 +259,7 @@ static inline void pxo_prep_contact(PxoConstraint* k, const PxoContacts* c, cons
     t0 = anormalize(t0);
     const v3 t1 = anormalize(v3cross(normal, t0));
     const v3 relTr = v3sub(bodyFrame0->p, bodyFrame1->p);
+    const float norVelT[2][2] = {{adot(linVel0, t0), adot(linVel1, t0)}, {adot(linVel0, t1), adot(linVel1, t1)}};   /* norVel00 / 01 / 10 / 11, DyTGSContactPrep.cpp:670-673 */
     const float frictionScale = (fp->anchorCount == 2) ? 0.5f : 1.f;
     for (int j = 0; j < fp->anchorCount; ++j) {
       const v3 ra = aqrot(bodyFrame0->q, fp->body0Anchors[j]), rb = aqrot(bodyFrame1->q, fp->body1Anchors[j]);
@@ -263,7 +274,10 @@ static inline void pxo_prep_contact(PxoConstraint* k, const PxoContacts* c, cons
         const float resp1 = adot(rbXnI, rbXnI) * angD1 - invMassNorLenSq1;
         const float unitResponse = resp0 + resp1;
         const float velMultiplier = (unitResponse > 0.f) ? (scale / unitResponse) : 0.f;
-        f->normal = tdir; f->error = adot(error, tdir); f->raXnI = raXnI; f->targetVel = 0.f; f->rbXnI = rbXnI;
+        float targetVel = 0.f;   /* kinematic bodies: their velocity along the tangent becomes the row's target velocity (:724-727, :761-764) */
+        if (b0->isKinematic) targetVel = targetVel - (norVelT[t][0] + adot(raXn, angVel0));
+        if (b1->isKinematic) targetVel = targetVel + (norVelT[t][1] + adot(rbXn, angVel1));
+        f->normal = tdir; f->error = adot(error, tdir); f->raXnI = raXnI; f->targetVel = targetVel; f->rbXnI = rbXnI;
         f->velMultiplier = velMultiplier; f->appliedForce = 0.f; f->frictionScale = frictionScale; f->biasScale = frictionBiasScale;
       }
     }

@@ -131,7 +131,7 @@ int main(int argc, char** argv) {
   const char* scenePath = argv[2];
   int steps = 100, threads = 1, warmup = 0;
   const char* gpuPlugin = nullptr; bool gpuBp = false, gpuDynamics = false, directGpuApi = false; int gpuBpShift = -1;
-  const char *statesPath = nullptr, *bpPath = nullptr, *contactsPath = nullptr, *hullsPath = nullptr, *orderPath = nullptr, *sleepPath = nullptr, *forcesPath = nullptr;
+  const char *statesPath = nullptr, *bpPath = nullptr, *contactsPath = nullptr, *hullsPath = nullptr, *orderPath = nullptr, *sleepPath = nullptr, *forcesPath = nullptr, *kinPath = nullptr;
   for (int i = 3; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--steps") steps = atoi(argv[++i]);
@@ -143,6 +143,7 @@ int main(int argc, char** argv) {
     else if (a == "--hulls") hullsPath = argv[++i];
     else if (a == "--order") orderPath = argv[++i];
     else if (a == "--forces") forcesPath = argv[++i];   // f32[blocks][nDyn][6] = force xyz, torque xyz: block s (mod blocks) is applied with addForce / addTorque(eFORCE) before step s
+    else if (a == "--kin-targets") kinPath = argv[++i];   // f32[blocks][nKinematic][7] = PxTransform (q.xyzw, p.xyz): block s is handed to setKinematicTarget before step s (no target once the blocks run out)
     else if (a == "--gpu-plugin") gpuPlugin = argv[++i];   // (GPU-enabled host build only) path of a libPhysXGpu_64.so to load through PxSetPhysXGpuLoadHook
     else if (a == "--gpu-bp") gpuBp = true;                // PxBroadPhaseType::eGPU (CPU dynamics)
     else if (a == "--gpu-dynamics") gpuDynamics = true;    // + PxSceneFlag::eENABLE_GPU_DYNAMICS
@@ -303,7 +304,7 @@ int main(int argc, char** argv) {
   }
 
   std::vector<PxRigidActor*> actors(H.nActors);
-  std::vector<PxRigidDynamic*> dyn;
+  std::vector<PxRigidDynamic*> dyn, kin;   // kin: the kinematic ones, in dynamic-body order
   std::vector<PxShape*> shapes(H.nActors);
   for (uint32_t i = 0; i < H.nActors; i++) {
     const PxbActorRec& r = recs[i];
@@ -343,6 +344,7 @@ int main(int argc, char** argv) {
       d->setSleepThreshold(H.sleepThreshold);
       if (H.sleepThreshold == 0.0f) d->setWakeCounter(1e9f);
       d->setRigidDynamicLockFlags(PxRigidDynamicLockFlags(PxU8((r.flags >> 8) & 0x3f)));
+      if (r.flags & PXB_ACTOR_KINEMATIC) { d->setRigidBodyFlag(PxRigidBodyFlag::eKINEMATIC, true); kin.push_back(d); }
       dyn.push_back(d);
     }
     actors[i] = a;
@@ -394,6 +396,7 @@ int main(int argc, char** argv) {
   PxBroadPhase* bp = nullptr; PxAABBManager* aabb = nullptr;
   if (fb) {
     PxBroadPhaseDesc bpd(PxBroadPhaseType::eABP);
+    bpd.mDiscardKinematicVsKinematic = true; bpd.mDiscardStaticVsKinematic = true;   // what a scene's broadphase is created with under PxPairFilteringMode::eDEFAULT (ScScene.cpp: kineKine / staticKine filtering != eKEEP)
     bp = PxCreateBroadPhase(bpd);
     aabb = PxCreateAABBManager(*bp);
   }
@@ -406,7 +409,7 @@ int main(int argc, char** argv) {
       memcpy(&bounds[i * 6], &b.minimum.x, 24);
       const bool isDyn = recs[i].flags & PXB_ACTOR_DYNAMIC;
       if (first) {
-        PxBpFilterGroup g = isDyn ? PxGetBroadPhaseDynamicFilterGroup(i) : PxGetBroadPhaseStaticFilterGroup();
+        PxBpFilterGroup g = (recs[i].flags & PXB_ACTOR_KINEMATIC) ? PxGetBroadPhaseKinematicFilterGroup(i) : isDyn ? PxGetBroadPhaseDynamicFilterGroup(i) : PxGetBroadPhaseStaticFilterGroup();
         aabb->addObject(i, b, g, shapeOffsets ? shapeOffsets[2 * i] : H.contactOffset);   // contact distance of the object = its shape's contact offset
       } else if (isDyn) {
         aabb->updateObject(i, &b, nullptr);
@@ -430,6 +433,8 @@ int main(int argc, char** argv) {
 
   std::vector<float> forces;
   if (forcesPath) { std::vector<uint8_t> fb_ = readFile(forcesPath); forces.resize(fb_.size() / 4); memcpy(forces.data(), fb_.data(), forces.size() * 4); }
+  std::vector<float> kinTargets;
+  if (kinPath) { std::vector<uint8_t> kb_ = readFile(kinPath); kinTargets.resize(kb_.size() / 4); memcpy(kinTargets.data(), kb_.data(), kinTargets.size() * 4); }
   inlineDispatcher.hook = [](void*) { sDump(); };
   dumpStates();
   double totalMs = 0; std::vector<double> stepMs;
@@ -443,6 +448,10 @@ int main(int argc, char** argv) {
         if (!F.isZero()) dyn[i]->addForce(F, PxForceMode::eFORCE);
         if (!T.isZero()) dyn[i]->addTorque(T, PxForceMode::eFORCE);
       }
+    }
+    if (!kin.empty() && size_t(s + 1) * kin.size() * 7 <= kinTargets.size()) {   // PxRigidDynamic::setKinematicTarget
+      const float* k = kinTargets.data() + size_t(s) * kin.size() * 7;
+      for (size_t i = 0; i < kin.size(); i++) if (k[i * 7] == k[i * 7]) /* NaN row: no target this step */ kin[i]->setKinematicTarget(PxTransform(PxVec3(k[i * 7 + 4], k[i * 7 + 5], k[i * 7 + 6]), PxQuat(k[i * 7], k[i * 7 + 1], k[i * 7 + 2], k[i * 7 + 3])));
     }
     auto t0 = std::chrono::steady_clock::now();
     scene->simulate(H.dt);

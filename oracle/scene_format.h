@@ -26,7 +26,9 @@
 #define PXB_SCENE_MAGIC 0x314e4353u /* "SCN1" */
 
 enum { PXB_GEOM_SPHERE = 0, PXB_GEOM_PLANE = 1, PXB_GEOM_CAPSULE = 2, PXB_GEOM_BOX = 3, PXB_GEOM_CONVEX = 5 };
-enum { PXB_ACTOR_DYNAMIC = 1u };
+enum { PXB_ACTOR_DYNAMIC = 1u,
+       PXB_ACTOR_KINEMATIC = 2u /* with PXB_ACTOR_DYNAMIC: PxRigidBodyFlag::eKINEMATIC -- moved by PxRigidDynamic::setKinematicTarget (ScKinematics.cpp:44-97), infinite mass in the solver,
+                                   no pairs against statics or other kinematics (PxPairFilteringMode::eDEFAULT, BpFiltering.cpp:36-48); it keeps its place in the dynamic-body order */ };
 enum { PXB_SOLVER_PGS = 0, PXB_SOLVER_TGS = 1 };
 
 typedef struct {

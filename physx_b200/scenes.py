@@ -876,3 +876,73 @@ def shape_offsets_mix(seed=29, **hdr):
     so[:, 0] = rng.uniform(0.03, 0.06, n); so[:, 1] = rng.uniform(-0.01, 0.025, n)
     so[0] = (0.02, 0.01)   # the ground plane
     return Scene(sc.header, sc.actors, shape_offsets=so)
+
+
+ACTOR_KINEMATIC = 2   # with ACTOR_DYNAMIC: PxRigidBodyFlag::eKINEMATIC (oracle/scene_format.h)
+
+
+def kinematic_mix(n_envs=0, env_pitch=12.0, **hdr):
+    """Kinematic bodies (PxRigidBodyFlag::eKINEMATIC, moved with setKinematicTarget): a conveyor platform that carries three boxes sideways, a lift that moves a
+    box and a sphere up and down, a paddle that rotates through a row of boxes and capsules standing on the ground, a kinematic that never gets a target (stands
+    still, carries a box) and one that passes through another kinematic and through the ground plane (no pairs: kinematic-kinematic and kinematic-static are
+    filtered).  n_envs > 0: the same group once per environment (environment ids, config-2 style); the ground plane is shared."""
+    groups = max(1, n_envs)
+    per = 5 + 3 + 2 + 6 + 1
+    a = _new_actors(groups * per)
+    he = np.float32(0.25)
+    for g in range(groups):
+        o = g * per
+        ox = np.float32(env_pitch * g)
+        k = np.arange(o, o + 5)
+        a["pos"][k[0]] = (ox + 0.0, 1.0, 0.0); a["dims"][k[0], :3] = (1.5, 0.1, 1.0)         # conveyor
+        a["pos"][k[1]] = (ox + 0.0, 0.6, 4.0); a["dims"][k[1], :3] = (0.8, 0.1, 0.8)         # lift
+        a["pos"][k[2]] = (ox + 4.0, 0.3, 0.0); a["dims"][k[2], :3] = (1.2, 0.3, 0.1)         # paddle (sweeps about the y axis)
+        a["pos"][k[3]] = (ox + 4.0, 0.8, 4.0); a["dims"][k[3], :3] = (0.6, 0.1, 0.6)         # no target
+        a["pos"][k[4]] = (ox + 4.0, 0.6, 4.0); a["dims"][k[4], :3] = (0.2, 0.2, 0.2)         # crosses the one above and the ground
+        b = np.arange(o + 5, o + 8)                                                            # boxes on the conveyor
+        for i, j in enumerate(b):
+            a["pos"][j] = (ox - 0.8 + 0.8 * i, 1.1 + he, -0.3 + 0.3 * i)
+        lift = np.arange(o + 8, o + 10)
+        a["pos"][lift[0]] = (ox - 0.3, 0.7 + he, 4.0); a["pos"][lift[1]] = (ox + 0.4, 0.7 + 0.2, 4.2)
+        row = np.arange(o + 10, o + 16)
+        for i, j in enumerate(row):
+            a["pos"][j] = (ox + 4.0 + 0.9 * np.cos(i), he if i % 2 == 0 else 0.2, 0.9 * np.sin(i) + (0.45 if i % 2 else -0.45))
+        top = o + 16
+        a["pos"][top] = (ox + 4.0, 0.9 + he, 4.0)
+        boxes = np.concatenate([b, lift[:1], row[0::2], [top]])
+        dims_k = a["dims"][k, :3].copy()
+        set_box(a, k, dims_k); set_box(a, boxes, np.array([he, he, he], dtype=np.float32))
+        set_sphere(a, lift[1:], np.float32(0.2))
+        set_capsule(a, row[1::2], np.float32(0.2), np.float32(0.25))
+        a["flags"][k] = ACTOR_DYNAMIC | ACTOR_KINEMATIC
+        if n_envs:
+            a["envId"][o:o + per] = g
+    return Scene(default_header(**hdr), add_ground_plane(a))
+
+
+def kinematic_targets(scene, steps):
+    """(steps, n_kinematic, 7) PxTransform (q.xyzw, p.xyz) handed to setKinematicTarget before each step of kinematic_mix; NaN rows = no target that step.
+    Conveyor: 1 m/s along x, stops after 2/3 of the run; lift: sinusoidal; paddle: 1.5 rad/s about y; fourth: never; fifth: sinks through the ground and rises again."""
+    kin = np.nonzero((scene.actors["flags"] & ACTOR_KINEMATIC) != 0)[0]
+    dt = float(scene.header["dt"])
+    out = np.full((steps, len(kin), 7), np.nan, np.float64)
+    for n, ai in enumerate(kin):
+        p0 = scene.actors["pos"][ai].astype(np.float64); role = n % 5
+        for t in range(steps):
+            time = (t + 1) * dt
+            q = np.array([0.0, 0.0, 0.0, 1.0]); p = p0.copy()
+            if role == 0:
+                if t >= (2 * steps) // 3:
+                    continue
+                p[0] += 1.0 * time
+            elif role == 1:
+                p[1] += 0.4 * np.sin(3.0 * time)
+            elif role == 2:
+                ang = 1.5 * time
+                q = np.array([0.0, np.sin(ang / 2), 0.0, np.cos(ang / 2)])
+            elif role == 3:
+                continue
+            else:
+                p[1] += 0.8 * np.sin(2.0 * time) - 0.3
+            out[t, n] = np.concatenate([q, p])
+    return out.astype(np.float32)

@@ -22,7 +22,7 @@ HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 LITE_FULL_STEPS = 4
 
 
-def run_reference(scene, steps, threads=1, forces=None, lite=False):
+def run_reference(scene, steps, threads=1, forces=None, lite=False, kin_targets=None):
     """lite: long-horizon fixtures keep the states, the island-manager order and the per-pair contact COUNTS of every step, but
     bounds / ABP events / contact points only for the first `LITE_FULL_STEPS` steps (fixture size)."""
     with tempfile.TemporaryDirectory() as d:
@@ -32,6 +32,9 @@ def run_reference(scene, steps, threads=1, forces=None, lite=False):
         if forces is not None:   # (blocks, n_dyn, 6) force xyz + torque xyz: block t % blocks is applied before step t
             np.ascontiguousarray(forces, dtype="<f4").tofile(d + "/forces")
             extra = ["--forces", d + "/forces"]
+        if kin_targets is not None:   # (steps, n_kinematic, 7) PxTransform rows for setKinematicTarget before each step (NaN row = no target)
+            np.ascontiguousarray(kin_targets, dtype="<f4").tofile(d + "/kin")
+            extra += ["--kin-targets", d + "/kin"]
         subprocess.run([HARNESS, "run", sp, "--steps", str(steps), "--threads", str(threads), "--states", d + "/st", "--order", d + "/ord",
                         "--bp", d + "/bp", "--contacts", d + "/con", "--sleep", d + "/sl"] + extra, check=True, capture_output=True)
         sl = np.fromfile(d + "/sl", dtype=[("wc", "<f4"), ("s", "<u4")]).reshape(steps, scene.n_dynamic)
@@ -63,7 +66,7 @@ def run_reference(scene, steps, threads=1, forces=None, lite=False):
             k = LITE_FULL_STEPS
             bounds, cr, de = bounds[:k], cr[:k], de[:k]; cro, deo = cro[:k + 1], deo[:k + 1]
             con_pts = con_pts[:con_off[k]]; pt_off = pt_off[:con_off[k] + 1]
-        return dict(scene=np.frombuffer(scene.tobytes(), np.uint8), forces=(np.zeros((0, nd, 6), np.float32) if forces is None else np.asarray(forces, np.float32)), states=states, wake=sl["wc"].copy(), asleep=sl["s"].copy(),
+        return dict(kin_targets=(np.zeros((0, 0, 7), np.float32) if kin_targets is None else np.asarray(kin_targets, np.float32)), scene=np.frombuffer(scene.tobytes(), np.uint8), forces=(np.zeros((0, nd, 6), np.float32) if forces is None else np.asarray(forces, np.float32)), states=states, wake=sl["wc"].copy(), asleep=sl["s"].copy(),
                     order=np.concatenate(order_flat) if order_flat else np.zeros((0, 2), np.uint32), order_off=np.array(order_off),
                     bounds=np.stack(bounds), created=np.concatenate(cr), created_off=np.array(cro), deleted=np.concatenate(de) if de else np.zeros((0, 2), np.uint32),
                     deleted_off=np.array(deo), con_pairs=np.array(con_pairs, np.uint32).reshape(-1, 3), con_off=np.array(con_off),
@@ -186,6 +189,15 @@ def main():
         data = run_reference(sc, 80, forces=scenes.test_forces(sc.n_dynamic))
         np.savez_compressed(os.path.join(out, name + ".npz"), **data)
         print(name, "bodies", sc.n_dynamic, "steps", 80, "bytes", os.path.getsize(os.path.join(out, name + ".npz")))
+    # kinematic bodies (PxRigidBodyFlag::eKINEMATIC + setKinematicTarget every step): conveyor, lift, rotating paddle, a kinematic without target, filtered kinematic pairs;
+    # device-wide and with environment ids
+    kinem = {"kinematic_mix": (scenes.kinematic_mix(), 120), "kinematic_envs_3": (scenes.kinematic_mix(n_envs=3), 90)}
+    for name, (sc, steps) in kinem.items():
+        if only and not any(name.startswith(o) for o in only):
+            continue
+        data = run_reference(sc, steps, kin_targets=scenes.kinematic_targets(sc, steps))
+        np.savez_compressed(os.path.join(out, name + ".npz"), **data)
+        print(name, "bodies", sc.n_dynamic, "steps", steps, "bytes", os.path.getsize(os.path.join(out, name + ".npz")))
     for name, (sc, steps) in cases.items():
         data = run_reference(sc, steps)
         np.savez_compressed(os.path.join(out, name + ".npz"), **data)

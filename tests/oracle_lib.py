@@ -35,6 +35,7 @@ def lib():
         L.pxo_debug_epa_calls.restype = u32
         L.pxo_scene_get_sleep.argtypes = [vp, vp, vp]
         L.pxo_scene_set_forces.argtypes = [vp, vp, vp]
+        L.pxo_scene_set_kinematic_targets.argtypes = [vp, vp, vp, u32]
         L.pxo_scene_compute_bounds.argtypes = [vp]
         L.pxo_scene_broadphase.argtypes = [vp]
         _LIB = L
@@ -79,6 +80,11 @@ class OracleScene:
         f = None if forces is None else np.ascontiguousarray(forces, dtype=np.float32)
         t = None if torques is None else np.ascontiguousarray(torques, dtype=np.float32)
         self.L.pxo_scene_set_forces(self.h, _p(f), _p(t))
+
+    def setKinematicTargets(self, dyn_indices, poses):
+        """PxRigidDynamic::setKinematicTarget: (n, 7) PxTransform rows (q.xyzw, p.xyz) for the kinematic bodies `dyn_indices`; consumed by the next step"""
+        i = np.ascontiguousarray(dyn_indices, dtype=np.uint32); p = np.ascontiguousarray(poses, dtype=np.float32)
+        assert self.L.pxo_scene_set_kinematic_targets(self.h, _p(i), _p(p), len(i)) == 0
 
     def step(self, order=None):
         if order is None or len(order) == 0:

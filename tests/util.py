@@ -91,3 +91,18 @@ LONG_HORIZON = {
     "pile_6x4x6": (2e-4, 1.5e-2, 6e-2),        # config 4 shape, exact first-fit in the reference's order, 60 steps: 1.4e-4 measured
     "pgs_pile_6x4x6": (2e-3, 2e-2, 8e-2),      # the same under PGS: 1.1e-3 measured (open item)
 }
+
+
+def kinematic_indices(sc):
+    """dynamic-body indices of the kinematic bodies of a scene (the rows of a golden's kin_targets)"""
+    from physx_b200 import scenes
+    dyn = np.nonzero((sc.actors["flags"] & scenes.ACTOR_DYNAMIC) != 0)[0]
+    return np.nonzero((sc.actors["flags"][dyn] & scenes.ACTOR_KINEMATIC) != 0)[0].astype(np.uint32)
+
+
+def golden_kin_targets(z, sc, t):
+    """(dynamic-body indices, (n, 7) PxTransform rows) of the kinematic targets set before step t (rows without a target that step are dropped)"""
+    idx = kinematic_indices(sc)
+    rows = z["kin_targets"][t] if t < len(z["kin_targets"]) else np.full((len(idx), 7), np.nan, np.float32)
+    keep = ~np.isnan(rows[:, 0])
+    return idx[keep], np.ascontiguousarray(rows[keep])
