@@ -30,7 +30,11 @@ typedef enum {
 
 /* PxGeometryType values used by the hot path (physx/include/geometry/PxGeometry.h:48-62) */
 enum { PXB_GEOM_SPHERE = 0, PXB_GEOM_PLANE = 1, PXB_GEOM_CAPSULE = 2, PXB_GEOM_BOX = 3, PXB_GEOM_CONVEXMESH = 5 };
-enum { PXB_ACTOR_DYNAMIC = 1u };
+enum { PXB_ACTOR_DYNAMIC = 1u,
+       PXB_ACTOR_KINEMATIC = 2u /* together with PXB_ACTOR_DYNAMIC: PxRigidBodyFlag::eKINEMATIC.  The body has infinite mass, is moved by pxb_scene_set_kinematic_targets and stands still in steps
+                                   without a target; it pushes / carries dynamic bodies with the velocity of its move (ScKinematics.cpp:44-97, DyTGSContactPrep.cpp:406-409, :724-727) and
+                                   generates no pairs against statics or other kinematics (PxPairFilteringMode::eDEFAULT).  It keeps its place in the dynamic-body order.  TGS solver, scenes
+                                   without sleeping; such scenes run on the device-wide path. */ };
 enum { PXB_SOLVER_PGS = 0, PXB_SOLVER_TGS = 1 };
 
 /* Scene description: the PxSceneDesc / PxGpuDynamicsMemoryConfig fields the hot path consumes
@@ -170,6 +174,12 @@ PXB_API int  pxb_set_rigid_dynamic_data_device(PxbScene* scene, const void* devD
  * the work waits for `startEvent` (NULL = none) and records `finishEvent` once done; without a finish event the call synchronises, as the reference does (PxgSimulationCore.cpp:2736-2850). */
 PXB_API int  pxb_get_rigid_dynamic_data_device_ev(PxbScene* scene, void* devData, const uint32_t* devIndices, int dataType, uint32_t nb, void* startEvent, void* finishEvent);
 PXB_API int  pxb_set_rigid_dynamic_data_device_ev(PxbScene* scene, const void* devData, const uint32_t* devIndices, int dataType, uint32_t nb, void* startEvent, void* finishEvent);
+/* PxRigidDynamic::setKinematicTarget (physx/include/PxRigidDynamic.h; NpRigidDynamic.cpp:129-158) for nb kinematic bodies: `indices` are dynamic-body indices, `poses` nb x 7 floats
+ * (PxTransform: q.xyzw, p.xyz; actor poses, normalised by the call).  The next pxb_scene_simulate moves the bodies there.  The reference's GPU pipeline receives the same data through
+ * PxsSimulationController::updateDynamic after Sc::Scene::kinematicsSetup (ScKinematics.cpp:117-160).  The _device variant takes device pointers, is stream-ordered on the scene stream and
+ * reports a bad index through the next pxb_scene_fetch_results. */
+PXB_API int  pxb_scene_set_kinematic_targets(PxbScene* scene, const uint32_t* indices, const float* poses, uint32_t nb);
+PXB_API int  pxb_scene_set_kinematic_targets_device(PxbScene* scene, const uint32_t* devIndices, const float* devPoses, uint32_t nb);
 /* Packed state convenience: 13 floats per dynamic body (pos3 quat4 linVel3 angVel3), dynamic-body order. */
 PXB_API int  pxb_scene_get_states(PxbScene* scene, float* out);
 PXB_API int  pxb_scene_set_states(PxbScene* scene, const float* in);

@@ -72,6 +72,8 @@ class Scene {
   bool fetchResults(bool block = true) { const int rc = pxb_scene_fetch_results(h_, block ? 1 : 0); check(rc); return rc == 0; }
   // PxDirectGPUAPI (host buffers; *_device / *_async variants are in the C header)
   void getRigidDynamicData(void* data, int dataType, uint32_t nb, const uint32_t* indices = nullptr) { check(pxb_get_rigid_dynamic_data(h_, data, indices, dataType, nb)); }
+  // PxRigidDynamic::setKinematicTarget for a batch of kinematic bodies (dynamic-body indices, PxTransform rows q.xyzw p.xyz)
+  void setKinematicTargets(const uint32_t* indices, const float* poses, uint32_t nb) { check(pxb_scene_set_kinematic_targets(h_, indices, poses, nb)); }
   // PxDirectGPUAPI::getRigidDynamicData(data, gpuIndices, dataType, nbElements, startEvent, finishEvent) on device memory (PxDirectGPUAPI.h:311-340)
   void getRigidDynamicDataDevice(void* devData, const uint32_t* devIndices, int dataType, uint32_t nb, void* startEvent = nullptr, void* finishEvent = nullptr) { check(pxb_get_rigid_dynamic_data_device_ev(h_, devData, devIndices, dataType, nb, startEvent, finishEvent)); }
   void setRigidDynamicDataDevice(const void* devData, const uint32_t* devIndices, int dataType, uint32_t nb, void* startEvent = nullptr, void* finishEvent = nullptr) { check(pxb_set_rigid_dynamic_data_device_ev(h_, devData, devIndices, dataType, nb, startEvent, finishEvent)); }

@@ -27,7 +27,7 @@ struct ActorRec {
 static_assert(sizeof(ActorRec) == 128, "actor record layout");
 
 enum Counter { C_NPAIRS_NEW = 0, C_NCREATED, C_NDELETED, C_FREE_HEAD, C_ERROR, C_NCON, C_NPART, C_REMAINING, C_NA, C_NORDER, C_NDYNCON, C_FREE_TAIL, C_FREE_SNAP, C_MAXCONENV, C_MAXPAIRENV, C_NGJK, C_NTOUCH_FOUND, C_NTOUCH_LOST, C_NGJK_QUERY, C_NGJK_FULL, C_NGJK_EPA, C_NBOXGEN, C_COUNT = 24 };
-enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8 };
+enum ErrorBits { E_PAIR_OVERFLOW = 1, E_COLOUR_OVERFLOW = 2, E_PARTITION_OVERFLOW = 4, E_UNSUPPORTED_PAIR = 8, E_BAD_INDEX = 16 /* a device-side index list named a body that does not exist / is not kinematic */ };
 
 struct GridParams { float ox, oy, oz, invCell; int nx, ny, nz; uint32_t keyBits; };
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
@@ -75,10 +75,13 @@ __device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d
 }
 // pair filter: closed-interval overlap on all axes (PxgIntegerAABB::intersects / ABP intersect2D semantics),
 // at least one dynamic actor (BpFiltering.h:99-114 groups), equal-or-invalid environment ids (broadphase.cu:62-80)
+// geomFlags word: bits 0..7 geometry type, 0x100 dynamic (PxRigidDynamic), 0x200 global / oversize object, 0x400 removed, 0x800 kinematic (PxRigidBodyFlag::eKINEMATIC),
+// bits 16..21 PxRigidDynamicLockFlags.  A kinematic body is a PxRigidDynamic that the solver treats like a static one (infinite mass, second body of its pairs).
+__device__ __forceinline__ bool gf_dynamic(uint32_t gf) { return (gf & 0x900u) == 0x100u; }
 __device__ __forceinline__ bool bp_test(const float4& amin, const float4& amax, const float4& bmin, const float4& bmax) {
   if (amin.x > bmax.x || bmin.x > amax.x || amin.y > bmax.y || bmin.y > amax.y || amin.z > bmax.z || bmin.z > amax.z) return false;
   const uint32_t fa = __float_as_uint(amax.w), fb = __float_as_uint(bmax.w);
-  if (!((fa | fb) & 0x100u)) return false;
+  if (!(gf_dynamic(fa) || gf_dynamic(fb))) return false;   // static-static, kinematic-static and kinematic-kinematic pairs are filtered (BpFiltering.cpp:36-48 with PxPairFilteringMode::eDEFAULT)
   const uint32_t ea = __float_as_uint(amin.w), eb = __float_as_uint(bmin.w);
   if (ea != NONE32 && eb != NONE32 && ea != eb) return false;
   return true;

@@ -71,6 +71,7 @@ struct PxbScene {
   // write is pending on the copy stream, so that its host-to-device copy overlaps the first part (which reads poses only)
   bool useGraph = true; cudaGraphExec_t graphExec[2][3] = {{0, 0, 0}, {0, 0, 0}}; float graphDt = 0.f; uint32_t graphLaunches[2][3] = {{0, 0, 0}, {0, 0, 0}};
   cudaStream_t copyStream = nullptr; cudaEvent_t velEvent = nullptr, orderEvent = nullptr; bool velPending = false;
+  bool anyKinematic = false; uint32_t nKin = 0; uint32_t* kinList = 0; float4 *kinP = 0, *kinQ = 0, *kinFtv = 0; uint32_t* kinHas = 0; std::vector<uint32_t> kinHost;   // kinematic bodies: actor list, pending targets (body frame), friction target velocities per pair
   bool bodyAccel = false; float4 *prevLin = 0, *prevAng = 0; float accelInvDt = 0.f;   // PxSceneFlag::eENABLE_BODY_ACCELERATIONS: velocities the last step started from
   bool profiling = false; cudaEvent_t ev[8] = {0, 0, 0, 0, 0, 0, 0, 0}; float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
   uint32_t hNPairs = 0, hNCreated = 0, hNDeleted = 0, hNCon = 0, hNPart = 0, hErr = 0;
@@ -328,7 +329,7 @@ __global__ void k_con_bodies(const uint32_t* __restrict__ counters_, uint32_t* _
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= counters_[C_NCON]) return;
   const uint2 b = pairBodies[conPair[c]];
-  const bool dyn1 = (geomFlags[b.y] & 0x100u) != 0;
+  const bool dyn1 = gf_dynamic(geomFlags[b.y]);   // static and kinematic bodies sit outside the partitioned body range
   conB0[c] = b.x; conB1[c] = dyn1 ? b.y : NONE32; conDone[c] = dyn1 ? 0u : 1u;
   atomicAdd(&bodyCnt[b.x], 1u);
   if (dyn1) { atomicAdd(&bodyCnt[b.y], 1u); atomicAdd(&counters[C_REMAINING], 1u); }
@@ -588,7 +589,7 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
-  if (!(geomFlags[a] & 0x100u)) return;   // removed actor
+  if (!gf_dynamic(geomFlags[a])) return;   // removed actor, kinematic body (KinematicCopyTGSTask: no gravity, no damping)
   const bool asleep = body_asleep(S, a);
   const float4 dm = damp[a]; const float4 ii = invInertia[a]; const float4 p4 = pos[a];
   v3 lv = V3(linVel[a]), av = V3(angVel[a]);
@@ -622,7 +623,7 @@ __global__ void k_finalize_bodies(uint32_t nDyn, const uint32_t* __restrict__ dy
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
-  if (body_asleep(S, a) || !(geomFlags[a] & 0x100u)) return;   // (removed actors lose their dynamic bit)
+  if (body_asleep(S, a) || !gf_dynamic(geomFlags[a])) return;   // (removed actors lose their dynamic bit; kinematic bodies move in k_kin_finalize)
   const float4 ib = sbIB[a];
   const m33 sI = load_sym(sbIA[a], ib);
   v3 p = V3(sbP[a]); q4 dq = Q4(sbQ[a]);
@@ -634,6 +635,44 @@ __global__ void k_finalize_bodies(uint32_t nDyn, const uint32_t* __restrict__ dy
   pos[a] = make_float4(p.x, p.y, p.z, invMass); quat[a] = F4(q);
   linVel[a] = F4(lv, 0.f); angVel[a] = F4(mmul(sI, as), 0.f);
   if (S.threshold > 0.f) { const float invDt = 1.0f / dt; sleep_check_dev(S, a, q, invInertia[a], invMass, dl * invDt, mmul(sI, da * invDt)); }   // motionVel of copyBackBodies
+}
+// Kinematic bodies (PxRigidBodyFlag::eKINEMATIC).  k_kin_set_targets = PxRigidDynamic::setKinematicTarget (NpRigidDynamic.cpp:129-158: normalised, moved into the
+// body frame); k_kin_setup = Sc::Scene::kinematicsSetup / BodySim::calculateKinematicVelocity (ScKinematics.cpp:44-97) at the start of the solver part of the step;
+// k_kin_finalize = BodySim::updateKinematicPose (ScKinematics.cpp:181-204) after it.  Bounds, contacts and solver rows of a step see the pose BEFORE the move.
+__global__ void k_kin_set_targets(uint32_t n, const uint32_t* __restrict__ idx, const float* __restrict__ poses, const uint32_t* __restrict__ dynActor, uint32_t nDyn, const uint32_t* __restrict__ geomFlags,
+                                  float4* __restrict__ kinP, float4* __restrict__ kinQ, uint32_t* __restrict__ kinHas, const float4* __restrict__ b2aP, const float4* __restrict__ b2aQ, uint32_t* __restrict__ counters) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= n) return;
+  const uint32_t d = idx[t];
+  if (d >= nDyn) { atomicOr(&counters[C_ERROR], (uint32_t)E_BAD_INDEX); return; }
+  const uint32_t a = dynActor[d];
+  if (!(geomFlags[a] & 0x800u)) { atomicOr(&counters[C_ERROR], (uint32_t)E_BAD_INDEX); return; }   // "Body must be kinematic!"
+  const float* o = poses + (size_t)t * 7;
+  q4 q = qnormalized(Q4(o[0], o[1], o[2], o[3])); v3 p = V3(o[4], o[5], o[6]);
+  if (b2aP) { const float4 bp = b2aP[a]; if (bp.w != 0.f) { p = qrot(q, V3(bp.x, bp.y, bp.z)) + p; q = qmul(q, Q4(b2aQ[a])); } }
+  kinP[a] = F4(p, 0.f); kinQ[a] = F4(q); kinHas[a] = 1u;
+}
+__global__ void k_kin_setup(uint32_t nKin, const uint32_t* __restrict__ kinList, const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ kinP, const float4* __restrict__ kinQ,
+                            const uint32_t* __restrict__ kinHas, float4* __restrict__ linVel, float4* __restrict__ angVel, float oneOverDt) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= nKin) return;
+  const uint32_t a = kinList[t];
+  if (!kinHas[a]) { linVel[a] = make_float4(0, 0, 0, 0); angVel[a] = make_float4(0, 0, 0, 0); return; }   // no target this step: the body stands still
+  const float4 c = pos[a]; const v3 tp = V3(kinP[a]);
+  linVel[a] = F4((tp - V3(c.x, c.y, c.z)) * oneOverDt, 0.f);
+  const q4 cq = Q4(quat[a]);
+  q4 q = qmul(Q4(kinQ[a]), Q4(-cq.x, -cq.y, -cq.z, cq.w));
+  if (q.w < 0.f) q = Q4(-q.x, -q.y, -q.z, -q.w);   // shortest arc
+  float angle; v3 axis;   // PxQuat::toRadiansAndUnitAxis (PxQuat.h:158-173)
+  const float s2 = q.x * q.x + q.y * q.y + q.z * q.z;
+  if (s2 < 1.0e-8f * 1.0e-8f) { angle = 0.f; axis = V3(1, 0, 0); }
+  else { const float rs = 1.0f / sqrtf(s2); axis = V3(q.x, q.y, q.z) * rs; angle = fabsf(q.w) < 1.0e-8f ? 3.14159265358979323846f : atan2f(s2 * rs, q.w) * 2.0f; }
+  angVel[a] = F4((axis * angle) * oneOverDt, 0.f);
+}
+__global__ void k_kin_finalize(uint32_t nKin, const uint32_t* __restrict__ kinList, float4* __restrict__ pos, float4* __restrict__ quat, const float4* __restrict__ kinP, const float4* __restrict__ kinQ,
+                               uint32_t* __restrict__ kinHas) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= nKin) return;
+  const uint32_t a = kinList[t];
+  if (!kinHas[a]) return;
+  const float4 p = kinP[a]; pos[a] = make_float4(p.x, p.y, p.z, 0.f); quat[a] = kinQ[a]; kinHas[a] = 0u;   // the velocity of the move stays readable until the next step
 }
 // a19: PxDirectGPUAPI get/set (gather/scatter by dynamic-body index)
 __global__ void k_rd_get(uint32_t nb, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ dynActor, int type, const float4* __restrict__ pos, const float4* __restrict__ quat,
@@ -863,7 +902,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
   if (!s) return;
   cudaStreamSynchronize(s->stream);
   drop_graphs(s);
-  void* ptrs[] = {s->prevLin, s->prevAng, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
+  void* ptrs[] = {s->kinList, s->kinP, s->kinQ, s->kinHas, s->kinFtv, s->prevLin, s->prevAng, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->filterData, s->shapeOff, s->tcPos, s->tcQuat, s->s2bP, s->s2bQ, s->b2aP, s->b2aQ, s->actorPos, s->actorQuat, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
@@ -903,6 +942,7 @@ static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
   s->envEligible = false;
   const char* em = getenv("PXB_ENV_MODE");
   if (s->envDisabled || (em && em[0] == '0')) return;
+  if (s->anyKinematic) return;   // kinematic bodies are built on the device-wide path only
   // A small scene without environment ids (BASELINE config 1: 100 boxes) is ONE environment: the whole step then runs on one SM in 5 launches
   // instead of ~36, which is what bounds a scene of that size.
   const bool single = !usesEnv && s->nA > 0 && s->nA <= ENV_MAX_LIST;
@@ -982,7 +1022,7 @@ static void rebuild_grid(PxbScene* s) {
     anyLocks |= ((r.flags >> 8) & 0x3fu) != 0;
     const float d = shape_diameter(r);
     const bool global = !std::isfinite(d) || d > largeThresh || (usesEnv && r.envId == NONE32);
-    gf[a] = (r.geomType & 0xff) | ((r.flags & PXB_ACTOR_DYNAMIC) ? 0x100u : 0u) | (global ? 0x200u : 0u) | (((r.flags >> 8) & 0x3fu) << 16);   // bits 16..21: PxRigidDynamicLockFlags
+    gf[a] = (r.geomType & 0xff) | ((r.flags & PXB_ACTOR_DYNAMIC) ? 0x100u : 0u) | (global ? 0x200u : 0u) | ((r.flags & PXB_ACTOR_KINEMATIC) ? 0x800u : 0u) | (((r.flags >> 8) & 0x3fu) << 16);   // bits 16..21: PxRigidDynamicLockFlags
     if (global) { s->largeHost.push_back(a); continue; }
     cell = std::max(cell, d);
     for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], r.pos[k]); mx[k] = std::max(mx[k], r.pos[k]); }
@@ -1001,6 +1041,12 @@ static void rebuild_grid(PxbScene* s) {
   while ((long double)envCount * g.nx * g.ny * g.nz > 4.0e18L) { if (g.nx >= g.ny && g.nx >= g.nz) g.nx = (g.nx + 1) / 2; else if (g.ny >= g.nz) g.ny = (g.ny + 1) / 2; else g.nz = (g.nz + 1) / 2; }
   g.keyBits = bits_for((uint64_t)envCount * (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz + 1);
   s->anyLocks = anyLocks;
+  s->anyKinematic = !s->kinHost.empty(); s->nKin = (uint32_t)s->kinHost.size();
+  if (s->anyKinematic && !s->kinP) {
+    if (dalloc(s->kinList, s->capA) || dalloc(s->kinP, s->capA) || dalloc(s->kinQ, s->capA) || dalloc(s->kinHas, s->capA) || dalloc(s->kinFtv, s->capPairs)) { s->abort = true; return; }
+    cudaMemsetAsync(s->kinHas, 0, 4 * (size_t)s->capA, s->stream);
+  }
+  if (s->nKin) cudaMemcpyAsync(s->kinList, s->kinHost.data(), 4 * (size_t)s->nKin, cudaMemcpyHostToDevice, s->stream);
   s->hasGjkPairs = (anyCapsule && anyBox) || anyConvex;   // k_narrowphase_gjk: capsule-box and hull pairs
   s->anyConvex = anyConvex;
   s->binPairs = __builtin_popcount(typeMask) >= 2 && !getenv("PXB_NO_PAIR_BINS");
@@ -1100,13 +1146,21 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
     if (r.geomType == PXB_GEOM_CONVEXMESH) { if (r.hullIdx >= s->nHulls) return fail(PXB_ERR_UNSUPPORTED, "convex actor without a cooked hull: call pxb_scene_set_convex_meshes first"); }
     else if (r.geomType != PXB_GEOM_BOX && r.geomType != PXB_GEOM_PLANE && r.geomType != PXB_GEOM_SPHERE && r.geomType != PXB_GEOM_CAPSULE)
       return fail(PXB_ERR_UNSUPPORTED, "geometry type not supported yet");
+    if (r.flags & PXB_ACTOR_KINEMATIC) {
+      if (!(r.flags & PXB_ACTOR_DYNAMIC)) return fail(PXB_ERR_INVALID, "PXB_ACTOR_KINEMATIC is a flag of dynamic actors (PxRigidBodyFlag::eKINEMATIC)");
+      if (s->desc.solverType == PXB_SOLVER_PGS) return fail(PXB_ERR_UNSUPPORTED, "kinematic bodies are built for the TGS solver only");
+      if (s->sleepThreshold > 0.f) return fail(PXB_ERR_UNSUPPORTED, "kinematic bodies in scenes with sleeping enabled are not built");
+      if (r.geomType == PXB_GEOM_PLANE) return fail(PXB_ERR_INVALID, "planes are static");
+    }
   }
   for (uint32_t i = 0; i < nb; ++i) {
     const ActorRec& r = in[i];
-    const bool dyn = r.flags & PXB_ACTOR_DYNAMIC;
+    const bool kin = (r.flags & PXB_ACTOR_KINEMATIC) != 0;
+    const bool dyn = (r.flags & PXB_ACTOR_DYNAMIC) && !kin;   // mass properties: a kinematic body has none (infinite mass and inertia)
     s->recs.push_back(r);
+    if (kin) s->kinHost.push_back(base + i);
     if (r.geomType == PXB_GEOM_CONVEXMESH) s->recs.back().dims[3] = s->hullDiam[r.hullIdx];   // bounding diameter for the broadphase grid
-    if (dyn) { s->dynIndex.push_back((int)s->nDyn); s->dynActor.push_back(base + i); s->nDyn++; } else s->dynIndex.push_back(-1);
+    if (dyn || kin) { s->dynIndex.push_back((int)s->nDyn); s->dynActor.push_back(base + i); s->nDyn++; } else s->dynIndex.push_back(-1);   // kinematic bodies keep their place in the dynamic-body order (they are PxRigidDynamic)
     const float invMass = (dyn && r.mass > 0.f) ? 1.0f / r.mass : 0.f;
     pos[i] = make_float4(r.pos[0], r.pos[1], r.pos[2], invMass);
     { const float sN = 1.0f / sqrtf(r.quat[0] * r.quat[0] + r.quat[1] * r.quat[1] + r.quat[2] * r.quat[2] + r.quat[3] * r.quat[3]);   // NpPhysics::createRigidDynamic / createRigidStatic store globalPose.getNormalized()
@@ -1240,6 +1294,7 @@ static int read_counters(PxbScene* s) {
   if (s->hErr & E_PAIR_OVERFLOW) return fail(PXB_ERR_CAPACITY, "broadphase pair capacity (maxPairs) exceeded");
   if (s->hErr & (E_COLOUR_OVERFLOW | E_PARTITION_OVERFLOW)) return fail(PXB_ERR_CAPACITY, "more than 64 dynamic colours / 160 partitions needed");
   if (s->hErr & E_UNSUPPORTED_PAIR) return fail(PXB_ERR_UNSUPPORTED, "a pair of an unsupported geometry type came into contact range");
+  if (s->hErr & E_BAD_INDEX) return fail(PXB_ERR_INVALID, "a kinematic target named a body that does not exist or is not kinematic");
   return PXB_OK;
 }
 
@@ -1248,6 +1303,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
   cudaStream_t st = s->stream; const uint32_t B = 256;
   s->launches = 0;
 #define MARK(i) do { if (s->profiling) CK(cudaEventRecord(s->ev[i], st)); } while (0)
+  if (s->nKin && phase != 1) LAUNCH(k_kin_setup, cdiv(s->nKin, 128), 128, s->nKin, s->kinList, s->pos, s->quat, s->kinP, s->kinQ, s->kinHas, s->linVel, s->angVel, 1.0f / dt);
   if (s->bodyAccel && phase != 1) {   // velocities this step starts from (integrationTGS.cu:124-131 keeps them in mBodySimPrevVelocities); after the join of a stream-ordered velocity write
     CK(cudaMemcpyAsync(s->prevLin, s->linVel, 16 * (size_t)s->nA, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(s->prevAng, s->angVel, 16 * (size_t)s->nA, cudaMemcpyDeviceToDevice, st));
   }
@@ -1364,12 +1420,13 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     PrepArgs PA;
     PA.counters = s->counters; PA.ordered = s->ordered; PA.conPair = s->conPair; PA.pairSlots = s->pairSlots[cur]; PA.pairBodies = s->pairBodies; PA.geomFlags = s->geomFlags; PA.cHdr = s->cHdr; PA.cPts = s->cPts;
     PA.pos = s->pos; PA.quat = s->quat; PA.linVel = s->linVel; PA.sbOrigAng = s->sbOrigAng; PA.invInertia = s->invInertia; PA.sbIA = s->sbIA; PA.sbIB = s->sbIB; PA.frictions = s->frictions; PA.P = P; PA.R = R; PA.M = material_args(s);
+    PA.angVel = s->angVel; PA.kinFtv = (s->nKin && !pgs) ? s->kinFtv : nullptr;
     pxb_launch_prep_rows(st, pgs, s->capPairs, PA); s->launches++;
     MARK(4);
     SolveArgs VA;
     VA.counters = s->counters; VA.partStart = s->partStart; VA.posIters = s->desc.posIters; VA.velIters = s->desc.velIters; VA.stepDt = P.stepDt; VA.R = R;
     VA.sbLin = s->sbLin; VA.sbAng = s->sbAng; VA.sbDLin = s->sbDLin; VA.sbDAng = s->sbDAng; VA.sbIA = s->sbIA; VA.sbIB = s->sbIB; VA.sbP = s->sbP; VA.sbQ = s->sbQ; VA.bodyHasCon = s->bodyHasCon;
-    VA.nDyn = s->nDyn; VA.dynActor = s->dynActorDev;
+    VA.nDyn = s->nDyn; VA.dynActor = s->dynActorDev; VA.kinFtv = (s->nKin && !pgs) ? s->kinFtv : nullptr;
     CK(pxb_launch_solve(st, pgs, pgs ? s->coopBlocksSolvePgs : s->coopBlocksSolve, VA)); s->launches++;
     MARK(5);
     pxb_launch_writeback_rows(st, s->capPairs, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions, s->contactData ? s->frReport : nullptr, s->pairBodies, s->pos, s->quat); s->launches++;
@@ -1383,6 +1440,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
   }
   LAUNCH(k_finalize_bodies, cdiv(s->nDyn, B), B, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->bodyHasCon,
          s->sbDLin, s->sbDAng, s->invInertia, SA, s->geomFlags);
+  if (s->nKin) LAUNCH(k_kin_finalize, cdiv(s->nKin, 128), 128, s->nKin, s->kinList, s->pos, s->quat, s->kinP, s->kinQ, s->kinHas);
   if (s->exportOn) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
   MARK(6);
   CK(cudaGetLastError());
@@ -1818,6 +1876,36 @@ PXB_API int pxb_get_rigid_dynamic_data_device_ev(PxbScene* s, void* devData, con
   return rd_events(s, devData, devIdx, type, nb, false, startEvent, finishEvent); }
 PXB_API int pxb_set_rigid_dynamic_data_device_ev(PxbScene* s, const void* devData, const uint32_t* devIdx, int type, uint32_t nb, void* startEvent, void* finishEvent) { DeviceGuard dg_(s);
   return rd_events(s, const_cast<void*>(devData), devIdx, type, nb, true, startEvent, finishEvent); }
+// PxRigidDynamic::setKinematicTarget for nb kinematic bodies: actor poses as PxTransform (q.xyzw, p.xyz); consumed by the next step.  A bad index is reported by that
+// step's fetchResults (the check runs on the device).
+static int kin_targets(PxbScene* s, const uint32_t* devIdx, const float* devPoses, uint32_t nb) {
+  if (!s->nKin || !s->kinP) return fail(PXB_ERR_INVALID, "the scene has no kinematic body (or has not been stepped / rebuilt since they were added)");
+  if (int rc = join_pending(s)) return rc;
+  cudaStream_t st = s->stream;
+  LAUNCH(k_kin_set_targets, cdiv(nb, 128), 128, nb, devIdx, devPoses, s->dynActorDev, s->nDyn, s->geomFlags, s->kinP, s->kinQ, s->kinHas, s->hasCom ? s->b2aP : (const float4*)nullptr, s->hasCom ? s->b2aQ : (const float4*)nullptr, s->counters);
+  CK(cudaGetLastError());
+  return PXB_OK;
+}
+PXB_API int pxb_scene_set_kinematic_targets_device(PxbScene* s, const uint32_t* devIndices, const float* devPoses, uint32_t nb) { DeviceGuard dg_(s);
+  if (!s || (nb && (!devIndices || !devPoses))) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running");
+  if (!nb) return PXB_OK;
+  if (s->gridDirty) { rebuild_grid(s); drop_graphs(s); }
+  return kin_targets(s, devIndices, devPoses, nb);
+}
+PXB_API int pxb_scene_set_kinematic_targets(PxbScene* s, const uint32_t* indices, const float* poses, uint32_t nb) { DeviceGuard dg_(s);
+  if (!s || (nb && (!indices || !poses))) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running");
+  if (!nb) return PXB_OK;
+  if (nb > s->capA) return fail(PXB_ERR_INVALID, "nb exceeds the actor capacity");
+  if (s->gridDirty) { rebuild_grid(s); drop_graphs(s); }
+  for (uint32_t i = 0; i < nb; ++i) { if (indices[i] >= s->nDyn || !(s->recs[s->dynActor[indices[i]]].flags & PXB_ACTOR_KINEMATIC)) return fail(PXB_ERR_INVALID, "setKinematicTarget: the body must be kinematic"); }
+  float* d = s->stage + (size_t)s->capA * 13;   // the 'set pose' staging region (7 floats per actor)
+  CK(cudaMemcpyAsync(d, poses, 28 * (size_t)nb, cudaMemcpyHostToDevice, s->stream)); CK(cudaMemcpyAsync(s->stageIdx, indices, 4 * (size_t)nb, cudaMemcpyHostToDevice, s->stream));
+  const int rc = kin_targets(s, s->stageIdx, d, nb);
+  CK(cudaStreamSynchronize(s->stream));   // the caller's buffers may be pageable: done with them on return
+  return rc;
+}
 static int rd_host(PxbScene* s, void* data, const uint32_t* idx, int type, uint32_t nb, bool set, bool async) {
   if (!s || !data) return fail(PXB_ERR_INVALID, "null argument");
   const bool accel = !set && (type == PXB_RD_LINEAR_ACCELERATION || type == PXB_RD_ANGULAR_ACCELERATION);

@@ -269,7 +269,8 @@ PXB_D void f4set(float4& v, int j, float x) { if (j == 0) v.x = x; else if (j ==
 // a14 into registers: same arithmetic as prep_constraint (createFinalizeSolverContactsStep, DyTGSContactPrep.cpp:1297-1490;
 // friction correlation DyFrictionCorrelation.cpp:56-330).
 __device__ __forceinline__ void prep_constraint_regs(RegRows& r, uint32_t i, uint32_t b0, uint32_t b1, const PrepBodies& B, const float4* __restrict__ cHdr,
-                                                     const float4* __restrict__ cPts, float4* __restrict__ frec, const SolverParams& P, const bool noFriction = false) {
+                                                     const float4* __restrict__ cPts, float4* __restrict__ frec, const SolverParams& P, const bool noFriction = false,
+                                                     const bool kin1 = false, float4* __restrict__ kinFtvOut = nullptr) {   // kin1: body B is kinematic (device-wide path only)
   Contacts con; const float4 h = cHdr[i]; con.normal = V3(h.x, h.y, h.z); con.count = __float_as_int(h.w);
 #pragma unroll
   for (int j = 0; j < 4; ++j) { const float4 p = cPts[(size_t)i * 4 + j]; con.point[j] = V3(p.x, p.y, p.z); con.sep[j] = p.w; }
@@ -292,13 +293,13 @@ __device__ __forceinline__ void prep_constraint_regs(RegRows& r, uint32_t i, uin
   const uint32_t numFriction = haveFriction ? (uint32_t)fp.anchorCount * 2u : 0u;
   r.h0 = F4(normal, maxPenBias);
   r.h1 = make_float4(invMass0_dom0, -invMass1_dom1, P.staticFriction, P.dynamicFriction);
-  r.h2 = make_uint4(b0, b1, (uint32_t)con.count | (numFriction << 8), i);
+  r.h2 = make_uint4(b0, b1, (uint32_t)con.count | (numFriction << 8) | (kin1 ? 0x10000u : 0u), i);   // bit 16: friction target velocities in the side table (kinematic body B)
   r.pc0 = r.pc1 = r.ap = r.fap = make_float4(0, 0, 0, 0); r.t0 = r.t1 = make_float4(0, 0, 0, 0); r.broken = 0u;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     r.pa[j] = r.pb[j] = make_float4(0, 0, 0, 0);
     if (j < con.count) {
-      SPoint s; prep_point(s, con.point[j], con.sep[j], normal, f0.p, f1.p, sI0, sI1, angVel0, angVel1, norVel0, norVel1, imn0, imn1, P, invDtp8);
+      SPoint s; prep_point(s, con.point[j], con.sep[j], normal, f0.p, f1.p, sI0, sI1, angVel0, angVel1, norVel0, norVel1, imn0, imn1, P, invDtp8, kin1);
       r.pa[j] = F4(s.raXnI, s.velMultiplier); r.pb[j] = F4(s.rbXnI, s.separation);
       f4set(r.pc0, j, s.biasCoefficient); f4set(r.pc1, j, s.targetVelocity);
     }
@@ -316,6 +317,7 @@ __device__ __forceinline__ void prep_constraint_regs(RegRows& r, uint32_t i, uin
     const v3 relTr = f0.p - f1.p;
     const float frictionScale = (fp.anchorCount == 2) ? 0.5f : 1.f;
     r.t0 = F4(t0, frictionScale); r.t1 = F4(t1, frictionBiasScale);
+    float4 ftv = make_float4(0, 0, 0, 0);   // friction target velocities (row = anchor * 2 + direction): the kinematic body's velocity along the tangent at the anchor (DyTGSContactPrep.cpp:724-727, :761-764)
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       if (j < fp.anchorCount) {
@@ -325,10 +327,12 @@ __device__ __forceinline__ void prep_constraint_regs(RegRows& r, uint32_t i, uin
         for (int t = 0; t < 2; ++t) {
           SFriction f; prep_friction_row(f, ra, rb, error, t == 0 ? t0 : t1, sI0, sI1, imn0, imn1, scale, frictionScale, frictionBiasScale);
           r.fa[j * 2 + t] = F4(f.raXnI, f.error); r.fb[j * 2 + t] = F4(f.rbXnI, f.velMultiplier);
+          if (kin1) { const v3 td = t == 0 ? t0 : t1; f4set(ftv, j * 2 + t, 0.f + (adot(linVel1, td) + adot(cross(rb, td), angVel1))); }
         }
       }
     }
-  }
+    if (kin1 && kinFtvOut) *kinFtvOut = ftv;
+  } else if (kin1 && kinFtvOut) *kinFtvOut = make_float4(0, 0, 0, 0);
 }
 
 // a15 on a register-resident record: same arithmetic and operation order as solve_constraint (solveContact,
@@ -343,8 +347,10 @@ PXB_D void fr_spill(const FrView& v, const RegRows& r) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) { v.p[(2 + j) * v.stride] = r.fa[j]; v.p[(6 + j) * v.stride] = r.fb[j]; }
 }
-template <bool FR>
-__device__ __forceinline__ void solve_constraint_regs(RegRows& r, const float minPen, const float elapsedTime, float4* bLin, float4* bAng, const float4* bDLin, const float4* bDAng, const FrView fr = FrView()) {
+// KIN (device-wide path, scenes with kinematic bodies): friction rows against a kinematic body carry target velocities, kept in a side table indexed by the pair
+template <bool FR, bool KIN = false>
+__device__ __forceinline__ void solve_constraint_regs(RegRows& r, const float minPen, const float elapsedTime, float4* bLin, float4* bAng, const float4* bDLin, const float4* bDAng, const FrView fr = FrView(),
+                                                      const float4* __restrict__ kinFtv = nullptr) {
   const uint32_t b0 = r.h2.x, b1 = r.h2.y;
   const int numNormal = (int)(r.h2.z & 0xff), numFriction = (int)((r.h2.z >> 8) & 0xff);
   const v3 n = V3(r.h0.x, r.h0.y, r.h0.z); const float maxPenBias = r.h0.w;
@@ -388,6 +394,8 @@ __device__ __forceinline__ void solve_constraint_regs(RegRows& r, const float mi
     const float frictionScale = T0.w, biasScale = T1.w;
     const v3 normal0 = V3(T0.x, T0.y, T0.z), normal1 = V3(T1.x, T1.y, T1.z);
     bool broken = false;
+    float4 ftv = make_float4(0, 0, 0, 0);
+    if (KIN && (r.h2.z & 0x10000u)) ftv = kinFtv[r.h2.w];
 #pragma unroll
     for (int j = 0; j < 4; j += 2) {
       if (j < numFriction) {
@@ -395,13 +403,16 @@ __device__ __forceinline__ void solve_constraint_regs(RegRows& r, const float mi
         const float4 A1 = FR ? fr.p[(3 + j) * fr.stride] : r.fa[j + 1], B1 = FR ? fr.p[(7 + j) * fr.stride] : r.fb[j + 1];
         const v3 raXnI0 = V3(A0.x, A0.y, A0.z), rbXnI0 = V3(B0.x, B0.y, B0.z), raXnI1 = V3(A1.x, A1.y, A1.z), rbXnI1 = V3(B1.x, B1.y, B1.z);
         const float applied0 = f4get(fap, j), applied1 = f4get(fap, j + 1);
-        const float deltaV0 = (adot(raXnI0, angMotion0) - adot(rbXnI0, angMotion1)) + adot(normal0, relMotion);
-        const float deltaV1 = (adot(raXnI1, angMotion0) - adot(rbXnI1, angMotion1)) + adot(normal1, relMotion);
-        const float bias0 = (A0.w + deltaV0) * biasScale, bias1 = (A1.w + deltaV1) * biasScale;
+        float deltaV0 = (adot(raXnI0, angMotion0) - adot(rbXnI0, angMotion1)) + adot(normal0, relMotion);
+        float deltaV1 = (adot(raXnI1, angMotion0) - adot(rbXnI1, angMotion1)) + adot(normal1, relMotion);
+        const float tv0 = KIN ? f4get(ftv, j) : 0.f, tv1 = KIN ? f4get(ftv, j + 1) : 0.f;
+        if (KIN) { deltaV0 = deltaV0 - tv0 * elapsedTime; deltaV1 = deltaV1 - tv1 * elapsedTime; }
+        float bias0 = (A0.w + deltaV0) * biasScale, bias1 = (A1.w + deltaV1) * biasScale;
         const float vm0 = B0.w, vm1 = B1.w;
         const v3 d0 = (vmul(linVel0, normal0) + vmul(angState0, raXnI0)) - (vmul(linVel1, normal0) + vmul(angState1, rbXnI0));
         const v3 d1 = (vmul(linVel0, normal1) + vmul(angState0, raXnI1)) - (vmul(linVel1, normal1) + vmul(angState1, rbXnI1));
         const float normalVel0 = (d0.x + d0.y) + d0.z, normalVel1 = (d1.x + d1.y) + d1.z;
+        if (KIN) { bias0 = bias0 - tv0; bias1 = bias1 - tv1; }
         const float tmp10 = applied0 - bias0 * vm0, tmp11 = applied1 - bias1 * vm1;
         const float total0 = tmp10 - normalVel0 * vm0, total1 = tmp11 - normalVel1 * vm1;
         const float total = sqrtf(total0 * total0 + total1 * total1);

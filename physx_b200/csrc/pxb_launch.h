@@ -12,10 +12,11 @@ void pxb_launch_env_solve(cudaStream_t st, const EnvSolveArgs& A, uint32_t threa
 struct PrepArgs {
   const uint32_t *counters, *ordered, *conPair, *pairSlots; const uint2* pairBodies; const uint32_t* geomFlags; const float4 *cHdr, *cPts, *pos, *quat, *linVel, *sbOrigAng, *invInertia, *sbIA, *sbIB;
   float4* frictions; SolverParams P; Rows R; MaterialArgs M;
+  const float4* angVel; float4* kinFtv;   // kinFtv: friction target velocities per pair, non-null in scenes with kinematic bodies
 };
 struct SolveArgs {
   uint32_t *counters, *partStart; uint32_t posIters, velIters; float stepDt; Rows R;
-  float4 *sbLin, *sbAng, *sbDLin, *sbDAng, *sbIA, *sbIB, *sbP, *sbQ; uint32_t* bodyHasCon; uint32_t nDyn; uint32_t* dynActor;
+  float4 *sbLin, *sbAng, *sbDLin, *sbDAng, *sbIA, *sbIB, *sbP, *sbQ; uint32_t* bodyHasCon; uint32_t nDyn; uint32_t* dynActor; const float4* kinFtv;
 };
 cudaError_t pxb_solve_occupancy(int* tgsCtasPerSm, int* pgsCtasPerSm);
 void pxb_launch_prep_rows(cudaStream_t st, bool pgs, uint32_t capPairs, const PrepArgs& A);

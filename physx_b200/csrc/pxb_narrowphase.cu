@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(128, PXB_NP_CTAS) k_narrowphase(const uint64_t
   const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
   uint32_t a0 = hi, a1 = lo;
   const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
-  if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
+  if (!gf_dynamic(gfHi)) { a0 = lo; a1 = hi; }   // a static or kinematic actor is body B (shouldSwapBodies, ScNPhaseCore.cpp:182-252)
   const float contactDist = (FILT && F.shapeOff) ? F.shapeOff[a0].x + F.shapeOff[a1].x : contactDistScene;   // sum of the two shapes' contact offsets
   if (FILT && F.data && filter_suppressed(F, a0, a1)) {   // eSUPPRESS: the pair stays a broadphase pair, there is no contact manager behind it
     cHdr[i] = make_float4(0, 0, 0, __int_as_float(0)); conFlag[i] = 0u; pairBodies[i] = make_uint2(a0, a1);
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128, PXB_GJK_CTAS) k_narrowphase_gjk(const uin
     const uint32_t lo = (uint32_t)(key >> bitsA), hi = (uint32_t)(key & ((1ull << bitsA) - 1ull));
     uint32_t a0 = hi, a1 = lo;
     const uint32_t gfHi = geomFlags[hi], gfLo = geomFlags[lo];
-    if (!(gfHi & 0x100u)) { a0 = lo; a1 = hi; }
+    if (!gf_dynamic(gfHi)) { a0 = lo; a1 = hi; }
     const uint32_t t0 = ((a0 == hi) ? gfHi : gfLo) & 0xff, t1 = ((a0 == hi) ? gfLo : gfHi) & 0xff;
     const float contactDist = shapeOff ? shapeOff[a0].x + shapeOff[a1].x : contactDistScene;
     const bool flip = t1 < t0;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void gjk_pair_setup(const NpArgs& A, uint32_t i, GjkP
   const uint32_t lo = (uint32_t)(P.key >> A.bitsA), hi = (uint32_t)(P.key & ((1ull << A.bitsA) - 1ull));
   P.a0 = hi; P.a1 = lo;
   const uint32_t gfHi = A.geomFlags[hi], gfLo = A.geomFlags[lo];
-  if (!(gfHi & 0x100u)) { P.a0 = lo; P.a1 = hi; }
+  if (!gf_dynamic(gfHi)) { P.a0 = lo; P.a1 = hi; }
   const uint32_t t0 = ((P.a0 == hi) ? gfHi : gfLo) & 0xff, t1 = ((P.a0 == hi) ? gfLo : gfHi) & 0xff;
   P.flip = t1 < t0;
   const uint32_t s0 = P.flip ? P.a1 : P.a0, s1 = P.flip ? P.a0 : P.a1;

@@ -208,12 +208,15 @@ template <bool PGS>
 __global__ void __launch_bounds__(128) k_prep_rows(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ ordered, const uint32_t* __restrict__ conPair, const uint32_t* __restrict__ pairSlots,
                        const uint2* __restrict__ pairBodies, const uint32_t* __restrict__ geomFlags, const float4* __restrict__ cHdr, const float4* __restrict__ cPts,
                        const float4* __restrict__ pos, const float4* __restrict__ quat, const float4* __restrict__ linVel, const float4* __restrict__ sbOrigAng,
-                       const float4* __restrict__ invInertia, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, float4* __restrict__ frictions, SolverParams P, Rows R, const MaterialArgs M) {
+                       const float4* __restrict__ invInertia, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB, float4* __restrict__ frictions, SolverParams P, Rows R, const MaterialArgs M,
+                       const float4* __restrict__ angVel, float4* __restrict__ kinFtv) {   // kinFtv: non-null in scenes with kinematic bodies (TGS only)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= counters[C_NCON]) return;
   const uint32_t c = ordered[k]; const uint32_t i = conPair[c];
   const uint2 bb = pairBodies[i]; const uint32_t b0 = bb.x, b1 = bb.y;
-  const bool dyn1 = (geomFlags[b1] & 0x100u) != 0;
+  const uint32_t gf1 = geomFlags[b1];
+  const bool dyn1 = gf_dynamic(gf1);
+  const bool kin1 = !PGS && kinFtv && (gf1 & 0x800u);   // kinematic body B: a static solver body whose velocity enters the rows as target velocity (copyToSolverBodyDataStepKinematic, DyTGSDynamics.cpp:245-274)
   RegRows r;
   if (__float_as_int(cHdr[i].w) == 0) {  // empty constraint kept only for the colouring (see k_flag_ordered)
     r.h0 = r.h1 = make_float4(0, 0, 0, 0); r.h2 = make_uint4(b0, dyn1 ? b1 : NONE32, 0u, i); r.pc0 = r.pc1 = r.ap = r.t0 = r.t1 = r.fap = make_float4(0, 0, 0, 0); r.broken = 0u;
@@ -230,20 +233,22 @@ __global__ void __launch_bounds__(128) k_prep_rows(const uint32_t* __restrict__ 
   B.angVel0 = V3(sbOrigAng[b0]); B.angVel1 = dyn1 ? V3(sbOrigAng[b1]) : V3(0, 0, 0);
   B.sI0 = load_sym(sbIA[b0], sbIB[b0]);
   if (dyn1) B.sI1 = load_sym(sbIA[b1], sbIB[b1]); else { B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
+  if (kin1) { B.pen1 = -invInertia[b1].w; B.linVel1 = V3(linVel[b1]); B.angVel1 = V3(angVel[b1]); }
   bool noFriction = false;
   if (M.matTab) noFriction = pair_material(M, b0, b1, P);   // material table: this pair's combined coefficients (P is this thread's copy)
   if (M.shapeOff) P.restDistance = M.shapeOff[b0].y + M.shapeOff[b1].y;   // per-shape rest offsets: the pair's rest distance is their sum (PxcNpWorkUnit::restDistance)
   if (PGS) prep_constraint_pgs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, noFriction);
-  else prep_constraint_regs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, noFriction);
+  else prep_constraint_regs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, noFriction, kin1, kin1 ? kinFtv + i : nullptr);
   rows_store(R, k, r);
 }
 
 // a15/a16: the whole TGS iteration loop in ONE cooperative launch (iterativeSolveIsland, DyTGSDynamics.cpp:2515-2793):
 // position iterations = {solve every partition in order; integrate the sub-step}, then velocity iterations.
 // Replaces solveBlockUnified x partitions x iterations + propagateAverageSolverBodyVelocityTGS (~65 launches in the reference).
+template <bool KIN>
 __global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve_tgs(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ partStart, uint32_t posIters, uint32_t velIters, float stepDt, Rows R,
                             float4* __restrict__ sbLin, float4* __restrict__ sbAng, float4* __restrict__ sbDLin, float4* __restrict__ sbDAng, const float4* __restrict__ sbIA, const float4* __restrict__ sbIB,
-                            float4* __restrict__ sbP, float4* __restrict__ sbQ, const uint32_t* __restrict__ bodyHasCon, uint32_t nDyn, const uint32_t* __restrict__ dynActor) {
+                            float4* __restrict__ sbP, float4* __restrict__ sbQ, const uint32_t* __restrict__ bodyHasCon, uint32_t nDyn, const uint32_t* __restrict__ dynActor, const float4* __restrict__ kinFtv) {
   cg::grid_group grid = cg::this_grid();
   const uint32_t nPart = counters[C_NPART];
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(256, PXB_SOLVE_CTAS_PER_SM) k_solve_tgs(const 
       for (uint32_t k = b + gtid; k < e; k += gsize) {
         RegRows r; rows_load(R, k, r);
         if ((r.h2.z & 0xff) == 0) continue;   // empty constraint kept only for the colouring
-        solve_constraint_regs<false>(r, minPen, elapsed, sbLin, sbAng, sbDLin, sbDAng);
+        solve_constraint_regs<false, KIN>(r, minPen, elapsed, sbLin, sbAng, sbDLin, sbDAng, FrView(), kinFtv);
         rows_store_state(R, k, r);
       }
       grid.sync();

@@ -173,7 +173,7 @@ struct SFriction { v3 normal; float error; v3 raXnI; float targetVel; v3 rbXnI; 
 
 PXB_D void prep_point(SPoint& s, v3 point, float separation, v3 normal, v3 p0, v3 p1, const m33& sI0, const m33& sI1,
                       v3 angVel0, v3 angVel1, float norVel0, float norVel1, float invMassNorLenSq0, float invMassNorLenSq1,
-                      const SolverParams& P, float invDtp8) {
+                      const SolverParams& P, float invDtp8, const bool kin1 = false) {
   const v3 ra = point - p0, rb = point - p1;
   const v3 raXn = cross(ra, normal), rbXn = cross(rb, normal);
   const float angV0 = adot(raXn, angVel0), angV1 = adot(rbXn, angVel1);
@@ -191,8 +191,9 @@ PXB_D void prep_point(SPoint& s, v3 point, float separation, v3 normal, v3 p0, v
   const float recipResponse = (unitResponse > 0.f) ? (1.f / unitResponse) : 0.f;
   const float biasCoeff = -(isSeparated ? P.invStepDt : invDtp8);
   float totalError = penetration;
-  const float targetVelocity = 0.f + (isGreater2 ? ((-vrel) * P.restitution) : 0.f);
+  float targetVelocity = 0.f + (isGreater2 ? ((-vrel) * P.restitution) : 0.f);
   totalError = targetVelocity * ratio + totalError;
+  if (kin1) targetVelocity = targetVelocity + vrel2;   // kinematic body B: its velocity along the normal is the row's target velocity (DyTGSContactPrep.cpp:406-409)
   s.raXnI = raXnI; s.rbXnI = rbXnI; s.velMultiplier = recipResponse; s.separation = totalError;
   s.biasCoefficient = biasCoeff; s.targetVelocity = targetVelocity; s.recipResponse = recipResponse; s.appliedForce = 0.f;
 }

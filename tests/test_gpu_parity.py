@@ -1378,3 +1378,74 @@ def test_acceleration_getters_and_events(env_path):
     assert bool((dst == 0.25).all())
     gpu.getRigidDynamicDataDeviceEv(engine.RD_ANGULAR_VELOCITY, dst.data_ptr(), nb)                  # no finish event: synchronous
     assert np.array_equal(dst.cpu().numpy(), gpu.getRigidDynamicData(engine.RD_ANGULAR_VELOCITY))
+
+
+# ---- kinematic bodies (PxRigidBodyFlag::eKINEMATIC, PxRigidDynamic::setKinematicTarget) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["kinematic_mix", "kinematic_envs_3"])
+def test_kinematic_bodies_gpu_matches_oracle_and_reference(oracle, name):
+    """Conveyor, lift, rotating paddle, a kinematic without target, kinematics crossing each other and the ground plane; targets before every step.  Teacher-forced from the
+    reference's states: kinematic poses equal to the targets bit for bit, kinematic velocities 1e-6 relative (atan2f of the device library), the reference's created / deleted
+    pairs and manifolds every step, dynamic bodies within pose 2e-5 / 2e-4 m/s / 2e-3 rad/s of the reference and within 1e-6 / 2e-5 of the oracle.  Free running for 40 steps:
+    GPU within 1e-4 of the reference.  Scenes with kinematic bodies run on the device-wide path (also with environment ids)."""
+    z, sc = util.load_golden(name)
+    kin = util.kinematic_indices(sc)
+    gpu, cpu = engine.Scene(sc), oracle.OracleScene(sc)
+    assert not gpu.uses_env_path
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setStates(z["states"][t]); cpu.setStates(z["states"][t])
+        i, p = util.golden_kin_targets(z, sc, t)
+        if len(i):
+            gpu.setKinematicTargets(i, p); cpu.setKinematicTargets(i, p)
+        gpu.setConstraintOrder(util.golden_order(z, t)); gpu.step(); cpu.step(util.golden_order(z, t))
+        st, ref, orc = gpu.getStates(), z["states"][t + 1], cpu.getStates()
+        assert np.array_equal(st[kin][:, :7], ref[kin][:, :7]), f"kinematic pose, step {t}"
+        assert np.abs(st[kin][:, 7:] - ref[kin][:, 7:]).max() <= 1e-6 * max(1.0, np.abs(ref[kin][:, 7:]).max()), f"kinematic velocity, step {t}"
+        assert np.array_equal(gpu.getCreatedPairs(), util.golden_created(z, t)) and np.array_equal(gpu.getDeletedPairs(), util.golden_deleted(z, t)), f"broadphase, step {t}"
+        assert util.contact_counts(gpu.getPairs(), gpu.getContacts()) == util.golden_contact_counts(z, t), f"manifolds, step {t}"
+        assert np.abs(st[:, :7] - ref[:, :7]).max() < 2e-5 and np.abs(st[:, 7:10] - ref[:, 7:10]).max() < 2e-4 and np.abs(st[:, 10:] - ref[:, 10:]).max() < 2e-3, f"vs reference, step {t}"
+        assert np.abs(st[:, :7] - orc[:, :7]).max() < 1e-6 and np.abs(st[:, 7:] - orc[:, 7:]).max() < 2e-5, f"vs oracle, step {t}"
+    gpu = engine.Scene(sc)
+    for t in range(40):
+        i, p = util.golden_kin_targets(z, sc, t)
+        if len(i):
+            gpu.setKinematicTargets(i, p)
+        gpu.setConstraintOrder(util.golden_order(z, t)); gpu.step()
+        assert np.abs(gpu.getStates()[:, :7] - z["states"][t + 1][:, :7]).max() < 1e-4, f"free running, step {t}"
+
+
+@pytest.mark.gpu
+def test_kinematic_targets_api():
+    """device-pointer variant == host variant (CUDA graph replay included: no constraint order given); errors: a non-kinematic body, an index out of range (reported by
+    fetchResults for the device variant), PGS / sleeping scenes, a kinematic flag on a static actor."""
+    import torch
+    z, sc = util.load_golden("kinematic_mix")
+    a, b = engine.Scene(sc), engine.Scene(sc)
+    for t in range(25):
+        i, p = util.golden_kin_targets(z, sc, t)
+        a.setKinematicTargets(i, p)
+        di, dp = torch.from_numpy(i.astype(np.int32)).cuda(), torch.from_numpy(p).cuda()
+        torch.cuda.synchronize()
+        b.setKinematicTargetsDevice(di.data_ptr(), dp.data_ptr(), len(i))
+        a.step(); b.step()
+        assert np.array_equal(a.getStates(), b.getStates()), f"step {t}"
+    kin = util.kinematic_indices(sc)
+    assert np.abs(a.getStates()[kin[0], 0] - z["states"][25][kin[0], 0]) == 0 and a.getStates()[kin[0], 7] > 0.9       # the conveyor is where its targets put it, at 1 m/s
+    a.step()                                                                                                              # no new target: it stands still
+    assert not a.getStates()[kin, 7:].any()
+    dyn = np.setdiff1d(np.arange(sc.n_dynamic), kin)
+    with pytest.raises(engine.PhysxB200Error):
+        a.setKinematicTargets(dyn[:1], p[:1])
+    with pytest.raises(engine.PhysxB200Error):
+        a.setKinematicTargets(np.array([10 ** 6], np.uint32), p[:1])
+    bad = torch.tensor([int(dyn[0])], dtype=torch.int32).cuda(); torch.cuda.synchronize()
+    a.setKinematicTargetsDevice(bad.data_ptr(), dp.data_ptr(), 1)
+    with pytest.raises(engine.PhysxB200Error):
+        a.step()
+    a.step()                                                                                                              # reported once, the scene carries on
+    for kw in (dict(solver=scenes.SOLVER_PGS), dict(sleep_threshold=0.005)):
+        with pytest.raises(engine.PhysxB200Error):
+            engine.Scene(scenes.kinematic_mix(**kw))
+    wrong = scenes.kinematic_mix(); wrong.actors["flags"][1] = scenes.ACTOR_KINEMATIC
+    with pytest.raises(engine.PhysxB200Error):
+        engine.Scene(wrong)
