@@ -942,7 +942,6 @@ static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
   s->envEligible = false;
   const char* em = getenv("PXB_ENV_MODE");
   if (s->envDisabled || (em && em[0] == '0')) return;
-  if (s->anyKinematic) return;   // kinematic bodies are built on the device-wide path only
   // A small scene without environment ids (BASELINE config 1: 100 boxes) is ONE environment: the whole step then runs on one SM in 5 launches
   // instead of ~36, which is what bounds a scene of that size.
   const bool single = !usesEnv && s->nA > 0 && s->nA <= ENV_MAX_LIST;
@@ -1358,13 +1357,14 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     A.conPair = s->conPair; A.conB0 = s->conB0; A.conB1 = s->conB1; A.conColour = s->conColour; A.ordered = s->ordered; A.broken = s->conDone;
     A.rowScratch = s->ptA;   // ptA|ptB|ptC|frA|frB|frC|frD are ONE allocation of 28 x cap float4 (scene_alloc); the environment path uses 25 of them
     A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour; A.S = SA;
-    const bool fusedExport = s->exportOn && s->envDynContiguous;
+    const bool fusedExport = s->exportOn && s->envDynContiguous && !s->nKin;   // kinematic bodies take their new pose after the kernel (k_kin_finalize): export afterwards
     A.exportTab = fusedExport ? s->exportTab : nullptr; A.envDyn = s->envDyn; A.dynActor = s->dynActorDev;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
-    A.M = material_args(s);
-    const bool ext = s->anyLocks || s->forcesUsed || s->nMaterials != 0 || s->hasShapeOff;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
+    A.M = material_args(s); A.kinFtv = (s->nKin && !pgs) ? s->kinFtv : nullptr;
+    const bool ext = s->anyLocks || s->forcesUsed || s->nMaterials != 0 || s->hasShapeOff || s->nKin != 0;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
     pxb_launch_env_solve(st, A, s->envSolveThreads, pgs, ext, smem);
     s->launches++;
+    if (s->nKin) LAUNCH(k_kin_finalize, cdiv(s->nKin, 128), 128, s->nKin, s->kinList, s->pos, s->quat, s->kinP, s->kinQ, s->kinHas);
     if (s->exportOn && !fusedExport) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
     MARK(5); MARK(6);
     CK(cudaGetLastError());

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
     }
     const float co = (LOCAL && A.shapeOff) ? A.shapeOff[a].x : A.contactOffset;   // every bound is inflated by its own shape's contact offset
     sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(env));
-    sMax[k] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf));
+    sMax[k] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf_dynamic(gf) ? gf : (gf & ~0x100u)));   // kinematic bodies pair with dynamic ones only, like statics (the test below reads the dynamic bit)
     sAct[k] = a;
   }
   __syncwarp();
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(ENV_BP_CTA_THREADS) k_env_bp_cta(const EnvBpAr
     }
     const float co = (LOCAL && A.shapeOff) ? A.shapeOff[a].x : A.contactOffset;   // every bound is inflated by its own shape's contact offset
     sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(env));
-    sMax[k] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf));
+    sMax[k] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf_dynamic(gf) ? gf : (gf & ~0x100u)));   // kinematic bodies pair with dynamic ones only, like statics (the test below reads the dynamic bit)
     sAct[k] = a;
   }
   __syncthreads();
@@ -240,6 +240,7 @@ struct EnvSolveArgs {
   uint32_t anyLocks;   // some actor carries PxRigidDynamicLockFlags (uniform fast path otherwise)
   float4 *extForce, *extTorque;   // pending eFORCE / eTORQUE writes (NULL until the application uses them)
   MaterialArgs M;   // material table (matTab NULL: the scene's single material in P)
+  float4* kinFtv;   // scenes with kinematic bodies (EXT instantiation, TGS): friction target velocities per pair index; NULL otherwise
   const ExportTable* exportTab; const uint2* envDyn; const uint32_t* dynActor;   // fused state export: targets, per environment {first dynamic-body index, count}
 };
 #ifdef PXB_ENV_TIMING
@@ -472,11 +473,13 @@ __device__ __forceinline__ void env_prep_one(const EnvSolveArgs& A, const ConLis
   B.linVel0 = V3(vLin[l0]); B.angVel0 = V3(vAng[l0]); B.sI0 = load_sym(bIA[l0], bIB[l0]);
   if (dyn1) { B.linVel1 = V3(vLin[l1]); B.angVel1 = V3(vAng[l1]); B.sI1 = load_sym(bIA[l1], bIB[l1]); }
   else { B.linVel1 = V3(0, 0, 0); B.angVel1 = V3(0, 0, 0); B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
-  if (EXT && (A.M.matTab || A.M.shapeOff)) {   // material table / per-shape rest offsets: this pair's own parameters (the plain instantiation carries none of this)
+  if (EXT && (A.M.matTab || A.M.shapeOff || A.kinFtv)) {   // material table / per-shape rest offsets / kinematic bodies: this pair's own parameters (the plain instantiation carries none of this)
     SolverParams Pm = A.P; const bool noFriction = A.M.matTab ? pair_material(A.M, bb.x, bb.y, Pm) : false;
     if (A.M.shapeOff) Pm.restDistance = A.M.shapeOff[bb.x].y + A.M.shapeOff[bb.y].y;
+    const bool kin1 = !PGS && A.kinFtv && (A.geomFlags[bb.y] & 0x800u);   // kinematic body B (see k_prep_rows)
+    if (kin1) { B.pen1 = -A.invInertia[bb.y].w; B.linVel1 = V3(A.linVel[bb.y]); B.angVel1 = V3(A.angVel[bb.y]); }
     if (PGS) prep_constraint_pgs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, Pm, noFriction);
-    else prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, Pm, noFriction);
+    else prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, Pm, noFriction, kin1, kin1 ? A.kinFtv + i : nullptr);
     return;
   }
   if (PGS) prep_constraint_pgs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.P);
@@ -554,8 +557,8 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
       const float minPen = vel ? 0.f : -FLT_MAX;
       for (uint32_t p = 0; p < nPart; ++p) {
         const uint32_t pb = sPartStart[p], pe = sPartStart[p + 1];
-        if (REG) { if (tid >= pb && tid < pe) solve_constraint_regs<true>(mine, minPen, elapsed, bLin, bAng, bDLin, bDAng, fr); }
-        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_regs<false>(r, minPen, elapsed, bLin, bAng, bDLin, bDAng); rows_store_state(R, k, r); }
+        if (REG) { if (tid >= pb && tid < pe) solve_constraint_regs<true, EXT>(mine, minPen, elapsed, bLin, bAng, bDLin, bDAng, fr, A.kinFtv); }   // EXT: friction target velocities of rows against kinematic bodies
+        else for (uint32_t k = pb + tid; k < pe; k += T) { RegRows r; rows_load(R, k, r); solve_constraint_regs<false, EXT>(r, minPen, elapsed, bLin, bAng, bDLin, bDAng, FrView(), A.kinFtv); rows_store_state(R, k, r); }
         __syncthreads();
       }
       if (!vel) {
@@ -598,7 +601,7 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
     const uint32_t a = list[b];
     bMask[b] = 0; bStat[b] = 0;
     const uint32_t gf = A.geomFlags[a];
-    if (!(gf & 0x100u) || body_asleep(A.S, a)) { bP[b] = make_float4(0, 0, 0, 0); continue; }   // statics and sleeping bodies take no part
+    if (!gf_dynamic(gf) || body_asleep(A.S, a)) { bP[b] = make_float4(0, 0, 0, 0); continue; }   // statics, kinematic and sleeping bodies take no part
     const float4 dm = A.damp[a]; const float4 ii = A.invInertia[a]; const float4 p4 = A.pos[a];
     v3 lv = V3(A.linVel[a]), av = V3(A.angVel[a]);
     if (EXT && A.extForce) {   // pending eFORCE / eTORQUE writes: consumed by this step
@@ -655,7 +658,7 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
     if (f) {
       const uint32_t k = off + __popc(bal & ((1u << lane) - 1u));
       const uint2 bb = A.pairBodies[base + t];
-      const uint32_t l0 = A.actorLocal[bb.x]; const uint32_t l1 = (A.geomFlags[bb.y] & 0x100u) ? A.actorLocal[bb.y] : NONE32;
+      const uint32_t l0 = A.actorLocal[bb.x]; const uint32_t l1 = gf_dynamic(A.geomFlags[bb.y]) ? A.actorLocal[bb.y] : NONE32;
       L.conPair[k] = t; L.b0[k] = l0; L.b1[k] = l1; L.colour[k] = prevCol;
       bP[l0].w = __uint_as_float(1u); if (l1 != NONE32) bP[l1].w = __uint_as_float(1u);   // hasConstraints (benign same-value races)
       if (l1 == NONE32) atomicAdd(&bStat[l0], 1u);
@@ -732,7 +735,7 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
   // a18: copyBackBodies (DyTGSDynamics.cpp:1549-1580); bodies without constraints take one full-dt step (:2573-2577)
   for (uint32_t b = tid; b < n; b += T) {
     const uint32_t a = list[b];
-    if (!(A.geomFlags[a] & 0x100u) || body_asleep(A.S, a)) continue;
+    if (!gf_dynamic(A.geomFlags[a]) || body_asleep(A.S, a)) continue;
     const float4 ib = bIB[b]; const uint32_t lock = EXT ? __float_as_uint(ib.z) : 0u;
     const m33 sI = load_sym(bIA[b], ib);
     if (PGS) {   // integrate (DyDynamics.cpp:1398-1423): every body, with or without constraints
