@@ -87,7 +87,8 @@ typedef struct {
   float    maxLinVel, maxAngVel;
   float    maxDepenetrationVel;
   uint32_t materialIndex; /* index into the table of pxb_scene_set_materials (ignored while no table is set) */
-  float    reserved1;
+  uint32_t aggregate;   /* PxAggregate membership: 0 = none, k > 0 = aggregate k; bit 31 set = the aggregate has self collisions enabled.  Members of an aggregate without self collisions
+                            generate no pairs among themselves (PxGetAggregateFilterHint, BpAABBManager.cpp aggregate self-collision pairs) */
 } PxbActorRec;
 
 typedef struct PxbScene PxbScene;

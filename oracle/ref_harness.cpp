@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 #include <algorithm>
 #include <chrono>
@@ -306,6 +307,14 @@ int main(int argc, char** argv) {
   std::vector<PxRigidActor*> actors(H.nActors);
   std::vector<PxRigidDynamic*> dyn, kin;   // kin: the kinematic ones, in dynamic-body order
   std::vector<PxShape*> shapes(H.nActors);
+  // PxAggregate per aggregate id (bit 31 of the id = self collisions): created and added to the scene up front, members join in record order
+  std::map<uint32_t, std::vector<uint32_t>> aggMembers; std::map<uint32_t, PxAggregate*> aggs;
+  for (uint32_t i = 0; i < H.nActors; i++) if (recs[i].aggregate) aggMembers[recs[i].aggregate].push_back(i);
+  for (auto& kv : aggMembers) {
+    const PxU32 n = PxU32(kv.second.size());
+    aggs[kv.first] = physics->createAggregate(n, n, PxGetAggregateFilterHint(PxAggregateType::eGENERIC, (kv.first & 0x80000000u) != 0));
+    scene->addAggregate(*aggs[kv.first]);
+  }
   for (uint32_t i = 0; i < H.nActors; i++) {
     const PxbActorRec& r = recs[i];
     PxTransform pose(PxVec3(r.pos[0], r.pos[1], r.pos[2]), PxQuat(r.quat[0], r.quat[1], r.quat[2], r.quat[3]));
@@ -348,7 +357,7 @@ int main(int argc, char** argv) {
       dyn.push_back(d);
     }
     actors[i] = a;
-    scene->addActor(*a);
+    if (r.aggregate) aggs[r.aggregate]->addActor(*a); else scene->addActor(*a);   // (an aggregate that is in the scene inserts the actor right away: actor ids stay in record order)
   }
 
   FILE* fs = statesPath ? fopen(statesPath, "wb") : nullptr;
@@ -358,6 +367,7 @@ int main(int argc, char** argv) {
   FILE* fsl = sleepPath ? fopen(sleepPath, "wb") : nullptr;
   static FILE* sFo; static PxScene* sScene; sFo = fo; sScene = scene;
   static void (*sDump)();
+  static uint32_t sIdShift; sIdShift = uint32_t(aggs.size());   // element ids: every aggregate took one from the pool before the first shape (they are created up front), shapes follow in record order
   auto dumpOrder = []() {
     FILE* fo = sFo; PxScene* scene = sScene;
     if (!fo) return;
@@ -370,7 +380,7 @@ int main(int argc, char** argv) {
       IG::EdgeIndex e = isl.mFirstEdge[IG::Edge::eCONTACT_MANAGER];
       while (e != IG_INVALID_EDGE) {
         PxsContactManager* cm = im->getContactManager(e);
-        if (cm) { edges.push_back(cm->getWorkUnit().mTransformCache0); edges.push_back(cm->getWorkUnit().mTransformCache1); }
+        if (cm) { edges.push_back(cm->getWorkUnit().mTransformCache0 - sIdShift); edges.push_back(cm->getWorkUnit().mTransformCache1 - sIdShift); }
         e = is.getEdge(e).mNextIslandEdge;
       }
     }
@@ -409,7 +419,9 @@ int main(int argc, char** argv) {
       memcpy(&bounds[i * 6], &b.minimum.x, 24);
       const bool isDyn = recs[i].flags & PXB_ACTOR_DYNAMIC;
       if (first) {
-        PxBpFilterGroup g = (recs[i].flags & PXB_ACTOR_KINEMATIC) ? PxGetBroadPhaseKinematicFilterGroup(i) : isDyn ? PxGetBroadPhaseDynamicFilterGroup(i) : PxGetBroadPhaseStaticFilterGroup();
+        // (standalone broadphase: objects of one filter group do not collide -- the members of an aggregate without self collisions share the group of its first member)
+        const uint32_t gid = (recs[i].aggregate && !(recs[i].aggregate & 0x80000000u)) ? aggMembers[recs[i].aggregate][0] : i;
+        PxBpFilterGroup g = (recs[i].flags & PXB_ACTOR_KINEMATIC) ? PxGetBroadPhaseKinematicFilterGroup(gid) : isDyn ? PxGetBroadPhaseDynamicFilterGroup(gid) : PxGetBroadPhaseStaticFilterGroup();
         aabb->addObject(i, b, g, shapeOffsets ? shapeOffsets[2 * i] : H.contactOffset);   // contact distance of the object = its shape's contact offset
       } else if (isDyn) {
         aabb->updateObject(i, &b, nullptr);

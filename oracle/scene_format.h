@@ -65,7 +65,8 @@ typedef struct {
   float    maxLinVel, maxAngVel;
   float    maxDepenetrationVel;
   uint32_t materialIndex; /* index into the scene's material table (ignored when the table is empty: the header's material applies) */
-  float    reserved1;
+  uint32_t aggregate;   /* PxAggregate membership: 0 = none, k > 0 = aggregate k; bit 31 set = the aggregate has self collisions enabled.  Members of an aggregate without self collisions
+                            generate no pairs among themselves (PxGetAggregateFilterHint, BpAABBManager.cpp aggregate self-collision pairs) */
 } PxbActorRec;
 
 /* One PxMaterial (physx/include/PxMaterial.h): bits = frictionCombineMode | restitutionCombineMode << 4 (PxCombineMode: 0 average, 1 min,

@@ -22,7 +22,7 @@ namespace cg = cooperative_groups;
 // host-side record (layout of oracle/scene_format.h::PxbActorRec, 128 bytes)
 struct ActorRec {
   uint32_t flags, geomType, envId, hullIdx;
-  float pos[3], quat[4], dims[4], linVel[3], angVel[3], mass, inertia[3], linDamping, angDamping, maxLinVel, maxAngVel, maxDepenetrationVel; uint32_t materialIndex; float reserved1;
+  float pos[3], quat[4], dims[4], linVel[3], angVel[3], mass, inertia[3], linDamping, angDamping, maxLinVel, maxAngVel, maxDepenetrationVel; uint32_t materialIndex; uint32_t aggregate;
 };
 static_assert(sizeof(ActorRec) == 128, "actor record layout");
 

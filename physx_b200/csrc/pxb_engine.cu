@@ -71,6 +71,7 @@ struct PxbScene {
   // write is pending on the copy stream, so that its host-to-device copy overlaps the first part (which reads poses only)
   bool useGraph = true; cudaGraphExec_t graphExec[2][3] = {{0, 0, 0}, {0, 0, 0}}; float graphDt = 0.f; uint32_t graphLaunches[2][3] = {{0, 0, 0}, {0, 0, 0}};
   cudaStream_t copyStream = nullptr; cudaEvent_t velEvent = nullptr, orderEvent = nullptr; bool velPending = false;
+  bool anyAggregate = false; uint32_t* aggId = 0;   // PxAggregate membership per actor (ActorRec::aggregate)
   bool anyKinematic = false; uint32_t nKin = 0; uint32_t* kinList = 0; float4 *kinP = 0, *kinQ = 0, *kinFtv = 0; uint32_t* kinHas = 0; std::vector<uint32_t> kinHost;   // kinematic bodies: actor list, pending targets (body frame), friction target velocities per pair
   bool bodyAccel = false; float4 *prevLin = 0, *prevAng = 0; float accelInvDt = 0.f;   // PxSceneFlag::eENABLE_BODY_ACCELERATIONS: velocities the last step started from
   bool profiling = false; cudaEvent_t ev[8] = {0, 0, 0, 0, 0, 0, 0, 0}; float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -154,7 +155,9 @@ __global__ void k_bp_gather(uint32_t nA, const uint32_t* __restrict__ sortedActo
 // pair, otherwise the 7 x 7 BpFilter table indexed by the 3-bit type in the group's low bits -- passed as a 49-bit mask; environment ids as in
 // broadphase.cu:62-80): amin.w = environment id, amax.w = filter group.
 struct EngineFilter {
+  const uint32_t* agg;   // per-actor PxAggregate id (NULL: the scene has none); members of one aggregate without self collisions never pair
   __device__ __forceinline__ bool operator()(const float4& amin, const float4& amax, const float4& bmin, const float4& bmax) const { return bp_test(amin, amax, bmin, bmax); }
+  __device__ __forceinline__ bool pairOk(uint32_t a, uint32_t b) const { if (!agg) return true; const uint32_t ga = agg[a]; return !(ga && ga == agg[b] && !(ga & 0x80000000u)); }
   __device__ __forceinline__ bool isLarge(const float4& amax, uint32_t) const { return (__float_as_uint(amax.w) & 0x200u) != 0; }
 };
 struct GroupFilter {
@@ -167,6 +170,7 @@ struct GroupFilter {
     return ea == NONE32 || eb == NONE32 || ea == eb;
   }
   __device__ __forceinline__ bool isLarge(const float4&, uint32_t a) const { return large[a] != 0u; }
+  __device__ __forceinline__ bool pairOk(uint32_t, uint32_t) const { return true; }
 };
 template <class F>
 __global__ void k_bp_pairs(uint32_t nA, const uint64_t* __restrict__ key, const uint32_t* __restrict__ sortedActor, const float4* __restrict__ sMin,
@@ -183,7 +187,7 @@ __global__ void k_bp_pairs(uint32_t nA, const uint64_t* __restrict__ key, const 
   {  // own row, forward
     const uint64_t last = r1 * nx + (uint64_t)x1;
     for (uint32_t j = i + 1; j < nA && key[j] <= last; ++j)
-      if (filter(amin, amax, sMin[j], sMax[j])) bp_emit(a, sortedActor[j], bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
+      if (filter(amin, amax, sMin[j], sMax[j]) && filter.pairOk(a, sortedActor[j])) bp_emit(a, sortedActor[j], bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
   }
   const int dzs[4] = {0, 1, 1, 1}, dys[4] = {1, -1, 0, 1};
 #pragma unroll
@@ -193,7 +197,7 @@ __global__ void k_bp_pairs(uint32_t nA, const uint64_t* __restrict__ key, const 
     const uint64_t rowBase = ((e * nz + (uint64_t)zz) * ny + (uint64_t)yy) * nx;
     const uint64_t first = rowBase + (uint64_t)x0, last = rowBase + (uint64_t)x1;
     for (uint32_t j = lower_bound_u64(key, nA, first); j < nA && key[j] <= last; ++j)
-      if (filter(amin, amax, sMin[j], sMax[j])) bp_emit(a, sortedActor[j], bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
+      if (filter(amin, amax, sMin[j], sMax[j]) && filter.pairOk(a, sortedActor[j])) bp_emit(a, sortedActor[j], bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
   }
 }
 // global / oversize objects (planes, shapes larger than a cell, env-less actors in env scenes) against everything
@@ -207,7 +211,7 @@ __global__ void k_bp_large(uint32_t nA, uint32_t nLarge, const uint32_t* __restr
   for (uint32_t l = 0; l < nLarge; ++l) {
     const uint32_t b = largeList[l];
     if (b == a || (aLarge && a > b)) continue;
-    if (filter(amin, amax, aabbMin[b], aabbMax[b])) bp_emit(a, b, bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
+    if (filter(amin, amax, aabbMin[b], aabbMax[b]) && filter.pairOk(a, b)) bp_emit(a, b, bitsA, pairKeys, &counters[C_NPAIRS_NEW], cap, &counters[C_ERROR]);
   }
 }
 __global__ void k_clamp_count(uint32_t* __restrict__ counters, uint32_t cap, uint32_t* __restrict__ nPairsCur) {
@@ -902,7 +906,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
   if (!s) return;
   cudaStreamSynchronize(s->stream);
   drop_graphs(s);
-  void* ptrs[] = {s->kinList, s->kinP, s->kinQ, s->kinHas, s->kinFtv, s->prevLin, s->prevAng, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
+  void* ptrs[] = {s->aggId, s->kinList, s->kinP, s->kinQ, s->kinHas, s->kinFtv, s->prevLin, s->prevAng, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->filterData, s->shapeOff, s->tcPos, s->tcQuat, s->s2bP, s->s2bQ, s->b2aP, s->b2aQ, s->actorPos, s->actorQuat, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
@@ -1040,6 +1044,13 @@ static void rebuild_grid(PxbScene* s) {
   while ((long double)envCount * g.nx * g.ny * g.nz > 4.0e18L) { if (g.nx >= g.ny && g.nx >= g.nz) g.nx = (g.nx + 1) / 2; else if (g.ny >= g.nz) g.ny = (g.ny + 1) / 2; else g.nz = (g.nz + 1) / 2; }
   g.keyBits = bits_for((uint64_t)envCount * (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz + 1);
   s->anyLocks = anyLocks;
+  { bool anyAgg = false; for (auto& r : s->recs) anyAgg |= r.aggregate != 0 && !(r.flags & ACTOR_REMOVED);
+    if (anyAgg) {
+      if (!s->aggId && dalloc(s->aggId, s->capA)) { s->abort = true; return; }
+      std::vector<uint32_t> ag(s->nA); for (uint32_t a = 0; a < s->nA; ++a) ag[a] = s->recs[a].aggregate;
+      cudaMemcpyAsync(s->aggId, ag.data(), 4 * (size_t)s->nA, cudaMemcpyHostToDevice, s->stream); cudaStreamSynchronize(s->stream);
+    }
+    if (anyAgg != s->anyAggregate) { s->anyAggregate = anyAgg; drop_graphs(s); } }
   s->anyKinematic = !s->kinHost.empty(); s->nKin = (uint32_t)s->kinHost.size();
   if (s->anyKinematic && !s->kinP) {
     if (dalloc(s->kinList, s->capA) || dalloc(s->kinP, s->capA) || dalloc(s->kinQ, s->capA) || dalloc(s->kinHas, s->capA) || dalloc(s->kinFtv, s->capPairs)) { s->abort = true; return; }
@@ -1151,6 +1162,7 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
       if (s->sleepThreshold > 0.f) return fail(PXB_ERR_UNSUPPORTED, "kinematic bodies in scenes with sleeping enabled are not built");
       if (r.geomType == PXB_GEOM_PLANE) return fail(PXB_ERR_INVALID, "planes are static");
     }
+    if ((r.aggregate & 0x7fffffffu) >= 0x40000000u) return fail(PXB_ERR_INVALID, "aggregate ids are 1 .. 2^30 - 1 (bit 31 = self collisions)");
   }
   for (uint32_t i = 0; i < nb; ++i) {
     const ActorRec& r = in[i];
@@ -1239,7 +1251,7 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     LAUNCH(k_env_begin, 1, 32, s->counters);
     EnvBpArgs A;
     A.nEnv = s->nEnv; A.maxList = s->envMaxList; A.bitsA = s->bitsA; A.cap = s->capPairs; A.ringMask = s->ringMask; A.externalTight = externalTight ? 1 : 0; A.contactOffset = s->desc.contactOffset;
-    A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight; A.hulls = hull_arrays(s); A.L = local_poses(s); A.shapeOff = s->hasShapeOff ? s->shapeOff : nullptr;
+    A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight; A.hulls = hull_arrays(s); A.L = local_poses(s); A.aggId = s->anyAggregate ? s->aggId : nullptr; A.shapeOff = s->hasShapeOff ? s->shapeOff : nullptr;
     A.oldKeys = s->pairKeys[prev]; A.oldSlots = s->pairSlots[prev]; A.oldSeg = s->envSeg[prev]; A.newKeys = s->pairKeys[cur]; A.newSlots = s->pairSlots[cur]; A.newSeg = s->envSeg[cur];
     A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions; A.slotColour = s->slotColour; A.touch = touch_lists(s);
     const size_t smem = (size_t)ENV_BP_WARPS * (s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t)) + ENV_BP_STAGE * sizeof(uint64_t));
@@ -1262,8 +1274,8 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
   const bool oddPasses = (((2 * s->bitsA + 7) / 8) & 1u) != 0;
   uint64_t* emit = oddPasses ? s->pairKeyAlt : s->pairKeys[cur];
   uint64_t* other = oddPasses ? s->pairKeys[cur] : s->pairKeyAlt;
-  LAUNCH(k_bp_pairs<EngineFilter>, cdiv(nA, 128), 128, nA, sk, sv, s->sMin, s->sMax, s->grid, s->bitsA, emit, s->counters, s->capPairs, EngineFilter());
-  if (s->nLarge) LAUNCH(k_bp_large<EngineFilter>, cdiv(nA, B), B, nA, s->nLarge, s->largeList, s->aabbMin, s->aabbMax, s->bitsA, emit, s->counters, s->capPairs, EngineFilter());
+  LAUNCH(k_bp_pairs<EngineFilter>, cdiv(nA, 128), 128, nA, sk, sv, s->sMin, s->sMax, s->grid, s->bitsA, emit, s->counters, s->capPairs, EngineFilter{s->anyAggregate ? s->aggId : nullptr});
+  if (s->nLarge) LAUNCH(k_bp_large<EngineFilter>, cdiv(nA, B), B, nA, s->nLarge, s->largeList, s->aabbMin, s->aabbMax, s->bitsA, emit, s->counters, s->capPairs, EngineFilter{s->anyAggregate ? s->aggId : nullptr});
   LAUNCH(k_clamp_count, 1, 32, s->counters, s->capPairs, s->nPairsDev + cur);
   radix_sort_pairs(emit, s->pairValTmp, other, s->pairValAlt, s->nPairsDev + cur, 2 * s->bitsA, s->rsTmp, st);
   s->launches += 3 * ((2 * s->bitsA + 7) / 8);

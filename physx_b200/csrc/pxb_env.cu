@@ -20,7 +20,7 @@ cudaError_t pxb_env_set_attributes(int solveSmemMax, int bpSmemMax) {
   return e;
 }
 void pxb_launch_env_bp(cudaStream_t st, const EnvBpArgs& A, bool hulls, size_t smem) {
-  const bool local = A.L.s2bP != nullptr || A.shapeOff != nullptr;
+  const bool local = A.L.s2bP != nullptr || A.shapeOff != nullptr || A.aggId != nullptr;
 #define BP_PICK(K, ...) do { if (hulls) { if (local) K<true, true>__VA_ARGS__; else K<true, false>__VA_ARGS__; } else { if (local) K<false, true>__VA_ARGS__; else K<false, false>__VA_ARGS__; } } while (0)
   if (A.nEnv <= PXB_ENV_BP_CTA_MAX_ENVS) {   // few environments: a CTA per environment (the warps share the rows), else the step is one warp's latency
     const size_t ctaSmem = (size_t)A.maxList * (2 * sizeof(float4) + 2 * sizeof(uint32_t));

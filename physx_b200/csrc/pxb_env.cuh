@@ -27,7 +27,7 @@ struct EnvBpArgs {
   const float4 *pos, *quat, *dims; const uint32_t *geomFlags, *envId; float* tight; HullArrays hulls;
   const uint64_t* oldKeys; const uint32_t* oldSlots; const uint2* oldSeg;
   uint64_t* newKeys; uint32_t* newSlots; uint2* newSeg;
-  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions; TouchLists touch; LocalPoses L; const float2* shapeOff;   // shapeOff: per-actor (contactOffset, restOffset), LOCAL instantiation only
+  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions; TouchLists touch; LocalPoses L; const uint32_t* aggId; const float2* shapeOff;   // shapeOff: per-actor (contactOffset, restOffset), LOCAL instantiation only
 };
 
 #define ENV_BP_STAGE 256   // pair keys staged per warp in shared memory before the segment base is known
@@ -35,9 +35,17 @@ struct EnvBpArgs {
 // branch-free AABB test of the environment path: closed-interval overlap on all axes (PxgIntegerAABB::intersects / ABP
 // intersect2D semantics) and at least one dynamic actor (BpFiltering.h:99-114).  Every list member is in the warp's own
 // environment or env-less, so the environment filter (broadphase.cu:62-80) always passes here.
+// AGG (the LOCAL instantiations): the .w of the minima carries an aggregate key -- the aggregate id for members of an aggregate without self collisions, a value
+// unique in the list otherwise -- and equal keys never pair.
+template <bool AGG = false>
 __device__ __forceinline__ bool env_bp_test(const float4& amin, const float4& amax, const float4& bmin, const float4& bmax) {
   const bool sep = (amin.x > bmax.x) | (bmin.x > amax.x) | (amin.y > bmax.y) | (bmin.y > amax.y) | (amin.z > bmax.z) | (bmin.z > amax.z);
-  return !sep & (((__float_as_uint(amax.w) | __float_as_uint(bmax.w)) & 0x100u) != 0);
+  const bool ok = !sep & (((__float_as_uint(amax.w) | __float_as_uint(bmax.w)) & 0x100u) != 0);
+  return AGG ? (ok & (__float_as_uint(amin.w) != __float_as_uint(bmin.w))) : ok;
+}
+__device__ __forceinline__ uint32_t env_agg_key(const uint32_t* __restrict__ aggId, uint32_t a, uint32_t k) {
+  const uint32_t g = aggId ? aggId[a] : 0u;
+  return (g && !(g & 0x80000000u)) ? g : (0x40000000u | k);
 }
 
 // a7: pair lifecycle of one environment against last frame's segment of the same environment (both sorted); `tid` of `stride` cooperating threads.
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
       if (own) for (int c = 0; c < 3; ++c) { A.tight[a * 6 + c] = mn[c]; A.tight[a * 6 + 3 + c] = mx[c]; }
     }
     const float co = (LOCAL && A.shapeOff) ? A.shapeOff[a].x : A.contactOffset;   // every bound is inflated by its own shape's contact offset
-    sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(env));
+    sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(LOCAL ? env_agg_key(A.aggId, a, k) : env));
     sMax[k] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf_dynamic(gf) ? gf : (gf & ~0x100u)));   // kinematic bodies pair with dynamic ones only, like statics (the test below reads the dynamic bit)
     sAct[k] = a;
   }
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
     const float4 amin = sMin[i], amax = sMax[i]; const uint64_t hiKey = (uint64_t)sAct[i] << A.bitsA;
     for (uint32_t j0 = i + 1; j0 < n; j0 += 32) {
       const uint32_t j = j0 + lane;
-      const bool hit = j < n && env_bp_test(amin, amax, sMin[j], sMax[j]);
+      const bool hit = j < n && env_bp_test<LOCAL>(amin, amax, sMin[j], sMax[j]);
       const uint32_t m = __ballot_sync(0xffffffffu, hit);
       if (m) {
         const uint32_t w = cnt + __popc(m & ((1u << lane) - 1u));
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
       const float4 amin = sMin[i], amax = sMax[i]; const uint64_t hiKey = (uint64_t)sAct[i] << A.bitsA;
       for (uint32_t j0 = i + 1; j0 < n; j0 += 32) {
         const uint32_t j = j0 + lane;
-        const bool hit = j < n && env_bp_test(amin, amax, sMin[j], sMax[j]);
+        const bool hit = j < n && env_bp_test<LOCAL>(amin, amax, sMin[j], sMax[j]);
         const uint32_t m = __ballot_sync(0xffffffffu, hit);
         if (hit) A.newKeys[base + w + __popc(m & ((1u << lane) - 1u))] = hiKey | sAct[j];
         w += __popc(m);
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(ENV_BP_CTA_THREADS) k_env_bp_cta(const EnvBpAr
       if (own) for (int c = 0; c < 3; ++c) { A.tight[a * 6 + c] = mn[c]; A.tight[a * 6 + 3 + c] = mx[c]; }
     }
     const float co = (LOCAL && A.shapeOff) ? A.shapeOff[a].x : A.contactOffset;   // every bound is inflated by its own shape's contact offset
-    sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(env));
+    sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(LOCAL ? env_agg_key(A.aggId, a, k) : env));
     sMax[k] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf_dynamic(gf) ? gf : (gf & ~0x100u)));   // kinematic bodies pair with dynamic ones only, like statics (the test below reads the dynamic bit)
     sAct[k] = a;
   }
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(ENV_BP_CTA_THREADS) k_env_bp_cta(const EnvBpAr
     uint32_t c = 0;
     if (i + 1 < n) {
       const float4 amin = sMin[i], amax = sMax[i];
-      for (uint32_t j0 = i + 1; j0 < n; j0 += 32) { const uint32_t j = j0 + lane; c += __popc(__ballot_sync(0xffffffffu, j < n && env_bp_test(amin, amax, sMin[j], sMax[j]))); }
+      for (uint32_t j0 = i + 1; j0 < n; j0 += 32) { const uint32_t j = j0 + lane; c += __popc(__ballot_sync(0xffffffffu, j < n && env_bp_test<LOCAL>(amin, amax, sMin[j], sMax[j]))); }
     }
     if (lane == 0) sRow[i] = c;
   }
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(ENV_BP_CTA_THREADS) k_env_bp_cta(const EnvBpAr
       uint32_t w = sRow[i];
       for (uint32_t j0 = i + 1; j0 < n; j0 += 32) {
         const uint32_t j = j0 + lane;
-        const bool hit = j < n && env_bp_test(amin, amax, sMin[j], sMax[j]);
+        const bool hit = j < n && env_bp_test<LOCAL>(amin, amax, sMin[j], sMax[j]);
         const uint32_t m = __ballot_sync(0xffffffffu, hit);
         if (hit) A.newKeys[base + w + __popc(m & ((1u << lane) - 1u))] = hiKey | sAct[j];
         w += __popc(m);

@@ -31,7 +31,7 @@ ACTOR_DTYPE = np.dtype([
     ("pos", "<f4", 3), ("quat", "<f4", 4), ("dims", "<f4", 4),
     ("linVel", "<f4", 3), ("angVel", "<f4", 3), ("mass", "<f4"), ("inertia", "<f4", 3),
     ("linDamping", "<f4"), ("angDamping", "<f4"), ("maxLinVel", "<f4"), ("maxAngVel", "<f4"),
-    ("maxDepenetrationVel", "<f4"), ("materialIndex", "<u4"), ("reserved1", "<f4"),
+    ("maxDepenetrationVel", "<f4"), ("materialIndex", "<u4"), ("aggregate", "<u4"),
 ])
 MATERIAL_DTYPE = np.dtype([("staticFriction", "<f4"), ("dynamicFriction", "<f4"), ("restitution", "<f4"), ("bits", "<u4")])
 COMBINE_AVERAGE, COMBINE_MIN, COMBINE_MULTIPLY, COMBINE_MAX = 0, 1, 2, 3
@@ -946,3 +946,33 @@ def kinematic_targets(scene, steps):
                 p[1] += 0.8 * np.sin(2.0 * time) - 0.3
             out[t, n] = np.concatenate([q, p])
     return out.astype(np.float32)
+
+
+AGGREGATE_SELF_COLLISION = 0x80000000   # ActorRec.aggregate bit 31
+
+
+def aggregates_mix(n_envs=0, env_pitch=8.0, seed=41, **hdr):
+    """PxAggregate membership (first half).  Per group: aggregate A = four boxes stacked with 40 % overlap and NO self collisions (they fall through
+    each other and come to rest side by side / on the free boxes), aggregate B = a column with 2 cm overlaps WITH self collisions (the overlaps are pushed apart, the column stands), three free boxes
+    and a sphere that collide with every member.  n_envs > 0: one group per environment."""
+    rng = np.random.RandomState(seed)
+    groups = max(1, n_envs)
+    per = 4 + 4 + 4
+    a = _new_actors(groups * per)
+    he = np.float32(0.25)
+    for g in range(groups):
+        o = g * per; ox = np.float32(env_pitch * g)
+        for k in range(4):
+            a["pos"][o + k] = (ox + 0.05 * k, he + 0.3 * k, 0.03 * k)
+            a["pos"][o + 4 + k] = (ox + 2.0 + 0.05 * k, he + 0.48 * k, -0.03 * k)
+        a["aggregate"][o:o + 4] = 2 * g + 1
+        a["aggregate"][o + 4:o + 8] = (2 * g + 2) | AGGREGATE_SELF_COLLISION
+        for k in range(3):
+            a["pos"][o + 8 + k] = (ox + 0.1 + 0.9 * k + rng.uniform(-0.05, 0.05), 2.2 + 0.6 * k, rng.uniform(-0.1, 0.1))
+        a["pos"][o + 11] = (ox + 0.3, 4.2, 0.1)
+        if n_envs:
+            a["envId"][o:o + per] = g
+    idx = np.arange(groups * per)
+    set_box(a, idx[(idx % per) != 11], np.array([he, he, he], dtype=np.float32))
+    set_sphere(a, idx[(idx % per) == 11], np.float32(0.3))
+    return Scene(default_header(**hdr), add_ground_plane(a))

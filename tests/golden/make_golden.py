@@ -198,6 +198,12 @@ def main():
         data = run_reference(sc, steps, kin_targets=scenes.kinematic_targets(sc, steps))
         np.savez_compressed(os.path.join(out, name + ".npz"), **data)
         print(name, "bodies", sc.n_dynamic, "steps", steps, "bytes", os.path.getsize(os.path.join(out, name + ".npz")))
+    # PxAggregate membership with and without self collisions (the harness creates real PxAggregates; its standalone broadphase gives the members of an aggregate
+    # without self collisions one filter group)
+    cases["aggregates_mix"] = (scenes.aggregates_mix(), 100)
+    cases["aggregates_envs_3"] = (scenes.aggregates_mix(n_envs=3), 80)
+    if only:
+        cases = {k: v for k, v in cases.items() if any(k.startswith(o) for o in only)}
     for name, (sc, steps) in cases.items():
         data = run_reference(sc, steps)
         np.savez_compressed(os.path.join(out, name + ".npz"), **data)

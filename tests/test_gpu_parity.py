@@ -1462,3 +1462,27 @@ def test_kinematic_targets_api():
     wrong = scenes.kinematic_mix(); wrong.actors["flags"][1] = scenes.ACTOR_KINEMATIC
     with pytest.raises(engine.PhysxB200Error):
         engine.Scene(wrong)
+
+
+# ---- PxAggregate membership (members of an aggregate without self collisions never pair) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,env_path", [("aggregates_mix", False), ("aggregates_mix", True), ("aggregates_envs_3", False), ("aggregates_envs_3", True)])
+def test_aggregates_gpu_matches_oracle_and_reference(oracle, name, env_path):
+    """Teacher-forced from the reference's states: created / deleted pairs and manifolds of the reference every step on both paths (aggregates_mix has no environment
+    ids and runs as one environment), states equal to the oracle's (1e-6 / 2e-5; device-wide path with the reference's solver order also within 2e-5 of the reference)."""
+    z, sc = util.load_golden(name)
+    gpu, cpu = engine.Scene(sc, env_path=env_path), oracle.OracleScene(sc)
+    for t in range(z["states"].shape[0] - 1):
+        gpu.setStates(z["states"][t]); cpu.setStates(z["states"][t])
+        order = None if env_path else util.golden_order(z, t)
+        gpu.setConstraintOrder(order); gpu.step(); cpu.step(order)
+        assert gpu.uses_env_path == env_path
+        st, ref, orc = gpu.getStates(), z["states"][t + 1], cpu.getStates()
+        assert np.array_equal(gpu.getCreatedPairs(), util.golden_created(z, t)) and np.array_equal(gpu.getDeletedPairs(), util.golden_deleted(z, t)), f"broadphase, step {t}"
+        assert util.contact_counts(gpu.getPairs(), gpu.getContacts()) == util.golden_contact_counts(z, t), f"manifolds, step {t}"
+        assert np.abs(st[:, :7] - orc[:, :7]).max() < 1e-6 and np.abs(st[:, 7:] - orc[:, 7:]).max() < 2e-5, f"vs oracle, step {t}"
+        if not env_path:
+            assert np.abs(st[:, :7] - ref[:, :7]).max() < 2e-5, f"vs reference, step {t}"
+    lib = gpu._lib
+    bad = sc.actors[1:2].copy(); bad["aggregate"] = 0x40000000
+    assert lib.pxb_scene_add_actors(gpu._h, bad.ctypes.data, 1) < 0
