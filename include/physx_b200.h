@@ -33,7 +33,7 @@ enum { PXB_GEOM_SPHERE = 0, PXB_GEOM_PLANE = 1, PXB_GEOM_CAPSULE = 2, PXB_GEOM_B
 enum { PXB_ACTOR_DYNAMIC = 1u,
        PXB_ACTOR_KINEMATIC = 2u /* together with PXB_ACTOR_DYNAMIC: PxRigidBodyFlag::eKINEMATIC.  The body has infinite mass, is moved by pxb_scene_set_kinematic_targets and stands still in steps
                                    without a target; it pushes / carries dynamic bodies with the velocity of its move (ScKinematics.cpp:44-97, DyTGSContactPrep.cpp:406-409, :724-727) and
-                                   generates no pairs against statics or other kinematics (PxPairFilteringMode::eDEFAULT).  It keeps its place in the dynamic-body order.  TGS solver, scenes
+                                   generates no pairs against statics or other kinematics (PxPairFilteringMode::eDEFAULT).  It keeps its place in the dynamic-body order.  TGS and PGS, scenes
                                    without sleeping; both paths (on the environment path the fused state export gives way to the export kernel). */ };
 enum { PXB_SOLVER_PGS = 0, PXB_SOLVER_TGS = 1 };
 

@@ -1051,6 +1051,7 @@ static void rebuild_grid(PxbScene* s) {
       cudaMemcpyAsync(s->aggId, ag.data(), 4 * (size_t)s->nA, cudaMemcpyHostToDevice, s->stream); cudaStreamSynchronize(s->stream);
     }
     if (anyAgg != s->anyAggregate) { s->anyAggregate = anyAgg; drop_graphs(s); } }
+  s->kinHost.clear(); for (uint32_t a = 0; a < s->nA; ++a) if ((s->recs[a].flags & PXB_ACTOR_KINEMATIC) && !(s->recs[a].flags & ACTOR_REMOVED)) s->kinHost.push_back(a);
   s->anyKinematic = !s->kinHost.empty(); s->nKin = (uint32_t)s->kinHost.size();
   if (s->anyKinematic && !s->kinP) {
     if (dalloc(s->kinList, s->capA) || dalloc(s->kinP, s->capA) || dalloc(s->kinQ, s->capA) || dalloc(s->kinHas, s->capA) || dalloc(s->kinFtv, s->capPairs)) { s->abort = true; return; }
@@ -1158,7 +1159,6 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
       return fail(PXB_ERR_UNSUPPORTED, "geometry type not supported yet");
     if (r.flags & PXB_ACTOR_KINEMATIC) {
       if (!(r.flags & PXB_ACTOR_DYNAMIC)) return fail(PXB_ERR_INVALID, "PXB_ACTOR_KINEMATIC is a flag of dynamic actors (PxRigidBodyFlag::eKINEMATIC)");
-      if (s->desc.solverType == PXB_SOLVER_PGS) return fail(PXB_ERR_UNSUPPORTED, "kinematic bodies are built for the TGS solver only");
       if (s->sleepThreshold > 0.f) return fail(PXB_ERR_UNSUPPORTED, "kinematic bodies in scenes with sleeping enabled are not built");
       if (r.geomType == PXB_GEOM_PLANE) return fail(PXB_ERR_INVALID, "planes are static");
     }
@@ -1169,7 +1169,6 @@ PXB_API int pxb_scene_add_actors(PxbScene* s, const void* recsIn, uint32_t nb) {
     const bool kin = (r.flags & PXB_ACTOR_KINEMATIC) != 0;
     const bool dyn = (r.flags & PXB_ACTOR_DYNAMIC) && !kin;   // mass properties: a kinematic body has none (infinite mass and inertia)
     s->recs.push_back(r);
-    if (kin) s->kinHost.push_back(base + i);
     if (r.geomType == PXB_GEOM_CONVEXMESH) s->recs.back().dims[3] = s->hullDiam[r.hullIdx];   // bounding diameter for the broadphase grid
     if (dyn || kin) { s->dynIndex.push_back((int)s->nDyn); s->dynActor.push_back(base + i); s->nDyn++; } else s->dynIndex.push_back(-1);   // kinematic bodies keep their place in the dynamic-body order (they are PxRigidDynamic)
     const float invMass = (dyn && r.mass > 0.f) ? 1.0f / r.mass : 0.f;
@@ -1372,7 +1371,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     const bool fusedExport = s->exportOn && s->envDynContiguous && !s->nKin;   // kinematic bodies take their new pose after the kernel (k_kin_finalize): export afterwards
     A.exportTab = fusedExport ? s->exportTab : nullptr; A.envDyn = s->envDyn; A.dynActor = s->dynActorDev;
     const size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
-    A.M = material_args(s); A.kinFtv = (s->nKin && !pgs) ? s->kinFtv : nullptr;
+    A.M = material_args(s); A.kinFtv = (s->nKin && !pgs) ? s->kinFtv : nullptr; A.kinOn = s->nKin ? 1u : 0u;
     const bool ext = s->anyLocks || s->forcesUsed || s->nMaterials != 0 || s->hasShapeOff || s->nKin != 0;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
     pxb_launch_env_solve(st, A, s->envSolveThreads, pgs, ext, smem);
     s->launches++;
@@ -1444,6 +1443,7 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     pxb_launch_writeback_rows(st, s->capPairs, s->counters, R, s->pairSlots[cur], s->cForce, s->frictions, s->contactData ? s->frReport : nullptr, s->pairBodies, s->pos, s->quat); s->launches++;
     if (pgs) {
       pxb_launch_finalize_bodies_pgs(st, s->nDyn, s->dynActorDev, dt, s->pos, s->quat, s->linVel, s->angVel, s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->invInertia, SA, s->geomFlags); s->launches++;
+      if (s->nKin) LAUNCH(k_kin_finalize, cdiv(s->nKin, 128), 128, s->nKin, s->kinList, s->pos, s->quat, s->kinP, s->kinQ, s->kinHas);
       if (s->exportOn) LAUNCH(k_states_export, cdiv(s->nDyn, 256), 256, s->nDyn, s->dynActorDev, s->pos, s->quat, s->linVel, s->angVel, s->exportTab);
       MARK(6);
       CK(cudaGetLastError());

@@ -248,7 +248,7 @@ struct EnvSolveArgs {
   uint32_t anyLocks;   // some actor carries PxRigidDynamicLockFlags (uniform fast path otherwise)
   float4 *extForce, *extTorque;   // pending eFORCE / eTORQUE writes (NULL until the application uses them)
   MaterialArgs M;   // material table (matTab NULL: the scene's single material in P)
-  float4* kinFtv;   // scenes with kinematic bodies (EXT instantiation, TGS): friction target velocities per pair index; NULL otherwise
+  float4* kinFtv; uint32_t kinOn;   // scenes with kinematic bodies (kinOn; EXT instantiation): TGS friction target velocities per pair index (NULL with PGS)
   const ExportTable* exportTab; const uint2* envDyn; const uint32_t* dynActor;   // fused state export: targets, per environment {first dynamic-body index, count}
 };
 #ifdef PXB_ENV_TIMING
@@ -481,13 +481,13 @@ __device__ __forceinline__ void env_prep_one(const EnvSolveArgs& A, const ConLis
   B.linVel0 = V3(vLin[l0]); B.angVel0 = V3(vAng[l0]); B.sI0 = load_sym(bIA[l0], bIB[l0]);
   if (dyn1) { B.linVel1 = V3(vLin[l1]); B.angVel1 = V3(vAng[l1]); B.sI1 = load_sym(bIA[l1], bIB[l1]); }
   else { B.linVel1 = V3(0, 0, 0); B.angVel1 = V3(0, 0, 0); B.sI1.c0 = B.sI1.c1 = B.sI1.c2 = V3(0, 0, 0); }
-  if (EXT && (A.M.matTab || A.M.shapeOff || A.kinFtv)) {   // material table / per-shape rest offsets / kinematic bodies: this pair's own parameters (the plain instantiation carries none of this)
+  if (EXT && (A.M.matTab || A.M.shapeOff || A.kinOn)) {   // material table / per-shape rest offsets / kinematic bodies: this pair's own parameters (the plain instantiation carries none of this)
     SolverParams Pm = A.P; const bool noFriction = A.M.matTab ? pair_material(A.M, bb.x, bb.y, Pm) : false;
     if (A.M.shapeOff) Pm.restDistance = A.M.shapeOff[bb.x].y + A.M.shapeOff[bb.y].y;
-    const bool kin1 = !PGS && A.kinFtv && (A.geomFlags[bb.y] & 0x800u);   // kinematic body B (see k_prep_rows)
+    const bool kin1 = A.kinOn && (A.geomFlags[bb.y] & 0x800u);   // kinematic body B (see k_prep_rows)
     if (kin1) { B.pen1 = -A.invInertia[bb.y].w; B.linVel1 = V3(A.linVel[bb.y]); B.angVel1 = V3(A.angVel[bb.y]); }
     if (PGS) prep_constraint_pgs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, Pm, noFriction);
-    else prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, Pm, noFriction, kin1, kin1 ? A.kinFtv + i : nullptr);
+    else prep_constraint_regs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, Pm, noFriction, kin1, (kin1 && A.kinFtv) ? A.kinFtv + i : nullptr);
     return;
   }
   if (PGS) prep_constraint_pgs(r, i, l0, l1, B, A.cHdr, A.cPts, A.frictions + (size_t)A.pairSlots[i] * PXB_FRICTION_F4, A.P);

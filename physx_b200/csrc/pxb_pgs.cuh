@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(128) k_prep_rows(const uint32_t* __restrict__ 
   const uint2 bb = pairBodies[i]; const uint32_t b0 = bb.x, b1 = bb.y;
   const uint32_t gf1 = geomFlags[b1];
   const bool dyn1 = gf_dynamic(gf1);
-  const bool kin1 = !PGS && kinFtv && (gf1 & 0x800u);   // kinematic body B: a static solver body whose velocity enters the rows as target velocity (copyToSolverBodyDataStepKinematic, DyTGSDynamics.cpp:245-274)
+  const bool kin1 = (gf1 & 0x800u) != 0;   // kinematic body B: a static solver body whose velocity enters the rows (TGS: as target velocity, copyToSolverBodyDataStepKinematic DyTGSDynamics.cpp:245-274; PGS: through the
+                                           // pre-solver velocities the rows are built from, KinematicCopyTask DyDynamics.cpp:1855-1870)
   RegRows r;
   if (__float_as_int(cHdr[i].w) == 0) {  // empty constraint kept only for the colouring (see k_flag_ordered)
     r.h0 = r.h1 = make_float4(0, 0, 0, 0); r.h2 = make_uint4(b0, dyn1 ? b1 : NONE32, 0u, i); r.pc0 = r.pc1 = r.ap = r.t0 = r.t1 = r.fap = make_float4(0, 0, 0, 0); r.broken = 0u;
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(128) k_prep_rows(const uint32_t* __restrict__ 
   if (M.matTab) noFriction = pair_material(M, b0, b1, P);   // material table: this pair's combined coefficients (P is this thread's copy)
   if (M.shapeOff) P.restDistance = M.shapeOff[b0].y + M.shapeOff[b1].y;   // per-shape rest offsets: the pair's rest distance is their sum (PxcNpWorkUnit::restDistance)
   if (PGS) prep_constraint_pgs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, noFriction);
-  else prep_constraint_regs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, noFriction, kin1, kin1 ? kinFtv + i : nullptr);
+  else prep_constraint_regs(r, i, b0, dyn1 ? b1 : NONE32, B, cHdr, cPts, frictions + (size_t)pairSlots[i] * PXB_FRICTION_F4, P, noFriction, kin1, (kin1 && kinFtv) ? kinFtv + i : nullptr);
   rows_store(R, k, r);
 }
 
@@ -340,7 +341,7 @@ __global__ void k_finalize_bodies_pgs(uint32_t nDyn, const uint32_t* __restrict_
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nDyn) return;
   const uint32_t a = dynActor[d];
-  if (body_asleep(S, a) || !(geomFlags[a] & 0x100u)) return;   // (removed actors lose their dynamic bit)
+  if (body_asleep(S, a) || !gf_dynamic(geomFlags[a])) return;   // (removed actors lose their dynamic bit; kinematic bodies move in k_kin_finalize)
   const float4 p4 = pos[a]; v3 p = V3(p4.x, p4.y, p4.z); q4 q = Q4(quat[a]); v3 lv = V3(linVel[a]), av = V3(angVel[a]);
   const m33 sI = load_sym(sbIA[a], sbIB[a]);
   v3 motionLin, motionAng;   // motionVelocityArray after integrateCore

@@ -191,7 +191,7 @@ def main():
         print(name, "bodies", sc.n_dynamic, "steps", 80, "bytes", os.path.getsize(os.path.join(out, name + ".npz")))
     # kinematic bodies (PxRigidBodyFlag::eKINEMATIC + setKinematicTarget every step): conveyor, lift, rotating paddle, a kinematic without target, filtered kinematic pairs;
     # device-wide and with environment ids
-    kinem = {"kinematic_mix": (scenes.kinematic_mix(), 120), "kinematic_envs_3": (scenes.kinematic_mix(n_envs=3), 90)}
+    kinem = {"kinematic_mix": (scenes.kinematic_mix(), 120), "kinematic_envs_3": (scenes.kinematic_mix(n_envs=3), 90), "pgs_kinematic_mix": (scenes.kinematic_mix(solver=scenes.SOLVER_PGS), 120)}
     for name, (sc, steps) in kinem.items():
         if only and not any(name.startswith(o) for o in only):
             continue

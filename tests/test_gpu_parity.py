@@ -1382,7 +1382,7 @@ def test_acceleration_getters_and_events(env_path):
 
 # ---- kinematic bodies (PxRigidBodyFlag::eKINEMATIC, PxRigidDynamic::setKinematicTarget) ----
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,env_path", [("kinematic_mix", False), ("kinematic_envs_3", False), ("kinematic_envs_3", True)])
+@pytest.mark.parametrize("name,env_path", [("kinematic_mix", False), ("kinematic_envs_3", False), ("kinematic_envs_3", True), ("pgs_kinematic_mix", False), ("pgs_kinematic_mix", True)])
 def test_kinematic_bodies_gpu_matches_oracle_and_reference(oracle, name, env_path):
     """Conveyor, lift, rotating paddle, a kinematic without target, kinematics crossing each other and the ground plane; targets before every step.  Teacher-forced from the
     reference's states: kinematic poses equal to the targets bit for bit, kinematic velocities 1e-6 relative (atan2f of the device library), the reference's created / deleted
@@ -1424,13 +1424,13 @@ def test_kinematic_bodies_gpu_matches_oracle_and_reference(oracle, name, env_pat
         if len(i):
             gpu.setKinematicTargets(i, p)
         gpu.setConstraintOrder(util.golden_order(z, t)); gpu.step()
-        assert np.abs(gpu.getStates()[:, :7] - z["states"][t + 1][:, :7]).max() < 1e-4, f"free running, step {t}"
+        assert np.abs(gpu.getStates()[:, :7] - z["states"][t + 1][:, :7]).max() < (2e-3 if name.startswith("pgs") else 1e-4), f"free running, step {t}"
 
 
 @pytest.mark.gpu
 def test_kinematic_targets_api():
     """device-pointer variant == host variant (CUDA graph replay included: no constraint order given); errors: a non-kinematic body, an index out of range (reported by
-    fetchResults for the device variant), PGS / sleeping scenes, a kinematic flag on a static actor."""
+    fetchResults for the device variant), scenes with sleeping, a kinematic flag on a static actor."""
     import torch
     z, sc = util.load_golden("kinematic_mix")
     a, b = engine.Scene(sc), engine.Scene(sc)
@@ -1456,9 +1456,8 @@ def test_kinematic_targets_api():
     with pytest.raises(engine.PhysxB200Error):
         a.step()
     a.step()                                                                                                              # reported once, the scene carries on
-    for kw in (dict(solver=scenes.SOLVER_PGS), dict(sleep_threshold=0.005)):
-        with pytest.raises(engine.PhysxB200Error):
-            engine.Scene(scenes.kinematic_mix(**kw))
+    with pytest.raises(engine.PhysxB200Error):
+        engine.Scene(scenes.kinematic_mix(sleep_threshold=0.005))
     wrong = scenes.kinematic_mix(); wrong.actors["flags"][1] = scenes.ACTOR_KINEMATIC
     with pytest.raises(engine.PhysxB200Error):
         engine.Scene(wrong)
