@@ -34,7 +34,9 @@ enum { PXB_ACTOR_DYNAMIC = 1u,
        PXB_ACTOR_KINEMATIC = 2u /* together with PXB_ACTOR_DYNAMIC: PxRigidBodyFlag::eKINEMATIC.  The body has infinite mass, is moved by pxb_scene_set_kinematic_targets and stands still in steps
                                    without a target; it pushes / carries dynamic bodies with the velocity of its move (ScKinematics.cpp:44-97, DyTGSContactPrep.cpp:406-409, :724-727) and
                                    generates no pairs against statics or other kinematics (PxPairFilteringMode::eDEFAULT).  It keeps its place in the dynamic-body order.  TGS and PGS, scenes
-                                   without sleeping; both paths (on the environment path the fused state export gives way to the export kernel). */ };
+                                   without sleeping; both paths (on the environment path the fused state export gives way to the export kernel). */,
+       PXB_ACTOR_DISABLE_GRAVITY = 4u, /* PxActorFlag::eDISABLE_GRAVITY (bodyCoreComputeUnconstrainedVelocity, DyBodyCoreIntegrator.h:55-59) */
+       PXB_ACTOR_GYROSCOPIC = 8u       /* PxRigidBodyFlag::eENABLE_GYROSCOPIC_FORCES (copyToSolverBodyDataStep DyTGSDynamics.cpp:177-193, copyToSolverBodyData DyRigidBodyToSolverBody.cpp:53-70) */ };
 enum { PXB_SOLVER_PGS = 0, PXB_SOLVER_TGS = 1 };
 
 /* Scene description: the PxSceneDesc / PxGpuDynamicsMemoryConfig fields the hot path consumes

@@ -66,10 +66,10 @@ static inline void pxo_transform_inertia(v3 invD, const m33* M, m33* out) { /* C
 }
 
 /* DyBodyCoreIntegrator.h:39-81 */
-static inline void pxo_unconstrained_velocity(v3 gravity, float dt, float linDamping, float angDamping, float maxLinVelSq, float maxAngVelSq, v3* lv, v3* av) {
+static inline void pxo_unconstrained_velocity(v3 gravity, float dt, float linDamping, float angDamping, float maxLinVelSq, float maxAngVelSq, v3* lv, v3* av, int disableGravity) {
   v3 l = *lv, a = *av;
   const float oml = 1.0f - linDamping * dt, oma = 1.0f - angDamping * dt;
-  l = v3add(l, v3scale(v3scale(gravity, dt), 1.0f)); /* gravity*dt*accelScale, accelScale = 1 */
+  if (!disableGravity) l = v3add(l, v3scale(v3scale(gravity, dt), 1.0f)); /* gravity*dt*accelScale, accelScale = 1; PxActorFlag::eDISABLE_GRAVITY skips the term */
   const float lm = oml >= 0.f ? oml : 0.f, am = oma >= 0.f ? oma : 0.f;
   l = v3scale(l, lm); a = v3scale(a, am);
   const float lsq = v3lensq(l); if (lsq > maxLinVelSq) l = v3scale(l, sqrtf(maxLinVelSq / lsq));
@@ -77,7 +77,21 @@ static inline void pxo_unconstrained_velocity(v3 gravity, float dt, float linDam
   *lv = l; *av = a;
 }
 
-/* DyTGSDynamics.cpp:154-243 (no gyroscopic forces, no lock flags) */
+/* PxRigidBodyFlag::eENABLE_GYROSCOPIC_FORCES: DyTGSDynamics.cpp:177-193 = DyRigidBodyToSolverBody.cpp:53-70 (scalar PxVec3 / PxQuat arithmetic) */
+static inline v3 pxo_gyroscopic(v3 av, v3 invInertia, q4 q, float dt) {
+  const v3 localInertia = V3(invInertia.x == 0.f ? 0.f : 1.f / invInertia.x, invInertia.y == 0.f ? 0.f : 1.f / invInertia.y, invInertia.z == 0.f ? 0.f : 1.f / invInertia.z);
+  const v3 localAngVel = q4rotinv(q, av);
+  const v3 origMom = v3mul(localInertia, localAngVel);
+  const v3 c = v3cross(localAngVel, origMom); const v3 torque = V3(-c.x, -c.y, -c.z);
+  v3 newMom = v3add(origMom, v3scale(torque, dt));
+  const float denom = sqrtf(newMom.x * newMom.x + newMom.y * newMom.y + newMom.z * newMom.z);
+  const float ratio = denom > 0.f ? sqrtf(origMom.x * origMom.x + origMom.y * origMom.y + origMom.z * origMom.z) / denom : 0.f;
+  newMom = v3scale(newMom, ratio);
+  const v3 newDeltaAngVel = q4rot(q, v3sub(v3mul(invInertia, newMom), localAngVel));
+  return v3add(av, newDeltaAngVel);
+}
+
+/* DyTGSDynamics.cpp:154-243 (gyroscopic forces: the caller applies pxo_gyroscopic to `av` first) */
 static inline v3 pxo_lock3(v3 v, uint32_t bits) { if (bits & 1u) v.x = 0.f; if (bits & 2u) v.y = 0.f; if (bits & 4u) v.z = 0.f; return v; }
 static inline void pxo_solver_body_init(PxoSolverBody* b, v3 lv, v3 av, float invMass, v3 invInertia, const xf* pose, float maxDepenVel, uint32_t lockFlags) {
   lv = pxo_lock3(lv, lockFlags & 7u); av = pxo_lock3(av, (lockFlags >> 3) & 7u);   /* DyTGSDynamics.cpp:195-222 */

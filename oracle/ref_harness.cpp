@@ -353,6 +353,8 @@ int main(int argc, char** argv) {
       d->setSleepThreshold(H.sleepThreshold);
       if (H.sleepThreshold == 0.0f) d->setWakeCounter(1e9f);
       d->setRigidDynamicLockFlags(PxRigidDynamicLockFlags(PxU8((r.flags >> 8) & 0x3f)));
+      if (r.flags & PXB_ACTOR_DISABLE_GRAVITY) d->setActorFlag(PxActorFlag::eDISABLE_GRAVITY, true);
+      if (r.flags & PXB_ACTOR_GYROSCOPIC) d->setRigidBodyFlag(PxRigidBodyFlag::eENABLE_GYROSCOPIC_FORCES, true);
       if (r.flags & PXB_ACTOR_KINEMATIC) { d->setRigidBodyFlag(PxRigidBodyFlag::eKINEMATIC, true); kin.push_back(d); }
       dyn.push_back(d);
     }

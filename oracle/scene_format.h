@@ -28,7 +28,10 @@
 enum { PXB_GEOM_SPHERE = 0, PXB_GEOM_PLANE = 1, PXB_GEOM_CAPSULE = 2, PXB_GEOM_BOX = 3, PXB_GEOM_CONVEX = 5 };
 enum { PXB_ACTOR_DYNAMIC = 1u,
        PXB_ACTOR_KINEMATIC = 2u /* with PXB_ACTOR_DYNAMIC: PxRigidBodyFlag::eKINEMATIC -- moved by PxRigidDynamic::setKinematicTarget (ScKinematics.cpp:44-97), infinite mass in the solver,
-                                   no pairs against statics or other kinematics (PxPairFilteringMode::eDEFAULT, BpFiltering.cpp:36-48); it keeps its place in the dynamic-body order */ };
+                                   no pairs against statics or other kinematics (PxPairFilteringMode::eDEFAULT, BpFiltering.cpp:36-48); it keeps its place in the dynamic-body order */,
+       PXB_ACTOR_DISABLE_GRAVITY = 4u /* PxActorFlag::eDISABLE_GRAVITY: no gravity term in the unconstrained velocity (DyBodyCoreIntegrator.h:55-59) */,
+       PXB_ACTOR_GYROSCOPIC = 8u /* PxRigidBodyFlag::eENABLE_GYROSCOPIC_FORCES: the body's angular velocity is advanced by the torque-free gyroscopic term when the solver
+                                    body is built (DyTGSDynamics.cpp:177-193, DyRigidBodyToSolverBody.cpp:53-70) */ };
 enum { PXB_SOLVER_PGS = 0, PXB_SOLVER_TGS = 1 };
 
 typedef struct {

@@ -76,6 +76,7 @@ __device__ __forceinline__ void tight_bounds(uint32_t type, v3 p, q4 q, float4 d
 // pair filter: closed-interval overlap on all axes (PxgIntegerAABB::intersects / ABP intersect2D semantics),
 // at least one dynamic actor (BpFiltering.h:99-114 groups), equal-or-invalid environment ids (broadphase.cu:62-80)
 // geomFlags word: bits 0..7 geometry type, 0x100 dynamic (PxRigidDynamic), 0x200 global / oversize object, 0x400 removed, 0x800 kinematic (PxRigidBodyFlag::eKINEMATIC),
+// 0x1000 PxActorFlag::eDISABLE_GRAVITY, 0x2000 PxRigidBodyFlag::eENABLE_GYROSCOPIC_FORCES,
 // bits 16..21 PxRigidDynamicLockFlags.  A kinematic body is a PxRigidDynamic that the solver treats like a static one (infinite mass, second body of its pairs).
 __device__ __forceinline__ bool gf_dynamic(uint32_t gf) { return (gf & 0x900u) == 0x100u; }
 __device__ __forceinline__ bool bp_test(const float4& amin, const float4& amax, const float4& bmin, const float4& bmax) {

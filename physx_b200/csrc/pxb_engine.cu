@@ -604,7 +604,9 @@ __global__ void k_preintegrate(uint32_t nDyn, const uint32_t* __restrict__ dynAc
       extForce[a] = make_float4(0, 0, 0, 0); extTorque[a] = make_float4(0, 0, 0, 0);
     }
   }
-  if (!asleep) unconstrained_velocity(V3(gx, gy, gz), dt, dm.x, dm.y, dm.z, dm.w, lv, av);
+  const uint32_t gfl = geomFlags[a];
+  if (!asleep) unconstrained_velocity((gfl & 0x1000u) ? V3(0, 0, 0) : V3(gx, gy, gz), dt, dm.x, dm.y, dm.z, dm.w, lv, av);   // eDISABLE_GRAVITY: no gravity term (adding the zero vector changes nothing)
+  if ((gfl & 0x2000u) && !asleep) av = gyroscopic(av, V3(ii.x, ii.y, ii.z), Q4(quat[a]), dt);
   // lock flags: TGS locks both velocities (copyToSolverBodyDataStep, DyTGSDynamics.cpp:195-222); PGS only the angular one (copyToSolverBodyData, DyRigidBodyToSolverBody.cpp:72-98)
   const uint32_t lock = (geomFlags[a] >> 16) & 0x3fu;
   if (lock && !asleep) { if (!pgs) lv = lock3(lv, lock & 7u); av = lock3(av, (lock >> 3) & 7u); }
@@ -1025,7 +1027,8 @@ static void rebuild_grid(PxbScene* s) {
     anyLocks |= ((r.flags >> 8) & 0x3fu) != 0;
     const float d = shape_diameter(r);
     const bool global = !std::isfinite(d) || d > largeThresh || (usesEnv && r.envId == NONE32);
-    gf[a] = (r.geomType & 0xff) | ((r.flags & PXB_ACTOR_DYNAMIC) ? 0x100u : 0u) | (global ? 0x200u : 0u) | ((r.flags & PXB_ACTOR_KINEMATIC) ? 0x800u : 0u) | (((r.flags >> 8) & 0x3fu) << 16);   // bits 16..21: PxRigidDynamicLockFlags
+    gf[a] = (r.geomType & 0xff) | ((r.flags & PXB_ACTOR_DYNAMIC) ? 0x100u : 0u) | (global ? 0x200u : 0u) | ((r.flags & PXB_ACTOR_KINEMATIC) ? 0x800u : 0u) | ((r.flags & PXB_ACTOR_DISABLE_GRAVITY) ? 0x1000u : 0u) | ((r.flags & PXB_ACTOR_GYROSCOPIC) ? 0x2000u : 0u) | (((r.flags >> 8) & 0x3fu) << 16);
+    anyLocks |= (r.flags & (PXB_ACTOR_DISABLE_GRAVITY | PXB_ACTOR_GYROSCOPIC)) != 0;   // the environment path serves these from its EXT instantiation, like lock flags   // bits 16..21: PxRigidDynamicLockFlags
     if (global) { s->largeHost.push_back(a); continue; }
     cell = std::max(cell, d);
     for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], r.pos[k]); mx[k] = std::max(mx[k], r.pos[k]); }

@@ -619,7 +619,8 @@ __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB
         A.extForce[a] = make_float4(0, 0, 0, 0); A.extTorque[a] = make_float4(0, 0, 0, 0);
       }
     }
-    unconstrained_velocity(V3(A.gx, A.gy, A.gz), A.dt, dm.x, dm.y, dm.z, dm.w, lv, av);
+    unconstrained_velocity((EXT && (gf & 0x1000u)) ? V3(0, 0, 0) : V3(A.gx, A.gy, A.gz), A.dt, dm.x, dm.y, dm.z, dm.w, lv, av);   // eDISABLE_GRAVITY
+    if (EXT && (gf & 0x2000u)) av = gyroscopic(av, V3(ii.x, ii.y, ii.z), Q4(A.quat[a]), A.dt);   // eENABLE_GYROSCOPIC_FORCES
     const uint32_t lock = EXT ? (gf >> 16) & 0x3fu : 0u;   // PxRigidDynamicLockFlags: TGS locks both velocities, PGS only the angular one (see k_preintegrate)
     if (EXT && lock) { if (!PGS) lv = lock3(lv, lock & 7u); av = lock3(av, (lock >> 3) & 7u); }
     const m33 rot = amfromq(Q4(A.quat[a]));

@@ -73,6 +73,20 @@ PXB_D void unconstrained_velocity(v3 gravity, float dt, float linDamping, float 
   lv = l; av = a;
 }
 
+// PxRigidBodyFlag::eENABLE_GYROSCOPIC_FORCES: the torque-free gyroscopic term applied to the angular velocity when the solver body is built
+// (copyToSolverBodyDataStep DyTGSDynamics.cpp:177-193 = copyToSolverBodyData DyRigidBodyToSolverBody.cpp:53-70; scalar PxVec3 / PxQuat arithmetic)
+PXB_D v3 gyroscopic(v3 av, v3 invInertia, q4 q, float dt) {
+  const v3 localInertia = V3(invInertia.x == 0.f ? 0.f : 1.f / invInertia.x, invInertia.y == 0.f ? 0.f : 1.f / invInertia.y, invInertia.z == 0.f ? 0.f : 1.f / invInertia.z);
+  const v3 localAngVel = qrotinv(q, av);
+  const v3 origMom = vmul(localInertia, localAngVel);
+  const v3 c = cross(localAngVel, origMom); const v3 torque = V3(-c.x, -c.y, -c.z);
+  v3 newMom = origMom + torque * dt;
+  const float denom = sqrtf(newMom.x * newMom.x + newMom.y * newMom.y + newMom.z * newMom.z);
+  const float ratio = denom > 0.f ? sqrtf(origMom.x * origMom.x + origMom.y * origMom.y + origMom.z * origMom.z) / denom : 0.f;
+  newMom = newMom * ratio;
+  return av + qrot(q, vmul(invInertia, newMom) - localAngVel);
+}
+
 // PxRigidDynamicLockFlag bits (linear x,y,z = 1,2,4; angular x,y,z = 8,16,32) travel in the unused .z lane of the body's second inertia float4
 PXB_D v3 lock3(v3 v, uint32_t bits) { if (bits & 1u) v.x = 0.f; if (bits & 2u) v.y = 0.f; if (bits & 4u) v.z = 0.f; return v; }
 // External force / torque for this step (PxDirectGPUAPI eFORCE / eTORQUE = PxRigidBody::addForce / addTorque(eFORCE)):

@@ -976,3 +976,27 @@ def aggregates_mix(n_envs=0, env_pitch=8.0, seed=41, **hdr):
     set_box(a, idx[(idx % per) != 11], np.array([he, he, he], dtype=np.float32))
     set_sphere(a, idx[(idx % per) == 11], np.float32(0.3))
     return Scene(default_header(**hdr), add_ground_plane(a))
+
+
+ACTOR_DISABLE_GRAVITY, ACTOR_GYROSCOPIC = 4, 8   # PxActorFlag::eDISABLE_GRAVITY, PxRigidBodyFlag::eENABLE_GYROSCOPIC_FORCES (oracle/scene_format.h)
+
+
+def body_flags_mix(n=16, seed=53, **hdr):
+    """Per-body flags of the pre-integration stage (a12): flat boxes and capsules (three different principal inertias) thrown up spinning about a non-principal axis --
+    every other one with eENABLE_GYROSCOPIC_FORCES -- and a row of bodies with eDISABLE_GRAVITY that float until something lands on them (some drift sideways)."""
+    rng = np.random.RandomState(seed)
+    a = _new_actors(n)
+    q = random_unit_quats(rng, n)
+    for i in range(n):
+        a["pos"][i] = (1.2 * (i % 8), 1.0 + 1.3 * (i // 8), 0.0)
+        a["quat"][i] = q[i]
+    flat = np.arange(0, n, 2); caps = np.arange(1, n, 2)
+    set_box(a, flat, np.array([0.1, 0.25, 0.4], dtype=np.float32))
+    set_capsule(a, caps, np.float32(0.12), np.float32(0.3))
+    a["angVel"][:] = rng.uniform(-6, 6, (n, 3)); a["linVel"][:, 1] = rng.uniform(0.5, 2.5, n)
+    a["angDamping"][:] = 0.0
+    a["flags"][np.arange(0, n, 4)] |= ACTOR_GYROSCOPIC; a["flags"][np.arange(1, n, 4)] |= ACTOR_GYROSCOPIC
+    upper = np.arange(n // 2, n)
+    a["flags"][upper[::2]] |= ACTOR_DISABLE_GRAVITY
+    a["linVel"][upper[::2], 1] = 0.0; a["linVel"][upper[::4], 0] = 0.4
+    return Scene(default_header(**hdr), add_ground_plane(a))

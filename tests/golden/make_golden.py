@@ -200,6 +200,9 @@ def main():
         print(name, "bodies", sc.n_dynamic, "steps", steps, "bytes", os.path.getsize(os.path.join(out, name + ".npz")))
     # PxAggregate membership with and without self collisions (the harness creates real PxAggregates; its standalone broadphase gives the members of an aggregate
     # without self collisions one filter group)
+    # per-body pre-integration flags: PxActorFlag::eDISABLE_GRAVITY, PxRigidBodyFlag::eENABLE_GYROSCOPIC_FORCES (TGS and PGS)
+    cases["body_flags_mix"] = (scenes.body_flags_mix(), 100)
+    cases["pgs_body_flags_mix"] = (scenes.body_flags_mix(solver=scenes.SOLVER_PGS), 100)
     cases["aggregates_mix"] = (scenes.aggregates_mix(), 100)
     cases["aggregates_envs_3"] = (scenes.aggregates_mix(n_envs=3), 80)
     if only:

@@ -1485,3 +1485,24 @@ def test_aggregates_gpu_matches_oracle_and_reference(oracle, name, env_path):
     lib = gpu._lib
     bad = sc.actors[1:2].copy(); bad["aggregate"] = 0x40000000
     assert lib.pxb_scene_add_actors(gpu._h, bad.ctypes.data, 1) < 0
+
+
+# ---- per-body pre-integration flags: eDISABLE_GRAVITY, eENABLE_GYROSCOPIC_FORCES ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["body_flags_mix", "pgs_body_flags_mix"])
+@pytest.mark.parametrize("env_path", [True, False])
+def test_body_flags_gpu_matches_oracle_and_reference(oracle, name, env_path):
+    """28 steps of free flight bit-identical to the REFERENCE on both paths and both solvers (gyroscopic term, gravity switch); then, re-synchronised to the oracle every
+    step, equal manifolds and states within TOL_STEP for the remaining steps (tumbling flat boxes: chaotic)."""
+    z, sc = util.load_golden(name)
+    gpu, cpu = engine.Scene(sc, env_path=env_path), oracle.OracleScene(sc)
+    for t in range(z["states"].shape[0] - 1):
+        order = None if env_path else util.golden_order(z, t)
+        gpu.setConstraintOrder(order); gpu.step(); cpu.step(order)
+        assert gpu.uses_env_path == env_path
+        a, b = gpu.getStates(), cpu.getStates()
+        if t < 28:
+            assert np.array_equal(a, z["states"][t + 1]), f"free flight vs reference, step {t}"
+        assert np.array_equal(gpu.getContacts()[:, 0], cpu.getContacts()[:, 0]), f"contact counts, step {t}"
+        assert np.abs(a - b).max() < TOL_STEP, f"states, step {t}"
+        cpu.setStates(a)
