@@ -71,6 +71,7 @@ struct PxbScene {
   // write is pending on the copy stream, so that its host-to-device copy overlaps the first part (which reads poses only)
   bool useGraph = true; cudaGraphExec_t graphExec[2][3] = {{0, 0, 0}, {0, 0, 0}}; float graphDt = 0.f; uint32_t graphLaunches[2][3] = {{0, 0, 0}, {0, 0, 0}};
   cudaStream_t copyStream = nullptr; cudaEvent_t velEvent = nullptr, orderEvent = nullptr; bool velPending = false;
+  uint32_t *candKeys = 0, *candCount = 0, candCap = 0; float4 *candRefMin = 0, *candRefMax = 0; bool candOn = true;   // k_env_bp temporal coherence: candidate pairs per environment + the bounds they were built from
   bool anyAggregate = false; uint32_t* aggId = 0;   // PxAggregate membership per actor (ActorRec::aggregate)
   bool anyKinematic = false; uint32_t nKin = 0; uint32_t* kinList = 0; float4 *kinP = 0, *kinQ = 0, *kinFtv = 0; uint32_t* kinHas = 0; std::vector<uint32_t> kinHost;   // kinematic bodies: actor list, pending targets (body frame), friction target velocities per pair
   bool bodyAccel = false; float4 *prevLin = 0, *prevAng = 0; float accelInvDt = 0.f;   // PxSceneFlag::eENABLE_BODY_ACCELERATIONS: velocities the last step started from
@@ -908,7 +909,7 @@ PXB_API void pxb_scene_release(PxbScene* s) { DeviceGuard dg_(s);
   if (!s) return;
   cudaStreamSynchronize(s->stream);
   drop_graphs(s);
-  void* ptrs[] = {s->aggId, s->kinList, s->kinP, s->kinQ, s->kinHas, s->kinFtv, s->prevLin, s->prevAng, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
+  void* ptrs[] = {s->candKeys, s->candCount, s->candRefMin, s->candRefMax, s->aggId, s->kinList, s->kinP, s->kinQ, s->kinHas, s->kinFtv, s->prevLin, s->prevAng, s->pos, s->quat, s->linVel, s->angVel, s->invInertia, s->damp, s->dims, s->aabbMin, s->aabbMax, s->geomFlags, s->envId, s->dynActorDev, s->largeList, s->tight,
                   s->sbLin, s->sbAng, s->sbDLin, s->sbDAng, s->sbIA, s->sbIB, s->sbP, s->sbQ, s->sbOrigAng, s->bodyCnt, s->bodyStart, s->bodyCursor, s->bodyNext, s->bodyMask, s->bodyHasCon,
                   s->cellKey, s->cellKeyAlt, s->cellVal, s->cellValAlt, s->sMin, s->sMax, s->pairKeys[0], s->pairKeys[1], s->pairSlots[0], s->pairSlots[1], s->pairKeyAlt, s->pairValTmp,
                   s->pairValAlt, s->nPairsDev, s->freeList, s->createdKeys, s->deletedKeys, s->manifolds, s->frictions, s->cHdr, s->cPts, s->pairBodies, s->cForce, s->gjkList, s->gjkQuery, s->gjkFull, s->gjkEpa, s->boxList, s->filterData, s->shapeOff, s->tcPos, s->tcQuat, s->s2bP, s->s2bQ, s->b2aP, s->b2aQ, s->actorPos, s->actorQuat, s->frReport, s->ccIdx, s->ccOff, s->ccCount, s->ccTotal, s->actorDyn, s->ccPatches, s->ccPoints, s->ccFriction, s->ccForces, s->pairOrder, s->npClass, s->npClassCount, s->conFlag, s->conIdx,
@@ -996,6 +997,15 @@ static void rebuild_env(PxbScene* s, bool usesEnv, uint32_t maxEnv) {
     s->envDynContiguous = contiguous;
   }
   s->nEnv = nEnv; s->envMaxList = maxList; s->envEligible = true;
+  {   // candidate lists of the broadphase (invalid until the first step of every environment builds them); without them k_env_bp enumerates all pairs every step
+    if (s->candKeys) cudaFree(s->candKeys); if (s->candCount) cudaFree(s->candCount); if (s->candRefMin) cudaFree(s->candRefMin); if (s->candRefMax) cudaFree(s->candRefMax);
+    s->candKeys = s->candCount = nullptr; s->candRefMin = s->candRefMax = nullptr;
+    const char* cc = getenv("PXB_ENV_BP_CAND"); s->candOn = !(cc && cc[0] == '0');
+    s->candCap = 8 * maxList;
+    if (s->candOn && (dalloc(s->candKeys, (size_t)nEnv * s->candCap) != cudaSuccess || dalloc(s->candCount, nEnv) != cudaSuccess || dalloc(s->candRefMin, list.size()) != cudaSuccess ||
+                      dalloc(s->candRefMax, list.size()) != cudaSuccess)) { cudaGetLastError(); if (s->candKeys) cudaFree(s->candKeys); s->candKeys = nullptr; }   // no memory: all pairs every step
+    if (s->candKeys) { cudaMemsetAsync(s->candCount, 0xff, 4 * (size_t)nEnv, s->stream); cudaStreamSynchronize(s->stream); }
+  }
 #ifdef PXB_ENV_TIMING
   if (s->envTiming) cudaFree(s->envTiming); cudaMalloc((void**)&s->envTiming, (size_t)nEnv * 16 * 8); cudaMemset(s->envTiming, 0, (size_t)nEnv * 16 * 8);
 #endif
@@ -1254,6 +1264,8 @@ static int run_broadphase(PxbScene* s, bool externalTight) {
     EnvBpArgs A;
     A.nEnv = s->nEnv; A.maxList = s->envMaxList; A.bitsA = s->bitsA; A.cap = s->capPairs; A.ringMask = s->ringMask; A.externalTight = externalTight ? 1 : 0; A.contactOffset = s->desc.contactOffset;
     A.envStart = s->envStart; A.envList = s->envList; A.pos = s->pos; A.quat = s->quat; A.dims = s->dims; A.geomFlags = s->geomFlags; A.envId = s->envId; A.tight = s->tight; A.hulls = hull_arrays(s); A.L = local_poses(s); A.aggId = s->anyAggregate ? s->aggId : nullptr; A.shapeOff = s->hasShapeOff ? s->shapeOff : nullptr;
+    A.candKeys = s->candKeys; A.candCount = s->candCount; A.refMin = s->candRefMin; A.refMax = s->candRefMax; A.candCap = s->candCap;
+    { const float co = std::max(s->desc.contactOffset, s->maxContactOffset); A.candMargin = 2.f * (co > 0.f ? co : 0.01f); }
     A.oldKeys = s->pairKeys[prev]; A.oldSlots = s->pairSlots[prev]; A.oldSeg = s->envSeg[prev]; A.newKeys = s->pairKeys[cur]; A.newSlots = s->pairSlots[cur]; A.newSeg = s->envSeg[cur];
     A.counters = s->counters; A.freeRing = s->freeList; A.createdKeys = s->createdKeys; A.deletedKeys = s->deletedKeys; A.manifolds = s->manifolds; A.frictions = s->frictions; A.slotColour = s->slotColour; A.touch = touch_lists(s);
     const size_t smem = (size_t)ENV_BP_WARPS * (s->envMaxList * (2 * sizeof(float4) + sizeof(uint32_t)) + ENV_BP_STAGE * sizeof(uint64_t));

@@ -27,7 +27,10 @@ struct EnvBpArgs {
   const float4 *pos, *quat, *dims; const uint32_t *geomFlags, *envId; float* tight; HullArrays hulls;
   const uint64_t* oldKeys; const uint32_t* oldSlots; const uint2* oldSeg;
   uint64_t* newKeys; uint32_t* newSlots; uint2* newSeg;
-  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions; TouchLists touch; LocalPoses L; const uint32_t* aggId; const float2* shapeOff;   // shapeOff: per-actor (contactOffset, restOffset), LOCAL instantiation only
+  uint32_t *counters, *freeRing, *slotColour; uint64_t *createdKeys, *deletedKeys; float4 *manifolds, *frictions; TouchLists touch; LocalPoses L; const uint32_t* aggId; const float2* shapeOff;
+  // temporal coherence of k_env_bp (NULL candKeys = off): per environment a list of candidate pairs (list positions i << 16 | j, ascending) whose bounds overlapped when expanded
+  // by candMargin, and the bounds that list was built from
+  uint32_t* candKeys; uint32_t* candCount; float4 *refMin, *refMax; uint32_t candCap; float candMargin;   // shapeOff: per-actor (contactOffset, restOffset), LOCAL instantiation only
 };
 
 #define ENV_BP_STAGE 256   // pair keys staged per warp in shared memory before the segment base is known
@@ -95,6 +98,8 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
   uint64_t* sStage = reinterpret_cast<uint64_t*>(envBpSmem + (size_t)ENV_BP_WARPS * 2 * A.maxList) + (size_t)warp * ENV_BP_STAGE;
   uint32_t* sAct = reinterpret_cast<uint32_t*>(envBpSmem + (size_t)ENV_BP_WARPS * 2 * A.maxList) + ENV_BP_WARPS * ENV_BP_STAGE * 2 + (size_t)warp * A.maxList;
   const uint32_t ls = A.envStart[e], n = A.envStart[e + 1] - ls;
+  const uint32_t nCand = A.candKeys ? A.candCount[e] : NONE32;   // NONE32: no valid candidate list
+  bool moved = false;
   // a1/a2: bounds of this environment's actors (+ the shared env-less statics), inflated, into shared memory
   for (uint32_t k = lane; k < n; k += 32) {
     const uint32_t a = A.envList[ls + k]; const uint32_t gf = A.geomFlags[a], env = A.envId[a];
@@ -112,22 +117,55 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
     sMin[k] = make_float4(mn[0] - co, mn[1] - co, mn[2] - co, __uint_as_float(LOCAL ? env_agg_key(A.aggId, a, k) : env));
     sMax[k] = make_float4(mx[0] + co, mx[1] + co, mx[2] + co, __uint_as_float(gf_dynamic(gf) ? gf : (gf & ~0x100u)));   // kinematic bodies pair with dynamic ones only, like statics (the test below reads the dynamic bit)
     sAct[k] = a;
+    if (nCand != NONE32) {   // has a face of this bound moved further than the candidate list allows?
+      const float4 rm = A.refMin[ls + k], rx = A.refMax[ls + k]; const float4 cm = sMin[k], cx = sMax[k]; const float lim = 0.9f * A.candMargin;
+      moved |= (fabsf(cm.x - rm.x) > lim) | (fabsf(cm.y - rm.y) > lim) | (fabsf(cm.z - rm.z) > lim) | (fabsf(cx.x - rx.x) > lim) | (fabsf(cx.y - rx.y) > lim) | (fabsf(cx.z - rx.z) > lim);
+    }
   }
   __syncwarp();
   // a4/a5: all pairs (i<j) of the list, row by row = ascending (lo,hi) key order because the list is sorted by actor
   // index.  Keys are staged in shared memory; one atomic reserves the environment's segment of the flat pair list.
+  // Temporal coherence (the role of the reference's INCREMENTAL sweep): while no bound has moved by more than the margin since the candidate list was built, every
+  // overlapping pair is a candidate (a.min <= b.max now implies a.min_ref - m <= b.max_ref + m), so only the candidates are tested -- with the same exact test, in the
+  // same ascending order: the pair set is identical.  Otherwise the all-pairs enumeration runs and rebuilds the list.
+  const bool useCand = nCand != NONE32 && !__any_sync(0xffffffffu, moved);
+  const uint32_t* candList = A.candKeys ? A.candKeys + (size_t)e * A.candCap : nullptr;
   uint32_t cnt = 0;
-  for (uint32_t i = 0; i + 1 < n; ++i) {
-    const float4 amin = sMin[i], amax = sMax[i]; const uint64_t hiKey = (uint64_t)sAct[i] << A.bitsA;
-    for (uint32_t j0 = i + 1; j0 < n; j0 += 32) {
-      const uint32_t j = j0 + lane;
-      const bool hit = j < n && env_bp_test<LOCAL>(amin, amax, sMin[j], sMax[j]);
+  if (useCand) {
+    for (uint32_t c0 = 0; c0 < nCand; c0 += 32) {
+      const uint32_t c = c0 + lane; uint32_t ij = 0; bool hit = false;
+      if (c < nCand) { ij = candList[c]; const uint32_t i = ij >> 16, j = ij & 0xffffu; hit = env_bp_test<LOCAL>(sMin[i], sMax[i], sMin[j], sMax[j]); }
       const uint32_t m = __ballot_sync(0xffffffffu, hit);
       if (m) {
         const uint32_t w = cnt + __popc(m & ((1u << lane) - 1u));
-        if (hit && w < ENV_BP_STAGE) sStage[w] = hiKey | sAct[j];
+        if (hit && w < ENV_BP_STAGE) sStage[w] = ((uint64_t)sAct[ij >> 16] << A.bitsA) | sAct[ij & 0xffffu];
         cnt += __popc(m);
       }
+    }
+  } else {
+    uint32_t ccnt = 0; uint32_t* cw = A.candKeys ? A.candKeys + (size_t)e * A.candCap : nullptr; const float m2 = cw ? 2.f * A.candMargin : 0.f;
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+      const float4 amin = sMin[i], amax = sMax[i]; const uint64_t hiKey = (uint64_t)sAct[i] << A.bitsA;
+      const float4 emin = make_float4(amin.x - m2, amin.y - m2, amin.z - m2, amin.w), emax = make_float4(amax.x + m2, amax.y + m2, amax.z + m2, amax.w);   // both bounds expanded by the margin
+      for (uint32_t j0 = i + 1; j0 < n; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool ch = j < n && env_bp_test<LOCAL>(emin, emax, sMin[j], sMax[j]);   // the expanded test first: a miss (the common case) is a miss of the exact test too
+        const uint32_t cmk = __ballot_sync(0xffffffffu, ch);
+        if (cmk) {
+          const bool hit = cw ? (ch && env_bp_test<LOCAL>(amin, amax, sMin[j], sMax[j])) : ch;   // (without candidate lists the margin is zero and the first test was the exact one)
+          const uint32_t m = __ballot_sync(0xffffffffu, hit);
+          if (m) {
+            const uint32_t w = cnt + __popc(m & ((1u << lane) - 1u));
+            if (hit && w < ENV_BP_STAGE) sStage[w] = hiKey | sAct[j];
+            cnt += __popc(m);
+          }
+          if (cw) { const uint32_t w = ccnt + __popc(cmk & ((1u << lane) - 1u)); if (ch && w < A.candCap) cw[w] = (i << 16) | j; ccnt += __popc(cmk); }
+        }
+      }
+    }
+    if (cw) {
+      if (lane == 0) A.candCount[e] = ccnt <= A.candCap ? ccnt : NONE32;   // too many candidates: this environment keeps enumerating all pairs
+      for (uint32_t k = lane; k < n; k += 32) { A.refMin[ls + k] = sMin[k]; A.refMax[ls + k] = sMax[k]; }
     }
   }
   uint32_t base = 0;
@@ -140,7 +178,16 @@ __global__ void __launch_bounds__(32 * ENV_BP_WARPS) k_env_bp(const EnvBpArgs A)
     cnt = 0;
   }
   if (cnt <= ENV_BP_STAGE) { for (uint32_t t = lane; t < cnt; t += 32) A.newKeys[base + t] = sStage[t]; }
-  else {   // more pairs than the staging area holds: enumerate again, straight into the segment
+  else if (useCand) {   // more pairs than the staging area holds: enumerate again, straight into the segment
+    uint32_t w = 0;
+    for (uint32_t c0 = 0; c0 < nCand; c0 += 32) {
+      const uint32_t c = c0 + lane; uint32_t ij = 0; bool hit = false;
+      if (c < nCand) { ij = candList[c]; const uint32_t i = ij >> 16, j = ij & 0xffffu; hit = env_bp_test<LOCAL>(sMin[i], sMax[i], sMin[j], sMax[j]); }
+      const uint32_t m = __ballot_sync(0xffffffffu, hit);
+      if (hit) A.newKeys[base + w + __popc(m & ((1u << lane) - 1u))] = ((uint64_t)sAct[ij >> 16] << A.bitsA) | sAct[ij & 0xffffu];
+      w += __popc(m);
+    }
+  } else {
     uint32_t w = 0;
     for (uint32_t i = 0; i + 1 < n; ++i) {
       const float4 amin = sMin[i], amax = sMax[i]; const uint64_t hiKey = (uint64_t)sAct[i] << A.bitsA;
