@@ -89,7 +89,7 @@ __device__ __forceinline__ bool bp_test(const float4& amin, const float4& amax, 
 }
 __device__ __forceinline__ void bp_emit(uint32_t a, uint32_t b, uint32_t bitsA, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt, uint32_t cap, uint32_t* __restrict__ err) {
   const uint32_t lo = min(a, b), hi = max(a, b);
-  const uint32_t idx = atomicAdd(cnt, 1u);
+  const uint32_t idx = atomicAdd(cnt, 1u);   // (a warp-aggregated increment was measured and changes nothing: config 4 broadphase stage 0.577 vs 0.578 ms, profiles/README.md)
   if (idx < cap) keys[idx] = ((uint64_t)lo << bitsA) | hi; else atomicOr(err, (uint32_t)E_PAIR_OVERFLOW);
 }
 __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__ k, uint32_t n, uint64_t v) {
