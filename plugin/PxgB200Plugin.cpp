@@ -14,7 +14,7 @@
 //                      bit-identical to the reference's ABP
 //   Bp::AABBManagerBase (lowlevelaabb/include/BpAABBManagerBase.h:175-390; reference: gpubroadphase/src/PxgAABBManager.cpp:501-1050): added /
 //                      updated / removed handle lists from the bitmaps, BroadPhaseUpdateData, created / destroyed AABBOverlap{userData} lists
-//                      per element type.  Aggregates are refused (createAggregate reports an error): SURVEY 8f rank f4.
+//                      per element type.  PxAggregates are flattened: their shapes enter the broadphase one by one, pairs inside an aggregate without self collisions are dropped.
 //   Bp::BoundsArray    createGpuBounds: the host class on pinned memory
 //
 // That is the scene configuration PxBroadPhaseType::eGPU with CPU dynamics (simulationcontroller/src/ScScene.cpp:786-916 creates exactly these
@@ -179,7 +179,7 @@ private:
 };
 
 // ------------------------------------------------------------------------------------------------------------------------------------------
-// Bp::AABBManagerBase without aggregates: bitmaps -> handle lists -> BroadPhaseUpdateData -> overlaps by element type
+// Bp::AABBManagerBase (aggregates flattened): bitmaps -> handle lists -> BroadPhaseUpdateData -> overlaps by element type
 class B200AABBManager : public Bp::AABBManagerBase
 {
 public:
@@ -189,21 +189,44 @@ public:
 
 	virtual void destroy() PX_OVERRIDE { PX_DELETE_THIS; }
 
-	virtual Bp::AggregateHandle createAggregate(Bp::BoundsIndex, Bp::FilterGroup::Enum, void*, PxU32, PxAggregateFilterHint, PxU32) PX_OVERRIDE
+	// PxAggregate: the grid broadphase needs no merged bound, so the shapes of an aggregate enter the broadphase one by one and the aggregate itself only keeps its
+	// entry (bounds index, group, user data) and its self-collision switch; pairs between two shapes of an aggregate WITHOUT self collisions are dropped when the
+	// created / deleted pairs are handed to the host (the reference computes an aggregate's self-collision pairs only when enabled, BpAABBManager.cpp Aggregate::mSelfCollisionPairs)
+	struct AggregateRec { Bp::BoundsIndex index; PxU32 nbShapes; bool selfCollisions; bool used; };
+	virtual Bp::AggregateHandle createAggregate(Bp::BoundsIndex index, Bp::FilterGroup::Enum group, void* userData, PxU32, PxAggregateFilterHint filterHint, PxU32) PX_OVERRIDE
 	{
-		B200_ERROR(PxErrorCode::eINVALID_OPERATION, "libPhysXGpu_64 (physx_b200): PxAggregate is not supported by this GPU broadphase yet");
-		return PX_INVALID_U32;
+		Bp::AggregateHandle handle = PX_INVALID_U32;
+		for(PxU32 i = 0; i < mAggregateRecs.size(); i++) if(!mAggregateRecs[i].used) { handle = i; break; }
+		if(handle == PX_INVALID_U32) { handle = mAggregateRecs.size(); mAggregateRecs.pushBack(AggregateRec()); }
+		AggregateRec& a = mAggregateRecs[handle];
+		a.index = index; a.nbShapes = 0; a.selfCollisions = PxGetAggregateSelfCollisionBit(filterHint) != 0; a.used = true;
+		initEntry(index, 0.0f, group, userData);
+		mVolumeData[index].setAggregate(handle);
+		mBoundsArray.setBounds(PxBounds3::empty(), index);	// (the aggregate's own bound is never in the broadphase)
+		return handle;
 	}
-	virtual bool destroyAggregate(Bp::BoundsIndex&, Bp::FilterGroup::Enum&, Bp::AggregateHandle) PX_OVERRIDE { return false; }
+	virtual bool destroyAggregate(Bp::BoundsIndex& index_, Bp::FilterGroup::Enum& group_, Bp::AggregateHandle handle) PX_OVERRIDE
+	{
+		if(handle >= mAggregateRecs.size() || !mAggregateRecs[handle].used)
+			return B200_ERROR(PxErrorCode::eINVALID_PARAMETER, "AABBManager::destroyAggregate - aggregateId out of bounds or already removed");
+		if(mAggregateRecs[handle].nbShapes)
+			return B200_ERROR(PxErrorCode::eINVALID_PARAMETER, "AABBManager::destroyAggregate - aggregate still has bounds that needs removed");
+		const Bp::BoundsIndex index = mAggregateRecs[handle].index;
+		index_ = index; group_ = mGroups[index];
+		resetEntry(index);
+		mAggregateRecs[handle].used = false;
+		return true;
+	}
 
 	virtual bool addBounds(Bp::BoundsIndex index, PxReal contactDistance, Bp::FilterGroup::Enum group, void* userData, Bp::AggregateHandle aggregateHandle, Bp::ElementType::Enum volumeType, PxU32 envID) PX_OVERRIDE
 	{
-		if(aggregateHandle != PX_INVALID_U32)
-			return B200_ERROR(PxErrorCode::eINVALID_OPERATION, "libPhysXGpu_64 (physx_b200): shapes of aggregates are not supported by this GPU broadphase yet");
+		if(aggregateHandle != PX_INVALID_U32 && (aggregateHandle >= mAggregateRecs.size() || !mAggregateRecs[aggregateHandle].used))
+			return B200_ERROR(PxErrorCode::eINVALID_PARAMETER, "AABBManager::addBounds - aggregateId out of bounds");
 		initEntry(index, contactDistance, group, userData, volumeType);
 		if(mEnvIDs.size() < mVolumeData.size()) mEnvIDs.resize(mVolumeData.size(), PX_INVALID_U32);	// environment ids: PxActor::setEnvironmentID, honoured on the GPU (broadphase.cu:62-80)
 		mEnvIDs[index] = PxI32(envID);
-		mVolumeData[index].setSingleActor();
+		if(aggregateHandle == PX_INVALID_U32) mVolumeData[index].setSingleActor();
+		else { mVolumeData[index].setAggregated(aggregateHandle); mAggregateRecs[aggregateHandle].nbShapes++; }
 		addBPEntry(index);
 		mPersistentStateChanged = true;
 		return true;
@@ -211,6 +234,7 @@ public:
 	virtual bool removeBounds(Bp::BoundsIndex index) PX_OVERRIDE
 	{
 		PX_ASSERT(index < mVolumeData.size());
+		if(mVolumeData[index].isAggregated()) { AggregateRec& a = mAggregateRecs[mVolumeData[index].getAggregateOwner()]; if(a.nbShapes) a.nbShapes--; }
 		const bool res = removeBPEntry(index);
 		resetEntry(index);
 		mPersistentStateChanged = true;
@@ -253,11 +277,11 @@ public:
 			for(PxU32 i = 0; i < nb; i++)
 			{	// a pair whose volume lost its user data was removed by the host already (BpAABBManager.cpp:1611-1617)
 				void* u0 = mVolumeData[pairs[i].mVolA].getUserData(); void* u1 = mVolumeData[pairs[i].mVolB].getUserData();
-				if(u0 && u1) output(mDestroyedOverlaps, pairs[i].mVolA, pairs[i].mVolB, u0, u1);
+				if(u0 && u1 && !insideQuietAggregate(pairs[i].mVolA, pairs[i].mVolB)) output(mDestroyedOverlaps, pairs[i].mVolA, pairs[i].mVolB, u0, u1);
 			}
 			pairs = mBroadPhase.getCreatedPairs(nb);
 			for(PxU32 i = 0; i < nb; i++)
-				output(mCreatedOverlaps, pairs[i].mVolA, pairs[i].mVolB, mVolumeData[pairs[i].mVolA].getUserData(), mVolumeData[pairs[i].mVolB].getUserData());
+				if(!insideQuietAggregate(pairs[i].mVolA, pairs[i].mVolB)) output(mCreatedOverlaps, pairs[i].mVolA, pairs[i].mVolB, mVolumeData[pairs[i].mVolA].getUserData(), mVolumeData[pairs[i].mVolB].getUserData());
 #if PX_ENABLE_SIM_STATS
 			mGpuDynamicsLostFoundPairsStats = PxMax(mGpuDynamicsLostFoundPairsStats, nb);
 #endif
@@ -271,6 +295,14 @@ public:
 	virtual void setPersistentStateChanged() PX_OVERRIDE { mPersistentStateChanged = true; }
 
 private:
+	// both volumes are shapes of the same aggregate and that aggregate has no self collisions
+	bool insideQuietAggregate(PxU32 a, PxU32 b) const
+	{
+		const Bp::VolumeData& va = mVolumeData[a]; const Bp::VolumeData& vb = mVolumeData[b];
+		if(!va.isAggregated() || !vb.isAggregated() || va.getAggregateOwner() != vb.getAggregateOwner()) return false;
+		return !mAggregateRecs[va.getAggregateOwner()].selfCollisions;
+	}
+	PxArray<AggregateRec> mAggregateRecs;
 	template <class Map, class List> void collect(const Map& map, List& out, bool updatedPass)
 	{
 		const PxU32* bits = map.getWords();
