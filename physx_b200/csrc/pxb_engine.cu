@@ -1385,7 +1385,8 @@ static int enqueue_step(PxbScene* s, float dt, int phase = 0) {
     A.counters = s->counters; A.timing = s->envTiming; A.slotColour = s->slotColour; A.S = SA;
     const bool fusedExport = s->exportOn && s->envDynContiguous && !s->nKin;   // kinematic bodies take their new pose after the kernel (k_kin_finalize): export afterwards
     A.exportTab = fusedExport ? s->exportTab : nullptr; A.envDyn = s->envDyn; A.dynActor = s->dynActorDev;
-    const size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
+    size_t smem = env_solve_smem(s->envMaxList, s->envConCap, s->envSolveThreads);
+    { static const char* pad = getenv("PXB_ENV_SMEM_PAD"); if (pad) smem += (size_t)atoi(pad); }   // experiment hook: padding the request lowers the CTAs per SM (wave quantisation A/B, profiles/README.md)
     A.M = material_args(s); A.kinFtv = (s->nKin && !pgs) ? s->kinFtv : nullptr; A.kinOn = s->nKin ? 1u : 0u;
     const bool ext = s->anyLocks || s->forcesUsed || s->nMaterials != 0 || s->hasShapeOff || s->nKin != 0;   // lock flags / external forces: the EXT instantiation; the plain one carries none of that code
     pxb_launch_env_solve(st, A, s->envSolveThreads, pgs, ext, smem);
