@@ -635,6 +635,8 @@ __device__ __forceinline__ void env_solve_body(const EnvSolveArgs& A, const Rows
 #define PXB_ENV_CTAS64 8
 #endif
 template <int T, bool PGS, bool EXT>   // EXT: scenes that use PxRigidDynamicLockFlags or eFORCE / eTORQUE writes (the plain instantiation carries none of that code)
+// (measured and not kept: a register cap of 144 = 7 CTAs/SM instead of the residency target -- solve 0.2006 vs 0.1937 ms on config 2, tools/gpu_run52.sh; the 320 B of stack are the
+//  dynamically indexed row arrays, not spills, so more registers buy nothing)
 __global__ void __launch_bounds__(T, (T <= 64 ? PXB_ENV_CTAS64 : (T <= 128 ? PXB_ENV_CTAS64 / 2 : 1))) k_env_solve(const EnvSolveArgs A) {
   extern __shared__ float4 envSmem[];
   __shared__ uint32_t sPartCnt[MAX_PARTITIONS + 1], sPartStart[MAX_PARTITIONS + 1], sWarp[T / 32 + 1], sMisc[4];
