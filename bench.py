@@ -473,6 +473,7 @@ def bench_ours(args):
             "details": {"bodies_total": total_bodies, "pairs_per_gpu": n_pairs, "constraints_per_gpu": P, "partitions": scene.num_partitions, "path": "environment (pxb_env.cuh)" if scene.uses_env_path else "device-wide",
                         "partitioning": ("relaxed (Jones-Plassmann rounds)" if relaxed else "exact first-fit (the reference's order-preserving greedy colouring)") if not scene.uses_env_path else "exact first-fit per environment",
                         **churn_stats,
+                        "env_broadphase": ("all pairs every step (PXB_ENV_BP_CAND=0)" if os.environ.get("PXB_ENV_BP_CAND", "1")[:1] == "0" else "temporal coherence: per-environment candidate pair lists, all-pairs rebuild when a bound moved beyond the margin (identical pair sets)") if scene.uses_env_path else None,
                         "settle_steps": SETTLE[cfg], "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_p95": per_step[min(len(per_step) - 1, int(len(per_step) * 0.95))],
                         "timing": "CUDA events on the scene stream per step, max over ranks; L2 flushed (256 MiB memset) between timed steps",
                         "multi_gpu": ("env-partitioned, one scene per GPU, per-step all-gather of the packed pose+linear+angular velocity tensor (13 floats/body) by " + str(gather_kind) + ", double-buffered on communication streams (overlaps the next step)") if gather is not None else ("independent replicas" if world > 1 else "single scene")},
