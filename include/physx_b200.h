@@ -183,6 +183,8 @@ PXB_API int  pxb_set_rigid_dynamic_data_device_ev(PxbScene* scene, const void* d
  * reports a bad index through the next pxb_scene_fetch_results. */
 PXB_API int  pxb_scene_set_kinematic_targets(PxbScene* scene, const uint32_t* indices, const float* poses, uint32_t nb);
 PXB_API int  pxb_scene_set_kinematic_targets_device(PxbScene* scene, const uint32_t* devIndices, const float* devPoses, uint32_t nb);
+/* PxScene::setGravity (physx/include/PxScene.h; NpScene.cpp:331-342): takes effect with the next pxb_scene_simulate. */
+PXB_API int  pxb_scene_set_gravity(PxbScene* scene, const float* gravity3);
 /* Packed state convenience: 13 floats per dynamic body (pos3 quat4 linVel3 angVel3), dynamic-body order. */
 PXB_API int  pxb_scene_get_states(PxbScene* scene, float* out);
 PXB_API int  pxb_scene_set_states(PxbScene* scene, const float* in);

@@ -1717,6 +1717,17 @@ PXB_API int pxb_scene_set_local_poses(PxbScene* s, uint32_t firstActor, uint32_t
   return PXB_OK;
 }
 
+// PxScene::setGravity (NpScene.cpp:331-342 -> Sc::Scene::mGravity, read by the next step's pre-integration): domain randomisation changes it between steps
+PXB_API int pxb_scene_set_gravity(PxbScene* s, const float* gravity3) { DeviceGuard dg_(s);
+  if (!s || !gravity3) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "PxScene::setGravity() not allowed while simulation is running");
+  if (!std::isfinite(gravity3[0]) || !std::isfinite(gravity3[1]) || !std::isfinite(gravity3[2])) return fail(PXB_ERR_INVALID, "gravity is not finite");
+  if (gravity3[0] == s->desc.gravity[0] && gravity3[1] == s->desc.gravity[1] && gravity3[2] == s->desc.gravity[2]) return PXB_OK;
+  s->desc.gravity[0] = gravity3[0]; s->desc.gravity[1] = gravity3[1]; s->desc.gravity[2] = gravity3[2];
+  drop_graphs(s);   // the vector travels in the kernel arguments
+  return PXB_OK;
+}
+
 // ---- f1: the default simulation filter shader on the device ----
 PXB_API int pxb_scene_set_filter_shader(PxbScene* s, const PxbFilterShaderConfig* cfg) { DeviceGuard dg_(s);
   if (!s) return fail(PXB_ERR_INVALID, "null argument");

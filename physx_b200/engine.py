@@ -32,7 +32,7 @@ EXPORTS = [
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
     "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait", "pxb_bp_create", "pxb_bp_release", "pxb_bp_update", "pxb_bp_fetch",
     "pxb_scene_set_materials", "pxb_scene_remove_actors", "pxb_tensor_read_device", "pxb_tensor_write_device", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost", "pxb_scene_enable_contact_data", "pxb_scene_copy_contact_data", "pxb_scene_set_local_poses", "pxb_scene_set_filter_shader", "pxb_scene_set_filter_data", "pxb_scene_set_shape_offsets",
-    "pxb_get_rigid_dynamic_data_device_ev", "pxb_set_rigid_dynamic_data_device_ev", "pxb_scene_set_kinematic_targets", "pxb_scene_set_kinematic_targets_device",
+    "pxb_get_rigid_dynamic_data_device_ev", "pxb_set_rigid_dynamic_data_device_ev", "pxb_scene_set_kinematic_targets", "pxb_scene_set_kinematic_targets_device", "pxb_scene_set_gravity",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
@@ -94,6 +94,7 @@ def load_library():
               "pxb_set_rigid_dynamic_data_device"):
         getattr(lib, f).argtypes = [vp, vp, vp, i32, u32]
     lib.pxb_scene_set_kinematic_targets.argtypes = [vp, vp, vp, u32]
+    lib.pxb_scene_set_gravity.argtypes = [vp, vp]
     lib.pxb_scene_set_kinematic_targets_device.argtypes = [vp, vp, vp, u32]
     for f in ("pxb_get_rigid_dynamic_data_device_ev", "pxb_set_rigid_dynamic_data_device_ev"):
         getattr(lib, f).argtypes = [vp, vp, vp, i32, u32, vp, vp]
@@ -245,6 +246,11 @@ class Scene:
         d = np.ascontiguousarray(data, dtype=np.float32)
         idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.uint32)
         _check(self._lib, self._lib.pxb_set_rigid_dynamic_data(self._h, _ptr(d), _ptr(idx), data_type, len(d)))
+
+    def setGravity(self, g):
+        """PxScene::setGravity: read by the next simulate."""
+        v = np.ascontiguousarray(g, dtype=np.float32).reshape(3)
+        _check(self._lib, self._lib.pxb_scene_set_gravity(self._h, _ptr(v)))
 
     def setKinematicTargets(self, indices, poses):
         """PxRigidDynamic::setKinematicTarget for the kinematic bodies `indices` (dynamic-body indices): (n, 7) PxTransform rows (q.xyzw, p.xyz), consumed by the next simulate."""

@@ -36,6 +36,7 @@ def lib():
         L.pxo_scene_get_sleep.argtypes = [vp, vp, vp]
         L.pxo_scene_set_forces.argtypes = [vp, vp, vp]
         L.pxo_scene_set_kinematic_targets.argtypes = [vp, vp, vp, u32]
+        L.pxo_scene_set_gravity.argtypes = [vp, vp]
         L.pxo_scene_compute_bounds.argtypes = [vp]
         L.pxo_scene_broadphase.argtypes = [vp]
         _LIB = L
@@ -80,6 +81,10 @@ class OracleScene:
         f = None if forces is None else np.ascontiguousarray(forces, dtype=np.float32)
         t = None if torques is None else np.ascontiguousarray(torques, dtype=np.float32)
         self.L.pxo_scene_set_forces(self.h, _p(f), _p(t))
+
+    def setGravity(self, g):
+        v = np.ascontiguousarray(g, dtype=np.float32).reshape(3)
+        self.L.pxo_scene_set_gravity(self.h, _p(v))
 
     def setKinematicTargets(self, dyn_indices, poses):
         """PxRigidDynamic::setKinematicTarget: (n, 7) PxTransform rows (q.xyzw, p.xyz) for the kinematic bodies `dyn_indices`; consumed by the next step"""

@@ -1506,3 +1506,29 @@ def test_body_flags_gpu_matches_oracle_and_reference(oracle, name, env_path):
         assert np.array_equal(gpu.getContacts()[:, 0], cpu.getContacts()[:, 0]), f"contact counts, step {t}"
         assert np.abs(a - b).max() < TOL_STEP, f"states, step {t}"
         cpu.setStates(a)
+
+
+# ---- PxScene::setGravity between steps ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_path", [True, False])
+def test_set_gravity_between_steps(oracle, env_path):
+    """The gravity vector is read by the next step's pre-integration (Sc::Scene::mGravity): GPU == oracle bit for bit through two changes (CUDA graphs are re-captured), and a
+    free-falling body's acceleration getter shows the new vector."""
+    sc = scenes.env_grid_stacks(n_envs=4, jitter=0.01)
+    sc.actors["pos"][5, 1] += 3.0                                   # one box in free fall
+    gpu, cpu = engine.Scene(sc, env_path=env_path, body_accelerations=True), oracle.OracleScene(sc)
+    dyn5 = 4                                                        # actor 5 is dynamic body 4 (actor 0 is the ground plane)
+    for t in range(12):
+        if t == 4:
+            gpu.setGravity([0.0, -3.0, 1.0]); cpu.setGravity([0.0, -3.0, 1.0])
+        if t == 8:
+            gpu.setGravity([0.0, -9.81, 0.0]); cpu.setGravity([0.0, -9.81, 0.0])
+        gpu.step(); cpu.step()
+        assert np.array_equal(gpu.getStates(), cpu.getStates()), f"step {t}"
+        if t in (5, 6):
+            acc = gpu.getRigidDynamicData(engine.RD_LINEAR_ACCELERATION)[dyn5]
+            assert np.abs(acc - np.array([0.0, -3.0, 1.0], np.float32)).max() < 1e-4, acc
+    gpu.simulate()
+    with pytest.raises(engine.PhysxB200Error):
+        gpu.setGravity([0, 0, 0])
+    gpu.fetchResults(True)
