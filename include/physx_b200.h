@@ -183,6 +183,9 @@ PXB_API int  pxb_set_rigid_dynamic_data_device_ev(PxbScene* scene, const void* d
  * reports a bad index through the next pxb_scene_fetch_results. */
 PXB_API int  pxb_scene_set_kinematic_targets(PxbScene* scene, const uint32_t* indices, const float* poses, uint32_t nb);
 PXB_API int  pxb_scene_set_kinematic_targets_device(PxbScene* scene, const uint32_t* devIndices, const float* devPoses, uint32_t nb);
+/* PxRigidBody::setMass / setMassSpaceInertiaTensor at run time for nb dynamic bodies (dynamic-body indices; 4 floats per body: mass, inertia xyz; 0 = infinite): domain randomisation
+ * of the mass properties between steps.  Not for kinematic bodies. */
+PXB_API int  pxb_scene_set_mass_properties(PxbScene* scene, const uint32_t* indices, const float* massInertia4, uint32_t nb);
 /* PxScene::setGravity (physx/include/PxScene.h; NpScene.cpp:331-342): takes effect with the next pxb_scene_simulate. */
 PXB_API int  pxb_scene_set_gravity(PxbScene* scene, const float* gravity3);
 /* Packed state convenience: 13 floats per dynamic body (pos3 quat4 linVel3 angVel3), dynamic-body order. */

@@ -72,6 +72,7 @@ class Scene {
   bool fetchResults(bool block = true) { const int rc = pxb_scene_fetch_results(h_, block ? 1 : 0); check(rc); return rc == 0; }
   // PxDirectGPUAPI (host buffers; *_device / *_async variants are in the C header)
   void getRigidDynamicData(void* data, int dataType, uint32_t nb, const uint32_t* indices = nullptr) { check(pxb_get_rigid_dynamic_data(h_, data, indices, dataType, nb)); }
+  void setMassProperties(const uint32_t* indices, const float* massInertia4, uint32_t nb) { check(pxb_scene_set_mass_properties(h_, indices, massInertia4, nb)); }   // PxRigidBody::setMass / setMassSpaceInertiaTensor
   void setGravity(const float g[3]) { check(pxb_scene_set_gravity(h_, g)); }   // PxScene::setGravity
   // PxRigidDynamic::setKinematicTarget for a batch of kinematic bodies (dynamic-body indices, PxTransform rows q.xyzw p.xyz)
   void setKinematicTargets(const uint32_t* indices, const float* poses, uint32_t nb) { check(pxb_scene_set_kinematic_targets(h_, indices, poses, nb)); }

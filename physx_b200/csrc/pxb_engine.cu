@@ -1717,6 +1717,34 @@ PXB_API int pxb_scene_set_local_poses(PxbScene* s, uint32_t firstActor, uint32_t
   return PXB_OK;
 }
 
+// PxRigidBody::setMass / setMassSpaceInertiaTensor at run time (NpRigidBodyTemplate.h: the core keeps inverse mass / inverse inertia; 0 = infinite): domain randomisation
+__global__ void k_set_mass(uint32_t n, const uint32_t* __restrict__ idx, const float* __restrict__ massInertia4, const uint32_t* __restrict__ dynActor, float4* __restrict__ pos, float4* __restrict__ invInertia) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= n) return;
+  const uint32_t a = dynActor[idx[t]]; const float* m = massInertia4 + (size_t)t * 4;
+  pos[a].w = m[0] > 0.f ? 1.0f / m[0] : 0.f;
+  const float w = invInertia[a].w;
+  invInertia[a] = make_float4(m[1] > 0.f ? 1.0f / m[1] : 0.f, m[2] > 0.f ? 1.0f / m[2] : 0.f, m[3] > 0.f ? 1.0f / m[3] : 0.f, w);
+}
+PXB_API int pxb_scene_set_mass_properties(PxbScene* s, const uint32_t* indices, const float* massInertia4, uint32_t nb) { DeviceGuard dg_(s);
+  if (!s || (nb && (!indices || !massInertia4))) return fail(PXB_ERR_INVALID, "null argument");
+  if (s->stepping) return fail(PXB_ERR_INVALID, "illegal while the simulation is running");
+  if (!nb) return PXB_OK;
+  if (nb > s->capA) return fail(PXB_ERR_INVALID, "nb exceeds the actor capacity");
+  for (uint32_t i = 0; i < nb; ++i) {
+    if (indices[i] >= s->nDyn) return fail(PXB_ERR_INVALID, "index out of range");
+    if (s->recs[s->dynActor[indices[i]]].flags & PXB_ACTOR_KINEMATIC) return fail(PXB_ERR_INVALID, "a kinematic body has no mass properties");
+    for (int k = 0; k < 4; ++k) if (!(massInertia4[4 * i + k] >= 0.f) || !std::isfinite(massInertia4[4 * i + k])) return fail(PXB_ERR_INVALID, "mass / inertia must be finite and >= 0 (0 = infinite)");
+  }
+  if (s->velPending) { CK(cudaStreamWaitEvent(s->stream, s->velEvent, 0)); s->velPending = false; }
+  cudaStream_t st = s->stream;
+  float* d = s->stage;   // staging: 4 floats per body fit the first region (7 per actor)
+  CK(cudaMemcpyAsync(d, massInertia4, 16 * (size_t)nb, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(s->stageIdx, indices, 4 * (size_t)nb, cudaMemcpyHostToDevice, st));
+  LAUNCH(k_set_mass, cdiv(nb, 128), 128, nb, s->stageIdx, d, s->dynActorDev, s->pos, s->invInertia);
+  CK(cudaStreamSynchronize(st));
+  for (uint32_t i = 0; i < nb; ++i) { ActorRec& r = s->recs[s->dynActor[indices[i]]]; r.mass = massInertia4[4 * i]; r.inertia[0] = massInertia4[4 * i + 1]; r.inertia[1] = massInertia4[4 * i + 2]; r.inertia[2] = massInertia4[4 * i + 3]; }
+  return PXB_OK;
+}
+
 // PxScene::setGravity (NpScene.cpp:331-342 -> Sc::Scene::mGravity, read by the next step's pre-integration): domain randomisation changes it between steps
 PXB_API int pxb_scene_set_gravity(PxbScene* s, const float* gravity3) { DeviceGuard dg_(s);
   if (!s || !gravity3) return fail(PXB_ERR_INVALID, "null argument");

@@ -32,7 +32,7 @@ EXPORTS = [
     "pxb_scene_get_states_device", "pxb_scene_uses_env_path", "pxb_scene_get_sleep_data", "pxb_get_rigid_dynamic_data_async", "pxb_set_rigid_dynamic_data_async", "pxb_scene_sync", "pxb_scatter_to_peers",
     "pxb_scene_set_state_export", "pxb_peer_signal", "pxb_peer_wait", "pxb_bp_create", "pxb_bp_release", "pxb_bp_update", "pxb_bp_fetch",
     "pxb_scene_set_materials", "pxb_scene_remove_actors", "pxb_tensor_read_device", "pxb_tensor_write_device", "pxb_scene_num_touch_found", "pxb_scene_num_touch_lost", "pxb_scene_get_touch_found", "pxb_scene_get_touch_lost", "pxb_scene_enable_contact_data", "pxb_scene_copy_contact_data", "pxb_scene_set_local_poses", "pxb_scene_set_filter_shader", "pxb_scene_set_filter_data", "pxb_scene_set_shape_offsets",
-    "pxb_get_rigid_dynamic_data_device_ev", "pxb_set_rigid_dynamic_data_device_ev", "pxb_scene_set_kinematic_targets", "pxb_scene_set_kinematic_targets_device", "pxb_scene_set_gravity",
+    "pxb_get_rigid_dynamic_data_device_ev", "pxb_set_rigid_dynamic_data_device_ev", "pxb_scene_set_kinematic_targets", "pxb_scene_set_kinematic_targets_device", "pxb_scene_set_gravity", "pxb_scene_set_mass_properties",
 ]
 
 RD_GLOBAL_POSE, RD_LINEAR_VELOCITY, RD_ANGULAR_VELOCITY, RD_FORCE, RD_TORQUE = 0, 1, 2, 3, 4   # PxRigidDynamicGPUAPIRead/WriteType
@@ -95,6 +95,7 @@ def load_library():
         getattr(lib, f).argtypes = [vp, vp, vp, i32, u32]
     lib.pxb_scene_set_kinematic_targets.argtypes = [vp, vp, vp, u32]
     lib.pxb_scene_set_gravity.argtypes = [vp, vp]
+    lib.pxb_scene_set_mass_properties.argtypes = [vp, vp, vp, u32]
     lib.pxb_scene_set_kinematic_targets_device.argtypes = [vp, vp, vp, u32]
     for f in ("pxb_get_rigid_dynamic_data_device_ev", "pxb_set_rigid_dynamic_data_device_ev"):
         getattr(lib, f).argtypes = [vp, vp, vp, i32, u32, vp, vp]
@@ -246,6 +247,12 @@ class Scene:
         d = np.ascontiguousarray(data, dtype=np.float32)
         idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.uint32)
         _check(self._lib, self._lib.pxb_set_rigid_dynamic_data(self._h, _ptr(d), _ptr(idx), data_type, len(d)))
+
+    def setMassProperties(self, indices, mass_inertia):
+        """PxRigidBody::setMass / setMassSpaceInertiaTensor for the dynamic bodies `indices`: (n, 4) rows (mass, inertia xyz)."""
+        i = np.ascontiguousarray(indices, dtype=np.uint32); m = np.ascontiguousarray(mass_inertia, dtype=np.float32)
+        assert m.shape == (len(i), 4)
+        _check(self._lib, self._lib.pxb_scene_set_mass_properties(self._h, _ptr(i), _ptr(m), len(i)))
 
     def setGravity(self, g):
         """PxScene::setGravity: read by the next simulate."""

@@ -37,6 +37,7 @@ def lib():
         L.pxo_scene_set_forces.argtypes = [vp, vp, vp]
         L.pxo_scene_set_kinematic_targets.argtypes = [vp, vp, vp, u32]
         L.pxo_scene_set_gravity.argtypes = [vp, vp]
+        L.pxo_scene_set_mass_properties.argtypes = [vp, vp, vp, u32]
         L.pxo_scene_compute_bounds.argtypes = [vp]
         L.pxo_scene_broadphase.argtypes = [vp]
         _LIB = L
@@ -81,6 +82,10 @@ class OracleScene:
         f = None if forces is None else np.ascontiguousarray(forces, dtype=np.float32)
         t = None if torques is None else np.ascontiguousarray(torques, dtype=np.float32)
         self.L.pxo_scene_set_forces(self.h, _p(f), _p(t))
+
+    def setMassProperties(self, dyn_indices, mass_inertia):
+        i = np.ascontiguousarray(dyn_indices, dtype=np.uint32); m = np.ascontiguousarray(mass_inertia, dtype=np.float32)
+        self.L.pxo_scene_set_mass_properties(self.h, _p(i), _p(m), len(i))
 
     def setGravity(self, g):
         v = np.ascontiguousarray(g, dtype=np.float32).reshape(3)

@@ -1532,3 +1532,35 @@ def test_set_gravity_between_steps(oracle, env_path):
     with pytest.raises(engine.PhysxB200Error):
         gpu.setGravity([0, 0, 0])
     gpu.fetchResults(True)
+
+
+# ---- PxRigidBody::setMass / setMassSpaceInertiaTensor between steps ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_path", [True, False])
+def test_set_mass_properties_between_steps(oracle, env_path):
+    """Mass randomisation between steps: GPU == oracle bit for bit after the change (the heavier boxes sink differently into the stacks below), the tensor front end reads the new
+    masses back, kinematic bodies and bad values are rejected."""
+    sc = scenes.env_grid_stacks(n_envs=4, jitter=0.01)
+    gpu, cpu = engine.Scene(sc, env_path=env_path), oracle.OracleScene(sc)
+    rng = np.random.RandomState(5)
+    idx = np.arange(0, sc.n_dynamic, 3, dtype=np.uint32)
+    dyn = np.nonzero(sc.actors["flags"] & 1)[0]
+    base = np.concatenate([sc.actors["mass"][dyn][idx, None], sc.actors["inertia"][dyn][idx]], axis=1)
+    for t in range(16):
+        if t in (3, 9):
+            m = (base * rng.uniform(0.3, 4.0, (len(idx), 1))).astype(np.float32)
+            gpu.setMassProperties(idx, m); cpu.setMassProperties(idx, m)
+        gpu.step(); cpu.step()
+        assert np.array_equal(gpu.getStates(), cpu.getStates()), f"step {t}"
+    ref = engine.Scene(sc, env_path=env_path)
+    for t in range(16):
+        ref.step()
+    assert np.abs(ref.getStates() - gpu.getStates()).max() > 1e-5                       # the change matters
+    with pytest.raises(engine.PhysxB200Error):
+        gpu.setMassProperties(idx[:1], np.array([[-1.0, 1, 1, 1]], np.float32))
+    with pytest.raises(engine.PhysxB200Error):
+        gpu.setMassProperties(np.array([10 ** 6], np.uint32), m[:1])
+    z, ksc = util.load_golden("kinematic_mix")
+    kin = util.kinematic_indices(ksc)
+    with pytest.raises(engine.PhysxB200Error):
+        engine.Scene(ksc).setMassProperties(kin[:1], m[:1])
