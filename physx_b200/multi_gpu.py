@@ -30,7 +30,8 @@ def shard_scene(scene: _scenes.Scene, world_size: int, rank: int) -> _scenes.Sce
     """Sub-scene with the actors of this rank's environments plus every env-less (shared) actor, e.g. the
     ground plane.  Actor order is preserved, so local dynamic-body order = global order restricted to the shard.
     Environment ids are rebased to start at 0 on every rank (the engine builds one CTA / warp per id up to the largest one),
-    and the convex hulls travel with the shard (point clouds and the cooked section; hull indices are unchanged)."""
+    and the convex hulls travel with the shard (point clouds and the cooked section; hull indices are unchanged), as do the per-actor
+    sections of the scene format.  Aggregate ids stay global (an aggregate lives inside one environment)."""
     env = scene.actors["envId"]
     n_envs = int(env[env != _scenes.NO_ENV].max()) + 1 if np.any(env != _scenes.NO_ENV) else 0
     lo, hi = env_range(n_envs, world_size, rank)
@@ -38,7 +39,10 @@ def shard_scene(scene: _scenes.Scene, world_size: int, rank: int) -> _scenes.Sce
     actors = scene.actors[keep].copy()
     own = actors["envId"] != _scenes.NO_ENV
     actors["envId"][own] -= np.uint32(lo)
-    return _scenes.Scene(scene.header, actors, scene.hulls, scene.cooked, scene.materials)
+    # per-actor sections travel with their actors (local poses, PxFilterData, per-shape offsets); kinematic flags and aggregate ids are fields of the actor records
+    rows = lambda x: None if x is None else x[keep].copy()
+    return _scenes.Scene(scene.header, actors, scene.hulls, scene.cooked, scene.materials, local_poses=rows(scene.local_poses), filter_config=scene.filter_config,
+                         filter_data=rows(scene.filter_data), shape_offsets=rows(scene.shape_offsets))
 
 
 def gather_layout(counts):

@@ -113,3 +113,31 @@ def test_state_all_gather_world2_gloo(counts):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_shard_scene_carries_per_actor_sections_and_flags():
+    """local poses, PxFilterData, per-shape offsets are sliced with the actors; kinematic flags and aggregate ids are fields of the actor records"""
+    from physx_b200 import scenes
+    sc = scenes.kinematic_mix(n_envs=4)
+    n = len(sc.actors)
+    lp = scenes.identity_local_poses(n); lp["shapeP"][:, 0] = np.arange(n)
+    fd = np.arange(4 * n, dtype=np.uint32).reshape(n, 4)
+    so = np.stack([0.02 + 0.001 * np.arange(n), np.zeros(n)], axis=1).astype(np.float32)
+    sc.actors["aggregate"][1:4] = 7
+    full = scenes.Scene(sc.header, sc.actors, local_poses=lp, filter_config=scenes.default_filter_config(), filter_data=fd, shape_offsets=so)
+    seen = 0
+    for rank in range(2):
+        sh = multi_gpu.shard_scene(full, 2, rank)
+        keep = np.nonzero((full.actors["envId"] == scenes.NO_ENV) | ((full.actors["envId"] >= 2 * rank) & (full.actors["envId"] < 2 * rank + 2)))[0]
+        assert len(sh.actors) == len(keep)
+        assert np.array_equal(sh.local_poses["shapeP"][:, 0], lp["shapeP"][keep, 0]) and np.array_equal(sh.filter_data, fd[keep]) and np.array_equal(sh.shape_offsets, so[keep])
+        assert np.array_equal(sh.actors["flags"], full.actors["flags"][keep]) and np.array_equal(sh.actors["aggregate"], full.actors["aggregate"][keep])
+        assert np.count_nonzero(sh.actors["flags"] & scenes.ACTOR_KINEMATIC) == 10 and sh.actors["envId"][sh.actors["envId"] != scenes.NO_ENV].max() == 1
+        rt = scenes.Scene.load  # round trip through the scene format keeps the sections
+        import tempfile
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            f.write(sh.tobytes()); f.flush()
+            back = rt(f.name)
+        assert np.array_equal(back.shape_offsets, sh.shape_offsets) and np.array_equal(back.filter_data, sh.filter_data)
+        seen += int((sh.actors["aggregate"] == 7).sum())
+    assert seen == 3
